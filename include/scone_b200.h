@@ -1,0 +1,167 @@
+/*
+ * scone_b200.h — C ABI of the B200-native SCoNe hot path (libscone_b200.so).
+ *
+ * The reference (nglaze00/SCoNe_GCN) is pure Python/JAX and has no FFI; the seam this library sits
+ * behind is the per-sample model function that Scone_GCN.setup vmaps
+ * (trajectory_analysis/scone_trajectory_model.py:256) and that Scone_GCN.loss / accuracy / train call
+ * (:46, :64, :307).  Each entry point below names the reference code it replaces.  All functions
+ *   - return 0 on success, non-zero on error (message: scone_last_error(), thread-local),
+ *   - never throw across the ABI, never allocate behind the caller's back except inside the opaque
+ *     handles (scone_complex, scone_model), and launch only on the stream they are given
+ *     (`stream` is a cudaStream_t passed as void*; NULL = legacy default stream),
+ *   - take plain pointers and sizes.  "dev" = device pointer, "host" = host pointer.
+ *
+ * Device layouts (fp32, row-major):
+ *   activations  H[e][t][c]  -> ((e * b) + t) * C + c      e < E edges, t < b trajectories, c < C channels
+ *   flows        X[e][t]     -> e * b + t                  (layer-0 input, C = 1)
+ *   weights      flat concatenation of the reference's weight list, each [C_in][C_out] row-major, in
+ *                list order W[0], W[1], ... (scone_trajectory_model.py:222-237).
+ */
+#ifndef SCONE_B200_H
+#define SCONE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCONE_B200_VERSION 100
+
+typedef struct scone_complex scone_complex;   /* simplicial complex: device-resident index arrays */
+typedef struct scone_model scone_model;       /* weights + Adam state + activation workspace     */
+
+enum { SCONE_MODEL_SCONE = 0, SCONE_MODEL_EBLI = 1, SCONE_MODEL_BUNCH = 2 };
+enum { SCONE_ACT_TANH = 0, SCONE_ACT_LEAKY_RELU = 1, SCONE_ACT_RELU = 2 };
+
+int scone_version(void);
+const char* scone_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Complex construction — replaces the dense operator assembly
+ *   L1_lower = B1.T @ B1 ; L1_upper = B2 @ B2.T ; ebli: L1, L1 @ L1      trajectory_experiments.py:239-253
+ *   nbrhoods / n_nbrs / B1_jax / Bconds_func                               trajectory_experiments.py:262-303
+ * Input is the signed incidence structure itself (what B1.npy / B2.npy encode,
+ * synthetic_data_gen.py:139-161): per edge its two end nodes and their B1 signs, per triangle its three
+ * edges and their B2 signs.  edge_signs == NULL means (-1,+1) (tail, head); `-flip_edges 1`
+ * (trajectory_experiments.py:214-219,242-244,290) is expressed by passing the flipped signs.
+ * All integer work is exact.  model selects which shift pair is built: scone -> (L_lower, L_upper),
+ * ebli -> (L1, L1^2).
+ * ------------------------------------------------------------------------------------------- */
+int scone_complex_create(int32_t n_nodes, int32_t n_edges, int32_t n_tris,
+                         const int32_t* edge_nodes /* host [E][2] */, const int8_t* edge_signs /* host [E][2] or NULL */,
+                         const int32_t* tri_edges /* host [F][3] */, const int8_t* tri_signs /* host [F][3] */,
+                         int32_t model, scone_complex** out);
+/* Same exact index construction, but WITHOUT touching a GPU: the handle only serves the copy-out getters
+ * below (bit-exact index parity tests on a CPU-only machine); every compute entry point refuses it. */
+int scone_complex_create_index_only(int32_t n_nodes, int32_t n_edges, int32_t n_tris,
+                                    const int32_t* edge_nodes, const int8_t* edge_signs,
+                                    const int32_t* tri_edges, const int8_t* tri_signs,
+                                    int32_t model, scone_complex** out);
+int scone_complex_destroy(scone_complex* cx);
+/* dims: N, E, F, D (max degree), nnz of shift 0, nnz of shift 1 */
+int scone_complex_dims(const scone_complex* cx, int32_t* n_nodes, int32_t* n_edges, int32_t* n_tris,
+                       int32_t* max_degree, int64_t* nnz0, int64_t* nnz1);
+/* copy-out (host buffers) for bit-exact parity tests */
+int scone_complex_get_shift_csr(const scone_complex* cx, int32_t which, int32_t* rowptr /* [E+1] */,
+                                int32_t* col /* [nnz] */, float* val /* [nnz] */);
+int scone_complex_get_nbrhoods(const scone_complex* cx, int32_t* nbrhoods /* [N][D], pad -1 */);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernel-level entry points (device pointers).  These are what a jax.ffi handler binds, one per
+ * custom call; INTEGRATION.md shows the shim.
+ * ------------------------------------------------------------------------------------------- */
+
+/* path_to_flow output (synthetic_data_gen.py:327-344) in sparse form -> dense X[E][b].
+ * Trajectory t owns entries [traj_ptr[t], traj_ptr[t+1]) of (flow_edge, flow_val). */
+int scone_flows_to_dense(const scone_complex* cx, int32_t b, const int32_t* traj_ptr_dev /* [b+1] */,
+                         const int32_t* flow_edge_dev, const float* flow_val_dev, float* X_dev /* [E][b] */,
+                         void* stream);
+
+/* One fused Hodge-Laplacian convolution layer, forward:
+ *   Hout = act(Hin W0 + (S0 Hin) W1 + (S1 Hin) W2)                       trajectory_experiments.py:145-149,163-167
+ * Hin [E][b][cin], Hout [E][b][cout], W* [cin][cout] (device). */
+int scone_layer_forward(const scone_complex* cx, int32_t act, int32_t b, int32_t cin, int32_t cout,
+                        const float* Hin_dev, const float* W0_dev, const float* W1_dev, const float* W2_dev,
+                        float* Hout_dev, void* stream);
+
+/* Backward of the same layer (what jax.grad derives from the lines above, scone_trajectory_model.py:307).
+ * G_dev = dL/dZ of this layer ( = dL/dHout * act'(Hout), already multiplied) [E][b][cout].
+ * Outputs:  Gprev_dev [E][b][cin] = dL/dZ of the previous layer = (dL/dHin) * act'(Hin)
+ *           (pass NULL for the first layer: the reference never differentiates w.r.t. the flows);
+ *           dW_dev [3][cin][cout] += sum over rows, reduced in a fixed order (deterministic, no atomics).
+ * workspace: scone_layer_backward_workspace_bytes(cin, cout) bytes, device. */
+int64_t scone_layer_backward_workspace_bytes(int32_t cin, int32_t cout);
+int scone_layer_backward(const scone_complex* cx, int32_t act, int32_t b, int32_t cin, int32_t cout,
+                         const float* G_dev, const float* Hin_dev,
+                         const float* W0_dev, const float* W1_dev, const float* W2_dev,
+                         float* Gprev_dev, float* dW_dev, int32_t accumulate, void* workspace_dev, void* stream);
+
+/* Readout + padded log-softmax (+ NLL and its gradient):
+ *   logits = Bcond(last_node) @ H_L @ w_out ; logits - logsumexp(logits)   trajectory_experiments.py:151-152,298-303
+ *   loss term  -sum(preds * y) over masked rows                            scone_trajectory_model.py:46,54
+ * logprobs_dev [b][D].  If GL_dev != NULL also writes GL = dL/dZ of the last conv layer
+ * [E][b][C] (zero except on edges incident to the neighbours of last_node), the w_out gradient
+ * (dwout_dev [C]), the masked NLL sum (*nll_sum_dev) and the mask count (*count_dev) — each reduced over
+ * trajectories in ascending order and added to the destination when accumulate != 0.
+ * workspace_dev: scone_readout_workspace(b, C) bytes (gradient mode only).
+ * target_idx_dev[t] = argmax of the one-hot target row; mask_dev[t] in {0,1}; scale multiplies the
+ * upstream gradient (1 / number of masked rows in the whole batch). */
+int64_t scone_readout_workspace(int32_t b, int32_t C);
+int scone_readout(const scone_complex* cx, int32_t act, int32_t b, int32_t C,
+                  const float* HL_dev, const float* wout_dev, const int32_t* last_nodes_dev,
+                  float* logprobs_dev,
+                  const int32_t* target_idx_dev, const float* mask_dev, float scale,
+                  float* GL_dev, float* dwout_dev, float* nll_sum_dev, float* count_dev, int32_t accumulate,
+                  void* workspace_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Model-level entry points — replace Scone_GCN.{setup, loss, accuracy, train's adam_step}
+ * (scone_trajectory_model.py:42-71,215-262,300-326) for -model scone / ebli.
+ * hidden[l] = channel count of layer l (the reference's hidden_layers[l][1]); micro_batch = number of
+ * trajectories resident per pass (activations are [E][micro_batch][C] per layer).
+ * ------------------------------------------------------------------------------------------- */
+int scone_model_create(const scone_complex* cx, int32_t n_layers, const int32_t* hidden, int32_t micro_batch,
+                       scone_model** out);
+int scone_model_destroy(scone_model* m);
+int64_t scone_model_num_params(const scone_model* m);
+int scone_model_set_weights(scone_model* m, const float* weights_host);     /* also resets Adam state */
+int scone_model_get_weights(const scone_model* m, float* weights_host);
+float* scone_model_weights_dev(scone_model* m);                              /* flat device weights      */
+float* scone_model_grads_dev(scone_model* m);                                /* flat [n_params + 2]: grads, nll_sum, count */
+
+/* Batched forward: log-probs for B trajectories given as sparse flows (HOST buffers; copies inside).
+ * Replaces self.model(weights, *shifts, *inputs) (scone_trajectory_model.py:46,64). */
+int scone_model_forward_host(scone_model* m, int32_t B, const int32_t* traj_ptr /* [B+1] */,
+                             const int32_t* flow_edge, const float* flow_val, const int32_t* last_nodes,
+                             float* logprobs_out /* [B][D] */, void* stream);
+/* Same with DEVICE buffers (inputs already resident). */
+int scone_model_forward_dev(scone_model* m, int32_t B, const int32_t* traj_ptr_dev, const int32_t* flow_edge_dev,
+                            const float* flow_val_dev, const int32_t* last_nodes_dev, float* logprobs_dev, void* stream);
+
+/* Loss + weight gradients over B trajectories (forward + backward, micro-batched), accumulating the
+ * UNNORMALISED sums into the model's flat gradient buffer [grads | nll_sum | count]:
+ *   grads += sum_t mask_t * d(-log p_t[target_t])/dW ;  nll_sum += ... ; count += sum(mask).
+ * Replaces grad(self.loss) minus the ridge term and the 1/sum(mask) factor, which scone_model_adam_step
+ * applies after the (optional) cross-GPU all-reduce of that buffer.  zero_first != 0 clears the buffer. */
+int scone_model_loss_grad_dev(scone_model* m, int32_t B, const int32_t* traj_ptr_dev, const int32_t* flow_edge_dev,
+                              const float* flow_val_dev, const int32_t* last_nodes_dev,
+                              const int32_t* target_idx_dev, const float* mask_dev, int32_t zero_first, void* stream);
+int scone_model_loss_grad_host(scone_model* m, int32_t B, const int32_t* traj_ptr, const int32_t* flow_edge,
+                               const float* flow_val, const int32_t* last_nodes,
+                               const int32_t* target_idx, const float* mask, int32_t zero_first, void* stream);
+/* Read back [grads | nll_sum | count] (host, n_params + 2 floats); synchronises the stream. */
+int scone_model_read_grads(scone_model* m, float* out_host, void* stream);
+
+/* Adam step on the accumulated buffer (upstream JAX `adam`, used at scone_trajectory_model.py:300,310):
+ *   g = grads / count + 2 * weight_decay * W ;  m,v update ;  W -= lr * mhat / (sqrt(vhat) + eps)
+ * step = 0-based iteration index i. */
+int scone_model_adam_step(scone_model* m, int32_t step, float lr, float weight_decay, void* stream);
+
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+int64_t scone_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCONE_B200_H */

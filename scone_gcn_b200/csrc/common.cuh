@@ -1,0 +1,77 @@
+// common.cuh — shared declarations for libscone_b200.so (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <vector>
+#include "scone_b200.h"
+
+void scone_set_error(const char* fmt, ...);
+extern std::atomic<long long> g_scone_launches;
+
+#define SCONE_CUDA(x)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (x);                                                                           \
+        if (e_ != cudaSuccess) {                                                                        \
+            scone_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_));         \
+            return 1;                                                                                   \
+        }                                                                                               \
+    } while (0)
+
+#define SCONE_REQUIRE(cond, ...)                                                                        \
+    do {                                                                                                \
+        if (!(cond)) {                                                                                  \
+            scone_set_error(__VA_ARGS__);                                                               \
+            return 2;                                                                                   \
+        }                                                                                               \
+    } while (0)
+
+#define SCONE_LAUNCHED()                                                                                \
+    do {                                                                                                \
+        g_scone_launches.fetch_add(1, std::memory_order_relaxed);                                       \
+        SCONE_CUDA(cudaGetLastError());                                                                 \
+    } while (0)
+
+// Integer-valued shift operator in CSR form.  ent[p] = {column, float bits of the coefficient};
+// columns ascending inside a row (fixed, deterministic summation order).
+struct DevCsr {
+    const int32_t* rowptr;
+    const int2* ent;
+};
+
+struct HostCsr {
+    std::vector<int32_t> rowptr;
+    std::vector<int32_t> col;
+    std::vector<float> val;
+};
+
+struct scone_complex {
+    int32_t N = 0, E = 0, F = 0, D = 0, model = 0;
+    int num_sms = 148;
+    bool host_only = false;                    // built by scone_complex_create_index_only: no device arrays
+    HostCsr hS[2];
+    std::vector<int32_t> h_nbrhoods;           // [N][D], pad -1
+    // device
+    int32_t* d_rowptr[2] = {nullptr, nullptr};
+    int2* d_ent[2] = {nullptr, nullptr};
+    int32_t* d_nbrhoods = nullptr;             // [N][D]
+    int32_t* d_inc_ptr = nullptr;              // [N+1]   B1 rows: node -> incident edges
+    int2* d_inc_ent = nullptr;                 // [2E]    {edge, float bits of sign}, edge ascending
+    DevCsr S(int k) const { return DevCsr{d_rowptr[k], d_ent[k]}; }
+};
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// internal kernels-level helpers implemented in scone_kernels.cu
+int scone_layer0_forward(const scone_complex* cx, int32_t act, int32_t b, int32_t cout, const float* X_dev,
+                         const float* W0, const float* W1, const float* W2, float* Hout, void* stream);
+int64_t scone_layer0_backward_workspace_bytes(int32_t cout);
+int scone_layer0_backward(const scone_complex* cx, int32_t b, int32_t cout, const float* G_dev, const float* X_dev,
+                          float* dW_dev, int32_t accumulate, void* workspace, void* stream);
+int64_t scone_readout_workspace_bytes(int32_t b, int32_t C);
+int scone_readout_ws(const scone_complex* cx, int32_t act, int32_t b, int32_t C, const float* HL, const float* wout,
+                     const int32_t* last_nodes, float* logprobs, const int32_t* target_idx, const float* mask,
+                     float scale, float* GL, float* dwout, float* nll_sum, float* count, int32_t accumulate,
+                     void* workspace, void* stream);
+int scone_adam_launch(float* W, float* m, float* v, const float* gradbuf, int64_t n, int32_t step, float lr,
+                      float wd, void* stream);

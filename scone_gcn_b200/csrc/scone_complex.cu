@@ -1,0 +1,283 @@
+// scone_complex.cu — host-side exact integer construction of the device-resident complex.
+//
+// Replaces the dense operator assembly of the reference
+//   L1_lower = B1.T @ B1, L1_upper = B2 @ B2.T, ebli: L1 = L_lower + L_upper, L1 @ L1
+//     (trajectory_analysis/trajectory_experiments.py:239-253)
+//   nbrhoods / B1_jax / Bconds_func (trajectory_experiments.py:272-303)
+// with CSR index arrays built from the signed incidence lists (2 nonzeros per B1 column, 3 per B2
+// column).  All arithmetic here is int32 and exact; coefficients are stored as fp32 (|v| <= 2^24).
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+std::atomic<long long> g_scone_launches{0};
+
+void scone_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* scone_last_error(void) { return g_err; }
+extern "C" int scone_version(void) { return SCONE_B200_VERSION; }
+extern "C" int64_t scone_launch_count(void) { return g_scone_launches.load(); }
+
+namespace {
+
+struct IntCsr {
+    std::vector<int32_t> rowptr, col, val;
+};
+
+// C = A * B for square int CSR matrices with sorted columns; drops exact zeros.
+IntCsr spgemm(const IntCsr& A, const IntCsr& B, int32_t n) {
+    IntCsr C;
+    C.rowptr.assign(n + 1, 0);
+    std::vector<int32_t> acc(n, 0), mark(n, -1), touched;
+    for (int32_t i = 0; i < n; ++i) {
+        touched.clear();
+        for (int32_t p = A.rowptr[i]; p < A.rowptr[i + 1]; ++p) {
+            int32_t k = A.col[p], a = A.val[p];
+            for (int32_t q = B.rowptr[k]; q < B.rowptr[k + 1]; ++q) {
+                int32_t j = B.col[q];
+                if (mark[j] != i) {
+                    mark[j] = i;
+                    acc[j] = 0;
+                    touched.push_back(j);
+                }
+                acc[j] += a * B.val[q];
+            }
+        }
+        std::sort(touched.begin(), touched.end());
+        for (int32_t j : touched)
+            if (acc[j] != 0) {
+                C.col.push_back(j);
+                C.val.push_back(acc[j]);
+            }
+        C.rowptr[i + 1] = (int32_t)C.col.size();
+    }
+    return C;
+}
+
+// C = A + B (sorted merge), drops exact zeros (the shared-triangle off-diagonals of L1 cancel).
+IntCsr spadd(const IntCsr& A, const IntCsr& B, int32_t n) {
+    IntCsr C;
+    C.rowptr.assign(n + 1, 0);
+    for (int32_t i = 0; i < n; ++i) {
+        int32_t p = A.rowptr[i], pe = A.rowptr[i + 1], q = B.rowptr[i], qe = B.rowptr[i + 1];
+        while (p < pe || q < qe) {
+            int32_t c, v;
+            if (q >= qe || (p < pe && A.col[p] < B.col[q])) { c = A.col[p]; v = A.val[p]; ++p; }
+            else if (p >= pe || B.col[q] < A.col[p]) { c = B.col[q]; v = B.val[q]; ++q; }
+            else { c = A.col[p]; v = A.val[p] + B.val[q]; ++p; ++q; }
+            if (v != 0) { C.col.push_back(c); C.val.push_back(v); }
+        }
+        C.rowptr[i + 1] = (int32_t)C.col.size();
+    }
+    return C;
+}
+
+// L = M^T M restricted to the structure "rows of M are simplices of the other dimension":
+// given for every column-simplex (edge) its incident row-simplices with signs, and for every
+// row-simplex its incident edges with signs, L[e][e'] = sum_r s(r,e) s(r,e').
+IntCsr gram(int32_t n_edges, const std::vector<std::vector<std::pair<int32_t, int32_t>>>& edge_to_rows,
+            const std::vector<std::vector<std::pair<int32_t, int32_t>>>& row_to_edges) {
+    IntCsr L;
+    L.rowptr.assign(n_edges + 1, 0);
+    std::map<int32_t, int32_t> acc;
+    for (int32_t e = 0; e < n_edges; ++e) {
+        acc.clear();
+        for (auto& rs : edge_to_rows[e])
+            for (auto& es : row_to_edges[rs.first]) acc[es.first] += rs.second * es.second;
+        for (auto& kv : acc)
+            if (kv.second != 0) { L.col.push_back(kv.first); L.val.push_back(kv.second); }
+        L.rowptr[e + 1] = (int32_t)L.col.size();
+    }
+    return L;
+}
+
+template <typename T>
+int upload(T** dst, const std::vector<T>& src) {
+    size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
+    SCONE_CUDA(cudaMalloc((void**)dst, bytes));
+    if (!src.empty()) SCONE_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+}  // namespace
+
+static int complex_create_impl(int32_t N, int32_t E, int32_t F, const int32_t* edge_nodes, const int8_t* edge_signs,
+                               const int32_t* tri_edges, const int8_t* tri_signs, int32_t model, bool upload_to_device,
+                               scone_complex** out) {
+    SCONE_REQUIRE(out != nullptr, "scone_complex_create: out is NULL");
+    *out = nullptr;
+    SCONE_REQUIRE(N > 0 && E > 0 && F >= 0, "scone_complex_create: bad sizes N=%d E=%d F=%d", N, E, F);
+    SCONE_REQUIRE(edge_nodes != nullptr && (F == 0 || (tri_edges != nullptr && tri_signs != nullptr)),
+                  "scone_complex_create: NULL index array");
+    SCONE_REQUIRE(model == SCONE_MODEL_SCONE || model == SCONE_MODEL_EBLI,
+                  "scone_complex_create: model must be scone (0) or ebli (1), got %d", model);
+    using PairList = std::vector<std::vector<std::pair<int32_t, int32_t>>>;
+    PairList edge_to_nodes(E), node_to_edges(N), edge_to_tris(E), tri_to_edges(F);
+    for (int32_t e = 0; e < E; ++e) {
+        for (int k = 0; k < 2; ++k) {
+            int32_t n = edge_nodes[2 * e + k];
+            SCONE_REQUIRE(n >= 0 && n < N, "scone_complex_create: edge %d has node %d outside [0,%d)", e, n, N);
+            int32_t s = edge_signs ? edge_signs[2 * e + k] : (k == 0 ? -1 : 1);
+            SCONE_REQUIRE(s == 1 || s == -1, "scone_complex_create: edge %d sign %d not +-1", e, s);
+            edge_to_nodes[e].push_back({n, s});
+            node_to_edges[n].push_back({e, s});          // e ascending by construction
+        }
+        SCONE_REQUIRE(edge_nodes[2 * e] != edge_nodes[2 * e + 1], "scone_complex_create: edge %d is a self loop", e);
+    }
+    for (int32_t f = 0; f < F; ++f)
+        for (int k = 0; k < 3; ++k) {
+            int32_t e = tri_edges[3 * f + k], s = tri_signs[3 * f + k];
+            SCONE_REQUIRE(e >= 0 && e < E, "scone_complex_create: triangle %d has edge %d outside [0,%d)", f, e, E);
+            SCONE_REQUIRE(s == 1 || s == -1, "scone_complex_create: triangle %d sign %d not +-1", f, s);
+            edge_to_tris[e].push_back({f, s});
+            tri_to_edges[f].push_back({e, s});
+        }
+
+    IntCsr Ll = gram(E, edge_to_nodes, node_to_edges);     // B1^T B1
+    IntCsr Lu = gram(E, edge_to_tris, tri_to_edges);       // B2 B2^T
+    IntCsr S0, S1;
+    if (model == SCONE_MODEL_SCONE) {
+        S0 = std::move(Ll);
+        S1 = std::move(Lu);
+    } else {
+        S0 = spadd(Ll, Lu, E);
+        S1 = spgemm(S0, S0, E);
+    }
+
+    scone_complex* cx = new scone_complex();
+    cx->N = N; cx->E = E; cx->F = F; cx->model = model;
+    IntCsr* src[2] = {&S0, &S1};
+    for (int k = 0; k < 2; ++k) {
+        cx->hS[k].rowptr = src[k]->rowptr;
+        cx->hS[k].col = src[k]->col;
+        cx->hS[k].val.resize(src[k]->val.size());
+        for (size_t i = 0; i < src[k]->val.size(); ++i) {
+            SCONE_REQUIRE(std::abs(src[k]->val[i]) < (1 << 24), "shift coefficient not exactly representable in fp32");
+            cx->hS[k].val[i] = (float)src[k]->val[i];
+        }
+    }
+    // neighbour table: sorted ascending, padded with -1 (trajectory_experiments.py:279)
+    std::vector<std::vector<int32_t>> nbrs(N);
+    for (int32_t e = 0; e < E; ++e) {
+        nbrs[edge_nodes[2 * e]].push_back(edge_nodes[2 * e + 1]);
+        nbrs[edge_nodes[2 * e + 1]].push_back(edge_nodes[2 * e]);
+    }
+    int32_t D = 0;
+    for (auto& v : nbrs) {
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+        D = std::max<int32_t>(D, (int32_t)v.size());
+    }
+    cx->D = D;
+    cx->h_nbrhoods.assign((size_t)N * std::max(D, 1), -1);
+    for (int32_t n = 0; n < N; ++n)
+        for (size_t j = 0; j < nbrs[n].size(); ++j) cx->h_nbrhoods[(size_t)n * D + j] = nbrs[n][j];
+
+    if (!upload_to_device) {                 // index-only handle: getters work, every device op is refused
+        cx->host_only = true;
+        *out = cx;
+        return 0;
+    }
+    int dev = 0;
+    cudaError_t ce = cudaGetDevice(&dev);
+    if (ce != cudaSuccess) {
+        scone_set_error("scone_complex_create: no CUDA device (%s); this library has no CPU path", cudaGetErrorString(ce));
+        delete cx;
+        return 3;
+    }
+    cudaDeviceGetAttribute(&cx->num_sms, cudaDevAttrMultiProcessorCount, dev);
+
+    int rc = 0;
+    for (int k = 0; k < 2 && !rc; ++k) {
+        std::vector<int2> ent(cx->hS[k].col.size());
+        for (size_t i = 0; i < ent.size(); ++i) {
+            int32_t bits;
+            memcpy(&bits, &cx->hS[k].val[i], 4);
+            ent[i] = make_int2(cx->hS[k].col[i], bits);
+        }
+        rc |= upload(&cx->d_rowptr[k], cx->hS[k].rowptr);
+        rc |= upload(&cx->d_ent[k], ent);
+    }
+    std::vector<int32_t> inc_ptr(N + 1, 0);
+    std::vector<int2> inc_ent;
+    inc_ent.reserve(2 * (size_t)E);
+    for (int32_t n = 0; n < N; ++n) {
+        for (auto& es : node_to_edges[n]) {
+            float s = (float)es.second;
+            int32_t bits;
+            memcpy(&bits, &s, 4);
+            inc_ent.push_back(make_int2(es.first, bits));
+        }
+        inc_ptr[n + 1] = (int32_t)inc_ent.size();
+    }
+    if (!rc) rc |= upload(&cx->d_inc_ptr, inc_ptr);
+    if (!rc) rc |= upload(&cx->d_inc_ent, inc_ent);
+    if (!rc) rc |= upload(&cx->d_nbrhoods, cx->h_nbrhoods);
+    if (rc) {
+        scone_complex_destroy(cx);
+        return rc;
+    }
+    *out = cx;
+    return 0;
+}
+
+extern "C" int scone_complex_create(int32_t N, int32_t E, int32_t F, const int32_t* edge_nodes, const int8_t* edge_signs,
+                                    const int32_t* tri_edges, const int8_t* tri_signs, int32_t model, scone_complex** out) {
+    return complex_create_impl(N, E, F, edge_nodes, edge_signs, tri_edges, tri_signs, model, true, out);
+}
+
+extern "C" int scone_complex_create_index_only(int32_t N, int32_t E, int32_t F, const int32_t* edge_nodes,
+                                               const int8_t* edge_signs, const int32_t* tri_edges, const int8_t* tri_signs,
+                                               int32_t model, scone_complex** out) {
+    return complex_create_impl(N, E, F, edge_nodes, edge_signs, tri_edges, tri_signs, model, false, out);
+}
+
+extern "C" int scone_complex_destroy(scone_complex* cx) {
+    if (!cx) return 0;
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(cx->d_rowptr[k]);
+        cudaFree(cx->d_ent[k]);
+    }
+    cudaFree(cx->d_nbrhoods);
+    cudaFree(cx->d_inc_ptr);
+    cudaFree(cx->d_inc_ent);
+    delete cx;
+    return 0;
+}
+
+extern "C" int scone_complex_dims(const scone_complex* cx, int32_t* N, int32_t* E, int32_t* F, int32_t* D, int64_t* nnz0,
+                                  int64_t* nnz1) {
+    SCONE_REQUIRE(cx != nullptr, "scone_complex_dims: NULL complex");
+    if (N) *N = cx->N;
+    if (E) *E = cx->E;
+    if (F) *F = cx->F;
+    if (D) *D = cx->D;
+    if (nnz0) *nnz0 = (int64_t)cx->hS[0].col.size();
+    if (nnz1) *nnz1 = (int64_t)cx->hS[1].col.size();
+    return 0;
+}
+
+extern "C" int scone_complex_get_shift_csr(const scone_complex* cx, int32_t which, int32_t* rowptr, int32_t* col,
+                                           float* val) {
+    SCONE_REQUIRE(cx != nullptr && (which == 0 || which == 1), "scone_complex_get_shift_csr: bad arguments");
+    const HostCsr& h = cx->hS[which];
+    if (rowptr) memcpy(rowptr, h.rowptr.data(), h.rowptr.size() * sizeof(int32_t));
+    if (col) memcpy(col, h.col.data(), h.col.size() * sizeof(int32_t));
+    if (val) memcpy(val, h.val.data(), h.val.size() * sizeof(float));
+    return 0;
+}
+
+extern "C" int scone_complex_get_nbrhoods(const scone_complex* cx, int32_t* nbrhoods) {
+    SCONE_REQUIRE(cx != nullptr && nbrhoods != nullptr, "scone_complex_get_nbrhoods: bad arguments");
+    memcpy(nbrhoods, cx->h_nbrhoods.data(), cx->h_nbrhoods.size() * sizeof(int32_t));
+    return 0;
+}

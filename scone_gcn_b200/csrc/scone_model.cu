@@ -1,0 +1,280 @@
+// scone_model.cu — model-level entry points: micro-batched forward / loss+grad / Adam.
+//
+// Replaces, for -model scone / ebli, the reference's
+//   Scone_GCN.setup + generate_weights shapes   scone_trajectory_model.py:215-262
+//   self.model(weights, *shifts, *inputs)       scone_trajectory_model.py:46,64   (vmap of scone_func / ebli_func)
+//   grad(self.loss) + adam update               scone_trajectory_model.py:300-326
+// Trajectories are processed in micro-batches of `micro_batch` so that the [E][b][C] activations of all
+// layers stay resident in HBM; weight gradients accumulate across micro-batches in one
+// flat device buffer [grads | nll_sum | count] that is the single all-reduce payload of a data-parallel step.
+#include <cstring>
+#include "common.cuh"
+
+struct scone_model {
+    const scone_complex* cx = nullptr;
+    int32_t L = 0, mb = 0, act = 0, cmax = 0;
+    std::vector<int32_t> hidden;              // channel count per conv layer
+    std::vector<int64_t> w_off;               // offsets of W[0..3L] in the flat buffer
+    int64_t n_params = 0;
+    float *d_w = nullptr, *d_m = nullptr, *d_v = nullptr, *d_grad = nullptr;     // d_grad: [n_params + 2]
+    float* d_X = nullptr;                     // [E][mb]
+    std::vector<float*> d_H;                  // H_1..H_L, [E][mb][C_l]
+    float* d_G[2] = {nullptr, nullptr};       // ping-pong dL/dZ, [E][mb][cmax]
+    void* d_ws = nullptr;                     // backward / readout workspace
+    float* d_logp = nullptr;                  // [mb][D]
+    // staging for the *_host entry points
+    int32_t *d_ptr = nullptr, *d_edge = nullptr, *d_last = nullptr, *d_tgt = nullptr;
+    float *d_val = nullptr, *d_mask = nullptr, *d_logp_all = nullptr;
+    int64_t cap_B = 0, cap_nnz = 0;
+};
+
+namespace {
+
+int ensure_staging(scone_model* m, int64_t B, int64_t nnz) {
+    if (B > m->cap_B) {
+        cudaFree(m->d_ptr); cudaFree(m->d_last); cudaFree(m->d_tgt); cudaFree(m->d_mask); cudaFree(m->d_logp_all);
+        int64_t cap = B + B / 4 + 16;
+        SCONE_CUDA(cudaMalloc((void**)&m->d_ptr, (cap + 1) * sizeof(int32_t)));
+        SCONE_CUDA(cudaMalloc((void**)&m->d_last, cap * sizeof(int32_t)));
+        SCONE_CUDA(cudaMalloc((void**)&m->d_tgt, cap * sizeof(int32_t)));
+        SCONE_CUDA(cudaMalloc((void**)&m->d_mask, cap * sizeof(float)));
+        SCONE_CUDA(cudaMalloc((void**)&m->d_logp_all, cap * (size_t)(m->cx->D > 0 ? m->cx->D : 1) * sizeof(float)));
+        m->cap_B = cap;
+    }
+    if (nnz > m->cap_nnz) {
+        cudaFree(m->d_edge); cudaFree(m->d_val);
+        int64_t cap = nnz + nnz / 4 + 16;
+        SCONE_CUDA(cudaMalloc((void**)&m->d_edge, cap * sizeof(int32_t)));
+        SCONE_CUDA(cudaMalloc((void**)&m->d_val, cap * sizeof(float)));
+        m->cap_nnz = cap;
+    }
+    return 0;
+}
+
+// forward over one micro-batch [off, off+b): X -> H_1 .. H_L (kept) ; returns 0 on success
+int forward_mb(scone_model* m, int32_t b, const int32_t* ptr, const int32_t* edge, const float* val, void* st) {
+    const scone_complex* cx = m->cx;
+    int rc = scone_flows_to_dense(cx, b, ptr, edge, val, m->d_X, st);
+    if (rc) return rc;
+    const float* in = m->d_X;
+    int cin = 1;
+    for (int l = 0; l < m->L; ++l) {
+        const int cout = m->hidden[l];
+        rc = scone_layer_forward(cx, m->act, b, cin, cout, in, m->d_w + m->w_off[3 * l], m->d_w + m->w_off[3 * l + 1],
+                                 m->d_w + m->w_off[3 * l + 2], m->d_H[l], st);
+        if (rc) return rc;
+        in = m->d_H[l];
+        cin = cout;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int scone_model_create(const scone_complex* cx, int32_t n_layers, const int32_t* hidden, int32_t micro_batch,
+                                  scone_model** out) {
+    SCONE_REQUIRE(out != nullptr, "scone_model_create: out is NULL");
+    *out = nullptr;
+    SCONE_REQUIRE(cx && hidden && n_layers >= 1 && micro_batch >= 1, "scone_model_create: bad arguments");
+    SCONE_REQUIRE(!cx->host_only, "scone_model_create: index-only complex has no device arrays");
+    scone_model* m = new scone_model();
+    m->cx = cx;
+    m->L = n_layers;
+    m->mb = micro_batch;
+    m->act = cx->model == SCONE_MODEL_EBLI ? SCONE_ACT_LEAKY_RELU : SCONE_ACT_TANH;
+    m->hidden.assign(hidden, hidden + n_layers);
+    int64_t off = 0;
+    int cin = 1;
+    for (int l = 0; l < n_layers; ++l) {
+        const int c = hidden[l];
+        if (!(c == 8 || c == 16 || c == 32 || c == 64)) {
+            scone_set_error("scone_model_create: hidden width %d of layer %d unsupported (8, 16, 32 or 64)", c, l);
+            delete m;
+            return 2;
+        }
+        if (l > 0 && !(c == cin || c == 2 * cin || 2 * c == cin)) {
+            scone_set_error("scone_model_create: consecutive widths %d -> %d unsupported (ratio must be 1/2, 1 or 2)", cin, c);
+            delete m;
+            return 2;
+        }
+        for (int k = 0; k < 3; ++k) {
+            m->w_off.push_back(off);
+            off += (int64_t)cin * c;
+        }
+        m->cmax = c > m->cmax ? c : m->cmax;
+        cin = c;
+    }
+    m->w_off.push_back(off);
+    off += cin;                               // W[-1]: [C_L][1]
+    m->n_params = off;
+    const size_t E = cx->E, mb = micro_batch;
+    int rc = 0;
+    auto alloc = [&](void** p, size_t bytes) {
+        if (rc) return;
+        cudaError_t e = cudaMalloc(p, bytes ? bytes : 4);
+        if (e != cudaSuccess) {
+            scone_set_error("scone_model_create: cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+            rc = 1;
+        }
+    };
+    alloc((void**)&m->d_w, off * sizeof(float));
+    alloc((void**)&m->d_m, off * sizeof(float));
+    alloc((void**)&m->d_v, off * sizeof(float));
+    alloc((void**)&m->d_grad, (off + 2) * sizeof(float));
+    alloc((void**)&m->d_X, E * mb * sizeof(float));
+    m->d_H.assign(n_layers, nullptr);
+    for (int l = 0; l < n_layers; ++l) alloc((void**)&m->d_H[l], E * mb * hidden[l] * sizeof(float));
+    for (int k = 0; k < 2; ++k) alloc((void**)&m->d_G[k], E * mb * m->cmax * sizeof(float));
+    int64_t ws = scone_readout_workspace_bytes(micro_batch, m->cmax);
+    cin = 1;
+    for (int l = 0; l < n_layers; ++l) {
+        int64_t w = scone_layer_backward_workspace_bytes(cin, hidden[l]);
+        ws = w > ws ? w : ws;
+        cin = hidden[l];
+    }
+    alloc(&m->d_ws, ws);
+    alloc((void**)&m->d_logp, mb * (size_t)(cx->D > 0 ? cx->D : 1) * sizeof(float));
+    if (!rc) {
+        cudaMemset(m->d_w, 0, off * sizeof(float));
+        cudaMemset(m->d_m, 0, off * sizeof(float));
+        cudaMemset(m->d_v, 0, off * sizeof(float));
+        cudaMemset(m->d_grad, 0, (off + 2) * sizeof(float));
+    }
+    if (rc) {
+        scone_model_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return 0;
+}
+
+extern "C" int scone_model_destroy(scone_model* m) {
+    if (!m) return 0;
+    cudaFree(m->d_w); cudaFree(m->d_m); cudaFree(m->d_v); cudaFree(m->d_grad); cudaFree(m->d_X);
+    for (float* p : m->d_H) cudaFree(p);
+    cudaFree(m->d_G[0]); cudaFree(m->d_G[1]); cudaFree(m->d_ws); cudaFree(m->d_logp);
+    cudaFree(m->d_ptr); cudaFree(m->d_edge); cudaFree(m->d_last); cudaFree(m->d_tgt); cudaFree(m->d_val);
+    cudaFree(m->d_mask); cudaFree(m->d_logp_all);
+    delete m;
+    return 0;
+}
+
+extern "C" int64_t scone_model_num_params(const scone_model* m) { return m ? m->n_params : -1; }
+extern "C" float* scone_model_weights_dev(scone_model* m) { return m ? m->d_w : nullptr; }
+extern "C" float* scone_model_grads_dev(scone_model* m) { return m ? m->d_grad : nullptr; }
+
+extern "C" int scone_model_set_weights(scone_model* m, const float* w) {
+    SCONE_REQUIRE(m && w, "scone_model_set_weights: NULL argument");
+    SCONE_CUDA(cudaMemcpy(m->d_w, w, m->n_params * sizeof(float), cudaMemcpyHostToDevice));
+    SCONE_CUDA(cudaMemset(m->d_m, 0, m->n_params * sizeof(float)));
+    SCONE_CUDA(cudaMemset(m->d_v, 0, m->n_params * sizeof(float)));
+    return 0;
+}
+
+extern "C" int scone_model_get_weights(const scone_model* m, float* w) {
+    SCONE_REQUIRE(m && w, "scone_model_get_weights: NULL argument");
+    SCONE_CUDA(cudaMemcpy(w, m->d_w, m->n_params * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int scone_model_forward_dev(scone_model* m, int32_t B, const int32_t* ptr, const int32_t* edge, const float* val,
+                                       const int32_t* last, float* logprobs, void* st) {
+    SCONE_REQUIRE(m && ptr && last && logprobs && B >= 0, "scone_model_forward_dev: bad arguments");
+    const scone_complex* cx = m->cx;
+    for (int32_t off = 0; off < B; off += m->mb) {
+        const int32_t b = B - off < m->mb ? B - off : m->mb;
+        int rc = forward_mb(m, b, ptr + off, edge, val, st);
+        if (rc) return rc;
+        rc = scone_readout_ws(cx, m->act, b, m->hidden[m->L - 1], m->d_H[m->L - 1], m->d_w + m->w_off[3 * m->L], last + off,
+                              logprobs + (size_t)off * cx->D, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, nullptr, 0,
+                              nullptr, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+extern "C" int scone_model_loss_grad_dev(scone_model* m, int32_t B, const int32_t* ptr, const int32_t* edge, const float* val,
+                                         const int32_t* last, const int32_t* tgt, const float* mask, int32_t zero_first,
+                                         void* st) {
+    SCONE_REQUIRE(m && ptr && last && tgt && mask && B >= 0, "scone_model_loss_grad_dev: bad arguments");
+    const scone_complex* cx = m->cx;
+    const int L = m->L;
+    cudaStream_t s = as_stream(st);
+    if (zero_first) SCONE_CUDA(cudaMemsetAsync(m->d_grad, 0, (m->n_params + 2) * sizeof(float), s));
+    for (int32_t off = 0; off < B; off += m->mb) {
+        const int32_t b = B - off < m->mb ? B - off : m->mb;
+        int rc = forward_mb(m, b, ptr + off, edge, val, st);
+        if (rc) return rc;
+        const int CL = m->hidden[L - 1];
+        float* G = m->d_G[0];
+        rc = scone_readout_ws(cx, m->act, b, CL, m->d_H[L - 1], m->d_w + m->w_off[3 * L], last + off, m->d_logp, tgt + off,
+                              mask + off, 1.f, G, m->d_grad + m->w_off[3 * L], m->d_grad + m->n_params,
+                              m->d_grad + m->n_params + 1, 1, m->d_ws, st);
+        if (rc) return rc;
+        int cur = 0;
+        for (int l = L - 1; l >= 0; --l) {
+            const int cout = m->hidden[l], cin = l > 0 ? m->hidden[l - 1] : 1;
+            const float* Hin = l > 0 ? m->d_H[l - 1] : m->d_X;
+            float* Gprev = l > 0 ? m->d_G[cur ^ 1] : nullptr;
+            rc = scone_layer_backward(cx, m->act, b, cin, cout, m->d_G[cur], Hin, m->d_w + m->w_off[3 * l],
+                                      m->d_w + m->w_off[3 * l + 1], m->d_w + m->w_off[3 * l + 2], Gprev,
+                                      m->d_grad + m->w_off[3 * l], 1, m->d_ws, st);
+            if (rc) return rc;
+            cur ^= 1;
+        }
+    }
+    return 0;
+}
+
+extern "C" int scone_model_forward_host(scone_model* m, int32_t B, const int32_t* ptr, const int32_t* edge, const float* val,
+                                        const int32_t* last, float* logprobs_out, void* st) {
+    SCONE_REQUIRE(m && ptr && last && logprobs_out && B >= 0, "scone_model_forward_host: bad arguments");
+    if (B == 0) return 0;
+    cudaStream_t s = as_stream(st);
+    const int64_t nnz = ptr[B];
+    int rc = ensure_staging(m, B, nnz);
+    if (rc) return rc;
+    SCONE_CUDA(cudaMemcpyAsync(m->d_ptr, ptr, (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    SCONE_CUDA(cudaMemcpyAsync(m->d_edge, edge, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    SCONE_CUDA(cudaMemcpyAsync(m->d_val, val, nnz * sizeof(float), cudaMemcpyHostToDevice, s));
+    SCONE_CUDA(cudaMemcpyAsync(m->d_last, last, B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    rc = scone_model_forward_dev(m, B, m->d_ptr, m->d_edge, m->d_val, m->d_last, m->d_logp_all, st);
+    if (rc) return rc;
+    SCONE_CUDA(cudaMemcpyAsync(logprobs_out, m->d_logp_all, (size_t)B * m->cx->D * sizeof(float), cudaMemcpyDeviceToHost, s));
+    SCONE_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+extern "C" int scone_model_loss_grad_host(scone_model* m, int32_t B, const int32_t* ptr, const int32_t* edge, const float* val,
+                                          const int32_t* last, const int32_t* tgt, const float* mask, int32_t zero_first,
+                                          void* st) {
+    SCONE_REQUIRE(m && ptr && last && tgt && mask && B >= 0, "scone_model_loss_grad_host: bad arguments");
+    cudaStream_t s = as_stream(st);
+    const int64_t nnz = B > 0 ? ptr[B] : 0;
+    int rc = ensure_staging(m, B, nnz);
+    if (rc) return rc;
+    SCONE_CUDA(cudaMemcpyAsync(m->d_ptr, ptr, (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (nnz) {
+        SCONE_CUDA(cudaMemcpyAsync(m->d_edge, edge, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        SCONE_CUDA(cudaMemcpyAsync(m->d_val, val, nnz * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
+    if (B) {
+        SCONE_CUDA(cudaMemcpyAsync(m->d_last, last, B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        SCONE_CUDA(cudaMemcpyAsync(m->d_tgt, tgt, B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        SCONE_CUDA(cudaMemcpyAsync(m->d_mask, mask, B * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
+    return scone_model_loss_grad_dev(m, B, m->d_ptr, m->d_edge, m->d_val, m->d_last, m->d_tgt, m->d_mask, zero_first, st);
+}
+
+extern "C" int scone_model_read_grads(scone_model* m, float* out, void* st) {
+    SCONE_REQUIRE(m && out, "scone_model_read_grads: NULL argument");
+    cudaStream_t s = as_stream(st);
+    SCONE_CUDA(cudaMemcpyAsync(out, m->d_grad, (m->n_params + 2) * sizeof(float), cudaMemcpyDeviceToHost, s));
+    SCONE_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+extern "C" int scone_model_adam_step(scone_model* m, int32_t step, float lr, float wd, void* st) {
+    SCONE_REQUIRE(m && step >= 0, "scone_model_adam_step: bad arguments");
+    return scone_adam_launch(m->d_w, m->d_m, m->d_v, m->d_grad, m->n_params, step, lr, wd, st);
+}

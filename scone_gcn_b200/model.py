@@ -1,0 +1,124 @@
+"""SconeModel — owner of a `scone_model*`: device weights, Adam state, activation workspace.
+
+Replaces vmap(scone_func / ebli_func) + grad(loss) + adam (scone_trajectory_model.py:42-56,256,300-326)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class SconeModel:
+    def __init__(self, cx, hidden, micro_batch=64):
+        self.cx = cx
+        self.hidden = [int(h) for h in hidden]
+        self.micro_batch = int(micro_batch)
+        L = _lib.lib()
+        harr = np.asarray(self.hidden, dtype=np.int32)
+        h = C.c_void_p()
+        _lib.check(L.scone_model_create(cx.handle, len(self.hidden), _lib.ptr(harr), self.micro_batch, C.byref(h)),
+                   'scone_model_create')
+        self.handle = h
+        self.n_params = L.scone_model_num_params(h)
+        self.shapes = []
+        cin = 1
+        for c in self.hidden:
+            self.shapes += [(cin, c)] * 3
+            cin = c
+        self.shapes.append((cin, 1))
+
+    # ---- weights ------------------------------------------------------------------------------
+    def flatten(self, weights):
+        assert len(weights) == len(self.shapes), 'wrong number of weights'
+        parts = []
+        for w, s in zip(weights, self.shapes):
+            w = np.asarray(w, dtype=np.float32)
+            assert w.shape == s, 'weight shape %s, expected %s' % (w.shape, s)
+            parts.append(w.ravel())
+        return np.ascontiguousarray(np.concatenate(parts))
+
+    def unflatten(self, flat):
+        out, off = [], 0
+        for s in self.shapes:
+            n = s[0] * s[1]
+            out.append(flat[off:off + n].reshape(s).copy())
+            off += n
+        return out
+
+    def set_weights(self, weights, reset_adam=True):
+        flat = self.flatten(weights)
+        if reset_adam:
+            _lib.check(_lib.lib().scone_model_set_weights(self.handle, _lib.ptr(flat)), 'scone_model_set_weights')
+        else:
+            _copy_host_to_dev(_lib.lib().scone_model_weights_dev(self.handle), flat)
+
+    def get_weights(self):
+        flat = np.zeros(self.n_params, np.float32)
+        _lib.check(_lib.lib().scone_model_get_weights(self.handle, _lib.ptr(flat)), 'scone_model_get_weights')
+        return self.unflatten(flat)
+
+    # ---- compute ------------------------------------------------------------------------------
+    def forward(self, traj_ptr, flow_edge, flow_val, last_nodes, stream=None):
+        """log-probs [B, D] (numpy) from HOST sparse flows."""
+        B = len(last_nodes)
+        out = np.zeros((B, self.cx.D), np.float32)
+        traj_ptr = np.ascontiguousarray(traj_ptr, np.int32)
+        flow_edge = np.ascontiguousarray(flow_edge, np.int32)
+        flow_val = np.ascontiguousarray(flow_val, np.float32)
+        last_nodes = np.ascontiguousarray(last_nodes, np.int32)
+        _lib.check(_lib.lib().scone_model_forward_host(self.handle, B, _lib.ptr(traj_ptr), _lib.ptr(flow_edge),
+                                                       _lib.ptr(flow_val), _lib.ptr(last_nodes), _lib.ptr(out), stream),
+                   'scone_model_forward_host')
+        return out
+
+    def loss_grad(self, traj_ptr, flow_edge, flow_val, last_nodes, target_idx, mask, zero_first=True, stream=None,
+                  read=True):
+        """Accumulate [grads | nll_sum | count] on the device from HOST inputs; optionally read it back."""
+        B = len(last_nodes)
+        a = [np.ascontiguousarray(traj_ptr, np.int32), np.ascontiguousarray(flow_edge, np.int32),
+             np.ascontiguousarray(flow_val, np.float32), np.ascontiguousarray(last_nodes, np.int32),
+             np.ascontiguousarray(target_idx, np.int32), np.ascontiguousarray(mask, np.float32)]
+        _lib.check(_lib.lib().scone_model_loss_grad_host(self.handle, B, *[_lib.ptr(x) for x in a], int(zero_first), stream),
+                   'scone_model_loss_grad_host')
+        return self.read_grads(stream) if read else None
+
+    def read_grads(self, stream=None):
+        buf = np.zeros(self.n_params + 2, np.float32)
+        _lib.check(_lib.lib().scone_model_read_grads(self.handle, _lib.ptr(buf), stream), 'scone_model_read_grads')
+        return buf
+
+    def adam_step(self, step, lr, weight_decay, stream=None):
+        _lib.check(_lib.lib().scone_model_adam_step(self.handle, int(step), float(lr), float(weight_decay), stream),
+                   'scone_model_adam_step')
+
+    def grads_tensor(self):
+        """torch view of the flat device buffer [grads | nll_sum | count] (for the NCCL all-reduce)."""
+        return _wrap_device_f32(_lib.lib().scone_model_grads_dev(self.handle), self.n_params + 2)
+
+    def weights_tensor(self):
+        return _wrap_device_f32(_lib.lib().scone_model_weights_dev(self.handle), self.n_params)
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                _lib.lib().scone_model_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class _CudaArray:
+    """Minimal __cuda_array_interface__ carrier so torch can alias library-owned device memory."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {'shape': (int(n),), 'typestr': '<f4', 'data': (int(ptr), False), 'version': 2}
+
+
+def _wrap_device_f32(ptr, n):
+    import torch
+    return torch.as_tensor(_CudaArray(ptr, n), device='cuda')
+
+
+def _copy_host_to_dev(ptr, flat):
+    import torch
+    _wrap_device_f32(ptr, len(flat)).copy_(torch.from_numpy(flat))

@@ -1,0 +1,197 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Tolerances are the north-star's: integer/index work bit-exact; log-probs within 1e-5, gradients within
+1e-4 (relative to the largest magnitude of the tensor), identical next-node accuracy.
+"""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import Dataset, load, weights_of
+from oracle import scone_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+LP_TOL = 1e-5
+GRAD_TOL = 1e-4
+
+
+def _mods():
+    import scone_gcn_b200 as sg
+    return sg
+
+
+def _relmax(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope='module')
+def small():
+    return Dataset('dataset_small.npz')
+
+
+@pytest.mark.parametrize('model', ['scone', 'ebli'])
+def test_index_arrays_bit_exact_on_device_handle(small, model):
+    sg = _mods()
+    cx = sg.SimplicialComplex.from_dense(small.B1, small.B2, model)
+    ref = so.shift_matrices(small.B1, small.B2, model)
+    for k in range(2):
+        assert np.array_equal(cx.shift_dense(k), ref[k])
+    nb, _, _ = so.neighbourhood_tables(small.B1, small.last_nodes)
+    assert np.array_equal(cx.nbrhoods, nb)
+
+
+@pytest.mark.parametrize('name,mb', [('model_small_scone_h16', 64), ('model_small_scone_h16', 7),
+                                     ('model_small_ebli_h16', 64), ('model_small_scone_h32', 16)])
+def test_forward_and_grads_vs_reference_golden(small, name, mb):
+    sg = _mods()
+    fx = load(name + '.npz')
+    model = str(fx['model'])
+    hidden = [int(h[1]) for h in fx['hidden']]
+    cx = sg.SimplicialComplex.from_dense(small.B1, small.B2, model)
+    net = sg.SconeModel(cx, hidden, micro_batch=mb)
+    ptr, fe, fv = sg.flows_to_csr(small.flows)
+    tgt = small.raw['targets_argmax']
+    mask = fx['batch_mask'].astype(np.float32)
+    wd = float(fx['wd'])
+    for tag in ('init', 'big'):
+        W = weights_of(fx, 'w_' + tag)
+        net.set_weights(W)
+        lp = net.forward(ptr, fe, fv, small.last_nodes)
+        ref = fx[tag + '_logprobs'][:, :, 0]
+        assert np.abs(lp - ref).max() <= LP_TOL * max(1.0, np.abs(ref).max()), (tag, np.abs(lp - ref).max())
+        buf = net.loss_grad(ptr, fe, fv, small.last_nodes, tgt, mask)
+        n = net.n_params
+        count = buf[n + 1]
+        assert count == mask.sum()
+        ridge = wd * sum(float((np.asarray(w, np.float64) ** 2).sum()) for w in W)
+        loss = buf[n] / count + ridge
+        assert loss == pytest.approx(float(fx[tag + '_loss_batch']), rel=2e-5)
+        grads = net.unflatten(buf[:n] / count)
+        for i, g in enumerate(grads):
+            g = g + 2 * wd * np.asarray(W[i], np.float32)
+            r = fx['%s_grad_%d' % (tag, i)]
+            assert _relmax(g, r) <= GRAD_TOL, (tag, i, _relmax(g, r))
+        # identical next-node accuracy (scone_trajectory_model.py:59-71)
+        pred = lp.copy()
+        nn = fx['n_nbrs']
+        for i in range(len(pred)):
+            pred[i, nn[i]:] = -100
+        for mname, m in (('train', small.train_mask), ('test', small.test_mask)):
+            acc = np.mean(np.argmax(pred[m == 1], axis=1) == tgt[m == 1])
+            assert acc == pytest.approx(float(fx['%s_acc_%s' % (tag, mname)]), abs=1e-7)
+
+
+def test_deterministic_and_microbatch_invariant_logprobs(small):
+    sg = _mods()
+    fx = load('model_small_scone_h16.npz')
+    cx = sg.SimplicialComplex.from_dense(small.B1, small.B2, 'scone')
+    ptr, fe, fv = sg.flows_to_csr(small.flows)
+    W = weights_of(fx, 'w_big')
+    outs, grads = [], []
+    for mb in (64, 64, 5):
+        net = sg.SconeModel(cx, [16, 16, 16], micro_batch=mb)
+        net.set_weights(W)
+        outs.append(net.forward(ptr, fe, fv, small.last_nodes))
+        grads.append(net.loss_grad(ptr, fe, fv, small.last_nodes, small.raw['targets_argmax'],
+                                   np.ones(small.n_traj, np.float32)))
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(grads[0], grads[1])       # run-to-run bit-exact
+    assert np.array_equal(outs[0], outs[2])            # per-trajectory results do not depend on the micro-batch
+    assert _relmax(grads[2], grads[0]) < 1e-5
+
+
+def test_default_complex_vs_reference_golden():
+    sg = _mods()
+    ds = Dataset('dataset_default.npz')
+    fx = load('model_default_scone_h16.npz')
+    cx = sg.SimplicialComplex.from_simplices(ds.N, ds.edges, ds.faces, 'scone')
+    assert (cx.N, cx.E, cx.F, cx.D) == (400, 1001, 649, 13)
+    net = sg.SconeModel(cx, [16, 16, 16], micro_batch=256)
+    ptr, fe, fv = sg.flows_to_csr(ds.flows)
+    tgt = ds.raw['targets_argmax']
+    mask = fx['batch_mask'].astype(np.float32)
+    for tag in ('init', 'big'):
+        W = weights_of(fx, 'w_' + tag)
+        net.set_weights(W)
+        lp = net.forward(ptr, fe, fv, ds.last_nodes)
+        ref = fx[tag + '_logprobs'][:, :, 0]
+        assert np.abs(lp - ref).max() <= LP_TOL * max(1.0, np.abs(ref).max())
+        buf = net.loss_grad(ptr, fe, fv, ds.last_nodes, tgt, mask)
+        n = net.n_params
+        grads = net.unflatten(buf[:n] / buf[n + 1])
+        for i, g in enumerate(grads):
+            g = g + 2 * float(fx['wd']) * np.asarray(W[i], np.float32)
+            assert _relmax(g, fx['%s_grad_%d' % (tag, i)]) <= GRAD_TOL, (tag, i)
+    assert float(fx['init_loss_train']) == pytest.approx(np.log(13), abs=1e-3)
+
+
+@pytest.mark.parametrize('cin,cout,act', [(16, 16, 0), (32, 32, 0), (8, 8, 1), (16, 32, 0), (32, 16, 2), (64, 64, 0),
+                                          (1, 16, 0), (1, 32, 1)])
+@pytest.mark.parametrize('b', [5, 32])
+def test_layer_kernels_dense_random_input(small, cin, cout, act, b):
+    """Kernel-level: one fused layer forward/backward on DENSE random features (no structural zeros)."""
+    sg = _mods()
+    from scone_gcn_b200 import _lib
+    L = _lib.lib()
+    cx = sg.SimplicialComplex.from_dense(small.B1, small.B2, 'scone')
+    E = cx.E
+    rs = np.random.RandomState(cin * 100 + cout + b)
+    Hin = rs.randn(E, b, cin).astype(np.float32)
+    W = [(rs.randn(cin, cout) * 0.3).astype(np.float32) for _ in range(3)]
+    G = rs.randn(E, b, cout).astype(np.float32)
+    S = [cx.shift_dense(0), cx.shift_dense(1)]
+    # fp64 reference
+    H64 = Hin.astype(np.float64)
+    T = [H64, np.einsum('ef,fbc->ebc', S[0], H64), np.einsum('ef,fbc->ebc', S[1], H64)]
+    Z = sum(T[k] @ W[k].astype(np.float64) for k in range(3))
+    actf = [np.tanh, lambda z: np.where(z >= 0, z, 0.01 * z), lambda z: np.maximum(z, 0)][act]
+    dact = [lambda h: 1 - h * h, lambda h: np.where(h >= 0, 1.0, 0.01), lambda h: (h > 0) * 1.0][act]
+    Href = actf(Z)
+    dev = torch.device('cuda')
+    tH, tG = torch.from_numpy(Hin).to(dev), torch.from_numpy(G).to(dev)
+    tW = [torch.from_numpy(w).to(dev) for w in W]
+    tout = torch.empty(E, b, cout, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.scone_layer_forward(cx.handle, act, b, cin, cout, _lib.dptr(tH), _lib.dptr(tW[0]), _lib.dptr(tW[1]),
+                                     _lib.dptr(tW[2]), _lib.dptr(tout), st), 'layer_forward')
+    out = tout.cpu().numpy()
+    assert np.abs(out - Href).max() <= 2e-5 * max(1.0, np.abs(Href).max())
+    # backward: G is dL/dZ
+    G64 = G.astype(np.float64)
+    A = [G64, np.einsum('ef,fbc->ebc', S[0], G64), np.einsum('ef,fbc->ebc', S[1], G64)]
+    dW_ref = np.stack([np.einsum('ebi,ebo->io', H64, A[k]) for k in range(3)])
+    ws = torch.empty(L.scone_layer_backward_workspace_bytes(cin, cout) // 4 + 16, device=dev)
+    tdW = torch.zeros(3, cin, cout, device=dev)
+    tGp = torch.empty(E, b, cin, device=dev) if cin > 1 else None
+    _lib.check(L.scone_layer_backward(cx.handle, act, b, cin, cout, _lib.dptr(tG), _lib.dptr(tH), _lib.dptr(tW[0]),
+                                      _lib.dptr(tW[1]), _lib.dptr(tW[2]), _lib.dptr(tGp), _lib.dptr(tdW), 0, _lib.dptr(ws), st),
+               'layer_backward')
+    assert _relmax(tdW.cpu().numpy(), dW_ref) <= 2e-5
+    if cin > 1:
+        dH = sum(A[k] @ W[k].astype(np.float64).T for k in range(3))
+        Gp_ref = dH * dact(H64)          # Hin plays the role of the previous layer's OUTPUT
+        assert _relmax(tGp.cpu().numpy(), Gp_ref) <= 2e-5
+    torch.cuda.synchronize()
+
+
+def test_training_matches_oracle_end_to_end(small):
+    """k Adam steps from the reference init / batch stream: same weights (1e-4) and identical accuracy."""
+    sg = _mods()
+    fx = load('model_small_scone_h16.npz')
+    from scone_gcn_b200.scone_trajectory_model import Scone_GCN
+    from scone_gcn_b200 import trajectory_experiments as te
+    np.random.seed(1030)
+    cx = sg.SimplicialComplex.from_dense(small.B1, small.B2, 'scone')
+    shifts = te.shift_handles(cx)
+    inputs = [te.Bconds(cx), small.last_nodes, small.flows]
+    net = Scone_GCN(int(fx['epochs']), float(fx['lr']), int(fx['batch_size']), float(fx['wd']), verbose=False)
+    in_axes = (None, None, None, None, 0, 0)
+    net.setup(te.scone_func, [(3, 16)] * 3, shifts, inputs, small.targets, in_axes, small.train_mask)
+    for a, r in zip(net.weights, weights_of(fx, 'w_init')):
+        assert np.array_equal(np.asarray(a), r)
+    res = net.train(inputs, small.targets, small.train_mask, small.test_mask, fx['n_nbrs'])
+    ref = fx['train_result']
+    assert res[0] == pytest.approx(ref[0], rel=1e-4) and res[2] == pytest.approx(ref[2], rel=1e-4)
+    assert res[1] == pytest.approx(ref[1], abs=1e-7) and res[3] == pytest.approx(ref[3], abs=1e-7)
+    for i, w in enumerate(net.weights):
+        assert _relmax(np.asarray(w), fx['w_trained_%d' % i]) <= 2e-3, i      # 9 Adam steps amplify fp32 noise
