@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py — SCoNe train trajectories/s on B200 (BASELINE.json metric), one JSON line on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg5|cfg4|cfg1]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one optimizer step of the 3-layer SCoNe (hidden 32) over one batch of synthetic trajectories on the
+named complex: sparse flows -> fused layer forwards -> readout/NLL -> fused layer backwards -> (all-reduce of
+the flat [grads | nll | count] buffer when N > 1) -> Adam.  Every trajectory in the batch contributes to the
+loss (mask all ones).  Weak scaling: the per-GPU batch is fixed and the complex is replicated.
+
+  value  whole-job trajectories/s with the batch already resident in HBM (device-timed, max over ranks)
+  e2e    same metric through the public host API (SconeModel.loss_grad + adam_step on pinned HOST buffers,
+         H2D of the batch and D2H of the loss inside the timed region)
+  roofline   the dominant kernel family, timed live with CUDA events on the launching stream
+  cpu_baseline  the oracle's sparse CPU port (oracle/scone_oracle.py) on a bounded sample, rank 0, N = 1 only
+--impl reference times that same CPU port as the whole arm (the reference's dense E x E formulation cannot be
+instantiated at E = 1M: 4 TB per operator; jax itself is not installable offline — see DESIGN.md).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (n_nodes for the generator, per-GPU batch, hidden, micro-batch)
+    'cfg5': dict(n_nodes=370000, batch=4096, hidden=32, micro_batch=64,
+                 desc='1M-edge synthetic holed Delaunay complex, 4096 trajectories per GPU (32768 at 8 GPUs), 3-layer SCoNe hidden 32'),
+    'cfg4': dict(n_nodes=110000, batch=4096, hidden=32, micro_batch=128,
+                 desc='~300k-edge synthetic complex, batch 4096, 3-layer SCoNe hidden 32'),
+    'cfg1': dict(n_nodes=400, batch=1000, hidden=16, micro_batch=256,
+                 desc='default synthetic complex (400 nodes), 1000 trajectories, 3-layer SCoNe hidden 16'),
+}
+KIND_NAMES = ['layer_fwd', 'layer_bwd', 'layer0_fwd', 'layer0_bwd', 'readout', 'flows_to_dense']
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        sm.sort()
+        load = [x for x in sm if mx and x > 0.3 * mx] or sm
+        return {'sm_mhz': (load[len(load) // 2] if load else None), 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def make_dataset(cfg, rank):
+    from scone_gcn_b200 import synthetic_data_gen as sdg
+    if cfg['n_nodes'] <= 1000:
+        import numpy as np
+        sys.path.insert(0, os.path.join(ROOT, 'tests'))
+        from golden_util import Dataset
+        ds = Dataset('dataset_default.npz')
+        sp = sdg.SparseDataset.from_dense(ds.flows, ds.B1, ds.B2, ds.targets, ds.train_mask, ds.test_mask, ds.last_nodes,
+                                          ds.target_nodes)
+        return sp
+    return sdg.generate_sparse_dataset(cfg['n_nodes'], cfg['batch'], seed=1030 + rank, n_waypoints=24)
+
+
+def tri_lists(sp):
+    from scone_gcn_b200.complex import incidence_lists_from_simplices
+    return incidence_lists_from_simplices(sp.edges, sp.faces)
+
+
+def cpu_port_run(sp, hidden, n_sample, repeats, seed=0):
+    """Oracle port (CPU, torch sparse, all host threads): fwd + bwd over `n_sample` trajectories; trajectories/s."""
+    import numpy as np
+    import torch
+    from oracle import scone_oracle as so
+    en, es, te, ts = tri_lists(sp)
+    orc = so.SparseOracle('scone', sp.edges, te, ts, int(sp.n_nodes))
+    rs = np.random.RandomState(1030)
+    shapes = [(1, hidden)] * 3 + [(hidden, hidden)] * 6 + [(hidden, 1)]
+    W = [0.01 * rs.randn(*s) for s in shapes]
+    E = len(sp.edges)
+    X = np.zeros((E, n_sample), np.float32)
+    for t in range(n_sample):
+        sl = slice(sp.traj_ptr[t], sp.traj_ptr[t + 1])
+        X[sp.flow_edge[sl], t] = sp.flow_val[sl]
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        orc.loss_and_grads(W, X, sp.last_nodes[:n_sample], sp.target_idx[:n_sample], np.ones(n_sample, np.float32))
+        times.append(time.perf_counter() - t0)
+    return n_sample / min(times), torch.get_num_threads(), times
+
+
+def run_reference(args, cfg, rank, world):
+    if rank != 0:
+        return
+    import torch
+    sp = make_dataset(cfg, 0)
+    n_sample = 2 if cfg['n_nodes'] > 200000 else (8 if cfg['n_nodes'] > 1000 else 64)
+    t0 = time.perf_counter()
+    tps, threads, times = cpu_port_run(sp, cfg['hidden'], n_sample, args.warmup + args.steps)
+    times = times[args.warmup:] or times
+    tps = n_sample / (sum(times) / len(times))
+    sample = '%d trajectories fwd+bwd per step on the same complex (E=%d), sparse CSR CPU port of the reference maths' % (
+        n_sample, len(sp.edges))
+    out = {'impl': 'reference', 'metric': 'SCoNe train trajectories/sec', 'value': tps, 'unit': 'trajectories/s',
+           'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(times) / len(times),
+           'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+           'config': {'workload': args.config + ': ' + cfg['desc'], 'E': int(len(sp.edges)), 'N': int(sp.n_nodes),
+                      'F': int(len(sp.faces)), 'sample_trajectories_per_step': n_sample},
+           'cpu_baseline': {'value': tps, 'unit': 'trajectories/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+           'e2e': {'value': tps, 'unit': 'trajectories/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+           'gpu_launches': 0,
+           'note': 'jax is not installable offline and the dense E x E reference formulation cannot be instantiated at this '
+                   'size; this is the oracle port (oracle/scone_oracle.py SparseOracle) on torch CPU sparse kernels'}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='cfg5', choices=sorted(CONFIGS))
+    ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch')
+    ap.add_argument('--micro-batch', type=int, default=0)
+    ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.batch:
+        cfg['batch'] = args.batch
+    if args.micro_batch:
+        cfg['micro_batch'] = args.micro_batch
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        return run_reference(args, cfg, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import scone_gcn_b200 as sg
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU path)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    L = sg.lib()
+
+    t_setup = time.time()
+    sp = make_dataset(cfg, rank)
+    B = sp.n_traj if args.config == 'cfg1' else cfg['batch']
+    cx = sg.SimplicialComplex.from_simplices(int(sp.n_nodes), sp.edges, sp.faces, 'scone')
+    C, mb = cfg['hidden'], min(cfg['micro_batch'], B)
+    net = sg.SconeModel(cx, [C, C, C], micro_batch=mb)
+    rs = np.random.RandomState(1030)                       # same init on every rank
+    net.set_weights([0.01 * rs.randn(*s) for s in net.shapes])
+    E, N, F, D = cx.E, cx.N, cx.F, cx.D
+    nnz = int(sp.traj_ptr[B])
+    # host batch in pinned memory (e2e) and its device copy (value)
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t
+    h = dict(ptr=pinned(sp.traj_ptr[:B + 1].astype(np.int32)), edge=pinned(sp.flow_edge[:nnz].astype(np.int32)),
+             val=pinned(sp.flow_val[:nnz].astype(np.float32)), last=pinned(sp.last_nodes[:B].astype(np.int32)),
+             tgt=pinned(sp.target_idx[:B].astype(np.int32)), mask=pinned(np.ones(B, np.float32)))
+    d = {k: v.to(dev) for k, v in h.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in h.values())
+    stream = torch.cuda.current_stream().cuda_stream
+    gbuf = net.grads_tensor()
+    from scone_gcn_b200 import _lib
+    lr, wd = 1e-3, 5e-5
+    step_no = [0]
+
+    def step_dev():
+        _lib.check(L.scone_model_loss_grad_dev(net.handle, B, _lib.dptr(d['ptr']), _lib.dptr(d['edge']), _lib.dptr(d['val']),
+                                               _lib.dptr(d['last']), _lib.dptr(d['tgt']), _lib.dptr(d['mask']), 1, stream))
+        if world > 1:
+            dist.all_reduce(gbuf)
+        net.adam_step(step_no[0], lr, wd, stream)
+        step_no[0] += 1
+
+    hp = {k: v.numpy() for k, v in h.items()}
+    loss_host = np.zeros(net.n_params + 2, np.float32)
+
+    def step_e2e():
+        net.loss_grad(hp['ptr'], hp['edge'], hp['val'], hp['last'], hp['tgt'], hp['mask'], zero_first=True, stream=stream, read=False)
+        if world > 1:
+            dist.all_reduce(gbuf)
+        net.adam_step(step_no[0], lr, wd, stream)
+        step_no[0] += 1
+        buf = net.read_grads(stream)                       # D2H of [grads | nll_sum | count]: the step's loss
+        return float(buf[-2] / buf[-1])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    setup_s = time.time() - t_setup
+
+    L.scone_profile_reset()
+    L.scone_profile_enable(1)
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = L.scone_launch_count()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step_dev()
+    ev1.record()
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = L.scone_launch_count() - launches0
+    L.scone_profile_enable(0)
+    clk = clocks.stop()
+    ms_per_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total / 1e3)
+
+    # per-kernel-family device time inside the timed region
+    import ctypes
+    fam = {}
+    for k, nme in enumerate(KIND_NAMES):
+        n_l, t_ms = ctypes.c_int64(), ctypes.c_double()
+        L.scone_profile_read(k, n_l, t_ms)
+        fam[nme] = (n_l.value, t_ms.value)
+    alg = {'layer_fwd': 4.0 * E * mb * (C + C), 'layer_bwd': 4.0 * E * mb * (C + C + C),
+           'layer0_fwd': 4.0 * E * mb * (1 + C), 'layer0_bwd': 4.0 * E * mb * (1 + C),
+           'readout': 4.0 * E * mb * C, 'flows_to_dense': 4.0 * E * mb}
+    peak, peak_src = load_peaks()
+    kernels = {}
+    tot_ms = sum(t for _, t in fam.values()) or 1.0
+    for nme, (n_l, t_ms) in fam.items():
+        if n_l:
+            avg = t_ms / n_l
+            kernels[nme] = {'launches': n_l, 'avg_ms': avg, 'achieved_gbs': alg[nme] / avg / 1e6,
+                            'frac': alg[nme] / avg / 1e6 / peak, 'share_of_kernel_time': t_ms / tot_ms}
+    dom = max(kernels, key=lambda k_: kernels[k_]['share_of_kernel_time'])
+    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': kernels[dom]['achieved_gbs'], 'peak': peak, 'unit': 'GB/s',
+                'frac': kernels[dom]['frac'], 'traffic': None, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': alg[dom],
+                'hodge_spmm_fwd_gbs': kernels.get('layer_fwd', {}).get('achieved_gbs'), 'kernels': kernels}
+
+    # end to end through the host API
+    barrier()
+    e2e_steps = max(1, args.e2e_steps)
+    step_e2e()
+    barrier()
+    ev0.record()
+    loss = None
+    for _ in range(e2e_steps):
+        loss = step_e2e()
+    ev1.record()
+    barrier()
+    e2e_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    e2e = {'value': world * B * e2e_steps / (e2e_ms / 1e3), 'unit': 'trajectories/s', 'h2d_bytes_per_step': h2d_bytes,
+           'd2h_bytes_per_step': int(4 * (net.n_params + 2)), 'steps': e2e_steps, 'last_loss': loss}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_sample = 2 if E > 500000 else (8 if E > 2000 else 64)
+        tps, threads, times = cpu_port_run(sp, C, n_sample, 2)
+        cpu_baseline = {'value': tps, 'unit': 'trajectories/s', 'cores': threads, 'kind': 'port',
+                        'sample': '%d trajectories fwd+bwd on the same complex (E=%d), best of 2; sparse CSR CPU port '
+                                  '(oracle/scone_oracle.py), torch CPU sparse kernels' % (n_sample, E)}
+    if rank == 0:
+        out = {'metric': 'SCoNe train trajectories/sec', 'value': value, 'unit': 'trajectories/s', 'n_gpus': world,
+               'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+               'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+               'config': {'workload': args.config + ': ' + cfg['desc'], 'N': N, 'E': E, 'F': F, 'D': D,
+                          'per_gpu_batch': B, 'global_batch': B * world, 'hidden': C, 'layers': 3, 'micro_batch': mb,
+                          'parallelism': 'dp%d (trajectory shards, complex replicated, one all-reduce of %d floats per step)'
+                                         % (world, net.n_params + 2),
+                          'l2_policy': 'inputs larger than L2: each micro-batch streams %.2f GB of activations'
+                                       % (4.0 * E * mb * C * 5 / 1e9),
+                          'generator_seed': 1030, 'mean_flow_nnz': nnz / B},
+               'roofline': roofline, 'e2e': e2e, 'cpu_baseline': cpu_baseline, 'gpu_launches': int(launches),
+               'clocks': clk, 'setup_s': setup_s}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

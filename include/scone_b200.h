@@ -158,6 +158,13 @@ int scone_model_read_grads(scone_model* m, float* out_host, void* stream);
  * step = 0-based iteration index i. */
 int scone_model_adam_step(scone_model* m, int32_t step, float lr, float weight_decay, void* stream);
 
+/* Optional per-kernel-family device timing (CUDA events recorded on the launching stream around each launch);
+ * off by default.  kind: 0 fused conv layer fwd, 1 fused conv layer bwd (+ its partial reduce), 2 first layer fwd,
+ * 3 first layer bwd, 4 readout (+memset/reduce), 5 flows->dense.  Used by bench.py for the roofline figures. */
+int scone_profile_enable(int32_t on);
+int scone_profile_reset(void);
+int scone_profile_read(int32_t kind, int64_t* launches, double* total_ms);
+
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t scone_launch_count(void);
 

@@ -290,13 +290,14 @@ def train(oracle, rng, weights, train_mask, test_mask, epochs, batch_size, step_
 # sparse formulation with hand-derived backward (scales to configs 4-5; scone / ebli)
 # ------------------------------------------------------------------------------------------------
 class SparseOracle:
-    """Same maths with SciPy CSR operators, layout H[E, b*C] (edge-major), hand-derived backward
-    (SURVEY.md Appendix A).  Used (a) to cross-check the CUDA kernels at sizes where dense E x E cannot
-    exist and (b) as the CPU baseline ('port') timed by bench.py."""
+    """Same maths with CSR operators (torch CPU sparse, multi-threaded), layout H[E, b, C] (edge-major),
+    hand-derived backward.  Used (a) to cross-check the CUDA kernels at sizes where a
+    dense E x E operator cannot exist and (b) as the CPU baseline ('port') timed by bench.py."""
 
     def __init__(self, model, edges, tri_edges, tri_signs, n_nodes, dtype=np.float32):
         """edges [E,2] (tail<head); tri_edges [F,3] edge ids; tri_signs [F,3] in {+1,-1}."""
         self.model, self.dt = model, dtype
+        self.tdt = torch.float32 if dtype == np.float32 else torch.float64
         edges = np.asarray(edges)
         E, F = len(edges), len(tri_edges)
         self.E, self.N = E, n_nodes
@@ -312,82 +313,90 @@ class SparseOracle:
             L1 = (Ll + Lu).tocsr()
             L1.eliminate_zeros()
             S = [L1, (L1 @ L1).tocsr()]
-        self.S = [s.astype(dtype) for s in S]
-        self.B1 = B1.tocsr().astype(dtype)
+        self.S = [self._tcsr(s) for s in S]
+        self.B1 = self._tcsr(B1.tocsr())
+        self.B1T = self._tcsr(B1.T.tocsr())
         adj = (abs(B1) @ abs(B1).T).tolil()
         adj.setdiag(0)
         adj = adj.tocsr()
         adj.eliminate_zeros()
+        adj.sort_indices()
         self.nbr_ptr, self.nbr_idx = adj.indptr, adj.indices           # sorted ascending per row
         self.D = int(np.diff(adj.indptr).max())
 
+    def _tcsr(self, m):
+        m.sort_indices()
+        return torch.sparse_csr_tensor(torch.as_tensor(m.indptr.astype(np.int64)), torch.as_tensor(m.indices.astype(np.int64)),
+                                       torch.as_tensor(m.data.astype(self.dt)), size=m.shape)
+
     def act(self, z):
         if self.model == 'scone':
-            return np.tanh(z)
-        return np.where(z >= 0, z, self.dt(0.01) * z)
+            return torch.tanh(z)
+        return torch.where(z >= 0, z, 0.01 * z)
 
     def dact(self, h):
         if self.model == 'scone':
             return 1 - h * h
-        return np.where(h >= 0, self.dt(1), self.dt(0.01))
+        one = torch.ones((), dtype=h.dtype)
+        return torch.where(h >= 0, one, 0.01 * one)
+
+    def _shift(self, k, H):
+        E, b, C = H.shape
+        return (self.S[k] @ H.reshape(E, b * C)).reshape(E, b, C)
 
     def forward(self, weights, X, last_nodes, keep=False):
         """X [E, b] dense flows (edge-major).  Returns log-probs [b, D] (+ saved activations)."""
-        W = [np.asarray(w, dtype=self.dt) for w in weights]
-        E, b = X.shape
-        L = (len(W) - 1) // 3
-        H = X.reshape(E, b, 1).astype(self.dt)
-        acts = [H]
-        for i in range(L):
-            C = H.shape[2]
-            flat = H.reshape(E, b * C)
-            T1 = (self.S[0] @ flat).reshape(E, b, C)
-            T2 = (self.S[1] @ flat).reshape(E, b, C)
-            H = self.act(H @ W[3 * i] + T1 @ W[3 * i + 1] + T2 @ W[3 * i + 2])
-            acts.append(H)
-        q = (H @ W[-1])[:, :, 0]                                        # [E, b]
-        div = self.B1 @ q                                               # [N, b]
-        logits = np.zeros((b, self.D), dtype=self.dt)
-        for t, n in enumerate(last_nodes):
-            nb = self.nbr_idx[self.nbr_ptr[n]:self.nbr_ptr[n + 1]]
-            logits[t, :len(nb)] = div[nb, t]
-        mx = logits.max(axis=1, keepdims=True)
-        lse = mx + np.log(np.exp(logits - mx).sum(axis=1, keepdims=True))
-        lp = logits - lse
-        return (lp, acts, logits) if keep else lp
+        with torch.no_grad():
+            W = [torch.as_tensor(np.asarray(w, dtype=self.dt)) for w in weights]
+            X = torch.as_tensor(np.asarray(X, dtype=self.dt))
+            E, b = X.shape
+            L = (len(W) - 1) // 3
+            H = X.reshape(E, b, 1)
+            acts = [H]
+            for i in range(L):
+                H = self.act(H @ W[3 * i] + self._shift(0, H) @ W[3 * i + 1] + self._shift(1, H) @ W[3 * i + 2])
+                acts.append(H)
+            q = (H @ W[-1])[:, :, 0]                                        # [E, b]
+            div = (self.B1 @ q).numpy()                                     # [N, b]
+            logits = np.zeros((b, self.D), dtype=self.dt)
+            for t, n in enumerate(last_nodes):
+                nb = self.nbr_idx[self.nbr_ptr[n]:self.nbr_ptr[n + 1]]
+                logits[t, :len(nb)] = div[nb, t]
+            mx = logits.max(axis=1, keepdims=True)
+            lse = mx + np.log(np.exp(logits - mx).sum(axis=1, keepdims=True))
+            lp = logits - lse
+        return (lp, acts, W) if keep else lp
 
     def loss_and_grads(self, weights, X, last_nodes, target_idx, mask, n_total=None):
-        """Returns (nll_sum, [dW] WITHOUT ridge and WITHOUT the 1/n factor unless n_total given)."""
-        W = [np.asarray(w, dtype=self.dt) for w in weights]
-        lp, acts, logits = self.forward(W, X, last_nodes, keep=True)
-        E, b = X.shape
-        L = (len(W) - 1) // 3
-        mask = np.asarray(mask, dtype=self.dt)
-        scale = self.dt(1.0 if n_total is None else 1.0 / n_total)
-        nll = -float((lp[np.arange(b), target_idx] * mask).sum())
-        dlogit = np.exp(lp)
-        dlogit[np.arange(b), target_idx] -= 1
-        dlogit *= (mask * scale)[:, None]
-        ddiv = np.zeros((self.N, b), dtype=self.dt)
-        for t, n in enumerate(last_nodes):
-            nb = self.nbr_idx[self.nbr_ptr[n]:self.nbr_ptr[n + 1]]
-            ddiv[nb, t] = dlogit[t, :len(nb)]
-        dq = self.B1.T @ ddiv                                           # [E, b]
-        HL = acts[-1]
-        grads = [None] * len(W)
-        grads[-1] = np.einsum('ebc,eb->c', HL, dq).reshape(-1, 1)
-        dH = dq[:, :, None] * W[-1][:, 0][None, None, :]
-        for i in range(L - 1, -1, -1):
-            Hin, Hout = acts[i], acts[i + 1]
-            G = dH * self.dact(Hout)
-            Cin, Cout = Hin.shape[2], Hout.shape[2]
-            Gf = G.reshape(E, b * Cout)
-            A1 = (self.S[0] @ Gf).reshape(E, b, Cout)
-            A2 = (self.S[1] @ Gf).reshape(E, b, Cout)
-            Hf = Hin.reshape(E * b, Cin)
-            grads[3 * i] = Hf.T @ G.reshape(E * b, Cout)
-            grads[3 * i + 1] = Hf.T @ A1.reshape(E * b, Cout)
-            grads[3 * i + 2] = Hf.T @ A2.reshape(E * b, Cout)
-            if i > 0:
-                dH = G @ W[3 * i].T + A1 @ W[3 * i + 1].T + A2 @ W[3 * i + 2].T
+        """Returns (nll_sum, [dW]) WITHOUT ridge; gradients are scaled by 1/n_total when it is given."""
+        lp, acts, W = self.forward(weights, X, last_nodes, keep=True)
+        with torch.no_grad():
+            E, b = acts[0].shape[:2]
+            L = (len(W) - 1) // 3
+            mask = np.asarray(mask, dtype=self.dt)
+            scale = self.dt(1.0 if n_total is None else 1.0 / n_total)
+            nll = -float((lp[np.arange(b), target_idx] * mask).sum())
+            dlogit = np.exp(lp)
+            dlogit[np.arange(b), target_idx] -= 1
+            dlogit *= (mask * scale)[:, None]
+            ddiv = np.zeros((self.N, b), dtype=self.dt)
+            for t, n in enumerate(last_nodes):
+                nb = self.nbr_idx[self.nbr_ptr[n]:self.nbr_ptr[n + 1]]
+                ddiv[nb, t] = dlogit[t, :len(nb)]
+            dq = self.B1T @ torch.as_tensor(ddiv)                           # [E, b]
+            HL = acts[-1]
+            grads = [None] * len(W)
+            grads[-1] = torch.einsum('ebc,eb->c', HL, dq).reshape(-1, 1).numpy()
+            dH = dq[:, :, None] * W[-1][:, 0][None, None, :]
+            for i in range(L - 1, -1, -1):
+                Hin, Hout = acts[i], acts[i + 1]
+                G = dH * self.dact(Hout)
+                Cin, Cout = Hin.shape[2], Hout.shape[2]
+                A1, A2 = self._shift(0, G), self._shift(1, G)
+                Hf = Hin.reshape(E * b, Cin)
+                grads[3 * i] = (Hf.T @ G.reshape(E * b, Cout)).numpy()
+                grads[3 * i + 1] = (Hf.T @ A1.reshape(E * b, Cout)).numpy()
+                grads[3 * i + 2] = (Hf.T @ A2.reshape(E * b, Cout)).numpy()
+                if i > 0:
+                    dH = G @ W[3 * i].T + A1 @ W[3 * i + 1].T + A2 @ W[3 * i + 2].T
         return nll, grads

@@ -25,6 +25,9 @@ SIGNATURES = {
     'scone_version': (C.c_int, []),
     'scone_last_error': (C.c_char_p, []),
     'scone_launch_count': (_i64, []),
+    'scone_profile_enable': (C.c_int, [_i32]),
+    'scone_profile_reset': (C.c_int, []),
+    'scone_profile_read': (C.c_int, [_i32, C.POINTER(_i64), C.POINTER(C.c_double)]),
     'scone_complex_create': (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, C.POINTER(_vp)]),
     'scone_complex_create_index_only': (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, C.POINTER(_vp)]),
     'scone_complex_destroy': (C.c_int, [_vp]),

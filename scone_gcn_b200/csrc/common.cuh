@@ -32,6 +32,18 @@ extern std::atomic<long long> g_scone_launches;
         SCONE_CUDA(cudaGetLastError());                                                                 \
     } while (0)
 
+// Optional per-kernel timing (CUDA events on the launching stream), off by default; bench.py's roofline uses it.
+enum { SCONE_K_LAYER_FWD = 0, SCONE_K_LAYER_BWD = 1, SCONE_K_LAYER0_FWD = 2, SCONE_K_LAYER0_BWD = 3, SCONE_K_READOUT = 4,
+       SCONE_K_OTHER = 5, SCONE_K_COUNT = 6 };
+extern bool g_scone_prof;
+void scone_prof_begin_impl(int kind, cudaStream_t st);
+void scone_prof_end_impl(int kind, cudaStream_t st);
+struct ScopedProf {
+    int kind; cudaStream_t st;
+    ScopedProf(int k, cudaStream_t s) : kind(k), st(s) { if (g_scone_prof) scone_prof_begin_impl(kind, st); }
+    ~ScopedProf() { if (g_scone_prof) scone_prof_end_impl(kind, st); }
+};
+
 // Integer-valued shift operator in CSR form.  ent[p] = {column, float bits of the coefficient};
 // columns ascending inside a row (fixed, deterministic summation order).
 struct DevCsr {

@@ -27,6 +27,55 @@ extern "C" const char* scone_last_error(void) { return g_err; }
 extern "C" int scone_version(void) { return SCONE_B200_VERSION; }
 extern "C" int64_t scone_launch_count(void) { return g_scone_launches.load(); }
 
+// ---- optional per-kernel timing ---------------------------------------------------------------
+bool g_scone_prof = false;
+namespace {
+struct ProfRec { int kind; cudaEvent_t a, b; };
+std::vector<ProfRec> g_prof_pending;
+std::vector<cudaEvent_t> g_prof_pool;
+double g_prof_ms[SCONE_K_COUNT] = {0};
+long long g_prof_n[SCONE_K_COUNT] = {0};
+cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void prof_collect() {
+    for (auto& r : g_prof_pending) {
+        cudaEventSynchronize(r.b);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { g_prof_ms[r.kind] += ms; g_prof_n[r.kind] += 1; }
+        g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b);
+    }
+    g_prof_pending.clear();
+}
+}  // namespace
+void scone_prof_begin_impl(int kind, cudaStream_t st) {
+    ProfRec r{kind, prof_event(), prof_event()};
+    cudaEventRecord(r.a, st);
+    g_prof_pending.push_back(r);
+}
+void scone_prof_end_impl(int kind, cudaStream_t st) {
+    for (size_t i = g_prof_pending.size(); i-- > 0;)
+        if (g_prof_pending[i].kind == kind) { cudaEventRecord(g_prof_pending[i].b, st); break; }
+}
+extern "C" int scone_profile_enable(int32_t on) {
+    prof_collect();
+    g_scone_prof = on != 0;
+    return 0;
+}
+extern "C" int scone_profile_reset(void) {
+    prof_collect();
+    for (int k = 0; k < SCONE_K_COUNT; ++k) { g_prof_ms[k] = 0; g_prof_n[k] = 0; }
+    return 0;
+}
+extern "C" int scone_profile_read(int32_t kind, int64_t* launches, double* total_ms) {
+    SCONE_REQUIRE(kind >= 0 && kind < SCONE_K_COUNT, "scone_profile_read: kind out of range");
+    prof_collect();
+    if (launches) *launches = g_prof_n[kind];
+    if (total_ms) *total_ms = g_prof_ms[kind];
+    return 0;
+}
+
 namespace {
 
 struct IntCsr {

@@ -590,6 +590,7 @@ int launch_fwd(const scone_complex* cx, int b, const float* Hin, const float* W0
     int occ = 1;
     SCONE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
     const int n_tiles = ((b + TT - 1) / TT) * ((cx->E + TE - 1) / TE);
+    ScopedProf prof(SCONE_K_LAYER_FWD, st);
     kern<<<grid_for(cx, n_tiles, occ > 0 ? occ : 1), kThreads, smem, st>>>(Hin, Hout, W0, W1, W2, cx->S(0), cx->S(1), cx->E, b);
     SCONE_LAUNCHED();
     return 0;
@@ -628,6 +629,7 @@ int launch_bwd(const scone_complex* cx, int b, const float* G, const float* Hin,
     const int n_tiles = ((b + Sh::TT - 1) / Sh::TT) * ((cx->E + Sh::TE - 1) / Sh::TE);
     int grid = grid_for(cx, n_tiles, occ);
     if (grid > kBwdMaxCtas) grid = kBwdMaxCtas;
+    ScopedProf prof(SCONE_K_LAYER_BWD, st);
     kern<<<grid, kThreads, smem, st>>>(G, Hin, Gprev, W0, W1, W2, ws, cx->S(0), cx->S(1), cx->E, b);
     SCONE_LAUNCHED();
     reduce_partials_kernel<<<(Sh::DW + 255) / 256, 256, 0, st>>>(ws, grid, Sh::DW, dW, accumulate);
@@ -715,6 +717,7 @@ static int launch_l0_fwd(const scone_complex* cx, int act, int b, const float* X
                          float* Hout, cudaStream_t st) {
     const int n_tiles = ((b + 31) / 32) * ((cx->E + kL0Edges - 1) / kL0Edges);
     const int grid = grid_for(cx, n_tiles, 6);
+    ScopedProf prof(SCONE_K_LAYER0_FWD, st);
     switch (act) {
         case SCONE_ACT_TANH:
             layer0_fwd_kernel<COUT, SCONE_ACT_TANH><<<grid, kThreads, 0, st>>>(X, Hout, W0, W1, W2, cx->S(0), cx->S(1), cx->E, b);
@@ -753,6 +756,7 @@ static int launch_l0_bwd(const scone_complex* cx, int b, const float* G, const f
     const int n_tiles = ((b + 31) / 32) * ((cx->E + kL0Edges - 1) / kL0Edges);
     int grid = grid_for(cx, n_tiles, 4);
     if (grid > kL0BwdCtas) grid = kL0BwdCtas;
+    ScopedProf prof(SCONE_K_LAYER0_BWD, st);
     layer0_bwd_kernel<COUT><<<grid, kThreads, 0, st>>>(X, G, ws, cx->S(0), cx->S(1), cx->E, b);
     SCONE_LAUNCHED();
     reduce_partials_kernel<<<(3 * COUT + 255) / 256, 256, 0, st>>>(ws, grid, 3 * COUT, dW, accumulate);
@@ -779,6 +783,7 @@ extern "C" int scone_flows_to_dense(const scone_complex* cx, int32_t b, const in
     SCONE_REQUIRE(cx && traj_ptr && X && b > 0, "scone_flows_to_dense: bad argument");
     SCONE_REQUIRE(!cx->host_only, "scone_flows_to_dense: index-only complex has no device arrays");
     cudaStream_t st = as_stream(stream);
+    ScopedProf prof(SCONE_K_OTHER, st);
     SCONE_CUDA(cudaMemsetAsync(X, 0, (size_t)cx->E * b * sizeof(float), st));
     flows_to_dense_kernel<<<(b * 32 + 255) / 256, 256, 0, st>>>(traj_ptr, flow_edge, flow_val, X, cx->E, b);
     SCONE_LAUNCHED();
@@ -795,6 +800,7 @@ int scone_readout_ws(const scone_complex* cx, int32_t act, int32_t b, int32_t C,
     SCONE_REQUIRE(C >= 1 && C <= 32 * kReadoutMaxCper, "scone_readout: C must be in [1,%d]", 32 * kReadoutMaxCper);
     SCONE_REQUIRE(cx->D <= kReadoutMaxD, "scone_readout: max degree %d exceeds %d", cx->D, kReadoutMaxD);
     cudaStream_t st = as_stream(stream);
+    ScopedProf prof(SCONE_K_READOUT, st);
     if (GL) {
         SCONE_REQUIRE(target_idx && mask && workspace, "scone_readout: gradient mode needs target_idx, mask, workspace");
         SCONE_CUDA(cudaMemsetAsync(GL, 0, (size_t)cx->E * b * C * sizeof(float), st));
