@@ -11,7 +11,7 @@
  *     (`stream` is a cudaStream_t passed as void*; NULL = legacy default stream),
  *   - take plain pointers and sizes.  "dev" = device pointer, "host" = host pointer.
  *
- * Device layouts (fp32, row-major):
+ * Device layouts (fp32, row-major; e = INTERNAL edge row, see scone_complex_get_edge_rank):
  *   activations  H[e][t][c]  -> ((e * b) + t) * C + c      e < E edges, t < b trajectories, c < C channels
  *   flows        X[e][t]     -> e * b + t                  (layer-0 input, C = 1)
  *   weights      flat concatenation of the reference's weight list, each [C_in][C_out] row-major, in
@@ -66,6 +66,11 @@ int scone_complex_dims(const scone_complex* cx, int32_t* n_nodes, int32_t* n_edg
 int scone_complex_get_shift_csr(const scone_complex* cx, int32_t which, int32_t* rowptr /* [E+1] */,
                                 int32_t* col /* [nnz] */, float* val /* [nnz] */);
 int scone_complex_get_nbrhoods(const scone_complex* cx, int32_t* nbrhoods /* [N][D], pad -1 */);
+/* Device tensors H[E][b][C], X[E][b] and the occupancy flags are stored in an INTERNAL edge order chosen for memory
+ * locality (Hilbert curve over two BFS distance fields); rank[e] is the internal row of the caller's edge e.  The
+ * model-level entry points and scone_flows_to_dense translate for the caller; only code that fills H directly
+ * (kernel-level tests, the jax.ffi layer ops) needs this map. */
+int scone_complex_get_edge_rank(const scone_complex* cx, int32_t* rank /* host [E] */);
 
 /* ---------------------------------------------------------------------------------------------
  * Kernel-level entry points (device pointers).  These are what a jax.ffi handler binds, one per
@@ -80,10 +85,17 @@ int scone_flows_to_dense(const scone_complex* cx, int32_t b, const int32_t* traj
 
 /* One fused Hodge-Laplacian convolution layer, forward:
  *   Hout = act(Hin W0 + (S0 Hin) W1 + (S1 Hin) W2)                       trajectory_experiments.py:145-149,163-167
- * Hin [E][b][cin], Hout [E][b][cout], W* [cin][cout] (device). */
+ * Hin [E][b][cin], Hout [E][b][cout], W* [cin][cout] (device).
+ * Occupancy flags (optional, NULL = none): occ[e*b + t] == 0 promises that row (e, t) of the tensor is entirely
+ * zero.  There is no bias and act(0) == 0, so activations are structurally zero outside the l-hop neighbourhood of a
+ * trajectory; with occ_in the kernel skips the gathers of flagged-zero neighbour rows and the FLOPs
+ * of all-zero tiles — results are bit-identical, every row is still read and written once.  occ_out receives the
+ * flags of Hout.  occ_scratch (E*b bytes, optional) lets the call first propagate the flags one hop (a byte-only
+ * pre-pass) so that whole tiles without any candidate row are zero-filled without touching the index arrays. */
 int scone_layer_forward(const scone_complex* cx, int32_t act, int32_t b, int32_t cin, int32_t cout,
                         const float* Hin_dev, const float* W0_dev, const float* W1_dev, const float* W2_dev,
-                        float* Hout_dev, void* stream);
+                        float* Hout_dev, const uint8_t* occ_in_dev, uint8_t* occ_out_dev, uint8_t* occ_scratch_dev,
+                        void* stream);
 
 /* Backward of the same layer (what jax.grad derives from the lines above, scone_trajectory_model.py:307).
  * G_dev = dL/dZ of this layer ( = dL/dHout * act'(Hout), already multiplied) [E][b][cout].
@@ -95,7 +107,9 @@ int64_t scone_layer_backward_workspace_bytes(int32_t cin, int32_t cout);
 int scone_layer_backward(const scone_complex* cx, int32_t act, int32_t b, int32_t cin, int32_t cout,
                          const float* G_dev, const float* Hin_dev,
                          const float* W0_dev, const float* W1_dev, const float* W2_dev,
-                         float* Gprev_dev, float* dW_dev, int32_t accumulate, void* workspace_dev, void* stream);
+                         float* Gprev_dev, float* dW_dev, int32_t accumulate, void* workspace_dev,
+                         const uint8_t* occ_g_dev, const uint8_t* occ_hin_dev, uint8_t* occ_gprev_dev,
+                         uint8_t* occ_scratch_dev, void* stream);
 
 /* Readout + padded log-softmax (+ NLL and its gradient):
  *   logits = Bcond(last_node) @ H_L @ w_out ; logits - logsumexp(logits)   trajectory_experiments.py:151-152,298-303
@@ -113,7 +127,7 @@ int scone_readout(const scone_complex* cx, int32_t act, int32_t b, int32_t C,
                   float* logprobs_dev,
                   const int32_t* target_idx_dev, const float* mask_dev, float scale,
                   float* GL_dev, float* dwout_dev, float* nll_sum_dev, float* count_dev, int32_t accumulate,
-                  void* workspace_dev, void* stream);
+                  void* workspace_dev, const uint8_t* occ_HL_dev, uint8_t* occ_GL_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Model-level entry points — replace Scone_GCN.{setup, loss, accuracy, train's adam_step}
@@ -157,6 +171,13 @@ int scone_model_read_grads(scone_model* m, float* out_host, void* stream);
  *   g = grads / count + 2 * weight_decay * W ;  m,v update ;  W -= lr * mhat / (sqrt(vhat) + eps)
  * step = 0-based iteration index i. */
 int scone_model_adam_step(scone_model* m, int32_t step, float lr, float weight_decay, void* stream);
+
+/* Flagged kernels write only the rows that can be non-zero.  With zero-fill ON (default) every output tensor is first
+ * bulk-zeroed, so it is a complete dense [E][b][C] array (the dense-streaming contract: each output byte written).
+ * With zero-fill OFF unflagged rows are left unwritten and every consumer must honour the flags (all kernels of this
+ * library do): traffic then scales with the support of the trajectories instead of E.  Results are identical. */
+int scone_set_zero_fill(int32_t on);
+int scone_get_zero_fill(void);
 
 /* Optional per-kernel-family device timing (CUDA events recorded on the launching stream around each launch);
  * off by default.  kind: 0 fused conv layer fwd, 1 fused conv layer bwd (+ its partial reduce), 2 first layer fwd,

@@ -34,12 +34,15 @@ SIGNATURES = {
     'scone_complex_dims': (C.c_int, [_vp] + [C.POINTER(_i32)] * 4 + [C.POINTER(_i64)] * 2),
     'scone_complex_get_shift_csr': (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
     'scone_complex_get_nbrhoods': (C.c_int, [_vp, _vp]),
+    'scone_complex_get_edge_rank': (C.c_int, [_vp, _vp]),
     'scone_flows_to_dense': (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
-    'scone_layer_forward': (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'scone_layer_forward': (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'scone_layer_backward_workspace_bytes': (_i64, [_i32, _i32]),
-    'scone_layer_backward': (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    'scone_layer_backward': (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     'scone_readout_workspace': (_i64, [_i32, _i32]),
-    'scone_readout': (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    'scone_readout': (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    'scone_set_zero_fill': (C.c_int, [_i32]),
+    'scone_get_zero_fill': (C.c_int, []),
     'scone_model_create': (C.c_int, [_vp, _i32, _vp, _i32, C.POINTER(_vp)]),
     'scone_model_destroy': (C.c_int, [_vp]),
     'scone_model_num_params': (_i64, [_vp]),

@@ -135,6 +135,13 @@ class SimplicialComplex:
         return M
 
     @property
+    def edge_rank(self):
+        """rank[e] = internal device row of the caller's edge e (device tensors are stored in a locality order)."""
+        a = np.zeros(self.E, np.int32)
+        _lib.check(_lib.lib().scone_complex_get_edge_rank(self.handle, _lib.ptr(a)))
+        return a
+
+    @property
     def nbrhoods(self):
         if self._nbrhoods is None:
             a = np.zeros((self.N, max(self.D, 1)), np.int32)

@@ -36,6 +36,7 @@ extern std::atomic<long long> g_scone_launches;
 enum { SCONE_K_LAYER_FWD = 0, SCONE_K_LAYER_BWD = 1, SCONE_K_LAYER0_FWD = 2, SCONE_K_LAYER0_BWD = 3, SCONE_K_READOUT = 4,
        SCONE_K_OTHER = 5, SCONE_K_COUNT = 6 };
 extern bool g_scone_prof;
+extern bool g_scone_zero_fill;   // flagged kernels: bulk zero-fill outputs (dense-streaming contract) or leave unflagged rows unwritten
 void scone_prof_begin_impl(int kind, cudaStream_t st);
 void scone_prof_end_impl(int kind, cudaStream_t st);
 struct ScopedProf {
@@ -63,12 +64,14 @@ struct scone_complex {
     bool host_only = false;                    // built by scone_complex_create_index_only: no device arrays
     HostCsr hS[2];
     std::vector<int32_t> h_nbrhoods;           // [N][D], pad -1
+    std::vector<int32_t> h_rank;               // [E] caller's edge id -> internal edge row
     // device
     int32_t* d_rowptr[2] = {nullptr, nullptr};
     int2* d_ent[2] = {nullptr, nullptr};
     int32_t* d_nbrhoods = nullptr;             // [N][D]
     int32_t* d_inc_ptr = nullptr;              // [N+1]   B1 rows: node -> incident edges
-    int2* d_inc_ent = nullptr;                 // [2E]    {edge, float bits of sign}, edge ascending
+    int2* d_inc_ent = nullptr;                 // [2E]    {internal edge id, float bits of sign}, ascending
+    int32_t* d_rank = nullptr;                 // [E]     caller's edge id -> internal (locality-ordered) edge row
     DevCsr S(int k) const { return DevCsr{d_rowptr[k], d_ent[k]}; }
 };
 
@@ -76,14 +79,14 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 
 // internal kernels-level helpers implemented in scone_kernels.cu
 int scone_layer0_forward(const scone_complex* cx, int32_t act, int32_t b, int32_t cout, const float* X_dev,
-                         const float* W0, const float* W1, const float* W2, float* Hout, void* stream);
+                         const float* W0, const float* W1, const float* W2, float* Hout, uint8_t* occ_out, void* stream);
 int64_t scone_layer0_backward_workspace_bytes(int32_t cout);
 int scone_layer0_backward(const scone_complex* cx, int32_t b, int32_t cout, const float* G_dev, const float* X_dev,
-                          float* dW_dev, int32_t accumulate, void* workspace, void* stream);
+                          float* dW_dev, int32_t accumulate, void* workspace, const uint8_t* occ_g, void* stream);
 int64_t scone_readout_workspace_bytes(int32_t b, int32_t C);
 int scone_readout_ws(const scone_complex* cx, int32_t act, int32_t b, int32_t C, const float* HL, const float* wout,
                      const int32_t* last_nodes, float* logprobs, const int32_t* target_idx, const float* mask,
                      float scale, float* GL, float* dwout, float* nll_sum, float* count, int32_t accumulate,
-                     void* workspace, void* stream);
+                     void* workspace, const uint8_t* occ_HL, uint8_t* occ_GL, void* stream);
 int scone_adam_launch(float* W, float* m, float* v, const float* gradbuf, int64_t n, int32_t step, float lr,
                       float wd, void* stream);

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include "common.cuh"
@@ -149,6 +150,84 @@ IntCsr gram(int32_t n_edges, const std::vector<std::vector<std::pair<int32_t, in
     return L;
 }
 
+// ---- internal edge order -------------------------------------------------------------------------------------------
+// Activations are private to the library, so edge rows may live in any order on the device.  The reference's order
+// (lexicographic over nodes sorted by x+y) spreads a spatial neighbourhood over the whole index range; a CTA tile of
+// consecutive edges then touches rows all over HBM/L2 and almost every tile intersects some trajectory's support.  We
+// sort edges along a Hilbert curve over two graph-distance fields (BFS from two peripheral landmarks), which needs no
+// coordinates and keeps mesh neighbourhoods in compact index ranges.
+uint64_t hilbert_d(uint32_t x, uint32_t y) {      // 16-bit coordinates -> position along the Hilbert curve
+    uint64_t d = 0;
+    for (uint32_t s = 1u << 15; s > 0; s >>= 1) {
+        uint32_t rx = (x & s) ? 1 : 0, ry = (y & s) ? 1 : 0;
+        d += (uint64_t)s * s * ((3 * rx) ^ ry);
+        if (ry == 0) {
+            if (rx == 1) { x = 65535u - x; y = 65535u - y; }
+            uint32_t t = x; x = y; y = t;
+        }
+    }
+    return d;
+}
+
+void bfs(const std::vector<int32_t>& ptr, const std::vector<int32_t>& adj, int32_t src, std::vector<int32_t>& dist,
+         std::vector<int32_t>& order) {
+    order.clear();
+    dist[src] = 0;
+    order.push_back(src);
+    for (size_t h = 0; h < order.size(); ++h) {
+        int32_t u = order[h];
+        for (int32_t p = ptr[u]; p < ptr[u + 1]; ++p) {
+            int32_t v = adj[p];
+            if (dist[v] < 0) { dist[v] = dist[u] + 1; order.push_back(v); }
+        }
+    }
+}
+
+// order[new] = old edge id
+std::vector<int32_t> locality_order(int32_t N, int32_t E, const int32_t* edge_nodes) {
+    std::vector<int32_t> ptr(N + 1, 0), adj(2 * (size_t)E);
+    for (int32_t e = 0; e < E; ++e) { ptr[edge_nodes[2 * e] + 1]++; ptr[edge_nodes[2 * e + 1] + 1]++; }
+    for (int32_t n = 0; n < N; ++n) ptr[n + 1] += ptr[n];
+    std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
+    for (int32_t e = 0; e < E; ++e) {
+        int32_t a = edge_nodes[2 * e], b = edge_nodes[2 * e + 1];
+        adj[fill[a]++] = b;
+        adj[fill[b]++] = a;
+    }
+    std::vector<int32_t> comp(N, -1), tmp(N, -1), d1(N, -1), d2(N, -1), d3(N, -1), ord, ord2;
+    std::vector<int64_t> cx(N, 0), cy(N, 0);
+    int64_t xoff = 0;
+    for (int32_t s0 = 0; s0 < N; ++s0) {
+        if (comp[s0] >= 0 || ptr[s0 + 1] == ptr[s0]) continue;
+        bfs(ptr, adj, s0, tmp, ord);
+        int32_t a = ord.back();                  // peripheral node
+        for (int32_t v : ord) comp[v] = s0;
+        bfs(ptr, adj, a, d1, ord2);
+        int32_t b = ord2.back();
+        bfs(ptr, adj, b, d2, ord2);
+        int32_t c = a;
+        int64_t best = -1;
+        for (int32_t v : ord) if ((int64_t)d1[v] + d2[v] > best) { best = (int64_t)d1[v] + d2[v]; c = v; }
+        bfs(ptr, adj, c, d3, ord2);
+        int64_t xmax = 0;
+        for (int32_t v : ord) { cx[v] = xoff + d1[v]; cy[v] = d3[v]; xmax = std::max<int64_t>(xmax, d1[v]); }
+        xoff += xmax + 2;                         // components side by side
+    }
+    int64_t mx = 1, my = 1;
+    for (int32_t n = 0; n < N; ++n) { mx = std::max(mx, cx[n]); my = std::max(my, cy[n]); }
+    const int64_t span = std::max(mx, my) * 2 + 1;   // edge key uses the sum of its end nodes (2 x midpoint)
+    std::vector<std::pair<uint64_t, int32_t>> key(E);
+    for (int32_t e = 0; e < E; ++e) {
+        int32_t a = edge_nodes[2 * e], b = edge_nodes[2 * e + 1];
+        uint32_t x = (uint32_t)(((cx[a] + cx[b]) * 65535) / span), y = (uint32_t)(((cy[a] + cy[b]) * 65535) / span);
+        key[e] = {hilbert_d(x, y), e};
+    }
+    std::sort(key.begin(), key.end());
+    std::vector<int32_t> order(E);
+    for (int32_t i = 0; i < E; ++i) order[i] = key[i].second;
+    return order;
+}
+
 template <typename T>
 int upload(T** dst, const std::vector<T>& src) {
     size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
@@ -231,6 +310,16 @@ static int complex_create_impl(int32_t N, int32_t E, int32_t F, const int32_t* e
     for (int32_t n = 0; n < N; ++n)
         for (size_t j = 0; j < nbrs[n].size(); ++j) cx->h_nbrhoods[(size_t)n * D + j] = nbrs[n][j];
 
+    // device arrays live in the internal (locality) edge order: rank[old] = new, order[new] = old
+    std::vector<int32_t> order(E), rank(E);
+    const char* no_reorder = getenv("SCONE_B200_NO_REORDER");
+    if (no_reorder && no_reorder[0] == '1') {
+        for (int32_t e = 0; e < E; ++e) order[e] = e;
+    } else {
+        order = locality_order(N, E, edge_nodes);
+    }
+    for (int32_t i = 0; i < E; ++i) rank[order[i]] = i;
+    cx->h_rank = rank;
     if (!upload_to_device) {                 // index-only handle: getters work, every device op is refused
         cx->host_only = true;
         *out = cx;
@@ -247,29 +336,45 @@ static int complex_create_impl(int32_t N, int32_t E, int32_t F, const int32_t* e
 
     int rc = 0;
     for (int k = 0; k < 2 && !rc; ++k) {
-        std::vector<int2> ent(cx->hS[k].col.size());
-        for (size_t i = 0; i < ent.size(); ++i) {
-            int32_t bits;
-            memcpy(&bits, &cx->hS[k].val[i], 4);
-            ent[i] = make_int2(cx->hS[k].col[i], bits);
+        const HostCsr& h = cx->hS[k];
+        std::vector<int32_t> rowptr(E + 1, 0);
+        std::vector<int2> ent(h.col.size());
+        std::vector<std::pair<int32_t, int32_t>> row;
+        size_t w = 0;
+        for (int32_t i = 0; i < E; ++i) {
+            const int32_t o = order[i];
+            row.clear();
+            for (int32_t p = h.rowptr[o]; p < h.rowptr[o + 1]; ++p) {
+                int32_t bits;
+                memcpy(&bits, &h.val[p], 4);
+                row.push_back({rank[h.col[p]], bits});
+            }
+            std::sort(row.begin(), row.end());           // ascending internal column: fixed summation order
+            for (auto& cv : row) ent[w++] = make_int2(cv.first, cv.second);
+            rowptr[i + 1] = (int32_t)w;
         }
-        rc |= upload(&cx->d_rowptr[k], cx->hS[k].rowptr);
+        rc |= upload(&cx->d_rowptr[k], rowptr);
         rc |= upload(&cx->d_ent[k], ent);
     }
     std::vector<int32_t> inc_ptr(N + 1, 0);
     std::vector<int2> inc_ent;
     inc_ent.reserve(2 * (size_t)E);
+    std::vector<std::pair<int32_t, int32_t>> row;
     for (int32_t n = 0; n < N; ++n) {
+        row.clear();
         for (auto& es : node_to_edges[n]) {
-            float s = (float)es.second;
+            float sgn = (float)es.second;
             int32_t bits;
-            memcpy(&bits, &s, 4);
-            inc_ent.push_back(make_int2(es.first, bits));
+            memcpy(&bits, &sgn, 4);
+            row.push_back({rank[es.first], bits});
         }
+        std::sort(row.begin(), row.end());
+        for (auto& cv : row) inc_ent.push_back(make_int2(cv.first, cv.second));
         inc_ptr[n + 1] = (int32_t)inc_ent.size();
     }
     if (!rc) rc |= upload(&cx->d_inc_ptr, inc_ptr);
     if (!rc) rc |= upload(&cx->d_inc_ent, inc_ent);
+    if (!rc) rc |= upload(&cx->d_rank, rank);
     if (!rc) rc |= upload(&cx->d_nbrhoods, cx->h_nbrhoods);
     if (rc) {
         scone_complex_destroy(cx);
@@ -299,6 +404,7 @@ extern "C" int scone_complex_destroy(scone_complex* cx) {
     cudaFree(cx->d_nbrhoods);
     cudaFree(cx->d_inc_ptr);
     cudaFree(cx->d_inc_ent);
+    cudaFree(cx->d_rank);
     delete cx;
     return 0;
 }
@@ -322,6 +428,12 @@ extern "C" int scone_complex_get_shift_csr(const scone_complex* cx, int32_t whic
     if (rowptr) memcpy(rowptr, h.rowptr.data(), h.rowptr.size() * sizeof(int32_t));
     if (col) memcpy(col, h.col.data(), h.col.size() * sizeof(int32_t));
     if (val) memcpy(val, h.val.data(), h.val.size() * sizeof(float));
+    return 0;
+}
+
+extern "C" int scone_complex_get_edge_rank(const scone_complex* cx, int32_t* rank) {
+    SCONE_REQUIRE(cx != nullptr && rank != nullptr, "scone_complex_get_edge_rank: bad arguments");
+    memcpy(rank, cx->h_rank.data(), cx->h_rank.size() * sizeof(int32_t));
     return 0;
 }
 

@@ -1,19 +1,23 @@
 // scone_kernels.cu — hand-written sm_100a kernels of the SCoNe hot path.
 //
-//   layer_fwd_kernel   Hout = act(Hin W0 + (S0 Hin) W1 + (S1 Hin) W2)      (trajectory_experiments.py:145-149)
-//   layer_bwd_kernel   Gprev = ((S_k G) W_k^T summed over k) * act'(Hin),  dW_k = Hin^T (S_k G)
-//   layer0_*           the C_in = 1 first layer (input = flows X[E][b])
-//   readout_kernel     Bcond(last) @ H_L @ w_out, padded log-softmax, NLL and its gradient
-//                      (trajectory_experiments.py:151-152,298-303; scone_trajectory_model.py:46,54)
-//   adam_kernel        JAX adam update (scone_trajectory_model.py:300,310)
+//   Hout = act(Hin W0 + (S0 Hin) W1 + (S1 Hin) W2)                           trajectory_experiments.py:145-149,163-167
+//   backward of the same (what jax.grad derives, scone_trajectory_model.py:307):
+//       A_k = S_k G,  Gprev = (sum_k A_k W_k^T) * act'(Hin),  dW_k = Hin^T A_k      (S_k symmetric)
+//   readout Bcond(last) @ H_L @ w_out, padded log-softmax, NLL + gradient       trajectory_experiments.py:151-152,298-303
+//   JAX adam update                                                             scone_trajectory_model.py:300,310
 //
-// Design: activations are H[E][b][C] fp32, one edge row = b*C contiguous floats.  A CTA
-// owns a tile of TE edges x 128 columns.  Phase 1: every warp owns whole output edge rows and gathers
-// the 1 + nnz(S0 row) + nnz(S1 row) neighbour rows with 128-bit coalesced loads in the CSR's fixed
-// (ascending) order — no atomics, deterministic — into shared memory.  Phase 2: the three C x C weight
-// products, the three-term sum and the activation run as a register-tiled contraction out of shared
-// memory, and the result is stored with 128-bit coalesced stores.  Weight gradients are accumulated in
-// registers across the tiles of a persistent CTA, written as per-CTA partials and reduced in CTA order.
+// Layout: activations H[E][b][C] fp32 (e = internal edge row), one edge row = b*C contiguous floats.  Two kernel
+// families implement the fused layer:
+//   * DENSE tile kernels (no occupancy information): a CTA owns 128 (edge, trajectory) rows; every warp gathers whole
+//     edge rows (1 + nnz(S0 row) + nnz(S1 row) neighbour rows, 128-bit coalesced loads, CSR order = fixed summation
+//     order, no atomics) into shared memory, then the 3C x C weight products + sum + activation run as a
+//     register-tiled contraction and are stored with 128-bit coalesced stores.
+//   * UNIT kernels (occupancy flags given): there is no bias and act(0) = 0, so activations are exactly zero outside the
+//     l-hop neighbourhood of a trajectory.  A byte-only pre-pass propagates the row flags one hop; CTAs classify
+//     blocks of 1024 (edge, trajectory-chunk) units, compact the candidates deterministically, and warps process the
+//     candidates autonomously (flag-aware gather, per-row contraction).  Skipping a zero row is exact.
+// Weight gradients are accumulated in registers in a data-independent thread mapping and a fixed row order, written
+// as per-CTA partials and reduced in CTA order: bit-reproducible run to run.
 #include <math_constants.h>
 #include "common.cuh"
 
@@ -21,8 +25,8 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kTileRows = 128;      // (edge, trajectory) rows per tile
-constexpr int kTileCols = 128;      // gathered columns per edge per tile (32 lanes x float4)
+constexpr int kTileRows = 128;      // (edge, trajectory) rows per dense tile
+constexpr int kTileCols = 128;      // gathered columns per edge per warp pass (32 lanes x float4)
 
 template <int ACT>
 __device__ __forceinline__ float act_fn(float z) {
@@ -49,10 +53,26 @@ __device__ __forceinline__ void fma4(float4& a, float s, const float4& v) {
     a.z = fmaf(s, v.z, a.z);
     a.w = fmaf(s, v.w, a.w);
 }
+__device__ __forceinline__ bool nz4(const float4& v) { return v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f; }
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
-// sum_p coef_p * H[col_p][colofs .. colofs+3] over one CSR row, ascending column order.
-__device__ __forceinline__ float4 gather_row4(const float* __restrict__ H, size_t rowlen, int colofs, DevCsr S, int e) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Row gathers: sum_p coef_p * H[col_p][colofs .. colofs+3] over one CSR row, ascending column order.
+// ---------------------------------------------------------------------------------------------------------------
+// Dense flavour: every neighbour row is loaded; 4 independent 128-bit loads in flight.
+__device__ __forceinline__ float4 gather_row4_dense(const float* __restrict__ H, size_t rowlen, int colofs, DevCsr S, int e) {
+    float4 acc = zero4();
     int p = __ldg(S.rowptr + e);
     const int end = __ldg(S.rowptr + e + 1);
     for (; p + 4 <= end; p += 4) {
@@ -74,6 +94,54 @@ __device__ __forceinline__ float4 gather_row4(const float* __restrict__ H, size_
     return acc;
 }
 
+// Flag-aware flavour: lanes fetch the row's (column, coefficient) entries in parallel and test whether neighbour row i
+// has a non-zero among this unit's TT trajectories; the warp then loads only the flagged neighbour rows.
+template <int TT>
+__device__ __forceinline__ float4 gather_row4_flagged(const float* __restrict__ H, size_t rowlen, int colofs, bool colok, DevCsr S,
+                                                      int e, const uint8_t* __restrict__ occ, int b, int t0, int jl) {
+    float4 acc = zero4();
+    const int lane = threadIdx.x & 31;
+    const int p0 = __ldg(S.rowptr + e), p1 = __ldg(S.rowptr + e + 1);
+    for (int base = p0; base < p1; base += 32) {
+        const int idx = base + lane;
+        int2 ent = make_int2(e, 0);
+        unsigned fm = 0;                                  // bit k: trajectory t0+k of neighbour row `idx` is flagged
+        if (idx < p1) {
+            ent = __ldg(S.ent + idx);
+            const uint8_t* f = occ + (size_t)ent.x * b + t0;
+#pragma unroll
+            for (int k = 0; k < TT; ++k)
+                if (t0 + k < b && __ldg(f + k) != 0) fm |= 1u << k;
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, fm != 0u);
+        while (mask) {
+            const int n = min(4, __popc(mask));          // warp-uniform
+            float c[4];
+            int col[4];
+            bool mine[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (u < n) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    col[u] = __shfl_sync(0xffffffffu, ent.x, src);
+                    c[u] = __int_as_float(__shfl_sync(0xffffffffu, ent.y, src));
+                    const unsigned nfm = __shfl_sync(0xffffffffu, fm, src);      // (all lanes take part in the shuffle)
+                    mine[u] = colok && ((nfm >> jl) & 1u);                       // unflagged rows are never read
+                }
+            }
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (u < n && mine[u]) v[u] = __ldg(reinterpret_cast<const float4*>(H + (size_t)col[u] * rowlen + colofs));
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (u < n && mine[u]) fma4(acc, c[u], v[u]);
+        }
+    }
+    return acc;
+}
+
 // scalar flavour for the flows X[E][b]
 __device__ __forceinline__ float gather_row1(const float* __restrict__ X, int b, int t, DevCsr S, int e) {
     float acc = 0.f;
@@ -86,10 +154,36 @@ __device__ __forceinline__ float gather_row1(const float* __restrict__ X, int b,
     return acc;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Register-tiled contraction out[128][NOUT] = T[128][KD] * Wm[KD][NOUT] from shared memory.
+// cand[e][t] = occ[e][t] | OR over the S0 / S1 neighbours e' of occ[e'][t]: the rows of the NEXT tensor that can be
+// non-zero (one-hop growth of the support).  One warp per edge, lanes across trajectories; pure byte traffic.
+__global__ void __launch_bounds__(256) occ_propagate_kernel(const uint8_t* __restrict__ occ, uint8_t* __restrict__ cand, DevCsr S0,
+                                                           DevCsr S1, int E, int b) {
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+    if (e >= E) return;
+    const int p0 = __ldg(S0.rowptr + e), p1 = __ldg(S0.rowptr + e + 1), q0 = __ldg(S1.rowptr + e), q1 = __ldg(S1.rowptr + e + 1);
+    if ((b & 3) == 0) {
+        const uint32_t* o32 = reinterpret_cast<const uint32_t*>(occ);
+        const int w = b >> 2;
+        for (int t = lane; t < w; t += 32) {
+            uint32_t acc = __ldg(o32 + (size_t)e * w + t);
+            for (int p = p0; p < p1; ++p) acc |= __ldg(o32 + (size_t)__ldg(S0.ent + p).x * w + t);
+            for (int p = q0; p < q1; ++p) acc |= __ldg(o32 + (size_t)__ldg(S1.ent + p).x * w + t);
+            reinterpret_cast<uint32_t*>(cand)[(size_t)e * w + t] = acc;
+        }
+    } else {
+        for (int t = lane; t < b; t += 32) {
+            uint8_t acc = __ldg(occ + (size_t)e * b + t);
+            for (int p = p0; p < p1; ++p) acc |= __ldg(occ + (size_t)__ldg(S0.ent + p).x * b + t);
+            for (int p = q0; p < q1; ++p) acc |= __ldg(occ + (size_t)__ldg(S1.ent + p).x * b + t);
+            cand[(size_t)e * b + t] = acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Register-tiled contraction out[128][NOUT] = T[128][KD] * Wm[KD][NOUT] from shared memory (dense tile kernels).
 // Thread (tx, ty): columns 4*tx .. 4*tx+3, rows ty + i*NRT (i < RT).
-// ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------------
 template <int KD, int NOUT, int LDT>
 struct TileGemm {
     static constexpr int NTX = NOUT / 4;
@@ -99,7 +193,7 @@ struct TileGemm {
     __device__ __forceinline__ static void run(const float* __restrict__ Ts, const float* __restrict__ Ws, float4 (&acc)[RT]) {
         const int tx = threadIdx.x % NTX, ty = threadIdx.x / NTX;
 #pragma unroll
-        for (int i = 0; i < RT; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < RT; ++i) acc[i] = zero4();
 #pragma unroll 2
         for (int kq = 0; kq < KD / 4; ++kq) {
             float4 w[4];
@@ -117,13 +211,43 @@ struct TileGemm {
     }
 };
 
-// =============================================================================================
-// Forward conv layer, C_in, C_out in {8,16,32,64}.
-// =============================================================================================
+// One output row x 4 columns: out[rho][4tx..4tx+3] = T[rho][:] * Wm[:][4tx..4tx+3]   (unit kernels)
+template <int KD, int NOUT, int LDT>
+__device__ __forceinline__ float4 row_gemm(const float* __restrict__ Ts, const float* __restrict__ Ws, int rho, int tx) {
+    float4 acc = zero4();
+#pragma unroll 4
+    for (int kq = 0; kq < KD / 4; ++kq) {
+        const float4 a = *reinterpret_cast<const float4*>(Ts + rho * LDT + 4 * kq);
+        const float4 w0 = *reinterpret_cast<const float4*>(Ws + (4 * kq + 0) * NOUT + 4 * tx);
+        const float4 w1 = *reinterpret_cast<const float4*>(Ws + (4 * kq + 1) * NOUT + 4 * tx);
+        const float4 w2 = *reinterpret_cast<const float4*>(Ws + (4 * kq + 2) * NOUT + 4 * tx);
+        const float4 w3 = *reinterpret_cast<const float4*>(Ws + (4 * kq + 3) * NOUT + 4 * tx);
+        fma4(acc, a.x, w0);
+        fma4(acc, a.y, w1);
+        fma4(acc, a.z, w2);
+        fma4(acc, a.w, w3);
+    }
+    return acc;
+}
+
+// lanes [g*NTX, (g+1)*NTX) of a warp hold one row's outputs; the group's first lane stores the row's flag.
+template <int NTX>
+__device__ __forceinline__ void store_row_flag(uint8_t* __restrict__ occ_out, size_t pos, bool valid, bool nz) {
+    const unsigned bal = __ballot_sync(0xffffffffu, nz);
+    const int lane = threadIdx.x & 31;
+    if (occ_out != nullptr && valid && (lane % NTX) == 0) {
+        const unsigned grp = (bal >> (lane - lane % NTX)) & ((NTX >= 32) ? 0xffffffffu : ((1u << NTX) - 1u));
+        occ_out[pos] = grp ? 1 : 0;
+    }
+}
+
+// =================================================================================================================
+// DENSE tile kernels
+// =================================================================================================================
 template <int CIN, int COUT, int ACT>
-__global__ void __launch_bounds__(kThreads) layer_fwd_kernel(const float* __restrict__ Hin, float* __restrict__ Hout,
-                                                            const float* __restrict__ W0, const float* __restrict__ W1,
-                                                            const float* __restrict__ W2, DevCsr S0, DevCsr S1, int E, int b) {
+__global__ void __launch_bounds__(kThreads) layer_fwd_dense_kernel(const float* __restrict__ Hin, float* __restrict__ Hout,
+                                                                  const float* __restrict__ W0, const float* __restrict__ W1,
+                                                                  const float* __restrict__ W2, DevCsr S0, DevCsr S1, int E, int b) {
     constexpr int TT = kTileCols / CIN;      // trajectories per tile
     constexpr int TE = kTileRows / TT;       // edges per tile
     constexpr int KD = 3 * CIN, LDT = KD + 4;
@@ -131,7 +255,6 @@ __global__ void __launch_bounds__(kThreads) layer_fwd_kernel(const float* __rest
     extern __shared__ __align__(16) float smem[];
     float* Ts = smem;                        // [128][LDT]
     float* Ws = smem + kTileRows * LDT;      // [KD][COUT]
-
     for (int i = threadIdx.x; i < CIN * COUT; i += kThreads) {
         Ws[i] = W0[i];
         Ws[CIN * COUT + i] = W1[i];
@@ -141,7 +264,7 @@ __global__ void __launch_bounds__(kThreads) layer_fwd_kernel(const float* __rest
     const size_t rowlen_in = (size_t)b * CIN, rowlen_out = (size_t)b * COUT;
     const int n_tb = (b + TT - 1) / TT, n_eb = (E + TE - 1) / TE;
     const int jl = (4 * lane) / CIN, cil = (4 * lane) % CIN;
-
+    const int tx = threadIdx.x % Gemm::NTX, ty = threadIdx.x / Gemm::NTX;
     for (int tile = blockIdx.x; tile < n_tb * n_eb; tile += gridDim.x) {
         const int tb = tile % n_tb, eb = tile / n_tb;
         const int e0 = eb * TE, t0 = tb * TT;
@@ -150,11 +273,11 @@ __global__ void __launch_bounds__(kThreads) layer_fwd_kernel(const float* __rest
         __syncthreads();                      // previous tile's contraction done (and Ws visible)
         for (int r = warp; r < TE; r += kWarps) {
             const int e = e0 + r;
-            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
+            float4 a0 = zero4(), a1 = a0, a2 = a0;
             if (e < E && colok) {
                 a0 = __ldg(reinterpret_cast<const float4*>(Hin + (size_t)e * rowlen_in + colofs));
-                a1 = gather_row4(Hin, rowlen_in, colofs, S0, e);
-                a2 = gather_row4(Hin, rowlen_in, colofs, S1, e);
+                a1 = gather_row4_dense(Hin, rowlen_in, colofs, S0, e);
+                a2 = gather_row4_dense(Hin, rowlen_in, colofs, S1, e);
             }
             float* dst = Ts + (r * TT + jl) * LDT + cil;
             *reinterpret_cast<float4*>(dst) = a0;
@@ -164,7 +287,6 @@ __global__ void __launch_bounds__(kThreads) layer_fwd_kernel(const float* __rest
         __syncthreads();
         float4 acc[Gemm::RT];
         Gemm::run(Ts, Ws, acc);
-        const int tx = threadIdx.x % Gemm::NTX, ty = threadIdx.x / Gemm::NTX;
 #pragma unroll
         for (int i = 0; i < Gemm::RT; ++i) {
             const int rho = ty + i * Gemm::NRT;
@@ -181,124 +303,36 @@ __global__ void __launch_bounds__(kThreads) layer_fwd_kernel(const float* __rest
     }
 }
 
-// =============================================================================================
-// Backward conv layer.  A_k = S_k G (k = 1,2; A_0 = G), Gprev = (sum_k A_k W_k^T) * act'(Hin),
-// dW_k[ci][co] = sum_rows Hin[row][ci] * A_k[row][co]   (S_k symmetric: (S_k Hin)^T G == Hin^T (S_k G)).
-// =============================================================================================
 template <int CIN, int COUT>
 struct BwdShape {
     static constexpr int TT = kTileCols / COUT, TE = kTileRows / TT;
     static constexpr int KD = 3 * COUT, LDA = KD + 4, LDH = CIN + 4;
-    static constexpr int UNITS = COUT * CIN / 4;                       // (co, ci-quad) pairs
-    static constexpr int UPT = UNITS >= kThreads ? UNITS / kThreads : 1;  // units per thread
+    static constexpr int UNITS = COUT * CIN / 4;                          // (co, ci-quad) pairs
+    static constexpr int UPT = UNITS >= kThreads ? UNITS / kThreads : 1;  // pairs per thread
     static constexpr int RS = UNITS >= kThreads ? 1 : kThreads / UNITS;   // row split
-    static constexpr size_t smem_floats = (size_t)kTileRows * LDA + (size_t)kTileRows * LDH + (size_t)KD * CIN;
     static constexpr int DW = 3 * CIN * COUT;
 };
 
-template <int CIN, int COUT, int ACT, bool WRITE_GPREV>
-__global__ void __launch_bounds__(kThreads) layer_bwd_kernel(const float* __restrict__ G, const float* __restrict__ Hin,
-                                                            float* __restrict__ Gprev, const float* __restrict__ W0,
-                                                            const float* __restrict__ W1, const float* __restrict__ W2,
-                                                            float* __restrict__ dw_partial, DevCsr S0, DevCsr S1, int E, int b) {
+// dw[u][k][q] += H[rho][4ciq+q] * A_k[rho][co] for one row; thread -> (co, ciq) mapping is data independent
+#define SCONE_DW_ROW(Hs_, As_, rho_)                                                                                      \
+    do {                                                                                                                  \
+        const float4 h_ = *reinterpret_cast<const float4*>((Hs_) + (rho_) * LDH + 4 * ciq);                               \
+        const float a0_ = (As_)[(rho_) * LDA + co], a1_ = (As_)[(rho_) * LDA + COUT + co],                                \
+                    a2_ = (As_)[(rho_) * LDA + 2 * COUT + co];                                                            \
+        dw[u][0][0] = fmaf(h_.x, a0_, dw[u][0][0]); dw[u][0][1] = fmaf(h_.y, a0_, dw[u][0][1]);                           \
+        dw[u][0][2] = fmaf(h_.z, a0_, dw[u][0][2]); dw[u][0][3] = fmaf(h_.w, a0_, dw[u][0][3]);                           \
+        dw[u][1][0] = fmaf(h_.x, a1_, dw[u][1][0]); dw[u][1][1] = fmaf(h_.y, a1_, dw[u][1][1]);                           \
+        dw[u][1][2] = fmaf(h_.z, a1_, dw[u][1][2]); dw[u][1][3] = fmaf(h_.w, a1_, dw[u][1][3]);                           \
+        dw[u][2][0] = fmaf(h_.x, a2_, dw[u][2][0]); dw[u][2][1] = fmaf(h_.y, a2_, dw[u][2][1]);                           \
+        dw[u][2][2] = fmaf(h_.z, a2_, dw[u][2][2]); dw[u][2][3] = fmaf(h_.w, a2_, dw[u][2][3]);                           \
+    } while (0)
+
+// per-CTA partial dw_partial[cta][k][ci][co]; row splits are combined in split order through shared memory
+template <int CIN, int COUT>
+__device__ __forceinline__ void write_dw_partial(float (&dw)[BwdShape<CIN, COUT>::UPT][3][4], float* __restrict__ red,
+                                                 float* __restrict__ dw_partial) {
     using Sh = BwdShape<CIN, COUT>;
-    constexpr int TT = Sh::TT, TE = Sh::TE, KD = Sh::KD, LDA = Sh::LDA, LDH = Sh::LDH;
-    using Gemm = TileGemm<KD, CIN, LDA>;
-    extern __shared__ __align__(16) float smem[];
-    float* As = smem;                          // [128][LDA]   rows = (edge, traj), cols = k*COUT + co
-    float* Hs = As + kTileRows * LDA;          // [128][LDH]
-    float* Wt = Hs + kTileRows * LDH;          // [KD][CIN]    Wt[k*COUT+co][ci] = W_k[ci][co]
-
-    for (int i = threadIdx.x; i < CIN * COUT; i += kThreads) {
-        const int ci = i / COUT, co = i % COUT;
-        Wt[(co)*CIN + ci] = W0[i];
-        Wt[(COUT + co) * CIN + ci] = W1[i];
-        Wt[(2 * COUT + co) * CIN + ci] = W2[i];
-    }
-    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    const size_t rowlen_g = (size_t)b * COUT, rowlen_h = (size_t)b * CIN;
-    const int n_tb = (b + TT - 1) / TT, n_eb = (E + TE - 1) / TE;
-    const int jl = (4 * lane) / COUT, col = (4 * lane) % COUT;
-
-    float dw[Sh::UPT][3][4];
-#pragma unroll
-    for (int u = 0; u < Sh::UPT; ++u)
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) dw[u][k][q] = 0.f;
-
-    for (int tile = blockIdx.x; tile < n_tb * n_eb; tile += gridDim.x) {
-        const int tb = tile % n_tb, eb = tile / n_tb;
-        const int e0 = eb * TE, t0 = tb * TT;
-        const int colofs = tb * kTileCols + 4 * lane;
-        const bool colok = colofs < (int)rowlen_g;
-        __syncthreads();
-        // phase 1a: gather A tile
-        for (int r = warp; r < TE; r += kWarps) {
-            const int e = e0 + r;
-            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
-            if (e < E && colok) {
-                a0 = __ldg(reinterpret_cast<const float4*>(G + (size_t)e * rowlen_g + colofs));
-                a1 = gather_row4(G, rowlen_g, colofs, S0, e);
-                a2 = gather_row4(G, rowlen_g, colofs, S1, e);
-            }
-            float* dst = As + (r * TT + jl) * LDA + col;
-            *reinterpret_cast<float4*>(dst) = a0;
-            *reinterpret_cast<float4*>(dst + COUT) = a1;
-            *reinterpret_cast<float4*>(dst + 2 * COUT) = a2;
-        }
-        // phase 1b: Hin tile (rows rho = r*TT + j, CIN columns)
-        for (int idx = threadIdx.x; idx < kTileRows * (CIN / 4); idx += kThreads) {
-            const int rho = idx / (CIN / 4), c4 = idx % (CIN / 4);
-            const int e = e0 + rho / TT, t = t0 + rho % TT;
-            float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e < E && t < b) h = __ldg(reinterpret_cast<const float4*>(Hin + (size_t)e * rowlen_h + (size_t)t * CIN + 4 * c4));
-            *reinterpret_cast<float4*>(Hs + rho * LDH + 4 * c4) = h;
-        }
-        __syncthreads();
-        // phase 2a: Gprev tile
-        if (WRITE_GPREV) {
-            float4 acc[Gemm::RT];
-            Gemm::run(As, Wt, acc);
-            const int tx = threadIdx.x % Gemm::NTX, ty = threadIdx.x / Gemm::NTX;
-#pragma unroll
-            for (int i = 0; i < Gemm::RT; ++i) {
-                const int rho = ty + i * Gemm::NRT;
-                const int e = e0 + rho / TT, t = t0 + rho % TT;
-                if (e < E && t < b) {
-                    const float4 h = *reinterpret_cast<const float4*>(Hs + rho * LDH + 4 * tx);
-                    float4 o;
-                    o.x = acc[i].x * dact_fn<ACT>(h.x);
-                    o.y = acc[i].y * dact_fn<ACT>(h.y);
-                    o.z = acc[i].z * dact_fn<ACT>(h.z);
-                    o.w = acc[i].w * dact_fn<ACT>(h.w);
-                    *reinterpret_cast<float4*>(Gprev + (size_t)e * rowlen_h + (size_t)t * CIN + 4 * tx) = o;
-                }
-            }
-        }
-        // phase 2b: weight-gradient accumulation (rows of zero-padded tiles contribute 0)
-#pragma unroll
-        for (int u = 0; u < Sh::UPT; ++u) {
-            const int unit = (Sh::UNITS >= kThreads) ? (int)threadIdx.x + u * kThreads : (int)threadIdx.x % Sh::UNITS;
-            const int split = (Sh::UNITS >= kThreads) ? 0 : (int)threadIdx.x / Sh::UNITS;
-            const int co = unit % COUT, ciq = unit / COUT;
-#pragma unroll 4
-            for (int rho = split; rho < kTileRows; rho += Sh::RS) {
-                const float4 h = *reinterpret_cast<const float4*>(Hs + rho * LDH + 4 * ciq);
-                const float a0 = As[rho * LDA + co], a1 = As[rho * LDA + COUT + co], a2 = As[rho * LDA + 2 * COUT + co];
-                dw[u][0][0] = fmaf(h.x, a0, dw[u][0][0]); dw[u][0][1] = fmaf(h.y, a0, dw[u][0][1]);
-                dw[u][0][2] = fmaf(h.z, a0, dw[u][0][2]); dw[u][0][3] = fmaf(h.w, a0, dw[u][0][3]);
-                dw[u][1][0] = fmaf(h.x, a1, dw[u][1][0]); dw[u][1][1] = fmaf(h.y, a1, dw[u][1][1]);
-                dw[u][1][2] = fmaf(h.z, a1, dw[u][1][2]); dw[u][1][3] = fmaf(h.w, a1, dw[u][1][3]);
-                dw[u][2][0] = fmaf(h.x, a2, dw[u][2][0]); dw[u][2][1] = fmaf(h.y, a2, dw[u][2][1]);
-                dw[u][2][2] = fmaf(h.z, a2, dw[u][2][2]); dw[u][2][3] = fmaf(h.w, a2, dw[u][2][3]);
-            }
-        }
-    }
-    // per-CTA partial: dw_partial[cta][k][ci][co]; row splits are combined in split order via smem
     __syncthreads();
-    float* red = smem;   // reuse: [RS][DW]
     float* outp = dw_partial + (size_t)blockIdx.x * Sh::DW;
 #pragma unroll
     for (int u = 0; u < Sh::UPT; ++u) {
@@ -324,6 +358,323 @@ __global__ void __launch_bounds__(kThreads) layer_bwd_kernel(const float* __rest
     }
 }
 
+template <int CIN, int COUT, int ACT, bool WRITE_GPREV>
+__global__ void __launch_bounds__(kThreads) layer_bwd_dense_kernel(const float* __restrict__ G, const float* __restrict__ Hin,
+                                                                  float* __restrict__ Gprev, const float* __restrict__ W0,
+                                                                  const float* __restrict__ W1, const float* __restrict__ W2,
+                                                                  float* __restrict__ dw_partial, DevCsr S0, DevCsr S1, int E, int b) {
+    using Sh = BwdShape<CIN, COUT>;
+    constexpr int TT = Sh::TT, TE = Sh::TE, KD = Sh::KD, LDA = Sh::LDA, LDH = Sh::LDH;
+    using Gemm = TileGemm<KD, CIN, LDA>;
+    extern __shared__ __align__(16) float smem[];
+    float* As = smem;                          // [128][LDA]   rows = (edge, traj), cols = k*COUT + co
+    float* Hs = As + kTileRows * LDA;          // [128][LDH]
+    float* Wt = Hs + kTileRows * LDH;          // [KD][CIN]    Wt[k*COUT+co][ci] = W_k[ci][co]
+    for (int i = threadIdx.x; i < CIN * COUT; i += kThreads) {
+        const int ci = i / COUT, co = i % COUT;
+        Wt[(co)*CIN + ci] = W0[i];
+        Wt[(COUT + co) * CIN + ci] = W1[i];
+        Wt[(2 * COUT + co) * CIN + ci] = W2[i];
+    }
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const size_t rowlen_g = (size_t)b * COUT, rowlen_h = (size_t)b * CIN;
+    const int n_tb = (b + TT - 1) / TT, n_eb = (E + TE - 1) / TE;
+    const int jl = (4 * lane) / COUT, col = (4 * lane) % COUT;
+    float dw[Sh::UPT][3][4];
+#pragma unroll
+    for (int u = 0; u < Sh::UPT; ++u)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dw[u][k][q] = 0.f;
+
+    for (int tile = blockIdx.x; tile < n_tb * n_eb; tile += gridDim.x) {
+        const int tb = tile % n_tb, eb = tile / n_tb;
+        const int e0 = eb * TE, t0 = tb * TT;
+        const int colofs = tb * kTileCols + 4 * lane;
+        const bool colok = colofs < (int)rowlen_g;
+        __syncthreads();
+        for (int r = warp; r < TE; r += kWarps) {
+            const int e = e0 + r;
+            float4 a0 = zero4(), a1 = a0, a2 = a0;
+            if (e < E && colok) {
+                a0 = __ldg(reinterpret_cast<const float4*>(G + (size_t)e * rowlen_g + colofs));
+                a1 = gather_row4_dense(G, rowlen_g, colofs, S0, e);
+                a2 = gather_row4_dense(G, rowlen_g, colofs, S1, e);
+            }
+            float* dst = As + (r * TT + jl) * LDA + col;
+            *reinterpret_cast<float4*>(dst) = a0;
+            *reinterpret_cast<float4*>(dst + COUT) = a1;
+            *reinterpret_cast<float4*>(dst + 2 * COUT) = a2;
+        }
+        for (int idx = threadIdx.x; idx < kTileRows * (CIN / 4); idx += kThreads) {
+            const int rho = idx / (CIN / 4), c4 = idx % (CIN / 4);
+            const int e = e0 + rho / TT, t = t0 + rho % TT;
+            float4 h = zero4();
+            if (e < E && t < b) h = __ldg(reinterpret_cast<const float4*>(Hin + (size_t)e * rowlen_h + (size_t)t * CIN + 4 * c4));
+            *reinterpret_cast<float4*>(Hs + rho * LDH + 4 * c4) = h;
+        }
+        __syncthreads();
+        if (WRITE_GPREV) {
+            float4 acc[Gemm::RT];
+            Gemm::run(As, Wt, acc);
+            const int tx = threadIdx.x % Gemm::NTX, ty = threadIdx.x / Gemm::NTX;
+#pragma unroll
+            for (int i = 0; i < Gemm::RT; ++i) {
+                const int rho = ty + i * Gemm::NRT;
+                const int e = e0 + rho / TT, t = t0 + rho % TT;
+                if (e < E && t < b) {
+                    const float4 h = *reinterpret_cast<const float4*>(Hs + rho * LDH + 4 * tx);
+                    float4 o;
+                    o.x = acc[i].x * dact_fn<ACT>(h.x);
+                    o.y = acc[i].y * dact_fn<ACT>(h.y);
+                    o.z = acc[i].z * dact_fn<ACT>(h.z);
+                    o.w = acc[i].w * dact_fn<ACT>(h.w);
+                    *reinterpret_cast<float4*>(Gprev + (size_t)e * rowlen_h + (size_t)t * CIN + 4 * tx) = o;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < Sh::UPT; ++u) {
+            const int unit = (Sh::UNITS >= kThreads) ? (int)threadIdx.x + u * kThreads : (int)threadIdx.x % Sh::UNITS;
+            const int split = (Sh::UNITS >= kThreads) ? 0 : (int)threadIdx.x / Sh::UNITS;
+            const int co = unit % COUT, ciq = unit / COUT;
+#pragma unroll 4
+            for (int rho = split; rho < kTileRows; rho += Sh::RS) SCONE_DW_ROW(Hs, As, rho);
+        }
+    }
+    write_dw_partial<CIN, COUT>(dw, smem, dw_partial);
+}
+
+// =================================================================================================================
+// UNIT kernels (occupancy flags)
+// =================================================================================================================
+constexpr int kUnitsPerBlock = 1024;          // units classified per CTA iteration (4 per thread)
+
+// Deterministic compaction of the units of one block whose TT flag bytes are not all zero.
+// unit u -> (edge e = u / nchunk, trajectories t0 = (u % nchunk) * TT ...).  list[] receives block-local unit
+// indices in ascending (slice, warp, lane) order.  Contains two __syncthreads().
+template <int TT>
+__device__ __forceinline__ int classify_units(const uint8_t* __restrict__ flags, long long unit0, long long n_units, int nchunk,
+                                              int b, uint16_t* __restrict__ list, int* __restrict__ wcount) {
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    unsigned bal[4];
+    bool on[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const long long u = unit0 + k * kThreads + threadIdx.x;
+        bool a = false;
+        if (u < n_units) {
+            const long long e = u / nchunk;
+            const int t0 = (int)(u - e * nchunk) * TT;
+            const uint8_t* f = flags + (size_t)e * b + t0;
+#pragma unroll
+            for (int kk = 0; kk < TT; ++kk)
+                if (t0 + kk < b) a |= (__ldg(f + kk) != 0);
+        }
+        on[k] = a;
+        bal[k] = __ballot_sync(0xffffffffu, a);
+        if (lane == 0) wcount[k * kWarps + warp] = __popc(bal[k]);
+    }
+    __syncthreads();
+    int total = 0;
+#pragma unroll
+    for (int j = 0; j < 4 * kWarps; ++j) total += wcount[j];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (on[k]) {
+            int base = 0;
+            for (int j = 0; j < k * kWarps + warp; ++j) base += wcount[j];
+            list[base + __popc(bal[k] & ((1u << lane) - 1u))] = (uint16_t)(k * kThreads + threadIdx.x);
+        }
+    }
+    __syncthreads();
+    return total;
+}
+
+// (own row, S0 row, S1 row) of unit (e, t0..t0+TT) into Ts rows [slot0 + j]; returns the ballot of non-zero lanes.
+template <int C, int LD>
+__device__ __forceinline__ unsigned gather_unit(const float* __restrict__ H, size_t rowlen, DevCsr S0, DevCsr S1, int b, int e,
+                                                int chunk, const uint8_t* __restrict__ occ, float* __restrict__ Ts, int slot0) {
+    constexpr int TT = kTileCols / C;
+    const int lane = threadIdx.x & 31;
+    const int jl = (4 * lane) / C, cl = (4 * lane) % C, t0 = chunk * TT;
+    const int colofs = chunk * kTileCols + 4 * lane;
+    const bool colok = colofs < (int)rowlen;
+    float4 a0 = zero4();
+    if (colok && __ldg(occ + (size_t)e * b + t0 + jl) != 0) a0 = __ldg(reinterpret_cast<const float4*>(H + (size_t)e * rowlen + colofs));
+    const float4 a1 = gather_row4_flagged<TT>(H, rowlen, colofs, colok, S0, e, occ, b, t0, jl);
+    const float4 a2 = gather_row4_flagged<TT>(H, rowlen, colofs, colok, S1, e, occ, b, t0, jl);
+    float* dst = Ts + (slot0 + jl) * LD + cl;
+    *reinterpret_cast<float4*>(dst) = a0;
+    *reinterpret_cast<float4*>(dst + C) = a1;
+    *reinterpret_cast<float4*>(dst + 2 * C) = a2;
+    return __ballot_sync(0xffffffffu, nz4(a0) || nz4(a1) || nz4(a2));
+}
+
+template <int CIN, int COUT, int ACT>
+__global__ void __launch_bounds__(kThreads) layer_fwd_units_kernel(const float* __restrict__ Hin, float* __restrict__ Hout,
+                                                                  const float* __restrict__ W0, const float* __restrict__ W1,
+                                                                  const float* __restrict__ W2, DevCsr S0, DevCsr S1, int E, int b,
+                                                                  const uint8_t* __restrict__ occ_in, uint8_t* __restrict__ occ_out,
+                                                                  const uint8_t* __restrict__ cand) {
+    constexpr int TT = kTileCols / CIN, KD = 3 * CIN, LDT = KD + 4, NTX = COUT / 4, NG = CIN / 4, ITEMS = TT * NTX;
+    extern __shared__ __align__(16) float smem[];
+    float* Ws = smem;                              // [KD][COUT]
+    float* Tw = smem + KD * COUT;                  // [kWarps][TT][LDT]
+    __shared__ uint16_t list[kUnitsPerBlock];
+    __shared__ int wcount[4 * kWarps];
+    for (int i = threadIdx.x; i < CIN * COUT; i += kThreads) {
+        Ws[i] = W0[i];
+        Ws[CIN * COUT + i] = W1[i];
+        Ws[2 * CIN * COUT + i] = W2[i];
+    }
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const size_t rowlen_in = (size_t)b * CIN, rowlen_out = (size_t)b * COUT;
+    const int nchunk = (b + TT - 1) / TT;
+    const long long n_units = (long long)E * nchunk;
+    const long long n_blocks = (n_units + kUnitsPerBlock - 1) / kUnitsPerBlock;
+    float* T = Tw + warp * TT * LDT;
+    for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        __syncthreads();                               // list / Ws hazards
+        const int n = classify_units<TT>(cand, blk * kUnitsPerBlock, n_units, nchunk, b, list, wcount);
+        for (int i = warp; i < n; i += kWarps) {
+            const long long u = blk * kUnitsPerBlock + list[i];
+            const int e = (int)(u / nchunk), chunk = (int)(u - (long long)e * nchunk), t0 = chunk * TT;
+            const unsigned bal = gather_unit<CIN, LDT>(Hin, rowlen_in, S0, S1, b, e, chunk, occ_in, T, 0);
+            if (bal == 0u) continue;                   // candidate by support, but numerically zero: output stays zero
+            __syncwarp();
+#pragma unroll
+            for (int p = 0; p < (ITEMS + 31) / 32; ++p) {
+                const int it = p * 32 + lane;
+                const int j = it / NTX, tx = it % NTX;
+                const bool live = it < ITEMS && t0 + j < b && ((bal >> (j * NG)) & ((NG >= 32) ? 0xffffffffu : ((1u << NG) - 1u))) != 0u;
+                float4 o = zero4();
+                if (live) {
+                    o = row_gemm<KD, COUT, LDT>(T, Ws, j, tx);
+                    o.x = act_fn<ACT>(o.x);
+                    o.y = act_fn<ACT>(o.y);
+                    o.z = act_fn<ACT>(o.z);
+                    o.w = act_fn<ACT>(o.w);
+                    *reinterpret_cast<float4*>(Hout + (size_t)e * rowlen_out + (size_t)(t0 + j) * COUT + 4 * tx) = o;
+                }
+                store_row_flag<NTX>(occ_out, (size_t)e * b + t0 + j, live, nz4(o));
+            }
+            __syncwarp();                              // T is reused by this warp's next unit
+        }
+    }
+}
+
+template <int CIN, int COUT>
+struct BwdUnitShape {
+    static constexpr int TT = kTileCols / COUT;
+    static constexpr int UC = 16;                        // units staged per dW round
+    static constexpr int RC = UC * TT;                   // staged rows
+    static constexpr int KD = 3 * COUT, LDA = KD + 4, LDH = CIN + 4;
+    static constexpr size_t smem_floats_layout = (size_t)KD * CIN + (size_t)RC * LDA + (size_t)RC * LDH;
+    static constexpr size_t red_floats = (size_t)BwdShape<CIN, COUT>::RS * BwdShape<CIN, COUT>::DW;
+    static constexpr size_t smem_floats = smem_floats_layout > red_floats ? smem_floats_layout : red_floats;
+};
+
+template <int CIN, int COUT, int ACT, bool WRITE_GPREV>
+__global__ void __launch_bounds__(kThreads) layer_bwd_units_kernel(const float* __restrict__ G, const float* __restrict__ Hin,
+                                                                  float* __restrict__ Gprev, const float* __restrict__ W0,
+                                                                  const float* __restrict__ W1, const float* __restrict__ W2,
+                                                                  float* __restrict__ dw_partial, DevCsr S0, DevCsr S1, int E, int b,
+                                                                  const uint8_t* __restrict__ occ_g, const uint8_t* __restrict__ occ_h,
+                                                                  uint8_t* __restrict__ occ_prev, const uint8_t* __restrict__ cand) {
+    using Sh = BwdShape<CIN, COUT>;
+    using Us = BwdUnitShape<CIN, COUT>;
+    constexpr int TT = Us::TT, UC = Us::UC, RC = Us::RC, KD = Us::KD, LDA = Us::LDA, LDH = Us::LDH;
+    constexpr int NTX = CIN / 4, NG = COUT / 4, ITEMS = TT * NTX;
+    extern __shared__ __align__(16) float smem[];
+    float* Wt = smem;                              // [KD][CIN]    Wt[k*COUT+co][ci] = W_k[ci][co]
+    float* Ar = Wt + KD * CIN;                     // [RC][LDA]
+    float* Hr = Ar + RC * LDA;                     // [RC][LDH]
+    __shared__ uint16_t list[kUnitsPerBlock];
+    __shared__ int wcount[4 * kWarps];
+    __shared__ uint8_t rowact[RC];
+    for (int i = threadIdx.x; i < CIN * COUT; i += kThreads) {
+        const int ci = i / COUT, co = i % COUT;
+        Wt[(co)*CIN + ci] = W0[i];
+        Wt[(COUT + co) * CIN + ci] = W1[i];
+        Wt[(2 * COUT + co) * CIN + ci] = W2[i];
+    }
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const size_t rowlen_g = (size_t)b * COUT, rowlen_h = (size_t)b * CIN;
+    const int nchunk = (b + TT - 1) / TT;
+    const long long n_units = (long long)E * nchunk;
+    const long long n_blocks = (n_units + kUnitsPerBlock - 1) / kUnitsPerBlock;
+    float dw[Sh::UPT][3][4];
+#pragma unroll
+    for (int u = 0; u < Sh::UPT; ++u)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dw[u][k][q] = 0.f;
+
+    for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        __syncthreads();
+        const int n = classify_units<TT>(cand, blk * kUnitsPerBlock, n_units, nchunk, b, list, wcount);
+        for (int c0 = 0; c0 < n; c0 += UC) {
+            const int nu = min(UC, n - c0);
+            // warp phase: stage (A rows, Hin rows) of up to UC units; Gprev rows of the non-zero A rows
+            for (int i = warp; i < nu; i += kWarps) {
+                const long long u = blk * kUnitsPerBlock + list[c0 + i];
+                const int e = (int)(u / nchunk), chunk = (int)(u - (long long)e * nchunk), t0 = chunk * TT;
+                const int slot0 = i * TT;
+                const unsigned bal = gather_unit<COUT, LDA>(G, rowlen_g, S0, S1, b, e, chunk, occ_g, Ar, slot0);
+#pragma unroll
+                for (int p = 0; p < (ITEMS + 31) / 32; ++p) {
+                    const int it = p * 32 + lane;
+                    const int j = it / NTX, hx = it % NTX;
+                    if (it < ITEMS) {
+                        const bool ra = t0 + j < b && ((bal >> (j * NG)) & ((NG >= 32) ? 0xffffffffu : ((1u << NG) - 1u))) != 0u;
+                        float4 h = zero4();
+                        if (ra && (occ_h == nullptr || __ldg(occ_h + (size_t)e * b + t0 + j) != 0))
+                            h = __ldg(reinterpret_cast<const float4*>(Hin + (size_t)e * rowlen_h + (size_t)(t0 + j) * CIN + 4 * hx));
+                        *reinterpret_cast<float4*>(Hr + (slot0 + j) * LDH + 4 * hx) = h;
+                        if (hx == 0) rowact[slot0 + j] = ra ? 1 : 0;
+                    }
+                }
+                __syncwarp();
+                if (WRITE_GPREV && bal != 0u) {
+#pragma unroll
+                    for (int p = 0; p < (ITEMS + 31) / 32; ++p) {
+                        const int it = p * 32 + lane;
+                        const int j = it / NTX, tx = it % NTX;
+                        const bool live = it < ITEMS && rowact[slot0 + j] != 0;
+                        float4 o = zero4();
+                        if (live) {
+                            o = row_gemm<KD, CIN, LDA>(Ar, Wt, slot0 + j, tx);
+                            const float4 h = *reinterpret_cast<const float4*>(Hr + (slot0 + j) * LDH + 4 * tx);
+                            o.x *= dact_fn<ACT>(h.x);
+                            o.y *= dact_fn<ACT>(h.y);
+                            o.z *= dact_fn<ACT>(h.z);
+                            o.w *= dact_fn<ACT>(h.w);
+                            *reinterpret_cast<float4*>(Gprev + (size_t)e * rowlen_h + (size_t)(t0 + j) * CIN + 4 * tx) = o;
+                        }
+                        store_row_flag<NTX>(occ_prev, (size_t)e * b + t0 + j, live, nz4(o));
+                    }
+                }
+            }
+            __syncthreads();
+            // CTA phase: weight gradients over the staged rows, ascending, fixed thread mapping
+            const int n_rows = nu * TT;
+#pragma unroll
+            for (int u = 0; u < Sh::UPT; ++u) {
+                const int unit = (Sh::UNITS >= kThreads) ? (int)threadIdx.x + u * kThreads : (int)threadIdx.x % Sh::UNITS;
+                const int split = (Sh::UNITS >= kThreads) ? 0 : (int)threadIdx.x / Sh::UNITS;
+                const int co = unit % COUT, ciq = unit / COUT;
+                for (int rho = split; rho < n_rows; rho += Sh::RS)
+                    if (rowact[rho]) SCONE_DW_ROW(Hr, Ar, rho);
+            }
+            __syncthreads();
+        }
+    }
+    write_dw_partial<CIN, COUT>(dw, smem, dw_partial);
+}
+
 // out[i] (+)= sum over parts p (ascending) of partial[p][i]
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int nparts, int n, float* __restrict__ out,
                                        int accumulate) {
@@ -334,9 +685,9 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int np
     out[i] = accumulate ? out[i] + s : s;
 }
 
-// =============================================================================================
+// =================================================================================================================
 // First layer (C_in = 1): input X[E][b].
-// =============================================================================================
+// =================================================================================================================
 constexpr int kL0Edges = 32;     // edges per tile; 32 trajectories per tile (lane = trajectory)
 
 __device__ __forceinline__ void layer0_gather(const float* __restrict__ X, DevCsr S0, DevCsr S1, int E, int b, int e0, int t0,
@@ -357,10 +708,12 @@ __device__ __forceinline__ void layer0_gather(const float* __restrict__ X, DevCs
     }
 }
 
+// write_zero_rows: false when the caller pre-zeroed Hout (or runs in sparse mode): only live rows are stored.
 template <int COUT, int ACT>
 __global__ void __launch_bounds__(kThreads) layer0_fwd_kernel(const float* __restrict__ X, float* __restrict__ Hout,
                                                              const float* __restrict__ W0, const float* __restrict__ W1,
-                                                             const float* __restrict__ W2, DevCsr S0, DevCsr S1, int E, int b) {
+                                                             const float* __restrict__ W2, DevCsr S0, DevCsr S1, int E, int b,
+                                                             uint8_t* __restrict__ occ_out, int write_zero_rows) {
     __shared__ float ts[3 * kL0Edges * 32];
     __shared__ __align__(16) float ws[3 * COUT];
     for (int i = threadIdx.x; i < COUT; i += kThreads) {
@@ -382,24 +735,30 @@ __global__ void __launch_bounds__(kThreads) layer0_fwd_kernel(const float* __res
             if (e < E && t < b) {
                 const float a0 = ts[(0 * kL0Edges + r) * 32 + j], a1 = ts[(1 * kL0Edges + r) * 32 + j],
                             a2 = ts[(2 * kL0Edges + r) * 32 + j];
-                const float4 w0 = *reinterpret_cast<const float4*>(ws + 4 * c4);
-                const float4 w1 = *reinterpret_cast<const float4*>(ws + COUT + 4 * c4);
-                const float4 w2 = *reinterpret_cast<const float4*>(ws + 2 * COUT + 4 * c4);
-                float4 o;
-                o.x = act_fn<ACT>(fmaf(a2, w2.x, fmaf(a1, w1.x, a0 * w0.x)));
-                o.y = act_fn<ACT>(fmaf(a2, w2.y, fmaf(a1, w1.y, a0 * w0.y)));
-                o.z = act_fn<ACT>(fmaf(a2, w2.z, fmaf(a1, w1.z, a0 * w0.z)));
-                o.w = act_fn<ACT>(fmaf(a2, w2.w, fmaf(a1, w1.w, a0 * w0.w)));
-                *reinterpret_cast<float4*>(Hout + ((size_t)e * b + t) * COUT + 4 * c4) = o;
+                const bool live = a0 != 0.f || a1 != 0.f || a2 != 0.f;      // act(0) == 0: zero rows need no math
+                if (live) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(ws + 4 * c4);
+                    const float4 w1 = *reinterpret_cast<const float4*>(ws + COUT + 4 * c4);
+                    const float4 w2 = *reinterpret_cast<const float4*>(ws + 2 * COUT + 4 * c4);
+                    float4 o;
+                    o.x = act_fn<ACT>(fmaf(a2, w2.x, fmaf(a1, w1.x, a0 * w0.x)));
+                    o.y = act_fn<ACT>(fmaf(a2, w2.y, fmaf(a1, w1.y, a0 * w0.y)));
+                    o.z = act_fn<ACT>(fmaf(a2, w2.z, fmaf(a1, w1.z, a0 * w0.z)));
+                    o.w = act_fn<ACT>(fmaf(a2, w2.w, fmaf(a1, w1.w, a0 * w0.w)));
+                    *reinterpret_cast<float4*>(Hout + ((size_t)e * b + t) * COUT + 4 * c4) = o;
+                } else if (write_zero_rows) {
+                    *reinterpret_cast<float4*>(Hout + ((size_t)e * b + t) * COUT + 4 * c4) = zero4();
+                }
+                if (occ_out != nullptr && c4 == 0 && (live || write_zero_rows)) occ_out[(size_t)e * b + t] = live ? 1 : 0;
             }
         }
     }
 }
 
-// dW_k[0][co] = sum_{e,t} (S_k X)[e][t] * G0[e][t][co]
+// dense: dW_k[0][co] = sum_{e,t} (S_k X)[e][t] * G0[e][t][co]
 template <int COUT>
-__global__ void __launch_bounds__(kThreads) layer0_bwd_kernel(const float* __restrict__ X, const float* __restrict__ G0,
-                                                             float* __restrict__ dw_partial, DevCsr S0, DevCsr S1, int E, int b) {
+__global__ void __launch_bounds__(kThreads) layer0_bwd_dense_kernel(const float* __restrict__ X, const float* __restrict__ G0,
+                                                                   float* __restrict__ dw_partial, DevCsr S0, DevCsr S1, int E, int b) {
     __shared__ float ts[3 * kL0Edges * 32];
     __shared__ float red[kThreads * 12];
     constexpr int C4 = COUT / 4;
@@ -434,7 +793,6 @@ __global__ void __launch_bounds__(kThreads) layer0_bwd_kernel(const float* __res
 #pragma unroll
         for (int q = 0; q < 4; ++q) red[threadIdx.x * 12 + k * 4 + q] = acc[k][q];
     __syncthreads();
-    // thread o < 3*COUT sums its (k, co) over the kThreads / C4 threads that own channel quad co/4, ascending
     for (int o = threadIdx.x; o < 3 * COUT; o += kThreads) {
         const int k = o / COUT, co = o % COUT, c4 = co / 4, q = co % 4;
         float s = 0.f;
@@ -443,39 +801,93 @@ __global__ void __launch_bounds__(kThreads) layer0_bwd_kernel(const float* __res
     }
 }
 
+// flagged: only the rows of G0 whose flag is set contribute.  Row (e, t): t_k = (S_k X)[e][t] by a lane-parallel gather
+// + fixed shuffle tree; per-warp accumulators, warps combined in warp order.
+template <int COUT>
+__global__ void __launch_bounds__(kThreads) layer0_bwd_rows_kernel(const float* __restrict__ X, const float* __restrict__ G0,
+                                                                  float* __restrict__ dw_partial, DevCsr S0, DevCsr S1, int E, int b,
+                                                                  const uint8_t* __restrict__ occ_g) {
+    constexpr int Q = (COUT + 31) / 32;
+    __shared__ uint16_t list[kUnitsPerBlock];
+    __shared__ int wcount[4 * kWarps];
+    __shared__ float red[kWarps][3 * COUT];
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    float acc[3][Q];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int q = 0; q < Q; ++q) acc[k][q] = 0.f;
+    const long long n_units = (long long)E * b;
+    const long long n_blocks = (n_units + kUnitsPerBlock - 1) / kUnitsPerBlock;
+    for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        __syncthreads();
+        const int n = classify_units<1>(occ_g, blk * kUnitsPerBlock, n_units, b, b, list, wcount);
+        for (int i = warp; i < n; i += kWarps) {
+            const long long u = blk * kUnitsPerBlock + list[i];
+            const int e = (int)(u / b), t = (int)(u - (long long)e * b);
+            float tk[3];
+            tk[0] = __ldg(X + (size_t)e * b + t);
+#pragma unroll
+            for (int k = 1; k < 3; ++k) {
+                const DevCsr S = k == 1 ? S0 : S1;
+                const int p0 = __ldg(S.rowptr + e), p1 = __ldg(S.rowptr + e + 1);
+                float part = 0.f;
+                for (int p = p0 + lane; p < p1; p += 32) {
+                    const int2 ent = __ldg(S.ent + p);
+                    part = fmaf(__int_as_float(ent.y), __ldg(X + (size_t)ent.x * b + t), part);
+                }
+                tk[k] = warp_sum(part);
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const int c = lane + 32 * q;
+                if (c < COUT) {
+                    const float g = __ldg(G0 + ((size_t)e * b + t) * COUT + c);
+                    acc[0][q] = fmaf(tk[0], g, acc[0][q]);
+                    acc[1][q] = fmaf(tk[1], g, acc[1][q]);
+                    acc[2][q] = fmaf(tk[2], g, acc[2][q]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+            if (lane + 32 * q < COUT) red[warp][k * COUT + lane + 32 * q] = acc[k][q];
+    __syncthreads();
+    for (int o = threadIdx.x; o < 3 * COUT; o += kThreads) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) s += red[w][o];
+        dw_partial[(size_t)blockIdx.x * 3 * COUT + o] = s;
+    }
+}
+
 // X[E][b] from sparse flows; one warp per trajectory (X pre-zeroed).
 __global__ void flows_to_dense_kernel(const int32_t* __restrict__ traj_ptr, const int32_t* __restrict__ flow_edge,
-                                      const float* __restrict__ flow_val, float* __restrict__ X, int E, int b) {
+                                      const float* __restrict__ flow_val, const int32_t* __restrict__ rank,
+                                      float* __restrict__ X, int E, int b) {
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
     if (t >= b) return;
     for (int p = traj_ptr[t] + lane; p < traj_ptr[t + 1]; p += 32) {
         const int e = flow_edge[p];
-        if (e >= 0 && e < E) X[(size_t)e * b + t] = flow_val[p];
+        if (e >= 0 && e < E) X[(size_t)rank[e] * b + t] = flow_val[p];
     }
 }
 
-// =============================================================================================
+// =================================================================================================================
 // Readout: one warp per trajectory.
-// =============================================================================================
+// =================================================================================================================
 constexpr int kReadoutMaxD = 128, kReadoutMaxCper = 4;   // D <= 128, C <= 128
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
 
 __global__ void __launch_bounds__(128) readout_kernel(const float* __restrict__ HL, const float* __restrict__ wout,
                                                      const int32_t* __restrict__ last_nodes, const int32_t* __restrict__ nbrhoods,
                                                      const int32_t* __restrict__ inc_ptr, const int2* __restrict__ inc_ent,
                                                      float* __restrict__ logprobs, const int32_t* __restrict__ target_idx,
                                                      const float* __restrict__ mask, float scale, float* __restrict__ GL,
-                                                     float* __restrict__ partial /* [b][C+2] */, int act, int N, int D, int b, int C) {
+                                                     float* __restrict__ partial /* [b][C+2] */, const uint8_t* __restrict__ occ_HL,
+                                                     uint8_t* __restrict__ occ_GL, int act, int N, int D, int b, int C) {
     __shared__ float s_logit[4][kReadoutMaxD];
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int t = blockIdx.x * 4 + warp;
@@ -495,6 +907,7 @@ __global__ void __launch_bounds__(128) readout_kernel(const float* __restrict__ 
             float z[kReadoutMaxCper] = {0.f, 0.f, 0.f, 0.f};
             for (int p = inc_ptr[nbr]; p < inc_ptr[nbr + 1]; ++p) {
                 const int2 es = inc_ent[p];
+                if (occ_HL != nullptr && occ_HL[(size_t)es.x * b + t] == 0) continue;      // row is exactly zero
                 const float* row = HL + ((size_t)es.x * b + t) * C;
 #pragma unroll
                 for (int q = 0; q < kReadoutMaxCper; ++q)
@@ -517,6 +930,20 @@ __global__ void __launch_bounds__(128) readout_kernel(const float* __restrict__ 
     for (int j = lane; j < D; j += 32) logprobs[(size_t)t * D + j] = logit[j] - lse;
     if (GL == nullptr) return;
 
+    // gradient: rows of GL touched by this trajectory are zeroed first (an edge can be incident to two neighbours),
+    // then accumulated in ascending (j, p) order by the same lane: deterministic, no atomics.
+    for (int j = 0; j < D; ++j) {
+        const int nbr = last_ok ? nbrhoods[(size_t)last * D + j] : -1;
+        if (nbr < 0) continue;
+        for (int p = inc_ptr[nbr]; p < inc_ptr[nbr + 1]; ++p) {
+            const size_t base = ((size_t)inc_ent[p].x * b + t) * C;
+#pragma unroll
+            for (int q = 0; q < kReadoutMaxCper; ++q)
+                if (lane + 32 * q < C) GL[base + lane + 32 * q] = 0.f;
+            if (occ_GL != nullptr && lane == 0) occ_GL[(size_t)inc_ent[p].x * b + t] = 1;
+        }
+    }
+    __syncwarp();
     const float mk = mask[t];
     const int y = target_idx[t];
     float dwl[kReadoutMaxCper] = {0.f, 0.f, 0.f, 0.f};
@@ -528,10 +955,11 @@ __global__ void __launch_bounds__(128) readout_kernel(const float* __restrict__ 
             const int2 es = inc_ent[p];
             const size_t base = ((size_t)es.x * b + t) * C;
             const float sdl = __int_as_float(es.y) * dl;
+            const bool hz = occ_HL != nullptr && occ_HL[(size_t)es.x * b + t] == 0;
 #pragma unroll
             for (int q = 0; q < kReadoutMaxCper; ++q)
                 if (lane + 32 * q < C) {
-                    const float h = HL[base + lane + 32 * q];
+                    const float h = hz ? 0.f : HL[base + lane + 32 * q];
                     dwl[q] = fmaf(sdl, h, dwl[q]);                                // z[j][c] * dlogit[j]
                     GL[base + lane + 32 * q] += sdl * w[q] * dact_rt(act, h);      // same lane, sequential: no race
                 }
@@ -571,67 +999,119 @@ __global__ void adam_kernel(float* __restrict__ W, float* __restrict__ m, float*
     W[i] = W[i] - lr * (mi / c1) / (sqrtf(vi / c2) + eps);
 }
 
-int grid_for(const scone_complex* cx, int n_tiles, int ctas_per_sm) {
-    int g = cx->num_sms * ctas_per_sm;
-    return n_tiles < g ? (n_tiles > 0 ? n_tiles : 1) : g;
+}  // namespace
+
+bool g_scone_zero_fill = true;
+
+namespace {
+
+// =================================================================================================================
+// launchers
+// =================================================================================================================
+int grid_for(const scone_complex* cx, long long n_work, int ctas_per_sm) {
+    long long g = (long long)cx->num_sms * ctas_per_sm;
+    if (n_work < g) g = n_work > 0 ? n_work : 1;
+    return (int)g;
+}
+
+template <typename K>
+int occupancy_of(K kern, size_t smem, int* out) {
+    int occ = 1;
+    SCONE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SCONE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
+    *out = occ > 0 ? occ : 1;
+    return 0;
+}
+
+int propagate(const scone_complex* cx, int b, const uint8_t* occ, uint8_t* cand, cudaStream_t st) {
+    occ_propagate_kernel<<<(int)(((long long)cx->E * 32 + 255) / 256), 256, 0, st>>>(occ, cand, cx->S(0), cx->S(1), cx->E, b);
+    SCONE_LAUNCHED();
+    return 0;
 }
 
 template <int CIN, int COUT, int ACT>
 int launch_fwd(const scone_complex* cx, int b, const float* Hin, const float* W0, const float* W1, const float* W2, float* Hout,
-               cudaStream_t st) {
+               const uint8_t* occ_in, uint8_t* occ_out, uint8_t* scratch, cudaStream_t st) {
     constexpr int TT = kTileCols / CIN, TE = kTileRows / TT, KD = 3 * CIN, LDT = KD + 4;
-    const size_t smem = ((size_t)kTileRows * LDT + (size_t)KD * COUT) * sizeof(float);
-    auto kern = layer_fwd_kernel<CIN, COUT, ACT>;
-    static bool configured = false;
-    if (!configured) {
-        SCONE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    int occ = 1;
-    SCONE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
-    const int n_tiles = ((b + TT - 1) / TT) * ((cx->E + TE - 1) / TE);
     ScopedProf prof(SCONE_K_LAYER_FWD, st);
-    kern<<<grid_for(cx, n_tiles, occ > 0 ? occ : 1), kThreads, smem, st>>>(Hin, Hout, W0, W1, W2, cx->S(0), cx->S(1), cx->E, b);
+    if (occ_in == nullptr) {                                  // dense path
+        const size_t smem = ((size_t)kTileRows * LDT + (size_t)KD * COUT) * sizeof(float);
+        auto kern = layer_fwd_dense_kernel<CIN, COUT, ACT>;
+        static int occ = 0;
+        if (!occ && occupancy_of(kern, smem, &occ)) return 1;
+        const long long n_tiles = (long long)((b + TT - 1) / TT) * ((cx->E + TE - 1) / TE);
+        kern<<<grid_for(cx, n_tiles, occ), kThreads, smem, st>>>(Hin, Hout, W0, W1, W2, cx->S(0), cx->S(1), cx->E, b);
+        SCONE_LAUNCHED();
+        if (occ_out) SCONE_CUDA(cudaMemsetAsync(occ_out, 1, (size_t)cx->E * b, st));   // no information: everything may be non-zero
+        return 0;
+    }
+    SCONE_REQUIRE(occ_out != nullptr && scratch != nullptr, "scone_layer_forward: occ_in needs occ_out and occ_scratch");
+    if (propagate(cx, b, occ_in, scratch, st)) return 1;
+    if (g_scone_zero_fill) SCONE_CUDA(cudaMemsetAsync(Hout, 0, (size_t)cx->E * b * COUT * sizeof(float), st));
+    SCONE_CUDA(cudaMemsetAsync(occ_out, 0, (size_t)cx->E * b, st));
+    const size_t smem = ((size_t)KD * COUT + (size_t)kWarps * TT * LDT) * sizeof(float);
+    auto kern = layer_fwd_units_kernel<CIN, COUT, ACT>;
+    static int occ = 0;
+    if (!occ && occupancy_of(kern, smem, &occ)) return 1;
+    const long long n_blocks = ((long long)cx->E * ((b + TT - 1) / TT) + kUnitsPerBlock - 1) / kUnitsPerBlock;
+    kern<<<grid_for(cx, n_blocks, occ), kThreads, smem, st>>>(Hin, Hout, W0, W1, W2, cx->S(0), cx->S(1), cx->E, b, occ_in, occ_out,
+                                                            scratch);
     SCONE_LAUNCHED();
     return 0;
 }
 
 template <int CIN, int COUT>
 int dispatch_fwd_act(const scone_complex* cx, int act, int b, const float* Hin, const float* W0, const float* W1, const float* W2,
-                     float* Hout, cudaStream_t st) {
+                     float* Hout, const uint8_t* occ_in, uint8_t* occ_out, uint8_t* scratch, cudaStream_t st) {
     switch (act) {
-        case SCONE_ACT_TANH: return launch_fwd<CIN, COUT, SCONE_ACT_TANH>(cx, b, Hin, W0, W1, W2, Hout, st);
-        case SCONE_ACT_LEAKY_RELU: return launch_fwd<CIN, COUT, SCONE_ACT_LEAKY_RELU>(cx, b, Hin, W0, W1, W2, Hout, st);
-        case SCONE_ACT_RELU: return launch_fwd<CIN, COUT, SCONE_ACT_RELU>(cx, b, Hin, W0, W1, W2, Hout, st);
+        case SCONE_ACT_TANH: return launch_fwd<CIN, COUT, SCONE_ACT_TANH>(cx, b, Hin, W0, W1, W2, Hout, occ_in, occ_out, scratch, st);
+        case SCONE_ACT_LEAKY_RELU: return launch_fwd<CIN, COUT, SCONE_ACT_LEAKY_RELU>(cx, b, Hin, W0, W1, W2, Hout, occ_in, occ_out, scratch, st);
+        case SCONE_ACT_RELU: return launch_fwd<CIN, COUT, SCONE_ACT_RELU>(cx, b, Hin, W0, W1, W2, Hout, occ_in, occ_out, scratch, st);
     }
     scone_set_error("unknown activation %d", act);
     return 2;
 }
 
-constexpr int kBwdMaxCtas = 148 * 4;     // upper bound on persistent CTAs (workspace sizing)
+constexpr int kBwdMaxCtas = 148 * 8;     // upper bound on persistent CTAs (workspace sizing)
 
 template <int CIN, int COUT, int ACT, bool WG>
 int launch_bwd(const scone_complex* cx, int b, const float* G, const float* Hin, const float* W0, const float* W1, const float* W2,
-               float* Gprev, float* dW, int accumulate, float* ws, cudaStream_t st) {
+               float* Gprev, float* dW, int accumulate, float* ws, const uint8_t* occ_g, const uint8_t* occ_h, uint8_t* occ_prev,
+               uint8_t* scratch, cudaStream_t st) {
     using Sh = BwdShape<CIN, COUT>;
-    size_t smem_f = Sh::smem_floats;
-    if ((size_t)Sh::RS * Sh::DW > smem_f) smem_f = (size_t)Sh::RS * Sh::DW;
-    const size_t smem = smem_f * sizeof(float);
-    auto kern = layer_bwd_kernel<CIN, COUT, ACT, WG>;
-    static bool configured = false;
-    if (!configured) {
-        SCONE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    int occ = 1;
-    SCONE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
-    if (occ < 1) occ = 1;
-    const int n_tiles = ((b + Sh::TT - 1) / Sh::TT) * ((cx->E + Sh::TE - 1) / Sh::TE);
-    int grid = grid_for(cx, n_tiles, occ);
-    if (grid > kBwdMaxCtas) grid = kBwdMaxCtas;
     ScopedProf prof(SCONE_K_LAYER_BWD, st);
-    kern<<<grid, kThreads, smem, st>>>(G, Hin, Gprev, W0, W1, W2, ws, cx->S(0), cx->S(1), cx->E, b);
-    SCONE_LAUNCHED();
+    int grid = 1;
+    if (occ_g == nullptr) {                                   // dense path
+        size_t smem_f = (size_t)kTileRows * Sh::LDA + (size_t)kTileRows * Sh::LDH + (size_t)Sh::KD * CIN;
+        if ((size_t)Sh::RS * Sh::DW > smem_f) smem_f = (size_t)Sh::RS * Sh::DW;
+        const size_t smem = smem_f * sizeof(float);
+        auto kern = layer_bwd_dense_kernel<CIN, COUT, ACT, WG>;
+        static int occ = 0;
+        if (!occ && occupancy_of(kern, smem, &occ)) return 1;
+        const long long n_tiles = (long long)((b + Sh::TT - 1) / Sh::TT) * ((cx->E + Sh::TE - 1) / Sh::TE);
+        grid = grid_for(cx, n_tiles, occ);
+        if (grid > kBwdMaxCtas) grid = kBwdMaxCtas;
+        kern<<<grid, kThreads, smem, st>>>(G, Hin, Gprev, W0, W1, W2, ws, cx->S(0), cx->S(1), cx->E, b);
+        SCONE_LAUNCHED();
+        if (WG && occ_prev) SCONE_CUDA(cudaMemsetAsync(occ_prev, 1, (size_t)cx->E * b, st));
+    } else {
+        using Us = BwdUnitShape<CIN, COUT>;
+        SCONE_REQUIRE(scratch != nullptr && (!WG || occ_prev != nullptr), "scone_layer_backward: occ_g needs occ_gprev and occ_scratch");
+        if (propagate(cx, b, occ_g, scratch, st)) return 1;
+        if (WG) {
+            if (g_scone_zero_fill) SCONE_CUDA(cudaMemsetAsync(Gprev, 0, (size_t)cx->E * b * CIN * sizeof(float), st));
+            SCONE_CUDA(cudaMemsetAsync(occ_prev, 0, (size_t)cx->E * b, st));
+        }
+        const size_t smem = Us::smem_floats * sizeof(float);
+        auto kern = layer_bwd_units_kernel<CIN, COUT, ACT, WG>;
+        static int occ = 0;
+        if (!occ && occupancy_of(kern, smem, &occ)) return 1;
+        const long long n_blocks = ((long long)cx->E * ((b + Us::TT - 1) / Us::TT) + kUnitsPerBlock - 1) / kUnitsPerBlock;
+        grid = grid_for(cx, n_blocks, occ);
+        if (grid > kBwdMaxCtas) grid = kBwdMaxCtas;
+        kern<<<grid, kThreads, smem, st>>>(G, Hin, Gprev, W0, W1, W2, ws, cx->S(0), cx->S(1), cx->E, b, occ_g, occ_h, occ_prev, scratch);
+        SCONE_LAUNCHED();
+    }
     reduce_partials_kernel<<<(Sh::DW + 255) / 256, 256, 0, st>>>(ws, grid, Sh::DW, dW, accumulate);
     SCONE_LAUNCHED();
     return 0;
@@ -639,11 +1119,14 @@ int launch_bwd(const scone_complex* cx, int b, const float* G, const float* Hin,
 
 template <int CIN, int COUT>
 int dispatch_bwd_act(const scone_complex* cx, int act, int b, const float* G, const float* Hin, const float* W0, const float* W1,
-                     const float* W2, float* Gprev, float* dW, int accumulate, float* ws, cudaStream_t st) {
-#define SCONE_BWD_CASE(A)                                                                                                    \
-    case A:                                                                                                                  \
-        return Gprev ? launch_bwd<CIN, COUT, A, true>(cx, b, G, Hin, W0, W1, W2, Gprev, dW, accumulate, ws, st)              \
-                     : launch_bwd<CIN, COUT, A, false>(cx, b, G, Hin, W0, W1, W2, Gprev, dW, accumulate, ws, st);
+                     const float* W2, float* Gprev, float* dW, int accumulate, float* ws, const uint8_t* occ_g, const uint8_t* occ_h,
+                     uint8_t* occ_prev, uint8_t* scratch, cudaStream_t st) {
+#define SCONE_BWD_CASE(A)                                                                                                          \
+    case A:                                                                                                                        \
+        return Gprev ? launch_bwd<CIN, COUT, A, true>(cx, b, G, Hin, W0, W1, W2, Gprev, dW, accumulate, ws, occ_g, occ_h, occ_prev, \
+                                                      scratch, st)                                                                 \
+                     : launch_bwd<CIN, COUT, A, false>(cx, b, G, Hin, W0, W1, W2, Gprev, dW, accumulate, ws, occ_g, occ_h, occ_prev, \
+                                                       scratch, st);
     switch (act) {
         SCONE_BWD_CASE(SCONE_ACT_TANH)
         SCONE_BWD_CASE(SCONE_ACT_LEAKY_RELU)
@@ -658,9 +1141,15 @@ bool width_ok(int c) { return c == 8 || c == 16 || c == 32 || c == 64; }
 
 }  // namespace
 
-// ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------------
 // C ABI
-// ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int scone_set_zero_fill(int32_t on) {
+    g_scone_zero_fill = on != 0;
+    return 0;
+}
+extern "C" int scone_get_zero_fill(void) { return g_scone_zero_fill ? 1 : 0; }
+
 #define SCONE_DISPATCH_WIDTHS(FN, ...)                                              \
     do {                                                                            \
         const int key_ = cin * 1000 + cout;                                         \
@@ -679,14 +1168,15 @@ bool width_ok(int c) { return c == 8 || c == 16 || c == 32 || c == 64; }
     } while (0)
 
 extern "C" int scone_layer_forward(const scone_complex* cx, int32_t act, int32_t b, int32_t cin, int32_t cout, const float* Hin,
-                                   const float* W0, const float* W1, const float* W2, float* Hout, void* stream) {
+                                   const float* W0, const float* W1, const float* W2, float* Hout, const uint8_t* occ_in,
+                                   uint8_t* occ_out, uint8_t* occ_scratch, void* stream) {
     SCONE_REQUIRE(cx && Hin && W0 && W1 && W2 && Hout, "scone_layer_forward: NULL argument");
     SCONE_REQUIRE(!cx->host_only, "scone_layer_forward: index-only complex has no device arrays");
     SCONE_REQUIRE(b > 0, "scone_layer_forward: b must be positive");
-    if (cin == 1) return scone_layer0_forward(cx, act, b, cout, Hin, W0, W1, W2, Hout, stream);
+    if (cin == 1) return scone_layer0_forward(cx, act, b, cout, Hin, W0, W1, W2, Hout, occ_out, stream);
     SCONE_REQUIRE(width_ok(cin) && width_ok(cout),
                   "scone_layer_forward: hidden widths must be in {8,16,32,64} with |log2 ratio| <= 1 (got %d -> %d)", cin, cout);
-    SCONE_DISPATCH_WIDTHS(dispatch_fwd_act, cx, act, b, Hin, W0, W1, W2, Hout, as_stream(stream));
+    SCONE_DISPATCH_WIDTHS(dispatch_fwd_act, cx, act, b, Hin, W0, W1, W2, Hout, occ_in, occ_out, occ_scratch, as_stream(stream));
     scone_set_error("scone_layer_forward: unsupported width pair %d -> %d", cin, cout);
     return 2;
 }
@@ -698,35 +1188,42 @@ extern "C" int64_t scone_layer_backward_workspace_bytes(int32_t cin, int32_t cou
 
 extern "C" int scone_layer_backward(const scone_complex* cx, int32_t act, int32_t b, int32_t cin, int32_t cout, const float* G,
                                     const float* Hin, const float* W0, const float* W1, const float* W2, float* Gprev, float* dW,
-                                    int32_t accumulate, void* workspace, void* stream) {
+                                    int32_t accumulate, void* workspace, const uint8_t* occ_g, const uint8_t* occ_hin,
+                                    uint8_t* occ_prev, uint8_t* occ_scratch, void* stream) {
     SCONE_REQUIRE(cx && G && Hin && dW && workspace, "scone_layer_backward: NULL argument");
     SCONE_REQUIRE(!cx->host_only, "scone_layer_backward: index-only complex has no device arrays");
     SCONE_REQUIRE(b > 0, "scone_layer_backward: b must be positive");
-    if (cin == 1) return scone_layer0_backward(cx, b, cout, G, Hin, dW, accumulate, workspace, stream);
+    if (cin == 1) return scone_layer0_backward(cx, b, cout, G, Hin, dW, accumulate, workspace, occ_g, stream);
     SCONE_REQUIRE(W0 && W1 && W2, "scone_layer_backward: NULL weights");
     SCONE_REQUIRE(width_ok(cin) && width_ok(cout),
                   "scone_layer_backward: hidden widths must be in {8,16,32,64} with |log2 ratio| <= 1 (got %d -> %d)", cin, cout);
-    SCONE_DISPATCH_WIDTHS(dispatch_bwd_act, cx, act, b, G, Hin, W0, W1, W2, Gprev, dW, accumulate, (float*)workspace,
-                          as_stream(stream));
+    SCONE_DISPATCH_WIDTHS(dispatch_bwd_act, cx, act, b, G, Hin, W0, W1, W2, Gprev, dW, accumulate, (float*)workspace, occ_g, occ_hin,
+                          occ_prev, occ_scratch, as_stream(stream));
     scone_set_error("scone_layer_backward: unsupported width pair %d -> %d", cin, cout);
     return 2;
 }
 
 template <int COUT>
 static int launch_l0_fwd(const scone_complex* cx, int act, int b, const float* X, const float* W0, const float* W1, const float* W2,
-                         float* Hout, cudaStream_t st) {
-    const int n_tiles = ((b + 31) / 32) * ((cx->E + kL0Edges - 1) / kL0Edges);
+                         float* Hout, uint8_t* occ_out, cudaStream_t st) {
+    const long long n_tiles = (long long)((b + 31) / 32) * ((cx->E + kL0Edges - 1) / kL0Edges);
     const int grid = grid_for(cx, n_tiles, 6);
     ScopedProf prof(SCONE_K_LAYER0_FWD, st);
+    int write_zero_rows = 1;
+    if (occ_out != nullptr) {              // flagged pipeline: bulk zero-fill (when enabled), the kernel stores live rows only
+        if (g_scone_zero_fill) SCONE_CUDA(cudaMemsetAsync(Hout, 0, (size_t)cx->E * b * COUT * sizeof(float), st));
+        SCONE_CUDA(cudaMemsetAsync(occ_out, 0, (size_t)cx->E * b, st));
+        write_zero_rows = 0;
+    }
     switch (act) {
         case SCONE_ACT_TANH:
-            layer0_fwd_kernel<COUT, SCONE_ACT_TANH><<<grid, kThreads, 0, st>>>(X, Hout, W0, W1, W2, cx->S(0), cx->S(1), cx->E, b);
+            layer0_fwd_kernel<COUT, SCONE_ACT_TANH><<<grid, kThreads, 0, st>>>(X, Hout, W0, W1, W2, cx->S(0), cx->S(1), cx->E, b, occ_out, write_zero_rows);
             break;
         case SCONE_ACT_LEAKY_RELU:
-            layer0_fwd_kernel<COUT, SCONE_ACT_LEAKY_RELU><<<grid, kThreads, 0, st>>>(X, Hout, W0, W1, W2, cx->S(0), cx->S(1), cx->E, b);
+            layer0_fwd_kernel<COUT, SCONE_ACT_LEAKY_RELU><<<grid, kThreads, 0, st>>>(X, Hout, W0, W1, W2, cx->S(0), cx->S(1), cx->E, b, occ_out, write_zero_rows);
             break;
         case SCONE_ACT_RELU:
-            layer0_fwd_kernel<COUT, SCONE_ACT_RELU><<<grid, kThreads, 0, st>>>(X, Hout, W0, W1, W2, cx->S(0), cx->S(1), cx->E, b);
+            layer0_fwd_kernel<COUT, SCONE_ACT_RELU><<<grid, kThreads, 0, st>>>(X, Hout, W0, W1, W2, cx->S(0), cx->S(1), cx->E, b, occ_out, write_zero_rows);
             break;
         default: scone_set_error("unknown activation %d", act); return 2;
     }
@@ -735,29 +1232,37 @@ static int launch_l0_fwd(const scone_complex* cx, int act, int b, const float* X
 }
 
 int scone_layer0_forward(const scone_complex* cx, int32_t act, int32_t b, int32_t cout, const float* X, const float* W0,
-                         const float* W1, const float* W2, float* Hout, void* stream) {
+                         const float* W1, const float* W2, float* Hout, uint8_t* occ_out, void* stream) {
     cudaStream_t st = as_stream(stream);
     switch (cout) {
-        case 8: return launch_l0_fwd<8>(cx, act, b, X, W0, W1, W2, Hout, st);
-        case 16: return launch_l0_fwd<16>(cx, act, b, X, W0, W1, W2, Hout, st);
-        case 32: return launch_l0_fwd<32>(cx, act, b, X, W0, W1, W2, Hout, st);
-        case 64: return launch_l0_fwd<64>(cx, act, b, X, W0, W1, W2, Hout, st);
+        case 8: return launch_l0_fwd<8>(cx, act, b, X, W0, W1, W2, Hout, occ_out, st);
+        case 16: return launch_l0_fwd<16>(cx, act, b, X, W0, W1, W2, Hout, occ_out, st);
+        case 32: return launch_l0_fwd<32>(cx, act, b, X, W0, W1, W2, Hout, occ_out, st);
+        case 64: return launch_l0_fwd<64>(cx, act, b, X, W0, W1, W2, Hout, occ_out, st);
     }
     scone_set_error("scone_layer_forward: first-layer width must be in {8,16,32,64} (got %d)", cout);
     return 2;
 }
 
-constexpr int kL0BwdCtas = 148 * 4;
+constexpr int kL0BwdCtas = 148 * 8;
 int64_t scone_layer0_backward_workspace_bytes(int32_t cout) { return (int64_t)kL0BwdCtas * 3 * cout * sizeof(float); }
 
 template <int COUT>
 static int launch_l0_bwd(const scone_complex* cx, int b, const float* G, const float* X, float* dW, int accumulate, float* ws,
-                         cudaStream_t st) {
-    const int n_tiles = ((b + 31) / 32) * ((cx->E + kL0Edges - 1) / kL0Edges);
-    int grid = grid_for(cx, n_tiles, 4);
-    if (grid > kL0BwdCtas) grid = kL0BwdCtas;
+                         const uint8_t* occ_g, cudaStream_t st) {
     ScopedProf prof(SCONE_K_LAYER0_BWD, st);
-    layer0_bwd_kernel<COUT><<<grid, kThreads, 0, st>>>(X, G, ws, cx->S(0), cx->S(1), cx->E, b);
+    int grid;
+    if (occ_g == nullptr) {
+        const long long n_tiles = (long long)((b + 31) / 32) * ((cx->E + kL0Edges - 1) / kL0Edges);
+        grid = grid_for(cx, n_tiles, 4);
+        if (grid > kL0BwdCtas) grid = kL0BwdCtas;
+        layer0_bwd_dense_kernel<COUT><<<grid, kThreads, 0, st>>>(X, G, ws, cx->S(0), cx->S(1), cx->E, b);
+    } else {
+        const long long n_blocks = ((long long)cx->E * b + kUnitsPerBlock - 1) / kUnitsPerBlock;
+        grid = grid_for(cx, n_blocks, 8);
+        if (grid > kL0BwdCtas) grid = kL0BwdCtas;
+        layer0_bwd_rows_kernel<COUT><<<grid, kThreads, 0, st>>>(X, G, ws, cx->S(0), cx->S(1), cx->E, b, occ_g);
+    }
     SCONE_LAUNCHED();
     reduce_partials_kernel<<<(3 * COUT + 255) / 256, 256, 0, st>>>(ws, grid, 3 * COUT, dW, accumulate);
     SCONE_LAUNCHED();
@@ -765,14 +1270,14 @@ static int launch_l0_bwd(const scone_complex* cx, int b, const float* G, const f
 }
 
 int scone_layer0_backward(const scone_complex* cx, int32_t b, int32_t cout, const float* G, const float* X, float* dW,
-                          int32_t accumulate, void* workspace, void* stream) {
+                          int32_t accumulate, void* workspace, const uint8_t* occ_g, void* stream) {
     cudaStream_t st = as_stream(stream);
     float* ws = (float*)workspace;
     switch (cout) {
-        case 8: return launch_l0_bwd<8>(cx, b, G, X, dW, accumulate, ws, st);
-        case 16: return launch_l0_bwd<16>(cx, b, G, X, dW, accumulate, ws, st);
-        case 32: return launch_l0_bwd<32>(cx, b, G, X, dW, accumulate, ws, st);
-        case 64: return launch_l0_bwd<64>(cx, b, G, X, dW, accumulate, ws, st);
+        case 8: return launch_l0_bwd<8>(cx, b, G, X, dW, accumulate, ws, occ_g, st);
+        case 16: return launch_l0_bwd<16>(cx, b, G, X, dW, accumulate, ws, occ_g, st);
+        case 32: return launch_l0_bwd<32>(cx, b, G, X, dW, accumulate, ws, occ_g, st);
+        case 64: return launch_l0_bwd<64>(cx, b, G, X, dW, accumulate, ws, occ_g, st);
     }
     scone_set_error("scone_layer_backward: first-layer width must be in {8,16,32,64} (got %d)", cout);
     return 2;
@@ -785,7 +1290,7 @@ extern "C" int scone_flows_to_dense(const scone_complex* cx, int32_t b, const in
     cudaStream_t st = as_stream(stream);
     ScopedProf prof(SCONE_K_OTHER, st);
     SCONE_CUDA(cudaMemsetAsync(X, 0, (size_t)cx->E * b * sizeof(float), st));
-    flows_to_dense_kernel<<<(b * 32 + 255) / 256, 256, 0, st>>>(traj_ptr, flow_edge, flow_val, X, cx->E, b);
+    flows_to_dense_kernel<<<(b * 32 + 255) / 256, 256, 0, st>>>(traj_ptr, flow_edge, flow_val, cx->d_rank, X, cx->E, b);
     SCONE_LAUNCHED();
     return 0;
 }
@@ -794,7 +1299,8 @@ int64_t scone_readout_workspace_bytes(int32_t b, int32_t C) { return (int64_t)b 
 
 int scone_readout_ws(const scone_complex* cx, int32_t act, int32_t b, int32_t C, const float* HL, const float* wout,
                      const int32_t* last_nodes, float* logprobs, const int32_t* target_idx, const float* mask, float scale,
-                     float* GL, float* dwout, float* nll_sum, float* count, int32_t accumulate, void* workspace, void* stream) {
+                     float* GL, float* dwout, float* nll_sum, float* count, int32_t accumulate, void* workspace,
+                     const uint8_t* occ_HL, uint8_t* occ_GL, void* stream) {
     SCONE_REQUIRE(cx && HL && wout && last_nodes && logprobs, "scone_readout: NULL argument");
     SCONE_REQUIRE(!cx->host_only, "scone_readout: index-only complex has no device arrays");
     SCONE_REQUIRE(C >= 1 && C <= 32 * kReadoutMaxCper, "scone_readout: C must be in [1,%d]", 32 * kReadoutMaxCper);
@@ -803,10 +1309,13 @@ int scone_readout_ws(const scone_complex* cx, int32_t act, int32_t b, int32_t C,
     ScopedProf prof(SCONE_K_READOUT, st);
     if (GL) {
         SCONE_REQUIRE(target_idx && mask && workspace, "scone_readout: gradient mode needs target_idx, mask, workspace");
-        SCONE_CUDA(cudaMemsetAsync(GL, 0, (size_t)cx->E * b * C * sizeof(float), st));
+        // without flags the consumer reads every row of GL: it must be dense zeros; with flags only when zero-fill is on
+        if (occ_GL == nullptr || g_scone_zero_fill) SCONE_CUDA(cudaMemsetAsync(GL, 0, (size_t)cx->E * b * C * sizeof(float), st));
+        if (occ_GL) SCONE_CUDA(cudaMemsetAsync(occ_GL, 0, (size_t)cx->E * b, st));
     }
     readout_kernel<<<(b + 3) / 4, 128, 0, st>>>(HL, wout, last_nodes, cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, logprobs,
-                                              target_idx, mask, scale, GL, (float*)workspace, act, cx->N, cx->D, b, C);
+                                              target_idx, mask, scale, GL, (float*)workspace, occ_HL, GL ? occ_GL : nullptr, act,
+                                              cx->N, cx->D, b, C);
     SCONE_LAUNCHED();
     if (GL) {
         readout_reduce_kernel<<<1, ((C + 2 + 31) / 32) * 32, 0, st>>>((const float*)workspace, b, C, dwout, nll_sum, count, accumulate);
@@ -820,9 +1329,9 @@ extern "C" int64_t scone_readout_workspace(int32_t b, int32_t C) { return scone_
 extern "C" int scone_readout(const scone_complex* cx, int32_t act, int32_t b, int32_t C, const float* HL, const float* wout,
                              const int32_t* last_nodes, float* logprobs, const int32_t* target_idx, const float* mask, float scale,
                              float* GL, float* dwout, float* nll_sum, float* count, int32_t accumulate, void* workspace,
-                             void* stream) {
+                             const uint8_t* occ_HL, uint8_t* occ_GL, void* stream) {
     return scone_readout_ws(cx, act, b, C, HL, wout, last_nodes, logprobs, target_idx, mask, scale, GL, dwout, nll_sum, count,
-                            accumulate, workspace, stream);
+                            accumulate, workspace, occ_HL, occ_GL, stream);
 }
 
 int scone_adam_launch(float* W, float* m, float* v, const float* gradbuf, int64_t n, int32_t step, float lr, float wd, void* stream) {

@@ -20,6 +20,9 @@ struct scone_model {
     float* d_X = nullptr;                     // [E][mb]
     std::vector<float*> d_H;                  // H_1..H_L, [E][mb][C_l]
     float* d_G[2] = {nullptr, nullptr};       // ping-pong dL/dZ, [E][mb][cmax]
+    std::vector<uint8_t*> d_occH;             // occupancy flags of H_1..H_L, [E][mb]
+    uint8_t* d_occG[2] = {nullptr, nullptr};  // occupancy flags of the dL/dZ buffers
+    uint8_t* d_occS = nullptr;                // one-hop propagated flags (scratch)
     void* d_ws = nullptr;                     // backward / readout workspace
     float* d_logp = nullptr;                  // [mb][D]
     // staging for the *_host entry points
@@ -61,7 +64,7 @@ int forward_mb(scone_model* m, int32_t b, const int32_t* ptr, const int32_t* edg
     for (int l = 0; l < m->L; ++l) {
         const int cout = m->hidden[l];
         rc = scone_layer_forward(cx, m->act, b, cin, cout, in, m->d_w + m->w_off[3 * l], m->d_w + m->w_off[3 * l + 1],
-                                 m->d_w + m->w_off[3 * l + 2], m->d_H[l], st);
+                                 m->d_w + m->w_off[3 * l + 2], m->d_H[l], l > 0 ? m->d_occH[l - 1] : nullptr, m->d_occH[l], m->d_occS, st);
         if (rc) return rc;
         in = m->d_H[l];
         cin = cout;
@@ -125,6 +128,10 @@ extern "C" int scone_model_create(const scone_complex* cx, int32_t n_layers, con
     m->d_H.assign(n_layers, nullptr);
     for (int l = 0; l < n_layers; ++l) alloc((void**)&m->d_H[l], E * mb * hidden[l] * sizeof(float));
     for (int k = 0; k < 2; ++k) alloc((void**)&m->d_G[k], E * mb * m->cmax * sizeof(float));
+    m->d_occH.assign(n_layers, nullptr);
+    for (int l = 0; l < n_layers; ++l) alloc((void**)&m->d_occH[l], E * mb);
+    for (int k = 0; k < 2; ++k) alloc((void**)&m->d_occG[k], E * mb);
+    alloc((void**)&m->d_occS, E * mb);
     int64_t ws = scone_readout_workspace_bytes(micro_batch, m->cmax);
     cin = 1;
     for (int l = 0; l < n_layers; ++l) {
@@ -152,6 +159,8 @@ extern "C" int scone_model_destroy(scone_model* m) {
     if (!m) return 0;
     cudaFree(m->d_w); cudaFree(m->d_m); cudaFree(m->d_v); cudaFree(m->d_grad); cudaFree(m->d_X);
     for (float* p : m->d_H) cudaFree(p);
+    for (uint8_t* p : m->d_occH) cudaFree(p);
+    cudaFree(m->d_occG[0]); cudaFree(m->d_occG[1]); cudaFree(m->d_occS);
     cudaFree(m->d_G[0]); cudaFree(m->d_G[1]); cudaFree(m->d_ws); cudaFree(m->d_logp);
     cudaFree(m->d_ptr); cudaFree(m->d_edge); cudaFree(m->d_last); cudaFree(m->d_tgt); cudaFree(m->d_val);
     cudaFree(m->d_mask); cudaFree(m->d_logp_all);
@@ -187,7 +196,7 @@ extern "C" int scone_model_forward_dev(scone_model* m, int32_t B, const int32_t*
         if (rc) return rc;
         rc = scone_readout_ws(cx, m->act, b, m->hidden[m->L - 1], m->d_H[m->L - 1], m->d_w + m->w_off[3 * m->L], last + off,
                               logprobs + (size_t)off * cx->D, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, nullptr, 0,
-                              nullptr, st);
+                              nullptr, m->d_occH[m->L - 1], nullptr, st);
         if (rc) return rc;
     }
     return 0;
@@ -209,7 +218,7 @@ extern "C" int scone_model_loss_grad_dev(scone_model* m, int32_t B, const int32_
         float* G = m->d_G[0];
         rc = scone_readout_ws(cx, m->act, b, CL, m->d_H[L - 1], m->d_w + m->w_off[3 * L], last + off, m->d_logp, tgt + off,
                               mask + off, 1.f, G, m->d_grad + m->w_off[3 * L], m->d_grad + m->n_params,
-                              m->d_grad + m->n_params + 1, 1, m->d_ws, st);
+                              m->d_grad + m->n_params + 1, 1, m->d_ws, m->d_occH[L - 1], m->d_occG[0], st);
         if (rc) return rc;
         int cur = 0;
         for (int l = L - 1; l >= 0; --l) {
@@ -218,7 +227,8 @@ extern "C" int scone_model_loss_grad_dev(scone_model* m, int32_t B, const int32_
             float* Gprev = l > 0 ? m->d_G[cur ^ 1] : nullptr;
             rc = scone_layer_backward(cx, m->act, b, cin, cout, m->d_G[cur], Hin, m->d_w + m->w_off[3 * l],
                                       m->d_w + m->w_off[3 * l + 1], m->d_w + m->w_off[3 * l + 2], Gprev,
-                                      m->d_grad + m->w_off[3 * l], 1, m->d_ws, st);
+                                      m->d_grad + m->w_off[3 * l], 1, m->d_ws, m->d_occG[cur], l > 0 ? m->d_occH[l - 1] : nullptr,
+                                      l > 0 ? m->d_occG[cur ^ 1] : nullptr, m->d_occS, st);
             if (rc) return rc;
             cur ^= 1;
         }

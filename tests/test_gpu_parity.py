@@ -148,13 +148,22 @@ def test_layer_kernels_dense_random_input(small, cin, cout, act, b):
     dact = [lambda h: 1 - h * h, lambda h: np.where(h >= 0, 1.0, 0.01), lambda h: (h > 0) * 1.0][act]
     Href = actf(Z)
     dev = torch.device('cuda')
-    tH, tG = torch.from_numpy(Hin).to(dev), torch.from_numpy(G).to(dev)
+    rank = torch.from_numpy(cx.edge_rank.astype(np.int64))          # caller's edge id -> internal device row
+
+    def to_dev(a):                                                   # rows in the library's internal order
+        t = torch.empty(a.shape, dtype=torch.float32)
+        t[rank] = torch.from_numpy(a)
+        return t.to(dev)
+
+    def from_dev(t):
+        return t.cpu()[rank].numpy()
+    tH, tG = to_dev(Hin), to_dev(G)
     tW = [torch.from_numpy(w).to(dev) for w in W]
     tout = torch.empty(E, b, cout, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     _lib.check(L.scone_layer_forward(cx.handle, act, b, cin, cout, _lib.dptr(tH), _lib.dptr(tW[0]), _lib.dptr(tW[1]),
-                                     _lib.dptr(tW[2]), _lib.dptr(tout), st), 'layer_forward')
-    out = tout.cpu().numpy()
+                                     _lib.dptr(tW[2]), _lib.dptr(tout), None, None, None, st), 'layer_forward')
+    out = from_dev(tout)
     assert np.abs(out - Href).max() <= 2e-5 * max(1.0, np.abs(Href).max())
     # backward: G is dL/dZ
     G64 = G.astype(np.float64)
@@ -164,14 +173,84 @@ def test_layer_kernels_dense_random_input(small, cin, cout, act, b):
     tdW = torch.zeros(3, cin, cout, device=dev)
     tGp = torch.empty(E, b, cin, device=dev) if cin > 1 else None
     _lib.check(L.scone_layer_backward(cx.handle, act, b, cin, cout, _lib.dptr(tG), _lib.dptr(tH), _lib.dptr(tW[0]),
-                                      _lib.dptr(tW[1]), _lib.dptr(tW[2]), _lib.dptr(tGp), _lib.dptr(tdW), 0, _lib.dptr(ws), st),
-               'layer_backward')
+                                      _lib.dptr(tW[1]), _lib.dptr(tW[2]), _lib.dptr(tGp), _lib.dptr(tdW), 0, _lib.dptr(ws),
+                                      None, None, None, None, st), 'layer_backward')
     assert _relmax(tdW.cpu().numpy(), dW_ref) <= 2e-5
     if cin > 1:
         dH = sum(A[k] @ W[k].astype(np.float64).T for k in range(3))
         Gp_ref = dH * dact(H64)          # Hin plays the role of the previous layer's OUTPUT
-        assert _relmax(tGp.cpu().numpy(), Gp_ref) <= 2e-5
+        assert _relmax(from_dev(tGp), Gp_ref) <= 2e-5
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize('cin,cout', [(16, 16), (32, 32), (16, 32), (64, 32)])
+def test_occupancy_flags_are_exact(small, cin, cout):
+    """Row-sparse features: the flagged kernels (skip zero neighbour rows / zero tiles) must reproduce the unflagged
+    kernels bit for bit, and the flags they emit must be a superset of the non-zero rows."""
+    sg = _mods()
+    from scone_gcn_b200 import _lib
+    L = _lib.lib()
+    cx = sg.SimplicialComplex.from_dense(small.B1, small.B2, 'scone')
+    E, b = cx.E, 19
+    dev = torch.device('cuda')
+    g = torch.Generator(device='cpu').manual_seed(cin + cout)
+    keep = (torch.rand(E, b, 1, generator=g) < 0.05).float()
+    H = (torch.randn(E, b, cin, generator=g) * keep).to(dev)
+    G = (torch.randn(E, b, cout, generator=g) * (torch.rand(E, b, 1, generator=g) < 0.03).float()).to(dev)
+    occH = (H.abs().amax(dim=2) > 0).to(torch.uint8).contiguous()
+    occG = (G.abs().amax(dim=2) > 0).to(torch.uint8).contiguous()
+    W = [(torch.randn(cin, cout, generator=g) * 0.3).to(dev) for _ in range(3)]
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    scratch = torch.empty(E, b, dtype=torch.uint8, device=dev)
+    for flagged in (0, 1, 2):
+        out = torch.full((E, b, cout), 7.0, device=dev)
+        occ_out = torch.full((E, b), 9, dtype=torch.uint8, device=dev)
+        _lib.check(L.scone_layer_forward(cx.handle, 0, b, cin, cout, _lib.dptr(H), _lib.dptr(W[0]), _lib.dptr(W[1]), _lib.dptr(W[2]),
+                                         _lib.dptr(out), _lib.dptr(occH) if flagged else None, _lib.dptr(occ_out),
+                                         _lib.dptr(scratch) if flagged else None, st))
+        ws = torch.empty(L.scone_layer_backward_workspace_bytes(cin, cout) // 4 + 16, device=dev)
+        dW = torch.zeros(3, cin, cout, device=dev)
+        Gp = torch.full((E, b, cin), 7.0, device=dev)
+        occ_p = torch.full((E, b), 9, dtype=torch.uint8, device=dev)
+        _lib.check(L.scone_layer_backward(cx.handle, 0, b, cin, cout, _lib.dptr(G), _lib.dptr(H), _lib.dptr(W[0]), _lib.dptr(W[1]),
+                                          _lib.dptr(W[2]), _lib.dptr(Gp), _lib.dptr(dW), 0, _lib.dptr(ws),
+                                          _lib.dptr(occG) if flagged else None, _lib.dptr(occH) if flagged == 2 else None,
+                                          _lib.dptr(occ_p), _lib.dptr(scratch) if flagged else None, st))
+        outs.append((out.cpu(), occ_out.cpu(), Gp.cpu(), occ_p.cpu(), dW.cpu()))
+    for k in (1, 2):
+        assert torch.equal(outs[0][0], outs[k][0]) and torch.equal(outs[0][2], outs[k][2])     # Hout, Gprev bit-identical
+        assert _relmax(outs[k][4].numpy(), outs[0][4].numpy()) < 1e-5                          # dW: other summation order
+        assert torch.equal(outs[k][1].bool(), outs[k][0].abs().amax(dim=2) > 0)               # flags == non-zero rows
+        assert torch.equal(outs[k][3].bool(), outs[k][2].abs().amax(dim=2) > 0)
+    assert torch.equal(outs[1][4], outs[2][4])
+    assert outs[0][1].min() == 1                                 # dense kernels carry no information: everything flagged
+    assert 0 < outs[1][1].float().mean() < 0.9
+
+
+@pytest.mark.parametrize('zero_fill', [1, 0])
+def test_model_results_identical_with_and_without_zero_fill(small, zero_fill):
+    """Sparse mode (unflagged rows never written) must give the same log-probs and gradients bit for bit."""
+    sg = _mods()
+    L = sg.lib()
+    fx = load('model_small_scone_h16.npz')
+    cx = sg.SimplicialComplex.from_dense(small.B1, small.B2, 'scone')
+    ptr, fe, fv = sg.flows_to_csr(small.flows)
+    W = weights_of(fx, 'w_big')
+    res = []
+    try:
+        for zf in (1, zero_fill):
+            L.scone_set_zero_fill(zf)
+            net = sg.SconeModel(cx, [16, 16, 16], micro_batch=32)
+            # poison the activation buffers so that a read of an unwritten row would show up
+            net.set_weights(W)
+            lp = net.forward(ptr, fe, fv, small.last_nodes)
+            buf = net.loss_grad(ptr, fe, fv, small.last_nodes, small.raw['targets_argmax'], np.ones(small.n_traj, np.float32))
+            res.append((lp, buf))
+    finally:
+        L.scone_set_zero_fill(1)
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert np.abs(res[0][0] - fx['big_logprobs'][:, :, 0]).max() < 1e-5
 
 
 def test_training_matches_oracle_end_to_end(small):

@@ -48,26 +48,35 @@ def report(name, ms, nbytes):
 
 W = [torch.randn(C, C, device=dev) * 0.2 for _ in range(3)]
 W1 = [torch.randn(1, C, device=dev) * 0.2 for _ in range(3)]
-for kind in ('dense-random', 'sparse-2pct'):
+for kind in ('dense-random', 'rows-2pct+flags', 'blob-1pct+flags'):
     H = torch.randn(E, b, C, device=dev)
-    if kind != 'dense-random':
+    if kind.startswith('rows'):
         H *= (torch.rand(E, 1, 1, device=dev) < 0.02)
+    if kind.startswith('blob'):          # spatially compact support, different per trajectory (what real activations look like)
+        mid = torch.empty(E, 2)
+        mid[torch.from_numpy(cx.edge_rank.astype(np.int64))] = torch.from_numpy(coords[edges].mean(axis=1)).float()
+        mid = mid.to(dev)
+        ctr = torch.rand(b, 2, device=dev)
+        H *= ((mid[:, None, :] - ctr[None, :, :]).norm(dim=2) < 0.056)[:, :, None]
+    occ = (H.abs().amax(dim=2) > 0).to(torch.uint8).contiguous() if 'flags' in kind else None
+    occ_o = torch.empty(E, b, dtype=torch.uint8, device=dev)
+    scr = torch.empty(E, b, dtype=torch.uint8, device=dev) if occ is not None else None
     out = torch.empty_like(H)
     X = torch.randn(E, b, device=dev)
     ms = timeit(lambda: _lib.check(L.scone_layer_forward(cx.handle, 0, b, C, C, _lib.dptr(H), _lib.dptr(W[0]), _lib.dptr(W[1]),
-                                                        _lib.dptr(W[2]), _lib.dptr(out), st)))
+                                                        _lib.dptr(W[2]), _lib.dptr(out), _lib.dptr(occ), _lib.dptr(occ_o), _lib.dptr(scr), st)))
     report('fwd %d->%d (%s)' % (C, C, kind), ms, 4 * E * b * 2 * C)
     ws = torch.empty(L.scone_layer_backward_workspace_bytes(C, C) // 4 + 16, device=dev)
     dW = torch.zeros(3, C, C, device=dev)
     ms = timeit(lambda: _lib.check(L.scone_layer_backward(cx.handle, 0, b, C, C, _lib.dptr(H), _lib.dptr(out), _lib.dptr(W[0]),
                                                          _lib.dptr(W[1]), _lib.dptr(W[2]), _lib.dptr(out), _lib.dptr(dW), 0,
-                                                         _lib.dptr(ws), st)))
+                                                         _lib.dptr(ws), _lib.dptr(occ), _lib.dptr(occ), _lib.dptr(occ_o), _lib.dptr(scr), st)))
     report('bwd %d->%d (%s)' % (C, C, kind), ms, 4 * E * b * 3 * C)
     ms = timeit(lambda: _lib.check(L.scone_layer_forward(cx.handle, 0, b, 1, C, _lib.dptr(X), _lib.dptr(W1[0]), _lib.dptr(W1[1]),
-                                                        _lib.dptr(W1[2]), _lib.dptr(out), st)))
+                                                        _lib.dptr(W1[2]), _lib.dptr(out), None, _lib.dptr(occ_o), None, st)))
     report('fwd 1->%d (%s)' % (C, kind), ms, 4 * E * b * (1 + C))
     ms = timeit(lambda: _lib.check(L.scone_layer_backward(cx.handle, 0, b, 1, C, _lib.dptr(H), _lib.dptr(X), None, None, None,
-                                                         None, _lib.dptr(dW), 0, _lib.dptr(ws), st)))
+                                                         None, _lib.dptr(dW), 0, _lib.dptr(ws), _lib.dptr(occ), None, None, None, st)))
     report('bwd 1->%d (%s)' % (C, kind), ms, 4 * E * b * (1 + C))
     del H, out
 a = torch.empty(E * b * C, device=dev)
