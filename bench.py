@@ -174,6 +174,7 @@ def main():
     ap.add_argument('--micro-batch', type=int, default=0)
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', dest='extras', action='store_false', help='skip the sparse-mode and dense-kernel extras')
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.batch:
@@ -285,9 +286,14 @@ def main():
         n_l, t_ms = ctypes.c_int64(), ctypes.c_double()
         L.scone_profile_read(k, n_l, t_ms)
         fam[nme] = (n_l.value, t_ms.value)
-    alg = {'layer_fwd': 4.0 * E * mb * (C + C), 'layer_bwd': 4.0 * E * mb * (C + C + C),
-           'layer0_fwd': 4.0 * E * mb * (1 + C), 'layer0_bwd': 4.0 * E * mb * (1 + C),
-           'readout': 4.0 * E * mb * C, 'flows_to_dense': 4.0 * E * mb}
+    # ALGORITHMIC bytes per launch of the flagged (default) kernels, DESIGN.md §4: the dense output tensor is written
+    # once (zero-fill + live rows), the one-byte row flags are read/written ~4x, and only flagged input rows are read
+    # (their bytes are NOT counted: < 2 % of the output on this workload) -- a conservative numerator.
+    fl = 4.0 * E * mb
+    alg = {'layer_fwd': 4.0 * E * mb * C + fl, 'layer_bwd': 4.0 * E * mb * C + fl,
+           'layer0_fwd': 4.0 * E * mb * (1 + C) + E * mb, 'layer0_bwd': 4.0 * E * mb + E * mb,
+           'readout': 4.0 * E * mb * C + E * mb, 'flows_to_dense': 4.0 * E * mb}
+    alg_dense = {'layer_fwd': 4.0 * E * mb * (C + C), 'layer_bwd': 4.0 * E * mb * (C + C + C)}
     peak, peak_src = load_peaks()
     kernels = {}
     tot_ms = sum(t for _, t in fam.values()) or 1.0
@@ -300,7 +306,8 @@ def main():
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': kernels[dom]['achieved_gbs'], 'peak': peak, 'unit': 'GB/s',
                 'frac': kernels[dom]['frac'], 'traffic': None, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': alg[dom],
-                'hodge_spmm_fwd_gbs': kernels.get('layer_fwd', {}).get('achieved_gbs'), 'kernels': kernels}
+                'hodge_spmm_fwd_gbs': kernels.get('layer_fwd', {}).get('achieved_gbs'), 'kernels': kernels,
+                'bytes_model': 'flagged kernels: dense output write + row flags; flagged input-row reads not counted'}
 
     # end to end through the host API
     barrier()
@@ -316,6 +323,60 @@ def main():
     e2e_ms = max_over_ranks(ev0.elapsed_time(ev1))
     e2e = {'value': world * B * e2e_steps / (e2e_ms / 1e3), 'unit': 'trajectories/s', 'h2d_bytes_per_step': h2d_bytes,
            'd2h_bytes_per_step': int(4 * (net.n_params + 2)), 'steps': e2e_steps, 'last_loss': loss}
+
+    # extra 1: the same step with zero-fill OFF (unflagged rows never written; results bit-identical, tests/)
+    sparse_mode = None
+    if args.extras:
+        L.scone_set_zero_fill(0)
+        try:
+            step_dev()
+            barrier()
+            ev0.record()
+            for _ in range(args.steps):
+                step_dev()
+            ev1.record()
+            barrier()
+            sm_ms = max_over_ranks(ev0.elapsed_time(ev1))
+            sparse_mode = {'value': world * B * args.steps / (sm_ms / 1e3), 'unit': 'trajectories/s',
+                           'ms_per_step': sm_ms / args.steps,
+                           'note': 'scone_set_zero_fill(0): traffic follows the support of the trajectories instead of E'}
+        finally:
+            L.scone_set_zero_fill(1)
+
+    # extra 2: the contracted DENSE-tile measurement (north-star / SURVEY 8d): one fused 32->32 layer on dense random
+    # features, no occupancy information, algorithmic bytes 4*E*b*(Cin+Cout) fwd and 4*E*b*(2*Cout+Cin) bwd
+    roofline_dense = None
+    if args.extras and rank == 0:
+        bd = min(mb, 64)
+        Hd = torch.randn(E, bd, C, device=dev)
+        Od = torch.empty_like(Hd)
+        Wd = [torch.randn(C, C, device=dev) * 0.2 for _ in range(3)]
+        wsd = torch.empty(L.scone_layer_backward_workspace_bytes(C, C) // 4 + 16, device=dev)
+        dWd = torch.zeros(3, C, C, device=dev)
+
+        def t_of(fn, it=3):
+            fn()
+            torch.cuda.synchronize()
+            best = 1e30
+            for _ in range(it):
+                a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                z.record()
+                torch.cuda.synchronize()
+                best = min(best, a.elapsed_time(z))
+            return best
+        f_ms = t_of(lambda: _lib.check(L.scone_layer_forward(cx.handle, 0, bd, C, C, _lib.dptr(Hd), _lib.dptr(Wd[0]), _lib.dptr(Wd[1]),
+                                                             _lib.dptr(Wd[2]), _lib.dptr(Od), None, None, None, stream)))
+        b_ms = t_of(lambda: _lib.check(L.scone_layer_backward(cx.handle, 0, bd, C, C, _lib.dptr(Hd), _lib.dptr(Od), _lib.dptr(Wd[0]),
+                                                              _lib.dptr(Wd[1]), _lib.dptr(Wd[2]), _lib.dptr(Od), _lib.dptr(dWd), 0,
+                                                              _lib.dptr(wsd), None, None, None, None, stream)))
+        fa, ba = 4.0 * E * bd * 2 * C / f_ms / 1e6, 4.0 * E * bd * 3 * C / b_ms / 1e6
+        roofline_dense = {'bound': 'hbm', 'unit': 'GB/s', 'peak': peak, 'b': bd,
+                          'layer_fwd': {'ms': f_ms, 'achieved': fa, 'frac': fa / peak},
+                          'layer_bwd': {'ms': b_ms, 'achieved': ba, 'frac': ba / peak},
+                          'note': 'dense random features, no flags: instruction/L1-bound SIMT product (profiles/); not in the timed region'}
+        del Hd, Od
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -335,7 +396,8 @@ def main():
                           'l2_policy': 'inputs larger than L2: each micro-batch streams %.2f GB of activations'
                                        % (4.0 * E * mb * C * 5 / 1e9),
                           'generator_seed': 1030, 'mean_flow_nnz': nnz / B},
-               'roofline': roofline, 'e2e': e2e, 'cpu_baseline': cpu_baseline, 'gpu_launches': int(launches),
+               'roofline': roofline, 'roofline_dense': roofline_dense, 'sparse_mode': sparse_mode, 'e2e': e2e,
+               'cpu_baseline': cpu_baseline, 'gpu_launches': int(launches),
                'clocks': clk, 'setup_s': setup_s}
         print(json.dumps(out), flush=True)
     if world > 1:
