@@ -195,6 +195,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        os.environ['NCCL_DEBUG_FILE'] = '/dev/stderr'       # keep stdout to the one JSON line (NCCL prints its version banner)
         dist.init_process_group('nccl', device_id=dev)
     L = sg.lib()
 
