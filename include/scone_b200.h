@@ -81,17 +81,19 @@ int scone_complex_get_edge_rank(const scone_complex* cx, int32_t* rank /* host [
  * Trajectory t owns entries [traj_ptr[t], traj_ptr[t+1]) of (flow_edge, flow_val). */
 int scone_flows_to_dense(const scone_complex* cx, int32_t b, const int32_t* traj_ptr_dev /* [b+1] */,
                          const int32_t* flow_edge_dev, const float* flow_val_dev, float* X_dev /* [E][b] */,
-                         void* stream);
+                         uint8_t* occ_X_dev /* [E][b] flags of X, or NULL */, void* stream);
 
 /* One fused Hodge-Laplacian convolution layer, forward:
  *   Hout = act(Hin W0 + (S0 Hin) W1 + (S1 Hin) W2)                       trajectory_experiments.py:145-149,163-167
  * Hin [E][b][cin], Hout [E][b][cout], W* [cin][cout] (device).
  * Occupancy flags (optional, NULL = none): occ[e*b + t] == 0 promises that row (e, t) of the tensor is entirely
- * zero.  There is no bias and act(0) == 0, so activations are structurally zero outside the l-hop neighbourhood of a
- * trajectory; with occ_in the kernel skips the gathers of flagged-zero neighbour rows and the FLOPs
- * of all-zero tiles — results are bit-identical, every row is still read and written once.  occ_out receives the
- * flags of Hout.  occ_scratch (E*b bytes, optional) lets the call first propagate the flags one hop (a byte-only
- * pre-pass) so that whole tiles without any candidate row are zero-filled without touching the index arrays. */
+ * zero (a superset of the non-zero rows is fine).  There is no bias and act(0) == 0, so activations are structurally
+ * zero outside the l-hop neighbourhood of a trajectory.  With occ_in the call (1) compacts the flagged
+ * units of the input into a worklist, (2) scatters the support one hop into occ_out, (3) compacts occ_out, and (4) runs
+ * one warp per candidate unit; unflagged neighbour rows are never read.  Results are bit-identical to the dense
+ * kernel.  occ_scratch: scone_occ_scratch_bytes(cx, b) bytes.  Without occ_in the dense tile kernel runs and occ_out
+ * (if given) is set to all ones. */
+int64_t scone_occ_scratch_bytes(const scone_complex* cx, int32_t b);
 int scone_layer_forward(const scone_complex* cx, int32_t act, int32_t b, int32_t cin, int32_t cout,
                         const float* Hin_dev, const float* W0_dev, const float* W1_dev, const float* W2_dev,
                         float* Hout_dev, const uint8_t* occ_in_dev, uint8_t* occ_out_dev, uint8_t* occ_scratch_dev,

@@ -35,7 +35,8 @@ SIGNATURES = {
     'scone_complex_get_shift_csr': (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
     'scone_complex_get_nbrhoods': (C.c_int, [_vp, _vp]),
     'scone_complex_get_edge_rank': (C.c_int, [_vp, _vp]),
-    'scone_flows_to_dense': (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    'scone_flows_to_dense': (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'scone_occ_scratch_bytes': (_i64, [_vp, _i32]),
     'scone_layer_forward': (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'scone_layer_backward_workspace_bytes': (_i64, [_i32, _i32]),
     'scone_layer_backward': (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -79,10 +79,12 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 
 // internal kernels-level helpers implemented in scone_kernels.cu
 int scone_layer0_forward(const scone_complex* cx, int32_t act, int32_t b, int32_t cout, const float* X_dev,
-                         const float* W0, const float* W1, const float* W2, float* Hout, uint8_t* occ_out, void* stream);
+                         const float* W0, const float* W1, const float* W2, float* Hout, const uint8_t* occ_in, uint8_t* occ_out,
+                         uint8_t* scratch, void* stream);
 int64_t scone_layer0_backward_workspace_bytes(int32_t cout);
 int scone_layer0_backward(const scone_complex* cx, int32_t b, int32_t cout, const float* G_dev, const float* X_dev,
-                          float* dW_dev, int32_t accumulate, void* workspace, const uint8_t* occ_g, void* stream);
+                          float* dW_dev, int32_t accumulate, void* workspace, const uint8_t* occ_g, uint8_t* scratch,
+                          void* stream);
 int64_t scone_readout_workspace_bytes(int32_t b, int32_t C);
 int scone_readout_ws(const scone_complex* cx, int32_t act, int32_t b, int32_t C, const float* HL, const float* wout,
                      const int32_t* last_nodes, float* logprobs, const int32_t* target_idx, const float* mask,

@@ -13,9 +13,9 @@
 //     order, no atomics) into shared memory, then the 3C x C weight products + sum + activation run as a
 //     register-tiled contraction and are stored with 128-bit coalesced stores.
 //   * UNIT kernels (occupancy flags given): there is no bias and act(0) = 0, so activations are exactly zero outside the
-//     l-hop neighbourhood of a trajectory.  A byte-only pre-pass propagates the row flags one hop; CTAs classify
-//     blocks of 1024 (edge, trajectory-chunk) units, compact the candidates deterministically, and warps process the
-//     candidates autonomously (flag-aware gather, per-row contraction).  Skipping a zero row is exact.
+//     l-hop neighbourhood of a trajectory.  The flagged (edge, trajectory-chunk) units of the input are compacted into a
+//     worklist (deterministic order), their support is scattered one hop into the output's flags, those are compacted
+//     again, and one warp per candidate unit does a flag-aware gather + per-row contraction.  Skipping a zero row is exact.
 // Weight gradients are accumulated in registers in a data-independent thread mapping and a fixed row order, written
 // as per-CTA partials and reduced in CTA order: bit-reproducible run to run.
 #include <math_constants.h>
@@ -152,32 +152,6 @@ __device__ __forceinline__ float gather_row1(const float* __restrict__ X, int b,
         acc = fmaf(__int_as_float(c0.y), __ldg(X + (size_t)c0.x * b + t), acc);
     }
     return acc;
-}
-
-// cand[e][t] = occ[e][t] | OR over the S0 / S1 neighbours e' of occ[e'][t]: the rows of the NEXT tensor that can be
-// non-zero (one-hop growth of the support).  One warp per edge, lanes across trajectories; pure byte traffic.
-__global__ void __launch_bounds__(256) occ_propagate_kernel(const uint8_t* __restrict__ occ, uint8_t* __restrict__ cand, DevCsr S0,
-                                                           DevCsr S1, int E, int b) {
-    const int e = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
-    if (e >= E) return;
-    const int p0 = __ldg(S0.rowptr + e), p1 = __ldg(S0.rowptr + e + 1), q0 = __ldg(S1.rowptr + e), q1 = __ldg(S1.rowptr + e + 1);
-    if ((b & 3) == 0) {
-        const uint32_t* o32 = reinterpret_cast<const uint32_t*>(occ);
-        const int w = b >> 2;
-        for (int t = lane; t < w; t += 32) {
-            uint32_t acc = __ldg(o32 + (size_t)e * w + t);
-            for (int p = p0; p < p1; ++p) acc |= __ldg(o32 + (size_t)__ldg(S0.ent + p).x * w + t);
-            for (int p = q0; p < q1; ++p) acc |= __ldg(o32 + (size_t)__ldg(S1.ent + p).x * w + t);
-            reinterpret_cast<uint32_t*>(cand)[(size_t)e * w + t] = acc;
-        }
-    } else {
-        for (int t = lane; t < b; t += 32) {
-            uint8_t acc = __ldg(occ + (size_t)e * b + t);
-            for (int p = p0; p < p1; ++p) acc |= __ldg(occ + (size_t)__ldg(S0.ent + p).x * b + t);
-            for (int p = q0; p < q1; ++p) acc |= __ldg(occ + (size_t)__ldg(S1.ent + p).x * b + t);
-            cand[(size_t)e * b + t] = acc;
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -448,16 +422,39 @@ __global__ void __launch_bounds__(kThreads) layer_bwd_dense_kernel(const float* 
 
 // =================================================================================================================
 // UNIT kernels (occupancy flags)
+//
+// occ[e][t] (one byte) == 0 promises that row (e, t) of a tensor is entirely zero (structural support, a superset of
+// the non-zero rows).  A unit is (edge e, chunk of TT = 128 / C consecutive trajectories) = 128 contiguous columns.
+// Per flagged launch:   worklist(in) = compaction of occ_in            (deterministic, ascending unit id)
+//                       occ_out      = one-hop scatter from worklist(in)   (idempotent byte stores of 1: no atomics)
+//                       worklist(out)= compaction of occ_out
+//                       one warp per worklist(out) entry does gather + contraction + store.
 // =================================================================================================================
-constexpr int kUnitsPerBlock = 1024;          // units classified per CTA iteration (4 per thread)
+constexpr int kCompactBlock = 1024;           // units per compaction CTA (4 per thread)
 
-// Deterministic compaction of the units of one block whose TT flag bytes are not all zero.
-// unit u -> (edge e = u / nchunk, trajectories t0 = (u % nchunk) * TT ...).  list[] receives block-local unit
-// indices in ascending (slice, warp, lane) order.  Contains two __syncthreads().
 template <int TT>
-__device__ __forceinline__ int classify_units(const uint8_t* __restrict__ flags, long long unit0, long long n_units, int nchunk,
-                                              int b, uint16_t* __restrict__ list, int* __restrict__ wcount) {
+__device__ __forceinline__ unsigned unit_row_mask(const uint8_t* __restrict__ flags, int e, int t0, int b) {
+    unsigned m = 0;
+    const uint8_t* f = flags + (size_t)e * b + t0;
+    if (TT == 4 && (b & 3) == 0) {             // aligned fast path: one 32-bit load
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(f));
+        m = ((w & 0xffu) ? 1u : 0u) | ((w & 0xff00u) ? 2u : 0u) | ((w & 0xff0000u) ? 4u : 0u) | ((w & 0xff000000u) ? 8u : 0u);
+    } else {
+#pragma unroll
+        for (int k = 0; k < TT; ++k)
+            if (t0 + k < b && __ldg(f + k) != 0) m |= 1u << k;
+    }
+    return m;
+}
+
+// pass 1 / pass 3 of the compaction: WRITE = false counts the flagged units of each 1024-unit block,
+// WRITE = true writes their ids at the block's offset (ascending order).
+template <int TT, bool WRITE>
+__global__ void __launch_bounds__(kThreads) compact_units_kernel(const uint8_t* __restrict__ flags, long long n_units, int nchunk, int b,
+                                                                int* __restrict__ block_counts, uint32_t* __restrict__ list) {
+    __shared__ int wcount[4 * kWarps];
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const long long unit0 = (long long)blockIdx.x * kCompactBlock;
     unsigned bal[4];
     bool on[4];
 #pragma unroll
@@ -465,31 +462,76 @@ __device__ __forceinline__ int classify_units(const uint8_t* __restrict__ flags,
         const long long u = unit0 + k * kThreads + threadIdx.x;
         bool a = false;
         if (u < n_units) {
-            const long long e = u / nchunk;
-            const int t0 = (int)(u - e * nchunk) * TT;
-            const uint8_t* f = flags + (size_t)e * b + t0;
-#pragma unroll
-            for (int kk = 0; kk < TT; ++kk)
-                if (t0 + kk < b) a |= (__ldg(f + kk) != 0);
+            const int e = (int)(u / nchunk);
+            a = unit_row_mask<TT>(flags, e, (int)(u - (long long)e * nchunk) * TT, b) != 0u;
         }
         on[k] = a;
         bal[k] = __ballot_sync(0xffffffffu, a);
         if (lane == 0) wcount[k * kWarps + warp] = __popc(bal[k]);
     }
     __syncthreads();
-    int total = 0;
-#pragma unroll
-    for (int j = 0; j < 4 * kWarps; ++j) total += wcount[j];
+    if (!WRITE) {
+        if (threadIdx.x == 0) {
+            int total = 0;
+            for (int j = 0; j < 4 * kWarps; ++j) total += wcount[j];
+            block_counts[blockIdx.x] = total;
+        }
+        return;
+    }
+    const int off = block_counts[blockIdx.x];          // exclusive prefix after the scan
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         if (on[k]) {
-            int base = 0;
+            int base = off;
             for (int j = 0; j < k * kWarps + warp; ++j) base += wcount[j];
-            list[base + __popc(bal[k] & ((1u << lane) - 1u))] = (uint16_t)(k * kThreads + threadIdx.x);
+            list[base + __popc(bal[k] & ((1u << lane) - 1u))] = (uint32_t)(unit0 + k * kThreads + threadIdx.x);
         }
     }
+}
+
+// in-place exclusive scan of block_counts[0..n) by one CTA; *total = sum
+__global__ void __launch_bounds__(1024) scan_counts_kernel(int* __restrict__ counts, int n, int* __restrict__ total) {
+    __shared__ int part[1024];
+    const int per = (n + 1023) / 1024;
+    const int lo = threadIdx.x * per, hi = min(n, lo + per);
+    int s = 0;
+    for (int i = lo; i < hi; ++i) s += counts[i];
+    part[threadIdx.x] = s;
     __syncthreads();
-    return total;
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < 1024; ++i) { const int v = part[i]; part[i] = run; run += v; }
+        *total = run;
+    }
+    __syncthreads();
+    int run = part[threadIdx.x];
+    for (int i = lo; i < hi; ++i) { const int v = counts[i]; counts[i] = run; run += v; }
+}
+
+// occ_out[e'][t] = 1 for every flagged row (e, t) of the input worklist and every e' in {e} + S0 row + S1 row.
+template <int TT>
+__global__ void __launch_bounds__(kThreads) scatter_support_kernel(const uint32_t* __restrict__ wl, const int* __restrict__ n_ptr,
+                                                                  const uint8_t* __restrict__ occ_in, uint8_t* __restrict__ occ_out,
+                                                                  DevCsr S0, DevCsr S1, int nchunk, int b) {
+    const int n = *n_ptr, lane = threadIdx.x % 32;
+    const long long nw = (long long)gridDim.x * kWarps;
+    for (long long i = (long long)blockIdx.x * kWarps + threadIdx.x / 32; i < n; i += nw) {
+        const uint32_t u = wl[i];
+        const int e = (int)(u / (uint32_t)nchunk), t0 = (int)(u - (uint32_t)e * (uint32_t)nchunk) * TT;
+        const unsigned m = unit_row_mask<TT>(occ_in, e, t0, b);
+        if (lane < TT && ((m >> lane) & 1u)) occ_out[(size_t)e * b + t0 + lane] = 1;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const DevCsr S = s == 0 ? S0 : S1;
+            const int p0 = __ldg(S.rowptr + e), p1 = __ldg(S.rowptr + e + 1);
+            for (int p = p0 + lane; p < p1; p += 32) {
+                uint8_t* dst = occ_out + (size_t)__ldg(S.ent + p).x * b + t0;
+#pragma unroll
+                for (int k = 0; k < TT; ++k)
+                    if ((m >> k) & 1u) dst[k] = 1;
+            }
+        }
+    }
 }
 
 // (own row, S0 row, S1 row) of unit (e, t0..t0+TT) into Ts rows [slot0 + j]; returns the ballot of non-zero lanes.
@@ -512,56 +554,53 @@ __device__ __forceinline__ unsigned gather_unit(const float* __restrict__ H, siz
     return __ballot_sync(0xffffffffu, nz4(a0) || nz4(a1) || nz4(a2));
 }
 
+// Forward: one warp per worklist unit.  Every flagged row of the unit is written (zeros when the gathered rows are
+// numerically zero), so that the output's flags (occ_out == the candidates) never point at unwritten memory.
 template <int CIN, int COUT, int ACT>
 __global__ void __launch_bounds__(kThreads) layer_fwd_units_kernel(const float* __restrict__ Hin, float* __restrict__ Hout,
                                                                   const float* __restrict__ W0, const float* __restrict__ W1,
                                                                   const float* __restrict__ W2, DevCsr S0, DevCsr S1, int E, int b,
-                                                                  const uint8_t* __restrict__ occ_in, uint8_t* __restrict__ occ_out,
-                                                                  const uint8_t* __restrict__ cand) {
+                                                                  const uint8_t* __restrict__ occ_in, const uint8_t* __restrict__ occ_out,
+                                                                  const uint32_t* __restrict__ wl, const int* __restrict__ n_ptr) {
     constexpr int TT = kTileCols / CIN, KD = 3 * CIN, LDT = KD + 4, NTX = COUT / 4, NG = CIN / 4, ITEMS = TT * NTX;
     extern __shared__ __align__(16) float smem[];
     float* Ws = smem;                              // [KD][COUT]
     float* Tw = smem + KD * COUT;                  // [kWarps][TT][LDT]
-    __shared__ uint16_t list[kUnitsPerBlock];
-    __shared__ int wcount[4 * kWarps];
     for (int i = threadIdx.x; i < CIN * COUT; i += kThreads) {
         Ws[i] = W0[i];
         Ws[CIN * COUT + i] = W1[i];
         Ws[2 * CIN * COUT + i] = W2[i];
     }
+    __syncthreads();
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const size_t rowlen_in = (size_t)b * CIN, rowlen_out = (size_t)b * COUT;
     const int nchunk = (b + TT - 1) / TT;
-    const long long n_units = (long long)E * nchunk;
-    const long long n_blocks = (n_units + kUnitsPerBlock - 1) / kUnitsPerBlock;
+    const int n = *n_ptr;
+    const long long nw = (long long)gridDim.x * kWarps;
     float* T = Tw + warp * TT * LDT;
-    for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        __syncthreads();                               // list / Ws hazards
-        const int n = classify_units<TT>(cand, blk * kUnitsPerBlock, n_units, nchunk, b, list, wcount);
-        for (int i = warp; i < n; i += kWarps) {
-            const long long u = blk * kUnitsPerBlock + list[i];
-            const int e = (int)(u / nchunk), chunk = (int)(u - (long long)e * nchunk), t0 = chunk * TT;
-            const unsigned bal = gather_unit<CIN, LDT>(Hin, rowlen_in, S0, S1, b, e, chunk, occ_in, T, 0);
-            if (bal == 0u) continue;                   // candidate by support, but numerically zero: output stays zero
-            __syncwarp();
+    for (long long i = (long long)blockIdx.x * kWarps + warp; i < n; i += nw) {
+        const uint32_t u = wl[i];
+        const int e = (int)(u / (uint32_t)nchunk), chunk = (int)(u - (uint32_t)e * (uint32_t)nchunk), t0 = chunk * TT;
+        const unsigned cm = unit_row_mask<TT>(occ_out, e, t0, b);          // candidate rows of this unit
+        const unsigned bal = gather_unit<CIN, LDT>(Hin, rowlen_in, S0, S1, b, e, chunk, occ_in, T, 0);
+        __syncwarp();
 #pragma unroll
-            for (int p = 0; p < (ITEMS + 31) / 32; ++p) {
-                const int it = p * 32 + lane;
-                const int j = it / NTX, tx = it % NTX;
-                const bool live = it < ITEMS && t0 + j < b && ((bal >> (j * NG)) & ((NG >= 32) ? 0xffffffffu : ((1u << NG) - 1u))) != 0u;
+        for (int p = 0; p < (ITEMS + 31) / 32; ++p) {
+            const int it = p * 32 + lane;
+            const int j = it / NTX, tx = it % NTX;
+            if (it < ITEMS && ((cm >> j) & 1u)) {
                 float4 o = zero4();
-                if (live) {
+                if (((bal >> (j * NG)) & ((NG >= 32) ? 0xffffffffu : ((1u << NG) - 1u))) != 0u) {
                     o = row_gemm<KD, COUT, LDT>(T, Ws, j, tx);
                     o.x = act_fn<ACT>(o.x);
                     o.y = act_fn<ACT>(o.y);
                     o.z = act_fn<ACT>(o.z);
                     o.w = act_fn<ACT>(o.w);
-                    *reinterpret_cast<float4*>(Hout + (size_t)e * rowlen_out + (size_t)(t0 + j) * COUT + 4 * tx) = o;
                 }
-                store_row_flag<NTX>(occ_out, (size_t)e * b + t0 + j, live, nz4(o));
+                *reinterpret_cast<float4*>(Hout + (size_t)e * rowlen_out + (size_t)(t0 + j) * COUT + 4 * tx) = o;
             }
-            __syncwarp();                              // T is reused by this warp's next unit
         }
+        __syncwarp();                              // T is reused by this warp's next unit
     }
 }
 
@@ -576,13 +615,16 @@ struct BwdUnitShape {
     static constexpr size_t smem_floats = smem_floats_layout > red_floats ? smem_floats_layout : red_floats;
 };
 
+// Backward: CTA c owns the contiguous worklist slice [c*per, (c+1)*per); rounds of UC units are staged by the warps
+// (A rows = G / S0 G / S1 G, Hin rows) and then all threads accumulate the weight gradients over the staged rows.
 template <int CIN, int COUT, int ACT, bool WRITE_GPREV>
 __global__ void __launch_bounds__(kThreads) layer_bwd_units_kernel(const float* __restrict__ G, const float* __restrict__ Hin,
                                                                   float* __restrict__ Gprev, const float* __restrict__ W0,
                                                                   const float* __restrict__ W1, const float* __restrict__ W2,
                                                                   float* __restrict__ dw_partial, DevCsr S0, DevCsr S1, int E, int b,
                                                                   const uint8_t* __restrict__ occ_g, const uint8_t* __restrict__ occ_h,
-                                                                  uint8_t* __restrict__ occ_prev, const uint8_t* __restrict__ cand) {
+                                                                  const uint8_t* __restrict__ occ_prev, const uint32_t* __restrict__ wl,
+                                                                  const int* __restrict__ n_ptr) {
     using Sh = BwdShape<CIN, COUT>;
     using Us = BwdUnitShape<CIN, COUT>;
     constexpr int TT = Us::TT, UC = Us::UC, RC = Us::RC, KD = Us::KD, LDA = Us::LDA, LDH = Us::LDH;
@@ -591,8 +633,6 @@ __global__ void __launch_bounds__(kThreads) layer_bwd_units_kernel(const float* 
     float* Wt = smem;                              // [KD][CIN]    Wt[k*COUT+co][ci] = W_k[ci][co]
     float* Ar = Wt + KD * CIN;                     // [RC][LDA]
     float* Hr = Ar + RC * LDA;                     // [RC][LDH]
-    __shared__ uint16_t list[kUnitsPerBlock];
-    __shared__ int wcount[4 * kWarps];
     __shared__ uint8_t rowact[RC];
     for (int i = threadIdx.x; i < CIN * COUT; i += kThreads) {
         const int ci = i / COUT, co = i % COUT;
@@ -603,8 +643,6 @@ __global__ void __launch_bounds__(kThreads) layer_bwd_units_kernel(const float* 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const size_t rowlen_g = (size_t)b * COUT, rowlen_h = (size_t)b * CIN;
     const int nchunk = (b + TT - 1) / TT;
-    const long long n_units = (long long)E * nchunk;
-    const long long n_blocks = (n_units + kUnitsPerBlock - 1) / kUnitsPerBlock;
     float dw[Sh::UPT][3][4];
 #pragma unroll
     for (int u = 0; u < Sh::UPT; ++u)
@@ -612,67 +650,159 @@ __global__ void __launch_bounds__(kThreads) layer_bwd_units_kernel(const float* 
         for (int k = 0; k < 3; ++k)
 #pragma unroll
             for (int q = 0; q < 4; ++q) dw[u][k][q] = 0.f;
-
-    for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        __syncthreads();
-        const int n = classify_units<TT>(cand, blk * kUnitsPerBlock, n_units, nchunk, b, list, wcount);
-        for (int c0 = 0; c0 < n; c0 += UC) {
-            const int nu = min(UC, n - c0);
-            // warp phase: stage (A rows, Hin rows) of up to UC units; Gprev rows of the non-zero A rows
-            for (int i = warp; i < nu; i += kWarps) {
-                const long long u = blk * kUnitsPerBlock + list[c0 + i];
-                const int e = (int)(u / nchunk), chunk = (int)(u - (long long)e * nchunk), t0 = chunk * TT;
-                const int slot0 = i * TT;
-                const unsigned bal = gather_unit<COUT, LDA>(G, rowlen_g, S0, S1, b, e, chunk, occ_g, Ar, slot0);
+    const int n = *n_ptr;
+    const int per = (n + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int lo = min(n, (int)blockIdx.x * per), hi = min(n, lo + per);
+    __syncthreads();
+    for (int c0 = lo; c0 < hi; c0 += UC) {
+        const int nu = min(UC, hi - c0);
+        for (int i = warp; i < nu; i += kWarps) {
+            const uint32_t u = wl[c0 + i];
+            const int e = (int)(u / (uint32_t)nchunk), chunk = (int)(u - (uint32_t)e * (uint32_t)nchunk), t0 = chunk * TT;
+            const int slot0 = i * TT;
+            const unsigned cm = WRITE_GPREV ? unit_row_mask<TT>(occ_prev, e, t0, b) : 0u;
+            const unsigned bal = gather_unit<COUT, LDA>(G, rowlen_g, S0, S1, b, e, chunk, occ_g, Ar, slot0);
+#pragma unroll
+            for (int p = 0; p < (ITEMS + 31) / 32; ++p) {
+                const int it = p * 32 + lane;
+                const int j = it / NTX, hx = it % NTX;
+                if (it < ITEMS) {
+                    const bool ra = t0 + j < b && ((bal >> (j * NG)) & ((NG >= 32) ? 0xffffffffu : ((1u << NG) - 1u))) != 0u;
+                    float4 h = zero4();
+                    if (ra && (occ_h == nullptr || __ldg(occ_h + (size_t)e * b + t0 + j) != 0))
+                        h = __ldg(reinterpret_cast<const float4*>(Hin + (size_t)e * rowlen_h + (size_t)(t0 + j) * CIN + 4 * hx));
+                    *reinterpret_cast<float4*>(Hr + (slot0 + j) * LDH + 4 * hx) = h;
+                    if (hx == 0) rowact[slot0 + j] = ra ? 1 : 0;
+                }
+            }
+            __syncwarp();
+            if (WRITE_GPREV) {
 #pragma unroll
                 for (int p = 0; p < (ITEMS + 31) / 32; ++p) {
                     const int it = p * 32 + lane;
-                    const int j = it / NTX, hx = it % NTX;
-                    if (it < ITEMS) {
-                        const bool ra = t0 + j < b && ((bal >> (j * NG)) & ((NG >= 32) ? 0xffffffffu : ((1u << NG) - 1u))) != 0u;
-                        float4 h = zero4();
-                        if (ra && (occ_h == nullptr || __ldg(occ_h + (size_t)e * b + t0 + j) != 0))
-                            h = __ldg(reinterpret_cast<const float4*>(Hin + (size_t)e * rowlen_h + (size_t)(t0 + j) * CIN + 4 * hx));
-                        *reinterpret_cast<float4*>(Hr + (slot0 + j) * LDH + 4 * hx) = h;
-                        if (hx == 0) rowact[slot0 + j] = ra ? 1 : 0;
-                    }
-                }
-                __syncwarp();
-                if (WRITE_GPREV && bal != 0u) {
-#pragma unroll
-                    for (int p = 0; p < (ITEMS + 31) / 32; ++p) {
-                        const int it = p * 32 + lane;
-                        const int j = it / NTX, tx = it % NTX;
-                        const bool live = it < ITEMS && rowact[slot0 + j] != 0;
+                    const int j = it / NTX, tx = it % NTX;
+                    if (it < ITEMS && ((cm >> j) & 1u)) {
                         float4 o = zero4();
-                        if (live) {
+                        if (rowact[slot0 + j]) {
                             o = row_gemm<KD, CIN, LDA>(Ar, Wt, slot0 + j, tx);
                             const float4 h = *reinterpret_cast<const float4*>(Hr + (slot0 + j) * LDH + 4 * tx);
                             o.x *= dact_fn<ACT>(h.x);
                             o.y *= dact_fn<ACT>(h.y);
                             o.z *= dact_fn<ACT>(h.z);
                             o.w *= dact_fn<ACT>(h.w);
-                            *reinterpret_cast<float4*>(Gprev + (size_t)e * rowlen_h + (size_t)(t0 + j) * CIN + 4 * tx) = o;
                         }
-                        store_row_flag<NTX>(occ_prev, (size_t)e * b + t0 + j, live, nz4(o));
+                        *reinterpret_cast<float4*>(Gprev + (size_t)e * rowlen_h + (size_t)(t0 + j) * CIN + 4 * tx) = o;
                     }
                 }
             }
-            __syncthreads();
-            // CTA phase: weight gradients over the staged rows, ascending, fixed thread mapping
-            const int n_rows = nu * TT;
-#pragma unroll
-            for (int u = 0; u < Sh::UPT; ++u) {
-                const int unit = (Sh::UNITS >= kThreads) ? (int)threadIdx.x + u * kThreads : (int)threadIdx.x % Sh::UNITS;
-                const int split = (Sh::UNITS >= kThreads) ? 0 : (int)threadIdx.x / Sh::UNITS;
-                const int co = unit % COUT, ciq = unit / COUT;
-                for (int rho = split; rho < n_rows; rho += Sh::RS)
-                    if (rowact[rho]) SCONE_DW_ROW(Hr, Ar, rho);
-            }
-            __syncthreads();
         }
+        __syncthreads();
+        const int n_rows = nu * TT;
+#pragma unroll
+        for (int u = 0; u < Sh::UPT; ++u) {
+            const int unit = (Sh::UNITS >= kThreads) ? (int)threadIdx.x + u * kThreads : (int)threadIdx.x % Sh::UNITS;
+            const int split = (Sh::UNITS >= kThreads) ? 0 : (int)threadIdx.x / Sh::UNITS;
+            const int co = unit % COUT, ciq = unit / COUT;
+            for (int rho = split; rho < n_rows; rho += Sh::RS)
+                if (rowact[rho]) SCONE_DW_ROW(Hr, Ar, rho);
+        }
+        __syncthreads();
     }
     write_dw_partial<CIN, COUT>(dw, smem, dw_partial);
+}
+
+// First layer on units: lanes (row j, channel quad c4); the scalar gathers of X are repeated by the COUT/4 lanes of a row
+// (broadcast loads).  Forward writes every candidate row; backward accumulates dW_k[0][co] over flagged rows of G0.
+template <int COUT>
+__device__ __forceinline__ void layer0_unit_rows(const float* __restrict__ X, DevCsr S0, DevCsr S1, int b, int e, int t, bool ok,
+                                                 float& a0, float& a1, float& a2) {
+    a0 = a1 = a2 = 0.f;
+    if (ok) {
+        a0 = __ldg(X + (size_t)e * b + t);
+        a1 = gather_row1(X, b, t, S0, e);
+        a2 = gather_row1(X, b, t, S1, e);
+    }
+}
+
+template <int COUT, int ACT>
+__global__ void __launch_bounds__(kThreads) layer0_fwd_units_kernel(const float* __restrict__ X, float* __restrict__ Hout,
+                                                                   const float* __restrict__ W0, const float* __restrict__ W1,
+                                                                   const float* __restrict__ W2, DevCsr S0, DevCsr S1, int E, int b,
+                                                                   const uint8_t* __restrict__ occ_out, const uint32_t* __restrict__ wl,
+                                                                   const int* __restrict__ n_ptr) {
+    constexpr int TT = kTileCols / COUT, C4 = COUT / 4;
+    __shared__ __align__(16) float ws[3 * COUT];
+    for (int i = threadIdx.x; i < COUT; i += kThreads) {
+        ws[i] = W0[i];
+        ws[COUT + i] = W1[i];
+        ws[2 * COUT + i] = W2[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x % 32, j = lane / C4, c4 = lane % C4;
+    const int nchunk = (b + TT - 1) / TT, n = *n_ptr;
+    const long long nw = (long long)gridDim.x * kWarps;
+    const float4 w0 = *reinterpret_cast<const float4*>(ws + 4 * c4);
+    const float4 w1 = *reinterpret_cast<const float4*>(ws + COUT + 4 * c4);
+    const float4 w2 = *reinterpret_cast<const float4*>(ws + 2 * COUT + 4 * c4);
+    for (long long i = (long long)blockIdx.x * kWarps + threadIdx.x / 32; i < n; i += nw) {
+        const uint32_t u = wl[i];
+        const int e = (int)(u / (uint32_t)nchunk), t = (int)(u - (uint32_t)e * (uint32_t)nchunk) * TT + j;
+        const bool ok = t < b && __ldg(occ_out + (size_t)e * b + t) != 0;
+        float a0, a1, a2;
+        layer0_unit_rows<COUT>(X, S0, S1, b, e, t, ok, a0, a1, a2);
+        if (ok) {
+            float4 o = zero4();
+            if (a0 != 0.f || a1 != 0.f || a2 != 0.f) {
+                o.x = act_fn<ACT>(fmaf(a2, w2.x, fmaf(a1, w1.x, a0 * w0.x)));
+                o.y = act_fn<ACT>(fmaf(a2, w2.y, fmaf(a1, w1.y, a0 * w0.y)));
+                o.z = act_fn<ACT>(fmaf(a2, w2.z, fmaf(a1, w1.z, a0 * w0.z)));
+                o.w = act_fn<ACT>(fmaf(a2, w2.w, fmaf(a1, w1.w, a0 * w0.w)));
+            }
+            *reinterpret_cast<float4*>(Hout + ((size_t)e * b + t) * COUT + 4 * c4) = o;
+        }
+    }
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(kThreads) layer0_bwd_units_kernel(const float* __restrict__ X, const float* __restrict__ G0,
+                                                                   float* __restrict__ dw_partial, DevCsr S0, DevCsr S1, int E, int b,
+                                                                   const uint8_t* __restrict__ occ_g, const uint32_t* __restrict__ wl,
+                                                                   const int* __restrict__ n_ptr) {
+    constexpr int TT = kTileCols / COUT, C4 = COUT / 4;
+    __shared__ float red[kThreads * 12];
+    const int lane = threadIdx.x % 32, j = lane / C4, c4 = lane % C4;
+    const int nchunk = (b + TT - 1) / TT, n = *n_ptr;
+    const long long nw = (long long)gridDim.x * kWarps;
+    float acc[3][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    for (long long i = (long long)blockIdx.x * kWarps + threadIdx.x / 32; i < n; i += nw) {
+        const uint32_t u = wl[i];
+        const int e = (int)(u / (uint32_t)nchunk), t = (int)(u - (uint32_t)e * (uint32_t)nchunk) * TT + j;
+        const bool ok = t < b && __ldg(occ_g + (size_t)e * b + t) != 0;
+        float a[3];
+        layer0_unit_rows<COUT>(X, S0, S1, b, e, t, ok, a[0], a[1], a[2]);
+        if (ok) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(G0 + ((size_t)e * b + t) * COUT + 4 * c4));
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                acc[k][0] = fmaf(a[k], g.x, acc[k][0]);
+                acc[k][1] = fmaf(a[k], g.y, acc[k][1]);
+                acc[k][2] = fmaf(a[k], g.z, acc[k][2]);
+                acc[k][3] = fmaf(a[k], g.w, acc[k][3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) red[threadIdx.x * 12 + k * 4 + q] = acc[k][q];
+    __syncthreads();
+    // thread o < 3*COUT sums its (k, co) over the threads that own channel quad co/4 (lane % C4 == co/4), ascending
+    for (int o = threadIdx.x; o < 3 * COUT; o += kThreads) {
+        const int k = o / COUT, co = o % COUT, q4 = co / 4, q = co % 4;
+        float s = 0.f;
+        for (int th = q4; th < kThreads; th += C4) s += red[th * 12 + k * 4 + q];
+        dw_partial[(size_t)blockIdx.x * 3 * COUT + o] = s;
+    }
 }
 
 // out[i] (+)= sum over parts p (ascending) of partial[p][i]
@@ -801,78 +931,18 @@ __global__ void __launch_bounds__(kThreads) layer0_bwd_dense_kernel(const float*
     }
 }
 
-// flagged: only the rows of G0 whose flag is set contribute.  Row (e, t): t_k = (S_k X)[e][t] by a lane-parallel gather
-// + fixed shuffle tree; per-warp accumulators, warps combined in warp order.
-template <int COUT>
-__global__ void __launch_bounds__(kThreads) layer0_bwd_rows_kernel(const float* __restrict__ X, const float* __restrict__ G0,
-                                                                  float* __restrict__ dw_partial, DevCsr S0, DevCsr S1, int E, int b,
-                                                                  const uint8_t* __restrict__ occ_g) {
-    constexpr int Q = (COUT + 31) / 32;
-    __shared__ uint16_t list[kUnitsPerBlock];
-    __shared__ int wcount[4 * kWarps];
-    __shared__ float red[kWarps][3 * COUT];
-    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    float acc[3][Q];
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-#pragma unroll
-        for (int q = 0; q < Q; ++q) acc[k][q] = 0.f;
-    const long long n_units = (long long)E * b;
-    const long long n_blocks = (n_units + kUnitsPerBlock - 1) / kUnitsPerBlock;
-    for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        __syncthreads();
-        const int n = classify_units<1>(occ_g, blk * kUnitsPerBlock, n_units, b, b, list, wcount);
-        for (int i = warp; i < n; i += kWarps) {
-            const long long u = blk * kUnitsPerBlock + list[i];
-            const int e = (int)(u / b), t = (int)(u - (long long)e * b);
-            float tk[3];
-            tk[0] = __ldg(X + (size_t)e * b + t);
-#pragma unroll
-            for (int k = 1; k < 3; ++k) {
-                const DevCsr S = k == 1 ? S0 : S1;
-                const int p0 = __ldg(S.rowptr + e), p1 = __ldg(S.rowptr + e + 1);
-                float part = 0.f;
-                for (int p = p0 + lane; p < p1; p += 32) {
-                    const int2 ent = __ldg(S.ent + p);
-                    part = fmaf(__int_as_float(ent.y), __ldg(X + (size_t)ent.x * b + t), part);
-                }
-                tk[k] = warp_sum(part);
-            }
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                const int c = lane + 32 * q;
-                if (c < COUT) {
-                    const float g = __ldg(G0 + ((size_t)e * b + t) * COUT + c);
-                    acc[0][q] = fmaf(tk[0], g, acc[0][q]);
-                    acc[1][q] = fmaf(tk[1], g, acc[1][q]);
-                    acc[2][q] = fmaf(tk[2], g, acc[2][q]);
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-#pragma unroll
-        for (int q = 0; q < Q; ++q)
-            if (lane + 32 * q < COUT) red[warp][k * COUT + lane + 32 * q] = acc[k][q];
-    __syncthreads();
-    for (int o = threadIdx.x; o < 3 * COUT; o += kThreads) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) s += red[w][o];
-        dw_partial[(size_t)blockIdx.x * 3 * COUT + o] = s;
-    }
-}
-
 // X[E][b] from sparse flows; one warp per trajectory (X pre-zeroed).
 __global__ void flows_to_dense_kernel(const int32_t* __restrict__ traj_ptr, const int32_t* __restrict__ flow_edge,
                                       const float* __restrict__ flow_val, const int32_t* __restrict__ rank,
-                                      float* __restrict__ X, int E, int b) {
+                                      float* __restrict__ X, uint8_t* __restrict__ occX, int E, int b) {
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
     if (t >= b) return;
     for (int p = traj_ptr[t] + lane; p < traj_ptr[t + 1]; p += 32) {
         const int e = flow_edge[p];
-        if (e >= 0 && e < E) X[(size_t)rank[e] * b + t] = flow_val[p];
+        if (e >= 0 && e < E) {
+            X[(size_t)rank[e] * b + t] = flow_val[p];
+            if (occX != nullptr) occX[(size_t)rank[e] * b + t] = 1;
+        }
     }
 }
 
@@ -1023,10 +1093,50 @@ int occupancy_of(K kern, size_t smem, int* out) {
     return 0;
 }
 
-int propagate(const scone_complex* cx, int b, const uint8_t* occ, uint8_t* cand, cudaStream_t st) {
-    occ_propagate_kernel<<<(int)(((long long)cx->E * 32 + 255) / 256), 256, 0, st>>>(occ, cand, cx->S(0), cx->S(1), cx->E, b);
+// scratch carved from the caller's occ_scratch buffer (scone_occ_scratch_bytes)
+struct UnitScratch {
+    uint32_t *wl_a, *wl_b;
+    int *counts, *n_a, *n_b;
+    uint8_t* occ_tmp;
+};
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+size_t max_units(const scone_complex* cx, int b) { return (size_t)cx->E * (size_t)((b + 1) / 2); }   // TT >= 2
+UnitScratch carve_scratch(const scone_complex* cx, int b, uint8_t* base) {
+    UnitScratch sc;
+    const size_t nu = max_units(cx, b);
+    size_t off = 0;
+    sc.wl_a = reinterpret_cast<uint32_t*>(base + off); off += align256(nu * 4);
+    sc.wl_b = reinterpret_cast<uint32_t*>(base + off); off += align256(nu * 4);
+    sc.counts = reinterpret_cast<int*>(base + off); off += align256((nu / kCompactBlock + 2) * 4);
+    sc.n_a = reinterpret_cast<int*>(base + off); off += 256;
+    sc.n_b = reinterpret_cast<int*>(base + off); off += 256;
+    sc.occ_tmp = base + off;
+    return sc;
+}
+
+template <int TT>
+int compact_units(const scone_complex* cx, int b, const uint8_t* flags, uint32_t* list, int* counts, int* n_ptr, cudaStream_t st) {
+    const int nchunk = (b + TT - 1) / TT;
+    const long long n_units = (long long)cx->E * nchunk;
+    const int nblk = (int)((n_units + kCompactBlock - 1) / kCompactBlock);
+    compact_units_kernel<TT, false><<<nblk, kThreads, 0, st>>>(flags, n_units, nchunk, b, counts, nullptr);
+    SCONE_LAUNCHED();
+    scan_counts_kernel<<<1, 1024, 0, st>>>(counts, nblk, n_ptr);
+    SCONE_LAUNCHED();
+    compact_units_kernel<TT, true><<<nblk, kThreads, 0, st>>>(flags, n_units, nchunk, b, counts, list);
     SCONE_LAUNCHED();
     return 0;
+}
+
+// worklist of occ_in -> one-hop scatter into occ_out -> worklist of occ_out (sc.wl_b / sc.n_b)
+template <int TT>
+int prepare_units(const scone_complex* cx, int b, const uint8_t* occ_in, uint8_t* occ_out, const UnitScratch& sc, cudaStream_t st) {
+    if (compact_units<TT>(cx, b, occ_in, sc.wl_a, sc.counts, sc.n_a, st)) return 1;
+    SCONE_CUDA(cudaMemsetAsync(occ_out, 0, (size_t)cx->E * b, st));
+    scatter_support_kernel<TT><<<cx->num_sms * 8, kThreads, 0, st>>>(sc.wl_a, sc.n_a, occ_in, occ_out, cx->S(0), cx->S(1),
+                                                                     (b + TT - 1) / TT, b);
+    SCONE_LAUNCHED();
+    return compact_units<TT>(cx, b, occ_out, sc.wl_b, sc.counts, sc.n_b, st);
 }
 
 template <int CIN, int COUT, int ACT>
@@ -1046,16 +1156,15 @@ int launch_fwd(const scone_complex* cx, int b, const float* Hin, const float* W0
         return 0;
     }
     SCONE_REQUIRE(occ_out != nullptr && scratch != nullptr, "scone_layer_forward: occ_in needs occ_out and occ_scratch");
-    if (propagate(cx, b, occ_in, scratch, st)) return 1;
+    const UnitScratch sc = carve_scratch(cx, b, scratch);
+    if (prepare_units<TT>(cx, b, occ_in, occ_out, sc, st)) return 1;
     if (g_scone_zero_fill) SCONE_CUDA(cudaMemsetAsync(Hout, 0, (size_t)cx->E * b * COUT * sizeof(float), st));
-    SCONE_CUDA(cudaMemsetAsync(occ_out, 0, (size_t)cx->E * b, st));
     const size_t smem = ((size_t)KD * COUT + (size_t)kWarps * TT * LDT) * sizeof(float);
     auto kern = layer_fwd_units_kernel<CIN, COUT, ACT>;
     static int occ = 0;
     if (!occ && occupancy_of(kern, smem, &occ)) return 1;
-    const long long n_blocks = ((long long)cx->E * ((b + TT - 1) / TT) + kUnitsPerBlock - 1) / kUnitsPerBlock;
-    kern<<<grid_for(cx, n_blocks, occ), kThreads, smem, st>>>(Hin, Hout, W0, W1, W2, cx->S(0), cx->S(1), cx->E, b, occ_in, occ_out,
-                                                            scratch);
+    kern<<<cx->num_sms * occ, kThreads, smem, st>>>(Hin, Hout, W0, W1, W2, cx->S(0), cx->S(1), cx->E, b, occ_in, occ_out, sc.wl_b,
+                                                  sc.n_b);
     SCONE_LAUNCHED();
     return 0;
 }
@@ -1097,19 +1206,18 @@ int launch_bwd(const scone_complex* cx, int b, const float* G, const float* Hin,
     } else {
         using Us = BwdUnitShape<CIN, COUT>;
         SCONE_REQUIRE(scratch != nullptr && (!WG || occ_prev != nullptr), "scone_layer_backward: occ_g needs occ_gprev and occ_scratch");
-        if (propagate(cx, b, occ_g, scratch, st)) return 1;
-        if (WG) {
-            if (g_scone_zero_fill) SCONE_CUDA(cudaMemsetAsync(Gprev, 0, (size_t)cx->E * b * CIN * sizeof(float), st));
-            SCONE_CUDA(cudaMemsetAsync(occ_prev, 0, (size_t)cx->E * b, st));
-        }
+        const UnitScratch sc = carve_scratch(cx, b, scratch);
+        uint8_t* cand = WG ? occ_prev : sc.occ_tmp;           // rows whose (G, S0 G, S1 G) can be non-zero
+        if (prepare_units<Us::TT>(cx, b, occ_g, cand, sc, st)) return 1;
+        if (WG && g_scone_zero_fill) SCONE_CUDA(cudaMemsetAsync(Gprev, 0, (size_t)cx->E * b * CIN * sizeof(float), st));
         const size_t smem = Us::smem_floats * sizeof(float);
         auto kern = layer_bwd_units_kernel<CIN, COUT, ACT, WG>;
         static int occ = 0;
         if (!occ && occupancy_of(kern, smem, &occ)) return 1;
-        const long long n_blocks = ((long long)cx->E * ((b + Us::TT - 1) / Us::TT) + kUnitsPerBlock - 1) / kUnitsPerBlock;
-        grid = grid_for(cx, n_blocks, occ);
+        grid = cx->num_sms * occ;
         if (grid > kBwdMaxCtas) grid = kBwdMaxCtas;
-        kern<<<grid, kThreads, smem, st>>>(G, Hin, Gprev, W0, W1, W2, ws, cx->S(0), cx->S(1), cx->E, b, occ_g, occ_h, occ_prev, scratch);
+        kern<<<grid, kThreads, smem, st>>>(G, Hin, Gprev, W0, W1, W2, ws, cx->S(0), cx->S(1), cx->E, b, occ_g, occ_h, cand, sc.wl_b,
+                                          sc.n_b);
         SCONE_LAUNCHED();
     }
     reduce_partials_kernel<<<(Sh::DW + 255) / 256, 256, 0, st>>>(ws, grid, Sh::DW, dW, accumulate);
@@ -1167,13 +1275,19 @@ extern "C" int scone_get_zero_fill(void) { return g_scone_zero_fill ? 1 : 0; }
         }                                                                           \
     } while (0)
 
+extern "C" int64_t scone_occ_scratch_bytes(const scone_complex* cx, int32_t b) {
+    if (!cx || b <= 0) return 0;
+    const size_t nu = max_units(cx, b);
+    return (int64_t)(2 * align256(nu * 4) + align256((nu / kCompactBlock + 2) * 4) + 512 + align256((size_t)cx->E * b));
+}
+
 extern "C" int scone_layer_forward(const scone_complex* cx, int32_t act, int32_t b, int32_t cin, int32_t cout, const float* Hin,
                                    const float* W0, const float* W1, const float* W2, float* Hout, const uint8_t* occ_in,
                                    uint8_t* occ_out, uint8_t* occ_scratch, void* stream) {
     SCONE_REQUIRE(cx && Hin && W0 && W1 && W2 && Hout, "scone_layer_forward: NULL argument");
     SCONE_REQUIRE(!cx->host_only, "scone_layer_forward: index-only complex has no device arrays");
     SCONE_REQUIRE(b > 0, "scone_layer_forward: b must be positive");
-    if (cin == 1) return scone_layer0_forward(cx, act, b, cout, Hin, W0, W1, W2, Hout, occ_out, stream);
+    if (cin == 1) return scone_layer0_forward(cx, act, b, cout, Hin, W0, W1, W2, Hout, occ_in, occ_out, occ_scratch, stream);
     SCONE_REQUIRE(width_ok(cin) && width_ok(cout),
                   "scone_layer_forward: hidden widths must be in {8,16,32,64} with |log2 ratio| <= 1 (got %d -> %d)", cin, cout);
     SCONE_DISPATCH_WIDTHS(dispatch_fwd_act, cx, act, b, Hin, W0, W1, W2, Hout, occ_in, occ_out, occ_scratch, as_stream(stream));
@@ -1193,7 +1307,7 @@ extern "C" int scone_layer_backward(const scone_complex* cx, int32_t act, int32_
     SCONE_REQUIRE(cx && G && Hin && dW && workspace, "scone_layer_backward: NULL argument");
     SCONE_REQUIRE(!cx->host_only, "scone_layer_backward: index-only complex has no device arrays");
     SCONE_REQUIRE(b > 0, "scone_layer_backward: b must be positive");
-    if (cin == 1) return scone_layer0_backward(cx, b, cout, G, Hin, dW, accumulate, workspace, occ_g, stream);
+    if (cin == 1) return scone_layer0_backward(cx, b, cout, G, Hin, dW, accumulate, workspace, occ_g, occ_scratch, stream);
     SCONE_REQUIRE(W0 && W1 && W2, "scone_layer_backward: NULL weights");
     SCONE_REQUIRE(width_ok(cin) && width_ok(cout),
                   "scone_layer_backward: hidden widths must be in {8,16,32,64} with |log2 ratio| <= 1 (got %d -> %d)", cin, cout);
@@ -1203,42 +1317,49 @@ extern "C" int scone_layer_backward(const scone_complex* cx, int32_t act, int32_
     return 2;
 }
 
-template <int COUT>
-static int launch_l0_fwd(const scone_complex* cx, int act, int b, const float* X, const float* W0, const float* W1, const float* W2,
-                         float* Hout, uint8_t* occ_out, cudaStream_t st) {
-    const long long n_tiles = (long long)((b + 31) / 32) * ((cx->E + kL0Edges - 1) / kL0Edges);
-    const int grid = grid_for(cx, n_tiles, 6);
+template <int COUT, int ACT>
+static int launch_l0_fwd_act(const scone_complex* cx, int b, const float* X, const float* W0, const float* W1, const float* W2,
+                             float* Hout, const uint8_t* occ_in, uint8_t* occ_out, uint8_t* scratch, cudaStream_t st) {
     ScopedProf prof(SCONE_K_LAYER0_FWD, st);
-    int write_zero_rows = 1;
-    if (occ_out != nullptr) {              // flagged pipeline: bulk zero-fill (when enabled), the kernel stores live rows only
-        if (g_scone_zero_fill) SCONE_CUDA(cudaMemsetAsync(Hout, 0, (size_t)cx->E * b * COUT * sizeof(float), st));
-        SCONE_CUDA(cudaMemsetAsync(occ_out, 0, (size_t)cx->E * b, st));
-        write_zero_rows = 0;
+    if (occ_in == nullptr) {               // dense: every row is computed; flags (if wanted) are value based
+        const long long n_tiles = (long long)((b + 31) / 32) * ((cx->E + kL0Edges - 1) / kL0Edges);
+        layer0_fwd_kernel<COUT, ACT><<<grid_for(cx, n_tiles, 6), kThreads, 0, st>>>(X, Hout, W0, W1, W2, cx->S(0), cx->S(1), cx->E, b,
+                                                                                   occ_out, 1);
+        SCONE_LAUNCHED();
+        return 0;
     }
-    switch (act) {
-        case SCONE_ACT_TANH:
-            layer0_fwd_kernel<COUT, SCONE_ACT_TANH><<<grid, kThreads, 0, st>>>(X, Hout, W0, W1, W2, cx->S(0), cx->S(1), cx->E, b, occ_out, write_zero_rows);
-            break;
-        case SCONE_ACT_LEAKY_RELU:
-            layer0_fwd_kernel<COUT, SCONE_ACT_LEAKY_RELU><<<grid, kThreads, 0, st>>>(X, Hout, W0, W1, W2, cx->S(0), cx->S(1), cx->E, b, occ_out, write_zero_rows);
-            break;
-        case SCONE_ACT_RELU:
-            layer0_fwd_kernel<COUT, SCONE_ACT_RELU><<<grid, kThreads, 0, st>>>(X, Hout, W0, W1, W2, cx->S(0), cx->S(1), cx->E, b, occ_out, write_zero_rows);
-            break;
-        default: scone_set_error("unknown activation %d", act); return 2;
-    }
+    SCONE_REQUIRE(occ_out != nullptr && scratch != nullptr, "scone_layer_forward: occ_in needs occ_out and occ_scratch");
+    constexpr int TT = kTileCols / COUT;
+    const UnitScratch sc = carve_scratch(cx, b, scratch);
+    if (prepare_units<TT>(cx, b, occ_in, occ_out, sc, st)) return 1;
+    if (g_scone_zero_fill) SCONE_CUDA(cudaMemsetAsync(Hout, 0, (size_t)cx->E * b * COUT * sizeof(float), st));
+    layer0_fwd_units_kernel<COUT, ACT><<<cx->num_sms * 8, kThreads, 0, st>>>(X, Hout, W0, W1, W2, cx->S(0), cx->S(1), cx->E, b, occ_out,
+                                                                            sc.wl_b, sc.n_b);
     SCONE_LAUNCHED();
     return 0;
 }
 
+template <int COUT>
+static int launch_l0_fwd(const scone_complex* cx, int act, int b, const float* X, const float* W0, const float* W1, const float* W2,
+                         float* Hout, const uint8_t* occ_in, uint8_t* occ_out, uint8_t* scratch, cudaStream_t st) {
+    switch (act) {
+        case SCONE_ACT_TANH: return launch_l0_fwd_act<COUT, SCONE_ACT_TANH>(cx, b, X, W0, W1, W2, Hout, occ_in, occ_out, scratch, st);
+        case SCONE_ACT_LEAKY_RELU: return launch_l0_fwd_act<COUT, SCONE_ACT_LEAKY_RELU>(cx, b, X, W0, W1, W2, Hout, occ_in, occ_out, scratch, st);
+        case SCONE_ACT_RELU: return launch_l0_fwd_act<COUT, SCONE_ACT_RELU>(cx, b, X, W0, W1, W2, Hout, occ_in, occ_out, scratch, st);
+    }
+    scone_set_error("unknown activation %d", act);
+    return 2;
+}
+
 int scone_layer0_forward(const scone_complex* cx, int32_t act, int32_t b, int32_t cout, const float* X, const float* W0,
-                         const float* W1, const float* W2, float* Hout, uint8_t* occ_out, void* stream) {
+                         const float* W1, const float* W2, float* Hout, const uint8_t* occ_in, uint8_t* occ_out, uint8_t* scratch,
+                         void* stream) {
     cudaStream_t st = as_stream(stream);
     switch (cout) {
-        case 8: return launch_l0_fwd<8>(cx, act, b, X, W0, W1, W2, Hout, occ_out, st);
-        case 16: return launch_l0_fwd<16>(cx, act, b, X, W0, W1, W2, Hout, occ_out, st);
-        case 32: return launch_l0_fwd<32>(cx, act, b, X, W0, W1, W2, Hout, occ_out, st);
-        case 64: return launch_l0_fwd<64>(cx, act, b, X, W0, W1, W2, Hout, occ_out, st);
+        case 8: return launch_l0_fwd<8>(cx, act, b, X, W0, W1, W2, Hout, occ_in, occ_out, scratch, st);
+        case 16: return launch_l0_fwd<16>(cx, act, b, X, W0, W1, W2, Hout, occ_in, occ_out, scratch, st);
+        case 32: return launch_l0_fwd<32>(cx, act, b, X, W0, W1, W2, Hout, occ_in, occ_out, scratch, st);
+        case 64: return launch_l0_fwd<64>(cx, act, b, X, W0, W1, W2, Hout, occ_in, occ_out, scratch, st);
     }
     scone_set_error("scone_layer_forward: first-layer width must be in {8,16,32,64} (got %d)", cout);
     return 2;
@@ -1249,7 +1370,7 @@ int64_t scone_layer0_backward_workspace_bytes(int32_t cout) { return (int64_t)kL
 
 template <int COUT>
 static int launch_l0_bwd(const scone_complex* cx, int b, const float* G, const float* X, float* dW, int accumulate, float* ws,
-                         const uint8_t* occ_g, cudaStream_t st) {
+                         const uint8_t* occ_g, uint8_t* scratch, cudaStream_t st) {
     ScopedProf prof(SCONE_K_LAYER0_BWD, st);
     int grid;
     if (occ_g == nullptr) {
@@ -1258,10 +1379,13 @@ static int launch_l0_bwd(const scone_complex* cx, int b, const float* G, const f
         if (grid > kL0BwdCtas) grid = kL0BwdCtas;
         layer0_bwd_dense_kernel<COUT><<<grid, kThreads, 0, st>>>(X, G, ws, cx->S(0), cx->S(1), cx->E, b);
     } else {
-        const long long n_blocks = ((long long)cx->E * b + kUnitsPerBlock - 1) / kUnitsPerBlock;
-        grid = grid_for(cx, n_blocks, 8);
+        SCONE_REQUIRE(scratch != nullptr, "scone_layer_backward: occ_g needs occ_scratch");
+        constexpr int TT = kTileCols / COUT;
+        const UnitScratch sc = carve_scratch(cx, b, scratch);
+        if (compact_units<TT>(cx, b, occ_g, sc.wl_b, sc.counts, sc.n_b, st)) return 1;
+        grid = cx->num_sms * 4;
         if (grid > kL0BwdCtas) grid = kL0BwdCtas;
-        layer0_bwd_rows_kernel<COUT><<<grid, kThreads, 0, st>>>(X, G, ws, cx->S(0), cx->S(1), cx->E, b, occ_g);
+        layer0_bwd_units_kernel<COUT><<<grid, kThreads, 0, st>>>(X, G, ws, cx->S(0), cx->S(1), cx->E, b, occ_g, sc.wl_b, sc.n_b);
     }
     SCONE_LAUNCHED();
     reduce_partials_kernel<<<(3 * COUT + 255) / 256, 256, 0, st>>>(ws, grid, 3 * COUT, dW, accumulate);
@@ -1270,27 +1394,28 @@ static int launch_l0_bwd(const scone_complex* cx, int b, const float* G, const f
 }
 
 int scone_layer0_backward(const scone_complex* cx, int32_t b, int32_t cout, const float* G, const float* X, float* dW,
-                          int32_t accumulate, void* workspace, const uint8_t* occ_g, void* stream) {
+                          int32_t accumulate, void* workspace, const uint8_t* occ_g, uint8_t* scratch, void* stream) {
     cudaStream_t st = as_stream(stream);
     float* ws = (float*)workspace;
     switch (cout) {
-        case 8: return launch_l0_bwd<8>(cx, b, G, X, dW, accumulate, ws, occ_g, st);
-        case 16: return launch_l0_bwd<16>(cx, b, G, X, dW, accumulate, ws, occ_g, st);
-        case 32: return launch_l0_bwd<32>(cx, b, G, X, dW, accumulate, ws, occ_g, st);
-        case 64: return launch_l0_bwd<64>(cx, b, G, X, dW, accumulate, ws, occ_g, st);
+        case 8: return launch_l0_bwd<8>(cx, b, G, X, dW, accumulate, ws, occ_g, scratch, st);
+        case 16: return launch_l0_bwd<16>(cx, b, G, X, dW, accumulate, ws, occ_g, scratch, st);
+        case 32: return launch_l0_bwd<32>(cx, b, G, X, dW, accumulate, ws, occ_g, scratch, st);
+        case 64: return launch_l0_bwd<64>(cx, b, G, X, dW, accumulate, ws, occ_g, scratch, st);
     }
     scone_set_error("scone_layer_backward: first-layer width must be in {8,16,32,64} (got %d)", cout);
     return 2;
 }
 
 extern "C" int scone_flows_to_dense(const scone_complex* cx, int32_t b, const int32_t* traj_ptr, const int32_t* flow_edge,
-                                    const float* flow_val, float* X, void* stream) {
+                                    const float* flow_val, float* X, uint8_t* occX, void* stream) {
     SCONE_REQUIRE(cx && traj_ptr && X && b > 0, "scone_flows_to_dense: bad argument");
     SCONE_REQUIRE(!cx->host_only, "scone_flows_to_dense: index-only complex has no device arrays");
     cudaStream_t st = as_stream(stream);
     ScopedProf prof(SCONE_K_OTHER, st);
     SCONE_CUDA(cudaMemsetAsync(X, 0, (size_t)cx->E * b * sizeof(float), st));
-    flows_to_dense_kernel<<<(b * 32 + 255) / 256, 256, 0, st>>>(traj_ptr, flow_edge, flow_val, cx->d_rank, X, cx->E, b);
+    if (occX) SCONE_CUDA(cudaMemsetAsync(occX, 0, (size_t)cx->E * b, st));
+    flows_to_dense_kernel<<<(b * 32 + 255) / 256, 256, 0, st>>>(traj_ptr, flow_edge, flow_val, cx->d_rank, X, occX, cx->E, b);
     SCONE_LAUNCHED();
     return 0;
 }

@@ -22,7 +22,8 @@ struct scone_model {
     float* d_G[2] = {nullptr, nullptr};       // ping-pong dL/dZ, [E][mb][cmax]
     std::vector<uint8_t*> d_occH;             // occupancy flags of H_1..H_L, [E][mb]
     uint8_t* d_occG[2] = {nullptr, nullptr};  // occupancy flags of the dL/dZ buffers
-    uint8_t* d_occS = nullptr;                // one-hop propagated flags (scratch)
+    uint8_t* d_occS = nullptr;                // worklists / counters scratch (scone_occ_scratch_bytes)
+    uint8_t* d_occX = nullptr;                // flags of the flows X
     void* d_ws = nullptr;                     // backward / readout workspace
     float* d_logp = nullptr;                  // [mb][D]
     // staging for the *_host entry points
@@ -57,14 +58,14 @@ int ensure_staging(scone_model* m, int64_t B, int64_t nnz) {
 // forward over one micro-batch [off, off+b): X -> H_1 .. H_L (kept) ; returns 0 on success
 int forward_mb(scone_model* m, int32_t b, const int32_t* ptr, const int32_t* edge, const float* val, void* st) {
     const scone_complex* cx = m->cx;
-    int rc = scone_flows_to_dense(cx, b, ptr, edge, val, m->d_X, st);
+    int rc = scone_flows_to_dense(cx, b, ptr, edge, val, m->d_X, m->d_occX, st);
     if (rc) return rc;
     const float* in = m->d_X;
     int cin = 1;
     for (int l = 0; l < m->L; ++l) {
         const int cout = m->hidden[l];
         rc = scone_layer_forward(cx, m->act, b, cin, cout, in, m->d_w + m->w_off[3 * l], m->d_w + m->w_off[3 * l + 1],
-                                 m->d_w + m->w_off[3 * l + 2], m->d_H[l], l > 0 ? m->d_occH[l - 1] : nullptr, m->d_occH[l], m->d_occS, st);
+                                 m->d_w + m->w_off[3 * l + 2], m->d_H[l], l > 0 ? m->d_occH[l - 1] : m->d_occX, m->d_occH[l], m->d_occS, st);
         if (rc) return rc;
         in = m->d_H[l];
         cin = cout;
@@ -131,7 +132,8 @@ extern "C" int scone_model_create(const scone_complex* cx, int32_t n_layers, con
     m->d_occH.assign(n_layers, nullptr);
     for (int l = 0; l < n_layers; ++l) alloc((void**)&m->d_occH[l], E * mb);
     for (int k = 0; k < 2; ++k) alloc((void**)&m->d_occG[k], E * mb);
-    alloc((void**)&m->d_occS, E * mb);
+    alloc((void**)&m->d_occS, (size_t)scone_occ_scratch_bytes(cx, micro_batch));
+    alloc((void**)&m->d_occX, E * mb);
     int64_t ws = scone_readout_workspace_bytes(micro_batch, m->cmax);
     cin = 1;
     for (int l = 0; l < n_layers; ++l) {
@@ -160,7 +162,7 @@ extern "C" int scone_model_destroy(scone_model* m) {
     cudaFree(m->d_w); cudaFree(m->d_m); cudaFree(m->d_v); cudaFree(m->d_grad); cudaFree(m->d_X);
     for (float* p : m->d_H) cudaFree(p);
     for (uint8_t* p : m->d_occH) cudaFree(p);
-    cudaFree(m->d_occG[0]); cudaFree(m->d_occG[1]); cudaFree(m->d_occS);
+    cudaFree(m->d_occG[0]); cudaFree(m->d_occG[1]); cudaFree(m->d_occS); cudaFree(m->d_occX);
     cudaFree(m->d_G[0]); cudaFree(m->d_G[1]); cudaFree(m->d_ws); cudaFree(m->d_logp);
     cudaFree(m->d_ptr); cudaFree(m->d_edge); cudaFree(m->d_last); cudaFree(m->d_tgt); cudaFree(m->d_val);
     cudaFree(m->d_mask); cudaFree(m->d_logp_all);

@@ -202,7 +202,7 @@ def test_occupancy_flags_are_exact(small, cin, cout):
     W = [(torch.randn(cin, cout, generator=g) * 0.3).to(dev) for _ in range(3)]
     st = torch.cuda.current_stream().cuda_stream
     outs = []
-    scratch = torch.empty(E, b, dtype=torch.uint8, device=dev)
+    scratch = torch.empty(L.scone_occ_scratch_bytes(cx.handle, b), dtype=torch.uint8, device=dev)
     for flagged in (0, 1, 2):
         out = torch.full((E, b, cout), 7.0, device=dev)
         occ_out = torch.full((E, b), 9, dtype=torch.uint8, device=dev)
@@ -221,8 +221,8 @@ def test_occupancy_flags_are_exact(small, cin, cout):
     for k in (1, 2):
         assert torch.equal(outs[0][0], outs[k][0]) and torch.equal(outs[0][2], outs[k][2])     # Hout, Gprev bit-identical
         assert _relmax(outs[k][4].numpy(), outs[0][4].numpy()) < 1e-5                          # dW: other summation order
-        assert torch.equal(outs[k][1].bool(), outs[k][0].abs().amax(dim=2) > 0)               # flags == non-zero rows
-        assert torch.equal(outs[k][3].bool(), outs[k][2].abs().amax(dim=2) > 0)
+        assert not ((outs[k][0].abs().amax(dim=2) > 0) & ~outs[k][1].bool()).any()            # flags cover the non-zero rows
+        assert not ((outs[k][2].abs().amax(dim=2) > 0) & ~outs[k][3].bool()).any()
     assert torch.equal(outs[1][4], outs[2][4])
     assert outs[0][1].min() == 1                                 # dense kernels carry no information: everything flagged
     assert 0 < outs[1][1].float().mean() < 0.9

@@ -59,10 +59,11 @@ for kind in ('dense-random', 'rows-2pct+flags', 'blob-1pct+flags'):
         ctr = torch.rand(b, 2, device=dev)
         H *= ((mid[:, None, :] - ctr[None, :, :]).norm(dim=2) < 0.056)[:, :, None]
     occ = (H.abs().amax(dim=2) > 0).to(torch.uint8).contiguous() if 'flags' in kind else None
+    X = H[:, :, 0].contiguous() if 'flags' in kind else torch.randn(E, b, device=dev)
     occ_o = torch.empty(E, b, dtype=torch.uint8, device=dev)
-    scr = torch.empty(E, b, dtype=torch.uint8, device=dev) if occ is not None else None
+    scr = torch.empty(L.scone_occ_scratch_bytes(cx.handle, b), dtype=torch.uint8, device=dev) if occ is not None else None
+    occX = (X != 0).to(torch.uint8).contiguous() if occ is not None else None
     out = torch.empty_like(H)
-    X = torch.randn(E, b, device=dev)
     ms = timeit(lambda: _lib.check(L.scone_layer_forward(cx.handle, 0, b, C, C, _lib.dptr(H), _lib.dptr(W[0]), _lib.dptr(W[1]),
                                                         _lib.dptr(W[2]), _lib.dptr(out), _lib.dptr(occ), _lib.dptr(occ_o), _lib.dptr(scr), st)))
     report('fwd %d->%d (%s)' % (C, C, kind), ms, 4 * E * b * 2 * C)
@@ -73,10 +74,10 @@ for kind in ('dense-random', 'rows-2pct+flags', 'blob-1pct+flags'):
                                                          _lib.dptr(ws), _lib.dptr(occ), _lib.dptr(occ), _lib.dptr(occ_o), _lib.dptr(scr), st)))
     report('bwd %d->%d (%s)' % (C, C, kind), ms, 4 * E * b * 3 * C)
     ms = timeit(lambda: _lib.check(L.scone_layer_forward(cx.handle, 0, b, 1, C, _lib.dptr(X), _lib.dptr(W1[0]), _lib.dptr(W1[1]),
-                                                        _lib.dptr(W1[2]), _lib.dptr(out), None, _lib.dptr(occ_o), None, st)))
+                                                        _lib.dptr(W1[2]), _lib.dptr(out), _lib.dptr(occX), _lib.dptr(occ_o), _lib.dptr(scr), st)))
     report('fwd 1->%d (%s)' % (C, kind), ms, 4 * E * b * (1 + C))
     ms = timeit(lambda: _lib.check(L.scone_layer_backward(cx.handle, 0, b, 1, C, _lib.dptr(H), _lib.dptr(X), None, None, None,
-                                                         None, _lib.dptr(dW), 0, _lib.dptr(ws), _lib.dptr(occ), None, None, None, st)))
+                                                         None, _lib.dptr(dW), 0, _lib.dptr(ws), _lib.dptr(occ), None, None, _lib.dptr(scr), st)))
     report('bwd 1->%d (%s)' % (C, kind), ms, 4 * E * b * (1 + C))
     del H, out
 a = torch.empty(E * b * C, device=dev)
