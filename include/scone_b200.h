@@ -183,7 +183,8 @@ int scone_get_zero_fill(void);
 
 /* Optional per-kernel-family device timing (CUDA events recorded on the launching stream around each launch);
  * off by default.  kind: 0 fused conv layer fwd, 1 fused conv layer bwd (+ its partial reduce), 2 first layer fwd,
- * 3 first layer bwd, 4 readout (+memset/reduce), 5 flows->dense.  Used by bench.py for the roofline figures. */
+ * 3 first layer bwd, 4 readout (+reduce), 5 flows->dense, 6 dense zero-fill of output tensors (on the model's side
+ * stream in the model-level calls).  Used by bench.py for the roofline figures. */
 int scone_profile_enable(int32_t on);
 int scone_profile_reset(void);
 int scone_profile_read(int32_t kind, int64_t* launches, double* total_ms);

@@ -34,7 +34,7 @@ extern std::atomic<long long> g_scone_launches;
 
 // Optional per-kernel timing (CUDA events on the launching stream), off by default; bench.py's roofline uses it.
 enum { SCONE_K_LAYER_FWD = 0, SCONE_K_LAYER_BWD = 1, SCONE_K_LAYER0_FWD = 2, SCONE_K_LAYER0_BWD = 3, SCONE_K_READOUT = 4,
-       SCONE_K_OTHER = 5, SCONE_K_COUNT = 6 };
+       SCONE_K_OTHER = 5, SCONE_K_FILL = 6, SCONE_K_COUNT = 7 };
 extern bool g_scone_prof;
 extern bool g_scone_zero_fill;   // flagged kernels: bulk zero-fill outputs (dense-streaming contract) or leave unflagged rows unwritten
 void scone_prof_begin_impl(int kind, cudaStream_t st);
@@ -44,6 +44,16 @@ struct ScopedProf {
     ScopedProf(int k, cudaStream_t s) : kind(k), st(s) { if (g_scone_prof) scone_prof_begin_impl(kind, st); }
     ~ScopedProf() { if (g_scone_prof) scone_prof_end_impl(kind, st); }
 };
+
+// Hints the model-level code gives to the next flagged kernel-level call on this thread (consumed by scone_hints_take):
+//   in_wl/in_tt   the previous call's output worklist (index in the scratch, unit width) describes occ_in -> no re-compaction
+//   skip_fill     the caller zero-fills the output tensor itself (e.g. on a side stream)
+// out_wl/out_tt are written back by the call.
+struct SconeLaunchHints {
+    int in_wl = -1, in_tt = 0, out_wl = -1, out_tt = 0;
+    bool skip_fill = false;
+};
+extern thread_local SconeLaunchHints g_scone_hints;
 
 // Integer-valued shift operator in CSR form.  ent[p] = {column, float bits of the coefficient};
 // columns ascending inside a row (fixed, deterministic summation order).
@@ -76,6 +86,7 @@ struct scone_complex {
 };
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+int scone_zero_fill(const scone_complex* cx, void* p, size_t bytes, cudaStream_t st);
 
 // internal kernels-level helpers implemented in scone_kernels.cu
 int scone_layer0_forward(const scone_complex* cx, int32_t act, int32_t b, int32_t cout, const float* X_dev,

@@ -19,6 +19,7 @@
 // Weight gradients are accumulated in registers in a data-independent thread mapping and a fixed row order, written
 // as per-CTA partials and reduced in CTA order: bit-reproducible run to run.
 #include <math_constants.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -805,6 +806,20 @@ __global__ void __launch_bounds__(kThreads) layer0_bwd_units_kernel(const float*
     }
 }
 
+// Dense zero-fill of an output tensor (128-bit streaming stores, grid-stride).  In the default (zero-fill ON) mode this is
+// where the HBM time of a step goes: every dense [E][b][C] tensor is written once per micro-batch.
+// One short-lived CTA per 32 KB chunk: SM slots turn over every few microseconds, so the (higher-priority) flag / unit
+// kernels of the main stream are scheduled in between instead of queueing behind a persistent fill.
+__global__ void __launch_bounds__(kThreads) zero_fill_kernel(float4* __restrict__ p, size_t n16) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t base = (size_t)blockIdx.x * ((size_t)kThreads * 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const size_t i = base + (size_t)k * kThreads + threadIdx.x;
+        if (i < n16) __stcs(p + i, z);
+    }
+}
+
 // out[i] (+)= sum over parts p (ascending) of partial[p][i]
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int nparts, int n, float* __restrict__ out,
                                        int accumulate) {
@@ -1072,6 +1087,7 @@ __global__ void adam_kernel(float* __restrict__ W, float* __restrict__ m, float*
 }  // namespace
 
 bool g_scone_zero_fill = true;
+thread_local SconeLaunchHints g_scone_hints;
 
 namespace {
 
@@ -1093,10 +1109,11 @@ int occupancy_of(K kern, size_t smem, int* out) {
     return 0;
 }
 
-// scratch carved from the caller's occ_scratch buffer (scone_occ_scratch_bytes)
+// scratch carved from the caller's occ_scratch buffer (scone_occ_scratch_bytes): two worklists (ping-pong), counters
 struct UnitScratch {
-    uint32_t *wl_a, *wl_b;
-    int *counts, *n_a, *n_b;
+    uint32_t* wl[2];
+    int* n[2];
+    int* counts;
     uint8_t* occ_tmp;
 };
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -1105,11 +1122,11 @@ UnitScratch carve_scratch(const scone_complex* cx, int b, uint8_t* base) {
     UnitScratch sc;
     const size_t nu = max_units(cx, b);
     size_t off = 0;
-    sc.wl_a = reinterpret_cast<uint32_t*>(base + off); off += align256(nu * 4);
-    sc.wl_b = reinterpret_cast<uint32_t*>(base + off); off += align256(nu * 4);
+    sc.wl[0] = reinterpret_cast<uint32_t*>(base + off); off += align256(nu * 4);
+    sc.wl[1] = reinterpret_cast<uint32_t*>(base + off); off += align256(nu * 4);
     sc.counts = reinterpret_cast<int*>(base + off); off += align256((nu / kCompactBlock + 2) * 4);
-    sc.n_a = reinterpret_cast<int*>(base + off); off += 256;
-    sc.n_b = reinterpret_cast<int*>(base + off); off += 256;
+    sc.n[0] = reinterpret_cast<int*>(base + off); off += 256;
+    sc.n[1] = reinterpret_cast<int*>(base + off); off += 256;
     sc.occ_tmp = base + off;
     return sc;
 }
@@ -1128,16 +1145,36 @@ int compact_units(const scone_complex* cx, int b, const uint8_t* flags, uint32_t
     return 0;
 }
 
-// worklist of occ_in -> one-hop scatter into occ_out -> worklist of occ_out (sc.wl_b / sc.n_b)
+// Input worklist: the caller's hint (the previous launch's output worklist, same flags, same TT) or a fresh compaction.
 template <int TT>
-int prepare_units(const scone_complex* cx, int b, const uint8_t* occ_in, uint8_t* occ_out, const UnitScratch& sc, cudaStream_t st) {
-    if (compact_units<TT>(cx, b, occ_in, sc.wl_a, sc.counts, sc.n_a, st)) return 1;
+int input_worklist(const scone_complex* cx, int b, const uint8_t* occ_in, const UnitScratch& sc, cudaStream_t st, int* in) {
+    SconeLaunchHints& h = g_scone_hints;
+    if (h.in_wl >= 0 && h.in_tt == TT) {
+        *in = h.in_wl;
+        return 0;
+    }
+    *in = 0;
+    return compact_units<TT>(cx, b, occ_in, sc.wl[0], sc.counts, sc.n[0], st);
+}
+
+// worklist(occ_in) -> one-hop scatter into occ_out -> worklist(occ_out); *out = index of that worklist in sc
+template <int TT>
+int prepare_units(const scone_complex* cx, int b, const uint8_t* occ_in, uint8_t* occ_out, const UnitScratch& sc, cudaStream_t st,
+                  int* out) {
+    int in = 0;
+    if (input_worklist<TT>(cx, b, occ_in, sc, st, &in)) return 1;
     SCONE_CUDA(cudaMemsetAsync(occ_out, 0, (size_t)cx->E * b, st));
-    scatter_support_kernel<TT><<<cx->num_sms * 8, kThreads, 0, st>>>(sc.wl_a, sc.n_a, occ_in, occ_out, cx->S(0), cx->S(1),
+    scatter_support_kernel<TT><<<cx->num_sms * 8, kThreads, 0, st>>>(sc.wl[in], sc.n[in], occ_in, occ_out, cx->S(0), cx->S(1),
                                                                      (b + TT - 1) / TT, b);
     SCONE_LAUNCHED();
-    return compact_units<TT>(cx, b, occ_out, sc.wl_b, sc.counts, sc.n_b, st);
+    *out = 1 - in;
+    g_scone_hints.out_wl = *out;
+    g_scone_hints.out_tt = TT;
+    return compact_units<TT>(cx, b, occ_out, sc.wl[*out], sc.counts, sc.n[*out], st);
 }
+
+bool zero_fill_here() { return g_scone_zero_fill && !g_scone_hints.skip_fill; }
+
 
 template <int CIN, int COUT, int ACT>
 int launch_fwd(const scone_complex* cx, int b, const float* Hin, const float* W0, const float* W1, const float* W2, float* Hout,
@@ -1157,14 +1194,15 @@ int launch_fwd(const scone_complex* cx, int b, const float* Hin, const float* W0
     }
     SCONE_REQUIRE(occ_out != nullptr && scratch != nullptr, "scone_layer_forward: occ_in needs occ_out and occ_scratch");
     const UnitScratch sc = carve_scratch(cx, b, scratch);
-    if (prepare_units<TT>(cx, b, occ_in, occ_out, sc, st)) return 1;
-    if (g_scone_zero_fill) SCONE_CUDA(cudaMemsetAsync(Hout, 0, (size_t)cx->E * b * COUT * sizeof(float), st));
+    int wo = 0;
+    if (prepare_units<TT>(cx, b, occ_in, occ_out, sc, st, &wo)) return 1;
+    if (zero_fill_here() && scone_zero_fill(cx, Hout, (size_t)cx->E * b * COUT * sizeof(float), st)) return 1;
     const size_t smem = ((size_t)KD * COUT + (size_t)kWarps * TT * LDT) * sizeof(float);
     auto kern = layer_fwd_units_kernel<CIN, COUT, ACT>;
     static int occ = 0;
     if (!occ && occupancy_of(kern, smem, &occ)) return 1;
-    kern<<<cx->num_sms * occ, kThreads, smem, st>>>(Hin, Hout, W0, W1, W2, cx->S(0), cx->S(1), cx->E, b, occ_in, occ_out, sc.wl_b,
-                                                  sc.n_b);
+    kern<<<cx->num_sms * occ, kThreads, smem, st>>>(Hin, Hout, W0, W1, W2, cx->S(0), cx->S(1), cx->E, b, occ_in, occ_out, sc.wl[wo],
+                                                  sc.n[wo]);
     SCONE_LAUNCHED();
     return 0;
 }
@@ -1208,16 +1246,17 @@ int launch_bwd(const scone_complex* cx, int b, const float* G, const float* Hin,
         SCONE_REQUIRE(scratch != nullptr && (!WG || occ_prev != nullptr), "scone_layer_backward: occ_g needs occ_gprev and occ_scratch");
         const UnitScratch sc = carve_scratch(cx, b, scratch);
         uint8_t* cand = WG ? occ_prev : sc.occ_tmp;           // rows whose (G, S0 G, S1 G) can be non-zero
-        if (prepare_units<Us::TT>(cx, b, occ_g, cand, sc, st)) return 1;
-        if (WG && g_scone_zero_fill) SCONE_CUDA(cudaMemsetAsync(Gprev, 0, (size_t)cx->E * b * CIN * sizeof(float), st));
+        int wo = 0;
+        if (prepare_units<Us::TT>(cx, b, occ_g, cand, sc, st, &wo)) return 1;
+        if (WG && zero_fill_here() && scone_zero_fill(cx, Gprev, (size_t)cx->E * b * CIN * sizeof(float), st)) return 1;
         const size_t smem = Us::smem_floats * sizeof(float);
         auto kern = layer_bwd_units_kernel<CIN, COUT, ACT, WG>;
         static int occ = 0;
         if (!occ && occupancy_of(kern, smem, &occ)) return 1;
         grid = cx->num_sms * occ;
         if (grid > kBwdMaxCtas) grid = kBwdMaxCtas;
-        kern<<<grid, kThreads, smem, st>>>(G, Hin, Gprev, W0, W1, W2, ws, cx->S(0), cx->S(1), cx->E, b, occ_g, occ_h, cand, sc.wl_b,
-                                          sc.n_b);
+        kern<<<grid, kThreads, smem, st>>>(G, Hin, Gprev, W0, W1, W2, ws, cx->S(0), cx->S(1), cx->E, b, occ_g, occ_h, cand, sc.wl[wo],
+                                          sc.n[wo]);
         SCONE_LAUNCHED();
     }
     reduce_partials_kernel<<<(Sh::DW + 255) / 256, 256, 0, st>>>(ws, grid, Sh::DW, dW, accumulate);
@@ -1249,6 +1288,27 @@ bool width_ok(int c) { return c == 8 || c == 16 || c == 32 || c == 64; }
 
 }  // namespace
 
+// zero-fill `bytes` (multiple of 16) at p on stream st with the library's own kernel
+int scone_zero_fill(const scone_complex* cx, void* p, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return 0;
+    if ((bytes & 15) || ((uintptr_t)p & 15)) {
+        SCONE_CUDA(cudaMemsetAsync(p, 0, bytes, st));
+        return 0;
+    }
+    ScopedProf prof(SCONE_K_FILL, st);
+    const size_t n16 = bytes / 16;
+    // the (unused) dynamic shared memory caps residency at ~4 fill CTAs per SM, leaving slots for the concurrent kernels
+    static bool configured = false;
+    const int fill_smem = getenv("SCONE_FILL_SMEM") ? atoi(getenv("SCONE_FILL_SMEM")) : 56 * 1024;
+    if (!configured) {
+        SCONE_CUDA(cudaFuncSetAttribute(zero_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    zero_fill_kernel<<<(unsigned)((n16 + (size_t)kThreads * 8 - 1) / ((size_t)kThreads * 8)), kThreads, fill_smem, st>>>(reinterpret_cast<float4*>(p), n16);
+    SCONE_LAUNCHED();
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------------------------
@@ -1275,6 +1335,15 @@ extern "C" int scone_get_zero_fill(void) { return g_scone_zero_fill ? 1 : 0; }
         }                                                                           \
     } while (0)
 
+// input hints are consumed by exactly one kernel-level call
+struct HintsReset {
+    ~HintsReset() {
+        g_scone_hints.in_wl = -1;
+        g_scone_hints.in_tt = 0;
+        g_scone_hints.skip_fill = false;
+    }
+};
+
 extern "C" int64_t scone_occ_scratch_bytes(const scone_complex* cx, int32_t b) {
     if (!cx || b <= 0) return 0;
     const size_t nu = max_units(cx, b);
@@ -1284,6 +1353,8 @@ extern "C" int64_t scone_occ_scratch_bytes(const scone_complex* cx, int32_t b) {
 extern "C" int scone_layer_forward(const scone_complex* cx, int32_t act, int32_t b, int32_t cin, int32_t cout, const float* Hin,
                                    const float* W0, const float* W1, const float* W2, float* Hout, const uint8_t* occ_in,
                                    uint8_t* occ_out, uint8_t* occ_scratch, void* stream) {
+    HintsReset hints_guard;
+    g_scone_hints.out_wl = -1;
     SCONE_REQUIRE(cx && Hin && W0 && W1 && W2 && Hout, "scone_layer_forward: NULL argument");
     SCONE_REQUIRE(!cx->host_only, "scone_layer_forward: index-only complex has no device arrays");
     SCONE_REQUIRE(b > 0, "scone_layer_forward: b must be positive");
@@ -1304,6 +1375,8 @@ extern "C" int scone_layer_backward(const scone_complex* cx, int32_t act, int32_
                                     const float* Hin, const float* W0, const float* W1, const float* W2, float* Gprev, float* dW,
                                     int32_t accumulate, void* workspace, const uint8_t* occ_g, const uint8_t* occ_hin,
                                     uint8_t* occ_prev, uint8_t* occ_scratch, void* stream) {
+    HintsReset hints_guard;
+    g_scone_hints.out_wl = -1;
     SCONE_REQUIRE(cx && G && Hin && dW && workspace, "scone_layer_backward: NULL argument");
     SCONE_REQUIRE(!cx->host_only, "scone_layer_backward: index-only complex has no device arrays");
     SCONE_REQUIRE(b > 0, "scone_layer_backward: b must be positive");
@@ -1331,10 +1404,11 @@ static int launch_l0_fwd_act(const scone_complex* cx, int b, const float* X, con
     SCONE_REQUIRE(occ_out != nullptr && scratch != nullptr, "scone_layer_forward: occ_in needs occ_out and occ_scratch");
     constexpr int TT = kTileCols / COUT;
     const UnitScratch sc = carve_scratch(cx, b, scratch);
-    if (prepare_units<TT>(cx, b, occ_in, occ_out, sc, st)) return 1;
-    if (g_scone_zero_fill) SCONE_CUDA(cudaMemsetAsync(Hout, 0, (size_t)cx->E * b * COUT * sizeof(float), st));
+    int wo = 0;
+    if (prepare_units<TT>(cx, b, occ_in, occ_out, sc, st, &wo)) return 1;
+    if (zero_fill_here() && scone_zero_fill(cx, Hout, (size_t)cx->E * b * COUT * sizeof(float), st)) return 1;
     layer0_fwd_units_kernel<COUT, ACT><<<cx->num_sms * 8, kThreads, 0, st>>>(X, Hout, W0, W1, W2, cx->S(0), cx->S(1), cx->E, b, occ_out,
-                                                                            sc.wl_b, sc.n_b);
+                                                                            sc.wl[wo], sc.n[wo]);
     SCONE_LAUNCHED();
     return 0;
 }
@@ -1382,10 +1456,11 @@ static int launch_l0_bwd(const scone_complex* cx, int b, const float* G, const f
         SCONE_REQUIRE(scratch != nullptr, "scone_layer_backward: occ_g needs occ_scratch");
         constexpr int TT = kTileCols / COUT;
         const UnitScratch sc = carve_scratch(cx, b, scratch);
-        if (compact_units<TT>(cx, b, occ_g, sc.wl_b, sc.counts, sc.n_b, st)) return 1;
+        int wi = 0;
+        if (input_worklist<TT>(cx, b, occ_g, sc, st, &wi)) return 1;
         grid = cx->num_sms * 4;
         if (grid > kL0BwdCtas) grid = kL0BwdCtas;
-        layer0_bwd_units_kernel<COUT><<<grid, kThreads, 0, st>>>(X, G, ws, cx->S(0), cx->S(1), cx->E, b, occ_g, sc.wl_b, sc.n_b);
+        layer0_bwd_units_kernel<COUT><<<grid, kThreads, 0, st>>>(X, G, ws, cx->S(0), cx->S(1), cx->E, b, occ_g, sc.wl[wi], sc.n[wi]);
     }
     SCONE_LAUNCHED();
     reduce_partials_kernel<<<(3 * COUT + 255) / 256, 256, 0, st>>>(ws, grid, 3 * COUT, dW, accumulate);
@@ -1426,6 +1501,8 @@ int scone_readout_ws(const scone_complex* cx, int32_t act, int32_t b, int32_t C,
                      const int32_t* last_nodes, float* logprobs, const int32_t* target_idx, const float* mask, float scale,
                      float* GL, float* dwout, float* nll_sum, float* count, int32_t accumulate, void* workspace,
                      const uint8_t* occ_HL, uint8_t* occ_GL, void* stream) {
+    HintsReset hints_guard;
+    g_scone_hints.out_wl = -1;
     SCONE_REQUIRE(cx && HL && wout && last_nodes && logprobs, "scone_readout: NULL argument");
     SCONE_REQUIRE(!cx->host_only, "scone_readout: index-only complex has no device arrays");
     SCONE_REQUIRE(C >= 1 && C <= 32 * kReadoutMaxCper, "scone_readout: C must be in [1,%d]", 32 * kReadoutMaxCper);
@@ -1435,7 +1512,7 @@ int scone_readout_ws(const scone_complex* cx, int32_t act, int32_t b, int32_t C,
     if (GL) {
         SCONE_REQUIRE(target_idx && mask && workspace, "scone_readout: gradient mode needs target_idx, mask, workspace");
         // without flags the consumer reads every row of GL: it must be dense zeros; with flags only when zero-fill is on
-        if (occ_GL == nullptr || g_scone_zero_fill) SCONE_CUDA(cudaMemsetAsync(GL, 0, (size_t)cx->E * b * C * sizeof(float), st));
+        if ((occ_GL == nullptr || zero_fill_here()) && scone_zero_fill(cx, GL, (size_t)cx->E * b * C * sizeof(float), st)) return 1;
         if (occ_GL) SCONE_CUDA(cudaMemsetAsync(occ_GL, 0, (size_t)cx->E * b, st));
     }
     readout_kernel<<<(b + 3) / 4, 128, 0, st>>>(HL, wout, last_nodes, cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, logprobs,

@@ -19,9 +19,14 @@ struct scone_model {
     float *d_w = nullptr, *d_m = nullptr, *d_v = nullptr, *d_grad = nullptr;     // d_grad: [n_params + 2]
     float* d_X = nullptr;                     // [E][mb]
     std::vector<float*> d_H;                  // H_1..H_L, [E][mb][C_l]
-    float* d_G[2] = {nullptr, nullptr};       // ping-pong dL/dZ, [E][mb][cmax]
+    std::vector<float*> d_G;                  // dL/dZ of layer l, [E][mb][C_l]
     std::vector<uint8_t*> d_occH;             // occupancy flags of H_1..H_L, [E][mb]
-    uint8_t* d_occG[2] = {nullptr, nullptr};  // occupancy flags of the dL/dZ buffers
+    std::vector<uint8_t*> d_occG;             // occupancy flags of the dL/dZ buffers
+    cudaStream_t side = nullptr;              // zero-fill of the next tensors overlaps the current kernels (lowest priority)
+    cudaStream_t compute = nullptr;           // all kernels of a model-level call (highest priority), forked from / joined to the caller's stream
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_begin = nullptr;
+    std::vector<cudaEvent_t> ev_fill;         // [2L]: H_1..H_L, G_{L-1}..G_0
     uint8_t* d_occS = nullptr;                // worklists / counters scratch (scone_occ_scratch_bytes)
     uint8_t* d_occX = nullptr;                // flags of the flows X
     void* d_ws = nullptr;                     // backward / readout workspace
@@ -55,18 +60,48 @@ int ensure_staging(scone_model* m, int64_t B, int64_t nnz) {
     return 0;
 }
 
+// Zero-fill of this micro-batch's dense tensors on the side stream (they are only written, never read, before their
+// consumer kernel runs): the fills overlap the small flag / unit kernels of the main stream.
+int start_fills(scone_model* m, int32_t b, bool with_grads, cudaStream_t s) {
+    if (!g_scone_zero_fill) return 0;
+    const size_t E = m->cx->E;
+    SCONE_CUDA(cudaEventRecord(m->ev_begin, s));              // everything that still reads the old contents is before this
+    SCONE_CUDA(cudaStreamWaitEvent(m->side, m->ev_begin, 0));
+    for (int l = 0; l < m->L; ++l) {
+        if (scone_zero_fill(m->cx, m->d_H[l], E * b * m->hidden[l] * sizeof(float), m->side)) return 1;
+        SCONE_CUDA(cudaEventRecord(m->ev_fill[l], m->side));
+    }
+    if (with_grads)
+        for (int l = m->L - 1; l >= 0; --l) {
+            if (scone_zero_fill(m->cx, m->d_G[l], E * b * m->hidden[l] * sizeof(float), m->side)) return 1;
+            SCONE_CUDA(cudaEventRecord(m->ev_fill[m->L + l], m->side));
+        }
+    return 0;
+}
+int wait_fill(scone_model* m, int idx, cudaStream_t s) {
+    if (!g_scone_zero_fill) return 0;
+    SCONE_CUDA(cudaStreamWaitEvent(s, m->ev_fill[idx], 0));
+    g_scone_hints.skip_fill = true;
+    return 0;
+}
+
 // forward over one micro-batch [off, off+b): X -> H_1 .. H_L (kept) ; returns 0 on success
 int forward_mb(scone_model* m, int32_t b, const int32_t* ptr, const int32_t* edge, const float* val, void* st) {
     const scone_complex* cx = m->cx;
     int rc = scone_flows_to_dense(cx, b, ptr, edge, val, m->d_X, m->d_occX, st);
     if (rc) return rc;
     const float* in = m->d_X;
-    int cin = 1;
+    int cin = 1, wl = -1, tt = 0;
     for (int l = 0; l < m->L; ++l) {
         const int cout = m->hidden[l];
+        if (wait_fill(m, l, as_stream(st))) return 1;
+        g_scone_hints.in_wl = wl;
+        g_scone_hints.in_tt = tt;
         rc = scone_layer_forward(cx, m->act, b, cin, cout, in, m->d_w + m->w_off[3 * l], m->d_w + m->w_off[3 * l + 1],
                                  m->d_w + m->w_off[3 * l + 2], m->d_H[l], l > 0 ? m->d_occH[l - 1] : m->d_occX, m->d_occH[l], m->d_occS, st);
         if (rc) return rc;
+        wl = g_scone_hints.out_wl;
+        tt = g_scone_hints.out_tt;
         in = m->d_H[l];
         cin = cout;
     }
@@ -128,10 +163,12 @@ extern "C" int scone_model_create(const scone_complex* cx, int32_t n_layers, con
     alloc((void**)&m->d_X, E * mb * sizeof(float));
     m->d_H.assign(n_layers, nullptr);
     for (int l = 0; l < n_layers; ++l) alloc((void**)&m->d_H[l], E * mb * hidden[l] * sizeof(float));
-    for (int k = 0; k < 2; ++k) alloc((void**)&m->d_G[k], E * mb * m->cmax * sizeof(float));
+    m->d_G.assign(n_layers, nullptr);
+    for (int l = 0; l < n_layers; ++l) alloc((void**)&m->d_G[l], E * mb * hidden[l] * sizeof(float));
     m->d_occH.assign(n_layers, nullptr);
     for (int l = 0; l < n_layers; ++l) alloc((void**)&m->d_occH[l], E * mb);
-    for (int k = 0; k < 2; ++k) alloc((void**)&m->d_occG[k], E * mb);
+    m->d_occG.assign(n_layers, nullptr);
+    for (int l = 0; l < n_layers; ++l) alloc((void**)&m->d_occG[l], E * mb);
     alloc((void**)&m->d_occS, (size_t)scone_occ_scratch_bytes(cx, micro_batch));
     alloc((void**)&m->d_occX, E * mb);
     int64_t ws = scone_readout_workspace_bytes(micro_batch, m->cmax);
@@ -144,6 +181,15 @@ extern "C" int scone_model_create(const scone_complex* cx, int32_t n_layers, con
     alloc(&m->d_ws, ws);
     alloc((void**)&m->d_logp, mb * (size_t)(cx->D > 0 ? cx->D : 1) * sizeof(float));
     if (!rc) {
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);      // lowest priority: compute CTAs are scheduled first
+        cudaStreamCreateWithPriority(&m->side, cudaStreamNonBlocking, prio_lo);
+        cudaStreamCreateWithPriority(&m->compute, cudaStreamNonBlocking, prio_hi);
+        cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&m->ev_begin, cudaEventDisableTiming);
+        m->ev_fill.assign(2 * n_layers, nullptr);
+        for (auto& e : m->ev_fill) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
         cudaMemset(m->d_w, 0, off * sizeof(float));
         cudaMemset(m->d_m, 0, off * sizeof(float));
         cudaMemset(m->d_v, 0, off * sizeof(float));
@@ -162,8 +208,16 @@ extern "C" int scone_model_destroy(scone_model* m) {
     cudaFree(m->d_w); cudaFree(m->d_m); cudaFree(m->d_v); cudaFree(m->d_grad); cudaFree(m->d_X);
     for (float* p : m->d_H) cudaFree(p);
     for (uint8_t* p : m->d_occH) cudaFree(p);
-    cudaFree(m->d_occG[0]); cudaFree(m->d_occG[1]); cudaFree(m->d_occS); cudaFree(m->d_occX);
-    cudaFree(m->d_G[0]); cudaFree(m->d_G[1]); cudaFree(m->d_ws); cudaFree(m->d_logp);
+    for (uint8_t* p : m->d_occG) cudaFree(p);
+    cudaFree(m->d_occS); cudaFree(m->d_occX);
+    for (float* p : m->d_G) cudaFree(p);
+    cudaFree(m->d_ws); cudaFree(m->d_logp);
+    if (m->side) cudaStreamDestroy(m->side);
+    if (m->compute) cudaStreamDestroy(m->compute);
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    if (m->ev_join) cudaEventDestroy(m->ev_join);
+    if (m->ev_begin) cudaEventDestroy(m->ev_begin);
+    for (auto e : m->ev_fill) if (e) cudaEventDestroy(e);
     cudaFree(m->d_ptr); cudaFree(m->d_edge); cudaFree(m->d_last); cudaFree(m->d_tgt); cudaFree(m->d_val);
     cudaFree(m->d_mask); cudaFree(m->d_logp_all);
     delete m;
@@ -188,54 +242,78 @@ extern "C" int scone_model_get_weights(const scone_model* m, float* w) {
     return 0;
 }
 
+// The caller's stream is forked into the model's high-priority compute stream (and joined back): block scheduling
+// then prefers the flag / unit kernels over the low-priority zero-fill CTAs, so the two really overlap.
+static int fork_to_compute(scone_model* m, void* user_st) {
+    SCONE_CUDA(cudaEventRecord(m->ev_fork, as_stream(user_st)));
+    SCONE_CUDA(cudaStreamWaitEvent(m->compute, m->ev_fork, 0));
+    return 0;
+}
+static int join_from_compute(scone_model* m, void* user_st) {
+    SCONE_CUDA(cudaEventRecord(m->ev_join, m->compute));
+    SCONE_CUDA(cudaStreamWaitEvent(as_stream(user_st), m->ev_join, 0));
+    return 0;
+}
+
 extern "C" int scone_model_forward_dev(scone_model* m, int32_t B, const int32_t* ptr, const int32_t* edge, const float* val,
-                                       const int32_t* last, float* logprobs, void* st) {
+                                       const int32_t* last, float* logprobs, void* user_st) {
     SCONE_REQUIRE(m && ptr && last && logprobs && B >= 0, "scone_model_forward_dev: bad arguments");
+    if (fork_to_compute(m, user_st)) return 1;
+    void* st = (void*)m->compute;
     const scone_complex* cx = m->cx;
     for (int32_t off = 0; off < B; off += m->mb) {
         const int32_t b = B - off < m->mb ? B - off : m->mb;
-        int rc = forward_mb(m, b, ptr + off, edge, val, st);
+        int rc = start_fills(m, b, false, as_stream(st));
+        if (rc) return rc;
+        rc = forward_mb(m, b, ptr + off, edge, val, st);
         if (rc) return rc;
         rc = scone_readout_ws(cx, m->act, b, m->hidden[m->L - 1], m->d_H[m->L - 1], m->d_w + m->w_off[3 * m->L], last + off,
                               logprobs + (size_t)off * cx->D, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, nullptr, 0,
                               nullptr, m->d_occH[m->L - 1], nullptr, st);
         if (rc) return rc;
     }
-    return 0;
+    return join_from_compute(m, user_st);
 }
 
 extern "C" int scone_model_loss_grad_dev(scone_model* m, int32_t B, const int32_t* ptr, const int32_t* edge, const float* val,
                                          const int32_t* last, const int32_t* tgt, const float* mask, int32_t zero_first,
-                                         void* st) {
+                                         void* user_st) {
     SCONE_REQUIRE(m && ptr && last && tgt && mask && B >= 0, "scone_model_loss_grad_dev: bad arguments");
+    if (fork_to_compute(m, user_st)) return 1;
+    void* st = (void*)m->compute;
     const scone_complex* cx = m->cx;
     const int L = m->L;
     cudaStream_t s = as_stream(st);
     if (zero_first) SCONE_CUDA(cudaMemsetAsync(m->d_grad, 0, (m->n_params + 2) * sizeof(float), s));
     for (int32_t off = 0; off < B; off += m->mb) {
         const int32_t b = B - off < m->mb ? B - off : m->mb;
-        int rc = forward_mb(m, b, ptr + off, edge, val, st);
+        int rc = start_fills(m, b, true, s);
+        if (rc) return rc;
+        rc = forward_mb(m, b, ptr + off, edge, val, st);
         if (rc) return rc;
         const int CL = m->hidden[L - 1];
-        float* G = m->d_G[0];
+        if (wait_fill(m, L + (L - 1), s)) return 1;
         rc = scone_readout_ws(cx, m->act, b, CL, m->d_H[L - 1], m->d_w + m->w_off[3 * L], last + off, m->d_logp, tgt + off,
-                              mask + off, 1.f, G, m->d_grad + m->w_off[3 * L], m->d_grad + m->n_params,
-                              m->d_grad + m->n_params + 1, 1, m->d_ws, m->d_occH[L - 1], m->d_occG[0], st);
+                              mask + off, 1.f, m->d_G[L - 1], m->d_grad + m->w_off[3 * L], m->d_grad + m->n_params,
+                              m->d_grad + m->n_params + 1, 1, m->d_ws, m->d_occH[L - 1], m->d_occG[L - 1], st);
         if (rc) return rc;
-        int cur = 0;
+        int wl = -1, tt = 0;
         for (int l = L - 1; l >= 0; --l) {
             const int cout = m->hidden[l], cin = l > 0 ? m->hidden[l - 1] : 1;
             const float* Hin = l > 0 ? m->d_H[l - 1] : m->d_X;
-            float* Gprev = l > 0 ? m->d_G[cur ^ 1] : nullptr;
-            rc = scone_layer_backward(cx, m->act, b, cin, cout, m->d_G[cur], Hin, m->d_w + m->w_off[3 * l],
-                                      m->d_w + m->w_off[3 * l + 1], m->d_w + m->w_off[3 * l + 2], Gprev,
-                                      m->d_grad + m->w_off[3 * l], 1, m->d_ws, m->d_occG[cur], l > 0 ? m->d_occH[l - 1] : nullptr,
-                                      l > 0 ? m->d_occG[cur ^ 1] : nullptr, m->d_occS, st);
+            if (l > 0 && wait_fill(m, L + (l - 1), s)) return 1;
+            g_scone_hints.in_wl = wl;
+            g_scone_hints.in_tt = tt;
+            rc = scone_layer_backward(cx, m->act, b, cin, cout, m->d_G[l], Hin, m->d_w + m->w_off[3 * l],
+                                      m->d_w + m->w_off[3 * l + 1], m->d_w + m->w_off[3 * l + 2], l > 0 ? m->d_G[l - 1] : nullptr,
+                                      m->d_grad + m->w_off[3 * l], 1, m->d_ws, m->d_occG[l], l > 0 ? m->d_occH[l - 1] : nullptr,
+                                      l > 0 ? m->d_occG[l - 1] : nullptr, m->d_occS, st);
             if (rc) return rc;
-            cur ^= 1;
+            wl = g_scone_hints.out_wl;
+            tt = g_scone_hints.out_tt;
         }
     }
-    return 0;
+    return join_from_compute(m, user_st);
 }
 
 extern "C" int scone_model_forward_host(scone_model* m, int32_t B, const int32_t* ptr, const int32_t* edge, const float* val,
