@@ -558,7 +558,7 @@ __device__ __forceinline__ unsigned gather_unit(const float* __restrict__ H, siz
 // Forward: one warp per worklist unit.  Every flagged row of the unit is written (zeros when the gathered rows are
 // numerically zero), so that the output's flags (occ_out == the candidates) never point at unwritten memory.
 template <int CIN, int COUT, int ACT>
-__global__ void __launch_bounds__(kThreads) layer_fwd_units_kernel(const float* __restrict__ Hin, float* __restrict__ Hout,
+__global__ void __launch_bounds__(kThreads, 3) layer_fwd_units_kernel(const float* __restrict__ Hin, float* __restrict__ Hout,
                                                                   const float* __restrict__ W0, const float* __restrict__ W1,
                                                                   const float* __restrict__ W2, DevCsr S0, DevCsr S1, int E, int b,
                                                                   const uint8_t* __restrict__ occ_in, const uint8_t* __restrict__ occ_out,
@@ -619,7 +619,7 @@ struct BwdUnitShape {
 // Backward: CTA c owns the contiguous worklist slice [c*per, (c+1)*per); rounds of UC units are staged by the warps
 // (A rows = G / S0 G / S1 G, Hin rows) and then all threads accumulate the weight gradients over the staged rows.
 template <int CIN, int COUT, int ACT, bool WRITE_GPREV>
-__global__ void __launch_bounds__(kThreads) layer_bwd_units_kernel(const float* __restrict__ G, const float* __restrict__ Hin,
+__global__ void __launch_bounds__(kThreads, 3) layer_bwd_units_kernel(const float* __restrict__ G, const float* __restrict__ Hin,
                                                                   float* __restrict__ Gprev, const float* __restrict__ W0,
                                                                   const float* __restrict__ W1, const float* __restrict__ W2,
                                                                   float* __restrict__ dw_partial, DevCsr S0, DevCsr S1, int E, int b,
