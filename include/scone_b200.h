@@ -174,6 +174,34 @@ int scone_model_read_grads(scone_model* m, float* out_host, void* stream);
  * step = 0-based iteration index i. */
 int scone_model_adam_step(scone_model* m, int32_t step, float lr, float weight_decay, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * SCCONV / "bunch" model (-model bunch): bunch_func (trajectory_experiments.py:173-203) over the seven weighted shift
+ * operators of compute_shift_matrices (bunch_model_matrices.py:118-135), given as generic float CSR matrices in the
+ * reference order S_00, S_10, S_01, S_11, S_21, S_12, S_22.  Edge rows keep the CALLER's order on this path.
+ * hidden[i] = width of hidden layer i; the model has n_hidden + 1 layers of 7 weights (the last maps to 1 channel),
+ * weights flat in list order.  Same [grads | nll_sum | count] / Adam contract as scone_model.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct scone_csr scone_csr;
+typedef struct scone_bunch scone_bunch;
+int scone_csr_create(int32_t rows, int32_t cols, const int32_t* rowptr /* host */, const int32_t* col, const float* val,
+                     scone_csr** out);
+int scone_csr_destroy(scone_csr* S);
+int scone_bunch_create(const scone_csr* const* S7, int32_t n_nodes, int32_t n_edges, int32_t n_tris, int32_t max_degree,
+                       const int32_t* nbrhoods /* host [N][D], pad -1 */, int32_t n_hidden, const int32_t* hidden,
+                       int32_t micro_batch, scone_bunch** out);
+int scone_bunch_destroy(scone_bunch* m);
+int64_t scone_bunch_num_params(const scone_bunch* m);
+float* scone_bunch_grads_dev(scone_bunch* m);
+int scone_bunch_set_weights(scone_bunch* m, const float* weights_host, int32_t reset_adam);
+int scone_bunch_get_weights(const scone_bunch* m, float* weights_host);
+int scone_bunch_forward_host(scone_bunch* m, int32_t B, const int32_t* traj_ptr, const int32_t* flow_edge, const float* flow_val,
+                             const int32_t* last_nodes, float* logprobs_out /* [B][D] */, void* stream);
+int scone_bunch_loss_grad_host(scone_bunch* m, int32_t B, const int32_t* traj_ptr, const int32_t* flow_edge, const float* flow_val,
+                               const int32_t* last_nodes, const int32_t* target_idx, const float* mask, int32_t zero_first,
+                               void* stream);
+int scone_bunch_read_grads(scone_bunch* m, float* out_host, void* stream);
+int scone_bunch_adam_step(scone_bunch* m, int32_t step, float lr, float weight_decay, void* stream);
+
 /* Flagged kernels write only the rows that can be non-zero.  With zero-fill ON (default) every output tensor is first
  * bulk-zeroed, so it is a complete dense [E][b][C] array (the dense-streaming contract: each output byte written).
  * With zero-fill OFF unflagged rows are left unwritten and every consumer must honour the flags (all kernels of this

@@ -44,6 +44,18 @@ SIGNATURES = {
     'scone_readout': (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     'scone_set_zero_fill': (C.c_int, [_i32]),
     'scone_get_zero_fill': (C.c_int, []),
+    'scone_csr_create': (C.c_int, [_i32, _i32, _vp, _vp, _vp, C.POINTER(_vp)]),
+    'scone_csr_destroy': (C.c_int, [_vp]),
+    'scone_bunch_create': (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, C.POINTER(_vp)]),
+    'scone_bunch_destroy': (C.c_int, [_vp]),
+    'scone_bunch_num_params': (_i64, [_vp]),
+    'scone_bunch_grads_dev': (_vp, [_vp]),
+    'scone_bunch_set_weights': (C.c_int, [_vp, _vp, _i32]),
+    'scone_bunch_get_weights': (C.c_int, [_vp, _vp]),
+    'scone_bunch_forward_host': (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'scone_bunch_loss_grad_host': (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    'scone_bunch_read_grads': (C.c_int, [_vp, _vp, _vp]),
+    'scone_bunch_adam_step': (C.c_int, [_vp, _i32, _f32, _f32, _vp]),
     'scone_model_create': (C.c_int, [_vp, _i32, _vp, _i32, C.POINTER(_vp)]),
     'scone_model_destroy': (C.c_int, [_vp]),
     'scone_model_num_params': (_i64, [_vp]),

@@ -18,6 +18,7 @@ import numpy as onp
 
 from .complex import flows_to_csr
 from .model import SconeModel
+from .bunch import BunchModel
 
 onp.random.seed(1030)          # scone_trajectory_model.py:15 — weight init and batch masks draw from this stream
 
@@ -186,7 +187,7 @@ class Scone_GCN():
         """
         self.model_type = model_type
         if model_type == 'bunch':
-            raise NotImplementedError('-model bunch is not on the CUDA path yet (SURVEY.md §8 A6)')
+            return self._setup_bunch(model, hidden_layers, shifts, inputs, y)
         cx = getattr(shifts[0], 'complex', None) or getattr(inputs[0], 'complex', None)
         if cx is None:
             raise TypeError('setup() needs the shift handles / Bconds returned by scone_gcn_b200.trajectory_experiments.'
@@ -212,6 +213,25 @@ class Scone_GCN():
         out_channels = onp.asarray(y).shape[-1]
         assert in_channels == 1 and out_channels == 1, 'the SCoNe path is defined for scalar flows / one-hot targets'
         self.generate_weights(in_channels, hidden_layers, out_channels)
+
+    def _setup_bunch(self, model, hidden_layers, shifts, inputs, y):
+        """-model bunch: 7 weighted CSR operators, inputs[0] is the padded neighbour table (trajectory_experiments.py:309)."""
+        for k, _ in hidden_layers:
+            if k != 7:
+                raise AssertionError('wrong number of weights')       # trajectory_experiments.py:178
+        if len(shifts) != 7 or not all(hasattr(s, 'handle') for s in shifts):
+            raise TypeError('setup(model_type="bunch") needs the 7 CsrOperator shifts returned by data_setup')
+        self.shifts = shifts
+        n = len(onp.asarray(inputs[1]))
+        mb = self.micro_batch or min(max(n, 1), 256)
+        self._net = BunchModel(shifts, onp.asarray(inputs[0]), [h[1] for h in hidden_layers], micro_batch=mb)
+        self.model_single = model
+
+        def batched(weights, *args):
+            return self._forward(weights, list(args[len(self.shifts):]))
+        batched.__name__ = getattr(model, '__name__', 'model')
+        self.model = batched
+        self.generate_weights(1, hidden_layers, onp.asarray(y).shape[-1])
 
     def train(self, inputs, y, train_mask, test_mask, n_nbrs):
         """

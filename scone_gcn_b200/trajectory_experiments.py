@@ -14,6 +14,8 @@ import numpy as onp
 
 from .complex import SimplicialComplex
 from .model import SconeModel
+from .bunch import BunchModel, CsrOperator
+from .bunch_model_matrices import compute_shift_matrices
 from .scone_trajectory_model import Scone_GCN
 from . import synthetic_data_gen as sdg
 
@@ -149,7 +151,19 @@ def bunch_func(weights, S_00, S_10, S_01, S_11, S_21, S_12, S_22, nbrhoods, last
     """
     Forward pass of the Bunch model                                       (trajectory_experiments.py:173-203)
     """
-    raise NotImplementedError('-model bunch is not on the CUDA path yet (SURVEY.md §8 A6)')
+    assert len(weights) % 7 == 0, 'wrong number of weights'
+    shifts = (S_00, S_10, S_01, S_11, S_21, S_12, S_22)
+    if not all(hasattr(s, 'handle') for s in shifts):
+        raise TypeError('the shift arguments must be the CsrOperator objects returned by data_setup')
+    hidden = tuple(int(onp.asarray(weights[7 * i]).shape[1]) for i in range(len(weights) // 7 - 1))
+    key = (tuple(id(s) for s in shifts), hidden)
+    net = _MODEL_CACHE.get(key)
+    if net is None:
+        net = _MODEL_CACHE[key] = BunchModel(shifts, onp.asarray(nbrhoods), hidden, micro_batch=1)
+    net.set_weights([onp.asarray(w) for w in weights], reset_adam=False)
+    from .complex import flows_to_csr
+    ptr, fe, fv = flows_to_csr(onp.asarray(flow).reshape(1, -1))
+    return net.forward(ptr, fe, fv, onp.asarray([int(last_node)], onp.int32)).reshape(-1, 1)
 
 
 def data_setup(hops=(1,), load=True, folder_suffix='schaub'):
@@ -177,7 +191,10 @@ def data_setup(hops=(1,), load=True, folder_suffix='schaub'):
     if model not in ('scone', 'ebli', 'bunch'):
         raise Exception('invalid model type')
     cx = SimplicialComplex.from_dense(B1, B2, model if model != 'bunch' else 'scone', flips=flips)
-    shifts = shift_handles(cx)
+    if model == 'bunch':
+        shifts = [CsrOperator(M) for M in compute_shift_matrices(B1, B2)]      # trajectory_experiments.py:255-257
+    else:
+        shifts = shift_handles(cx)
 
     e = onp.nonzero(B1.T)[1]
     edges = onp.array_split(e, len(e) / 2)
