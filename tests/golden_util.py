@@ -32,7 +32,8 @@ class Dataset:
         self.B2 = dense_from_nz(d['B2_nz'], d['B2_val'], (self.E, self.F))
         self.n_traj = len(d['last_nodes'])
         self.flows = dense_from_nz(d['flows_nz'], d['flows_val'], (self.n_traj, self.E)).reshape(self.n_traj, self.E, 1)
-        self.rev_flows = dense_from_nz(d['rev_flows_nz'], d['rev_flows_val'], (self.n_traj, self.E)).reshape(self.n_traj, self.E, 1)
+        if 'rev_flows_nz' in d.files:
+            self.rev_flows = dense_from_nz(d['rev_flows_nz'], d['rev_flows_val'], (self.n_traj, self.E)).reshape(self.n_traj, self.E, 1)
         self.targets = np.zeros((self.n_traj, self.D, 1))
         self.targets[np.arange(self.n_traj), d['targets_argmax'], 0] = 1.0
         self.train_mask = d['train_mask'].astype(np.int64)

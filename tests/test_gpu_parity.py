@@ -274,3 +274,30 @@ def test_training_matches_oracle_end_to_end(small):
     assert res[1] == pytest.approx(ref[1], abs=1e-7) and res[3] == pytest.approx(ref[3], abs=1e-7)
     for i, w in enumerate(net.weights):
         assert _relmax(np.asarray(w), fx['w_trained_%d' % i]) <= 2e-3, i      # 9 Adam steps amplify fp32 noise
+
+
+def test_default_complex_training_matches_oracle():
+    """cfg1: 3 epochs (24 Adam steps) of the default run from the reference init and batch stream; the oracle runs the
+    reference formulation (dense E x E, forward over all 1000 trajectories, autograd) on the CPU beside it."""
+    sg = _mods()
+    from scone_gcn_b200.scone_trajectory_model import Scone_GCN
+    from scone_gcn_b200 import trajectory_experiments as te
+    ds = Dataset('dataset_default.npz')
+    fx = load('model_default_scone_h16.npz')
+    epochs, bs, lr, wd = 3, 100, 1e-3, 5e-5
+    # oracle
+    orc = so.DenseOracle('scone', so.shift_matrices(ds.B1, ds.B2, 'scone'), ds.B1, ds.last_nodes, ds.flows, ds.targets)
+    rng = np.random.RandomState(1030)
+    W0 = so.generate_weights(rng, 1, [(3, 16)] * 3, 1, 'scone')
+    Wo, res_o = so.train(orc, rng, W0, ds.train_mask, ds.test_mask, epochs, bs, lr, wd)
+    # CUDA path through the reference API
+    np.random.seed(1030)
+    cx = sg.SimplicialComplex.from_simplices(ds.N, ds.edges, ds.faces, 'scone')
+    inputs = [te.Bconds(cx), ds.last_nodes, ds.flows]
+    net = Scone_GCN(epochs, lr, bs, wd, verbose=False)
+    net.setup(te.scone_func, [(3, 16)] * 3, te.shift_handles(cx), inputs, ds.targets, None, ds.train_mask)
+    res = net.train(inputs, ds.targets, ds.train_mask, ds.test_mask, fx['n_nbrs'])
+    assert res[0] == pytest.approx(res_o[0], rel=1e-4) and res[2] == pytest.approx(res_o[2], rel=1e-4)
+    assert res[1] == pytest.approx(res_o[1], abs=1e-9) and res[3] == pytest.approx(res_o[3], abs=1e-9)   # identical accuracy
+    for a, b in zip(net.weights, Wo):
+        assert _relmax(np.asarray(a), b) <= 5e-3
