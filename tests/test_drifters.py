@@ -61,4 +61,17 @@ def test_drifter_training_matches_oracle():
     n_nbrs = np.array([len(so.adjacency_from_B1(ds.B1)[n]) for n in ds.last_nodes])
     res = net.train(inputs, ds.targets, ds.train_mask, ds.test_mask, n_nbrs)
     assert res[0] == pytest.approx(res_o[0], rel=1e-4) and res[2] == pytest.approx(res_o[2], rel=1e-4)
-    assert res[1] == pytest.approx(res_o[1], abs=1e-9) and res[3] == pytest.approx(res_o[3], abs=1e-9)
+    # 20 Adam steps from 0.01-scale weights leave the 6 logits nearly tied, so the argmax is only required to agree where
+    # the oracle's own top-2 margin is above fp32 noise; everywhere else the predictions must be identical
+    import torch
+    with torch.no_grad():
+        lp_o = orc.forward(Wo).numpy()[:, :, 0]
+    lp = net._forward(net.weights, inputs)[:, :, 0]
+    assert np.abs(lp - lp_o).max() < 1e-4
+    for i in range(len(lp)):
+        lp[i, n_nbrs[i]:] = -100
+        lp_o[i, n_nbrs[i]:] = -100
+    top2 = np.sort(lp_o, axis=1)[:, -2:]
+    decided = (top2[:, 1] - top2[:, 0]) > 1e-4
+    assert decided.sum() > 0 and np.array_equal(np.argmax(lp, axis=1)[decided], np.argmax(lp_o, axis=1)[decided])
+    assert abs(res[1] - res_o[1]) <= (~decided).mean() + 1e-9 and abs(res[3] - res_o[3]) <= (~decided).mean() * 5 + 1e-9
