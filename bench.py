@@ -97,6 +97,24 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
+def ncu_traffic(kernel, E, mb, C):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full`
+    capture (profiles/prof_fill_r1m_raw.csv: cfg5, b=64) -- only reported when this run has the same launch shape."""
+    if kernel != 'zero_fill' or (E, mb, C) != (999308, 64, 32):
+        return None
+    try:
+        import csv
+        rows = list(csv.reader(open(os.path.join(ROOT, 'profiles', 'prof_fill_r1m_raw.csv'))))
+        hdr, unit, val = rows[0], rows[1], rows[2]
+        tot = 0.0
+        for name in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            i = hdr.index(name)
+            tot += float(val[i]) * {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[unit[i]]
+        return tot
+    except Exception:
+        return None
+
+
 def make_dataset(cfg, rank):
     from scone_gcn_b200 import synthetic_data_gen as sdg
     if cfg['n_nodes'] <= 1000:
@@ -304,7 +322,7 @@ def main():
     dom = max(kernels, key=lambda k_: kernels[k_]['share_of_kernel_time'])
     fills_ms = fam['zero_fill'][1]
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': kernels[dom].get('achieved_gbs'), 'peak': peak, 'unit': 'GB/s',
-                'frac': kernels[dom].get('frac'), 'traffic': None, 'peak_source': peak_src,
+                'frac': kernels[dom].get('frac'), 'traffic': ncu_traffic(dom, E, mb, C), 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': alg.get(dom),
                 'fill_time_share_of_step': fills_ms / (ms_total or 1.0), 'kernels': kernels,
                 'bytes_model': 'zero_fill_kernel: 4*E*b*C bytes written per launch, 6 launches per micro-batch (H_1..H_3, G_2..G_0); '
