@@ -193,6 +193,7 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', dest='extras', action='store_false', help='skip the sparse-mode and dense-kernel extras')
+    ap.add_argument('--zero-fill', type=int, default=1, help='timed region with dense zero-fill of the outputs on (1) or off (0)')
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.batch:
@@ -274,6 +275,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    L.scone_set_zero_fill(args.zero_fill)
     for _ in range(args.warmup):
         step_dev()
     barrier()

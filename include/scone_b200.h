@@ -209,6 +209,13 @@ int scone_bunch_adam_step(scone_bunch* m, int32_t step, float lr, float weight_d
 int scone_set_zero_fill(int32_t on);
 int scone_get_zero_fill(void);
 
+/* Dense (no occupancy flags) fused layer kernels: 1 (default) = slab kernels for widths 16 / 32 (merged-row gather straight
+ * into mma.sync fragments, 3xTF32 tensor-core product, fp32-grade accuracy), a warp owning 16 trajectories of one edge;
+ * 2 = the same with 8 trajectories of two edges per warp; 0 = the fp32 SIMT tile kernels for every width (bit-identical to
+ * the flagged unit kernels; used by the tests that assert that identity). */
+int scone_set_dense_kernel(int32_t which);
+int scone_get_dense_kernel(void);
+
 /* Optional per-kernel-family device timing (CUDA events recorded on the launching stream around each launch);
  * off by default.  kind: 0 fused conv layer fwd, 1 fused conv layer bwd (+ its partial reduce), 2 first layer fwd,
  * 3 first layer bwd, 4 readout (+reduce), 5 flows->dense, 6 dense zero-fill of output tensors (on the model's side

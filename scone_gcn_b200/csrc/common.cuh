@@ -82,6 +82,10 @@ struct scone_complex {
     int32_t* d_inc_ptr = nullptr;              // [N+1]   B1 rows: node -> incident edges
     int2* d_inc_ent = nullptr;                 // [2E]    {internal edge id, float bits of sign}, ascending
     int32_t* d_rank = nullptr;                 // [E]     caller's edge id -> internal (locality-ordered) edge row
+    // merged operator rows (slab kernels): union of the S0 / S1 patterns (+ the diagonal), columns ascending,
+    // ent = {internal column, (c1 << 16) | (c0 & 0xffff)} with both integer coefficients as int16
+    int32_t* d_mptr = nullptr;                 // [E+1]
+    int2* d_ment = nullptr;
     DevCsr S(int k) const { return DevCsr{d_rowptr[k], d_ent[k]}; }
 };
 
@@ -101,5 +105,10 @@ int scone_readout_ws(const scone_complex* cx, int32_t act, int32_t b, int32_t C,
                      const int32_t* last_nodes, float* logprobs, const int32_t* target_idx, const float* mask,
                      float scale, float* GL, float* dwout, float* nll_sum, float* count, int32_t accumulate,
                      void* workspace, const uint8_t* occ_HL, uint8_t* occ_GL, void* stream);
+// slab kernels (scone_slab.cu): dense fused layer for widths 16 / 32, tensor-core product
+extern int g_scone_dense_kernel;
+bool scone_slab_supported(const scone_complex* cx, int cin, int cout);
+int scone_slab_forward(const scone_complex* cx, int act, int b, int cin, int cout, const float* Hin, const float* W0, const float* W1,
+                       const float* W2, float* Hout, cudaStream_t st);
 int scone_adam_launch(float* W, float* m, float* v, const float* gradbuf, int64_t n, int32_t step, float lr,
                       float wd, void* stream);

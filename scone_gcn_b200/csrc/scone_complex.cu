@@ -356,6 +356,36 @@ static int complex_create_impl(int32_t N, int32_t E, int32_t F, const int32_t* e
         rc |= upload(&cx->d_rowptr[k], rowptr);
         rc |= upload(&cx->d_ent[k], ent);
     }
+    {   // merged rows: one pass over a neighbour row feeds the own-row term and both operator sums
+        std::vector<int32_t> mptr(E + 1, 0);
+        std::vector<int2> ment;
+        ment.reserve(cx->hS[0].col.size() + (size_t)E);
+        std::map<int32_t, std::pair<int32_t, int32_t>> mrow;
+        bool fits = true;
+        for (int32_t i = 0; i < E; ++i) {
+            const int32_t o = order[i];
+            mrow.clear();
+            mrow[i] = {0, 0};                            // the diagonal is always present (own-row term)
+            for (int k = 0; k < 2; ++k) {
+                const HostCsr& h = cx->hS[k];
+                for (int32_t p = h.rowptr[o]; p < h.rowptr[o + 1]; ++p) {
+                    const int32_t v = (int32_t)h.val[p];
+                    if (v < -32768 || v > 32767) fits = false;
+                    auto& cc = mrow[rank[h.col[p]]];
+                    (k == 0 ? cc.first : cc.second) = v;
+                }
+            }
+            for (auto& kv : mrow) {
+                const uint32_t pk = ((uint32_t)(uint16_t)(int16_t)kv.second.second << 16) | (uint32_t)(uint16_t)(int16_t)kv.second.first;
+                ment.push_back(make_int2(kv.first, (int32_t)pk));
+            }
+            mptr[i + 1] = (int32_t)ment.size();
+        }
+        if (fits && !rc) {                               // coefficients beyond int16: the slab kernels are simply not used
+            rc |= upload(&cx->d_mptr, mptr);
+            rc |= upload(&cx->d_ment, ment);
+        }
+    }
     std::vector<int32_t> inc_ptr(N + 1, 0);
     std::vector<int2> inc_ent;
     inc_ent.reserve(2 * (size_t)E);
@@ -405,6 +435,8 @@ extern "C" int scone_complex_destroy(scone_complex* cx) {
     cudaFree(cx->d_inc_ptr);
     cudaFree(cx->d_inc_ent);
     cudaFree(cx->d_rank);
+    cudaFree(cx->d_mptr);
+    cudaFree(cx->d_ment);
     delete cx;
     return 0;
 }

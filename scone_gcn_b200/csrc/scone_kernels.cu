@@ -1302,6 +1302,11 @@ int launch_fwd(const scone_complex* cx, int b, const float* Hin, const float* W0
     constexpr int TT = kTileCols / CIN, TE = kTileRows / TT, KD = 3 * CIN, LDT = KD + 4;
     ScopedProf prof(SCONE_K_LAYER_FWD, st);
     if (occ_in == nullptr) {                                  // dense path
+        if (scone_slab_supported(cx, CIN, COUT)) {            // slab kernel: merged-row gather into mma fragments, 3xTF32 product
+            if (scone_slab_forward(cx, ACT, b, CIN, COUT, Hin, W0, W1, W2, Hout, st)) return 1;
+            if (occ_out) SCONE_CUDA(cudaMemsetAsync(occ_out, 1, (size_t)cx->E * b, st));
+            return 0;
+        }
         const long long n_tiles = (long long)((b + TT - 1) / TT) * ((cx->E + TE - 1) / TE);
         // Opt-in experiment (SCONE_B200_DENSE_MMA=1, widths <= 32): measured SLOWER than the SIMT product on B200 (3.38 vs
         // 2.96 ms at E=270k, b=32, C=32) because the dense kernel is bound by L1/LSU wavefronts of the 17-row gather and of

@@ -203,6 +203,7 @@ def test_occupancy_flags_are_exact(small, cin, cout):
     st = torch.cuda.current_stream().cuda_stream
     outs = []
     scratch = torch.empty(L.scone_occ_scratch_bytes(cx.handle, b), dtype=torch.uint8, device=dev)
+    L.scone_set_dense_kernel(0)          # the bit-identity holds against the fp32 SIMT dense kernels (same arithmetic)
     for flagged in (0, 1, 2):
         out = torch.full((E, b, cout), 7.0, device=dev)
         occ_out = torch.full((E, b), 9, dtype=torch.uint8, device=dev)
@@ -218,6 +219,7 @@ def test_occupancy_flags_are_exact(small, cin, cout):
                                           _lib.dptr(occG) if flagged else None, _lib.dptr(occH) if flagged == 2 else None,
                                           _lib.dptr(occ_p), _lib.dptr(scratch) if flagged else None, st))
         outs.append((out.cpu(), occ_out.cpu(), Gp.cpu(), occ_p.cpu(), dW.cpu()))
+    L.scone_set_dense_kernel(1)
     for k in (1, 2):
         assert torch.equal(outs[0][0], outs[k][0]) and torch.equal(outs[0][2], outs[k][2])     # Hout, Gprev bit-identical
         assert _relmax(outs[k][4].numpy(), outs[0][4].numpy()) < 1e-5                          # dW: other summation order
@@ -226,6 +228,36 @@ def test_occupancy_flags_are_exact(small, cin, cout):
     assert torch.equal(outs[1][4], outs[2][4])
     assert outs[0][1].min() == 1                                 # dense kernels carry no information: everything flagged
     assert 0 < outs[1][1].float().mean() < 0.9
+
+
+@pytest.mark.parametrize('cin,cout,act', [(16, 16, 0), (32, 32, 0), (16, 32, 1), (32, 16, 2)])
+@pytest.mark.parametrize('b', [3, 16, 40])
+def test_slab_kernels_match_simt_dense_kernels(small, cin, cout, act, b):
+    """The tensor-core slab kernels (3xTF32, both slab shapes) against the fp32 SIMT dense kernels on the same input:
+    same gather order, product within fp32 rounding noise; ragged trajectory counts included."""
+    sg = _mods()
+    from scone_gcn_b200 import _lib
+    L = _lib.lib()
+    cx = sg.SimplicialComplex.from_dense(small.B1, small.B2, 'scone')
+    E = cx.E
+    dev = torch.device('cuda')
+    g = torch.Generator(device='cpu').manual_seed(7 * cin + cout + b)
+    H = torch.randn(E, b, cin, generator=g).to(dev)
+    W = [(torch.randn(cin, cout, generator=g) * 0.3).to(dev) for _ in range(3)]
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    try:
+        for which in (0, 1, 2):
+            L.scone_set_dense_kernel(which)
+            out = torch.full((E, b, cout), 7.0, device=dev)
+            _lib.check(L.scone_layer_forward(cx.handle, act, b, cin, cout, _lib.dptr(H), _lib.dptr(W[0]), _lib.dptr(W[1]),
+                                             _lib.dptr(W[2]), _lib.dptr(out), None, None, None, st))
+            outs.append(out.cpu().numpy())
+    finally:
+        L.scone_set_dense_kernel(1)
+    scale = max(1.0, np.abs(outs[0]).max())
+    for k in (1, 2):
+        assert np.abs(outs[k] - outs[0]).max() <= 4e-6 * scale, (k, np.abs(outs[k] - outs[0]).max())
 
 
 @pytest.mark.parametrize('zero_fill', [1, 0])
