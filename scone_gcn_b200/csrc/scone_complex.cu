@@ -152,35 +152,37 @@ IntCsr gram(int32_t n_edges, const std::vector<std::vector<std::pair<int32_t, in
 
 // ---- internal edge order -------------------------------------------------------------------------------------------
 // Activations are private to the library, so edge rows may live in any order on the device.  The reference's order
-// (lexicographic over nodes sorted by x+y) spreads a spatial neighbourhood over the whole index range; a CTA tile of
-// consecutive edges then touches rows all over HBM/L2 and almost every tile intersects some trajectory's support.  We
-// sort edges along a Hilbert curve over two graph-distance fields (BFS from two peripheral landmarks), which needs no
-// coordinates and keeps mesh neighbourhoods in compact index ranges.
-uint64_t hilbert_d(uint32_t x, uint32_t y) {      // 16-bit coordinates -> position along the Hilbert curve
-    uint64_t d = 0;
-    for (uint32_t s = 1u << 15; s > 0; s >>= 1) {
-        uint32_t rx = (x & s) ? 1 : 0, ry = (y & s) ? 1 : 0;
-        d += (uint64_t)s * s * ((3 * rx) ^ ry);
-        if (ry == 0) {
-            if (rx == 1) { x = 65535u - x; y = 65535u - y; }
-            uint32_t t = x; x = y; y = t;
-        }
-    }
-    return d;
-}
+// (lexicographic over nodes sorted by x+y) spreads a spatial neighbourhood over the whole index range: a window of 256
+// consecutive edges touches ~1170 distinct neighbour rows on the 100k-node complex.  We order the NODES by recursive
+// breadth-first bisection of the graph (no coordinates needed): inside a part, breadth-first search from a
+// pseudo-peripheral node, the first half of the visit order goes left, the second half right, recurse; edges follow their
+// earlier end node.  Every index window is then a compact patch of the mesh at every scale (256 edges -> ~450 distinct
+// neighbour rows, within 15 % of a Hilbert curve over the true coordinates), which is what lets the gathers of
+// consecutive edges hit in L1 / L2.  (BFS-distance embeddings are not usable here: the long convex-hull edges of a
+// Delaunay complex are hop-distance shortcuts around the whole boundary.)
+struct BfsScratch {
+    std::vector<int32_t> stamp, queue;
+    int32_t cur = 0;
+};
 
-void bfs(const std::vector<int32_t>& ptr, const std::vector<int32_t>& adj, int32_t src, std::vector<int32_t>& dist,
-         std::vector<int32_t>& order) {
-    order.clear();
-    dist[src] = 0;
-    order.push_back(src);
-    for (size_t h = 0; h < order.size(); ++h) {
-        int32_t u = order[h];
+// BFS inside the part perm[lo, hi) (membership: lo <= pos[v] < hi) from src; visit order in sc.queue; returns #visited
+int32_t bfs_part(const std::vector<int32_t>& ptr, const std::vector<int32_t>& adj, const std::vector<int32_t>& pos, int32_t lo,
+                 int32_t hi, int32_t src, BfsScratch& sc) {
+    ++sc.cur;
+    sc.queue.clear();
+    sc.queue.push_back(src);
+    sc.stamp[src] = sc.cur;
+    for (size_t h = 0; h < sc.queue.size(); ++h) {
+        const int32_t u = sc.queue[h];
         for (int32_t p = ptr[u]; p < ptr[u + 1]; ++p) {
-            int32_t v = adj[p];
-            if (dist[v] < 0) { dist[v] = dist[u] + 1; order.push_back(v); }
+            const int32_t v = adj[p];
+            if (sc.stamp[v] != sc.cur && pos[v] >= lo && pos[v] < hi) {
+                sc.stamp[v] = sc.cur;
+                sc.queue.push_back(v);
+            }
         }
     }
+    return (int32_t)sc.queue.size();
 }
 
 // order[new] = old edge id
@@ -194,33 +196,46 @@ std::vector<int32_t> locality_order(int32_t N, int32_t E, const int32_t* edge_no
         adj[fill[a]++] = b;
         adj[fill[b]++] = a;
     }
-    std::vector<int32_t> comp(N, -1), tmp(N, -1), d1(N, -1), d2(N, -1), d3(N, -1), ord, ord2;
-    std::vector<int64_t> cx(N, 0), cy(N, 0);
-    int64_t xoff = 0;
-    for (int32_t s0 = 0; s0 < N; ++s0) {
-        if (comp[s0] >= 0 || ptr[s0 + 1] == ptr[s0]) continue;
-        bfs(ptr, adj, s0, tmp, ord);
-        int32_t a = ord.back();                  // peripheral node
-        for (int32_t v : ord) comp[v] = s0;
-        bfs(ptr, adj, a, d1, ord2);
-        int32_t b = ord2.back();
-        bfs(ptr, adj, b, d2, ord2);
-        int32_t c = a;
-        int64_t best = -1;
-        for (int32_t v : ord) if ((int64_t)d1[v] + d2[v] > best) { best = (int64_t)d1[v] + d2[v]; c = v; }
-        bfs(ptr, adj, c, d3, ord2);
-        int64_t xmax = 0;
-        for (int32_t v : ord) { cx[v] = xoff + d1[v]; cy[v] = d3[v]; xmax = std::max<int64_t>(xmax, d1[v]); }
-        xoff += xmax + 2;                         // components side by side
+    // perm: connected nodes first (isolated nodes carry no edge rows), pos = inverse
+    std::vector<int32_t> perm, pos(N);
+    perm.reserve(N);
+    for (int32_t n = 0; n < N; ++n) if (ptr[n + 1] > ptr[n]) perm.push_back(n);
+    const int32_t n_conn = (int32_t)perm.size();
+    for (int32_t n = 0; n < N; ++n) if (ptr[n + 1] == ptr[n]) perm.push_back(n);
+    for (int32_t i = 0; i < N; ++i) pos[perm[i]] = i;
+    BfsScratch sc;
+    sc.stamp.assign(N, 0);
+    constexpr int32_t kLeaf = 16;
+    std::vector<std::pair<int32_t, int32_t>> stack;
+    stack.push_back({0, n_conn});
+    std::vector<int32_t> rest;
+    while (!stack.empty()) {
+        const int32_t lo = stack.back().first, hi = stack.back().second;
+        stack.pop_back();
+        if (hi - lo <= kLeaf) continue;
+        int32_t cnt = bfs_part(ptr, adj, pos, lo, hi, perm[lo], sc);
+        if (cnt < hi - lo) {                         // disconnected part: [component of perm[lo]] [everything else]
+            rest.clear();
+            for (int32_t i = lo; i < hi; ++i) if (sc.stamp[perm[i]] != sc.cur) rest.push_back(perm[i]);
+            for (int32_t i = 0; i < cnt; ++i) perm[lo + i] = sc.queue[i];
+            for (size_t i = 0; i < rest.size(); ++i) perm[lo + cnt + (int32_t)i] = rest[i];
+            for (int32_t i = lo; i < hi; ++i) pos[perm[i]] = i;
+            stack.push_back({lo + cnt, hi});
+            stack.push_back({lo, lo + cnt});
+            continue;
+        }
+        const int32_t far = sc.queue.back();         // pseudo-peripheral node of the part
+        cnt = bfs_part(ptr, adj, pos, lo, hi, far, sc);
+        for (int32_t i = 0; i < cnt; ++i) perm[lo + i] = sc.queue[i];
+        for (int32_t i = lo; i < hi; ++i) pos[perm[i]] = i;
+        const int32_t mid = lo + (hi - lo) / 2;
+        stack.push_back({mid, hi});
+        stack.push_back({lo, mid});
     }
-    int64_t mx = 1, my = 1;
-    for (int32_t n = 0; n < N; ++n) { mx = std::max(mx, cx[n]); my = std::max(my, cy[n]); }
-    const int64_t span = std::max(mx, my) * 2 + 1;   // edge key uses the sum of its end nodes (2 x midpoint)
     std::vector<std::pair<uint64_t, int32_t>> key(E);
     for (int32_t e = 0; e < E; ++e) {
-        int32_t a = edge_nodes[2 * e], b = edge_nodes[2 * e + 1];
-        uint32_t x = (uint32_t)(((cx[a] + cx[b]) * 65535) / span), y = (uint32_t)(((cy[a] + cy[b]) * 65535) / span);
-        key[e] = {hilbert_d(x, y), e};
+        const uint32_t pa = (uint32_t)pos[edge_nodes[2 * e]], pb = (uint32_t)pos[edge_nodes[2 * e + 1]];
+        key[e] = {((uint64_t)std::min(pa, pb) << 32) | std::max(pa, pb), e};
     }
     std::sort(key.begin(), key.end());
     std::vector<int32_t> order(E);
