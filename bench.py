@@ -13,7 +13,10 @@ loss (mask all ones).  Weak scaling: the per-GPU batch is fixed and the complex 
   value  whole-job trajectories/s with the batch already resident in HBM (device-timed, max over ranks)
   e2e    same metric through the public host API (SconeModel.loss_grad + adam_step on pinned HOST buffers,
          H2D of the batch and D2H of the loss inside the timed region)
-  roofline   the dominant kernel family, timed live with CUDA events on the launching stream
+  roofline   the dominant kernel family, timed live with CUDA events on the launching stream; bytes follow the
+             device-counted rows the flagged unit kernels produce (support of the trajectories)
+  other_mode the same step with the dense zero-fill switched the other way (dense-stream mode: zero_fill_kernel at
+             ~0.9 of the measured HBM peak is then the dominant kernel)
   cpu_baseline  the oracle's sparse CPU port (oracle/scone_oracle.py) on a bounded sample, rank 0, N = 1 only
 --impl reference times that same CPU port as the whole arm (the reference's dense E x E formulation cannot be
 instantiated at E = 1M: 4 TB per operator; jax itself is not installable offline — see DESIGN.md).
@@ -193,7 +196,7 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', dest='extras', action='store_false', help='skip the sparse-mode and dense-kernel extras')
-    ap.add_argument('--zero-fill', type=int, default=1, help='timed region with dense zero-fill of the outputs on (1) or off (0)')
+    ap.add_argument('--zero-fill', type=int, default=0, help='timed region with dense zero-fill of the outputs on (1) or off (0)')
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.batch:
@@ -275,7 +278,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    L.scone_set_zero_fill(args.zero_fill)
+    net.set_zero_fill(args.zero_fill)
     for _ in range(args.warmup):
         step_dev()
     barrier()
@@ -302,33 +305,59 @@ def main():
 
     # per-kernel-family device time inside the timed region
     import ctypes
-    fam = {}
-    for k, nme in enumerate(KIND_NAMES):
-        n_l, t_ms = ctypes.c_int64(), ctypes.c_double()
-        L.scone_profile_read(k, n_l, t_ms)
-        fam[nme] = (n_l.value, t_ms.value)
-    # ALGORITHMIC bytes.  Default (zero-fill ON) mode: every dense [E][b][C] tensor is written once per
-    # micro-batch by zero_fill_kernel (side stream) -- that is where the HBM time goes; the flag / unit kernels of the
-    # main stream touch only one-byte row flags (E*b per pass) and the flagged rows (< 2 % of a tensor here), run
-    # concurrently with the fills, and are latency / issue bound (no HBM fraction is claimed for them).
-    alg = {'zero_fill': 4.0 * E * mb * C}
+
+    def read_families():
+        fam_ = {}
+        for k, nme in enumerate(KIND_NAMES):
+            n_l, t_ms = ctypes.c_int64(), ctypes.c_double()
+            L.scone_profile_read(k, n_l, t_ms)
+            fam_[nme] = (n_l.value, t_ms.value)
+        rows_ = {}
+        for k, nme in ((0, 'layer_fwd'), (1, 'layer_bwd')):
+            r = ctypes.c_int64()
+            L.scone_profile_read_rows(k, r)
+            rows_[nme] = r.value
+        return fam_, rows_
+    fam, rows = read_families()
+    # ALGORITHMIC bytes.  The flagged unit kernels produce only the (edge, trajectory) rows inside the
+    # trajectories' support (counted on the device): per produced row a fused layer forward reads one input row and
+    # writes one output row (4*(Cin+Cout) bytes), a backward reads G and Hin rows and writes Gprev (4*(2*Cin+Cout));
+    # neighbour re-reads are cache-served, exactly as in the dense formula of SURVEY 8(d).  zero_fill (dense-stream mode
+    # only) writes 4*E*b*C bytes per launch.
     peak, peak_src = load_peaks()
-    kernels = {}
-    tot_ms = sum(t for _, t in fam.values()) or 1.0
-    for nme, (n_l, t_ms) in fam.items():
-        if n_l:
-            avg = t_ms / n_l
-            kernels[nme] = {'launches': n_l, 'avg_ms': avg, 'share_of_kernel_time': t_ms / tot_ms}
-            if nme in alg:
-                kernels[nme].update({'achieved_gbs': alg[nme] / avg / 1e6, 'frac': alg[nme] / avg / 1e6 / peak})
+
+    def kernel_table(fam_, rows_):
+        alg_ = {'zero_fill': 4.0 * E * mb * C}
+        if fam_['layer_fwd'][0]:
+            alg_['layer_fwd'] = rows_['layer_fwd'] * 4.0 * 2 * C / fam_['layer_fwd'][0]
+        if fam_['layer_bwd'][0]:
+            alg_['layer_bwd'] = rows_['layer_bwd'] * 4.0 * 3 * C / fam_['layer_bwd'][0]
+        tot_ms_ = sum(t for _, t in fam_.values()) or 1.0
+        ks = {}
+        for nme, (n_l, t_ms) in fam_.items():
+            if n_l:
+                avg = t_ms / n_l
+                ks[nme] = {'launches': n_l, 'avg_ms': avg, 'share_of_kernel_time': t_ms / tot_ms_}
+                if nme in alg_:
+                    ks[nme].update({'algorithmic_bytes_per_launch': alg_[nme], 'achieved_gbs': alg_[nme] / avg / 1e6,
+                                    'frac': alg_[nme] / avg / 1e6 / peak})
+        return ks
+    kernels = kernel_table(fam, rows)
     dom = max(kernels, key=lambda k_: kernels[k_]['share_of_kernel_time'])
-    fills_ms = fam['zero_fill'][1]
+    dense_bytes_per_traj = 4.0 * E * (15 * C + 2)
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': kernels[dom].get('achieved_gbs'), 'peak': peak, 'unit': 'GB/s',
                 'frac': kernels[dom].get('frac'), 'traffic': ncu_traffic(dom, E, mb, C), 'peak_source': peak_src,
-                'algorithmic_bytes_per_launch': alg.get(dom),
-                'fill_time_share_of_step': fills_ms / (ms_total or 1.0), 'kernels': kernels,
-                'bytes_model': 'zero_fill_kernel: 4*E*b*C bytes written per launch, 6 launches per micro-batch (H_1..H_3, G_2..G_0); '
-                               'timed with CUDA events on the side stream it runs on, while the main-stream kernels run concurrently'}
+                'algorithmic_bytes_per_launch': kernels[dom].get('algorithmic_bytes_per_launch'),
+                'rows_per_step': {k_: v_ / args.steps for k_, v_ in rows.items()},
+                'dense_rows_per_step': float(E) * B * 2,
+                'kernels': kernels,
+                'dense_equivalent': {'bytes_per_trajectory': dense_bytes_per_traj,
+                                     'effective_gbs': dense_bytes_per_traj * value / world / 1e9,
+                                     'note': 'SURVEY 8(d) dense formula 4*E*(15C+2) bytes per trajectory times the measured per-GPU '
+                                             'trajectories/s: what a dense-streaming implementation would have to move to match'},
+                'bytes_model': 'layer_fwd / layer_bwd: rows produced (device-counted) x 4*(Cin+Cout) / 4*(2*Cin+Cout) bytes per launch; the family '
+                               'time includes its worklist kernels (scatter, compaction); these kernels are L2-latency / issue bound, not HBM bound '
+                               '(profiles/); zero_fill (dense-stream mode): 4*E*b*C bytes per launch'}
 
     # end to end through the host API
     barrier()
@@ -345,24 +374,32 @@ def main():
     e2e = {'value': world * B * e2e_steps / (e2e_ms / 1e3), 'unit': 'trajectories/s', 'h2d_bytes_per_step': h2d_bytes,
            'd2h_bytes_per_step': int(4 * (net.n_params + 2)), 'steps': e2e_steps, 'last_loss': loss}
 
-    # extra 1: the same step with zero-fill OFF (unflagged rows never written; results bit-identical, tests/)
-    sparse_mode = None
+    # extra 1: the same step in the OTHER mode (results bit-identical, tests/): dense-stream mode bulk-zeroes every dense
+    # [E][b][C] tensor once per micro-batch (zero_fill_kernel on a side stream is then the HBM-bound dominant kernel)
+    other_mode = None
     if args.extras:
-        L.scone_set_zero_fill(0)
+        net.set_zero_fill(1 - args.zero_fill)
         try:
             step_dev()
             barrier()
+            L.scone_profile_reset()
+            L.scone_profile_enable(1)
             ev0.record()
             for _ in range(args.steps):
                 step_dev()
             ev1.record()
             barrier()
+            L.scone_profile_enable(0)
             sm_ms = max_over_ranks(ev0.elapsed_time(ev1))
-            sparse_mode = {'value': world * B * args.steps / (sm_ms / 1e3), 'unit': 'trajectories/s',
-                           'ms_per_step': sm_ms / args.steps,
-                           'note': 'scone_set_zero_fill(0): traffic follows the support of the trajectories instead of E'}
+            fam2, rows2 = read_families()
+            k2 = kernel_table(fam2, rows2)
+            other_mode = {'zero_fill': 1 - args.zero_fill, 'value': world * B * args.steps / (sm_ms / 1e3), 'unit': 'trajectories/s',
+                          'ms_per_step': sm_ms / args.steps,
+                          'zero_fill_kernel': k2.get('zero_fill'),
+                          'note': 'zero_fill=1: every activation / gradient tensor is a complete dense array (each byte written once per '
+                                  'micro-batch by zero_fill_kernel, timed on its side stream); zero_fill=0: rows outside the support are never written'}
         finally:
-            L.scone_set_zero_fill(1)
+            net.set_zero_fill(args.zero_fill)
 
     # extra 2: the contracted DENSE-tile measurement (north-star / SURVEY 8d): one fused 32->32 layer on dense random
     # features, no occupancy information, algorithmic bytes 4*E*b*(Cin+Cout) fwd and 4*E*b*(2*Cout+Cin) bwd
@@ -396,7 +433,9 @@ def main():
         roofline_dense = {'bound': 'hbm', 'unit': 'GB/s', 'peak': peak, 'b': bd,
                           'layer_fwd': {'ms': f_ms, 'achieved': fa, 'frac': fa / peak},
                           'layer_bwd': {'ms': b_ms, 'achieved': ba, 'frac': ba / peak},
-                          'note': 'dense random features, no flags: instruction/L1-bound SIMT product (profiles/); not in the timed region'}
+                          'note': 'one fused 32->32 layer on dense random features, no flags (every row computed): forward = slab kernel '
+                                  '(merged-row gather into mma.sync fragments, 3xTF32 product), backward = fp32 SIMT tile kernel; '
+                                  'algorithmic bytes 4*E*b*(Cin+Cout) / 4*E*b*(2*Cout+Cin); not in the timed region'}
         del Hd, Od
 
     cpu_baseline = None
@@ -412,12 +451,13 @@ def main():
                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                'config': {'workload': args.config + ': ' + cfg['desc'], 'N': N, 'E': E, 'F': F, 'D': D,
                           'per_gpu_batch': B, 'global_batch': B * world, 'hidden': C, 'layers': 3, 'micro_batch': mb,
+                          'zero_fill': args.zero_fill,
                           'parallelism': 'dp%d (trajectory shards, complex replicated, one all-reduce of %d floats per step)'
                                          % (world, net.n_params + 2),
-                          'l2_policy': 'inputs larger than L2: each micro-batch streams %.2f GB of activations'
-                                       % (4.0 * E * mb * C * 5 / 1e9),
+                          'l2_policy': 'inputs larger than L2: the activation / gradient tensors of one micro-batch span %.2f GB '
+                                       'and every step walks %d micro-batches' % (4.0 * E * mb * C * 6 / 1e9, (B + mb - 1) // mb),
                           'generator_seed': 1030, 'mean_flow_nnz': nnz / B},
-               'roofline': roofline, 'roofline_dense': roofline_dense, 'sparse_mode': sparse_mode, 'e2e': e2e,
+               'roofline': roofline, 'roofline_dense': roofline_dense, 'other_mode': other_mode, 'e2e': e2e,
                'cpu_baseline': cpu_baseline, 'gpu_launches': int(launches),
                'clocks': clk, 'setup_s': setup_s}
         print(json.dumps(out), flush=True)

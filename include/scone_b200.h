@@ -141,6 +141,11 @@ int scone_model_create(const scone_complex* cx, int32_t n_layers, const int32_t*
                        scone_model** out);
 int scone_model_destroy(scone_model* m);
 int64_t scone_model_num_params(const scone_model* m);
+/* The model-level calls keep their activation / gradient tensors private, so by default (0) unflagged rows are never written
+ * and traffic follows the support of the trajectories; 1 = bulk zero-fill every tensor once per micro-batch (complete dense
+ * [E][b][C] arrays, the dense-streaming formulation).  Results are bit-identical either way. */
+int scone_model_set_zero_fill(scone_model* m, int32_t on);
+int scone_model_get_zero_fill(const scone_model* m);
 int scone_model_set_weights(scone_model* m, const float* weights_host);     /* also resets Adam state */
 int scone_model_get_weights(const scone_model* m, float* weights_host);
 float* scone_model_weights_dev(scone_model* m);                              /* flat device weights      */
@@ -202,7 +207,7 @@ int scone_bunch_loss_grad_host(scone_bunch* m, int32_t B, const int32_t* traj_pt
 int scone_bunch_read_grads(scone_bunch* m, float* out_host, void* stream);
 int scone_bunch_adam_step(scone_bunch* m, int32_t step, float lr, float weight_decay, void* stream);
 
-/* Flagged kernels write only the rows that can be non-zero.  With zero-fill ON (default) every output tensor is first
+/* KERNEL-LEVEL calls: flagged kernels write only the rows that can be non-zero.  With zero-fill ON (default) every output tensor is first
  * bulk-zeroed, so it is a complete dense [E][b][C] array (the dense-streaming contract: each output byte written).
  * With zero-fill OFF unflagged rows are left unwritten and every consumer must honour the flags (all kernels of this
  * library do): traffic then scales with the support of the trajectories instead of E.  Results are identical. */
@@ -223,6 +228,9 @@ int scone_get_dense_kernel(void);
 int scone_profile_enable(int32_t on);
 int scone_profile_reset(void);
 int scone_profile_read(int32_t kind, int64_t* launches, double* total_ms);
+/* (edge, trajectory) rows the flagged unit kernels of kind 0 (layer fwd) / 1 (layer bwd) produced since the last reset, counted
+ * on the device while profiling is on: the support-aware work behind bench.py's byte accounting. */
+int scone_profile_read_rows(int32_t kind, int64_t* rows);
 
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t scone_launch_count(void);

@@ -28,6 +28,7 @@ SIGNATURES = {
     'scone_profile_enable': (C.c_int, [_i32]),
     'scone_profile_reset': (C.c_int, []),
     'scone_profile_read': (C.c_int, [_i32, C.POINTER(_i64), C.POINTER(C.c_double)]),
+    'scone_profile_read_rows': (C.c_int, [_i32, C.POINTER(_i64)]),
     'scone_complex_create': (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, C.POINTER(_vp)]),
     'scone_complex_create_index_only': (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, C.POINTER(_vp)]),
     'scone_complex_destroy': (C.c_int, [_vp]),
@@ -61,6 +62,8 @@ SIGNATURES = {
     'scone_model_create': (C.c_int, [_vp, _i32, _vp, _i32, C.POINTER(_vp)]),
     'scone_model_destroy': (C.c_int, [_vp]),
     'scone_model_num_params': (_i64, [_vp]),
+    'scone_model_set_zero_fill': (C.c_int, [_vp, _i32]),
+    'scone_model_get_zero_fill': (C.c_int, [_vp]),
     'scone_model_set_weights': (C.c_int, [_vp, _vp]),
     'scone_model_get_weights': (C.c_int, [_vp, _vp]),
     'scone_model_weights_dev': (_vp, [_vp]),

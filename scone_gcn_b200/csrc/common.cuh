@@ -39,6 +39,8 @@ extern bool g_scone_prof;
 extern bool g_scone_zero_fill;   // flagged kernels: bulk zero-fill outputs (dense-streaming contract) or leave unflagged rows unwritten
 void scone_prof_begin_impl(int kind, cudaStream_t st);
 void scone_prof_end_impl(int kind, cudaStream_t st);
+// device counter of the (edge, trajectory) rows a unit kernel family produced while profiling is on (NULL when off)
+unsigned long long* scone_prof_row_counter(int kind);
 struct ScopedProf {
     int kind; cudaStream_t st;
     ScopedProf(int k, cudaStream_t s) : kind(k), st(s) { if (g_scone_prof) scone_prof_begin_impl(kind, st); }
@@ -49,10 +51,16 @@ struct ScopedProf {
 //   in_wl/in_tt   the previous call's output worklist (index in the scratch, unit width) describes occ_in -> no re-compaction
 //   skip_fill     the caller zero-fills the output tensor itself (e.g. on a side stream)
 // out_wl/out_tt are written back by the call.
+//   in_bm         quad bitmap of occ_in (bit (e*b + t)/4 set <=> one of the 4 flag bytes is set): compaction reads it instead
+//                 of the E*b flag bytes
+//   out_bm        quad bitmap the producer call (scone_flows_to_dense, scone_readout) should set next to the flags it writes
 struct SconeLaunchHints {
     int in_wl = -1, in_tt = 0, out_wl = -1, out_tt = 0;
     bool skip_fill = false;
+    const uint32_t* in_bm = nullptr;
+    uint32_t* out_bm = nullptr;
 };
+static inline size_t scone_bitmap_words(size_t E, size_t b) { return (E * b / 4 + 31) / 32 + 1; }
 extern thread_local SconeLaunchHints g_scone_hints;
 
 // Integer-valued shift operator in CSR form.  ent[p] = {column, float bits of the coefficient};

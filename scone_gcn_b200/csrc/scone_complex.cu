@@ -59,14 +59,34 @@ void scone_prof_end_impl(int kind, cudaStream_t st) {
     for (size_t i = g_prof_pending.size(); i-- > 0;)
         if (g_prof_pending[i].kind == kind) { cudaEventRecord(g_prof_pending[i].b, st); break; }
 }
+static unsigned long long* g_prof_rows_dev = nullptr;      // [SCONE_K_COUNT]
+unsigned long long* scone_prof_row_counter(int kind) {
+    return (g_scone_prof && g_prof_rows_dev) ? g_prof_rows_dev + kind : nullptr;
+}
 extern "C" int scone_profile_enable(int32_t on) {
     prof_collect();
+    if (on && !g_prof_rows_dev) {
+        SCONE_CUDA(cudaMalloc((void**)&g_prof_rows_dev, SCONE_K_COUNT * sizeof(unsigned long long)));
+        SCONE_CUDA(cudaMemset(g_prof_rows_dev, 0, SCONE_K_COUNT * sizeof(unsigned long long)));
+    }
     g_scone_prof = on != 0;
     return 0;
 }
 extern "C" int scone_profile_reset(void) {
     prof_collect();
     for (int k = 0; k < SCONE_K_COUNT; ++k) { g_prof_ms[k] = 0; g_prof_n[k] = 0; }
+    if (g_prof_rows_dev) SCONE_CUDA(cudaMemset(g_prof_rows_dev, 0, SCONE_K_COUNT * sizeof(unsigned long long)));
+    return 0;
+}
+/* rows produced by the flagged unit kernels of `kind` (0 fwd, 1 bwd) since the last reset; synchronises the device */
+extern "C" int scone_profile_read_rows(int32_t kind, int64_t* rows) {
+    SCONE_REQUIRE(kind >= 0 && kind < SCONE_K_COUNT && rows, "scone_profile_read_rows: bad arguments");
+    *rows = 0;
+    if (!g_prof_rows_dev) return 0;
+    unsigned long long v = 0;
+    SCONE_CUDA(cudaDeviceSynchronize());
+    SCONE_CUDA(cudaMemcpy(&v, g_prof_rows_dev + kind, sizeof(v), cudaMemcpyDeviceToHost));
+    *rows = (int64_t)v;
     return 0;
 }
 extern "C" int scone_profile_read(int32_t kind, int64_t* launches, double* total_ms) {

@@ -630,10 +630,21 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(int* __restrict__ cou
 }
 
 // occ_out[e'][t] = 1 for every flagged row (e, t) of the input worklist and every e' in {e} + S0 row + S1 row.
+// quad bitmap: bit (e*b + t) / 4 is set when one of the 4 flag bytes of that aligned quad is set (b % 4 == 0).  Setting a bit
+// is idempotent (atomicOr), so the bitmap — like the flags — does not depend on the order of the writers.
+__device__ __forceinline__ void bitmap_set_quads(uint32_t* __restrict__ bm, size_t row0, unsigned m, int tt) {
+    for (int k = 0; k < tt; k += 4)
+        if ((m >> k) & 0xfu) {
+            const size_t q = (row0 + k) >> 2;
+            const uint32_t bit = 1u << (q & 31);
+            if (!(bm[q >> 5] & bit)) atomicOr(bm + (q >> 5), bit);
+        }
+}
+
 template <int TT>
 __global__ void __launch_bounds__(kThreads) scatter_support_kernel(const uint32_t* __restrict__ wl, const int* __restrict__ n_ptr,
                                                                   const uint8_t* __restrict__ occ_in, uint8_t* __restrict__ occ_out,
-                                                                  DevCsr S0, DevCsr S1, int nchunk, int b) {
+                                                                  uint32_t* __restrict__ bm_out, DevCsr S0, DevCsr S1, int nchunk, int b) {
     const int n = *n_ptr, lane = threadIdx.x % 32;
     const long long nw = (long long)gridDim.x * kWarps;
     for (long long i = (long long)blockIdx.x * kWarps + threadIdx.x / 32; i < n; i += nw) {
@@ -641,18 +652,80 @@ __global__ void __launch_bounds__(kThreads) scatter_support_kernel(const uint32_
         const int e = (int)(u / (uint32_t)nchunk), t0 = (int)(u - (uint32_t)e * (uint32_t)nchunk) * TT;
         const unsigned m = unit_row_mask<TT>(occ_in, e, t0, b);
         if (lane < TT && ((m >> lane) & 1u)) occ_out[(size_t)e * b + t0 + lane] = 1;
+        if (bm_out != nullptr && lane == 0) bitmap_set_quads(bm_out, (size_t)e * b + t0, m, TT);
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             const DevCsr S = s == 0 ? S0 : S1;
             const int p0 = __ldg(S.rowptr + e), p1 = __ldg(S.rowptr + e + 1);
             for (int p = p0 + lane; p < p1; p += 32) {
-                uint8_t* dst = occ_out + (size_t)__ldg(S.ent + p).x * b + t0;
+                const size_t row0 = (size_t)__ldg(S.ent + p).x * b + t0;
+                uint8_t* dst = occ_out + row0;
 #pragma unroll
                 for (int k = 0; k < TT; ++k)
                     if ((m >> k) & 1u) dst[k] = 1;
+                if (bm_out != nullptr) bitmap_set_quads(bm_out, row0, m, TT);
             }
         }
     }
+}
+
+// Worklist of the flagged units from the quad bitmap, ascending unit id, in ONE launch: CTA c owns a contiguous slice of
+// bitmap words; it counts, publishes its total (ticket = ready bit | count), sums the tickets of the CTAs before it
+// (decoupled look-back; lower block indices are dispatched first), then writes its ids.  A unit of TT trajectories is
+// R = TT/4 adjacent quads (b % TT == 0).  tickets[] must be zero at launch.
+template <int R>
+__device__ __forceinline__ uint32_t collapse_quads(uint32_t w) {
+    if (R == 1) return w;
+    if (R == 2) return (w | (w >> 1)) & 0x55555555u;
+    return (w | (w >> 1) | (w >> 2) | (w >> 3)) & 0x11111111u;
+}
+
+template <int R>
+__global__ void __launch_bounds__(kThreads) compact_bitmap_kernel(const uint32_t* __restrict__ bm, long long n_words,
+                                                                 uint32_t* __restrict__ list, int* __restrict__ n_out,
+                                                                 unsigned long long* __restrict__ tickets) {
+    __shared__ int s_scan[kThreads];
+    __shared__ long long s_prefix;
+    const long long per_cta = (n_words + gridDim.x - 1) / gridDim.x;
+    const long long lo = (long long)blockIdx.x * per_cta, hi = lo + per_cta < n_words ? lo + per_cta : n_words;
+    const long long per_thr = (per_cta + kThreads - 1) / kThreads;
+    long long w0 = lo + (long long)threadIdx.x * per_thr, w1 = w0 + per_thr;
+    if (w0 > hi) w0 = hi;
+    if (w1 > hi) w1 = hi;
+    int cnt = 0;
+    for (long long w = w0; w < w1; ++w) cnt += __popc(collapse_quads<R>(__ldg(bm + w)));
+    s_scan[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int o = 1; o < kThreads; o <<= 1) {             // inclusive scan
+        const int v = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0;
+        __syncthreads();
+        s_scan[threadIdx.x] += v;
+        __syncthreads();
+    }
+    const int total = s_scan[kThreads - 1];
+    if (threadIdx.x == 0) {
+        atomicExch(tickets + blockIdx.x, (1ull << 63) | (unsigned long long)(unsigned)total);
+        s_prefix = 0;
+    }
+    __syncthreads();
+    long long part = 0;
+    for (int c = threadIdx.x; c < (int)blockIdx.x; c += kThreads) {
+        unsigned long long t;
+        do { t = atomicAdd(tickets + c, 0ull); } while (!(t >> 63));
+        part += (long long)(t & 0xffffffffull);
+    }
+    if (part) atomicAdd((unsigned long long*)&s_prefix, (unsigned long long)part);
+    __syncthreads();
+    long long off = s_prefix + s_scan[threadIdx.x] - cnt;
+    for (long long w = w0; w < w1; ++w) {
+        uint32_t c = collapse_quads<R>(__ldg(bm + w));
+        while (c) {
+            const int pbit = __ffs(c) - 1;
+            c &= c - 1;
+            list[off++] = (uint32_t)((w * 32 + pbit) / R);
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *n_out = (int)(s_prefix + total);
 }
 
 // (own row, S0 row, S1 row) of unit (e, t0..t0+TT) into Ts rows [slot0 + j]; returns the ballot of non-zero lanes.
@@ -682,8 +755,10 @@ __global__ void __launch_bounds__(kThreads, 3) layer_fwd_units_kernel(const floa
                                                                   const float* __restrict__ W0, const float* __restrict__ W1,
                                                                   const float* __restrict__ W2, DevCsr S0, DevCsr S1, int E, int b,
                                                                   const uint8_t* __restrict__ occ_in, const uint8_t* __restrict__ occ_out,
-                                                                  const uint32_t* __restrict__ wl, const int* __restrict__ n_ptr) {
+                                                                  const uint32_t* __restrict__ wl, const int* __restrict__ n_ptr,
+                                                                  unsigned long long* __restrict__ row_counter) {
     constexpr int TT = kTileCols / CIN, KD = 3 * CIN, LDT = KD + 4, NTX = COUT / 4, NG = CIN / 4, ITEMS = TT * NTX;
+    unsigned rows_done = 0;
     extern __shared__ __align__(16) float smem[];
     float* Ws = smem;                              // [KD][COUT]
     float* Tw = smem + KD * COUT;                  // [kWarps][TT][LDT]
@@ -703,6 +778,7 @@ __global__ void __launch_bounds__(kThreads, 3) layer_fwd_units_kernel(const floa
         const uint32_t u = wl[i];
         const int e = (int)(u / (uint32_t)nchunk), chunk = (int)(u - (uint32_t)e * (uint32_t)nchunk), t0 = chunk * TT;
         const unsigned cm = unit_row_mask<TT>(occ_out, e, t0, b);          // candidate rows of this unit
+        rows_done += __popc(cm);
         const unsigned bal = gather_unit<CIN, LDT>(Hin, rowlen_in, S0, S1, b, e, chunk, occ_in, T, 0);
         __syncwarp();
 #pragma unroll
@@ -723,6 +799,7 @@ __global__ void __launch_bounds__(kThreads, 3) layer_fwd_units_kernel(const floa
         }
         __syncwarp();                              // T is reused by this warp's next unit
     }
+    if (row_counter != nullptr && lane == 0 && rows_done) atomicAdd(row_counter, (unsigned long long)rows_done);
 }
 
 template <int CIN, int COUT>
@@ -745,9 +822,10 @@ __global__ void __launch_bounds__(kThreads, 3) layer_bwd_units_kernel(const floa
                                                                   float* __restrict__ dw_partial, DevCsr S0, DevCsr S1, int E, int b,
                                                                   const uint8_t* __restrict__ occ_g, const uint8_t* __restrict__ occ_h,
                                                                   const uint8_t* __restrict__ occ_prev, const uint32_t* __restrict__ wl,
-                                                                  const int* __restrict__ n_ptr) {
+                                                                  const int* __restrict__ n_ptr, unsigned long long* __restrict__ row_counter) {
     using Sh = BwdShape<CIN, COUT>;
     using Us = BwdUnitShape<CIN, COUT>;
+    unsigned rows_done = 0;
     constexpr int TT = Us::TT, UC = Us::UC, RC = Us::RC, KD = Us::KD, LDA = Us::LDA, LDH = Us::LDH;
     constexpr int NTX = CIN / 4, NG = COUT / 4, ITEMS = TT * NTX;
     extern __shared__ __align__(16) float smem[];
@@ -783,6 +861,7 @@ __global__ void __launch_bounds__(kThreads, 3) layer_bwd_units_kernel(const floa
             const int slot0 = i * TT;
             const unsigned cm = WRITE_GPREV ? unit_row_mask<TT>(occ_prev, e, t0, b) : 0u;
             const unsigned bal = gather_unit<COUT, LDA>(G, rowlen_g, S0, S1, b, e, chunk, occ_g, Ar, slot0);
+            rows_done += __popc(unit_row_mask<TT>(WRITE_GPREV ? occ_prev : occ_g, e, t0, b));
 #pragma unroll
             for (int p = 0; p < (ITEMS + 31) / 32; ++p) {
                 const int it = p * 32 + lane;
@@ -829,6 +908,7 @@ __global__ void __launch_bounds__(kThreads, 3) layer_bwd_units_kernel(const floa
         }
         __syncthreads();
     }
+    if (row_counter != nullptr && lane == 0 && rows_done) atomicAdd(row_counter, (unsigned long long)rows_done);
     write_dw_partial<CIN, COUT>(dw, smem, dw_partial);
 }
 
@@ -941,13 +1021,26 @@ __global__ void __launch_bounds__(kThreads) zero_fill_kernel(float4* __restrict_
 }
 
 // out[i] (+)= sum over parts p (ascending) of partial[p][i]
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nparts, int n, float* __restrict__ out,
-                                       int accumulate) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+// 256 threads = 32 outputs x 8 slices of the parts; slice sums (ascending p inside a slice) are combined in slice order:
+// a fixed summation tree, independent of the launch shape of the producer only through nparts.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int nparts, int n,
+                                                             float* __restrict__ out, int accumulate) {
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    const int per = (nparts + 7) / 8;
+    const int p0 = slice * per, p1 = min(nparts, p0 + per);
     float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * n + i];
-    out[i] = accumulate ? out[i] + s : s;
+    if (i < n)
+        for (int p = p0; p < p1; ++p) s += partial[(size_t)p * n + i];
+    red[slice][lane] = s;
+    __syncthreads();
+    if (slice == 0 && i < n) {
+        float t = red[0][lane];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) t += red[k][lane];
+        out[i] = accumulate ? out[i] + t : t;
+    }
 }
 
 // =================================================================================================================
@@ -1069,14 +1162,16 @@ __global__ void __launch_bounds__(kThreads) layer0_bwd_dense_kernel(const float*
 // X[E][b] from sparse flows; one warp per trajectory (X pre-zeroed).
 __global__ void flows_to_dense_kernel(const int32_t* __restrict__ traj_ptr, const int32_t* __restrict__ flow_edge,
                                       const float* __restrict__ flow_val, const int32_t* __restrict__ rank,
-                                      float* __restrict__ X, uint8_t* __restrict__ occX, int E, int b) {
+                                      float* __restrict__ X, uint8_t* __restrict__ occX, uint32_t* __restrict__ bm, int E, int b) {
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
     if (t >= b) return;
     for (int p = traj_ptr[t] + lane; p < traj_ptr[t + 1]; p += 32) {
         const int e = flow_edge[p];
         if (e >= 0 && e < E) {
-            X[(size_t)rank[e] * b + t] = flow_val[p];
-            if (occX != nullptr) occX[(size_t)rank[e] * b + t] = 1;
+            const size_t row = (size_t)rank[e] * b + t;
+            X[row] = flow_val[p];
+            if (occX != nullptr) occX[row] = 1;
+            if (bm != nullptr) atomicOr(bm + (row >> 7), 1u << ((row >> 2) & 31));
         }
     }
 }
@@ -1092,7 +1187,8 @@ __global__ void __launch_bounds__(128) readout_kernel(const float* __restrict__ 
                                                      float* __restrict__ logprobs, const int32_t* __restrict__ target_idx,
                                                      const float* __restrict__ mask, float scale, float* __restrict__ GL,
                                                      float* __restrict__ partial /* [b][C+2] */, const uint8_t* __restrict__ occ_HL,
-                                                     uint8_t* __restrict__ occ_GL, int act, int N, int D, int b, int C) {
+                                                     uint8_t* __restrict__ occ_GL, uint32_t* __restrict__ bm_GL, int act, int N, int D,
+                                                     int b, int C) {
     __shared__ float s_logit[4][kReadoutMaxD];
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int t = blockIdx.x * 4 + warp;
@@ -1145,7 +1241,11 @@ __global__ void __launch_bounds__(128) readout_kernel(const float* __restrict__ 
 #pragma unroll
             for (int q = 0; q < kReadoutMaxCper; ++q)
                 if (lane + 32 * q < C) GL[base + lane + 32 * q] = 0.f;
-            if (occ_GL != nullptr && lane == 0) occ_GL[(size_t)inc_ent[p].x * b + t] = 1;
+            if (occ_GL != nullptr && lane == 0) {
+                const size_t row = (size_t)inc_ent[p].x * b + t;
+                occ_GL[row] = 1;
+                if (bm_GL != nullptr) atomicOr(bm_GL + (row >> 7), 1u << ((row >> 2) & 31));
+            }
         }
     }
     __syncwarp();
@@ -1234,8 +1334,11 @@ struct UnitScratch {
     uint32_t* wl[2];
     int* n[2];
     int* counts;
+    uint32_t* bm;                       // quad bitmap of the flags a call produces (scatter -> compaction)
+    unsigned long long* tickets;        // look-back tickets of compact_bitmap_kernel
     uint8_t* occ_tmp;
 };
+constexpr int kTicketSlots = 1024;
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 size_t max_units(const scone_complex* cx, int b) { return (size_t)cx->E * (size_t)((b + 1) / 2); }   // TT >= 2
 UnitScratch carve_scratch(const scone_complex* cx, int b, uint8_t* base) {
@@ -1247,6 +1350,8 @@ UnitScratch carve_scratch(const scone_complex* cx, int b, uint8_t* base) {
     sc.counts = reinterpret_cast<int*>(base + off); off += align256((nu / kCompactBlock + 2) * 4);
     sc.n[0] = reinterpret_cast<int*>(base + off); off += 256;
     sc.n[1] = reinterpret_cast<int*>(base + off); off += 256;
+    sc.bm = reinterpret_cast<uint32_t*>(base + off); off += align256(scone_bitmap_words(cx->E, b) * 4);
+    sc.tickets = reinterpret_cast<unsigned long long*>(base + off); off += align256(kTicketSlots * 8);
     sc.occ_tmp = base + off;
     return sc;
 }
@@ -1265,6 +1370,22 @@ int compact_units(const scone_complex* cx, int b, const uint8_t* flags, uint32_t
     return 0;
 }
 
+// The same worklist from the quad bitmap of the flags (TT in {4, 8, 16}, b % TT == 0): one launch over E*b/32 bytes.
+bool bitmap_ok(int tt, int b) { return (tt == 4 || tt == 8 || tt == 16) && b % tt == 0; }
+
+template <int TT>
+int compact_bitmap(const scone_complex* cx, int b, const uint32_t* bm, uint32_t* list, int* n_ptr, unsigned long long* tickets,
+                   cudaStream_t st) {
+    constexpr int R = TT >= 4 ? TT / 4 : 1;
+    const long long n_words = ((long long)cx->E * b / 4 + 31) / 32;
+    int grid = cx->num_sms < kTicketSlots ? cx->num_sms : kTicketSlots;
+    if (n_words < grid) grid = n_words > 0 ? (int)n_words : 1;
+    SCONE_CUDA(cudaMemsetAsync(tickets, 0, (size_t)grid * 8, st));
+    compact_bitmap_kernel<R><<<grid, kThreads, 0, st>>>(bm, n_words, list, n_ptr, tickets);
+    SCONE_LAUNCHED();
+    return 0;
+}
+
 // Input worklist: the caller's hint (the previous launch's output worklist, same flags, same TT) or a fresh compaction.
 template <int TT>
 int input_worklist(const scone_complex* cx, int b, const uint8_t* occ_in, const UnitScratch& sc, cudaStream_t st, int* in) {
@@ -1274,6 +1395,7 @@ int input_worklist(const scone_complex* cx, int b, const uint8_t* occ_in, const 
         return 0;
     }
     *in = 0;
+    if (h.in_bm != nullptr && bitmap_ok(TT, b)) return compact_bitmap<TT>(cx, b, h.in_bm, sc.wl[0], sc.n[0], sc.tickets, st);
     return compact_units<TT>(cx, b, occ_in, sc.wl[0], sc.counts, sc.n[0], st);
 }
 
@@ -1284,12 +1406,15 @@ int prepare_units(const scone_complex* cx, int b, const uint8_t* occ_in, uint8_t
     int in = 0;
     if (input_worklist<TT>(cx, b, occ_in, sc, st, &in)) return 1;
     SCONE_CUDA(cudaMemsetAsync(occ_out, 0, (size_t)cx->E * b, st));
-    scatter_support_kernel<TT><<<cx->num_sms * 8, kThreads, 0, st>>>(sc.wl[in], sc.n[in], occ_in, occ_out, cx->S(0), cx->S(1),
+    uint32_t* bm = bitmap_ok(TT, b) ? sc.bm : nullptr;
+    if (bm) SCONE_CUDA(cudaMemsetAsync(bm, 0, scone_bitmap_words(cx->E, b) * 4, st));
+    scatter_support_kernel<TT><<<cx->num_sms * 8, kThreads, 0, st>>>(sc.wl[in], sc.n[in], occ_in, occ_out, bm, cx->S(0), cx->S(1),
                                                                      (b + TT - 1) / TT, b);
     SCONE_LAUNCHED();
     *out = 1 - in;
     g_scone_hints.out_wl = *out;
     g_scone_hints.out_tt = TT;
+    if (bm) return compact_bitmap<TT>(cx, b, bm, sc.wl[*out], sc.n[*out], sc.tickets, st);
     return compact_units<TT>(cx, b, occ_out, sc.wl[*out], sc.counts, sc.n[*out], st);
 }
 
@@ -1339,7 +1464,7 @@ int launch_fwd(const scone_complex* cx, int b, const float* Hin, const float* W0
     static int occ = 0;
     if (!occ && occupancy_of(kern, smem, &occ)) return 1;
     kern<<<cx->num_sms * occ, kThreads, smem, st>>>(Hin, Hout, W0, W1, W2, cx->S(0), cx->S(1), cx->E, b, occ_in, occ_out, sc.wl[wo],
-                                                  sc.n[wo]);
+                                                  sc.n[wo], scone_prof_row_counter(SCONE_K_LAYER_FWD));
     SCONE_LAUNCHED();
     return 0;
 }
@@ -1393,10 +1518,10 @@ int launch_bwd(const scone_complex* cx, int b, const float* G, const float* Hin,
         grid = cx->num_sms * occ;
         if (grid > kBwdMaxCtas) grid = kBwdMaxCtas;
         kern<<<grid, kThreads, smem, st>>>(G, Hin, Gprev, W0, W1, W2, ws, cx->S(0), cx->S(1), cx->E, b, occ_g, occ_h, cand, sc.wl[wo],
-                                          sc.n[wo]);
+                                          sc.n[wo], scone_prof_row_counter(SCONE_K_LAYER_BWD));
         SCONE_LAUNCHED();
     }
-    reduce_partials_kernel<<<(Sh::DW + 255) / 256, 256, 0, st>>>(ws, grid, Sh::DW, dW, accumulate);
+    reduce_partials_kernel<<<(Sh::DW + 31) / 32, 256, 0, st>>>(ws, grid, Sh::DW, dW, accumulate);
     SCONE_LAUNCHED();
     return 0;
 }
@@ -1478,13 +1603,16 @@ struct HintsReset {
         g_scone_hints.in_wl = -1;
         g_scone_hints.in_tt = 0;
         g_scone_hints.skip_fill = false;
+        g_scone_hints.in_bm = nullptr;
+        g_scone_hints.out_bm = nullptr;
     }
 };
 
 extern "C" int64_t scone_occ_scratch_bytes(const scone_complex* cx, int32_t b) {
     if (!cx || b <= 0) return 0;
     const size_t nu = max_units(cx, b);
-    return (int64_t)(2 * align256(nu * 4) + align256((nu / kCompactBlock + 2) * 4) + 512 + align256((size_t)cx->E * b));
+    return (int64_t)(2 * align256(nu * 4) + align256((nu / kCompactBlock + 2) * 4) + 512 + align256(scone_bitmap_words(cx->E, b) * 4) +
+                     align256(kTicketSlots * 8) + align256((size_t)cx->E * b));
 }
 
 extern "C" int scone_layer_forward(const scone_complex* cx, int32_t act, int32_t b, int32_t cin, int32_t cout, const float* Hin,
@@ -1600,7 +1728,7 @@ static int launch_l0_bwd(const scone_complex* cx, int b, const float* G, const f
         layer0_bwd_units_kernel<COUT><<<grid, kThreads, 0, st>>>(X, G, ws, cx->S(0), cx->S(1), cx->E, b, occ_g, sc.wl[wi], sc.n[wi]);
     }
     SCONE_LAUNCHED();
-    reduce_partials_kernel<<<(3 * COUT + 255) / 256, 256, 0, st>>>(ws, grid, 3 * COUT, dW, accumulate);
+    reduce_partials_kernel<<<(3 * COUT + 31) / 32, 256, 0, st>>>(ws, grid, 3 * COUT, dW, accumulate);
     SCONE_LAUNCHED();
     return 0;
 }
@@ -1627,7 +1755,10 @@ extern "C" int scone_flows_to_dense(const scone_complex* cx, int32_t b, const in
     ScopedProf prof(SCONE_K_OTHER, st);
     SCONE_CUDA(cudaMemsetAsync(X, 0, (size_t)cx->E * b * sizeof(float), st));
     if (occX) SCONE_CUDA(cudaMemsetAsync(occX, 0, (size_t)cx->E * b, st));
-    flows_to_dense_kernel<<<(b * 32 + 255) / 256, 256, 0, st>>>(traj_ptr, flow_edge, flow_val, cx->d_rank, X, occX, cx->E, b);
+    uint32_t* bm = (occX != nullptr && b % 4 == 0) ? g_scone_hints.out_bm : nullptr;
+    g_scone_hints.out_bm = nullptr;
+    if (bm) SCONE_CUDA(cudaMemsetAsync(bm, 0, scone_bitmap_words(cx->E, b) * 4, st));
+    flows_to_dense_kernel<<<(b * 32 + 255) / 256, 256, 0, st>>>(traj_ptr, flow_edge, flow_val, cx->d_rank, X, occX, bm, cx->E, b);
     SCONE_LAUNCHED();
     return 0;
 }
@@ -1652,8 +1783,11 @@ int scone_readout_ws(const scone_complex* cx, int32_t act, int32_t b, int32_t C,
         if ((occ_GL == nullptr || zero_fill_here()) && scone_zero_fill(cx, GL, (size_t)cx->E * b * C * sizeof(float), st)) return 1;
         if (occ_GL) SCONE_CUDA(cudaMemsetAsync(occ_GL, 0, (size_t)cx->E * b, st));
     }
+    uint32_t* bm = (GL && occ_GL && b % 4 == 0) ? g_scone_hints.out_bm : nullptr;
+    g_scone_hints.out_bm = nullptr;
+    if (bm) SCONE_CUDA(cudaMemsetAsync(bm, 0, scone_bitmap_words(cx->E, b) * 4, st));
     readout_kernel<<<(b + 3) / 4, 128, 0, st>>>(HL, wout, last_nodes, cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, logprobs,
-                                              target_idx, mask, scale, GL, (float*)workspace, occ_HL, GL ? occ_GL : nullptr, act,
+                                              target_idx, mask, scale, GL, (float*)workspace, occ_HL, GL ? occ_GL : nullptr, bm, act,
                                               cx->N, cx->D, b, C);
     SCONE_LAUNCHED();
     if (GL) {

@@ -29,6 +29,8 @@ struct scone_model {
     std::vector<cudaEvent_t> ev_fill;         // [2L]: H_1..H_L, G_{L-1}..G_0
     uint8_t* d_occS = nullptr;                // worklists / counters scratch (scone_occ_scratch_bytes)
     uint8_t* d_occX = nullptr;                // flags of the flows X
+    uint32_t *d_bmX = nullptr, *d_bmG = nullptr;   // quad bitmaps of the flags of X and of G_L (compaction reads these)
+    bool zero_fill = false;                   // dense zero-fill of every activation / gradient tensor (scone_model_set_zero_fill)
     void* d_ws = nullptr;                     // backward / readout workspace
     float* d_logp = nullptr;                  // [mb][D]
     // staging for the *_host entry points
@@ -63,7 +65,7 @@ int ensure_staging(scone_model* m, int64_t B, int64_t nnz) {
 // Zero-fill of this micro-batch's dense tensors on the side stream (they are only written, never read, before their
 // consumer kernel runs): the fills overlap the small flag / unit kernels of the main stream.
 int start_fills(scone_model* m, int32_t b, bool with_grads, cudaStream_t s) {
-    if (!g_scone_zero_fill) return 0;
+    if (!m->zero_fill) return 0;
     const size_t E = m->cx->E;
     SCONE_CUDA(cudaEventRecord(m->ev_begin, s));              // everything that still reads the old contents is before this
     SCONE_CUDA(cudaStreamWaitEvent(m->side, m->ev_begin, 0));
@@ -79,15 +81,16 @@ int start_fills(scone_model* m, int32_t b, bool with_grads, cudaStream_t s) {
     return 0;
 }
 int wait_fill(scone_model* m, int idx, cudaStream_t s) {
-    if (!g_scone_zero_fill) return 0;
+    g_scone_hints.skip_fill = true;          // the kernel-level call never fills: either the side stream did, or nobody does
+    if (!m->zero_fill) return 0;
     SCONE_CUDA(cudaStreamWaitEvent(s, m->ev_fill[idx], 0));
-    g_scone_hints.skip_fill = true;
     return 0;
 }
 
 // forward over one micro-batch [off, off+b): X -> H_1 .. H_L (kept) ; returns 0 on success
 int forward_mb(scone_model* m, int32_t b, const int32_t* ptr, const int32_t* edge, const float* val, void* st) {
     const scone_complex* cx = m->cx;
+    g_scone_hints.out_bm = m->d_bmX;
     int rc = scone_flows_to_dense(cx, b, ptr, edge, val, m->d_X, m->d_occX, st);
     if (rc) return rc;
     const float* in = m->d_X;
@@ -97,6 +100,7 @@ int forward_mb(scone_model* m, int32_t b, const int32_t* ptr, const int32_t* edg
         if (wait_fill(m, l, as_stream(st))) return 1;
         g_scone_hints.in_wl = wl;
         g_scone_hints.in_tt = tt;
+        if (l == 0) g_scone_hints.in_bm = m->d_bmX;
         rc = scone_layer_forward(cx, m->act, b, cin, cout, in, m->d_w + m->w_off[3 * l], m->d_w + m->w_off[3 * l + 1],
                                  m->d_w + m->w_off[3 * l + 2], m->d_H[l], l > 0 ? m->d_occH[l - 1] : m->d_occX, m->d_occH[l], m->d_occS, st);
         if (rc) return rc;
@@ -171,6 +175,8 @@ extern "C" int scone_model_create(const scone_complex* cx, int32_t n_layers, con
     for (int l = 0; l < n_layers; ++l) alloc((void**)&m->d_occG[l], E * mb);
     alloc((void**)&m->d_occS, (size_t)scone_occ_scratch_bytes(cx, micro_batch));
     alloc((void**)&m->d_occX, E * mb);
+    alloc((void**)&m->d_bmX, scone_bitmap_words(E, mb) * 4);
+    alloc((void**)&m->d_bmG, scone_bitmap_words(E, mb) * 4);
     int64_t ws = scone_readout_workspace_bytes(micro_batch, m->cmax);
     cin = 1;
     for (int l = 0; l < n_layers; ++l) {
@@ -209,7 +215,7 @@ extern "C" int scone_model_destroy(scone_model* m) {
     for (float* p : m->d_H) cudaFree(p);
     for (uint8_t* p : m->d_occH) cudaFree(p);
     for (uint8_t* p : m->d_occG) cudaFree(p);
-    cudaFree(m->d_occS); cudaFree(m->d_occX);
+    cudaFree(m->d_occS); cudaFree(m->d_occX); cudaFree(m->d_bmX); cudaFree(m->d_bmG);
     for (float* p : m->d_G) cudaFree(p);
     cudaFree(m->d_ws); cudaFree(m->d_logp);
     if (m->side) cudaStreamDestroy(m->side);
@@ -225,6 +231,12 @@ extern "C" int scone_model_destroy(scone_model* m) {
 }
 
 extern "C" int64_t scone_model_num_params(const scone_model* m) { return m ? m->n_params : -1; }
+extern "C" int scone_model_set_zero_fill(scone_model* m, int32_t on) {
+    SCONE_REQUIRE(m != nullptr, "scone_model_set_zero_fill: NULL model");
+    m->zero_fill = on != 0;
+    return 0;
+}
+extern "C" int scone_model_get_zero_fill(const scone_model* m) { return m && m->zero_fill ? 1 : 0; }
 extern "C" float* scone_model_weights_dev(scone_model* m) { return m ? m->d_w : nullptr; }
 extern "C" float* scone_model_grads_dev(scone_model* m) { return m ? m->d_grad : nullptr; }
 
@@ -293,6 +305,7 @@ extern "C" int scone_model_loss_grad_dev(scone_model* m, int32_t B, const int32_
         if (rc) return rc;
         const int CL = m->hidden[L - 1];
         if (wait_fill(m, L + (L - 1), s)) return 1;
+        g_scone_hints.out_bm = m->d_bmG;
         rc = scone_readout_ws(cx, m->act, b, CL, m->d_H[L - 1], m->d_w + m->w_off[3 * L], last + off, m->d_logp, tgt + off,
                               mask + off, 1.f, m->d_G[L - 1], m->d_grad + m->w_off[3 * L], m->d_grad + m->n_params,
                               m->d_grad + m->n_params + 1, 1, m->d_ws, m->d_occH[L - 1], m->d_occG[L - 1], st);
@@ -304,6 +317,7 @@ extern "C" int scone_model_loss_grad_dev(scone_model* m, int32_t B, const int32_
             if (l > 0 && wait_fill(m, L + (l - 1), s)) return 1;
             g_scone_hints.in_wl = wl;
             g_scone_hints.in_tt = tt;
+            if (l == L - 1) g_scone_hints.in_bm = m->d_bmG;
             rc = scone_layer_backward(cx, m->act, b, cin, cout, m->d_G[l], Hin, m->d_w + m->w_off[3 * l],
                                       m->d_w + m->w_off[3 * l + 1], m->d_w + m->w_off[3 * l + 2], l > 0 ? m->d_G[l - 1] : nullptr,
                                       m->d_grad + m->w_off[3 * l], 1, m->d_ws, m->d_occG[l], l > 0 ? m->d_occH[l - 1] : nullptr,

@@ -270,17 +270,13 @@ def test_model_results_identical_with_and_without_zero_fill(small, zero_fill):
     ptr, fe, fv = sg.flows_to_csr(small.flows)
     W = weights_of(fx, 'w_big')
     res = []
-    try:
-        for zf in (1, zero_fill):
-            L.scone_set_zero_fill(zf)
-            net = sg.SconeModel(cx, [16, 16, 16], micro_batch=32)
-            # poison the activation buffers so that a read of an unwritten row would show up
-            net.set_weights(W)
-            lp = net.forward(ptr, fe, fv, small.last_nodes)
-            buf = net.loss_grad(ptr, fe, fv, small.last_nodes, small.raw['targets_argmax'], np.ones(small.n_traj, np.float32))
-            res.append((lp, buf))
-    finally:
-        L.scone_set_zero_fill(1)
+    for zf in (1, zero_fill):
+        net = sg.SconeModel(cx, [16, 16, 16], micro_batch=32, zero_fill=bool(zf))
+        assert L.scone_model_get_zero_fill(net.handle) == zf
+        net.set_weights(W)
+        lp = net.forward(ptr, fe, fv, small.last_nodes)
+        buf = net.loss_grad(ptr, fe, fv, small.last_nodes, small.raw['targets_argmax'], np.ones(small.n_traj, np.float32))
+        res.append((lp, buf))
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
     assert np.abs(res[0][0] - fx['big_logprobs'][:, :, 0]).max() < 1e-5
 
