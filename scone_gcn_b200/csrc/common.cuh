@@ -51,16 +51,15 @@ struct ScopedProf {
 //   in_wl/in_tt   the previous call's output worklist (index in the scratch, unit width) describes occ_in -> no re-compaction
 //   skip_fill     the caller zero-fills the output tensor itself (e.g. on a side stream)
 // out_wl/out_tt are written back by the call.
-//   in_bm         quad bitmap of occ_in (bit (e*b + t)/4 set <=> one of the 4 flag bytes is set): compaction reads it instead
-//                 of the E*b flag bytes
-//   out_bm        quad bitmap the producer call (scone_flows_to_dense, scone_readout) should set next to the flags it writes
+//   in_bm         row bitmap of occ_in (bit e*b + t set <=> flag byte set): compaction reads it instead of the E*b flag bytes
+//   out_bm        row bitmap the producer call (scone_flows_to_dense, scone_readout) should set next to the flags it writes
 struct SconeLaunchHints {
     int in_wl = -1, in_tt = 0, out_wl = -1, out_tt = 0;
     bool skip_fill = false;
     const uint32_t* in_bm = nullptr;
     uint32_t* out_bm = nullptr;
 };
-static inline size_t scone_bitmap_words(size_t E, size_t b) { return (E * b / 4 + 31) / 32 + 1; }
+static inline size_t scone_bitmap_words(size_t E, size_t b) { return (E * b + 31) / 32 + 1; }
 extern thread_local SconeLaunchHints g_scone_hints;
 
 // Integer-valued shift operator in CSR form.  ent[p] = {column, float bits of the coefficient};
@@ -118,5 +117,8 @@ extern int g_scone_dense_kernel;
 bool scone_slab_supported(const scone_complex* cx, int cin, int cout);
 int scone_slab_forward(const scone_complex* cx, int act, int b, int cin, int cout, const float* Hin, const float* W0, const float* W1,
                        const float* W2, float* Hout, cudaStream_t st);
+int scone_slab_forward_rows(const scone_complex* cx, int act, int b, int cin, int cout, const float* Hin, const float* W0,
+                            const float* W1, const float* W2, float* Hout, const uint8_t* occ_in, const uint32_t* rows,
+                            const int* n_rows_dev, unsigned long long* row_counter, cudaStream_t st);
 int scone_adam_launch(float* W, float* m, float* v, const float* gradbuf, int64_t n, int32_t step, float lr,
                       float wd, void* stream);

@@ -630,15 +630,13 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(int* __restrict__ cou
 }
 
 // occ_out[e'][t] = 1 for every flagged row (e, t) of the input worklist and every e' in {e} + S0 row + S1 row.
-// quad bitmap: bit (e*b + t) / 4 is set when one of the 4 flag bytes of that aligned quad is set (b % 4 == 0).  Setting a bit
-// is idempotent (atomicOr), so the bitmap — like the flags — does not depend on the order of the writers.
-__device__ __forceinline__ void bitmap_set_quads(uint32_t* __restrict__ bm, size_t row0, unsigned m, int tt) {
-    for (int k = 0; k < tt; k += 4)
-        if ((m >> k) & 0xfu) {
-            const size_t q = (row0 + k) >> 2;
-            const uint32_t bit = 1u << (q & 31);
-            if (!(bm[q >> 5] & bit)) atomicOr(bm + (q >> 5), bit);
-        }
+// row bitmap: bit e*b + t mirrors the flag byte of row (e, t).  Setting bits is idempotent (atomicOr), so the bitmap — like
+// the flags — does not depend on the order of the writers.  A unit's tt <= 16 rows start at a multiple of tt (b % tt == 0),
+// so they sit in one 32-bit word.
+__device__ __forceinline__ void bitmap_set_rows(uint32_t* __restrict__ bm, size_t row0, unsigned m) {
+    const uint32_t bits = m << (row0 & 31);
+    uint32_t* w = bm + (row0 >> 5);
+    if ((*w & bits) != bits) atomicOr(w, bits);
 }
 
 template <int TT>
@@ -652,7 +650,7 @@ __global__ void __launch_bounds__(kThreads) scatter_support_kernel(const uint32_
         const int e = (int)(u / (uint32_t)nchunk), t0 = (int)(u - (uint32_t)e * (uint32_t)nchunk) * TT;
         const unsigned m = unit_row_mask<TT>(occ_in, e, t0, b);
         if (lane < TT && ((m >> lane) & 1u)) occ_out[(size_t)e * b + t0 + lane] = 1;
-        if (bm_out != nullptr && lane == 0) bitmap_set_quads(bm_out, (size_t)e * b + t0, m, TT);
+        if (bm_out != nullptr && lane == 0) bitmap_set_rows(bm_out, (size_t)e * b + t0, m);
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             const DevCsr S = s == 0 ? S0 : S1;
@@ -663,21 +661,24 @@ __global__ void __launch_bounds__(kThreads) scatter_support_kernel(const uint32_
 #pragma unroll
                 for (int k = 0; k < TT; ++k)
                     if ((m >> k) & 1u) dst[k] = 1;
-                if (bm_out != nullptr) bitmap_set_quads(bm_out, row0, m, TT);
+                if (bm_out != nullptr) bitmap_set_rows(bm_out, row0, m);
             }
         }
     }
 }
 
-// Worklist of the flagged units from the quad bitmap, ascending unit id, in ONE launch: CTA c owns a contiguous slice of
-// bitmap words; it counts, publishes its total (ticket = ready bit | count), sums the tickets of the CTAs before it
-// (decoupled look-back; lower block indices are dispatched first), then writes its ids.  A unit of TT trajectories is
-// R = TT/4 adjacent quads (b % TT == 0).  tickets[] must be zero at launch.
-template <int R>
+// Worklist of the flagged units (or rows, G = 1) from the row bitmap, ascending id, in ONE launch: CTA c owns a contiguous
+// slice of bitmap words; it counts, publishes its total (ticket = ready bit | count), sums the tickets of the CTAs before it
+// (decoupled look-back; lower block indices are dispatched first), then writes its ids.  A unit is G = TT adjacent rows
+// (b % TT == 0, TT in {4, 8, 16}).  tickets[] must be zero at launch.
+template <int G>
 __device__ __forceinline__ uint32_t collapse_quads(uint32_t w) {
-    if (R == 1) return w;
-    if (R == 2) return (w | (w >> 1)) & 0x55555555u;
-    return (w | (w >> 1) | (w >> 2) | (w >> 3)) & 0x11111111u;
+    if (G == 1) return w;
+    w = (w | (w >> 1) | (w >> 2) | (w >> 3)) & 0x11111111u;
+    if (G == 4) return w;
+    w = (w | (w >> 4)) & 0x01010101u;
+    if (G == 8) return w;
+    return (w | (w >> 8)) & 0x00010001u;
 }
 
 template <int R>
@@ -1171,7 +1172,7 @@ __global__ void flows_to_dense_kernel(const int32_t* __restrict__ traj_ptr, cons
             const size_t row = (size_t)rank[e] * b + t;
             X[row] = flow_val[p];
             if (occX != nullptr) occX[row] = 1;
-            if (bm != nullptr) atomicOr(bm + (row >> 7), 1u << ((row >> 2) & 31));
+            if (bm != nullptr) atomicOr(bm + (row >> 5), 1u << (row & 31));
         }
     }
 }
@@ -1244,7 +1245,7 @@ __global__ void __launch_bounds__(128) readout_kernel(const float* __restrict__ 
             if (occ_GL != nullptr && lane == 0) {
                 const size_t row = (size_t)inc_ent[p].x * b + t;
                 occ_GL[row] = 1;
-                if (bm_GL != nullptr) atomicOr(bm_GL + (row >> 7), 1u << ((row >> 2) & 31));
+                if (bm_GL != nullptr) atomicOr(bm_GL + (row >> 5), 1u << (row & 31));
             }
         }
     }
@@ -1334,13 +1335,13 @@ struct UnitScratch {
     uint32_t* wl[2];
     int* n[2];
     int* counts;
-    uint32_t* bm;                       // quad bitmap of the flags a call produces (scatter -> compaction)
+    uint32_t* bm;                       // row bitmap of the flags a call produces (scatter -> compaction)
     unsigned long long* tickets;        // look-back tickets of compact_bitmap_kernel
     uint8_t* occ_tmp;
 };
 constexpr int kTicketSlots = 1024;
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-size_t max_units(const scone_complex* cx, int b) { return (size_t)cx->E * (size_t)((b + 1) / 2); }   // TT >= 2
+size_t max_units(const scone_complex* cx, int b) { return (size_t)cx->E * (size_t)b; }   // a worklist may also hold row ids
 UnitScratch carve_scratch(const scone_complex* cx, int b, uint8_t* base) {
     UnitScratch sc;
     const size_t nu = max_units(cx, b);
@@ -1376,8 +1377,8 @@ bool bitmap_ok(int tt, int b) { return (tt == 4 || tt == 8 || tt == 16) && b % t
 template <int TT>
 int compact_bitmap(const scone_complex* cx, int b, const uint32_t* bm, uint32_t* list, int* n_ptr, unsigned long long* tickets,
                    cudaStream_t st) {
-    constexpr int R = TT >= 4 ? TT / 4 : 1;
-    const long long n_words = ((long long)cx->E * b / 4 + 31) / 32;
+    constexpr int R = TT;                // TT = 1: row list
+    const long long n_words = ((long long)cx->E * b + 31) / 32;
     int grid = cx->num_sms < kTicketSlots ? cx->num_sms : kTicketSlots;
     if (n_words < grid) grid = n_words > 0 ? (int)n_words : 1;
     SCONE_CUDA(cudaMemsetAsync(tickets, 0, (size_t)grid * 8, st));
@@ -1459,6 +1460,14 @@ int launch_fwd(const scone_complex* cx, int b, const float* Hin, const float* W0
     int wo = 0;
     if (prepare_units<TT>(cx, b, occ_in, occ_out, sc, st, &wo)) return 1;
     if (zero_fill_here() && scone_zero_fill(cx, Hout, (size_t)cx->E * b * COUT * sizeof(float), st)) return 1;
+    if (scone_slab_supported(cx, CIN, COUT) && bitmap_ok(TT, b)) {
+        // candidate ROWS of the output (row bitmap of occ_out, still in the scratch) -> compacted list -> row-list kernel.  The
+        // list goes where the consumed input worklist was; the output unit worklist (hint for the next call) stays intact.
+        const int wi = 1 - wo;
+        if (compact_bitmap<1>(cx, b, sc.bm, sc.wl[wi], sc.n[wi], sc.tickets, st)) return 1;
+        return scone_slab_forward_rows(cx, ACT, b, CIN, COUT, Hin, W0, W1, W2, Hout, occ_in, sc.wl[wi], sc.n[wi],
+                                       scone_prof_row_counter(SCONE_K_LAYER_FWD), st);
+    }
     const size_t smem = ((size_t)KD * COUT + (size_t)kWarps * TT * LDT) * sizeof(float);
     auto kern = layer_fwd_units_kernel<CIN, COUT, ACT>;
     static int occ = 0;

@@ -395,7 +395,171 @@ int dispatch_fwd_act(const scone_complex* cx, int act, int ts, int b, const floa
     return 2;
 }
 
+// =================================================================================================================
+// Row-list forward (occupancy flags given): the same gather -> fragments -> 3xTF32 product pipeline on a COMPACTED list of
+// candidate rows.  rows[] holds the ids e*b + t of the rows of Hout that can be non-zero (ascending: the output's row
+// bitmap compacted by compact_bitmap_kernel); a warp takes 16 consecutive list entries.  Lane group q (the LPR = C/4 lanes
+// that cover one row) walks the merged operator row of ITS row; a neighbour row is loaded only if its flag byte in occ_in
+// is set (unflagged rows are exact zeros and — with zero-fill off — may never have been written).  All 16 rows' k-th
+// neighbours are in flight together.  Each row's result is independent of the other rows in its slab and uses the same
+// summation order and mma sequence as the dense slab kernel: bit-identical to it.
+// =================================================================================================================
+template <int CIN, int COUT, int ACT>
+__global__ void __launch_bounds__(kSlabThreads, 1) layer_fwd_rows_kernel(const float* __restrict__ Hin, float* __restrict__ Hout,
+                                                                        const float* __restrict__ W0, const float* __restrict__ W1,
+                                                                        const float* __restrict__ W2, const int32_t* __restrict__ mptr,
+                                                                        const int2* __restrict__ ment, const uint8_t* __restrict__ occ_in,
+                                                                        const uint32_t* __restrict__ rows, const int* __restrict__ n_ptr,
+                                                                        int b, unsigned long long* __restrict__ row_counter) {
+    using G = SlabGeom<CIN, 16>;
+    constexpr int NT = COUT / 8, NL = G::NL, Q = G::Q, LPR = CIN / 4;      // Q rows per warp-wide load, LPR lanes per row
+    extern __shared__ __align__(16) uint4 Bf[];
+    stage_weight_fragments<CIN, COUT, 16, false>(Bf, W0, W1, W2);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tig = lane & 3, g = lane >> 2;
+    const int gq = lane / LPR, cq = lane % LPR;
+    const unsigned rowbytes = (unsigned)b * CIN * 4u;
+    const char* Hb = reinterpret_cast<const char*>(Hin);
+    const int n = *n_ptr;
+    const int n_slabs = (n + 15) / 16;
+    const int n_tiles = (n_slabs + kSlabWarps - 1) / kSlabWarps;
+    const int per = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const int lo = blockIdx.x * per, hi = min(n_tiles, lo + per);
+    if (row_counter != nullptr && threadIdx.x == 0 && lo < hi)
+        atomicAdd(row_counter, (unsigned long long)(min(n, hi * kSlabWarps * 16) - lo * kSlabWarps * 16));
+    for (int tile = lo; tile < hi; ++tile) {
+        const int slab = tile * kSlabWarps + warp;
+        if (slab >= n_slabs) continue;
+        // this lane's row in each load slot
+        uint32_t rid[NL];
+        int len[NL], p0[NL], tq[NL];
+        const char* P[NL];
+        bool own[NL];
+        int maxlen = 0;
+#pragma unroll
+        for (int i = 0; i < NL; ++i) {
+            const int li = slab * 16 + i * Q + gq;
+            const bool valid = li < n;
+            rid[i] = valid ? __ldg(rows + li) : 0u;
+            const int e = (int)(rid[i] / (unsigned)b);
+            tq[i] = (int)(rid[i] - (unsigned)e * (unsigned)b);
+            const int cpos = (CIN == 32 && i >= 2) ? (cq ^ 4) : cq;
+            P[i] = Hb + (size_t)((unsigned)(tq[i] * CIN + 4 * cpos) * 4u);
+            p0[i] = valid ? __ldg(mptr + e) : 0;
+            len[i] = valid ? __ldg(mptr + e + 1) - p0[i] : 0;
+            own[i] = valid && __ldg(occ_in + rid[i]) != 0;
+            maxlen = max(maxlen, len[i]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+        u64 acc[3][NL][2];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int i = 0; i < NL; ++i) acc[k][i][0] = acc[k][i][1] = 0ull;
+#pragma unroll
+        for (int i = 0; i < NL; ++i)
+            if (own[i]) ldg128(reinterpret_cast<const float*>(P[i] + (size_t)(rid[i] / (unsigned)b) * rowbytes), acc[0][i][0], acc[0][i][1]);
+        for (int k = 0; k < maxlen; ++k) {
+            int2 ent[NL];
+            bool on[NL];
+#pragma unroll
+            for (int i = 0; i < NL; ++i) {
+                on[i] = k < len[i];
+                ent[i] = on[i] ? __ldg(ment + p0[i] + k) : make_int2(0, 0);
+            }
+#pragma unroll
+            for (int i = 0; i < NL; ++i) on[i] = on[i] && __ldg(occ_in + (size_t)(unsigned)ent[i].x * b + tq[i]) != 0;
+            u64 v[NL][2];
+#pragma unroll
+            for (int i = 0; i < NL; ++i) {
+                v[i][0] = v[i][1] = 0ull;
+                if (on[i]) ldg128(reinterpret_cast<const float*>(P[i] + (size_t)(unsigned)ent[i].x * rowbytes), v[i][0], v[i][1]);
+            }
+#pragma unroll
+            for (int i = 0; i < NL; ++i) {
+                const float c0 = (float)(short)(ent[i].y & 0xffff), c1 = (float)(ent[i].y >> 16);
+                const u64 q0 = bcast2(c0), q1 = bcast2(c1);
+                ffma2(acc[1][i][0], q0, v[i][0]);
+                ffma2(acc[1][i][1], q0, v[i][1]);
+                ffma2(acc[2][i][0], q1, v[i][0]);
+                ffma2(acc[2][i][1], q1, v[i][1]);
+            }
+        }
+        float d[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) d[nt][0] = d[nt][1] = d[nt][2] = d[nt][3] = 0.f;
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+            float fr[G::KS][4];
+            slab_fragments<CIN, 16>(acc[term], fr);
+            slab_mma_term<G::KS, NT>(d, fr, Bf + term * G::KS * NT * 32);
+        }
+        slab_activate<ACT, NT>(d);
+        // fragment row r (0: row g, 1: row g + 8) is this lane's own row of slot 2*(g&1) + r (width 32) / slot r (width 16)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            uint32_t orow;
+            int oli;
+            if (CIN == 32) {
+                const bool odd = g & 1;
+                orow = odd ? rid[2 + r] : rid[r];
+                oli = slab * 16 + (odd ? 2 + r : r) * Q + gq;
+            } else {
+                orow = rid[r];
+                oli = slab * 16 + r * Q + gq;
+            }
+            if (oli < n) {
+                float* dst = Hout + (size_t)orow * COUT + 2 * tig;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) *reinterpret_cast<float2*>(dst + nt * 8) = make_float2(d[nt][2 * r], d[nt][2 * r + 1]);
+            }
+        }
+    }
+}
+
+template <int CIN, int COUT, int ACT>
+int launch_fwd_rows(const scone_complex* cx, int b, const float* Hin, const float* W0, const float* W1, const float* W2, float* Hout,
+                    const uint8_t* occ_in, const uint32_t* rows, const int* n_ptr, unsigned long long* row_counter, cudaStream_t st) {
+    using G = SlabGeom<CIN, 16>;
+    constexpr int NT = COUT / 8;
+    const size_t smem = (size_t)3 * G::KS * NT * 32 * sizeof(uint4);
+    auto kern = layer_fwd_rows_kernel<CIN, COUT, ACT>;
+    static bool configured = false;
+    if (!configured) {
+        SCONE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    kern<<<cx->num_sms, kSlabThreads, smem, st>>>(Hin, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, occ_in, rows, n_ptr, b, row_counter);
+    SCONE_LAUNCHED();
+    return 0;
+}
+
+template <int CIN, int COUT>
+int dispatch_rows_act(const scone_complex* cx, int act, int b, const float* Hin, const float* W0, const float* W1, const float* W2,
+                      float* Hout, const uint8_t* occ_in, const uint32_t* rows, const int* n_ptr, unsigned long long* rc, cudaStream_t st) {
+    switch (act) {
+        case SCONE_ACT_TANH: return launch_fwd_rows<CIN, COUT, SCONE_ACT_TANH>(cx, b, Hin, W0, W1, W2, Hout, occ_in, rows, n_ptr, rc, st);
+        case SCONE_ACT_LEAKY_RELU: return launch_fwd_rows<CIN, COUT, SCONE_ACT_LEAKY_RELU>(cx, b, Hin, W0, W1, W2, Hout, occ_in, rows, n_ptr, rc, st);
+        case SCONE_ACT_RELU: return launch_fwd_rows<CIN, COUT, SCONE_ACT_RELU>(cx, b, Hin, W0, W1, W2, Hout, occ_in, rows, n_ptr, rc, st);
+    }
+    scone_set_error("unknown activation %d", act);
+    return 2;
+}
+
 }  // namespace
+
+// Flagged fused layer forward over a compacted row list (see layer_fwd_rows_kernel); the caller checked scone_slab_supported.
+int scone_slab_forward_rows(const scone_complex* cx, int act, int b, int cin, int cout, const float* Hin, const float* W0,
+                            const float* W1, const float* W2, float* Hout, const uint8_t* occ_in, const uint32_t* rows,
+                            const int* n_rows_dev, unsigned long long* row_counter, cudaStream_t st) {
+    if (cin == 16 && cout == 16) return dispatch_rows_act<16, 16>(cx, act, b, Hin, W0, W1, W2, Hout, occ_in, rows, n_rows_dev, row_counter, st);
+    if (cin == 16 && cout == 32) return dispatch_rows_act<16, 32>(cx, act, b, Hin, W0, W1, W2, Hout, occ_in, rows, n_rows_dev, row_counter, st);
+    if (cin == 32 && cout == 16) return dispatch_rows_act<32, 16>(cx, act, b, Hin, W0, W1, W2, Hout, occ_in, rows, n_rows_dev, row_counter, st);
+    if (cin == 32 && cout == 32) return dispatch_rows_act<32, 32>(cx, act, b, Hin, W0, W1, W2, Hout, occ_in, rows, n_rows_dev, row_counter, st);
+    scone_set_error("scone_slab_forward_rows: unsupported widths %d -> %d", cin, cout);
+    return 2;
+}
 
 int g_scone_dense_kernel = 1;   // 0: fp32 SIMT tile kernels; 1: slab kernels, 16 trajectories x 1 edge per slab; 2: slab, 8 x 2
 
