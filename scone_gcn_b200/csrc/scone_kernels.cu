@@ -685,30 +685,26 @@ template <int R>
 __global__ void __launch_bounds__(kThreads) compact_bitmap_kernel(const uint32_t* __restrict__ bm, long long n_words,
                                                                  uint32_t* __restrict__ list, int* __restrict__ n_out,
                                                                  unsigned long long* __restrict__ tickets) {
-    __shared__ int s_scan[kThreads];
+    __shared__ int s_warp[kWarps];
     __shared__ long long s_prefix;
-    const long long per_cta = (n_words + gridDim.x - 1) / gridDim.x;
+    __shared__ int s_total;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long per_cta = ((n_words + gridDim.x - 1) / gridDim.x + kThreads - 1) / kThreads * kThreads;   // whole chunks
     const long long lo = (long long)blockIdx.x * per_cta, hi = lo + per_cta < n_words ? lo + per_cta : n_words;
-    const long long per_thr = (per_cta + kThreads - 1) / kThreads;
-    long long w0 = lo + (long long)threadIdx.x * per_thr, w1 = w0 + per_thr;
-    if (w0 > hi) w0 = hi;
-    if (w1 > hi) w1 = hi;
+    // pass 1: count (coalesced, strided over the slice)
     int cnt = 0;
-    for (long long w = w0; w < w1; ++w) cnt += __popc(collapse_quads<R>(__ldg(bm + w)));
-    s_scan[threadIdx.x] = cnt;
+    for (long long w = lo + threadIdx.x; w < hi; w += kThreads) cnt += __popc(collapse_quads<R>(__ldg(bm + w)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) s_warp[warp] = cnt;
+    if (threadIdx.x == 0) s_prefix = 0;
     __syncthreads();
-    for (int o = 1; o < kThreads; o <<= 1) {             // inclusive scan
-        const int v = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0;
-        __syncthreads();
-        s_scan[threadIdx.x] += v;
-        __syncthreads();
-    }
-    const int total = s_scan[kThreads - 1];
     if (threadIdx.x == 0) {
+        int total = 0;
+        for (int k = 0; k < kWarps; ++k) total += s_warp[k];
+        s_total = total;
         atomicExch(tickets + blockIdx.x, (1ull << 63) | (unsigned long long)(unsigned)total);
-        s_prefix = 0;
     }
-    __syncthreads();
     long long part = 0;
     for (int c = threadIdx.x; c < (int)blockIdx.x; c += kThreads) {
         unsigned long long t;
@@ -717,16 +713,37 @@ __global__ void __launch_bounds__(kThreads) compact_bitmap_kernel(const uint32_t
     }
     if (part) atomicAdd((unsigned long long*)&s_prefix, (unsigned long long)part);
     __syncthreads();
-    long long off = s_prefix + s_scan[threadIdx.x] - cnt;
-    for (long long w = w0; w < w1; ++w) {
-        uint32_t c = collapse_quads<R>(__ldg(bm + w));
+    long long base = s_prefix;
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *n_out = (int)(base + s_total);
+    // pass 2: chunks of kThreads words; block-exclusive scan of the per-word counts, ids written in ascending order
+    for (long long w0 = lo; w0 < hi; w0 += kThreads) {
+        const long long w = w0 + threadIdx.x;
+        uint32_t c = w < hi ? collapse_quads<R>(__ldg(bm + w)) : 0u;
+        const int n = __popc(c);
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        __syncthreads();                                  // s_warp of the previous chunk fully consumed
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int woff = 0, ctot = 0;
+#pragma unroll
+        for (int k = 0; k < kWarps; ++k) {
+            const int v = s_warp[k];
+            if (k < warp) woff += v;
+            ctot += v;
+        }
+        long long off = base + woff + incl - n;
         while (c) {
             const int pbit = __ffs(c) - 1;
             c &= c - 1;
             list[off++] = (uint32_t)((w * 32 + pbit) / R);
         }
+        base += ctot;
     }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *n_out = (int)(s_prefix + total);
 }
 
 // (own row, S0 row, S1 row) of unit (e, t0..t0+TT) into Ts rows [slot0 + j]; returns the ballot of non-zero lanes.
@@ -1178,11 +1195,15 @@ __global__ void flows_to_dense_kernel(const int32_t* __restrict__ traj_ptr, cons
 }
 
 // =================================================================================================================
-// Readout: one warp per trajectory.
+// Readout: one CTA per trajectory.
 // =================================================================================================================
 constexpr int kReadoutMaxD = 128, kReadoutMaxCper = 4;   // D <= 128, C <= 128
 
-__global__ void __launch_bounds__(128) readout_kernel(const float* __restrict__ HL, const float* __restrict__ wout,
+// One CTA (4 warps) per trajectory; warp w owns the neighbour slots j = w, w + 4, ...  A row of GL receives at most two
+// contributions (an edge has two end nodes), added with atomicAdd onto a zeroed row: a + b == b + a, so the result does not
+// depend on the order (deterministic without serialising the warps).
+constexpr int kReadoutWarps = 4;
+__global__ void __launch_bounds__(32 * kReadoutWarps) readout_kernel(const float* __restrict__ HL, const float* __restrict__ wout,
                                                      const int32_t* __restrict__ last_nodes, const int32_t* __restrict__ nbrhoods,
                                                      const int32_t* __restrict__ inc_ptr, const int2* __restrict__ inc_ent,
                                                      float* __restrict__ logprobs, const int32_t* __restrict__ target_idx,
@@ -1190,18 +1211,18 @@ __global__ void __launch_bounds__(128) readout_kernel(const float* __restrict__ 
                                                      float* __restrict__ partial /* [b][C+2] */, const uint8_t* __restrict__ occ_HL,
                                                      uint8_t* __restrict__ occ_GL, uint32_t* __restrict__ bm_GL, int act, int N, int D,
                                                      int b, int C) {
-    __shared__ float s_logit[4][kReadoutMaxD];
+    __shared__ float logit[kReadoutMaxD];
+    __shared__ float s_dw[kReadoutWarps][32 * kReadoutMaxCper];
+    __shared__ float s_lse;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    const int t = blockIdx.x * 4 + warp;
-    if (t >= b) return;
-    float* logit = s_logit[warp];
+    const int t = blockIdx.x;
     const int last = last_nodes[t];
     const bool last_ok = last >= 0 && last < N;
     float w[kReadoutMaxCper];
 #pragma unroll
     for (int q = 0; q < kReadoutMaxCper; ++q) w[q] = (lane + 32 * q < C) ? wout[lane + 32 * q] : 0.f;
 
-    for (int j = 0; j < D; ++j) {
+    for (int j = warp; j < D; j += kReadoutWarps) {
         const int nbr = last_ok ? nbrhoods[(size_t)last * D + j] : -1;
         float l = 0.f;                                     // padded slot: row -1 of B1_jax = zeros -> logit 0
         if (nbr >= 0) {
@@ -1221,39 +1242,40 @@ __global__ void __launch_bounds__(128) readout_kernel(const float* __restrict__ 
         }
         if (lane == 0) logit[j] = l;
     }
-    __syncwarp();
-    float mx = -CUDART_INF_F;
-    for (int j = lane; j < D; j += 32) mx = fmaxf(mx, logit[j]);
-    mx = warp_max(mx);
-    float se = 0.f;
-    for (int j = lane; j < D; j += 32) se += expf(logit[j] - mx);
-    se = warp_sum(se);
-    const float lse = mx + logf(se);
-    for (int j = lane; j < D; j += 32) logprobs[(size_t)t * D + j] = logit[j] - lse;
+    __syncthreads();
+    if (warp == 0) {
+        float mx = -CUDART_INF_F;
+        for (int j = lane; j < D; j += 32) mx = fmaxf(mx, logit[j]);
+        mx = warp_max(mx);
+        float se = 0.f;
+        for (int j = lane; j < D; j += 32) se += expf(logit[j] - mx);
+        se = warp_sum(se);
+        const float lse_ = mx + logf(se);
+        for (int j = lane; j < D; j += 32) logprobs[(size_t)t * D + j] = logit[j] - lse_;
+        if (lane == 0) s_lse = lse_;
+    }
     if (GL == nullptr) return;
-
-    // gradient: rows of GL touched by this trajectory are zeroed first (an edge can be incident to two neighbours),
-    // then accumulated in ascending (j, p) order by the same lane: deterministic, no atomics.
-    for (int j = 0; j < D; ++j) {
+    // gradient: the rows of GL this trajectory touches are zeroed and flagged first ...
+    for (int j = warp; j < D; j += kReadoutWarps) {
         const int nbr = last_ok ? nbrhoods[(size_t)last * D + j] : -1;
         if (nbr < 0) continue;
         for (int p = inc_ptr[nbr]; p < inc_ptr[nbr + 1]; ++p) {
-            const size_t base = ((size_t)inc_ent[p].x * b + t) * C;
+            const size_t row = (size_t)inc_ent[p].x * b + t;
 #pragma unroll
             for (int q = 0; q < kReadoutMaxCper; ++q)
-                if (lane + 32 * q < C) GL[base + lane + 32 * q] = 0.f;
+                if (lane + 32 * q < C) GL[row * C + lane + 32 * q] = 0.f;
             if (occ_GL != nullptr && lane == 0) {
-                const size_t row = (size_t)inc_ent[p].x * b + t;
                 occ_GL[row] = 1;
                 if (bm_GL != nullptr) atomicOr(bm_GL + (row >> 5), 1u << (row & 31));
             }
         }
     }
-    __syncwarp();
+    __syncthreads();                                       // ... (also publishes s_lse) then accumulated
+    const float lse = s_lse;
     const float mk = mask[t];
     const int y = target_idx[t];
     float dwl[kReadoutMaxCper] = {0.f, 0.f, 0.f, 0.f};
-    for (int j = 0; j < D; ++j) {
+    for (int j = warp; j < D; j += kReadoutWarps) {
         const int nbr = last_ok ? nbrhoods[(size_t)last * D + j] : -1;
         if (nbr < 0) continue;
         const float dl = mk * scale * (expf(logit[j] - lse) - (j == y ? 1.f : 0.f));
@@ -1267,17 +1289,26 @@ __global__ void __launch_bounds__(128) readout_kernel(const float* __restrict__ 
                 if (lane + 32 * q < C) {
                     const float h = hz ? 0.f : HL[base + lane + 32 * q];
                     dwl[q] = fmaf(sdl, h, dwl[q]);                                // z[j][c] * dlogit[j]
-                    GL[base + lane + 32 * q] += sdl * w[q] * dact_rt(act, h);      // same lane, sequential: no race
+                    atomicAdd(GL + base + lane + 32 * q, sdl * w[q] * dact_rt(act, h));
                 }
         }
     }
-    float* pt = partial + (size_t)t * (C + 2);
 #pragma unroll
-    for (int q = 0; q < kReadoutMaxCper; ++q)
-        if (lane + 32 * q < C) pt[lane + 32 * q] = dwl[q];
-    if (lane == 0) {
-        pt[C] = (y >= 0 && y < D) ? -mk * (logit[y] - lse) : 0.f;
-        pt[C + 1] = mk;
+    for (int q = 0; q < kReadoutMaxCper; ++q) s_dw[warp][lane + 32 * q] = dwl[q];
+    __syncthreads();
+    if (warp == 0) {
+        float* pt = partial + (size_t)t * (C + 2);
+#pragma unroll
+        for (int q = 0; q < kReadoutMaxCper; ++q)
+            if (lane + 32 * q < C) {
+                float sacc = s_dw[0][lane + 32 * q];
+                for (int k = 1; k < kReadoutWarps; ++k) sacc += s_dw[k][lane + 32 * q];
+                pt[lane + 32 * q] = sacc;
+            }
+        if (lane == 0) {
+            pt[C] = (y >= 0 && y < D) ? -mk * (logit[y] - lse) : 0.f;
+            pt[C + 1] = mk;
+        }
     }
 }
 
@@ -1379,8 +1410,9 @@ int compact_bitmap(const scone_complex* cx, int b, const uint32_t* bm, uint32_t*
                    cudaStream_t st) {
     constexpr int R = TT;                // TT = 1: row list
     const long long n_words = ((long long)cx->E * b + 31) / 32;
-    int grid = cx->num_sms < kTicketSlots ? cx->num_sms : kTicketSlots;
-    if (n_words < grid) grid = n_words > 0 ? (int)n_words : 1;
+    int grid = cx->num_sms * 4 < kTicketSlots ? cx->num_sms * 4 : kTicketSlots;
+    if (n_words < (long long)grid * kThreads) grid = (int)((n_words + kThreads - 1) / kThreads);
+    if (grid < 1) grid = 1;
     SCONE_CUDA(cudaMemsetAsync(tickets, 0, (size_t)grid * 8, st));
     compact_bitmap_kernel<R><<<grid, kThreads, 0, st>>>(bm, n_words, list, n_ptr, tickets);
     SCONE_LAUNCHED();
@@ -1795,7 +1827,7 @@ int scone_readout_ws(const scone_complex* cx, int32_t act, int32_t b, int32_t C,
     uint32_t* bm = (GL && occ_GL && b % 4 == 0) ? g_scone_hints.out_bm : nullptr;
     g_scone_hints.out_bm = nullptr;
     if (bm) SCONE_CUDA(cudaMemsetAsync(bm, 0, scone_bitmap_words(cx->E, b) * 4, st));
-    readout_kernel<<<(b + 3) / 4, 128, 0, st>>>(HL, wout, last_nodes, cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, logprobs,
+    readout_kernel<<<b, 32 * kReadoutWarps, 0, st>>>(HL, wout, last_nodes, cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, logprobs,
                                               target_idx, mask, scale, GL, (float*)workspace, occ_HL, GL ? occ_GL : nullptr, bm, act,
                                               cx->N, cx->D, b, C);
     SCONE_LAUNCHED();
