@@ -59,7 +59,7 @@ struct SconeLaunchHints {
     const uint32_t* in_bm = nullptr;
     uint32_t* out_bm = nullptr;
 };
-static inline size_t scone_bitmap_words(size_t E, size_t b) { return (E * b + 31) / 32 + 1; }
+static inline size_t scone_bitmap_words(size_t E, size_t b) { return ((E * b + 31) / 32 + 7) / 4 * 4; }   // padded to whole uint4
 extern thread_local SconeLaunchHints g_scone_hints;
 
 // Integer-valued shift operator in CSR form.  ent[p] = {column, float bits of the coefficient};

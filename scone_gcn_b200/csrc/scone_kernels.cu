@@ -685,15 +685,28 @@ template <int R>
 __global__ void __launch_bounds__(kThreads) compact_bitmap_kernel(const uint32_t* __restrict__ bm, long long n_words,
                                                                  uint32_t* __restrict__ list, int* __restrict__ n_out,
                                                                  unsigned long long* __restrict__ tickets) {
+    constexpr int kChunk = 4 * kThreads;                  // words per chunk: one 128-bit load per thread
     __shared__ int s_warp[kWarps];
     __shared__ long long s_prefix;
     __shared__ int s_total;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long per_cta = ((n_words + gridDim.x - 1) / gridDim.x + kThreads - 1) / kThreads * kThreads;   // whole chunks
+    const long long per_cta = ((n_words + gridDim.x - 1) / gridDim.x + kChunk - 1) / kChunk * kChunk;   // whole chunks
     const long long lo = (long long)blockIdx.x * per_cta, hi = lo + per_cta < n_words ? lo + per_cta : n_words;
-    // pass 1: count (coalesced, strided over the slice)
+    auto load4 = [&](long long w, uint32_t (&c)[4]) {     // words w .. w+3 (w % 4 == 0), zero beyond hi; the bitmap is padded
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (w < hi) v = __ldg(reinterpret_cast<const uint4*>(bm + w));
+        c[0] = collapse_quads<R>(v.x);
+        c[1] = w + 1 < hi ? collapse_quads<R>(v.y) : 0u;
+        c[2] = w + 2 < hi ? collapse_quads<R>(v.z) : 0u;
+        c[3] = w + 3 < hi ? collapse_quads<R>(v.w) : 0u;
+    };
+    // pass 1: count
     int cnt = 0;
-    for (long long w = lo + threadIdx.x; w < hi; w += kThreads) cnt += __popc(collapse_quads<R>(__ldg(bm + w)));
+    for (long long w = lo + 4 * threadIdx.x; w < hi; w += kChunk) {
+        uint32_t c[4];
+        load4(w, c);
+        cnt += __popc(c[0]) + __popc(c[1]) + __popc(c[2]) + __popc(c[3]);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (lane == 0) s_warp[warp] = cnt;
@@ -714,12 +727,15 @@ __global__ void __launch_bounds__(kThreads) compact_bitmap_kernel(const uint32_t
     if (part) atomicAdd((unsigned long long*)&s_prefix, (unsigned long long)part);
     __syncthreads();
     long long base = s_prefix;
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *n_out = (int)(base + s_total);
-    // pass 2: chunks of kThreads words; block-exclusive scan of the per-word counts, ids written in ascending order
-    for (long long w0 = lo; w0 < hi; w0 += kThreads) {
-        const long long w = w0 + threadIdx.x;
-        uint32_t c = w < hi ? collapse_quads<R>(__ldg(bm + w)) : 0u;
-        const int n = __popc(c);
+    const int total = s_total;
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *n_out = (int)(base + total);
+    if (total == 0) return;                               // (uniform) nothing flagged in this slice
+    // pass 2: block-exclusive scan of the per-thread counts of a chunk, ids written in ascending order
+    for (long long w0 = lo; w0 < hi; w0 += kChunk) {
+        const long long w = w0 + 4 * threadIdx.x;
+        uint32_t c[4];
+        load4(w, c);
+        const int n = __popc(c[0]) + __popc(c[1]) + __popc(c[2]) + __popc(c[3]);
         int incl = n;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -737,10 +753,14 @@ __global__ void __launch_bounds__(kThreads) compact_bitmap_kernel(const uint32_t
             ctot += v;
         }
         long long off = base + woff + incl - n;
-        while (c) {
-            const int pbit = __ffs(c) - 1;
-            c &= c - 1;
-            list[off++] = (uint32_t)((w * 32 + pbit) / R);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t cc = c[q];
+            while (cc) {
+                const int pbit = __ffs(cc) - 1;
+                cc &= cc - 1;
+                list[off++] = (uint32_t)(((w + q) * 32 + pbit) / R);
+            }
         }
         base += ctot;
     }
@@ -1411,7 +1431,7 @@ int compact_bitmap(const scone_complex* cx, int b, const uint32_t* bm, uint32_t*
     constexpr int R = TT;                // TT = 1: row list
     const long long n_words = ((long long)cx->E * b + 31) / 32;
     int grid = cx->num_sms * 4 < kTicketSlots ? cx->num_sms * 4 : kTicketSlots;
-    if (n_words < (long long)grid * kThreads) grid = (int)((n_words + kThreads - 1) / kThreads);
+    if (n_words < (long long)grid * 4 * kThreads) grid = (int)((n_words + 4 * kThreads - 1) / (4 * kThreads));
     if (grid < 1) grid = 1;
     SCONE_CUDA(cudaMemsetAsync(tickets, 0, (size_t)grid * 8, st));
     compact_bitmap_kernel<R><<<grid, kThreads, 0, st>>>(bm, n_words, list, n_ptr, tickets);
