@@ -146,6 +146,11 @@ int64_t scone_model_num_params(const scone_model* m);
  * [E][b][C] arrays, the dense-streaming formulation).  Results are bit-identical either way. */
 int scone_model_set_zero_fill(scone_model* m, int32_t on);
 int scone_model_get_zero_fill(const scone_model* m);
+/* Model-level pipeline: 1 (default when every hidden width is 16 or 32) = row lists: each tensor carries a row bitmap, producers
+ * mark the candidate rows of the next tensor, per layer one bitmap compaction + one row-list kernel (tensor-core product);
+ * 0 = unit kernels over byte flags (every width; fp32 SIMT).  zero_fill = 1 always uses 0.  Same results within fp32 rounding. */
+int scone_model_set_pipeline(scone_model* m, int32_t which);
+int scone_model_get_pipeline(const scone_model* m);
 int scone_model_set_weights(scone_model* m, const float* weights_host);     /* also resets Adam state */
 int scone_model_get_weights(const scone_model* m, float* weights_host);
 float* scone_model_weights_dev(scone_model* m);                              /* flat device weights      */

@@ -64,6 +64,8 @@ SIGNATURES = {
     'scone_model_num_params': (_i64, [_vp]),
     'scone_model_set_zero_fill': (C.c_int, [_vp, _i32]),
     'scone_model_get_zero_fill': (C.c_int, [_vp]),
+    'scone_model_set_pipeline': (C.c_int, [_vp, _i32]),
+    'scone_model_get_pipeline': (C.c_int, [_vp]),
     'scone_model_set_weights': (C.c_int, [_vp, _vp]),
     'scone_model_get_weights': (C.c_int, [_vp, _vp]),
     'scone_model_weights_dev': (_vp, [_vp]),

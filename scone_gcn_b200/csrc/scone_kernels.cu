@@ -633,6 +633,7 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(int* __restrict__ cou
 // row bitmap: bit e*b + t mirrors the flag byte of row (e, t).  Setting bits is idempotent (atomicOr), so the bitmap — like
 // the flags — does not depend on the order of the writers.  A unit's tt <= 16 rows start at a multiple of tt (b % tt == 0),
 // so they sit in one 32-bit word.
+__device__ __forceinline__ bool bitmap_test_row(const uint32_t* __restrict__ bm, size_t row) { return (bm[row >> 5] >> (row & 31)) & 1u; }
 __device__ __forceinline__ void bitmap_set_rows(uint32_t* __restrict__ bm, size_t row0, unsigned m) {
     const uint32_t bits = m << (row0 & 31);
     uint32_t* w = bm + (row0 >> 5);
@@ -1230,7 +1231,10 @@ __global__ void __launch_bounds__(32 * kReadoutWarps) readout_kernel(const float
                                                      const float* __restrict__ mask, float scale, float* __restrict__ GL,
                                                      float* __restrict__ partial /* [b][C+2] */, const uint8_t* __restrict__ occ_HL,
                                                      uint8_t* __restrict__ occ_GL, uint32_t* __restrict__ bm_GL, int act, int N, int D,
-                                                     int b, int C) {
+                                                     int b, int C, const uint32_t* __restrict__ bm_HL, uint32_t* __restrict__ bm_cand,
+                                                     const int32_t* __restrict__ mptr, const int2* __restrict__ ment) {
+    // bm_HL != NULL: the row bitmap of H_L replaces the flag bytes; bm_cand != NULL: every row of G_L this trajectory touches
+    // also marks the candidate rows one hop further (its merged operator row) for the first backward layer
     __shared__ float logit[kReadoutMaxD];
     __shared__ float s_dw[kReadoutWarps][32 * kReadoutMaxCper];
     __shared__ float s_lse;
@@ -1250,7 +1254,8 @@ __global__ void __launch_bounds__(32 * kReadoutWarps) readout_kernel(const float
             float z[kReadoutMaxCper] = {0.f, 0.f, 0.f, 0.f};
             for (int p = inc_ptr[nbr]; p < inc_ptr[nbr + 1]; ++p) {
                 const int2 es = inc_ent[p];
-                if (occ_HL != nullptr && occ_HL[(size_t)es.x * b + t] == 0) continue;      // row is exactly zero
+                if (bm_HL != nullptr ? !bitmap_test_row(bm_HL, (size_t)es.x * b + t)
+                                     : (occ_HL != nullptr && occ_HL[(size_t)es.x * b + t] == 0)) continue;      // row is exactly zero
                 const float* row = HL + ((size_t)es.x * b + t) * C;
 #pragma unroll
                 for (int q = 0; q < kReadoutMaxCper; ++q)
@@ -1284,9 +1289,14 @@ __global__ void __launch_bounds__(32 * kReadoutWarps) readout_kernel(const float
 #pragma unroll
             for (int q = 0; q < kReadoutMaxCper; ++q)
                 if (lane + 32 * q < C) GL[row * C + lane + 32 * q] = 0.f;
-            if (occ_GL != nullptr && lane == 0) {
-                occ_GL[row] = 1;
-                if (bm_GL != nullptr) atomicOr(bm_GL + (row >> 5), 1u << (row & 31));
+            if (occ_GL != nullptr && lane == 0) occ_GL[row] = 1;
+            if (bm_GL != nullptr && lane == 0) atomicOr(bm_GL + (row >> 5), 1u << (row & 31));
+            if (bm_cand != nullptr) {
+                const int e = inc_ent[p].x;
+                for (int q = mptr[e] + lane; q < mptr[e + 1]; q += 32) {
+                    const size_t crow = (size_t)(unsigned)ment[q].x * b + t;
+                    atomicOr(bm_cand + (crow >> 5), 1u << (crow & 31));
+                }
             }
         }
     }
@@ -1303,7 +1313,8 @@ __global__ void __launch_bounds__(32 * kReadoutWarps) readout_kernel(const float
             const int2 es = inc_ent[p];
             const size_t base = ((size_t)es.x * b + t) * C;
             const float sdl = __int_as_float(es.y) * dl;
-            const bool hz = occ_HL != nullptr && occ_HL[(size_t)es.x * b + t] == 0;
+            const bool hz = bm_HL != nullptr ? !bitmap_test_row(bm_HL, (size_t)es.x * b + t)
+                                             : (occ_HL != nullptr && occ_HL[(size_t)es.x * b + t] == 0);
 #pragma unroll
             for (int q = 0; q < kReadoutMaxCper; ++q)
                 if (lane + 32 * q < C) {
@@ -1518,7 +1529,7 @@ int launch_fwd(const scone_complex* cx, int b, const float* Hin, const float* W0
         const int wi = 1 - wo;
         if (compact_bitmap<1>(cx, b, sc.bm, sc.wl[wi], sc.n[wi], sc.tickets, st)) return 1;
         return scone_slab_forward_rows(cx, ACT, b, CIN, COUT, Hin, W0, W1, W2, Hout, occ_in, sc.wl[wi], sc.n[wi],
-                                       scone_prof_row_counter(SCONE_K_LAYER_FWD), st);
+                                       scone_prof_row_counter(SCONE_K_LAYER_FWD), nullptr, nullptr, st);
     }
     const size_t smem = ((size_t)KD * COUT + (size_t)kWarps * TT * LDT) * sizeof(float);
     auto kern = layer_fwd_units_kernel<CIN, COUT, ACT>;
@@ -1611,6 +1622,13 @@ bool width_ok(int c) { return c == 8 || c == 16 || c == 32 || c == 64; }
 
 }  // namespace
 
+// ascending list of the set bits of a row bitmap (ids e*b + t) and their count, both on the device; tickets: kTicketSlots * 8 bytes
+int scone_compact_rows(const scone_complex* cx, int b, const uint32_t* bm, uint32_t* list, int* n_dev, unsigned long long* tickets,
+                       cudaStream_t st) {
+    return compact_bitmap<1>(cx, b, bm, list, n_dev, tickets, st);
+}
+size_t scone_ticket_bytes() { return (size_t)kTicketSlots * 8; }
+
 // zero-fill `bytes` (multiple of 16) at p on stream st with the library's own kernel
 int scone_zero_fill(const scone_complex* cx, void* p, size_t bytes, cudaStream_t st) {
     if (bytes == 0) return 0;
@@ -1666,6 +1684,7 @@ struct HintsReset {
         g_scone_hints.skip_fill = false;
         g_scone_hints.in_bm = nullptr;
         g_scone_hints.out_bm = nullptr;
+        g_scone_hints.cand_bm = nullptr;
     }
 };
 
@@ -1841,15 +1860,20 @@ int scone_readout_ws(const scone_complex* cx, int32_t act, int32_t b, int32_t C,
     if (GL) {
         SCONE_REQUIRE(target_idx && mask && workspace, "scone_readout: gradient mode needs target_idx, mask, workspace");
         // without flags the consumer reads every row of GL: it must be dense zeros; with flags only when zero-fill is on
-        if ((occ_GL == nullptr || zero_fill_here()) && scone_zero_fill(cx, GL, (size_t)cx->E * b * C * sizeof(float), st)) return 1;
+        const bool flagged = occ_GL != nullptr || g_scone_hints.out_bm != nullptr;
+        if ((!flagged || zero_fill_here()) && scone_zero_fill(cx, GL, (size_t)cx->E * b * C * sizeof(float), st)) return 1;
         if (occ_GL) SCONE_CUDA(cudaMemsetAsync(occ_GL, 0, (size_t)cx->E * b, st));
     }
-    uint32_t* bm = (GL && occ_GL && b % 4 == 0) ? g_scone_hints.out_bm : nullptr;
+    const uint32_t* bm_HL = g_scone_hints.in_bm;           // row-bitmap pipeline: bits instead of flag bytes
+    uint32_t* bm_cand = GL ? g_scone_hints.cand_bm : nullptr;
+    uint32_t* bm = (GL && (occ_GL || bm_HL)) ? g_scone_hints.out_bm : nullptr;
     g_scone_hints.out_bm = nullptr;
+    g_scone_hints.cand_bm = nullptr;
     if (bm) SCONE_CUDA(cudaMemsetAsync(bm, 0, scone_bitmap_words(cx->E, b) * 4, st));
+    if (bm_cand) SCONE_CUDA(cudaMemsetAsync(bm_cand, 0, scone_bitmap_words(cx->E, b) * 4, st));
     readout_kernel<<<b, 32 * kReadoutWarps, 0, st>>>(HL, wout, last_nodes, cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, logprobs,
                                               target_idx, mask, scale, GL, (float*)workspace, occ_HL, GL ? occ_GL : nullptr, bm, act,
-                                              cx->N, cx->D, b, C);
+                                              cx->N, cx->D, b, C, bm_HL, bm_cand, cx->d_mptr, cx->d_ment);
     SCONE_LAUNCHED();
     if (GL) {
         readout_reduce_kernel<<<1, ((C + 2 + 31) / 32) * 32, 0, st>>>((const float*)workspace, b, C, dwout, nll_sum, count, accumulate);

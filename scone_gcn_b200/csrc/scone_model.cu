@@ -31,6 +31,15 @@ struct scone_model {
     uint8_t* d_occX = nullptr;                // flags of the flows X
     uint32_t *d_bmX = nullptr, *d_bmG = nullptr;   // quad bitmaps of the flags of X and of G_L (compaction reads these)
     bool zero_fill = false;                   // dense zero-fill of every activation / gradient tensor (scone_model_set_zero_fill)
+    // bitmap-native row-list pipeline (scone_rows.cu): row bitmaps per tensor, one row list, compact A rows for the dW GEMM
+    bool rows_ok = false, use_rows = false, x_clean = false;
+    std::vector<uint32_t*> d_bmH, d_bmGr;
+    uint32_t* d_rows = nullptr;
+    int* d_nrows = nullptr;
+    int* d_overflow = nullptr;
+    unsigned long long* d_tickets = nullptr;
+    float* d_Abuf = nullptr;
+    int a_cap = 0;
     void* d_ws = nullptr;                     // backward / readout workspace
     float* d_logp = nullptr;                  // [mb][D]
     // staging for the *_host entry points
@@ -112,6 +121,66 @@ int forward_mb(scone_model* m, int32_t b, const int32_t* ptr, const int32_t* edg
     return 0;
 }
 
+// ---- row-list pipeline -------------------------------------------------------------------------------------------
+int rows_forward_mb(scone_model* m, int32_t b, const int32_t* ptr, const int32_t* edge, const float* val, cudaStream_t s) {
+    const scone_complex* cx = m->cx;
+    const size_t bm_bytes = scone_bitmap_words(cx->E, b) * 4;
+    if (!m->x_clean) {                                     // X must be all-zero outside the flows (no flag test in the first layer)
+        SCONE_CUDA(cudaMemsetAsync(m->d_X, 0, (size_t)cx->E * m->mb * sizeof(float), s));
+        m->x_clean = true;
+    }
+    {
+        ScopedProf prof(SCONE_K_OTHER, s);
+        SCONE_CUDA(cudaMemsetAsync(m->d_bmX, 0, bm_bytes, s));
+        SCONE_CUDA(cudaMemsetAsync(m->d_bmH[0], 0, bm_bytes, s));
+        if (scone_rows_flows(cx, b, ptr, edge, val, m->d_X, m->d_bmX, m->d_bmH[0], false, s)) return 1;
+    }
+    int cin = 1;
+    for (int l = 0; l < m->L; ++l) {
+        const int cout = m->hidden[l];
+        ScopedProf prof(l == 0 ? SCONE_K_LAYER0_FWD : SCONE_K_LAYER_FWD, s);
+        if (scone_compact_rows(cx, b, m->d_bmH[l], m->d_rows, m->d_nrows, m->d_tickets, s)) return 1;
+        uint32_t* next = l + 1 < m->L ? m->d_bmH[l + 1] : nullptr;
+        if (next) SCONE_CUDA(cudaMemsetAsync(next, 0, bm_bytes, s));
+        const float *W0 = m->d_w + m->w_off[3 * l], *W1 = m->d_w + m->w_off[3 * l + 1], *W2 = m->d_w + m->w_off[3 * l + 2];
+        int rc;
+        if (l == 0)
+            rc = scone_rows_layer0_forward(cx, m->act, b, cout, m->d_X, W0, W1, W2, m->d_H[0], m->d_rows, m->d_nrows, next, s);
+        else
+            rc = scone_slab_forward_rows(cx, m->act, b, cin, cout, m->d_H[l - 1], W0, W1, W2, m->d_H[l], nullptr, m->d_rows, m->d_nrows,
+                                         scone_prof_row_counter(SCONE_K_LAYER_FWD), m->d_bmH[l - 1], next, s);
+        if (rc) return rc;
+        cin = cout;
+    }
+    return 0;
+}
+
+int rows_clear_x(scone_model* m, int32_t b, const int32_t* ptr, const int32_t* edge, const float* val, cudaStream_t s) {
+    ScopedProf prof(SCONE_K_OTHER, s);
+    return scone_rows_flows(m->cx, b, ptr, edge, val, m->d_X, nullptr, nullptr, true, s);
+}
+
+int rows_backward_mb(scone_model* m, int32_t b, cudaStream_t s) {
+    const scone_complex* cx = m->cx;
+    const int L = m->L;
+    const size_t bm_bytes = scone_bitmap_words(cx->E, b) * 4;
+    for (int l = L - 1; l >= 1; --l) {
+        ScopedProf prof(SCONE_K_LAYER_BWD, s);
+        if (scone_compact_rows(cx, b, m->d_bmGr[l - 1], m->d_rows, m->d_nrows, m->d_tickets, s)) return 1;
+        uint32_t* next = l >= 2 ? m->d_bmGr[l - 2] : nullptr;
+        if (next) SCONE_CUDA(cudaMemsetAsync(next, 0, bm_bytes, s));
+        int rc = scone_rows_backward(cx, m->act, b, m->hidden[l - 1], m->hidden[l], m->d_G[l], m->d_H[l - 1], m->d_G[l - 1], m->d_Abuf,
+                                     m->d_w + m->w_off[3 * l], m->d_w + m->w_off[3 * l + 1], m->d_w + m->w_off[3 * l + 2], m->d_rows,
+                                     m->d_nrows, m->d_bmGr[l], m->d_bmH[l - 1], next, m->a_cap, m->d_overflow,
+                                     m->d_grad + m->w_off[3 * l], 1, (float*)m->d_ws, s);
+        if (rc) return rc;
+    }
+    ScopedProf prof(SCONE_K_LAYER0_BWD, s);
+    if (L == 1 && scone_compact_rows(cx, b, m->d_bmGr[0], m->d_rows, m->d_nrows, m->d_tickets, s)) return 1;
+    return scone_rows_layer0_backward(cx, b, m->hidden[0], m->d_X, m->d_G[0], m->d_rows, m->d_nrows, m->d_grad + m->w_off[0], 1,
+                                      (float*)m->d_ws, s);
+}
+
 }  // namespace
 
 extern "C" int scone_model_create(const scone_complex* cx, int32_t n_layers, const int32_t* hidden, int32_t micro_batch,
@@ -177,7 +246,25 @@ extern "C" int scone_model_create(const scone_complex* cx, int32_t n_layers, con
     alloc((void**)&m->d_occX, E * mb);
     alloc((void**)&m->d_bmX, scone_bitmap_words(E, mb) * 4);
     alloc((void**)&m->d_bmG, scone_bitmap_words(E, mb) * 4);
+    m->rows_ok = scone_rows_supported(cx, n_layers, hidden) && E * mb < ((size_t)1 << 31);
+    if (m->rows_ok) {
+        m->d_bmH.assign(n_layers, nullptr);
+        m->d_bmGr.assign(n_layers, nullptr);
+        for (int l = 0; l < n_layers; ++l) {
+            alloc((void**)&m->d_bmH[l], scone_bitmap_words(E, mb) * 4);
+            alloc((void**)&m->d_bmGr[l], scone_bitmap_words(E, mb) * 4);
+        }
+        alloc((void**)&m->d_rows, E * mb * sizeof(uint32_t));
+        alloc((void**)&m->d_nrows, 256);
+        alloc((void**)&m->d_overflow, 256);
+        alloc((void**)&m->d_tickets, scone_ticket_bytes());
+        const size_t cap = E * mb < (size_t)6000000 ? E * mb : (size_t)6000000;     // rows of the compact A buffer (backward)
+        m->a_cap = (int)cap;
+        alloc((void**)&m->d_Abuf, cap * 3 * (size_t)m->cmax * sizeof(float));
+        m->use_rows = true;
+    }
     int64_t ws = scone_readout_workspace_bytes(micro_batch, m->cmax);
+    if (scone_rows_dw_workspace_bytes(m->cmax, m->cmax) > ws) ws = scone_rows_dw_workspace_bytes(m->cmax, m->cmax);
     cin = 1;
     for (int l = 0; l < n_layers; ++l) {
         int64_t w = scone_layer_backward_workspace_bytes(cin, hidden[l]);
@@ -200,6 +287,7 @@ extern "C" int scone_model_create(const scone_complex* cx, int32_t n_layers, con
         cudaMemset(m->d_m, 0, off * sizeof(float));
         cudaMemset(m->d_v, 0, off * sizeof(float));
         cudaMemset(m->d_grad, 0, (off + 2) * sizeof(float));
+        if (m->d_overflow) cudaMemset(m->d_overflow, 0, 256);
     }
     if (rc) {
         scone_model_destroy(m);
@@ -216,6 +304,9 @@ extern "C" int scone_model_destroy(scone_model* m) {
     for (uint8_t* p : m->d_occH) cudaFree(p);
     for (uint8_t* p : m->d_occG) cudaFree(p);
     cudaFree(m->d_occS); cudaFree(m->d_occX); cudaFree(m->d_bmX); cudaFree(m->d_bmG);
+    for (uint32_t* p : m->d_bmH) cudaFree(p);
+    for (uint32_t* p : m->d_bmGr) cudaFree(p);
+    cudaFree(m->d_rows); cudaFree(m->d_nrows); cudaFree(m->d_overflow); cudaFree(m->d_tickets); cudaFree(m->d_Abuf);
     for (float* p : m->d_G) cudaFree(p);
     cudaFree(m->d_ws); cudaFree(m->d_logp);
     if (m->side) cudaStreamDestroy(m->side);
@@ -237,6 +328,13 @@ extern "C" int scone_model_set_zero_fill(scone_model* m, int32_t on) {
     return 0;
 }
 extern "C" int scone_model_get_zero_fill(const scone_model* m) { return m && m->zero_fill ? 1 : 0; }
+extern "C" int scone_model_set_pipeline(scone_model* m, int32_t which) {
+    SCONE_REQUIRE(m != nullptr && (which == 0 || which == 1), "scone_model_set_pipeline: 0 (unit kernels, byte flags) or 1 (row lists, bitmaps)");
+    SCONE_REQUIRE(which == 0 || m->rows_ok, "scone_model_set_pipeline: the row-list pipeline needs hidden widths in {16, 32}");
+    m->use_rows = which == 1;
+    return 0;
+}
+extern "C" int scone_model_get_pipeline(const scone_model* m) { return m && m->use_rows && !m->zero_fill ? 1 : 0; }
 extern "C" float* scone_model_weights_dev(scone_model* m) { return m ? m->d_w : nullptr; }
 extern "C" float* scone_model_grads_dev(scone_model* m) { return m ? m->d_grad : nullptr; }
 
@@ -273,9 +371,24 @@ extern "C" int scone_model_forward_dev(scone_model* m, int32_t B, const int32_t*
     if (fork_to_compute(m, user_st)) return 1;
     void* st = (void*)m->compute;
     const scone_complex* cx = m->cx;
+    const bool rows = m->use_rows && !m->zero_fill;
     for (int32_t off = 0; off < B; off += m->mb) {
         const int32_t b = B - off < m->mb ? B - off : m->mb;
-        int rc = start_fills(m, b, false, as_stream(st));
+        int rc;
+        if (rows) {
+            rc = rows_forward_mb(m, b, ptr + off, edge, val, as_stream(st));
+            if (rc) return rc;
+            g_scone_hints.in_bm = m->d_bmH[m->L - 1];
+            rc = scone_readout_ws(cx, m->act, b, m->hidden[m->L - 1], m->d_H[m->L - 1], m->d_w + m->w_off[3 * m->L], last + off,
+                                  logprobs + (size_t)off * cx->D, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, nullptr, 0,
+                                  nullptr, nullptr, nullptr, st);
+            if (rc) return rc;
+            rc = rows_clear_x(m, b, ptr + off, edge, val, as_stream(st));
+            if (rc) return rc;
+            continue;
+        }
+        m->x_clean = false;
+        rc = start_fills(m, b, false, as_stream(st));
         if (rc) return rc;
         rc = forward_mb(m, b, ptr + off, edge, val, st);
         if (rc) return rc;
@@ -297,9 +410,29 @@ extern "C" int scone_model_loss_grad_dev(scone_model* m, int32_t B, const int32_
     const int L = m->L;
     cudaStream_t s = as_stream(st);
     if (zero_first) SCONE_CUDA(cudaMemsetAsync(m->d_grad, 0, (m->n_params + 2) * sizeof(float), s));
+    const bool rows = m->use_rows && !m->zero_fill;
     for (int32_t off = 0; off < B; off += m->mb) {
         const int32_t b = B - off < m->mb ? B - off : m->mb;
-        int rc = start_fills(m, b, true, s);
+        int rc;
+        if (rows) {
+            rc = rows_forward_mb(m, b, ptr + off, edge, val, s);
+            if (rc) return rc;
+            g_scone_hints.skip_fill = true;
+            g_scone_hints.in_bm = m->d_bmH[L - 1];
+            g_scone_hints.out_bm = m->d_bmGr[L - 1];
+            g_scone_hints.cand_bm = L >= 2 ? m->d_bmGr[L - 2] : nullptr;
+            rc = scone_readout_ws(cx, m->act, b, m->hidden[L - 1], m->d_H[L - 1], m->d_w + m->w_off[3 * L], last + off, m->d_logp,
+                                  tgt + off, mask + off, 1.f, m->d_G[L - 1], m->d_grad + m->w_off[3 * L], m->d_grad + m->n_params,
+                                  m->d_grad + m->n_params + 1, 1, m->d_ws, nullptr, nullptr, st);
+            if (rc) return rc;
+            rc = rows_backward_mb(m, b, s);
+            if (rc) return rc;
+            rc = rows_clear_x(m, b, ptr + off, edge, val, s);
+            if (rc) return rc;
+            continue;
+        }
+        m->x_clean = false;
+        rc = start_fills(m, b, true, s);
         if (rc) return rc;
         rc = forward_mb(m, b, ptr + off, edge, val, st);
         if (rc) return rc;
@@ -374,7 +507,15 @@ extern "C" int scone_model_read_grads(scone_model* m, float* out, void* st) {
     SCONE_REQUIRE(m && out, "scone_model_read_grads: NULL argument");
     cudaStream_t s = as_stream(st);
     SCONE_CUDA(cudaMemcpyAsync(out, m->d_grad, (m->n_params + 2) * sizeof(float), cudaMemcpyDeviceToHost, s));
+    int overflow = 0;
+    if (m->d_overflow) SCONE_CUDA(cudaMemcpyAsync(&overflow, m->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
     SCONE_CUDA(cudaStreamSynchronize(s));
+    if (overflow) {
+        cudaMemset(m->d_overflow, 0, sizeof(int));
+        scone_set_error("scone_model: a backward pass had more than %d candidate rows in one micro-batch (compact A buffer); the gradients "
+                        "are incomplete — use a smaller micro-batch or scone_model_set_pipeline(m, 0)", m->a_cap);
+        return 4;
+    }
     return 0;
 }
 

@@ -1,0 +1,536 @@
+// scone_rows.cu — the bitmap-native row-list pipeline behind the model-level entry points (widths 16 / 32).
+//
+// Every activation / gradient tensor carries a ROW BITMAP (bit e*b + t set <=> row (e, t) may be non-zero and has been
+// written).  A kernel that produces rows of one tensor also marks — while it walks the merged operator rows anyway —
+// the candidate rows of the NEXT tensor one hop further (idempotent atomicOr: the bitmap does not depend on the order of
+// the writers).  Per layer the pipeline is then: clear the next bitmap, compact the current one into an ascending row list
+// (one launch, deterministic), run one row-list kernel.  No per-layer scatter kernel, no byte flags, nothing proportional to
+// E*b except the E*b/8-byte bitmaps.
+//
+//   flows          X rows + bits, candidate bits of H_1                       synthetic_data_gen.py:327-344 (path_to_flow)
+//   first layer    H_1 = act(X w0 + (S0 X) w1 + (S1 X) w2)                    trajectory_experiments.py:145-149 (i = 0)
+//   conv layers    layer_fwd_rows_kernel (scone_slab.cu)                      trajectory_experiments.py:145-149
+//   backward       A_k = S_k G, Gprev = (sum_k A_k W_k^T) * act'(Hin); dW_k = Hin^T A_k     (jax.grad, scone_trajectory_model.py:307)
+//   first layer bwd  dW_k[0][:] = sum_rows (S_k X)[row] * G_1[row][:]
+#include <cstdlib>
+#include "common.cuh"
+
+namespace {
+
+#include "slab_common.cuh"
+
+template <int ACT>
+__device__ __forceinline__ float act_scalar(float z) {
+    if (ACT == SCONE_ACT_TANH) return scone_tanh(z);
+    if (ACT == SCONE_ACT_LEAKY_RELU) return z >= 0.f ? z : 0.01f * z;
+    return fmaxf(z, 0.f);
+}
+template <int ACT>
+__device__ __forceinline__ float dact_out(float h) {       // derivative through the OUTPUT h = act(z)
+    if (ACT == SCONE_ACT_TANH) return 1.f - h * h;
+    if (ACT == SCONE_ACT_LEAKY_RELU) return h >= 0.f ? 1.f : 0.01f;
+    return h > 0.f ? 1.f : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// flows: one CTA per trajectory.  X[row] = value, bit of X, and the candidate bits of H_1 (the row itself is in its own
+// merged operator row).  CLEAR = true undoes the X writes after the step (X stays all-zero between micro-batches, so the
+// first-layer gathers need no flag test and X needs no E*b memset).
+// ---------------------------------------------------------------------------------------------------------------
+template <bool CLEAR>
+__global__ void __launch_bounds__(128) rows_flows_kernel(const int32_t* __restrict__ traj_ptr, const int32_t* __restrict__ flow_edge,
+                                                        const float* __restrict__ flow_val, const int32_t* __restrict__ rank,
+                                                        float* __restrict__ X, uint32_t* __restrict__ bmX, uint32_t* __restrict__ bm_next,
+                                                        const int32_t* __restrict__ mptr, const int2* __restrict__ ment, int E, int b) {
+    const int t = blockIdx.x;
+    for (int p = traj_ptr[t] + threadIdx.x; p < traj_ptr[t + 1]; p += blockDim.x) {
+        const int eo = flow_edge[p];
+        if (eo < 0 || eo >= E) continue;
+        const int e = rank[eo];
+        const size_t row = (size_t)e * b + t;
+        if (CLEAR) {
+            X[row] = 0.f;
+            continue;
+        }
+        X[row] = flow_val[p];
+        bit_set(bmX, row);
+        for (int q = mptr[e]; q < mptr[e + 1]; ++q) bit_set(bm_next, (size_t)(unsigned)ment[q].x * b + t);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// first layer forward over a row list: lane = row for the scalar gathers of X (no flag test: X is zero off its support), then
+// the 32 rows of the warp are written one after the other with lane = channel (coalesced).  Gather order = merged row order
+// = ascending columns for both sums, same as the unit kernels.
+// ---------------------------------------------------------------------------------------------------------------
+template <int COUT, int ACT>
+__global__ void __launch_bounds__(256) rows_layer0_fwd_kernel(const float* __restrict__ X, float* __restrict__ Hout,
+                                                             const float* __restrict__ W0, const float* __restrict__ W1,
+                                                             const float* __restrict__ W2, const int32_t* __restrict__ mptr,
+                                                             const int2* __restrict__ ment, const uint32_t* __restrict__ rows,
+                                                             const int* __restrict__ n_ptr, int b, uint32_t* __restrict__ bm_next) {
+    static_assert(COUT == 16 || COUT == 32, "first-layer row kernel: widths 16 / 32");
+    constexpr int RPI = 32 / COUT;                        // rows written per iteration of the store loop
+    const int lane = threadIdx.x & 31;
+    const int n = *n_ptr;
+    const int c = lane % COUT;
+    const float w0 = W0[c], w1 = W1[c], w2 = W2[c];
+    const int n_groups = (n + 31) / 32;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int grp = gw; grp < n_groups; grp += nw) {
+        const int li = grp * 32 + lane;
+        uint32_t rid = 0;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        if (li < n) {
+            rid = __ldg(rows + li);
+            const int e = (int)(rid / (unsigned)b), t = (int)(rid - (unsigned)e * (unsigned)b);
+            a0 = __ldg(X + rid);
+            const int p1 = __ldg(mptr + e + 1);
+            for (int p = __ldg(mptr + e); p < p1; ++p) {
+                const int2 en = __ldg(ment + p);
+                const size_t nrow = (size_t)(unsigned)en.x * b + t;
+                const float x = __ldg(X + nrow);
+                a1 = fmaf((float)(short)(en.y & 0xffff), x, a1);
+                a2 = fmaf((float)(en.y >> 16), x, a2);
+                if (bm_next != nullptr) bit_set(bm_next, nrow);
+            }
+        }
+        const int cnt = min(32, n - grp * 32);
+        for (int r0 = 0; r0 < cnt; r0 += RPI) {
+            const int r = r0 + lane / COUT;
+            const float s0 = __shfl_sync(0xffffffffu, a0, r & 31), s1 = __shfl_sync(0xffffffffu, a1, r & 31),
+                        s2 = __shfl_sync(0xffffffffu, a2, r & 31);
+            const uint32_t orow = __shfl_sync(0xffffffffu, rid, r & 31);
+            if (r < cnt) Hout[(size_t)orow * COUT + c] = act_scalar<ACT>(fmaf(s2, w2, fmaf(s1, w1, s0 * w0)));
+        }
+    }
+}
+
+// first layer backward: one warp per row of G_1; lanes split the merged operator row for the two scalar gathers (fixed
+// butterfly sum), then lane = channel.  Per-CTA partials [3][COUT], reduced by reduce order (deterministic).
+template <int COUT>
+__global__ void __launch_bounds__(256) rows_layer0_bwd_kernel(const float* __restrict__ X, const float* __restrict__ G,
+                                                             const int32_t* __restrict__ mptr, const int2* __restrict__ ment,
+                                                             const uint32_t* __restrict__ rows, const int* __restrict__ n_ptr, int b,
+                                                             float* __restrict__ partial /* [grid][3*COUT] */) {
+    __shared__ float red[8][3 * 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = *n_ptr;
+    const int per = (n + gridDim.x - 1) / gridDim.x;          // contiguous slice per CTA, rows strided over its warps
+    const int lo = min(n, (int)blockIdx.x * per), hi = min(n, lo + per);
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+    for (int li = lo + warp; li < hi; li += 8) {
+        const uint32_t rid = __ldg(rows + li);
+        const int e = (int)(rid / (unsigned)b), t = (int)(rid - (unsigned)e * (unsigned)b);
+        const int p0 = __ldg(mptr + e), p1 = __ldg(mptr + e + 1);
+        float a1 = 0.f, a2 = 0.f;
+        for (int p = p0 + lane; p < p1; p += 32) {
+            const int2 en = __ldg(ment + p);
+            const float x = __ldg(X + (size_t)(unsigned)en.x * b + t);
+            a1 = fmaf((float)(short)(en.y & 0xffff), x, a1);
+            a2 = fmaf((float)(en.y >> 16), x, a2);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        }
+        const float a0 = __ldg(X + rid);
+        if (lane < COUT) {
+            const float g = __ldg(G + (size_t)rid * COUT + lane);
+            acc0 = fmaf(a0, g, acc0);
+            acc1 = fmaf(a1, g, acc1);
+            acc2 = fmaf(a2, g, acc2);
+        }
+    }
+    red[warp][lane] = acc0;
+    red[warp][32 + lane] = acc1;
+    red[warp][64 + lane] = acc2;
+    __syncthreads();
+    for (int o = threadIdx.x; o < 3 * COUT; o += blockDim.x) {
+        const int k = o / COUT, c = o % COUT;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][k * 32 + c];
+        partial[(size_t)blockIdx.x * 3 * COUT + o] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward over a row list (the candidate rows of Gprev = rows where S G can be non-zero): same gather as the forward row
+// kernel on G (flag test = row bitmap of G), the three gathered terms A_k are (1) stored compactly, row i of the list at
+// Abuf[i][3*COUT], for the weight-gradient GEMM, (2) contracted with W^T on the tensor cores (3xTF32) into
+// Gprev = (sum_k A_k W_k^T) * act'(Hin) with Hin rows read through the row bitmap of H_{l-1} (an unflagged row is an exact
+// zero: act'(0)).  Candidate bits of the tensor one hop further are set on the way.
+// ---------------------------------------------------------------------------------------------------------------
+template <int CIN, int COUT, int ACT>
+__global__ void __launch_bounds__(kSlabThreads, 1) rows_bwd_kernel(const float* __restrict__ Gin, const float* __restrict__ Hin,
+                                                                  float* __restrict__ Gprev, float* __restrict__ Abuf,
+                                                                  const float* __restrict__ W0, const float* __restrict__ W1,
+                                                                  const float* __restrict__ W2, const int32_t* __restrict__ mptr,
+                                                                  const int2* __restrict__ ment, const uint32_t* __restrict__ rows,
+                                                                  const int* __restrict__ n_ptr, int b, const uint32_t* __restrict__ bmG,
+                                                                  const uint32_t* __restrict__ bmH, uint32_t* __restrict__ bm_next,
+                                                                  int a_cap, int* __restrict__ overflow,
+                                                                  unsigned long long* __restrict__ row_counter) {
+    using G = SlabGeom<COUT, 16>;                          // the gathered tensor has COUT channels
+    constexpr int NT = CIN / 8, NL = G::NL, Q = G::Q, LPR = COUT / 4;
+    extern __shared__ __align__(16) uint4 Bf[];
+    stage_weight_fragments<COUT, CIN, 16, true>(Bf, W0, W1, W2);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tig = lane & 3, g = lane >> 2;
+    const int gq = lane / LPR, cq = lane % LPR;
+    const unsigned rowbytes = (unsigned)b * COUT * 4u;
+    const char* Gb = reinterpret_cast<const char*>(Gin);
+    int n = *n_ptr;
+    if (n > a_cap) {                                       // the compact A buffer cannot hold this many rows: flag it (host raises)
+        if (blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1;
+        n = a_cap;
+    }
+    const int n_slabs = (n + 15) / 16;
+    const int n_tiles = (n_slabs + kSlabWarps - 1) / kSlabWarps;
+    const int per = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const int lo = blockIdx.x * per, hi = min(n_tiles, lo + per);
+    if (row_counter != nullptr && threadIdx.x == 0 && lo < hi)
+        atomicAdd(row_counter, (unsigned long long)(min(n, hi * kSlabWarps * 16) - lo * kSlabWarps * 16));
+    for (int tile = lo; tile < hi; ++tile) {
+        const int slab = tile * kSlabWarps + warp;
+        if (slab >= n_slabs) continue;
+        uint32_t rid[NL];
+        int len[NL], p0[NL], tq[NL], cpos[NL];
+        const char* P[NL];
+        bool own[NL], valid[NL];
+        int maxlen = 0;
+#pragma unroll
+        for (int i = 0; i < NL; ++i) {
+            const int li = slab * 16 + i * Q + gq;
+            valid[i] = li < n;
+            rid[i] = valid[i] ? __ldg(rows + li) : 0u;
+            const int e = (int)(rid[i] / (unsigned)b);
+            tq[i] = (int)(rid[i] - (unsigned)e * (unsigned)b);
+            cpos[i] = (COUT == 32 && i >= 2) ? (cq ^ 4) : cq;
+            P[i] = Gb + (size_t)((unsigned)(tq[i] * COUT + 4 * cpos[i]) * 4u);
+            p0[i] = valid[i] ? __ldg(mptr + e) : 0;
+            len[i] = valid[i] ? __ldg(mptr + e + 1) - p0[i] : 0;
+            own[i] = valid[i] && bit_test(bmG, rid[i]);
+            maxlen = max(maxlen, len[i]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+        u64 acc[3][NL][2];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int i = 0; i < NL; ++i) acc[k][i][0] = acc[k][i][1] = 0ull;
+#pragma unroll
+        for (int i = 0; i < NL; ++i)
+            if (own[i]) ldg128(reinterpret_cast<const float*>(P[i] + (size_t)(rid[i] / (unsigned)b) * rowbytes), acc[0][i][0], acc[0][i][1]);
+        for (int k = 0; k < maxlen; ++k) {
+            int2 ent[NL];
+            bool on[NL];
+#pragma unroll
+            for (int i = 0; i < NL; ++i) {
+                on[i] = k < len[i];
+                ent[i] = on[i] ? __ldg(ment + p0[i] + k) : make_int2(0, 0);
+            }
+#pragma unroll
+            for (int i = 0; i < NL; ++i) {
+                const size_t nrow = (size_t)(unsigned)ent[i].x * b + tq[i];
+                if (bm_next != nullptr && on[i] && cq == 0) bit_set(bm_next, nrow);
+                on[i] = on[i] && bit_test(bmG, nrow);
+            }
+            u64 v[NL][2];
+#pragma unroll
+            for (int i = 0; i < NL; ++i) {
+                v[i][0] = v[i][1] = 0ull;
+                if (on[i]) ldg128(reinterpret_cast<const float*>(P[i] + (size_t)(unsigned)ent[i].x * rowbytes), v[i][0], v[i][1]);
+            }
+#pragma unroll
+            for (int i = 0; i < NL; ++i) {
+                const float c0 = (float)(short)(ent[i].y & 0xffff), c1 = (float)(ent[i].y >> 16);
+                const u64 q0 = bcast2(c0), q1 = bcast2(c1);
+                ffma2(acc[1][i][0], q0, v[i][0]);
+                ffma2(acc[1][i][1], q0, v[i][1]);
+                ffma2(acc[2][i][0], q1, v[i][0]);
+                ffma2(acc[2][i][1], q1, v[i][1]);
+            }
+        }
+        // (1) the gathered terms, row li of the list -> Abuf[li][term * COUT + channel]
+#pragma unroll
+        for (int i = 0; i < NL; ++i)
+            if (valid[i]) {
+                float* dst = Abuf + (size_t)(slab * 16 + i * Q + gq) * (3 * COUT) + 4 * cpos[i];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    float4 o;
+                    unpack2(acc[k][i][0], o.x, o.y);
+                    unpack2(acc[k][i][1], o.z, o.w);
+                    *reinterpret_cast<float4*>(dst + k * COUT) = o;
+                }
+            }
+        // (2) Gprev
+        float d[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) d[nt][0] = d[nt][1] = d[nt][2] = d[nt][3] = 0.f;
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+            float fr[G::KS][4];
+            slab_fragments<COUT, 16>(acc[term], fr);
+            slab_mma_term<G::KS, NT>(d, fr, Bf + term * G::KS * NT * 32);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            uint32_t orow;
+            bool ok;
+            if (COUT == 32) {
+                const bool odd = g & 1;
+                orow = odd ? rid[2 + r] : rid[r];
+                ok = odd ? valid[2 + r] : valid[r];
+            } else {
+                orow = rid[r];
+                ok = valid[r];
+            }
+            if (ok) {
+                const bool hset = bit_test(bmH, orow);
+                const float* hsrc = Hin + (size_t)orow * CIN + 2 * tig;
+                float* dst = Gprev + (size_t)orow * CIN + 2 * tig;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    float2 h = make_float2(0.f, 0.f);
+                    if (hset) h = __ldg(reinterpret_cast<const float2*>(hsrc + nt * 8));
+                    *reinterpret_cast<float2*>(dst + nt * 8) =
+                        make_float2(d[nt][2 * r] * dact_out<ACT>(h.x), d[nt][2 * r + 1] * dact_out<ACT>(h.y));
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradients dW_k[ci][co] = sum_i Hin[rows[i]][ci] * A_k[i][co]: a tall-skinny GEMM (M = CIN, N = 3*COUT, K = rows)
+// on mma.sync with the 3xTF32 split of both operands.  CTA c owns a contiguous slice of the list; its 8 warps own disjoint
+// (m-tile, n-tile) sets and all walk the slice in k-steps of 8 rows (fixed order), operands fetched straight from global
+// memory in fragment layout (each 32-bit load fills whole 32-byte sectors; the 8 warps share the rows through L1).
+// Per-CTA partials, reduced over CTAs in a fixed tree: deterministic.
+// ---------------------------------------------------------------------------------------------------------------
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256) rows_dw_kernel(const float* __restrict__ Hin, const uint32_t* __restrict__ bmH,
+                                                     const float* __restrict__ Abuf, const uint32_t* __restrict__ rows,
+                                                     const int* __restrict__ n_ptr, int a_cap, float* __restrict__ partial /* [grid][3*CIN*COUT] */) {
+    constexpr int MT = CIN / 16, NTT = 3 * COUT / 8;       // m-tiles, n-tiles
+    constexpr int TILES = MT * NTT;
+    constexpr int TPW = TILES >= 24 ? 3 : (TILES >= 12 ? 2 : 1);   // (m, n) tiles per warp; TILES / TPW <= 8 warps work
+    static_assert(TILES % TPW == 0 && TILES / TPW <= 8, "tile count must split over at most 8 warps");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tig = lane & 3, g = lane >> 2;
+    if (warp >= TILES / TPW) return;                       // (no CTA barrier below)
+    int n = *n_ptr;
+    if (n > a_cap) n = a_cap;
+    const int n_steps = (n + 7) / 8;
+    const int per = (n_steps + gridDim.x - 1) / gridDim.x;
+    const int lo = min(n_steps, (int)blockIdx.x * per), hi = min(n_steps, lo + per);
+    // this warp's tiles: consecutive n-tiles of one m-tile
+    const int t0 = warp * TPW;
+    const int mt = t0 / NTT, nt0 = t0 % NTT;
+    static_assert(NTT % TPW == 0, "a warp's tiles must share one m-tile");
+    float acc[TPW][4];
+#pragma unroll
+    for (int j = 0; j < TPW; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    for (int s = lo; s < hi; ++s) {
+        const int i0 = s * 8 + tig, i1 = i0 + 4;           // list positions of this lane's two k rows
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        if (i0 < n) {
+            const uint32_t r = __ldg(rows + i0);
+            if (bit_test(bmH, r)) {
+                a[0] = __ldg(Hin + (size_t)r * CIN + mt * 16 + g);
+                a[1] = __ldg(Hin + (size_t)r * CIN + mt * 16 + g + 8);
+            }
+        }
+        if (i1 < n) {
+            const uint32_t r = __ldg(rows + i1);
+            if (bit_test(bmH, r)) {
+                a[2] = __ldg(Hin + (size_t)r * CIN + mt * 16 + g);
+                a[3] = __ldg(Hin + (size_t)r * CIN + mt * 16 + g + 8);
+            }
+        }
+        uint32_t ahi[4], alo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) split_tf32(a[q], ahi[q], alo[q]);
+#pragma unroll
+        for (int j = 0; j < TPW; ++j) {
+            const int ncol = (nt0 + j) * 8 + g;
+            const float b0 = i0 < n ? __ldg(Abuf + (size_t)i0 * (3 * COUT) + ncol) : 0.f;
+            const float b1 = i1 < n ? __ldg(Abuf + (size_t)i1 * (3 * COUT) + ncol) : 0.f;
+            uint32_t bh0, bl0, bh1, bl1;
+            split_tf32(b0, bh0, bl0);
+            split_tf32(b1, bh1, bl1);
+            mma_tf32(acc[j], alo, bh0, bh1);
+            mma_tf32(acc[j], ahi, bl0, bl1);
+            mma_tf32(acc[j], ahi, bh0, bh1);
+        }
+    }
+    // D fragment (m = ci, n = k*COUT + co): c0,c1 -> (ci = g, n = 2*tig, +1); c2,c3 -> (ci = g + 8, ...)
+    float* outp = partial + (size_t)blockIdx.x * (3 * CIN * COUT);
+#pragma unroll
+    for (int j = 0; j < TPW; ++j) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int ci = mt * 16 + g + (q >> 1) * 8;
+            const int ncol = (nt0 + j) * 8 + 2 * tig + (q & 1);
+            const int k = ncol / COUT, co = ncol % COUT;
+            outp[(k * CIN + ci) * COUT + co] = acc[j][q];
+        }
+    }
+}
+
+// out[i] (+)= sum over parts (fixed tree): 256 threads = 32 outputs x 8 slices
+__global__ void __launch_bounds__(256) rows_reduce_kernel(const float* __restrict__ partial, int nparts, int n, float* __restrict__ out,
+                                                         int accumulate) {
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    const int per = (nparts + 7) / 8;
+    const int p0 = slice * per, p1 = min(nparts, p0 + per);
+    float s = 0.f;
+    if (i < n)
+        for (int p = p0; p < p1; ++p) s += partial[(size_t)p * n + i];
+    red[slice][lane] = s;
+    __syncthreads();
+    if (slice == 0 && i < n) {
+        float t = red[0][lane];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) t += red[k][lane];
+        out[i] = accumulate ? out[i] + t : t;
+    }
+}
+
+constexpr int kDwCtas = 148 * 2;
+
+template <int CIN, int COUT, int ACT>
+int launch_rows_bwd(const scone_complex* cx, int b, const float* G, const float* Hin, float* Gprev, float* Abuf, const float* W0,
+                    const float* W1, const float* W2, const uint32_t* rows, const int* n_ptr, const uint32_t* bmG, const uint32_t* bmH,
+                    uint32_t* bm_next, int a_cap, int* overflow, cudaStream_t st) {
+    using Gm = SlabGeom<COUT, 16>;
+    constexpr int NT = CIN / 8;
+    const size_t smem = (size_t)3 * Gm::KS * NT * 32 * sizeof(uint4);
+    auto kern = rows_bwd_kernel<CIN, COUT, ACT>;
+    static bool configured = false;
+    if (!configured) {
+        SCONE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    kern<<<cx->num_sms, kSlabThreads, smem, st>>>(G, Hin, Gprev, Abuf, W0, W1, W2, cx->d_mptr, cx->d_ment, rows, n_ptr, b, bmG, bmH,
+                                                  bm_next, a_cap, overflow, scone_prof_row_counter(SCONE_K_LAYER_BWD));
+    SCONE_LAUNCHED();
+    return 0;
+}
+
+template <int CIN, int COUT>
+int dispatch_rows_bwd(const scone_complex* cx, int act, int b, const float* G, const float* Hin, float* Gprev, float* Abuf,
+                      const float* W0, const float* W1, const float* W2, const uint32_t* rows, const int* n_ptr, const uint32_t* bmG,
+                      const uint32_t* bmH, uint32_t* bm_next, int a_cap, int* overflow, cudaStream_t st) {
+    switch (act) {
+        case SCONE_ACT_TANH:
+            return launch_rows_bwd<CIN, COUT, SCONE_ACT_TANH>(cx, b, G, Hin, Gprev, Abuf, W0, W1, W2, rows, n_ptr, bmG, bmH, bm_next, a_cap, overflow, st);
+        case SCONE_ACT_LEAKY_RELU:
+            return launch_rows_bwd<CIN, COUT, SCONE_ACT_LEAKY_RELU>(cx, b, G, Hin, Gprev, Abuf, W0, W1, W2, rows, n_ptr, bmG, bmH, bm_next, a_cap, overflow, st);
+        case SCONE_ACT_RELU:
+            return launch_rows_bwd<CIN, COUT, SCONE_ACT_RELU>(cx, b, G, Hin, Gprev, Abuf, W0, W1, W2, rows, n_ptr, bmG, bmH, bm_next, a_cap, overflow, st);
+    }
+    scone_set_error("unknown activation %d", act);
+    return 2;
+}
+
+template <int CIN, int COUT>
+int launch_rows_dw(const scone_complex* cx, const float* Hin, const uint32_t* bmH, const float* Abuf, const uint32_t* rows,
+                   const int* n_ptr, int a_cap, float* dW, int accumulate, float* ws, cudaStream_t st) {
+    rows_dw_kernel<CIN, COUT><<<kDwCtas, 256, 0, st>>>(Hin, bmH, Abuf, rows, n_ptr, a_cap, ws);
+    SCONE_LAUNCHED();
+    constexpr int DW = 3 * CIN * COUT;
+    rows_reduce_kernel<<<(DW + 31) / 32, 256, 0, st>>>(ws, kDwCtas, DW, dW, accumulate);
+    SCONE_LAUNCHED();
+    return 0;
+}
+
+template <int COUT>
+int launch_rows_l0_fwd(const scone_complex* cx, int act, int b, const float* X, const float* W0, const float* W1, const float* W2,
+                       float* Hout, const uint32_t* rows, const int* n_ptr, uint32_t* bm_next, cudaStream_t st) {
+    const int grid = cx->num_sms * 4;
+    switch (act) {
+        case SCONE_ACT_TANH:
+            rows_layer0_fwd_kernel<COUT, SCONE_ACT_TANH><<<grid, 256, 0, st>>>(X, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, rows, n_ptr, b, bm_next);
+            break;
+        case SCONE_ACT_LEAKY_RELU:
+            rows_layer0_fwd_kernel<COUT, SCONE_ACT_LEAKY_RELU><<<grid, 256, 0, st>>>(X, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, rows, n_ptr, b, bm_next);
+            break;
+        case SCONE_ACT_RELU:
+            rows_layer0_fwd_kernel<COUT, SCONE_ACT_RELU><<<grid, 256, 0, st>>>(X, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, rows, n_ptr, b, bm_next);
+            break;
+        default: scone_set_error("unknown activation %d", act); return 2;
+    }
+    SCONE_LAUNCHED();
+    return 0;
+}
+
+}  // namespace
+
+bool scone_rows_supported(const scone_complex* cx, int n_layers, const int32_t* hidden) {
+    if (g_scone_dense_kernel == 0 || cx->d_mptr == nullptr) return false;
+    for (int l = 0; l < n_layers; ++l)
+        if (hidden[l] != 16 && hidden[l] != 32) return false;
+    return true;
+}
+int64_t scone_rows_dw_workspace_bytes(int cin, int cout) { return (int64_t)kDwCtas * 3 * (cin > 1 ? cin : 1) * cout * sizeof(float); }
+
+int scone_rows_flows(const scone_complex* cx, int b, const int32_t* traj_ptr, const int32_t* flow_edge, const float* flow_val, float* X,
+                     uint32_t* bmX, uint32_t* bm_next, bool clear, cudaStream_t st) {
+    if (clear)
+        rows_flows_kernel<true><<<b, 128, 0, st>>>(traj_ptr, flow_edge, flow_val, cx->d_rank, X, bmX, bm_next, cx->d_mptr, cx->d_ment, cx->E, b);
+    else
+        rows_flows_kernel<false><<<b, 128, 0, st>>>(traj_ptr, flow_edge, flow_val, cx->d_rank, X, bmX, bm_next, cx->d_mptr, cx->d_ment, cx->E, b);
+    SCONE_LAUNCHED();
+    return 0;
+}
+
+int scone_rows_layer0_forward(const scone_complex* cx, int act, int b, int cout, const float* X, const float* W0, const float* W1,
+                              const float* W2, float* Hout, const uint32_t* rows, const int* n_dev, uint32_t* bm_next, cudaStream_t st) {
+    if (cout == 16) return launch_rows_l0_fwd<16>(cx, act, b, X, W0, W1, W2, Hout, rows, n_dev, bm_next, st);
+    if (cout == 32) return launch_rows_l0_fwd<32>(cx, act, b, X, W0, W1, W2, Hout, rows, n_dev, bm_next, st);
+    scone_set_error("scone_rows_layer0_forward: unsupported width %d", cout);
+    return 2;
+}
+
+int scone_rows_layer0_backward(const scone_complex* cx, int b, int cout, const float* X, const float* G, const uint32_t* rows,
+                               const int* n_dev, float* dW, int accumulate, float* ws, cudaStream_t st) {
+    if (cout == 16)
+        rows_layer0_bwd_kernel<16><<<kDwCtas, 256, 0, st>>>(X, G, cx->d_mptr, cx->d_ment, rows, n_dev, b, ws);
+    else if (cout == 32)
+        rows_layer0_bwd_kernel<32><<<kDwCtas, 256, 0, st>>>(X, G, cx->d_mptr, cx->d_ment, rows, n_dev, b, ws);
+    else {
+        scone_set_error("scone_rows_layer0_backward: unsupported width %d", cout);
+        return 2;
+    }
+    SCONE_LAUNCHED();
+    rows_reduce_kernel<<<(3 * cout + 31) / 32, 256, 0, st>>>(ws, kDwCtas, 3 * cout, dW, accumulate);
+    SCONE_LAUNCHED();
+    return 0;
+}
+
+int scone_rows_backward(const scone_complex* cx, int act, int b, int cin, int cout, const float* G, const float* Hin, float* Gprev,
+                        float* Abuf, const float* W0, const float* W1, const float* W2, const uint32_t* rows, const int* n_dev,
+                        const uint32_t* bmG, const uint32_t* bmH, uint32_t* bm_next, int a_cap, int* overflow_dev, float* dW,
+                        int accumulate, float* ws, cudaStream_t st) {
+#define SCONE_RB_CASE(CI, CO)                                                                                                     \
+    if (cin == CI && cout == CO) {                                                                                                \
+        if (dispatch_rows_bwd<CI, CO>(cx, act, b, G, Hin, Gprev, Abuf, W0, W1, W2, rows, n_dev, bmG, bmH, bm_next, a_cap,          \
+                                      overflow_dev, st))                                                                          \
+            return 1;                                                                                                             \
+        return launch_rows_dw<CI, CO>(cx, Hin, bmH, Abuf, rows, n_dev, a_cap, dW, accumulate, ws, st);                             \
+    }
+    SCONE_RB_CASE(16, 16)
+    SCONE_RB_CASE(16, 32)
+    SCONE_RB_CASE(32, 16)
+    SCONE_RB_CASE(32, 32)
+#undef SCONE_RB_CASE
+    scone_set_error("scone_rows_backward: unsupported widths %d -> %d", cin, cout);
+    return 2;
+}
