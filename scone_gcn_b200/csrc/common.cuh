@@ -120,8 +120,8 @@ int scone_slab_forward(const scone_complex* cx, int act, int b, int cin, int cou
                        const float* W2, float* Hout, cudaStream_t st);
 int scone_slab_forward_rows(const scone_complex* cx, int act, int b, int cin, int cout, const float* Hin, const float* W0,
                             const float* W1, const float* W2, float* Hout, const uint8_t* occ_in, const uint32_t* rows,
-                            const int* n_rows_dev, unsigned long long* row_counter, const uint32_t* bm_in, uint32_t* bm_next,
-                            cudaStream_t st);
+                            const int* n_rows_dev, unsigned long long* row_counter, const uint32_t* bm_in, cudaStream_t st);
+int scone_rows_mark(const scone_complex* cx, int b, const uint32_t* rows, const int* n_dev, uint32_t* bm_next, cudaStream_t st);
 // bitmap-native row-list pipeline (scone_rows.cu, scone_slab.cu)
 bool scone_rows_supported(const scone_complex* cx, int n_layers, const int32_t* hidden);
 int64_t scone_rows_dw_workspace_bytes(int cin, int cout);
@@ -136,7 +136,7 @@ int scone_rows_layer0_backward(const scone_complex* cx, int b, int cout, const f
                                const int* n_dev, float* dW, int accumulate, float* ws, cudaStream_t st);
 int scone_rows_backward(const scone_complex* cx, int act, int b, int cin, int cout, const float* G, const float* Hin, float* Gprev,
                         float* Abuf, const float* W0, const float* W1, const float* W2, const uint32_t* rows, const int* n_dev,
-                        const uint32_t* bmG, const uint32_t* bmH, uint32_t* bm_next, int a_cap, int* overflow_dev, float* dW,
-                        int accumulate, float* ws, cudaStream_t st);
+                        const uint32_t* bmG, const uint32_t* bmH, int a_cap, int* overflow_dev, float* dW, int accumulate, float* ws,
+                        cudaStream_t st);
 int scone_adam_launch(float* W, float* m, float* v, const float* gradbuf, int64_t n, int32_t step, float lr,
                       float wd, void* stream);

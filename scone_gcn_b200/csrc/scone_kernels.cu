@@ -1529,7 +1529,7 @@ int launch_fwd(const scone_complex* cx, int b, const float* Hin, const float* W0
         const int wi = 1 - wo;
         if (compact_bitmap<1>(cx, b, sc.bm, sc.wl[wi], sc.n[wi], sc.tickets, st)) return 1;
         return scone_slab_forward_rows(cx, ACT, b, CIN, COUT, Hin, W0, W1, W2, Hout, occ_in, sc.wl[wi], sc.n[wi],
-                                       scone_prof_row_counter(SCONE_K_LAYER_FWD), nullptr, nullptr, st);
+                                       scone_prof_row_counter(SCONE_K_LAYER_FWD), nullptr, st);
     }
     const size_t smem = ((size_t)KD * COUT + (size_t)kWarps * TT * LDT) * sizeof(float);
     auto kern = layer_fwd_units_kernel<CIN, COUT, ACT>;

@@ -146,9 +146,11 @@ int rows_forward_mb(scone_model* m, int32_t b, const int32_t* ptr, const int32_t
         int rc;
         if (l == 0)
             rc = scone_rows_layer0_forward(cx, m->act, b, cout, m->d_X, W0, W1, W2, m->d_H[0], m->d_rows, m->d_nrows, next, s);
-        else
+        else {
+            if (next && scone_rows_mark(cx, b, m->d_rows, m->d_nrows, next, s)) return 1;
             rc = scone_slab_forward_rows(cx, m->act, b, cin, cout, m->d_H[l - 1], W0, W1, W2, m->d_H[l], nullptr, m->d_rows, m->d_nrows,
-                                         scone_prof_row_counter(SCONE_K_LAYER_FWD), m->d_bmH[l - 1], next, s);
+                                         scone_prof_row_counter(SCONE_K_LAYER_FWD), m->d_bmH[l - 1], s);
+        }
         if (rc) return rc;
         cin = cout;
     }
@@ -168,10 +170,13 @@ int rows_backward_mb(scone_model* m, int32_t b, cudaStream_t s) {
         ScopedProf prof(SCONE_K_LAYER_BWD, s);
         if (scone_compact_rows(cx, b, m->d_bmGr[l - 1], m->d_rows, m->d_nrows, m->d_tickets, s)) return 1;
         uint32_t* next = l >= 2 ? m->d_bmGr[l - 2] : nullptr;
-        if (next) SCONE_CUDA(cudaMemsetAsync(next, 0, bm_bytes, s));
+        if (next) {
+            SCONE_CUDA(cudaMemsetAsync(next, 0, bm_bytes, s));
+            if (scone_rows_mark(cx, b, m->d_rows, m->d_nrows, next, s)) return 1;
+        }
         int rc = scone_rows_backward(cx, m->act, b, m->hidden[l - 1], m->hidden[l], m->d_G[l], m->d_H[l - 1], m->d_G[l - 1], m->d_Abuf,
                                      m->d_w + m->w_off[3 * l], m->d_w + m->w_off[3 * l + 1], m->d_w + m->w_off[3 * l + 2], m->d_rows,
-                                     m->d_nrows, m->d_bmGr[l], m->d_bmH[l - 1], next, m->a_cap, m->d_overflow,
+                                     m->d_nrows, m->d_bmGr[l], m->d_bmH[l - 1], m->a_cap, m->d_overflow,
                                      m->d_grad + m->w_off[3 * l], 1, (float*)m->d_ws, s);
         if (rc) return rc;
     }

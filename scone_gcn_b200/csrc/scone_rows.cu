@@ -58,6 +58,19 @@ __global__ void __launch_bounds__(128) rows_flows_kernel(const int32_t* __restri
     }
 }
 
+// candidate rows one hop further: lane = row of the list, every entry of its merged operator row marks (column, t) in bm_next
+__global__ void __launch_bounds__(256) rows_mark_kernel(const uint32_t* __restrict__ rows, const int* __restrict__ n_ptr,
+                                                       const int32_t* __restrict__ mptr, const int2* __restrict__ ment, int b,
+                                                       uint32_t* __restrict__ bm_next) {
+    const int n = *n_ptr;
+    for (int li = blockIdx.x * blockDim.x + threadIdx.x; li < n; li += gridDim.x * blockDim.x) {
+        const uint32_t rid = __ldg(rows + li);
+        const unsigned e = rid / (unsigned)b, t = rid - e * (unsigned)b;
+        const int p1 = __ldg(mptr + e + 1);
+        for (int p = __ldg(mptr + e); p < p1; ++p) bit_set(bm_next, (unsigned)__ldg(ment + p).x * (unsigned)b + t);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // first layer forward over a row list: lane = row for the scalar gathers of X (no flag test: X is zero off its support), then
 // the 32 rows of the warp are written one after the other with lane = channel (coalesced).  Gather order = merged row order
@@ -161,7 +174,7 @@ __global__ void __launch_bounds__(256) rows_layer0_bwd_kernel(const float* __res
 // kernel on G (flag test = row bitmap of G), the three gathered terms A_k are (1) stored compactly, row i of the list at
 // Abuf[i][3*COUT], for the weight-gradient GEMM, (2) contracted with W^T on the tensor cores (3xTF32) into
 // Gprev = (sum_k A_k W_k^T) * act'(Hin) with Hin rows read through the row bitmap of H_{l-1} (an unflagged row is an exact
-// zero: act'(0)).  Candidate bits of the tensor one hop further are set on the way.
+// zero: act'(0)).
 // ---------------------------------------------------------------------------------------------------------------
 template <int CIN, int COUT, int ACT>
 __global__ void __launch_bounds__(kSlabThreads, 1) rows_bwd_kernel(const float* __restrict__ Gin, const float* __restrict__ Hin,
@@ -170,8 +183,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) rows_bwd_kernel(const float* 
                                                                   const float* __restrict__ W2, const int32_t* __restrict__ mptr,
                                                                   const int2* __restrict__ ment, const uint32_t* __restrict__ rows,
                                                                   const int* __restrict__ n_ptr, int b, const uint32_t* __restrict__ bmG,
-                                                                  const uint32_t* __restrict__ bmH, uint32_t* __restrict__ bm_next,
-                                                                  int a_cap, int* __restrict__ overflow,
+                                                                  const uint32_t* __restrict__ bmH, int a_cap, int* __restrict__ overflow,
                                                                   unsigned long long* __restrict__ row_counter) {
     using G = SlabGeom<COUT, 16>;                          // the gathered tensor has COUT channels
     constexpr int NT = CIN / 8, NL = G::NL, Q = G::Q, LPR = COUT / 4;
@@ -234,11 +246,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) rows_bwd_kernel(const float* 
                 ent[i] = on[i] ? __ldg(ment + p0[i] + k) : make_int2(0, 0);
             }
 #pragma unroll
-            for (int i = 0; i < NL; ++i) {
-                const size_t nrow = (size_t)(unsigned)ent[i].x * b + tq[i];
-                if (bm_next != nullptr && on[i] && cq == 0) bit_set(bm_next, nrow);
-                on[i] = on[i] && bit_test(bmG, nrow);
-            }
+            for (int i = 0; i < NL; ++i) on[i] = on[i] && bit_test(bmG, (unsigned)ent[i].x * (unsigned)b + (unsigned)tq[i]);
             u64 v[NL][2];
 #pragma unroll
             for (int i = 0; i < NL; ++i) {
@@ -408,7 +416,7 @@ constexpr int kDwCtas = 148 * 2;
 template <int CIN, int COUT, int ACT>
 int launch_rows_bwd(const scone_complex* cx, int b, const float* G, const float* Hin, float* Gprev, float* Abuf, const float* W0,
                     const float* W1, const float* W2, const uint32_t* rows, const int* n_ptr, const uint32_t* bmG, const uint32_t* bmH,
-                    uint32_t* bm_next, int a_cap, int* overflow, cudaStream_t st) {
+                    int a_cap, int* overflow, cudaStream_t st) {
     using Gm = SlabGeom<COUT, 16>;
     constexpr int NT = CIN / 8;
     const size_t smem = (size_t)3 * Gm::KS * NT * 32 * sizeof(uint4);
@@ -419,7 +427,7 @@ int launch_rows_bwd(const scone_complex* cx, int b, const float* G, const float*
         configured = true;
     }
     kern<<<cx->num_sms, kSlabThreads, smem, st>>>(G, Hin, Gprev, Abuf, W0, W1, W2, cx->d_mptr, cx->d_ment, rows, n_ptr, b, bmG, bmH,
-                                                  bm_next, a_cap, overflow, scone_prof_row_counter(SCONE_K_LAYER_BWD));
+                                                  a_cap, overflow, scone_prof_row_counter(SCONE_K_LAYER_BWD));
     SCONE_LAUNCHED();
     return 0;
 }
@@ -427,14 +435,14 @@ int launch_rows_bwd(const scone_complex* cx, int b, const float* G, const float*
 template <int CIN, int COUT>
 int dispatch_rows_bwd(const scone_complex* cx, int act, int b, const float* G, const float* Hin, float* Gprev, float* Abuf,
                       const float* W0, const float* W1, const float* W2, const uint32_t* rows, const int* n_ptr, const uint32_t* bmG,
-                      const uint32_t* bmH, uint32_t* bm_next, int a_cap, int* overflow, cudaStream_t st) {
+                      const uint32_t* bmH, int a_cap, int* overflow, cudaStream_t st) {
     switch (act) {
         case SCONE_ACT_TANH:
-            return launch_rows_bwd<CIN, COUT, SCONE_ACT_TANH>(cx, b, G, Hin, Gprev, Abuf, W0, W1, W2, rows, n_ptr, bmG, bmH, bm_next, a_cap, overflow, st);
+            return launch_rows_bwd<CIN, COUT, SCONE_ACT_TANH>(cx, b, G, Hin, Gprev, Abuf, W0, W1, W2, rows, n_ptr, bmG, bmH, a_cap, overflow, st);
         case SCONE_ACT_LEAKY_RELU:
-            return launch_rows_bwd<CIN, COUT, SCONE_ACT_LEAKY_RELU>(cx, b, G, Hin, Gprev, Abuf, W0, W1, W2, rows, n_ptr, bmG, bmH, bm_next, a_cap, overflow, st);
+            return launch_rows_bwd<CIN, COUT, SCONE_ACT_LEAKY_RELU>(cx, b, G, Hin, Gprev, Abuf, W0, W1, W2, rows, n_ptr, bmG, bmH, a_cap, overflow, st);
         case SCONE_ACT_RELU:
-            return launch_rows_bwd<CIN, COUT, SCONE_ACT_RELU>(cx, b, G, Hin, Gprev, Abuf, W0, W1, W2, rows, n_ptr, bmG, bmH, bm_next, a_cap, overflow, st);
+            return launch_rows_bwd<CIN, COUT, SCONE_ACT_RELU>(cx, b, G, Hin, Gprev, Abuf, W0, W1, W2, rows, n_ptr, bmG, bmH, a_cap, overflow, st);
     }
     scone_set_error("unknown activation %d", act);
     return 2;
@@ -491,6 +499,12 @@ int scone_rows_flows(const scone_complex* cx, int b, const int32_t* traj_ptr, co
     return 0;
 }
 
+int scone_rows_mark(const scone_complex* cx, int b, const uint32_t* rows, const int* n_dev, uint32_t* bm_next, cudaStream_t st) {
+    rows_mark_kernel<<<cx->num_sms * 8, 256, 0, st>>>(rows, n_dev, cx->d_mptr, cx->d_ment, b, bm_next);
+    SCONE_LAUNCHED();
+    return 0;
+}
+
 int scone_rows_layer0_forward(const scone_complex* cx, int act, int b, int cout, const float* X, const float* W0, const float* W1,
                               const float* W2, float* Hout, const uint32_t* rows, const int* n_dev, uint32_t* bm_next, cudaStream_t st) {
     if (cout == 16) return launch_rows_l0_fwd<16>(cx, act, b, X, W0, W1, W2, Hout, rows, n_dev, bm_next, st);
@@ -517,11 +531,11 @@ int scone_rows_layer0_backward(const scone_complex* cx, int b, int cout, const f
 
 int scone_rows_backward(const scone_complex* cx, int act, int b, int cin, int cout, const float* G, const float* Hin, float* Gprev,
                         float* Abuf, const float* W0, const float* W1, const float* W2, const uint32_t* rows, const int* n_dev,
-                        const uint32_t* bmG, const uint32_t* bmH, uint32_t* bm_next, int a_cap, int* overflow_dev, float* dW,
-                        int accumulate, float* ws, cudaStream_t st) {
+                        const uint32_t* bmG, const uint32_t* bmH, int a_cap, int* overflow_dev, float* dW, int accumulate, float* ws,
+                        cudaStream_t st) {
 #define SCONE_RB_CASE(CI, CO)                                                                                                     \
     if (cin == CI && cout == CO) {                                                                                                \
-        if (dispatch_rows_bwd<CI, CO>(cx, act, b, G, Hin, Gprev, Abuf, W0, W1, W2, rows, n_dev, bmG, bmH, bm_next, a_cap,          \
+        if (dispatch_rows_bwd<CI, CO>(cx, act, b, G, Hin, Gprev, Abuf, W0, W1, W2, rows, n_dev, bmG, bmH, a_cap,                   \
                                       overflow_dev, st))                                                                          \
             return 1;                                                                                                             \
         return launch_rows_dw<CI, CO>(cx, Hin, bmH, Abuf, rows, n_dev, a_cap, dW, accumulate, ws, st);                             \

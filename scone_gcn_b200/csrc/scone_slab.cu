@@ -118,7 +118,8 @@ int dispatch_fwd_act(const scone_complex* cx, int act, int ts, int b, const floa
 // candidate rows.  rows[] holds the ids e*b + t of the rows of Hout that can be non-zero (ascending: the output's row
 // bitmap compacted by compact_bitmap_kernel); a warp takes 16 consecutive list entries.  Lane group q (the LPR = C/4 lanes
 // that cover one row) walks the merged operator row of ITS row; a neighbour row is loaded only if its flag byte in occ_in
-// is set (unflagged rows are exact zeros and — with zero-fill off — may never have been written).  All 16 rows' k-th
+// (or, in the bitmap pipeline, its bit in bm_in) is set (unflagged rows are exact zeros and — with zero-fill off — may never
+// have been written).  All 16 rows' k-th
 // neighbours are in flight together.  Each row's result is independent of the other rows in its slab and uses the same
 // summation order and mma sequence as the dense slab kernel: bit-identical to it.
 // =================================================================================================================
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) layer_fwd_rows_kernel(const f
                                                                         const int2* __restrict__ ment, const uint8_t* __restrict__ occ_in,
                                                                         const uint32_t* __restrict__ rows, const int* __restrict__ n_ptr,
                                                                         int b, unsigned long long* __restrict__ row_counter,
-                                                                        const uint32_t* __restrict__ bm_in, uint32_t* __restrict__ bm_next) {
+                                                                        const uint32_t* __restrict__ bm_in) {
     using G = SlabGeom<CIN, 16>;
     constexpr int NT = COUT / 8, NL = G::NL, Q = G::Q, LPR = CIN / 4;      // Q rows per warp-wide load, LPR lanes per row
     extern __shared__ __align__(16) uint4 Bf[];
@@ -189,8 +190,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) layer_fwd_rows_kernel(const f
             }
 #pragma unroll
             for (int i = 0; i < NL; ++i) {
-                const size_t nrow = (size_t)(unsigned)ent[i].x * b + tq[i];
-                if (bm_next != nullptr && on[i] && cq == 0) bit_set(bm_next, nrow);       // one hop further: candidates of the next layer
+                const unsigned nrow = (unsigned)ent[i].x * (unsigned)b + (unsigned)tq[i];       // E*b < 2^32
                 on[i] = on[i] && (bm_in != nullptr ? bit_test(bm_in, nrow) : __ldg(occ_in + nrow) != 0);
             }
             u64 v[NL][2];
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) layer_fwd_rows_kernel(const f
 template <int CIN, int COUT, int ACT>
 int launch_fwd_rows(const scone_complex* cx, int b, const float* Hin, const float* W0, const float* W1, const float* W2, float* Hout,
                     const uint8_t* occ_in, const uint32_t* rows, const int* n_ptr, unsigned long long* row_counter,
-                    const uint32_t* bm_in, uint32_t* bm_next, cudaStream_t st) {
+                    const uint32_t* bm_in, cudaStream_t st) {
     using G = SlabGeom<CIN, 16>;
     constexpr int NT = COUT / 8;
     const size_t smem = (size_t)3 * G::KS * NT * 32 * sizeof(uint4);
@@ -255,7 +255,7 @@ int launch_fwd_rows(const scone_complex* cx, int b, const float* Hin, const floa
         configured = true;
     }
     kern<<<cx->num_sms, kSlabThreads, smem, st>>>(Hin, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, occ_in, rows, n_ptr, b, row_counter,
-                                                  bm_in, bm_next);
+                                                  bm_in);
     SCONE_LAUNCHED();
     return 0;
 }
@@ -263,11 +263,11 @@ int launch_fwd_rows(const scone_complex* cx, int b, const float* Hin, const floa
 template <int CIN, int COUT>
 int dispatch_rows_act(const scone_complex* cx, int act, int b, const float* Hin, const float* W0, const float* W1, const float* W2,
                       float* Hout, const uint8_t* occ_in, const uint32_t* rows, const int* n_ptr, unsigned long long* rc,
-                      const uint32_t* bm_in, uint32_t* bm_next, cudaStream_t st) {
+                      const uint32_t* bm_in, cudaStream_t st) {
     switch (act) {
-        case SCONE_ACT_TANH: return launch_fwd_rows<CIN, COUT, SCONE_ACT_TANH>(cx, b, Hin, W0, W1, W2, Hout, occ_in, rows, n_ptr, rc, bm_in, bm_next, st);
-        case SCONE_ACT_LEAKY_RELU: return launch_fwd_rows<CIN, COUT, SCONE_ACT_LEAKY_RELU>(cx, b, Hin, W0, W1, W2, Hout, occ_in, rows, n_ptr, rc, bm_in, bm_next, st);
-        case SCONE_ACT_RELU: return launch_fwd_rows<CIN, COUT, SCONE_ACT_RELU>(cx, b, Hin, W0, W1, W2, Hout, occ_in, rows, n_ptr, rc, bm_in, bm_next, st);
+        case SCONE_ACT_TANH: return launch_fwd_rows<CIN, COUT, SCONE_ACT_TANH>(cx, b, Hin, W0, W1, W2, Hout, occ_in, rows, n_ptr, rc, bm_in, st);
+        case SCONE_ACT_LEAKY_RELU: return launch_fwd_rows<CIN, COUT, SCONE_ACT_LEAKY_RELU>(cx, b, Hin, W0, W1, W2, Hout, occ_in, rows, n_ptr, rc, bm_in, st);
+        case SCONE_ACT_RELU: return launch_fwd_rows<CIN, COUT, SCONE_ACT_RELU>(cx, b, Hin, W0, W1, W2, Hout, occ_in, rows, n_ptr, rc, bm_in, st);
     }
     scone_set_error("unknown activation %d", act);
     return 2;
@@ -278,11 +278,10 @@ int dispatch_rows_act(const scone_complex* cx, int act, int b, const float* Hin,
 // Flagged fused layer forward over a compacted row list (see layer_fwd_rows_kernel); the caller checked scone_slab_supported.
 int scone_slab_forward_rows(const scone_complex* cx, int act, int b, int cin, int cout, const float* Hin, const float* W0,
                             const float* W1, const float* W2, float* Hout, const uint8_t* occ_in, const uint32_t* rows,
-                            const int* n_rows_dev, unsigned long long* row_counter, const uint32_t* bm_in, uint32_t* bm_next,
-                            cudaStream_t st) {
+                            const int* n_rows_dev, unsigned long long* row_counter, const uint32_t* bm_in, cudaStream_t st) {
 #define SCONE_ROWS_CASE(CI, CO)                                                                                                 \
     if (cin == CI && cout == CO)                                                                                                \
-        return dispatch_rows_act<CI, CO>(cx, act, b, Hin, W0, W1, W2, Hout, occ_in, rows, n_rows_dev, row_counter, bm_in, bm_next, st);
+        return dispatch_rows_act<CI, CO>(cx, act, b, Hin, W0, W1, W2, Hout, occ_in, rows, n_rows_dev, row_counter, bm_in, st);
     SCONE_ROWS_CASE(16, 16)
     SCONE_ROWS_CASE(16, 32)
     SCONE_ROWS_CASE(32, 16)
