@@ -100,20 +100,33 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-def ncu_traffic(kernel, E, mb, C):
+def ncu_traffic(kernel, E, mb, C, zero_fill):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full`
-    capture (profiles/prof_fill_r1m_raw.csv: cfg5, b=64) -- only reported when this run has the same launch shape."""
-    if kernel != 'zero_fill' or (E, mb, C) != (999308, 64, 32):
+    captures -- only reported when this run has the same launch shape as the capture (cfg5).
+      zero_fill  profiles/prof_fill_r1m_raw.csv       (dense-stream mode, b = 64)
+      layer_fwd  profiles/prof_rows_fwd_r1t_raw.csv   (row-list pipeline, b = 128: the two layer_fwd_rows_kernel launches of
+                                                       one micro-batch, averaged)"""
+    src = None
+    if kernel == 'zero_fill' and (E, mb, C) == (999308, 64, 32):
+        src = 'prof_fill_r1m_raw.csv'
+    if kernel == 'layer_fwd' and not zero_fill and (E, mb, C) == (999308, 128, 32):
+        src = 'prof_rows_fwd_r1t_raw.csv'
+    if src is None:
         return None
     try:
         import csv
-        rows = list(csv.reader(open(os.path.join(ROOT, 'profiles', 'prof_fill_r1m_raw.csv'))))
-        hdr, unit, val = rows[0], rows[1], rows[2]
-        tot = 0.0
-        for name in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
-            i = hdr.index(name)
-            tot += float(val[i]) * {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[unit[i]]
-        return tot
+        rows = list(csv.reader(open(os.path.join(ROOT, 'profiles', src))))
+        hdr, unit = rows[0], rows[1]
+        scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+        tot, n = 0.0, 0
+        for val in rows[2:]:
+            if len(val) < len(hdr):
+                continue
+            for name in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+                i = hdr.index(name)
+                tot += float(val[i]) * scale[unit[i]]
+            n += 1
+        return tot / n if n else None
     except Exception:
         return None
 
@@ -346,7 +359,7 @@ def main():
     dom = max(kernels, key=lambda k_: kernels[k_]['share_of_kernel_time'])
     dense_bytes_per_traj = 4.0 * E * (15 * C + 2)
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': kernels[dom].get('achieved_gbs'), 'peak': peak, 'unit': 'GB/s',
-                'frac': kernels[dom].get('frac'), 'traffic': ncu_traffic(dom, E, mb, C), 'peak_source': peak_src,
+                'frac': kernels[dom].get('frac'), 'traffic': ncu_traffic(dom, E, mb, C, args.zero_fill), 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': kernels[dom].get('algorithmic_bytes_per_launch'),
                 'rows_per_step': {k_: v_ / args.steps for k_, v_ in rows.items()},
                 'dense_rows_per_step': float(E) * B * 2,
@@ -356,8 +369,10 @@ def main():
                                      'note': 'SURVEY 8(d) dense formula 4*E*(15C+2) bytes per trajectory times the measured per-GPU '
                                              'trajectories/s: what a dense-streaming implementation would have to move to match'},
                 'bytes_model': 'layer_fwd / layer_bwd: rows produced (device-counted) x 4*(Cin+Cout) / 4*(2*Cin+Cout) bytes per launch; the family '
-                               'time includes its worklist kernels (scatter, compaction); these kernels are L2-latency / issue bound, not HBM bound '
-                               '(profiles/); zero_fill (dense-stream mode): 4*E*b*C bytes per launch'}
+                               'time includes its bitmap compaction, candidate marking and (backward) the weight-gradient GEMM; these kernels are '
+                               'L2-latency / issue bound on ~0.5 M rows per launch, not HBM bound (profiles/prof_rows_fwd_r1t_*); '
+                               'zero_fill (dense-stream mode): 4*E*b*C bytes per launch',
+                'pipeline': 'row lists + bitmaps' if L.scone_model_get_pipeline(net.handle) else 'unit kernels + byte flags'}
 
     # end to end through the host API
     barrier()
