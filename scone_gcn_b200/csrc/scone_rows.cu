@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) rows_bwd_kernel(const float* 
             tq[i] = (int)(rid[i] - (unsigned)e * (unsigned)b);
             cpos[i] = (COUT == 32 && i >= 2) ? (cq ^ 4) : cq;
             P[i] = Gb + (size_t)((unsigned)(tq[i] * COUT + 4 * cpos[i]) * 4u);
+            asm volatile("" : "+l"(P[i]));
             p0[i] = valid[i] ? __ldg(mptr + e) : 0;
             len[i] = valid[i] ? __ldg(mptr + e + 1) - p0[i] : 0;
             own[i] = valid[i] && bit_test(bmG, rid[i]);
@@ -246,7 +247,10 @@ __global__ void __launch_bounds__(kSlabThreads, 1) rows_bwd_kernel(const float* 
                 ent[i] = on[i] ? __ldg(ment + p0[i] + k) : make_int2(0, 0);
             }
 #pragma unroll
-            for (int i = 0; i < NL; ++i) on[i] = on[i] && bit_test(bmG, (unsigned)ent[i].x * (unsigned)b + (unsigned)tq[i]);
+            for (int i = 0; i < NL; ++i) {                 // branch-free bit test (entry {0,0} of an idle lane tests row tq: in range)
+                const unsigned nrow = (unsigned)ent[i].x * (unsigned)b + (unsigned)tq[i];
+                on[i] = on[i] && ((__ldg(bmG + (nrow >> 5)) >> (nrow & 31)) & 1u) != 0u;
+            }
             u64 v[NL][2];
 #pragma unroll
             for (int i = 0; i < NL; ++i) {

@@ -123,7 +123,7 @@ int dispatch_fwd_act(const scone_complex* cx, int act, int ts, int b, const floa
 // neighbours are in flight together.  Each row's result is independent of the other rows in its slab and uses the same
 // summation order and mma sequence as the dense slab kernel: bit-identical to it.
 // =================================================================================================================
-template <int CIN, int COUT, int ACT>
+template <int CIN, int COUT, int ACT, bool BITS>
 __global__ void __launch_bounds__(kSlabThreads, 1) layer_fwd_rows_kernel(const float* __restrict__ Hin, float* __restrict__ Hout,
                                                                         const float* __restrict__ W0, const float* __restrict__ W1,
                                                                         const float* __restrict__ W2, const int32_t* __restrict__ mptr,
@@ -165,9 +165,10 @@ __global__ void __launch_bounds__(kSlabThreads, 1) layer_fwd_rows_kernel(const f
             tq[i] = (int)(rid[i] - (unsigned)e * (unsigned)b);
             const int cpos = (CIN == 32 && i >= 2) ? (cq ^ 4) : cq;
             P[i] = Hb + (size_t)((unsigned)(tq[i] * CIN + 4 * cpos) * 4u);
+            asm volatile("" : "+l"(P[i]));                 // keep base + lane offset folded: one IMAD.WIDE per load address
             p0[i] = valid ? __ldg(mptr + e) : 0;
             len[i] = valid ? __ldg(mptr + e + 1) - p0[i] : 0;
-            own[i] = valid && (bm_in != nullptr ? bit_test(bm_in, rid[i]) : __ldg(occ_in + rid[i]) != 0);
+            own[i] = valid && (BITS ? bit_test(bm_in, rid[i]) : __ldg(occ_in + rid[i]) != 0);
             maxlen = max(maxlen, len[i]);
         }
 #pragma unroll
@@ -189,9 +190,10 @@ __global__ void __launch_bounds__(kSlabThreads, 1) layer_fwd_rows_kernel(const f
                 ent[i] = on[i] ? __ldg(ment + p0[i] + k) : make_int2(0, 0);
             }
 #pragma unroll
-            for (int i = 0; i < NL; ++i) {
+            for (int i = 0; i < NL; ++i) {                 // branch-free flag test (entry {0,0} of an idle lane tests row tq: in range)
                 const unsigned nrow = (unsigned)ent[i].x * (unsigned)b + (unsigned)tq[i];       // E*b < 2^32
-                on[i] = on[i] && (bm_in != nullptr ? bit_test(bm_in, nrow) : __ldg(occ_in + nrow) != 0);
+                const unsigned f = BITS ? (__ldg(bm_in + (nrow >> 5)) >> (nrow & 31)) & 1u : (unsigned)__ldg(occ_in + nrow);
+                on[i] = on[i] && f != 0u;
             }
             u64 v[NL][2];
 #pragma unroll
@@ -248,14 +250,18 @@ int launch_fwd_rows(const scone_complex* cx, int b, const float* Hin, const floa
     using G = SlabGeom<CIN, 16>;
     constexpr int NT = COUT / 8;
     const size_t smem = (size_t)3 * G::KS * NT * 32 * sizeof(uint4);
-    auto kern = layer_fwd_rows_kernel<CIN, COUT, ACT>;
     static bool configured = false;
     if (!configured) {
-        SCONE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCONE_CUDA(cudaFuncSetAttribute(layer_fwd_rows_kernel<CIN, COUT, ACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCONE_CUDA(cudaFuncSetAttribute(layer_fwd_rows_kernel<CIN, COUT, ACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    kern<<<cx->num_sms, kSlabThreads, smem, st>>>(Hin, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, occ_in, rows, n_ptr, b, row_counter,
-                                                  bm_in);
+    if (bm_in != nullptr)
+        layer_fwd_rows_kernel<CIN, COUT, ACT, true><<<cx->num_sms, kSlabThreads, smem, st>>>(Hin, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment,
+                                                                                           occ_in, rows, n_ptr, b, row_counter, bm_in);
+    else
+        layer_fwd_rows_kernel<CIN, COUT, ACT, false><<<cx->num_sms, kSlabThreads, smem, st>>>(Hin, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment,
+                                                                                            occ_in, rows, n_ptr, b, row_counter, bm_in);
     SCONE_LAUNCHED();
     return 0;
 }
