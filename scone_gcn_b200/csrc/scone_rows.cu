@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) rows_bwd_kernel(const float* 
 #pragma unroll
         for (int i = 0; i < NL; ++i)
             if (own[i]) ldg128(reinterpret_cast<const float*>(P[i] + (size_t)(rid[i] / (unsigned)b) * rowbytes), acc[0][i][0], acc[0][i][1]);
+#pragma unroll 2
         for (int k = 0; k < maxlen; ++k) {
             int2 ent[NL];
             bool on[NL];
