@@ -278,126 +278,6 @@ __global__ void __launch_bounds__(kThreads) layer_fwd_dense_kernel(const float* 
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Tensor-core flavour of the dense forward layer: the 3C x C product runs on mma.sync m16n8k8 TF32 with the 3xTF32 split
-// (a = a_hi + a_lo, w = w_hi + w_lo;  a w ~ a_lo w_hi + a_hi w_lo + a_hi w_hi, fp32 accumulate), which keeps fp32-grade
-// accuracy (~2^-21 relative) — plain TF32 / BF16 would break the 1e-5 tolerance.  Each warp owns a 16-row slab of the
-// tile (the rows it gathered itself), so the tile loop needs no CTA barrier: warps run through
-// gather -> split -> mma -> activation -> coalesced store on their own.
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-template <int CIN, int COUT>
-struct FwdMmaShape {
-    static constexpr int TT = kTileCols / CIN, TE = kTileRows / TT;      // tile = TE edges x TT trajectories = 128 rows
-    static constexpr int EPW = 16 / TT;                                  // edges per warp slab (16 rows)
-    static constexpr int KD = 3 * CIN, LDT = KD + 4, LDW = COUT + 8, NT = COUT / 8;
-    static_assert(TT <= 16 && CIN % 8 == 0 && COUT % 8 == 0, "mma path needs widths that are multiples of 8 (>= 8)");
-    static constexpr size_t smem_floats = (size_t)2 * KD * LDW + (size_t)kWarps * 16 * LDT;
-};
-
-template <int CIN, int COUT, int ACT>
-__global__ void __launch_bounds__(kThreads) layer_fwd_dense_mma_kernel(const float* __restrict__ Hin, float* __restrict__ Hout,
-                                                                      const float* __restrict__ W0, const float* __restrict__ W1,
-                                                                      const float* __restrict__ W2, DevCsr S0, DevCsr S1, int E, int b) {
-    using Sh = FwdMmaShape<CIN, COUT>;
-    constexpr int TT = Sh::TT, TE = Sh::TE, EPW = Sh::EPW, KD = Sh::KD, LDT = Sh::LDT, LDW = Sh::LDW, NT = Sh::NT;
-    extern __shared__ __align__(16) float smem[];
-    uint32_t* Whi = reinterpret_cast<uint32_t*>(smem);            // [KD][LDW]  tf32(w)
-    uint32_t* Wlo = Whi + KD * LDW;                               // [KD][LDW]  tf32(w - tf32(w))
-    float* Tw = smem + 2 * KD * LDW;                              // [kWarps][16][LDT]
-    for (int i = threadIdx.x; i < 3 * CIN * COUT; i += kThreads) {
-        const int k = i / COUT, co = i % COUT;                    // k = term * CIN + ci
-        const float* Wsrc = k < CIN ? W0 : (k < 2 * CIN ? W1 : W2);
-        const float w = Wsrc[(k % CIN) * COUT + co];
-        const uint32_t hi = to_tf32(w);
-        Whi[k * LDW + co] = hi;
-        Wlo[k * LDW + co] = to_tf32(w - __uint_as_float(hi));
-    }
-    __syncthreads();
-    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, g = lane >> 2, tig = lane & 3;
-    const size_t rowlen_in = (size_t)b * CIN, rowlen_out = (size_t)b * COUT;
-    const int n_tb = (b + TT - 1) / TT, n_eb = (E + TE - 1) / TE;
-    const int jl = (4 * lane) / CIN, cil = (4 * lane) % CIN;
-    float* T = Tw + warp * 16 * LDT;
-
-    for (int tile = blockIdx.x; tile < n_tb * n_eb; tile += gridDim.x) {
-        const int tb = tile % n_tb, eb = tile / n_tb;
-        const int e0 = eb * TE + warp * EPW, t0 = tb * TT;
-        const int colofs = tb * kTileCols + 4 * lane;
-        const bool colok = colofs < (int)rowlen_in;
-        // gather this warp's EPW edges (16 rows)
-#pragma unroll
-        for (int r = 0; r < EPW; ++r) {
-            const int e = e0 + r;
-            float4 a0 = zero4(), a1 = a0, a2 = a0;
-            if (e < E && colok) {
-                a0 = __ldg(reinterpret_cast<const float4*>(Hin + (size_t)e * rowlen_in + colofs));
-                a1 = gather_row4_dense(Hin, rowlen_in, colofs, S0, e);
-                a2 = gather_row4_dense(Hin, rowlen_in, colofs, S1, e);
-            }
-            float* dst = T + (r * TT + jl) * LDT + cil;
-            *reinterpret_cast<float4*>(dst) = a0;
-            *reinterpret_cast<float4*>(dst + CIN) = a1;
-            *reinterpret_cast<float4*>(dst + 2 * CIN) = a2;
-        }
-        __syncwarp();
-        float acc[NT][4];
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-#pragma unroll 2
-        for (int ks = 0; ks < KD / 8; ++ks) {
-            const int k0 = ks * 8;
-            float af[4];
-            af[0] = T[g * LDT + k0 + tig];
-            af[1] = T[(g + 8) * LDT + k0 + tig];
-            af[2] = T[g * LDT + k0 + tig + 4];
-            af[3] = T[(g + 8) * LDT + k0 + tig + 4];
-            uint32_t ahi[4], alo[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                ahi[q] = to_tf32(af[q]);
-                alo[q] = to_tf32(af[q] - __uint_as_float(ahi[q]));
-            }
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-                const int wi0 = (k0 + tig) * LDW + nt * 8 + g, wi1 = (k0 + tig + 4) * LDW + nt * 8 + g;
-                const uint32_t bh0 = Whi[wi0], bh1 = Whi[wi1], bl0 = Wlo[wi0], bl1 = Wlo[wi1];
-                mma_tf32(acc[nt], alo, bh0, bh1);
-                mma_tf32(acc[nt], ahi, bl0, bl1);
-                mma_tf32(acc[nt], ahi, bh0, bh1);
-            }
-        }
-        __syncwarp();                       // all lanes finished reading T: reuse its first COUT columns for the outputs
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            *reinterpret_cast<float2*>(T + g * LDT + nt * 8 + 2 * tig) = make_float2(act_fn<ACT>(acc[nt][0]), act_fn<ACT>(acc[nt][1]));
-            *reinterpret_cast<float2*>(T + (g + 8) * LDT + nt * 8 + 2 * tig) = make_float2(act_fn<ACT>(acc[nt][2]), act_fn<ACT>(acc[nt][3]));
-        }
-        __syncwarp();
-        // coalesced 128-bit stores: 16 rows x COUT floats
-        constexpr int Q = COUT / 4;                       // float4 per row
-#pragma unroll
-        for (int it = lane; it < 16 * Q; it += 32) {
-            const int rho = it / Q, c4 = it % Q;
-            const int e = e0 + rho / TT, t = t0 + rho % TT;
-            if (e < E && t < b)
-                *reinterpret_cast<float4*>(Hout + (size_t)e * rowlen_out + (size_t)t * COUT + 4 * c4) =
-                    *reinterpret_cast<const float4*>(T + rho * LDT + 4 * c4);
-        }
-        __syncwarp();                       // T is rewritten by the next tile's gather
-    }
-}
-
 template <int CIN, int COUT>
 struct BwdShape {
     static constexpr int TT = kTileCols / COUT, TE = kTileRows / TT;
@@ -729,7 +609,10 @@ __global__ void __launch_bounds__(kThreads) compact_bitmap_kernel(const uint32_t
     __syncthreads();
     long long base = s_prefix;
     const int total = s_total;
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *n_out = (int)(base + total);
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        n_out[0] = (int)(base + total);
+        n_out[1] = 0;                                     // tile counter of the row-list kernel that consumes this list
+    }
     if (total == 0) return;                               // (uniform) nothing flagged in this slice
     // pass 2: block-exclusive scan of the per-thread counts of a chunk, ids written in ascending order
     for (long long w0 = lo; w0 < hi; w0 += kChunk) {
@@ -1497,17 +1380,7 @@ int launch_fwd(const scone_complex* cx, int b, const float* Hin, const float* W0
             return 0;
         }
         const long long n_tiles = (long long)((b + TT - 1) / TT) * ((cx->E + TE - 1) / TE);
-        // Opt-in experiment (SCONE_B200_DENSE_MMA=1, widths <= 32): measured SLOWER than the SIMT product on B200 (3.38 vs
-        // 2.96 ms at E=270k, b=32, C=32) because the dense kernel is bound by L1/LSU wavefronts of the 17-row gather and of
-        // the shared-memory operand fetches, not by FMA issue; kept for the next round's two-hop / tcgen05 work.
-        static const bool use_mma = getenv("SCONE_B200_DENSE_MMA") && getenv("SCONE_B200_DENSE_MMA")[0] == '1';
-        if (use_mma && CIN <= 32 && COUT <= 32) {             // 3xTF32 tensor-core product, barrier-free warps
-            const size_t smem = FwdMmaShape<CIN, COUT>::smem_floats * sizeof(float);
-            auto kern = layer_fwd_dense_mma_kernel<CIN, COUT, ACT>;
-            static int occ = 0;
-            if (!occ && occupancy_of(kern, smem, &occ)) return 1;
-            kern<<<grid_for(cx, n_tiles, occ), kThreads, smem, st>>>(Hin, Hout, W0, W1, W2, cx->S(0), cx->S(1), cx->E, b);
-        } else {                                              // fp32 SIMT register-tiled product
+        {                                                     // fp32 SIMT register-tiled product
             const size_t smem = ((size_t)kTileRows * LDT + (size_t)KD * COUT) * sizeof(float);
             auto kern = layer_fwd_dense_kernel<CIN, COUT, ACT>;
             static int occ = 0;

@@ -143,11 +143,17 @@ __global__ void __launch_bounds__(kSlabThreads, 1) layer_fwd_rows_kernel(const f
     const int n = *n_ptr;
     const int n_slabs = (n + 15) / 16;
     const int n_tiles = (n_slabs + kSlabWarps - 1) / kSlabWarps;
-    const int per = (n_tiles + gridDim.x - 1) / gridDim.x;
-    const int lo = blockIdx.x * per, hi = min(n_tiles, lo + per);
-    if (row_counter != nullptr && threadIdx.x == 0 && lo < hi)
-        atomicAdd(row_counter, (unsigned long long)(min(n, hi * kSlabWarps * 16) - lo * kSlabWarps * 16));
-    for (int tile = lo; tile < hi; ++tile) {
+    if (row_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(row_counter, (unsigned long long)n);
+    // tiles (16 consecutive slabs, one per warp) are handed out dynamically: n_ptr[1] is a counter the compaction kernel zeroed
+    // (per-tile cost varies with how many distinct edges a slab mixes; a static split left SMs idle for a third of the kernel)
+    __shared__ int s_tile;
+    int* tile_counter = const_cast<int*>(n_ptr) + 1;
+    for (;;) {
+        __syncthreads();                                  // every warp is done with the previous s_tile
+        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= n_tiles) break;
         const int slab = tile * kSlabWarps + warp;
         if (slab >= n_slabs) continue;
         // this lane's row in each load slot
