@@ -34,9 +34,9 @@ sys.path.insert(0, ROOT)
 
 CONFIGS = {
     # name: (n_nodes for the generator, per-GPU batch, hidden, micro-batch)
-    'cfg5': dict(n_nodes=370000, batch=4096, hidden=32, micro_batch=128,
+    'cfg5': dict(n_nodes=370000, batch=4096, hidden=32, micro_batch=2048,
                  desc='1M-edge synthetic holed Delaunay complex, 4096 trajectories per GPU (32768 at 8 GPUs), 3-layer SCoNe hidden 32'),
-    'cfg4': dict(n_nodes=110000, batch=4096, hidden=32, micro_batch=128,
+    'cfg4': dict(n_nodes=110000, batch=4096, hidden=32, micro_batch=4096,
                  desc='~300k-edge synthetic complex, batch 4096, 3-layer SCoNe hidden 32'),
     'cfg1': dict(n_nodes=400, batch=1000, hidden=16, micro_batch=256,
                  desc='default synthetic complex (400 nodes), 1000 trajectories, 3-layer SCoNe hidden 16'),
@@ -372,7 +372,8 @@ def main():
                                'time includes its bitmap compaction, candidate marking and (backward) the weight-gradient GEMM; these kernels are '
                                'L2-latency / issue bound on ~0.5 M rows per launch, not HBM bound (profiles/prof_rows_fwd_r1t_*); '
                                'zero_fill (dense-stream mode): 4*E*b*C bytes per launch',
-                'pipeline': 'row lists + bitmaps' if L.scone_model_get_pipeline(net.handle) else 'unit kernels + byte flags'}
+                'pipeline': {2: 'row lists, compact tensors', 1: 'row lists, dense tensors', 0: 'unit kernels, byte flags'}[
+                    L.scone_model_get_pipeline(net.handle)]}
 
     # end to end through the host API
     barrier()
@@ -393,28 +394,35 @@ def main():
     # [E][b][C] tensor once per micro-batch (zero_fill_kernel on a side stream is then the HBM-bound dominant kernel)
     other_mode = None
     if args.extras:
-        net.set_zero_fill(1 - args.zero_fill)
-        try:
-            step_dev()
-            barrier()
-            L.scone_profile_reset()
-            L.scone_profile_enable(1)
-            ev0.record()
-            for _ in range(args.steps):
-                step_dev()
-            ev1.record()
-            barrier()
-            L.scone_profile_enable(0)
-            sm_ms = max_over_ranks(ev0.elapsed_time(ev1))
-            fam2, rows2 = read_families()
-            k2 = kernel_table(fam2, rows2)
-            other_mode = {'zero_fill': 1 - args.zero_fill, 'value': world * B * args.steps / (sm_ms / 1e3), 'unit': 'trajectories/s',
-                          'ms_per_step': sm_ms / args.steps,
-                          'zero_fill_kernel': k2.get('zero_fill'),
-                          'note': 'zero_fill=1: every activation / gradient tensor is a complete dense array (each byte written once per '
-                                  'micro-batch by zero_fill_kernel, timed on its side stream); zero_fill=0: rows outside the support are never written'}
-        finally:
-            net.set_zero_fill(args.zero_fill)
+        mb2 = min(64, B)                                    # dense tensors: 6 x E x mb2 x C x 4 bytes must fit
+        net2 = sg.SconeModel(cx, [C, C, C], micro_batch=mb2, zero_fill=not args.zero_fill)
+        net2.set_weights(net.get_weights())
+
+        def step_other():
+            _lib.check(L.scone_model_loss_grad_dev(net2.handle, B, _lib.dptr(d['ptr']), _lib.dptr(d['edge']), _lib.dptr(d['val']),
+                                                   _lib.dptr(d['last']), _lib.dptr(d['tgt']), _lib.dptr(d['mask']), 1, stream))
+            net2.adam_step(step_no[0], lr, wd, stream)
+        step_other()
+        barrier()
+        L.scone_profile_reset()
+        L.scone_profile_enable(1)
+        ev0.record()
+        for _ in range(args.steps):
+            step_other()
+        ev1.record()
+        barrier()
+        L.scone_profile_enable(0)
+        sm_ms = max_over_ranks(ev0.elapsed_time(ev1))
+        fam2, rows2 = read_families()
+        mb_main, mb = mb, mb2
+        k2 = kernel_table(fam2, rows2)
+        mb = mb_main
+        other_mode = {'zero_fill': 1 - args.zero_fill, 'micro_batch': mb2, 'value': world * B * args.steps / (sm_ms / 1e3),
+                      'unit': 'trajectories/s', 'ms_per_step': sm_ms / args.steps, 'zero_fill_kernel': k2.get('zero_fill'),
+                      'note': 'zero_fill=1 (dense-stream mode, unit kernels): every activation / gradient tensor is a complete dense array '
+                              '(each byte written once per micro-batch by zero_fill_kernel, timed on its side stream); zero_fill=0: rows '
+                              'outside the support are never written'}
+        del net2
 
     # extra 2: the contracted DENSE-tile measurement (north-star / SURVEY 8d): one fused 32->32 layer on dense random
     # features, no occupancy information, algorithmic bytes 4*E*b*(Cin+Cout) fwd and 4*E*b*(2*Cout+Cin) bwd

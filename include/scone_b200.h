@@ -146,9 +146,14 @@ int64_t scone_model_num_params(const scone_model* m);
  * [E][b][C] arrays, the dense-streaming formulation).  Results are bit-identical either way. */
 int scone_model_set_zero_fill(scone_model* m, int32_t on);
 int scone_model_get_zero_fill(const scone_model* m);
-/* Model-level pipeline: 1 (default when every hidden width is 16 or 32) = row lists: each tensor carries a row bitmap, producers
- * mark the candidate rows of the next tensor, per layer one bitmap compaction + one row-list kernel (tensor-core product);
- * 0 = unit kernels over byte flags (every width; fp32 SIMT).  zero_fill = 1 always uses 0.  Same results within fp32 rounding. */
+/* Model-level pipeline (same results within fp32 rounding; buffers of a pipeline are allocated on first use):
+ *   2 (default when every hidden width is 16 or 32) = row lists over COMPACT tensors: each tensor carries a row bitmap, row r is
+ *     stored at index rank(r) = its position in the compacted row list, producers mark the candidate rows of the next tensor,
+ *     per layer one bitmap compaction + one row-list kernel (tensor-core product).  Memory and traffic follow the support of
+ *     the trajectories, so micro_batch can be thousands (E * micro_batch < 2^31).  A compact tensor holds at most 32 M rows and
+ *     the backward's A buffer 6 M rows per micro-batch; beyond that scone_model_read_grads reports an error.
+ *   1 = the same row-list kernels over dense [E][micro_batch][C] tensors.
+ *   0 = unit kernels over byte flags and dense tensors (every width; fp32 SIMT).  zero_fill = 1 always uses 0. */
 int scone_model_set_pipeline(scone_model* m, int32_t which);
 int scone_model_get_pipeline(const scone_model* m);
 int scone_model_set_weights(scone_model* m, const float* weights_host);     /* also resets Adam state */

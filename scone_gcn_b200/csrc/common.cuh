@@ -120,23 +120,34 @@ int scone_slab_forward(const scone_complex* cx, int act, int b, int cin, int cou
                        const float* W2, float* Hout, cudaStream_t st);
 int scone_slab_forward_rows(const scone_complex* cx, int act, int b, int cin, int cout, const float* Hin, const float* W0,
                             const float* W1, const float* W2, float* Hout, const uint8_t* occ_in, const uint32_t* rows,
-                            const int* n_rows_dev, unsigned long long* row_counter, const uint32_t* bm_in, cudaStream_t st);
-int scone_rows_mark(const scone_complex* cx, int b, const uint32_t* rows, const int* n_dev, uint32_t* bm_next, cudaStream_t st);
+                            const int* n_rows_dev, unsigned long long* row_counter, const uint32_t* bm_in, const uint32_t* pref_in,
+                            int out_cap, int* overflow_dev, cudaStream_t st);
+int scone_rows_mark(const scone_complex* cx, int b, const uint32_t* rows, const int* n_dev, uint32_t* bm_next, int list_cap,
+                    cudaStream_t st);
 // bitmap-native row-list pipeline (scone_rows.cu, scone_slab.cu)
 bool scone_rows_supported(const scone_complex* cx, int n_layers, const int32_t* hidden);
 int64_t scone_rows_dw_workspace_bytes(int cin, int cout);
 size_t scone_ticket_bytes();
 int scone_compact_rows(const scone_complex* cx, int b, const uint32_t* bm, uint32_t* list, int* n_dev, unsigned long long* tickets,
-                       cudaStream_t st);
+                       cudaStream_t st, uint32_t* pref_out = nullptr, long long list_cap = (1ll << 62));
 int scone_rows_flows(const scone_complex* cx, int b, const int32_t* traj_ptr, const int32_t* flow_edge, const float* flow_val, float* X,
                      uint32_t* bmX, uint32_t* bm_next, bool clear, cudaStream_t st);
 int scone_rows_layer0_forward(const scone_complex* cx, int act, int b, int cout, const float* X, const float* W0, const float* W1,
-                              const float* W2, float* Hout, const uint32_t* rows, const int* n_dev, uint32_t* bm_next, cudaStream_t st);
+                              const float* W2, float* Hout, const uint32_t* rows, const int* n_dev, uint32_t* bm_next, int out_cap,
+                              int* overflow_dev, cudaStream_t st);
 int scone_rows_layer0_backward(const scone_complex* cx, int b, int cout, const float* X, const float* G, const uint32_t* rows,
-                               const int* n_dev, float* dW, int accumulate, float* ws, cudaStream_t st);
+                               const int* n_dev, float* dW, int accumulate, float* ws, int g_cap, cudaStream_t st);
 int scone_rows_backward(const scone_complex* cx, int act, int b, int cin, int cout, const float* G, const float* Hin, float* Gprev,
                         float* Abuf, const float* W0, const float* W1, const float* W2, const uint32_t* rows, const int* n_dev,
                         const uint32_t* bmG, const uint32_t* bmH, int a_cap, int* overflow_dev, float* dW, int accumulate, float* ws,
-                        cudaStream_t st);
+                        const uint32_t* prefG, const uint32_t* prefH, cudaStream_t st);
+int scone_rows_readout_forward(const scone_complex* cx, int b, int C, const float* HL, const float* wout, const int32_t* last_nodes,
+                               float* logprobs, const uint32_t* bmH, const uint32_t* prefH, uint32_t* bmG, uint32_t* bm_cand,
+                               cudaStream_t st);
+int scone_rows_readout_backward(const scone_complex* cx, int act, int b, int C, const float* HL, const float* wout,
+                                const int32_t* last_nodes, const float* logprobs, const int32_t* target_idx, const float* mask,
+                                float scale, float* GL, const int* n_dev, int g_cap, int* overflow_dev, float* dwout, float* nll_sum,
+                                float* count, int accumulate, float* ws, const uint32_t* bmH, const uint32_t* prefH, const uint32_t* bmG,
+                                const uint32_t* prefG, cudaStream_t st);
 int scone_adam_launch(float* W, float* m, float* v, const float* gradbuf, int64_t n, int32_t step, float lr,
                       float wd, void* stream);

@@ -565,7 +565,11 @@ __device__ __forceinline__ uint32_t collapse_quads(uint32_t w) {
 template <int R>
 __global__ void __launch_bounds__(kThreads) compact_bitmap_kernel(const uint32_t* __restrict__ bm, long long n_words,
                                                                  uint32_t* __restrict__ list, int* __restrict__ n_out,
-                                                                 unsigned long long* __restrict__ tickets) {
+                                                                 unsigned long long* __restrict__ tickets,
+                                                                 uint32_t* __restrict__ pref_out, long long list_cap) {
+    // pref_out (optional, R == 1): pref_out[w] = number of set bits before word w = list index of word w's first set bit; the
+    // rank of row r is then pref_out[r >> 5] + popc(bm[r >> 5] & ((1 << (r & 31)) - 1)).  Words of slices without any set bit
+    // are not written (their rank is never asked for).
     constexpr int kChunk = 4 * kThreads;                  // words per chunk: one 128-bit load per thread
     __shared__ int s_warp[kWarps];
     __shared__ long long s_prefix;
@@ -640,10 +644,12 @@ __global__ void __launch_bounds__(kThreads) compact_bitmap_kernel(const uint32_t
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             uint32_t cc = c[q];
+            if (pref_out != nullptr && w + q < hi) pref_out[w + q] = (uint32_t)off;
             while (cc) {
                 const int pbit = __ffs(cc) - 1;
                 cc &= cc - 1;
-                list[off++] = (uint32_t)(((w + q) * 32 + pbit) / R);
+                if (off < list_cap) list[off] = (uint32_t)(((w + q) * 32 + pbit) / R);     // (*n_out still reports the full count)
+                ++off;
             }
         }
         base += ctot;
@@ -1321,14 +1327,14 @@ bool bitmap_ok(int tt, int b) { return (tt == 4 || tt == 8 || tt == 16) && b % t
 
 template <int TT>
 int compact_bitmap(const scone_complex* cx, int b, const uint32_t* bm, uint32_t* list, int* n_ptr, unsigned long long* tickets,
-                   cudaStream_t st) {
+                   cudaStream_t st, uint32_t* pref_out = nullptr, long long list_cap = (1ll << 62)) {
     constexpr int R = TT;                // TT = 1: row list
     const long long n_words = ((long long)cx->E * b + 31) / 32;
     int grid = cx->num_sms * 4 < kTicketSlots ? cx->num_sms * 4 : kTicketSlots;
     if (n_words < (long long)grid * 4 * kThreads) grid = (int)((n_words + 4 * kThreads - 1) / (4 * kThreads));
     if (grid < 1) grid = 1;
     SCONE_CUDA(cudaMemsetAsync(tickets, 0, (size_t)grid * 8, st));
-    compact_bitmap_kernel<R><<<grid, kThreads, 0, st>>>(bm, n_words, list, n_ptr, tickets);
+    compact_bitmap_kernel<R><<<grid, kThreads, 0, st>>>(bm, n_words, list, n_ptr, tickets, pref_out, list_cap);
     SCONE_LAUNCHED();
     return 0;
 }
@@ -1402,7 +1408,7 @@ int launch_fwd(const scone_complex* cx, int b, const float* Hin, const float* W0
         const int wi = 1 - wo;
         if (compact_bitmap<1>(cx, b, sc.bm, sc.wl[wi], sc.n[wi], sc.tickets, st)) return 1;
         return scone_slab_forward_rows(cx, ACT, b, CIN, COUT, Hin, W0, W1, W2, Hout, occ_in, sc.wl[wi], sc.n[wi],
-                                       scone_prof_row_counter(SCONE_K_LAYER_FWD), nullptr, st);
+                                       scone_prof_row_counter(SCONE_K_LAYER_FWD), nullptr, nullptr, 0, nullptr, st);
     }
     const size_t smem = ((size_t)KD * COUT + (size_t)kWarps * TT * LDT) * sizeof(float);
     auto kern = layer_fwd_units_kernel<CIN, COUT, ACT>;
@@ -1497,8 +1503,8 @@ bool width_ok(int c) { return c == 8 || c == 16 || c == 32 || c == 64; }
 
 // ascending list of the set bits of a row bitmap (ids e*b + t) and their count, both on the device; tickets: kTicketSlots * 8 bytes
 int scone_compact_rows(const scone_complex* cx, int b, const uint32_t* bm, uint32_t* list, int* n_dev, unsigned long long* tickets,
-                       cudaStream_t st) {
-    return compact_bitmap<1>(cx, b, bm, list, n_dev, tickets, st);
+                       cudaStream_t st, uint32_t* pref_out, long long list_cap) {
+    return compact_bitmap<1>(cx, b, bm, list, n_dev, tickets, st, pref_out, list_cap);
 }
 size_t scone_ticket_bytes() { return (size_t)kTicketSlots * 8; }
 

@@ -32,8 +32,14 @@ struct scone_model {
     uint32_t *d_bmX = nullptr, *d_bmG = nullptr;   // quad bitmaps of the flags of X and of G_L (compaction reads these)
     bool zero_fill = false;                   // dense zero-fill of every activation / gradient tensor (scone_model_set_zero_fill)
     // bitmap-native row-list pipeline (scone_rows.cu): row bitmaps per tensor, one row list, compact A rows for the dW GEMM
-    bool rows_ok = false, use_rows = false, x_clean = false;
-    std::vector<uint32_t*> d_bmH, d_bmGr;
+    // pipeline: 0 unit kernels + byte flags (dense [E][mb][C] tensors), 1 row lists over the dense tensors, 2 row lists over
+    // COMPACT tensors (row r of a tensor at index rank(r) of its bitmap = its position in the compacted row list)
+    bool rows_ok = false, x_clean = false, dense_ready = false, rows_ready = false, compact_ready = false;
+    int pipeline = 0;
+    std::vector<uint32_t*> d_bmH, d_bmGr, d_prefH, d_prefG;
+    std::vector<float*> d_cH, d_cG;           // compact tensors [row_cap][C_l]
+    int row_cap = 0;                          // rows a compact tensor / the row list can hold
+    size_t rows_list_cap = 0;
     uint32_t* d_rows = nullptr;
     int* d_nrows = nullptr;
     int* d_overflow = nullptr;
@@ -121,10 +127,92 @@ int forward_mb(scone_model* m, int32_t b, const int32_t* ptr, const int32_t* edg
     return 0;
 }
 
+// ---- buffers of the active pipeline, allocated on first use ----------------------------------------------------------
+int dev_alloc(void** p, size_t bytes, const char* what) {
+    if (*p) return 0;
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 4);
+    if (e != cudaSuccess) {
+        scone_set_error("scone_model: cudaMalloc(%zu bytes) for %s failed: %s", bytes, what, cudaGetErrorString(e));
+        *p = nullptr;
+        return 1;
+    }
+    return 0;
+}
+#define SCONE_ALLOC(p, bytes, what)                      \
+    do {                                                 \
+        if (dev_alloc((void**)&(p), (bytes), (what))) return 1; \
+    } while (0)
+
+int ensure_buffers(scone_model* m) {
+    const scone_complex* cx = m->cx;
+    const size_t E = cx->E, mb = m->mb;
+    const int L = m->L;
+    const int pl = m->zero_fill ? 0 : m->pipeline;
+    if (pl <= 1 && !m->dense_ready) {                      // dense [E][mb][C] tensors (+ byte flags for the unit kernels)
+        for (int l = 0; l < L; ++l) {
+            SCONE_ALLOC(m->d_H[l], E * mb * m->hidden[l] * sizeof(float), "dense activations");
+            SCONE_ALLOC(m->d_G[l], E * mb * m->hidden[l] * sizeof(float), "dense gradients");
+            SCONE_ALLOC(m->d_occH[l], E * mb, "flags");
+            SCONE_ALLOC(m->d_occG[l], E * mb, "flags");
+        }
+        SCONE_ALLOC(m->d_occS, (size_t)scone_occ_scratch_bytes(cx, m->mb), "worklist scratch");
+        SCONE_ALLOC(m->d_occX, E * mb, "flags");
+        SCONE_ALLOC(m->d_bmX, scone_bitmap_words(E, mb) * 4, "bitmap");
+        SCONE_ALLOC(m->d_bmG, scone_bitmap_words(E, mb) * 4, "bitmap");
+        m->dense_ready = true;
+    }
+    if (pl >= 1 && !m->rows_ready) {                       // row bitmaps, the row list, the compact A buffer
+        const size_t bm_bytes = scone_bitmap_words(E, mb) * 4;
+        m->d_bmH.resize(L, nullptr);
+        m->d_bmGr.resize(L, nullptr);
+        SCONE_ALLOC(m->d_bmX, bm_bytes, "bitmap");
+        for (int l = 0; l < L; ++l) {
+            SCONE_ALLOC(m->d_bmH[l], bm_bytes, "bitmap");
+            SCONE_ALLOC(m->d_bmGr[l], bm_bytes, "bitmap");
+        }
+        SCONE_ALLOC(m->d_nrows, 256, "counters");
+        SCONE_ALLOC(m->d_overflow, 256, "counters");
+        SCONE_CUDA(cudaMemset(m->d_overflow, 0, 256));
+        SCONE_ALLOC(m->d_tickets, scone_ticket_bytes(), "tickets");
+        const size_t acap = E * mb < (size_t)6000000 ? E * mb : (size_t)6000000;    // rows of the compact A buffer (backward)
+        m->a_cap = (int)acap;
+        SCONE_ALLOC(m->d_Abuf, acap * 3 * (size_t)m->cmax * sizeof(float), "A buffer");
+        const size_t rcap = E * mb < (size_t)32000000 ? E * mb : (size_t)32000000;   // rows of a compact tensor
+        m->row_cap = (int)rcap;
+        m->rows_ready = true;
+    }
+    if (pl >= 1) {                                         // the row list: every row under pipeline 1, row_cap rows under 2
+        const size_t need = pl == 1 ? E * mb : (size_t)m->row_cap;
+        if (need > m->rows_list_cap) {
+            cudaFree(m->d_rows);
+            m->d_rows = nullptr;
+            SCONE_ALLOC(m->d_rows, need * sizeof(uint32_t), "row list");
+            m->rows_list_cap = need;
+        }
+    }
+    if (pl == 2 && !m->compact_ready) {
+        const size_t bm_bytes = scone_bitmap_words(E, mb) * 4;
+        m->d_prefH.resize(L, nullptr);
+        m->d_prefG.resize(L, nullptr);
+        m->d_cH.resize(L, nullptr);
+        m->d_cG.resize(L, nullptr);
+        for (int l = 0; l < L; ++l) {
+            SCONE_ALLOC(m->d_prefH[l], bm_bytes, "rank prefix");
+            SCONE_ALLOC(m->d_prefG[l], bm_bytes, "rank prefix");
+            SCONE_ALLOC(m->d_cH[l], (size_t)m->row_cap * m->hidden[l] * sizeof(float), "compact activations");
+            SCONE_ALLOC(m->d_cG[l], (size_t)m->row_cap * m->hidden[l] * sizeof(float), "compact gradients");
+        }
+        m->compact_ready = true;
+    }
+    return 0;
+}
+
 // ---- row-list pipeline -------------------------------------------------------------------------------------------
 int rows_forward_mb(scone_model* m, int32_t b, const int32_t* ptr, const int32_t* edge, const float* val, cudaStream_t s) {
     const scone_complex* cx = m->cx;
+    const bool compact = m->pipeline == 2;
     const size_t bm_bytes = scone_bitmap_words(cx->E, b) * 4;
+    const long long list_cap = compact ? (long long)m->row_cap : (1ll << 62);
     if (!m->x_clean) {                                     // X must be all-zero outside the flows (no flag test in the first layer)
         SCONE_CUDA(cudaMemsetAsync(m->d_X, 0, (size_t)cx->E * m->mb * sizeof(float), s));
         m->x_clean = true;
@@ -139,18 +227,23 @@ int rows_forward_mb(scone_model* m, int32_t b, const int32_t* ptr, const int32_t
     for (int l = 0; l < m->L; ++l) {
         const int cout = m->hidden[l];
         ScopedProf prof(l == 0 ? SCONE_K_LAYER0_FWD : SCONE_K_LAYER_FWD, s);
-        if (scone_compact_rows(cx, b, m->d_bmH[l], m->d_rows, m->d_nrows, m->d_tickets, s)) return 1;
+        if (scone_compact_rows(cx, b, m->d_bmH[l], m->d_rows, m->d_nrows, m->d_tickets, s, compact ? m->d_prefH[l] : nullptr, list_cap))
+            return 1;
         uint32_t* next = l + 1 < m->L ? m->d_bmH[l + 1] : nullptr;
-        if (next) SCONE_CUDA(cudaMemsetAsync(next, 0, bm_bytes, s));
+        if (next) {
+            SCONE_CUDA(cudaMemsetAsync(next, 0, bm_bytes, s));
+            if (scone_rows_mark(cx, b, m->d_rows, m->d_nrows, next, compact ? m->row_cap : 0x7fffffff, s)) return 1;
+        }
         const float *W0 = m->d_w + m->w_off[3 * l], *W1 = m->d_w + m->w_off[3 * l + 1], *W2 = m->d_w + m->w_off[3 * l + 2];
+        float* Hout = compact ? m->d_cH[l] : m->d_H[l];
         int rc;
         if (l == 0)
-            rc = scone_rows_layer0_forward(cx, m->act, b, cout, m->d_X, W0, W1, W2, m->d_H[0], m->d_rows, m->d_nrows, next, s);
-        else {
-            if (next && scone_rows_mark(cx, b, m->d_rows, m->d_nrows, next, s)) return 1;
-            rc = scone_slab_forward_rows(cx, m->act, b, cin, cout, m->d_H[l - 1], W0, W1, W2, m->d_H[l], nullptr, m->d_rows, m->d_nrows,
-                                         scone_prof_row_counter(SCONE_K_LAYER_FWD), m->d_bmH[l - 1], s);
-        }
+            rc = scone_rows_layer0_forward(cx, m->act, b, cout, m->d_X, W0, W1, W2, Hout, m->d_rows, m->d_nrows, nullptr,
+                                           compact ? m->row_cap : 0, m->d_overflow, s);
+        else
+            rc = scone_slab_forward_rows(cx, m->act, b, cin, cout, compact ? m->d_cH[l - 1] : m->d_H[l - 1], W0, W1, W2, Hout, nullptr,
+                                         m->d_rows, m->d_nrows, scone_prof_row_counter(SCONE_K_LAYER_FWD), m->d_bmH[l - 1],
+                                         compact ? m->d_prefH[l - 1] : nullptr, m->row_cap, m->d_overflow, s);
         if (rc) return rc;
         cin = cout;
     }
@@ -162,28 +255,73 @@ int rows_clear_x(scone_model* m, int32_t b, const int32_t* ptr, const int32_t* e
     return scone_rows_flows(m->cx, b, ptr, edge, val, m->d_X, nullptr, nullptr, true, s);
 }
 
+// readout on the row-list pipelines; grad = false: log-probs only
+int rows_readout(scone_model* m, int32_t b, const int32_t* last, float* logprobs, bool grad, const int32_t* tgt, const float* mask,
+                 cudaStream_t s) {
+    const scone_complex* cx = m->cx;
+    const int L = m->L, CL = m->hidden[L - 1];
+    const float* wout = m->d_w + m->w_off[3 * L];
+    ScopedProf prof(SCONE_K_READOUT, s);
+    if (m->pipeline == 1) {
+        g_scone_hints.skip_fill = true;
+        g_scone_hints.in_bm = m->d_bmH[L - 1];
+        if (grad) {
+            g_scone_hints.out_bm = m->d_bmGr[L - 1];
+            g_scone_hints.cand_bm = L >= 2 ? m->d_bmGr[L - 2] : nullptr;
+            return scone_readout_ws(cx, m->act, b, CL, m->d_H[L - 1], wout, last, logprobs, tgt, mask, 1.f, m->d_G[L - 1],
+                                    m->d_grad + m->w_off[3 * L], m->d_grad + m->n_params, m->d_grad + m->n_params + 1, 1, m->d_ws, nullptr,
+                                    nullptr, s);
+        }
+        return scone_readout_ws(cx, m->act, b, CL, m->d_H[L - 1], wout, last, logprobs, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr,
+                                nullptr, 0, nullptr, nullptr, nullptr, s);
+    }
+    const size_t bm_bytes = scone_bitmap_words(cx->E, b) * 4;
+    uint32_t *bmG = nullptr, *cand = nullptr;
+    if (grad) {
+        bmG = m->d_bmGr[L - 1];
+        SCONE_CUDA(cudaMemsetAsync(bmG, 0, bm_bytes, s));
+        if (L >= 2) {
+            cand = m->d_bmGr[L - 2];
+            SCONE_CUDA(cudaMemsetAsync(cand, 0, bm_bytes, s));
+        }
+    }
+    if (scone_rows_readout_forward(cx, b, CL, m->d_cH[L - 1], wout, last, logprobs, m->d_bmH[L - 1], m->d_prefH[L - 1], bmG, cand, s)) return 1;
+    if (!grad) return 0;
+    if (scone_compact_rows(cx, b, bmG, m->d_rows, m->d_nrows, m->d_tickets, s, m->d_prefG[L - 1], m->row_cap)) return 1;
+    return scone_rows_readout_backward(cx, m->act, b, CL, m->d_cH[L - 1], wout, last, logprobs, tgt, mask, 1.f, m->d_cG[L - 1], m->d_nrows,
+                                       m->row_cap, m->d_overflow, m->d_grad + m->w_off[3 * L], m->d_grad + m->n_params,
+                                       m->d_grad + m->n_params + 1, 1, (float*)m->d_ws, m->d_bmH[L - 1], m->d_prefH[L - 1], bmG,
+                                       m->d_prefG[L - 1], s);
+}
+
 int rows_backward_mb(scone_model* m, int32_t b, cudaStream_t s) {
     const scone_complex* cx = m->cx;
     const int L = m->L;
+    const bool compact = m->pipeline == 2;
     const size_t bm_bytes = scone_bitmap_words(cx->E, b) * 4;
+    const long long list_cap = compact ? (long long)m->row_cap : (1ll << 62);
+    const int a_cap = compact && m->row_cap < m->a_cap ? m->row_cap : m->a_cap;
     for (int l = L - 1; l >= 1; --l) {
         ScopedProf prof(SCONE_K_LAYER_BWD, s);
-        if (scone_compact_rows(cx, b, m->d_bmGr[l - 1], m->d_rows, m->d_nrows, m->d_tickets, s)) return 1;
+        if (scone_compact_rows(cx, b, m->d_bmGr[l - 1], m->d_rows, m->d_nrows, m->d_tickets, s, compact ? m->d_prefG[l - 1] : nullptr, list_cap))
+            return 1;
         uint32_t* next = l >= 2 ? m->d_bmGr[l - 2] : nullptr;
         if (next) {
             SCONE_CUDA(cudaMemsetAsync(next, 0, bm_bytes, s));
-            if (scone_rows_mark(cx, b, m->d_rows, m->d_nrows, next, s)) return 1;
+            if (scone_rows_mark(cx, b, m->d_rows, m->d_nrows, next, compact ? m->row_cap : 0x7fffffff, s)) return 1;
         }
-        int rc = scone_rows_backward(cx, m->act, b, m->hidden[l - 1], m->hidden[l], m->d_G[l], m->d_H[l - 1], m->d_G[l - 1], m->d_Abuf,
+        int rc = scone_rows_backward(cx, m->act, b, m->hidden[l - 1], m->hidden[l], compact ? m->d_cG[l] : m->d_G[l],
+                                     compact ? m->d_cH[l - 1] : m->d_H[l - 1], compact ? m->d_cG[l - 1] : m->d_G[l - 1], m->d_Abuf,
                                      m->d_w + m->w_off[3 * l], m->d_w + m->w_off[3 * l + 1], m->d_w + m->w_off[3 * l + 2], m->d_rows,
-                                     m->d_nrows, m->d_bmGr[l], m->d_bmH[l - 1], m->a_cap, m->d_overflow,
-                                     m->d_grad + m->w_off[3 * l], 1, (float*)m->d_ws, s);
+                                     m->d_nrows, m->d_bmGr[l], m->d_bmH[l - 1], a_cap, m->d_overflow, m->d_grad + m->w_off[3 * l], 1,
+                                     (float*)m->d_ws, compact ? m->d_prefG[l] : nullptr, compact ? m->d_prefH[l - 1] : nullptr, s);
         if (rc) return rc;
     }
     ScopedProf prof(SCONE_K_LAYER0_BWD, s);
-    if (L == 1 && scone_compact_rows(cx, b, m->d_bmGr[0], m->d_rows, m->d_nrows, m->d_tickets, s)) return 1;
-    return scone_rows_layer0_backward(cx, b, m->hidden[0], m->d_X, m->d_G[0], m->d_rows, m->d_nrows, m->d_grad + m->w_off[0], 1,
-                                      (float*)m->d_ws, s);
+    if (L == 1 && !compact && scone_compact_rows(cx, b, m->d_bmGr[0], m->d_rows, m->d_nrows, m->d_tickets, s)) return 1;
+    // (compact, L == 1: the list of G_0's rows is still the one the readout compacted)
+    return scone_rows_layer0_backward(cx, b, m->hidden[0], m->d_X, compact ? m->d_cG[0] : m->d_G[0], m->d_rows, m->d_nrows,
+                                      m->d_grad + m->w_off[0], 1, (float*)m->d_ws, compact ? m->row_cap : 0, s);
 }
 
 }  // namespace
@@ -240,34 +378,11 @@ extern "C" int scone_model_create(const scone_complex* cx, int32_t n_layers, con
     alloc((void**)&m->d_grad, (off + 2) * sizeof(float));
     alloc((void**)&m->d_X, E * mb * sizeof(float));
     m->d_H.assign(n_layers, nullptr);
-    for (int l = 0; l < n_layers; ++l) alloc((void**)&m->d_H[l], E * mb * hidden[l] * sizeof(float));
     m->d_G.assign(n_layers, nullptr);
-    for (int l = 0; l < n_layers; ++l) alloc((void**)&m->d_G[l], E * mb * hidden[l] * sizeof(float));
     m->d_occH.assign(n_layers, nullptr);
-    for (int l = 0; l < n_layers; ++l) alloc((void**)&m->d_occH[l], E * mb);
     m->d_occG.assign(n_layers, nullptr);
-    for (int l = 0; l < n_layers; ++l) alloc((void**)&m->d_occG[l], E * mb);
-    alloc((void**)&m->d_occS, (size_t)scone_occ_scratch_bytes(cx, micro_batch));
-    alloc((void**)&m->d_occX, E * mb);
-    alloc((void**)&m->d_bmX, scone_bitmap_words(E, mb) * 4);
-    alloc((void**)&m->d_bmG, scone_bitmap_words(E, mb) * 4);
     m->rows_ok = scone_rows_supported(cx, n_layers, hidden) && E * mb < ((size_t)1 << 31);
-    if (m->rows_ok) {
-        m->d_bmH.assign(n_layers, nullptr);
-        m->d_bmGr.assign(n_layers, nullptr);
-        for (int l = 0; l < n_layers; ++l) {
-            alloc((void**)&m->d_bmH[l], scone_bitmap_words(E, mb) * 4);
-            alloc((void**)&m->d_bmGr[l], scone_bitmap_words(E, mb) * 4);
-        }
-        alloc((void**)&m->d_rows, E * mb * sizeof(uint32_t));
-        alloc((void**)&m->d_nrows, 256);
-        alloc((void**)&m->d_overflow, 256);
-        alloc((void**)&m->d_tickets, scone_ticket_bytes());
-        const size_t cap = E * mb < (size_t)6000000 ? E * mb : (size_t)6000000;     // rows of the compact A buffer (backward)
-        m->a_cap = (int)cap;
-        alloc((void**)&m->d_Abuf, cap * 3 * (size_t)m->cmax * sizeof(float));
-        m->use_rows = true;
-    }
+    m->pipeline = m->rows_ok ? 2 : 0;
     int64_t ws = scone_readout_workspace_bytes(micro_batch, m->cmax);
     if (scone_rows_dw_workspace_bytes(m->cmax, m->cmax) > ws) ws = scone_rows_dw_workspace_bytes(m->cmax, m->cmax);
     cin = 1;
@@ -292,8 +407,8 @@ extern "C" int scone_model_create(const scone_complex* cx, int32_t n_layers, con
         cudaMemset(m->d_m, 0, off * sizeof(float));
         cudaMemset(m->d_v, 0, off * sizeof(float));
         cudaMemset(m->d_grad, 0, (off + 2) * sizeof(float));
-        if (m->d_overflow) cudaMemset(m->d_overflow, 0, 256);
     }
+    if (!rc) rc = ensure_buffers(m);
     if (rc) {
         scone_model_destroy(m);
         return rc;
@@ -311,6 +426,10 @@ extern "C" int scone_model_destroy(scone_model* m) {
     cudaFree(m->d_occS); cudaFree(m->d_occX); cudaFree(m->d_bmX); cudaFree(m->d_bmG);
     for (uint32_t* p : m->d_bmH) cudaFree(p);
     for (uint32_t* p : m->d_bmGr) cudaFree(p);
+    for (uint32_t* p : m->d_prefH) cudaFree(p);
+    for (uint32_t* p : m->d_prefG) cudaFree(p);
+    for (float* p : m->d_cH) cudaFree(p);
+    for (float* p : m->d_cG) cudaFree(p);
     cudaFree(m->d_rows); cudaFree(m->d_nrows); cudaFree(m->d_overflow); cudaFree(m->d_tickets); cudaFree(m->d_Abuf);
     for (float* p : m->d_G) cudaFree(p);
     cudaFree(m->d_ws); cudaFree(m->d_logp);
@@ -330,16 +449,22 @@ extern "C" int64_t scone_model_num_params(const scone_model* m) { return m ? m->
 extern "C" int scone_model_set_zero_fill(scone_model* m, int32_t on) {
     SCONE_REQUIRE(m != nullptr, "scone_model_set_zero_fill: NULL model");
     m->zero_fill = on != 0;
-    return 0;
+    return ensure_buffers(m);
 }
 extern "C" int scone_model_get_zero_fill(const scone_model* m) { return m && m->zero_fill ? 1 : 0; }
 extern "C" int scone_model_set_pipeline(scone_model* m, int32_t which) {
-    SCONE_REQUIRE(m != nullptr && (which == 0 || which == 1), "scone_model_set_pipeline: 0 (unit kernels, byte flags) or 1 (row lists, bitmaps)");
-    SCONE_REQUIRE(which == 0 || m->rows_ok, "scone_model_set_pipeline: the row-list pipeline needs hidden widths in {16, 32}");
-    m->use_rows = which == 1;
+    SCONE_REQUIRE(m != nullptr && which >= 0 && which <= 2,
+                  "scone_model_set_pipeline: 0 (unit kernels, byte flags), 1 (row lists, dense tensors) or 2 (row lists, compact tensors)");
+    SCONE_REQUIRE(which == 0 || m->rows_ok, "scone_model_set_pipeline: the row-list pipelines need hidden widths in {16, 32}");
+    const int old = m->pipeline;
+    m->pipeline = which;
+    if (ensure_buffers(m)) {
+        m->pipeline = old;
+        return 1;
+    }
     return 0;
 }
-extern "C" int scone_model_get_pipeline(const scone_model* m) { return m && m->use_rows && !m->zero_fill ? 1 : 0; }
+extern "C" int scone_model_get_pipeline(const scone_model* m) { return m ? (m->zero_fill ? 0 : m->pipeline) : -1; }
 extern "C" float* scone_model_weights_dev(scone_model* m) { return m ? m->d_w : nullptr; }
 extern "C" float* scone_model_grads_dev(scone_model* m) { return m ? m->d_grad : nullptr; }
 
@@ -376,17 +501,14 @@ extern "C" int scone_model_forward_dev(scone_model* m, int32_t B, const int32_t*
     if (fork_to_compute(m, user_st)) return 1;
     void* st = (void*)m->compute;
     const scone_complex* cx = m->cx;
-    const bool rows = m->use_rows && !m->zero_fill;
+    const bool rows = m->pipeline >= 1 && !m->zero_fill;
     for (int32_t off = 0; off < B; off += m->mb) {
         const int32_t b = B - off < m->mb ? B - off : m->mb;
         int rc;
         if (rows) {
             rc = rows_forward_mb(m, b, ptr + off, edge, val, as_stream(st));
             if (rc) return rc;
-            g_scone_hints.in_bm = m->d_bmH[m->L - 1];
-            rc = scone_readout_ws(cx, m->act, b, m->hidden[m->L - 1], m->d_H[m->L - 1], m->d_w + m->w_off[3 * m->L], last + off,
-                                  logprobs + (size_t)off * cx->D, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, nullptr, 0,
-                                  nullptr, nullptr, nullptr, st);
+            rc = rows_readout(m, b, last + off, logprobs + (size_t)off * cx->D, false, nullptr, nullptr, as_stream(st));
             if (rc) return rc;
             rc = rows_clear_x(m, b, ptr + off, edge, val, as_stream(st));
             if (rc) return rc;
@@ -415,20 +537,14 @@ extern "C" int scone_model_loss_grad_dev(scone_model* m, int32_t B, const int32_
     const int L = m->L;
     cudaStream_t s = as_stream(st);
     if (zero_first) SCONE_CUDA(cudaMemsetAsync(m->d_grad, 0, (m->n_params + 2) * sizeof(float), s));
-    const bool rows = m->use_rows && !m->zero_fill;
+    const bool rows = m->pipeline >= 1 && !m->zero_fill;
     for (int32_t off = 0; off < B; off += m->mb) {
         const int32_t b = B - off < m->mb ? B - off : m->mb;
         int rc;
         if (rows) {
             rc = rows_forward_mb(m, b, ptr + off, edge, val, s);
             if (rc) return rc;
-            g_scone_hints.skip_fill = true;
-            g_scone_hints.in_bm = m->d_bmH[L - 1];
-            g_scone_hints.out_bm = m->d_bmGr[L - 1];
-            g_scone_hints.cand_bm = L >= 2 ? m->d_bmGr[L - 2] : nullptr;
-            rc = scone_readout_ws(cx, m->act, b, m->hidden[L - 1], m->d_H[L - 1], m->d_w + m->w_off[3 * L], last + off, m->d_logp,
-                                  tgt + off, mask + off, 1.f, m->d_G[L - 1], m->d_grad + m->w_off[3 * L], m->d_grad + m->n_params,
-                                  m->d_grad + m->n_params + 1, 1, m->d_ws, nullptr, nullptr, st);
+            rc = rows_readout(m, b, last + off, m->d_logp, true, tgt + off, mask + off, s);
             if (rc) return rc;
             rc = rows_backward_mb(m, b, s);
             if (rc) return rc;

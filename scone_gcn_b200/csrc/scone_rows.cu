@@ -61,8 +61,8 @@ __global__ void __launch_bounds__(128) rows_flows_kernel(const int32_t* __restri
 // candidate rows one hop further: lane = row of the list, every entry of its merged operator row marks (column, t) in bm_next
 __global__ void __launch_bounds__(256) rows_mark_kernel(const uint32_t* __restrict__ rows, const int* __restrict__ n_ptr,
                                                        const int32_t* __restrict__ mptr, const int2* __restrict__ ment, int b,
-                                                       uint32_t* __restrict__ bm_next) {
-    const int n = *n_ptr;
+                                                       uint32_t* __restrict__ bm_next, int list_cap) {
+    const int n = min(*n_ptr, list_cap);
     for (int li = blockIdx.x * blockDim.x + threadIdx.x; li < n; li += gridDim.x * blockDim.x) {
         const uint32_t rid = __ldg(rows + li);
         const unsigned e = rid / (unsigned)b, t = rid - e * (unsigned)b;
@@ -76,16 +76,21 @@ __global__ void __launch_bounds__(256) rows_mark_kernel(const uint32_t* __restri
 // the 32 rows of the warp are written one after the other with lane = channel (coalesced).  Gather order = merged row order
 // = ascending columns for both sums, same as the unit kernels.
 // ---------------------------------------------------------------------------------------------------------------
-template <int COUT, int ACT>
+template <int COUT, int ACT, bool COMPACT>
 __global__ void __launch_bounds__(256) rows_layer0_fwd_kernel(const float* __restrict__ X, float* __restrict__ Hout,
                                                              const float* __restrict__ W0, const float* __restrict__ W1,
                                                              const float* __restrict__ W2, const int32_t* __restrict__ mptr,
                                                              const int2* __restrict__ ment, const uint32_t* __restrict__ rows,
-                                                             const int* __restrict__ n_ptr, int b, uint32_t* __restrict__ bm_next) {
+                                                             const int* __restrict__ n_ptr, int b, uint32_t* __restrict__ bm_next,
+                                                             int out_cap, int* __restrict__ overflow) {
     static_assert(COUT == 16 || COUT == 32, "first-layer row kernel: widths 16 / 32");
     constexpr int RPI = 32 / COUT;                        // rows written per iteration of the store loop
     const int lane = threadIdx.x & 31;
-    const int n = *n_ptr;
+    int n = *n_ptr;
+    if (COMPACT && n > out_cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1;
+        n = out_cap;
+    }
     const int c = lane % COUT;
     const float w0 = W0[c], w1 = W1[c], w2 = W2[c];
     const int n_groups = (n + 31) / 32;
@@ -114,21 +119,22 @@ __global__ void __launch_bounds__(256) rows_layer0_fwd_kernel(const float* __res
             const float s0 = __shfl_sync(0xffffffffu, a0, r & 31), s1 = __shfl_sync(0xffffffffu, a1, r & 31),
                         s2 = __shfl_sync(0xffffffffu, a2, r & 31);
             const uint32_t orow = __shfl_sync(0xffffffffu, rid, r & 31);
-            if (r < cnt) Hout[(size_t)orow * COUT + c] = act_scalar<ACT>(fmaf(s2, w2, fmaf(s1, w1, s0 * w0)));
+            if (r < cnt) Hout[(size_t)(COMPACT ? (uint32_t)(grp * 32 + r) : orow) * COUT + c] = act_scalar<ACT>(fmaf(s2, w2, fmaf(s1, w1, s0 * w0)));
         }
     }
 }
 
 // first layer backward: one warp per row of G_1; lanes split the merged operator row for the two scalar gathers (fixed
 // butterfly sum), then lane = channel.  Per-CTA partials [3][COUT], reduced by reduce order (deterministic).
-template <int COUT>
+template <int COUT, bool COMPACT>
 __global__ void __launch_bounds__(256) rows_layer0_bwd_kernel(const float* __restrict__ X, const float* __restrict__ G,
                                                              const int32_t* __restrict__ mptr, const int2* __restrict__ ment,
                                                              const uint32_t* __restrict__ rows, const int* __restrict__ n_ptr, int b,
-                                                             float* __restrict__ partial /* [grid][3*COUT] */) {
+                                                             float* __restrict__ partial /* [grid][3*COUT] */, int cap) {
     __shared__ float red[8][3 * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n = *n_ptr;
+    int n = *n_ptr;
+    if (COMPACT && n > cap) n = cap;
     const int per = (n + gridDim.x - 1) / gridDim.x;          // contiguous slice per CTA, rows strided over its warps
     const int lo = min(n, (int)blockIdx.x * per), hi = min(n, lo + per);
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
@@ -150,7 +156,7 @@ __global__ void __launch_bounds__(256) rows_layer0_bwd_kernel(const float* __res
         }
         const float a0 = __ldg(X + rid);
         if (lane < COUT) {
-            const float g = __ldg(G + (size_t)rid * COUT + lane);
+            const float g = __ldg(G + (size_t)(COMPACT ? (uint32_t)li : rid) * COUT + lane);
             acc0 = fmaf(a0, g, acc0);
             acc1 = fmaf(a1, g, acc1);
             acc2 = fmaf(a2, g, acc2);
@@ -176,7 +182,7 @@ __global__ void __launch_bounds__(256) rows_layer0_bwd_kernel(const float* __res
 // Gprev = (sum_k A_k W_k^T) * act'(Hin) with Hin rows read through the row bitmap of H_{l-1} (an unflagged row is an exact
 // zero: act'(0)).
 // ---------------------------------------------------------------------------------------------------------------
-template <int CIN, int COUT, int ACT>
+template <int CIN, int COUT, int ACT, bool COMPACT>
 __global__ void __launch_bounds__(kSlabThreads, 1) rows_bwd_kernel(const float* __restrict__ Gin, const float* __restrict__ Hin,
                                                                   float* __restrict__ Gprev, float* __restrict__ Abuf,
                                                                   const float* __restrict__ W0, const float* __restrict__ W1,
@@ -184,7 +190,8 @@ __global__ void __launch_bounds__(kSlabThreads, 1) rows_bwd_kernel(const float* 
                                                                   const int2* __restrict__ ment, const uint32_t* __restrict__ rows,
                                                                   const int* __restrict__ n_ptr, int b, const uint32_t* __restrict__ bmG,
                                                                   const uint32_t* __restrict__ bmH, int a_cap, int* __restrict__ overflow,
-                                                                  unsigned long long* __restrict__ row_counter) {
+                                                                  unsigned long long* __restrict__ row_counter,
+                                                                  const uint32_t* __restrict__ prefG, const uint32_t* __restrict__ prefH) {
     using G = SlabGeom<COUT, 16>;                          // the gathered tensor has COUT channels
     constexpr int NT = CIN / 8, NL = G::NL, Q = G::Q, LPR = COUT / 4;
     extern __shared__ __align__(16) uint4 Bf[];
@@ -192,7 +199,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) rows_bwd_kernel(const float* 
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tig = lane & 3, g = lane >> 2;
     const int gq = lane / LPR, cq = lane % LPR;
-    const unsigned rowbytes = (unsigned)b * COUT * 4u;
+    const unsigned rowbytes = COMPACT ? COUT * 4u : (unsigned)b * COUT * 4u;
     const char* Gb = reinterpret_cast<const char*>(Gin);
     int n = *n_ptr;
     if (n > a_cap) {                                       // the compact A buffer cannot hold this many rows: flag it (host raises)
@@ -213,6 +220,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) rows_bwd_kernel(const float* 
         const int slab = tile * kSlabWarps + warp;
         if (slab >= n_slabs) continue;
         uint32_t rid[NL];
+        unsigned oidx[NL];
         int len[NL], p0[NL], tq[NL], cpos[NL];
         const char* P[NL];
         bool own[NL], valid[NL];
@@ -225,11 +233,16 @@ __global__ void __launch_bounds__(kSlabThreads, 1) rows_bwd_kernel(const float* 
             const int e = (int)(rid[i] / (unsigned)b);
             tq[i] = (int)(rid[i] - (unsigned)e * (unsigned)b);
             cpos[i] = (COUT == 32 && i >= 2) ? (cq ^ 4) : cq;
-            P[i] = Gb + (size_t)((unsigned)(tq[i] * COUT + 4 * cpos[i]) * 4u);
+            P[i] = Gb + (size_t)((unsigned)((COMPACT ? 0 : tq[i] * COUT) + 4 * cpos[i]) * 4u);
             asm volatile("" : "+l"(P[i]));
             p0[i] = valid[i] ? __ldg(mptr + e) : 0;
             len[i] = valid[i] ? __ldg(mptr + e + 1) - p0[i] : 0;
-            own[i] = valid[i] && bit_test(bmG, rid[i]);
+            if (COMPACT) {
+                own[i] = rank_lookup(bmG, prefG, rid[i], oidx[i]) && valid[i];
+            } else {
+                oidx[i] = (unsigned)e;
+                own[i] = valid[i] && bit_test(bmG, rid[i]);
+            }
             maxlen = max(maxlen, len[i]);
         }
 #pragma unroll
@@ -241,7 +254,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) rows_bwd_kernel(const float* 
             for (int i = 0; i < NL; ++i) acc[k][i][0] = acc[k][i][1] = 0ull;
 #pragma unroll
         for (int i = 0; i < NL; ++i)
-            if (own[i]) ldg128(reinterpret_cast<const float*>(P[i] + (size_t)(rid[i] / (unsigned)b) * rowbytes), acc[0][i][0], acc[0][i][1]);
+            if (own[i]) ldg128(reinterpret_cast<const float*>(P[i] + (size_t)oidx[i] * rowbytes), acc[0][i][0], acc[0][i][1]);
 #pragma unroll 2
         for (int k = 0; k < maxlen; ++k) {
             int2 ent[NL];
@@ -251,16 +264,22 @@ __global__ void __launch_bounds__(kSlabThreads, 1) rows_bwd_kernel(const float* 
                 on[i] = k < len[i];
                 ent[i] = on[i] ? __ldg(ment + p0[i] + k) : make_int2(0, 0);
             }
+            unsigned gidx[NL];
 #pragma unroll
             for (int i = 0; i < NL; ++i) {                 // branch-free bit test (entry {0,0} of an idle lane tests row tq: in range)
                 const unsigned nrow = (unsigned)ent[i].x * (unsigned)b + (unsigned)tq[i];
-                on[i] = on[i] && ((__ldg(bmG + (nrow >> 5)) >> (nrow & 31)) & 1u) != 0u;
+                if (COMPACT) {
+                    on[i] = rank_lookup(bmG, prefG, nrow, gidx[i]) && on[i];
+                } else {
+                    on[i] = on[i] && ((__ldg(bmG + (nrow >> 5)) >> (nrow & 31)) & 1u) != 0u;
+                    gidx[i] = (unsigned)ent[i].x;
+                }
             }
             u64 v[NL][2];
 #pragma unroll
             for (int i = 0; i < NL; ++i) {
                 v[i][0] = v[i][1] = 0ull;
-                if (on[i]) ldg128(reinterpret_cast<const float*>(P[i] + (size_t)(unsigned)ent[i].x * rowbytes), v[i][0], v[i][1]);
+                if (on[i]) ldg128(reinterpret_cast<const float*>(P[i] + (size_t)gidx[i] * rowbytes), v[i][0], v[i][1]);
             }
 #pragma unroll
             for (int i = 0; i < NL; ++i) {
@@ -299,18 +318,22 @@ __global__ void __launch_bounds__(kSlabThreads, 1) rows_bwd_kernel(const float* 
         for (int r = 0; r < 2; ++r) {
             uint32_t orow;
             bool ok;
+            int oslot;
             if (COUT == 32) {
                 const bool odd = g & 1;
+                oslot = odd ? 2 + r : r;
                 orow = odd ? rid[2 + r] : rid[r];
                 ok = odd ? valid[2 + r] : valid[r];
             } else {
+                oslot = r;
                 orow = rid[r];
                 ok = valid[r];
             }
             if (ok) {
-                const bool hset = bit_test(bmH, orow);
-                const float* hsrc = Hin + (size_t)orow * CIN + 2 * tig;
-                float* dst = Gprev + (size_t)orow * CIN + 2 * tig;
+                unsigned hidx = orow;
+                const bool hset = COMPACT ? rank_lookup(bmH, prefH, orow, hidx) : bit_test(bmH, orow);
+                const float* hsrc = Hin + (size_t)hidx * CIN + 2 * tig;
+                float* dst = Gprev + (size_t)(COMPACT ? (uint32_t)(slab * 16 + oslot * Q + gq) : orow) * CIN + 2 * tig;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     float2 h = make_float2(0.f, 0.f);
@@ -330,10 +353,11 @@ __global__ void __launch_bounds__(kSlabThreads, 1) rows_bwd_kernel(const float* 
 // memory in fragment layout (each 32-bit load fills whole 32-byte sectors; the 8 warps share the rows through L1).
 // Per-CTA partials, reduced over CTAs in a fixed tree: deterministic.
 // ---------------------------------------------------------------------------------------------------------------
-template <int CIN, int COUT>
+template <int CIN, int COUT, bool COMPACT>
 __global__ void __launch_bounds__(256) rows_dw_kernel(const float* __restrict__ Hin, const uint32_t* __restrict__ bmH,
                                                      const float* __restrict__ Abuf, const uint32_t* __restrict__ rows,
-                                                     const int* __restrict__ n_ptr, int a_cap, float* __restrict__ partial /* [grid][3*CIN*COUT] */) {
+                                                     const int* __restrict__ n_ptr, int a_cap, float* __restrict__ partial /* [grid][3*CIN*COUT] */,
+                                                     const uint32_t* __restrict__ prefH) {
     constexpr int MT = CIN / 16, NTT = 3 * COUT / 8;       // m-tiles, n-tiles
     constexpr int TILES = MT * NTT;
     constexpr int TPW = TILES >= 24 ? 3 : (TILES >= 12 ? 2 : 1);   // (m, n) tiles per warp; TILES / TPW <= 8 warps work
@@ -356,15 +380,15 @@ __global__ void __launch_bounds__(256) rows_dw_kernel(const float* __restrict__ 
         const int i0 = s * 8 + tig, i1 = i0 + 4;           // list positions of this lane's two k rows
         float a[4] = {0.f, 0.f, 0.f, 0.f};
         if (i0 < n) {
-            const uint32_t r = __ldg(rows + i0);
-            if (bit_test(bmH, r)) {
+            unsigned r = __ldg(rows + i0);
+            if (COMPACT ? rank_lookup(bmH, prefH, r, r) : bit_test(bmH, r)) {
                 a[0] = __ldg(Hin + (size_t)r * CIN + mt * 16 + g);
                 a[1] = __ldg(Hin + (size_t)r * CIN + mt * 16 + g + 8);
             }
         }
         if (i1 < n) {
-            const uint32_t r = __ldg(rows + i1);
-            if (bit_test(bmH, r)) {
+            unsigned r = __ldg(rows + i1);
+            if (COMPACT ? rank_lookup(bmH, prefH, r, r) : bit_test(bmH, r)) {
                 a[2] = __ldg(Hin + (size_t)r * CIN + mt * 16 + g);
                 a[3] = __ldg(Hin + (size_t)r * CIN + mt * 16 + g + 8);
             }
@@ -420,23 +444,197 @@ __global__ void __launch_bounds__(256) rows_reduce_kernel(const float* __restric
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Readout for compact storage, in two kernels around the compaction of G_L's bitmap:
+//   rows_readout_fwd_kernel   logits -> padded log-softmax (trajectory_experiments.py:151-152,298-303); with `grad` also the bits
+//                             of the rows of G_L this trajectory touches and the candidate bits one hop further
+//   rows_readout_bwd_kernel   dl_j = mask * scale * (exp(logp_j) - [j == y]); adds s(e, nbr_j) * dl_j * w * act'(h) onto row rank(e, t)
+//                             of the zeroed compact G_L (at most two contributions per row: a + b == b + a, deterministic), the
+//                             w_out gradient partials, the NLL term and the mask count.
+// One CTA (4 warps) per trajectory, warps split the neighbour slots (same arithmetic as readout_kernel).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kRoWarps = 4, kRoMaxD = 128, kRoMaxCper = 4;
+
+__global__ void __launch_bounds__(32 * kRoWarps) rows_readout_fwd_kernel(const float* __restrict__ HL, const float* __restrict__ wout,
+                                                                        const int32_t* __restrict__ last_nodes, const int32_t* __restrict__ nbrhoods,
+                                                                        const int32_t* __restrict__ inc_ptr, const int2* __restrict__ inc_ent,
+                                                                        float* __restrict__ logprobs, const uint32_t* __restrict__ bmH,
+                                                                        const uint32_t* __restrict__ prefH, uint32_t* __restrict__ bmG,
+                                                                        uint32_t* __restrict__ bm_cand, const int32_t* __restrict__ mptr,
+                                                                        const int2* __restrict__ ment, int N, int D, int b, int C) {
+    __shared__ float logit[kRoMaxD];
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int t = blockIdx.x;
+    const int last = last_nodes[t];
+    const bool last_ok = last >= 0 && last < N;
+    float w[kRoMaxCper];
+#pragma unroll
+    for (int q = 0; q < kRoMaxCper; ++q) w[q] = (lane + 32 * q < C) ? wout[lane + 32 * q] : 0.f;
+    for (int j = warp; j < D; j += kRoWarps) {
+        const int nbr = last_ok ? nbrhoods[(size_t)last * D + j] : -1;
+        float l = 0.f;
+        if (nbr >= 0) {
+            float part = 0.f;
+            float z[kRoMaxCper] = {0.f, 0.f, 0.f, 0.f};
+            for (int p = inc_ptr[nbr]; p < inc_ptr[nbr + 1]; ++p) {
+                const int2 es = inc_ent[p];
+                const unsigned row = (unsigned)es.x * (unsigned)b + (unsigned)t;
+                if (bmG != nullptr) {                      // gradient wanted: this row of G_L will be written
+                    if (lane == 0) bit_set(bmG, row);
+                    if (bm_cand != nullptr)
+                        for (int q = mptr[es.x] + lane; q < mptr[es.x + 1]; q += 32) bit_set(bm_cand, (unsigned)ment[q].x * (unsigned)b + (unsigned)t);
+                }
+                unsigned idx;
+                if (!rank_lookup(bmH, prefH, row, idx)) continue;      // row is exactly zero
+                const float* hrow = HL + (size_t)idx * C;
+#pragma unroll
+                for (int q = 0; q < kRoMaxCper; ++q)
+                    if (lane + 32 * q < C) z[q] = fmaf(__int_as_float(es.y), hrow[lane + 32 * q], z[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < kRoMaxCper; ++q) part = fmaf(z[q], w[q], part);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            l = part;
+        }
+        if (lane == 0) logit[j] = l;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float mx = -3.4e38f;
+        for (int j = lane; j < D; j += 32) mx = fmaxf(mx, logit[j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float se = 0.f;
+        for (int j = lane; j < D; j += 32) se += expf(logit[j] - mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+        const float lse = mx + logf(se);
+        for (int j = lane; j < D; j += 32) logprobs[(size_t)t * D + j] = logit[j] - lse;
+    }
+}
+
+// zero the first min(*n, cap) rows of a compact tensor (row = C floats)
+__global__ void __launch_bounds__(256) rows_zero_kernel(float4* __restrict__ T, const int* __restrict__ n_ptr, int cap, int c4,
+                                                       int* __restrict__ overflow) {
+    int n = *n_ptr;
+    if (n > cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1;
+        n = cap;
+    }
+    const size_t total = (size_t)n * c4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        T[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(32 * kRoWarps) rows_readout_bwd_kernel(const float* __restrict__ HL, const float* __restrict__ wout,
+                                                                        const int32_t* __restrict__ last_nodes, const int32_t* __restrict__ nbrhoods,
+                                                                        const int32_t* __restrict__ inc_ptr, const int2* __restrict__ inc_ent,
+                                                                        const float* __restrict__ logprobs, const int32_t* __restrict__ target_idx,
+                                                                        const float* __restrict__ mask, float scale, float* __restrict__ GL,
+                                                                        float* __restrict__ partial /* [b][C+2] */, const uint32_t* __restrict__ bmH,
+                                                                        const uint32_t* __restrict__ prefH, const uint32_t* __restrict__ bmG,
+                                                                        const uint32_t* __restrict__ prefG, int g_cap, int act, int N, int D, int b, int C) {
+    __shared__ float s_dw[kRoWarps][32 * kRoMaxCper];
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int t = blockIdx.x;
+    const int last = last_nodes[t];
+    const bool last_ok = last >= 0 && last < N;
+    float w[kRoMaxCper];
+#pragma unroll
+    for (int q = 0; q < kRoMaxCper; ++q) w[q] = (lane + 32 * q < C) ? wout[lane + 32 * q] : 0.f;
+    const float mk = mask[t];
+    const int y = target_idx[t];
+    float dwl[kRoMaxCper] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = warp; j < D; j += kRoWarps) {
+        const int nbr = last_ok ? nbrhoods[(size_t)last * D + j] : -1;
+        if (nbr < 0) continue;
+        const float dl = mk * scale * (expf(logprobs[(size_t)t * D + j]) - (j == y ? 1.f : 0.f));
+        for (int p = inc_ptr[nbr]; p < inc_ptr[nbr + 1]; ++p) {
+            const int2 es = inc_ent[p];
+            const unsigned row = (unsigned)es.x * (unsigned)b + (unsigned)t;
+            unsigned hidx, gidx;
+            const bool hset = rank_lookup(bmH, prefH, row, hidx);
+            rank_lookup(bmG, prefG, row, gidx);
+            if ((int)gidx >= g_cap) continue;              // overflow already flagged by rows_zero_kernel
+            const float sdl = __int_as_float(es.y) * dl;
+#pragma unroll
+            for (int q = 0; q < kRoMaxCper; ++q)
+                if (lane + 32 * q < C) {
+                    const float h = hset ? HL[(size_t)hidx * C + lane + 32 * q] : 0.f;
+                    dwl[q] = fmaf(sdl, h, dwl[q]);
+                    const float da = act == SCONE_ACT_TANH ? 1.f - h * h : (act == SCONE_ACT_LEAKY_RELU ? (h >= 0.f ? 1.f : 0.01f) : (h > 0.f ? 1.f : 0.f));
+                    atomicAdd(GL + (size_t)gidx * C + lane + 32 * q, sdl * w[q] * da);
+                }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kRoMaxCper; ++q) s_dw[warp][lane + 32 * q] = dwl[q];
+    __syncthreads();
+    if (warp == 0) {
+        float* pt = partial + (size_t)t * (C + 2);
+#pragma unroll
+        for (int q = 0; q < kRoMaxCper; ++q)
+            if (lane + 32 * q < C) {
+                float sacc = s_dw[0][lane + 32 * q];
+                for (int k = 1; k < kRoWarps; ++k) sacc += s_dw[k][lane + 32 * q];
+                pt[lane + 32 * q] = sacc;
+            }
+        if (lane == 0) {
+            pt[C] = (y >= 0 && y < D) ? -mk * logprobs[(size_t)t * D + y] : 0.f;
+            pt[C + 1] = mk;
+        }
+    }
+}
+
+// dwout[c] (+)= sum_t partial[t][c]; nll (+)= sum_t partial[t][C]; count (+)= sum_t partial[t][C+1]  (t ascending, 8 fixed slices)
+__global__ void __launch_bounds__(256) rows_readout_reduce_kernel(const float* __restrict__ partial, int b, int C, float* __restrict__ dwout,
+                                                                 float* __restrict__ nll, float* __restrict__ count, int accumulate) {
+    __shared__ float red[8][64];
+    const int c = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    for (int c0 = 0; c0 < C + 2; c0 += 32) {
+        const int cc = c0 + c;
+        const int per = (b + 7) / 8;
+        const int t0 = slice * per, t1 = min(b, t0 + per);
+        float s = 0.f;
+        if (cc < C + 2)
+            for (int t = t0; t < t1; ++t) s += partial[(size_t)t * (C + 2) + cc];
+        __syncthreads();
+        red[slice][c] = s;
+        __syncthreads();
+        if (slice == 0 && cc < C + 2) {
+            float tsum = red[0][c];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) tsum += red[k][c];
+            float* dst = cc < C ? dwout + cc : (cc == C ? nll : count);
+            *dst = accumulate ? *dst + tsum : tsum;
+        }
+    }
+}
+
 constexpr int kDwCtas = 148 * 2;
 
 template <int CIN, int COUT, int ACT>
 int launch_rows_bwd(const scone_complex* cx, int b, const float* G, const float* Hin, float* Gprev, float* Abuf, const float* W0,
                     const float* W1, const float* W2, const uint32_t* rows, const int* n_ptr, const uint32_t* bmG, const uint32_t* bmH,
-                    int a_cap, int* overflow, cudaStream_t st) {
+                    int a_cap, int* overflow, const uint32_t* prefG, const uint32_t* prefH, cudaStream_t st) {
     using Gm = SlabGeom<COUT, 16>;
     constexpr int NT = CIN / 8;
     const size_t smem = (size_t)3 * Gm::KS * NT * 32 * sizeof(uint4);
-    auto kern = rows_bwd_kernel<CIN, COUT, ACT>;
     static bool configured = false;
     if (!configured) {
-        SCONE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCONE_CUDA(cudaFuncSetAttribute(rows_bwd_kernel<CIN, COUT, ACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCONE_CUDA(cudaFuncSetAttribute(rows_bwd_kernel<CIN, COUT, ACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    kern<<<cx->num_sms, kSlabThreads, smem, st>>>(G, Hin, Gprev, Abuf, W0, W1, W2, cx->d_mptr, cx->d_ment, rows, n_ptr, b, bmG, bmH,
-                                                  a_cap, overflow, scone_prof_row_counter(SCONE_K_LAYER_BWD));
+    if (prefG != nullptr)
+        rows_bwd_kernel<CIN, COUT, ACT, true><<<cx->num_sms, kSlabThreads, smem, st>>>(G, Hin, Gprev, Abuf, W0, W1, W2, cx->d_mptr, cx->d_ment, rows,
+                                                                                     n_ptr, b, bmG, bmH, a_cap, overflow,
+                                                                                     scone_prof_row_counter(SCONE_K_LAYER_BWD), prefG, prefH);
+    else
+        rows_bwd_kernel<CIN, COUT, ACT, false><<<cx->num_sms, kSlabThreads, smem, st>>>(G, Hin, Gprev, Abuf, W0, W1, W2, cx->d_mptr, cx->d_ment, rows,
+                                                                                      n_ptr, b, bmG, bmH, a_cap, overflow,
+                                                                                      scone_prof_row_counter(SCONE_K_LAYER_BWD), prefG, prefH);
     SCONE_LAUNCHED();
     return 0;
 }
@@ -444,14 +642,14 @@ int launch_rows_bwd(const scone_complex* cx, int b, const float* G, const float*
 template <int CIN, int COUT>
 int dispatch_rows_bwd(const scone_complex* cx, int act, int b, const float* G, const float* Hin, float* Gprev, float* Abuf,
                       const float* W0, const float* W1, const float* W2, const uint32_t* rows, const int* n_ptr, const uint32_t* bmG,
-                      const uint32_t* bmH, int a_cap, int* overflow, cudaStream_t st) {
+                      const uint32_t* bmH, int a_cap, int* overflow, const uint32_t* prefG, const uint32_t* prefH, cudaStream_t st) {
     switch (act) {
         case SCONE_ACT_TANH:
-            return launch_rows_bwd<CIN, COUT, SCONE_ACT_TANH>(cx, b, G, Hin, Gprev, Abuf, W0, W1, W2, rows, n_ptr, bmG, bmH, a_cap, overflow, st);
+            return launch_rows_bwd<CIN, COUT, SCONE_ACT_TANH>(cx, b, G, Hin, Gprev, Abuf, W0, W1, W2, rows, n_ptr, bmG, bmH, a_cap, overflow, prefG, prefH, st);
         case SCONE_ACT_LEAKY_RELU:
-            return launch_rows_bwd<CIN, COUT, SCONE_ACT_LEAKY_RELU>(cx, b, G, Hin, Gprev, Abuf, W0, W1, W2, rows, n_ptr, bmG, bmH, a_cap, overflow, st);
+            return launch_rows_bwd<CIN, COUT, SCONE_ACT_LEAKY_RELU>(cx, b, G, Hin, Gprev, Abuf, W0, W1, W2, rows, n_ptr, bmG, bmH, a_cap, overflow, prefG, prefH, st);
         case SCONE_ACT_RELU:
-            return launch_rows_bwd<CIN, COUT, SCONE_ACT_RELU>(cx, b, G, Hin, Gprev, Abuf, W0, W1, W2, rows, n_ptr, bmG, bmH, a_cap, overflow, st);
+            return launch_rows_bwd<CIN, COUT, SCONE_ACT_RELU>(cx, b, G, Hin, Gprev, Abuf, W0, W1, W2, rows, n_ptr, bmG, bmH, a_cap, overflow, prefG, prefH, st);
     }
     scone_set_error("unknown activation %d", act);
     return 2;
@@ -459,8 +657,11 @@ int dispatch_rows_bwd(const scone_complex* cx, int act, int b, const float* G, c
 
 template <int CIN, int COUT>
 int launch_rows_dw(const scone_complex* cx, const float* Hin, const uint32_t* bmH, const float* Abuf, const uint32_t* rows,
-                   const int* n_ptr, int a_cap, float* dW, int accumulate, float* ws, cudaStream_t st) {
-    rows_dw_kernel<CIN, COUT><<<kDwCtas, 256, 0, st>>>(Hin, bmH, Abuf, rows, n_ptr, a_cap, ws);
+                   const int* n_ptr, int a_cap, float* dW, int accumulate, float* ws, const uint32_t* prefH, cudaStream_t st) {
+    if (prefH != nullptr)
+        rows_dw_kernel<CIN, COUT, true><<<kDwCtas, 256, 0, st>>>(Hin, bmH, Abuf, rows, n_ptr, a_cap, ws, prefH);
+    else
+        rows_dw_kernel<CIN, COUT, false><<<kDwCtas, 256, 0, st>>>(Hin, bmH, Abuf, rows, n_ptr, a_cap, ws, prefH);
     SCONE_LAUNCHED();
     constexpr int DW = 3 * CIN * COUT;
     rows_reduce_kernel<<<(DW + 31) / 32, 256, 0, st>>>(ws, kDwCtas, DW, dW, accumulate);
@@ -468,24 +669,28 @@ int launch_rows_dw(const scone_complex* cx, const float* Hin, const uint32_t* bm
     return 0;
 }
 
-template <int COUT>
-int launch_rows_l0_fwd(const scone_complex* cx, int act, int b, const float* X, const float* W0, const float* W1, const float* W2,
-                       float* Hout, const uint32_t* rows, const int* n_ptr, uint32_t* bm_next, cudaStream_t st) {
-    const int grid = cx->num_sms * 4;
-    switch (act) {
-        case SCONE_ACT_TANH:
-            rows_layer0_fwd_kernel<COUT, SCONE_ACT_TANH><<<grid, 256, 0, st>>>(X, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, rows, n_ptr, b, bm_next);
-            break;
-        case SCONE_ACT_LEAKY_RELU:
-            rows_layer0_fwd_kernel<COUT, SCONE_ACT_LEAKY_RELU><<<grid, 256, 0, st>>>(X, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, rows, n_ptr, b, bm_next);
-            break;
-        case SCONE_ACT_RELU:
-            rows_layer0_fwd_kernel<COUT, SCONE_ACT_RELU><<<grid, 256, 0, st>>>(X, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, rows, n_ptr, b, bm_next);
-            break;
-        default: scone_set_error("unknown activation %d", act); return 2;
-    }
+template <int COUT, int ACT>
+int launch_rows_l0_fwd_act(const scone_complex* cx, int b, const float* X, const float* W0, const float* W1, const float* W2, float* Hout,
+                           const uint32_t* rows, const int* n_ptr, uint32_t* bm_next, int out_cap, int* overflow, cudaStream_t st) {
+    const int grid = cx->num_sms * 8;
+    if (out_cap > 0)
+        rows_layer0_fwd_kernel<COUT, ACT, true><<<grid, 256, 0, st>>>(X, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, rows, n_ptr, b, bm_next, out_cap, overflow);
+    else
+        rows_layer0_fwd_kernel<COUT, ACT, false><<<grid, 256, 0, st>>>(X, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, rows, n_ptr, b, bm_next, out_cap, overflow);
     SCONE_LAUNCHED();
     return 0;
+}
+
+template <int COUT>
+int launch_rows_l0_fwd(const scone_complex* cx, int act, int b, const float* X, const float* W0, const float* W1, const float* W2,
+                       float* Hout, const uint32_t* rows, const int* n_ptr, uint32_t* bm_next, int out_cap, int* overflow, cudaStream_t st) {
+    switch (act) {
+        case SCONE_ACT_TANH: return launch_rows_l0_fwd_act<COUT, SCONE_ACT_TANH>(cx, b, X, W0, W1, W2, Hout, rows, n_ptr, bm_next, out_cap, overflow, st);
+        case SCONE_ACT_LEAKY_RELU: return launch_rows_l0_fwd_act<COUT, SCONE_ACT_LEAKY_RELU>(cx, b, X, W0, W1, W2, Hout, rows, n_ptr, bm_next, out_cap, overflow, st);
+        case SCONE_ACT_RELU: return launch_rows_l0_fwd_act<COUT, SCONE_ACT_RELU>(cx, b, X, W0, W1, W2, Hout, rows, n_ptr, bm_next, out_cap, overflow, st);
+    }
+    scone_set_error("unknown activation %d", act);
+    return 2;
 }
 
 }  // namespace
@@ -508,46 +713,53 @@ int scone_rows_flows(const scone_complex* cx, int b, const int32_t* traj_ptr, co
     return 0;
 }
 
-int scone_rows_mark(const scone_complex* cx, int b, const uint32_t* rows, const int* n_dev, uint32_t* bm_next, cudaStream_t st) {
-    rows_mark_kernel<<<cx->num_sms * 8, 256, 0, st>>>(rows, n_dev, cx->d_mptr, cx->d_ment, b, bm_next);
+int scone_rows_mark(const scone_complex* cx, int b, const uint32_t* rows, const int* n_dev, uint32_t* bm_next, int list_cap,
+                    cudaStream_t st) {
+    rows_mark_kernel<<<cx->num_sms * 8, 256, 0, st>>>(rows, n_dev, cx->d_mptr, cx->d_ment, b, bm_next, list_cap);
     SCONE_LAUNCHED();
     return 0;
 }
 
+// out_cap > 0: compact storage (row rows[i] of Hout at index i, at most out_cap rows)
 int scone_rows_layer0_forward(const scone_complex* cx, int act, int b, int cout, const float* X, const float* W0, const float* W1,
-                              const float* W2, float* Hout, const uint32_t* rows, const int* n_dev, uint32_t* bm_next, cudaStream_t st) {
-    if (cout == 16) return launch_rows_l0_fwd<16>(cx, act, b, X, W0, W1, W2, Hout, rows, n_dev, bm_next, st);
-    if (cout == 32) return launch_rows_l0_fwd<32>(cx, act, b, X, W0, W1, W2, Hout, rows, n_dev, bm_next, st);
+                              const float* W2, float* Hout, const uint32_t* rows, const int* n_dev, uint32_t* bm_next, int out_cap,
+                              int* overflow_dev, cudaStream_t st) {
+    if (cout == 16) return launch_rows_l0_fwd<16>(cx, act, b, X, W0, W1, W2, Hout, rows, n_dev, bm_next, out_cap, overflow_dev, st);
+    if (cout == 32) return launch_rows_l0_fwd<32>(cx, act, b, X, W0, W1, W2, Hout, rows, n_dev, bm_next, out_cap, overflow_dev, st);
     scone_set_error("scone_rows_layer0_forward: unsupported width %d", cout);
     return 2;
 }
 
+// g_cap > 0: G is compact (row rows[i] at index i)
 int scone_rows_layer0_backward(const scone_complex* cx, int b, int cout, const float* X, const float* G, const uint32_t* rows,
-                               const int* n_dev, float* dW, int accumulate, float* ws, cudaStream_t st) {
-    if (cout == 16)
-        rows_layer0_bwd_kernel<16><<<kDwCtas, 256, 0, st>>>(X, G, cx->d_mptr, cx->d_ment, rows, n_dev, b, ws);
-    else if (cout == 32)
-        rows_layer0_bwd_kernel<32><<<kDwCtas, 256, 0, st>>>(X, G, cx->d_mptr, cx->d_ment, rows, n_dev, b, ws);
+                               const int* n_dev, float* dW, int accumulate, float* ws, int g_cap, cudaStream_t st) {
+#define SCONE_L0B(CO)                                                                                                         \
+    if (g_cap > 0) rows_layer0_bwd_kernel<CO, true><<<kDwCtas, 256, 0, st>>>(X, G, cx->d_mptr, cx->d_ment, rows, n_dev, b, ws, g_cap); \
+    else rows_layer0_bwd_kernel<CO, false><<<kDwCtas, 256, 0, st>>>(X, G, cx->d_mptr, cx->d_ment, rows, n_dev, b, ws, g_cap);
+    if (cout == 16) { SCONE_L0B(16) }
+    else if (cout == 32) { SCONE_L0B(32) }
     else {
         scone_set_error("scone_rows_layer0_backward: unsupported width %d", cout);
         return 2;
     }
+#undef SCONE_L0B
     SCONE_LAUNCHED();
     rows_reduce_kernel<<<(3 * cout + 31) / 32, 256, 0, st>>>(ws, kDwCtas, 3 * cout, dW, accumulate);
     SCONE_LAUNCHED();
     return 0;
 }
 
+// prefG / prefH != NULL: compact storage of G, Hin, Gprev (a_cap then also bounds the rows of Gprev)
 int scone_rows_backward(const scone_complex* cx, int act, int b, int cin, int cout, const float* G, const float* Hin, float* Gprev,
                         float* Abuf, const float* W0, const float* W1, const float* W2, const uint32_t* rows, const int* n_dev,
                         const uint32_t* bmG, const uint32_t* bmH, int a_cap, int* overflow_dev, float* dW, int accumulate, float* ws,
-                        cudaStream_t st) {
+                        const uint32_t* prefG, const uint32_t* prefH, cudaStream_t st) {
 #define SCONE_RB_CASE(CI, CO)                                                                                                     \
     if (cin == CI && cout == CO) {                                                                                                \
-        if (dispatch_rows_bwd<CI, CO>(cx, act, b, G, Hin, Gprev, Abuf, W0, W1, W2, rows, n_dev, bmG, bmH, a_cap,                   \
-                                      overflow_dev, st))                                                                          \
+        if (dispatch_rows_bwd<CI, CO>(cx, act, b, G, Hin, Gprev, Abuf, W0, W1, W2, rows, n_dev, bmG, bmH, a_cap, overflow_dev,      \
+                                      prefG, prefH, st))                                                                          \
             return 1;                                                                                                             \
-        return launch_rows_dw<CI, CO>(cx, Hin, bmH, Abuf, rows, n_dev, a_cap, dW, accumulate, ws, st);                             \
+        return launch_rows_dw<CI, CO>(cx, Hin, bmH, Abuf, rows, n_dev, a_cap, dW, accumulate, ws, prefH, st);                       \
     }
     SCONE_RB_CASE(16, 16)
     SCONE_RB_CASE(16, 32)
@@ -556,4 +768,32 @@ int scone_rows_backward(const scone_complex* cx, int act, int b, int cin, int co
 #undef SCONE_RB_CASE
     scone_set_error("scone_rows_backward: unsupported widths %d -> %d", cin, cout);
     return 2;
+}
+
+// Readout over compact storage (see rows_readout_*_kernel).  Forward: log-probs; with bmG != NULL also the bits of G_L's rows and
+// (bm_cand != NULL) the candidate bits one hop further — the caller cleared both bitmaps.
+int scone_rows_readout_forward(const scone_complex* cx, int b, int C, const float* HL, const float* wout, const int32_t* last_nodes,
+                               float* logprobs, const uint32_t* bmH, const uint32_t* prefH, uint32_t* bmG, uint32_t* bm_cand,
+                               cudaStream_t st) {
+    SCONE_REQUIRE(C >= 1 && C <= 32 * kRoMaxCper && cx->D <= kRoMaxD, "scone_rows_readout: C <= %d and max degree <= %d", 32 * kRoMaxCper, kRoMaxD);
+    rows_readout_fwd_kernel<<<b, 32 * kRoWarps, 0, st>>>(HL, wout, last_nodes, cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, logprobs, bmH,
+                                                        prefH, bmG, bm_cand, cx->d_mptr, cx->d_ment, cx->N, cx->D, b, C);
+    SCONE_LAUNCHED();
+    return 0;
+}
+
+// Gradient part, after bmG was compacted (prefG, n_dev = number of rows of G_L): zero the rows, accumulate, reduce the partials.
+int scone_rows_readout_backward(const scone_complex* cx, int act, int b, int C, const float* HL, const float* wout,
+                                const int32_t* last_nodes, const float* logprobs, const int32_t* target_idx, const float* mask,
+                                float scale, float* GL, const int* n_dev, int g_cap, int* overflow_dev, float* dwout, float* nll_sum,
+                                float* count, int accumulate, float* ws, const uint32_t* bmH, const uint32_t* prefH, const uint32_t* bmG,
+                                const uint32_t* prefG, cudaStream_t st) {
+    rows_zero_kernel<<<cx->num_sms * 4, 256, 0, st>>>(reinterpret_cast<float4*>(GL), n_dev, g_cap, C / 4, overflow_dev);
+    SCONE_LAUNCHED();
+    rows_readout_bwd_kernel<<<b, 32 * kRoWarps, 0, st>>>(HL, wout, last_nodes, cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, logprobs, target_idx,
+                                                        mask, scale, GL, ws, bmH, prefH, bmG, prefG, g_cap, act, cx->N, cx->D, b, C);
+    SCONE_LAUNCHED();
+    rows_readout_reduce_kernel<<<1, 256, 0, st>>>(ws, b, C, dwout, nll_sum, count, accumulate);
+    SCONE_LAUNCHED();
+    return 0;
 }

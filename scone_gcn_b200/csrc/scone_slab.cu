@@ -123,14 +123,19 @@ int dispatch_fwd_act(const scone_complex* cx, int act, int ts, int b, const floa
 // neighbours are in flight together.  Each row's result is independent of the other rows in its slab and uses the same
 // summation order and mma sequence as the dense slab kernel: bit-identical to it.
 // =================================================================================================================
-template <int CIN, int COUT, int ACT, bool BITS>
+// COMPACT (with BITS): tensors are stored compactly — row r of Hin at index rank(r) in (bm_in, pref_in), row rows[i] of Hout at
+// index i — so memory and traffic follow the support and a micro-batch can hold thousands of trajectories.
+template <int CIN, int COUT, int ACT, bool BITS, bool COMPACT>
 __global__ void __launch_bounds__(kSlabThreads, 1) layer_fwd_rows_kernel(const float* __restrict__ Hin, float* __restrict__ Hout,
                                                                         const float* __restrict__ W0, const float* __restrict__ W1,
                                                                         const float* __restrict__ W2, const int32_t* __restrict__ mptr,
                                                                         const int2* __restrict__ ment, const uint8_t* __restrict__ occ_in,
                                                                         const uint32_t* __restrict__ rows, const int* __restrict__ n_ptr,
                                                                         int b, unsigned long long* __restrict__ row_counter,
-                                                                        const uint32_t* __restrict__ bm_in) {
+                                                                        const uint32_t* __restrict__ bm_in,
+                                                                        const uint32_t* __restrict__ pref_in, int out_cap,
+                                                                        int* __restrict__ overflow) {
+    static_assert(!COMPACT || BITS, "compact storage is addressed through the row bitmaps");
     using G = SlabGeom<CIN, 16>;
     constexpr int NT = COUT / 8, NL = G::NL, Q = G::Q, LPR = CIN / 4;      // Q rows per warp-wide load, LPR lanes per row
     extern __shared__ __align__(16) uint4 Bf[];
@@ -138,9 +143,13 @@ __global__ void __launch_bounds__(kSlabThreads, 1) layer_fwd_rows_kernel(const f
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tig = lane & 3, g = lane >> 2;
     const int gq = lane / LPR, cq = lane % LPR;
-    const unsigned rowbytes = (unsigned)b * CIN * 4u;
+    const unsigned rowbytes = COMPACT ? CIN * 4u : (unsigned)b * CIN * 4u;    // stride of the gather index (compact row / edge row)
     const char* Hb = reinterpret_cast<const char*>(Hin);
-    const int n = *n_ptr;
+    int n = *n_ptr;
+    if (COMPACT && n > out_cap) {                          // the compact output cannot hold this many rows: flag it (host raises)
+        if (blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1;
+        n = out_cap;
+    }
     const int n_slabs = (n + 15) / 16;
     const int n_tiles = (n_slabs + kSlabWarps - 1) / kSlabWarps;
     if (row_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(row_counter, (unsigned long long)n);
@@ -158,6 +167,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) layer_fwd_rows_kernel(const f
         if (slab >= n_slabs) continue;
         // this lane's row in each load slot
         uint32_t rid[NL];
+        unsigned oidx[NL];                                 // index of the own row in Hin's storage
         int len[NL], p0[NL], tq[NL];
         const char* P[NL];
         bool own[NL];
@@ -170,11 +180,16 @@ __global__ void __launch_bounds__(kSlabThreads, 1) layer_fwd_rows_kernel(const f
             const int e = (int)(rid[i] / (unsigned)b);
             tq[i] = (int)(rid[i] - (unsigned)e * (unsigned)b);
             const int cpos = (CIN == 32 && i >= 2) ? (cq ^ 4) : cq;
-            P[i] = Hb + (size_t)((unsigned)(tq[i] * CIN + 4 * cpos) * 4u);
+            P[i] = Hb + (size_t)((unsigned)((COMPACT ? 0 : tq[i] * CIN) + 4 * cpos) * 4u);
             asm volatile("" : "+l"(P[i]));                 // keep base + lane offset folded: one IMAD.WIDE per load address
             p0[i] = valid ? __ldg(mptr + e) : 0;
             len[i] = valid ? __ldg(mptr + e + 1) - p0[i] : 0;
-            own[i] = valid && (BITS ? bit_test(bm_in, rid[i]) : __ldg(occ_in + rid[i]) != 0);
+            if (COMPACT) {
+                own[i] = rank_lookup(bm_in, pref_in, rid[i], oidx[i]) && valid;
+            } else {
+                oidx[i] = (unsigned)e;
+                own[i] = valid && (BITS ? bit_test(bm_in, rid[i]) : __ldg(occ_in + rid[i]) != 0);
+            }
             maxlen = max(maxlen, len[i]);
         }
 #pragma unroll
@@ -186,7 +201,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) layer_fwd_rows_kernel(const f
             for (int i = 0; i < NL; ++i) acc[k][i][0] = acc[k][i][1] = 0ull;
 #pragma unroll
         for (int i = 0; i < NL; ++i)
-            if (own[i]) ldg128(reinterpret_cast<const float*>(P[i] + (size_t)(rid[i] / (unsigned)b) * rowbytes), acc[0][i][0], acc[0][i][1]);
+            if (own[i]) ldg128(reinterpret_cast<const float*>(P[i] + (size_t)oidx[i] * rowbytes), acc[0][i][0], acc[0][i][1]);
 #pragma unroll 2
         for (int k = 0; k < maxlen; ++k) {
             int2 ent[NL];
@@ -196,17 +211,23 @@ __global__ void __launch_bounds__(kSlabThreads, 1) layer_fwd_rows_kernel(const f
                 on[i] = k < len[i];
                 ent[i] = on[i] ? __ldg(ment + p0[i] + k) : make_int2(0, 0);
             }
+            unsigned gidx[NL];                             // gather index of the neighbour row: its edge, or its compact rank
 #pragma unroll
             for (int i = 0; i < NL; ++i) {                 // branch-free flag test (entry {0,0} of an idle lane tests row tq: in range)
                 const unsigned nrow = (unsigned)ent[i].x * (unsigned)b + (unsigned)tq[i];       // E*b < 2^32
-                const unsigned f = BITS ? (__ldg(bm_in + (nrow >> 5)) >> (nrow & 31)) & 1u : (unsigned)__ldg(occ_in + nrow);
-                on[i] = on[i] && f != 0u;
+                if (COMPACT) {
+                    on[i] = rank_lookup(bm_in, pref_in, nrow, gidx[i]) && on[i];
+                } else {
+                    const unsigned f = BITS ? (__ldg(bm_in + (nrow >> 5)) >> (nrow & 31)) & 1u : (unsigned)__ldg(occ_in + nrow);
+                    on[i] = on[i] && f != 0u;
+                    gidx[i] = (unsigned)ent[i].x;
+                }
             }
             u64 v[NL][2];
 #pragma unroll
             for (int i = 0; i < NL; ++i) {
                 v[i][0] = v[i][1] = 0ull;
-                if (on[i]) ldg128(reinterpret_cast<const float*>(P[i] + (size_t)(unsigned)ent[i].x * rowbytes), v[i][0], v[i][1]);
+                if (on[i]) ldg128(reinterpret_cast<const float*>(P[i] + (size_t)gidx[i] * rowbytes), v[i][0], v[i][1]);
             }
 #pragma unroll
             for (int i = 0; i < NL; ++i) {
@@ -242,7 +263,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) layer_fwd_rows_kernel(const f
                 oli = slab * 16 + r * Q + gq;
             }
             if (oli < n) {
-                float* dst = Hout + (size_t)orow * COUT + 2 * tig;
+                float* dst = Hout + (size_t)(COMPACT ? (uint32_t)oli : orow) * COUT + 2 * tig;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) *reinterpret_cast<float2*>(dst + nt * 8) = make_float2(d[nt][2 * r], d[nt][2 * r + 1]);
             }
@@ -253,22 +274,24 @@ __global__ void __launch_bounds__(kSlabThreads, 1) layer_fwd_rows_kernel(const f
 template <int CIN, int COUT, int ACT>
 int launch_fwd_rows(const scone_complex* cx, int b, const float* Hin, const float* W0, const float* W1, const float* W2, float* Hout,
                     const uint8_t* occ_in, const uint32_t* rows, const int* n_ptr, unsigned long long* row_counter,
-                    const uint32_t* bm_in, cudaStream_t st) {
+                    const uint32_t* bm_in, const uint32_t* pref_in, int out_cap, int* overflow, cudaStream_t st) {
     using G = SlabGeom<CIN, 16>;
     constexpr int NT = COUT / 8;
     const size_t smem = (size_t)3 * G::KS * NT * 32 * sizeof(uint4);
     static bool configured = false;
     if (!configured) {
-        SCONE_CUDA(cudaFuncSetAttribute(layer_fwd_rows_kernel<CIN, COUT, ACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SCONE_CUDA(cudaFuncSetAttribute(layer_fwd_rows_kernel<CIN, COUT, ACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCONE_CUDA(cudaFuncSetAttribute(layer_fwd_rows_kernel<CIN, COUT, ACT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCONE_CUDA(cudaFuncSetAttribute(layer_fwd_rows_kernel<CIN, COUT, ACT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCONE_CUDA(cudaFuncSetAttribute(layer_fwd_rows_kernel<CIN, COUT, ACT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    if (bm_in != nullptr)
-        layer_fwd_rows_kernel<CIN, COUT, ACT, true><<<cx->num_sms, kSlabThreads, smem, st>>>(Hin, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment,
-                                                                                           occ_in, rows, n_ptr, b, row_counter, bm_in);
-    else
-        layer_fwd_rows_kernel<CIN, COUT, ACT, false><<<cx->num_sms, kSlabThreads, smem, st>>>(Hin, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment,
-                                                                                            occ_in, rows, n_ptr, b, row_counter, bm_in);
+#define SCONE_ROWS_LAUNCH(BITS_, COMPACT_)                                                                                          \
+    layer_fwd_rows_kernel<CIN, COUT, ACT, BITS_, COMPACT_><<<cx->num_sms, kSlabThreads, smem, st>>>(                                \
+        Hin, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, occ_in, rows, n_ptr, b, row_counter, bm_in, pref_in, out_cap, overflow)
+    if (bm_in != nullptr && pref_in != nullptr) SCONE_ROWS_LAUNCH(true, true);
+    else if (bm_in != nullptr) SCONE_ROWS_LAUNCH(true, false);
+    else SCONE_ROWS_LAUNCH(false, false);
+#undef SCONE_ROWS_LAUNCH
     SCONE_LAUNCHED();
     return 0;
 }
@@ -276,11 +299,11 @@ int launch_fwd_rows(const scone_complex* cx, int b, const float* Hin, const floa
 template <int CIN, int COUT>
 int dispatch_rows_act(const scone_complex* cx, int act, int b, const float* Hin, const float* W0, const float* W1, const float* W2,
                       float* Hout, const uint8_t* occ_in, const uint32_t* rows, const int* n_ptr, unsigned long long* rc,
-                      const uint32_t* bm_in, cudaStream_t st) {
+                      const uint32_t* bm_in, const uint32_t* pref_in, int out_cap, int* overflow, cudaStream_t st) {
     switch (act) {
-        case SCONE_ACT_TANH: return launch_fwd_rows<CIN, COUT, SCONE_ACT_TANH>(cx, b, Hin, W0, W1, W2, Hout, occ_in, rows, n_ptr, rc, bm_in, st);
-        case SCONE_ACT_LEAKY_RELU: return launch_fwd_rows<CIN, COUT, SCONE_ACT_LEAKY_RELU>(cx, b, Hin, W0, W1, W2, Hout, occ_in, rows, n_ptr, rc, bm_in, st);
-        case SCONE_ACT_RELU: return launch_fwd_rows<CIN, COUT, SCONE_ACT_RELU>(cx, b, Hin, W0, W1, W2, Hout, occ_in, rows, n_ptr, rc, bm_in, st);
+        case SCONE_ACT_TANH: return launch_fwd_rows<CIN, COUT, SCONE_ACT_TANH>(cx, b, Hin, W0, W1, W2, Hout, occ_in, rows, n_ptr, rc, bm_in, pref_in, out_cap, overflow, st);
+        case SCONE_ACT_LEAKY_RELU: return launch_fwd_rows<CIN, COUT, SCONE_ACT_LEAKY_RELU>(cx, b, Hin, W0, W1, W2, Hout, occ_in, rows, n_ptr, rc, bm_in, pref_in, out_cap, overflow, st);
+        case SCONE_ACT_RELU: return launch_fwd_rows<CIN, COUT, SCONE_ACT_RELU>(cx, b, Hin, W0, W1, W2, Hout, occ_in, rows, n_ptr, rc, bm_in, pref_in, out_cap, overflow, st);
     }
     scone_set_error("unknown activation %d", act);
     return 2;
@@ -291,10 +314,11 @@ int dispatch_rows_act(const scone_complex* cx, int act, int b, const float* Hin,
 // Flagged fused layer forward over a compacted row list (see layer_fwd_rows_kernel); the caller checked scone_slab_supported.
 int scone_slab_forward_rows(const scone_complex* cx, int act, int b, int cin, int cout, const float* Hin, const float* W0,
                             const float* W1, const float* W2, float* Hout, const uint8_t* occ_in, const uint32_t* rows,
-                            const int* n_rows_dev, unsigned long long* row_counter, const uint32_t* bm_in, cudaStream_t st) {
+                            const int* n_rows_dev, unsigned long long* row_counter, const uint32_t* bm_in, const uint32_t* pref_in,
+                            int out_cap, int* overflow_dev, cudaStream_t st) {
 #define SCONE_ROWS_CASE(CI, CO)                                                                                                 \
     if (cin == CI && cout == CO)                                                                                                \
-        return dispatch_rows_act<CI, CO>(cx, act, b, Hin, W0, W1, W2, Hout, occ_in, rows, n_rows_dev, row_counter, bm_in, st);
+        return dispatch_rows_act<CI, CO>(cx, act, b, Hin, W0, W1, W2, Hout, occ_in, rows, n_rows_dev, row_counter, bm_in, pref_in, out_cap, overflow_dev, st);
     SCONE_ROWS_CASE(16, 16)
     SCONE_ROWS_CASE(16, 32)
     SCONE_ROWS_CASE(32, 16)

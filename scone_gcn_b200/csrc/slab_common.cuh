@@ -26,6 +26,15 @@ __device__ __forceinline__ void bit_set(uint32_t* __restrict__ bm, size_t row) {
     const uint32_t bit = 1u << (row & 31);
     if (!(*w & bit)) atomicOr(w, bit);
 }
+// compact storage: row r of a tensor lives at index rank(r) = pref[r >> 5] + popc(bm[r >> 5] & bits below r) = its position in
+// the compacted row list; returns whether the row exists (bit set)
+__device__ __forceinline__ bool rank_lookup(const uint32_t* __restrict__ bm, const uint32_t* __restrict__ pref, unsigned row,
+                                            unsigned& idx) {
+    const uint32_t w = __ldg(bm + (row >> 5));
+    const unsigned sh = row & 31u;
+    idx = __ldg(pref + (row >> 5)) + (unsigned)__popc(w & ((1u << sh) - 1u));
+    return (w >> sh) & 1u;
+}
 __device__ __forceinline__ uint32_t to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
