@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256) rows_layer0_bwd_kernel(const float* __res
 // zero: act'(0)).
 // ---------------------------------------------------------------------------------------------------------------
 template <int CIN, int COUT, int ACT, bool COMPACT>
-__global__ void __launch_bounds__(kSlabThreads, 1) rows_bwd_kernel(const float* __restrict__ Gin, const float* __restrict__ Hin,
+__global__ void __launch_bounds__(kRowsThreads, 1) rows_bwd_kernel(const float* __restrict__ Gin, const float* __restrict__ Hin,
                                                                   float* __restrict__ Gprev, float* __restrict__ Abuf,
                                                                   const float* __restrict__ W0, const float* __restrict__ W1,
                                                                   const float* __restrict__ W2, const int32_t* __restrict__ mptr,
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) rows_bwd_kernel(const float* 
         n = a_cap;
     }
     const int n_slabs = (n + 15) / 16;
-    const int n_tiles = (n_slabs + kSlabWarps - 1) / kSlabWarps;
+    const int n_tiles = (n_slabs + kRowsWarps - 1) / kRowsWarps;
     if (row_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(row_counter, (unsigned long long)n);
     __shared__ int s_tile;                                 // dynamic tiles, see layer_fwd_rows_kernel
     int* tile_counter = const_cast<int*>(n_ptr) + 1;
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) rows_bwd_kernel(const float* 
         __syncthreads();
         const int tile = s_tile;
         if (tile >= n_tiles) break;
-        const int slab = tile * kSlabWarps + warp;
+        const int slab = tile * kRowsWarps + warp;
         if (slab >= n_slabs) continue;
         uint32_t rid[NL];
         unsigned oidx[NL];
@@ -628,11 +628,11 @@ int launch_rows_bwd(const scone_complex* cx, int b, const float* G, const float*
         configured = true;
     }
     if (prefG != nullptr)
-        rows_bwd_kernel<CIN, COUT, ACT, true><<<cx->num_sms, kSlabThreads, smem, st>>>(G, Hin, Gprev, Abuf, W0, W1, W2, cx->d_mptr, cx->d_ment, rows,
+        rows_bwd_kernel<CIN, COUT, ACT, true><<<cx->num_sms, kRowsThreads, smem, st>>>(G, Hin, Gprev, Abuf, W0, W1, W2, cx->d_mptr, cx->d_ment, rows,
                                                                                      n_ptr, b, bmG, bmH, a_cap, overflow,
                                                                                      scone_prof_row_counter(SCONE_K_LAYER_BWD), prefG, prefH);
     else
-        rows_bwd_kernel<CIN, COUT, ACT, false><<<cx->num_sms, kSlabThreads, smem, st>>>(G, Hin, Gprev, Abuf, W0, W1, W2, cx->d_mptr, cx->d_ment, rows,
+        rows_bwd_kernel<CIN, COUT, ACT, false><<<cx->num_sms, kRowsThreads, smem, st>>>(G, Hin, Gprev, Abuf, W0, W1, W2, cx->d_mptr, cx->d_ment, rows,
                                                                                       n_ptr, b, bmG, bmH, a_cap, overflow,
                                                                                       scone_prof_row_counter(SCONE_K_LAYER_BWD), prefG, prefH);
     SCONE_LAUNCHED();

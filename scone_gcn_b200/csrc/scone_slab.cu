@@ -126,7 +126,7 @@ int dispatch_fwd_act(const scone_complex* cx, int act, int ts, int b, const floa
 // COMPACT (with BITS): tensors are stored compactly — row r of Hin at index rank(r) in (bm_in, pref_in), row rows[i] of Hout at
 // index i — so memory and traffic follow the support and a micro-batch can hold thousands of trajectories.
 template <int CIN, int COUT, int ACT, bool BITS, bool COMPACT>
-__global__ void __launch_bounds__(kSlabThreads, 1) layer_fwd_rows_kernel(const float* __restrict__ Hin, float* __restrict__ Hout,
+__global__ void __launch_bounds__(kRowsThreads, 1) layer_fwd_rows_kernel(const float* __restrict__ Hin, float* __restrict__ Hout,
                                                                         const float* __restrict__ W0, const float* __restrict__ W1,
                                                                         const float* __restrict__ W2, const int32_t* __restrict__ mptr,
                                                                         const int2* __restrict__ ment, const uint8_t* __restrict__ occ_in,
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) layer_fwd_rows_kernel(const f
         n = out_cap;
     }
     const int n_slabs = (n + 15) / 16;
-    const int n_tiles = (n_slabs + kSlabWarps - 1) / kSlabWarps;
+    const int n_tiles = (n_slabs + kRowsWarps - 1) / kRowsWarps;
     if (row_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(row_counter, (unsigned long long)n);
     // tiles (16 consecutive slabs, one per warp) are handed out dynamically: n_ptr[1] is a counter the compaction kernel zeroed
     // (per-tile cost varies with how many distinct edges a slab mixes; a static split left SMs idle for a third of the kernel)
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) layer_fwd_rows_kernel(const f
         __syncthreads();
         const int tile = s_tile;
         if (tile >= n_tiles) break;
-        const int slab = tile * kSlabWarps + warp;
+        const int slab = tile * kRowsWarps + warp;
         if (slab >= n_slabs) continue;
         // this lane's row in each load slot
         uint32_t rid[NL];
@@ -286,7 +286,7 @@ int launch_fwd_rows(const scone_complex* cx, int b, const float* Hin, const floa
         configured = true;
     }
 #define SCONE_ROWS_LAUNCH(BITS_, COMPACT_)                                                                                          \
-    layer_fwd_rows_kernel<CIN, COUT, ACT, BITS_, COMPACT_><<<cx->num_sms, kSlabThreads, smem, st>>>(                                \
+    layer_fwd_rows_kernel<CIN, COUT, ACT, BITS_, COMPACT_><<<cx->num_sms, kRowsThreads, smem, st>>>(                                \
         Hin, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, occ_in, rows, n_ptr, b, row_counter, bm_in, pref_in, out_cap, overflow)
     if (bm_in != nullptr && pref_in != nullptr) SCONE_ROWS_LAUNCH(true, true);
     else if (bm_in != nullptr) SCONE_ROWS_LAUNCH(true, false);
