@@ -104,13 +104,13 @@ def ncu_traffic(kernel, E, mb, C, zero_fill):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full`
     captures -- only reported when this run has the same launch shape as the capture (cfg5).
       zero_fill  profiles/prof_fill_r1m_raw.csv       (dense-stream mode, b = 64)
-      layer_fwd  profiles/prof_rows_fwd_r1t_raw.csv   (row-list pipeline, b = 128: the two layer_fwd_rows_kernel launches of
-                                                       one micro-batch, averaged)"""
+      layer_fwd  profiles/prof_rows_fwd_r1x_raw.csv   (compact row-list pipeline, b = 2048: the two layer_fwd_rows_kernel
+                                                       launches of one micro-batch, averaged)"""
     src = None
     if kernel == 'zero_fill' and (E, mb, C) == (999308, 64, 32):
         src = 'prof_fill_r1m_raw.csv'
-    if kernel == 'layer_fwd' and not zero_fill and (E, mb, C) == (999308, 128, 32):
-        src = 'prof_rows_fwd_r1t_raw.csv'
+    if kernel == 'layer_fwd' and not zero_fill and (E, mb, C) == (999308, 2048, 32):
+        src = 'prof_rows_fwd_r1x_raw.csv'
     if src is None:
         return None
     try:
@@ -370,7 +370,7 @@ def main():
                                              'trajectories/s: what a dense-streaming implementation would have to move to match'},
                 'bytes_model': 'layer_fwd / layer_bwd: rows produced (device-counted) x 4*(Cin+Cout) / 4*(2*Cin+Cout) bytes per launch; the family '
                                'time includes its bitmap compaction, candidate marking and (backward) the weight-gradient GEMM; these kernels are '
-                               'L2-latency / issue bound on ~0.5 M rows per launch, not HBM bound (profiles/prof_rows_fwd_r1t_*); '
+                               'L1 / issue bound (rank lookups and gathers are cache-served), not HBM bound (profiles/prof_rows_fwd_r1x_*); '
                                'zero_fill (dense-stream mode): 4*E*b*C bytes per launch',
                 'pipeline': {2: 'row lists, compact tensors', 1: 'row lists, dense tensors', 0: 'unit kernels, byte flags'}[
                     L.scone_model_get_pipeline(net.handle)]}

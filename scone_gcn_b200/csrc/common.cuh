@@ -60,7 +60,7 @@ struct SconeLaunchHints {
     uint32_t* out_bm = nullptr;
     uint32_t* cand_bm = nullptr;     // readout: also mark the candidate rows one hop beyond the rows of G_L it writes
 };
-static inline size_t scone_bitmap_words(size_t E, size_t b) { return ((E * b + 31) / 32 + 7) / 4 * 4; }   // padded to whole uint4
+static inline size_t scone_bitmap_words(size_t E, size_t b) { return ((E * b + 31) / 32 + 31) / 16 * 16; }   // padded to whole 64-byte groups
 extern thread_local SconeLaunchHints g_scone_hints;
 
 // Integer-valued shift operator in CSR form.  ent[p] = {column, float bits of the coefficient};

@@ -568,29 +568,34 @@ __global__ void __launch_bounds__(kThreads) compact_bitmap_kernel(const uint32_t
                                                                  unsigned long long* __restrict__ tickets,
                                                                  uint32_t* __restrict__ pref_out, long long list_cap) {
     // pref_out (optional, R == 1): pref_out[w] = number of set bits before word w = list index of word w's first set bit; the
-    // rank of row r is then pref_out[r >> 5] + popc(bm[r >> 5] & ((1 << (r & 31)) - 1)).  Words of slices without any set bit
-    // are not written (their rank is never asked for).
-    constexpr int kChunk = 4 * kThreads;                  // words per chunk: one 128-bit load per thread
+    // rank of row r is then pref_out[r >> 5] + popc(bm[r >> 5] & ((1 << (r & 31)) - 1)).  Only words with a set bit are written
+    // (the rank of a row whose bit is clear is never used).
+    constexpr int WPT = 16;                               // words per thread and chunk: four 128-bit loads in flight
+    constexpr int kChunk = WPT * kThreads;
     __shared__ int s_warp[kWarps];
     __shared__ long long s_prefix;
     __shared__ int s_total;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long per_cta = ((n_words + gridDim.x - 1) / gridDim.x + kChunk - 1) / kChunk * kChunk;   // whole chunks
     const long long lo = (long long)blockIdx.x * per_cta, hi = lo + per_cta < n_words ? lo + per_cta : n_words;
-    auto load4 = [&](long long w, uint32_t (&c)[4]) {     // words w .. w+3 (w % 4 == 0), zero beyond hi; the bitmap is padded
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (w < hi) v = __ldg(reinterpret_cast<const uint4*>(bm + w));
-        c[0] = collapse_quads<R>(v.x);
-        c[1] = w + 1 < hi ? collapse_quads<R>(v.y) : 0u;
-        c[2] = w + 2 < hi ? collapse_quads<R>(v.z) : 0u;
-        c[3] = w + 3 < hi ? collapse_quads<R>(v.w) : 0u;
+    auto load16 = [&](long long w, uint32_t (&c)[WPT]) {  // words w .. w+15 (w % 16 == 0), zero beyond hi; the bitmap is padded
+#pragma unroll
+        for (int v4 = 0; v4 < WPT / 4; ++v4) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (w + 4 * v4 < hi) v = __ldg(reinterpret_cast<const uint4*>(bm + w + 4 * v4));
+            c[4 * v4 + 0] = collapse_quads<R>(v.x);
+            c[4 * v4 + 1] = w + 4 * v4 + 1 < hi ? collapse_quads<R>(v.y) : 0u;
+            c[4 * v4 + 2] = w + 4 * v4 + 2 < hi ? collapse_quads<R>(v.z) : 0u;
+            c[4 * v4 + 3] = w + 4 * v4 + 3 < hi ? collapse_quads<R>(v.w) : 0u;
+        }
     };
     // pass 1: count
     int cnt = 0;
-    for (long long w = lo + 4 * threadIdx.x; w < hi; w += kChunk) {
-        uint32_t c[4];
-        load4(w, c);
-        cnt += __popc(c[0]) + __popc(c[1]) + __popc(c[2]) + __popc(c[3]);
+    for (long long w = lo + (long long)WPT * threadIdx.x; w < hi; w += kChunk) {
+        uint32_t c[WPT];
+        load16(w, c);
+#pragma unroll
+        for (int q = 0; q < WPT; ++q) cnt += __popc(c[q]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -620,10 +625,12 @@ __global__ void __launch_bounds__(kThreads) compact_bitmap_kernel(const uint32_t
     if (total == 0) return;                               // (uniform) nothing flagged in this slice
     // pass 2: block-exclusive scan of the per-thread counts of a chunk, ids written in ascending order
     for (long long w0 = lo; w0 < hi; w0 += kChunk) {
-        const long long w = w0 + 4 * threadIdx.x;
-        uint32_t c[4];
-        load4(w, c);
-        const int n = __popc(c[0]) + __popc(c[1]) + __popc(c[2]) + __popc(c[3]);
+        const long long w = w0 + (long long)WPT * threadIdx.x;
+        uint32_t c[WPT];
+        load16(w, c);
+        int n = 0;
+#pragma unroll
+        for (int q = 0; q < WPT; ++q) n += __popc(c[q]);
         int incl = n;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -641,15 +648,18 @@ __global__ void __launch_bounds__(kThreads) compact_bitmap_kernel(const uint32_t
             ctot += v;
         }
         long long off = base + woff + incl - n;
+        if (n) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint32_t cc = c[q];
-            if (pref_out != nullptr && w + q < hi) pref_out[w + q] = (uint32_t)off;
-            while (cc) {
-                const int pbit = __ffs(cc) - 1;
-                cc &= cc - 1;
-                if (off < list_cap) list[off] = (uint32_t)(((w + q) * 32 + pbit) / R);     // (*n_out still reports the full count)
-                ++off;
+            for (int q = 0; q < WPT; ++q) {
+                uint32_t cc = c[q];
+                if (cc == 0u) continue;
+                if (pref_out != nullptr) pref_out[w + q] = (uint32_t)off;
+                while (cc) {
+                    const int pbit = __ffs(cc) - 1;
+                    cc &= cc - 1;
+                    if (off < list_cap) list[off] = (uint32_t)(((w + q) * 32 + pbit) / R);     // (*n_out still reports the full count)
+                    ++off;
+                }
             }
         }
         base += ctot;
@@ -1331,7 +1341,7 @@ int compact_bitmap(const scone_complex* cx, int b, const uint32_t* bm, uint32_t*
     constexpr int R = TT;                // TT = 1: row list
     const long long n_words = ((long long)cx->E * b + 31) / 32;
     int grid = cx->num_sms * 4 < kTicketSlots ? cx->num_sms * 4 : kTicketSlots;
-    if (n_words < (long long)grid * 4 * kThreads) grid = (int)((n_words + 4 * kThreads - 1) / (4 * kThreads));
+    if (n_words < (long long)grid * 16 * kThreads) grid = (int)((n_words + 16 * kThreads - 1) / (16 * kThreads));
     if (grid < 1) grid = 1;
     SCONE_CUDA(cudaMemsetAsync(tickets, 0, (size_t)grid * 8, st));
     compact_bitmap_kernel<R><<<grid, kThreads, 0, st>>>(bm, n_words, list, n_ptr, tickets, pref_out, list_cap);
