@@ -41,7 +41,7 @@ CONFIGS = {
     'cfg1': dict(n_nodes=400, batch=1000, hidden=16, micro_batch=256,
                  desc='default synthetic complex (400 nodes), 1000 trajectories, 3-layer SCoNe hidden 16'),
 }
-KIND_NAMES = ['layer_fwd', 'layer_bwd', 'layer0_fwd', 'layer0_bwd', 'readout', 'flows_to_dense', 'zero_fill']
+KIND_NAMES = ['layer_fwd', 'layer_bwd', 'layer0_fwd', 'layer0_bwd', 'readout', 'flows_to_dense', 'zero_fill', 'cone']
 
 
 def load_peaks():
@@ -372,7 +372,7 @@ def main():
                                'time includes its bitmap compaction, candidate marking and (backward) the weight-gradient GEMM; these kernels are '
                                'L1 / issue bound (rank lookups and gathers are cache-served), not HBM bound (profiles/prof_rows_fwd_r1x_*); '
                                'zero_fill (dense-stream mode): 4*E*b*C bytes per launch',
-                'pipeline': {2: 'row lists, compact tensors', 1: 'row lists, dense tensors', 0: 'unit kernels, byte flags'}[
+                'pipeline': {3: 'row lists over the readout cone, compact tensors', 2: 'row lists, compact tensors', 1: 'row lists, dense tensors', 0: 'unit kernels, byte flags'}[
                     L.scone_model_get_pipeline(net.handle)]}
 
     # end to end through the host API

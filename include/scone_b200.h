@@ -147,7 +147,12 @@ int64_t scone_model_num_params(const scone_model* m);
 int scone_model_set_zero_fill(scone_model* m, int32_t on);
 int scone_model_get_zero_fill(const scone_model* m);
 /* Model-level pipeline (same results within fp32 rounding; buffers of a pipeline are allocated on first use):
- *   2 (default when every hidden width is 16 or 32) = row lists over COMPACT tensors: each tensor carries a row bitmap, row r is
+ *   3 (default when every hidden width is 16 or 32) = pipeline 2's kernels restricted to the READOUT CONE: the log-probs of a
+ *     trajectory read H_L only at the edges incident to the neighbours of its last node (trajectory_experiments.py:151,298-303),
+ *     H_{L-1} one hop around those, and so on; the cone of layer l is both the rows of H_l the forward must produce and the rows
+ *     of G_l the backward produces, so each layer has one bitmap / rank prefix / row list, built from last_nodes before the
+ *     forward.  Log-probs and gradients are bit-identical to pipeline 2 (test).
+ *   2 = row lists over COMPACT tensors, whole support: each tensor carries a row bitmap, row r is
  *     stored at index rank(r) = its position in the compacted row list, producers mark the candidate rows of the next tensor,
  *     per layer one bitmap compaction + one row-list kernel (tensor-core product).  Memory and traffic follow the support of
  *     the trajectories, so micro_batch can be thousands (E * micro_batch < 2^31).  A compact tensor holds at most 32 M rows and

@@ -34,7 +34,7 @@ extern std::atomic<long long> g_scone_launches;
 
 // Optional per-kernel timing (CUDA events on the launching stream), off by default; bench.py's roofline uses it.
 enum { SCONE_K_LAYER_FWD = 0, SCONE_K_LAYER_BWD = 1, SCONE_K_LAYER0_FWD = 2, SCONE_K_LAYER0_BWD = 3, SCONE_K_READOUT = 4,
-       SCONE_K_OTHER = 5, SCONE_K_FILL = 6, SCONE_K_COUNT = 7 };
+       SCONE_K_OTHER = 5, SCONE_K_FILL = 6, SCONE_K_CONE = 7, SCONE_K_COUNT = 8 };
 extern bool g_scone_prof;
 extern bool g_scone_zero_fill;   // flagged kernels: bulk zero-fill outputs (dense-streaming contract) or leave unflagged rows unwritten
 void scone_prof_begin_impl(int kind, cudaStream_t st);
@@ -124,6 +124,7 @@ int scone_slab_forward_rows(const scone_complex* cx, int act, int b, int cin, in
                             int out_cap, int* overflow_dev, cudaStream_t st);
 int scone_rows_mark(const scone_complex* cx, int b, const uint32_t* rows, const int* n_dev, uint32_t* bm_next, int list_cap,
                     cudaStream_t st);
+int scone_rows_cone(const scone_complex* cx, int b, const int32_t* last_nodes, uint32_t* bm_top, uint32_t* bm_cand, cudaStream_t st);
 // bitmap-native row-list pipeline (scone_rows.cu, scone_slab.cu)
 bool scone_rows_supported(const scone_complex* cx, int n_layers, const int32_t* hidden);
 int64_t scone_rows_dw_workspace_bytes(int cin, int cout);

@@ -33,7 +33,8 @@ struct scone_model {
     bool zero_fill = false;                   // dense zero-fill of every activation / gradient tensor (scone_model_set_zero_fill)
     // bitmap-native row-list pipeline (scone_rows.cu): row bitmaps per tensor, one row list, compact A rows for the dW GEMM
     // pipeline: 0 unit kernels + byte flags (dense [E][mb][C] tensors), 1 row lists over the dense tensors, 2 row lists over
-    // COMPACT tensors (row r of a tensor at index rank(r) of its bitmap = its position in the compacted row list)
+    // COMPACT tensors (row r of a tensor at index rank(r) of its bitmap = its position in the compacted row list), 3 the same
+    // kernels over the READOUT CONE only: H_l and G_l share one row set per layer, the rows that can reach the log-probs
     bool rows_ok = false, x_clean = false, dense_ready = false, rows_ready = false, compact_ready = false;
     int pipeline = 0;
     std::vector<uint32_t*> d_bmH, d_bmGr, d_prefH, d_prefG;
@@ -41,7 +42,8 @@ struct scone_model {
     int row_cap = 0;                          // rows a compact tensor / the row list can hold
     size_t rows_list_cap = 0;
     uint32_t* d_rows = nullptr;
-    int* d_nrows = nullptr;
+    std::vector<uint32_t*> d_rowsC;           // pipeline 3: the cone's row list per layer (forward and backward walk the same list)
+    int* d_nrows = nullptr;                   // {count, tile counter} pairs: [0] the shared list, [1 + l] the cone list of layer l
     int* d_overflow = nullptr;
     unsigned long long* d_tickets = nullptr;
     float* d_Abuf = nullptr;
@@ -165,12 +167,8 @@ int ensure_buffers(scone_model* m) {
         const size_t bm_bytes = scone_bitmap_words(E, mb) * 4;
         m->d_bmH.resize(L, nullptr);
         m->d_bmGr.resize(L, nullptr);
-        SCONE_ALLOC(m->d_bmX, bm_bytes, "bitmap");
-        for (int l = 0; l < L; ++l) {
-            SCONE_ALLOC(m->d_bmH[l], bm_bytes, "bitmap");
-            SCONE_ALLOC(m->d_bmGr[l], bm_bytes, "bitmap");
-        }
-        SCONE_ALLOC(m->d_nrows, 256, "counters");
+        for (int l = 0; l < L; ++l) SCONE_ALLOC(m->d_bmGr[l], bm_bytes, "bitmap");
+        SCONE_ALLOC(m->d_nrows, 8 * (size_t)(L + 1), "counters");
         SCONE_ALLOC(m->d_overflow, 256, "counters");
         SCONE_CUDA(cudaMemset(m->d_overflow, 0, 256));
         SCONE_ALLOC(m->d_tickets, scone_ticket_bytes(), "tickets");
@@ -181,7 +179,12 @@ int ensure_buffers(scone_model* m) {
         m->row_cap = (int)rcap;
         m->rows_ready = true;
     }
-    if (pl >= 1) {                                         // the row list: every row under pipeline 1, row_cap rows under 2
+    if (pl == 1 || pl == 2) {                              // bitmaps of X and the activations (the cone pipeline has none)
+        const size_t bm_bytes = scone_bitmap_words(E, mb) * 4;
+        SCONE_ALLOC(m->d_bmX, bm_bytes, "bitmap");
+        for (int l = 0; l < L; ++l) SCONE_ALLOC(m->d_bmH[l], bm_bytes, "bitmap");
+    }
+    if (pl == 1 || pl == 2) {                              // the row list: every row under pipeline 1, row_cap rows under 2
         const size_t need = pl == 1 ? E * mb : (size_t)m->row_cap;
         if (need > m->rows_list_cap) {
             cudaFree(m->d_rows);
@@ -190,19 +193,20 @@ int ensure_buffers(scone_model* m) {
             m->rows_list_cap = need;
         }
     }
-    if (pl == 2 && !m->compact_ready) {
+    if (pl >= 2) {                                         // compact tensors + rank prefixes (allocated once, shared by 2 and 3)
         const size_t bm_bytes = scone_bitmap_words(E, mb) * 4;
         m->d_prefH.resize(L, nullptr);
         m->d_prefG.resize(L, nullptr);
         m->d_cH.resize(L, nullptr);
         m->d_cG.resize(L, nullptr);
+        m->d_rowsC.resize(L, nullptr);
         for (int l = 0; l < L; ++l) {
-            SCONE_ALLOC(m->d_prefH[l], bm_bytes, "rank prefix");
+            if (pl == 2) SCONE_ALLOC(m->d_prefH[l], bm_bytes, "rank prefix");
             SCONE_ALLOC(m->d_prefG[l], bm_bytes, "rank prefix");
             SCONE_ALLOC(m->d_cH[l], (size_t)m->row_cap * m->hidden[l] * sizeof(float), "compact activations");
             SCONE_ALLOC(m->d_cG[l], (size_t)m->row_cap * m->hidden[l] * sizeof(float), "compact gradients");
+            if (pl == 3) SCONE_ALLOC(m->d_rowsC[l], (size_t)m->row_cap * sizeof(uint32_t), "cone row list");
         }
-        m->compact_ready = true;
     }
     return 0;
 }
@@ -324,6 +328,96 @@ int rows_backward_mb(scone_model* m, int32_t b, cudaStream_t s) {
                                       m->d_grad + m->w_off[0], 1, (float*)m->d_ws, compact ? m->row_cap : 0, s);
 }
 
+// ---- cone-pruned row-list pipeline (3) -----------------------------------------------------------------------------
+// The log-probs of trajectory t read H_L only at the edges incident to the neighbours of its last node; H_{L-1} is needed one
+// hop around those rows, and so on: the receptive cone.  Layer l's cone C_l is at once the set of rows of H_l the forward has
+// to produce and the set of rows of G_l the backward produces (it is what rows_backward_mb derives as candidate rows), so each
+// layer has ONE bitmap / rank prefix / row list, built from last_nodes before the forward.  Every row the cone keeps is
+// computed exactly as in pipeline 2 (all its neighbours are in the cone below it; a cone row outside the flows' support
+// evaluates to act(0) = 0, which is what pipeline 2 reads for an absent row), so log-probs and gradients do not change.
+int* cone_n(scone_model* m, int l) { return m->d_nrows + 2 * (1 + l); }
+
+int cone_build_mb(scone_model* m, int32_t b, const int32_t* last, cudaStream_t s) {
+    const scone_complex* cx = m->cx;
+    const int L = m->L;
+    const size_t bm_bytes = scone_bitmap_words(cx->E, b) * 4;
+    ScopedProf prof(SCONE_K_CONE, s);
+    SCONE_CUDA(cudaMemsetAsync(m->d_bmGr[L - 1], 0, bm_bytes, s));
+    if (L >= 2) SCONE_CUDA(cudaMemsetAsync(m->d_bmGr[L - 2], 0, bm_bytes, s));
+    if (scone_rows_cone(cx, b, last, m->d_bmGr[L - 1], L >= 2 ? m->d_bmGr[L - 2] : nullptr, s)) return 1;
+    for (int l = L - 1; l >= 0; --l) {
+        if (scone_compact_rows(cx, b, m->d_bmGr[l], m->d_rowsC[l], cone_n(m, l), m->d_tickets, s, m->d_prefG[l], m->row_cap)) return 1;
+        if (l >= 1 && l <= L - 2) {                        // (the readout cone already marked layer L-2)
+            SCONE_CUDA(cudaMemsetAsync(m->d_bmGr[l - 1], 0, bm_bytes, s));
+            if (scone_rows_mark(cx, b, m->d_rowsC[l], cone_n(m, l), m->d_bmGr[l - 1], m->row_cap, s)) return 1;
+        }
+    }
+    return 0;
+}
+
+int cone_forward_mb(scone_model* m, int32_t b, const int32_t* ptr, const int32_t* edge, const float* val, cudaStream_t s) {
+    const scone_complex* cx = m->cx;
+    if (!m->x_clean) {
+        SCONE_CUDA(cudaMemsetAsync(m->d_X, 0, (size_t)cx->E * m->mb * sizeof(float), s));
+        m->x_clean = true;
+    }
+    {
+        ScopedProf prof(SCONE_K_OTHER, s);
+        if (scone_rows_flows(cx, b, ptr, edge, val, m->d_X, nullptr, nullptr, false, s)) return 1;
+    }
+    int cin = 1;
+    for (int l = 0; l < m->L; ++l) {
+        const int cout = m->hidden[l];
+        ScopedProf prof(l == 0 ? SCONE_K_LAYER0_FWD : SCONE_K_LAYER_FWD, s);
+        const float *W0 = m->d_w + m->w_off[3 * l], *W1 = m->d_w + m->w_off[3 * l + 1], *W2 = m->d_w + m->w_off[3 * l + 2];
+        int rc;
+        if (l == 0)
+            rc = scone_rows_layer0_forward(cx, m->act, b, cout, m->d_X, W0, W1, W2, m->d_cH[0], m->d_rowsC[0], cone_n(m, 0), nullptr,
+                                           m->row_cap, m->d_overflow, s);
+        else
+            rc = scone_slab_forward_rows(cx, m->act, b, cin, cout, m->d_cH[l - 1], W0, W1, W2, m->d_cH[l], nullptr, m->d_rowsC[l],
+                                         cone_n(m, l), scone_prof_row_counter(SCONE_K_LAYER_FWD), m->d_bmGr[l - 1], m->d_prefG[l - 1],
+                                         m->row_cap, m->d_overflow, s);
+        if (rc) return rc;
+        cin = cout;
+    }
+    return 0;
+}
+
+int cone_readout(scone_model* m, int32_t b, const int32_t* last, float* logprobs, bool grad, const int32_t* tgt, const float* mask,
+                 cudaStream_t s) {
+    const scone_complex* cx = m->cx;
+    const int L = m->L, CL = m->hidden[L - 1];
+    const float* wout = m->d_w + m->w_off[3 * L];
+    ScopedProf prof(SCONE_K_READOUT, s);
+    if (scone_rows_readout_forward(cx, b, CL, m->d_cH[L - 1], wout, last, logprobs, m->d_bmGr[L - 1], m->d_prefG[L - 1], nullptr, nullptr, s))
+        return 1;
+    if (!grad) return 0;
+    return scone_rows_readout_backward(cx, m->act, b, CL, m->d_cH[L - 1], wout, last, logprobs, tgt, mask, 1.f, m->d_cG[L - 1],
+                                       cone_n(m, L - 1), m->row_cap, m->d_overflow, m->d_grad + m->w_off[3 * L], m->d_grad + m->n_params,
+                                       m->d_grad + m->n_params + 1, 1, (float*)m->d_ws, m->d_bmGr[L - 1], m->d_prefG[L - 1],
+                                       m->d_bmGr[L - 1], m->d_prefG[L - 1], s);
+}
+
+int cone_backward_mb(scone_model* m, int32_t b, cudaStream_t s) {
+    const scone_complex* cx = m->cx;
+    const int L = m->L;
+    const int a_cap = m->row_cap < m->a_cap ? m->row_cap : m->a_cap;
+    // the forward consumed the tile counters of the lists it walked: zero the counter of every list again
+    SCONE_CUDA(cudaMemset2DAsync(m->d_nrows + 1, 2 * sizeof(int), 0, sizeof(int), (size_t)(L + 1), s));
+    for (int l = L - 1; l >= 1; --l) {
+        ScopedProf prof(SCONE_K_LAYER_BWD, s);
+        int rc = scone_rows_backward(cx, m->act, b, m->hidden[l - 1], m->hidden[l], m->d_cG[l], m->d_cH[l - 1], m->d_cG[l - 1], m->d_Abuf,
+                                     m->d_w + m->w_off[3 * l], m->d_w + m->w_off[3 * l + 1], m->d_w + m->w_off[3 * l + 2], m->d_rowsC[l - 1],
+                                     cone_n(m, l - 1), m->d_bmGr[l], m->d_bmGr[l - 1], a_cap, m->d_overflow, m->d_grad + m->w_off[3 * l], 1,
+                                     (float*)m->d_ws, m->d_prefG[l], m->d_prefG[l - 1], s);
+        if (rc) return rc;
+    }
+    ScopedProf prof(SCONE_K_LAYER0_BWD, s);
+    return scone_rows_layer0_backward(cx, b, m->hidden[0], m->d_X, m->d_cG[0], m->d_rowsC[0], cone_n(m, 0), m->d_grad + m->w_off[0], 1,
+                                      (float*)m->d_ws, m->row_cap, s);
+}
+
 }  // namespace
 
 extern "C" int scone_model_create(const scone_complex* cx, int32_t n_layers, const int32_t* hidden, int32_t micro_batch,
@@ -382,7 +476,7 @@ extern "C" int scone_model_create(const scone_complex* cx, int32_t n_layers, con
     m->d_occH.assign(n_layers, nullptr);
     m->d_occG.assign(n_layers, nullptr);
     m->rows_ok = scone_rows_supported(cx, n_layers, hidden) && E * mb < ((size_t)1 << 31);
-    m->pipeline = m->rows_ok ? 2 : 0;
+    m->pipeline = m->rows_ok ? 3 : 0;
     int64_t ws = scone_readout_workspace_bytes(micro_batch, m->cmax);
     if (scone_rows_dw_workspace_bytes(m->cmax, m->cmax) > ws) ws = scone_rows_dw_workspace_bytes(m->cmax, m->cmax);
     cin = 1;
@@ -430,6 +524,7 @@ extern "C" int scone_model_destroy(scone_model* m) {
     for (uint32_t* p : m->d_prefG) cudaFree(p);
     for (float* p : m->d_cH) cudaFree(p);
     for (float* p : m->d_cG) cudaFree(p);
+    for (uint32_t* p : m->d_rowsC) cudaFree(p);
     cudaFree(m->d_rows); cudaFree(m->d_nrows); cudaFree(m->d_overflow); cudaFree(m->d_tickets); cudaFree(m->d_Abuf);
     for (float* p : m->d_G) cudaFree(p);
     cudaFree(m->d_ws); cudaFree(m->d_logp);
@@ -453,8 +548,9 @@ extern "C" int scone_model_set_zero_fill(scone_model* m, int32_t on) {
 }
 extern "C" int scone_model_get_zero_fill(const scone_model* m) { return m && m->zero_fill ? 1 : 0; }
 extern "C" int scone_model_set_pipeline(scone_model* m, int32_t which) {
-    SCONE_REQUIRE(m != nullptr && which >= 0 && which <= 2,
-                  "scone_model_set_pipeline: 0 (unit kernels, byte flags), 1 (row lists, dense tensors) or 2 (row lists, compact tensors)");
+    SCONE_REQUIRE(m != nullptr && which >= 0 && which <= 3,
+                  "scone_model_set_pipeline: 0 (unit kernels, byte flags), 1 (row lists, dense tensors), 2 (row lists, compact tensors) or "
+                  "3 (compact row lists over the readout cone)");
     SCONE_REQUIRE(which == 0 || m->rows_ok, "scone_model_set_pipeline: the row-list pipelines need hidden widths in {16, 32}");
     const int old = m->pipeline;
     m->pipeline = which;
@@ -505,6 +601,17 @@ extern "C" int scone_model_forward_dev(scone_model* m, int32_t B, const int32_t*
     for (int32_t off = 0; off < B; off += m->mb) {
         const int32_t b = B - off < m->mb ? B - off : m->mb;
         int rc;
+        if (rows && m->pipeline == 3) {
+            rc = cone_build_mb(m, b, last + off, as_stream(st));
+            if (rc) return rc;
+            rc = cone_forward_mb(m, b, ptr + off, edge, val, as_stream(st));
+            if (rc) return rc;
+            rc = cone_readout(m, b, last + off, logprobs + (size_t)off * cx->D, false, nullptr, nullptr, as_stream(st));
+            if (rc) return rc;
+            rc = rows_clear_x(m, b, ptr + off, edge, val, as_stream(st));
+            if (rc) return rc;
+            continue;
+        }
         if (rows) {
             rc = rows_forward_mb(m, b, ptr + off, edge, val, as_stream(st));
             if (rc) return rc;
@@ -541,6 +648,19 @@ extern "C" int scone_model_loss_grad_dev(scone_model* m, int32_t B, const int32_
     for (int32_t off = 0; off < B; off += m->mb) {
         const int32_t b = B - off < m->mb ? B - off : m->mb;
         int rc;
+        if (rows && m->pipeline == 3) {
+            rc = cone_build_mb(m, b, last + off, s);
+            if (rc) return rc;
+            rc = cone_forward_mb(m, b, ptr + off, edge, val, s);
+            if (rc) return rc;
+            rc = cone_readout(m, b, last + off, m->d_logp, true, tgt + off, mask + off, s);
+            if (rc) return rc;
+            rc = cone_backward_mb(m, b, s);
+            if (rc) return rc;
+            rc = rows_clear_x(m, b, ptr + off, edge, val, s);
+            if (rc) return rc;
+            continue;
+        }
         if (rows) {
             rc = rows_forward_mb(m, b, ptr + off, edge, val, s);
             if (rc) return rc;

@@ -53,8 +53,9 @@ __global__ void __launch_bounds__(128) rows_flows_kernel(const int32_t* __restri
             continue;
         }
         X[row] = flow_val[p];
-        bit_set(bmX, row);
-        for (int q = mptr[e]; q < mptr[e + 1]; ++q) bit_set(bm_next, (size_t)(unsigned)ment[q].x * b + t);
+        if (bmX != nullptr) bit_set(bmX, row);
+        if (bm_next != nullptr)
+            for (int q = mptr[e]; q < mptr[e + 1]; ++q) bit_set(bm_next, (size_t)(unsigned)ment[q].x * b + t);
     }
 }
 
@@ -68,6 +69,30 @@ __global__ void __launch_bounds__(256) rows_mark_kernel(const uint32_t* __restri
         const unsigned e = rid / (unsigned)b, t = rid - e * (unsigned)b;
         const int p1 = __ldg(mptr + e + 1);
         for (int p = __ldg(mptr + e); p < p1; ++p) bit_set(bm_next, (unsigned)__ldg(ment + p).x * (unsigned)b + t);
+    }
+}
+
+// Receptive cone of the readout (pure geometry: last node + complex).  The log-probs of trajectory t depend on H_L only at the
+// edges incident to the neighbours of its last node (trajectory_experiments.py:151,298-303); those rows are the top of the cone
+// (bm_top), the rows one hop further (bm_cand) are all that H_{L-1} has to provide, and so on down (rows_mark_kernel).  Rows
+// outside the cone reach neither the log-probs nor any weight gradient, so the cone-pruned pipeline never computes them.
+__global__ void __launch_bounds__(128) rows_cone_kernel(const int32_t* __restrict__ last_nodes, const int32_t* __restrict__ nbrhoods,
+                                                       const int32_t* __restrict__ inc_ptr, const int2* __restrict__ inc_ent,
+                                                       uint32_t* __restrict__ bm_top, uint32_t* __restrict__ bm_cand,
+                                                       const int32_t* __restrict__ mptr, const int2* __restrict__ ment, int N, int D, int b) {
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int t = blockIdx.x;
+    const int last = last_nodes[t];
+    if (last < 0 || last >= N) return;
+    for (int j = warp; j < D; j += 4) {
+        const int nbr = nbrhoods[(size_t)last * D + j];
+        if (nbr < 0) continue;
+        for (int p = inc_ptr[nbr]; p < inc_ptr[nbr + 1]; ++p) {
+            const int e = inc_ent[p].x;
+            if (lane == 0) bit_set(bm_top, (unsigned)e * (unsigned)b + (unsigned)t);
+            if (bm_cand != nullptr)
+                for (int q = mptr[e] + lane; q < mptr[e + 1]; q += 32) bit_set(bm_cand, (unsigned)ment[q].x * (unsigned)b + (unsigned)t);
+        }
     }
 }
 
@@ -716,6 +741,13 @@ int scone_rows_flows(const scone_complex* cx, int b, const int32_t* traj_ptr, co
 int scone_rows_mark(const scone_complex* cx, int b, const uint32_t* rows, const int* n_dev, uint32_t* bm_next, int list_cap,
                     cudaStream_t st) {
     rows_mark_kernel<<<cx->num_sms * 8, 256, 0, st>>>(rows, n_dev, cx->d_mptr, cx->d_ment, b, bm_next, list_cap);
+    SCONE_LAUNCHED();
+    return 0;
+}
+
+int scone_rows_cone(const scone_complex* cx, int b, const int32_t* last_nodes, uint32_t* bm_top, uint32_t* bm_cand, cudaStream_t st) {
+    rows_cone_kernel<<<b, 128, 0, st>>>(last_nodes, cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, bm_top, bm_cand, cx->d_mptr, cx->d_ment,
+                                       cx->N, cx->D, b);
     SCONE_LAUNCHED();
     return 0;
 }

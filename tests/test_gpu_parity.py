@@ -293,20 +293,21 @@ def test_model_results_identical_with_and_without_zero_fill(small, zero_fill):
 @pytest.mark.parametrize('model,hidden,mb', [('scone', [16, 16, 16], 32), ('scone', [32, 32, 32], 7), ('ebli', [16, 32, 16], 64),
                                              ('scone', [32], 16), ('scone', [16, 32], 5)])
 def test_row_list_pipeline_matches_unit_kernel_pipeline(small, model, hidden, mb):
-    """Model level: the bitmap-native row-list pipelines (tensor-core kernels; 2 = compact tensors, 1 = dense tensors) against
-    the unit-kernel pipeline (0: fp32 SIMT, byte flags): log-probs within 1e-5, gradients within 1e-4 of the largest entry;
-    run-to-run bit-exact; and interleaving the pipelines on one model (X must be re-cleaned) changes nothing."""
+    """Model level: the bitmap-native row-list pipelines (tensor-core kernels; 3 = compact tensors over the readout cone,
+    2 = compact tensors over the whole support, 1 = dense tensors) against the unit-kernel pipeline (0: fp32 SIMT, byte flags):
+    log-probs within 1e-5, gradients within 1e-4 of the largest entry; run-to-run bit-exact; interleaving the pipelines on one
+    model (X must be re-cleaned) changes nothing; and pruning to the cone changes no bit of the log-probs or the gradients."""
     sg = _mods()
     L = sg.lib()
     cx = sg.SimplicialComplex.from_dense(small.B1, small.B2, model)
     ptr, fe, fv = sg.flows_to_csr(small.flows)
     net = sg.SconeModel(cx, hidden, micro_batch=mb)
-    assert L.scone_model_get_pipeline(net.handle) == 2             # default: row lists over compact tensors
+    assert L.scone_model_get_pipeline(net.handle) == 3             # default: compact row lists over the readout cone
     rs = np.random.RandomState(len(hidden) * 10 + mb)
     net.set_weights([0.1 * rs.randn(*s_) for s_ in net.shapes])
     mask = (rs.rand(small.n_traj) < 0.7).astype(np.float32)
     out = {}
-    for which in (2, 1, 0, 2, 1):
+    for which in (3, 2, 1, 0, 3, 2, 1):
         _lib_check = __import__('scone_gcn_b200')._lib.check
         _lib_check(L.scone_model_set_pipeline(net.handle, which), 'set_pipeline')
         lp = net.forward(ptr, fe, fv, small.last_nodes)
@@ -315,8 +316,9 @@ def test_row_list_pipeline_matches_unit_kernel_pipeline(small, model, hidden, mb
             assert np.array_equal(out[which][0], lp) and np.array_equal(out[which][1], buf)
         out[which] = (lp, buf)
     assert np.array_equal(out[2][0], out[1][0])                    # compact vs dense addressing: same arithmetic per row
+    assert np.array_equal(out[3][0], out[2][0]) and np.array_equal(out[3][1], out[2][1])     # cone pruning: nothing changes
     n = net.n_params
-    for which in (1, 2):
+    for which in (1, 2, 3):
         assert np.abs(out[which][0] - out[0][0]).max() <= 1e-5 * max(1.0, np.abs(out[0][0]).max())
         assert out[which][1][n + 1] == out[0][1][n + 1] == mask.sum()
         assert abs(out[which][1][n] - out[0][1][n]) <= 1e-5 * max(1.0, abs(out[0][1][n]))
