@@ -54,50 +54,93 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).  The timed region of
+    this bench is tens of milliseconds, shorter than one `nvidia-smi` invocation, so the sampler polls NVML in-process
+    (nvidia_ml_py, ~1 kHz, own thread); `nvidia-smi -lms` is the fallback when NVML cannot be loaded."""
     Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.nv, self.h = [], None, index, None, None
+        self.running, self.th, self.source = False, None, None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(',')[self.index])
+                except Exception:
+                    idx = self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.running, self.source = True, 'nvml'
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nv = None
+        try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = 'nvidia-smi'
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv = self.nv
+        bits = [(getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8), 'hw_slowdown'),
+                (getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40), 'hw_thermal_slowdown'),
+                (getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20), 'sw_thermal_slowdown'),
+                (getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4), 'sw_power_cap')]
+        get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while self.running:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = int(get_reasons(self.h))
+                self.rows.append([sm, self.mx, 0.0] + ['Active' if r & bit else 'Not Active' for bit, _ in bits])
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(',')])
 
     def stop(self):
-        if not self.proc:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=3)
-        except Exception:
-            self.proc.kill()
+        if self.nv is not None:
+            self.running = False
+            self.th.join(timeout=2)
+        elif self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=3)
+            except Exception:
+                self.proc.kill()
+        else:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no NVML, no nvidia-smi'], 'samples': 0}
         sm, mx, reasons = [], None, set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
-                for nme, v in zip(names, r[3:7]):
-                    if v.lower().startswith('active'):
+                for nme, v in zip(self.NAMES, r[3:7]):
+                    if str(v).lower().startswith('active'):
                         reasons.add(nme)
             except Exception:
                 pass
         sm.sort()
         load = [x for x in sm if mx and x > 0.3 * mx] or sm
         return {'sm_mhz': (load[len(load) // 2] if load else None), 'sm_max_mhz': mx, 'reasons': sorted(reasons),
-                'samples': len(sm)}
+                'samples': len(sm), 'source': self.source}
 
 
 def ncu_traffic(kernel, E, mb, C, zero_fill):
@@ -200,8 +243,8 @@ def run_reference(args, cfg, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=3)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='cfg5', choices=sorted(CONFIGS))
     ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch')

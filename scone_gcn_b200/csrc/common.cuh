@@ -123,8 +123,13 @@ int scone_slab_forward_rows(const scone_complex* cx, int act, int b, int cin, in
                             const int* n_rows_dev, unsigned long long* row_counter, const uint32_t* bm_in, const uint32_t* pref_in,
                             int out_cap, int* overflow_dev, cudaStream_t st);
 int scone_rows_mark(const scone_complex* cx, int b, const uint32_t* rows, const int* n_dev, uint32_t* bm_next, int list_cap,
+                    cudaStream_t st, size_t sum_off = 0);
+// cone pipeline: two-level bitmaps (summary words at bm + sum_off, sum_off = 0: none)
+int scone_rows_cone(const scone_complex* cx, int b, const int32_t* last_nodes, uint32_t* bm_top, uint32_t* bm_cand, size_t sum_off,
                     cudaStream_t st);
-int scone_rows_cone(const scone_complex* cx, int b, const int32_t* last_nodes, uint32_t* bm_top, uint32_t* bm_cand, cudaStream_t st);
+int scone_compact_rows_summary(const scone_complex* cx, int b, const uint32_t* bm, size_t sum_off, uint32_t* list, int* n_dev,
+                               unsigned long long* tickets, cudaStream_t st, uint32_t* pref_out, long long list_cap);
+int scone_clear_summary(const scone_complex* cx, int b, uint32_t* bm, size_t sum_off, cudaStream_t st);
 // bitmap-native row-list pipeline (scone_rows.cu, scone_slab.cu)
 bool scone_rows_supported(const scone_complex* cx, int n_layers, const int32_t* hidden);
 int64_t scone_rows_dw_workspace_bytes(int cin, int cout);
@@ -141,7 +146,7 @@ int scone_rows_layer0_backward(const scone_complex* cx, int b, int cout, const f
 int scone_rows_backward(const scone_complex* cx, int act, int b, int cin, int cout, const float* G, const float* Hin, float* Gprev,
                         float* Abuf, const float* W0, const float* W1, const float* W2, const uint32_t* rows, const int* n_dev,
                         const uint32_t* bmG, const uint32_t* bmH, int a_cap, int* overflow_dev, float* dW, int accumulate, float* ws,
-                        const uint32_t* prefG, const uint32_t* prefH, cudaStream_t st);
+                        const uint32_t* prefG, const uint32_t* prefH, bool hin_by_list, cudaStream_t st);
 int scone_rows_readout_forward(const scone_complex* cx, int b, int C, const float* HL, const float* wout, const int32_t* last_nodes,
                                float* logprobs, const uint32_t* bmH, const uint32_t* prefH, uint32_t* bmG, uint32_t* bm_cand,
                                cudaStream_t st);

@@ -36,6 +36,8 @@ struct scone_model {
     // COMPACT tensors (row r of a tensor at index rank(r) of its bitmap = its position in the compacted row list), 3 the same
     // kernels over the READOUT CONE only: H_l and G_l share one row set per layer, the rows that can reach the log-probs
     bool rows_ok = false, x_clean = false, dense_ready = false, rows_ready = false, compact_ready = false;
+    bool cone_clean = false;                  // pipeline 3: the two-level bitmaps d_bmGr are all-zero between micro-batches
+    size_t sum_off = 0, bmg_bytes = 0;        // summary words of d_bmGr[l] start at word sum_off; bytes of one d_bmGr allocation
     int pipeline = 0;
     std::vector<uint32_t*> d_bmH, d_bmGr, d_prefH, d_prefG;
     std::vector<float*> d_cH, d_cG;           // compact tensors [row_cap][C_l]
@@ -167,7 +169,9 @@ int ensure_buffers(scone_model* m) {
         const size_t bm_bytes = scone_bitmap_words(E, mb) * 4;
         m->d_bmH.resize(L, nullptr);
         m->d_bmGr.resize(L, nullptr);
-        for (int l = 0; l < L; ++l) SCONE_ALLOC(m->d_bmGr[l], bm_bytes, "bitmap");
+        m->sum_off = scone_bitmap_words(E, mb);             // + one summary bit per bitmap word (cone pipeline)
+        m->bmg_bytes = bm_bytes + ((m->sum_off + 31) / 32 + 16) * 4;
+        for (int l = 0; l < L; ++l) SCONE_ALLOC(m->d_bmGr[l], m->bmg_bytes, "bitmap");
         SCONE_ALLOC(m->d_nrows, 8 * (size_t)(L + 1), "counters");
         SCONE_ALLOC(m->d_overflow, 256, "counters");
         SCONE_CUDA(cudaMemset(m->d_overflow, 0, 256));
@@ -217,6 +221,7 @@ int rows_forward_mb(scone_model* m, int32_t b, const int32_t* ptr, const int32_t
     const bool compact = m->pipeline == 2;
     const size_t bm_bytes = scone_bitmap_words(cx->E, b) * 4;
     const long long list_cap = compact ? (long long)m->row_cap : (1ll << 62);
+    m->cone_clean = false;                                 // pipelines 1 / 2 use d_bmGr as plain bitmaps
     if (!m->x_clean) {                                     // X must be all-zero outside the flows (no flag test in the first layer)
         SCONE_CUDA(cudaMemsetAsync(m->d_X, 0, (size_t)cx->E * m->mb * sizeof(float), s));
         m->x_clean = true;
@@ -318,7 +323,7 @@ int rows_backward_mb(scone_model* m, int32_t b, cudaStream_t s) {
                                      compact ? m->d_cH[l - 1] : m->d_H[l - 1], compact ? m->d_cG[l - 1] : m->d_G[l - 1], m->d_Abuf,
                                      m->d_w + m->w_off[3 * l], m->d_w + m->w_off[3 * l + 1], m->d_w + m->w_off[3 * l + 2], m->d_rows,
                                      m->d_nrows, m->d_bmGr[l], m->d_bmH[l - 1], a_cap, m->d_overflow, m->d_grad + m->w_off[3 * l], 1,
-                                     (float*)m->d_ws, compact ? m->d_prefG[l] : nullptr, compact ? m->d_prefH[l - 1] : nullptr, s);
+                                     (float*)m->d_ws, compact ? m->d_prefG[l] : nullptr, compact ? m->d_prefH[l - 1] : nullptr, false, s);
         if (rc) return rc;
     }
     ScopedProf prof(SCONE_K_LAYER0_BWD, s);
@@ -340,18 +345,28 @@ int* cone_n(scone_model* m, int l) { return m->d_nrows + 2 * (1 + l); }
 int cone_build_mb(scone_model* m, int32_t b, const int32_t* last, cudaStream_t s) {
     const scone_complex* cx = m->cx;
     const int L = m->L;
-    const size_t bm_bytes = scone_bitmap_words(cx->E, b) * 4;
     ScopedProf prof(SCONE_K_CONE, s);
-    SCONE_CUDA(cudaMemsetAsync(m->d_bmGr[L - 1], 0, bm_bytes, s));
-    if (L >= 2) SCONE_CUDA(cudaMemsetAsync(m->d_bmGr[L - 2], 0, bm_bytes, s));
-    if (scone_rows_cone(cx, b, last, m->d_bmGr[L - 1], L >= 2 ? m->d_bmGr[L - 2] : nullptr, s)) return 1;
-    for (int l = L - 1; l >= 0; --l) {
-        if (scone_compact_rows(cx, b, m->d_bmGr[l], m->d_rowsC[l], cone_n(m, l), m->d_tickets, s, m->d_prefG[l], m->row_cap)) return 1;
-        if (l >= 1 && l <= L - 2) {                        // (the readout cone already marked layer L-2)
-            SCONE_CUDA(cudaMemsetAsync(m->d_bmGr[l - 1], 0, bm_bytes, s));
-            if (scone_rows_mark(cx, b, m->d_rowsC[l], cone_n(m, l), m->d_bmGr[l - 1], m->row_cap, s)) return 1;
-        }
+    if (!m->cone_clean) {                                  // once: afterwards every micro-batch clears exactly what it set
+        for (int l = 0; l < L; ++l) SCONE_CUDA(cudaMemsetAsync(m->d_bmGr[l], 0, m->bmg_bytes, s));
     }
+    m->cone_clean = false;                                 // until cone_clear_mb has run (an error return in between leaves bits set)
+    if (scone_rows_cone(cx, b, last, m->d_bmGr[L - 1], L >= 2 ? m->d_bmGr[L - 2] : nullptr, m->sum_off, s)) return 1;
+    for (int l = L - 1; l >= 0; --l) {
+        if (scone_compact_rows_summary(cx, b, m->d_bmGr[l], m->sum_off, m->d_rowsC[l], cone_n(m, l), m->d_tickets, s, m->d_prefG[l],
+                                       m->row_cap))
+            return 1;
+        if (l >= 1 && l <= L - 2)                          // (the readout cone already marked layer L-2)
+            if (scone_rows_mark(cx, b, m->d_rowsC[l], cone_n(m, l), m->d_bmGr[l - 1], m->row_cap, s, m->sum_off)) return 1;
+    }
+    return 0;
+}
+
+// end of a micro-batch: the bitmaps go back to all-zero (cost follows the cone, not E*b)
+int cone_clear_mb(scone_model* m, int32_t b, cudaStream_t s) {
+    ScopedProf prof(SCONE_K_CONE, s);
+    for (int l = 0; l < m->L; ++l)
+        if (scone_clear_summary(m->cx, b, m->d_bmGr[l], m->sum_off, s)) return 1;
+    m->cone_clean = true;
     return 0;
 }
 
@@ -410,7 +425,7 @@ int cone_backward_mb(scone_model* m, int32_t b, cudaStream_t s) {
         int rc = scone_rows_backward(cx, m->act, b, m->hidden[l - 1], m->hidden[l], m->d_cG[l], m->d_cH[l - 1], m->d_cG[l - 1], m->d_Abuf,
                                      m->d_w + m->w_off[3 * l], m->d_w + m->w_off[3 * l + 1], m->d_w + m->w_off[3 * l + 2], m->d_rowsC[l - 1],
                                      cone_n(m, l - 1), m->d_bmGr[l], m->d_bmGr[l - 1], a_cap, m->d_overflow, m->d_grad + m->w_off[3 * l], 1,
-                                     (float*)m->d_ws, m->d_prefG[l], m->d_prefG[l - 1], s);
+                                     (float*)m->d_ws, m->d_prefG[l], m->d_prefG[l - 1], true, s);
         if (rc) return rc;
     }
     ScopedProf prof(SCONE_K_LAYER0_BWD, s);
@@ -610,6 +625,8 @@ extern "C" int scone_model_forward_dev(scone_model* m, int32_t B, const int32_t*
             if (rc) return rc;
             rc = rows_clear_x(m, b, ptr + off, edge, val, as_stream(st));
             if (rc) return rc;
+            rc = cone_clear_mb(m, b, as_stream(st));
+            if (rc) return rc;
             continue;
         }
         if (rows) {
@@ -658,6 +675,8 @@ extern "C" int scone_model_loss_grad_dev(scone_model* m, int32_t B, const int32_
             rc = cone_backward_mb(m, b, s);
             if (rc) return rc;
             rc = rows_clear_x(m, b, ptr + off, edge, val, s);
+            if (rc) return rc;
+            rc = cone_clear_mb(m, b, s);
             if (rc) return rc;
             continue;
         }

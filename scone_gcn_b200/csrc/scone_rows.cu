@@ -62,13 +62,119 @@ __global__ void __launch_bounds__(128) rows_flows_kernel(const int32_t* __restri
 // candidate rows one hop further: lane = row of the list, every entry of its merged operator row marks (column, t) in bm_next
 __global__ void __launch_bounds__(256) rows_mark_kernel(const uint32_t* __restrict__ rows, const int* __restrict__ n_ptr,
                                                        const int32_t* __restrict__ mptr, const int2* __restrict__ ment, int b,
-                                                       uint32_t* __restrict__ bm_next, int list_cap) {
+                                                       uint32_t* __restrict__ bm_next, int list_cap, size_t sum_off) {
     const int n = min(*n_ptr, list_cap);
+    uint32_t* bm1 = sum_off ? bm_next + sum_off : nullptr;
     for (int li = blockIdx.x * blockDim.x + threadIdx.x; li < n; li += gridDim.x * blockDim.x) {
         const uint32_t rid = __ldg(rows + li);
         const unsigned e = rid / (unsigned)b, t = rid - e * (unsigned)b;
         const int p1 = __ldg(mptr + e + 1);
-        for (int p = __ldg(mptr + e); p < p1; ++p) bit_set(bm_next, (unsigned)__ldg(ment + p).x * (unsigned)b + t);
+        for (int p = __ldg(mptr + e); p < p1; ++p) bit_set2(bm_next, bm1, (unsigned)__ldg(ment + p).x * (unsigned)b + t);
+    }
+}
+
+// Compaction of a SPARSE two-level bitmap (see bit_set2): same contract as compact_bitmap_kernel (ascending row list, count, rank
+// prefix per non-empty word, one launch, per-CTA totals + decoupled look-back over tickets, deterministic) but the CTAs scan the
+// summary words and touch only the bitmap words whose summary bit is set.  tickets[] must be zero at launch.
+__global__ void __launch_bounds__(256) compact_summary_kernel(const uint32_t* __restrict__ bm, const uint32_t* __restrict__ bm1,
+                                                             long long n1_words, uint32_t* __restrict__ list, int* __restrict__ n_out,
+                                                             unsigned long long* __restrict__ tickets, uint32_t* __restrict__ pref_out,
+                                                             long long list_cap) {
+    __shared__ int s_warp[8];
+    __shared__ long long s_prefix;
+    __shared__ int s_total;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long per_cta = ((n1_words + gridDim.x - 1) / gridDim.x + 255) / 256 * 256;     // whole chunks of 256 summary words
+    const long long lo = (long long)blockIdx.x * per_cta, hi = lo + per_cta < n1_words ? lo + per_cta : n1_words;
+    auto count_word = [&](long long w1) {                 // set bits below summary word w1
+        int c = 0;
+        uint32_t sm = w1 < hi ? __ldg(bm1 + w1) : 0u;
+        while (sm) {
+            const int q = __ffs(sm) - 1;
+            sm &= sm - 1;
+            c += __popc(__ldg(bm + w1 * 32 + q));
+        }
+        return c;
+    };
+    int cnt = 0;
+    for (long long w1 = lo + threadIdx.x; w1 < hi; w1 += 256) cnt += count_word(w1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) s_warp[warp] = cnt;
+    if (threadIdx.x == 0) s_prefix = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int total = 0;
+        for (int k = 0; k < 8; ++k) total += s_warp[k];
+        s_total = total;
+        atomicExch(tickets + blockIdx.x, (1ull << 63) | (unsigned long long)(unsigned)total);
+    }
+    long long part = 0;
+    for (int c = threadIdx.x; c < (int)blockIdx.x; c += 256) {
+        unsigned long long t;
+        do { t = atomicAdd(tickets + c, 0ull); } while (!(t >> 63));
+        part += (long long)(t & 0xffffffffull);
+    }
+    if (part) atomicAdd((unsigned long long*)&s_prefix, (unsigned long long)part);
+    __syncthreads();
+    long long base = s_prefix;
+    const int total = s_total;
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        n_out[0] = (int)(base + total);
+        n_out[1] = 0;                                     // tile counter of the row-list kernel that consumes this list
+    }
+    if (total == 0) return;                               // (uniform) nothing set in this slice
+    for (long long w0 = lo; w0 < hi; w0 += 256) {
+        const long long w1 = w0 + threadIdx.x;
+        const int n = count_word(w1);
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        __syncthreads();                                  // s_warp of the previous chunk fully consumed
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int woff = 0, ctot = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int v = s_warp[k];
+            if (k < warp) woff += v;
+            ctot += v;
+        }
+        if (n) {
+            long long off = base + woff + incl - n;
+            uint32_t sm = __ldg(bm1 + w1);
+            while (sm) {
+                const int q = __ffs(sm) - 1;
+                sm &= sm - 1;
+                const long long w = w1 * 32 + q;
+                uint32_t cc = __ldg(bm + w);
+                if (pref_out != nullptr) pref_out[w] = (uint32_t)off;
+                while (cc) {
+                    const int pbit = __ffs(cc) - 1;
+                    cc &= cc - 1;
+                    if (off < list_cap) list[off] = (uint32_t)(w * 32 + pbit);
+                    ++off;
+                }
+            }
+        }
+        base += ctot;
+    }
+}
+
+// back to all-zero: every bitmap word under a set summary bit, then the summary word
+__global__ void __launch_bounds__(256) clear_summary_kernel(uint32_t* __restrict__ bm, uint32_t* __restrict__ bm1, long long n1_words) {
+    for (long long w1 = (long long)blockIdx.x * blockDim.x + threadIdx.x; w1 < n1_words; w1 += (long long)gridDim.x * blockDim.x) {
+        uint32_t sm = bm1[w1];
+        if (sm == 0u) continue;
+        while (sm) {
+            const int q = __ffs(sm) - 1;
+            sm &= sm - 1;
+            bm[w1 * 32 + q] = 0u;
+        }
+        bm1[w1] = 0u;
     }
 }
 
@@ -79,19 +185,22 @@ __global__ void __launch_bounds__(256) rows_mark_kernel(const uint32_t* __restri
 __global__ void __launch_bounds__(128) rows_cone_kernel(const int32_t* __restrict__ last_nodes, const int32_t* __restrict__ nbrhoods,
                                                        const int32_t* __restrict__ inc_ptr, const int2* __restrict__ inc_ent,
                                                        uint32_t* __restrict__ bm_top, uint32_t* __restrict__ bm_cand,
-                                                       const int32_t* __restrict__ mptr, const int2* __restrict__ ment, int N, int D, int b) {
+                                                       const int32_t* __restrict__ mptr, const int2* __restrict__ ment, int N, int D, int b,
+                                                       size_t sum_off) {
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int t = blockIdx.x;
     const int last = last_nodes[t];
     if (last < 0 || last >= N) return;
+    uint32_t* top1 = sum_off ? bm_top + sum_off : nullptr;
+    uint32_t* cand1 = sum_off && bm_cand != nullptr ? bm_cand + sum_off : nullptr;
     for (int j = warp; j < D; j += 4) {
         const int nbr = nbrhoods[(size_t)last * D + j];
         if (nbr < 0) continue;
         for (int p = inc_ptr[nbr]; p < inc_ptr[nbr + 1]; ++p) {
             const int e = inc_ent[p].x;
-            if (lane == 0) bit_set(bm_top, (unsigned)e * (unsigned)b + (unsigned)t);
+            if (lane == 0) bit_set2(bm_top, top1, (unsigned)e * (unsigned)b + (unsigned)t);
             if (bm_cand != nullptr)
-                for (int q = mptr[e] + lane; q < mptr[e + 1]; q += 32) bit_set(bm_cand, (unsigned)ment[q].x * (unsigned)b + (unsigned)t);
+                for (int q = mptr[e] + lane; q < mptr[e + 1]; q += 32) bit_set2(bm_cand, cand1, (unsigned)ment[q].x * (unsigned)b + (unsigned)t);
         }
     }
 }
@@ -149,53 +258,71 @@ __global__ void __launch_bounds__(256) rows_layer0_fwd_kernel(const float* __res
     }
 }
 
-// first layer backward: one warp per row of G_1; lanes split the merged operator row for the two scalar gathers (fixed
-// butterfly sum), then lane = channel.  Per-CTA partials [3][COUT], reduced by reduce order (deterministic).
+// first layer backward: dW_k[0][c] = sum_rows a_k[row] * G_1[row][c] with a_0 = X[row], a_1 = (S0 X)[row], a_2 = (S1 X)[row].  A warp
+// takes 32 consecutive list rows: lane = row for the scalar gathers of X (exact small integers), then lane = channel walks the 32
+// rows (coalesced G rows, a_k by shuffle).  Fixed row -> warp mapping and order; per-CTA partials [3][COUT] (reduced by
+// rows_reduce_kernel): deterministic.
 template <int COUT, bool COMPACT>
 __global__ void __launch_bounds__(256) rows_layer0_bwd_kernel(const float* __restrict__ X, const float* __restrict__ G,
                                                              const int32_t* __restrict__ mptr, const int2* __restrict__ ment,
                                                              const uint32_t* __restrict__ rows, const int* __restrict__ n_ptr, int b,
                                                              float* __restrict__ partial /* [grid][3*COUT] */, int cap) {
+    static_assert(COUT == 16 || COUT == 32, "first-layer row kernel: widths 16 / 32");
+    constexpr int RPI = 32 / COUT;                             // rows per iteration of the channel loop
     __shared__ float red[8][3 * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int n = *n_ptr;
     if (COMPACT && n > cap) n = cap;
-    const int per = (n + gridDim.x - 1) / gridDim.x;          // contiguous slice per CTA, rows strided over its warps
-    const int lo = min(n, (int)blockIdx.x * per), hi = min(n, lo + per);
+    const int n_groups = (n + 31) / 32;
+    const int per = (n_groups + gridDim.x - 1) / gridDim.x;   // contiguous slice of 32-row groups per CTA, strided over its warps
+    const int lo = min(n_groups, (int)blockIdx.x * per), hi = min(n_groups, lo + per);
+    const int c = lane % COUT, sub = lane / COUT;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
-    for (int li = lo + warp; li < hi; li += 8) {
-        const uint32_t rid = __ldg(rows + li);
-        const int e = (int)(rid / (unsigned)b), t = (int)(rid - (unsigned)e * (unsigned)b);
-        const int p0 = __ldg(mptr + e), p1 = __ldg(mptr + e + 1);
-        float a1 = 0.f, a2 = 0.f;
-        for (int p = p0 + lane; p < p1; p += 32) {
-            const int2 en = __ldg(ment + p);
-            const float x = __ldg(X + (size_t)(unsigned)en.x * b + t);
-            a1 = fmaf((float)(short)(en.y & 0xffff), x, a1);
-            a2 = fmaf((float)(en.y >> 16), x, a2);
+    for (int grp = lo + warp; grp < hi; grp += 8) {
+        const int li = grp * 32 + lane;
+        uint32_t rid = 0;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        if (li < n) {
+            rid = __ldg(rows + li);
+            const int e = (int)(rid / (unsigned)b), t = (int)(rid - (unsigned)e * (unsigned)b);
+            a0 = __ldg(X + rid);
+            const int p1 = __ldg(mptr + e + 1);
+            for (int p = __ldg(mptr + e); p < p1; ++p) {
+                const int2 en = __ldg(ment + p);
+                const float x = __ldg(X + (size_t)(unsigned)en.x * b + t);
+                a1 = fmaf((float)(short)(en.y & 0xffff), x, a1);
+                a2 = fmaf((float)(en.y >> 16), x, a2);
+            }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        const int cnt = min(32, n - grp * 32);
+#pragma unroll 4
+        for (int r0 = 0; r0 < cnt; r0 += RPI) {
+            const int r = r0 + sub;
+            const float s0 = __shfl_sync(0xffffffffu, a0, r & 31), s1 = __shfl_sync(0xffffffffu, a1, r & 31),
+                        s2 = __shfl_sync(0xffffffffu, a2, r & 31);
+            const uint32_t orow = __shfl_sync(0xffffffffu, rid, r & 31);
+            if (r < cnt) {
+                const float gv = __ldg(G + (size_t)(COMPACT ? (uint32_t)(grp * 32 + r) : orow) * COUT + c);
+                acc0 = fmaf(s0, gv, acc0);
+                acc1 = fmaf(s1, gv, acc1);
+                acc2 = fmaf(s2, gv, acc2);
+            }
         }
-        const float a0 = __ldg(X + rid);
-        if (lane < COUT) {
-            const float g = __ldg(G + (size_t)(COMPACT ? (uint32_t)li : rid) * COUT + lane);
-            acc0 = fmaf(a0, g, acc0);
-            acc1 = fmaf(a1, g, acc1);
-            acc2 = fmaf(a2, g, acc2);
-        }
+    }
+    if (RPI == 2) {                                            // the two half-warps hold alternate rows of the same channels
+        acc0 += __shfl_down_sync(0xffffffffu, acc0, 16);
+        acc1 += __shfl_down_sync(0xffffffffu, acc1, 16);
+        acc2 += __shfl_down_sync(0xffffffffu, acc2, 16);
     }
     red[warp][lane] = acc0;
     red[warp][32 + lane] = acc1;
     red[warp][64 + lane] = acc2;
     __syncthreads();
     for (int o = threadIdx.x; o < 3 * COUT; o += blockDim.x) {
-        const int k = o / COUT, c = o % COUT;
+        const int k = o / COUT, cc = o % COUT;
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) s += red[w][k * 32 + c];
+        for (int w = 0; w < 8; ++w) s += red[w][k * 32 + cc];
         partial[(size_t)blockIdx.x * 3 * COUT + o] = s;
     }
 }
@@ -378,7 +505,11 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rows_bwd_kernel(const float* 
 // memory in fragment layout (each 32-bit load fills whole 32-byte sectors; the 8 warps share the rows through L1).
 // Per-CTA partials, reduced over CTAs in a fixed tree: deterministic.
 // ---------------------------------------------------------------------------------------------------------------
-template <int CIN, int COUT, bool COMPACT>
+// IDENT: Hin is stored in the order of this very list (cone pipeline: row rows[i] of Hin at index i) — no rank lookup.
+// The k-loop is software-pipelined UNR steps deep: all operand loads of UNR consecutive k-steps are issued before the first
+// product (the loop was bound by the rows -> bitmap / prefix -> operand load chain, one chain per step); the mma order is the
+// plain ascending k order either way.
+template <int CIN, int COUT, bool COMPACT, bool IDENT>
 __global__ void __launch_bounds__(256) rows_dw_kernel(const float* __restrict__ Hin, const uint32_t* __restrict__ bmH,
                                                      const float* __restrict__ Abuf, const uint32_t* __restrict__ rows,
                                                      const int* __restrict__ n_ptr, int a_cap, float* __restrict__ partial /* [grid][3*CIN*COUT] */,
@@ -386,6 +517,7 @@ __global__ void __launch_bounds__(256) rows_dw_kernel(const float* __restrict__ 
     constexpr int MT = CIN / 16, NTT = 3 * COUT / 8;       // m-tiles, n-tiles
     constexpr int TILES = MT * NTT;
     constexpr int TPW = TILES >= 24 ? 3 : (TILES >= 12 ? 2 : 1);   // (m, n) tiles per warp; TILES / TPW <= 8 warps work
+    constexpr int UNR = 4;
     static_assert(TILES % TPW == 0 && TILES / TPW <= 8, "tile count must split over at most 8 warps");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tig = lane & 3, g = lane >> 2;
     if (warp >= TILES / TPW) return;                       // (no CTA barrier below)
@@ -401,37 +533,55 @@ __global__ void __launch_bounds__(256) rows_dw_kernel(const float* __restrict__ 
     float acc[TPW][4];
 #pragma unroll
     for (int j = 0; j < TPW; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-    for (int s = lo; s < hi; ++s) {
-        const int i0 = s * 8 + tig, i1 = i0 + 4;           // list positions of this lane's two k rows
-        float a[4] = {0.f, 0.f, 0.f, 0.f};
-        if (i0 < n) {
-            unsigned r = __ldg(rows + i0);
-            if (COMPACT ? rank_lookup(bmH, prefH, r, r) : bit_test(bmH, r)) {
-                a[0] = __ldg(Hin + (size_t)r * CIN + mt * 16 + g);
-                a[1] = __ldg(Hin + (size_t)r * CIN + mt * 16 + g + 8);
+    const float* Hc = Hin + mt * 16 + g;
+    const float* Ac = Abuf + nt0 * 8 + g;
+    for (int s0 = lo; s0 < hi; s0 += UNR) {
+        float a[UNR][4], bv[UNR][TPW][2];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int i0 = (s0 + u) * 8 + tig, i1 = i0 + 4;           // list positions of this lane's two k rows
+            const bool ok0 = s0 + u < hi && i0 < n, ok1 = s0 + u < hi && i1 < n;
+            a[u][0] = a[u][1] = a[u][2] = a[u][3] = 0.f;
+            unsigned r0 = (unsigned)i0, r1 = (unsigned)i1;
+            bool h0 = ok0, h1 = ok1;
+            if (!IDENT) {
+                if (ok0) {
+                    r0 = __ldg(rows + i0);
+                    h0 = COMPACT ? rank_lookup(bmH, prefH, r0, r0) : bit_test(bmH, r0);
+                }
+                if (ok1) {
+                    r1 = __ldg(rows + i1);
+                    h1 = COMPACT ? rank_lookup(bmH, prefH, r1, r1) : bit_test(bmH, r1);
+                }
+            }
+            if (h0) {
+                a[u][0] = __ldg(Hc + (size_t)r0 * CIN);
+                a[u][1] = __ldg(Hc + (size_t)r0 * CIN + 8);
+            }
+            if (h1) {
+                a[u][2] = __ldg(Hc + (size_t)r1 * CIN);
+                a[u][3] = __ldg(Hc + (size_t)r1 * CIN + 8);
+            }
+#pragma unroll
+            for (int j = 0; j < TPW; ++j) {
+                bv[u][j][0] = ok0 ? __ldg(Ac + (size_t)i0 * (3 * COUT) + j * 8) : 0.f;
+                bv[u][j][1] = ok1 ? __ldg(Ac + (size_t)i1 * (3 * COUT) + j * 8) : 0.f;
             }
         }
-        if (i1 < n) {
-            unsigned r = __ldg(rows + i1);
-            if (COMPACT ? rank_lookup(bmH, prefH, r, r) : bit_test(bmH, r)) {
-                a[2] = __ldg(Hin + (size_t)r * CIN + mt * 16 + g);
-                a[3] = __ldg(Hin + (size_t)r * CIN + mt * 16 + g + 8);
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            uint32_t ahi[4], alo[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) split_tf32(a[u][q], ahi[q], alo[q]);
+#pragma unroll
+            for (int j = 0; j < TPW; ++j) {
+                uint32_t bh0, bl0, bh1, bl1;
+                split_tf32(bv[u][j][0], bh0, bl0);
+                split_tf32(bv[u][j][1], bh1, bl1);
+                mma_tf32(acc[j], alo, bh0, bh1);
+                mma_tf32(acc[j], ahi, bl0, bl1);
+                mma_tf32(acc[j], ahi, bh0, bh1);
             }
-        }
-        uint32_t ahi[4], alo[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) split_tf32(a[q], ahi[q], alo[q]);
-#pragma unroll
-        for (int j = 0; j < TPW; ++j) {
-            const int ncol = (nt0 + j) * 8 + g;
-            const float b0 = i0 < n ? __ldg(Abuf + (size_t)i0 * (3 * COUT) + ncol) : 0.f;
-            const float b1 = i1 < n ? __ldg(Abuf + (size_t)i1 * (3 * COUT) + ncol) : 0.f;
-            uint32_t bh0, bl0, bh1, bl1;
-            split_tf32(b0, bh0, bl0);
-            split_tf32(b1, bh1, bl1);
-            mma_tf32(acc[j], alo, bh0, bh1);
-            mma_tf32(acc[j], ahi, bl0, bl1);
-            mma_tf32(acc[j], ahi, bh0, bh1);
         }
     }
     // D fragment (m = ci, n = k*COUT + co): c0,c1 -> (ci = g, n = 2*tig, +1); c2,c3 -> (ci = g + 8, ...)
@@ -682,11 +832,14 @@ int dispatch_rows_bwd(const scone_complex* cx, int act, int b, const float* G, c
 
 template <int CIN, int COUT>
 int launch_rows_dw(const scone_complex* cx, const float* Hin, const uint32_t* bmH, const float* Abuf, const uint32_t* rows,
-                   const int* n_ptr, int a_cap, float* dW, int accumulate, float* ws, const uint32_t* prefH, cudaStream_t st) {
-    if (prefH != nullptr)
-        rows_dw_kernel<CIN, COUT, true><<<kDwCtas, 256, 0, st>>>(Hin, bmH, Abuf, rows, n_ptr, a_cap, ws, prefH);
+                   const int* n_ptr, int a_cap, float* dW, int accumulate, float* ws, const uint32_t* prefH, bool hin_by_list,
+                   cudaStream_t st) {
+    if (hin_by_list)
+        rows_dw_kernel<CIN, COUT, true, true><<<kDwCtas, 256, 0, st>>>(Hin, bmH, Abuf, rows, n_ptr, a_cap, ws, prefH);
+    else if (prefH != nullptr)
+        rows_dw_kernel<CIN, COUT, true, false><<<kDwCtas, 256, 0, st>>>(Hin, bmH, Abuf, rows, n_ptr, a_cap, ws, prefH);
     else
-        rows_dw_kernel<CIN, COUT, false><<<kDwCtas, 256, 0, st>>>(Hin, bmH, Abuf, rows, n_ptr, a_cap, ws, prefH);
+        rows_dw_kernel<CIN, COUT, false, false><<<kDwCtas, 256, 0, st>>>(Hin, bmH, Abuf, rows, n_ptr, a_cap, ws, prefH);
     SCONE_LAUNCHED();
     constexpr int DW = 3 * CIN * COUT;
     rows_reduce_kernel<<<(DW + 31) / 32, 256, 0, st>>>(ws, kDwCtas, DW, dW, accumulate);
@@ -739,15 +892,41 @@ int scone_rows_flows(const scone_complex* cx, int b, const int32_t* traj_ptr, co
 }
 
 int scone_rows_mark(const scone_complex* cx, int b, const uint32_t* rows, const int* n_dev, uint32_t* bm_next, int list_cap,
-                    cudaStream_t st) {
-    rows_mark_kernel<<<cx->num_sms * 8, 256, 0, st>>>(rows, n_dev, cx->d_mptr, cx->d_ment, b, bm_next, list_cap);
+                    cudaStream_t st, size_t sum_off) {
+    rows_mark_kernel<<<cx->num_sms * 8, 256, 0, st>>>(rows, n_dev, cx->d_mptr, cx->d_ment, b, bm_next, list_cap, sum_off);
     SCONE_LAUNCHED();
     return 0;
 }
 
-int scone_rows_cone(const scone_complex* cx, int b, const int32_t* last_nodes, uint32_t* bm_top, uint32_t* bm_cand, cudaStream_t st) {
+int scone_rows_cone(const scone_complex* cx, int b, const int32_t* last_nodes, uint32_t* bm_top, uint32_t* bm_cand, size_t sum_off,
+                    cudaStream_t st) {
     rows_cone_kernel<<<b, 128, 0, st>>>(last_nodes, cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, bm_top, bm_cand, cx->d_mptr, cx->d_ment,
-                                       cx->N, cx->D, b);
+                                       cx->N, cx->D, b, sum_off);
+    SCONE_LAUNCHED();
+    return 0;
+}
+
+// two-level bitmaps: the summary words of bm start at bm + sum_off
+static long long summary_words(const scone_complex* cx, int b) { return (((long long)cx->E * b + 31) / 32 + 31) / 32; }
+
+int scone_compact_rows_summary(const scone_complex* cx, int b, const uint32_t* bm, size_t sum_off, uint32_t* list, int* n_dev,
+                               unsigned long long* tickets, cudaStream_t st, uint32_t* pref_out, long long list_cap) {
+    const long long n1 = summary_words(cx, b);
+    int grid = cx->num_sms * 4 < 1024 ? cx->num_sms * 4 : 1024;
+    if (n1 < (long long)grid * 256) grid = (int)((n1 + 255) / 256);
+    if (grid < 1) grid = 1;
+    SCONE_CUDA(cudaMemsetAsync(tickets, 0, (size_t)grid * 8, st));
+    compact_summary_kernel<<<grid, 256, 0, st>>>(bm, bm + sum_off, n1, list, n_dev, tickets, pref_out, list_cap);
+    SCONE_LAUNCHED();
+    return 0;
+}
+
+int scone_clear_summary(const scone_complex* cx, int b, uint32_t* bm, size_t sum_off, cudaStream_t st) {
+    const long long n1 = summary_words(cx, b);
+    long long grid = (n1 + 255) / 256;
+    if (grid > cx->num_sms * 8) grid = cx->num_sms * 8;
+    if (grid < 1) grid = 1;
+    clear_summary_kernel<<<(int)grid, 256, 0, st>>>(bm, bm + sum_off, n1);
     SCONE_LAUNCHED();
     return 0;
 }
@@ -781,17 +960,18 @@ int scone_rows_layer0_backward(const scone_complex* cx, int b, int cout, const f
     return 0;
 }
 
-// prefG / prefH != NULL: compact storage of G, Hin, Gprev (a_cap then also bounds the rows of Gprev)
+// prefG / prefH != NULL: compact storage of G, Hin, Gprev (a_cap then also bounds the rows of Gprev); hin_by_list: Hin's row set
+// IS this list (cone pipeline), row rows[i] at index i
 int scone_rows_backward(const scone_complex* cx, int act, int b, int cin, int cout, const float* G, const float* Hin, float* Gprev,
                         float* Abuf, const float* W0, const float* W1, const float* W2, const uint32_t* rows, const int* n_dev,
                         const uint32_t* bmG, const uint32_t* bmH, int a_cap, int* overflow_dev, float* dW, int accumulate, float* ws,
-                        const uint32_t* prefG, const uint32_t* prefH, cudaStream_t st) {
+                        const uint32_t* prefG, const uint32_t* prefH, bool hin_by_list, cudaStream_t st) {
 #define SCONE_RB_CASE(CI, CO)                                                                                                     \
     if (cin == CI && cout == CO) {                                                                                                \
         if (dispatch_rows_bwd<CI, CO>(cx, act, b, G, Hin, Gprev, Abuf, W0, W1, W2, rows, n_dev, bmG, bmH, a_cap, overflow_dev,      \
                                       prefG, prefH, st))                                                                          \
             return 1;                                                                                                             \
-        return launch_rows_dw<CI, CO>(cx, Hin, bmH, Abuf, rows, n_dev, a_cap, dW, accumulate, ws, prefH, st);                       \
+        return launch_rows_dw<CI, CO>(cx, Hin, bmH, Abuf, rows, n_dev, a_cap, dW, accumulate, ws, prefH, hin_by_list, st);          \
     }
     SCONE_RB_CASE(16, 16)
     SCONE_RB_CASE(16, 32)

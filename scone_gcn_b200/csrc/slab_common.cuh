@@ -28,6 +28,16 @@ __device__ __forceinline__ void bit_set(uint32_t* __restrict__ bm, size_t row) {
     const uint32_t bit = 1u << (row & 31);
     if (!(*w & bit)) atomicOr(w, bit);
 }
+// two-level bitmap: bm1 = one summary bit per 32-bit word of bm, set by whoever turns a word non-zero; the compaction and the
+// clearing of a sparse bitmap then scan 1/32 of its bytes (compact_summary_kernel, clear_summary_kernel in scone_rows.cu)
+__device__ __forceinline__ void bit_set2(uint32_t* __restrict__ bm, uint32_t* __restrict__ bm1, size_t row) {
+    const size_t widx = row >> 5;
+    uint32_t* w = bm + widx;
+    const uint32_t bit = 1u << (row & 31);
+    if (!(*w & bit)) {
+        if (atomicOr(w, bit) == 0u && bm1 != nullptr) atomicOr(bm1 + (widx >> 5), 1u << (widx & 31));
+    }
+}
 // compact storage: row r of a tensor lives at index rank(r) = pref[r >> 5] + popc(bm[r >> 5] & bits below r) = its position in
 // the compacted row list; returns whether the row exists (bit set)
 __device__ __forceinline__ bool rank_lookup(const uint32_t* __restrict__ bm, const uint32_t* __restrict__ pref, unsigned row,
