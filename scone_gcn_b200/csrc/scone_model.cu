@@ -230,7 +230,7 @@ int rows_forward_mb(scone_model* m, int32_t b, const int32_t* ptr, const int32_t
         ScopedProf prof(SCONE_K_OTHER, s);
         SCONE_CUDA(cudaMemsetAsync(m->d_bmX, 0, bm_bytes, s));
         SCONE_CUDA(cudaMemsetAsync(m->d_bmH[0], 0, bm_bytes, s));
-        if (scone_rows_flows(cx, b, ptr, edge, val, m->d_X, m->d_bmX, m->d_bmH[0], false, s)) return 1;
+        if (scone_rows_flows(cx, b, ptr, edge, val, m->d_X, m->d_bmX, m->d_bmH[0], false, compact, s)) return 1;
     }
     int cin = 1;
     for (int l = 0; l < m->L; ++l) {
@@ -241,7 +241,7 @@ int rows_forward_mb(scone_model* m, int32_t b, const int32_t* ptr, const int32_t
         uint32_t* next = l + 1 < m->L ? m->d_bmH[l + 1] : nullptr;
         if (next) {
             SCONE_CUDA(cudaMemsetAsync(next, 0, bm_bytes, s));
-            if (scone_rows_mark(cx, b, m->d_rows, m->d_nrows, next, compact ? m->row_cap : 0x7fffffff, s)) return 1;
+            if (scone_rows_mark(cx, b, m->d_rows, m->d_nrows, next, compact ? m->row_cap : 0x7fffffff, s, compact)) return 1;
         }
         const float *W0 = m->d_w + m->w_off[3 * l], *W1 = m->d_w + m->w_off[3 * l + 1], *W2 = m->d_w + m->w_off[3 * l + 2];
         float* Hout = compact ? m->d_cH[l] : m->d_H[l];
@@ -261,7 +261,7 @@ int rows_forward_mb(scone_model* m, int32_t b, const int32_t* ptr, const int32_t
 
 int rows_clear_x(scone_model* m, int32_t b, const int32_t* ptr, const int32_t* edge, const float* val, cudaStream_t s) {
     ScopedProf prof(SCONE_K_OTHER, s);
-    return scone_rows_flows(m->cx, b, ptr, edge, val, m->d_X, nullptr, nullptr, true, s);
+    return scone_rows_flows(m->cx, b, ptr, edge, val, m->d_X, nullptr, nullptr, true, m->pipeline >= 2, s);
 }
 
 // readout on the row-list pipelines; grad = false: log-probs only
@@ -317,7 +317,7 @@ int rows_backward_mb(scone_model* m, int32_t b, cudaStream_t s) {
         uint32_t* next = l >= 2 ? m->d_bmGr[l - 2] : nullptr;
         if (next) {
             SCONE_CUDA(cudaMemsetAsync(next, 0, bm_bytes, s));
-            if (scone_rows_mark(cx, b, m->d_rows, m->d_nrows, next, compact ? m->row_cap : 0x7fffffff, s)) return 1;
+            if (scone_rows_mark(cx, b, m->d_rows, m->d_nrows, next, compact ? m->row_cap : 0x7fffffff, s, compact)) return 1;
         }
         int rc = scone_rows_backward(cx, m->act, b, m->hidden[l - 1], m->hidden[l], compact ? m->d_cG[l] : m->d_G[l],
                                      compact ? m->d_cH[l - 1] : m->d_H[l - 1], compact ? m->d_cG[l - 1] : m->d_G[l - 1], m->d_Abuf,
@@ -356,7 +356,7 @@ int cone_build_mb(scone_model* m, int32_t b, const int32_t* last, cudaStream_t s
                                        m->row_cap))
             return 1;
         if (l >= 1 && l <= L - 2)                          // (the readout cone already marked layer L-2)
-            if (scone_rows_mark(cx, b, m->d_rowsC[l], cone_n(m, l), m->d_bmGr[l - 1], m->row_cap, s, m->sum_off)) return 1;
+            if (scone_rows_mark(cx, b, m->d_rowsC[l], cone_n(m, l), m->d_bmGr[l - 1], m->row_cap, s, true, m->sum_off)) return 1;
     }
     return 0;
 }
@@ -378,7 +378,7 @@ int cone_forward_mb(scone_model* m, int32_t b, const int32_t* ptr, const int32_t
     }
     {
         ScopedProf prof(SCONE_K_OTHER, s);
-        if (scone_rows_flows(cx, b, ptr, edge, val, m->d_X, nullptr, nullptr, false, s)) return 1;
+        if (scone_rows_flows(cx, b, ptr, edge, val, m->d_X, nullptr, nullptr, false, true, s)) return 1;
     }
     int cin = 1;
     for (int l = 0; l < m->L; ++l) {

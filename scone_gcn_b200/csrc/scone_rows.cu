@@ -19,6 +19,8 @@ namespace {
 
 #include "slab_common.cuh"
 
+constexpr int kRoWarps = 4, kRoMaxD = 128, kRoMaxCper = 4;     // readout / cone kernels: max degree, channels per lane
+
 template <int ACT>
 __device__ __forceinline__ float act_scalar(float z) {
     if (ACT == SCONE_ACT_TANH) return scone_tanh(z);
@@ -41,13 +43,15 @@ template <bool CLEAR>
 __global__ void __launch_bounds__(128) rows_flows_kernel(const int32_t* __restrict__ traj_ptr, const int32_t* __restrict__ flow_edge,
                                                         const float* __restrict__ flow_val, const int32_t* __restrict__ rank,
                                                         float* __restrict__ X, uint32_t* __restrict__ bmX, uint32_t* __restrict__ bm_next,
-                                                        const int32_t* __restrict__ mptr, const int2* __restrict__ ment, int E, int b) {
+                                                        const int32_t* __restrict__ mptr, const int2* __restrict__ ment, int E, int b,
+                                                        bool tmaj) {
     const int t = blockIdx.x;
+    const size_t se = tmaj ? 1 : (size_t)b, toff = tmaj ? (size_t)t * E : (size_t)t;     // row id = e * se + toff (see RowIds)
     for (int p = traj_ptr[t] + threadIdx.x; p < traj_ptr[t + 1]; p += blockDim.x) {
         const int eo = flow_edge[p];
         if (eo < 0 || eo >= E) continue;
         const int e = rank[eo];
-        const size_t row = (size_t)e * b + t;
+        const size_t row = (size_t)e * se + toff;
         if (CLEAR) {
             X[row] = 0.f;
             continue;
@@ -55,21 +59,23 @@ __global__ void __launch_bounds__(128) rows_flows_kernel(const int32_t* __restri
         X[row] = flow_val[p];
         if (bmX != nullptr) bit_set(bmX, row);
         if (bm_next != nullptr)
-            for (int q = mptr[e]; q < mptr[e + 1]; ++q) bit_set(bm_next, (size_t)(unsigned)ment[q].x * b + t);
+            for (int q = mptr[e]; q < mptr[e + 1]; ++q) bit_set(bm_next, (size_t)(unsigned)ment[q].x * se + toff);
     }
 }
 
 // candidate rows one hop further: lane = row of the list, every entry of its merged operator row marks (column, t) in bm_next
 __global__ void __launch_bounds__(256) rows_mark_kernel(const uint32_t* __restrict__ rows, const int* __restrict__ n_ptr,
                                                        const int32_t* __restrict__ mptr, const int2* __restrict__ ment, int b,
-                                                       uint32_t* __restrict__ bm_next, int list_cap, size_t sum_off) {
+                                                       uint32_t* __restrict__ bm_next, int list_cap, size_t sum_off, int E, bool tmaj) {
     const int n = min(*n_ptr, list_cap);
+    const unsigned dv = tmaj ? (unsigned)E : (unsigned)b, se = tmaj ? 1u : (unsigned)b;
     uint32_t* bm1 = sum_off ? bm_next + sum_off : nullptr;
     for (int li = blockIdx.x * blockDim.x + threadIdx.x; li < n; li += gridDim.x * blockDim.x) {
         const uint32_t rid = __ldg(rows + li);
-        const unsigned e = rid / (unsigned)b, t = rid - e * (unsigned)b;
+        const unsigned q = rid / dv, r = rid - q * dv;
+        const unsigned e = tmaj ? r : q, toff = tmaj ? rid - r : r;
         const int p1 = __ldg(mptr + e + 1);
-        for (int p = __ldg(mptr + e); p < p1; ++p) bit_set2(bm_next, bm1, (unsigned)__ldg(ment + p).x * (unsigned)b + t);
+        for (int p = __ldg(mptr + e); p < p1; ++p) bit_set2(bm_next, bm1, (unsigned)__ldg(ment + p).x * se + toff);
     }
 }
 
@@ -80,24 +86,40 @@ __global__ void __launch_bounds__(256) compact_summary_kernel(const uint32_t* __
                                                              long long n1_words, uint32_t* __restrict__ list, int* __restrict__ n_out,
                                                              unsigned long long* __restrict__ tickets, uint32_t* __restrict__ pref_out,
                                                              long long list_cap) {
+    constexpr int WPT = 4, kChunk = WPT * 256;            // summary words per thread (one 128-bit load) and per CTA iteration
     __shared__ int s_warp[8];
     __shared__ long long s_prefix;
     __shared__ int s_total;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long per_cta = ((n1_words + gridDim.x - 1) / gridDim.x + 255) / 256 * 256;     // whole chunks of 256 summary words
+    const long long per_cta = ((n1_words + gridDim.x - 1) / gridDim.x + kChunk - 1) / kChunk * kChunk;     // whole chunks
     const long long lo = (long long)blockIdx.x * per_cta, hi = lo + per_cta < n1_words ? lo + per_cta : n1_words;
-    auto count_word = [&](long long w1) {                 // set bits below summary word w1
+    auto load4 = [&](long long w1, uint32_t (&sm)[WPT]) { // summary words w1 .. w1+3 (w1 % 4 == 0; the summary is padded), zero beyond hi
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (w1 < hi) v = __ldg(reinterpret_cast<const uint4*>(bm1 + w1));
+        sm[0] = v.x;
+        sm[1] = w1 + 1 < hi ? v.y : 0u;
+        sm[2] = w1 + 2 < hi ? v.z : 0u;
+        sm[3] = w1 + 3 < hi ? v.w : 0u;
+    };
+    auto count4 = [&](long long w1, const uint32_t (&sm)[WPT]) {
         int c = 0;
-        uint32_t sm = w1 < hi ? __ldg(bm1 + w1) : 0u;
-        while (sm) {
-            const int q = __ffs(sm) - 1;
-            sm &= sm - 1;
-            c += __popc(__ldg(bm + w1 * 32 + q));
+#pragma unroll
+        for (int k = 0; k < WPT; ++k) {
+            uint32_t m = sm[k];
+            while (m) {
+                const int q = __ffs(m) - 1;
+                m &= m - 1;
+                c += __popc(__ldg(bm + (w1 + k) * 32 + q));
+            }
         }
         return c;
     };
     int cnt = 0;
-    for (long long w1 = lo + threadIdx.x; w1 < hi; w1 += 256) cnt += count_word(w1);
+    for (long long w1 = lo + (long long)WPT * threadIdx.x; w1 < hi; w1 += kChunk) {
+        uint32_t sm[WPT];
+        load4(w1, sm);
+        cnt += count4(w1, sm);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (lane == 0) s_warp[warp] = cnt;
@@ -124,9 +146,11 @@ __global__ void __launch_bounds__(256) compact_summary_kernel(const uint32_t* __
         n_out[1] = 0;                                     // tile counter of the row-list kernel that consumes this list
     }
     if (total == 0) return;                               // (uniform) nothing set in this slice
-    for (long long w0 = lo; w0 < hi; w0 += 256) {
-        const long long w1 = w0 + threadIdx.x;
-        const int n = count_word(w1);
+    for (long long w0 = lo; w0 < hi; w0 += kChunk) {
+        const long long w1 = w0 + (long long)WPT * threadIdx.x;
+        uint32_t sm[WPT];
+        load4(w1, sm);
+        const int n = count4(w1, sm);
         int incl = n;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -145,18 +169,21 @@ __global__ void __launch_bounds__(256) compact_summary_kernel(const uint32_t* __
         }
         if (n) {
             long long off = base + woff + incl - n;
-            uint32_t sm = __ldg(bm1 + w1);
-            while (sm) {
-                const int q = __ffs(sm) - 1;
-                sm &= sm - 1;
-                const long long w = w1 * 32 + q;
-                uint32_t cc = __ldg(bm + w);
-                if (pref_out != nullptr) pref_out[w] = (uint32_t)off;
-                while (cc) {
-                    const int pbit = __ffs(cc) - 1;
-                    cc &= cc - 1;
-                    if (off < list_cap) list[off] = (uint32_t)(w * 32 + pbit);
-                    ++off;
+#pragma unroll
+            for (int k = 0; k < WPT; ++k) {
+                uint32_t m = sm[k];
+                while (m) {
+                    const int q = __ffs(m) - 1;
+                    m &= m - 1;
+                    const long long w = (w1 + k) * 32 + q;
+                    uint32_t cc = __ldg(bm + w);
+                    if (pref_out != nullptr) pref_out[w] = (uint32_t)off;
+                    while (cc) {
+                        const int pbit = __ffs(cc) - 1;
+                        cc &= cc - 1;
+                        if (off < list_cap) list[off] = (uint32_t)(w * 32 + pbit);
+                        ++off;
+                    }
                 }
             }
         }
@@ -182,25 +209,41 @@ __global__ void __launch_bounds__(256) clear_summary_kernel(uint32_t* __restrict
 // edges incident to the neighbours of its last node (trajectory_experiments.py:151,298-303); those rows are the top of the cone
 // (bm_top), the rows one hop further (bm_cand) are all that H_{L-1} has to provide, and so on down (rows_mark_kernel).  Rows
 // outside the cone reach neither the log-probs nor any weight gradient, so the cone-pruned pipeline never computes them.
-__global__ void __launch_bounds__(128) rows_cone_kernel(const int32_t* __restrict__ last_nodes, const int32_t* __restrict__ nbrhoods,
+__global__ void __launch_bounds__(256) rows_cone_kernel(const int32_t* __restrict__ last_nodes, const int32_t* __restrict__ nbrhoods,
                                                        const int32_t* __restrict__ inc_ptr, const int2* __restrict__ inc_ent,
                                                        uint32_t* __restrict__ bm_top, uint32_t* __restrict__ bm_cand,
-                                                       const int32_t* __restrict__ mptr, const int2* __restrict__ ment, int N, int D, int b,
+                                                       const int32_t* __restrict__ mptr, const int2* __restrict__ ment, int N, int D, int E,
                                                        size_t sum_off) {
-    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    // one CTA per trajectory; the (neighbour, incident edge) pairs are flattened over quads of threads, a quad's lanes split the
+    // merged operator row of its edge: every load / atomicOr of a trajectory is in flight at once (idempotent, order-free)
+    __shared__ int s_ptr[kRoMaxD], s_off[kRoMaxD + 1];
     const int t = blockIdx.x;
     const int last = last_nodes[t];
     if (last < 0 || last >= N) return;
     uint32_t* top1 = sum_off ? bm_top + sum_off : nullptr;
     uint32_t* cand1 = sum_off && bm_cand != nullptr ? bm_cand + sum_off : nullptr;
-    for (int j = warp; j < D; j += 4) {
+    for (int j = threadIdx.x; j < D; j += blockDim.x) {
         const int nbr = nbrhoods[(size_t)last * D + j];
-        if (nbr < 0) continue;
-        for (int p = inc_ptr[nbr]; p < inc_ptr[nbr + 1]; ++p) {
-            const int e = inc_ent[p].x;
-            if (lane == 0) bit_set2(bm_top, top1, (unsigned)e * (unsigned)b + (unsigned)t);
-            if (bm_cand != nullptr)
-                for (int q = mptr[e] + lane; q < mptr[e + 1]; q += 32) bit_set2(bm_cand, cand1, (unsigned)ment[q].x * (unsigned)b + (unsigned)t);
+        s_ptr[j] = nbr >= 0 ? inc_ptr[nbr] : 0;
+        s_off[j + 1] = nbr >= 0 ? inc_ptr[nbr + 1] - inc_ptr[nbr] : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_off[0] = 0;
+        for (int j = 0; j < D; ++j) s_off[j + 1] += s_off[j];
+    }
+    __syncthreads();
+    const int total = s_off[D];
+    const unsigned tbase = (unsigned)t * (unsigned)E;
+    const int ql = threadIdx.x & 3;
+    for (int i = threadIdx.x >> 2; i < total; i += blockDim.x >> 2) {
+        int j = 0;
+        while (s_off[j + 1] <= i) ++j;
+        const int e = inc_ent[s_ptr[j] + (i - s_off[j])].x;
+        if (ql == 0) bit_set2(bm_top, top1, tbase + (unsigned)e);
+        if (bm_cand != nullptr) {
+            const int p1 = mptr[e + 1];
+            for (int q = mptr[e] + ql; q < p1; q += 4) bit_set2(bm_cand, cand1, tbase + (unsigned)ment[q].x);
         }
     }
 }
@@ -216,7 +259,7 @@ __global__ void __launch_bounds__(256) rows_layer0_fwd_kernel(const float* __res
                                                              const float* __restrict__ W2, const int32_t* __restrict__ mptr,
                                                              const int2* __restrict__ ment, const uint32_t* __restrict__ rows,
                                                              const int* __restrict__ n_ptr, int b, uint32_t* __restrict__ bm_next,
-                                                             int out_cap, int* __restrict__ overflow) {
+                                                             int out_cap, int* __restrict__ overflow, int E) {
     static_assert(COUT == 16 || COUT == 32, "first-layer row kernel: widths 16 / 32");
     constexpr int RPI = 32 / COUT;                        // rows written per iteration of the store loop
     const int lane = threadIdx.x & 31;
@@ -235,12 +278,13 @@ __global__ void __launch_bounds__(256) rows_layer0_fwd_kernel(const float* __res
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
         if (li < n) {
             rid = __ldg(rows + li);
-            const int e = (int)(rid / (unsigned)b), t = (int)(rid - (unsigned)e * (unsigned)b);
+            const RowIds<COMPACT> ids(rid, b, E);
+            const int e = (int)ids.e;
             a0 = __ldg(X + rid);
             const int p1 = __ldg(mptr + e + 1);
             for (int p = __ldg(mptr + e); p < p1; ++p) {
                 const int2 en = __ldg(ment + p);
-                const size_t nrow = (size_t)(unsigned)en.x * b + t;
+                const size_t nrow = ids.row((unsigned)en.x);
                 const float x = __ldg(X + nrow);
                 a1 = fmaf((float)(short)(en.y & 0xffff), x, a1);
                 a2 = fmaf((float)(en.y >> 16), x, a2);
@@ -266,7 +310,7 @@ template <int COUT, bool COMPACT>
 __global__ void __launch_bounds__(256) rows_layer0_bwd_kernel(const float* __restrict__ X, const float* __restrict__ G,
                                                              const int32_t* __restrict__ mptr, const int2* __restrict__ ment,
                                                              const uint32_t* __restrict__ rows, const int* __restrict__ n_ptr, int b,
-                                                             float* __restrict__ partial /* [grid][3*COUT] */, int cap) {
+                                                             float* __restrict__ partial /* [grid][3*COUT] */, int cap, int E) {
     static_assert(COUT == 16 || COUT == 32, "first-layer row kernel: widths 16 / 32");
     constexpr int RPI = 32 / COUT;                             // rows per iteration of the channel loop
     __shared__ float red[8][3 * 32];
@@ -284,12 +328,13 @@ __global__ void __launch_bounds__(256) rows_layer0_bwd_kernel(const float* __res
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
         if (li < n) {
             rid = __ldg(rows + li);
-            const int e = (int)(rid / (unsigned)b), t = (int)(rid - (unsigned)e * (unsigned)b);
+            const RowIds<COMPACT> ids(rid, b, E);
+            const int e = (int)ids.e;
             a0 = __ldg(X + rid);
             const int p1 = __ldg(mptr + e + 1);
             for (int p = __ldg(mptr + e); p < p1; ++p) {
                 const int2 en = __ldg(ment + p);
-                const float x = __ldg(X + (size_t)(unsigned)en.x * b + t);
+                const float x = __ldg(X + ids.row((unsigned)en.x));
                 a1 = fmaf((float)(short)(en.y & 0xffff), x, a1);
                 a2 = fmaf((float)(en.y >> 16), x, a2);
             }
@@ -343,7 +388,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rows_bwd_kernel(const float* 
                                                                   const int* __restrict__ n_ptr, int b, const uint32_t* __restrict__ bmG,
                                                                   const uint32_t* __restrict__ bmH, int a_cap, int* __restrict__ overflow,
                                                                   unsigned long long* __restrict__ row_counter,
-                                                                  const uint32_t* __restrict__ prefG, const uint32_t* __restrict__ prefH) {
+                                                                  const uint32_t* __restrict__ prefG, const uint32_t* __restrict__ prefH, int E) {
     using G = SlabGeom<COUT, 16>;                          // the gathered tensor has COUT channels
     constexpr int NT = CIN / 8, NL = G::NL, Q = G::Q, LPR = COUT / 4;
     extern __shared__ __align__(16) uint4 Bf[];
@@ -382,8 +427,9 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rows_bwd_kernel(const float* 
             const int li = slab * 16 + i * Q + gq;
             valid[i] = li < n;
             rid[i] = valid[i] ? __ldg(rows + li) : 0u;
-            const int e = (int)(rid[i] / (unsigned)b);
-            tq[i] = (int)(rid[i] - (unsigned)e * (unsigned)b);
+            const RowIds<COMPACT> ids(rid[i], b, E);
+            const int e = (int)ids.e;
+            tq[i] = (int)ids.toff;                         // e-major: t; trajectory-major: t * E
             cpos[i] = (COUT == 32 && i >= 2) ? (cq ^ 4) : cq;
             P[i] = Gb + (size_t)((unsigned)((COMPACT ? 0 : tq[i] * COUT) + 4 * cpos[i]) * 4u);
             asm volatile("" : "+l"(P[i]));
@@ -419,7 +465,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rows_bwd_kernel(const float* 
             unsigned gidx[NL];
 #pragma unroll
             for (int i = 0; i < NL; ++i) {                 // branch-free bit test (entry {0,0} of an idle lane tests row tq: in range)
-                const unsigned nrow = (unsigned)ent[i].x * (unsigned)b + (unsigned)tq[i];
+                const unsigned nrow = RowIds<COMPACT>::row_of((unsigned)ent[i].x, (unsigned)tq[i], b);
                 if (COMPACT) {
                     on[i] = rank_lookup(bmG, prefG, nrow, gidx[i]) && on[i];
                 } else {
@@ -628,7 +674,6 @@ __global__ void __launch_bounds__(256) rows_reduce_kernel(const float* __restric
 //                             w_out gradient partials, the NLL term and the mask count.
 // One CTA (4 warps) per trajectory, warps split the neighbour slots (same arithmetic as readout_kernel).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kRoWarps = 4, kRoMaxD = 128, kRoMaxCper = 4;
 
 __global__ void __launch_bounds__(32 * kRoWarps) rows_readout_fwd_kernel(const float* __restrict__ HL, const float* __restrict__ wout,
                                                                         const int32_t* __restrict__ last_nodes, const int32_t* __restrict__ nbrhoods,
@@ -636,7 +681,7 @@ __global__ void __launch_bounds__(32 * kRoWarps) rows_readout_fwd_kernel(const f
                                                                         float* __restrict__ logprobs, const uint32_t* __restrict__ bmH,
                                                                         const uint32_t* __restrict__ prefH, uint32_t* __restrict__ bmG,
                                                                         uint32_t* __restrict__ bm_cand, const int32_t* __restrict__ mptr,
-                                                                        const int2* __restrict__ ment, int N, int D, int b, int C) {
+                                                                        const int2* __restrict__ ment, int N, int D, int E, int C) {
     __shared__ float logit[kRoMaxD];
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int t = blockIdx.x;
@@ -653,11 +698,11 @@ __global__ void __launch_bounds__(32 * kRoWarps) rows_readout_fwd_kernel(const f
             float z[kRoMaxCper] = {0.f, 0.f, 0.f, 0.f};
             for (int p = inc_ptr[nbr]; p < inc_ptr[nbr + 1]; ++p) {
                 const int2 es = inc_ent[p];
-                const unsigned row = (unsigned)es.x * (unsigned)b + (unsigned)t;
+                const unsigned row = (unsigned)t * (unsigned)E + (unsigned)es.x;      // compact tensors: trajectory-major row ids
                 if (bmG != nullptr) {                      // gradient wanted: this row of G_L will be written
                     if (lane == 0) bit_set(bmG, row);
                     if (bm_cand != nullptr)
-                        for (int q = mptr[es.x] + lane; q < mptr[es.x + 1]; q += 32) bit_set(bm_cand, (unsigned)ment[q].x * (unsigned)b + (unsigned)t);
+                        for (int q = mptr[es.x] + lane; q < mptr[es.x + 1]; q += 32) bit_set(bm_cand, (unsigned)t * (unsigned)E + (unsigned)ment[q].x);
                 }
                 unsigned idx;
                 if (!rank_lookup(bmH, prefH, row, idx)) continue;      // row is exactly zero
@@ -709,7 +754,7 @@ __global__ void __launch_bounds__(32 * kRoWarps) rows_readout_bwd_kernel(const f
                                                                         const float* __restrict__ mask, float scale, float* __restrict__ GL,
                                                                         float* __restrict__ partial /* [b][C+2] */, const uint32_t* __restrict__ bmH,
                                                                         const uint32_t* __restrict__ prefH, const uint32_t* __restrict__ bmG,
-                                                                        const uint32_t* __restrict__ prefG, int g_cap, int act, int N, int D, int b, int C) {
+                                                                        const uint32_t* __restrict__ prefG, int g_cap, int act, int N, int D, int E, int C) {
     __shared__ float s_dw[kRoWarps][32 * kRoMaxCper];
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int t = blockIdx.x;
@@ -727,7 +772,7 @@ __global__ void __launch_bounds__(32 * kRoWarps) rows_readout_bwd_kernel(const f
         const float dl = mk * scale * (expf(logprobs[(size_t)t * D + j]) - (j == y ? 1.f : 0.f));
         for (int p = inc_ptr[nbr]; p < inc_ptr[nbr + 1]; ++p) {
             const int2 es = inc_ent[p];
-            const unsigned row = (unsigned)es.x * (unsigned)b + (unsigned)t;
+            const unsigned row = (unsigned)t * (unsigned)E + (unsigned)es.x;
             unsigned hidx, gidx;
             const bool hset = rank_lookup(bmH, prefH, row, hidx);
             rank_lookup(bmG, prefG, row, gidx);
@@ -805,11 +850,11 @@ int launch_rows_bwd(const scone_complex* cx, int b, const float* G, const float*
     if (prefG != nullptr)
         rows_bwd_kernel<CIN, COUT, ACT, true><<<cx->num_sms, kRowsThreads, smem, st>>>(G, Hin, Gprev, Abuf, W0, W1, W2, cx->d_mptr, cx->d_ment, rows,
                                                                                      n_ptr, b, bmG, bmH, a_cap, overflow,
-                                                                                     scone_prof_row_counter(SCONE_K_LAYER_BWD), prefG, prefH);
+                                                                                     scone_prof_row_counter(SCONE_K_LAYER_BWD), prefG, prefH, cx->E);
     else
         rows_bwd_kernel<CIN, COUT, ACT, false><<<cx->num_sms, kRowsThreads, smem, st>>>(G, Hin, Gprev, Abuf, W0, W1, W2, cx->d_mptr, cx->d_ment, rows,
                                                                                       n_ptr, b, bmG, bmH, a_cap, overflow,
-                                                                                      scone_prof_row_counter(SCONE_K_LAYER_BWD), prefG, prefH);
+                                                                                      scone_prof_row_counter(SCONE_K_LAYER_BWD), prefG, prefH, cx->E);
     SCONE_LAUNCHED();
     return 0;
 }
@@ -852,9 +897,9 @@ int launch_rows_l0_fwd_act(const scone_complex* cx, int b, const float* X, const
                            const uint32_t* rows, const int* n_ptr, uint32_t* bm_next, int out_cap, int* overflow, cudaStream_t st) {
     const int grid = cx->num_sms * 8;
     if (out_cap > 0)
-        rows_layer0_fwd_kernel<COUT, ACT, true><<<grid, 256, 0, st>>>(X, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, rows, n_ptr, b, bm_next, out_cap, overflow);
+        rows_layer0_fwd_kernel<COUT, ACT, true><<<grid, 256, 0, st>>>(X, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, rows, n_ptr, b, bm_next, out_cap, overflow, cx->E);
     else
-        rows_layer0_fwd_kernel<COUT, ACT, false><<<grid, 256, 0, st>>>(X, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, rows, n_ptr, b, bm_next, out_cap, overflow);
+        rows_layer0_fwd_kernel<COUT, ACT, false><<<grid, 256, 0, st>>>(X, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, rows, n_ptr, b, bm_next, out_cap, overflow, cx->E);
     SCONE_LAUNCHED();
     return 0;
 }
@@ -882,26 +927,27 @@ bool scone_rows_supported(const scone_complex* cx, int n_layers, const int32_t* 
 int64_t scone_rows_dw_workspace_bytes(int cin, int cout) { return (int64_t)kDwCtas * 3 * (cin > 1 ? cin : 1) * cout * sizeof(float); }
 
 int scone_rows_flows(const scone_complex* cx, int b, const int32_t* traj_ptr, const int32_t* flow_edge, const float* flow_val, float* X,
-                     uint32_t* bmX, uint32_t* bm_next, bool clear, cudaStream_t st) {
+                     uint32_t* bmX, uint32_t* bm_next, bool clear, bool tmaj, cudaStream_t st) {
     if (clear)
-        rows_flows_kernel<true><<<b, 128, 0, st>>>(traj_ptr, flow_edge, flow_val, cx->d_rank, X, bmX, bm_next, cx->d_mptr, cx->d_ment, cx->E, b);
+        rows_flows_kernel<true><<<b, 128, 0, st>>>(traj_ptr, flow_edge, flow_val, cx->d_rank, X, bmX, bm_next, cx->d_mptr, cx->d_ment, cx->E, b, tmaj);
     else
-        rows_flows_kernel<false><<<b, 128, 0, st>>>(traj_ptr, flow_edge, flow_val, cx->d_rank, X, bmX, bm_next, cx->d_mptr, cx->d_ment, cx->E, b);
+        rows_flows_kernel<false><<<b, 128, 0, st>>>(traj_ptr, flow_edge, flow_val, cx->d_rank, X, bmX, bm_next, cx->d_mptr, cx->d_ment, cx->E, b, tmaj);
     SCONE_LAUNCHED();
     return 0;
 }
 
 int scone_rows_mark(const scone_complex* cx, int b, const uint32_t* rows, const int* n_dev, uint32_t* bm_next, int list_cap,
-                    cudaStream_t st, size_t sum_off) {
-    rows_mark_kernel<<<cx->num_sms * 8, 256, 0, st>>>(rows, n_dev, cx->d_mptr, cx->d_ment, b, bm_next, list_cap, sum_off);
+                    cudaStream_t st, bool tmaj, size_t sum_off) {
+    rows_mark_kernel<<<cx->num_sms * 8, 256, 0, st>>>(rows, n_dev, cx->d_mptr, cx->d_ment, b, bm_next, list_cap, sum_off, cx->E, tmaj);
     SCONE_LAUNCHED();
     return 0;
 }
 
 int scone_rows_cone(const scone_complex* cx, int b, const int32_t* last_nodes, uint32_t* bm_top, uint32_t* bm_cand, size_t sum_off,
                     cudaStream_t st) {
-    rows_cone_kernel<<<b, 128, 0, st>>>(last_nodes, cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, bm_top, bm_cand, cx->d_mptr, cx->d_ment,
-                                       cx->N, cx->D, b, sum_off);
+    SCONE_REQUIRE(cx->D <= kRoMaxD, "scone_rows_cone: max degree <= %d", kRoMaxD);
+    rows_cone_kernel<<<b, 256, 0, st>>>(last_nodes, cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, bm_top, bm_cand, cx->d_mptr, cx->d_ment,
+                                       cx->N, cx->D, cx->E, sum_off);
     SCONE_LAUNCHED();
     return 0;
 }
@@ -913,7 +959,7 @@ int scone_compact_rows_summary(const scone_complex* cx, int b, const uint32_t* b
                                unsigned long long* tickets, cudaStream_t st, uint32_t* pref_out, long long list_cap) {
     const long long n1 = summary_words(cx, b);
     int grid = cx->num_sms * 4 < 1024 ? cx->num_sms * 4 : 1024;
-    if (n1 < (long long)grid * 256) grid = (int)((n1 + 255) / 256);
+    if (n1 < (long long)grid * 1024) grid = (int)((n1 + 1023) / 1024);
     if (grid < 1) grid = 1;
     SCONE_CUDA(cudaMemsetAsync(tickets, 0, (size_t)grid * 8, st));
     compact_summary_kernel<<<grid, 256, 0, st>>>(bm, bm + sum_off, n1, list, n_dev, tickets, pref_out, list_cap);
@@ -945,8 +991,8 @@ int scone_rows_layer0_forward(const scone_complex* cx, int act, int b, int cout,
 int scone_rows_layer0_backward(const scone_complex* cx, int b, int cout, const float* X, const float* G, const uint32_t* rows,
                                const int* n_dev, float* dW, int accumulate, float* ws, int g_cap, cudaStream_t st) {
 #define SCONE_L0B(CO)                                                                                                         \
-    if (g_cap > 0) rows_layer0_bwd_kernel<CO, true><<<kDwCtas, 256, 0, st>>>(X, G, cx->d_mptr, cx->d_ment, rows, n_dev, b, ws, g_cap); \
-    else rows_layer0_bwd_kernel<CO, false><<<kDwCtas, 256, 0, st>>>(X, G, cx->d_mptr, cx->d_ment, rows, n_dev, b, ws, g_cap);
+    if (g_cap > 0) rows_layer0_bwd_kernel<CO, true><<<kDwCtas, 256, 0, st>>>(X, G, cx->d_mptr, cx->d_ment, rows, n_dev, b, ws, g_cap, cx->E); \
+    else rows_layer0_bwd_kernel<CO, false><<<kDwCtas, 256, 0, st>>>(X, G, cx->d_mptr, cx->d_ment, rows, n_dev, b, ws, g_cap, cx->E);
     if (cout == 16) { SCONE_L0B(16) }
     else if (cout == 32) { SCONE_L0B(32) }
     else {
@@ -989,7 +1035,7 @@ int scone_rows_readout_forward(const scone_complex* cx, int b, int C, const floa
                                cudaStream_t st) {
     SCONE_REQUIRE(C >= 1 && C <= 32 * kRoMaxCper && cx->D <= kRoMaxD, "scone_rows_readout: C <= %d and max degree <= %d", 32 * kRoMaxCper, kRoMaxD);
     rows_readout_fwd_kernel<<<b, 32 * kRoWarps, 0, st>>>(HL, wout, last_nodes, cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, logprobs, bmH,
-                                                        prefH, bmG, bm_cand, cx->d_mptr, cx->d_ment, cx->N, cx->D, b, C);
+                                                        prefH, bmG, bm_cand, cx->d_mptr, cx->d_ment, cx->N, cx->D, cx->E, C);
     SCONE_LAUNCHED();
     return 0;
 }
@@ -1003,7 +1049,7 @@ int scone_rows_readout_backward(const scone_complex* cx, int act, int b, int C, 
     rows_zero_kernel<<<cx->num_sms * 4, 256, 0, st>>>(reinterpret_cast<float4*>(GL), n_dev, g_cap, C / 4, overflow_dev);
     SCONE_LAUNCHED();
     rows_readout_bwd_kernel<<<b, 32 * kRoWarps, 0, st>>>(HL, wout, last_nodes, cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, logprobs, target_idx,
-                                                        mask, scale, GL, ws, bmH, prefH, bmG, prefG, g_cap, act, cx->N, cx->D, b, C);
+                                                        mask, scale, GL, ws, bmH, prefH, bmG, prefG, g_cap, act, cx->N, cx->D, cx->E, C);
     SCONE_LAUNCHED();
     rows_readout_reduce_kernel<<<1, 256, 0, st>>>(ws, b, C, dwout, nll_sum, count, accumulate);
     SCONE_LAUNCHED();

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) layer_fwd_rows_kernel(const f
                                                                         int b, unsigned long long* __restrict__ row_counter,
                                                                         const uint32_t* __restrict__ bm_in,
                                                                         const uint32_t* __restrict__ pref_in, int out_cap,
-                                                                        int* __restrict__ overflow) {
+                                                                        int* __restrict__ overflow, int E) {
     static_assert(!COMPACT || BITS, "compact storage is addressed through the row bitmaps");
     using G = SlabGeom<CIN, 16>;
     constexpr int NT = COUT / 8, NL = G::NL, Q = G::Q, LPR = CIN / 4;      // Q rows per warp-wide load, LPR lanes per row
@@ -177,8 +177,9 @@ __global__ void __launch_bounds__(kRowsThreads, 1) layer_fwd_rows_kernel(const f
             const int li = slab * 16 + i * Q + gq;
             const bool valid = li < n;
             rid[i] = valid ? __ldg(rows + li) : 0u;
-            const int e = (int)(rid[i] / (unsigned)b);
-            tq[i] = (int)(rid[i] - (unsigned)e * (unsigned)b);
+            const RowIds<COMPACT> ids(rid[i], b, E);
+            const int e = (int)ids.e;
+            tq[i] = (int)ids.toff;                         // e-major: t; trajectory-major (compact): t * E
             const int cpos = (CIN == 32 && i >= 2) ? (cq ^ 4) : cq;
             P[i] = Hb + (size_t)((unsigned)((COMPACT ? 0 : tq[i] * CIN) + 4 * cpos) * 4u);
             asm volatile("" : "+l"(P[i]));                 // keep base + lane offset folded: one IMAD.WIDE per load address
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) layer_fwd_rows_kernel(const f
             unsigned gidx[NL];                             // gather index of the neighbour row: its edge, or its compact rank
 #pragma unroll
             for (int i = 0; i < NL; ++i) {                 // branch-free flag test (entry {0,0} of an idle lane tests row tq: in range)
-                const unsigned nrow = (unsigned)ent[i].x * (unsigned)b + (unsigned)tq[i];       // E*b < 2^32
+                const unsigned nrow = RowIds<COMPACT>::row_of((unsigned)ent[i].x, (unsigned)tq[i], b);       // E*b < 2^32
                 if (COMPACT) {
                     on[i] = rank_lookup(bm_in, pref_in, nrow, gidx[i]) && on[i];
                 } else {
@@ -287,7 +288,7 @@ int launch_fwd_rows(const scone_complex* cx, int b, const float* Hin, const floa
     }
 #define SCONE_ROWS_LAUNCH(BITS_, COMPACT_)                                                                                          \
     layer_fwd_rows_kernel<CIN, COUT, ACT, BITS_, COMPACT_><<<cx->num_sms, kRowsThreads, smem, st>>>(                                \
-        Hin, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, occ_in, rows, n_ptr, b, row_counter, bm_in, pref_in, out_cap, overflow)
+        Hin, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, occ_in, rows, n_ptr, b, row_counter, bm_in, pref_in, out_cap, overflow, cx->E)
     if (bm_in != nullptr && pref_in != nullptr) SCONE_ROWS_LAUNCH(true, true);
     else if (bm_in != nullptr) SCONE_ROWS_LAUNCH(true, false);
     else SCONE_ROWS_LAUNCH(false, false);

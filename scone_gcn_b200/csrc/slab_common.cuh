@@ -28,6 +28,30 @@ __device__ __forceinline__ void bit_set(uint32_t* __restrict__ bm, size_t row) {
     const uint32_t bit = 1u << (row & 31);
     if (!(*w & bit)) atomicOr(w, bit);
 }
+// Row ids.  Dense tensors [E][b][C] (pipeline 1) number their rows edge-major, id = e * b + t.  COMPACT tensors (pipelines 2 / 3) are
+// numbered TRAJECTORY-major, id = t * E + e: the rows of one trajectory are a few clusters of the locality-ordered edge range, so
+// a slab's 16 list rows, their neighbour rows, the bitmap / prefix words of the rank lookups and the X entries of the first layer
+// are cache neighbours (edge-major ids put every (e', t) in its own 128-byte line).  toff is what a neighbour's id adds to its
+// edge term: t (edge-major) or t * E (trajectory-major).
+template <bool TMAJ>
+struct RowIds {
+    unsigned e, toff;
+    __device__ __forceinline__ RowIds(unsigned rid, int b, int E) {
+        if (TMAJ) {
+            const unsigned t = rid / (unsigned)E;
+            toff = t * (unsigned)E;
+            e = rid - toff;
+        } else {
+            e = rid / (unsigned)b;
+            toff = rid - e * (unsigned)b;
+        }
+        this->b = (unsigned)b;
+    }
+    unsigned b;
+    __device__ __forceinline__ unsigned row(unsigned edge) const { return TMAJ ? toff + edge : edge * b + toff; }
+    static __device__ __forceinline__ unsigned row_of(unsigned edge, unsigned toff_, int b_) { return TMAJ ? toff_ + edge : edge * (unsigned)b_ + toff_; }
+};
+
 // two-level bitmap: bm1 = one summary bit per 32-bit word of bm, set by whoever turns a word non-zero; the compaction and the
 // clearing of a sparse bitmap then scan 1/32 of its bytes (compact_summary_kernel, clear_summary_kernel in scone_rows.cu)
 __device__ __forceinline__ void bit_set2(uint32_t* __restrict__ bm, uint32_t* __restrict__ bm1, size_t row) {
