@@ -19,7 +19,8 @@ namespace {
 
 #include "slab_common.cuh"
 
-constexpr int kRoWarps = 4, kRoMaxD = 128, kRoMaxCper = 4;     // readout / cone kernels: max degree, channels per lane
+constexpr int kRoWarps = 8, kRoMaxD = 128, kRoMaxCper = 4;     // readout / cone kernels: max degree, channels per lane
+constexpr int kRoItems = 1024;                                  // (neighbour, incident edge) pairs of a trajectory staged in shared memory
 
 template <int ACT>
 __device__ __forceinline__ float act_scalar(float z) {
@@ -82,18 +83,68 @@ __global__ void __launch_bounds__(256) rows_mark_kernel(const uint32_t* __restri
 // Compaction of a SPARSE two-level bitmap (see bit_set2): same contract as compact_bitmap_kernel (ascending row list, count, rank
 // prefix per non-empty word, one launch, per-CTA totals + decoupled look-back over tickets, deterministic) but the CTAs scan the
 // summary words and touch only the bitmap words whose summary bit is set.  tickets[] must be zero at launch.
+constexpr int kSumWpt = 4, kSumChunk = kSumWpt * 256, kSumMaxChunks = 64;
+// A warp walks its 128 summary words of a chunk (4 per lane, ascending = lane-major) COOPERATIVELY: for every non-empty summary
+// word the 32 lanes load the 32 bitmap words under it (one 128-byte line) at once.  With trajectory-major row ids the set bits
+// of a sparse bitmap sit in a few dense clusters; a thread-per-word walk left all the work to a handful of threads.
+// WRITE = false: returns this lane's share of the count (sum over the warp = rows under the warp's words).
+// WRITE = true: rows are written from list index `off` on (ascending), prefixes for the non-empty bitmap words.
+template <bool WRITE>
+__device__ __forceinline__ long long summary_walk(const uint32_t* __restrict__ bm, long long w1_lane, const uint32_t (&sm)[kSumWpt],
+                                                  long long off, uint32_t* __restrict__ list, uint32_t* __restrict__ pref_out,
+                                                  long long list_cap) {
+    const int lane = threadIdx.x & 31;
+    long long cnt = 0;
+    unsigned mask = __ballot_sync(0xffffffffu, (sm[0] | sm[1] | sm[2] | sm[3]) != 0u);
+    while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const long long w1s = __shfl_sync(0xffffffffu, w1_lane, src);
+#pragma unroll
+        for (int k = 0; k < kSumWpt; ++k) {
+            const uint32_t word = __shfl_sync(0xffffffffu, sm[k], src);
+            if (word == 0u) continue;                     // (uniform)
+            const long long w = (w1s + k) * 32 + lane;    // this lane's bitmap word
+            uint32_t cc = (word >> lane) & 1u ? __ldg(bm + w) : 0u;
+            const int c = __popc(cc);
+            if (!WRITE) {
+                cnt += c;
+            } else {
+                int incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                long long o2 = off + incl - c;
+                if (c) {
+                    if (pref_out != nullptr) pref_out[w] = (uint32_t)o2;
+                    while (cc) {
+                        const int pbit = __ffs(cc) - 1;
+                        cc &= cc - 1;
+                        if (o2 < list_cap) list[o2] = (uint32_t)(w * 32 + pbit);
+                        ++o2;
+                    }
+                }
+                off += __shfl_sync(0xffffffffu, incl, 31);
+            }
+        }
+    }
+    return WRITE ? off : cnt;
+}
+
 __global__ void __launch_bounds__(256) compact_summary_kernel(const uint32_t* __restrict__ bm, const uint32_t* __restrict__ bm1,
                                                              long long n1_words, uint32_t* __restrict__ list, int* __restrict__ n_out,
                                                              unsigned long long* __restrict__ tickets, uint32_t* __restrict__ pref_out,
                                                              long long list_cap) {
-    constexpr int WPT = 4, kChunk = WPT * 256;            // summary words per thread (one 128-bit load) and per CTA iteration
-    __shared__ int s_warp[8];
+    __shared__ int s_cnt[kSumMaxChunks * 8];              // rows under (chunk, warp), chunk-major = ascending
     __shared__ long long s_prefix;
     __shared__ int s_total;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long per_cta = ((n1_words + gridDim.x - 1) / gridDim.x + kChunk - 1) / kChunk * kChunk;     // whole chunks
+    const long long per_cta = ((n1_words + gridDim.x - 1) / gridDim.x + kSumChunk - 1) / kSumChunk * kSumChunk;     // whole chunks
     const long long lo = (long long)blockIdx.x * per_cta, hi = lo + per_cta < n1_words ? lo + per_cta : n1_words;
-    auto load4 = [&](long long w1, uint32_t (&sm)[WPT]) { // summary words w1 .. w1+3 (w1 % 4 == 0; the summary is padded), zero beyond hi
+    const int n_chunks = hi > lo ? (int)((hi - lo + kSumChunk - 1) / kSumChunk) : 0;
+    auto load4 = [&](long long w1, uint32_t (&sm)[kSumWpt]) {   // summary words w1 .. w1+3 (w1 % 4 == 0; the summary is padded), zero beyond hi
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if (w1 < hi) v = __ldg(reinterpret_cast<const uint4*>(bm1 + w1));
         sm[0] = v.x;
@@ -101,33 +152,20 @@ __global__ void __launch_bounds__(256) compact_summary_kernel(const uint32_t* __
         sm[2] = w1 + 2 < hi ? v.z : 0u;
         sm[3] = w1 + 3 < hi ? v.w : 0u;
     };
-    auto count4 = [&](long long w1, const uint32_t (&sm)[WPT]) {
-        int c = 0;
-#pragma unroll
-        for (int k = 0; k < WPT; ++k) {
-            uint32_t m = sm[k];
-            while (m) {
-                const int q = __ffs(m) - 1;
-                m &= m - 1;
-                c += __popc(__ldg(bm + (w1 + k) * 32 + q));
-            }
-        }
-        return c;
-    };
-    int cnt = 0;
-    for (long long w1 = lo + (long long)WPT * threadIdx.x; w1 < hi; w1 += kChunk) {
-        uint32_t sm[WPT];
+    for (int c = 0; c < n_chunks; ++c) {
+        const long long w1 = lo + (long long)c * kSumChunk + (long long)kSumWpt * threadIdx.x;
+        uint32_t sm[kSumWpt];
         load4(w1, sm);
-        cnt += count4(w1, sm);
-    }
+        int cnt = (int)summary_walk<false>(bm, w1, sm, 0, nullptr, nullptr, 0);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0) s_warp[warp] = cnt;
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) s_cnt[c * 8 + warp] = cnt;
+    }
     if (threadIdx.x == 0) s_prefix = 0;
     __syncthreads();
     if (threadIdx.x == 0) {
         int total = 0;
-        for (int k = 0; k < 8; ++k) total += s_warp[k];
+        for (int k = 0; k < n_chunks * 8; ++k) total += s_cnt[k];
         s_total = total;
         atomicExch(tickets + blockIdx.x, (1ull << 63) | (unsigned long long)(unsigned)total);
     }
@@ -139,55 +177,23 @@ __global__ void __launch_bounds__(256) compact_summary_kernel(const uint32_t* __
     }
     if (part) atomicAdd((unsigned long long*)&s_prefix, (unsigned long long)part);
     __syncthreads();
-    long long base = s_prefix;
+    const long long base = s_prefix;
     const int total = s_total;
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
         n_out[0] = (int)(base + total);
         n_out[1] = 0;                                     // tile counter of the row-list kernel that consumes this list
     }
     if (total == 0) return;                               // (uniform) nothing set in this slice
-    for (long long w0 = lo; w0 < hi; w0 += kChunk) {
-        const long long w1 = w0 + (long long)WPT * threadIdx.x;
-        uint32_t sm[WPT];
+    for (int c = 0; c < n_chunks; ++c) {
+        if (s_cnt[c * 8 + warp] == 0) continue;           // (warp-uniform)
+        int before = 0;                                   // rows of this CTA before (c, warp)
+        for (int k = lane; k < c * 8 + warp; k += 32) before += s_cnt[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+        const long long w1 = lo + (long long)c * kSumChunk + (long long)kSumWpt * threadIdx.x;
+        uint32_t sm[kSumWpt];
         load4(w1, sm);
-        const int n = count4(w1, sm);
-        int incl = n;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        __syncthreads();                                  // s_warp of the previous chunk fully consumed
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        int woff = 0, ctot = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int v = s_warp[k];
-            if (k < warp) woff += v;
-            ctot += v;
-        }
-        if (n) {
-            long long off = base + woff + incl - n;
-#pragma unroll
-            for (int k = 0; k < WPT; ++k) {
-                uint32_t m = sm[k];
-                while (m) {
-                    const int q = __ffs(m) - 1;
-                    m &= m - 1;
-                    const long long w = (w1 + k) * 32 + q;
-                    uint32_t cc = __ldg(bm + w);
-                    if (pref_out != nullptr) pref_out[w] = (uint32_t)off;
-                    while (cc) {
-                        const int pbit = __ffs(cc) - 1;
-                        cc &= cc - 1;
-                        if (off < list_cap) list[off] = (uint32_t)(w * 32 + pbit);
-                        ++off;
-                    }
-                }
-            }
-        }
-        base += ctot;
+        summary_walk<true>(bm, w1, sm, base + before, list, pref_out, list_cap);
     }
 }
 
@@ -306,14 +312,15 @@ __global__ void __launch_bounds__(256) rows_layer0_fwd_kernel(const float* __res
 // takes 32 consecutive list rows: lane = row for the scalar gathers of X (exact small integers), then lane = channel walks the 32
 // rows (coalesced G rows, a_k by shuffle).  Fixed row -> warp mapping and order; per-CTA partials [3][COUT] (reduced by
 // rows_reduce_kernel): deterministic.
+constexpr int kL0bWarps = 32;      // the gathers are latency-bound: full occupancy (2 CTAs x 32 warps per SM)
 template <int COUT, bool COMPACT>
-__global__ void __launch_bounds__(256) rows_layer0_bwd_kernel(const float* __restrict__ X, const float* __restrict__ G,
+__global__ void __launch_bounds__(32 * kL0bWarps) rows_layer0_bwd_kernel(const float* __restrict__ X, const float* __restrict__ G,
                                                              const int32_t* __restrict__ mptr, const int2* __restrict__ ment,
                                                              const uint32_t* __restrict__ rows, const int* __restrict__ n_ptr, int b,
                                                              float* __restrict__ partial /* [grid][3*COUT] */, int cap, int E) {
     static_assert(COUT == 16 || COUT == 32, "first-layer row kernel: widths 16 / 32");
     constexpr int RPI = 32 / COUT;                             // rows per iteration of the channel loop
-    __shared__ float red[8][3 * 32];
+    __shared__ float red[kL0bWarps][3 * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int n = *n_ptr;
     if (COMPACT && n > cap) n = cap;
@@ -322,7 +329,7 @@ __global__ void __launch_bounds__(256) rows_layer0_bwd_kernel(const float* __res
     const int lo = min(n_groups, (int)blockIdx.x * per), hi = min(n_groups, lo + per);
     const int c = lane % COUT, sub = lane / COUT;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
-    for (int grp = lo + warp; grp < hi; grp += 8) {
+    for (int grp = lo + warp; grp < hi; grp += kL0bWarps) {
         const int li = grp * 32 + lane;
         uint32_t rid = 0;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
@@ -367,7 +374,7 @@ __global__ void __launch_bounds__(256) rows_layer0_bwd_kernel(const float* __res
         const int k = o / COUT, cc = o % COUT;
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) s += red[w][k * 32 + cc];
+        for (int w = 0; w < kL0bWarps; ++w) s += red[w][k * 32 + cc];
         partial[(size_t)blockIdx.x * 3 * COUT + o] = s;
     }
 }
@@ -675,6 +682,38 @@ __global__ void __launch_bounds__(256) rows_reduce_kernel(const float* __restric
 // One CTA (4 warps) per trajectory, warps split the neighbour slots (same arithmetic as readout_kernel).
 // ---------------------------------------------------------------------------------------------------------------
 
+// The (neighbour slot j, incident edge) pairs of a trajectory are flattened: a first phase resolves every pair's row (sign, rank
+// in H_L's storage, rank in G_L's) with one thread per pair — all lookups in flight at once — into shared memory; the second
+// phase (warp per neighbour slot, rows in ascending pair order: the summation order of the sequential version) then issues its
+// row loads four deep.  Pairs beyond kRoItems are resolved on the fly.
+struct RoItem {
+    int hidx;        // rank of the row in H_L's storage, -1: the row is exactly zero
+    int gidx;        // rank in G_L's storage (backward)
+    float sign;
+};
+struct RoPairs {
+    int s_ptr[kRoMaxD], s_off[kRoMaxD + 1];
+    __device__ __forceinline__ int setup(const int32_t* __restrict__ nbrhoods, const int32_t* __restrict__ inc_ptr, int last, bool last_ok, int D) {
+        for (int j = threadIdx.x; j < D; j += blockDim.x) {
+            const int nbr = last_ok ? nbrhoods[(size_t)last * D + j] : -1;
+            s_ptr[j] = nbr >= 0 ? inc_ptr[nbr] : -1;
+            s_off[j + 1] = nbr >= 0 ? inc_ptr[nbr + 1] - inc_ptr[nbr] : 0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_off[0] = 0;
+            for (int j = 0; j < D; ++j) s_off[j + 1] += s_off[j];
+        }
+        __syncthreads();
+        return s_off[D];
+    }
+    __device__ __forceinline__ int slot_of(int i) const {
+        int j = 0;
+        while (s_off[j + 1] <= i) ++j;
+        return j;
+    }
+};
+
 __global__ void __launch_bounds__(32 * kRoWarps) rows_readout_fwd_kernel(const float* __restrict__ HL, const float* __restrict__ wout,
                                                                         const int32_t* __restrict__ last_nodes, const int32_t* __restrict__ nbrhoods,
                                                                         const int32_t* __restrict__ inc_ptr, const int2* __restrict__ inc_ent,
@@ -683,34 +722,61 @@ __global__ void __launch_bounds__(32 * kRoWarps) rows_readout_fwd_kernel(const f
                                                                         uint32_t* __restrict__ bm_cand, const int32_t* __restrict__ mptr,
                                                                         const int2* __restrict__ ment, int N, int D, int E, int C) {
     __shared__ float logit[kRoMaxD];
+    __shared__ RoPairs pairs;
+    __shared__ RoItem items[kRoItems];
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int t = blockIdx.x;
     const int last = last_nodes[t];
     const bool last_ok = last >= 0 && last < N;
+    const unsigned tbase = (unsigned)t * (unsigned)E;      // compact tensors: trajectory-major row ids
+    const int total = pairs.setup(nbrhoods, inc_ptr, last, last_ok, D);
+    auto resolve = [&](int i, int j) {
+        const int2 es = inc_ent[pairs.s_ptr[j] + (i - pairs.s_off[j])];
+        RoItem it;
+        unsigned idx;
+        it.hidx = rank_lookup(bmH, prefH, tbase + (unsigned)es.x, idx) ? (int)idx : -1;
+        it.gidx = es.x;
+        it.sign = __int_as_float(es.y);
+        return it;
+    };
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const RoItem it = resolve(i, pairs.slot_of(i));
+        if (i < kRoItems) items[i] = it;
+        if (bmG != nullptr) {                              // gradient wanted (pipeline 2): this row of G_L will be written
+            bit_set(bmG, tbase + (unsigned)it.gidx);
+            if (bm_cand != nullptr)
+                for (int q = mptr[it.gidx]; q < mptr[it.gidx + 1]; ++q) bit_set(bm_cand, tbase + (unsigned)ment[q].x);
+        }
+    }
+    __syncthreads();
     float w[kRoMaxCper];
 #pragma unroll
     for (int q = 0; q < kRoMaxCper; ++q) w[q] = (lane + 32 * q < C) ? wout[lane + 32 * q] : 0.f;
     for (int j = warp; j < D; j += kRoWarps) {
-        const int nbr = last_ok ? nbrhoods[(size_t)last * D + j] : -1;
         float l = 0.f;
-        if (nbr >= 0) {
-            float part = 0.f;
+        if (pairs.s_ptr[j] >= 0) {
             float z[kRoMaxCper] = {0.f, 0.f, 0.f, 0.f};
-            for (int p = inc_ptr[nbr]; p < inc_ptr[nbr + 1]; ++p) {
-                const int2 es = inc_ent[p];
-                const unsigned row = (unsigned)t * (unsigned)E + (unsigned)es.x;      // compact tensors: trajectory-major row ids
-                if (bmG != nullptr) {                      // gradient wanted: this row of G_L will be written
-                    if (lane == 0) bit_set(bmG, row);
-                    if (bm_cand != nullptr)
-                        for (int q = mptr[es.x] + lane; q < mptr[es.x + 1]; q += 32) bit_set(bm_cand, (unsigned)t * (unsigned)E + (unsigned)ment[q].x);
-                }
-                unsigned idx;
-                if (!rank_lookup(bmH, prefH, row, idx)) continue;      // row is exactly zero
-                const float* hrow = HL + (size_t)idx * C;
+            const int i1 = pairs.s_off[j + 1];
+            for (int i0 = pairs.s_off[j]; i0 < i1; i0 += 4) {
+                RoItem it[4];
+                float hv[4][kRoMaxCper];
 #pragma unroll
-                for (int q = 0; q < kRoMaxCper; ++q)
-                    if (lane + 32 * q < C) z[q] = fmaf(__int_as_float(es.y), hrow[lane + 32 * q], z[q]);
+                for (int u = 0; u < 4; ++u) {
+                    it[u].hidx = -1;
+                    it[u].sign = 0.f;
+                    if (i0 + u < i1) it[u] = i0 + u < kRoItems ? items[i0 + u] : resolve(i0 + u, j);
+#pragma unroll
+                    for (int q = 0; q < kRoMaxCper; ++q)
+                        hv[u][q] = (it[u].hidx >= 0 && lane + 32 * q < C) ? __ldg(HL + (size_t)it[u].hidx * C + lane + 32 * q) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (it[u].hidx >= 0) {                 // (an absent row is skipped, not added as 0: same sums as before)
+#pragma unroll
+                        for (int q = 0; q < kRoMaxCper; ++q) z[q] = fmaf(it[u].sign, hv[u][q], z[q]);
+                    }
             }
+            float part = 0.f;
 #pragma unroll
             for (int q = 0; q < kRoMaxCper; ++q) part = fmaf(z[q], w[q], part);
 #pragma unroll
@@ -756,10 +822,28 @@ __global__ void __launch_bounds__(32 * kRoWarps) rows_readout_bwd_kernel(const f
                                                                         const uint32_t* __restrict__ prefH, const uint32_t* __restrict__ bmG,
                                                                         const uint32_t* __restrict__ prefG, int g_cap, int act, int N, int D, int E, int C) {
     __shared__ float s_dw[kRoWarps][32 * kRoMaxCper];
+    __shared__ RoPairs pairs;
+    __shared__ RoItem items[kRoItems];
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int t = blockIdx.x;
     const int last = last_nodes[t];
     const bool last_ok = last >= 0 && last < N;
+    const unsigned tbase = (unsigned)t * (unsigned)E;
+    const int total = pairs.setup(nbrhoods, inc_ptr, last, last_ok, D);
+    auto resolve = [&](int i, int j) {
+        const int2 es = inc_ent[pairs.s_ptr[j] + (i - pairs.s_off[j])];
+        const unsigned row = tbase + (unsigned)es.x;
+        RoItem it;
+        unsigned hidx, gidx;
+        it.hidx = rank_lookup(bmH, prefH, row, hidx) ? (int)hidx : -1;
+        if (bmG == bmH && prefG == prefH) gidx = hidx;     // cone pipeline: G_L and H_L share their row set
+        else rank_lookup(bmG, prefG, row, gidx);
+        it.gidx = (int)gidx;
+        it.sign = __int_as_float(es.y);
+        return it;
+    };
+    for (int i = threadIdx.x; i < total && i < kRoItems; i += blockDim.x) items[i] = resolve(i, pairs.slot_of(i));
+    __syncthreads();
     float w[kRoMaxCper];
 #pragma unroll
     for (int q = 0; q < kRoMaxCper; ++q) w[q] = (lane + 32 * q < C) ? wout[lane + 32 * q] : 0.f;
@@ -767,25 +851,35 @@ __global__ void __launch_bounds__(32 * kRoWarps) rows_readout_bwd_kernel(const f
     const int y = target_idx[t];
     float dwl[kRoMaxCper] = {0.f, 0.f, 0.f, 0.f};
     for (int j = warp; j < D; j += kRoWarps) {
-        const int nbr = last_ok ? nbrhoods[(size_t)last * D + j] : -1;
-        if (nbr < 0) continue;
+        if (pairs.s_ptr[j] < 0) continue;
         const float dl = mk * scale * (expf(logprobs[(size_t)t * D + j]) - (j == y ? 1.f : 0.f));
-        for (int p = inc_ptr[nbr]; p < inc_ptr[nbr + 1]; ++p) {
-            const int2 es = inc_ent[p];
-            const unsigned row = (unsigned)t * (unsigned)E + (unsigned)es.x;
-            unsigned hidx, gidx;
-            const bool hset = rank_lookup(bmH, prefH, row, hidx);
-            rank_lookup(bmG, prefG, row, gidx);
-            if ((int)gidx >= g_cap) continue;              // overflow already flagged by rows_zero_kernel
-            const float sdl = __int_as_float(es.y) * dl;
+        const int i1 = pairs.s_off[j + 1];
+        for (int i0 = pairs.s_off[j]; i0 < i1; i0 += 4) {
+            RoItem it[4];
+            float hv[4][kRoMaxCper];
 #pragma unroll
-            for (int q = 0; q < kRoMaxCper; ++q)
-                if (lane + 32 * q < C) {
-                    const float h = hset ? HL[(size_t)hidx * C + lane + 32 * q] : 0.f;
-                    dwl[q] = fmaf(sdl, h, dwl[q]);
-                    const float da = act == SCONE_ACT_TANH ? 1.f - h * h : (act == SCONE_ACT_LEAKY_RELU ? (h >= 0.f ? 1.f : 0.01f) : (h > 0.f ? 1.f : 0.f));
-                    atomicAdd(GL + (size_t)gidx * C + lane + 32 * q, sdl * w[q] * da);
-                }
+            for (int u = 0; u < 4; ++u) {
+                it[u].hidx = -1;
+                it[u].gidx = g_cap;                        // (skipped below)
+                it[u].sign = 0.f;
+                if (i0 + u < i1) it[u] = i0 + u < kRoItems ? items[i0 + u] : resolve(i0 + u, j);
+#pragma unroll
+                for (int q = 0; q < kRoMaxCper; ++q)
+                    hv[u][q] = (it[u].hidx >= 0 && lane + 32 * q < C) ? __ldg(HL + (size_t)it[u].hidx * C + lane + 32 * q) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i0 + u >= i1 || it[u].gidx >= g_cap) continue;      // overflow already flagged by rows_zero_kernel
+                const float sdl = it[u].sign * dl;
+#pragma unroll
+                for (int q = 0; q < kRoMaxCper; ++q)
+                    if (lane + 32 * q < C) {
+                        const float h = hv[u][q];
+                        dwl[q] = fmaf(sdl, h, dwl[q]);
+                        const float da = act == SCONE_ACT_TANH ? 1.f - h * h : (act == SCONE_ACT_LEAKY_RELU ? (h >= 0.f ? 1.f : 0.01f) : (h > 0.f ? 1.f : 0.f));
+                        atomicAdd(GL + (size_t)it[u].gidx * C + lane + 32 * q, sdl * w[q] * da);
+                    }
+            }
         }
     }
 #pragma unroll
@@ -807,28 +901,28 @@ __global__ void __launch_bounds__(32 * kRoWarps) rows_readout_bwd_kernel(const f
     }
 }
 
-// dwout[c] (+)= sum_t partial[t][c]; nll (+)= sum_t partial[t][C]; count (+)= sum_t partial[t][C+1]  (t ascending, 8 fixed slices)
+// dwout[c] (+)= sum_t partial[t][c]; nll (+)= sum_t partial[t][C]; count (+)= sum_t partial[t][C+1]: one warp per output, lane l sums
+// t = l, l + 32, ... in ascending order, then a fixed butterfly — deterministic
 __global__ void __launch_bounds__(256) rows_readout_reduce_kernel(const float* __restrict__ partial, int b, int C, float* __restrict__ dwout,
                                                                  float* __restrict__ nll, float* __restrict__ count, int accumulate) {
-    __shared__ float red[8][64];
-    const int c = threadIdx.x & 31, slice = threadIdx.x >> 5;
-    for (int c0 = 0; c0 < C + 2; c0 += 32) {
-        const int cc = c0 + c;
-        const int per = (b + 7) / 8;
-        const int t0 = slice * per, t1 = min(b, t0 + per);
-        float s = 0.f;
-        if (cc < C + 2)
-            for (int t = t0; t < t1; ++t) s += partial[(size_t)t * (C + 2) + cc];
-        __syncthreads();
-        red[slice][c] = s;
-        __syncthreads();
-        if (slice == 0 && cc < C + 2) {
-            float tsum = red[0][c];
+    const int lane = threadIdx.x & 31;
+    const int cc = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (cc >= C + 2) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int t = lane;
+    for (; t + 96 < b; t += 128) {
+        s0 += partial[(size_t)t * (C + 2) + cc];
+        s1 += partial[(size_t)(t + 32) * (C + 2) + cc];
+        s2 += partial[(size_t)(t + 64) * (C + 2) + cc];
+        s3 += partial[(size_t)(t + 96) * (C + 2) + cc];
+    }
+    for (; t < b; t += 32) s0 += partial[(size_t)t * (C + 2) + cc];
+    float s = (s0 + s1) + (s2 + s3);
 #pragma unroll
-            for (int k = 1; k < 8; ++k) tsum += red[k][c];
-            float* dst = cc < C ? dwout + cc : (cc == C ? nll : count);
-            *dst = accumulate ? *dst + tsum : tsum;
-        }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        float* dst = cc < C ? dwout + cc : (cc == C ? nll : count);
+        *dst = accumulate ? *dst + s : s;
     }
 }
 
@@ -959,8 +1053,9 @@ int scone_compact_rows_summary(const scone_complex* cx, int b, const uint32_t* b
                                unsigned long long* tickets, cudaStream_t st, uint32_t* pref_out, long long list_cap) {
     const long long n1 = summary_words(cx, b);
     int grid = cx->num_sms * 4 < 1024 ? cx->num_sms * 4 : 1024;
-    if (n1 < (long long)grid * 1024) grid = (int)((n1 + 1023) / 1024);
+    if (n1 < (long long)grid * kSumChunk) grid = (int)((n1 + kSumChunk - 1) / kSumChunk);
     if (grid < 1) grid = 1;
+    SCONE_REQUIRE((n1 + grid - 1) / grid <= (long long)kSumMaxChunks * kSumChunk, "scone_compact_rows_summary: bitmap too large for %d CTAs", grid);
     SCONE_CUDA(cudaMemsetAsync(tickets, 0, (size_t)grid * 8, st));
     compact_summary_kernel<<<grid, 256, 0, st>>>(bm, bm + sum_off, n1, list, n_dev, tickets, pref_out, list_cap);
     SCONE_LAUNCHED();
@@ -991,8 +1086,8 @@ int scone_rows_layer0_forward(const scone_complex* cx, int act, int b, int cout,
 int scone_rows_layer0_backward(const scone_complex* cx, int b, int cout, const float* X, const float* G, const uint32_t* rows,
                                const int* n_dev, float* dW, int accumulate, float* ws, int g_cap, cudaStream_t st) {
 #define SCONE_L0B(CO)                                                                                                         \
-    if (g_cap > 0) rows_layer0_bwd_kernel<CO, true><<<kDwCtas, 256, 0, st>>>(X, G, cx->d_mptr, cx->d_ment, rows, n_dev, b, ws, g_cap, cx->E); \
-    else rows_layer0_bwd_kernel<CO, false><<<kDwCtas, 256, 0, st>>>(X, G, cx->d_mptr, cx->d_ment, rows, n_dev, b, ws, g_cap, cx->E);
+    if (g_cap > 0) rows_layer0_bwd_kernel<CO, true><<<kDwCtas, 32 * kL0bWarps, 0, st>>>(X, G, cx->d_mptr, cx->d_ment, rows, n_dev, b, ws, g_cap, cx->E); \
+    else rows_layer0_bwd_kernel<CO, false><<<kDwCtas, 32 * kL0bWarps, 0, st>>>(X, G, cx->d_mptr, cx->d_ment, rows, n_dev, b, ws, g_cap, cx->E);
     if (cout == 16) { SCONE_L0B(16) }
     else if (cout == 32) { SCONE_L0B(32) }
     else {
@@ -1051,7 +1146,7 @@ int scone_rows_readout_backward(const scone_complex* cx, int act, int b, int C, 
     rows_readout_bwd_kernel<<<b, 32 * kRoWarps, 0, st>>>(HL, wout, last_nodes, cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, logprobs, target_idx,
                                                         mask, scale, GL, ws, bmH, prefH, bmG, prefG, g_cap, act, cx->N, cx->D, cx->E, C);
     SCONE_LAUNCHED();
-    rows_readout_reduce_kernel<<<1, 256, 0, st>>>(ws, b, C, dwout, nll_sum, count, accumulate);
+    rows_readout_reduce_kernel<<<(C + 2 + 7) / 8, 256, 0, st>>>(ws, b, C, dwout, nll_sum, count, accumulate);
     SCONE_LAUNCHED();
     return 0;
 }
