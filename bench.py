@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 
 CONFIGS = {
     # name: (n_nodes for the generator, per-GPU batch, hidden, micro-batch)
-    'cfg5': dict(n_nodes=370000, batch=4096, hidden=32, micro_batch=2048,
+    'cfg5': dict(n_nodes=370000, batch=4096, hidden=32, micro_batch=4096,
                  desc='1M-edge synthetic holed Delaunay complex, 4096 trajectories per GPU (32768 at 8 GPUs), 3-layer SCoNe hidden 32'),
     'cfg4': dict(n_nodes=110000, batch=4096, hidden=32, micro_batch=4096,
                  desc='~300k-edge synthetic complex, batch 4096, 3-layer SCoNe hidden 32'),

@@ -490,8 +490,14 @@ extern "C" int scone_model_create(const scone_complex* cx, int32_t n_layers, con
     m->d_G.assign(n_layers, nullptr);
     m->d_occH.assign(n_layers, nullptr);
     m->d_occG.assign(n_layers, nullptr);
-    m->rows_ok = scone_rows_supported(cx, n_layers, hidden) && E * mb < ((size_t)1 << 31);
+    // row ids are 32-bit: unsigned (E * mb < 2^32) in the compact trajectory-major pipelines, E * mb < 2^31 elsewhere
+    m->rows_ok = scone_rows_supported(cx, n_layers, hidden) && E * mb < ((size_t)1 << 32);
     m->pipeline = m->rows_ok ? 3 : 0;
+    if (!m->rows_ok && E * mb >= ((size_t)1 << 31)) {
+        scone_set_error("scone_model_create: E * micro_batch = %zu needs the row-list pipeline (widths 16 / 32, E * micro_batch < 2^32)", E * mb);
+        delete m;
+        return 2;
+    }
     int64_t ws = scone_readout_workspace_bytes(micro_batch, m->cmax);
     if (scone_rows_dw_workspace_bytes(m->cmax, m->cmax) > ws) ws = scone_rows_dw_workspace_bytes(m->cmax, m->cmax);
     cin = 1;
@@ -558,6 +564,7 @@ extern "C" int scone_model_destroy(scone_model* m) {
 extern "C" int64_t scone_model_num_params(const scone_model* m) { return m ? m->n_params : -1; }
 extern "C" int scone_model_set_zero_fill(scone_model* m, int32_t on) {
     SCONE_REQUIRE(m != nullptr, "scone_model_set_zero_fill: NULL model");
+    SCONE_REQUIRE(!on || (size_t)m->cx->E * m->mb < ((size_t)1 << 31), "scone_model_set_zero_fill: E * micro_batch >= 2^31 runs on pipeline 3 only");
     m->zero_fill = on != 0;
     return ensure_buffers(m);
 }
@@ -567,6 +574,8 @@ extern "C" int scone_model_set_pipeline(scone_model* m, int32_t which) {
                   "scone_model_set_pipeline: 0 (unit kernels, byte flags), 1 (row lists, dense tensors), 2 (row lists, compact tensors) or "
                   "3 (compact row lists over the readout cone)");
     SCONE_REQUIRE(which == 0 || m->rows_ok, "scone_model_set_pipeline: the row-list pipelines need hidden widths in {16, 32}");
+    SCONE_REQUIRE(which == 3 || (size_t)m->cx->E * m->mb < ((size_t)1 << 31),
+                  "scone_model_set_pipeline: E * micro_batch >= 2^31 runs on pipeline 3 only");
     const int old = m->pipeline;
     m->pipeline = which;
     if (ensure_buffers(m)) {

@@ -83,8 +83,8 @@ __global__ void __launch_bounds__(256) rows_mark_kernel(const uint32_t* __restri
 // Compaction of a SPARSE two-level bitmap (see bit_set2): same contract as compact_bitmap_kernel (ascending row list, count, rank
 // prefix per non-empty word, one launch, per-CTA totals + decoupled look-back over tickets, deterministic) but the CTAs scan the
 // summary words and touch only the bitmap words whose summary bit is set.  tickets[] must be zero at launch.
-constexpr int kSumWpt = 4, kSumChunk = kSumWpt * 256, kSumMaxChunks = 64;
-// A warp walks its 128 summary words of a chunk (4 per lane, ascending = lane-major) COOPERATIVELY: for every non-empty summary
+constexpr int kSumWpt = 16, kSumChunk = kSumWpt * 256, kSumMaxChunks = 64;
+// A warp walks its 512 summary words of a chunk (16 per lane, ascending = lane-major) COOPERATIVELY: for every non-empty summary
 // word the 32 lanes load the 32 bitmap words under it (one 128-byte line) at once.  With trajectory-major row ids the set bits
 // of a sparse bitmap sit in a few dense clusters; a thread-per-word walk left all the work to a handful of threads.
 // WRITE = false: returns this lane's share of the count (sum over the warp = rows under the warp's words).
@@ -95,7 +95,10 @@ __device__ __forceinline__ long long summary_walk(const uint32_t* __restrict__ b
                                                   long long list_cap) {
     const int lane = threadIdx.x & 31;
     long long cnt = 0;
-    unsigned mask = __ballot_sync(0xffffffffu, (sm[0] | sm[1] | sm[2] | sm[3]) != 0u);
+    uint32_t any = 0u;
+#pragma unroll
+    for (int k = 0; k < kSumWpt; ++k) any |= sm[k];
+    unsigned mask = __ballot_sync(0xffffffffu, any != 0u);
     while (mask) {
         const int src = __ffs(mask) - 1;
         mask &= mask - 1;
@@ -144,13 +147,16 @@ __global__ void __launch_bounds__(256) compact_summary_kernel(const uint32_t* __
     const long long per_cta = ((n1_words + gridDim.x - 1) / gridDim.x + kSumChunk - 1) / kSumChunk * kSumChunk;     // whole chunks
     const long long lo = (long long)blockIdx.x * per_cta, hi = lo + per_cta < n1_words ? lo + per_cta : n1_words;
     const int n_chunks = hi > lo ? (int)((hi - lo + kSumChunk - 1) / kSumChunk) : 0;
-    auto load4 = [&](long long w1, uint32_t (&sm)[kSumWpt]) {   // summary words w1 .. w1+3 (w1 % 4 == 0; the summary is padded), zero beyond hi
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (w1 < hi) v = __ldg(reinterpret_cast<const uint4*>(bm1 + w1));
-        sm[0] = v.x;
-        sm[1] = w1 + 1 < hi ? v.y : 0u;
-        sm[2] = w1 + 2 < hi ? v.z : 0u;
-        sm[3] = w1 + 3 < hi ? v.w : 0u;
+    auto load4 = [&](long long w1, uint32_t (&sm)[kSumWpt]) {   // summary words w1 .. w1+15 (w1 % 16 == 0; the summary is padded), zero beyond hi
+#pragma unroll
+        for (int v4 = 0; v4 < kSumWpt / 4; ++v4) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (w1 + 4 * v4 < hi) v = __ldg(reinterpret_cast<const uint4*>(bm1 + w1 + 4 * v4));
+            sm[4 * v4 + 0] = v.x;
+            sm[4 * v4 + 1] = w1 + 4 * v4 + 1 < hi ? v.y : 0u;
+            sm[4 * v4 + 2] = w1 + 4 * v4 + 2 < hi ? v.z : 0u;
+            sm[4 * v4 + 3] = w1 + 4 * v4 + 3 < hi ? v.w : 0u;
+        }
     };
     for (int c = 0; c < n_chunks; ++c) {
         const long long w1 = lo + (long long)c * kSumChunk + (long long)kSumWpt * threadIdx.x;
@@ -172,7 +178,7 @@ __global__ void __launch_bounds__(256) compact_summary_kernel(const uint32_t* __
     long long part = 0;
     for (int c = threadIdx.x; c < (int)blockIdx.x; c += 256) {
         unsigned long long t;
-        do { t = atomicAdd(tickets + c, 0ull); } while (!(t >> 63));
+        do { t = *reinterpret_cast<volatile unsigned long long*>(tickets + c); } while (!(t >> 63));
         part += (long long)(t & 0xffffffffull);
     }
     if (part) atomicAdd((unsigned long long*)&s_prefix, (unsigned long long)part);
@@ -401,7 +407,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rows_bwd_kernel(const float* 
     extern __shared__ __align__(16) uint4 Bf[];
     stage_weight_fragments<COUT, CIN, 16, true>(Bf, W0, W1, W2);
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tig = lane & 3, g = lane >> 2;
+    const int lane = threadIdx.x & 31, tig = lane & 3, g = lane >> 2;
     const int gq = lane / LPR, cq = lane % LPR;
     const unsigned rowbytes = COMPACT ? COUT * 4u : (unsigned)b * COUT * 4u;
     const char* Gb = reinterpret_cast<const char*>(Gin);
@@ -411,18 +417,16 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rows_bwd_kernel(const float* 
         n = a_cap;
     }
     const int n_slabs = (n + 15) / 16;
-    const int n_tiles = (n_slabs + kRowsWarps - 1) / kRowsWarps;
+    const int n_minis = (n_slabs + kRowsMini - 1) / kRowsMini;
     if (row_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(row_counter, (unsigned long long)n);
-    __shared__ int s_tile;                                 // dynamic tiles, see layer_fwd_rows_kernel
-    int* tile_counter = const_cast<int*>(n_ptr) + 1;
+    int* tile_counter = const_cast<int*>(n_ptr) + 1;       // per-warp dynamic mini-tiles, see layer_fwd_rows_kernel
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1);
-        __syncthreads();
-        const int tile = s_tile;
-        if (tile >= n_tiles) break;
-        const int slab = tile * kRowsWarps + warp;
-        if (slab >= n_slabs) continue;
+        int mini = 0;
+        if (lane == 0) mini = atomicAdd(tile_counter, 1);
+        mini = __shfl_sync(0xffffffffu, mini, 0);
+        if (mini >= n_minis) break;
+        const int slab_end = min(n_slabs, (mini + 1) * kRowsMini);
+        for (int slab = mini * kRowsMini; slab < slab_end; ++slab) {
         uint32_t rid[NL];
         unsigned oidx[NL];
         int len[NL], p0[NL], tq[NL], cpos[NL];
@@ -547,6 +551,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rows_bwd_kernel(const float* 
                         make_float2(d[nt][2 * r] * dact_out<ACT>(h.x), d[nt][2 * r + 1] * dact_out<ACT>(h.y));
                 }
             }
+        }
         }
     }
 }

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) layer_fwd_rows_kernel(const f
     extern __shared__ __align__(16) uint4 Bf[];
     stage_weight_fragments<CIN, COUT, 16, false>(Bf, W0, W1, W2);
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tig = lane & 3, g = lane >> 2;
+    const int lane = threadIdx.x & 31, tig = lane & 3, g = lane >> 2;
     const int gq = lane / LPR, cq = lane % LPR;
     const unsigned rowbytes = COMPACT ? CIN * 4u : (unsigned)b * CIN * 4u;    // stride of the gather index (compact row / edge row)
     const char* Hb = reinterpret_cast<const char*>(Hin);
@@ -151,20 +151,20 @@ __global__ void __launch_bounds__(kRowsThreads, 1) layer_fwd_rows_kernel(const f
         n = out_cap;
     }
     const int n_slabs = (n + 15) / 16;
-    const int n_tiles = (n_slabs + kRowsWarps - 1) / kRowsWarps;
+    const int n_minis = (n_slabs + kRowsMini - 1) / kRowsMini;
     if (row_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(row_counter, (unsigned long long)n);
-    // tiles (16 consecutive slabs, one per warp) are handed out dynamically: n_ptr[1] is a counter the compaction kernel zeroed
-    // (per-tile cost varies with how many distinct edges a slab mixes; a static split left SMs idle for a third of the kernel)
-    __shared__ int s_tile;
+    // every WARP takes kRowsMini consecutive slabs at a time from a global counter (n_ptr[1], zeroed by the compaction kernel): slab
+    // cost varies (longest merged row of its 16 rows, cache misses); a static split left SMs idle for a third of the kernel and
+    // CTA-wide tiles made 15 warps wait for the slowest at every tile.  Consecutive slabs stay in one warp: their rows are
+    // neighbours (same trajectory, nearby edges) and share gathered rows through L1.
     int* tile_counter = const_cast<int*>(n_ptr) + 1;
     for (;;) {
-        __syncthreads();                                  // every warp is done with the previous s_tile
-        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1);
-        __syncthreads();
-        const int tile = s_tile;
-        if (tile >= n_tiles) break;
-        const int slab = tile * kRowsWarps + warp;
-        if (slab >= n_slabs) continue;
+        int mini = 0;
+        if (lane == 0) mini = atomicAdd(tile_counter, 1);
+        mini = __shfl_sync(0xffffffffu, mini, 0);
+        if (mini >= n_minis) break;
+        const int slab_end = min(n_slabs, (mini + 1) * kRowsMini);
+        for (int slab = mini * kRowsMini; slab < slab_end; ++slab) {
         // this lane's row in each load slot
         uint32_t rid[NL];
         unsigned oidx[NL];                                 // index of the own row in Hin's storage
@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) layer_fwd_rows_kernel(const f
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) *reinterpret_cast<float2*>(dst + nt * 8) = make_float2(d[nt][2 * r], d[nt][2 * r + 1]);
             }
+        }
         }
     }
 }

@@ -8,6 +8,7 @@ constexpr int kSlabWarps = 16;
 constexpr int kSlabThreads = kSlabWarps * 32;
 constexpr int kRowsWarps = 16;            // row-list kernels (measured: 20 warps at <= 96 registers is 9 % slower than 16 at 128)
 constexpr int kRowsThreads = kRowsWarps * 32;
+constexpr int kRowsMini = 1;              // consecutive slabs a warp takes per grab of the dynamic counter
 
 __device__ __forceinline__ u64 bcast2(float c) {
     u64 r;

@@ -100,6 +100,47 @@ def test_deterministic_and_microbatch_invariant_logprobs(small):
     assert _relmax(grads[2], grads[0]) < 1e-5
 
 
+def test_row_ids_beyond_2_31_microbatch_invariant():
+    """Maximum sizes: ONE micro-batch whose trajectory-major row ids t*E + e run past 2^31 (E * micro_batch in (2^31, 2^32), the
+    cfg5 bench shape) against the same trajectories in micro-batches of 1024.  The batch tiles 256 generated trajectories, so
+    every tile must reproduce the first one bit for bit; gradients agree within fp32 summation noise."""
+    sg = _mods()
+    from scone_gcn_b200 import synthetic_data_gen as sdg
+    sp = sdg.generate_sparse_dataset(50000, 256, seed=7, n_waypoints=8)
+    cx = sg.SimplicialComplex.from_simplices(int(sp.n_nodes), sp.edges, sp.faces, 'scone')
+    base = 256
+    tiles = int(2.25e9 // cx.E) // base + 1
+    B = tiles * base
+    assert (1 << 31) < cx.E * B < (1 << 32)
+    nnz = int(sp.traj_ptr[base])
+    ptr = np.concatenate([[0], np.cumsum(np.tile(np.diff(sp.traj_ptr[:base + 1]), tiles))]).astype(np.int32)
+    fe = np.tile(sp.flow_edge[:nnz], tiles).astype(np.int32)
+    fv = np.tile(sp.flow_val[:nnz], tiles).astype(np.float32)
+    last = np.tile(sp.last_nodes[:base], tiles).astype(np.int32)
+    tgt = np.tile(sp.target_idx[:base], tiles).astype(np.int32)
+    rs = np.random.RandomState(3)
+    mask = (rs.rand(B) < 0.8).astype(np.float32)
+    res = []
+    for mb in (B, 1024):
+        net = sg.SconeModel(cx, [16, 16, 16], micro_batch=mb)
+        if mb == B:
+            rs_w = np.random.RandomState(11)
+            W = [0.2 * rs_w.randn(*s_) for s_ in net.shapes]
+        net.set_weights(W)
+        lp = net.forward(ptr, fe, fv, last)
+        buf = net.loss_grad(ptr, fe, fv, last, tgt, mask)
+        res.append((lp, buf))
+        del net
+        torch.cuda.empty_cache()
+    lp_big, lp_small = res[0][0], res[1][0]
+    assert np.isfinite(lp_big).all() and np.abs(lp_big).max() > 0
+    assert np.array_equal(lp_big, lp_small)
+    assert np.array_equal(lp_big.reshape(tiles, base, -1), np.broadcast_to(lp_big[:base], (tiles, base, lp_big.shape[1])))
+    n = len(res[0][1]) - 2
+    assert res[0][1][n + 1] == res[1][1][n + 1] == mask.sum()
+    assert _relmax(res[0][1][:n + 1], res[1][1][:n + 1]) < 1e-4
+
+
 def test_default_complex_vs_reference_golden():
     sg = _mods()
     ds = Dataset('dataset_default.npz')
