@@ -123,10 +123,10 @@ int scone_slab_forward_rows(const scone_complex* cx, int act, int b, int cin, in
                             const int* n_rows_dev, unsigned long long* row_counter, const uint32_t* bm_in, const uint32_t* pref_in,
                             int out_cap, int* overflow_dev, cudaStream_t st);
 int scone_rows_mark(const scone_complex* cx, int b, const uint32_t* rows, const int* n_dev, uint32_t* bm_next, int list_cap,
-                    cudaStream_t st, bool tmaj, size_t sum_off = 0);
+                    cudaStream_t st, bool tmaj, size_t sum_off = 0, const uint32_t* bm_filter = nullptr);
 // cone pipeline: two-level bitmaps (summary words at bm + sum_off, sum_off = 0: none)
-int scone_rows_cone(const scone_complex* cx, int b, const int32_t* last_nodes, uint32_t* bm_top, uint32_t* bm_cand, size_t sum_off,
-                    cudaStream_t st);
+int scone_rows_cone(const scone_complex* cx, int b, const int32_t* last_nodes, uint32_t* const* bm_levels, int n_levels, size_t sum_off,
+                    int* overflow_dev, cudaStream_t st);
 int scone_compact_rows_summary(const scone_complex* cx, int b, const uint32_t* bm, size_t sum_off, uint32_t* list, int* n_dev,
                                unsigned long long* tickets, cudaStream_t st, uint32_t* pref_out, long long list_cap);
 int scone_clear_summary(const scone_complex* cx, int b, uint32_t* bm, size_t sum_off, cudaStream_t st);
@@ -137,7 +137,8 @@ size_t scone_ticket_bytes();
 int scone_compact_rows(const scone_complex* cx, int b, const uint32_t* bm, uint32_t* list, int* n_dev, unsigned long long* tickets,
                        cudaStream_t st, uint32_t* pref_out = nullptr, long long list_cap = (1ll << 62));
 int scone_rows_flows(const scone_complex* cx, int b, const int32_t* traj_ptr, const int32_t* flow_edge, const float* flow_val, float* X,
-                     uint32_t* bmX, uint32_t* bm_next, bool clear, bool tmaj, cudaStream_t st);
+                     uint32_t* bmX, uint32_t* bm_next, bool clear, bool tmaj, cudaStream_t st, const uint32_t* bm_filter = nullptr,
+                     size_t sum_off = 0);
 int scone_rows_layer0_forward(const scone_complex* cx, int act, int b, int cout, const float* X, const float* W0, const float* W1,
                               const float* W2, float* Hout, const uint32_t* rows, const int* n_dev, uint32_t* bm_next, int out_cap,
                               int* overflow_dev, cudaStream_t st);

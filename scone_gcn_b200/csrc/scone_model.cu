@@ -40,6 +40,7 @@ struct scone_model {
     size_t sum_off = 0, bmg_bytes = 0;        // summary words of d_bmGr[l] start at word sum_off; bytes of one d_bmGr allocation
     int pipeline = 0;
     std::vector<uint32_t*> d_bmH, d_bmGr, d_prefH, d_prefG;
+    std::vector<uint32_t*> d_bmC;             // pipeline 3: geometric cone per layer (d_bmGr[l] then holds the LIVE rows: cone & support)
     std::vector<float*> d_cH, d_cG;           // compact tensors [row_cap][C_l]
     int row_cap = 0;                          // rows a compact tensor / the row list can hold
     size_t rows_list_cap = 0;
@@ -210,6 +211,10 @@ int ensure_buffers(scone_model* m) {
             SCONE_ALLOC(m->d_cH[l], (size_t)m->row_cap * m->hidden[l] * sizeof(float), "compact activations");
             SCONE_ALLOC(m->d_cG[l], (size_t)m->row_cap * m->hidden[l] * sizeof(float), "compact gradients");
             if (pl == 3) SCONE_ALLOC(m->d_rowsC[l], (size_t)m->row_cap * sizeof(uint32_t), "cone row list");
+            if (pl == 3) {
+                m->d_bmC.resize(L, nullptr);
+                SCONE_ALLOC(m->d_bmC[l], m->bmg_bytes, "cone bitmap");
+            }
         }
     }
     return 0;
@@ -335,28 +340,42 @@ int rows_backward_mb(scone_model* m, int32_t b, cudaStream_t s) {
 
 // ---- cone-pruned row-list pipeline (3) -----------------------------------------------------------------------------
 // The log-probs of trajectory t read H_L only at the edges incident to the neighbours of its last node; H_{L-1} is needed one
-// hop around those rows, and so on: the receptive cone.  Layer l's cone C_l is at once the set of rows of H_l the forward has
-// to produce and the set of rows of G_l the backward produces (it is what rows_backward_mb derives as candidate rows), so each
-// layer has ONE bitmap / rank prefix / row list, built from last_nodes before the forward.  Every row the cone keeps is
-// computed exactly as in pipeline 2 (all its neighbours are in the cone below it; a cone row outside the flows' support
-// evaluates to act(0) = 0, which is what pipeline 2 reads for an absent row), so log-probs and gradients do not change.
+// hop around those rows, and so on: the receptive cone (geometry only: d_bmC[l], built from last_nodes).  Inside the cone only
+// the rows in the structural support of the flows can be non-zero; the LIVE rows of layer l (d_bmGr[l]) are the cone rows with a
+// live neighbour one layer below (layer 0: a flow entry in their merged operator row) — marked layer by layer, each list
+// compacted once.  A live row is computed exactly as in pipeline 2 (its live neighbours are pipeline 2's present neighbours
+// inside the cone; everything it reads outside is an exact zero there too), so the log-probs are bit-identical.  The backward
+// walks the same lists: G_l outside the cone is never needed, and G_l on a cone row outside the support multiplies exact zeros
+// in every weight gradient and only feeds such rows further down — dropping it leaves every sum's non-zero terms unchanged.
+// Each layer has ONE bitmap / rank prefix / row list for H_l and G_l.
 int* cone_n(scone_model* m, int l) { return m->d_nrows + 2 * (1 + l); }
 
-int cone_build_mb(scone_model* m, int32_t b, const int32_t* last, cudaStream_t s) {
+int cone_build_mb(scone_model* m, int32_t b, const int32_t* ptr, const int32_t* edge, const float* val, const int32_t* last,
+                  cudaStream_t s) {
     const scone_complex* cx = m->cx;
     const int L = m->L;
+    if (!m->x_clean) {
+        SCONE_CUDA(cudaMemsetAsync(m->d_X, 0, (size_t)cx->E * m->mb * sizeof(float), s));
+        m->x_clean = true;
+    }
     ScopedProf prof(SCONE_K_CONE, s);
     if (!m->cone_clean) {                                  // once: afterwards every micro-batch clears exactly what it set
-        for (int l = 0; l < L; ++l) SCONE_CUDA(cudaMemsetAsync(m->d_bmGr[l], 0, m->bmg_bytes, s));
+        for (int l = 0; l < L; ++l) {
+            SCONE_CUDA(cudaMemsetAsync(m->d_bmGr[l], 0, m->bmg_bytes, s));
+            SCONE_CUDA(cudaMemsetAsync(m->d_bmC[l], 0, m->bmg_bytes, s));
+        }
     }
     m->cone_clean = false;                                 // until cone_clear_mb has run (an error return in between leaves bits set)
-    if (scone_rows_cone(cx, b, last, m->d_bmGr[L - 1], L >= 2 ? m->d_bmGr[L - 2] : nullptr, m->sum_off, s)) return 1;
-    for (int l = L - 1; l >= 0; --l) {
+    if (scone_rows_cone(cx, b, last, m->d_bmC.data(), L, m->sum_off, m->d_overflow, s)) return 1;
+    // flows -> X, live rows of H_1
+    if (scone_rows_flows(cx, b, ptr, edge, val, m->d_X, nullptr, m->d_bmGr[0], false, true, s, m->d_bmC[0], m->sum_off)) return 1;
+    for (int l = 0; l < L; ++l) {
         if (scone_compact_rows_summary(cx, b, m->d_bmGr[l], m->sum_off, m->d_rowsC[l], cone_n(m, l), m->d_tickets, s, m->d_prefG[l],
                                        m->row_cap))
             return 1;
-        if (l >= 1 && l <= L - 2)                          // (the readout cone already marked layer L-2)
-            if (scone_rows_mark(cx, b, m->d_rowsC[l], cone_n(m, l), m->d_bmGr[l - 1], m->row_cap, s, true, m->sum_off)) return 1;
+        if (l + 1 < L)
+            if (scone_rows_mark(cx, b, m->d_rowsC[l], cone_n(m, l), m->d_bmGr[l + 1], m->row_cap, s, true, m->sum_off, m->d_bmC[l + 1]))
+                return 1;
     }
     return 0;
 }
@@ -364,22 +383,16 @@ int cone_build_mb(scone_model* m, int32_t b, const int32_t* last, cudaStream_t s
 // end of a micro-batch: the bitmaps go back to all-zero (cost follows the cone, not E*b)
 int cone_clear_mb(scone_model* m, int32_t b, cudaStream_t s) {
     ScopedProf prof(SCONE_K_CONE, s);
-    for (int l = 0; l < m->L; ++l)
+    for (int l = 0; l < m->L; ++l) {
         if (scone_clear_summary(m->cx, b, m->d_bmGr[l], m->sum_off, s)) return 1;
+        if (scone_clear_summary(m->cx, b, m->d_bmC[l], m->sum_off, s)) return 1;
+    }
     m->cone_clean = true;
     return 0;
 }
 
-int cone_forward_mb(scone_model* m, int32_t b, const int32_t* ptr, const int32_t* edge, const float* val, cudaStream_t s) {
+int cone_forward_mb(scone_model* m, int32_t b, cudaStream_t s) {
     const scone_complex* cx = m->cx;
-    if (!m->x_clean) {
-        SCONE_CUDA(cudaMemsetAsync(m->d_X, 0, (size_t)cx->E * m->mb * sizeof(float), s));
-        m->x_clean = true;
-    }
-    {
-        ScopedProf prof(SCONE_K_OTHER, s);
-        if (scone_rows_flows(cx, b, ptr, edge, val, m->d_X, nullptr, nullptr, false, true, s)) return 1;
-    }
     int cin = 1;
     for (int l = 0; l < m->L; ++l) {
         const int cout = m->hidden[l];
@@ -546,6 +559,7 @@ extern "C" int scone_model_destroy(scone_model* m) {
     for (float* p : m->d_cH) cudaFree(p);
     for (float* p : m->d_cG) cudaFree(p);
     for (uint32_t* p : m->d_rowsC) cudaFree(p);
+    for (uint32_t* p : m->d_bmC) cudaFree(p);
     cudaFree(m->d_rows); cudaFree(m->d_nrows); cudaFree(m->d_overflow); cudaFree(m->d_tickets); cudaFree(m->d_Abuf);
     for (float* p : m->d_G) cudaFree(p);
     cudaFree(m->d_ws); cudaFree(m->d_logp);
@@ -626,9 +640,9 @@ extern "C" int scone_model_forward_dev(scone_model* m, int32_t B, const int32_t*
         const int32_t b = B - off < m->mb ? B - off : m->mb;
         int rc;
         if (rows && m->pipeline == 3) {
-            rc = cone_build_mb(m, b, last + off, as_stream(st));
+            rc = cone_build_mb(m, b, ptr + off, edge, val, last + off, as_stream(st));
             if (rc) return rc;
-            rc = cone_forward_mb(m, b, ptr + off, edge, val, as_stream(st));
+            rc = cone_forward_mb(m, b, as_stream(st));
             if (rc) return rc;
             rc = cone_readout(m, b, last + off, logprobs + (size_t)off * cx->D, false, nullptr, nullptr, as_stream(st));
             if (rc) return rc;
@@ -675,9 +689,9 @@ extern "C" int scone_model_loss_grad_dev(scone_model* m, int32_t B, const int32_
         const int32_t b = B - off < m->mb ? B - off : m->mb;
         int rc;
         if (rows && m->pipeline == 3) {
-            rc = cone_build_mb(m, b, last + off, s);
+            rc = cone_build_mb(m, b, ptr + off, edge, val, last + off, s);
             if (rc) return rc;
-            rc = cone_forward_mb(m, b, ptr + off, edge, val, s);
+            rc = cone_forward_mb(m, b, s);
             if (rc) return rc;
             rc = cone_readout(m, b, last + off, m->d_logp, true, tgt + off, mask + off, s);
             if (rc) return rc;
@@ -747,7 +761,16 @@ extern "C" int scone_model_forward_host(scone_model* m, int32_t B, const int32_t
     rc = scone_model_forward_dev(m, B, m->d_ptr, m->d_edge, m->d_val, m->d_last, m->d_logp_all, st);
     if (rc) return rc;
     SCONE_CUDA(cudaMemcpyAsync(logprobs_out, m->d_logp_all, (size_t)B * m->cx->D * sizeof(float), cudaMemcpyDeviceToHost, s));
+    int overflow = 0;
+    if (m->d_overflow) SCONE_CUDA(cudaMemcpyAsync(&overflow, m->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
     SCONE_CUDA(cudaStreamSynchronize(s));
+    if (overflow) {
+        cudaMemset(m->d_overflow, 0, sizeof(int));
+        scone_set_error("scone_model: a micro-batch exceeded a row-list capacity (%d rows per compact tensor, %d cone edges per trajectory "
+                        "and layer); the log-probs are incomplete — use a smaller micro-batch or scone_model_set_pipeline(m, 2 / 0)",
+                        m->row_cap, 3072);
+        return 4;
+    }
     return 0;
 }
 
@@ -781,8 +804,9 @@ extern "C" int scone_model_read_grads(scone_model* m, float* out, void* st) {
     SCONE_CUDA(cudaStreamSynchronize(s));
     if (overflow) {
         cudaMemset(m->d_overflow, 0, sizeof(int));
-        scone_set_error("scone_model: a backward pass had more than %d candidate rows in one micro-batch (compact A buffer); the gradients "
-                        "are incomplete — use a smaller micro-batch or scone_model_set_pipeline(m, 0)", m->a_cap);
+        scone_set_error("scone_model: a micro-batch exceeded a row-list capacity (%d rows per compact tensor, %d rows of the backward's A "
+                        "buffer, 3072 cone edges per trajectory and layer); the gradients are incomplete — use a smaller micro-batch or "
+                        "scone_model_set_pipeline(m, 2 / 0)", m->row_cap, m->a_cap);
         return 4;
     }
     return 0;

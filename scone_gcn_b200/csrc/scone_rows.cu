@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(128) rows_flows_kernel(const int32_t* __restri
                                                         const float* __restrict__ flow_val, const int32_t* __restrict__ rank,
                                                         float* __restrict__ X, uint32_t* __restrict__ bmX, uint32_t* __restrict__ bm_next,
                                                         const int32_t* __restrict__ mptr, const int2* __restrict__ ment, int E, int b,
-                                                        bool tmaj) {
+                                                        bool tmaj, const uint32_t* __restrict__ bm_filter, size_t sum_off) {
     const int t = blockIdx.x;
     const size_t se = tmaj ? 1 : (size_t)b, toff = tmaj ? (size_t)t * E : (size_t)t;     // row id = e * se + toff (see RowIds)
     for (int p = traj_ptr[t] + threadIdx.x; p < traj_ptr[t + 1]; p += blockDim.x) {
@@ -59,15 +59,21 @@ __global__ void __launch_bounds__(128) rows_flows_kernel(const int32_t* __restri
         }
         X[row] = flow_val[p];
         if (bmX != nullptr) bit_set(bmX, row);
-        if (bm_next != nullptr)
-            for (int q = mptr[e]; q < mptr[e + 1]; ++q) bit_set(bm_next, (size_t)(unsigned)ment[q].x * se + toff);
+        if (bm_next != nullptr) {
+            uint32_t* next1 = sum_off ? bm_next + sum_off : nullptr;
+            for (int q = mptr[e]; q < mptr[e + 1]; ++q) {        // candidate rows of H_1; with a filter only those inside it (the cone)
+                const size_t nrow = (size_t)(unsigned)ment[q].x * se + toff;
+                if (bm_filter == nullptr || bit_test(bm_filter, nrow)) bit_set2(bm_next, next1, nrow);
+            }
+        }
     }
 }
 
 // candidate rows one hop further: lane = row of the list, every entry of its merged operator row marks (column, t) in bm_next
 __global__ void __launch_bounds__(256) rows_mark_kernel(const uint32_t* __restrict__ rows, const int* __restrict__ n_ptr,
                                                        const int32_t* __restrict__ mptr, const int2* __restrict__ ment, int b,
-                                                       uint32_t* __restrict__ bm_next, int list_cap, size_t sum_off, int E, bool tmaj) {
+                                                       uint32_t* __restrict__ bm_next, int list_cap, size_t sum_off, int E, bool tmaj,
+                                                       const uint32_t* __restrict__ bm_filter) {
     const int n = min(*n_ptr, list_cap);
     const unsigned dv = tmaj ? (unsigned)E : (unsigned)b, se = tmaj ? 1u : (unsigned)b;
     uint32_t* bm1 = sum_off ? bm_next + sum_off : nullptr;
@@ -76,7 +82,10 @@ __global__ void __launch_bounds__(256) rows_mark_kernel(const uint32_t* __restri
         const unsigned q = rid / dv, r = rid - q * dv;
         const unsigned e = tmaj ? r : q, toff = tmaj ? rid - r : r;
         const int p1 = __ldg(mptr + e + 1);
-        for (int p = __ldg(mptr + e); p < p1; ++p) bit_set2(bm_next, bm1, (unsigned)__ldg(ment + p).x * se + toff);
+        for (int p = __ldg(mptr + e); p < p1; ++p) {
+            const unsigned nrow = (unsigned)__ldg(ment + p).x * se + toff;
+            if (bm_filter == nullptr || bit_test(bm_filter, nrow)) bit_set2(bm_next, bm1, nrow);
+        }
     }
 }
 
@@ -218,45 +227,80 @@ __global__ void __launch_bounds__(256) clear_summary_kernel(uint32_t* __restrict
 }
 
 // Receptive cone of the readout (pure geometry: last node + complex).  The log-probs of trajectory t depend on H_L only at the
-// edges incident to the neighbours of its last node (trajectory_experiments.py:151,298-303); those rows are the top of the cone
-// (bm_top), the rows one hop further (bm_cand) are all that H_{L-1} has to provide, and so on down (rows_mark_kernel).  Rows
-// outside the cone reach neither the log-probs nor any weight gradient, so the cone-pruned pipeline never computes them.
+// edges incident to the neighbours of its last node (trajectory_experiments.py:151,298-303): the top of the cone.  H_{L-1} has to
+// provide the rows one hop around those, and so on down.  Rows outside the cone reach neither the log-probs nor any weight
+// gradient; the cone pipeline never computes them.  One CTA per trajectory builds the bitmaps of ALL levels: the edges that
+// turned a bit on at level l (atomicOr reports it: an exact, duplicate-free list in shared memory) are expanded into level
+// l - 1.  A (neighbour, edge) or (edge, merged row) expansion is split over a quad of threads.  bm[l]: bitmap of level l
+// (tensor H_{l+1}), trajectory-major ids, summary words at + sum_off.
+constexpr int kConeCap = 3072;           // edges per level and trajectory staged in shared memory (2 lists)
+constexpr int kConeMaxLevels = 8;
+struct ConeBitmaps {
+    uint32_t* bm[kConeMaxLevels];
+};
 __global__ void __launch_bounds__(256) rows_cone_kernel(const int32_t* __restrict__ last_nodes, const int32_t* __restrict__ nbrhoods,
                                                        const int32_t* __restrict__ inc_ptr, const int2* __restrict__ inc_ent,
-                                                       uint32_t* __restrict__ bm_top, uint32_t* __restrict__ bm_cand,
-                                                       const int32_t* __restrict__ mptr, const int2* __restrict__ ment, int N, int D, int E,
-                                                       size_t sum_off) {
-    // one CTA per trajectory; the (neighbour, incident edge) pairs are flattened over quads of threads, a quad's lanes split the
-    // merged operator row of its edge: every load / atomicOr of a trajectory is in flight at once (idempotent, order-free)
+                                                       ConeBitmaps cone, int n_levels, const int32_t* __restrict__ mptr,
+                                                       const int2* __restrict__ ment, int N, int D, int E, size_t sum_off,
+                                                       int* __restrict__ overflow) {
     __shared__ int s_ptr[kRoMaxD], s_off[kRoMaxD + 1];
+    __shared__ int s_list[2][kConeCap];
+    __shared__ int s_n[2];
     const int t = blockIdx.x;
     const int last = last_nodes[t];
     if (last < 0 || last >= N) return;
-    uint32_t* top1 = sum_off ? bm_top + sum_off : nullptr;
-    uint32_t* cand1 = sum_off && bm_cand != nullptr ? bm_cand + sum_off : nullptr;
     for (int j = threadIdx.x; j < D; j += blockDim.x) {
         const int nbr = nbrhoods[(size_t)last * D + j];
         s_ptr[j] = nbr >= 0 ? inc_ptr[nbr] : 0;
         s_off[j + 1] = nbr >= 0 ? inc_ptr[nbr + 1] - inc_ptr[nbr] : 0;
     }
+    if (threadIdx.x == 0) s_n[0] = s_n[1] = 0;
     __syncthreads();
     if (threadIdx.x == 0) {
         s_off[0] = 0;
         for (int j = 0; j < D; ++j) s_off[j + 1] += s_off[j];
     }
     __syncthreads();
-    const int total = s_off[D];
     const unsigned tbase = (unsigned)t * (unsigned)E;
-    const int ql = threadIdx.x & 3;
-    for (int i = threadIdx.x >> 2; i < total; i += blockDim.x >> 2) {
+    // sets bit (e, t) of level lv; true if this call turned it on
+    auto turn_on = [&](int lv, int e) {
+        uint32_t* bm = cone.bm[lv];
+        const size_t row = (size_t)tbase + (unsigned)e, widx = row >> 5;
+        const uint32_t bit = 1u << (row & 31);
+        if (bm[widx] & bit) return false;
+        const uint32_t old = atomicOr(bm + widx, bit);
+        if (old == 0u) atomicOr(bm + sum_off + (widx >> 5), 1u << (widx & 31));
+        return (old & bit) == 0u;
+    };
+    auto push = [&](int which, int e) {
+        const int pos = atomicAdd(&s_n[which], 1);
+        if (pos < kConeCap) s_list[which][pos] = e;
+        else *overflow = 1;                               // (host: scone_model_read_grads / forward_host report it)
+    };
+    // top level: edges incident to the neighbours of the last node
+    int lv = n_levels - 1, cur = 0;
+    for (int i = threadIdx.x; i < s_off[D]; i += blockDim.x) {
         int j = 0;
         while (s_off[j + 1] <= i) ++j;
         const int e = inc_ent[s_ptr[j] + (i - s_off[j])].x;
-        if (ql == 0) bit_set2(bm_top, top1, tbase + (unsigned)e);
-        if (bm_cand != nullptr) {
+        if (turn_on(lv, e) && lv > 0) push(cur, e);
+    }
+    // one hop down per level
+    const int ql = threadIdx.x & 3;
+    for (--lv; lv >= 0; --lv) {
+        __syncthreads();
+        const int n_cur = min(s_n[cur], kConeCap);
+        if (threadIdx.x == 0) s_n[1 - cur] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x >> 2; i < n_cur; i += blockDim.x >> 2) {
+            const int e = s_list[cur][i];
             const int p1 = mptr[e + 1];
-            for (int q = mptr[e] + ql; q < p1; q += 4) bit_set2(bm_cand, cand1, tbase + (unsigned)ment[q].x);
+            for (int q = mptr[e] + ql; q < p1; q += 4) {
+                const int e2 = ment[q].x;
+                if (turn_on(lv, e2) && lv > 0) push(1 - cur, e2);
+            }
         }
+        cur = 1 - cur;
     }
 }
 
@@ -841,9 +885,12 @@ __global__ void __launch_bounds__(32 * kRoWarps) rows_readout_bwd_kernel(const f
         RoItem it;
         unsigned hidx, gidx;
         it.hidx = rank_lookup(bmH, prefH, row, hidx) ? (int)hidx : -1;
-        if (bmG == bmH && prefG == prefH) gidx = hidx;     // cone pipeline: G_L and H_L share their row set
-        else rank_lookup(bmG, prefG, row, gidx);
-        it.gidx = (int)gidx;
+        if (bmG == bmH && prefG == prefH) {                // cone pipeline: G_L and H_L share their (live) row set; an absent row
+            it.gidx = it.hidx >= 0 ? it.hidx : g_cap;      // is outside the flows' support: its gradient reaches no weight — skipped
+        } else {
+            rank_lookup(bmG, prefG, row, gidx);
+            it.gidx = (int)gidx;
+        }
         it.sign = __int_as_float(es.y);
         return it;
     };
@@ -1026,27 +1073,32 @@ bool scone_rows_supported(const scone_complex* cx, int n_layers, const int32_t* 
 int64_t scone_rows_dw_workspace_bytes(int cin, int cout) { return (int64_t)kDwCtas * 3 * (cin > 1 ? cin : 1) * cout * sizeof(float); }
 
 int scone_rows_flows(const scone_complex* cx, int b, const int32_t* traj_ptr, const int32_t* flow_edge, const float* flow_val, float* X,
-                     uint32_t* bmX, uint32_t* bm_next, bool clear, bool tmaj, cudaStream_t st) {
+                     uint32_t* bmX, uint32_t* bm_next, bool clear, bool tmaj, cudaStream_t st, const uint32_t* bm_filter, size_t sum_off) {
     if (clear)
-        rows_flows_kernel<true><<<b, 128, 0, st>>>(traj_ptr, flow_edge, flow_val, cx->d_rank, X, bmX, bm_next, cx->d_mptr, cx->d_ment, cx->E, b, tmaj);
+        rows_flows_kernel<true><<<b, 128, 0, st>>>(traj_ptr, flow_edge, flow_val, cx->d_rank, X, bmX, bm_next, cx->d_mptr, cx->d_ment, cx->E, b, tmaj,
+                                                   bm_filter, sum_off);
     else
-        rows_flows_kernel<false><<<b, 128, 0, st>>>(traj_ptr, flow_edge, flow_val, cx->d_rank, X, bmX, bm_next, cx->d_mptr, cx->d_ment, cx->E, b, tmaj);
+        rows_flows_kernel<false><<<b, 128, 0, st>>>(traj_ptr, flow_edge, flow_val, cx->d_rank, X, bmX, bm_next, cx->d_mptr, cx->d_ment, cx->E, b, tmaj,
+                                                    bm_filter, sum_off);
     SCONE_LAUNCHED();
     return 0;
 }
 
 int scone_rows_mark(const scone_complex* cx, int b, const uint32_t* rows, const int* n_dev, uint32_t* bm_next, int list_cap,
-                    cudaStream_t st, bool tmaj, size_t sum_off) {
-    rows_mark_kernel<<<cx->num_sms * 8, 256, 0, st>>>(rows, n_dev, cx->d_mptr, cx->d_ment, b, bm_next, list_cap, sum_off, cx->E, tmaj);
+                    cudaStream_t st, bool tmaj, size_t sum_off, const uint32_t* bm_filter) {
+    rows_mark_kernel<<<cx->num_sms * 8, 256, 0, st>>>(rows, n_dev, cx->d_mptr, cx->d_ment, b, bm_next, list_cap, sum_off, cx->E, tmaj, bm_filter);
     SCONE_LAUNCHED();
     return 0;
 }
 
-int scone_rows_cone(const scone_complex* cx, int b, const int32_t* last_nodes, uint32_t* bm_top, uint32_t* bm_cand, size_t sum_off,
-                    cudaStream_t st) {
+int scone_rows_cone(const scone_complex* cx, int b, const int32_t* last_nodes, uint32_t* const* bm_levels, int n_levels, size_t sum_off,
+                    int* overflow_dev, cudaStream_t st) {
     SCONE_REQUIRE(cx->D <= kRoMaxD, "scone_rows_cone: max degree <= %d", kRoMaxD);
-    rows_cone_kernel<<<b, 256, 0, st>>>(last_nodes, cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, bm_top, bm_cand, cx->d_mptr, cx->d_ment,
-                                       cx->N, cx->D, cx->E, sum_off);
+    SCONE_REQUIRE(n_levels >= 1 && n_levels <= kConeMaxLevels && sum_off > 0, "scone_rows_cone: 1..%d levels, two-level bitmaps", kConeMaxLevels);
+    ConeBitmaps cone;
+    for (int l = 0; l < kConeMaxLevels; ++l) cone.bm[l] = l < n_levels ? bm_levels[l] : nullptr;
+    rows_cone_kernel<<<b, 256, 0, st>>>(last_nodes, cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, cone, n_levels, cx->d_mptr, cx->d_ment, cx->N,
+                                       cx->D, cx->E, sum_off, overflow_dev);
     SCONE_LAUNCHED();
     return 0;
 }

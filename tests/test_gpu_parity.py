@@ -337,7 +337,7 @@ def test_row_list_pipeline_matches_unit_kernel_pipeline(small, model, hidden, mb
     """Model level: the bitmap-native row-list pipelines (tensor-core kernels; 3 = compact tensors over the readout cone,
     2 = compact tensors over the whole support, 1 = dense tensors) against the unit-kernel pipeline (0: fp32 SIMT, byte flags):
     log-probs within 1e-5, gradients within 1e-4 of the largest entry; run-to-run bit-exact; interleaving the pipelines on one
-    model (X must be re-cleaned) changes nothing; and pruning to the cone changes no bit of the log-probs or the gradients."""
+    model (X must be re-cleaned) changes nothing; and pruning to the cone changes no bit of the log-probs (gradients: 1e-5)."""
     sg = _mods()
     L = sg.lib()
     cx = sg.SimplicialComplex.from_dense(small.B1, small.B2, model)
@@ -357,8 +357,16 @@ def test_row_list_pipeline_matches_unit_kernel_pipeline(small, model, hidden, mb
             assert np.array_equal(out[which][0], lp) and np.array_equal(out[which][1], buf)
         out[which] = (lp, buf)
     assert np.array_equal(out[2][0], out[1][0])                    # compact vs dense addressing: same arithmetic per row
-    assert np.array_equal(out[3][0], out[2][0]) and np.array_equal(out[3][1], out[2][1])     # cone pruning: nothing changes
+    # cone pruning: the log-probs do not change by a bit; the weight gradients lose only exact-zero terms (their sums are grouped
+    # differently: fp32 summation noise)
+    assert np.array_equal(out[3][0], out[2][0])
     n = net.n_params
+    assert np.array_equal(out[3][1][n:], out[2][1][n:])
+    off = 0
+    for shp in net.shapes:
+        k = shp[0] * shp[1]
+        assert np.abs(out[3][1][off:off + k] - out[2][1][off:off + k]).max() <= 1e-5 * max(np.abs(out[2][1][off:off + k]).max(), 1e-30), shp
+        off += k
     for which in (1, 2, 3):
         assert np.abs(out[which][0] - out[0][0]).max() <= 1e-5 * max(1.0, np.abs(out[0][0]).max())
         assert out[which][1][n + 1] == out[0][1][n + 1] == mask.sum()
