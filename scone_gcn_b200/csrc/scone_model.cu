@@ -383,10 +383,9 @@ int cone_build_mb(scone_model* m, int32_t b, const int32_t* ptr, const int32_t* 
 // end of a micro-batch: the bitmaps go back to all-zero (cost follows the cone, not E*b)
 int cone_clear_mb(scone_model* m, int32_t b, cudaStream_t s) {
     ScopedProf prof(SCONE_K_CONE, s);
-    for (int l = 0; l < m->L; ++l) {
-        if (scone_clear_summary(m->cx, b, m->d_bmGr[l], m->sum_off, s)) return 1;
-        if (scone_clear_summary(m->cx, b, m->d_bmC[l], m->sum_off, s)) return 1;
-    }
+    std::vector<uint32_t*> bms(m->d_bmGr);
+    bms.insert(bms.end(), m->d_bmC.begin(), m->d_bmC.end());
+    if (scone_clear_summary(m->cx, b, bms.data(), (int)bms.size(), m->sum_off, s)) return 1;
     m->cone_clean = true;
     return 0;
 }

@@ -41,27 +41,31 @@ __device__ __forceinline__ float dact_out(float h) {       // derivative through
 // first-layer gathers need no flag test and X needs no E*b memset).
 // ---------------------------------------------------------------------------------------------------------------
 template <bool CLEAR>
-__global__ void __launch_bounds__(128) rows_flows_kernel(const int32_t* __restrict__ traj_ptr, const int32_t* __restrict__ flow_edge,
+__global__ void __launch_bounds__(256) rows_flows_kernel(const int32_t* __restrict__ traj_ptr, const int32_t* __restrict__ flow_edge,
                                                         const float* __restrict__ flow_val, const int32_t* __restrict__ rank,
                                                         float* __restrict__ X, uint32_t* __restrict__ bmX, uint32_t* __restrict__ bm_next,
                                                         const int32_t* __restrict__ mptr, const int2* __restrict__ ment, int E, int b,
                                                         bool tmaj, const uint32_t* __restrict__ bm_filter, size_t sum_off) {
-    const int t = blockIdx.x;
+    // a quad of threads per flow entry: lane 0 of the quad writes X, the four lanes split the entry's merged operator row
+    const int t = blockIdx.x, ql = threadIdx.x & 3;
     const size_t se = tmaj ? 1 : (size_t)b, toff = tmaj ? (size_t)t * E : (size_t)t;     // row id = e * se + toff (see RowIds)
-    for (int p = traj_ptr[t] + threadIdx.x; p < traj_ptr[t + 1]; p += blockDim.x) {
+    uint32_t* next1 = sum_off && bm_next != nullptr ? bm_next + sum_off : nullptr;
+    for (int p = traj_ptr[t] + (threadIdx.x >> 2); p < traj_ptr[t + 1]; p += blockDim.x >> 2) {
         const int eo = flow_edge[p];
         if (eo < 0 || eo >= E) continue;
         const int e = rank[eo];
         const size_t row = (size_t)e * se + toff;
         if (CLEAR) {
-            X[row] = 0.f;
+            if (ql == 0) X[row] = 0.f;
             continue;
         }
-        X[row] = flow_val[p];
-        if (bmX != nullptr) bit_set(bmX, row);
+        if (ql == 0) {
+            X[row] = flow_val[p];
+            if (bmX != nullptr) bit_set(bmX, row);
+        }
         if (bm_next != nullptr) {
-            uint32_t* next1 = sum_off ? bm_next + sum_off : nullptr;
-            for (int q = mptr[e]; q < mptr[e + 1]; ++q) {        // candidate rows of H_1; with a filter only those inside it (the cone)
+            const int q1 = mptr[e + 1];
+            for (int q = mptr[e] + ql; q < q1; q += 4) {         // candidate rows of H_1; with a filter only those inside it (the cone)
                 const size_t nrow = (size_t)(unsigned)ment[q].x * se + toff;
                 if (bm_filter == nullptr || bit_test(bm_filter, nrow)) bit_set2(bm_next, next1, nrow);
             }
@@ -69,7 +73,8 @@ __global__ void __launch_bounds__(128) rows_flows_kernel(const int32_t* __restri
     }
 }
 
-// candidate rows one hop further: lane = row of the list, every entry of its merged operator row marks (column, t) in bm_next
+// candidate rows one hop further: a quad of threads per row of the list splits its merged operator row; every entry marks
+// (column, t) in bm_next — with a filter only inside it (idempotent atomicOr: the bitmap does not depend on the order)
 __global__ void __launch_bounds__(256) rows_mark_kernel(const uint32_t* __restrict__ rows, const int* __restrict__ n_ptr,
                                                        const int32_t* __restrict__ mptr, const int2* __restrict__ ment, int b,
                                                        uint32_t* __restrict__ bm_next, int list_cap, size_t sum_off, int E, bool tmaj,
@@ -77,12 +82,13 @@ __global__ void __launch_bounds__(256) rows_mark_kernel(const uint32_t* __restri
     const int n = min(*n_ptr, list_cap);
     const unsigned dv = tmaj ? (unsigned)E : (unsigned)b, se = tmaj ? 1u : (unsigned)b;
     uint32_t* bm1 = sum_off ? bm_next + sum_off : nullptr;
-    for (int li = blockIdx.x * blockDim.x + threadIdx.x; li < n; li += gridDim.x * blockDim.x) {
+    const int ql = threadIdx.x & 3;
+    for (int li = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; li < n; li += (gridDim.x * blockDim.x) >> 2) {
         const uint32_t rid = __ldg(rows + li);
         const unsigned q = rid / dv, r = rid - q * dv;
         const unsigned e = tmaj ? r : q, toff = tmaj ? rid - r : r;
         const int p1 = __ldg(mptr + e + 1);
-        for (int p = __ldg(mptr + e); p < p1; ++p) {
+        for (int p = __ldg(mptr + e) + ql; p < p1; p += 4) {
             const unsigned nrow = (unsigned)__ldg(ment + p).x * se + toff;
             if (bm_filter == nullptr || bit_test(bm_filter, nrow)) bit_set2(bm_next, bm1, nrow);
         }
@@ -212,8 +218,14 @@ __global__ void __launch_bounds__(256) compact_summary_kernel(const uint32_t* __
     }
 }
 
-// back to all-zero: every bitmap word under a set summary bit, then the summary word
-__global__ void __launch_bounds__(256) clear_summary_kernel(uint32_t* __restrict__ bm, uint32_t* __restrict__ bm1, long long n1_words) {
+// back to all-zero: every bitmap word under a set summary bit, then the summary word; blockIdx.y = which bitmap
+constexpr int kClearMax = 16;
+struct ClearList {
+    uint32_t* bm[kClearMax];
+};
+__global__ void __launch_bounds__(256) clear_summary_kernel(ClearList list, size_t sum_off, long long n1_words) {
+    uint32_t* bm = list.bm[blockIdx.y];
+    uint32_t* bm1 = bm + sum_off;
     for (long long w1 = (long long)blockIdx.x * blockDim.x + threadIdx.x; w1 < n1_words; w1 += (long long)gridDim.x * blockDim.x) {
         uint32_t sm = bm1[w1];
         if (sm == 0u) continue;
@@ -709,8 +721,18 @@ __global__ void __launch_bounds__(256) rows_reduce_kernel(const float* __restric
     const int per = (nparts + 7) / 8;
     const int p0 = slice * per, p1 = min(nparts, p0 + per);
     float s = 0.f;
-    if (i < n)
-        for (int p = p0; p < p1; ++p) s += partial[(size_t)p * n + i];
+    if (i < n) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;     // four loads in flight; fixed grouping
+        int p = p0;
+        for (; p + 3 < p1; p += 4) {
+            s0 += partial[(size_t)p * n + i];
+            s1 += partial[(size_t)(p + 1) * n + i];
+            s2 += partial[(size_t)(p + 2) * n + i];
+            s3 += partial[(size_t)(p + 3) * n + i];
+        }
+        for (; p < p1; ++p) s0 += partial[(size_t)p * n + i];
+        s = (s0 + s1) + (s2 + s3);
+    }
     red[slice][lane] = s;
     __syncthreads();
     if (slice == 0 && i < n) {
@@ -1075,10 +1097,10 @@ int64_t scone_rows_dw_workspace_bytes(int cin, int cout) { return (int64_t)kDwCt
 int scone_rows_flows(const scone_complex* cx, int b, const int32_t* traj_ptr, const int32_t* flow_edge, const float* flow_val, float* X,
                      uint32_t* bmX, uint32_t* bm_next, bool clear, bool tmaj, cudaStream_t st, const uint32_t* bm_filter, size_t sum_off) {
     if (clear)
-        rows_flows_kernel<true><<<b, 128, 0, st>>>(traj_ptr, flow_edge, flow_val, cx->d_rank, X, bmX, bm_next, cx->d_mptr, cx->d_ment, cx->E, b, tmaj,
+        rows_flows_kernel<true><<<b, 256, 0, st>>>(traj_ptr, flow_edge, flow_val, cx->d_rank, X, bmX, bm_next, cx->d_mptr, cx->d_ment, cx->E, b, tmaj,
                                                    bm_filter, sum_off);
     else
-        rows_flows_kernel<false><<<b, 128, 0, st>>>(traj_ptr, flow_edge, flow_val, cx->d_rank, X, bmX, bm_next, cx->d_mptr, cx->d_ment, cx->E, b, tmaj,
+        rows_flows_kernel<false><<<b, 256, 0, st>>>(traj_ptr, flow_edge, flow_val, cx->d_rank, X, bmX, bm_next, cx->d_mptr, cx->d_ment, cx->E, b, tmaj,
                                                     bm_filter, sum_off);
     SCONE_LAUNCHED();
     return 0;
@@ -1119,13 +1141,18 @@ int scone_compact_rows_summary(const scone_complex* cx, int b, const uint32_t* b
     return 0;
 }
 
-int scone_clear_summary(const scone_complex* cx, int b, uint32_t* bm, size_t sum_off, cudaStream_t st) {
+int scone_clear_summary(const scone_complex* cx, int b, uint32_t* const* bms, int count, size_t sum_off, cudaStream_t st) {
     const long long n1 = summary_words(cx, b);
     long long grid = (n1 + 255) / 256;
-    if (grid > cx->num_sms * 8) grid = cx->num_sms * 8;
+    if (grid > cx->num_sms * 4) grid = cx->num_sms * 4;
     if (grid < 1) grid = 1;
-    clear_summary_kernel<<<(int)grid, 256, 0, st>>>(bm, bm + sum_off, n1);
-    SCONE_LAUNCHED();
+    for (int i0 = 0; i0 < count; i0 += kClearMax) {
+        ClearList list;
+        const int k = count - i0 < kClearMax ? count - i0 : kClearMax;
+        for (int i = 0; i < kClearMax; ++i) list.bm[i] = i < k ? bms[i0 + i] : nullptr;
+        clear_summary_kernel<<<dim3((unsigned)grid, (unsigned)k), 256, 0, st>>>(list, sum_off, n1);
+        SCONE_LAUNCHED();
+    }
     return 0;
 }
 
