@@ -143,27 +143,28 @@ class ClockSampler:
                 'samples': len(sm), 'source': self.source}
 
 
-def ncu_traffic(kernel, E, mb, C, zero_fill):
+def ncu_traffic(kernel, E, mb, C, zero_fill, pipeline=3):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full`
     captures -- only reported when this run has the same launch shape as the capture (cfg5).
       zero_fill  profiles/prof_fill_r1m_raw.csv       (dense-stream mode, b = 64)
-      layer_fwd  profiles/prof_rows_fwd_r1x_raw.csv   (compact row-list pipeline, b = 2048: the two layer_fwd_rows_kernel
-                                                       launches of one micro-batch, averaged)"""
-    src = None
+      layer_fwd / layer_bwd  profiles/prof_cone_r1z9_raw.csv   (cone pipeline, b = 4096: the two layer_fwd_rows_kernel /
+                                                       rows_bwd_kernel launches of one step, averaged)"""
+    src, pat = None, None
     if kernel == 'zero_fill' and (E, mb, C) == (999308, 64, 32):
         src = 'prof_fill_r1m_raw.csv'
-    if kernel == 'layer_fwd' and not zero_fill and (E, mb, C) == (999308, 2048, 32):
-        src = 'prof_rows_fwd_r1x_raw.csv'
+    if kernel in ('layer_fwd', 'layer_bwd') and not zero_fill and pipeline == 3 and (E, mb, C) == (999308, 4096, 32):
+        src, pat = 'prof_cone_r1z9_raw.csv', {'layer_fwd': 'layer_fwd_rows_kernel', 'layer_bwd': 'rows_bwd_kernel'}[kernel]
     if src is None:
         return None
     try:
         import csv
         rows = list(csv.reader(open(os.path.join(ROOT, 'profiles', src))))
         hdr, unit = rows[0], rows[1]
+        kn = hdr.index('Kernel Name') if 'Kernel Name' in hdr else None
         scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
         tot, n = 0.0, 0
         for val in rows[2:]:
-            if len(val) < len(hdr):
+            if len(val) < len(hdr) or (pat and (kn is None or pat not in val[kn])):
                 continue
             for name in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
                 i = hdr.index(name)
@@ -249,7 +250,7 @@ def main():
     ap.add_argument('--config', default='cfg5', choices=sorted(CONFIGS))
     ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch')
     ap.add_argument('--micro-batch', type=int, default=0)
-    ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--e2e-steps', type=int, default=20)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', dest='extras', action='store_false', help='skip the sparse-mode and dense-kernel extras')
     ap.add_argument('--zero-fill', type=int, default=0, help='timed region with dense zero-fill of the outputs on (1) or off (0)')
@@ -399,10 +400,16 @@ def main():
                                     'frac': alg_[nme] / avg / 1e6 / peak})
         return ks
     kernels = kernel_table(fam, rows)
-    dom = max(kernels, key=lambda k_: kernels[k_]['share_of_kernel_time'])
+    # the roofline is quoted for the tensor-moving family with the largest share (the families with a byte model); `cone` is the
+    # bit-level set-up of the row lists (integer work, latency-bound: cone / live-row marking, compaction, clearing)
+    largest = max(kernels, key=lambda k_: kernels[k_]['share_of_kernel_time'])
+    with_bytes = [k_ for k_ in kernels if 'achieved_gbs' in kernels[k_]]
+    dom = max(with_bytes or kernels, key=lambda k_: kernels[k_]['share_of_kernel_time'])
+    pipeline_id = L.scone_model_get_pipeline(net.handle)
     dense_bytes_per_traj = 4.0 * E * (15 * C + 2)
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': kernels[dom].get('achieved_gbs'), 'peak': peak, 'unit': 'GB/s',
-                'frac': kernels[dom].get('frac'), 'traffic': ncu_traffic(dom, E, mb, C, args.zero_fill), 'peak_source': peak_src,
+                'frac': kernels[dom].get('frac'), 'traffic': ncu_traffic(dom, E, mb, C, args.zero_fill, pipeline_id), 'peak_source': peak_src,
+                'largest_family': largest,
                 'algorithmic_bytes_per_launch': kernels[dom].get('algorithmic_bytes_per_launch'),
                 'rows_per_step': {k_: v_ / args.steps for k_, v_ in rows.items()},
                 'dense_rows_per_step': float(E) * B * 2,
@@ -411,12 +418,13 @@ def main():
                                      'effective_gbs': dense_bytes_per_traj * value / world / 1e9,
                                      'note': 'SURVEY 8(d) dense formula 4*E*(15C+2) bytes per trajectory times the measured per-GPU '
                                              'trajectories/s: what a dense-streaming implementation would have to move to match'},
-                'bytes_model': 'layer_fwd / layer_bwd: rows produced (device-counted) x 4*(Cin+Cout) / 4*(2*Cin+Cout) bytes per launch; the family '
-                               'time includes its bitmap compaction, candidate marking and (backward) the weight-gradient GEMM; these kernels are '
-                               'L1 / issue bound (rank lookups and gathers are cache-served), not HBM bound (profiles/prof_rows_fwd_r1x_*); '
-                               'zero_fill (dense-stream mode): 4*E*b*C bytes per launch',
+                'bytes_model': 'layer_fwd / layer_bwd: rows produced (device-counted) x 4*(Cin+Cout) / 4*(2*Cin+Cout) bytes per launch; the backward '
+                               'family time includes the weight-gradient GEMM and its reduction; cone = bit-level set-up of the row lists '
+                               '(receptive cone, live rows, compaction, clearing). The row kernels are latency / issue bound (16 warps per SM, '
+                               'dependent entry -> bitmap -> row loads; profiles/prof_cone_r1z9_*), not HBM bound; zero_fill (dense-stream '
+                               'mode): 4*E*b*C bytes per launch',
                 'pipeline': {3: 'row lists over the readout cone, compact tensors', 2: 'row lists, compact tensors', 1: 'row lists, dense tensors', 0: 'unit kernels, byte flags'}[
-                    L.scone_model_get_pipeline(net.handle)]}
+                    pipeline_id]}
 
     # end to end through the host API
     barrier()
@@ -449,8 +457,9 @@ def main():
         barrier()
         L.scone_profile_reset()
         L.scone_profile_enable(1)
+        other_steps = min(args.steps, 5)
         ev0.record()
-        for _ in range(args.steps):
+        for _ in range(other_steps):
             step_other()
         ev1.record()
         barrier()
@@ -460,8 +469,8 @@ def main():
         mb_main, mb = mb, mb2
         k2 = kernel_table(fam2, rows2)
         mb = mb_main
-        other_mode = {'zero_fill': 1 - args.zero_fill, 'micro_batch': mb2, 'value': world * B * args.steps / (sm_ms / 1e3),
-                      'unit': 'trajectories/s', 'ms_per_step': sm_ms / args.steps, 'zero_fill_kernel': k2.get('zero_fill'),
+        other_mode = {'zero_fill': 1 - args.zero_fill, 'micro_batch': mb2, 'value': world * B * other_steps / (sm_ms / 1e3),
+                      'unit': 'trajectories/s', 'ms_per_step': sm_ms / other_steps, 'steps': other_steps, 'zero_fill_kernel': k2.get('zero_fill'),
                       'note': 'zero_fill=1 (dense-stream mode, unit kernels): every activation / gradient tensor is a complete dense array '
                               '(each byte written once per micro-batch by zero_fill_kernel, timed on its side stream); zero_fill=0: rows '
                               'outside the support are never written'}

@@ -767,7 +767,7 @@ extern "C" int scone_model_forward_host(scone_model* m, int32_t B, const int32_t
         cudaMemset(m->d_overflow, 0, sizeof(int));
         scone_set_error("scone_model: a micro-batch exceeded a row-list capacity (%d rows per compact tensor, %d cone edges per trajectory "
                         "and layer); the log-probs are incomplete — use a smaller micro-batch or scone_model_set_pipeline(m, 2 / 0)",
-                        m->row_cap, 3072);
+                        m->row_cap, 2048);
         return 4;
     }
     return 0;
@@ -804,7 +804,7 @@ extern "C" int scone_model_read_grads(scone_model* m, float* out, void* st) {
     if (overflow) {
         cudaMemset(m->d_overflow, 0, sizeof(int));
         scone_set_error("scone_model: a micro-batch exceeded a row-list capacity (%d rows per compact tensor, %d rows of the backward's A "
-                        "buffer, 3072 cone edges per trajectory and layer); the gradients are incomplete — use a smaller micro-batch or "
+                        "buffer, 2048 cone edges per trajectory and layer); the gradients are incomplete — use a smaller micro-batch or "
                         "scone_model_set_pipeline(m, 2 / 0)", m->row_cap, m->a_cap);
         return 4;
     }

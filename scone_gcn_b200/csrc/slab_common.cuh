@@ -59,8 +59,9 @@ __device__ __forceinline__ void bit_set2(uint32_t* __restrict__ bm, uint32_t* __
     const size_t widx = row >> 5;
     uint32_t* w = bm + widx;
     const uint32_t bit = 1u << (row & 31);
-    if (!(*w & bit)) {
-        if (atomicOr(w, bit) == 0u && bm1 != nullptr) atomicOr(bm1 + (widx >> 5), 1u << (widx & 31));
+    if (!(*w & bit)) {                                   // both atomics are fire-and-forget (RED): nothing waits on their result
+        atomicOr(w, bit);
+        if (bm1 != nullptr) atomicOr(bm1 + (widx >> 5), 1u << (widx & 31));
     }
 }
 // compact storage: row r of a tensor lives at index rank(r) = pref[r >> 5] + popc(bm[r >> 5] & bits below r) = its position in
