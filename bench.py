@@ -38,7 +38,7 @@ CONFIGS = {
                  desc='1M-edge synthetic holed Delaunay complex, 4096 trajectories per GPU (32768 at 8 GPUs), 3-layer SCoNe hidden 32'),
     'cfg4': dict(n_nodes=110000, batch=4096, hidden=32, micro_batch=4096,
                  desc='~300k-edge synthetic complex, batch 4096, 3-layer SCoNe hidden 32'),
-    'cfg1': dict(n_nodes=400, batch=1000, hidden=16, micro_batch=256,
+    'cfg1': dict(n_nodes=400, batch=1000, hidden=16, micro_batch=1000,
                  desc='default synthetic complex (400 nodes), 1000 trajectories, 3-layer SCoNe hidden 16'),
 }
 KIND_NAMES = ['layer_fwd', 'layer_bwd', 'layer0_fwd', 'layer0_bwd', 'readout', 'flows_to_dense', 'zero_fill', 'cone']

@@ -98,28 +98,28 @@ __global__ void __launch_bounds__(256) rows_mark_kernel(const uint32_t* __restri
 // Compaction of a SPARSE two-level bitmap (see bit_set2): same contract as compact_bitmap_kernel (ascending row list, count, rank
 // prefix per non-empty word, one launch, per-CTA totals + decoupled look-back over tickets, deterministic) but the CTAs scan the
 // summary words and touch only the bitmap words whose summary bit is set.  tickets[] must be zero at launch.
-constexpr int kSumWpt = 16, kSumChunk = kSumWpt * 256, kSumMaxChunks = 64;
-// A warp walks its 512 summary words of a chunk (16 per lane, ascending = lane-major) COOPERATIVELY: for every non-empty summary
+constexpr int kSumMaxChunks = 64;       // chunks (WPT * 256 summary words) per CTA
+// A warp walks its 32 * WPT summary words of a chunk (WPT per lane, ascending = lane-major) COOPERATIVELY: for every non-empty summary
 // word the 32 lanes load the 32 bitmap words under it (one 128-byte line) at once.  With trajectory-major row ids the set bits
 // of a sparse bitmap sit in a few dense clusters; a thread-per-word walk left all the work to a handful of threads.
 // WRITE = false: returns this lane's share of the count (sum over the warp = rows under the warp's words).
 // WRITE = true: rows are written from list index `off` on (ascending), prefixes for the non-empty bitmap words.
-template <bool WRITE>
-__device__ __forceinline__ long long summary_walk(const uint32_t* __restrict__ bm, long long w1_lane, const uint32_t (&sm)[kSumWpt],
+template <bool WRITE, int WPT>
+__device__ __forceinline__ long long summary_walk(const uint32_t* __restrict__ bm, long long w1_lane, const uint32_t (&sm)[WPT],
                                                   long long off, uint32_t* __restrict__ list, uint32_t* __restrict__ pref_out,
                                                   long long list_cap) {
     const int lane = threadIdx.x & 31;
     long long cnt = 0;
     uint32_t any = 0u;
 #pragma unroll
-    for (int k = 0; k < kSumWpt; ++k) any |= sm[k];
+    for (int k = 0; k < WPT; ++k) any |= sm[k];
     unsigned mask = __ballot_sync(0xffffffffu, any != 0u);
     while (mask) {
         const int src = __ffs(mask) - 1;
         mask &= mask - 1;
         const long long w1s = __shfl_sync(0xffffffffu, w1_lane, src);
 #pragma unroll
-        for (int k = 0; k < kSumWpt; ++k) {
+        for (int k = 0; k < WPT; ++k) {
             const uint32_t word = __shfl_sync(0xffffffffu, sm[k], src);
             if (word == 0u) continue;                     // (uniform)
             const long long w = (w1s + k) * 32 + lane;    // this lane's bitmap word
@@ -151,10 +151,13 @@ __device__ __forceinline__ long long summary_walk(const uint32_t* __restrict__ b
     return WRITE ? off : cnt;
 }
 
+// WPT (summary words per thread: 16, 4 or 1) is chosen by the launcher so that small bitmaps still spread over warps / CTAs.
+template <int WPT>
 __global__ void __launch_bounds__(256) compact_summary_kernel(const uint32_t* __restrict__ bm, const uint32_t* __restrict__ bm1,
                                                              long long n1_words, uint32_t* __restrict__ list, int* __restrict__ n_out,
                                                              unsigned long long* __restrict__ tickets, uint32_t* __restrict__ pref_out,
                                                              long long list_cap) {
+    constexpr int kSumWpt = WPT, kSumChunk = WPT * 256;
     __shared__ int s_cnt[kSumMaxChunks * 8];              // rows under (chunk, warp), chunk-major = ascending
     __shared__ long long s_prefix;
     __shared__ int s_total;
@@ -162,22 +165,26 @@ __global__ void __launch_bounds__(256) compact_summary_kernel(const uint32_t* __
     const long long per_cta = ((n1_words + gridDim.x - 1) / gridDim.x + kSumChunk - 1) / kSumChunk * kSumChunk;     // whole chunks
     const long long lo = (long long)blockIdx.x * per_cta, hi = lo + per_cta < n1_words ? lo + per_cta : n1_words;
     const int n_chunks = hi > lo ? (int)((hi - lo + kSumChunk - 1) / kSumChunk) : 0;
-    auto load4 = [&](long long w1, uint32_t (&sm)[kSumWpt]) {   // summary words w1 .. w1+15 (w1 % 16 == 0; the summary is padded), zero beyond hi
+    auto load4 = [&](long long w1, uint32_t (&sm)[kSumWpt]) {   // summary words w1 .. w1+WPT-1 (w1 % WPT == 0; the summary is padded), zero beyond hi
+        if (WPT == 1) {
+            sm[0] = w1 < hi ? __ldg(bm1 + w1) : 0u;
+        } else {
 #pragma unroll
-        for (int v4 = 0; v4 < kSumWpt / 4; ++v4) {
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (w1 + 4 * v4 < hi) v = __ldg(reinterpret_cast<const uint4*>(bm1 + w1 + 4 * v4));
-            sm[4 * v4 + 0] = v.x;
-            sm[4 * v4 + 1] = w1 + 4 * v4 + 1 < hi ? v.y : 0u;
-            sm[4 * v4 + 2] = w1 + 4 * v4 + 2 < hi ? v.z : 0u;
-            sm[4 * v4 + 3] = w1 + 4 * v4 + 3 < hi ? v.w : 0u;
+            for (int v4 = 0; v4 < (WPT + 3) / 4; ++v4) {
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (w1 + 4 * v4 < hi) v = __ldg(reinterpret_cast<const uint4*>(bm1 + w1 + 4 * v4));
+                sm[(4 * v4 + 0) % WPT] = v.x;
+                sm[(4 * v4 + 1) % WPT] = w1 + 4 * v4 + 1 < hi ? v.y : 0u;
+                sm[(4 * v4 + 2) % WPT] = w1 + 4 * v4 + 2 < hi ? v.z : 0u;
+                sm[(4 * v4 + 3) % WPT] = w1 + 4 * v4 + 3 < hi ? v.w : 0u;
+            }
         }
     };
     uint32_t sm[kSumWpt];                                  // (one chunk per CTA — the usual case — is loaded once for both passes)
     for (int c = 0; c < n_chunks; ++c) {
         const long long w1 = lo + (long long)c * kSumChunk + (long long)kSumWpt * threadIdx.x;
         load4(w1, sm);
-        int cnt = (int)summary_walk<false>(bm, w1, sm, 0, nullptr, nullptr, 0);
+        int cnt = (int)summary_walk<false, WPT>(bm, w1, sm, 0, nullptr, nullptr, 0);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         if (lane == 0) s_cnt[c * 8 + warp] = cnt;
@@ -213,7 +220,7 @@ __global__ void __launch_bounds__(256) compact_summary_kernel(const uint32_t* __
         for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
         const long long w1 = lo + (long long)c * kSumChunk + (long long)kSumWpt * threadIdx.x;
         if (n_chunks > 1) load4(w1, sm);
-        summary_walk<true>(bm, w1, sm, base + before, list, pref_out, list_cap);
+        summary_walk<true, WPT>(bm, w1, sm, base + before, list, pref_out, list_cap);
     }
 }
 
@@ -1146,12 +1153,18 @@ static long long summary_words(const scone_complex* cx, int b) { return (((long 
 int scone_compact_rows_summary(const scone_complex* cx, int b, const uint32_t* bm, size_t sum_off, uint32_t* list, int* n_dev,
                                unsigned long long* tickets, cudaStream_t st, uint32_t* pref_out, long long list_cap) {
     const long long n1 = summary_words(cx, b);
-    int grid = cx->num_sms * 4 < 1024 ? cx->num_sms * 4 : 1024;     // (1024 single-chunk CTAs measured slower: 48 vs 34 us)
-    if (n1 < (long long)grid * kSumChunk) grid = (int)((n1 + kSumChunk - 1) / kSumChunk);
+    const int max_grid = cx->num_sms * 4 < 1024 ? cx->num_sms * 4 : 1024;     // (1024 single-chunk CTAs measured slower: 48 vs 34 us)
+    // summary words per thread: 16 when that still fills the GPU, else 4, else 1 (a small / dense bitmap must not end up in one warp)
+    const int wpt = n1 >= (long long)16 * 256 * cx->num_sms ? 16 : (n1 >= (long long)4 * 256 * cx->num_sms ? 4 : 1);
+    const long long chunk = (long long)wpt * 256;
+    int grid = max_grid;
+    if (n1 < (long long)grid * chunk) grid = (int)((n1 + chunk - 1) / chunk);
     if (grid < 1) grid = 1;
-    SCONE_REQUIRE((n1 + grid - 1) / grid <= (long long)kSumMaxChunks * kSumChunk, "scone_compact_rows_summary: bitmap too large for %d CTAs", grid);
+    SCONE_REQUIRE((n1 + grid - 1) / grid <= (long long)kSumMaxChunks * chunk, "scone_compact_rows_summary: bitmap too large for %d CTAs", grid);
     SCONE_CUDA(cudaMemsetAsync(tickets, 0, (size_t)grid * 8, st));
-    compact_summary_kernel<<<grid, 256, 0, st>>>(bm, bm + sum_off, n1, list, n_dev, tickets, pref_out, list_cap);
+    if (wpt == 16) compact_summary_kernel<16><<<grid, 256, 0, st>>>(bm, bm + sum_off, n1, list, n_dev, tickets, pref_out, list_cap);
+    else if (wpt == 4) compact_summary_kernel<4><<<grid, 256, 0, st>>>(bm, bm + sum_off, n1, list, n_dev, tickets, pref_out, list_cap);
+    else compact_summary_kernel<1><<<grid, 256, 0, st>>>(bm, bm + sum_off, n1, list, n_dev, tickets, pref_out, list_cap);
     SCONE_LAUNCHED();
     return 0;
 }

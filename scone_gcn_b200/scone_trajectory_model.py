@@ -198,8 +198,12 @@ class Scone_GCN():
         self.shifts = shifts
         self._cx = cx.with_model(model_type)
         n = len(onp.asarray(inputs[1]))
-        mb = self.micro_batch or min(max(n, 1), 256)
-        self._net = SconeModel(self._cx, [h[1] for h in hidden_layers], micro_batch=mb)
+        widths = [h[1] for h in hidden_layers]
+        # widths 16 / 32 run on the compact row-list pipeline (memory follows the trajectories' support): thousands of
+        # trajectories per micro-batch; other widths keep dense [E][micro_batch][C] tensors resident
+        cap = 4096 if all(w in (16, 32) for w in widths) and self._cx.E * 4096 < 2 ** 32 else 256
+        mb = self.micro_batch or min(max(n, 1), cap)
+        self._net = SconeModel(self._cx, widths, micro_batch=mb)
         self.model_single = model
 
         def batched(weights, *args):
