@@ -151,7 +151,11 @@ int scone_model_get_zero_fill(const scone_model* m);
  *     trajectory read H_L only at the edges incident to the neighbours of its last node (trajectory_experiments.py:151,298-303),
  *     H_{L-1} one hop around those, and so on; the cone of layer l is both the rows of H_l the forward must produce and the rows
  *     of G_l the backward produces, so each layer has one bitmap / rank prefix / row list, built from last_nodes before the
- *     forward.  Log-probs and gradients are bit-identical to pipeline 2 (test).
+ *     forward; inside the cone only the rows in the structural support of the flows (LIVE rows) are computed.  Log-probs are
+ *     bit-identical to pipeline 2, gradients equal up to the grouping of the fp32 sums (tests).  Row ids are 32-bit unsigned:
+ *     E * micro_batch < 2^32 (2^31 for the other pipelines).  Capacities per micro-batch: 32 M rows per compact tensor, 6 M rows
+ *     of the backward's A buffer, 2048 cone edges per trajectory and layer; beyond them scone_model_read_grads /
+ *     scone_model_forward_host report an error (complexes with max degree > 32 therefore start on pipeline 2).
  *   2 = row lists over COMPACT tensors, whole support: each tensor carries a row bitmap, row r is
  *     stored at index rank(r) = its position in the compacted row list, producers mark the candidate rows of the next tensor,
  *     per layer one bitmap compaction + one row-list kernel (tensor-core product).  Memory and traffic follow the support of

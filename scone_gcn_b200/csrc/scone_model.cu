@@ -504,7 +504,9 @@ extern "C" int scone_model_create(const scone_complex* cx, int32_t n_layers, con
     m->d_occG.assign(n_layers, nullptr);
     // row ids are 32-bit: unsigned (E * mb < 2^32) in the compact trajectory-major pipelines, E * mb < 2^31 elsewhere
     m->rows_ok = scone_rows_supported(cx, n_layers, hidden) && E * mb < ((size_t)1 << 32);
-    m->pipeline = m->rows_ok ? 3 : 0;
+    // the cone kernel stages at most 2048 edges per trajectory and level in shared memory: the top level alone has up to D * D
+    // edges, so complexes with very high degrees start on the whole-support pipeline (the cone would report an overflow)
+    m->pipeline = m->rows_ok ? ((cx->D <= 32 || E * mb >= ((size_t)1 << 31)) ? 3 : 2) : 0;
     if (!m->rows_ok && E * mb >= ((size_t)1 << 31)) {
         scone_set_error("scone_model_create: E * micro_batch = %zu needs the row-list pipeline (widths 16 / 32, E * micro_batch < 2^32)", E * mb);
         delete m;

@@ -1109,7 +1109,7 @@ int launch_rows_l0_fwd(const scone_complex* cx, int act, int b, const float* X, 
 }  // namespace
 
 bool scone_rows_supported(const scone_complex* cx, int n_layers, const int32_t* hidden) {
-    if (g_scone_dense_kernel == 0 || cx->d_mptr == nullptr) return false;
+    if (g_scone_dense_kernel == 0 || cx->d_mptr == nullptr || cx->D > kRoMaxD) return false;   // (readout / cone kernels: degree <= kRoMaxD)
     for (int l = 0; l < n_layers; ++l)
         if (hidden[l] != 16 && hidden[l] != 32) return false;
     return true;
