@@ -129,7 +129,7 @@ int scone_rows_cone(const scone_complex* cx, int b, const int32_t* last_nodes, u
                     int* overflow_dev, cudaStream_t st);
 int scone_compact_rows_summary(const scone_complex* cx, int b, const uint32_t* bm, size_t sum_off, uint32_t* list, int* n_dev,
                                unsigned long long* tickets, cudaStream_t st, uint32_t* pref_out, long long list_cap);
-int scone_clear_summary(const scone_complex* cx, int b, uint32_t* const* bms, int count, size_t sum_off, cudaStream_t st);
+int scone_clear_summary(const scone_complex* cx, int b, uint32_t* const* bms, int count, int master, size_t sum_off, cudaStream_t st);
 // bitmap-native row-list pipeline (scone_rows.cu, scone_slab.cu)
 bool scone_rows_supported(const scone_complex* cx, int n_layers, const int32_t* hidden);
 int64_t scone_rows_dw_workspace_bytes(int cin, int cout);

@@ -383,9 +383,9 @@ int cone_build_mb(scone_model* m, int32_t b, const int32_t* ptr, const int32_t* 
 // end of a micro-batch: the bitmaps go back to all-zero (cost follows the cone, not E*b)
 int cone_clear_mb(scone_model* m, int32_t b, cudaStream_t s) {
     ScopedProf prof(SCONE_K_CONE, s);
-    std::vector<uint32_t*> bms(m->d_bmGr);
-    bms.insert(bms.end(), m->d_bmC.begin(), m->d_bmC.end());
-    if (scone_clear_summary(m->cx, b, bms.data(), (int)bms.size(), m->sum_off, s)) return 1;
+    std::vector<uint32_t*> bms(m->d_bmC);                 // [0] = the lowest cone level: contains every other bitmap of the step
+    bms.insert(bms.end(), m->d_bmGr.begin(), m->d_bmGr.end());
+    if (scone_clear_summary(m->cx, b, bms.data(), (int)bms.size(), 0, m->sum_off, s)) return 1;
     m->cone_clean = true;
     return 0;
 }
@@ -767,6 +767,7 @@ extern "C" int scone_model_forward_host(scone_model* m, int32_t B, const int32_t
     SCONE_CUDA(cudaStreamSynchronize(s));
     if (overflow) {
         cudaMemset(m->d_overflow, 0, sizeof(int));
+        m->cone_clean = false;                             // a truncated cone list: the clearing may have missed bits
         scone_set_error("scone_model: a micro-batch exceeded a row-list capacity (%d rows per compact tensor, %d cone edges per trajectory "
                         "and layer); the log-probs are incomplete — use a smaller micro-batch or scone_model_set_pipeline(m, 2 / 0)",
                         m->row_cap, 2048);
@@ -805,6 +806,7 @@ extern "C" int scone_model_read_grads(scone_model* m, float* out, void* st) {
     SCONE_CUDA(cudaStreamSynchronize(s));
     if (overflow) {
         cudaMemset(m->d_overflow, 0, sizeof(int));
+        m->cone_clean = false;
         scone_set_error("scone_model: a micro-batch exceeded a row-list capacity (%d rows per compact tensor, %d rows of the backward's A "
                         "buffer, 2048 cone edges per trajectory and layer); the gradients are incomplete — use a smaller micro-batch or "
                         "scone_model_set_pipeline(m, 2 / 0)", m->row_cap, m->a_cap);

@@ -224,17 +224,18 @@ __global__ void __launch_bounds__(256) compact_summary_kernel(const uint32_t* __
     }
 }
 
-// back to all-zero: every bitmap word under a set summary bit, then the summary word; blockIdx.y = which bitmap
+// back to all-zero.  `master` is the summary of a bitmap that contains every bit set in any bitmap of the list (the lowest cone
+// level): for each of its set bits the word is zeroed in ALL bitmaps, then the summary word in all of them.  One scan of one
+// summary instead of one per bitmap.
 constexpr int kClearMax = 16;
 struct ClearList {
     uint32_t* bm[kClearMax];
 };
-__global__ void __launch_bounds__(256) clear_summary_kernel(ClearList list, size_t sum_off, long long n1_words) {
-    uint32_t* bm = list.bm[blockIdx.y];
-    uint32_t* bm1 = bm + sum_off;                         // 64-byte aligned, padded to whole 16-byte groups
-    const long long n4 = (n1_words + 3) / 4;
+__global__ void __launch_bounds__(256) clear_summary_kernel(ClearList list, int count, uint32_t* __restrict__ master, size_t sum_off,
+                                                           long long n1_words) {
+    const long long n4 = (n1_words + 3) / 4;              // summaries are 64-byte aligned and padded to whole 16-byte groups
     for (long long g4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; g4 < n4; g4 += (long long)gridDim.x * blockDim.x) {
-        const uint4 v = *reinterpret_cast<const uint4*>(bm1 + 4 * g4);
+        const uint4 v = *reinterpret_cast<const uint4*>(master + 4 * g4);
         if ((v.x | v.y | v.z | v.w) == 0u) continue;
         const uint32_t sm4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -243,10 +244,10 @@ __global__ void __launch_bounds__(256) clear_summary_kernel(ClearList list, size
             while (sm) {
                 const int q = __ffs(sm) - 1;
                 sm &= sm - 1;
-                bm[(4 * g4 + k) * 32 + q] = 0u;
+                for (int i = 0; i < count; ++i) list.bm[i][(4 * g4 + k) * 32 + q] = 0u;
             }
         }
-        *reinterpret_cast<uint4*>(bm1 + 4 * g4) = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = 0; i < count; ++i) *reinterpret_cast<uint4*>(list.bm[i] + sum_off + 4 * g4) = make_uint4(0u, 0u, 0u, 0u);
     }
 }
 
@@ -302,7 +303,9 @@ __global__ void __launch_bounds__(256) rows_cone_kernel(const int32_t* __restric
                 uint32_t* bm = cone.bm[lv];
                 const size_t row = tbase + (unsigned)e, widx = row >> 5;
                 atomicOr(bm + widx, 1u << (row & 31));
-                atomicOr(bm + sum_off + (widx >> 5), 1u << (widx & 31));
+                // only the lowest level keeps summary bits: it contains every level above it (a merged operator row holds its own
+                // diagonal) and every live row, so its summary is the one the clearing kernel scans
+                if (lv == 0) atomicOr(bm + sum_off + (widx >> 5), 1u << (widx & 31));
                 if (lv > 0) {
                     const int pos = atomicAdd(&s_n[which], 1);
                     if (pos < kConeCap) s_list[which][pos] = e;
@@ -1169,18 +1172,17 @@ int scone_compact_rows_summary(const scone_complex* cx, int b, const uint32_t* b
     return 0;
 }
 
-int scone_clear_summary(const scone_complex* cx, int b, uint32_t* const* bms, int count, size_t sum_off, cudaStream_t st) {
+// bms[0 .. count): two-level bitmaps to clear; bms[master] must contain every bit set in any of them and carry the summary bits
+int scone_clear_summary(const scone_complex* cx, int b, uint32_t* const* bms, int count, int master, size_t sum_off, cudaStream_t st) {
+    SCONE_REQUIRE(count >= 1 && count <= kClearMax && master >= 0 && master < count, "scone_clear_summary: 1..%d bitmaps", kClearMax);
     const long long n1 = summary_words(cx, b);
-    long long grid = (n1 + 255) / 256;
-    if (grid > cx->num_sms * 4) grid = cx->num_sms * 4;
+    long long grid = ((n1 + 3) / 4 + 255) / 256;
+    if (grid > cx->num_sms * 8) grid = cx->num_sms * 8;
     if (grid < 1) grid = 1;
-    for (int i0 = 0; i0 < count; i0 += kClearMax) {
-        ClearList list;
-        const int k = count - i0 < kClearMax ? count - i0 : kClearMax;
-        for (int i = 0; i < kClearMax; ++i) list.bm[i] = i < k ? bms[i0 + i] : nullptr;
-        clear_summary_kernel<<<dim3((unsigned)grid, (unsigned)k), 256, 0, st>>>(list, sum_off, n1);
-        SCONE_LAUNCHED();
-    }
+    ClearList list;
+    for (int i = 0; i < kClearMax; ++i) list.bm[i] = i < count ? bms[i] : nullptr;
+    clear_summary_kernel<<<(unsigned)grid, 256, 0, st>>>(list, count, bms[master] + sum_off, sum_off, n1);
+    SCONE_LAUNCHED();
     return 0;
 }
 
