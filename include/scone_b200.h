@@ -190,6 +190,16 @@ int scone_model_loss_grad_dev(scone_model* m, int32_t B, const int32_t* traj_ptr
 int scone_model_loss_grad_host(scone_model* m, int32_t B, const int32_t* traj_ptr, const int32_t* flow_edge,
                                const float* flow_val, const int32_t* last_nodes,
                                const int32_t* target_idx, const float* mask, int32_t zero_first, void* stream);
+/* Next-node accuracy on the device (scone_trajectory_model.py:59-71): for every trajectory with mask != 0 the prediction is
+ * argmax_j of (j < n_nbrs[t] ? logprobs[t][j] : -100) over ALL D slots — the first maximum wins, a NaN wins over numbers, as
+ * NumPy / JAX argmax — compared with target_idx[t].  out[0] = correct predictions, out[1] = masked trajectories (integers:
+ * accuracy = out[0] / out[1], identical to np.mean(pred_choice == target_choice)).  out_dev is overwritten. */
+int scone_accuracy_dev(int32_t B, int32_t D, const float* logprobs_dev, const int32_t* n_nbrs_dev,
+                       const int32_t* target_idx_dev, const float* mask_dev, int32_t* out_dev /* [2] */, void* stream);
+/* Forward + accuracy from HOST buffers (micro-batched forward, the log-probs never leave the device); out_host[2] as above. */
+int scone_model_accuracy_host(scone_model* m, int32_t B, const int32_t* traj_ptr, const int32_t* flow_edge,
+                              const float* flow_val, const int32_t* last_nodes, const int32_t* n_nbrs,
+                              const int32_t* target_idx, const float* mask, int32_t* out_host /* [2] */, void* stream);
 /* Read back [grads | nll_sum | count] (host, n_params + 2 floats); synchronises the stream. */
 int scone_model_read_grads(scone_model* m, float* out_host, void* stream);
 

@@ -74,6 +74,8 @@ SIGNATURES = {
     'scone_model_forward_dev': (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     'scone_model_loss_grad_dev': (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     'scone_model_loss_grad_host': (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    'scone_accuracy_dev': (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'scone_model_accuracy_host': (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'scone_model_read_grads': (C.c_int, [_vp, _vp, _vp]),
     'scone_model_adam_step': (C.c_int, [_vp, _i32, _f32, _f32, _vp]),
 }

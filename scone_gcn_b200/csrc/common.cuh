@@ -156,5 +156,7 @@ int scone_rows_readout_backward(const scone_complex* cx, int act, int b, int C, 
                                 float scale, float* GL, const int* n_dev, int g_cap, int* overflow_dev, float* dwout, float* nll_sum,
                                 float* count, int accumulate, float* ws, const uint32_t* bmH, const uint32_t* prefH, const uint32_t* bmG,
                                 const uint32_t* prefG, cudaStream_t st);
+int scone_accuracy_launch(int B, int D, const float* logprobs, const int32_t* n_nbrs, const int32_t* target_idx, const float* mask,
+                          int32_t* out, cudaStream_t st);
 int scone_adam_launch(float* W, float* m, float* v, const float* gradbuf, int64_t n, int32_t step, float lr,
                       float wd, void* stream);

@@ -54,7 +54,7 @@ struct scone_model {
     void* d_ws = nullptr;                     // backward / readout workspace
     float* d_logp = nullptr;                  // [mb][D]
     // staging for the *_host entry points
-    int32_t *d_ptr = nullptr, *d_edge = nullptr, *d_last = nullptr, *d_tgt = nullptr;
+    int32_t *d_ptr = nullptr, *d_edge = nullptr, *d_last = nullptr, *d_tgt = nullptr, *d_nn = nullptr, *d_acc = nullptr;
     float *d_val = nullptr, *d_mask = nullptr, *d_logp_all = nullptr;
     int64_t cap_B = 0, cap_nnz = 0;
 };
@@ -63,11 +63,13 @@ namespace {
 
 int ensure_staging(scone_model* m, int64_t B, int64_t nnz) {
     if (B > m->cap_B) {
-        cudaFree(m->d_ptr); cudaFree(m->d_last); cudaFree(m->d_tgt); cudaFree(m->d_mask); cudaFree(m->d_logp_all);
+        cudaFree(m->d_ptr); cudaFree(m->d_last); cudaFree(m->d_tgt); cudaFree(m->d_mask); cudaFree(m->d_logp_all); cudaFree(m->d_nn);
         int64_t cap = B + B / 4 + 16;
         SCONE_CUDA(cudaMalloc((void**)&m->d_ptr, (cap + 1) * sizeof(int32_t)));
         SCONE_CUDA(cudaMalloc((void**)&m->d_last, cap * sizeof(int32_t)));
         SCONE_CUDA(cudaMalloc((void**)&m->d_tgt, cap * sizeof(int32_t)));
+        SCONE_CUDA(cudaMalloc((void**)&m->d_nn, cap * sizeof(int32_t)));
+        if (!m->d_acc) SCONE_CUDA(cudaMalloc((void**)&m->d_acc, 2 * sizeof(int32_t)));
         SCONE_CUDA(cudaMalloc((void**)&m->d_mask, cap * sizeof(float)));
         SCONE_CUDA(cudaMalloc((void**)&m->d_logp_all, cap * (size_t)(m->cx->D > 0 ? m->cx->D : 1) * sizeof(float)));
         m->cap_B = cap;
@@ -571,7 +573,7 @@ extern "C" int scone_model_destroy(scone_model* m) {
     if (m->ev_begin) cudaEventDestroy(m->ev_begin);
     for (auto e : m->ev_fill) if (e) cudaEventDestroy(e);
     cudaFree(m->d_ptr); cudaFree(m->d_edge); cudaFree(m->d_last); cudaFree(m->d_tgt); cudaFree(m->d_val);
-    cudaFree(m->d_mask); cudaFree(m->d_logp_all);
+    cudaFree(m->d_mask); cudaFree(m->d_logp_all); cudaFree(m->d_nn); cudaFree(m->d_acc);
     delete m;
     return 0;
 }
@@ -771,6 +773,49 @@ extern "C" int scone_model_forward_host(scone_model* m, int32_t B, const int32_t
         scone_set_error("scone_model: a micro-batch exceeded a row-list capacity (%d rows per compact tensor, %d cone edges per trajectory "
                         "and layer); the log-probs are incomplete — use a smaller micro-batch or scone_model_set_pipeline(m, 2 / 0)",
                         m->row_cap, 2048);
+        return 4;
+    }
+    return 0;
+}
+
+extern "C" int scone_accuracy_dev(int32_t B, int32_t D, const float* logprobs, const int32_t* n_nbrs, const int32_t* target_idx,
+                                  const float* mask, int32_t* out, void* st) {
+    SCONE_REQUIRE(B >= 0 && D >= 1 && out && (B == 0 || (logprobs && n_nbrs && target_idx && mask)), "scone_accuracy_dev: bad arguments");
+    return scone_accuracy_launch(B, D, logprobs, n_nbrs, target_idx, mask, out, as_stream(st));
+}
+
+extern "C" int scone_model_accuracy_host(scone_model* m, int32_t B, const int32_t* ptr, const int32_t* edge, const float* val,
+                                         const int32_t* last, const int32_t* n_nbrs, const int32_t* tgt, const float* mask,
+                                         int32_t* out_host, void* st) {
+    SCONE_REQUIRE(m && out_host && B >= 0 && (B == 0 || (ptr && last && n_nbrs && tgt && mask)), "scone_model_accuracy_host: bad arguments");
+    out_host[0] = out_host[1] = 0;
+    if (B == 0) return 0;
+    cudaStream_t s = as_stream(st);
+    const int64_t nnz = ptr[B];
+    int rc = ensure_staging(m, B, nnz);
+    if (rc) return rc;
+    SCONE_CUDA(cudaMemcpyAsync(m->d_ptr, ptr, (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (nnz) {
+        SCONE_CUDA(cudaMemcpyAsync(m->d_edge, edge, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        SCONE_CUDA(cudaMemcpyAsync(m->d_val, val, nnz * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
+    SCONE_CUDA(cudaMemcpyAsync(m->d_last, last, B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    SCONE_CUDA(cudaMemcpyAsync(m->d_nn, n_nbrs, B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    SCONE_CUDA(cudaMemcpyAsync(m->d_tgt, tgt, B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    SCONE_CUDA(cudaMemcpyAsync(m->d_mask, mask, B * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = scone_model_forward_dev(m, B, m->d_ptr, m->d_edge, m->d_val, m->d_last, m->d_logp_all, st);
+    if (rc) return rc;
+    rc = scone_accuracy_launch(B, m->cx->D, m->d_logp_all, m->d_nn, m->d_tgt, m->d_mask, m->d_acc, s);
+    if (rc) return rc;
+    SCONE_CUDA(cudaMemcpyAsync(out_host, m->d_acc, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    int overflow = 0;
+    if (m->d_overflow) SCONE_CUDA(cudaMemcpyAsync(&overflow, m->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
+    SCONE_CUDA(cudaStreamSynchronize(s));
+    if (overflow) {
+        cudaMemset(m->d_overflow, 0, sizeof(int));
+        m->cone_clean = false;
+        scone_set_error("scone_model: a micro-batch exceeded a row-list capacity; the accuracy is incomplete — use a smaller micro-batch or "
+                        "scone_model_set_pipeline(m, 2 / 0)");
         return 4;
     }
     return 0;

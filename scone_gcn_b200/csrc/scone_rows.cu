@@ -1025,6 +1025,38 @@ __global__ void __launch_bounds__(256) rows_readout_reduce_kernel(const float* _
     }
 }
 
+// Next-node accuracy (scone_trajectory_model.py:59-71): thread = trajectory.  preds[t][n_nbrs[t]:] = -100, argmax over all D slots
+// (first maximum; a NaN beats numbers, as NumPy), compared with the target; integer counts (atomicAdd on ints is exact).
+__global__ void __launch_bounds__(256) accuracy_kernel(const float* __restrict__ logprobs, const int32_t* __restrict__ n_nbrs,
+                                                      const int32_t* __restrict__ target_idx, const float* __restrict__ mask, int B, int D,
+                                                      int32_t* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int correct = 0, counted = 0;
+    if (t < B && mask[t] != 0.f) {
+        const int n = n_nbrs[t];
+        float best = 0.f;
+        int arg = 0;
+        for (int j = 0; j < D; ++j) {
+            const float v = j < n ? logprobs[(size_t)t * D + j] : -100.f;
+            if (j == 0 || v > best || (v != v && best == best)) {
+                best = v;
+                arg = j;
+            }
+        }
+        counted = 1;
+        correct = arg == target_idx[t] ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        correct += __shfl_xor_sync(0xffffffffu, correct, o);
+        counted += __shfl_xor_sync(0xffffffffu, counted, o);
+    }
+    if ((threadIdx.x & 31) == 0 && counted) {
+        atomicAdd(out, correct);
+        atomicAdd(out + 1, counted);
+    }
+}
+
 constexpr int kDwCtas = 148 * 2;
 
 template <int CIN, int COUT, int ACT>
@@ -1110,6 +1142,16 @@ int launch_rows_l0_fwd(const scone_complex* cx, int act, int b, const float* X, 
 }
 
 }  // namespace
+
+int scone_accuracy_launch(int B, int D, const float* logprobs, const int32_t* n_nbrs, const int32_t* target_idx, const float* mask,
+                          int32_t* out, cudaStream_t st) {
+    SCONE_CUDA(cudaMemsetAsync(out, 0, 2 * sizeof(int32_t), st));
+    if (B > 0) {
+        accuracy_kernel<<<(B + 255) / 256, 256, 0, st>>>(logprobs, n_nbrs, target_idx, mask, B, D, out);
+        SCONE_LAUNCHED();
+    }
+    return 0;
+}
 
 bool scone_rows_supported(const scone_complex* cx, int n_layers, const int32_t* hidden) {
     if (g_scone_dense_kernel == 0 || cx->d_mptr == nullptr || cx->D > kRoMaxD) return false;   // (readout / cone kernels: degree <= kRoMaxD)

@@ -89,6 +89,19 @@ class SconeModel:
                    'scone_model_loss_grad_host')
         return self.read_grads(stream) if read else None
 
+    def accuracy(self, traj_ptr, flow_edge, flow_val, last_nodes, n_nbrs, target_idx, mask, stream=None):
+        """(correct, counted) over the trajectories with mask != 0: forward + argmax on the device
+        (scone_trajectory_model.py:59-71; slots >= n_nbrs count as -100, first maximum wins)."""
+        B = len(last_nodes)
+        a = [np.ascontiguousarray(traj_ptr, np.int32), np.ascontiguousarray(flow_edge, np.int32),
+             np.ascontiguousarray(flow_val, np.float32), np.ascontiguousarray(last_nodes, np.int32),
+             np.ascontiguousarray(n_nbrs, np.int32), np.ascontiguousarray(target_idx, np.int32),
+             np.ascontiguousarray(mask, np.float32)]
+        out = np.zeros(2, np.int32)
+        _lib.check(_lib.lib().scone_model_accuracy_host(self.handle, B, *[_lib.ptr(x) for x in a], _lib.ptr(out), stream),
+                   'scone_model_accuracy_host')
+        return int(out[0]), int(out[1])
+
     def read_grads(self, stream=None):
         buf = np.zeros(self.n_params + 2, np.float32)
         _lib.check(_lib.lib().scone_model_read_grads(self.handle, _lib.ptr(buf), stream), 'scone_model_read_grads')

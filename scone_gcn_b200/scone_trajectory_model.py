@@ -116,6 +116,16 @@ class Scone_GCN():
         Computes ratio of correct predictions                             (scone_trajectory_model.py:59-71)
         """
         mask = onp.asarray(mask)
+        if hasattr(self._net, 'accuracy') and not self.forward_all:
+            # forward + mask-to--100 + argmax + compare on the device; only two integers come back.  Only the masked
+            # trajectories are run (the same numbers as forwarding all of them and selecting, quirk Q4).
+            rows = onp.nonzero(mask == 1)[0]
+            p = self._prepared(inputs)
+            self._push(self.weights)
+            yv = onp.asarray(y)
+            tgt = onp.argmax(yv.reshape(yv.shape[0], -1)[rows], axis=1)
+            correct, counted = self._net.accuracy(*p.select(rows), onp.asarray(n_nbrs)[rows], tgt, onp.ones(len(rows), onp.float32))
+            return onp.float64(correct) / onp.float64(counted) if counted else onp.float64('nan')
         target_choice = onp.argmax(onp.asarray(y)[mask == 1], axis=1)
         preds = onp.array(self._forward(self.weights, inputs))
         return self._accuracy_from(preds, target_choice, mask, n_nbrs)

@@ -141,6 +141,33 @@ def test_row_ids_beyond_2_31_microbatch_invariant():
     assert _relmax(res[0][1][:n + 1], res[1][1][:n + 1]) < 1e-4
 
 
+@pytest.mark.parametrize('scale', [0.0, 0.3])
+def test_device_accuracy_matches_numpy(small, scale):
+    """Evaluation on the device: forward + mask-to--100 + argmax + compare (scone_trajectory_model.py:59-71) against
+    the same steps in NumPy on the returned log-probs — integer counts, exact; scale 0 = all log-probs tie (first maximum)."""
+    sg = _mods()
+    from scone_gcn_b200.scone_trajectory_model import Scone_GCN
+    cx = sg.SimplicialComplex.from_dense(small.B1, small.B2, 'scone')
+    ptr, fe, fv = sg.flows_to_csr(small.flows)
+    net = sg.SconeModel(cx, [16, 16, 16], micro_batch=13)
+    rs = np.random.RandomState(4)
+    net.set_weights([scale * rs.randn(*s_) for s_ in net.shapes])
+    _, n_nbrs, _ = so.neighbourhood_tables(small.B1, small.last_nodes)
+    tgt = small.raw['targets_argmax']
+    for mask in (np.ones(small.n_traj, np.float32), (rs.rand(small.n_traj) < 0.5).astype(np.float32)):
+        lp = net.forward(ptr, fe, fv, small.last_nodes)
+        ref = Scone_GCN._accuracy_from(lp[:, :, None], tgt[mask == 1][:, None], mask, n_nbrs)     # [n, 1] like argmax(y[mask == 1], axis=1)
+        correct, counted = net.accuracy(ptr, fe, fv, small.last_nodes, n_nbrs, tgt, mask)
+        assert counted == int(mask.sum())
+        assert correct / counted == ref
+    # fewer valid slots than the true degree: the -100 masking decides
+    half = np.maximum(1, np.asarray(n_nbrs) // 2)
+    mask = np.ones(small.n_traj, np.float32)
+    ref = Scone_GCN._accuracy_from(net.forward(ptr, fe, fv, small.last_nodes)[:, :, None], tgt[:, None], mask, half)
+    correct, counted = net.accuracy(ptr, fe, fv, small.last_nodes, half, tgt, mask)
+    assert correct / counted == ref
+
+
 def test_default_complex_vs_reference_golden():
     sg = _mods()
     ds = Dataset('dataset_default.npz')
