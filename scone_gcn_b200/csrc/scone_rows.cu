@@ -1,17 +1,23 @@
-// scone_rows.cu — the bitmap-native row-list pipeline behind the model-level entry points (widths 16 / 32).
+// scone_rows.cu — the bitmap-native row-list pipelines behind the model-level entry points (widths 16 / 32).
 //
-// Every activation / gradient tensor carries a ROW BITMAP (bit e*b + t set <=> row (e, t) may be non-zero and has been
-// written).  A kernel that produces rows of one tensor also marks — while it walks the merged operator rows anyway —
-// the candidate rows of the NEXT tensor one hop further (idempotent atomicOr: the bitmap does not depend on the order of
-// the writers).  Per layer the pipeline is then: clear the next bitmap, compact the current one into an ascending row list
-// (one launch, deterministic), run one row-list kernel.  No per-layer scatter kernel, no byte flags, nothing proportional to
-// E*b except the E*b/8-byte bitmaps.
+// A tensor is a ROW BITMAP (bit set <=> the row may be non-zero and has been written), an ascending row list, a rank prefix per
+// bitmap word and a compact array [rows][C]; row ids are trajectory-major (t*E + e) for compact tensors, edge-major (e*b + t)
+// over dense tensors (RowIds, slab_common.cuh).  Two orchestrations (scone_model.cu) use the kernels below:
+//   pipeline 3 (default)  one row set per layer shared by H_l and G_l: the LIVE rows = receptive cone of the readout (geometry,
+//                         rows_cone_kernel) & structural support of the flows (marked layer by layer); two-level bitmaps
+//                         (summary bit per word) so that compaction and clearing never scan E*b bits
+//   pipelines 2 / 1       every tensor has its own bitmap over its whole support; producers mark the candidate rows of the next
+//                         tensor one hop further; per layer: clear, compact (scone_kernels.cu), run one row-list kernel
+// Marking is an idempotent atomicOr (the bitmap does not depend on the order of the writers); lists are ascending: deterministic.
 //
-//   flows          X rows + bits, candidate bits of H_1                       synthetic_data_gen.py:327-344 (path_to_flow)
+//   cone           rows of H_L the log-probs read, one hop down per layer   trajectory_experiments.py:151,298-303 (Bconds_func)
+//   flows          X rows (+ live / candidate bits of H_1)                    synthetic_data_gen.py:327-344 (path_to_flow)
 //   first layer    H_1 = act(X w0 + (S0 X) w1 + (S1 X) w2)                    trajectory_experiments.py:145-149 (i = 0)
 //   conv layers    layer_fwd_rows_kernel (scone_slab.cu)                      trajectory_experiments.py:145-149
+//   readout        logits, padded log-softmax, NLL gradient                   trajectory_experiments.py:151-152
 //   backward       A_k = S_k G, Gprev = (sum_k A_k W_k^T) * act'(Hin); dW_k = Hin^T A_k     (jax.grad, scone_trajectory_model.py:307)
 //   first layer bwd  dW_k[0][:] = sum_rows (S_k X)[row] * G_1[row][:]
+//   accuracy       mask-to--100 + argmax + compare                            scone_trajectory_model.py:59-71
 #include <cstdlib>
 #include "common.cuh"
 
