@@ -1,0 +1,57 @@
+"""UNVALIDATED (written at the end of round 1 without GPU budget; the oracle half was run on the CPU): CUDA path vs the oracle on
+hand-built complexes: single triangle, two triangles sharing an edge, a path with no triangles, isolated nodes,
+a last node with maximum degree, a last node with degree 1 — log-probs 1e-5, gradients 1e-4, for scone and ebli."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import scone_oracle as so
+from test_index_tiny_complexes import CASES
+
+pytestmark = pytest.mark.gpu
+
+
+def tiny_problem(name, seed=0):
+    """flows [B, E, 1] with entries in {-1, 0, 1}, one trajectory ending at every node (isolated ones included)."""
+    n, edges, faces = CASES[name]
+    edges, faces = np.asarray(edges, np.int64).reshape(-1, 2), np.asarray(faces, np.int64).reshape(-1, 3)
+    B1, B2 = so.incidence_matrices(n, edges, faces)
+    rs = np.random.RandomState(seed)
+    E = len(edges)
+    last_nodes = np.arange(n)
+    flows = rs.choice([-1.0, 0.0, 1.0], size=(n, E, 1), p=[0.3, 0.4, 0.3])
+    flows[0] = 0.0                                                   # an empty trajectory: all logits 0
+    nb, n_nbrs, _ = so.neighbourhood_tables(B1, last_nodes)
+    D = nb.shape[1]
+    tgt = np.array([rs.randint(0, max(1, k)) for k in n_nbrs])
+    targets = np.zeros((n, D, 1))
+    targets[np.arange(n), tgt, 0] = 1.0
+    return n, edges, faces, B1, B2, last_nodes, flows, targets, tgt
+
+
+@pytest.mark.parametrize('model', ['scone', 'ebli'])
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_tiny_complex_forward_and_grads_vs_oracle(name, model):
+    import scone_gcn_b200 as sg
+    n, edges, faces, B1, B2, last_nodes, flows, targets, tgt = tiny_problem(name)
+    cx = sg.SimplicialComplex.from_simplices(n, edges, faces, model)
+    hidden = [16, 16]
+    net = sg.SconeModel(cx, hidden, micro_batch=4)
+    rs = np.random.RandomState(1)
+    W = [0.4 * rs.randn(*s_) for s_ in net.shapes]
+    net.set_weights(W)
+    ptr, fe, fv = sg.flows_to_csr(flows)
+    lp = net.forward(ptr, fe, fv, last_nodes)
+    orc = so.DenseOracle(model, so.shift_matrices(B1, B2, model), B1, last_nodes, flows, targets)
+    with torch.no_grad():
+        ref = orc.forward(W).numpy()[:, :, 0]
+    assert np.abs(lp - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+    mask = np.ones(n, np.float32)
+    mask[1] = 0.0
+    buf = net.loss_grad(ptr, fe, fv, last_nodes, tgt, mask)
+    k = net.n_params
+    assert buf[k + 1] == mask.sum()
+    _, g_ref = orc.loss_and_grads(W, mask, 0.0)
+    grads = net.unflatten(buf[:k] / buf[k + 1])
+    for a, r in zip(grads, g_ref):
+        assert np.abs(a - r).max() <= 1e-4 * max(np.abs(r).max(), 1e-30)
