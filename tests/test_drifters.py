@@ -43,35 +43,43 @@ def test_jld2_reader_on_the_reference_file(tmp_path):
 
 @pytest.mark.gpu
 def test_drifter_training_matches_oracle():
-    """cfg2: SCoNe on the drifter complex, 5 epochs from the reference init: loss and identical next-node accuracy."""
+    """cfg2: SCoNe on the drifter complex, 5 epochs (20 Adam steps) from 30 x the reference init (0.3-scale weights: the six
+    logits are then well separated, so next-node accuracy is DECIDED): same losses, identical argmax on every trajectory whose
+    oracle top-2 margin is above fp32 noise (>= 98 % of them; the rest are exact structural ties, logits equal to ~1e-7, where
+    the reference's own argmax is rounding noise), accuracies equal up to those rows."""
     import scone_gcn_b200 as sg
     from oracle import scone_oracle as so
     from scone_gcn_b200.scone_trajectory_model import Scone_GCN
     from scone_gcn_b200 import trajectory_experiments as te
+    import torch
     ds = Dataset('dataset_drifters.npz')
-    epochs, bs, lr, wd = 5, 40, 1e-3, 5e-5
+    epochs, bs, lr, wd, scale = 5, 40, 1e-3, 5e-5, 30.0
     orc = so.DenseOracle('scone', so.shift_matrices(ds.B1, ds.B2, 'scone'), ds.B1, ds.last_nodes, ds.flows, ds.targets)
     rng = np.random.RandomState(1030)
-    Wo, res_o = so.train(orc, rng, so.generate_weights(rng, 1, [(3, 16)] * 3, 1, 'scone'), ds.train_mask, ds.test_mask, epochs, bs, lr, wd)
+    W0 = [scale * w for w in so.generate_weights(rng, 1, [(3, 16)] * 3, 1, 'scone')]
+    Wo, res_o = so.train(orc, rng, W0, ds.train_mask, ds.test_mask, epochs, bs, lr, wd)
     np.random.seed(1030)
     cx = sg.SimplicialComplex.from_dense(ds.B1, ds.B2, 'scone')
     inputs = [te.Bconds(cx), ds.last_nodes, ds.flows]
     net = Scone_GCN(epochs, lr, bs, wd, verbose=False)
     net.setup(te.scone_func, [(3, 16)] * 3, te.shift_handles(cx), inputs, ds.targets, None, ds.train_mask)
+    net.weights = [scale * w for w in net.weights]
+    for a, b in zip(net.weights, W0):
+        assert np.array_equal(a, b)
     n_nbrs = np.array([len(so.adjacency_from_B1(ds.B1)[n]) for n in ds.last_nodes])
     res = net.train(inputs, ds.targets, ds.train_mask, ds.test_mask, n_nbrs)
-    assert res[0] == pytest.approx(res_o[0], rel=1e-4) and res[2] == pytest.approx(res_o[2], rel=1e-4)
-    # 20 Adam steps from 0.01-scale weights leave the 6 logits nearly tied, so the argmax is only required to agree where
-    # the oracle's own top-2 margin is above fp32 noise; everywhere else the predictions must be identical
-    import torch
+    assert res[0] == pytest.approx(res_o[0], rel=2e-5) and res[2] == pytest.approx(res_o[2], rel=2e-5)
     with torch.no_grad():
         lp_o = orc.forward(Wo).numpy()[:, :, 0]
     lp = net._forward(net.weights, inputs)[:, :, 0]
-    assert np.abs(lp - lp_o).max() < 1e-4
+    assert np.abs(lp - lp_o).max() < 2e-5 * max(1.0, np.abs(lp_o).max())
     for i in range(len(lp)):
         lp[i, n_nbrs[i]:] = -100
         lp_o[i, n_nbrs[i]:] = -100
     top2 = np.sort(lp_o, axis=1)[:, -2:]
-    decided = (top2[:, 1] - top2[:, 0]) > 1e-4
-    assert decided.sum() > 0 and np.array_equal(np.argmax(lp, axis=1)[decided], np.argmax(lp_o, axis=1)[decided])
-    assert abs(res[1] - res_o[1]) <= (~decided).mean() + 1e-9 and abs(res[3] - res_o[3]) <= (~decided).mean() * 5 + 1e-9
+    decided = (top2[:, 1] - top2[:, 0]) > 1e-5
+    assert decided.mean() >= 0.98
+    assert np.array_equal(np.argmax(lp, axis=1)[decided], np.argmax(lp_o, axis=1)[decided])
+    n_tr, n_te = ds.train_mask.sum(), ds.test_mask.sum()
+    assert abs(res[1] - res_o[1]) <= ((~decided) & (ds.train_mask == 1)).sum() / n_tr + 1e-9
+    assert abs(res[3] - res_o[3]) <= ((~decided) & (ds.test_mask == 1)).sum() / n_te + 1e-9
