@@ -1,4 +1,4 @@
-"""UNVALIDATED (written at the end of round 1 without GPU budget; the oracle half was run on the CPU): CUDA path vs the oracle on
+"""CUDA path vs the oracle on
 hand-built complexes: single triangle, two triangles sharing an edge, a path with no triangles, isolated nodes,
 a last node with maximum degree, a last node with degree 1 — log-probs 1e-5, gradients 1e-4, for scone and ebli."""
 import numpy as np
@@ -53,5 +53,8 @@ def test_tiny_complex_forward_and_grads_vs_oracle(name, model):
     assert buf[k + 1] == mask.sum()
     _, g_ref = orc.loss_and_grads(W, mask, 0.0)
     grads = net.unflatten(buf[:k] / buf[k + 1])
+    gmax = max(np.abs(r).max() for r in g_ref)
     for a, r in zip(grads, g_ref):
-        assert np.abs(a - r).max() <= 1e-4 * max(np.abs(r).max(), 1e-30)
+        # per weight array, relative to its largest entry; an array whose true gradient is zero up to fp32 cancellation
+        # noise (|g| ~ 1e-9 on these 3-6 edge complexes) is held to the noise floor of the whole gradient instead
+        assert np.abs(a - r).max() <= 1e-4 * max(np.abs(r).max(), 1e-3 * gmax, 1e-30)
