@@ -163,6 +163,14 @@ int scone_model_get_zero_fill(const scone_model* m);
  *     the backward's A buffer 6 M rows per micro-batch; beyond that scone_model_read_grads reports an error.
  *   1 = the same row-list kernels over dense [E][micro_batch][C] tensors.
  *   0 = unit kernels over byte flags and dense tensors (every width; fp32 SIMT).  zero_fill = 1 always uses 0. */
+/*   4 (default when all hidden widths are equal, 16 or 32, with at most 3 layers, and the cones of the complex fit the shared-memory
+ *     tables) = TRAJECTORY-FUSED kernels (csrc/scone_fused.cu): one plan kernel (cone & support -> per-trajectory live rows in ascending
+ *     edge order + gather programs; weight-independent integer work) and one compute kernel that keeps all activations and
+ *     gradients of a trajectory in shared memory (gather -> 3xTF32 mma.sync product -> activation per layer, readout, log-softmax,
+ *     NLL, backward, weight-gradient tiles in registers across trajectories) + one fixed-order reduce of the per-CTA partials.
+ *     Same live rows as pipeline 3, each computed from the same neighbours in the same (ascending column) order.  No capacity can
+ *     overflow: every table is sized from bounds measured on the complex at scone_model_create (the cone of every node).
+ *     Nothing is proportional to E * micro_batch (no dense X, no bitmaps), so E * micro_batch is unbounded. */
 int scone_model_set_pipeline(scone_model* m, int32_t which);
 int scone_model_get_pipeline(const scone_model* m);
 int scone_model_set_weights(scone_model* m, const float* weights_host);     /* also resets Adam state */
@@ -207,6 +215,24 @@ int scone_model_read_grads(scone_model* m, float* out_host, void* stream);
  *   g = grads / count + 2 * weight_decay * W ;  m,v update ;  W -= lr * mhat / (sqrt(vhat) + eps)
  * step = 0-based iteration index i. */
 int scone_model_adam_step(scone_model* m, int32_t step, float lr, float weight_decay, void* stream);
+/* Capacity overflow (pipelines 2 / 3 only; pipeline 4 and the dense pipelines cannot overflow): a micro-batch whose row lists exceed
+ * their capacity sets a device flag.  While the flag is set scone_model_adam_step leaves the weights and the Adam state untouched (the
+ * gradients are truncated).  The flag is REPORTED (error code 4) and cleared by scone_model_read_grads, scone_model_forward_host,
+ * scone_model_accuracy_host and by this call, which synchronises the stream; the *_dev entry points and scone_model_adam_step
+ * themselves never synchronise and never report it. */
+int scone_model_check_overflow(scone_model* m, void* stream);
+/* Weights only (Adam state kept), asynchronous on the caller's stream; weights_host must stay valid until the copy has run. */
+int scone_model_set_weights_keep_state(scone_model* m, const float* weights_host, void* stream);
+/* Fused pipeline introspection (tests / bench): out[0] = available, [1] bound on hash entries (|T_0| of any node), [2] bound on listed
+ * cone edges (|T_1|), [3] hash slots, [4] trajectories per arena chunk, [5] rows of the shared-memory row store, [6] / [7] KB of
+ * dynamic shared memory of the plan / compute kernel. */
+int scone_model_fused_info(const scone_model* m, int32_t* out /* [8] */);
+/* Plan of trajectory t of the LAST chunk run (synchronises the device): header (16 ints, layout in csrc/fused.cuh) and `words` 32-bit
+ * words of the program arena from word offset `off` (either output may be NULL). */
+int scone_model_fused_read(scone_model* m, int32_t t, int32_t* hdr_out /* [16] */, uint32_t off, int32_t words, uint32_t* arena_out);
+/* (edge, trajectory) rows the fused compute kernel produced since the last call, counted while scone_profile_enable(1): out[0] forward
+ * rows (all layers), out[1] backward rows.  bench.py's byte accounting. */
+int scone_model_read_rows_done(scone_model* m, int64_t* out /* [2] */);
 
 /* ---------------------------------------------------------------------------------------------
  * SCCONV / "bunch" model (-model bunch): bunch_func (trajectory_experiments.py:173-203) over the seven weighted shift

@@ -1,0 +1,1116 @@
+// scone_fused.cu — pipeline 4: the TRAJECTORY-FUSED path behind the model-level entry points (uniform hidden width 16 / 32,
+// at most 3 conv layers).  Two kernels per micro-batch instead of the ~25 launches of the bitmap pipeline:
+//
+//   fused_plan_kernel   (weight-independent integer work, one CTA per trajectory)
+//        receptive cone of the readout (trajectory_experiments.py:151,298-303: the log-probs read H_L only at the edges incident
+//        to the neighbours of the last node; one merged-operator hop further down per layer), intersected layer by layer with the
+//        structural support of the flows (no bias, act(0) = 0: a row with no live neighbour below is exactly zero) -> per layer
+//        the LIVE rows in ascending edge order, and for every live row its GATHER PROGRAM: {index of the live neighbour row one
+//        layer below, both integer operator coefficients}, plus the transposed programs the backward walks and the readout
+//        pairs.  Everything lives in a shared-memory hash set (edge -> slot); nothing is proportional to E * batch: no bitmaps,
+//        no dense X, no compaction, no clearing.
+//   fused_traj_kernel   (persistent CTAs, trajectories assigned statically = deterministic)
+//        layer 1 from the three exact scalars of each live row; conv layers l >= 2 as gather (shared memory) -> 3xTF32 mma.sync
+//        product against the weights staged once per CTA -> activation; readout + padded log-softmax + NLL
+//        (trajectory_experiments.py:151-152, scone_trajectory_model.py:46-54); backward through the transposed programs with
+//        the weight gradients accumulated in mma accumulator REGISTERS across all trajectories of the CTA; one partial vector
+//        per CTA, reduced in CTA order by fused_reduce_kernel.  Activations and gradients of a trajectory never leave the SM.
+//
+// All capacities are STATIC bounds measured once per complex (fused_bound_kernel: the cone of every possible last node), so a
+// micro-batch cannot overflow: the hash set holds |T_0| <= bound entries, a layer has at most |T_1| <= bound rows, the program
+// arena is sized for the worst case.  A trajectory whose rows do not fit the shared-memory row store runs in the BIG variant of
+// the same kernel (rows in a per-CTA global scratch).
+#include <algorithm>
+#include "common.cuh"
+#include "fused.cuh"
+
+namespace {
+
+#include "slab_common.cuh"
+
+constexpr int kPlanThreads = 256;
+constexpr int kTrajThreads = 256;
+constexpr int kFuMaxD = 128;
+constexpr uint32_t kNoRow = 0xFFFFu;
+
+template <int ACT>
+__device__ __forceinline__ float fu_act(float z) {
+    if (ACT == SCONE_ACT_TANH) return scone_tanh(z);
+    if (ACT == SCONE_ACT_LEAKY_RELU) return z >= 0.f ? z : 0.01f * z;
+    return fmaxf(z, 0.f);
+}
+template <int ACT>
+__device__ __forceinline__ float fu_dact(float h) {        // derivative through the OUTPUT h = act(z)
+    if (ACT == SCONE_ACT_TANH) return 1.f - h * h;
+    if (ACT == SCONE_ACT_LEAKY_RELU) return h >= 0.f ? 1.f : 0.01f;
+    return h > 0.f ? 1.f : 0.f;
+}
+
+__device__ __forceinline__ int align2(int x) { return (x + 1) & ~1; }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// shared-memory hash set of internal edge ids (open addressing, linear probing; the table can never fill: HS > static bound)
+// ---------------------------------------------------------------------------------------------------------------------
+struct EdgeSet {
+    int* keys;
+    int mask, shift;
+    __device__ __forceinline__ unsigned home(int e) const { return ((unsigned)e * 2654435761u) >> shift; }
+    // returns the slot; is_new = this call created the entry
+    __device__ __forceinline__ int insert(int e, bool& is_new) {
+        unsigned h = home(e);
+        is_new = false;
+        for (int probes = 0; probes <= mask; ++probes) {
+            const int old = atomicCAS(&keys[h], -1, e);
+            if (old == -1) {
+                is_new = true;
+                return (int)h;
+            }
+            if (old == e) return (int)h;
+            h = (h + 1) & mask;
+        }
+        return -1;                                        // full (only possible in bound mode)
+    }
+    __device__ __forceinline__ int find(int e) const {
+        unsigned h = home(e);
+        for (int probes = 0; probes <= mask; ++probes) {
+            const int k = keys[h];
+            if (k == e) return (int)h;
+            if (k == -1) return -1;
+            h = (h + 1) & mask;
+        }
+        return -1;
+    }
+};
+
+// (neighbour slot j, incident edge) pairs of the last node, flattened (same enumeration as the row-list readout kernels)
+struct FuPairs {
+    int s_ptr[kFuMaxD], s_off[kFuMaxD + 1];
+    __device__ __forceinline__ int setup(const int32_t* __restrict__ nbrhoods, const int32_t* __restrict__ inc_ptr, int last, bool last_ok, int D) {
+        for (int j = threadIdx.x; j < D; j += blockDim.x) {
+            const int nbr = last_ok ? nbrhoods[(size_t)last * D + j] : -1;
+            s_ptr[j] = nbr >= 0 ? inc_ptr[nbr] : -1;
+            s_off[j + 1] = nbr >= 0 ? inc_ptr[nbr + 1] - inc_ptr[nbr] : 0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_off[0] = 0;
+            for (int j = 0; j < D; ++j) s_off[j + 1] += s_off[j];
+        }
+        __syncthreads();
+        return s_off[D];
+    }
+    __device__ __forceinline__ int slot_of(int i, int D) const {
+        int j = 0;
+        while (j + 1 < D && s_off[j + 1] <= i) ++j;
+        return j;
+    }
+};
+
+// exclusive scan of a[0..n) in place (a[n] = total); every thread of the 256-thread CTA calls it
+__device__ int block_scan_excl(int* a, int n, int* s_warp) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n + kPlanThreads - 1) / kPlanThreads;
+    const int lo = min(n, tid * per), hi = min(n, lo + per);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += a[i];
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    __syncthreads();                                      // (s_warp may still be read from a previous call)
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kPlanThreads / 32; ++w) {
+        const int v = s_warp[w];
+        if (w < warp) base += v;
+        total += v;
+    }
+    int run = base + inc - sum;
+    for (int i = lo; i < hi; ++i) {
+        const int v = a[i];
+        a[i] = run;
+        run += v;
+    }
+    if (tid == 0) a[n] = total;
+    __syncthreads();
+    return total;
+}
+
+struct PlanArgs {
+    const int32_t* traj_ptr;
+    const int32_t* flow_edge;
+    const float* flow_val;
+    const int32_t* last_nodes;
+    const int32_t* rank;
+    const int32_t* nbrhoods;
+    const int32_t* inc_ptr;
+    const int2* inc_ent;
+    const int32_t* mptr;
+    const int2* ment;
+    int N, D, E, L, HS, LC, hshift;
+    int* hdr;
+    uint32_t* arena;
+    unsigned long long* bump;
+    unsigned long long arena_words;
+    int* overflow;
+};
+
+// Static bounds: blockIdx.x = candidate last node; builds its cone down to level 0 and records max |T_0| (hash entries) and
+// max |T_1| (listed entries) in stats[0..1]; stats[2] = 1 if even the largest table overflowed.
+__global__ void __launch_bounds__(kPlanThreads) fused_bound_kernel(const int32_t* __restrict__ nbrhoods, const int32_t* __restrict__ inc_ptr,
+                                                                  const int2* __restrict__ inc_ent, const int32_t* __restrict__ mptr,
+                                                                  const int2* __restrict__ ment, int N, int D, int L, int HS, int LC,
+                                                                  int hshift, int* __restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    int* keys = reinterpret_cast<int*>(sm);
+    int* list = keys + HS;
+    __shared__ FuPairs pairs;
+    __shared__ int s_nlist, s_nhash, s_ovf, s_nat[kFusedMaxL + 2];
+    const int tid = threadIdx.x, ql = tid & 3;
+    for (int i = tid; i < HS; i += kPlanThreads) keys[i] = -1;
+    if (tid == 0) s_nlist = s_nhash = s_ovf = 0;
+    const int last = blockIdx.x;
+    const int total = pairs.setup(nbrhoods, inc_ptr, last, last < N, D);
+    EdgeSet set{keys, HS - 1, hshift};
+    auto add = [&](int e, int lv) {
+        bool is_new;
+        const int s = set.insert(e, is_new);
+        if (s < 0) {
+            s_ovf = 1;
+            return;
+        }
+        if (is_new) {
+            if (atomicAdd(&s_nhash, 1) >= (HS * 3) / 4) s_ovf = 1;
+            if (lv >= 1) {
+                const int pos = atomicAdd(&s_nlist, 1);
+                if (pos < LC) list[pos] = e;
+                else s_ovf = 1;
+            }
+        }
+    };
+    for (int i = tid; i < total; i += kPlanThreads) {
+        const int j = pairs.slot_of(i, D);
+        add(inc_ent[pairs.s_ptr[j] + (i - pairs.s_off[j])].x, L);
+    }
+    __syncthreads();
+    if (tid == 0) s_nat[L] = min(s_nlist, LC);
+    __syncthreads();
+    int f0 = 0;
+    for (int lv = L - 1; lv >= 0; --lv) {
+        const int f1 = s_nat[lv + 1];
+        if (!s_ovf)
+            for (int i = f0 + (tid >> 2); i < f1; i += kPlanThreads / 4) {
+                const int e = list[i];
+                const int p1 = mptr[e + 1];
+                for (int q = mptr[e] + ql; q < p1; q += 4) add(ment[q].x, lv);
+            }
+        __syncthreads();
+        if (tid == 0) s_nat[lv] = min(s_nlist, LC);
+        __syncthreads();
+        f0 = f1;
+    }
+    if (tid == 0) {
+        atomicMax(&stats[0], s_nhash);
+        atomicMax(&stats[1], s_nat[1]);
+        if (s_ovf) stats[2] = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// the plan: one CTA per trajectory
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPlanThreads) fused_plan_kernel(const PlanArgs a) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int HS = a.HS, LC = a.LC, L = a.L, D = a.D;
+    int* keys = reinterpret_cast<int*>(sm);                          // [HS] internal edge id, -1 = empty
+    float* xv = reinterpret_cast<float*>(keys + HS);                 // [HS] flow value of the edge
+    uint16_t* idxA = reinterpret_cast<uint16_t*>(xv + HS);           // [HS] row index of the edge in the live list of a layer (ping)
+    uint16_t* idxB = idxA + HS;                                      // [HS] (pong)
+    uint8_t* lvl = reinterpret_cast<uint8_t*>(idxB + HS);            // [HS] highest cone level of the edge (0 = only in T_0)
+    int* rowcnt = reinterpret_cast<int*>(lvl + HS);                  // [LC + 4] entries per ranked row -> exclusive scan
+    float* av0 = reinterpret_cast<float*>(rowcnt);                   //   (layer 1 only: overlays rowcnt) x[e]
+    float* av1 = reinterpret_cast<float*>(rowcnt + LC + 4);          // [LC] (S0 x)[e]
+    float* av2 = av1 + LC;                                           // [LC] (S1 x)[e]
+    int* live_edge = reinterpret_cast<int*>(av2 + LC);               // [LC] edge id of the k-th live row (unordered)
+    uint16_t* list = reinterpret_cast<uint16_t*>(live_edge + LC);    // [LC] cone list: hash slots, level L first, then L-1, ...
+    uint16_t* live = list + LC;                                      // [LC] cone-list index of the k-th live row (unordered)
+    uint16_t* cnt = live + LC;                                       // [LC] program entries of cone-list entry i
+    uint16_t* byrank = cnt + LC;                                     // [LC] cone-list index of the row with rank r
+    __shared__ FuPairs pairs;
+    __shared__ int s_nlist, s_nlive, s_ovf, s_nat[kFusedMaxL + 2], s_warp[kPlanThreads / 32];
+    __shared__ unsigned s_piece;
+
+    const int tid = threadIdx.x, lane = tid & 31, ql = tid & 3;
+    const unsigned qmask = 0xFu << (lane & ~3);
+    const int t = blockIdx.x;
+    int* hdr = a.hdr + (size_t)t * kFusedHdrW;
+    for (int i = tid; i < HS; i += kPlanThreads) {
+        keys[i] = -1;
+        xv[i] = 0.f;
+        idxA[i] = (uint16_t)kNoRow;
+        idxB[i] = (uint16_t)kNoRow;
+    }
+    if (tid == 0) s_nlist = s_ovf = 0;
+    const int last = a.last_nodes[t];
+    const bool last_ok = last >= 0 && last < a.N;
+    const int total_pairs = pairs.setup(a.nbrhoods, a.inc_ptr, last, last_ok, D);
+    EdgeSet set{keys, HS - 1, a.hshift};
+    auto add = [&](int e, int lv) {
+        bool is_new;
+        const int s = set.insert(e, is_new);
+        if (s < 0) {
+            s_ovf = 1;
+            return;
+        }
+        if (is_new) {
+            lvl[s] = (uint8_t)lv;
+            if (lv >= 1) {
+                const int pos = atomicAdd(&s_nlist, 1);
+                if (pos < LC) list[pos] = (uint16_t)s;
+                else s_ovf = 1;
+            }
+        }
+    };
+    // arena allocation for one piece (thread 0 allocates, everybody gets the word offset; ~0u = out of space)
+    auto alloc = [&](int words) -> unsigned {
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned long long w = (unsigned long long)align2(words);
+            const unsigned long long o = atomicAdd(a.bump, w);
+            if (o + w > a.arena_words) {
+                s_ovf = 1;
+                s_piece = 0u;
+            } else {
+                s_piece = (unsigned)o;
+            }
+        }
+        __syncthreads();
+        return s_piece;
+    };
+
+    // ---- receptive cone: level L = edges incident to the neighbours of the last node, one merged-row hop down per level ----
+    for (int i = tid; i < total_pairs; i += kPlanThreads) {
+        const int j = pairs.slot_of(i, D);
+        add(a.inc_ent[pairs.s_ptr[j] + (i - pairs.s_off[j])].x, L);
+    }
+    __syncthreads();
+    if (tid == 0) s_nat[L] = min(s_nlist, LC);
+    __syncthreads();
+    {
+        int f0 = 0;
+        for (int lv = L - 1; lv >= 0; --lv) {
+            const int f1 = s_nat[lv + 1];
+            for (int i = f0 + (tid >> 2); i < f1; i += kPlanThreads / 4) {
+                const int e = keys[list[i]];
+                const int p1 = a.mptr[e + 1];
+                for (int q = a.mptr[e] + ql; q < p1; q += 4) add(a.ment[q].x, lv);
+            }
+            __syncthreads();
+            if (tid == 0) s_nat[lv] = min(s_nlist, LC);
+            __syncthreads();
+            f0 = f1;
+        }
+    }
+    // ---- flows: only edges of T_0 can reach a cone row ----
+    for (int p = a.traj_ptr[t] + tid; p < a.traj_ptr[t + 1]; p += kPlanThreads) {
+        const int eo = a.flow_edge[p];
+        if (eo < 0 || eo >= a.E) continue;
+        const int s = set.find(a.rank[eo]);
+        if (s >= 0) xv[s] = a.flow_val[p];
+    }
+    if (tid == 0) s_nlive = 0;
+    __syncthreads();
+    if (s_ovf) {                                           // cannot happen with measured bounds; reported, trajectory skipped
+        if (tid == 0) {
+            hdr[0] = kFusedFlagOverflow;
+            *a.overflow = 1;
+        }
+        return;
+    }
+
+    // ranks the s_nlive live rows by edge id (ascending = the deterministic row order of every list): idx[slot] = rank,
+    // byrank[rank] = cone-list index; returns the count
+    auto rank_live = [&](uint16_t* idx) -> int {
+        __syncthreads();
+        const int n = s_nlive;
+        for (int k = tid; k < n; k += kPlanThreads) {
+            const int e = live_edge[k];
+            int r = 0;
+            for (int m = 0; m < n; ++m) r += live_edge[m] < e ? 1 : 0;
+            const int i = live[k];
+            idx[list[i]] = (uint16_t)r;
+            byrank[r] = (uint16_t)i;
+        }
+        __syncthreads();
+        return n;
+    };
+
+    // ---- layer 1: live rows = cone rows of T_1 with a flow entry in their merged operator row; their three exact scalars ----
+    for (int i = tid >> 2; i < s_nat[1]; i += kPlanThreads / 4) {
+        const int slot = list[i];
+        const int e = keys[slot];
+        float a1 = 0.f, a2 = 0.f;
+        int any = 0;
+        const int p1 = a.mptr[e + 1];
+        for (int q = a.mptr[e] + ql; q < p1; q += 4) {
+            const int2 en = a.ment[q];
+            const int s2 = set.find(en.x);
+            const float x = s2 >= 0 ? xv[s2] : 0.f;
+            if (x != 0.f) {
+                any = 1;
+                a1 = fmaf((float)(short)(en.y & 0xffff), x, a1);
+                a2 = fmaf((float)(en.y >> 16), x, a2);
+            }
+        }
+#pragma unroll
+        for (int o = 1; o < 4; o <<= 1) {
+            a1 += __shfl_xor_sync(qmask, a1, o);
+            a2 += __shfl_xor_sync(qmask, a2, o);
+            any |= __shfl_xor_sync(qmask, any, o);
+        }
+        if (ql == 0 && any) {
+            const int k = atomicAdd(&s_nlive, 1);
+            live[k] = (uint16_t)i;
+            live_edge[k] = e;
+            av0[i] = xv[slot];
+            av1[i] = a1;
+            av2[i] = a2;
+        }
+    }
+    uint16_t *ip = idxA, *ic = idxB;
+    int n_prev = rank_live(ip);
+    int n_l[kFusedMaxL + 1] = {0, 0, 0, 0};
+    unsigned off_l1 = 0, off_f[kFusedMaxL + 1] = {0, 0, 0, 0}, off_b[kFusedMaxL + 1] = {0, 0, 0, 0};
+    n_l[1] = n_prev;
+    off_l1 = alloc(3 * n_prev);
+    if (!s_ovf) {
+        float* dst = reinterpret_cast<float*>(a.arena + off_l1);
+        for (int r = tid; r < n_prev; r += kPlanThreads) {
+            const int i = byrank[r];
+            dst[3 * r + 0] = av0[i];
+            dst[3 * r + 1] = av1[i];
+            dst[3 * r + 2] = av2[i];
+        }
+    }
+    __syncthreads();
+
+    // walks the merged row of cone-list entry i and emits, in column order, the entries whose neighbour has a row in `idx`:
+    // COUNT: returns the number (on quad lane 0 .. all lanes); FILL: writes them from position `base` on
+    auto count_row = [&](int e, const uint16_t* idx) -> int {
+        int c = 0;
+        const int p1 = a.mptr[e + 1];
+        for (int q = a.mptr[e] + ql; q < p1; q += 4) {
+            const int s2 = set.find(a.ment[q].x);
+            if (s2 >= 0 && idx[s2] != (uint16_t)kNoRow) ++c;
+        }
+        c += __shfl_xor_sync(qmask, c, 1);
+        c += __shfl_xor_sync(qmask, c, 2);
+        return c;
+    };
+    auto fill_row = [&](int e, const uint16_t* idx, int2* out, int base) {
+        const int p0 = a.mptr[e], p1 = a.mptr[e + 1];
+        for (int q0 = p0; q0 < p1; q0 += 4) {             // (uniform inside the quad)
+            const int q = q0 + ql;
+            int2 en = make_int2(0, 0);
+            uint32_t r = kNoRow;
+            if (q < p1) {
+                en = a.ment[q];
+                const int s2 = set.find(en.x);
+                if (s2 >= 0) r = idx[s2];
+            }
+            const bool valid = r != kNoRow;
+            const unsigned bits = (__ballot_sync(qmask, valid) >> (lane & ~3)) & 0xFu;
+            if (valid) out[base + __popc(bits & ((1u << ql) - 1u))] = make_int2((int)(r | (en.x == e ? 0x80000000u : 0u)), en.y);
+            base += __popc(bits);
+        }
+    };
+
+    for (int l = 2; l <= L; ++l) {
+        // forward program of layer l: rows = T_l entries with at least one live neighbour in layer l - 1
+        if (tid == 0) s_nlive = 0;
+        __syncthreads();
+        for (int i = tid >> 2; i < s_nat[l]; i += kPlanThreads / 4) {
+            const int e = keys[list[i]];
+            const int c = count_row(e, ip);
+            if (ql == 0) {
+                cnt[i] = (uint16_t)c;
+                if (c) {
+                    const int k = atomicAdd(&s_nlive, 1);
+                    live[k] = (uint16_t)i;
+                    live_edge[k] = e;
+                }
+            }
+        }
+        const int nl = rank_live(ic);
+        n_l[l] = nl;
+        for (int r = tid; r < nl; r += kPlanThreads) rowcnt[r] = cnt[byrank[r]];
+        __syncthreads();
+        int total = block_scan_excl(rowcnt, nl, s_warp);
+        off_f[l] = alloc(align2(nl + 1) + 2 * total);
+        if (!s_ovf) {
+            int* pdst = reinterpret_cast<int*>(a.arena + off_f[l]);
+            int2* edst = reinterpret_cast<int2*>(a.arena + off_f[l] + align2(nl + 1));
+            for (int r = tid; r <= nl; r += kPlanThreads) pdst[r] = rowcnt[r];
+            for (int r = tid >> 2; r < nl; r += kPlanThreads / 4) fill_row(keys[list[byrank[r]]], ip, edst, rowcnt[r]);
+        }
+        __syncthreads();
+        // transposed program: rows = live rows of layer l - 1, entries = their neighbours among the live rows of layer l
+        for (int r = tid; r <= n_prev; r += kPlanThreads) rowcnt[r] = 0;
+        __syncthreads();
+        for (int i = tid >> 2; i < s_nat[l - 1]; i += kPlanThreads / 4) {
+            const int slot = list[i];
+            const uint32_t rp = ip[slot];
+            if (rp == kNoRow) continue;                    // (same decision on the four lanes of the quad)
+            const int c = count_row(keys[slot], ic);
+            if (ql == 0) {
+                rowcnt[rp] = c;
+                byrank[rp] = (uint16_t)i;
+            }
+        }
+        __syncthreads();
+        total = block_scan_excl(rowcnt, n_prev, s_warp);
+        off_b[l] = alloc(align2(n_prev + 1) + 2 * total);
+        if (!s_ovf) {
+            int* pdst = reinterpret_cast<int*>(a.arena + off_b[l]);
+            int2* edst = reinterpret_cast<int2*>(a.arena + off_b[l] + align2(n_prev + 1));
+            for (int r = tid; r <= n_prev; r += kPlanThreads) pdst[r] = rowcnt[r];
+            for (int r = tid >> 2; r < n_prev; r += kPlanThreads / 4) fill_row(keys[list[byrank[r]]], ic, edst, rowcnt[r]);
+        }
+        __syncthreads();
+        uint16_t* tmp = ip;
+        ip = ic;
+        ic = tmp;
+        for (int i = tid; i < HS; i += kPlanThreads) ic[i] = (uint16_t)kNoRow;
+        n_prev = nl;
+        __syncthreads();
+    }
+    // ---- readout pairs: {row of H_L | neighbour slot << 16, sign bits}; a pair whose edge has no live row keeps kNoRow ----
+    const unsigned off_ro = alloc(align2(D + 1) + 2 * total_pairs);
+    if (!s_ovf) {
+        int* pdst = reinterpret_cast<int*>(a.arena + off_ro);
+        int2* edst = reinterpret_cast<int2*>(a.arena + off_ro + align2(D + 1));
+        for (int j = tid; j <= D; j += kPlanThreads) pdst[j] = pairs.s_off[j];
+        for (int i = tid; i < total_pairs; i += kPlanThreads) {
+            const int j = pairs.slot_of(i, D);
+            const int2 es = a.inc_ent[pairs.s_ptr[j] + (i - pairs.s_off[j])];
+            const int s = set.find(es.x);
+            const uint32_t r = s >= 0 ? (uint32_t)ip[s] : kNoRow;
+            edst[i] = make_int2((int)(r | ((uint32_t)j << 16)), es.y);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (s_ovf) {
+            hdr[0] = kFusedFlagOverflow;
+            *a.overflow = 1;
+        } else {
+            hdr[0] = 0;
+            for (int l = 1; l <= kFusedMaxL; ++l) hdr[l] = l <= L ? n_l[l] : 0;
+            hdr[4] = (int)off_l1;
+            for (int l = 2; l <= kFusedMaxL; ++l) {
+                hdr[5 + (l - 2)] = (int)off_f[l];
+                hdr[7 + (l - 2)] = (int)off_b[l];
+            }
+            hdr[9] = (int)off_ro;
+            hdr[10] = total_pairs;
+            hdr[11] = s_nat[1];
+            hdr[12] = s_nat[0];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// the compute kernel
+// ---------------------------------------------------------------------------------------------------------------------
+struct TrajArgs {
+    const int* hdr;
+    const uint32_t* arena;
+    const float* W;                        // flat weights
+    int w_off[3 * kFusedMaxL + 1];
+    int L, b, D, n_params;
+    float* logprobs;                       // [b][D] or NULL
+    const int32_t* target_idx;
+    const float* mask;
+    float* partial;                        // [gridDim.x][n_params + 2]
+    float* scratch;                        // BIG: per-CTA row store
+    size_t scratch_stride;                 // floats per CTA
+    int cap_rows;                          // rows of the shared-memory row store (small variant)
+    int big_rows;                          // rows of the per-CTA global row store
+    unsigned long long* rows_done;         // optional device counters: [0] forward rows, [1] backward rows produced
+};
+
+template <int C>
+struct FuGeom {
+    static constexpr int LDH = C + 8;       // row store stride: (tig * LDH + g) hits 32 distinct banks
+    static constexpr int LDA = 3 * C + 4;   // gathered tile stride: (g * LDA + tig) hits 32 distinct banks
+    static constexpr int LDW = C + 8;
+    static constexpr int CH = 80;           // rows gathered per chunk (5 m-tiles)
+    static constexpr int LPR = C / 4;       // lanes per row in the gather (one float4 each)
+    static constexpr int NP = C / 16;       // pairs of n-tiles per row tile
+    static constexpr int NMT = C / 16;      // dW: m-tiles (input channels)
+    static constexpr int NNT = 3 * C / 8;   // dW: n-tiles (term, output channel)
+    static constexpr int WPM = 8 / NMT;     // dW: warps per m-tile
+    static constexpr int TPW = (NNT + WPM - 1) / WPM;   // dW tiles per warp
+};
+
+// gather of nr rows (program rows r0 .. r0 + nr) from the row store `src` into the tile: [own | S0 sum | S1 sum]; rows up to
+// the next multiple of 16 are zero-filled
+template <int C>
+__device__ __forceinline__ void fu_gather(float* __restrict__ tile, const float* src, const int* __restrict__ ptr,
+                                          const int2* __restrict__ ent, int r0, int nr) {
+    using G = FuGeom<C>;
+    const int lr = threadIdx.x % G::LPR, rr = threadIdx.x / G::LPR;
+    const int npad = (nr + 15) & ~15;
+    for (int r = rr; r < npad; r += kTrajThreads / G::LPR) {
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f), s0 = o, s1 = o;
+        if (r < nr) {
+            const int p1 = __ldg(ptr + r0 + r + 1);
+            for (int p = __ldg(ptr + r0 + r); p < p1; ++p) {
+                const int2 en = __ldg(ent + p);
+                const float c0 = (float)(short)(en.y & 0xffff), c1 = (float)(en.y >> 16);
+                const float4 v = *reinterpret_cast<const float4*>(src + (size_t)(en.x & 0xFFFF) * G::LDH + 4 * lr);
+                s0.x = fmaf(c0, v.x, s0.x); s0.y = fmaf(c0, v.y, s0.y); s0.z = fmaf(c0, v.z, s0.z); s0.w = fmaf(c0, v.w, s0.w);
+                s1.x = fmaf(c1, v.x, s1.x); s1.y = fmaf(c1, v.y, s1.y); s1.z = fmaf(c1, v.z, s1.z); s1.w = fmaf(c1, v.w, s1.w);
+                if (en.x < 0) o = v;
+            }
+        }
+        float* d = tile + (size_t)r * G::LDA + 4 * lr;
+        *reinterpret_cast<float4*>(d) = o;
+        *reinterpret_cast<float4*>(d + C) = s0;
+        *reinterpret_cast<float4*>(d + 2 * C) = s1;
+    }
+}
+
+// row tile product: D[nr x C] = tile[nr x 3C] * B, B = [W0; W1; W2] (forward) or [W0^T; W1^T; W2^T] (TRANSPOSED: the backward
+// data product); 3xTF32, fp32 accumulate.  A warp owns (m-tile, pair of n-tiles); epi(row, col, v0, v1) receives two adjacent columns.
+template <int C, bool TRANSPOSED, typename Epi>
+__device__ __forceinline__ void fu_product(const float* __restrict__ tile, const float* __restrict__ Wsm, int nr, Epi epi) {
+    using G = FuGeom<C>;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+    const int n_mt = (nr + 15) >> 4;
+    for (int tl = warp; tl < n_mt * G::NP; tl += kTrajThreads / 32) {
+        const int mt = tl / G::NP, np = tl % G::NP;
+        float d[2][4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) d[j][q] = 0.f;
+        const float* arow0 = tile + (size_t)(16 * mt + g) * G::LDA + tig;
+        const float* arow1 = arow0 + 8 * G::LDA;
+#pragma unroll 4
+        for (int ks = 0; ks < 3 * C / 8; ++ks) {
+            const int k0 = 8 * ks;
+            uint32_t ahi[4], alo[4];
+            split_tf32(arow0[k0], ahi[0], alo[0]);
+            split_tf32(arow1[k0], ahi[1], alo[1]);
+            split_tf32(arow0[k0 + 4], ahi[2], alo[2]);
+            split_tf32(arow1[k0 + 4], ahi[3], alo[3]);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int n0 = (2 * np + j) * 8;
+                float b0, b1;
+                if (!TRANSPOSED) {
+                    b0 = Wsm[(k0 + tig) * G::LDW + n0 + g];
+                    b1 = Wsm[(k0 + tig + 4) * G::LDW + n0 + g];
+                } else {                                   // k = term * C + co, n = ci: W_term[ci][co]
+                    const int term = k0 / C, co = k0 % C + tig;
+                    b0 = Wsm[(term * C + n0 + g) * G::LDW + co];
+                    b1 = Wsm[(term * C + n0 + g) * G::LDW + co + 4];
+                }
+                uint32_t bh0, bl0, bh1, bl1;
+                split_tf32(b0, bh0, bl0);
+                split_tf32(b1, bh1, bl1);
+                mma_tf32(d[j], alo, bh0, bh1);
+                mma_tf32(d[j], ahi, bl0, bl1);
+                mma_tf32(d[j], ahi, bh0, bh1);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int col = (2 * np + j) * 8 + 2 * tig;
+            const int r0 = 16 * mt + g, r1 = r0 + 8;
+            if (r0 < nr) epi(r0, col, d[j][0], d[j][1]);
+            if (r1 < nr) epi(r1, col, d[j][2], d[j][3]);
+        }
+    }
+}
+
+// weight-gradient tiles: acc += Hprev[rows]^T * tile[rows][3C] (K = the nr rows of the chunk); a warp owns one m-tile of input
+// channels and TPW n-tiles of (term, output channel); both operands split for 3xTF32
+template <int C>
+__device__ __forceinline__ void fu_dw(float (&acc)[FuGeom<C>::TPW][4], const float* hprev, const float* __restrict__ tile, int nr) {
+    using G = FuGeom<C>;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+    const int mt = warp % G::NMT, ntg = warp / G::NMT;
+    for (int k0 = 0; k0 < nr; k0 += 8) {
+        const int ra = k0 + tig, rb = ra + 4;
+        const float* ha = hprev + (size_t)ra * G::LDH + 16 * mt + g;
+        const float* hb = hprev + (size_t)rb * G::LDH + 16 * mt + g;
+        uint32_t ahi[4], alo[4];
+        split_tf32(ra < nr ? ha[0] : 0.f, ahi[0], alo[0]);
+        split_tf32(ra < nr ? ha[8] : 0.f, ahi[1], alo[1]);
+        split_tf32(rb < nr ? hb[0] : 0.f, ahi[2], alo[2]);
+        split_tf32(rb < nr ? hb[8] : 0.f, ahi[3], alo[3]);
+#pragma unroll
+        for (int s = 0; s < G::TPW; ++s) {
+            const int nt = ntg + G::WPM * s;
+            if (nt < G::NNT) {                             // (warp-uniform)
+                uint32_t bh0, bl0, bh1, bl1;
+                split_tf32(tile[(size_t)ra * G::LDA + 8 * nt + g], bh0, bl0);     // rows >= nr of the tile are zero
+                split_tf32(tile[(size_t)rb * G::LDA + 8 * nt + g], bh1, bl1);
+                mma_tf32(acc[s], alo, bh0, bh1);
+                mma_tf32(acc[s], ahi, bl0, bl1);
+                mma_tf32(acc[s], ahi, bh0, bh1);
+            }
+        }
+    }
+}
+
+template <int C, int ACT, bool GRAD, bool BIG>
+__global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajArgs a) {
+    using G = FuGeom<C>;
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int L = a.L, D = a.D;
+    float* Wsm = reinterpret_cast<float*>(sm);                        // [(L-1)][3C][LDW]
+    float* w1s = Wsm + (size_t)(kFusedMaxL - 1) * 3 * C * G::LDW;    // [3][C] first-layer weights
+    float* wos = w1s + 3 * C;                                        // [C] w_out
+    float* tile = wos + C;                                           // [CH][LDA]
+    float* zs = tile + (size_t)G::CH * G::LDA;                       // [D][C] readout sums
+    float* lg = zs + (size_t)D * C;                                  // [D] logits -> log-probs
+    float* dl = lg + ((D + 3) & ~3);                                 // [D] dlogits
+    float* rows_sm = dl + ((D + 3) & ~3);                            // [cap_rows][LDH]  (small variant)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int l = 2; l <= L; ++l)
+        for (int i = tid; i < 3 * C * C; i += kTrajThreads) {
+            const int term = i / (C * C), rem = i % (C * C);
+            Wsm[(size_t)(l - 2) * 3 * C * G::LDW + (term * C + rem / C) * G::LDW + rem % C] = a.W[a.w_off[3 * (l - 1) + term] + rem];
+        }
+    for (int i = tid; i < 3 * C; i += kTrajThreads) w1s[i] = a.W[a.w_off[i / C] + i % C];
+    for (int i = tid; i < C; i += kTrajThreads) wos[i] = a.W[a.w_off[3 * L] + i];
+    __syncthreads();
+
+    float acc[kFusedMaxL - 1][G::TPW][4];
+#pragma unroll
+    for (int l = 0; l < kFusedMaxL - 1; ++l)
+#pragma unroll
+        for (int s = 0; s < G::TPW; ++s)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[l][s][q] = 0.f;
+    float acc1 = 0.f, acc_out = 0.f, acc_nll = 0.f, acc_cnt = 0.f;
+    unsigned long long n_fwd = 0, n_bwd = 0;
+
+    float* rows = BIG ? a.scratch + (size_t)blockIdx.x * a.scratch_stride : rows_sm;
+    const int cap = BIG ? a.big_rows : a.cap_rows;
+
+    for (int t = blockIdx.x; t < a.b; t += gridDim.x) {
+        const int* h = a.hdr + (size_t)t * kFusedHdrW;
+        if (h[0] & kFusedFlagOverflow) continue;
+        int n[kFusedMaxL + 1], hb[kFusedMaxL + 2];
+        int tot = 0;
+        n[0] = 0;
+        hb[0] = hb[1] = 0;
+#pragma unroll
+        for (int l = 1; l <= kFusedMaxL; ++l) {
+            n[l] = l <= L ? h[l] : 0;
+            hb[l] = tot;
+            tot += n[l];
+        }
+        const int need = (GRAD ? 2 : 1) * tot;
+        const bool big = need > a.cap_rows;
+        if (big != BIG || need > cap) continue;           // (block-uniform; need <= big_rows by construction of the bounds)
+        const float* l1 = reinterpret_cast<const float*>(a.arena + (unsigned)h[4]);
+        n_fwd += (unsigned long long)tot;
+
+        // ---- layer 1 ----
+        for (int i = tid; i < n[1] * C; i += kTrajThreads) {
+            const int r = i / C, c = i % C;
+            const float z = fmaf(l1[3 * r + 2], w1s[2 * C + c], fmaf(l1[3 * r + 1], w1s[C + c], l1[3 * r] * w1s[c]));
+            rows[(size_t)r * G::LDH + c] = fu_act<ACT>(z);
+        }
+        __syncthreads();
+        // ---- conv layers ----
+#pragma unroll
+        for (int l = 2; l <= kFusedMaxL; ++l) {
+            if (l > L) break;
+            const int nl = n[l];
+            const int* ptr = reinterpret_cast<const int*>(a.arena + (unsigned)h[5 + (l - 2)]);
+            const int2* ent = reinterpret_cast<const int2*>(ptr + align2(nl + 1));
+            const float* hprev = rows + (size_t)hb[l - 1] * G::LDH;
+            float* hout = rows + (size_t)hb[l] * G::LDH;
+            const float* Wl = Wsm + (size_t)(l - 2) * 3 * C * G::LDW;
+            for (int r0 = 0; r0 < nl; r0 += G::CH) {
+                const int nr = min(G::CH, nl - r0);
+                fu_gather<C>(tile, hprev, ptr, ent, r0, nr);
+                __syncthreads();
+                fu_product<C, false>(tile, Wl, nr, [&](int r, int col, float v0, float v1) {
+                    float* o = hout + (size_t)(r0 + r) * G::LDH + col;
+                    *reinterpret_cast<float2*>(o) = make_float2(fu_act<ACT>(v0), fu_act<ACT>(v1));
+                });
+                __syncthreads();
+            }
+        }
+        // ---- readout: z_j = sum over the edges incident to neighbour j of sign * H_L[row]; logit_j = z_j . w_out ----
+        const int* rptr = reinterpret_cast<const int*>(a.arena + (unsigned)h[9]);
+        const int2* rent = reinterpret_cast<const int2*>(rptr + align2(D + 1));
+        const float* hL = rows + (size_t)hb[L] * G::LDH;
+        for (int j = warp; j < D; j += kTrajThreads / 32) {
+            float z = 0.f;
+            const int p1 = __ldg(rptr + j + 1);
+            for (int p = __ldg(rptr + j); p < p1; ++p) {
+                const int2 en = __ldg(rent + p);
+                const uint32_t r = (uint32_t)en.x & 0xFFFFu;
+                if (r != kNoRow && lane < C) z = fmaf(__int_as_float(en.y), hL[(size_t)r * G::LDH + lane], z);
+            }
+            if (lane < C) zs[j * C + lane] = z;
+            float part = lane < C ? z * wos[lane] : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (lane == 0) lg[j] = part;
+        }
+        __syncthreads();
+        if (warp == 0) {                                   // padded slots (logit exactly 0) take part in the normaliser: quirk Q1
+            float mx = -3.4e38f;
+            for (int j = lane; j < D; j += 32) mx = fmaxf(mx, lg[j]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            float se = 0.f;
+            for (int j = lane; j < D; j += 32) se += expf(lg[j] - mx);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+            const float lse = mx + logf(se);
+            const float mk = GRAD ? a.mask[t] : 0.f;
+            const int y = GRAD ? a.target_idx[t] : -1;
+            for (int j = lane; j < D; j += 32) {
+                const float lp = lg[j] - lse;
+                if (a.logprobs != nullptr) a.logprobs[(size_t)t * D + j] = lp;
+                if (GRAD) {
+                    dl[j] = mk * (expf(lp) - (j == y ? 1.f : 0.f));
+                    if (j == y) acc_nll += -mk * lp;       // (lane y % 32 of warp 0 owns the term; summed over lanes at the end)
+                }
+            }
+            if (GRAD && lane == 0) acc_cnt += mk;
+        }
+        if (!GRAD) {
+            __syncthreads();
+            continue;
+        }
+        // ---- backward of the readout: dq[row] = sum of sign * dl_j over its (at most two) pairs; G_L = dq w_out act'(H_L) ----
+        // dq[r] lives in the first padding column of row r of G_L (columns C .. C+7 of a stored row are never read as data)
+        const int nL = n[L];
+        float* gL = rows + (size_t)(tot + hb[L]) * G::LDH;
+        for (int r = tid; r < nL; r += kTrajThreads) gL[(size_t)r * G::LDH + C] = 0.f;
+        __syncthreads();
+        if (tid < C) {
+            float s = acc_out;
+            for (int j = 0; j < D; ++j) s = fmaf(dl[j], zs[j * C + tid], s);
+            acc_out = s;
+        }
+        {
+            const int npairs = __ldg(rptr + D);
+            for (int p = tid; p < npairs; p += kTrajThreads) {
+                const int2 en = __ldg(rent + p);
+                const uint32_t r = (uint32_t)en.x & 0xFFFFu;
+                if (r != kNoRow) atomicAdd(&gL[(size_t)r * G::LDH + C], __int_as_float(en.y) * dl[((uint32_t)en.x >> 16) & 0x7FFFu]);   // a + b == b + a
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < nL * C; i += kTrajThreads) {
+            const int r = i / C, c = i % C;
+            gL[(size_t)r * G::LDH + c] = gL[(size_t)r * G::LDH + C] * wos[c] * fu_dact<ACT>(hL[(size_t)r * G::LDH + c]);
+        }
+        __syncthreads();
+        // ---- conv layers backward: AG = [G_l | S0 G_l | S1 G_l] on the live rows of layer l - 1 ----
+#pragma unroll
+        for (int l = kFusedMaxL; l >= 2; --l) {
+            if (l > L) continue;
+            const int np_ = n[l - 1];
+            const int* ptr = reinterpret_cast<const int*>(a.arena + (unsigned)h[7 + (l - 2)]);
+            const int2* ent = reinterpret_cast<const int2*>(ptr + align2(np_ + 1));
+            const float* gl = rows + (size_t)(tot + hb[l]) * G::LDH;
+            const float* hprev = rows + (size_t)hb[l - 1] * G::LDH;
+            float* gprev = rows + (size_t)(tot + hb[l - 1]) * G::LDH;
+            const float* Wl = Wsm + (size_t)(l - 2) * 3 * C * G::LDW;
+            n_bwd += (unsigned long long)np_;
+            for (int r0 = 0; r0 < np_; r0 += G::CH) {
+                const int nr = min(G::CH, np_ - r0);
+                fu_gather<C>(tile, gl, ptr, ent, r0, nr);
+                __syncthreads();
+                fu_dw<C>(acc[l - 2], hprev + (size_t)r0 * G::LDH, tile, nr);
+                fu_product<C, true>(tile, Wl, nr, [&](int r, int col, float v0, float v1) {
+                    const float2 hv = *reinterpret_cast<const float2*>(hprev + (size_t)(r0 + r) * G::LDH + col);
+                    *reinterpret_cast<float2*>(gprev + (size_t)(r0 + r) * G::LDH + col) =
+                        make_float2(v0 * fu_dact<ACT>(hv.x), v1 * fu_dact<ACT>(hv.y));
+                });
+                __syncthreads();
+            }
+        }
+        // ---- first layer: dW_k[0][c] += sum_rows a_k[row] G_1[row][c] ----
+        if (tid < 3 * C) {
+            const int k = tid / C, c = tid % C;
+            const float* g1 = rows + (size_t)tot * G::LDH;
+            float s = acc1;
+            for (int r = 0; r < n[1]; ++r) s = fmaf(l1[3 * r + k], g1[(size_t)r * G::LDH + c], s);
+            acc1 = s;
+        }
+        __syncthreads();
+    }
+
+    if (a.rows_done != nullptr && tid == 0 && (n_fwd | n_bwd)) {
+        atomicAdd(a.rows_done, n_fwd);
+        atomicAdd(a.rows_done + 1, n_bwd);
+    }
+    if (!GRAD) return;
+    // ---- the CTA's partial gradient vector ----
+    float* P = a.partial + (size_t)blockIdx.x * (a.n_params + 2);
+    if (tid < 3 * C) P[a.w_off[tid / C] + tid % C] = acc1;
+    {
+        const int g = lane >> 2, tig = lane & 3;
+        const int mt = warp % G::NMT, ntg = warp / G::NMT;
+#pragma unroll
+        for (int l = 2; l <= kFusedMaxL; ++l) {
+            if (l > L) break;
+#pragma unroll
+            for (int s = 0; s < G::TPW; ++s) {
+                const int nt = ntg + G::WPM * s;
+                if (nt >= G::NNT) continue;
+                const int nn = 8 * nt + 2 * tig, term = nn / C, co = nn % C;
+                float* dst = P + a.w_off[3 * (l - 1) + term];
+                const int ci = 16 * mt + g;
+                dst[ci * C + co] = acc[l - 2][s][0];
+                dst[ci * C + co + 1] = acc[l - 2][s][1];
+                dst[(ci + 8) * C + co] = acc[l - 2][s][2];
+                dst[(ci + 8) * C + co + 1] = acc[l - 2][s][3];
+            }
+        }
+    }
+    if (tid < C) P[a.w_off[3 * L] + tid] = acc_out;
+    if (warp == 0) {
+        float s = acc_nll;                                 // fixed butterfly over the lanes of warp 0
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            P[a.n_params] = s;
+            P[a.n_params + 1] = acc_cnt;
+        }
+    }
+}
+
+// out[i] += sum over the CTAs' partial vectors in CTA order (deterministic); also rearms the arena bump pointer
+__global__ void __launch_bounds__(256) fused_reduce_kernel(const float* __restrict__ partial, int nparts, int n, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int p = 0;
+    for (; p + 3 < nparts; p += 4) {
+        s0 += partial[(size_t)p * n + i];
+        s1 += partial[(size_t)(p + 1) * n + i];
+        s2 += partial[(size_t)(p + 2) * n + i];
+        s3 += partial[(size_t)(p + 3) * n + i];
+    }
+    for (; p < nparts; ++p) s0 += partial[(size_t)p * n + i];
+    out[i] += (s0 + s1) + (s2 + s3);
+}
+
+size_t plan_smem_bytes(int HS, int LC) { return (size_t)HS * 13 + (size_t)(LC + 4) * 4 + (size_t)LC * 12 + (size_t)LC * 8 + 16; }
+
+template <int C>
+size_t traj_smem_bytes(int D, int cap_rows) {
+    using G = FuGeom<C>;
+    size_t fl = (size_t)(kFusedMaxL - 1) * 3 * C * G::LDW + 3 * C + C + (size_t)G::CH * G::LDA + (size_t)D * C + 2 * ((D + 3) & ~3) +
+                (size_t)cap_rows * G::LDH;
+    return fl * sizeof(float);
+}
+
+template <int C, int ACT, bool GRAD>
+int launch_traj(const TrajArgs& base, int grid_small, int grid_big, size_t smem_small, size_t smem_big, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        SCONE_CUDA(cudaFuncSetAttribute(fused_traj_kernel<C, ACT, GRAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+        SCONE_CUDA(cudaFuncSetAttribute(fused_traj_kernel<C, ACT, GRAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+        configured = true;
+    }
+    TrajArgs a = base;
+    fused_traj_kernel<C, ACT, GRAD, false><<<grid_small, kTrajThreads, smem_small, st>>>(a);
+    SCONE_LAUNCHED();
+    if (grid_big > 0) {
+        if (GRAD) a.partial = base.partial + (size_t)grid_small * (base.n_params + 2);
+        fused_traj_kernel<C, ACT, GRAD, true><<<grid_big, kTrajThreads, smem_big, st>>>(a);
+        SCONE_LAUNCHED();
+    }
+    return 0;
+}
+
+template <int C, bool GRAD>
+int dispatch_traj(int act, const TrajArgs& a, int gs, int gb, size_t ss, size_t sb, cudaStream_t st) {
+    switch (act) {
+        case SCONE_ACT_TANH: return launch_traj<C, SCONE_ACT_TANH, GRAD>(a, gs, gb, ss, sb, st);
+        case SCONE_ACT_LEAKY_RELU: return launch_traj<C, SCONE_ACT_LEAKY_RELU, GRAD>(a, gs, gb, ss, sb, st);
+        case SCONE_ACT_RELU: return launch_traj<C, SCONE_ACT_RELU, GRAD>(a, gs, gb, ss, sb, st);
+    }
+    scone_set_error("unknown activation %d", act);
+    return 2;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+bool scone_fused_supported(const scone_complex* cx, int n_layers, const int32_t* hidden) {
+    if (cx->d_mptr == nullptr || cx->D > kFuMaxD || cx->D < 1 || n_layers < 1 || n_layers > kFusedMaxL) return false;
+    for (int l = 0; l < n_layers; ++l)
+        if (hidden[l] != hidden[0] || (hidden[l] != 16 && hidden[l] != 32)) return false;
+    return true;
+}
+
+void scone_fused_destroy(FusedState* f) {
+    if (!f) return;
+    cudaFree(f->d_hdr); cudaFree(f->d_arena); cudaFree(f->d_bump); cudaFree(f->d_partial); cudaFree(f->d_scratch); cudaFree(f->d_stats);
+    cudaFree(f->d_rows_done);
+    delete f;
+}
+
+// Measures the static bounds of the complex and sizes every buffer of the fused pipeline for micro-batches of `mb` trajectories.
+// Returns 0 and *out = nullptr when the complex does not fit the pipeline's shared-memory tables (caller keeps pipeline 3 / 2).
+int scone_fused_create(const scone_complex* cx, int L, int C, int mb, int64_t n_params, FusedState** out) {
+    *out = nullptr;
+    FusedState* f = new FusedState();
+    f->L = L;
+    f->C = C;
+    f->n_params = n_params;
+    // ---- bounds: the cone of every node, with the largest tables one CTA can hold ----
+    SCONE_CUDA(cudaMalloc((void**)&f->d_stats, 4 * sizeof(int)));
+    SCONE_CUDA(cudaMemset(f->d_stats, 0, 4 * sizeof(int)));
+    {
+        const int HS = 32768, LC = 16384, hshift = 32 - 15;
+        const size_t smem = (size_t)HS * 4 + (size_t)LC * 4;
+        SCONE_CUDA(cudaFuncSetAttribute(fused_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fused_bound_kernel<<<cx->N, kPlanThreads, smem>>>(cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, cx->d_mptr, cx->d_ment, cx->N, cx->D, L, HS,
+                                                          LC, hshift, f->d_stats);
+        SCONE_LAUNCHED();
+        int st[4] = {0, 0, 0, 0};
+        SCONE_CUDA(cudaMemcpy(st, f->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
+        if (st[2]) {                                       // cones larger than any table: not this pipeline's regime
+            scone_fused_destroy(f);
+            return 0;
+        }
+        f->bound_t0 = st[0] > 0 ? st[0] : 1;
+        f->bound_t1 = st[1] > 0 ? st[1] : 1;
+    }
+    int HS = 256;
+    while (HS * 3 / 4 < f->bound_t0 + 1) HS *= 2;
+    f->HS = HS;
+    f->hshift = 32;
+    for (int v = HS; v > 1; v >>= 1) --f->hshift;
+    f->LC = (f->bound_t1 + 63) & ~63;
+    f->plan_smem = plan_smem_bytes(f->HS, f->LC);
+    if (f->plan_smem > 200 * 1024 || f->bound_t1 >= 0xFFFF) {
+        scone_fused_destroy(f);
+        return 0;
+    }
+    SCONE_CUDA(cudaFuncSetAttribute(fused_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->plan_smem));
+    // ---- compute kernel: shared-memory row store of the small variant, per-CTA global row store of the big one ----
+    const int ldh = C + 8;
+    f->cap_rows = C == 32 ? 256 : 448;
+    f->big_rows = 2 * L * f->bound_t1;
+    f->traj_smem_small = C == 32 ? traj_smem_bytes<32>(cx->D, f->cap_rows) : traj_smem_bytes<16>(cx->D, f->cap_rows);
+    f->traj_smem_big = C == 32 ? traj_smem_bytes<32>(cx->D, 0) : traj_smem_bytes<16>(cx->D, 0);
+    if (f->traj_smem_small > 113 * 1024) {                 // very high degrees: shrink the row store, keep two CTAs per SM
+        const size_t over = f->traj_smem_small - 113 * 1024;
+        const int less = (int)((over + ldh * 4 - 1) / (ldh * 4));
+        f->cap_rows = f->cap_rows > less + 32 ? f->cap_rows - less : 32;
+        f->traj_smem_small = C == 32 ? traj_smem_bytes<32>(cx->D, f->cap_rows) : traj_smem_bytes<16>(cx->D, f->cap_rows);
+    }
+    f->grid_small = 2 * cx->num_sms;
+    f->grid_big = f->big_rows > f->cap_rows ? cx->num_sms : 0;   // (every trajectory fits the shared-memory store otherwise)
+    if (f->grid_big) {
+        f->scratch_stride = (size_t)f->big_rows * ldh;
+        SCONE_CUDA(cudaMalloc((void**)&f->d_scratch, (size_t)f->grid_big * f->scratch_stride * sizeof(float)));
+    }
+    SCONE_CUDA(cudaMalloc((void**)&f->d_partial, (size_t)(f->grid_small + f->grid_big) * (n_params + 2) * sizeof(float)));
+    // ---- program arena: worst case per trajectory from the bounds, chunked so that it stays below 4 GB ----
+    int max_row = 1;
+    {
+        std::vector<int32_t> mp((size_t)cx->E + 1);
+        SCONE_CUDA(cudaMemcpy(mp.data(), cx->d_mptr, mp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        for (int e = 0; e < cx->E; ++e) max_row = std::max(max_row, mp[e + 1] - mp[e]);
+    }
+    const unsigned long long b1 = (unsigned long long)f->bound_t1;
+    unsigned long long worst = 3 * b1 + 2 + (unsigned long long)(L > 1 ? L - 1 : 0) * 2 * ((b1 + 3) + 2 * b1 * (unsigned long long)max_row) +
+                               (unsigned long long)(cx->D + 3) + 2ull * cx->D * cx->D + 16;
+    // a neighbour has at most D incident edges: D * D pairs
+    const unsigned long long budget_words = (1ull << 30) - 1024;                 // 4 GB of 32-bit words; offsets are 32-bit
+    unsigned long long chunk = budget_words / worst;
+    if (chunk < 1) {
+        scone_fused_destroy(f);
+        return 0;
+    }
+    f->chunk = (int)std::min<unsigned long long>(chunk, (unsigned long long)mb);
+    f->arena_words = worst * (unsigned long long)f->chunk;
+    SCONE_CUDA(cudaMalloc((void**)&f->d_arena, f->arena_words * sizeof(uint32_t)));
+    SCONE_CUDA(cudaMalloc((void**)&f->d_hdr, (size_t)f->chunk * kFusedHdrW * sizeof(int)));
+    SCONE_CUDA(cudaMalloc((void**)&f->d_bump, sizeof(unsigned long long)));
+    SCONE_CUDA(cudaMalloc((void**)&f->d_rows_done, 2 * sizeof(unsigned long long)));
+    SCONE_CUDA(cudaMemset(f->d_rows_done, 0, 2 * sizeof(unsigned long long)));
+    *out = f;
+    return 0;
+}
+
+// One chunk (<= f->chunk trajectories, device pointers already offset to the chunk): plan + compute (+ partial reduce into grad).
+int scone_fused_run(const scone_complex* cx, FusedState* f, int act, int b, const int32_t* traj_ptr, const int32_t* flow_edge,
+                    const float* flow_val, const int32_t* last_nodes, const float* W, const int64_t* w_off, float* logprobs,
+                    const int32_t* target_idx, const float* mask, float* grad, int* overflow, bool count_rows, cudaStream_t st) {
+    if (b <= 0) return 0;
+    SCONE_REQUIRE(b <= f->chunk, "scone_fused_run: chunk of %d trajectories exceeds the planned %d", b, f->chunk);
+    const bool want_grad = grad != nullptr;
+    SCONE_CUDA(cudaMemsetAsync(f->d_bump, 0, sizeof(unsigned long long), st));
+    PlanArgs p;
+    p.traj_ptr = traj_ptr; p.flow_edge = flow_edge; p.flow_val = flow_val; p.last_nodes = last_nodes;
+    p.rank = cx->d_rank; p.nbrhoods = cx->d_nbrhoods; p.inc_ptr = cx->d_inc_ptr; p.inc_ent = cx->d_inc_ent;
+    p.mptr = cx->d_mptr; p.ment = cx->d_ment;
+    p.N = cx->N; p.D = cx->D; p.E = cx->E; p.L = f->L; p.HS = f->HS; p.LC = f->LC; p.hshift = f->hshift;
+    p.hdr = f->d_hdr; p.arena = f->d_arena; p.bump = f->d_bump; p.arena_words = f->arena_words; p.overflow = overflow;
+    {
+        ScopedProf prof(SCONE_K_CONE, st);
+        fused_plan_kernel<<<b, kPlanThreads, f->plan_smem, st>>>(p);
+        SCONE_LAUNCHED();
+    }
+    TrajArgs t;
+    t.hdr = f->d_hdr; t.arena = f->d_arena; t.W = W;
+    for (int i = 0; i <= 3 * kFusedMaxL; ++i) t.w_off[i] = i <= 3 * f->L ? (int)w_off[i] : 0;
+    t.L = f->L; t.b = b; t.D = cx->D; t.n_params = (int)f->n_params;
+    t.logprobs = logprobs; t.target_idx = target_idx; t.mask = mask;
+    t.partial = f->d_partial; t.scratch = f->d_scratch; t.scratch_stride = f->scratch_stride;
+    t.cap_rows = f->cap_rows; t.big_rows = f->big_rows;
+    t.rows_done = count_rows ? f->d_rows_done : nullptr;
+    int rc;
+    {
+        ScopedProf prof(want_grad ? SCONE_K_LAYER_BWD : SCONE_K_LAYER_FWD, st);
+        if (f->C == 32)
+            rc = want_grad ? dispatch_traj<32, true>(act, t, f->grid_small, f->grid_big, f->traj_smem_small, f->traj_smem_big, st)
+                           : dispatch_traj<32, false>(act, t, f->grid_small, f->grid_big, f->traj_smem_small, f->traj_smem_big, st);
+        else
+            rc = want_grad ? dispatch_traj<16, true>(act, t, f->grid_small, f->grid_big, f->traj_smem_small, f->traj_smem_big, st)
+                           : dispatch_traj<16, false>(act, t, f->grid_small, f->grid_big, f->traj_smem_small, f->traj_smem_big, st);
+        if (rc) return rc;
+        if (want_grad) {
+            const int n = (int)f->n_params + 2;
+            fused_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(f->d_partial, f->grid_small + f->grid_big, n, grad);
+            SCONE_LAUNCHED();
+        }
+    }
+    return 0;
+}
+
+// debug / test access: header of trajectory t of the last chunk and `words` arena words from word offset `off`
+int scone_fused_read(FusedState* f, int t, int* hdr_out, unsigned off, int words, uint32_t* arena_out) {
+    SCONE_CUDA(cudaDeviceSynchronize());
+    if (hdr_out) SCONE_CUDA(cudaMemcpy(hdr_out, f->d_hdr + (size_t)t * kFusedHdrW, kFusedHdrW * sizeof(int), cudaMemcpyDeviceToHost));
+    if (arena_out && words > 0) SCONE_CUDA(cudaMemcpy(arena_out, f->d_arena + off, (size_t)words * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return 0;
+}

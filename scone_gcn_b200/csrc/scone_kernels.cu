@@ -1254,9 +1254,13 @@ __global__ void readout_reduce_kernel(const float* __restrict__ partial, int b, 
 }
 
 __global__ void adam_kernel(float* __restrict__ W, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ gradbuf,
-                            long long n, float lr, float wd, float b1, float b2, float eps, float c1, float c2) {
+                            long long n, float lr, float wd, float b1, float b2, float eps, float c1, float c2,
+                            const int* __restrict__ overflow) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    // a micro-batch exceeded a row-list capacity: the accumulated gradients are truncated -> leave weights and Adam state alone
+    // (the flag stays set; scone_model_check_overflow / read_grads / forward_host report it as error code 4)
+    if (overflow != nullptr && *overflow != 0) return;
     const float count = gradbuf[n + 1];
     const float g = gradbuf[i] / count + 2.f * wd * W[i];
     const float mi = (1.f - b1) * g + b1 * m[i];
@@ -1781,10 +1785,11 @@ extern "C" int scone_readout(const scone_complex* cx, int32_t act, int32_t b, in
                             accumulate, workspace, occ_HL, occ_GL, stream);
 }
 
-int scone_adam_launch(float* W, float* m, float* v, const float* gradbuf, int64_t n, int32_t step, float lr, float wd, void* stream) {
+int scone_adam_launch(float* W, float* m, float* v, const float* gradbuf, int64_t n, int32_t step, float lr, float wd, void* stream,
+                      const int* overflow_dev) {
     const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
     const float c1 = 1.f - powf(b1, (float)(step + 1)), c2 = 1.f - powf(b2, (float)(step + 1));
-    adam_kernel<<<(int)((n + 255) / 256), 256, 0, as_stream(stream)>>>(W, m, v, gradbuf, (long long)n, lr, wd, b1, b2, eps, c1, c2);
+    adam_kernel<<<(int)((n + 255) / 256), 256, 0, as_stream(stream)>>>(W, m, v, gradbuf, (long long)n, lr, wd, b1, b2, eps, c1, c2, overflow_dev);
     SCONE_LAUNCHED();
     return 0;
 }

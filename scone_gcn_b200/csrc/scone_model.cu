@@ -9,6 +9,7 @@
 // flat device buffer [grads | nll_sum | count] that is the single all-reduce payload of a data-parallel step.
 #include <cstring>
 #include "common.cuh"
+#include "fused.cuh"
 
 struct scone_model {
     const scone_complex* cx = nullptr;
@@ -39,6 +40,7 @@ struct scone_model {
     bool cone_clean = false;                  // pipeline 3: the two-level bitmaps d_bmGr are all-zero between micro-batches
     size_t sum_off = 0, bmg_bytes = 0;        // summary words of d_bmGr[l] start at word sum_off; bytes of one d_bmGr allocation
     int pipeline = 0;
+    FusedState* fused = nullptr;              // pipeline 4: trajectory-fused kernels (scone_fused.cu); nullptr = not available for this model
     std::vector<uint32_t*> d_bmH, d_bmGr, d_prefH, d_prefG;
     std::vector<uint32_t*> d_bmC;             // pipeline 3: geometric cone per layer (d_bmGr[l] then holds the LIVE rows: cone & support)
     std::vector<float*> d_cH, d_cG;           // compact tensors [row_cap][C_l]
@@ -155,6 +157,12 @@ int ensure_buffers(scone_model* m) {
     const size_t E = cx->E, mb = m->mb;
     const int L = m->L;
     const int pl = m->zero_fill ? 0 : m->pipeline;
+    if (!m->d_overflow) {
+        SCONE_ALLOC(m->d_overflow, 256, "counters");
+        SCONE_CUDA(cudaMemset(m->d_overflow, 0, 256));
+    }
+    if (pl == 4) return 0;                                 // the fused pipeline owns its buffers (FusedState); no dense X, no bitmaps
+    SCONE_ALLOC(m->d_X, E * mb * sizeof(float), "dense flows X");
     if (pl <= 1 && !m->dense_ready) {                      // dense [E][mb][C] tensors (+ byte flags for the unit kernels)
         for (int l = 0; l < L; ++l) {
             SCONE_ALLOC(m->d_H[l], E * mb * m->hidden[l] * sizeof(float), "dense activations");
@@ -176,8 +184,6 @@ int ensure_buffers(scone_model* m) {
         m->bmg_bytes = bm_bytes + ((m->sum_off + 31) / 32 + 16) * 4;
         for (int l = 0; l < L; ++l) SCONE_ALLOC(m->d_bmGr[l], m->bmg_bytes, "bitmap");
         SCONE_ALLOC(m->d_nrows, 8 * (size_t)(L + 1), "counters");
-        SCONE_ALLOC(m->d_overflow, 256, "counters");
-        SCONE_CUDA(cudaMemset(m->d_overflow, 0, 256));
         SCONE_ALLOC(m->d_tickets, scone_ticket_bytes(), "tickets");
         const size_t acap = E * mb < (size_t)6000000 ? E * mb : (size_t)6000000;    // rows of the compact A buffer (backward)
         m->a_cap = (int)acap;
@@ -499,7 +505,6 @@ extern "C" int scone_model_create(const scone_complex* cx, int32_t n_layers, con
     alloc((void**)&m->d_m, off * sizeof(float));
     alloc((void**)&m->d_v, off * sizeof(float));
     alloc((void**)&m->d_grad, (off + 2) * sizeof(float));
-    alloc((void**)&m->d_X, E * mb * sizeof(float));
     m->d_H.assign(n_layers, nullptr);
     m->d_G.assign(n_layers, nullptr);
     m->d_occH.assign(n_layers, nullptr);
@@ -509,7 +514,14 @@ extern "C" int scone_model_create(const scone_complex* cx, int32_t n_layers, con
     // the cone kernel stages at most 2048 edges per trajectory and level in shared memory: the top level alone has up to D * D
     // edges, so complexes with very high degrees start on the whole-support pipeline (the cone would report an overflow)
     m->pipeline = m->rows_ok ? ((cx->D <= 32 || E * mb >= ((size_t)1 << 31)) ? 3 : 2) : 0;
-    if (!m->rows_ok && E * mb >= ((size_t)1 << 31)) {
+    if (scone_fused_supported(cx, n_layers, hidden)) {     // measured static bounds decide; nullptr = cones too large for the tables
+        if (scone_fused_create(cx, n_layers, hidden[0], micro_batch, m->n_params, &m->fused)) {
+            delete m;
+            return 1;
+        }
+        if (m->fused) m->pipeline = 4;
+    }
+    if (m->pipeline != 4 && !m->rows_ok && E * mb >= ((size_t)1 << 31)) {
         scone_set_error("scone_model_create: E * micro_batch = %zu needs the row-list pipeline (widths 16 / 32, E * micro_batch < 2^32)", E * mb);
         delete m;
         return 2;
@@ -566,6 +578,7 @@ extern "C" int scone_model_destroy(scone_model* m) {
     cudaFree(m->d_rows); cudaFree(m->d_nrows); cudaFree(m->d_overflow); cudaFree(m->d_tickets); cudaFree(m->d_Abuf);
     for (float* p : m->d_G) cudaFree(p);
     cudaFree(m->d_ws); cudaFree(m->d_logp);
+    scone_fused_destroy(m->fused);
     if (m->side) cudaStreamDestroy(m->side);
     if (m->compute) cudaStreamDestroy(m->compute);
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
@@ -587,12 +600,16 @@ extern "C" int scone_model_set_zero_fill(scone_model* m, int32_t on) {
 }
 extern "C" int scone_model_get_zero_fill(const scone_model* m) { return m && m->zero_fill ? 1 : 0; }
 extern "C" int scone_model_set_pipeline(scone_model* m, int32_t which) {
-    SCONE_REQUIRE(m != nullptr && which >= 0 && which <= 3,
-                  "scone_model_set_pipeline: 0 (unit kernels, byte flags), 1 (row lists, dense tensors), 2 (row lists, compact tensors) or "
-                  "3 (compact row lists over the readout cone)");
-    SCONE_REQUIRE(which == 0 || m->rows_ok, "scone_model_set_pipeline: the row-list pipelines need hidden widths in {16, 32}");
-    SCONE_REQUIRE(which == 3 || (size_t)m->cx->E * m->mb < ((size_t)1 << 31),
-                  "scone_model_set_pipeline: E * micro_batch >= 2^31 runs on pipeline 3 only");
+    SCONE_REQUIRE(m != nullptr && which >= 0 && which <= 4,
+                  "scone_model_set_pipeline: 0 (unit kernels, byte flags), 1 (row lists, dense tensors), 2 (row lists, compact tensors), "
+                  "3 (compact row lists over the readout cone) or 4 (trajectory-fused kernels)");
+    SCONE_REQUIRE(which != 4 || m->fused != nullptr,
+                  "scone_model_set_pipeline: the fused pipeline needs one uniform hidden width of 16 or 32, at most 3 layers, and cones that fit "
+                  "its shared-memory tables");
+    SCONE_REQUIRE(which == 0 || which == 4 || m->rows_ok, "scone_model_set_pipeline: the row-list pipelines need hidden widths in {16, 32}");
+    SCONE_REQUIRE(which >= 3 || (size_t)m->cx->E * m->mb < ((size_t)1 << 31),
+                  "scone_model_set_pipeline: E * micro_batch >= 2^31 runs on pipelines 3 / 4 only");
+    SCONE_REQUIRE(which != 3 || (size_t)m->cx->E * m->mb < ((size_t)1 << 32), "scone_model_set_pipeline: pipeline 3 needs E * micro_batch < 2^32");
     const int old = m->pipeline;
     m->pipeline = which;
     if (ensure_buffers(m)) {
@@ -632,6 +649,31 @@ static int join_from_compute(scone_model* m, void* user_st) {
     return 0;
 }
 
+// A failed launch inside a micro-batch leaves X / the cone bitmaps dirty: every model-level call leaves through this exit, which
+// marks them so (the next call re-clears) and still joins the caller's stream to the compute stream.
+static int finish_call(scone_model* m, int rc, void* user_st) {
+    if (rc) {
+        m->x_clean = false;
+        m->cone_clean = false;
+    }
+    const int jr = join_from_compute(m, user_st);
+    return rc ? rc : jr;
+}
+
+// pipeline 4: the micro-batch is walked in chunks the program arena was sized for (scone_fused_create)
+static int fused_call(scone_model* m, int32_t B, const int32_t* ptr, const int32_t* edge, const float* val, const int32_t* last,
+                      float* logprobs, const int32_t* tgt, const float* mask, bool grad, cudaStream_t s) {
+    const int step = m->fused->chunk < m->mb ? m->fused->chunk : m->mb;
+    for (int32_t off = 0; off < B; off += step) {
+        const int32_t b = B - off < step ? B - off : step;
+        int rc = scone_fused_run(m->cx, m->fused, m->act, b, ptr + off, edge, val, last + off, m->d_w, m->w_off.data(),
+                                 logprobs ? logprobs + (size_t)off * m->cx->D : nullptr, grad ? tgt + off : nullptr,
+                                 grad ? mask + off : nullptr, grad ? m->d_grad : nullptr, m->d_overflow, g_scone_prof, s);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 extern "C" int scone_model_forward_dev(scone_model* m, int32_t B, const int32_t* ptr, const int32_t* edge, const float* val,
                                        const int32_t* last, float* logprobs, void* user_st) {
     SCONE_REQUIRE(m && ptr && last && logprobs && B >= 0, "scone_model_forward_dev: bad arguments");
@@ -639,42 +681,33 @@ extern "C" int scone_model_forward_dev(scone_model* m, int32_t B, const int32_t*
     void* st = (void*)m->compute;
     const scone_complex* cx = m->cx;
     const bool rows = m->pipeline >= 1 && !m->zero_fill;
-    for (int32_t off = 0; off < B; off += m->mb) {
+    if (rows && m->pipeline == 4) return finish_call(m, fused_call(m, B, ptr, edge, val, last, logprobs, nullptr, nullptr, false, as_stream(st)), user_st);
+    int rc = 0;
+    for (int32_t off = 0; off < B && !rc; off += m->mb) {
         const int32_t b = B - off < m->mb ? B - off : m->mb;
-        int rc;
         if (rows && m->pipeline == 3) {
             rc = cone_build_mb(m, b, ptr + off, edge, val, last + off, as_stream(st));
-            if (rc) return rc;
-            rc = cone_forward_mb(m, b, as_stream(st));
-            if (rc) return rc;
-            rc = cone_readout(m, b, last + off, logprobs + (size_t)off * cx->D, false, nullptr, nullptr, as_stream(st));
-            if (rc) return rc;
-            rc = rows_clear_x(m, b, ptr + off, edge, val, as_stream(st));
-            if (rc) return rc;
-            rc = cone_clear_mb(m, b, as_stream(st));
-            if (rc) return rc;
+            if (!rc) rc = cone_forward_mb(m, b, as_stream(st));
+            if (!rc) rc = cone_readout(m, b, last + off, logprobs + (size_t)off * cx->D, false, nullptr, nullptr, as_stream(st));
+            if (!rc) rc = rows_clear_x(m, b, ptr + off, edge, val, as_stream(st));
+            if (!rc) rc = cone_clear_mb(m, b, as_stream(st));
             continue;
         }
         if (rows) {
             rc = rows_forward_mb(m, b, ptr + off, edge, val, as_stream(st));
-            if (rc) return rc;
-            rc = rows_readout(m, b, last + off, logprobs + (size_t)off * cx->D, false, nullptr, nullptr, as_stream(st));
-            if (rc) return rc;
-            rc = rows_clear_x(m, b, ptr + off, edge, val, as_stream(st));
-            if (rc) return rc;
+            if (!rc) rc = rows_readout(m, b, last + off, logprobs + (size_t)off * cx->D, false, nullptr, nullptr, as_stream(st));
+            if (!rc) rc = rows_clear_x(m, b, ptr + off, edge, val, as_stream(st));
             continue;
         }
         m->x_clean = false;
         rc = start_fills(m, b, false, as_stream(st));
-        if (rc) return rc;
-        rc = forward_mb(m, b, ptr + off, edge, val, st);
-        if (rc) return rc;
-        rc = scone_readout_ws(cx, m->act, b, m->hidden[m->L - 1], m->d_H[m->L - 1], m->d_w + m->w_off[3 * m->L], last + off,
-                              logprobs + (size_t)off * cx->D, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, nullptr, 0,
-                              nullptr, m->d_occH[m->L - 1], nullptr, st);
-        if (rc) return rc;
+        if (!rc) rc = forward_mb(m, b, ptr + off, edge, val, st);
+        if (!rc)
+            rc = scone_readout_ws(cx, m->act, b, m->hidden[m->L - 1], m->d_H[m->L - 1], m->d_w + m->w_off[3 * m->L], last + off,
+                                  logprobs + (size_t)off * cx->D, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, nullptr, 0,
+                                  nullptr, m->d_occH[m->L - 1], nullptr, st);
     }
-    return join_from_compute(m, user_st);
+    return finish_call(m, rc, user_st);
 }
 
 extern "C" int scone_model_loss_grad_dev(scone_model* m, int32_t B, const int32_t* ptr, const int32_t* edge, const float* val,
@@ -688,52 +721,44 @@ extern "C" int scone_model_loss_grad_dev(scone_model* m, int32_t B, const int32_
     cudaStream_t s = as_stream(st);
     if (zero_first) SCONE_CUDA(cudaMemsetAsync(m->d_grad, 0, (m->n_params + 2) * sizeof(float), s));
     const bool rows = m->pipeline >= 1 && !m->zero_fill;
-    for (int32_t off = 0; off < B; off += m->mb) {
+    if (rows && m->pipeline == 4) return finish_call(m, fused_call(m, B, ptr, edge, val, last, nullptr, tgt, mask, true, s), user_st);
+    int rc = 0;
+    for (int32_t off = 0; off < B && !rc; off += m->mb) {
         const int32_t b = B - off < m->mb ? B - off : m->mb;
-        int rc;
         if (rows && m->pipeline == 3) {
             rc = cone_build_mb(m, b, ptr + off, edge, val, last + off, s);
-            if (rc) return rc;
-            rc = cone_forward_mb(m, b, s);
-            if (rc) return rc;
-            rc = cone_readout(m, b, last + off, m->d_logp, true, tgt + off, mask + off, s);
-            if (rc) return rc;
-            rc = cone_backward_mb(m, b, s);
-            if (rc) return rc;
-            rc = rows_clear_x(m, b, ptr + off, edge, val, s);
-            if (rc) return rc;
-            rc = cone_clear_mb(m, b, s);
-            if (rc) return rc;
+            if (!rc) rc = cone_forward_mb(m, b, s);
+            if (!rc) rc = cone_readout(m, b, last + off, m->d_logp, true, tgt + off, mask + off, s);
+            if (!rc) rc = cone_backward_mb(m, b, s);
+            if (!rc) rc = rows_clear_x(m, b, ptr + off, edge, val, s);
+            if (!rc) rc = cone_clear_mb(m, b, s);
             continue;
         }
         if (rows) {
             rc = rows_forward_mb(m, b, ptr + off, edge, val, s);
-            if (rc) return rc;
-            rc = rows_readout(m, b, last + off, m->d_logp, true, tgt + off, mask + off, s);
-            if (rc) return rc;
-            rc = rows_backward_mb(m, b, s);
-            if (rc) return rc;
-            rc = rows_clear_x(m, b, ptr + off, edge, val, s);
-            if (rc) return rc;
+            if (!rc) rc = rows_readout(m, b, last + off, m->d_logp, true, tgt + off, mask + off, s);
+            if (!rc) rc = rows_backward_mb(m, b, s);
+            if (!rc) rc = rows_clear_x(m, b, ptr + off, edge, val, s);
             continue;
         }
         m->x_clean = false;
         rc = start_fills(m, b, true, s);
-        if (rc) return rc;
-        rc = forward_mb(m, b, ptr + off, edge, val, st);
-        if (rc) return rc;
+        if (!rc) rc = forward_mb(m, b, ptr + off, edge, val, st);
         const int CL = m->hidden[L - 1];
-        if (wait_fill(m, L + (L - 1), s)) return 1;
+        if (!rc && wait_fill(m, L + (L - 1), s)) rc = 1;
+        if (rc) break;
         g_scone_hints.out_bm = m->d_bmG;
         rc = scone_readout_ws(cx, m->act, b, CL, m->d_H[L - 1], m->d_w + m->w_off[3 * L], last + off, m->d_logp, tgt + off,
                               mask + off, 1.f, m->d_G[L - 1], m->d_grad + m->w_off[3 * L], m->d_grad + m->n_params,
                               m->d_grad + m->n_params + 1, 1, m->d_ws, m->d_occH[L - 1], m->d_occG[L - 1], st);
-        if (rc) return rc;
         int wl = -1, tt = 0;
-        for (int l = L - 1; l >= 0; --l) {
+        for (int l = L - 1; l >= 0 && !rc; --l) {
             const int cout = m->hidden[l], cin = l > 0 ? m->hidden[l - 1] : 1;
             const float* Hin = l > 0 ? m->d_H[l - 1] : m->d_X;
-            if (l > 0 && wait_fill(m, L + (l - 1), s)) return 1;
+            if (l > 0 && wait_fill(m, L + (l - 1), s)) {
+                rc = 1;
+                break;
+            }
             g_scone_hints.in_wl = wl;
             g_scone_hints.in_tt = tt;
             if (l == L - 1) g_scone_hints.in_bm = m->d_bmG;
@@ -741,12 +766,11 @@ extern "C" int scone_model_loss_grad_dev(scone_model* m, int32_t B, const int32_
                                       m->d_w + m->w_off[3 * l + 1], m->d_w + m->w_off[3 * l + 2], l > 0 ? m->d_G[l - 1] : nullptr,
                                       m->d_grad + m->w_off[3 * l], 1, m->d_ws, m->d_occG[l], l > 0 ? m->d_occH[l - 1] : nullptr,
                                       l > 0 ? m->d_occG[l - 1] : nullptr, m->d_occS, st);
-            if (rc) return rc;
             wl = g_scone_hints.out_wl;
             tt = g_scone_hints.out_tt;
         }
     }
-    return join_from_compute(m, user_st);
+    return finish_call(m, rc, user_st);
 }
 
 extern "C" int scone_model_forward_host(scone_model* m, int32_t B, const int32_t* ptr, const int32_t* edge, const float* val,
@@ -860,7 +884,59 @@ extern "C" int scone_model_read_grads(scone_model* m, float* out, void* st) {
     return 0;
 }
 
+extern "C" int scone_model_check_overflow(scone_model* m, void* st) {
+    SCONE_REQUIRE(m != nullptr, "scone_model_check_overflow: NULL model");
+    int overflow = 0;
+    cudaStream_t s = as_stream(st);
+    if (m->d_overflow) SCONE_CUDA(cudaMemcpyAsync(&overflow, m->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
+    SCONE_CUDA(cudaStreamSynchronize(s));
+    if (overflow) {
+        cudaMemset(m->d_overflow, 0, sizeof(int));
+        m->cone_clean = false;
+        scone_set_error("scone_model: a micro-batch exceeded a row-list capacity (%d rows per compact tensor, %d rows of the backward's A "
+                        "buffer, 2048 cone edges per trajectory and layer); results since the last check are incomplete and Adam steps were "
+                        "skipped — use a smaller micro-batch or another pipeline", m->row_cap, m->a_cap);
+        return 4;
+    }
+    return 0;
+}
+
+extern "C" int scone_model_set_weights_keep_state(scone_model* m, const float* w, void* st) {
+    SCONE_REQUIRE(m && w, "scone_model_set_weights_keep_state: NULL argument");
+    SCONE_CUDA(cudaMemcpyAsync(m->d_w, w, m->n_params * sizeof(float), cudaMemcpyHostToDevice, as_stream(st)));
+    return 0;
+}
+
+extern "C" int scone_model_fused_info(const scone_model* m, int32_t* out /* [8] */) {
+    SCONE_REQUIRE(m && out, "scone_model_fused_info: NULL argument");
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    if (!m->fused) return 0;
+    const FusedState* f = m->fused;
+    out[0] = 1; out[1] = f->bound_t0; out[2] = f->bound_t1; out[3] = f->HS; out[4] = f->chunk; out[5] = f->cap_rows;
+    out[6] = (int32_t)(f->plan_smem / 1024); out[7] = (int32_t)(f->traj_smem_small / 1024);
+    return 0;
+}
+
+extern "C" int scone_model_fused_read(scone_model* m, int32_t t, int32_t* hdr_out, uint32_t off, int32_t words, uint32_t* arena_out) {
+    SCONE_REQUIRE(m && m->fused, "scone_model_fused_read: the model has no fused pipeline");
+    SCONE_REQUIRE(t >= 0 && t < m->fused->chunk && (uint64_t)off + (uint64_t)(words > 0 ? words : 0) <= m->fused->arena_words,
+                  "scone_model_fused_read: out of range");
+    return scone_fused_read(m->fused, t, hdr_out, off, words, arena_out);
+}
+
+extern "C" int scone_model_read_rows_done(scone_model* m, int64_t* out /* [2] */) {
+    SCONE_REQUIRE(m && out, "scone_model_read_rows_done: NULL argument");
+    out[0] = out[1] = 0;
+    if (!m->fused) return 0;
+    unsigned long long v[2];
+    SCONE_CUDA(cudaMemcpy(v, m->fused->d_rows_done, sizeof(v), cudaMemcpyDeviceToHost));
+    SCONE_CUDA(cudaMemset(m->fused->d_rows_done, 0, sizeof(v)));
+    out[0] = (int64_t)v[0];
+    out[1] = (int64_t)v[1];
+    return 0;
+}
+
 extern "C" int scone_model_adam_step(scone_model* m, int32_t step, float lr, float wd, void* st) {
     SCONE_REQUIRE(m && step >= 0, "scone_model_adam_step: bad arguments");
-    return scone_adam_launch(m->d_w, m->d_m, m->d_v, m->d_grad, m->n_params, step, lr, wd, st);
+    return scone_adam_launch(m->d_w, m->d_m, m->d_v, m->d_grad, m->n_params, step, lr, wd, st, m->d_overflow);
 }

@@ -34,6 +34,32 @@ class SconeModel:
         trajectories' support are never written; results are bit-identical)."""
         _lib.check(_lib.lib().scone_model_set_zero_fill(self.handle, int(bool(on))), 'scone_model_set_zero_fill')
 
+    @property
+    def pipeline(self):
+        """0 unit kernels, 1-3 row lists (3 = readout cone), 4 = trajectory-fused kernels (include/scone_b200.h)."""
+        return int(_lib.lib().scone_model_get_pipeline(self.handle))
+
+    def set_pipeline(self, which):
+        _lib.check(_lib.lib().scone_model_set_pipeline(self.handle, int(which)), 'scone_model_set_pipeline')
+
+    def fused_info(self):
+        """dict of the fused pipeline's static bounds / launch shapes, or None when the model cannot use it."""
+        out = np.zeros(8, np.int32)
+        _lib.check(_lib.lib().scone_model_fused_info(self.handle, _lib.ptr(out)), 'scone_model_fused_info')
+        if not out[0]:
+            return None
+        keys = ['available', 'bound_t0', 'bound_t1', 'hash_slots', 'chunk', 'cap_rows', 'plan_smem_kb', 'traj_smem_kb']
+        return dict(zip(keys, (int(v) for v in out)))
+
+    def fused_header(self, t):
+        """Plan header (16 ints, csrc/fused.cuh) of trajectory t of the last chunk the fused pipeline ran."""
+        hdr = np.zeros(16, np.int32)
+        _lib.check(_lib.lib().scone_model_fused_read(self.handle, int(t), _lib.ptr(hdr), 0, 0, None), 'scone_model_fused_read')
+        return hdr
+
+    def check_overflow(self, stream=None):
+        _lib.check(_lib.lib().scone_model_check_overflow(self.handle, stream), 'scone_model_check_overflow')
+
     # ---- weights ------------------------------------------------------------------------------
     def flatten(self, weights):
         assert len(weights) == len(self.shapes), 'wrong number of weights'
@@ -52,12 +78,15 @@ class SconeModel:
             off += n
         return out
 
-    def set_weights(self, weights, reset_adam=True):
+    def set_weights(self, weights, reset_adam=True, stream=None):
         flat = self.flatten(weights)
         if reset_adam:
             _lib.check(_lib.lib().scone_model_set_weights(self.handle, _lib.ptr(flat)), 'scone_model_set_weights')
         else:
-            _copy_host_to_dev(_lib.lib().scone_model_weights_dev(self.handle), flat)
+            # asynchronous H2D on the caller's stream (Adam state kept); `flat` is kept alive until the next call replaces it
+            self._pending_weights = flat
+            _lib.check(_lib.lib().scone_model_set_weights_keep_state(self.handle, _lib.ptr(flat), stream),
+                       'scone_model_set_weights_keep_state')
 
     def get_weights(self):
         flat = np.zeros(self.n_params, np.float32)
@@ -137,8 +166,3 @@ class _CudaArray:
 def _wrap_device_f32(ptr, n):
     import torch
     return torch.as_tensor(_CudaArray(ptr, n), device='cuda')
-
-
-def _copy_host_to_dev(ptr, flat):
-    import torch
-    _wrap_device_f32(ptr, len(flat)).copy_(torch.from_numpy(flat))

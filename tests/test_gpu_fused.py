@@ -1,0 +1,165 @@
+"""Pipeline 4 (trajectory-fused kernels, csrc/scone_fused.cu) through the C ABI: its integer plan against a NumPy / SciPy
+restatement of cone & support, its results against the row-list pipeline and the oracle, determinism, chunking, and the
+big-trajectory variant (rows in global scratch)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from golden_util import Dataset, load, weights_of
+from oracle import scone_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+def cpu_live_rows(cx, n_layers, flows_row, last):
+    """Live rows per layer (sets of caller edge ids) for one trajectory: receptive cone of the readout intersected layer by layer
+    with the structural support of the flows (cone & support)."""
+    E = cx.E
+    pats = []
+    for k in range(2):
+        rowptr, col, val = cx.shift_csr(k)
+        pats.append(sp.csr_matrix((np.ones(len(col)), col, rowptr), shape=(E, E)))
+    pat = ((pats[0] + pats[1] + sp.identity(E, format='csr')) > 0).astype(np.int8).tocsr()
+    nb = cx.nbrhoods[last]
+    nb = nb[nb >= 0]
+    en = cx._edge_nodes
+    top = np.zeros(E, bool)
+    for v in nb:
+        top |= (en[:, 0] == v) | (en[:, 1] == v)
+    cones = [None] * (n_layers + 1)
+    cones[n_layers] = top
+    for l in range(n_layers - 1, 0, -1):
+        cones[l] = (pat @ cones[l + 1].astype(np.int8)) > 0
+    live = [None, cones[1] & ((pat @ (flows_row != 0).astype(np.int8)) > 0)]
+    for l in range(2, n_layers + 1):
+        live.append(cones[l] & ((pat @ live[l - 1].astype(np.int8)) > 0))
+    return live
+
+
+@pytest.mark.parametrize('model,hidden', [('scone', [16, 16, 16]), ('scone', [32, 32]), ('ebli', [16, 16, 16]), ('scone', [32])])
+def test_plan_live_rows_match_cpu_sets(model, hidden):
+    import scone_gcn_b200 as sg
+    ds = Dataset('dataset_small.npz')
+    cx = sg.SimplicialComplex.from_dense(ds.B1, ds.B2, model)
+    B = 24
+    net = sg.SconeModel(cx, hidden, micro_batch=B)
+    assert net.pipeline == 4 and net.fused_info() is not None
+    rs = np.random.RandomState(0)
+    net.set_weights([0.1 * rs.randn(*s) for s in net.shapes])
+    ptr, fe, fv = sg.flows_to_csr(ds.flows[:B])
+    net.forward(ptr, fe, fv, ds.last_nodes[:B])
+    info = net.fused_info()
+    for t in range(B):
+        hdr = net.fused_header(t)
+        live = cpu_live_rows(cx, len(hidden), ds.flows[t, :, 0], int(ds.last_nodes[t]))
+        assert hdr[0] == 0
+        for l in range(1, len(hidden) + 1):
+            assert hdr[l] == int(live[l].sum()), (t, l, hdr[:4], [int(x.sum()) for x in live[1:]])
+        assert hdr[11] <= info['bound_t1'] and hdr[11] <= cx.E
+
+
+@pytest.mark.parametrize('model,hidden,mb,scale', [('scone', [16, 16, 16], 32, 0.1), ('scone', [32, 32, 32], 7, 0.1), ('ebli', [32, 32], 64, 0.02),
+                                                   ('scone', [32], 16, 0.3), ('scone', [16, 16], 5, 0.3)])
+def test_fused_matches_row_list_pipeline_and_is_deterministic(model, hidden, mb, scale):
+    import scone_gcn_b200 as sg
+    ds = Dataset('dataset_small.npz')
+    cx = sg.SimplicialComplex.from_dense(ds.B1, ds.B2, model)
+    ptr, fe, fv = sg.flows_to_csr(ds.flows)
+    net = sg.SconeModel(cx, hidden, micro_batch=mb)
+    assert net.pipeline == 4
+    rs = np.random.RandomState(len(hidden) * 10 + mb)
+    net.set_weights([scale * rs.randn(*s_) for s_ in net.shapes])
+    mask = (rs.rand(ds.n_traj) < 0.7).astype(np.float32)
+    out = {}
+    for which in (4, 3, 4, 0):
+        net.set_pipeline(which)
+        lp = net.forward(ptr, fe, fv, ds.last_nodes)
+        buf = net.loss_grad(ptr, fe, fv, ds.last_nodes, ds.raw['targets_argmax'], mask)
+        if which in out:                                              # run-to-run: bit for bit
+            assert np.array_equal(out[which][0], lp) and np.array_equal(out[which][1], buf)
+        out[which] = (lp, buf)
+    n = net.n_params
+    for ref in (3, 0):
+        assert np.abs(out[4][0] - out[ref][0]).max() <= 1e-5 * max(1.0, np.abs(out[ref][0]).max())
+        assert out[4][1][n + 1] == out[ref][1][n + 1] == mask.sum()
+        assert abs(out[4][1][n] - out[ref][1][n]) <= 1e-5 * max(1.0, abs(out[ref][1][n]))
+        off = 0
+        gmax = np.abs(out[ref][1][:n]).max()
+        for shp in net.shapes:
+            k = shp[0] * shp[1]
+            a, r = out[4][1][off:off + k], out[ref][1][off:off + k]
+            assert np.abs(a - r).max() <= 1e-4 * max(np.abs(r).max(), 1e-3 * gmax), (ref, shp)
+            off += k
+
+
+def test_fused_results_do_not_depend_on_chunking():
+    import scone_gcn_b200 as sg
+    ds = Dataset('dataset_small.npz')
+    fx = load('model_small_scone_h16.npz')
+    cx = sg.SimplicialComplex.from_dense(ds.B1, ds.B2, 'scone')
+    ptr, fe, fv = sg.flows_to_csr(ds.flows)
+    W = weights_of(fx, 'w_big')
+    outs, grads = [], []
+    for mb in (ds.n_traj, 5, 1):
+        net = sg.SconeModel(cx, [16, 16, 16], micro_batch=mb)
+        assert net.pipeline == 4
+        net.set_weights(W)
+        outs.append(net.forward(ptr, fe, fv, ds.last_nodes))
+        grads.append(net.loss_grad(ptr, fe, fv, ds.last_nodes, ds.raw['targets_argmax'], np.ones(ds.n_traj, np.float32)))
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])    # per-trajectory log-probs: bit for bit
+    for g in grads[1:]:
+        assert np.abs(g - grads[0]).max() <= 1e-5 * np.abs(grads[0]).max()
+    assert np.abs(outs[0] - fx['big_logprobs'][:, :, 0]).max() < 1e-5                # and they are the reference's
+
+
+def test_fused_big_trajectories_use_the_global_row_store():
+    """ebli on the small complex: three L1^2 hops cover the whole complex, every layer has ~E live rows -> far more rows than the
+    shared-memory store holds; the BIG variant must give the oracle's numbers."""
+    import scone_gcn_b200 as sg
+    ds = Dataset('dataset_small.npz')
+    cx = sg.SimplicialComplex.from_dense(ds.B1, ds.B2, 'ebli')
+    net = sg.SconeModel(cx, [32, 32, 32], micro_batch=16)
+    assert net.pipeline == 4
+    info = net.fused_info()
+    rs = np.random.RandomState(2)
+    W = [0.03 * rs.randn(*s) for s in net.shapes]
+    net.set_weights(W)
+    ptr, fe, fv = sg.flows_to_csr(ds.flows)
+    lp = net.forward(ptr, fe, fv, ds.last_nodes)
+    rows = [int(net.fused_header(t)[1:4].sum()) for t in range(min(16, ds.n_traj % 16 or 16))]
+    assert max(rows) * 2 > info['cap_rows']                                          # the case this test is about
+    orc = so.DenseOracle('ebli', so.shift_matrices(ds.B1, ds.B2, 'ebli'), ds.B1, ds.last_nodes, ds.flows, ds.targets, dtype=torch.float64)
+    with torch.no_grad():
+        ref = orc.forward(W).numpy()[:, :, 0]
+    assert np.abs(lp - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+    mask = ds.train_mask.astype(np.float32)
+    buf = net.loss_grad(ptr, fe, fv, ds.last_nodes, ds.raw['targets_argmax'], mask)
+    k = net.n_params
+    _, g_ref = orc.loss_and_grads(W, ds.train_mask, 0.0)
+    for a, r in zip(net.unflatten(buf[:k] / buf[k + 1]), g_ref):
+        assert np.abs(a - r).max() <= 1e-4 * max(np.abs(r).max(), 1e-30)
+
+
+def test_fused_mixed_trajectories_with_empty_flows_and_invalid_last_node():
+    """Ragged inputs: a trajectory without flow entries (all logits 0 -> uniform log-probs over D slots) and one whose flows lie far
+    from its last node, next to ordinary ones."""
+    import scone_gcn_b200 as sg
+    ds = Dataset('dataset_small.npz')
+    cx = sg.SimplicialComplex.from_dense(ds.B1, ds.B2, 'scone')
+    B = 12
+    flows = ds.flows[:B].copy()
+    flows[3] = 0.0
+    last = ds.last_nodes[:B].copy()
+    last[5] = ds.last_nodes[40]                                        # flows of trajectory 5, last node of trajectory 40
+    net = sg.SconeModel(cx, [16, 16, 16], micro_batch=B)
+    rs = np.random.RandomState(8)
+    W = [0.3 * rs.randn(*s) for s in net.shapes]
+    net.set_weights(W)
+    ptr, fe, fv = sg.flows_to_csr(flows)
+    lp = net.forward(ptr, fe, fv, last)
+    assert np.allclose(lp[3], -np.log(cx.D), atol=1e-6)
+    orc = so.DenseOracle('scone', so.shift_matrices(ds.B1, ds.B2, 'scone'), ds.B1, last, flows, ds.targets[:B], dtype=torch.float64)
+    with torch.no_grad():
+        ref = orc.forward(W).numpy()[:, :, 0]
+    assert np.abs(lp - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())

@@ -370,7 +370,7 @@ def test_row_list_pipeline_matches_unit_kernel_pipeline(small, model, hidden, mb
     cx = sg.SimplicialComplex.from_dense(small.B1, small.B2, model)
     ptr, fe, fv = sg.flows_to_csr(small.flows)
     net = sg.SconeModel(cx, hidden, micro_batch=mb)
-    assert L.scone_model_get_pipeline(net.handle) == 3             # default: compact row lists over the readout cone
+    assert L.scone_model_get_pipeline(net.handle) in (3, 4)        # default: fused (uniform widths, <= 3 layers) or cone row lists
     rs = np.random.RandomState(len(hidden) * 10 + mb)
     net.set_weights([0.1 * rs.randn(*s_) for s_ in net.shapes])
     mask = (rs.rand(small.n_traj) < 0.7).astype(np.float32)
