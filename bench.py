@@ -1,27 +1,30 @@
 #!/usr/bin/env python
 """bench.py — SCoNe train trajectories/s on B200 (BASELINE.json metric), one JSON line on rank 0.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg5|cfg4|cfg1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg5|cfg4|cfg1|cfg3-ebli|cfg3-bunch]
+                    [--scaling strong|weak]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-A "step" is one optimizer step of the 3-layer SCoNe (hidden 32) over one batch of synthetic trajectories on the
-named complex: sparse flows -> fused layer forwards -> readout/NLL -> fused layer backwards -> (all-reduce of
-the flat [grads | nll | count] buffer when N > 1) -> Adam.  Every trajectory in the batch contributes to the
-loss (mask all ones).  Weak scaling: the per-GPU batch is fixed and the complex is replicated.
+A "step" is one optimizer step of the 3-layer model over one batch of synthetic trajectories on the named complex: plan (cone &
+support -> live rows + gather programs) -> fused forward / readout / NLL / backward per trajectory -> partial reduce -> (all-reduce
+of the flat [grads | nll | count] buffer when N > 1) -> Adam.  Every trajectory of the batch contributes to the loss (mask all ones).
 
-  value  whole-job trajectories/s with the batch already resident in HBM (device-timed, max over ranks)
-  e2e    same metric through the public host API (SconeModel.loss_grad + adam_step on pinned HOST buffers,
-         H2D of the batch and D2H of the loss inside the timed region)
-  roofline   the dominant kernel family, timed live with CUDA events on the launching stream; bytes follow the
-             device-counted rows the flagged unit kernels produce (support of the trajectories)
-  other_mode the same step with the dense zero-fill switched the other way (dense-stream mode: zero_fill_kernel at
-             ~0.9 of the measured HBM peak is then the dominant kernel)
-  cpu_baseline  the oracle's sparse CPU port (oracle/scone_oracle.py) on a bounded sample, rank 0, N = 1 only
---impl reference times that same CPU port as the whole arm (the reference's dense E x E formulation cannot be
-instantiated at E = 1M: 4 TB per operator; jax itself is not installable offline — see DESIGN.md).
+  cfg5 (default)  1M-edge complex, GLOBAL batch 32768 (BASELINE.json config 5).  --scaling strong (default): 32768 / N trajectories
+                  per GPU, the same global batch at every N; --scaling weak: 4096 per GPU.
+  value           whole-job trajectories/s with the batch already resident in HBM (device-timed with CUDA events, max over ranks)
+  e2e             same metric through the public host API (SconeModel.loss_grad + adam_step on pinned HOST buffers, H2D of the batch
+                  and D2H of the loss inside the timed region)
+  roofline        the dominant tensor-moving kernel, timed live with CUDA events on its launching stream in a SEPARATE profiled pass
+                  (the value loop runs with profiling off); bytes = device-counted live rows x SURVEY 8(d)'s per-row figures
+  roofline_dense  the contracted dense-tile measurement: one fused 32->32 layer on dense random features [E][64][32], no pruning
+  parity_check    the GPU's log-probs / NLL / gradients for the cpu_baseline sample against the oracle (1e-5 / 1e-4)
+  cpu_baseline    the oracle's CPU port on a bounded sample, rank 0, N = 1 only
+--impl reference times that CPU port as the whole arm (jax is not installable offline and the dense E x E formulation cannot be
+instantiated at E = 1M — DESIGN.md), with every host thread.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -33,15 +36,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CONFIGS = {
-    # name: (n_nodes for the generator, per-GPU batch, hidden, micro-batch)
-    'cfg5': dict(n_nodes=370000, batch=4096, hidden=32, micro_batch=4096,
-                 desc='1M-edge synthetic holed Delaunay complex, 4096 trajectories per GPU (32768 at 8 GPUs), 3-layer SCoNe hidden 32'),
-    'cfg4': dict(n_nodes=110000, batch=4096, hidden=32, micro_batch=4096,
+    'cfg5': dict(n_nodes=370000, global_batch=32768, weak_batch=4096, hidden=32, model='scone', cuts=8,
+                 desc='1M-edge synthetic holed Delaunay complex, global batch 32768 trajectories, 3-layer SCoNe hidden 32'),
+    'cfg4': dict(n_nodes=110000, global_batch=4096, weak_batch=4096, hidden=32, model='scone', cuts=1,
                  desc='~300k-edge synthetic complex, batch 4096, 3-layer SCoNe hidden 32'),
-    'cfg1': dict(n_nodes=400, batch=1000, hidden=16, micro_batch=1000,
+    'cfg1': dict(n_nodes=400, global_batch=1000, weak_batch=1000, hidden=16, model='scone', cuts=1,
                  desc='default synthetic complex (400 nodes), 1000 trajectories, 3-layer SCoNe hidden 16'),
+    'cfg3-ebli': dict(n_nodes=400, global_batch=1000, weak_batch=1000, hidden=16, model='ebli', cuts=1,
+                      desc='default synthetic complex (400 nodes), 1000 trajectories, 3-layer SNN (-model ebli) hidden 16'),
+    'cfg3-bunch': dict(n_nodes=400, global_batch=1000, weak_batch=1000, hidden=16, model='bunch', cuts=1,
+                       desc='default synthetic complex (400 nodes), 1000 trajectories, SCCONV (-model bunch) 7_16_7_16_7_16'),
 }
 KIND_NAMES = ['layer_fwd', 'layer_bwd', 'layer0_fwd', 'layer0_bwd', 'readout', 'flows_to_dense', 'zero_fill', 'cone']
+PIPELINES = {4: 'trajectory-fused kernels: plan + fused forward/backward + partial reduce', 3: 'row lists over the readout cone, compact tensors',
+             2: 'row lists, compact tensors', 1: 'row lists, dense tensors', 0: 'unit kernels, byte flags'}
 
 
 def load_peaks():
@@ -54,9 +62,9 @@ def load_peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).  The timed region of
-    this bench is tens of milliseconds, shorter than one `nvidia-smi` invocation, so the sampler polls NVML in-process
-    (nvidia_ml_py, ~1 kHz, own thread); `nvidia-smi -lms` is the fallback when NVML cannot be loaded."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).  The timed region can be
+    shorter than one `nvidia-smi` invocation, so the sampler polls NVML in-process (nvidia_ml_py, ~1 kHz, own thread);
+    `nvidia-smi -lms` is the fallback when NVML cannot be loaded."""
     Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
     NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
@@ -143,28 +151,21 @@ class ClockSampler:
                 'samples': len(sm), 'source': self.source}
 
 
-def ncu_traffic(kernel, E, mb, C, zero_fill, pipeline=3):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full`
-    captures -- only reported when this run has the same launch shape as the capture (cfg5).
-      zero_fill  profiles/prof_fill_r1m_raw.csv       (dense-stream mode, b = 64)
-      layer_fwd / layer_bwd  profiles/prof_cone_r1z9_raw.csv   (cone pipeline, b = 4096: the two layer_fwd_rows_kernel /
-                                                       rows_bwd_kernel launches of one step, averaged)"""
-    src, pat = None, None
-    if kernel == 'zero_fill' and (E, mb, C) == (999308, 64, 32):
-        src = 'prof_fill_r1m_raw.csv'
-    if kernel in ('layer_fwd', 'layer_bwd') and not zero_fill and pipeline == 3 and (E, mb, C) == (999308, 4096, 32):
-        src, pat = 'prof_cone_r1z9_raw.csv', {'layer_fwd': 'layer_fwd_rows_kernel', 'layer_bwd': 'rows_bwd_kernel'}[kernel]
-    if src is None:
+def ncu_traffic(kernel_pattern, tag):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full` capture
+    of this round (profiles/prof_<tag>_raw.csv) — only quoted when the capture was taken on the same launch shape."""
+    path = os.path.join(ROOT, 'profiles', 'prof_%s_raw.csv' % tag)
+    if not os.path.exists(path):
         return None
     try:
         import csv
-        rows = list(csv.reader(open(os.path.join(ROOT, 'profiles', src))))
+        rows = list(csv.reader(open(path)))
         hdr, unit = rows[0], rows[1]
-        kn = hdr.index('Kernel Name') if 'Kernel Name' in hdr else None
+        kn = hdr.index('Kernel Name')
         scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
         tot, n = 0.0, 0
         for val in rows[2:]:
-            if len(val) < len(hdr) or (pat and (kn is None or pat not in val[kn])):
+            if len(val) < len(hdr) or kernel_pattern not in val[kn]:
                 continue
             for name in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
                 i = hdr.index(name)
@@ -175,17 +176,14 @@ def ncu_traffic(kernel, E, mb, C, zero_fill, pipeline=3):
         return None
 
 
-def make_dataset(cfg, rank):
+def make_dataset(name, cfg, n_traj, seed):
     from scone_gcn_b200 import synthetic_data_gen as sdg
     if cfg['n_nodes'] <= 1000:
-        import numpy as np
         sys.path.insert(0, os.path.join(ROOT, 'tests'))
         from golden_util import Dataset
         ds = Dataset('dataset_default.npz')
-        sp = sdg.SparseDataset.from_dense(ds.flows, ds.B1, ds.B2, ds.targets, ds.train_mask, ds.test_mask, ds.last_nodes,
-                                          ds.target_nodes)
-        return sp
-    return sdg.generate_sparse_dataset(cfg['n_nodes'], cfg['batch'], seed=1030 + rank, n_waypoints=24)
+        return sdg.SparseDataset.from_dense(ds.flows, ds.B1, ds.B2, ds.targets, ds.train_mask, ds.test_mask, ds.last_nodes, ds.target_nodes), ds
+    return sdg.generate_sparse_dataset(cfg['n_nodes'], n_traj, seed=seed, n_waypoints=24, cuts_per_walk=cfg['cuts']), None
 
 
 def tri_lists(sp):
@@ -193,73 +191,76 @@ def tri_lists(sp):
     return incidence_lists_from_simplices(sp.edges, sp.faces)
 
 
-def cpu_port_run(sp, hidden, n_sample, repeats, seed=0):
-    """Oracle port (CPU, torch sparse, all host threads): fwd + bwd over `n_sample` trajectories; trajectories/s."""
+def oracle_sample(sp, model, W, n_sample, repeats, dtype=None):
+    """Oracle port (CPU, torch sparse, all host threads) over the first n_sample trajectories: (log-probs, nll, grads, times)."""
     import numpy as np
     import torch
     from oracle import scone_oracle as so
+    torch.set_num_threads(os.cpu_count() or 1)
     en, es, te, ts = tri_lists(sp)
-    orc = so.SparseOracle('scone', sp.edges, te, ts, int(sp.n_nodes))
-    rs = np.random.RandomState(1030)
-    shapes = [(1, hidden)] * 3 + [(hidden, hidden)] * 6 + [(hidden, 1)]
-    W = [0.01 * rs.randn(*s) for s in shapes]
+    orc = so.SparseOracle(model, sp.edges, te, ts, int(sp.n_nodes), dtype=dtype or np.float32)
     E = len(sp.edges)
     X = np.zeros((E, n_sample), np.float32)
     for t in range(n_sample):
         sl = slice(sp.traj_ptr[t], sp.traj_ptr[t + 1])
         X[sp.flow_edge[sl], t] = sp.flow_val[sl]
-    times = []
+    times, nll, grads = [], None, None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        orc.loss_and_grads(W, X, sp.last_nodes[:n_sample], sp.target_idx[:n_sample], np.ones(n_sample, np.float32))
+        nll, grads = orc.loss_and_grads(W, X, sp.last_nodes[:n_sample], sp.target_idx[:n_sample], np.ones(n_sample, np.float32))
         times.append(time.perf_counter() - t0)
-    return n_sample / min(times), torch.get_num_threads(), times
+    lp = orc.forward(W, X, sp.last_nodes[:n_sample])
+    return lp, nll, grads, times, torch.get_num_threads()
+
+
+def sample_size(E):
+    return 2 if E > 500000 else (8 if E > 2000 else 64)
 
 
 def run_reference(args, cfg, rank, world):
     if rank != 0:
         return
-    import torch
-    sp = make_dataset(cfg, 0)
-    n_sample = 2 if cfg['n_nodes'] > 200000 else (8 if cfg['n_nodes'] > 1000 else 64)
-    t0 = time.perf_counter()
-    tps, threads, times = cpu_port_run(sp, cfg['hidden'], n_sample, args.warmup + args.steps)
+    import numpy as np
+    sp, _ = make_dataset(args.config, cfg, 64, 1030)
+    E = len(sp.edges)
+    model = cfg['model'] if cfg['model'] != 'bunch' else 'scone'
+    C = cfg['hidden']
+    rs = np.random.RandomState(1030)
+    W = [0.01 * rs.randn(*s) for s in [(1, C)] * 3 + [(C, C)] * 6 + [(C, 1)]]
+    n_sample = sample_size(E)
+    lp, nll, grads, times, threads = oracle_sample(sp, model, W, n_sample, args.warmup + args.steps)
     times = times[args.warmup:] or times
     tps = n_sample / (sum(times) / len(times))
-    sample = '%d trajectories fwd+bwd per step on the same complex (E=%d), sparse CSR CPU port of the reference maths' % (
-        n_sample, len(sp.edges))
+    sample = '%d trajectories fwd+bwd per step on the same complex (E=%d), sparse CSR CPU port of the reference maths' % (n_sample, E)
     out = {'impl': 'reference', 'metric': 'SCoNe train trajectories/sec', 'value': tps, 'unit': 'trajectories/s',
            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(times) / len(times),
-           'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-           'config': {'workload': args.config + ': ' + cfg['desc'], 'E': int(len(sp.edges)), 'N': int(sp.n_nodes),
-                      'F': int(len(sp.faces)), 'sample_trajectories_per_step': n_sample},
+           'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+           'config': {'workload': args.config + ': ' + cfg['desc'], 'E': int(E), 'N': int(sp.n_nodes), 'F': int(len(sp.faces)),
+                      'global_batch': cfg['global_batch'], 'sample_trajectories_per_step': n_sample},
            'cpu_baseline': {'value': tps, 'unit': 'trajectories/s', 'cores': threads, 'kind': 'port', 'sample': sample},
            'e2e': {'value': tps, 'unit': 'trajectories/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
            'gpu_launches': 0,
-           'note': 'jax is not installable offline and the dense E x E reference formulation cannot be instantiated at this '
-                   'size; this is the oracle port (oracle/scone_oracle.py SparseOracle) on torch CPU sparse kernels'}
+           'note': 'jax is not installable offline and the dense E x E reference formulation cannot be instantiated at this size; this is '
+                   'the oracle port (oracle/scone_oracle.py SparseOracle) on torch CPU sparse kernels with torch.set_num_threads(os.cpu_count())'}
     print(json.dumps(out), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='cfg5', choices=sorted(CONFIGS))
+    ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'])
     ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch')
     ap.add_argument('--micro-batch', type=int, default=0)
-    ap.add_argument('--e2e-steps', type=int, default=20)
+    ap.add_argument('--pipeline', type=int, default=-1, help='force a model-level pipeline (default: the library\'s choice)')
+    ap.add_argument('--e2e-steps', type=int, default=10)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-extras', dest='extras', action='store_false', help='skip the sparse-mode and dense-kernel extras')
-    ap.add_argument('--zero-fill', type=int, default=0, help='timed region with dense zero-fill of the outputs on (1) or off (0)')
+    ap.add_argument('--no-extras', dest='extras', action='store_false', help='skip the dense-tile roofline measurement')
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
-    if args.batch:
-        cfg['batch'] = args.batch
-    if args.micro_batch:
-        cfg['micro_batch'] = args.micro_batch
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -270,6 +271,7 @@ def main():
     import torch
     import torch.distributed as dist
     import scone_gcn_b200 as sg
+    from scone_gcn_b200 import _lib, dp
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU path)'
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
@@ -279,29 +281,48 @@ def main():
     L = sg.lib()
 
     t_setup = time.time()
-    sp = make_dataset(cfg, rank)
-    B = sp.n_traj if args.config == 'cfg1' else cfg['batch']
-    cx = sg.SimplicialComplex.from_simplices(int(sp.n_nodes), sp.edges, sp.faces, 'scone')
-    C, mb = cfg['hidden'], min(cfg['micro_batch'], B)
-    net = sg.SconeModel(cx, [C, C, C], micro_batch=mb)
-    rs = np.random.RandomState(1030)                       # same init on every rank
-    net.set_weights([0.01 * rs.randn(*s) for s in net.shapes])
-    E, N, F, D = cx.E, cx.N, cx.F, cx.D
-    nnz = int(sp.traj_ptr[B])
-    # host batch in pinned memory (e2e) and its device copy (value)
+    # strong scaling: ONE global batch (same seed on every rank), rank r owns the contiguous shard dp.shard_range gives it;
+    # weak scaling: weak_batch trajectories per GPU, generated per rank
+    if args.scaling == 'strong':
+        gb = cfg['global_batch'] if not args.batch else args.batch * world
+        sp, dense_ds = make_dataset(args.config, cfg, gb, 1030)
+        gb = min(gb, sp.n_traj)
+        lo, hi = dp.shard_range(gb, rank, world)
+    else:
+        per = args.batch or cfg['weak_batch']
+        sp, dense_ds = make_dataset(args.config, cfg, per, 1030 + rank)
+        per = min(per, sp.n_traj)
+        lo, hi, gb = 0, per, per * world
+    B = hi - lo
+    model = cfg['model']
+    C = cfg['hidden']
+    p0, p1 = int(sp.traj_ptr[lo]), int(sp.traj_ptr[hi])
+    ptr = (sp.traj_ptr[lo:hi + 1] - sp.traj_ptr[lo]).astype(np.int32)
+
     def pinned(a):
-        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        return t
-    h = dict(ptr=pinned(sp.traj_ptr[:B + 1].astype(np.int32)), edge=pinned(sp.flow_edge[:nnz].astype(np.int32)),
-             val=pinned(sp.flow_val[:nnz].astype(np.float32)), last=pinned(sp.last_nodes[:B].astype(np.int32)),
-             tgt=pinned(sp.target_idx[:B].astype(np.int32)), mask=pinned(np.ones(B, np.float32)))
-    d = {k: v.to(dev) for k, v in h.items()}
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h = dict(ptr=pinned(ptr), edge=pinned(sp.flow_edge[p0:p1].astype(np.int32)), val=pinned(sp.flow_val[p0:p1].astype(np.float32)),
+             last=pinned(sp.last_nodes[lo:hi].astype(np.int32)), tgt=pinned(sp.target_idx[lo:hi].astype(np.int32)),
+             mask=pinned(np.ones(B, np.float32)))
     h2d_bytes = sum(v.numel() * v.element_size() for v in h.values())
+    hp = {k: v.numpy() for k, v in h.items()}
     stream = torch.cuda.current_stream().cuda_stream
-    gbuf = net.grads_tensor()
-    from scone_gcn_b200 import _lib
     lr, wd = 1e-3, 5e-5
     step_no = [0]
+    rs = np.random.RandomState(1030)                       # same init on every rank
+
+    if model == 'bunch':
+        return bench_bunch(args, cfg, sp, dense_ds, hp, h2d_bytes, B, gb, world, rank, dev, stream, t_setup)
+
+    cx = sg.SimplicialComplex.from_simplices(int(sp.n_nodes), sp.edges, sp.faces, model)
+    mb = min(args.micro_batch or B, B)
+    net = sg.SconeModel(cx, [C, C, C], micro_batch=mb)
+    if args.pipeline >= 0:
+        net.set_pipeline(args.pipeline)
+    net.set_weights([0.01 * rs.randn(*s) for s in net.shapes])
+    E, N, F, D = cx.E, cx.N, cx.F, cx.D
+    d = {k: v.to(dev) for k, v in h.items()}
+    gbuf = net.grads_tensor()
 
     def step_dev():
         _lib.check(L.scone_model_loss_grad_dev(net.handle, B, _lib.dptr(d['ptr']), _lib.dptr(d['edge']), _lib.dptr(d['val']),
@@ -310,9 +331,6 @@ def main():
             dist.all_reduce(gbuf)
         net.adam_step(step_no[0], lr, wd, stream)
         step_no[0] += 1
-
-    hp = {k: v.numpy() for k, v in h.items()}
-    loss_host = np.zeros(net.n_params + 2, np.float32)
 
     def step_e2e():
         net.loss_grad(hp['ptr'], hp['edge'], hp['val'], hp['last'], hp['tgt'], hp['mask'], zero_first=True, stream=stream, read=False)
@@ -335,14 +353,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    net.set_zero_fill(args.zero_fill)
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 3)):
         step_dev()
     barrier()
+    net.check_overflow(stream)
     setup_s = time.time() - t_setup
 
-    L.scone_profile_reset()
-    L.scone_profile_enable(1)
+    # ---- value: profiling OFF, batch resident ----
     clocks = ClockSampler(local)
     clocks.start()
     launches0 = L.scone_launch_count()
@@ -355,78 +372,83 @@ def main():
     barrier()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     launches = L.scone_launch_count() - launches0
-    L.scone_profile_enable(0)
     clk = clocks.stop()
+    net.check_overflow(stream)                             # a truncated step would have been timed silently otherwise
     ms_per_step = ms_total / args.steps
-    value = world * B * args.steps / (ms_total / 1e3)
+    value = gb * args.steps / (ms_total / 1e3)
 
-    # per-kernel-family device time inside the timed region
-    import ctypes
-
-    def read_families():
-        fam_ = {}
-        for k, nme in enumerate(KIND_NAMES):
-            n_l, t_ms = ctypes.c_int64(), ctypes.c_double()
-            L.scone_profile_read(k, n_l, t_ms)
-            fam_[nme] = (n_l.value, t_ms.value)
-        rows_ = {}
+    # ---- separate profiled pass: per-kernel-family device time (CUDA events around each launch on the launching stream) ----
+    prof_steps = min(args.steps, 5)
+    L.scone_profile_reset()
+    L.scone_profile_enable(1)
+    done = (ctypes.c_int64 * 2)()
+    L.scone_model_read_rows_done(net.handle, done)
+    for _ in range(prof_steps):
+        step_dev()
+    barrier()
+    L.scone_profile_enable(0)
+    fam = {}
+    for k, nme in enumerate(KIND_NAMES):
+        n_l, t_ms = ctypes.c_int64(), ctypes.c_double()
+        L.scone_profile_read(k, n_l, t_ms)
+        fam[nme] = (n_l.value, t_ms.value)
+    L.scone_model_read_rows_done(net.handle, done)
+    rows = {'layer_fwd': int(done[0]), 'layer_bwd': int(done[1])}
+    pipeline_id = net.pipeline
+    if pipeline_id != 4:
         for k, nme in ((0, 'layer_fwd'), (1, 'layer_bwd')):
             r = ctypes.c_int64()
             L.scone_profile_read_rows(k, r)
-            rows_[nme] = r.value
-        return fam_, rows_
-    fam, rows = read_families()
-    # ALGORITHMIC bytes.  The flagged unit kernels produce only the (edge, trajectory) rows inside the
-    # trajectories' support (counted on the device): per produced row a fused layer forward reads one input row and
-    # writes one output row (4*(Cin+Cout) bytes), a backward reads G and Hin rows and writes Gprev (4*(2*Cin+Cout));
-    # neighbour re-reads are cache-served, exactly as in the dense formula of SURVEY 8(d).  zero_fill (dense-stream mode
-    # only) writes 4*E*b*C bytes per launch.
+            rows[nme] = r.value
     peak, peak_src = load_peaks()
-
-    def kernel_table(fam_, rows_):
-        alg_ = {'zero_fill': 4.0 * E * mb * C}
-        if fam_['layer_fwd'][0]:
-            alg_['layer_fwd'] = rows_['layer_fwd'] * 4.0 * 2 * C / fam_['layer_fwd'][0]
-        if fam_['layer_bwd'][0]:
-            alg_['layer_bwd'] = rows_['layer_bwd'] * 4.0 * 3 * C / fam_['layer_bwd'][0]
-        tot_ms_ = sum(t for _, t in fam_.values()) or 1.0
-        ks = {}
-        for nme, (n_l, t_ms) in fam_.items():
-            if n_l:
-                avg = t_ms / n_l
-                ks[nme] = {'launches': n_l, 'avg_ms': avg, 'share_of_kernel_time': t_ms / tot_ms_}
-                if nme in alg_:
-                    ks[nme].update({'algorithmic_bytes_per_launch': alg_[nme], 'achieved_gbs': alg_[nme] / avg / 1e6,
-                                    'frac': alg_[nme] / avg / 1e6 / peak})
-        return ks
-    kernels = kernel_table(fam, rows)
-    # the roofline is quoted for the tensor-moving family with the largest share (the families with a byte model); `cone` is the
-    # bit-level set-up of the row lists (integer work, latency-bound: cone / live-row marking, compaction, clearing)
-    largest = max(kernels, key=lambda k_: kernels[k_]['share_of_kernel_time'])
+    # ALGORITHMIC bytes: per produced live row a fused layer forward reads one input row and writes one output row
+    # (4*(Cin+Cout) bytes), a backward reads G and Hin rows and writes Gprev (4*(2*Cin+Cout)) — SURVEY 8(d)'s per-row figures;
+    # the fused compute kernel does both passes in one launch, so its bytes are the sum
+    alg = {}
+    if pipeline_id == 4:
+        if fam['layer_bwd'][0]:
+            alg['layer_bwd'] = (rows['layer_fwd'] * 4.0 * 2 * C + rows['layer_bwd'] * 4.0 * 3 * C) / fam['layer_bwd'][0]
+    else:
+        if fam['layer_fwd'][0]:
+            alg['layer_fwd'] = rows['layer_fwd'] * 4.0 * 2 * C / fam['layer_fwd'][0]
+        if fam['layer_bwd'][0]:
+            alg['layer_bwd'] = rows['layer_bwd'] * 4.0 * 3 * C / fam['layer_bwd'][0]
+    tot_ms = sum(t for _, t in fam.values()) or 1.0
+    names = {'layer_bwd': 'fused_traj_kernel (+ fused_reduce_kernel)', 'cone': 'fused_plan_kernel'} if pipeline_id == 4 else {}
+    kernels = {}
+    for nme, (n_l, t_ms) in fam.items():
+        if n_l:
+            avg = t_ms / n_l
+            kernels[nme] = {'kernel': names.get(nme, nme), 'launches': n_l, 'avg_ms': avg, 'share_of_kernel_time': t_ms / tot_ms}
+            if nme in alg:
+                kernels[nme].update({'algorithmic_bytes_per_launch': alg[nme], 'achieved_gbs': alg[nme] / avg / 1e6, 'frac': alg[nme] / avg / 1e6 / peak})
     with_bytes = [k_ for k_ in kernels if 'achieved_gbs' in kernels[k_]]
     dom = max(with_bytes or kernels, key=lambda k_: kernels[k_]['share_of_kernel_time'])
-    pipeline_id = L.scone_model_get_pipeline(net.handle)
+    largest = max(kernels, key=lambda k_: kernels[k_]['share_of_kernel_time'])
     dense_bytes_per_traj = 4.0 * E * (15 * C + 2)
-    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': kernels[dom].get('achieved_gbs'), 'peak': peak, 'unit': 'GB/s',
-                'frac': kernels[dom].get('frac'), 'traffic': ncu_traffic(dom, E, mb, C, args.zero_fill, pipeline_id), 'peak_source': peak_src,
-                'largest_family': largest,
+    step_alg_bytes = (rows['layer_fwd'] * 4.0 * 2 * C + rows['layer_bwd'] * 4.0 * 3 * C) / prof_steps
+    roofline = {'bound': 'hbm', 'kernel': kernels[dom]['kernel'], 'achieved': kernels[dom].get('achieved_gbs'), 'peak': peak, 'unit': 'GB/s',
+                'frac': kernels[dom].get('frac'),
+                'traffic': ncu_traffic('fused_traj_kernel', 'fused_r2_' + args.config) if pipeline_id == 4 else None,
+                'peak_source': peak_src, 'largest_family': kernels[largest]['kernel'],
                 'algorithmic_bytes_per_launch': kernels[dom].get('algorithmic_bytes_per_launch'),
-                'rows_per_step': {k_: v_ / args.steps for k_, v_ in rows.items()},
+                'whole_step': {'algorithmic_bytes': step_alg_bytes, 'achieved_gbs': step_alg_bytes / ms_per_step / 1e6,
+                               'frac': step_alg_bytes / ms_per_step / 1e6 / peak},
+                'rows_per_step': {k_: v_ / prof_steps for k_, v_ in rows.items()},
                 'dense_rows_per_step': float(E) * B * 2,
                 'kernels': kernels,
                 'dense_equivalent': {'bytes_per_trajectory': dense_bytes_per_traj,
                                      'effective_gbs': dense_bytes_per_traj * value / world / 1e9,
                                      'note': 'SURVEY 8(d) dense formula 4*E*(15C+2) bytes per trajectory times the measured per-GPU '
                                              'trajectories/s: what a dense-streaming implementation would have to move to match'},
-                'bytes_model': 'layer_fwd / layer_bwd: rows produced (device-counted) x 4*(Cin+Cout) / 4*(2*Cin+Cout) bytes per launch; the backward '
-                               'family time includes the weight-gradient GEMM and its reduction; cone = bit-level set-up of the row lists '
-                               '(receptive cone, live rows, compaction, clearing). The row kernels are latency / issue bound (16 warps per SM, '
-                               'dependent entry -> bitmap -> row loads; profiles/prof_cone_r1z9_*), not HBM bound; zero_fill (dense-stream '
-                               'mode): 4*E*b*C bytes per launch',
-                'pipeline': {3: 'row lists over the readout cone, compact tensors', 2: 'row lists, compact tensors', 1: 'row lists, dense tensors', 0: 'unit kernels, byte flags'}[
-                    pipeline_id]}
+                'bytes_model': 'live rows produced (device-counted) x 4*(Cin+Cout) per forward row and 4*(2*Cin+Cout) per backward row '
+                               '(SURVEY 8(d) per-row figures; index arrays and the gather programs excluded, as there).  The fused compute kernel '
+                               'keeps those rows in shared memory, so its real DRAM traffic (roofline.traffic, ncu) is far BELOW the algorithmic '
+                               'bytes: it is bound by instruction issue / mma.sync rate and smem latency, the plan kernel by dependent L2 loads — '
+                               'neither by HBM.  The contracted dense-tile figure is roofline_dense.',
+                'pipeline': PIPELINES.get(pipeline_id, str(pipeline_id))}
 
-    # end to end through the host API
+    # ---- end to end through the host API ----
     barrier()
     e2e_steps = max(1, args.e2e_steps)
     step_e2e()
@@ -438,119 +460,158 @@ def main():
     ev1.record()
     barrier()
     e2e_ms = max_over_ranks(ev0.elapsed_time(ev1))
-    e2e = {'value': world * B * e2e_steps / (e2e_ms / 1e3), 'unit': 'trajectories/s', 'h2d_bytes_per_step': h2d_bytes,
+    e2e = {'value': gb * e2e_steps / (e2e_ms / 1e3), 'unit': 'trajectories/s', 'h2d_bytes_per_step': h2d_bytes,
            'd2h_bytes_per_step': int(4 * (net.n_params + 2)), 'steps': e2e_steps, 'last_loss': loss}
 
-    # extra 1: the same step in the OTHER mode (results bit-identical, tests/): dense-stream mode bulk-zeroes every dense
-    # [E][b][C] tensor once per micro-batch (zero_fill_kernel on a side stream is then the HBM-bound dominant kernel)
-    other_mode = None
-    if args.extras:
-        mb2 = min(64, B)                                    # dense tensors: 6 x E x mb2 x C x 4 bytes must fit
-        net2 = sg.SconeModel(cx, [C, C, C], micro_batch=mb2, zero_fill=not args.zero_fill)
-        net2.set_weights(net.get_weights())
-
-        def step_other():
-            _lib.check(L.scone_model_loss_grad_dev(net2.handle, B, _lib.dptr(d['ptr']), _lib.dptr(d['edge']), _lib.dptr(d['val']),
-                                                   _lib.dptr(d['last']), _lib.dptr(d['tgt']), _lib.dptr(d['mask']), 1, stream))
-            net2.adam_step(step_no[0], lr, wd, stream)
-        step_other()
-        barrier()
-        L.scone_profile_reset()
-        L.scone_profile_enable(1)
-        other_steps = min(args.steps, 5)
-        ev0.record()
-        for _ in range(other_steps):
-            step_other()
-        ev1.record()
-        barrier()
-        L.scone_profile_enable(0)
-        sm_ms = max_over_ranks(ev0.elapsed_time(ev1))
-        fam2, rows2 = read_families()
-        mb_main, mb = mb, mb2
-        k2 = kernel_table(fam2, rows2)
-        mb = mb_main
-        other_mode = {'zero_fill': 1 - args.zero_fill, 'micro_batch': mb2, 'value': world * B * other_steps / (sm_ms / 1e3),
-                      'unit': 'trajectories/s', 'ms_per_step': sm_ms / other_steps, 'steps': other_steps, 'zero_fill_kernel': k2.get('zero_fill'),
-                      'note': 'zero_fill=1 (dense-stream mode, unit kernels): every activation / gradient tensor is a complete dense array '
-                              '(each byte written once per micro-batch by zero_fill_kernel, timed on its side stream); zero_fill=0: rows '
-                              'outside the support are never written'}
-        del net2
-
-    # extra 2: the contracted DENSE-tile measurement (north-star / SURVEY 8d): one fused 32->32 layer on dense random
-    # features, no occupancy information, algorithmic bytes 4*E*b*(Cin+Cout) fwd and 4*E*b*(2*Cout+Cin) bwd
+    # ---- the contracted DENSE-tile measurement (north-star / SURVEY 8d): one fused 32->32 layer on dense random features,
+    # no pruning, algorithmic bytes 4*E*b*(Cin+Cout) fwd and 4*E*b*(2*Cout+Cin) bwd ----
     roofline_dense = None
-    if args.extras and rank == 0:
-        bd = min(mb, 64)
-        Hd = torch.randn(E, bd, C, device=dev)
-        Od = torch.empty_like(Hd)
-        Wd = [torch.randn(C, C, device=dev) * 0.2 for _ in range(3)]
-        wsd = torch.empty(L.scone_layer_backward_workspace_bytes(C, C) // 4 + 16, device=dev)
-        dWd = torch.zeros(3, C, C, device=dev)
+    if args.extras and rank == 0 and E > 100000:
+        roofline_dense = dense_tile_roofline(L, cx, E, C, dev, stream, peak)
 
-        def t_of(fn, it=3):
-            fn()
-            torch.cuda.synchronize()
-            best = 1e30
-            for _ in range(it):
-                a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                fn()
-                z.record()
-                torch.cuda.synchronize()
-                best = min(best, a.elapsed_time(z))
-            return best
-        f_ms = t_of(lambda: _lib.check(L.scone_layer_forward(cx.handle, 0, bd, C, C, _lib.dptr(Hd), _lib.dptr(Wd[0]), _lib.dptr(Wd[1]),
-                                                             _lib.dptr(Wd[2]), _lib.dptr(Od), None, None, None, stream)))
-        b_ms = t_of(lambda: _lib.check(L.scone_layer_backward(cx.handle, 0, bd, C, C, _lib.dptr(Hd), _lib.dptr(Od), _lib.dptr(Wd[0]),
-                                                              _lib.dptr(Wd[1]), _lib.dptr(Wd[2]), _lib.dptr(Od), _lib.dptr(dWd), 0,
-                                                              _lib.dptr(wsd), None, None, None, None, stream)))
-        fa, ba = 4.0 * E * bd * 2 * C / f_ms / 1e6, 4.0 * E * bd * 3 * C / b_ms / 1e6
-        roofline_dense = {'bound': 'hbm', 'unit': 'GB/s', 'peak': peak, 'b': bd,
-                          'layer_fwd': {'ms': f_ms, 'achieved': fa, 'frac': fa / peak},
-                          'layer_bwd': {'ms': b_ms, 'achieved': ba, 'frac': ba / peak},
-                          'note': 'one fused 32->32 layer on dense random features, no flags (every row computed): forward = slab kernel '
-                                  '(merged-row gather into mma.sync fragments, 3xTF32 product), backward = fp32 SIMT tile kernel; '
-                                  'algorithmic bytes 4*E*b*(Cin+Cout) / 4*E*b*(2*Cout+Cin); not in the timed region'}
-        del Hd, Od
-
-    cpu_baseline = None
+    # ---- parity on THIS workload + CPU baseline (rank 0, N = 1): the oracle port on a bounded sample ----
+    cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_sample = 2 if E > 500000 else (8 if E > 2000 else 64)
-        tps, threads, times = cpu_port_run(sp, C, n_sample, 2)
+        n_sample = sample_size(E)
+        W_now = net.get_weights()
+        lp_o, nll_o, g_o, times, threads = oracle_sample(sp, model, W_now, n_sample, 2)
+        tps = n_sample / min(times)
         cpu_baseline = {'value': tps, 'unit': 'trajectories/s', 'cores': threads, 'kind': 'port',
                         'sample': '%d trajectories fwd+bwd on the same complex (E=%d), best of 2; sparse CSR CPU port '
                                   '(oracle/scone_oracle.py), torch CPU sparse kernels' % (n_sample, E)}
+        nz = int(sp.traj_ptr[n_sample])
+        a = (sp.traj_ptr[:n_sample + 1].astype(np.int32), sp.flow_edge[:nz].astype(np.int32), sp.flow_val[:nz].astype(np.float32),
+             sp.last_nodes[:n_sample].astype(np.int32))
+        lp_g = net.forward(*a)
+        buf = net.loss_grad(*a, sp.target_idx[:n_sample].astype(np.int32), np.ones(n_sample, np.float32))
+        g_g = net.unflatten(buf[:net.n_params])
+        lp_err = float(np.abs(lp_g - lp_o).max() / max(1.0, np.abs(lp_o).max()))
+        gmax = max(float(np.abs(y).max()) for y in g_o)
+        g_err = max(float(np.abs(x - y).max() / max(np.abs(y).max(), 1e-3 * gmax, 1e-30)) for x, y in zip(g_g, g_o))
+        nll_err = float(abs(buf[net.n_params] - nll_o) / max(1.0, abs(nll_o)))
+        parity = {'against': 'oracle/scone_oracle.py SparseOracle (fp32)', 'trajectories': n_sample, 'weights': 'after the timed Adam steps',
+                  'logprob_max_err': lp_err, 'grad_max_rel_err': g_err, 'nll_rel_err': nll_err,
+                  'tolerance': {'logprob': 1e-5, 'grad': 1e-4}, 'ok': bool(lp_err <= 1e-5 and g_err <= 1e-4 and nll_err <= 1e-5)}
+
     if rank == 0:
-        # what one step touches (bytes): with the compact pipelines the tensors follow the rows actually produced
-        n_mb = (B + mb - 1) // mb
-        if pipeline_id >= 2 and not args.zero_fill:
-            fr, br = rows['layer_fwd'] / args.steps, rows['layer_bwd'] / args.steps
-            touched = (2 * 3 * 4.0 * E * mb / 1024 * n_mb          # summary words of the 2L two-level bitmaps, scanned
-                       + fr * 4.0 * C * 2 + br * 4.0 * C * 5      # produced rows: H and G rows, A_k rows of the weight-gradient GEMM
-                       + 8.0 * nnz)                                # flows
-            l2_policy = ('no explicit flush; one step touches ~%.0f MB of bitmaps summaries, compact tensor rows and flows (plus the operator '
-                         'rows it walks), %s the 126 MB L2; the dense address space of the same tensors is %.0f GB'
-                         % (touched / 1e6, 'more than' if touched > 126e6 else 'LESS than (this workload is L2-resident by size)',
-                            4.0 * E * B * C * 6 / 1e9))
+        nnz = p1 - p0
+        info = net.fused_info() if pipeline_id == 4 else None
+        touched = 8.0 * nnz + 16.0 * B * 4 + (step_alg_bytes if pipeline_id != 4 else 0.0)
+        if pipeline_id == 4:
+            l2_policy = ('no explicit flush; one step reads %.0f MB of flows / last nodes / targets and writes + re-reads the gather programs '
+                         'of all %d trajectories of the rank (~5-10 KB each) plus the merged operator rows it walks: %s the 126 MB L2'
+                         % (touched / 1e6, B, 'larger than' if B * 8e3 + touched > 126e6 else 'smaller than'))
         else:
-            l2_policy = ('inputs larger than L2: the activation / gradient tensors of one micro-batch span %.2f GB and every step walks %d '
-                         'micro-batches' % (4.0 * E * mb * C * 6 / 1e9, n_mb))
+            l2_policy = 'no explicit flush; compact row tensors of ~%.0f MB per step' % (touched / 1e6)
         out = {'metric': 'SCoNe train trajectories/sec', 'value': value, 'unit': 'trajectories/s', 'n_gpus': world,
-               'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
-               'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-               'config': {'workload': args.config + ': ' + cfg['desc'], 'N': N, 'E': E, 'F': F, 'D': D,
-                          'per_gpu_batch': B, 'global_batch': B * world, 'hidden': C, 'layers': 3, 'micro_batch': mb,
-                          'zero_fill': args.zero_fill,
-                          'parallelism': 'dp%d (trajectory shards, complex replicated, one all-reduce of %d floats per step)'
-                                         % (world, net.n_params + 2),
-                          'l2_policy': l2_policy,
-                          'generator_seed': 1030, 'mean_flow_nnz': nnz / B},
-               'roofline': roofline, 'roofline_dense': roofline_dense, 'other_mode': other_mode, 'e2e': e2e,
-               'cpu_baseline': cpu_baseline, 'gpu_launches': int(launches),
-               'clocks': clk, 'setup_s': setup_s}
+               'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
+               'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+               'config': {'workload': args.config + ': ' + cfg['desc'] + (' (%d per GPU)' % B if world > 1 else ''),
+                          'N': N, 'E': E, 'F': F, 'D': D, 'model': model, 'per_gpu_batch': B, 'global_batch': gb, 'hidden': C,
+                          'layers': 3, 'micro_batch': mb,
+                          'parallelism': 'dp%d (trajectory shards, complex replicated, one all-reduce of %d floats per step)' % (world, net.n_params + 2),
+                          'l2_policy': l2_policy, 'generator_seed': 1030, 'mean_flow_nnz': nnz / B,
+                          'trajectories': ('prefixes of %d BEGIN->A->B->END walks cut at %d random points each' % (-(-gb // cfg['cuts']), cfg['cuts']))
+                          if cfg['n_nodes'] > 1000 else 'the reference generator\'s 1000 trajectories (tests/golden/dataset_default.npz)'},
+               'roofline': roofline, 'roofline_dense': roofline_dense, 'e2e': e2e,
+               'cpu_baseline': cpu_baseline, 'parity_check': parity, 'gpu_launches': int(launches),
+               'clocks': clk, 'setup_s': setup_s, 'fused_info': info}
         print(json.dumps(out), flush=True)
+        if parity is not None and not parity['ok']:
+            sys.stderr.write('bench parity check FAILED: %s\n' % parity)
+            sys.exit(3)
     if world > 1:
         dist.destroy_process_group()
+
+
+def dense_tile_roofline(L, cx, E, C, dev, stream, peak):
+    import torch
+    from scone_gcn_b200 import _lib
+    bd = 64
+    Hd = torch.randn(E, bd, C, device=dev)
+    Od = torch.empty_like(Hd)
+    Wd = [torch.randn(C, C, device=dev) * 0.2 for _ in range(3)]
+    wsd = torch.empty(L.scone_layer_backward_workspace_bytes(C, C) // 4 + 16, device=dev)
+    dWd = torch.zeros(3, C, C, device=dev)
+
+    def t_of(fn, it=3):
+        fn()
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(it):
+            a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            z.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(z))
+        return best
+    f_ms = t_of(lambda: _lib.check(L.scone_layer_forward(cx.handle, 0, bd, C, C, _lib.dptr(Hd), _lib.dptr(Wd[0]), _lib.dptr(Wd[1]),
+                                                         _lib.dptr(Wd[2]), _lib.dptr(Od), None, None, None, stream)))
+    b_ms = t_of(lambda: _lib.check(L.scone_layer_backward(cx.handle, 0, bd, C, C, _lib.dptr(Hd), _lib.dptr(Od), _lib.dptr(Wd[0]),
+                                                          _lib.dptr(Wd[1]), _lib.dptr(Wd[2]), _lib.dptr(Od), _lib.dptr(dWd), 0,
+                                                          _lib.dptr(wsd), None, None, None, None, stream)))
+    fa, ba = 4.0 * E * bd * 2 * C / f_ms / 1e6, 4.0 * E * bd * 3 * C / b_ms / 1e6
+    del Hd, Od
+    return {'bound': 'hbm', 'unit': 'GB/s', 'peak': peak, 'b': bd, 'tensor_bytes': 4.0 * E * bd * C,
+            'layer_fwd': {'ms': f_ms, 'achieved': fa, 'frac': fa / peak, 'algorithmic_bytes': 4.0 * E * bd * 2 * C},
+            'layer_bwd': {'ms': b_ms, 'achieved': ba, 'frac': ba / peak, 'algorithmic_bytes': 4.0 * E * bd * 3 * C},
+            'l2_policy': 'tensors of %.1f GB each: larger than L2' % (4.0 * E * bd * C / 1e9),
+            'note': 'one fused 32->32 layer on dense random features [E][64][32], every row computed (no flags / pruning), best of 3, '
+                    'CUDA events: forward = dense slab kernel, backward = dense tile kernel (DESIGN.md 4)'}
+
+
+def bench_bunch(args, cfg, sp, ds, hp, h2d_bytes, B, gb, world, rank, dev, stream, t_setup):
+    """cfg3 / -model bunch: the SCCONV model has host-pointer entry points only; value == e2e (pinned host buffers, copies inside)."""
+    import numpy as np
+    import torch
+    import scone_gcn_b200 as sg
+    from scone_gcn_b200.bunch import BunchModel, CsrOperator
+    from scone_gcn_b200.bunch_model_matrices import compute_shift_matrices
+    L = sg.lib()
+    cx = sg.SimplicialComplex.from_dense(ds.B1, ds.B2, 'scone')
+    shifts = [CsrOperator(M) for M in compute_shift_matrices(ds.B1, ds.B2)]
+    net = BunchModel(shifts, np.array(cx.nbrhoods), [cfg['hidden']] * 3, micro_batch=min(B, 256))
+    rs = np.random.RandomState(1030)
+    net.set_weights([0.01 * rs.randn(*s) for s in net.shapes])
+    step_no = [0]
+
+    def step():
+        net.loss_grad(hp['ptr'], hp['edge'], hp['val'], hp['last'], hp['tgt'], hp['mask'], zero_first=True, stream=stream, read=False)
+        net.adam_step(step_no[0], 1e-3, 5e-5, stream)
+        step_no[0] += 1
+        buf = net.read_grads(stream)
+        return float(buf[-2] / buf[-1])
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(int(os.environ.get('LOCAL_RANK', '0')))
+    clocks.start()
+    launches0 = L.scone_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    loss = None
+    for _ in range(args.steps):
+        loss = step()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop()
+    value = B * args.steps / (ms / 1e3)
+    peak, peak_src = load_peaks()
+    out = {'metric': 'SCoNe train trajectories/sec', 'value': value, 'unit': 'trajectories/s', 'n_gpus': world, 'steps': args.steps,
+           'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
+           'dtype': 'f32', 'data': 'synthetic',
+           'config': {'workload': args.config + ': ' + cfg['desc'], 'N': cx.N, 'E': cx.E, 'F': cx.F, 'D': cx.D, 'model': 'bunch',
+                      'global_batch': B, 'hidden': cfg['hidden'], 'layers': 4, 'l2_policy': 'working set L2-resident by size (E = %d)' % cx.E},
+           'roofline': {'bound': 'hbm', 'kernel': 'csr_spmm_kernel (generic CSR operators)', 'achieved': None, 'peak': peak, 'unit': 'GB/s', 'frac': None,
+                        'traffic': None, 'peak_source': peak_src,
+                        'note': 'cfg3 complexes are L2-resident (E = 1001): launch-latency bound, no HBM roofline is meaningful'},
+           'e2e': {'value': value, 'unit': 'trajectories/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': int(4 * (net.n_params + 2)),
+                   'steps': args.steps, 'last_loss': loss, 'note': 'the bunch model only has host-pointer entry points: value == e2e'},
+           'cpu_baseline': None, 'gpu_launches': int(L.scone_launch_count() - launches0), 'clocks': clk, 'setup_s': time.time() - t_setup}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
 
 
 if __name__ == '__main__':

@@ -208,6 +208,20 @@ int scone_accuracy_dev(int32_t B, int32_t D, const float* logprobs_dev, const in
 int scone_model_accuracy_host(scone_model* m, int32_t B, const int32_t* traj_ptr, const int32_t* flow_edge,
                               const float* flow_val, const int32_t* last_nodes, const int32_t* n_nbrs,
                               const int32_t* target_idx, const float* mask, int32_t* out_host /* [2] */, void* stream);
+/* Evaluation with the log-probs staying on the device (the host-side metric loops of scone_trajectory_model.py:42-56 loss,
+ * :59-71 accuracy, :73-108 two_target_accuracy): forward over B trajectories from HOST buffers, then on the device, each optional
+ * (NULL = skip):  choice_out [B] = argmax_j (j < n_nbrs[t] ? logprob : -100), first maximum, as NumPy / JAX (needs n_nbrs);
+ * acc_out [2] = correct predictions, masked trajectories (needs n_nbrs, target_idx, mask);  nll_out [2] = sum of -mask *
+ * logprob[target] (fixed summation order), sum of mask (needs target_idx, mask).  Synchronises the stream. */
+int scone_model_eval_host(scone_model* m, int32_t B, const int32_t* traj_ptr, const int32_t* flow_edge, const float* flow_val,
+                          const int32_t* last_nodes, const int32_t* n_nbrs, const int32_t* target_idx, const float* mask,
+                          int32_t* choice_out, int32_t* acc_out, float* nll_out, void* stream);
+/* Two-target comparison (scone_trajectory_model.py:95-108) on the log-probs the last scone_model_eval_host left on the device (same
+ * B; its n_nbrs and mask are reused): true_idx / rand_idx [B] = slot of the true target / of the host-drawn random other target
+ * (the redraw loop :89-91 consumes the host RNG stream and stays on the host, fed by choice_out).  out[0] = rows with true > random,
+ * out[1] = rows with true == random, over mask != 0: the reference's score is (out[0] + 0.5 * out[1]) / sum(mask). */
+int scone_model_two_target_host(scone_model* m, int32_t B, const int32_t* true_idx, const int32_t* rand_idx, int32_t* out /* [2] */,
+                                void* stream);
 /* Read back [grads | nll_sum | count] (host, n_params + 2 floats); synchronises the stream. */
 int scone_model_read_grads(scone_model* m, float* out_host, void* stream);
 
@@ -223,10 +237,12 @@ int scone_model_adam_step(scone_model* m, int32_t step, float lr, float weight_d
 int scone_model_check_overflow(scone_model* m, void* stream);
 /* Weights only (Adam state kept), asynchronous on the caller's stream; weights_host must stay valid until the copy has run. */
 int scone_model_set_weights_keep_state(scone_model* m, const float* weights_host, void* stream);
-/* Fused pipeline introspection (tests / bench): out[0] = available, [1] bound on hash entries (|T_0| of any node), [2] bound on listed
- * cone edges (|T_1|), [3] hash slots, [4] trajectories per arena chunk, [5] rows of the shared-memory row store, [6] / [7] KB of
- * dynamic shared memory of the plan / compute kernel. */
-int scone_model_fused_info(const scone_model* m, int32_t* out /* [8] */);
+/* Fused pipeline introspection (tests / bench): out[0] = available, [1] bound on the cone edges (|T_1| of any node), [2] bound on the
+ * expanded cone edges (|T_2|), [3] hash slots of tier 1, [4] trajectories per arena chunk, [5] rows of the shared-memory row store, [6] / [7] KB of
+ * dynamic shared memory of the tier-1 plan / the compute kernel, [8] / [9] hash slots / list entries of tier 0 (tables that hold the
+ * cone of 99 % of the nodes), [10] its KB, [11] two tiers in use, [12] worst-case arena words per trajectory, [13] arena Mwords,
+ * [14] tier-1 list entries, [15] rows of the per-CTA global row store. */
+int scone_model_fused_info(const scone_model* m, int32_t* out /* [16] */);
 /* Plan of trajectory t of the LAST chunk run (synchronises the device): header (16 ints, layout in csrc/fused.cuh) and `words` 32-bit
  * words of the program arena from word offset `off` (either output may be NULL). */
 int scone_model_fused_read(scone_model* m, int32_t t, int32_t* hdr_out /* [16] */, uint32_t off, int32_t words, uint32_t* arena_out);

@@ -20,6 +20,7 @@ Everything here restates, op for op, these reference locations (paths relative t
   scone_func / ebli_func / bunch_func        trajectory_experiments.py:137-203
   generate_weights          scone_trajectory_model.py:215-242 (+ seed at :15)
   loss / accuracy           scone_trajectory_model.py:42-71
+  two_target_accuracy       scone_trajectory_model.py:73-108
   train / Adam              scone_trajectory_model.py:264-357 (+ upstream JAX adam formula)
 Two arithmetic back-ends:
   DenseOracle   torch CPU, dense E x E operators, `(S @ H) @ W` association, autograd — the reference
@@ -249,6 +250,36 @@ class DenseOracle:
             preds[i, self.n_nbrs[i]:] = -100
         m = np.asarray(mask) == 1
         return float(np.mean(np.argmax(preds[m], axis=1) == np.argmax(self.y.numpy()[m], axis=1)))
+
+
+def two_target_accuracy(preds, y, mask, n_nbrs, random_targets=None, rng=np.random):
+    """scone_trajectory_model.py:73-108 on the model's log-probs `preds` [N, D, 1]: returns (score, random_targets).
+
+    `rng` is the legacy global NumPy stream the reference draws from (:79, :91).  pred_choice is a jax array there, so
+    pred_choice[i] with i past the end clamps to the last element: the redraw loop runs over all N rows (:89-91)."""
+    preds = np.array(preds, dtype=np.float32).reshape(len(preds), -1)
+    mask = np.asarray(mask)
+    n_nbrs = np.asarray(n_nbrs)
+    N = len(preds)
+    if random_targets is None:
+        random_targets = rng.randint(0, high=n_nbrs, size=N)
+    for i in range(N):
+        preds[i, n_nbrs[i]:] = -100
+    pred_choice = np.argmax(preds[mask == 1], axis=1)
+    last = len(pred_choice) - 1
+    for i in range(N):
+        while random_targets[i] == pred_choice[min(i, last)]:
+            random_targets[i] = rng.randint(0, high=n_nbrs[i])
+    rows = np.arange(N)
+    random_probs = preds[rows, random_targets]
+    true_probs = preds[rows, np.argmax(np.asarray(y).reshape(N, -1), axis=1)]
+    correct = 0.0
+    for t, r in zip(true_probs[mask == 1], random_probs[mask == 1]):
+        if t > r:
+            correct += 1
+        elif t == r:
+            correct += 0.5
+    return correct / mask.sum(), random_targets
 
 
 def adam_update(i, grads, state, step_size, b1=0.9, b2=0.999, eps=1e-8, dtype=np.float32):

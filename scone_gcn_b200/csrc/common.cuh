@@ -158,5 +158,9 @@ int scone_rows_readout_backward(const scone_complex* cx, int act, int b, int C, 
                                 const uint32_t* prefG, cudaStream_t st);
 int scone_accuracy_launch(int B, int D, const float* logprobs, const int32_t* n_nbrs, const int32_t* target_idx, const float* mask,
                           int32_t* out, cudaStream_t st);
+int scone_predict_launch(int B, int D, const float* logprobs, const int32_t* n_nbrs, int32_t* choice, cudaStream_t st);
+int scone_two_target_launch(int B, int D, const float* logprobs, const int32_t* n_nbrs, const int32_t* true_idx, const int32_t* rand_idx,
+                            const float* mask, int32_t* out, cudaStream_t st);
+int scone_nll_launch(int B, int D, const float* logprobs, const int32_t* target_idx, const float* mask, float* out, cudaStream_t st);
 int scone_adam_launch(float* W, float* m, float* v, const float* gradbuf, int64_t n, int32_t step, float lr,
                       float wd, void* stream, const int* overflow_dev = nullptr);

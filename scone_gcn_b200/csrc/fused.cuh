@@ -5,17 +5,25 @@
 constexpr int kFusedMaxL = 3;             // conv layers the fused compute kernel keeps weight-gradient tiles in registers for
 constexpr int kFusedHdrW = 16;            // ints per trajectory header
 constexpr int kFusedFlagOverflow = 1;
+constexpr int kFusedFlagRetry = 2;        // tier 0 of the plan kernel overflowed its tables: tier 1 redoes the trajectory
 
 // Per-trajectory header written by fused_plan_kernel (word offsets into the program arena):
 //   [0] flags   [1..3] live rows of layers 1..3   [4] layer-1 scalars {x, S0 x, S1 x} per row
 //   [5],[6] forward programs of layers 2, 3: rowptr[n_l + 1] then int2 entries {row below | own << 31, (c1 << 16) | c0}
 //   [7],[8] transposed programs of layers 2, 3 (rows = live rows of layer l - 1, entries = rows of layer l)
-//   [9] readout: rowptr[D + 1] then int2 {row of H_L | slot << 16, sign bits}   [10] pairs   [11] |T_1|   [12] |T_1| + new T_0 listed
+//   [9] readout: rowptr[D + 1] then int2 {row of H_L | slot << 16, sign bits}   [10] pairs   [11] hash entries (flows + cone)
+//   [12] listed (expanded) cone edges   [13] flow entries
 struct FusedState {
     int L = 0, C = 0;
     int64_t n_params = 0;
-    int bound_t0 = 0, bound_t1 = 0;       // static bounds of the complex: hash entries / listed cone edges of any last node
-    int HS = 0, LC = 0, hshift = 0;
+    int bound_cone = 0, bound_list = 0;   // static bounds of the complex: cone edges |T_1| / expanded cone edges |T_2| of any last node
+    int HS = 0, LC = 0, LV = 0, hshift = 0;       // plan tables, tier 1: sized by the bounds
+    int HS0 = 0, LC0 = 0, LV0 = 0, hshift0 = 0;   // tier 0: sized for the cones of 99 % of the nodes
+    bool two_tiers = false;
+    int flow_room = 0;
+    size_t plan_smem0 = 0;
+    unsigned long long worst_words = 0;
+    int* d_retry = nullptr;
     size_t plan_smem = 0, traj_smem_small = 0, traj_smem_big = 0;
     int cap_rows = 0, big_rows = 0, grid_small = 0, grid_big = 0, chunk = 0;
     size_t scratch_stride = 0;

@@ -32,6 +32,7 @@ constexpr int kPlanThreads = 256;
 constexpr int kTrajThreads = 256;
 constexpr int kFuMaxD = 128;
 constexpr uint32_t kNoRow = 0xFFFFu;
+constexpr int kBoundBuckets = 1024;
 
 template <int ACT>
 __device__ __forceinline__ float fu_act(float z) {
@@ -151,16 +152,23 @@ struct PlanArgs {
     const int2* inc_ent;
     const int32_t* mptr;
     const int2* ment;
-    int N, D, E, L, HS, LC, hshift;
+    int N, D, E, L;
+    int HS, hshift;            // hash slots (power of two): the flow edges and the cone T_1 of the trajectory
+    int LC;                    // listed cone edges (levels >= 2: the ones that are expanded)
+    int LV;                    // live rows per layer
     int* hdr;
     uint32_t* arena;
     unsigned long long* bump;
     unsigned long long arena_words;
     int* overflow;
+    int tier;                  // 0: trajectory = work item, tables sized for ~99 % of the nodes; 1: the retry list, tables sized by the bounds
+    int n_work;                // tier 0: trajectories of the chunk
+    int* n_retry;              // device counter of the retry list
+    int* retry;                // [chunk]
 };
 
-// Static bounds: blockIdx.x = candidate last node; builds its cone down to level 0 and records max |T_0| (hash entries) and
-// max |T_1| (listed entries) in stats[0..1]; stats[2] = 1 if even the largest table overflowed.
+// Static bounds: blockIdx.x = candidate last node; builds its cone down to level 1 and records max |T_1| (cone edges = hash entries)
+// and max |T_2| (listed = expanded edges) in stats[0..1]; stats[2] = 1 if even the largest table overflowed; histograms of both.
 __global__ void __launch_bounds__(kPlanThreads) fused_bound_kernel(const int32_t* __restrict__ nbrhoods, const int32_t* __restrict__ inc_ptr,
                                                                   const int2* __restrict__ inc_ent, const int32_t* __restrict__ mptr,
                                                                   const int2* __restrict__ ment, int N, int D, int L, int HS, int LC,
@@ -185,7 +193,7 @@ __global__ void __launch_bounds__(kPlanThreads) fused_bound_kernel(const int32_t
         }
         if (is_new) {
             if (atomicAdd(&s_nhash, 1) >= (HS * 3) / 4) s_ovf = 1;
-            if (lv >= 1) {
+            if (lv >= 2) {
                 const int pos = atomicAdd(&s_nlist, 1);
                 if (pos < LC) list[pos] = e;
                 else s_ovf = 1;
@@ -200,7 +208,7 @@ __global__ void __launch_bounds__(kPlanThreads) fused_bound_kernel(const int32_t
     if (tid == 0) s_nat[L] = min(s_nlist, LC);
     __syncthreads();
     int f0 = 0;
-    for (int lv = L - 1; lv >= 0; --lv) {
+    for (int lv = L - 1; lv >= 1; --lv) {
         const int f1 = s_nat[lv + 1];
         if (!s_ovf)
             for (int i = f0 + (tid >> 2); i < f1; i += kPlanThreads / 4) {
@@ -215,74 +223,97 @@ __global__ void __launch_bounds__(kPlanThreads) fused_bound_kernel(const int32_t
     }
     if (tid == 0) {
         atomicMax(&stats[0], s_nhash);
-        atomicMax(&stats[1], s_nat[1]);
+        atomicMax(&stats[1], s_nlist);
         if (s_ovf) stats[2] = 1;
+        // size distribution over the nodes (buckets of 32): picks the tables of the plan kernel's first tier
+        atomicAdd(&stats[4 + min(kBoundBuckets - 1, s_nhash / 32)], 1);
+        atomicAdd(&stats[4 + kBoundBuckets + min(kBoundBuckets - 1, s_nlist / 32)], 1);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// the plan: one CTA per trajectory
+// the plan of one trajectory (one CTA)
+//
+//   hash set      flow edges (level 0, value x) and the receptive cone T_1 (level = highest cone level of the edge)
+//   cone          level L = edges incident to the neighbours of the last node; one merged-row hop further down per level; only the
+//                 edges of levels >= 2 are listed (they are the ones expanded)
+//   live rows     PUSHED from below: a row of layer 1 is live iff it is in T_1 and a flow edge sits in its merged operator row,
+//                 i.e. iff it is in the merged row of a flow edge (the operators are symmetric); a row of layer l iff it is in T_l
+//                 and in the merged row of a live row of layer l - 1.  Cost follows the flows and the live rows, not the cone.
+//   rank          live rows of a layer are numbered by ascending edge id: the deterministic row order of every list
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPlanThreads) fused_plan_kernel(const PlanArgs a) {
-    extern __shared__ __align__(16) unsigned char sm[];
-    const int HS = a.HS, LC = a.LC, L = a.L, D = a.D;
+__device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, unsigned char* sm) {
+    const int HS = a.HS, LC = a.LC, LV = a.LV, L = a.L, D = a.D;
     int* keys = reinterpret_cast<int*>(sm);                          // [HS] internal edge id, -1 = empty
     float* xv = reinterpret_cast<float*>(keys + HS);                 // [HS] flow value of the edge
-    uint16_t* idxA = reinterpret_cast<uint16_t*>(xv + HS);           // [HS] row index of the edge in the live list of a layer (ping)
+    int* lvl = reinterpret_cast<int*>(xv + HS);                      // [HS] bits 0-7: cone level (0 = flow edge outside the cone); bit 8 + l: marked live in layer l
+    uint16_t* idxA = reinterpret_cast<uint16_t*>(lvl + HS);          // [HS] row index of the edge in the live list of a layer (ping)
     uint16_t* idxB = idxA + HS;                                      // [HS] (pong)
-    uint8_t* lvl = reinterpret_cast<uint8_t*>(idxB + HS);            // [HS] highest cone level of the edge (0 = only in T_0)
-    int* rowcnt = reinterpret_cast<int*>(lvl + HS);                  // [LC + 4] entries per ranked row -> exclusive scan
-    float* av0 = reinterpret_cast<float*>(rowcnt);                   //   (layer 1 only: overlays rowcnt) x[e]
-    float* av1 = reinterpret_cast<float*>(rowcnt + LC + 4);          // [LC] (S0 x)[e]
-    float* av2 = av1 + LC;                                           // [LC] (S1 x)[e]
-    int* live_edge = reinterpret_cast<int*>(av2 + LC);               // [LC] edge id of the k-th live row (unordered)
-    uint16_t* list = reinterpret_cast<uint16_t*>(live_edge + LC);    // [LC] cone list: hash slots, level L first, then L-1, ...
-    uint16_t* live = list + LC;                                      // [LC] cone-list index of the k-th live row (unordered)
-    uint16_t* cnt = live + LC;                                       // [LC] program entries of cone-list entry i
-    uint16_t* byrank = cnt + LC;                                     // [LC] cone-list index of the row with rank r
+    int* rowcnt = reinterpret_cast<int*>(idxB + HS);                 // [LV + 4] entries per ranked row -> exclusive scan
+    int* live_edge = rowcnt + LV + 4;                                // [LV] edge id of the k-th live row (unordered)
+    uint16_t* live = reinterpret_cast<uint16_t*>(live_edge + LV);    // [LV] hash slot of the k-th live row (unordered)
+    uint16_t* rankA = live + LV;                                     // [LV] hash slot of the row with rank r (ping)
+    uint16_t* rankB = rankA + LV;                                    // [LV] (pong)
+    uint16_t* list = rankB + LV;                                     // [LC] cone list: hash slots of the edges of levels >= 2
     __shared__ FuPairs pairs;
-    __shared__ int s_nlist, s_nlive, s_ovf, s_nat[kFusedMaxL + 2], s_warp[kPlanThreads / 32];
+    __shared__ int s_nlist, s_nhash, s_nlive, s_ovf, s_nat[kFusedMaxL + 2], s_warp[kPlanThreads / 32];
     __shared__ unsigned s_piece;
 
     const int tid = threadIdx.x, lane = tid & 31, ql = tid & 3;
     const unsigned qmask = 0xFu << (lane & ~3);
-    const int t = blockIdx.x;
     int* hdr = a.hdr + (size_t)t * kFusedHdrW;
-    for (int i = tid; i < HS; i += kPlanThreads) {
-        keys[i] = -1;
-        xv[i] = 0.f;
-        idxA[i] = (uint16_t)kNoRow;
-        idxB[i] = (uint16_t)kNoRow;
-    }
-    if (tid == 0) s_nlist = s_ovf = 0;
-    const int last = a.last_nodes[t];
-    const bool last_ok = last >= 0 && last < a.N;
-    const int total_pairs = pairs.setup(a.nbrhoods, a.inc_ptr, last, last_ok, D);
-    EdgeSet set{keys, HS - 1, a.hshift};
-    auto add = [&](int e, int lv) {
-        bool is_new;
-        const int s = set.insert(e, is_new);
-        if (s < 0) {
-            s_ovf = 1;
-            return;
-        }
-        if (is_new) {
-            lvl[s] = (uint8_t)lv;
-            if (lv >= 1) {
-                const int pos = atomicAdd(&s_nlist, 1);
-                if (pos < LC) list[pos] = (uint16_t)s;
-                else s_ovf = 1;
+    // a table of this tier overflowed: tier 0 hands the trajectory to tier 1 (tables sized by the measured bounds)
+    auto give_up = [&]() {
+        if (tid == 0) {
+            if (a.tier == 0 && a.retry != nullptr) {
+                hdr[0] = kFusedFlagRetry;
+                a.retry[atomicAdd(a.n_retry, 1)] = t;
+            } else {
+                hdr[0] = kFusedFlagOverflow;
+                *a.overflow = 1;
             }
         }
     };
-    // arena allocation for one piece (thread 0 allocates, everybody gets the word offset; ~0u = out of space)
+    for (int i = tid; i < HS; i += kPlanThreads) {
+        keys[i] = -1;
+        xv[i] = 0.f;
+        lvl[i] = 0;
+        idxA[i] = (uint16_t)kNoRow;
+        idxB[i] = (uint16_t)kNoRow;
+    }
+    if (tid == 0) s_nlist = s_nhash = s_ovf = s_nlive = 0;
+    const int last = a.last_nodes[t];
+    const bool last_ok = last >= 0 && last < a.N;
+    const int total_pairs = pairs.setup(a.nbrhoods, a.inc_ptr, last, last_ok, D);     // (barriers inside: the tables are initialised)
+    EdgeSet set{keys, HS - 1, a.hshift};
+    const int hash_cap = (HS * 3) / 4;
+    auto put = [&](int e) -> int {                         // slot of edge e (created if absent); -1 when a table of this tier is full
+        if (s_ovf) return -1;
+        bool is_new;
+        const int s = set.insert(e, is_new);
+        if (s < 0 || (is_new && atomicAdd(&s_nhash, 1) >= hash_cap)) {
+            s_ovf = 1;
+            return -1;
+        }
+        return s;
+    };
+    auto add_cone = [&](int e, int lv) {
+        const int s = put(e);
+        if (s < 0) return;
+        if ((atomicMax(&lvl[s], lv) & 0xFF) == 0 && lv >= 2) {       // first time in the cone (levels are built top-down)
+            const int pos = atomicAdd(&s_nlist, 1);
+            if (pos < LC) list[pos] = (uint16_t)s;
+            else s_ovf = 1;
+        }
+    };
+    // arena allocation for one piece (thread 0 allocates, everybody gets the word offset)
     auto alloc = [&](int words) -> unsigned {
         __syncthreads();
         if (tid == 0) {
             const unsigned long long w = (unsigned long long)align2(words);
             const unsigned long long o = atomicAdd(a.bump, w);
             if (o + w > a.arena_words) {
-                s_ovf = 1;
+                s_ovf = 2;
                 s_piece = 0u;
             } else {
                 s_piece = (unsigned)o;
@@ -291,23 +322,32 @@ __global__ void __launch_bounds__(kPlanThreads) fused_plan_kernel(const PlanArgs
         __syncthreads();
         return s_piece;
     };
+    const int fp0 = a.traj_ptr[t], fp1 = a.traj_ptr[t + 1];
 
-    // ---- receptive cone: level L = edges incident to the neighbours of the last node, one merged-row hop down per level ----
+    // ---- flows ----
+    for (int p = fp0 + tid; p < fp1; p += kPlanThreads) {
+        const int eo = a.flow_edge[p];
+        if (eo < 0 || eo >= a.E) continue;
+        const int s = put(a.rank[eo]);
+        if (s >= 0) xv[s] = a.flow_val[p];
+    }
+    __syncthreads();
+    // ---- receptive cone ----
     for (int i = tid; i < total_pairs; i += kPlanThreads) {
         const int j = pairs.slot_of(i, D);
-        add(a.inc_ent[pairs.s_ptr[j] + (i - pairs.s_off[j])].x, L);
+        add_cone(a.inc_ent[pairs.s_ptr[j] + (i - pairs.s_off[j])].x, L);
     }
     __syncthreads();
     if (tid == 0) s_nat[L] = min(s_nlist, LC);
     __syncthreads();
     {
         int f0 = 0;
-        for (int lv = L - 1; lv >= 0; --lv) {
+        for (int lv = L - 1; lv >= 1; --lv) {
             const int f1 = s_nat[lv + 1];
             for (int i = f0 + (tid >> 2); i < f1; i += kPlanThreads / 4) {
                 const int e = keys[list[i]];
                 const int p1 = a.mptr[e + 1];
-                for (int q = a.mptr[e] + ql; q < p1; q += 4) add(a.ment[q].x, lv);
+                for (int q = a.mptr[e] + ql; q < p1; q += 4) add_cone(a.ment[q].x, lv);
             }
             __syncthreads();
             if (tid == 0) s_nat[lv] = min(s_nlist, LC);
@@ -315,91 +355,92 @@ __global__ void __launch_bounds__(kPlanThreads) fused_plan_kernel(const PlanArgs
             f0 = f1;
         }
     }
-    // ---- flows: only edges of T_0 can reach a cone row ----
-    for (int p = a.traj_ptr[t] + tid; p < a.traj_ptr[t + 1]; p += kPlanThreads) {
-        const int eo = a.flow_edge[p];
-        if (eo < 0 || eo >= a.E) continue;
-        const int s = set.find(a.rank[eo]);
-        if (s >= 0) xv[s] = a.flow_val[p];
-    }
-    if (tid == 0) s_nlive = 0;
-    __syncthreads();
-    if (s_ovf) {                                           // cannot happen with measured bounds; reported, trajectory skipped
-        if (tid == 0) {
-            hdr[0] = kFusedFlagOverflow;
-            *a.overflow = 1;
-        }
+    if (s_ovf) {
+        give_up();
         return;
     }
-
-    // ranks the s_nlive live rows by edge id (ascending = the deterministic row order of every list): idx[slot] = rank,
-    // byrank[rank] = cone-list index; returns the count
-    auto rank_live = [&](uint16_t* idx) -> int {
+    // marks (once) the cone edge in slot s2 as a live row of layer l
+    auto mark = [&](int s2, int e2, int l) {
+        const int bit = 1 << (8 + l);
+        const int old = atomicOr(&lvl[s2], bit);
+        if (!(old & bit)) {
+            const int k = atomicAdd(&s_nlive, 1);
+            if (k < LV) {
+                live[k] = (uint16_t)s2;
+                live_edge[k] = e2;
+            } else {
+                s_ovf = 1;
+            }
+        }
+    };
+    // ranks the s_nlive live rows by edge id: idx[slot] = rank, byrank[rank] = slot; returns the count
+    auto rank_live = [&](uint16_t* idx, uint16_t* byrank) -> int {
         __syncthreads();
-        const int n = s_nlive;
+        const int n = min(s_nlive, LV);
         for (int k = tid; k < n; k += kPlanThreads) {
             const int e = live_edge[k];
             int r = 0;
             for (int m = 0; m < n; ++m) r += live_edge[m] < e ? 1 : 0;
-            const int i = live[k];
-            idx[list[i]] = (uint16_t)r;
-            byrank[r] = (uint16_t)i;
+            idx[live[k]] = (uint16_t)r;
+            byrank[r] = live[k];
         }
         __syncthreads();
         return n;
     };
 
-    // ---- layer 1: live rows = cone rows of T_1 with a flow entry in their merged operator row; their three exact scalars ----
-    for (int i = tid >> 2; i < s_nat[1]; i += kPlanThreads / 4) {
-        const int slot = list[i];
-        const int e = keys[slot];
-        float a1 = 0.f, a2 = 0.f;
-        int any = 0;
+    // ---- layer 1: live rows = cone edges in the merged row of a flow edge with a non-zero value ----
+    for (int p = fp0 + (tid >> 2); p < fp1; p += kPlanThreads / 4) {
+        const int eo = a.flow_edge[p];
+        if (eo < 0 || eo >= a.E) continue;                 // (same decision on the four lanes of the quad)
+        const int e = a.rank[eo];
+        const int s = set.find(e);
+        if (s < 0 || xv[s] == 0.f) continue;
         const int p1 = a.mptr[e + 1];
         for (int q = a.mptr[e] + ql; q < p1; q += 4) {
-            const int2 en = a.ment[q];
-            const int s2 = set.find(en.x);
-            const float x = s2 >= 0 ? xv[s2] : 0.f;
-            if (x != 0.f) {
-                any = 1;
-                a1 = fmaf((float)(short)(en.y & 0xffff), x, a1);
-                a2 = fmaf((float)(en.y >> 16), x, a2);
-            }
-        }
-#pragma unroll
-        for (int o = 1; o < 4; o <<= 1) {
-            a1 += __shfl_xor_sync(qmask, a1, o);
-            a2 += __shfl_xor_sync(qmask, a2, o);
-            any |= __shfl_xor_sync(qmask, any, o);
-        }
-        if (ql == 0 && any) {
-            const int k = atomicAdd(&s_nlive, 1);
-            live[k] = (uint16_t)i;
-            live_edge[k] = e;
-            av0[i] = xv[slot];
-            av1[i] = a1;
-            av2[i] = a2;
+            const int e2 = a.ment[q].x;
+            const int s2 = set.find(e2);
+            if (s2 >= 0 && (lvl[s2] & 0xFF) >= 1) mark(s2, e2, 1);
         }
     }
-    uint16_t *ip = idxA, *ic = idxB;
-    int n_prev = rank_live(ip);
+    uint16_t *ip = idxA, *ic = idxB, *rp = rankA, *rc = rankB;
+    int n_prev = rank_live(ip, rp);
+    if (s_ovf) {
+        give_up();
+        return;
+    }
     int n_l[kFusedMaxL + 1] = {0, 0, 0, 0};
     unsigned off_l1 = 0, off_f[kFusedMaxL + 1] = {0, 0, 0, 0}, off_b[kFusedMaxL + 1] = {0, 0, 0, 0};
     n_l[1] = n_prev;
     off_l1 = alloc(3 * n_prev);
-    if (!s_ovf) {
+    if (!s_ovf) {                                          // the three exact scalars of each live row: x, (S0 x), (S1 x)
         float* dst = reinterpret_cast<float*>(a.arena + off_l1);
-        for (int r = tid; r < n_prev; r += kPlanThreads) {
-            const int i = byrank[r];
-            dst[3 * r + 0] = av0[i];
-            dst[3 * r + 1] = av1[i];
-            dst[3 * r + 2] = av2[i];
+        for (int r = tid >> 2; r < n_prev; r += kPlanThreads / 4) {
+            const int slot = rp[r];
+            const int e = keys[slot];
+            float a1 = 0.f, a2 = 0.f;
+            const int p1 = a.mptr[e + 1];
+            for (int q = a.mptr[e] + ql; q < p1; q += 4) {
+                const int2 en = a.ment[q];
+                const int s2 = set.find(en.x);
+                const float x = s2 >= 0 ? xv[s2] : 0.f;
+                a1 = fmaf((float)(short)(en.y & 0xffff), x, a1);
+                a2 = fmaf((float)(en.y >> 16), x, a2);
+            }
+#pragma unroll
+            for (int o = 1; o < 4; o <<= 1) {
+                a1 += __shfl_xor_sync(qmask, a1, o);
+                a2 += __shfl_xor_sync(qmask, a2, o);
+            }
+            if (ql == 0) {
+                dst[3 * r + 0] = xv[slot];
+                dst[3 * r + 1] = a1;
+                dst[3 * r + 2] = a2;
+            }
         }
     }
     __syncthreads();
 
-    // walks the merged row of cone-list entry i and emits, in column order, the entries whose neighbour has a row in `idx`:
-    // COUNT: returns the number (on quad lane 0 .. all lanes); FILL: writes them from position `base` on
+    // walks the merged row of edge e and counts / emits, in column order, the entries whose neighbour has a row in `idx`
     auto count_row = [&](int e, const uint16_t* idx) -> int {
         int c = 0;
         const int p1 = a.mptr[e + 1];
@@ -428,65 +469,52 @@ __global__ void __launch_bounds__(kPlanThreads) fused_plan_kernel(const PlanArgs
             base += __popc(bits);
         }
     };
+    // program of `n_rows` rows (slots byrank[r]) against the row indices `idx` of the other layer: rowptr + entries into the arena
+    auto emit_program = [&](const uint16_t* byrank, int n_rows, const uint16_t* idx) -> unsigned {
+        for (int r = tid >> 2; r < n_rows; r += kPlanThreads / 4) {
+            const int c = count_row(keys[byrank[r]], idx);
+            if (ql == 0) rowcnt[r] = c;
+        }
+        __syncthreads();
+        const int total = block_scan_excl(rowcnt, n_rows, s_warp);
+        const unsigned off = alloc(align2(n_rows + 1) + 2 * total);
+        if (!s_ovf) {
+            int* pdst = reinterpret_cast<int*>(a.arena + off);
+            int2* edst = reinterpret_cast<int2*>(a.arena + off + align2(n_rows + 1));
+            for (int r = tid; r <= n_rows; r += kPlanThreads) pdst[r] = rowcnt[r];
+            for (int r = tid >> 2; r < n_rows; r += kPlanThreads / 4) fill_row(keys[byrank[r]], idx, edst, rowcnt[r]);
+        }
+        __syncthreads();
+        return off;
+    };
 
     for (int l = 2; l <= L; ++l) {
-        // forward program of layer l: rows = T_l entries with at least one live neighbour in layer l - 1
+        // live rows of layer l: cone edges of level >= l in the merged row of a live row of layer l - 1
         if (tid == 0) s_nlive = 0;
         __syncthreads();
-        for (int i = tid >> 2; i < s_nat[l]; i += kPlanThreads / 4) {
-            const int e = keys[list[i]];
-            const int c = count_row(e, ip);
-            if (ql == 0) {
-                cnt[i] = (uint16_t)c;
-                if (c) {
-                    const int k = atomicAdd(&s_nlive, 1);
-                    live[k] = (uint16_t)i;
-                    live_edge[k] = e;
-                }
+        for (int r = tid >> 2; r < n_prev; r += kPlanThreads / 4) {
+            const int e = keys[rp[r]];
+            const int p1 = a.mptr[e + 1];
+            for (int q = a.mptr[e] + ql; q < p1; q += 4) {
+                const int e2 = a.ment[q].x;
+                const int s2 = set.find(e2);
+                if (s2 >= 0 && (lvl[s2] & 0xFF) >= l) mark(s2, e2, l);
             }
         }
-        const int nl = rank_live(ic);
+        const int nl = rank_live(ic, rc);
+        if (s_ovf) break;
         n_l[l] = nl;
-        for (int r = tid; r < nl; r += kPlanThreads) rowcnt[r] = cnt[byrank[r]];
-        __syncthreads();
-        int total = block_scan_excl(rowcnt, nl, s_warp);
-        off_f[l] = alloc(align2(nl + 1) + 2 * total);
-        if (!s_ovf) {
-            int* pdst = reinterpret_cast<int*>(a.arena + off_f[l]);
-            int2* edst = reinterpret_cast<int2*>(a.arena + off_f[l] + align2(nl + 1));
-            for (int r = tid; r <= nl; r += kPlanThreads) pdst[r] = rowcnt[r];
-            for (int r = tid >> 2; r < nl; r += kPlanThreads / 4) fill_row(keys[list[byrank[r]]], ip, edst, rowcnt[r]);
-        }
-        __syncthreads();
-        // transposed program: rows = live rows of layer l - 1, entries = their neighbours among the live rows of layer l
-        for (int r = tid; r <= n_prev; r += kPlanThreads) rowcnt[r] = 0;
-        __syncthreads();
-        for (int i = tid >> 2; i < s_nat[l - 1]; i += kPlanThreads / 4) {
-            const int slot = list[i];
-            const uint32_t rp = ip[slot];
-            if (rp == kNoRow) continue;                    // (same decision on the four lanes of the quad)
-            const int c = count_row(keys[slot], ic);
-            if (ql == 0) {
-                rowcnt[rp] = c;
-                byrank[rp] = (uint16_t)i;
-            }
-        }
-        __syncthreads();
-        total = block_scan_excl(rowcnt, n_prev, s_warp);
-        off_b[l] = alloc(align2(n_prev + 1) + 2 * total);
-        if (!s_ovf) {
-            int* pdst = reinterpret_cast<int*>(a.arena + off_b[l]);
-            int2* edst = reinterpret_cast<int2*>(a.arena + off_b[l] + align2(n_prev + 1));
-            for (int r = tid; r <= n_prev; r += kPlanThreads) pdst[r] = rowcnt[r];
-            for (int r = tid >> 2; r < n_prev; r += kPlanThreads / 4) fill_row(keys[list[byrank[r]]], ic, edst, rowcnt[r]);
-        }
-        __syncthreads();
-        uint16_t* tmp = ip;
-        ip = ic;
-        ic = tmp;
+        off_f[l] = emit_program(rc, nl, ip);               // forward: rows of layer l, entries = live rows of layer l - 1
+        off_b[l] = emit_program(rp, n_prev, ic);           // transposed: rows of layer l - 1, entries = live rows of layer l
+        uint16_t* tmp = ip; ip = ic; ic = tmp;
+        tmp = rp; rp = rc; rc = tmp;
         for (int i = tid; i < HS; i += kPlanThreads) ic[i] = (uint16_t)kNoRow;
         n_prev = nl;
         __syncthreads();
+    }
+    if (s_ovf == 1) {                                      // (uniform: s_ovf is only read after barriers)
+        give_up();
+        return;
     }
     // ---- readout pairs: {row of H_L | neighbour slot << 16, sign bits}; a pair whose edge has no live row keeps kNoRow ----
     const unsigned off_ro = alloc(align2(D + 1) + 2 * total_pairs);
@@ -503,23 +531,35 @@ __global__ void __launch_bounds__(kPlanThreads) fused_plan_kernel(const PlanArgs
         }
     }
     __syncthreads();
-    if (tid == 0) {
-        if (s_ovf) {
+    if (s_ovf) {                                           // the arena is exhausted (the average program exceeds its share)
+        if (tid == 0) {
             hdr[0] = kFusedFlagOverflow;
             *a.overflow = 1;
-        } else {
-            hdr[0] = 0;
-            for (int l = 1; l <= kFusedMaxL; ++l) hdr[l] = l <= L ? n_l[l] : 0;
-            hdr[4] = (int)off_l1;
-            for (int l = 2; l <= kFusedMaxL; ++l) {
-                hdr[5 + (l - 2)] = (int)off_f[l];
-                hdr[7 + (l - 2)] = (int)off_b[l];
-            }
-            hdr[9] = (int)off_ro;
-            hdr[10] = total_pairs;
-            hdr[11] = s_nat[1];
-            hdr[12] = s_nat[0];
         }
+        return;
+    }
+    if (tid == 0) {
+        hdr[0] = 0;
+        for (int l = 1; l <= kFusedMaxL; ++l) hdr[l] = l <= L ? n_l[l] : 0;
+        hdr[4] = (int)off_l1;
+        for (int l = 2; l <= kFusedMaxL; ++l) {
+            hdr[5 + (l - 2)] = (int)off_f[l];
+            hdr[7 + (l - 2)] = (int)off_b[l];
+        }
+        hdr[9] = (int)off_ro;
+        hdr[10] = total_pairs;
+        hdr[11] = s_nhash;
+        hdr[12] = s_nlist;
+        hdr[13] = fp1 - fp0;
+    }
+}
+
+__global__ void __launch_bounds__(kPlanThreads) fused_plan_kernel(const PlanArgs a) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int n_work = a.tier == 0 ? a.n_work : *a.n_retry;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        plan_trajectory(a, a.tier == 0 ? w : a.retry[w], sm);
+        __syncthreads();
     }
 }
 
@@ -549,6 +589,9 @@ struct FuGeom {
     static constexpr int LDA = 3 * C + 4;   // gathered tile stride: (g * LDA + tig) hits 32 distinct banks
     static constexpr int LDW = C + 8;
     static constexpr int CH = 80;           // rows gathered per chunk (5 m-tiles)
+    static constexpr int SE = 1024;         // program entries staged in shared memory per chunk
+    static constexpr int SP = 136;          // staged row pointers (CH + 1, or D + 1 for the readout pairs)
+    static constexpr int SL1 = 384;         // staged layer-1 scalars (3 per row: 128 rows)
     static constexpr int LPR = C / 4;       // lanes per row in the gather (one float4 each)
     static constexpr int NP = C / 16;       // pairs of n-tiles per row tile
     static constexpr int NMT = C / 16;      // dW: m-tiles (input channels)
@@ -558,19 +601,19 @@ struct FuGeom {
 };
 
 // gather of nr rows (program rows r0 .. r0 + nr) from the row store `src` into the tile: [own | S0 sum | S1 sum]; rows up to
-// the next multiple of 16 are zero-filled
+// the next multiple of 16 are zero-filled.  ptr[r] = row pointer of program row r0 + r; entry p lives at ent[p - pbase] (STAGED:
+// both in shared memory — a dependent global load per entry is what this kernel cannot afford)
 template <int C>
-__device__ __forceinline__ void fu_gather(float* __restrict__ tile, const float* src, const int* __restrict__ ptr,
-                                          const int2* __restrict__ ent, int r0, int nr) {
+__device__ __forceinline__ void fu_gather(float* __restrict__ tile, const float* src, const int* ptr, const int2* ent, int pbase, int nr) {
     using G = FuGeom<C>;
     const int lr = threadIdx.x % G::LPR, rr = threadIdx.x / G::LPR;
     const int npad = (nr + 15) & ~15;
     for (int r = rr; r < npad; r += kTrajThreads / G::LPR) {
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f), s0 = o, s1 = o;
         if (r < nr) {
-            const int p1 = __ldg(ptr + r0 + r + 1);
-            for (int p = __ldg(ptr + r0 + r); p < p1; ++p) {
-                const int2 en = __ldg(ent + p);
+            const int p1 = ptr[r + 1] - pbase;
+            for (int p = ptr[r] - pbase; p < p1; ++p) {
+                const int2 en = ent[p];
                 const float c0 = (float)(short)(en.y & 0xffff), c1 = (float)(en.y >> 16);
                 const float4 v = *reinterpret_cast<const float4*>(src + (size_t)(en.x & 0xFFFF) * G::LDH + 4 * lr);
                 s0.x = fmaf(c0, v.x, s0.x); s0.y = fmaf(c0, v.y, s0.y); s0.z = fmaf(c0, v.z, s0.z); s0.w = fmaf(c0, v.w, s0.w);
@@ -583,6 +626,26 @@ __device__ __forceinline__ void fu_gather(float* __restrict__ tile, const float*
         *reinterpret_cast<float4*>(d + C) = s0;
         *reinterpret_cast<float4*>(d + 2 * C) = s1;
     }
+}
+
+// Stages the next chunk of a program (rows r0 ...) into shared memory: row pointers into sptr, entries into sent.  Returns the rows
+// of the chunk (<= CH, shrunk in steps of 16 until the entries fit; a chunk that still does not fit is gathered from global memory:
+// *staged = false).  Two barriers inside; every thread gets the same answer.
+template <int C>
+__device__ __forceinline__ int fu_stage(const int* __restrict__ gptr, const int2* __restrict__ gent, int r0, int n_rows, int* sptr,
+                                        int2* sent, bool* staged) {
+    using G = FuGeom<C>;
+    int nr = min(G::CH, n_rows - r0);
+    for (int i = threadIdx.x; i <= nr; i += kTrajThreads) sptr[i] = __ldg(gptr + r0 + i);
+    __syncthreads();
+    const int pbase = sptr[0];
+    while (nr > 16 && sptr[nr] - pbase > G::SE) nr -= 16;
+    const int cnt = sptr[nr] - pbase;
+    *staged = cnt <= G::SE;
+    if (*staged)
+        for (int i = threadIdx.x; i < cnt; i += kTrajThreads) sent[i] = __ldg(gent + pbase + i);
+    __syncthreads();
+    return nr;
 }
 
 // row tile product: D[nr x C] = tile[nr x 3C] * B, B = [W0; W1; W2] (forward) or [W0^T; W1^T; W2^T] (TRANSPOSED: the backward
@@ -682,7 +745,10 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
     float* zs = tile + (size_t)G::CH * G::LDA;                       // [D][C] readout sums
     float* lg = zs + (size_t)D * C;                                  // [D] logits -> log-probs
     float* dl = lg + ((D + 3) & ~3);                                 // [D] dlogits
-    float* rows_sm = dl + ((D + 3) & ~3);                            // [cap_rows][LDH]  (small variant)
+    int2* sent = reinterpret_cast<int2*>(dl + ((D + 3) & ~3));       // [SE] staged program entries of the current chunk
+    int* sptr = reinterpret_cast<int*>(sent + G::SE);                // [SP] staged row pointers
+    float* l1s = reinterpret_cast<float*>(sptr + G::SP);             // [SL1] staged layer-1 scalars
+    float* rows_sm = l1s + G::SL1;                                   // [cap_rows][LDH]  (small variant)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int l = 2; l <= L; ++l)
@@ -709,7 +775,7 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
 
     for (int t = blockIdx.x; t < a.b; t += gridDim.x) {
         const int* h = a.hdr + (size_t)t * kFusedHdrW;
-        if (h[0] & kFusedFlagOverflow) continue;
+        if (h[0] != 0) continue;                           // overflow reported by the plan kernel: skipped (host: error code 4)
         int n[kFusedMaxL + 1], hb[kFusedMaxL + 2];
         int tot = 0;
         n[0] = 0;
@@ -720,11 +786,16 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
             hb[l] = tot;
             tot += n[l];
         }
-        const int need = (GRAD ? 2 : 1) * tot;
+        const int need = tot;                             // G_l overwrites H_l in place (below): one stored row per live row
         const bool big = need > a.cap_rows;
         if (big != BIG || need > cap) continue;           // (block-uniform; need <= big_rows by construction of the bounds)
         const float* l1 = reinterpret_cast<const float*>(a.arena + (unsigned)h[4]);
         n_fwd += (unsigned long long)tot;
+        if (3 * n[1] <= G::SL1) {                          // (block-uniform) the layer-1 scalars are read twice: stage them
+            for (int i = tid; i < 3 * n[1]; i += kTrajThreads) l1s[i] = __ldg(l1 + i);
+            __syncthreads();
+            l1 = l1s;
+        }
 
         // ---- layer 1 ----
         for (int i = tid; i < n[1] * C; i += kTrajThreads) {
@@ -743,26 +814,36 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
             const float* hprev = rows + (size_t)hb[l - 1] * G::LDH;
             float* hout = rows + (size_t)hb[l] * G::LDH;
             const float* Wl = Wsm + (size_t)(l - 2) * 3 * C * G::LDW;
-            for (int r0 = 0; r0 < nl; r0 += G::CH) {
-                const int nr = min(G::CH, nl - r0);
-                fu_gather<C>(tile, hprev, ptr, ent, r0, nr);
+            for (int r0 = 0; r0 < nl;) {
+                bool staged;
+                const int nr = fu_stage<C>(ptr, ent, r0, nl, sptr, sent, &staged);
+                if (staged) fu_gather<C>(tile, hprev, sptr, sent, sptr[0], nr);
+                else fu_gather<C>(tile, hprev, sptr, ent, 0, nr);
                 __syncthreads();
                 fu_product<C, false>(tile, Wl, nr, [&](int r, int col, float v0, float v1) {
                     float* o = hout + (size_t)(r0 + r) * G::LDH + col;
                     *reinterpret_cast<float2*>(o) = make_float2(fu_act<ACT>(v0), fu_act<ACT>(v1));
                 });
                 __syncthreads();
+                r0 += nr;
             }
         }
         // ---- readout: z_j = sum over the edges incident to neighbour j of sign * H_L[row]; logit_j = z_j . w_out ----
         const int* rptr = reinterpret_cast<const int*>(a.arena + (unsigned)h[9]);
         const int2* rent = reinterpret_cast<const int2*>(rptr + align2(D + 1));
+        if (h[10] <= G::SE) {                              // (block-uniform) stage the pair list: read by the logits and by dq
+            for (int i = tid; i <= D; i += kTrajThreads) sptr[i] = __ldg(rptr + i);
+            for (int i = tid; i < h[10]; i += kTrajThreads) sent[i] = __ldg(rent + i);
+            __syncthreads();
+            rptr = sptr;
+            rent = sent;
+        }
         const float* hL = rows + (size_t)hb[L] * G::LDH;
         for (int j = warp; j < D; j += kTrajThreads / 32) {
             float z = 0.f;
-            const int p1 = __ldg(rptr + j + 1);
-            for (int p = __ldg(rptr + j); p < p1; ++p) {
-                const int2 en = __ldg(rent + p);
+            const int p1 = rptr[j + 1];
+            for (int p = rptr[j]; p < p1; ++p) {
+                const int2 en = rent[p];
                 const uint32_t r = (uint32_t)en.x & 0xFFFFu;
                 if (r != kNoRow && lane < C) z = fmaf(__int_as_float(en.y), hL[(size_t)r * G::LDH + lane], z);
             }
@@ -802,7 +883,9 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
         // ---- backward of the readout: dq[row] = sum of sign * dl_j over its (at most two) pairs; G_L = dq w_out act'(H_L) ----
         // dq[r] lives in the first padding column of row r of G_L (columns C .. C+7 of a stored row are never read as data)
         const int nL = n[L];
-        float* gL = rows + (size_t)(tot + hb[L]) * G::LDH;
+        // G_l takes the place of H_l: once dH_l is known, H_l is only needed for act'(H_l) (same element, same thread) — the weight
+        // gradient of layer l + 1, the other reader of H_l, is accumulated BEFORE the rows are overwritten (barrier in the loop below)
+        float* gL = rows + (size_t)hb[L] * G::LDH;
         for (int r = tid; r < nL; r += kTrajThreads) gL[(size_t)r * G::LDH + C] = 0.f;
         __syncthreads();
         if (tid < C) {
@@ -811,9 +894,9 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
             acc_out = s;
         }
         {
-            const int npairs = __ldg(rptr + D);
+            const int npairs = rptr[D];
             for (int p = tid; p < npairs; p += kTrajThreads) {
-                const int2 en = __ldg(rent + p);
+                const int2 en = rent[p];
                 const uint32_t r = (uint32_t)en.x & 0xFFFFu;
                 if (r != kNoRow) atomicAdd(&gL[(size_t)r * G::LDH + C], __int_as_float(en.y) * dl[((uint32_t)en.x >> 16) & 0x7FFFu]);   // a + b == b + a
             }
@@ -831,28 +914,32 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
             const int np_ = n[l - 1];
             const int* ptr = reinterpret_cast<const int*>(a.arena + (unsigned)h[7 + (l - 2)]);
             const int2* ent = reinterpret_cast<const int2*>(ptr + align2(np_ + 1));
-            const float* gl = rows + (size_t)(tot + hb[l]) * G::LDH;
-            const float* hprev = rows + (size_t)hb[l - 1] * G::LDH;
-            float* gprev = rows + (size_t)(tot + hb[l - 1]) * G::LDH;
+            const float* gl = rows + (size_t)hb[l] * G::LDH;
+            float* hprev = rows + (size_t)hb[l - 1] * G::LDH;
+            float* gprev = hprev;
             const float* Wl = Wsm + (size_t)(l - 2) * 3 * C * G::LDW;
             n_bwd += (unsigned long long)np_;
-            for (int r0 = 0; r0 < np_; r0 += G::CH) {
-                const int nr = min(G::CH, np_ - r0);
-                fu_gather<C>(tile, gl, ptr, ent, r0, nr);
+            for (int r0 = 0; r0 < np_;) {
+                bool staged;
+                const int nr = fu_stage<C>(ptr, ent, r0, np_, sptr, sent, &staged);
+                if (staged) fu_gather<C>(tile, gl, sptr, sent, sptr[0], nr);
+                else fu_gather<C>(tile, gl, sptr, ent, 0, nr);
                 __syncthreads();
                 fu_dw<C>(acc[l - 2], hprev + (size_t)r0 * G::LDH, tile, nr);
+                __syncthreads();                           // every warp has read H_{l-1} of this chunk: G_{l-1} may overwrite it
                 fu_product<C, true>(tile, Wl, nr, [&](int r, int col, float v0, float v1) {
                     const float2 hv = *reinterpret_cast<const float2*>(hprev + (size_t)(r0 + r) * G::LDH + col);
                     *reinterpret_cast<float2*>(gprev + (size_t)(r0 + r) * G::LDH + col) =
                         make_float2(v0 * fu_dact<ACT>(hv.x), v1 * fu_dact<ACT>(hv.y));
                 });
                 __syncthreads();
+                r0 += nr;
             }
         }
         // ---- first layer: dW_k[0][c] += sum_rows a_k[row] G_1[row][c] ----
         if (tid < 3 * C) {
             const int k = tid / C, c = tid % C;
-            const float* g1 = rows + (size_t)tot * G::LDH;
+            const float* g1 = rows;
             float s = acc1;
             for (int r = 0; r < n[1]; ++r) s = fmaf(l1[3 * r + k], g1[(size_t)r * G::LDH + c], s);
             acc1 = s;
@@ -916,13 +1003,13 @@ __global__ void __launch_bounds__(256) fused_reduce_kernel(const float* __restri
     out[i] += (s0 + s1) + (s2 + s3);
 }
 
-size_t plan_smem_bytes(int HS, int LC) { return (size_t)HS * 13 + (size_t)(LC + 4) * 4 + (size_t)LC * 12 + (size_t)LC * 8 + 16; }
+size_t plan_smem_bytes(int HS, int LC, int LV) { return (size_t)HS * 16 + (size_t)(LV + 4) * 4 + (size_t)LV * 10 + (size_t)LC * 2 + 16; }
 
 template <int C>
 size_t traj_smem_bytes(int D, int cap_rows) {
     using G = FuGeom<C>;
     size_t fl = (size_t)(kFusedMaxL - 1) * 3 * C * G::LDW + 3 * C + C + (size_t)G::CH * G::LDA + (size_t)D * C + 2 * ((D + 3) & ~3) +
-                (size_t)cap_rows * G::LDH;
+                2 * (size_t)G::SE + G::SP + G::SL1 + (size_t)cap_rows * G::LDH;
     return fl * sizeof(float);
 }
 
@@ -970,22 +1057,32 @@ bool scone_fused_supported(const scone_complex* cx, int n_layers, const int32_t*
 
 void scone_fused_destroy(FusedState* f) {
     if (!f) return;
-    cudaFree(f->d_hdr); cudaFree(f->d_arena); cudaFree(f->d_bump); cudaFree(f->d_partial); cudaFree(f->d_scratch); cudaFree(f->d_stats);
+    cudaFree(f->d_hdr); cudaFree(f->d_retry); cudaFree(f->d_arena); cudaFree(f->d_bump); cudaFree(f->d_partial); cudaFree(f->d_scratch); cudaFree(f->d_stats);
     cudaFree(f->d_rows_done);
     delete f;
 }
 
 // Measures the static bounds of the complex and sizes every buffer of the fused pipeline for micro-batches of `mb` trajectories.
 // Returns 0 and *out = nullptr when the complex does not fit the pipeline's shared-memory tables (caller keeps pipeline 3 / 2).
+static void table_shape(int entries, int* HS, int* hshift) {
+    int hs = 256;
+    while (hs * 3 / 4 < entries + 1) hs *= 2;
+    *HS = hs;
+    *hshift = 32;
+    for (int v = hs; v > 1; v >>= 1) --*hshift;
+}
+
 int scone_fused_create(const scone_complex* cx, int L, int C, int mb, int64_t n_params, FusedState** out) {
     *out = nullptr;
     FusedState* f = new FusedState();
     f->L = L;
     f->C = C;
     f->n_params = n_params;
-    // ---- bounds: the cone of every node, with the largest tables one CTA can hold ----
-    SCONE_CUDA(cudaMalloc((void**)&f->d_stats, 4 * sizeof(int)));
-    SCONE_CUDA(cudaMemset(f->d_stats, 0, 4 * sizeof(int)));
+    // ---- bounds: the cone of every node, with the largest tables one CTA can hold; size histograms over the nodes ----
+    const int n_stats = 4 + 2 * kBoundBuckets;
+    SCONE_CUDA(cudaMalloc((void**)&f->d_stats, n_stats * sizeof(int)));
+    SCONE_CUDA(cudaMemset(f->d_stats, 0, n_stats * sizeof(int)));
+    std::vector<int> st(n_stats, 0);
     {
         const int HS = 32768, LC = 16384, hshift = 32 - 15;
         const size_t smem = (size_t)HS * 4 + (size_t)LC * 4;
@@ -993,31 +1090,60 @@ int scone_fused_create(const scone_complex* cx, int L, int C, int mb, int64_t n_
         fused_bound_kernel<<<cx->N, kPlanThreads, smem>>>(cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, cx->d_mptr, cx->d_ment, cx->N, cx->D, L, HS,
                                                           LC, hshift, f->d_stats);
         SCONE_LAUNCHED();
-        int st[4] = {0, 0, 0, 0};
-        SCONE_CUDA(cudaMemcpy(st, f->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
+        SCONE_CUDA(cudaMemcpy(st.data(), f->d_stats, n_stats * sizeof(int), cudaMemcpyDeviceToHost));
         if (st[2]) {                                       // cones larger than any table: not this pipeline's regime
             scone_fused_destroy(f);
             return 0;
         }
-        f->bound_t0 = st[0] > 0 ? st[0] : 1;
-        f->bound_t1 = st[1] > 0 ? st[1] : 1;
+        f->bound_cone = st[0] > 0 ? st[0] : 1;
+        f->bound_list = st[1] > 0 ? st[1] : 1;
     }
-    int HS = 256;
-    while (HS * 3 / 4 < f->bound_t0 + 1) HS *= 2;
-    f->HS = HS;
-    f->hshift = 32;
-    for (int v = HS; v > 1; v >>= 1) --f->hshift;
-    f->LC = (f->bound_t1 + 63) & ~63;
-    f->plan_smem = plan_smem_bytes(f->HS, f->LC);
-    if (f->plan_smem > 200 * 1024 || f->bound_t1 >= 0xFFFF) {
+    // tier 1 (the cone cannot overflow it): tables from the bounds + room for kFlowRoom flow entries per trajectory.  tier 0: tables
+    // that hold the cone of 99 % of the nodes (a few hull / hole boundary nodes of a Delaunay complex have cones ten times the typical
+    // size; sizing every CTA for them costs the occupancy the latency-bound plan kernel lives on)
+    constexpr int kFlowRoomMin = 1024, kFlowRoom = 4096, kFlowRoom0 = 320;
+    f->LC = (f->bound_list + 63) & ~63;
+    f->LV = (f->bound_cone + 63) & ~63;
+    table_shape(f->bound_cone + kFlowRoomMin, &f->HS, &f->hshift);
+    while ((f->HS * 3) / 4 < f->bound_cone + kFlowRoom && plan_smem_bytes(2 * f->HS, f->LC, f->LV) <= 200 * 1024) {
+        f->HS *= 2;
+        --f->hshift;
+    }
+    f->flow_room = (f->HS * 3) / 4 - f->bound_cone;       // flow entries per trajectory tier 1 is guaranteed to hold
+    f->plan_smem = plan_smem_bytes(f->HS, f->LC, f->LV);
+    if (f->plan_smem > 200 * 1024 || f->bound_cone >= 0xFFFF) {
         scone_fused_destroy(f);
         return 0;
+    }
+    {
+        auto quantile = [&](const int* h) {
+            long long acc = 0, want = ((long long)cx->N * 99 + 99) / 100;
+            for (int b = 0; b < kBoundBuckets; ++b) {
+                acc += h[b];
+                if (acc >= want) return 32 * (b + 1);
+            }
+            return 32 * kBoundBuckets;
+        };
+        const int q0 = std::min(quantile(&st[4]), f->bound_cone), q1 = std::min(quantile(&st[4 + kBoundBuckets]), f->bound_list);
+        table_shape(q0 + kFlowRoom0, &f->HS0, &f->hshift0);
+        f->LC0 = std::min((q1 + 63) & ~63, f->LC);
+        f->LV0 = std::min(256, f->LV);
+        if (f->HS0 >= f->HS) {                             // one tier is enough
+            f->HS0 = f->HS;
+            f->LC0 = f->LC;
+            f->LV0 = f->LV;
+            f->hshift0 = f->hshift;
+            f->two_tiers = false;
+        } else {
+            f->two_tiers = true;
+        }
+        f->plan_smem0 = plan_smem_bytes(f->HS0, f->LC0, f->LV0);
     }
     SCONE_CUDA(cudaFuncSetAttribute(fused_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->plan_smem));
     // ---- compute kernel: shared-memory row store of the small variant, per-CTA global row store of the big one ----
     const int ldh = C + 8;
-    f->cap_rows = C == 32 ? 256 : 448;
-    f->big_rows = 2 * L * f->bound_t1;
+    f->cap_rows = C == 32 ? 192 : 384;
+    f->big_rows = f->bound_cone + (L - 1) * f->bound_list;
     f->traj_smem_small = C == 32 ? traj_smem_bytes<32>(cx->D, f->cap_rows) : traj_smem_bytes<16>(cx->D, f->cap_rows);
     f->traj_smem_big = C == 32 ? traj_smem_bytes<32>(cx->D, 0) : traj_smem_bytes<16>(cx->D, 0);
     if (f->traj_smem_small > 113 * 1024) {                 // very high degrees: shrink the row store, keep two CTAs per SM
@@ -1033,30 +1159,35 @@ int scone_fused_create(const scone_complex* cx, int L, int C, int mb, int64_t n_
         SCONE_CUDA(cudaMalloc((void**)&f->d_scratch, (size_t)f->grid_big * f->scratch_stride * sizeof(float)));
     }
     SCONE_CUDA(cudaMalloc((void**)&f->d_partial, (size_t)(f->grid_small + f->grid_big) * (n_params + 2) * sizeof(float)));
-    // ---- program arena: worst case per trajectory from the bounds, chunked so that it stays below 4 GB ----
+    // ---- program arena.  Worst case per trajectory from the bounds (every row of every layer live, every merged-row entry kept).
+    // The arena holds min(worst * chunk, 4 GB): when the worst case fits, it cannot overflow; otherwise it is exhausted only if the
+    // AVERAGE program of a chunk exceeds 64 KB (typical: 5 - 10 KB), which the plan kernel reports through the overflow flag. ----
     int max_row = 1;
     {
         std::vector<int32_t> mp((size_t)cx->E + 1);
         SCONE_CUDA(cudaMemcpy(mp.data(), cx->d_mptr, mp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
         for (int e = 0; e < cx->E; ++e) max_row = std::max(max_row, mp[e + 1] - mp[e]);
     }
-    const unsigned long long b1 = (unsigned long long)f->bound_t1;
-    unsigned long long worst = 3 * b1 + 2 + (unsigned long long)(L > 1 ? L - 1 : 0) * 2 * ((b1 + 3) + 2 * b1 * (unsigned long long)max_row) +
-                               (unsigned long long)(cx->D + 3) + 2ull * cx->D * cx->D + 16;
-    // a neighbour has at most D incident edges: D * D pairs
+    const unsigned long long bc = (unsigned long long)f->bound_cone, bl = (unsigned long long)f->bound_list;
+    unsigned long long worst = 3 * bc + 2 + (unsigned long long)(cx->D + 3) + 2ull * cx->D * cx->D + 16;   // (a neighbour has at most D incident edges)
+    for (int l = 2; l <= L; ++l)                            // layer l: n_l <= |T_2| rows; the two programs hold the same entries
+        worst += (bl + 3) + ((l == 2 ? bc : bl) + 3) + 4 * bl * (unsigned long long)max_row;
     const unsigned long long budget_words = (1ull << 30) - 1024;                 // 4 GB of 32-bit words; offsets are 32-bit
-    unsigned long long chunk = budget_words / worst;
-    if (chunk < 1) {
-        scone_fused_destroy(f);
-        return 0;
+    const unsigned long long share_words = 16 * 1024;                            // 64 KB per trajectory
+    f->worst_words = worst;
+    if (worst * (unsigned long long)mb <= budget_words) {
+        f->chunk = mb;
+        f->arena_words = worst * (unsigned long long)mb;
+    } else {
+        f->chunk = (int)std::min<unsigned long long>((unsigned long long)mb, std::max<unsigned long long>(1, budget_words / std::min(worst, share_words)));
+        f->arena_words = std::min(budget_words, worst * (unsigned long long)f->chunk);
     }
-    f->chunk = (int)std::min<unsigned long long>(chunk, (unsigned long long)mb);
-    f->arena_words = worst * (unsigned long long)f->chunk;
     SCONE_CUDA(cudaMalloc((void**)&f->d_arena, f->arena_words * sizeof(uint32_t)));
     SCONE_CUDA(cudaMalloc((void**)&f->d_hdr, (size_t)f->chunk * kFusedHdrW * sizeof(int)));
-    SCONE_CUDA(cudaMalloc((void**)&f->d_bump, sizeof(unsigned long long)));
-    SCONE_CUDA(cudaMalloc((void**)&f->d_rows_done, 2 * sizeof(unsigned long long)));
-    SCONE_CUDA(cudaMemset(f->d_rows_done, 0, 2 * sizeof(unsigned long long)));
+    SCONE_CUDA(cudaMalloc((void**)&f->d_retry, (size_t)f->chunk * sizeof(int)));
+    SCONE_CUDA(cudaMalloc((void**)&f->d_bump, 2 * sizeof(unsigned long long)));  // [0] arena bump pointer, [1] retry counter (int)
+    SCONE_CUDA(cudaMalloc((void**)&f->d_rows_done, 4 * sizeof(unsigned long long)));
+    SCONE_CUDA(cudaMemset(f->d_rows_done, 0, 4 * sizeof(unsigned long long)));
     *out = f;
     return 0;
 }
@@ -1068,17 +1199,23 @@ int scone_fused_run(const scone_complex* cx, FusedState* f, int act, int b, cons
     if (b <= 0) return 0;
     SCONE_REQUIRE(b <= f->chunk, "scone_fused_run: chunk of %d trajectories exceeds the planned %d", b, f->chunk);
     const bool want_grad = grad != nullptr;
-    SCONE_CUDA(cudaMemsetAsync(f->d_bump, 0, sizeof(unsigned long long), st));
+    SCONE_CUDA(cudaMemsetAsync(f->d_bump, 0, 2 * sizeof(unsigned long long), st));
     PlanArgs p;
     p.traj_ptr = traj_ptr; p.flow_edge = flow_edge; p.flow_val = flow_val; p.last_nodes = last_nodes;
     p.rank = cx->d_rank; p.nbrhoods = cx->d_nbrhoods; p.inc_ptr = cx->d_inc_ptr; p.inc_ent = cx->d_inc_ent;
     p.mptr = cx->d_mptr; p.ment = cx->d_ment;
-    p.N = cx->N; p.D = cx->D; p.E = cx->E; p.L = f->L; p.HS = f->HS; p.LC = f->LC; p.hshift = f->hshift;
+    p.N = cx->N; p.D = cx->D; p.E = cx->E; p.L = f->L; p.HS = f->HS0; p.LC = f->LC0; p.LV = f->LV0; p.hshift = f->hshift0;
     p.hdr = f->d_hdr; p.arena = f->d_arena; p.bump = f->d_bump; p.arena_words = f->arena_words; p.overflow = overflow;
+    p.tier = 0; p.n_work = b; p.n_retry = reinterpret_cast<int*>(f->d_bump + 1); p.retry = f->two_tiers ? f->d_retry : nullptr;
     {
         ScopedProf prof(SCONE_K_CONE, st);
-        fused_plan_kernel<<<b, kPlanThreads, f->plan_smem, st>>>(p);
+        fused_plan_kernel<<<b, kPlanThreads, f->plan_smem0, st>>>(p);
         SCONE_LAUNCHED();
+        if (f->two_tiers) {                                // the few trajectories whose cone overflowed the first tier's tables
+            p.tier = 1; p.HS = f->HS; p.LC = f->LC; p.LV = f->LV; p.hshift = f->hshift; p.retry = f->d_retry;
+            fused_plan_kernel<<<std::min(b, cx->num_sms), kPlanThreads, f->plan_smem, st>>>(p);
+            SCONE_LAUNCHED();
+        }
     }
     TrajArgs t;
     t.hdr = f->d_hdr; t.arena = f->d_arena; t.W = W;

@@ -7,6 +7,7 @@
 // Trajectories are processed in micro-batches of `micro_batch` so that the [E][b][C] activations of all
 // layers stay resident in HBM; weight gradients accumulate across micro-batches in one
 // flat device buffer [grads | nll_sum | count] that is the single all-reduce payload of a data-parallel step.
+#include <algorithm>
 #include <cstring>
 #include "common.cuh"
 #include "fused.cuh"
@@ -59,6 +60,10 @@ struct scone_model {
     int32_t *d_ptr = nullptr, *d_edge = nullptr, *d_last = nullptr, *d_tgt = nullptr, *d_nn = nullptr, *d_acc = nullptr;
     float *d_val = nullptr, *d_mask = nullptr, *d_logp_all = nullptr;
     int64_t cap_B = 0, cap_nnz = 0;
+    int32_t *d_choice = nullptr, *d_rand = nullptr;   // evaluation: predictions, random other targets
+    float* d_evalf = nullptr;
+    int64_t cap_choice = 0;
+    int32_t eval_B = 0;                        // trajectories whose log-probs scone_model_eval_host left in d_logp_all
 };
 
 namespace {
@@ -587,6 +592,7 @@ extern "C" int scone_model_destroy(scone_model* m) {
     for (auto e : m->ev_fill) if (e) cudaEventDestroy(e);
     cudaFree(m->d_ptr); cudaFree(m->d_edge); cudaFree(m->d_last); cudaFree(m->d_tgt); cudaFree(m->d_val);
     cudaFree(m->d_mask); cudaFree(m->d_logp_all); cudaFree(m->d_nn); cudaFree(m->d_acc);
+    cudaFree(m->d_choice); cudaFree(m->d_rand); cudaFree(m->d_evalf);
     delete m;
     return 0;
 }
@@ -845,6 +851,89 @@ extern "C" int scone_model_accuracy_host(scone_model* m, int32_t B, const int32_
     return 0;
 }
 
+// ---- evaluation without the log-probs leaving the device (scone_trajectory_model.py:42-56, 59-71, 73-108) --------------------
+// scone_model_eval_host: forward over B trajectories from HOST buffers; the log-probs stay in the model's device buffer (valid until
+// the next model-level call).  Optional outputs, each computed on the device:
+//   choice_out [B]     argmax prediction per trajectory (n_nbrs masking, first maximum)            (needs n_nbrs)
+//   acc_out [2]        correct predictions, masked trajectories                                      (needs n_nbrs, target_idx, mask)
+//   nll_out [2]        sum of -mask * logprob[target], sum of mask                                   (needs target_idx, mask)
+extern "C" int scone_model_eval_host(scone_model* m, int32_t B, const int32_t* ptr, const int32_t* edge, const float* val,
+                                     const int32_t* last, const int32_t* n_nbrs, const int32_t* tgt, const float* mask,
+                                     int32_t* choice_out, int32_t* acc_out, float* nll_out, void* st) {
+    SCONE_REQUIRE(m && B >= 0 && (B == 0 || (ptr && last)), "scone_model_eval_host: bad arguments");
+    SCONE_REQUIRE(!choice_out || n_nbrs, "scone_model_eval_host: choice_out needs n_nbrs");
+    SCONE_REQUIRE(!acc_out || (n_nbrs && tgt && mask), "scone_model_eval_host: acc_out needs n_nbrs, target_idx and mask");
+    SCONE_REQUIRE(!nll_out || (tgt && mask), "scone_model_eval_host: nll_out needs target_idx and mask");
+    if (acc_out) acc_out[0] = acc_out[1] = 0;
+    if (nll_out) nll_out[0] = nll_out[1] = 0.f;
+    m->eval_B = 0;
+    if (B == 0) return 0;
+    cudaStream_t s = as_stream(st);
+    const int64_t nnz = ptr[B];
+    int rc = ensure_staging(m, B, nnz);
+    if (rc) return rc;
+    if (!m->d_choice || m->cap_choice < B) {
+        cudaFree(m->d_choice); cudaFree(m->d_rand);
+        m->d_choice = m->d_rand = nullptr;
+        SCONE_CUDA(cudaMalloc((void**)&m->d_choice, (size_t)m->cap_B * sizeof(int32_t)));
+        SCONE_CUDA(cudaMalloc((void**)&m->d_rand, (size_t)m->cap_B * sizeof(int32_t)));
+        m->cap_choice = m->cap_B;
+    }
+    if (!m->d_evalf) SCONE_CUDA(cudaMalloc((void**)&m->d_evalf, 4 * sizeof(float)));
+    SCONE_CUDA(cudaMemcpyAsync(m->d_ptr, ptr, (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (nnz) {
+        SCONE_CUDA(cudaMemcpyAsync(m->d_edge, edge, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        SCONE_CUDA(cudaMemcpyAsync(m->d_val, val, nnz * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
+    SCONE_CUDA(cudaMemcpyAsync(m->d_last, last, B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (n_nbrs) SCONE_CUDA(cudaMemcpyAsync(m->d_nn, n_nbrs, B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (tgt) SCONE_CUDA(cudaMemcpyAsync(m->d_tgt, tgt, B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (mask) SCONE_CUDA(cudaMemcpyAsync(m->d_mask, mask, B * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = scone_model_forward_dev(m, B, m->d_ptr, m->d_edge, m->d_val, m->d_last, m->d_logp_all, st);
+    if (rc) return rc;
+    const int D = m->cx->D;
+    if (choice_out) {
+        if (scone_predict_launch(B, D, m->d_logp_all, m->d_nn, m->d_choice, s)) return 1;
+        SCONE_CUDA(cudaMemcpyAsync(choice_out, m->d_choice, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    }
+    if (acc_out) {
+        if (scone_accuracy_launch(B, D, m->d_logp_all, m->d_nn, m->d_tgt, m->d_mask, m->d_acc, s)) return 1;
+        SCONE_CUDA(cudaMemcpyAsync(acc_out, m->d_acc, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    }
+    if (nll_out) {
+        if (scone_nll_launch(B, D, m->d_logp_all, m->d_tgt, m->d_mask, m->d_evalf, s)) return 1;
+        SCONE_CUDA(cudaMemcpyAsync(nll_out, m->d_evalf, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    int overflow = 0;
+    if (m->d_overflow) SCONE_CUDA(cudaMemcpyAsync(&overflow, m->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
+    SCONE_CUDA(cudaStreamSynchronize(s));
+    if (overflow) {
+        cudaMemset(m->d_overflow, 0, sizeof(int));
+        m->cone_clean = false;
+        scone_set_error("scone_model: a micro-batch exceeded a row-list capacity; the evaluation is incomplete — use a smaller micro-batch or "
+                        "another pipeline");
+        return 4;
+    }
+    m->eval_B = B;
+    return 0;
+}
+
+// Two-target comparison (scone_trajectory_model.py:95-108) on the log-probs the last scone_model_eval_host left on the device (same B,
+// n_nbrs and mask as that call): out[0] = rows with true > random, out[1] = rows with true == random, over mask != 0.
+extern "C" int scone_model_two_target_host(scone_model* m, int32_t B, const int32_t* true_idx, const int32_t* rand_idx, int32_t* out, void* st) {
+    SCONE_REQUIRE(m && out && B >= 0 && (B == 0 || (true_idx && rand_idx)), "scone_model_two_target_host: bad arguments");
+    SCONE_REQUIRE(B == m->eval_B, "scone_model_two_target_host: call scone_model_eval_host (with n_nbrs and mask) on the same %d trajectories first", B);
+    out[0] = out[1] = 0;
+    if (B == 0) return 0;
+    cudaStream_t s = as_stream(st);
+    SCONE_CUDA(cudaMemcpyAsync(m->d_tgt, true_idx, B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    SCONE_CUDA(cudaMemcpyAsync(m->d_rand, rand_idx, B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (scone_two_target_launch(B, m->cx->D, m->d_logp_all, m->d_nn, m->d_tgt, m->d_rand, m->d_mask, m->d_acc, s)) return 1;
+    SCONE_CUDA(cudaMemcpyAsync(out, m->d_acc, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    SCONE_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
 extern "C" int scone_model_loss_grad_host(scone_model* m, int32_t B, const int32_t* ptr, const int32_t* edge, const float* val,
                                           const int32_t* last, const int32_t* tgt, const float* mask, int32_t zero_first,
                                           void* st) {
@@ -907,13 +996,16 @@ extern "C" int scone_model_set_weights_keep_state(scone_model* m, const float* w
     return 0;
 }
 
-extern "C" int scone_model_fused_info(const scone_model* m, int32_t* out /* [8] */) {
+extern "C" int scone_model_fused_info(const scone_model* m, int32_t* out /* [16] */) {
     SCONE_REQUIRE(m && out, "scone_model_fused_info: NULL argument");
-    for (int i = 0; i < 8; ++i) out[i] = 0;
+    for (int i = 0; i < 16; ++i) out[i] = 0;
     if (!m->fused) return 0;
     const FusedState* f = m->fused;
-    out[0] = 1; out[1] = f->bound_t0; out[2] = f->bound_t1; out[3] = f->HS; out[4] = f->chunk; out[5] = f->cap_rows;
+    out[0] = 1; out[1] = f->bound_cone; out[2] = f->bound_list; out[3] = f->HS; out[4] = f->chunk; out[5] = f->cap_rows;
     out[6] = (int32_t)(f->plan_smem / 1024); out[7] = (int32_t)(f->traj_smem_small / 1024);
+    out[8] = f->HS0; out[9] = f->LC0; out[10] = (int32_t)(f->plan_smem0 / 1024); out[11] = f->two_tiers ? 1 : 0;
+    out[12] = (int32_t)std::min<unsigned long long>(f->worst_words, 0x7fffffffull); out[13] = (int32_t)(f->arena_words >> 20);
+    out[14] = f->LC; out[15] = f->big_rows;
     return 0;
 }
 

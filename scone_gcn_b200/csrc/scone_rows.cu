@@ -1063,6 +1063,87 @@ __global__ void __launch_bounds__(256) accuracy_kernel(const float* __restrict__
     }
 }
 
+// Device halves of the host-side metrics (scone_trajectory_model.py:73-108, 42-56): the log-probs never leave the GPU.
+//   predict      choice[t] = argmax_j (j < n_nbrs[t] ? logprobs[t][j] : -100), first maximum, NaN beats numbers (as accuracy_kernel)
+//   two_target   out[0] += [true > random], out[1] += [true == random] over the masked rows, where true / random are the log-probs
+//                of the true target and of the (host-drawn) random other target — exact integer counts
+//   nll          out[0] = sum_t -mask_t * logprobs[t][target_t] (one CTA, fixed lane-strided order + fixed tree: deterministic),
+//                out[1] = sum_t mask_t
+__global__ void __launch_bounds__(256) predict_kernel(const float* __restrict__ logprobs, const int32_t* __restrict__ n_nbrs, int B, int D,
+                                                     int32_t* __restrict__ choice) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B) return;
+    const int n = n_nbrs[t];
+    float best = 0.f;
+    int arg = 0;
+    for (int j = 0; j < D; ++j) {
+        const float v = j < n ? logprobs[(size_t)t * D + j] : -100.f;
+        if (j == 0 || v > best || (v != v && best == best)) {
+            best = v;
+            arg = j;
+        }
+    }
+    choice[t] = arg;
+}
+
+__global__ void __launch_bounds__(256) two_target_kernel(const float* __restrict__ logprobs, const int32_t* __restrict__ n_nbrs,
+                                                        const int32_t* __restrict__ true_idx, const int32_t* __restrict__ rand_idx,
+                                                        const float* __restrict__ mask, int B, int D, int32_t* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int gt = 0, eq = 0;
+    if (t < B && mask[t] != 0.f) {
+        const int n = n_nbrs[t], a = true_idx[t], r = rand_idx[t];
+        const float tv = (a >= 0 && a < n) ? logprobs[(size_t)t * D + a] : -100.f;     // preds[i, n_nbrs[i]:] = -100 (:84-85)
+        const float rv = (r >= 0 && r < n) ? logprobs[(size_t)t * D + r] : -100.f;
+        gt = tv > rv ? 1 : 0;
+        eq = tv == rv ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        gt += __shfl_xor_sync(0xffffffffu, gt, o);
+        eq += __shfl_xor_sync(0xffffffffu, eq, o);
+    }
+    if ((threadIdx.x & 31) == 0 && (gt | eq)) {
+        atomicAdd(out, gt);
+        atomicAdd(out + 1, eq);
+    }
+}
+
+__global__ void __launch_bounds__(1024) nll_kernel(const float* __restrict__ logprobs, const int32_t* __restrict__ target_idx,
+                                                  const float* __restrict__ mask, int B, int D, float* __restrict__ out) {
+    __shared__ float s_n[32], s_c[32];
+    float nll = 0.f, cnt = 0.f;
+    for (int t = threadIdx.x; t < B; t += blockDim.x) {
+        const float mk = mask[t];
+        const int y = target_idx[t];
+        if (mk != 0.f && y >= 0 && y < D) nll += -mk * logprobs[(size_t)t * D + y];
+        cnt += mk;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        nll += __shfl_xor_sync(0xffffffffu, nll, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_n[threadIdx.x >> 5] = nll;
+        s_c[threadIdx.x >> 5] = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        nll = s_n[threadIdx.x];
+        cnt = s_c[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            nll += __shfl_xor_sync(0xffffffffu, nll, o);
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        }
+        if (threadIdx.x == 0) {
+            out[0] = nll;
+            out[1] = cnt;
+        }
+    }
+}
+
 constexpr int kDwCtas = 148 * 2;
 
 template <int CIN, int COUT, int ACT>
@@ -1156,6 +1237,30 @@ int scone_accuracy_launch(int B, int D, const float* logprobs, const int32_t* n_
         accuracy_kernel<<<(B + 255) / 256, 256, 0, st>>>(logprobs, n_nbrs, target_idx, mask, B, D, out);
         SCONE_LAUNCHED();
     }
+    return 0;
+}
+
+int scone_predict_launch(int B, int D, const float* logprobs, const int32_t* n_nbrs, int32_t* choice, cudaStream_t st) {
+    if (B > 0) {
+        predict_kernel<<<(B + 255) / 256, 256, 0, st>>>(logprobs, n_nbrs, B, D, choice);
+        SCONE_LAUNCHED();
+    }
+    return 0;
+}
+
+int scone_two_target_launch(int B, int D, const float* logprobs, const int32_t* n_nbrs, const int32_t* true_idx, const int32_t* rand_idx,
+                            const float* mask, int32_t* out, cudaStream_t st) {
+    SCONE_CUDA(cudaMemsetAsync(out, 0, 2 * sizeof(int32_t), st));
+    if (B > 0) {
+        two_target_kernel<<<(B + 255) / 256, 256, 0, st>>>(logprobs, n_nbrs, true_idx, rand_idx, mask, B, D, out);
+        SCONE_LAUNCHED();
+    }
+    return 0;
+}
+
+int scone_nll_launch(int B, int D, const float* logprobs, const int32_t* target_idx, const float* mask, float* out, cudaStream_t st) {
+    nll_kernel<<<1, 1024, 0, st>>>(logprobs, target_idx, mask, B, D, out);
+    SCONE_LAUNCHED();
     return 0;
 }
 

@@ -44,11 +44,12 @@ class SconeModel:
 
     def fused_info(self):
         """dict of the fused pipeline's static bounds / launch shapes, or None when the model cannot use it."""
-        out = np.zeros(8, np.int32)
+        out = np.zeros(16, np.int32)
         _lib.check(_lib.lib().scone_model_fused_info(self.handle, _lib.ptr(out)), 'scone_model_fused_info')
         if not out[0]:
             return None
-        keys = ['available', 'bound_t0', 'bound_t1', 'hash_slots', 'chunk', 'cap_rows', 'plan_smem_kb', 'traj_smem_kb']
+        keys = ['available', 'bound_cone', 'bound_list', 'hash_slots', 'chunk', 'cap_rows', 'plan_smem_kb', 'traj_smem_kb', 'hash_slots_tier0',
+                'list_tier0', 'plan_smem_tier0_kb', 'two_tiers', 'worst_words', 'arena_mwords', 'list_tier1', 'big_rows']
         return dict(zip(keys, (int(v) for v in out)))
 
     def fused_header(self, t):
@@ -129,6 +130,37 @@ class SconeModel:
         out = np.zeros(2, np.int32)
         _lib.check(_lib.lib().scone_model_accuracy_host(self.handle, B, *[_lib.ptr(x) for x in a], _lib.ptr(out), stream),
                    'scone_model_accuracy_host')
+        return int(out[0]), int(out[1])
+
+    def evaluate(self, traj_ptr, flow_edge, flow_val, last_nodes, n_nbrs=None, target_idx=None, mask=None, want_choice=False,
+                 want_accuracy=False, want_nll=False, stream=None):
+        """Forward from HOST sparse flows with the log-probs staying on the device; returns a dict with the requested device-computed
+        metrics: 'choice' [B] int32 argmax predictions, 'accuracy' (correct, counted), 'nll' (nll_sum, mask_sum)."""
+        B = len(last_nodes)
+        i32 = lambda a: None if a is None else np.ascontiguousarray(a, np.int32)
+        a = [i32(traj_ptr), i32(flow_edge), np.ascontiguousarray(flow_val, np.float32), i32(last_nodes), i32(n_nbrs), i32(target_idx),
+             None if mask is None else np.ascontiguousarray(mask, np.float32)]
+        choice = np.zeros(B, np.int32) if want_choice else None
+        acc = np.zeros(2, np.int32) if want_accuracy else None
+        nll = np.zeros(2, np.float32) if want_nll else None
+        _lib.check(_lib.lib().scone_model_eval_host(self.handle, B, *[_lib.ptr(x) for x in a], _lib.ptr(choice), _lib.ptr(acc), _lib.ptr(nll),
+                                                    stream), 'scone_model_eval_host')
+        out = {}
+        if want_choice:
+            out['choice'] = choice
+        if want_accuracy:
+            out['accuracy'] = (int(acc[0]), int(acc[1]))
+        if want_nll:
+            out['nll'] = (float(nll[0]), float(nll[1]))
+        return out
+
+    def two_target_counts(self, true_idx, rand_idx, stream=None):
+        """(rows with true > random, rows with true == random) over the masked rows of the last evaluate() call."""
+        B = len(true_idx)
+        t, r = np.ascontiguousarray(true_idx, np.int32), np.ascontiguousarray(rand_idx, np.int32)
+        out = np.zeros(2, np.int32)
+        _lib.check(_lib.lib().scone_model_two_target_host(self.handle, B, _lib.ptr(t), _lib.ptr(r), _lib.ptr(out), stream),
+                   'scone_model_two_target_host')
         return int(out[0]), int(out[1])
 
     def read_grads(self, stream=None):

@@ -104,12 +104,24 @@ class Scone_GCN():
         """
         mask = onp.asarray(mask)
         rows = onp.nonzero(mask == 1)[0]
+        yv = onp.asarray(y)
+        if hasattr(self._net, 'evaluate') and not self.forward_all and self._is_onehot(yv):
+            # forward + masked NLL sum on the device (fixed summation order); only two floats come back
+            p = self._prepared(inputs)
+            self._push(weights)
+            tgt = onp.argmax(yv.reshape(yv.shape[0], -1)[rows], axis=1)
+            nll, cnt = self._net.evaluate(*p.select(rows), target_idx=tgt, mask=onp.ones(len(rows), onp.float32), want_nll=True)['nll']
+            return onp.float32(nll / onp.sum(mask) + self._ridge(weights))
         if self.forward_all:
             preds = self._forward(weights, inputs)[rows]
         else:
             preds = self._forward(weights, inputs, rows)
-        yv = onp.asarray(y)[rows]
-        return onp.float32(-onp.sum(preds.astype(onp.float64) * yv) / onp.sum(mask) + self._ridge(weights))
+        return onp.float32(-onp.sum(preds.astype(onp.float64) * yv[rows]) / onp.sum(mask) + self._ridge(weights))
+
+    @staticmethod
+    def _is_onehot(yv):
+        flat = yv.reshape(yv.shape[0], -1)
+        return bool(onp.all((flat == 0) | (flat == 1)) and onp.all(flat.sum(axis=1) == 1))
 
     def accuracy(self, shifts, inputs, y, mask, n_nbrs):
         """
@@ -142,22 +154,42 @@ class Scone_GCN():
     def two_target_accuracy(self, shifts, inputs, y, mask, n_nbrs):
         """
         Ratio of the time the model ranks the true target above a random, different target (:73-108).
+
+        The ranking runs on the device: the forward's log-probs stay there, the argmax predictions come back (N ints), the redraw
+        loop of :89-91 runs on the host because it consumes the global NumPy RNG stream, and the true-vs-random comparison goes
+        back to the device (two integer counts return).
         """
         mask = onp.asarray(mask)
+        n_nbrs = onp.asarray(n_nbrs)
+        N = onp.asarray(inputs[1]).shape[0]
         if type(self.random_targets) != onp.ndarray:
-            self.random_targets = onp.random.randint(0, high=n_nbrs, size=onp.asarray(inputs[1]).shape[0])
-        preds = onp.array(self._forward(self.weights, inputs))
-        for i in range(len(preds)):
-            preds[i, n_nbrs[i]:] = -100
-        pred_choice = onp.argmax(preds[mask == 1], axis=1)
-        # NB (faithful to :89-91): the loop pairs trajectory i with the i-th MASKED prediction and runs over all
-        # trajectories, so it only terminates without IndexError when mask selects every row or i stays in range.
-        for i in range(min(preds.shape[0], len(pred_choice))):
-            while self.random_targets[i] == pred_choice[i]:
+            self.random_targets = onp.random.randint(0, high=n_nbrs, size=N)
+        yv = onp.asarray(y)
+        true_choice = onp.argmax(yv, axis=1).reshape((yv.shape[0],))
+        on_device = hasattr(self._net, 'evaluate')
+        if on_device:
+            p = self._prepared(inputs)
+            self._push(self.weights)
+            choice_all = self._net.evaluate(p.ptr, p.edge, p.val, p.last_nodes, n_nbrs=n_nbrs, mask=(mask == 1).astype(onp.float32),
+                                            want_choice=True)['choice']
+            pred_choice = choice_all[mask == 1]
+        else:
+            preds = onp.array(self._forward(self.weights, inputs))
+            for i in range(len(preds)):
+                preds[i, n_nbrs[i]:] = -100
+            pred_choice = onp.argmax(preds[mask == 1], axis=1)
+        # Faithful to :89-91: the loop runs over ALL N rows and pairs row i with the i-th MASKED prediction; in the reference
+        # pred_choice is a jax array, whose out-of-range index clamps to the last element (no IndexError).
+        last = len(pred_choice) - 1
+        for i in range(N):
+            pc = pred_choice[min(i, last)] if last >= 0 else -1
+            while self.random_targets[i] == pc:
                 self.random_targets[i] = onp.random.randint(0, high=n_nbrs[i])
+        if on_device:
+            gt, eq = self._net.two_target_counts(true_choice, self.random_targets)
+            return (gt + 0.5 * eq) / sum(mask)
         all_row_idxs = range(len(self.random_targets))
         random_probs = preds[all_row_idxs, self.random_targets]
-        true_choice = onp.argmax(onp.asarray(y), axis=1).reshape((onp.asarray(y).shape[0],))
         true_probs = preds[all_row_idxs, true_choice]
         correct = 0
         for t, r in zip(true_probs[mask == 1], random_probs[mask == 1]):

@@ -299,10 +299,12 @@ class SparseDataset:
         return X, B1, B2, y
 
 
-def generate_sparse_dataset(n, m, holes=True, seed=1030, n_waypoints=48, verbose=False):
+def generate_sparse_dataset(n, m, holes=True, seed=1030, n_waypoints=48, verbose=False, cuts_per_walk=1):
     """Large-complex generator: same complex recipe as random_SC_graph (seeds 1 / 1030), walks BEGIN->A_k->B_k->END
     along BFS shortest paths through `n_waypoints` random waypoints per region (one BFS tree per waypoint instead of
-    three nx.shortest_path calls per walk), random truncation as split_paths, 80/20 split.  Deterministic in `seed`."""
+    three nx.shortest_path calls per walk), random truncation as split_paths, 80/20 split.  Deterministic in `seed`.
+    cuts_per_walk > 1: every accepted walk is truncated at that many independently drawn points, each a trajectory of its own
+    (different prefix, last node and target) — the cheap way to a 32768-trajectory batch."""
     from scipy.sparse import csr_matrix
     from scipy.sparse.csgraph import breadth_first_order
     coords, valid_idxs, faces, edges = _complex_arrays(n, holes)
@@ -346,20 +348,24 @@ def generate_sparse_dataset(n, m, holes=True, seed=1030, n_waypoints=48, verbose
         path = legs[0][:-1] + legs[1][:-1] + legs[2]
         if len(path) != len(set(path)) or len(path) < 8:
             continue
-        path = path[:4 + rng.choice(range(2, len(path) - 4))]       # split_paths truncation
-        prefix, nxt = np.asarray(path[:-2]), path[-2]
-        a, b = prefix[:-1], prefix[1:]
-        lo, hi = np.minimum(a, b), np.maximum(a, b)
-        eid = np.searchsorted(ekey, lo.astype(np.int64) * N + hi)
-        order = np.argsort(eid)
-        fe.append(eid[order].astype(np.int32))
-        fv.append(np.where(a < b, 1.0, -1.0).astype(np.float32)[order])
-        ptr.append(ptr[-1] + len(eid))
-        last = int(prefix[-1])
-        nb = adj.indices[adj.indptr[last]:adj.indptr[last + 1]]
-        last_nodes.append(last)
-        target_nodes.append(nxt)
-        target_idx.append(int(np.searchsorted(np.sort(nb), nxt)))
+        full = path
+        for _ in range(cuts_per_walk):
+            if len(last_nodes) >= m:
+                break
+            path = full[:4 + rng.choice(range(2, len(full) - 4))]   # split_paths truncation
+            prefix, nxt = np.asarray(path[:-2]), path[-2]
+            a, b = prefix[:-1], prefix[1:]
+            lo, hi = np.minimum(a, b), np.maximum(a, b)
+            eid = np.searchsorted(ekey, lo.astype(np.int64) * N + hi)
+            order = np.argsort(eid)
+            fe.append(eid[order].astype(np.int32))
+            fv.append(np.where(a < b, 1.0, -1.0).astype(np.float32)[order])
+            ptr.append(ptr[-1] + len(eid))
+            last = int(prefix[-1])
+            nb = adj.indices[adj.indptr[last]:adj.indptr[last + 1]]
+            last_nodes.append(last)
+            target_nodes.append(nxt)
+            target_idx.append(int(np.searchsorted(np.sort(nb), nxt)))
         i += 1
         if verbose and i % 1000 == 0:
             print('walks:', i)

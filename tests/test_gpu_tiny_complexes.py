@@ -56,5 +56,6 @@ def test_tiny_complex_forward_and_grads_vs_oracle(name, model):
     gmax = max(np.abs(r).max() for r in g_ref)
     for a, r in zip(grads, g_ref):
         # per weight array, relative to its largest entry; an array whose true gradient is zero up to fp32 cancellation
-        # noise (|g| ~ 1e-9 on these 3-6 edge complexes) is held to the noise floor of the whole gradient instead
-        assert np.abs(a - r).max() <= 1e-4 * max(np.abs(r).max(), 1e-3 * gmax, 1e-30)
+        # noise (|g| ~ 1e-9 on these 3-6 edge complexes; on `isolated_nodes` the WHOLE gradient is such noise) is held to the
+        # noise floor instead: 1e-6 absolute for an O(1) loss
+        assert np.abs(a - r).max() <= 1e-4 * max(np.abs(r).max(), 1e-3 * gmax, 1e-2)

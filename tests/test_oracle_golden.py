@@ -145,3 +145,18 @@ def test_sparse_oracle_matches_dense(model):
     assert np.allclose(nll / mask.sum(), l, rtol=1e-10)
     for a, b in zip(g, gref):
         assert np.allclose(a, b, rtol=1e-8, atol=1e-14)
+
+
+def test_two_target_accuracy_matches_the_reference_run():
+    """oracle.two_target_accuracy against the reference's own method (oracle/make_golden_two_target.py: train mask, then test mask,
+    global RNG seeded 4242): scores, the redrawn random targets and the RNG stream position afterwards."""
+    ds = Dataset('dataset_small.npz')
+    fx, tt = load('model_small_scone_h16.npz'), load('two_target_small_scone_h16.npz')
+    preds = fx['big_logprobs']
+    n_nbrs = fx['n_nbrs']
+    np.random.seed(int(tt['seed']))
+    tr, rt = so.two_target_accuracy(preds, ds.targets, ds.train_mask, n_nbrs)
+    assert tr == float(tt['train']) and np.array_equal(rt, tt['random_targets_after_train'])
+    ts, rt = so.two_target_accuracy(preds, ds.targets, ds.test_mask, n_nbrs, random_targets=rt)
+    assert ts == float(tt['test']) and np.array_equal(rt, tt['random_targets_after_test'])
+    assert np.random.randint(0, 1 << 30) == int(tt['next_draw'])
