@@ -16,6 +16,7 @@ Differences that are deliberate and results-identical:
 """
 import numpy as onp
 
+from . import dp
 from .complex import flows_to_csr
 from .model import SconeModel
 from .bunch import BunchModel
@@ -45,14 +46,18 @@ class _Prepared:
 
 
 class Scone_GCN():
-    def __init__(self, epochs, step_size, batch_size, weight_decay, verbose=True, micro_batch=None, forward_all=False):
+    def __init__(self, epochs, step_size, batch_size, weight_decay, verbose=True, micro_batch=None, forward_all=False,
+                 data_parallel=None):
         """
         :param epochs: # of training epochs
         :param step_size: step size for use in training model
         :param batch_size: # of data points to train over in each gradient step
         :param verbose: whether to print training progress
         :param weight_decay: ridge regularization constant
-        (micro_batch / forward_all: B200-side knobs, not in the reference)
+        (micro_batch / forward_all / data_parallel: B200-side knobs, not in the reference.  data_parallel=None: on when a
+         torch.distributed process group with more than one rank exists — every rank runs the same script with the same RNG
+         stream, computes the gradient of its contiguous share of each batch, and the flat [grads | nll | count] buffer is
+         all-reduced (NCCL over NVLink) before the replicated Adam step: SURVEY 8(e))
         """
         self.random_targets = None
         self.trained = False
@@ -67,6 +72,7 @@ class Scone_GCN():
         self.verbose = verbose
         self.micro_batch = micro_batch
         self.forward_all = forward_all
+        self.data_parallel = data_parallel
         self._net = None
         self._prep_cache = {}
 
@@ -293,6 +299,9 @@ class Scone_GCN():
 
         self._net.set_weights([onp.asarray(w) for w in self.weights], reset_adam=True)     # init_fun(self.weights)
         self.adam_state = self._net
+        use_dp = dp.is_distributed() if self.data_parallel is None else bool(self.data_parallel)
+        if use_dp and not hasattr(self._net, 'grads_tensor'):
+            raise NotImplementedError('data-parallel training is implemented for -model scone / ebli')
         unshuffled_batch_mask = onp.array([1] * self.batch_size + [0] * (N - self.batch_size))
         train_loss = train_acc = test_loss = test_acc = None
 
@@ -306,8 +315,13 @@ class Scone_GCN():
             else:
                 rows = onp.nonzero(batch_mask)[0]
                 m = onp.ones(len(rows), onp.float32)
+            if use_dp:                                     # this rank's contiguous share of the batch (same rows on every rank)
+                keep = dp.shard_rows(onp.arange(len(rows)))
+                rows, m = rows[keep], m[keep]
             ptr, fe, fv, last = p.select(rows)
             self._net.loss_grad(ptr, fe, fv, last, target_idx[rows], m, zero_first=True, read=False)
+            if use_dp:                                     # the one exchange of the step: [grads | nll_sum | count], summed over ranks
+                dp.allreduce_sum_(self._net.grads_tensor())
             self._net.adam_step(i, self.step_size, self.weight_decay)
 
             if i % n_batches == n_batches - 1:

@@ -225,6 +225,10 @@ def train_model():
     """
     Trains a model to predict the next node in each input path           (trajectory_experiments.py:313-513)
     """
+    # launched under torchrun (WORLD_SIZE > 1): one process per GPU, the batch of every step is sharded over the ranks and the
+    # weight gradients all-reduced (Scone_GCN.train); a plain `python trajectory_experiments.py ...` run is unchanged
+    from . import dp as _dp
+    _dp.init_from_env()
     inputs_all, y_all, train_mask, test_mask, shifts, G_undir, E_lookup, nbrhoods, n_nbrs, target_nodes_all, prefixes = \
         data_setup(hops=(1, 2), load=HYPERPARAMS['load_data'], folder_suffix=HYPERPARAMS['data_folder_suffix'])
     (inputs_1hop, inputs_2hop), (y_1hop, y_2hop) = inputs_all, y_all

@@ -60,3 +60,26 @@ def test_two_rank_allreduce_matches_single_process(tmp_path):
     nll, g = orc.loss_and_grads(W, ds.flows[:, :, 0].T.copy(), ds.last_nodes, ds.raw['targets_argmax'], mask)
     ref = np.concatenate([x.ravel() for x in g] + [np.array([nll, mask.sum()])])
     assert np.allclose(got, ref, rtol=1e-10, atol=1e-12)
+
+
+def _shard_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from scone_gcn_b200 import dp
+    assert dp.init_from_env() == (rank, world) and dp.is_distributed()
+    rows = np.arange(100, 137)                              # the batch rows every rank derives from the shared RNG stream
+    mine = dp.shard_rows(rows)
+    t = torch.zeros(137, dtype=torch.float64)
+    t[mine] = 1.0
+    dp.allreduce_sum_(t)                                    # every row owned exactly once
+    if rank == 0:
+        np.save(out, t.numpy())
+    dist.destroy_process_group()
+
+
+def test_product_sharding_covers_every_batch_row_once(tmp_path):
+    """Scone_GCN.train shards each batch with dp.shard_rows and all-reduces with dp.allreduce_sum_ (world_size 2, gloo)."""
+    out = str(tmp_path / 'own.npy')
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_shard_worker, args=(2, port, out), nprocs=2, join=True)
+    own = np.load(out)
+    assert np.array_equal(own[100:137], np.ones(37)) and own[:100].sum() == 0
