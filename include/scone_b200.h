@@ -290,6 +290,10 @@ int scone_get_zero_fill(void);
  * 2 = the same with 8 trajectories of two edges per warp; 0 = the fp32 SIMT tile kernels for every width (bit-identical to
  * the flagged unit kernels; used by the tests that assert that identity). */
 int scone_set_dense_kernel(int32_t which);
+/* 3 = tcgen05 / TMEM tiles (csrc/scone_umma.cu) for 32 -> 32 layers with b % 16 == 0: the slab gather feeds 128-row tcgen05.mma.kind::tf32
+ * tiles (A written to TMEM with tcgen05.st straight from the gather's registers, weights in shared memory, D read back with tcgen05.ld);
+ * other shapes fall back to 1.  scone_umma_status synchronises the stream and returns 3 if a launch reported an mbarrier time-out. */
+int scone_umma_status(void* stream);
 int scone_get_dense_kernel(void);
 
 /* Optional per-kernel-family device timing (CUDA events recorded on the launching stream around each launch);

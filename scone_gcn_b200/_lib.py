@@ -47,6 +47,7 @@ SIGNATURES = {
     'scone_get_zero_fill': (C.c_int, []),
     'scone_set_dense_kernel': (C.c_int, [_i32]),
     'scone_get_dense_kernel': (C.c_int, []),
+    'scone_umma_status': (C.c_int, [_vp]),
     'scone_csr_create': (C.c_int, [_i32, _i32, _vp, _vp, _vp, C.POINTER(_vp)]),
     'scone_csr_destroy': (C.c_int, [_vp]),
     'scone_bunch_create': (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, C.POINTER(_vp)]),

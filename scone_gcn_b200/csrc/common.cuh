@@ -113,6 +113,11 @@ int scone_readout_ws(const scone_complex* cx, int32_t act, int32_t b, int32_t C,
                      const int32_t* last_nodes, float* logprobs, const int32_t* target_idx, const float* mask,
                      float scale, float* GL, float* dwout, float* nll_sum, float* count, int32_t accumulate,
                      void* workspace, const uint8_t* occ_HL, uint8_t* occ_GL, void* stream);
+// tcgen05 dense layer (scone_umma.cu)
+bool scone_umma_supported(const scone_complex* cx, int cin, int cout, int b);
+int scone_umma_forward(const scone_complex* cx, int act, int b, const float* Hin, const float* W0, const float* W1, const float* W2,
+                       float* Hout, cudaStream_t st);
+int scone_umma_check(cudaStream_t st);
 // slab kernels (scone_slab.cu): dense fused layer for widths 16 / 32, tensor-core product
 extern int g_scone_dense_kernel;
 bool scone_slab_supported(const scone_complex* cx, int cin, int cout);

@@ -330,7 +330,8 @@ int scone_slab_forward_rows(const scone_complex* cx, int act, int b, int cin, in
     return 2;
 }
 
-int g_scone_dense_kernel = 1;   // 0: fp32 SIMT tile kernels; 1: slab kernels, 16 trajectories x 1 edge per slab; 2: slab, 8 x 2
+int g_scone_dense_kernel = 1;   // 0: fp32 SIMT tile kernels; 1: slab kernels, 16 trajectories x 1 edge per slab; 2: slab, 8 x 2;
+                                // 3: tcgen05 tiles of 128 rows for 32 -> 32 with b % 16 == 0 (scone_umma.cu), slab 16 x 1 elsewhere
 
 bool scone_slab_supported(const scone_complex* cx, int cin, int cout) {
     return g_scone_dense_kernel != 0 && cx->d_mptr != nullptr && (cin == 16 || cin == 32) && (cout == 16 || cout == 32);
@@ -341,6 +342,8 @@ static int slab_ts() { return g_scone_dense_kernel == 2 ? 8 : 16; }
 // Dense fused layer forward on the slab kernels; the caller checked scone_slab_supported.
 int scone_slab_forward(const scone_complex* cx, int act, int b, int cin, int cout, const float* Hin, const float* W0, const float* W1,
                        const float* W2, float* Hout, cudaStream_t st) {
+    if (g_scone_dense_kernel == 3 && scone_umma_supported(cx, cin, cout, b))      // tcgen05 / TMEM product (scone_umma.cu)
+        return scone_umma_forward(cx, act, b, Hin, W0, W1, W2, Hout, st);
     const int ts = slab_ts();
     if (cin == 16 && cout == 16) return dispatch_fwd_act<16, 16>(cx, act, ts, b, Hin, W0, W1, W2, Hout, st);
     if (cin == 16 && cout == 32) return dispatch_fwd_act<16, 32>(cx, act, ts, b, Hin, W0, W1, W2, Hout, st);
@@ -351,7 +354,7 @@ int scone_slab_forward(const scone_complex* cx, int act, int b, int cin, int cou
 }
 
 extern "C" int scone_set_dense_kernel(int32_t which) {
-    SCONE_REQUIRE(which >= 0 && which <= 2, "scone_set_dense_kernel: 0 (fp32 SIMT tiles), 1 (slab 16x1) or 2 (slab 8x2)");
+    SCONE_REQUIRE(which >= 0 && which <= 3, "scone_set_dense_kernel: 0 (fp32 SIMT tiles), 1 (slab 16x1), 2 (slab 8x2) or 3 (tcgen05 tiles)");
     g_scone_dense_kernel = which;
     return 0;
 }

@@ -1,0 +1,259 @@
+// scone_umma.cu — the dense fused Hodge-Laplacian layer (width 32 -> 32) on the 5th-generation tensor cores (tcgen05 / TMEM):
+//
+//   Hout = act(Hin W0 + (S0 Hin) W1 + (S1 Hin) W2)                           trajectory_experiments.py:145-149,163-167
+//
+// Same gather as the slab kernel (scone_slab.cu: one pass over the merged operator row, warp-wide 128-bit loads, packed FFMA2
+// sums whose registers are mma A fragments), but the product runs as M = 128 tcgen05.mma tiles instead of per-warp mma.sync:
+//   * a GROUP of 8 warps owns a tile of 128 rows (8 consecutive edges x 16 trajectories); warp w of the group writes its 16 gathered
+//     rows, split hi / lo for 3xTF32, with tcgen05.st.16x128b.x2 into TMEM lanes 32 (w % 4) + 16 (w / 4) .. + 15 — the fragment
+//     registers {a0, a1, a2, a3} of a k-step ARE that instruction's register layout, so the gathered rows go registers -> TMEM,
+//     never through shared memory;
+//   * one elected thread issues 36 tcgen05.mma.kind::tf32 (A from TMEM, B = the 96 x 32 weight stack hi / lo in shared memory,
+//     no-swizzle K-major canonical layout, staged once per CTA): D[128][32] (fp32, TMEM) = A_lo B_hi + A_hi B_lo + A_hi B_hi;
+//     tcgen05.commit arrives on an mbarrier;
+//   * every warp reads its 16 rows of D back with tcgen05.ld.16x256b.x4 (the mma C-fragment layout), applies the activation and
+//     stores 64-bit pairs exactly as the slab kernel does.
+// Two groups per CTA (16 warps, one persistent CTA per SM) with private TMEM regions (2 x (96 + 96 + 32) = 448 of 512 columns) and
+// private barriers: while one group's tile is in the tensor core the other group gathers.  Weights are read once per 128 rows
+// (mma.sync: once per 16 rows) and the tensor instruction stream is one thread's, not every warp's.
+// Every wait is bounded: a protocol error sets *err and the kernel runs on (wrong results, reported by the host) instead of hanging.
+#include <cstdlib>
+#include "common.cuh"
+
+namespace {
+
+#include "slab_common.cuh"
+
+constexpr int kUmmaWarps = 16, kUmmaThreads = kUmmaWarps * 32, kGroupWarps = 8;
+constexpr int kC = 32;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColsAhi = 0, kColsAlo = 96, kColsD = 192, kColsGroup = 224;
+// f32 accumulate, tf32 x tf32, A / B K-major, N = 32, M = 128 (UMMA instruction descriptor, cute/arch/mma_sm100_desc.hpp)
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t kLbo = 512, kSbo = 128;               // bytes: K-direction / N-direction stride between 8 x 16 B core matrices
+constexpr int kSpinLimit = 4000000;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_st_16x128b_x2(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+    asm volatile("tcgen05.st.sync.aligned.16x128b.x2.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+__device__ __forceinline__ void tc_ld_16x256b_x4(uint32_t taddr, float (&d)[4][4]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d[nt][q] = __uint_as_float(r[4 * nt + q]);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(kIdesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {       // no-swizzle K-major descriptor, version 1 (Blackwell)
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((kLbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((kSbo >> 4) & 0x3FFF) << 32) |
+           ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void group_barrier(int group) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(kGroupWarps * 32) : "memory");
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(kUmmaThreads, 1) layer_fwd_umma_kernel(const float* __restrict__ Hin, float* __restrict__ Hout,
+                                                                        const float* __restrict__ W0, const float* __restrict__ W1,
+                                                                        const float* __restrict__ W2, const int32_t* __restrict__ mptr,
+                                                                        const int2* __restrict__ ment, int E, int b, int* __restrict__ err) {
+    constexpr int TS = 16;
+    using G = SlabGeom<kC, TS>;
+    constexpr int NT = kC / 8;
+    // B operand: [hi | lo][k-chunk 24][n-group 4][8 rows][4 floats]; element (n, k) of the stacked weights, k = 32 term + 8 s + kappa
+    // <-> input channel chan(s, kappa) of W_term (the k order of the gather's fragments)
+    __shared__ __align__(128) float Bs[2][24 * 4 * 32];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ uint32_t s_tmem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tig = lane & 3;
+    const int group = warp / kGroupWarps, gw = warp % kGroupWarps;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+    }
+    for (int i = threadIdx.x; i < 96 * kC; i += kUmmaThreads) {
+        const int k = i / kC, n = i % kC;
+        const int term = k / 32, s = (k % 32) / 8, kappa = k % 8;
+        const float* W = term == 0 ? W0 : (term == 1 ? W1 : W2);
+        const float w = W[G::chan(s, kappa) * kC + n];
+        const uint32_t hi = to_tf32(w), lo = to_tf32(w - __uint_as_float(hi));
+        const int off = (k / 4) * 128 + (n / 8) * 32 + (n % 8) * 4 + (k % 4);
+        Bs[0][off] = __uint_as_float(hi);
+        Bs[1][off] = __uint_as_float(lo);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes of Bs -> the tensor core's async proxy
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = s_tmem + (uint32_t)group * kColsGroup;
+    const uint32_t lane_base = (uint32_t)(32 * (gw & 3) + 16 * (gw >> 2)) << 16;       // this warp's 16 TMEM lanes of the tile
+    const uint32_t bhi = smem_u32(&Bs[0][0]), blo = smem_u32(&Bs[1][0]);
+
+    const unsigned rowbytes_in = (unsigned)b * kC * 4u;
+    const size_t rowlen_out = (size_t)b * kC;
+    const int n_ts = (b + TS - 1) / TS;
+    const int tiles_per_ts = (E + kGroupWarps - 1) / kGroupWarps;        // a tile = 8 consecutive edges x one slab of 16 trajectories
+    const long long n_tiles = (long long)n_ts * tiles_per_ts;
+    const long long per = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const long long lo = (long long)blockIdx.x * per, hi = lo + per < n_tiles ? lo + per : n_tiles;
+    uint32_t phase = 0;
+    for (long long tile = lo + group; tile < hi; tile += 2) {
+        const int ts = (int)(tile / tiles_per_ts);
+        const int e0 = (int)(tile - (long long)ts * tiles_per_ts) * kGroupWarps + gw, t0 = ts * TS;
+        const bool live = e0 < E;                          // (a dead slab still takes part in the barriers; its rows are never stored)
+        u64 acc[3][G::NL][2];
+        if (live) {
+            slab_gather<kC, TS>(Hin, rowbytes_in, mptr, ment, E, b, e0, t0, acc);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int i = 0; i < G::NL; ++i) acc[k][i][0] = acc[k][i][1] = 0ull;
+        }
+        // fragments of every (term, k-step), split for 3xTF32, straight into TMEM: columns 32 term + 8 s .. + 7 of A_hi / A_lo
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+            float fr[G::KS][4];
+            slab_fragments<kC, TS>(acc[term], fr);
+#pragma unroll
+            for (int s = 0; s < G::KS; ++s) {
+                uint32_t ah[4], al[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) split_tf32(fr[s][q], ah[q], al[q]);
+                const uint32_t col = (uint32_t)(32 * term + 8 * s);
+                tc_st_16x128b_x2(tbase + kColsAhi + col + lane_base, ah[0], ah[1], ah[2], ah[3]);
+                tc_st_16x128b_x2(tbase + kColsAlo + col + lane_base, al[0], al[1], al[2], al[3]);
+            }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        group_barrier(group);                              // all 128 rows of A are in TMEM; every warp has drained D of the last tile
+        if (gw == 0 && lane == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {                 // K = 96 in steps of 8: two 16-byte k-chunks of B per step
+                const uint64_t dh = umma_desc(bhi + (uint32_t)j * 2 * kLbo), dl = umma_desc(blo + (uint32_t)j * 2 * kLbo);
+                umma_tf32_ts(tbase + kColsD, tbase + kColsAlo + 8 * j, dh, j > 0 ? 1u : 0u);
+                umma_tf32_ts(tbase + kColsD, tbase + kColsAhi + 8 * j, dl, 1u);
+                umma_tf32_ts(tbase + kColsD, tbase + kColsAhi + 8 * j, dh, 1u);
+            }
+            umma_commit(&s_bar[group]);
+        }
+        {
+            int spins = 0;
+            while (!mbar_try_wait(&s_bar[group], phase)) {
+                if (++spins > kSpinLimit) {
+                    *err = 1;
+                    break;
+                }
+            }
+        }
+        phase ^= 1u;
+        tc_fence_after();
+        float d[NT][4];
+        tc_ld_16x256b_x4(tbase + kColsD + lane_base, d);
+        tc_fence_before();                                 // (ordered before the next tile's group barrier -> before the next MMA writes D)
+        if (live) {
+            slab_activate<ACT, NT>(d);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                int e, t;
+                slab_row<kC, TS>(r, e0, t0, e, t);
+                if (e < E && t < b) {
+                    float* dst = Hout + (size_t)e * rowlen_out + (size_t)t * kC + 2 * tig;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+                        *reinterpret_cast<float2*>(dst + nt * 8) = make_float2(d[nt][2 * r], d[nt][2 * r + 1]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(kTmemCols));
+}
+
+int* g_umma_err = nullptr;
+
+}  // namespace
+
+bool scone_umma_supported(const scone_complex* cx, int cin, int cout, int b) {
+    return cx->d_mptr != nullptr && cin == 32 && cout == 32 && b % 16 == 0;
+}
+
+// Hout = act(Hin W0 + (S0 Hin) W1 + (S1 Hin) W2) over dense [E][b][32] tensors.  Returns 3 if the kernel reported a tcgen05 protocol
+// time-out on an earlier launch (checked lazily: the flag of the PREVIOUS launch is read, so the call itself stays asynchronous).
+int scone_umma_forward(const scone_complex* cx, int act, int b, const float* Hin, const float* W0, const float* W1, const float* W2,
+                       float* Hout, cudaStream_t st) {
+    if (!g_umma_err) {
+        SCONE_CUDA(cudaMalloc((void**)&g_umma_err, sizeof(int)));
+        SCONE_CUDA(cudaMemset(g_umma_err, 0, sizeof(int)));
+    }
+    const int n_ts = (b + 15) / 16;
+    const long long n_tiles = (long long)n_ts * ((cx->E + kGroupWarps - 1) / kGroupWarps);
+    const int grid = (int)(n_tiles < cx->num_sms ? n_tiles : cx->num_sms);
+    switch (act) {
+        case SCONE_ACT_TANH:
+            layer_fwd_umma_kernel<SCONE_ACT_TANH><<<grid, kUmmaThreads, 0, st>>>(Hin, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, cx->E, b, g_umma_err);
+            break;
+        case SCONE_ACT_LEAKY_RELU:
+            layer_fwd_umma_kernel<SCONE_ACT_LEAKY_RELU><<<grid, kUmmaThreads, 0, st>>>(Hin, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, cx->E, b, g_umma_err);
+            break;
+        case SCONE_ACT_RELU:
+            layer_fwd_umma_kernel<SCONE_ACT_RELU><<<grid, kUmmaThreads, 0, st>>>(Hin, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, cx->E, b, g_umma_err);
+            break;
+        default:
+            scone_set_error("unknown activation %d", act);
+            return 2;
+    }
+    SCONE_LAUNCHED();
+    return 0;
+}
+
+int scone_umma_check(cudaStream_t st) {
+    if (!g_umma_err) return 0;
+    int e = 0;
+    SCONE_CUDA(cudaMemcpyAsync(&e, g_umma_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SCONE_CUDA(cudaStreamSynchronize(st));
+    if (e) {
+        cudaMemset(g_umma_err, 0, sizeof(int));
+        scone_set_error("layer_fwd_umma_kernel: an mbarrier wait timed out (tcgen05 protocol error); results of that launch are invalid");
+        return 3;
+    }
+    return 0;
+}
