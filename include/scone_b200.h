@@ -241,7 +241,7 @@ int scone_model_set_weights_keep_state(scone_model* m, const float* weights_host
  * expanded cone edges (|T_2|), [3] hash slots of tier 1, [4] trajectories per arena chunk, [5] rows of the shared-memory row store, [6] / [7] KB of
  * dynamic shared memory of the tier-1 plan / the compute kernel, [8] / [9] hash slots / list entries of tier 0 (tables that hold the
  * cone of 99 % of the nodes), [10] its KB, [11] two tiers in use, [12] worst-case arena words per trajectory, [13] arena Mwords,
- * [14] tier-1 list entries, [15] rows of the per-CTA global row store. */
+ * [14] tier-1 list entries, [15] trajectories of the last chunk the first tier handed to the second (synchronises the device). */
 int scone_model_fused_info(const scone_model* m, int32_t* out /* [16] */);
 /* Plan of trajectory t of the LAST chunk run (synchronises the device): header (16 ints, layout in csrc/fused.cuh) and `words` 32-bit
  * words of the program arena from word offset `off` (either output may be NULL). */

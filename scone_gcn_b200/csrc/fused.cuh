@@ -17,8 +17,8 @@ struct FusedState {
     int L = 0, C = 0;
     int64_t n_params = 0;
     int bound_cone = 0, bound_list = 0;   // static bounds of the complex: cone edges |T_1| / expanded cone edges |T_2| of any last node
-    int HS = 0, LC = 0, LV = 0, hshift = 0;       // plan tables, tier 1: sized by the bounds
-    int HS0 = 0, LC0 = 0, LV0 = 0, hshift0 = 0;   // tier 0: sized for the cones of 99 % of the nodes
+    int HS = 0, LC = 0, LV = 0, EC = 0, hshift = 0;        // plan tables, tier 1: sized by the bounds
+    int HS0 = 0, LC0 = 0, LV0 = 0, EC0 = 0, hshift0 = 0;   // tier 0: sized for the cones of 99 % of the nodes
     bool two_tiers = false;
     int flow_room = 0;
     size_t plan_smem0 = 0;
@@ -43,4 +43,5 @@ void scone_fused_destroy(FusedState* f);
 int scone_fused_run(const scone_complex* cx, FusedState* f, int act, int b, const int32_t* traj_ptr, const int32_t* flow_edge,
                     const float* flow_val, const int32_t* last_nodes, const float* W, const int64_t* w_off, float* logprobs,
                     const int32_t* target_idx, const float* mask, float* grad, int* overflow, bool count_rows, cudaStream_t st);
+int scone_fused_last_retries(FusedState* f);
 int scone_fused_read(FusedState* f, int t, int* hdr_out, unsigned off, int words, uint32_t* arena_out);

@@ -21,6 +21,7 @@
 // arena is sized for the worst case.  A trajectory whose rows do not fit the shared-memory row store runs in the BIG variant of
 // the same kernel (rows in a per-CTA global scratch).
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "fused.cuh"
 
@@ -71,15 +72,15 @@ struct EdgeSet {
         }
         return -1;                                        // full (only possible in bound mode)
     }
-    __device__ __forceinline__ int find(int e) const {
+    __device__ __forceinline__ int find(int e) const {    // (the table always has empty slots: load <= 3/4)
         unsigned h = home(e);
-        for (int probes = 0; probes <= mask; ++probes) {
-            const int k = keys[h];
-            if (k == e) return (int)h;
+        int k = keys[h];
+        while (k != e) {
             if (k == -1) return -1;
             h = (h + 1) & mask;
+            k = keys[h];
         }
-        return -1;
+        return (int)h;
     }
 };
 
@@ -156,6 +157,7 @@ struct PlanArgs {
     int HS, hshift;            // hash slots (power of two): the flow edges and the cone T_1 of the trajectory
     int LC;                    // listed cone edges (levels >= 2: the ones that are expanded)
     int LV;                    // live rows per layer
+    int EC;                    // merged-row entries of the live rows of one layer (slot buffer)
     int* hdr;
     uint32_t* arena;
     unsigned long long* bump;
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(kPlanThreads) fused_bound_kernel(const int32_t
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// the plan of one trajectory (one CTA)
+// the plan of one trajectory (one CTA of THREADS threads)
 //
 //   hash set      flow edges (level 0, value x) and the receptive cone T_1 (level = highest cone level of the edge)
 //   cone          level L = edges incident to the neighbours of the last node; one merged-row hop further down per level; only the
@@ -241,22 +243,62 @@ __global__ void __launch_bounds__(kPlanThreads) fused_bound_kernel(const int32_t
 //                 i.e. iff it is in the merged row of a flow edge (the operators are symmetric); a row of layer l iff it is in T_l
 //                 and in the merged row of a live row of layer l - 1.  Cost follows the flows and the live rows, not the cone.
 //   rank          live rows of a layer are numbered by ascending edge id: the deterministic row order of every list
+//   one scan      the merged rows of the live rows of a layer are walked ONCE (global loads + hash lookups); the hash slot of every
+//                 entry is kept in shared memory (ebuf) and serves the layer's forward program (or the layer-1 scalars), the marking
+//                 of the next layer's live rows and the next layer's transposed program
 // ---------------------------------------------------------------------------------------------------------------------
+template <int THREADS>
+__device__ int block_scan_excl_t(int* a, int n, int* s_warp) {   // exclusive scan of a[0..n) in place (a[n] = total)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n + THREADS - 1) / THREADS;
+    const int lo = min(n, tid * per), hi = min(n, lo + per);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += a[i];
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    __syncthreads();                                      // (s_warp may still be read from a previous call)
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) {
+        const int v = s_warp[w];
+        if (w < warp) base += v;
+        total += v;
+    }
+    int run = base + inc - sum;
+    for (int i = lo; i < hi; ++i) {
+        const int v = a[i];
+        a[i] = run;
+        run += v;
+    }
+    if (tid == 0) a[n] = total;
+    __syncthreads();
+    return total;
+}
+
+template <int THREADS>
 __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, unsigned char* sm) {
-    const int HS = a.HS, LC = a.LC, LV = a.LV, L = a.L, D = a.D;
+    constexpr int QUADS = THREADS / 4;
+    const int HS = a.HS, LC = a.LC, LV = a.LV, EC = a.EC, L = a.L, D = a.D;
     int* keys = reinterpret_cast<int*>(sm);                          // [HS] internal edge id, -1 = empty
     float* xv = reinterpret_cast<float*>(keys + HS);                 // [HS] flow value of the edge
     int* lvl = reinterpret_cast<int*>(xv + HS);                      // [HS] bits 0-7: cone level (0 = flow edge outside the cone); bit 8 + l: marked live in layer l
-    uint16_t* idxA = reinterpret_cast<uint16_t*>(lvl + HS);          // [HS] row index of the edge in the live list of a layer (ping)
-    uint16_t* idxB = idxA + HS;                                      // [HS] (pong)
-    int* rowcnt = reinterpret_cast<int*>(idxB + HS);                 // [LV + 4] entries per ranked row -> exclusive scan
-    int* live_edge = rowcnt + LV + 4;                                // [LV] edge id of the k-th live row (unordered)
+    uint16_t* idx0 = reinterpret_cast<uint16_t*>(lvl + HS);          // [3][HS] row index of the edge in the live list of layer l: idx0 + (l % 3) * HS
+    int* rowcnt = reinterpret_cast<int*>(idx0 + 3 * HS);             // [LV + 4] entries per ranked row -> exclusive scan
+    int* erow = rowcnt + LV + 4;                                     // [LV + 4] start of the row's entries in ebuf
+    int* live_edge = erow + LV + 4;                                  // [LV] edge id of the k-th live row (unordered)
     uint16_t* live = reinterpret_cast<uint16_t*>(live_edge + LV);    // [LV] hash slot of the k-th live row (unordered)
     uint16_t* rankA = live + LV;                                     // [LV] hash slot of the row with rank r (ping)
     uint16_t* rankB = rankA + LV;                                    // [LV] (pong)
     uint16_t* list = rankB + LV;                                     // [LC] cone list: hash slots of the edges of levels >= 2
+    uint16_t* ebuf = list + LC;                                      // [EC] hash slot of every merged-row entry of the scanned rows
     __shared__ FuPairs pairs;
-    __shared__ int s_nlist, s_nhash, s_nlive, s_ovf, s_nat[kFusedMaxL + 2], s_warp[kPlanThreads / 32];
+    __shared__ int s_nlist, s_nhash, s_nlive, s_ovf, s_nat[kFusedMaxL + 2], s_warp[THREADS / 32];
     __shared__ unsigned s_piece;
 
     const int tid = threadIdx.x, lane = tid & 31, ql = tid & 3;
@@ -274,13 +316,12 @@ __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, 
             }
         }
     };
-    for (int i = tid; i < HS; i += kPlanThreads) {
+    for (int i = tid; i < HS; i += THREADS) {
         keys[i] = -1;
         xv[i] = 0.f;
         lvl[i] = 0;
-        idxA[i] = (uint16_t)kNoRow;
-        idxB[i] = (uint16_t)kNoRow;
     }
+    for (int i = tid; i < 3 * HS; i += THREADS) idx0[i] = (uint16_t)kNoRow;
     if (tid == 0) s_nlist = s_nhash = s_ovf = s_nlive = 0;
     const int last = a.last_nodes[t];
     const bool last_ok = last >= 0 && last < a.N;
@@ -325,7 +366,7 @@ __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, 
     const int fp0 = a.traj_ptr[t], fp1 = a.traj_ptr[t + 1];
 
     // ---- flows ----
-    for (int p = fp0 + tid; p < fp1; p += kPlanThreads) {
+    for (int p = fp0 + tid; p < fp1; p += THREADS) {
         const int eo = a.flow_edge[p];
         if (eo < 0 || eo >= a.E) continue;
         const int s = put(a.rank[eo]);
@@ -333,7 +374,7 @@ __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, 
     }
     __syncthreads();
     // ---- receptive cone ----
-    for (int i = tid; i < total_pairs; i += kPlanThreads) {
+    for (int i = tid; i < total_pairs; i += THREADS) {
         const int j = pairs.slot_of(i, D);
         add_cone(a.inc_ent[pairs.s_ptr[j] + (i - pairs.s_off[j])].x, L);
     }
@@ -344,7 +385,7 @@ __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, 
         int f0 = 0;
         for (int lv = L - 1; lv >= 1; --lv) {
             const int f1 = s_nat[lv + 1];
-            for (int i = f0 + (tid >> 2); i < f1; i += kPlanThreads / 4) {
+            for (int i = f0 + (tid >> 2); i < f1; i += QUADS) {
                 const int e = keys[list[i]];
                 const int p1 = a.mptr[e + 1];
                 for (int q = a.mptr[e] + ql; q < p1; q += 4) add_cone(a.ment[q].x, lv);
@@ -360,14 +401,14 @@ __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, 
         return;
     }
     // marks (once) the cone edge in slot s2 as a live row of layer l
-    auto mark = [&](int s2, int e2, int l) {
+    auto mark = [&](int s2, int l) {
         const int bit = 1 << (8 + l);
         const int old = atomicOr(&lvl[s2], bit);
         if (!(old & bit)) {
             const int k = atomicAdd(&s_nlive, 1);
             if (k < LV) {
                 live[k] = (uint16_t)s2;
-                live_edge[k] = e2;
+                live_edge[k] = keys[s2];
             } else {
                 s_ovf = 1;
             }
@@ -377,7 +418,7 @@ __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, 
     auto rank_live = [&](uint16_t* idx, uint16_t* byrank) -> int {
         __syncthreads();
         const int n = min(s_nlive, LV);
-        for (int k = tid; k < n; k += kPlanThreads) {
+        for (int k = tid; k < n; k += THREADS) {
             const int e = live_edge[k];
             int r = 0;
             for (int m = 0; m < n; ++m) r += live_edge[m] < e ? 1 : 0;
@@ -389,7 +430,7 @@ __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, 
     };
 
     // ---- layer 1: live rows = cone edges in the merged row of a flow edge with a non-zero value ----
-    for (int p = fp0 + (tid >> 2); p < fp1; p += kPlanThreads / 4) {
+    for (int p = fp0 + (tid >> 2); p < fp1; p += QUADS) {
         const int eo = a.flow_edge[p];
         if (eo < 0 || eo >= a.E) continue;                 // (same decision on the four lanes of the quad)
         const int e = a.rank[eo];
@@ -397,136 +438,159 @@ __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, 
         if (s < 0 || xv[s] == 0.f) continue;
         const int p1 = a.mptr[e + 1];
         for (int q = a.mptr[e] + ql; q < p1; q += 4) {
-            const int e2 = a.ment[q].x;
-            const int s2 = set.find(e2);
-            if (s2 >= 0 && (lvl[s2] & 0xFF) >= 1) mark(s2, e2, 1);
+            const int s2 = set.find(a.ment[q].x);
+            if (s2 >= 0 && (lvl[s2] & 0xFF) >= 1) mark(s2, 1);
         }
     }
-    uint16_t *ip = idxA, *ic = idxB, *rp = rankA, *rc = rankB;
-    int n_prev = rank_live(ip, rp);
+    uint16_t *rcur = rankA, *rnext = rankB;
+    int n_cur = rank_live(idx0 + 1 * HS, rcur);
     if (s_ovf) {
         give_up();
         return;
     }
     int n_l[kFusedMaxL + 1] = {0, 0, 0, 0};
     unsigned off_l1 = 0, off_f[kFusedMaxL + 1] = {0, 0, 0, 0}, off_b[kFusedMaxL + 1] = {0, 0, 0, 0};
-    n_l[1] = n_prev;
-    off_l1 = alloc(3 * n_prev);
-    if (!s_ovf) {                                          // the three exact scalars of each live row: x, (S0 x), (S1 x)
-        float* dst = reinterpret_cast<float*>(a.arena + off_l1);
-        for (int r = tid >> 2; r < n_prev; r += kPlanThreads / 4) {
-            const int slot = rp[r];
-            const int e = keys[slot];
-            float a1 = 0.f, a2 = 0.f;
-            const int p1 = a.mptr[e + 1];
-            for (int q = a.mptr[e] + ql; q < p1; q += 4) {
-                const int2 en = a.ment[q];
-                const int s2 = set.find(en.x);
-                const float x = s2 >= 0 ? xv[s2] : 0.f;
-                a1 = fmaf((float)(short)(en.y & 0xffff), x, a1);
-                a2 = fmaf((float)(en.y >> 16), x, a2);
-            }
-#pragma unroll
-            for (int o = 1; o < 4; o <<= 1) {
-                a1 += __shfl_xor_sync(qmask, a1, o);
-                a2 += __shfl_xor_sync(qmask, a2, o);
-            }
-            if (ql == 0) {
-                dst[3 * r + 0] = xv[slot];
-                dst[3 * r + 1] = a1;
-                dst[3 * r + 2] = a2;
-            }
-        }
-    }
-    __syncthreads();
 
-    // walks the merged row of edge e and counts / emits, in column order, the entries whose neighbour has a row in `idx`
-    auto count_row = [&](int e, const uint16_t* idx) -> int {
-        int c = 0;
-        const int p1 = a.mptr[e + 1];
-        for (int q = a.mptr[e] + ql; q < p1; q += 4) {
-            const int s2 = set.find(a.ment[q].x);
-            if (s2 >= 0 && idx[s2] != (uint16_t)kNoRow) ++c;
-        }
-        c += __shfl_xor_sync(qmask, c, 1);
-        c += __shfl_xor_sync(qmask, c, 2);
-        return c;
-    };
-    auto fill_row = [&](int e, const uint16_t* idx, int2* out, int base) {
-        const int p0 = a.mptr[e], p1 = a.mptr[e + 1];
-        for (int q0 = p0; q0 < p1; q0 += 4) {             // (uniform inside the quad)
-            const int q = q0 + ql;
-            int2 en = make_int2(0, 0);
-            uint32_t r = kNoRow;
-            if (q < p1) {
-                en = a.ment[q];
-                const int s2 = set.find(en.x);
-                if (s2 >= 0) r = idx[s2];
-            }
-            const bool valid = r != kNoRow;
-            const unsigned bits = (__ballot_sync(qmask, valid) >> (lane & ~3)) & 0xFu;
-            if (valid) out[base + __popc(bits & ((1u << ql) - 1u))] = make_int2((int)(r | (en.x == e ? 0x80000000u : 0u)), en.y);
-            base += __popc(bits);
-        }
-    };
-    // program of `n_rows` rows (slots byrank[r]) against the row indices `idx` of the other layer: rowptr + entries into the arena
+    // program of the n_cur scanned rows against the row indices `idx`: rowptr + entries {row | own << 31, coefficients} into the
+    // arena, entries in column order (count pass, scan, fill pass — all over the shared-memory slot buffer)
     auto emit_program = [&](const uint16_t* byrank, int n_rows, const uint16_t* idx) -> unsigned {
-        for (int r = tid >> 2; r < n_rows; r += kPlanThreads / 4) {
-            const int c = count_row(keys[byrank[r]], idx);
+        for (int r = tid >> 2; r < n_rows; r += QUADS) {
+            const int b0 = erow[r], b1 = erow[r + 1];
+            int c = 0;
+            for (int i = b0 + ql; i < b1; i += 4) {
+                const uint32_t s2 = ebuf[i];
+                if (s2 != kNoRow && idx[s2] != (uint16_t)kNoRow) ++c;
+            }
+            c += __shfl_xor_sync(qmask, c, 1);
+            c += __shfl_xor_sync(qmask, c, 2);
             if (ql == 0) rowcnt[r] = c;
         }
         __syncthreads();
-        const int total = block_scan_excl(rowcnt, n_rows, s_warp);
+        const int total = block_scan_excl_t<THREADS>(rowcnt, n_rows, s_warp);
         const unsigned off = alloc(align2(n_rows + 1) + 2 * total);
         if (!s_ovf) {
             int* pdst = reinterpret_cast<int*>(a.arena + off);
             int2* edst = reinterpret_cast<int2*>(a.arena + off + align2(n_rows + 1));
-            for (int r = tid; r <= n_rows; r += kPlanThreads) pdst[r] = rowcnt[r];
-            for (int r = tid >> 2; r < n_rows; r += kPlanThreads / 4) fill_row(keys[byrank[r]], idx, edst, rowcnt[r]);
+            for (int r = tid; r <= n_rows; r += THREADS) pdst[r] = rowcnt[r];
+            for (int r = tid >> 2; r < n_rows; r += QUADS) {
+                const int e = keys[byrank[r]];
+                const int p0 = a.mptr[e], b0 = erow[r], b1 = erow[r + 1];
+                int base = rowcnt[r];
+                for (int i0 = b0; i0 < b1; i0 += 4) {     // (uniform inside the quad)
+                    const int i = i0 + ql;
+                    uint32_t rr = kNoRow;
+                    if (i < b1) {
+                        const uint32_t s2 = ebuf[i];
+                        if (s2 != kNoRow) rr = idx[s2];
+                    }
+                    const bool valid = rr != kNoRow;
+                    const unsigned bits = (__ballot_sync(qmask, valid) >> (lane & ~3)) & 0xFu;
+                    if (valid) {
+                        const int2 en = a.ment[p0 + (i - b0)];
+                        edst[base + __popc(bits & ((1u << ql) - 1u))] = make_int2((int)(rr | (en.x == e ? 0x80000000u : 0u)), en.y);
+                    }
+                    base += __popc(bits);
+                }
+            }
         }
         __syncthreads();
         return off;
     };
 
-    for (int l = 2; l <= L; ++l) {
-        // live rows of layer l: cone edges of level >= l in the merged row of a live row of layer l - 1
-        if (tid == 0) s_nlive = 0;
+    for (int l = 1; l <= L; ++l) {
+        uint16_t* idx_prev = idx0 + ((l + 2) % 3) * HS;   // layer l - 1
+        uint16_t* idx_next = idx0 + ((l + 1) % 3) * HS;   // layer l + 1
+        n_l[l] = n_cur;
+        // ---- the one scan of the live rows of layer l: slot of every merged-row entry -> ebuf ----
+        for (int r = tid; r < n_cur; r += THREADS) {
+            const int e = keys[rcur[r]];
+            rowcnt[r] = a.mptr[e + 1] - a.mptr[e];
+        }
         __syncthreads();
-        for (int r = tid >> 2; r < n_prev; r += kPlanThreads / 4) {
-            const int e = keys[rp[r]];
-            const int p1 = a.mptr[e + 1];
-            for (int q = a.mptr[e] + ql; q < p1; q += 4) {
-                const int e2 = a.ment[q].x;
-                const int s2 = set.find(e2);
-                if (s2 >= 0 && (lvl[s2] & 0xFF) >= l) mark(s2, e2, l);
+        const int n_ent = block_scan_excl_t<THREADS>(rowcnt, n_cur, s_warp);
+        if (n_ent > EC) {                                  // (uniform) this tier's entry buffer is too small
+            if (tid == 0) s_ovf = 1;
+            __syncthreads();
+            break;
+        }
+        for (int r = tid; r <= n_cur; r += THREADS) erow[r] = rowcnt[r];
+        __syncthreads();
+        for (int r = tid >> 2; r < n_cur; r += QUADS) {
+            const int e = keys[rcur[r]];
+            const int p0 = a.mptr[e], b0 = erow[r], len = erow[r + 1] - b0;
+            for (int i = ql; i < len; i += 4) {
+                const int s2 = set.find(a.ment[p0 + i].x);
+                ebuf[b0 + i] = s2 >= 0 ? (uint16_t)s2 : (uint16_t)kNoRow;
             }
         }
-        const int nl = rank_live(ic, rc);
-        if (s_ovf) break;
-        n_l[l] = nl;
-        off_f[l] = emit_program(rc, nl, ip);               // forward: rows of layer l, entries = live rows of layer l - 1
-        off_b[l] = emit_program(rp, n_prev, ic);           // transposed: rows of layer l - 1, entries = live rows of layer l
-        uint16_t* tmp = ip; ip = ic; ic = tmp;
-        tmp = rp; rp = rc; rc = tmp;
-        for (int i = tid; i < HS; i += kPlanThreads) ic[i] = (uint16_t)kNoRow;
-        n_prev = nl;
         __syncthreads();
+        if (l == 1) {
+            // the three exact scalars of each live row: x, (S0 x), (S1 x)
+            off_l1 = alloc(3 * n_cur);
+            if (!s_ovf) {
+                float* dst = reinterpret_cast<float*>(a.arena + off_l1);
+                for (int r = tid >> 2; r < n_cur; r += QUADS) {
+                    const int slot = rcur[r];
+                    const int e = keys[slot];
+                    const int p0 = a.mptr[e], b0 = erow[r], len = erow[r + 1] - b0;
+                    float a1 = 0.f, a2 = 0.f;
+                    for (int i = ql; i < len; i += 4) {
+                        const uint32_t s2 = ebuf[b0 + i];
+                        const float x = s2 != kNoRow ? xv[s2] : 0.f;
+                        if (x != 0.f) {
+                            const int pk = a.ment[p0 + i].y;
+                            a1 = fmaf((float)(short)(pk & 0xffff), x, a1);
+                            a2 = fmaf((float)(pk >> 16), x, a2);
+                        }
+                    }
+#pragma unroll
+                    for (int o = 1; o < 4; o <<= 1) {
+                        a1 += __shfl_xor_sync(qmask, a1, o);
+                        a2 += __shfl_xor_sync(qmask, a2, o);
+                    }
+                    if (ql == 0) {
+                        dst[3 * r + 0] = xv[slot];
+                        dst[3 * r + 1] = a1;
+                        dst[3 * r + 2] = a2;
+                    }
+                }
+            }
+            __syncthreads();
+        } else {
+            off_f[l] = emit_program(rcur, n_cur, idx_prev);       // forward: rows of layer l, entries = live rows of layer l - 1
+        }
+        if (l == L) break;
+        // ---- live rows of layer l + 1: cone edges of level >= l + 1 among the scanned entries ----
+        if (tid == 0) s_nlive = 0;
+        for (int i = tid; i < HS; i += THREADS) idx_next[i] = (uint16_t)kNoRow;
+        __syncthreads();
+        for (int i = tid; i < n_ent; i += THREADS) {
+            const uint32_t s2 = ebuf[i];
+            if (s2 != kNoRow && (lvl[s2] & 0xFF) >= l + 1) mark((int)s2, l + 1);
+        }
+        const int n_next = rank_live(idx_next, rnext);
+        if (s_ovf) break;
+        off_b[l + 1] = emit_program(rcur, n_cur, idx_next);       // transposed program of layer l + 1: rows of layer l
+        uint16_t* tmp = rcur; rcur = rnext; rnext = tmp;
+        n_cur = n_next;
     }
+    __syncthreads();
     if (s_ovf == 1) {                                      // (uniform: s_ovf is only read after barriers)
         give_up();
         return;
     }
     // ---- readout pairs: {row of H_L | neighbour slot << 16, sign bits}; a pair whose edge has no live row keeps kNoRow ----
+    const uint16_t* idxL = idx0 + (L % 3) * HS;
     const unsigned off_ro = alloc(align2(D + 1) + 2 * total_pairs);
     if (!s_ovf) {
         int* pdst = reinterpret_cast<int*>(a.arena + off_ro);
         int2* edst = reinterpret_cast<int2*>(a.arena + off_ro + align2(D + 1));
-        for (int j = tid; j <= D; j += kPlanThreads) pdst[j] = pairs.s_off[j];
-        for (int i = tid; i < total_pairs; i += kPlanThreads) {
+        for (int j = tid; j <= D; j += THREADS) pdst[j] = pairs.s_off[j];
+        for (int i = tid; i < total_pairs; i += THREADS) {
             const int j = pairs.slot_of(i, D);
             const int2 es = a.inc_ent[pairs.s_ptr[j] + (i - pairs.s_off[j])];
             const int s = set.find(es.x);
-            const uint32_t r = s >= 0 ? (uint32_t)ip[s] : kNoRow;
+            const uint32_t r = s >= 0 ? (uint32_t)idxL[s] : kNoRow;
             edst[i] = make_int2((int)(r | ((uint32_t)j << 16)), es.y);
         }
     }
@@ -554,11 +618,12 @@ __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, 
     }
 }
 
-__global__ void __launch_bounds__(kPlanThreads) fused_plan_kernel(const PlanArgs a) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) fused_plan_kernel(const PlanArgs a) {
     extern __shared__ __align__(16) unsigned char sm[];
     const int n_work = a.tier == 0 ? a.n_work : *a.n_retry;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        plan_trajectory(a, a.tier == 0 ? w : a.retry[w], sm);
+        plan_trajectory<THREADS>(a, a.tier == 0 ? w : a.retry[w], sm);
         __syncthreads();
     }
 }
@@ -1003,7 +1068,9 @@ __global__ void __launch_bounds__(256) fused_reduce_kernel(const float* __restri
     out[i] += (s0 + s1) + (s2 + s3);
 }
 
-size_t plan_smem_bytes(int HS, int LC, int LV) { return (size_t)HS * 16 + (size_t)(LV + 4) * 4 + (size_t)LV * 10 + (size_t)LC * 2 + 16; }
+size_t plan_smem_bytes(int HS, int LC, int LV, int EC) {
+    return (size_t)HS * 18 + (size_t)(LV + 4) * 8 + (size_t)LV * 10 + (size_t)LC * 2 + (size_t)EC * 2 + 16;
+}
 
 template <int C>
 size_t traj_smem_bytes(int D, int cap_rows) {
@@ -1098,20 +1165,33 @@ int scone_fused_create(const scone_complex* cx, int L, int C, int mb, int64_t n_
         f->bound_cone = st[0] > 0 ? st[0] : 1;
         f->bound_list = st[1] > 0 ? st[1] : 1;
     }
-    // tier 1 (the cone cannot overflow it): tables from the bounds + room for kFlowRoom flow entries per trajectory.  tier 0: tables
-    // that hold the cone of 99 % of the nodes (a few hull / hole boundary nodes of a Delaunay complex have cones ten times the typical
-    // size; sizing every CTA for them costs the occupancy the latency-bound plan kernel lives on)
-    constexpr int kFlowRoomMin = 1024, kFlowRoom = 4096, kFlowRoom0 = 320;
+    int max_row = 1;
+    {
+        std::vector<int32_t> mp((size_t)cx->E + 1);
+        SCONE_CUDA(cudaMemcpy(mp.data(), cx->d_mptr, mp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        for (int e = 0; e < cx->E; ++e) max_row = std::max(max_row, mp[e + 1] - mp[e]);
+    }
+    // tier 1 (the cone cannot overflow it; 1024 threads per trajectory): tables from the bounds + room for kFlowRoom flow entries per
+    // trajectory, slot buffer for every merged-row entry of a full layer.  tier 0 (256 threads): tables that hold the cone of 99 % of
+    // the nodes (a few hull / hole boundary nodes of a Delaunay complex have cones ten times the typical size; sizing every CTA for
+    // them costs the occupancy the plan kernel lives on)
+    constexpr int kFlowRoom = 512, kFlowRoom0 = 320, kMaxPlanSmem = 200 * 1024;
     f->LC = (f->bound_list + 63) & ~63;
     f->LV = (f->bound_cone + 63) & ~63;
-    table_shape(f->bound_cone + kFlowRoomMin, &f->HS, &f->hshift);
-    while ((f->HS * 3) / 4 < f->bound_cone + kFlowRoom && plan_smem_bytes(2 * f->HS, f->LC, f->LV) <= 200 * 1024) {
-        f->HS *= 2;
-        --f->hshift;
-    }
+    table_shape(f->bound_cone + kFlowRoom, &f->HS, &f->hshift);
     f->flow_room = (f->HS * 3) / 4 - f->bound_cone;       // flow entries per trajectory tier 1 is guaranteed to hold
-    f->plan_smem = plan_smem_bytes(f->HS, f->LC, f->LV);
-    if (f->plan_smem > 200 * 1024 || f->bound_cone >= 0xFFFF) {
+    // slot buffer: every merged-row entry of the live rows of one layer.  The worst case (every cone edge live, every row of maximum
+    // length) rarely fits next to the tables; the buffer then takes what is left of the shared-memory budget (tens of thousands of
+    // entries against a few thousand for the largest trajectories seen) and a layer beyond it is reported through the overflow flag
+    f->EC = (int)std::min<long long>((long long)f->bound_cone * max_row, 1ll << 30);
+    f->EC = (f->EC + 63) & ~63;
+    {
+        const size_t fixed = plan_smem_bytes(f->HS, f->LC, f->LV, 0);
+        if (fixed + 2 * (size_t)f->EC > (size_t)kMaxPlanSmem && fixed + 2 * 16384 <= (size_t)kMaxPlanSmem)
+            f->EC = (int)(((size_t)kMaxPlanSmem - fixed) / 2) & ~63;
+    }
+    f->plan_smem = plan_smem_bytes(f->HS, f->LC, f->LV, f->EC);
+    if (f->plan_smem > (size_t)kMaxPlanSmem || f->bound_cone >= 0xFFFF || f->HS > 32768) {
         scone_fused_destroy(f);
         return 0;
     }
@@ -1126,20 +1206,38 @@ int scone_fused_create(const scone_complex* cx, int L, int C, int mb, int64_t n_
         };
         const int q0 = std::min(quantile(&st[4]), f->bound_cone), q1 = std::min(quantile(&st[4 + kBoundBuckets]), f->bound_list);
         table_shape(q0 + kFlowRoom0, &f->HS0, &f->hshift0);
-        f->LC0 = std::min((q1 + 63) & ~63, f->LC);
-        f->LV0 = std::min(256, f->LV);
+        // (measured on the 1M-edge bench complex, tools/sweep_plan_tiers.sh: the expanded-edge list overflows first — trajectories end
+        // on better-connected nodes than the average node — so the list gets twice the quantile; 192 live rows / 3072 entries per layer
+        // hold all but the trajectories the compute kernel sends to its big variant anyway)
+        f->LC0 = std::min(std::max(2 * ((q1 + 63) & ~63), 256), f->LC);
+        f->LV0 = std::min(192, f->LV);
+        f->EC0 = std::min(3072, f->EC);
         if (f->HS0 >= f->HS) {                             // one tier is enough
             f->HS0 = f->HS;
             f->LC0 = f->LC;
             f->LV0 = f->LV;
+            f->EC0 = f->EC;
             f->hshift0 = f->hshift;
             f->two_tiers = false;
         } else {
             f->two_tiers = true;
         }
-        f->plan_smem0 = plan_smem_bytes(f->HS0, f->LC0, f->LV0);
+        // tuning overrides (profiling experiments): SCONE_FUSED_HS0 / _LV0 / _EC0 / _LC0
+        auto env_int = [](const char* name, int dflt) {
+            const char* v = getenv(name);
+            return v && *v ? atoi(v) : dflt;
+        };
+        if (f->two_tiers) {
+            const int hs0 = env_int("SCONE_FUSED_HS0", f->HS0);
+            if (hs0 != f->HS0 && hs0 >= 256 && hs0 <= f->HS && (hs0 & (hs0 - 1)) == 0) table_shape((hs0 * 3) / 4 - 1, &f->HS0, &f->hshift0);
+            f->LV0 = std::min(env_int("SCONE_FUSED_LV0", f->LV0), f->LV);
+            f->EC0 = std::min(env_int("SCONE_FUSED_EC0", f->EC0), f->EC);
+            f->LC0 = std::min(env_int("SCONE_FUSED_LC0", f->LC0), f->LC);
+        }
+        f->plan_smem0 = plan_smem_bytes(f->HS0, f->LC0, f->LV0, f->EC0);
     }
-    SCONE_CUDA(cudaFuncSetAttribute(fused_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->plan_smem));
+    SCONE_CUDA(cudaFuncSetAttribute(fused_plan_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPlanSmem));
+    SCONE_CUDA(cudaFuncSetAttribute(fused_plan_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPlanSmem));
     // ---- compute kernel: shared-memory row store of the small variant, per-CTA global row store of the big one ----
     const int ldh = C + 8;
     f->cap_rows = C == 32 ? 192 : 384;
@@ -1153,7 +1251,7 @@ int scone_fused_create(const scone_complex* cx, int L, int C, int mb, int64_t n_
         f->traj_smem_small = C == 32 ? traj_smem_bytes<32>(cx->D, f->cap_rows) : traj_smem_bytes<16>(cx->D, f->cap_rows);
     }
     f->grid_small = 2 * cx->num_sms;
-    f->grid_big = f->big_rows > f->cap_rows ? cx->num_sms : 0;   // (every trajectory fits the shared-memory store otherwise)
+    f->grid_big = f->big_rows > f->cap_rows ? 2 * cx->num_sms : 0;   // (every trajectory fits the shared-memory store otherwise)
     if (f->grid_big) {
         f->scratch_stride = (size_t)f->big_rows * ldh;
         SCONE_CUDA(cudaMalloc((void**)&f->d_scratch, (size_t)f->grid_big * f->scratch_stride * sizeof(float)));
@@ -1162,12 +1260,6 @@ int scone_fused_create(const scone_complex* cx, int L, int C, int mb, int64_t n_
     // ---- program arena.  Worst case per trajectory from the bounds (every row of every layer live, every merged-row entry kept).
     // The arena holds min(worst * chunk, 4 GB): when the worst case fits, it cannot overflow; otherwise it is exhausted only if the
     // AVERAGE program of a chunk exceeds 64 KB (typical: 5 - 10 KB), which the plan kernel reports through the overflow flag. ----
-    int max_row = 1;
-    {
-        std::vector<int32_t> mp((size_t)cx->E + 1);
-        SCONE_CUDA(cudaMemcpy(mp.data(), cx->d_mptr, mp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-        for (int e = 0; e < cx->E; ++e) max_row = std::max(max_row, mp[e + 1] - mp[e]);
-    }
     const unsigned long long bc = (unsigned long long)f->bound_cone, bl = (unsigned long long)f->bound_list;
     unsigned long long worst = 3 * bc + 2 + (unsigned long long)(cx->D + 3) + 2ull * cx->D * cx->D + 16;   // (a neighbour has at most D incident edges)
     for (int l = 2; l <= L; ++l)                            // layer l: n_l <= |T_2| rows; the two programs hold the same entries
@@ -1204,16 +1296,20 @@ int scone_fused_run(const scone_complex* cx, FusedState* f, int act, int b, cons
     p.traj_ptr = traj_ptr; p.flow_edge = flow_edge; p.flow_val = flow_val; p.last_nodes = last_nodes;
     p.rank = cx->d_rank; p.nbrhoods = cx->d_nbrhoods; p.inc_ptr = cx->d_inc_ptr; p.inc_ent = cx->d_inc_ent;
     p.mptr = cx->d_mptr; p.ment = cx->d_ment;
-    p.N = cx->N; p.D = cx->D; p.E = cx->E; p.L = f->L; p.HS = f->HS0; p.LC = f->LC0; p.LV = f->LV0; p.hshift = f->hshift0;
+    p.N = cx->N; p.D = cx->D; p.E = cx->E; p.L = f->L; p.HS = f->HS0; p.LC = f->LC0; p.LV = f->LV0; p.EC = f->EC0; p.hshift = f->hshift0;
     p.hdr = f->d_hdr; p.arena = f->d_arena; p.bump = f->d_bump; p.arena_words = f->arena_words; p.overflow = overflow;
     p.tier = 0; p.n_work = b; p.n_retry = reinterpret_cast<int*>(f->d_bump + 1); p.retry = f->two_tiers ? f->d_retry : nullptr;
     {
         ScopedProf prof(SCONE_K_CONE, st);
-        fused_plan_kernel<<<b, kPlanThreads, f->plan_smem0, st>>>(p);
-        SCONE_LAUNCHED();
-        if (f->two_tiers) {                                // the few trajectories whose cone overflowed the first tier's tables
-            p.tier = 1; p.HS = f->HS; p.LC = f->LC; p.LV = f->LV; p.hshift = f->hshift; p.retry = f->d_retry;
-            fused_plan_kernel<<<std::min(b, cx->num_sms), kPlanThreads, f->plan_smem, st>>>(p);
+        if (f->two_tiers) {
+            fused_plan_kernel<256><<<b, 256, f->plan_smem0, st>>>(p);
+            SCONE_LAUNCHED();
+            // the few trajectories whose cone overflowed the first tier's tables: 1024 threads each
+            p.tier = 1; p.HS = f->HS; p.LC = f->LC; p.LV = f->LV; p.EC = f->EC; p.hshift = f->hshift; p.retry = f->d_retry;
+            fused_plan_kernel<1024><<<std::min(b, cx->num_sms), 1024, f->plan_smem, st>>>(p);
+            SCONE_LAUNCHED();
+        } else {
+            fused_plan_kernel<256><<<b, 256, f->plan_smem0, st>>>(p);
             SCONE_LAUNCHED();
         }
     }
@@ -1245,6 +1341,13 @@ int scone_fused_run(const scone_complex* cx, FusedState* f, int act, int b, cons
 }
 
 // debug / test access: header of trajectory t of the last chunk and `words` arena words from word offset `off`
+int scone_fused_last_retries(FusedState* f) {
+    unsigned long long v[2] = {0, 0};
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpy(v, f->d_bump, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int)(v[1] & 0xffffffffull);
+}
+
 int scone_fused_read(FusedState* f, int t, int* hdr_out, unsigned off, int words, uint32_t* arena_out) {
     SCONE_CUDA(cudaDeviceSynchronize());
     if (hdr_out) SCONE_CUDA(cudaMemcpy(hdr_out, f->d_hdr + (size_t)t * kFusedHdrW, kFusedHdrW * sizeof(int), cudaMemcpyDeviceToHost));

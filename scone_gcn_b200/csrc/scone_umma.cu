@@ -24,7 +24,7 @@ namespace {
 
 #include "slab_common.cuh"
 
-constexpr int kUmmaWarps = 16, kUmmaThreads = kUmmaWarps * 32, kGroupWarps = 8;
+constexpr int kGatherWarps = 16, kGroupWarps = 8, kUmmaThreads = (kGatherWarps + 1) * 32;      // + one MMA-issuing warp
 constexpr int kC = 32;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColsAhi = 0, kColsAlo = 96, kColsD = 192, kColsGroup = 224;
@@ -55,6 +55,9 @@ __device__ __forceinline__ void tc_ld_16x256b_x4(uint32_t taddr, float (&d)[4][4
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
@@ -62,6 +65,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
                  : "r"(smem_u32(bar)), "r"(parity)
                  : "memory");
     return ok != 0;
+}
+// bounded wait: a protocol error sets *err and lets the kernel run on instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err) {
+    int spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > kSpinLimit) {
+            *err = 1;
+            break;
+        }
+    }
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -77,10 +90,14 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {       // no-swiz
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((kLbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((kSbo >> 4) & 0x3FFF) << 32) |
            ((uint64_t)1 << 46);
 }
-__device__ __forceinline__ void group_barrier(int group) {
-    asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(kGroupWarps * 32) : "memory");
-}
 
+// Pipeline.  16 gather warps in two groups of 8 (group = one 128-row MMA tile = 8 consecutive edges x 16 trajectories) + 1 MMA warp.
+//   gather warp, per iteration:   [gather slab i+1 into registers]  while the tensor core works on tile i
+//                                 wait D_full(i) -> tcgen05.ld -> activation -> store          (its 16 rows of tile i)
+//                                 split + tcgen05.st slab i+1 into TMEM -> arrive on A_full    (8 arrivals complete a tile)
+//   MMA warp, per iteration and group:  wait A_full -> 36 tcgen05.mma -> tcgen05.commit -> D_full
+// D may be overwritten by tile i+1 only after all 8 warps read tile i: they arrive on A_full(i+1) after their tcgen05.ld completed.
+// A may be overwritten by slab i+1 only after the MMAs of tile i finished: the warp waited on D_full(i) first.
 template <int ACT>
 __global__ void __launch_bounds__(kUmmaThreads, 1) layer_fwd_umma_kernel(const float* __restrict__ Hin, float* __restrict__ Hout,
                                                                         const float* __restrict__ W0, const float* __restrict__ W1,
@@ -92,18 +109,19 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) layer_fwd_umma_kernel(const f
     // B operand: [hi | lo][k-chunk 24][n-group 4][8 rows][4 floats]; element (n, k) of the stacked weights, k = 32 term + 8 s + kappa
     // <-> input channel chan(s, kappa) of W_term (the k order of the gather's fragments)
     __shared__ __align__(128) float Bs[2][24 * 4 * 32];
-    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ __align__(8) uint64_t s_afull[2], s_dfull[2];
     __shared__ uint32_t s_tmem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tig = lane & 3;
-    const int group = warp / kGroupWarps, gw = warp % kGroupWarps;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (threadIdx.x == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+        mbar_init(&s_afull[0], kGroupWarps);
+        mbar_init(&s_afull[1], kGroupWarps);
+        mbar_init(&s_dfull[0], 1);
+        mbar_init(&s_dfull[1], 1);
     }
     for (int i = threadIdx.x; i < 96 * kC; i += kUmmaThreads) {
         const int k = i / kC, n = i % kC;
@@ -120,86 +138,113 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) layer_fwd_umma_kernel(const f
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tbase = s_tmem + (uint32_t)group * kColsGroup;
-    const uint32_t lane_base = (uint32_t)(32 * (gw & 3) + 16 * (gw >> 2)) << 16;       // this warp's 16 TMEM lanes of the tile
-    const uint32_t bhi = smem_u32(&Bs[0][0]), blo = smem_u32(&Bs[1][0]);
 
-    const unsigned rowbytes_in = (unsigned)b * kC * 4u;
-    const size_t rowlen_out = (size_t)b * kC;
     const int n_ts = (b + TS - 1) / TS;
-    const int tiles_per_ts = (E + kGroupWarps - 1) / kGroupWarps;        // a tile = 8 consecutive edges x one slab of 16 trajectories
+    const int tiles_per_ts = (E + kGatherWarps - 1) / kGatherWarps;      // a CTA tile = 16 consecutive edges x one slab of 16 trajectories
     const long long n_tiles = (long long)n_ts * tiles_per_ts;
     const long long per = (n_tiles + gridDim.x - 1) / gridDim.x;
     const long long lo = (long long)blockIdx.x * per, hi = lo + per < n_tiles ? lo + per : n_tiles;
-    uint32_t phase = 0;
-    for (long long tile = lo + group; tile < hi; tile += 2) {
-        const int ts = (int)(tile / tiles_per_ts);
-        const int e0 = (int)(tile - (long long)ts * tiles_per_ts) * kGroupWarps + gw, t0 = ts * TS;
-        const bool live = e0 < E;                          // (a dead slab still takes part in the barriers; its rows are never stored)
-        u64 acc[3][G::NL][2];
-        if (live) {
-            slab_gather<kC, TS>(Hin, rowbytes_in, mptr, ment, E, b, e0, t0, acc);
-        } else {
+
+    if (warp == kGatherWarps) {
+        // ---- MMA warp ----
+        const uint32_t bhi = smem_u32(&Bs[0][0]), blo = smem_u32(&Bs[1][0]);
+        uint32_t phase = 0;
+        for (long long tile = lo; tile < hi; ++tile) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
+            for (int group = 0; group < 2; ++group) {
+                mbar_wait(&s_afull[group], phase, err);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t tbase = s_tmem + (uint32_t)group * kColsGroup;
 #pragma unroll
-                for (int i = 0; i < G::NL; ++i) acc[k][i][0] = acc[k][i][1] = 0ull;
-        }
-        // fragments of every (term, k-step), split for 3xTF32, straight into TMEM: columns 32 term + 8 s .. + 7 of A_hi / A_lo
-#pragma unroll
-        for (int term = 0; term < 3; ++term) {
-            float fr[G::KS][4];
-            slab_fragments<kC, TS>(acc[term], fr);
-#pragma unroll
-            for (int s = 0; s < G::KS; ++s) {
-                uint32_t ah[4], al[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) split_tf32(fr[s][q], ah[q], al[q]);
-                const uint32_t col = (uint32_t)(32 * term + 8 * s);
-                tc_st_16x128b_x2(tbase + kColsAhi + col + lane_base, ah[0], ah[1], ah[2], ah[3]);
-                tc_st_16x128b_x2(tbase + kColsAlo + col + lane_base, al[0], al[1], al[2], al[3]);
+                    for (int j = 0; j < 12; ++j) {         // K = 96 in steps of 8: two 16-byte k-chunks of B per step
+                        const uint64_t dh = umma_desc(bhi + (uint32_t)j * 2 * kLbo), dl = umma_desc(blo + (uint32_t)j * 2 * kLbo);
+                        umma_tf32_ts(tbase + kColsD, tbase + kColsAlo + 8 * j, dh, j > 0 ? 1u : 0u);
+                        umma_tf32_ts(tbase + kColsD, tbase + kColsAhi + 8 * j, dl, 1u);
+                        umma_tf32_ts(tbase + kColsD, tbase + kColsAhi + 8 * j, dh, 1u);
+                    }
+                    umma_commit(&s_dfull[group]);
+                }
+                __syncwarp();
             }
+            phase ^= 1u;
         }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        group_barrier(group);                              // all 128 rows of A are in TMEM; every warp has drained D of the last tile
-        if (gw == 0 && lane == 0) {
-            tc_fence_after();
+    } else {
+        // ---- gather warps ----
+        const int group = warp / kGroupWarps, gw = warp % kGroupWarps;
+        const uint32_t tbase = s_tmem + (uint32_t)group * kColsGroup;
+        const uint32_t lane_base = (uint32_t)(32 * (gw & 3) + 16 * (gw >> 2)) << 16;   // this warp's 16 TMEM lanes of the tile
+        const unsigned rowbytes_in = (unsigned)b * kC * 4u;
+        const size_t rowlen_out = (size_t)b * kC;
+        uint32_t phase = 0;
+        int pe0 = 0, pt0 = 0;                              // slab whose product is in flight
+        bool pending = false, plive = false;
+        for (long long tile = lo; tile <= hi; ++tile) {
+            const bool have = tile < hi;
+            int e0 = 0, t0 = 0;
+            bool live = false;
+            u64 acc[3][G::NL][2];
+            if (have) {
+                const int ts = (int)(tile / tiles_per_ts);
+                e0 = (int)(tile - (long long)ts * tiles_per_ts) * kGatherWarps + warp;
+                t0 = ts * TS;
+                live = e0 < E;                             // (a dead slab still takes part in the barriers; its rows are never stored)
+                if (live) {
+                    slab_gather<kC, TS>(Hin, rowbytes_in, mptr, ment, E, b, e0, t0, acc);
+                } else {
 #pragma unroll
-            for (int j = 0; j < 12; ++j) {                 // K = 96 in steps of 8: two 16-byte k-chunks of B per step
-                const uint64_t dh = umma_desc(bhi + (uint32_t)j * 2 * kLbo), dl = umma_desc(blo + (uint32_t)j * 2 * kLbo);
-                umma_tf32_ts(tbase + kColsD, tbase + kColsAlo + 8 * j, dh, j > 0 ? 1u : 0u);
-                umma_tf32_ts(tbase + kColsD, tbase + kColsAhi + 8 * j, dl, 1u);
-                umma_tf32_ts(tbase + kColsD, tbase + kColsAhi + 8 * j, dh, 1u);
-            }
-            umma_commit(&s_bar[group]);
-        }
-        {
-            int spins = 0;
-            while (!mbar_try_wait(&s_bar[group], phase)) {
-                if (++spins > kSpinLimit) {
-                    *err = 1;
-                    break;
+                    for (int k = 0; k < 3; ++k)
+#pragma unroll
+                        for (int i = 0; i < G::NL; ++i) acc[k][i][0] = acc[k][i][1] = 0ull;
                 }
             }
-        }
-        phase ^= 1u;
-        tc_fence_after();
-        float d[NT][4];
-        tc_ld_16x256b_x4(tbase + kColsD + lane_base, d);
-        tc_fence_before();                                 // (ordered before the next tile's group barrier -> before the next MMA writes D)
-        if (live) {
-            slab_activate<ACT, NT>(d);
+            if (pending) {                                 // epilogue of the previous slab: its tile has been in the tensor core meanwhile
+                mbar_wait(&s_dfull[group], phase, err);
+                phase ^= 1u;
+                tc_fence_after();
+                float d[NT][4];
+                tc_ld_16x256b_x4(tbase + kColsD + lane_base, d);
+                if (plive) {
+                    slab_activate<ACT, NT>(d);
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                int e, t;
-                slab_row<kC, TS>(r, e0, t0, e, t);
-                if (e < E && t < b) {
-                    float* dst = Hout + (size_t)e * rowlen_out + (size_t)t * kC + 2 * tig;
+                    for (int r = 0; r < 2; ++r) {
+                        int e, t;
+                        slab_row<kC, TS>(r, pe0, pt0, e, t);
+                        if (e < E && t < b) {
+                            float* dst = Hout + (size_t)e * rowlen_out + (size_t)t * kC + 2 * tig;
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt)
-                        *reinterpret_cast<float2*>(dst + nt * 8) = make_float2(d[nt][2 * r], d[nt][2 * r + 1]);
+                            for (int nt = 0; nt < NT; ++nt)
+                                *reinterpret_cast<float2*>(dst + nt * 8) = make_float2(d[nt][2 * r], d[nt][2 * r + 1]);
+                        }
+                    }
                 }
+            }
+            if (have) {
+                // fragments of every (term, k-step), split for 3xTF32, straight into TMEM: columns 32 term + 8 s .. + 7 of A_hi / A_lo
+#pragma unroll
+                for (int term = 0; term < 3; ++term) {
+                    float fr[G::KS][4];
+                    slab_fragments<kC, TS>(acc[term], fr);
+#pragma unroll
+                    for (int s = 0; s < G::KS; ++s) {
+                        uint32_t ah[4], al[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) split_tf32(fr[s][q], ah[q], al[q]);
+                        const uint32_t col = (uint32_t)(32 * term + 8 * s);
+                        tc_st_16x128b_x2(tbase + kColsAhi + col + lane_base, ah[0], ah[1], ah[2], ah[3]);
+                        tc_st_16x128b_x2(tbase + kColsAlo + col + lane_base, al[0], al[1], al[2], al[3]);
+                    }
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_afull[group]);
+                pending = true;
+                plive = live;
+                pe0 = e0;
+                pt0 = t0;
+            } else {
+                pending = false;
             }
         }
     }
@@ -225,7 +270,7 @@ int scone_umma_forward(const scone_complex* cx, int act, int b, const float* Hin
         SCONE_CUDA(cudaMemset(g_umma_err, 0, sizeof(int)));
     }
     const int n_ts = (b + 15) / 16;
-    const long long n_tiles = (long long)n_ts * ((cx->E + kGroupWarps - 1) / kGroupWarps);
+    const long long n_tiles = (long long)n_ts * ((cx->E + kGatherWarps - 1) / kGatherWarps);
     const int grid = (int)(n_tiles < cx->num_sms ? n_tiles : cx->num_sms);
     switch (act) {
         case SCONE_ACT_TANH:
