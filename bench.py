@@ -448,6 +448,32 @@ def main():
                                'neither by HBM.  The contracted dense-tile figure is roofline_dense.',
                 'pipeline': PIPELINES.get(pipeline_id, str(pipeline_id))}
 
+    # ---- epoch >= 2 of a training run: the batch's plans are already on the device (weight-independent: Scone_GCN.train plans its
+    # dataset once, scone_model_plan_*), a step runs only the compute kernel + reduce (+ all-reduce) + Adam.  Reported next to
+    # `value`, never instead of it: `value` plans every step. ----
+    plans_cached = None
+    if pipeline_id == 4:
+        _lib.check(L.scone_model_plan_dev(net.handle, B, _lib.dptr(d['ptr']), _lib.dptr(d['edge']), _lib.dptr(d['val']), _lib.dptr(d['last']), stream))
+
+        def step_planned():
+            _lib.check(L.scone_model_loss_grad_planned_dev(net.handle, B, None, _lib.dptr(d['tgt']), _lib.dptr(d['mask']), 1, stream))
+            if world > 1:
+                dist.all_reduce(gbuf)
+            net.adam_step(step_no[0], lr, wd, stream)
+            step_no[0] += 1
+        for _ in range(3):
+            step_planned()
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            step_planned()
+        ev1.record()
+        barrier()
+        pc_ms = max_over_ranks(ev0.elapsed_time(ev1))
+        plans_cached = {'value': gb * args.steps / (pc_ms / 1e3), 'unit': 'trajectories/s', 'ms_per_step': pc_ms / args.steps, 'steps': args.steps,
+                        'note': 'the same step with the plans of the batch kept from an earlier step (a dataset revisited every epoch is planned '
+                                'once); compute kernel + partial reduce + Adam only'}
+
     # ---- end to end through the host API ----
     barrier()
     e2e_steps = max(1, args.e2e_steps)
@@ -513,7 +539,7 @@ def main():
                           'l2_policy': l2_policy, 'generator_seed': 1030, 'mean_flow_nnz': nnz / B,
                           'trajectories': ('prefixes of %d BEGIN->A->B->END walks cut at %d random points each' % (-(-gb // cfg['cuts']), cfg['cuts']))
                           if cfg['n_nodes'] > 1000 else 'the reference generator\'s 1000 trajectories (tests/golden/dataset_default.npz)'},
-               'roofline': roofline, 'roofline_dense': roofline_dense, 'e2e': e2e,
+               'roofline': roofline, 'roofline_dense': roofline_dense, 'plans_cached': plans_cached, 'e2e': e2e,
                'cpu_baseline': cpu_baseline, 'parity_check': parity, 'gpu_launches': int(launches),
                'clocks': clk, 'setup_s': setup_s, 'fused_info': info}
         print(json.dumps(out), flush=True)

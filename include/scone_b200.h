@@ -229,6 +229,21 @@ int scone_model_read_grads(scone_model* m, float* out_host, void* stream);
  *   g = grads / count + 2 * weight_decay * W ;  m,v update ;  W -= lr * mhat / (sqrt(vhat) + eps)
  * step = 0-based iteration index i. */
 int scone_model_adam_step(scone_model* m, int32_t step, float lr, float weight_decay, void* stream);
+/* Planned sets (pipeline 4).  The plan of a trajectory — receptive cone, live rows, gather programs — depends on the complex, the
+ * flows and the last node, not on the weights: a dataset that is revisited every epoch (Scone_GCN.train samples its batches from the
+ * same N trajectories for `epochs` epochs, scone_trajectory_model.py:318-322) is planned ONCE and every step runs only the compute
+ * kernel on the rows of its batch.  scone_model_plan_* builds and keeps the plan of B trajectories (replacing the previous set);
+ * *_planned_* take rows[n] = indices into that set (NULL = its first n trajectories), target_idx / mask / logprobs indexed by batch
+ * position.  Same results as the unplanned entry points, bit for bit (the same kernels on the same programs). */
+int scone_model_plan_host(scone_model* m, int32_t B, const int32_t* traj_ptr, const int32_t* flow_edge, const float* flow_val,
+                          const int32_t* last_nodes, void* stream);
+int scone_model_plan_dev(scone_model* m, int32_t B, const int32_t* traj_ptr_dev, const int32_t* flow_edge_dev, const float* flow_val_dev,
+                         const int32_t* last_nodes_dev, void* stream);
+int scone_model_loss_grad_planned_host(scone_model* m, int32_t n, const int32_t* rows, const int32_t* target_idx, const float* mask,
+                                       int32_t zero_first, void* stream);
+int scone_model_loss_grad_planned_dev(scone_model* m, int32_t n, const int32_t* rows_dev, const int32_t* target_idx_dev, const float* mask_dev,
+                                      int32_t zero_first, void* stream);
+int scone_model_forward_planned_host(scone_model* m, int32_t n, const int32_t* rows, float* logprobs_out /* [n][D] */, void* stream);
 /* Capacity overflow (pipelines 2 / 3 only; pipeline 4 and the dense pipelines cannot overflow): a micro-batch whose row lists exceed
  * their capacity sets a device flag.  While the flag is set scone_model_adam_step leaves the weights and the Adam state untouched (the
  * gradients are truncated).  The flag is REPORTED (error code 4) and cleared by scone_model_read_grads, scone_model_forward_host,

@@ -82,6 +82,11 @@ SIGNATURES = {
     'scone_model_two_target_host': (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp]),
     'scone_model_adam_step': (C.c_int, [_vp, _i32, _f32, _f32, _vp]),
     'scone_model_check_overflow': (C.c_int, [_vp, _vp]),
+    'scone_model_plan_host': (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    'scone_model_plan_dev': (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    'scone_model_loss_grad_planned_host': (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _vp]),
+    'scone_model_loss_grad_planned_dev': (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _vp]),
+    'scone_model_forward_planned_host': (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
     'scone_model_set_weights_keep_state': (C.c_int, [_vp, _vp, _vp]),
     'scone_model_fused_info': (C.c_int, [_vp, _vp]),
     'scone_model_fused_read': (C.c_int, [_vp, _i32, _vp, C.c_uint32, _i32, _vp]),

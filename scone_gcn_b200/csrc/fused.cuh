@@ -35,6 +35,12 @@ struct FusedState {
     float* d_scratch = nullptr;
     int* d_stats = nullptr;
     unsigned long long* d_rows_done = nullptr;
+    // planned set (scone_fused_plan_set): headers + programs of a whole dataset, kept across calls
+    int* d_set_hdr = nullptr;
+    uint32_t* d_set_arena = nullptr;
+    unsigned long long* d_set_bump = nullptr;
+    unsigned long long set_arena_words = 0;
+    int set_cap = 0, set_n = 0;
 };
 
 bool scone_fused_supported(const scone_complex* cx, int n_layers, const int32_t* hidden);
@@ -43,5 +49,9 @@ void scone_fused_destroy(FusedState* f);
 int scone_fused_run(const scone_complex* cx, FusedState* f, int act, int b, const int32_t* traj_ptr, const int32_t* flow_edge,
                     const float* flow_val, const int32_t* last_nodes, const float* W, const int64_t* w_off, float* logprobs,
                     const int32_t* target_idx, const float* mask, float* grad, int* overflow, bool count_rows, cudaStream_t st);
+int scone_fused_plan_set(const scone_complex* cx, FusedState* f, int B, const int32_t* traj_ptr, const int32_t* flow_edge,
+                         const float* flow_val, const int32_t* last_nodes, int* overflow, cudaStream_t st);
+int scone_fused_run_planned(const scone_complex* cx, FusedState* f, int act, int n, const int32_t* rows_dev, const float* W, const int64_t* w_off,
+                            float* logprobs, const int32_t* target_idx, const float* mask, float* grad, bool count_rows, cudaStream_t st);
 int scone_fused_last_retries(FusedState* f);
 int scone_fused_read(FusedState* f, int t, int* hdr_out, unsigned off, int words, uint32_t* arena_out);

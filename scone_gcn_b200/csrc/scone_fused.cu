@@ -634,6 +634,7 @@ __global__ void __launch_bounds__(THREADS) fused_plan_kernel(const PlanArgs a) {
 struct TrajArgs {
     const int* hdr;
     const uint32_t* arena;
+    const int32_t* rows;                   // planned set: trajectory t of the batch is entry rows[t] of the set (NULL: t itself)
     const float* W;                        // flat weights
     int w_off[3 * kFusedMaxL + 1];
     int L, b, D, n_params;
@@ -674,22 +675,29 @@ __device__ __forceinline__ void fu_gather(float* __restrict__ tile, const float*
     const int lr = threadIdx.x % G::LPR, rr = threadIdx.x / G::LPR;
     const int npad = (nr + 15) & ~15;
     for (int r = rr; r < npad; r += kTrajThreads / G::LPR) {
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f), s0 = o, s1 = o;
+        u64 s0a = 0ull, s0b = 0ull, s1a = 0ull, s1b = 0ull;       // packed pairs: (x, y) and (z, w) of the row's float4 chunk
+        int own = -1;
         if (r < nr) {
             const int p1 = ptr[r + 1] - pbase;
             for (int p = ptr[r] - pbase; p < p1; ++p) {
                 const int2 en = ent[p];
                 const float c0 = (float)(short)(en.y & 0xffff), c1 = (float)(en.y >> 16);
-                const float4 v = *reinterpret_cast<const float4*>(src + (size_t)(en.x & 0xFFFF) * G::LDH + 4 * lr);
-                s0.x = fmaf(c0, v.x, s0.x); s0.y = fmaf(c0, v.y, s0.y); s0.z = fmaf(c0, v.z, s0.z); s0.w = fmaf(c0, v.w, s0.w);
-                s1.x = fmaf(c1, v.x, s1.x); s1.y = fmaf(c1, v.y, s1.y); s1.z = fmaf(c1, v.z, s1.z); s1.w = fmaf(c1, v.w, s1.w);
-                if (en.x < 0) o = v;
+                const float* vp = src + (size_t)(en.x & 0xFFFF) * G::LDH + 4 * lr;
+                const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(vp);
+                const u64 q0 = bcast2(c0), q1 = bcast2(c1);
+                ffma2(s0a, q0, v.x);
+                ffma2(s0b, q0, v.y);
+                ffma2(s1a, q1, v.x);
+                ffma2(s1b, q1, v.y);
+                own = en.x < 0 ? (en.x & 0xFFFF) : own;
             }
         }
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (own >= 0) o = *reinterpret_cast<const float4*>(src + (size_t)own * G::LDH + 4 * lr);
         float* d = tile + (size_t)r * G::LDA + 4 * lr;
         *reinterpret_cast<float4*>(d) = o;
-        *reinterpret_cast<float4*>(d + C) = s0;
-        *reinterpret_cast<float4*>(d + 2 * C) = s1;
+        *reinterpret_cast<ulonglong2*>(d + C) = make_ulonglong2(s0a, s0b);
+        *reinterpret_cast<ulonglong2*>(d + 2 * C) = make_ulonglong2(s1a, s1b);
     }
 }
 
@@ -839,7 +847,7 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
     const int cap = BIG ? a.big_rows : a.cap_rows;
 
     for (int t = blockIdx.x; t < a.b; t += gridDim.x) {
-        const int* h = a.hdr + (size_t)t * kFusedHdrW;
+        const int* h = a.hdr + (size_t)(a.rows != nullptr ? a.rows[t] : t) * kFusedHdrW;
         if (h[0] != 0) continue;                           // overflow reported by the plan kernel: skipped (host: error code 4)
         int n[kFusedMaxL + 1], hb[kFusedMaxL + 2];
         int tot = 0;
@@ -1124,7 +1132,7 @@ bool scone_fused_supported(const scone_complex* cx, int n_layers, const int32_t*
 
 void scone_fused_destroy(FusedState* f) {
     if (!f) return;
-    cudaFree(f->d_hdr); cudaFree(f->d_retry); cudaFree(f->d_arena); cudaFree(f->d_bump); cudaFree(f->d_partial); cudaFree(f->d_scratch); cudaFree(f->d_stats);
+    cudaFree(f->d_hdr); cudaFree(f->d_retry); cudaFree(f->d_arena); cudaFree(f->d_set_hdr); cudaFree(f->d_set_arena); cudaFree(f->d_set_bump); cudaFree(f->d_bump); cudaFree(f->d_partial); cudaFree(f->d_scratch); cudaFree(f->d_stats);
     cudaFree(f->d_rows_done);
     delete f;
 }
@@ -1314,7 +1322,7 @@ int scone_fused_run(const scone_complex* cx, FusedState* f, int act, int b, cons
         }
     }
     TrajArgs t;
-    t.hdr = f->d_hdr; t.arena = f->d_arena; t.W = W;
+    t.hdr = f->d_hdr; t.arena = f->d_arena; t.rows = nullptr; t.W = W;
     for (int i = 0; i <= 3 * kFusedMaxL; ++i) t.w_off[i] = i <= 3 * f->L ? (int)w_off[i] : 0;
     t.L = f->L; t.b = b; t.D = cx->D; t.n_params = (int)f->n_params;
     t.logprobs = logprobs; t.target_idx = target_idx; t.mask = mask;
@@ -1336,6 +1344,83 @@ int scone_fused_run(const scone_complex* cx, FusedState* f, int act, int b, cons
             fused_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(f->d_partial, f->grid_small + f->grid_big, n, grad);
             SCONE_LAUNCHED();
         }
+    }
+    return 0;
+}
+
+// ---- planned sets: the plan is weight-independent, so a dataset that is revisited every epoch is planned ONCE --------------------
+// Plans B trajectories into the set's own arena (kept until the next scone_fused_plan_set / destroy).
+int scone_fused_plan_set(const scone_complex* cx, FusedState* f, int B, const int32_t* traj_ptr, const int32_t* flow_edge,
+                         const float* flow_val, const int32_t* last_nodes, int* overflow, cudaStream_t st) {
+    if (B > f->set_cap) {
+        cudaFree(f->d_set_hdr);
+        cudaFree(f->d_set_arena);
+        f->d_set_hdr = nullptr;
+        f->d_set_arena = nullptr;
+        f->set_cap = 0;
+        const unsigned long long budget_words = (1ull << 30) - 1024;
+        f->set_arena_words = std::min(budget_words, f->worst_words * (unsigned long long)B);
+        SCONE_CUDA(cudaMalloc((void**)&f->d_set_hdr, (size_t)B * kFusedHdrW * sizeof(int)));
+        SCONE_CUDA(cudaMalloc((void**)&f->d_set_arena, f->set_arena_words * sizeof(uint32_t)));
+        if (!f->d_set_bump) SCONE_CUDA(cudaMalloc((void**)&f->d_set_bump, 2 * sizeof(unsigned long long)));
+        f->set_cap = B;
+    }
+    f->set_n = 0;
+    SCONE_CUDA(cudaMemsetAsync(f->d_set_bump, 0, 2 * sizeof(unsigned long long), st));
+    PlanArgs p;
+    p.flow_edge = flow_edge; p.flow_val = flow_val;
+    p.rank = cx->d_rank; p.nbrhoods = cx->d_nbrhoods; p.inc_ptr = cx->d_inc_ptr; p.inc_ent = cx->d_inc_ent;
+    p.mptr = cx->d_mptr; p.ment = cx->d_ment;
+    p.N = cx->N; p.D = cx->D; p.E = cx->E; p.L = f->L;
+    p.arena = f->d_set_arena; p.bump = f->d_set_bump; p.arena_words = f->set_arena_words; p.overflow = overflow;
+    p.n_retry = reinterpret_cast<int*>(f->d_set_bump + 1);
+    ScopedProf prof(SCONE_K_CONE, st);
+    for (int off = 0; off < B; off += f->chunk) {
+        const int b = std::min(f->chunk, B - off);
+        SCONE_CUDA(cudaMemsetAsync(f->d_set_bump + 1, 0, sizeof(unsigned long long), st));       // retry counter only: the arena keeps growing
+        p.traj_ptr = traj_ptr + off; p.last_nodes = last_nodes + off; p.hdr = f->d_set_hdr + (size_t)off * kFusedHdrW;
+        p.tier = 0; p.n_work = b; p.retry = f->two_tiers ? f->d_retry : nullptr;
+        p.HS = f->HS0; p.LC = f->LC0; p.LV = f->LV0; p.EC = f->EC0; p.hshift = f->hshift0;
+        fused_plan_kernel<256><<<b, 256, f->plan_smem0, st>>>(p);
+        SCONE_LAUNCHED();
+        if (f->two_tiers) {
+            p.tier = 1; p.HS = f->HS; p.LC = f->LC; p.LV = f->LV; p.EC = f->EC; p.hshift = f->hshift; p.retry = f->d_retry;
+            fused_plan_kernel<1024><<<std::min(b, cx->num_sms), 1024, f->plan_smem, st>>>(p);
+            SCONE_LAUNCHED();
+        }
+    }
+    f->set_n = B;
+    return 0;
+}
+
+// Compute kernel over n trajectories of the planned set (rows_dev[t] = index into the set; NULL = the first n of the set).
+int scone_fused_run_planned(const scone_complex* cx, FusedState* f, int act, int n, const int32_t* rows_dev, const float* W, const int64_t* w_off,
+                            float* logprobs, const int32_t* target_idx, const float* mask, float* grad, bool count_rows, cudaStream_t st) {
+    if (n <= 0) return 0;
+    SCONE_REQUIRE(f->set_n > 0, "scone_fused_run_planned: no planned set (call scone_model_plan_* first)");
+    SCONE_REQUIRE(rows_dev != nullptr || n <= f->set_n, "scone_fused_run_planned: %d trajectories requested, the planned set holds %d", n, f->set_n);
+    const bool want_grad = grad != nullptr;
+    TrajArgs t;
+    t.hdr = f->d_set_hdr; t.arena = f->d_set_arena; t.rows = rows_dev; t.W = W;
+    for (int i = 0; i <= 3 * kFusedMaxL; ++i) t.w_off[i] = i <= 3 * f->L ? (int)w_off[i] : 0;
+    t.L = f->L; t.b = n; t.D = cx->D; t.n_params = (int)f->n_params;
+    t.logprobs = logprobs; t.target_idx = target_idx; t.mask = mask;
+    t.partial = f->d_partial; t.scratch = f->d_scratch; t.scratch_stride = f->scratch_stride;
+    t.cap_rows = f->cap_rows; t.big_rows = f->big_rows;
+    t.rows_done = count_rows ? f->d_rows_done : nullptr;
+    ScopedProf prof(want_grad ? SCONE_K_LAYER_BWD : SCONE_K_LAYER_FWD, st);
+    int rc;
+    if (f->C == 32)
+        rc = want_grad ? dispatch_traj<32, true>(act, t, f->grid_small, f->grid_big, f->traj_smem_small, f->traj_smem_big, st)
+                       : dispatch_traj<32, false>(act, t, f->grid_small, f->grid_big, f->traj_smem_small, f->traj_smem_big, st);
+    else
+        rc = want_grad ? dispatch_traj<16, true>(act, t, f->grid_small, f->grid_big, f->traj_smem_small, f->traj_smem_big, st)
+                       : dispatch_traj<16, false>(act, t, f->grid_small, f->grid_big, f->traj_smem_small, f->traj_smem_big, st);
+    if (rc) return rc;
+    if (want_grad) {
+        const int np = (int)f->n_params + 2;
+        fused_reduce_kernel<<<(np + 255) / 256, 256, 0, st>>>(f->d_partial, f->grid_small + f->grid_big, np, grad);
+        SCONE_LAUNCHED();
     }
     return 0;
 }

@@ -973,6 +973,80 @@ extern "C" int scone_model_read_grads(scone_model* m, float* out, void* st) {
     return 0;
 }
 
+// ---- planned sets (pipeline 4): plan a dataset once, run only the compute kernel on rows of it every step ----------------------
+extern "C" int scone_model_plan_dev(scone_model* m, int32_t B, const int32_t* ptr, const int32_t* edge, const float* val, const int32_t* last,
+                                    void* user_st) {
+    SCONE_REQUIRE(m && B >= 0 && (B == 0 || (ptr && last)), "scone_model_plan_dev: bad arguments");
+    SCONE_REQUIRE(m->fused != nullptr, "scone_model_plan_dev: planned sets need the fused pipeline (uniform width 16 / 32, <= 3 layers)");
+    if (fork_to_compute(m, user_st)) return 1;
+    const int rc = scone_fused_plan_set(m->cx, m->fused, B, ptr, edge, val, last, m->d_overflow, m->compute);
+    return finish_call(m, rc, user_st);
+}
+
+extern "C" int scone_model_plan_host(scone_model* m, int32_t B, const int32_t* ptr, const int32_t* edge, const float* val, const int32_t* last,
+                                     void* st) {
+    SCONE_REQUIRE(m && B >= 0 && (B == 0 || (ptr && last)), "scone_model_plan_host: bad arguments");
+    SCONE_REQUIRE(m->fused != nullptr, "scone_model_plan_host: planned sets need the fused pipeline (uniform width 16 / 32, <= 3 layers)");
+    cudaStream_t s = as_stream(st);
+    const int64_t nnz = B > 0 ? ptr[B] : 0;
+    // the plan reads its inputs only while it is built: the staging buffers of the *_host entry points serve
+    int rc = ensure_staging(m, B, nnz);
+    if (rc) return rc;
+    SCONE_CUDA(cudaMemcpyAsync(m->d_ptr, ptr, (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (nnz) {
+        SCONE_CUDA(cudaMemcpyAsync(m->d_edge, edge, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        SCONE_CUDA(cudaMemcpyAsync(m->d_val, val, nnz * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
+    if (B) SCONE_CUDA(cudaMemcpyAsync(m->d_last, last, B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    rc = scone_model_plan_dev(m, B, m->d_ptr, m->d_edge, m->d_val, m->d_last, st);
+    if (rc) return rc;
+    return scone_model_check_overflow(m, st);
+}
+
+extern "C" int scone_model_loss_grad_planned_dev(scone_model* m, int32_t n, const int32_t* rows_dev, const int32_t* tgt_dev, const float* mask_dev,
+                                                 int32_t zero_first, void* user_st) {
+    SCONE_REQUIRE(m && n >= 0 && (n == 0 || (tgt_dev && mask_dev)), "scone_model_loss_grad_planned_dev: bad arguments");
+    SCONE_REQUIRE(m->fused != nullptr, "scone_model_loss_grad_planned_dev: no fused pipeline");
+    if (fork_to_compute(m, user_st)) return 1;
+    cudaStream_t s = m->compute;
+    if (zero_first) SCONE_CUDA(cudaMemsetAsync(m->d_grad, 0, (m->n_params + 2) * sizeof(float), s));
+    const int rc = scone_fused_run_planned(m->cx, m->fused, m->act, n, rows_dev, m->d_w, m->w_off.data(), nullptr, tgt_dev, mask_dev, m->d_grad,
+                                           g_scone_prof, s);
+    return finish_call(m, rc, user_st);
+}
+
+extern "C" int scone_model_loss_grad_planned_host(scone_model* m, int32_t n, const int32_t* rows, const int32_t* tgt, const float* mask,
+                                                  int32_t zero_first, void* st) {
+    SCONE_REQUIRE(m && n >= 0 && (n == 0 || (tgt && mask)), "scone_model_loss_grad_planned_host: bad arguments");
+    cudaStream_t s = as_stream(st);
+    int rc = ensure_staging(m, n, 0);
+    if (rc) return rc;
+    if (n) {
+        if (rows) SCONE_CUDA(cudaMemcpyAsync(m->d_nn, rows, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        SCONE_CUDA(cudaMemcpyAsync(m->d_tgt, tgt, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        SCONE_CUDA(cudaMemcpyAsync(m->d_mask, mask, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
+    return scone_model_loss_grad_planned_dev(m, n, rows ? m->d_nn : nullptr, m->d_tgt, m->d_mask, zero_first, st);
+}
+
+extern "C" int scone_model_forward_planned_host(scone_model* m, int32_t n, const int32_t* rows, float* logprobs_out, void* st) {
+    SCONE_REQUIRE(m && n >= 0 && (n == 0 || logprobs_out), "scone_model_forward_planned_host: bad arguments");
+    SCONE_REQUIRE(m->fused != nullptr, "scone_model_forward_planned_host: no fused pipeline");
+    if (n == 0) return 0;
+    cudaStream_t s = as_stream(st);
+    int rc = ensure_staging(m, n, 0);
+    if (rc) return rc;
+    if (rows) SCONE_CUDA(cudaMemcpyAsync(m->d_nn, rows, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (fork_to_compute(m, st)) return 1;
+    rc = scone_fused_run_planned(m->cx, m->fused, m->act, n, rows ? m->d_nn : nullptr, m->d_w, m->w_off.data(), m->d_logp_all, nullptr, nullptr,
+                                 nullptr, false, m->compute);
+    rc = finish_call(m, rc, st);
+    if (rc) return rc;
+    SCONE_CUDA(cudaMemcpyAsync(logprobs_out, m->d_logp_all, (size_t)n * m->cx->D * sizeof(float), cudaMemcpyDeviceToHost, s));
+    SCONE_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
 extern "C" int scone_model_check_overflow(scone_model* m, void* st) {
     SCONE_REQUIRE(m != nullptr, "scone_model_check_overflow: NULL model");
     int overflow = 0;

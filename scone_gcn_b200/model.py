@@ -22,6 +22,7 @@ class SconeModel:
         if zero_fill:
             self.set_zero_fill(True)
         self.n_params = L.scone_model_num_params(h)
+        self.planned = 0
         self.shapes = []
         cin = 1
         for c in self.hidden:
@@ -131,6 +132,36 @@ class SconeModel:
         _lib.check(_lib.lib().scone_model_accuracy_host(self.handle, B, *[_lib.ptr(x) for x in a], _lib.ptr(out), stream),
                    'scone_model_accuracy_host')
         return int(out[0]), int(out[1])
+
+    # ---- planned sets (pipeline 4): plan a dataset once, run only the compute kernel on rows of it every step -------------------
+    def plan(self, traj_ptr, flow_edge, flow_val, last_nodes, stream=None):
+        """Builds and keeps the (weight-independent) plan of these trajectories; returns False when the model has no fused pipeline."""
+        if self.pipeline != 4:
+            return False
+        B = len(last_nodes)
+        a = [np.ascontiguousarray(traj_ptr, np.int32), np.ascontiguousarray(flow_edge, np.int32),
+             np.ascontiguousarray(flow_val, np.float32), np.ascontiguousarray(last_nodes, np.int32)]
+        _lib.check(_lib.lib().scone_model_plan_host(self.handle, B, *[_lib.ptr(x) for x in a], stream), 'scone_model_plan_host')
+        self.planned = B
+        return True
+
+    def loss_grad_planned(self, rows, target_idx, mask, zero_first=True, stream=None, read=True):
+        """loss_grad over rows (indices into the planned set; None = its first len(target_idx) trajectories)."""
+        n = len(target_idx)
+        r = None if rows is None else np.ascontiguousarray(rows, np.int32)
+        t, k = np.ascontiguousarray(target_idx, np.int32), np.ascontiguousarray(mask, np.float32)
+        _lib.check(_lib.lib().scone_model_loss_grad_planned_host(self.handle, n, _lib.ptr(r), _lib.ptr(t), _lib.ptr(k), int(zero_first), stream),
+                   'scone_model_loss_grad_planned_host')
+        return self.read_grads(stream) if read else None
+
+    def forward_planned(self, rows=None, n=None, stream=None):
+        """log-probs [n, D] of rows of the planned set (None = all of it)."""
+        r = None if rows is None else np.ascontiguousarray(rows, np.int32)
+        n = len(r) if r is not None else (self.planned if n is None else n)
+        out = np.zeros((n, self.cx.D), np.float32)
+        _lib.check(_lib.lib().scone_model_forward_planned_host(self.handle, n, _lib.ptr(r), _lib.ptr(out), stream),
+                   'scone_model_forward_planned_host')
+        return out
 
     def evaluate(self, traj_ptr, flow_edge, flow_val, last_nodes, n_nbrs=None, target_idx=None, mask=None, want_choice=False,
                  want_accuracy=False, want_nll=False, stream=None):

@@ -298,6 +298,9 @@ class Scone_GCN():
         target_idx = onp.argmax(yv.reshape(N, -1), axis=1).astype(onp.int32)
 
         self._net.set_weights([onp.asarray(w) for w in self.weights], reset_adam=True)     # init_fun(self.weights)
+        # the batches of every epoch are drawn from the same N trajectories: their plans (receptive cone, live rows, gather
+        # programs — weight-independent) are built once; each step then runs only the compute kernel on the rows of its batch
+        planned = bool(getattr(self._net, 'plan', None)) and not self.forward_all and self._net.plan(p.ptr, p.edge, p.val, p.last_nodes)
         self.adam_state = self._net
         use_dp = dp.is_distributed() if self.data_parallel is None else bool(self.data_parallel)
         if use_dp and not hasattr(self._net, 'grads_tensor'):
@@ -318,15 +321,18 @@ class Scone_GCN():
             if use_dp:                                     # this rank's contiguous share of the batch (same rows on every rank)
                 keep = dp.shard_rows(onp.arange(len(rows)))
                 rows, m = rows[keep], m[keep]
-            ptr, fe, fv, last = p.select(rows)
-            self._net.loss_grad(ptr, fe, fv, last, target_idx[rows], m, zero_first=True, read=False)
+            if planned:
+                self._net.loss_grad_planned(rows, target_idx[rows], m, zero_first=True, read=False)
+            else:
+                ptr, fe, fv, last = p.select(rows)
+                self._net.loss_grad(ptr, fe, fv, last, target_idx[rows], m, zero_first=True, read=False)
             if use_dp:                                     # the one exchange of the step: [grads | nll_sum | count], summed over ranks
                 dp.allreduce_sum_(self._net.grads_tensor())
             self._net.adam_step(i, self.step_size, self.weight_decay)
 
             if i % n_batches == n_batches - 1:
                 self.weights = self._net.get_weights()
-                preds = self._forward(self.weights, inputs)
+                preds = self._net.forward_planned()[:, :, None] if planned else self._forward(self.weights, inputs)
                 ridge = self._ridge(self.weights)
 
                 def _loss(mask):

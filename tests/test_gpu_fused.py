@@ -163,3 +163,30 @@ def test_fused_mixed_trajectories_with_empty_flows_and_invalid_last_node():
     with torch.no_grad():
         ref = orc.forward(W).numpy()[:, :, 0]
     assert np.abs(lp - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+
+
+def test_planned_set_gives_the_same_bits_as_planning_every_call():
+    """scone_model_plan_* + *_planned_*: plan the dataset once, run batches by row index — bit-identical to the unplanned entry points
+    (the same kernels on the same programs), for arbitrary row subsets in arbitrary order."""
+    import scone_gcn_b200 as sg
+    ds = Dataset('dataset_small.npz')
+    fx = load('model_small_scone_h16.npz')
+    cx = sg.SimplicialComplex.from_dense(ds.B1, ds.B2, 'scone')
+    ptr, fe, fv = sg.flows_to_csr(ds.flows)
+    net = sg.SconeModel(cx, [16, 16, 16], micro_batch=ds.n_traj)
+    net.set_weights(weights_of(fx, 'w_big'))
+    tgt = ds.raw['targets_argmax'].astype(np.int32)
+    ref_lp = net.forward(ptr, fe, fv, ds.last_nodes)
+    assert net.plan(ptr, fe, fv, ds.last_nodes)
+    assert np.array_equal(net.forward_planned(), ref_lp)
+    rs = np.random.RandomState(1)
+    rows = rs.permutation(ds.n_traj)[:23]
+    assert np.array_equal(net.forward_planned(rows), ref_lp[rows])
+    mask = (rs.rand(len(rows)) < 0.8).astype(np.float32)
+    got = net.loss_grad_planned(rows, tgt[rows], mask)
+    from scone_gcn_b200.scone_trajectory_model import _Prepared
+    sel = _Prepared([None, ds.last_nodes, (ptr, fe, fv)]).select(rows)
+    ref = net.loss_grad(*sel, tgt[rows], mask)
+    assert np.array_equal(got, ref)
+    # an intervening unplanned call (its own chunk arena) does not disturb the set
+    assert np.array_equal(net.forward_planned(rows), ref_lp[rows])
