@@ -252,11 +252,12 @@ int scone_model_forward_planned_host(scone_model* m, int32_t n, const int32_t* r
 int scone_model_check_overflow(scone_model* m, void* stream);
 /* Weights only (Adam state kept), asynchronous on the caller's stream; weights_host must stay valid until the copy has run. */
 int scone_model_set_weights_keep_state(scone_model* m, const float* weights_host, void* stream);
-/* Fused pipeline introspection (tests / bench): out[0] = available, [1] bound on the cone edges (|T_1| of any node), [2] bound on the
- * expanded cone edges (|T_2|), [3] hash slots of tier 1, [4] trajectories per arena chunk, [5] rows of the shared-memory row store, [6] / [7] KB of
- * dynamic shared memory of the tier-1 plan / the compute kernel, [8] / [9] hash slots / list entries of tier 0 (tables that hold the
- * cone of 99 % of the nodes), [10] its KB, [11] two tiers in use, [12] worst-case arena words per trajectory, [13] arena Mwords,
- * [14] tier-1 list entries, [15] trajectories of the last chunk the first tier handed to the second (synchronises the device). */
+/* Fused pipeline introspection (tests / bench): out[0] = available, [1] bound on |T_0| (hash entries: the cone of any node down to the
+ * ring whose flows can reach it), [2] bound on |T_1| (rows a layer can have), [3] hash slots of tier 1, [4] trajectories per arena
+ * chunk, [5] rows of the shared-memory row store, [6] / [7] KB of dynamic shared memory of the tier-1 plan / the compute kernel,
+ * [8] / [9] hash slots / live rows per layer of tier 0 (tables that hold the cone of ~99 % of the nodes), [10] its KB, [11] two tiers in
+ * use, [12] worst-case arena words per trajectory, [13] arena Mwords, [14] K entries of the per-complex cone table,
+ * [15] trajectories of the last chunk the first tier handed to the second (synchronises the device). */
 int scone_model_fused_info(const scone_model* m, int32_t* out /* [16] */);
 /* Plan of trajectory t of the LAST chunk run (synchronises the device): header (16 ints, layout in csrc/fused.cuh) and `words` 32-bit
  * words of the program arena from word offset `off` (either output may be NULL). */

@@ -12,13 +12,16 @@ constexpr int kFusedFlagRetry = 2;        // tier 0 of the plan kernel overflowe
 //   [5],[6] forward programs of layers 2, 3: rowptr[n_l + 1] then int2 entries {row below | own << 31, (c1 << 16) | c0}
 //   [7],[8] transposed programs of layers 2, 3 (rows = live rows of layer l - 1, entries = rows of layer l)
 //   [9] readout: rowptr[D + 1] then int2 {row of H_L | slot << 16, sign bits}   [10] pairs   [11] hash entries (flows + cone)
-//   [12] listed (expanded) cone edges   [13] flow entries
+//   [12] unused   [13] flow entries
 struct FusedState {
     int L = 0, C = 0;
     int64_t n_params = 0;
-    int bound_cone = 0, bound_list = 0;   // static bounds of the complex: cone edges |T_1| / expanded cone edges |T_2| of any last node
-    int HS = 0, LC = 0, LV = 0, EC = 0, hshift = 0;        // plan tables, tier 1: sized by the bounds
-    int HS0 = 0, LC0 = 0, LV0 = 0, EC0 = 0, hshift0 = 0;   // tier 0: sized for the cones of 99 % of the nodes
+    int bound_cone = 0, bound_list = 0;   // static bounds of the complex: |T_0| (hash entries) / |T_1| (rows of a layer) of any last node
+    unsigned* d_cone_ptr = nullptr;       // cone table: T_0 of every node, entries edge | level << 30
+    uint32_t* d_cone_ent = nullptr;
+    unsigned long long cone_entries = 0;
+    int HS = 0, LV = 0, EC = 0, hshift = 0;        // plan tables, tier 1: sized by the bounds
+    int HS0 = 0, LV0 = 0, EC0 = 0, hshift0 = 0;   // tier 0: sized for the cones of 99 % of the nodes
     bool two_tiers = false;
     int flow_room = 0;
     size_t plan_smem0 = 0;

@@ -155,7 +155,8 @@ struct PlanArgs {
     const int2* ment;
     int N, D, E, L;
     int HS, hshift;            // hash slots (power of two): the flow edges and the cone T_1 of the trajectory
-    int LC;                    // listed cone edges (levels >= 2: the ones that are expanded)
+    const unsigned* cone_ptr;  // cone table: entries of node n at cone_ent[cone_ptr[n] .. cone_ptr[n + 1])
+    const uint32_t* cone_ent;  //   edge | level << 30
     int LV;                    // live rows per layer
     int EC;                    // merged-row entries of the live rows of one layer (slot buffer)
     int* hdr;
@@ -169,23 +170,29 @@ struct PlanArgs {
     int* retry;                // [chunk]
 };
 
-// Static bounds: blockIdx.x = candidate last node; builds its cone down to level 1 and records max |T_1| (cone edges = hash entries)
-// and max |T_2| (listed = expanded edges) in stats[0..1]; stats[2] = 1 if even the largest table overflowed; histograms of both.
-__global__ void __launch_bounds__(kPlanThreads) fused_bound_kernel(const int32_t* __restrict__ nbrhoods, const int32_t* __restrict__ inc_ptr,
-                                                                  const int2* __restrict__ inc_ent, const int32_t* __restrict__ mptr,
-                                                                  const int2* __restrict__ ment, int N, int D, int L, int HS, int LC,
-                                                                  int hshift, int* __restrict__ stats) {
+// The receptive cone depends on the complex and the last node only: it is built ONCE per complex for every node (cone table) and a
+// plan just loads the cone of its last node.  blockIdx.x = node: level L = edges incident to its neighbours, one merged-row hop
+// further down per level, down to level 0 (T_0 = the edges whose flow value can reach a row of T_1).  Two passes:
+//   cone_ent == NULL   count: cnt[node] = |T_0|; stats[0] = max |T_0|, stats[1] = max |T_1| (rows a layer can have), stats[2] = 1 if
+//                      even the largest tables overflowed, histogram of |T_0| in buckets of 32 from stats[4] on
+//   cone_ent != NULL   fill: entries (edge | level << 30) at cone_ptr[node] .. (order = arrival order: nothing depends on it)
+__global__ void __launch_bounds__(kPlanThreads) fused_cone_kernel(const int32_t* __restrict__ nbrhoods, const int32_t* __restrict__ inc_ptr,
+                                                                 const int2* __restrict__ inc_ent, const int32_t* __restrict__ mptr,
+                                                                 const int2* __restrict__ ment, int N, int D, int L, int HS, int LC,
+                                                                 int hshift, int* __restrict__ stats, int* __restrict__ cnt,
+                                                                 const unsigned* __restrict__ cone_ptr, uint32_t* __restrict__ cone_ent) {
     extern __shared__ __align__(16) unsigned char sm[];
     int* keys = reinterpret_cast<int*>(sm);
     int* list = keys + HS;
     __shared__ FuPairs pairs;
-    __shared__ int s_nlist, s_nhash, s_ovf, s_nat[kFusedMaxL + 2];
+    __shared__ int s_nlist, s_nhash, s_n1, s_ovf, s_nat[kFusedMaxL + 2];
     const int tid = threadIdx.x, ql = tid & 3;
     for (int i = tid; i < HS; i += kPlanThreads) keys[i] = -1;
-    if (tid == 0) s_nlist = s_nhash = s_ovf = 0;
-    const int last = blockIdx.x;
-    const int total = pairs.setup(nbrhoods, inc_ptr, last, last < N, D);
+    if (tid == 0) s_nlist = s_nhash = s_n1 = s_ovf = 0;
+    const int node = blockIdx.x;
+    const int total = pairs.setup(nbrhoods, inc_ptr, node, node < N, D);
     EdgeSet set{keys, HS - 1, hshift};
+    uint32_t* out = cone_ent != nullptr ? cone_ent + cone_ptr[node] : nullptr;
     auto add = [&](int e, int lv) {
         bool is_new;
         const int s = set.insert(e, is_new);
@@ -194,8 +201,11 @@ __global__ void __launch_bounds__(kPlanThreads) fused_bound_kernel(const int32_t
             return;
         }
         if (is_new) {
-            if (atomicAdd(&s_nhash, 1) >= (HS * 3) / 4) s_ovf = 1;
-            if (lv >= 2) {
+            const int k = atomicAdd(&s_nhash, 1);
+            if (k >= (HS * 3) / 4) s_ovf = 1;
+            else if (out != nullptr) out[k] = (uint32_t)e | ((uint32_t)lv << 30);
+            if (lv >= 1) {                                  // level 0 edges are not expanded
+                atomicAdd(&s_n1, 1);
                 const int pos = atomicAdd(&s_nlist, 1);
                 if (pos < LC) list[pos] = e;
                 else s_ovf = 1;
@@ -210,7 +220,7 @@ __global__ void __launch_bounds__(kPlanThreads) fused_bound_kernel(const int32_t
     if (tid == 0) s_nat[L] = min(s_nlist, LC);
     __syncthreads();
     int f0 = 0;
-    for (int lv = L - 1; lv >= 1; --lv) {
+    for (int lv = L - 1; lv >= 0; --lv) {
         const int f1 = s_nat[lv + 1];
         if (!s_ovf)
             for (int i = f0 + (tid >> 2); i < f1; i += kPlanThreads / 4) {
@@ -223,22 +233,21 @@ __global__ void __launch_bounds__(kPlanThreads) fused_bound_kernel(const int32_t
         __syncthreads();
         f0 = f1;
     }
-    if (tid == 0) {
+    if (tid == 0 && cone_ent == nullptr) {
+        cnt[node] = s_nhash;
         atomicMax(&stats[0], s_nhash);
-        atomicMax(&stats[1], s_nlist);
+        atomicMax(&stats[1], s_n1);
         if (s_ovf) stats[2] = 1;
-        // size distribution over the nodes (buckets of 32): picks the tables of the plan kernel's first tier
         atomicAdd(&stats[4 + min(kBoundBuckets - 1, s_nhash / 32)], 1);
-        atomicAdd(&stats[4 + kBoundBuckets + min(kBoundBuckets - 1, s_nlist / 32)], 1);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // the plan of one trajectory (one CTA of THREADS threads)
 //
-//   hash set      flow edges (level 0, value x) and the receptive cone T_1 (level = highest cone level of the edge)
-//   cone          level L = edges incident to the neighbours of the last node; one merged-row hop further down per level; only the
-//                 edges of levels >= 2 are listed (they are the ones expanded)
+//   hash set      T_0 of the last node, loaded from the cone table (level = highest cone level of the edge; level 0 = the ring whose
+//                 flow values can reach a row of T_1); the flow entries of the trajectory that fall into it get their value x —
+//                 the rest of the path is too far from the last node to matter and is never touched again
 //   live rows     PUSHED from below: a row of layer 1 is live iff it is in T_1 and a flow edge sits in its merged operator row,
 //                 i.e. iff it is in the merged row of a flow edge (the operators are symmetric); a row of layer l iff it is in T_l
 //                 and in the merged row of a live row of layer l - 1.  Cost follows the flows and the live rows, not the cone.
@@ -284,7 +293,7 @@ __device__ int block_scan_excl_t(int* a, int n, int* s_warp) {   // exclusive sc
 template <int THREADS>
 __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, unsigned char* sm) {
     constexpr int QUADS = THREADS / 4;
-    const int HS = a.HS, LC = a.LC, LV = a.LV, EC = a.EC, L = a.L, D = a.D;
+    const int HS = a.HS, LV = a.LV, EC = a.EC, L = a.L, D = a.D;
     int* keys = reinterpret_cast<int*>(sm);                          // [HS] internal edge id, -1 = empty
     float* xv = reinterpret_cast<float*>(keys + HS);                 // [HS] flow value of the edge
     int* lvl = reinterpret_cast<int*>(xv + HS);                      // [HS] bits 0-7: cone level (0 = flow edge outside the cone); bit 8 + l: marked live in layer l
@@ -295,10 +304,9 @@ __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, 
     uint16_t* live = reinterpret_cast<uint16_t*>(live_edge + LV);    // [LV] hash slot of the k-th live row (unordered)
     uint16_t* rankA = live + LV;                                     // [LV] hash slot of the row with rank r (ping)
     uint16_t* rankB = rankA + LV;                                    // [LV] (pong)
-    uint16_t* list = rankB + LV;                                     // [LC] cone list: hash slots of the edges of levels >= 2
-    uint16_t* ebuf = list + LC;                                      // [EC] hash slot of every merged-row entry of the scanned rows
+    uint16_t* ebuf = rankB + LV;                                      // [EC] hash slot of every merged-row entry of the scanned rows
     __shared__ FuPairs pairs;
-    __shared__ int s_nlist, s_nhash, s_nlive, s_ovf, s_nat[kFusedMaxL + 2], s_warp[THREADS / 32];
+    __shared__ int s_nhash, s_nlive, s_ovf, s_warp[THREADS / 32];
     __shared__ unsigned s_piece;
 
     const int tid = threadIdx.x, lane = tid & 31, ql = tid & 3;
@@ -322,31 +330,12 @@ __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, 
         lvl[i] = 0;
     }
     for (int i = tid; i < 3 * HS; i += THREADS) idx0[i] = (uint16_t)kNoRow;
-    if (tid == 0) s_nlist = s_nhash = s_ovf = s_nlive = 0;
+    if (tid == 0) s_nhash = s_ovf = s_nlive = 0;
     const int last = a.last_nodes[t];
     const bool last_ok = last >= 0 && last < a.N;
     const int total_pairs = pairs.setup(a.nbrhoods, a.inc_ptr, last, last_ok, D);     // (barriers inside: the tables are initialised)
     EdgeSet set{keys, HS - 1, a.hshift};
     const int hash_cap = (HS * 3) / 4;
-    auto put = [&](int e) -> int {                         // slot of edge e (created if absent); -1 when a table of this tier is full
-        if (s_ovf) return -1;
-        bool is_new;
-        const int s = set.insert(e, is_new);
-        if (s < 0 || (is_new && atomicAdd(&s_nhash, 1) >= hash_cap)) {
-            s_ovf = 1;
-            return -1;
-        }
-        return s;
-    };
-    auto add_cone = [&](int e, int lv) {
-        const int s = put(e);
-        if (s < 0) return;
-        if ((atomicMax(&lvl[s], lv) & 0xFF) == 0 && lv >= 2) {       // first time in the cone (levels are built top-down)
-            const int pos = atomicAdd(&s_nlist, 1);
-            if (pos < LC) list[pos] = (uint16_t)s;
-            else s_ovf = 1;
-        }
-    };
     // arena allocation for one piece (thread 0 allocates, everybody gets the word offset)
     auto alloc = [&](int words) -> unsigned {
         __syncthreads();
@@ -365,41 +354,31 @@ __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, 
     };
     const int fp0 = a.traj_ptr[t], fp1 = a.traj_ptr[t + 1];
 
-    // ---- flows ----
+    // ---- the cone of the last node, from the table ----
+    {
+        const unsigned c0 = last_ok ? a.cone_ptr[last] : 0u, c1 = last_ok ? a.cone_ptr[last + 1] : 0u;
+        const int n_cone = (int)(c1 - c0);
+        if (n_cone > hash_cap) {                           // (uniform) this tier's table is too small
+            give_up();
+            return;
+        }
+        for (int i = tid; i < n_cone; i += THREADS) {
+            const uint32_t en = a.cone_ent[c0 + i];
+            bool is_new;
+            const int s = set.insert((int)(en & 0x3FFFFFFFu), is_new);
+            lvl[s] = (int)(en >> 30);
+        }
+        if (tid == 0) s_nhash = n_cone;
+    }
+    __syncthreads();
+    // ---- flows: only edges of T_0 can reach a cone row ----
     for (int p = fp0 + tid; p < fp1; p += THREADS) {
         const int eo = a.flow_edge[p];
         if (eo < 0 || eo >= a.E) continue;
-        const int s = put(a.rank[eo]);
+        const int s = set.find(a.rank[eo]);
         if (s >= 0) xv[s] = a.flow_val[p];
     }
     __syncthreads();
-    // ---- receptive cone ----
-    for (int i = tid; i < total_pairs; i += THREADS) {
-        const int j = pairs.slot_of(i, D);
-        add_cone(a.inc_ent[pairs.s_ptr[j] + (i - pairs.s_off[j])].x, L);
-    }
-    __syncthreads();
-    if (tid == 0) s_nat[L] = min(s_nlist, LC);
-    __syncthreads();
-    {
-        int f0 = 0;
-        for (int lv = L - 1; lv >= 1; --lv) {
-            const int f1 = s_nat[lv + 1];
-            for (int i = f0 + (tid >> 2); i < f1; i += QUADS) {
-                const int e = keys[list[i]];
-                const int p1 = a.mptr[e + 1];
-                for (int q = a.mptr[e] + ql; q < p1; q += 4) add_cone(a.ment[q].x, lv);
-            }
-            __syncthreads();
-            if (tid == 0) s_nat[lv] = min(s_nlist, LC);
-            __syncthreads();
-            f0 = f1;
-        }
-    }
-    if (s_ovf) {
-        give_up();
-        return;
-    }
     // marks (once) the cone edge in slot s2 as a live row of layer l
     auto mark = [&](int s2, int l) {
         const int bit = 1 << (8 + l);
@@ -613,7 +592,7 @@ __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, 
         hdr[9] = (int)off_ro;
         hdr[10] = total_pairs;
         hdr[11] = s_nhash;
-        hdr[12] = s_nlist;
+        hdr[12] = 0;
         hdr[13] = fp1 - fp0;
     }
 }
@@ -730,11 +709,11 @@ __device__ __forceinline__ void fu_product(const float* __restrict__ tile, const
     const int n_mt = (nr + 15) >> 4;
     for (int tl = warp; tl < n_mt * G::NP; tl += kTrajThreads / 32) {
         const int mt = tl / G::NP, np = tl % G::NP;
-        float d[2][4];
+        float d[2][4], dx[2][4];                          // dx: the two small cross terms (a_lo w_hi + a_hi w_lo): an independent mma chain
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) d[j][q] = 0.f;
+            for (int q = 0; q < 4; ++q) d[j][q] = dx[j][q] = 0.f;
         const float* arow0 = tile + (size_t)(16 * mt + g) * G::LDA + tig;
         const float* arow1 = arow0 + 8 * G::LDA;
 #pragma unroll 4
@@ -760,11 +739,15 @@ __device__ __forceinline__ void fu_product(const float* __restrict__ tile, const
                 uint32_t bh0, bl0, bh1, bl1;
                 split_tf32(b0, bh0, bl0);
                 split_tf32(b1, bh1, bl1);
-                mma_tf32(d[j], alo, bh0, bh1);
-                mma_tf32(d[j], ahi, bl0, bl1);
+                mma_tf32(dx[j], alo, bh0, bh1);
+                mma_tf32(dx[j], ahi, bl0, bl1);
                 mma_tf32(d[j], ahi, bh0, bh1);
             }
         }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) d[j][q] += dx[j][q];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int col = (2 * np + j) * 8 + 2 * tig;
@@ -1076,8 +1059,8 @@ __global__ void __launch_bounds__(256) fused_reduce_kernel(const float* __restri
     out[i] += (s0 + s1) + (s2 + s3);
 }
 
-size_t plan_smem_bytes(int HS, int LC, int LV, int EC) {
-    return (size_t)HS * 18 + (size_t)(LV + 4) * 8 + (size_t)LV * 10 + (size_t)LC * 2 + (size_t)EC * 2 + 16;
+size_t plan_smem_bytes(int HS, int LV, int EC) {
+    return (size_t)HS * 18 + (size_t)(LV + 4) * 8 + (size_t)LV * 10 + (size_t)EC * 2 + 16;
 }
 
 template <int C>
@@ -1132,7 +1115,7 @@ bool scone_fused_supported(const scone_complex* cx, int n_layers, const int32_t*
 
 void scone_fused_destroy(FusedState* f) {
     if (!f) return;
-    cudaFree(f->d_hdr); cudaFree(f->d_retry); cudaFree(f->d_arena); cudaFree(f->d_set_hdr); cudaFree(f->d_set_arena); cudaFree(f->d_set_bump); cudaFree(f->d_bump); cudaFree(f->d_partial); cudaFree(f->d_scratch); cudaFree(f->d_stats);
+    cudaFree(f->d_hdr); cudaFree(f->d_retry); cudaFree(f->d_arena); cudaFree(f->d_set_hdr); cudaFree(f->d_set_arena); cudaFree(f->d_set_bump); cudaFree(f->d_cone_ptr); cudaFree(f->d_cone_ent); cudaFree(f->d_bump); cudaFree(f->d_partial); cudaFree(f->d_scratch); cudaFree(f->d_stats);
     cudaFree(f->d_rows_done);
     delete f;
 }
@@ -1149,29 +1132,53 @@ static void table_shape(int entries, int* HS, int* hshift) {
 
 int scone_fused_create(const scone_complex* cx, int L, int C, int mb, int64_t n_params, FusedState** out) {
     *out = nullptr;
+    if ((unsigned)cx->E >= (1u << 30)) return 0;           // cone table entries carry the level in their top two bits
     FusedState* f = new FusedState();
     f->L = L;
     f->C = C;
     f->n_params = n_params;
-    // ---- bounds: the cone of every node, with the largest tables one CTA can hold; size histograms over the nodes ----
-    const int n_stats = 4 + 2 * kBoundBuckets;
+    // ---- the cone table: T_0 of every node (weight- and data-independent geometry of the complex), built in two passes with the
+    // largest tables one CTA can hold; its sizes are the static bounds of the pipeline ----
+    const int n_stats = 4 + kBoundBuckets;
     SCONE_CUDA(cudaMalloc((void**)&f->d_stats, n_stats * sizeof(int)));
     SCONE_CUDA(cudaMemset(f->d_stats, 0, n_stats * sizeof(int)));
     std::vector<int> st(n_stats, 0);
     {
         const int HS = 32768, LC = 16384, hshift = 32 - 15;
         const size_t smem = (size_t)HS * 4 + (size_t)LC * 4;
-        SCONE_CUDA(cudaFuncSetAttribute(fused_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fused_bound_kernel<<<cx->N, kPlanThreads, smem>>>(cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, cx->d_mptr, cx->d_ment, cx->N, cx->D, L, HS,
-                                                          LC, hshift, f->d_stats);
+        int* d_cnt = nullptr;
+        SCONE_CUDA(cudaMalloc((void**)&d_cnt, ((size_t)cx->N + 1) * sizeof(int)));
+        SCONE_CUDA(cudaFuncSetAttribute(fused_cone_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fused_cone_kernel<<<cx->N, kPlanThreads, smem>>>(cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, cx->d_mptr, cx->d_ment, cx->N, cx->D, L, HS, LC,
+                                                         hshift, f->d_stats, d_cnt, nullptr, nullptr);
         SCONE_LAUNCHED();
         SCONE_CUDA(cudaMemcpy(st.data(), f->d_stats, n_stats * sizeof(int), cudaMemcpyDeviceToHost));
-        if (st[2]) {                                       // cones larger than any table: not this pipeline's regime
+        std::vector<int> cnt((size_t)cx->N);
+        SCONE_CUDA(cudaMemcpy(cnt.data(), d_cnt, (size_t)cx->N * sizeof(int), cudaMemcpyDeviceToHost));
+        cudaFree(d_cnt);
+        unsigned long long total = 0;
+        for (int v : cnt) total += (unsigned long long)v;
+        if (st[2] || total >= (1ull << 32)) {             // cones larger than any table: not this pipeline's regime
             scone_fused_destroy(f);
             return 0;
         }
-        f->bound_cone = st[0] > 0 ? st[0] : 1;
-        f->bound_list = st[1] > 0 ? st[1] : 1;
+        std::vector<unsigned> ptr((size_t)cx->N + 1);
+        unsigned run = 0;
+        for (int n = 0; n < cx->N; ++n) {
+            ptr[n] = run;
+            run += (unsigned)cnt[n];
+        }
+        ptr[cx->N] = run;
+        f->cone_entries = total;
+        SCONE_CUDA(cudaMalloc((void**)&f->d_cone_ptr, ptr.size() * sizeof(unsigned)));
+        SCONE_CUDA(cudaMalloc((void**)&f->d_cone_ent, (size_t)(total ? total : 1) * sizeof(uint32_t)));
+        SCONE_CUDA(cudaMemcpy(f->d_cone_ptr, ptr.data(), ptr.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+        fused_cone_kernel<<<cx->N, kPlanThreads, smem>>>(cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, cx->d_mptr, cx->d_ment, cx->N, cx->D, L, HS, LC,
+                                                         hshift, f->d_stats, nullptr, f->d_cone_ptr, f->d_cone_ent);
+        SCONE_LAUNCHED();
+        SCONE_CUDA(cudaDeviceSynchronize());
+        f->bound_cone = st[0] > 0 ? st[0] : 1;            // |T_0|: hash entries
+        f->bound_list = st[1] > 0 ? st[1] : 1;            // |T_1|: rows a layer can have
     }
     int max_row = 1;
     {
@@ -1179,59 +1186,49 @@ int scone_fused_create(const scone_complex* cx, int L, int C, int mb, int64_t n_
         SCONE_CUDA(cudaMemcpy(mp.data(), cx->d_mptr, mp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
         for (int e = 0; e < cx->E; ++e) max_row = std::max(max_row, mp[e + 1] - mp[e]);
     }
-    // tier 1 (the cone cannot overflow it; 1024 threads per trajectory): tables from the bounds + room for kFlowRoom flow entries per
-    // trajectory, slot buffer for every merged-row entry of a full layer.  tier 0 (256 threads): tables that hold the cone of 99 % of
-    // the nodes (a few hull / hole boundary nodes of a Delaunay complex have cones ten times the typical size; sizing every CTA for
-    // them costs the occupancy the plan kernel lives on)
-    constexpr int kFlowRoom = 512, kFlowRoom0 = 320, kMaxPlanSmem = 200 * 1024;
-    f->LC = (f->bound_list + 63) & ~63;
-    f->LV = (f->bound_cone + 63) & ~63;
-    table_shape(f->bound_cone + kFlowRoom, &f->HS, &f->hshift);
-    f->flow_room = (f->HS * 3) / 4 - f->bound_cone;       // flow entries per trajectory tier 1 is guaranteed to hold
+    // tier 1 (cannot overflow its tables; 1024 threads per trajectory): hash for the largest T_0, live rows up to the largest T_1.
+    // tier 0 (256 threads): tables that hold T_0 of 99 % of the nodes (a few hull / hole boundary nodes of a Delaunay complex have
+    // cones ten times the typical size; sizing every CTA for them costs the occupancy the plan kernel lives on)
+    constexpr int kMaxPlanSmem = 225 * 1024;
+    f->LV = (f->bound_list + 63) & ~63;
+    table_shape(f->bound_cone, &f->HS, &f->hshift);
     // slot buffer: every merged-row entry of the live rows of one layer.  The worst case (every cone edge live, every row of maximum
     // length) rarely fits next to the tables; the buffer then takes what is left of the shared-memory budget (tens of thousands of
     // entries against a few thousand for the largest trajectories seen) and a layer beyond it is reported through the overflow flag
-    f->EC = (int)std::min<long long>((long long)f->bound_cone * max_row, 1ll << 30);
+    f->EC = (int)std::min<long long>((long long)f->bound_list * max_row, 1ll << 30);
     f->EC = (f->EC + 63) & ~63;
     {
-        const size_t fixed = plan_smem_bytes(f->HS, f->LC, f->LV, 0);
-        if (fixed + 2 * (size_t)f->EC > (size_t)kMaxPlanSmem && fixed + 2 * 16384 <= (size_t)kMaxPlanSmem)
+        const size_t fixed = plan_smem_bytes(f->HS, f->LV, 0);
+        if (fixed + 2 * (size_t)f->EC > (size_t)kMaxPlanSmem && fixed + 2 * 8192 <= (size_t)kMaxPlanSmem)
             f->EC = (int)(((size_t)kMaxPlanSmem - fixed) / 2) & ~63;
     }
-    f->plan_smem = plan_smem_bytes(f->HS, f->LC, f->LV, f->EC);
-    if (f->plan_smem > (size_t)kMaxPlanSmem || f->bound_cone >= 0xFFFF || f->HS > 32768) {
+    f->plan_smem = plan_smem_bytes(f->HS, f->LV, f->EC);
+    if (f->plan_smem > (size_t)kMaxPlanSmem || f->bound_list >= 0xFFFF || f->HS > 32768) {
         scone_fused_destroy(f);
         return 0;
     }
     {
-        auto quantile = [&](const int* h) {
-            long long acc = 0, want = ((long long)cx->N * 99 + 99) / 100;
-            for (int b = 0; b < kBoundBuckets; ++b) {
-                acc += h[b];
-                if (acc >= want) return 32 * (b + 1);
+        long long acc = 0, want = ((long long)cx->N * 99 + 99) / 100;
+        int q0 = 32 * kBoundBuckets;
+        for (int b = 0; b < kBoundBuckets; ++b) {
+            acc += st[4 + b];
+            if (acc >= want) {
+                q0 = 32 * (b + 1);
+                break;
             }
-            return 32 * kBoundBuckets;
-        };
-        const int q0 = std::min(quantile(&st[4]), f->bound_cone), q1 = std::min(quantile(&st[4 + kBoundBuckets]), f->bound_list);
-        table_shape(q0 + kFlowRoom0, &f->HS0, &f->hshift0);
-        // (measured on the 1M-edge bench complex, tools/sweep_plan_tiers.sh: the expanded-edge list overflows first — trajectories end
-        // on better-connected nodes than the average node — so the list gets twice the quantile; 192 live rows / 3072 entries per layer
-        // hold all but the trajectories the compute kernel sends to its big variant anyway)
-        f->LC0 = std::min(std::max(2 * ((q1 + 63) & ~63), 256), f->LC);
+        }
+        // (tools/sweep_plan_tiers.sh on the 1M-edge bench complex: 1024 slots / 27 KB per CTA beat 2048 / 45 KB although twice as
+        // many trajectories go to the second tier — occupancy is what the first tier lives on; 192 live rows / 3072 entries per
+        // layer hold all but the trajectories the compute kernel sends to its big variant anyway)
+        table_shape(std::min(q0, f->bound_cone), &f->HS0, &f->hshift0);
         f->LV0 = std::min(192, f->LV);
         f->EC0 = std::min(3072, f->EC);
-        if (f->HS0 >= f->HS) {                             // one tier is enough
+        f->two_tiers = f->HS0 < f->HS || f->LV0 < f->LV || f->EC0 < f->EC;
+        if (!f->two_tiers) {
             f->HS0 = f->HS;
-            f->LC0 = f->LC;
-            f->LV0 = f->LV;
-            f->EC0 = f->EC;
             f->hshift0 = f->hshift;
-            f->two_tiers = false;
-        } else {
-            f->two_tiers = true;
         }
-        // tuning overrides (profiling experiments): SCONE_FUSED_HS0 / _LV0 / _EC0 / _LC0
-        auto env_int = [](const char* name, int dflt) {
+        auto env_int = [](const char* name, int dflt) {    // tuning overrides (profiling experiments)
             const char* v = getenv(name);
             return v && *v ? atoi(v) : dflt;
         };
@@ -1240,16 +1237,15 @@ int scone_fused_create(const scone_complex* cx, int L, int C, int mb, int64_t n_
             if (hs0 != f->HS0 && hs0 >= 256 && hs0 <= f->HS && (hs0 & (hs0 - 1)) == 0) table_shape((hs0 * 3) / 4 - 1, &f->HS0, &f->hshift0);
             f->LV0 = std::min(env_int("SCONE_FUSED_LV0", f->LV0), f->LV);
             f->EC0 = std::min(env_int("SCONE_FUSED_EC0", f->EC0), f->EC);
-            f->LC0 = std::min(env_int("SCONE_FUSED_LC0", f->LC0), f->LC);
         }
-        f->plan_smem0 = plan_smem_bytes(f->HS0, f->LC0, f->LV0, f->EC0);
+        f->plan_smem0 = plan_smem_bytes(f->HS0, f->LV0, f->EC0);
     }
     SCONE_CUDA(cudaFuncSetAttribute(fused_plan_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPlanSmem));
     SCONE_CUDA(cudaFuncSetAttribute(fused_plan_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPlanSmem));
     // ---- compute kernel: shared-memory row store of the small variant, per-CTA global row store of the big one ----
     const int ldh = C + 8;
     f->cap_rows = C == 32 ? 192 : 384;
-    f->big_rows = f->bound_cone + (L - 1) * f->bound_list;
+    f->big_rows = L * f->bound_list;
     f->traj_smem_small = C == 32 ? traj_smem_bytes<32>(cx->D, f->cap_rows) : traj_smem_bytes<16>(cx->D, f->cap_rows);
     f->traj_smem_big = C == 32 ? traj_smem_bytes<32>(cx->D, 0) : traj_smem_bytes<16>(cx->D, 0);
     if (f->traj_smem_small > 113 * 1024) {                 // very high degrees: shrink the row store, keep two CTAs per SM
@@ -1268,10 +1264,10 @@ int scone_fused_create(const scone_complex* cx, int L, int C, int mb, int64_t n_
     // ---- program arena.  Worst case per trajectory from the bounds (every row of every layer live, every merged-row entry kept).
     // The arena holds min(worst * chunk, 4 GB): when the worst case fits, it cannot overflow; otherwise it is exhausted only if the
     // AVERAGE program of a chunk exceeds 64 KB (typical: 5 - 10 KB), which the plan kernel reports through the overflow flag. ----
-    const unsigned long long bc = (unsigned long long)f->bound_cone, bl = (unsigned long long)f->bound_list;
-    unsigned long long worst = 3 * bc + 2 + (unsigned long long)(cx->D + 3) + 2ull * cx->D * cx->D + 16;   // (a neighbour has at most D incident edges)
-    for (int l = 2; l <= L; ++l)                            // layer l: n_l <= |T_2| rows; the two programs hold the same entries
-        worst += (bl + 3) + ((l == 2 ? bc : bl) + 3) + 4 * bl * (unsigned long long)max_row;
+    const unsigned long long bl = (unsigned long long)f->bound_list;
+    unsigned long long worst = 3 * bl + 2 + (unsigned long long)(cx->D + 3) + 2ull * cx->D * cx->D + 16;   // (a neighbour has at most D incident edges)
+    for (int l = 2; l <= L; ++l)                            // layer l: n_l <= |T_1| rows; the two programs hold the same entries
+        worst += 2 * (bl + 3) + 4 * bl * (unsigned long long)max_row;
     const unsigned long long budget_words = (1ull << 30) - 1024;                 // 4 GB of 32-bit words; offsets are 32-bit
     const unsigned long long share_words = 16 * 1024;                            // 64 KB per trajectory
     f->worst_words = worst;
@@ -1303,8 +1299,8 @@ int scone_fused_run(const scone_complex* cx, FusedState* f, int act, int b, cons
     PlanArgs p;
     p.traj_ptr = traj_ptr; p.flow_edge = flow_edge; p.flow_val = flow_val; p.last_nodes = last_nodes;
     p.rank = cx->d_rank; p.nbrhoods = cx->d_nbrhoods; p.inc_ptr = cx->d_inc_ptr; p.inc_ent = cx->d_inc_ent;
-    p.mptr = cx->d_mptr; p.ment = cx->d_ment;
-    p.N = cx->N; p.D = cx->D; p.E = cx->E; p.L = f->L; p.HS = f->HS0; p.LC = f->LC0; p.LV = f->LV0; p.EC = f->EC0; p.hshift = f->hshift0;
+    p.mptr = cx->d_mptr; p.ment = cx->d_ment; p.cone_ptr = f->d_cone_ptr; p.cone_ent = f->d_cone_ent;
+    p.N = cx->N; p.D = cx->D; p.E = cx->E; p.L = f->L; p.HS = f->HS0; p.LV = f->LV0; p.EC = f->EC0; p.hshift = f->hshift0;
     p.hdr = f->d_hdr; p.arena = f->d_arena; p.bump = f->d_bump; p.arena_words = f->arena_words; p.overflow = overflow;
     p.tier = 0; p.n_work = b; p.n_retry = reinterpret_cast<int*>(f->d_bump + 1); p.retry = f->two_tiers ? f->d_retry : nullptr;
     {
@@ -1313,7 +1309,7 @@ int scone_fused_run(const scone_complex* cx, FusedState* f, int act, int b, cons
             fused_plan_kernel<256><<<b, 256, f->plan_smem0, st>>>(p);
             SCONE_LAUNCHED();
             // the few trajectories whose cone overflowed the first tier's tables: 1024 threads each
-            p.tier = 1; p.HS = f->HS; p.LC = f->LC; p.LV = f->LV; p.EC = f->EC; p.hshift = f->hshift; p.retry = f->d_retry;
+            p.tier = 1; p.HS = f->HS; p.LV = f->LV; p.EC = f->EC; p.hshift = f->hshift; p.retry = f->d_retry;
             fused_plan_kernel<1024><<<std::min(b, cx->num_sms), 1024, f->plan_smem, st>>>(p);
             SCONE_LAUNCHED();
         } else {
@@ -1370,7 +1366,7 @@ int scone_fused_plan_set(const scone_complex* cx, FusedState* f, int B, const in
     PlanArgs p;
     p.flow_edge = flow_edge; p.flow_val = flow_val;
     p.rank = cx->d_rank; p.nbrhoods = cx->d_nbrhoods; p.inc_ptr = cx->d_inc_ptr; p.inc_ent = cx->d_inc_ent;
-    p.mptr = cx->d_mptr; p.ment = cx->d_ment;
+    p.mptr = cx->d_mptr; p.ment = cx->d_ment; p.cone_ptr = f->d_cone_ptr; p.cone_ent = f->d_cone_ent;
     p.N = cx->N; p.D = cx->D; p.E = cx->E; p.L = f->L;
     p.arena = f->d_set_arena; p.bump = f->d_set_bump; p.arena_words = f->set_arena_words; p.overflow = overflow;
     p.n_retry = reinterpret_cast<int*>(f->d_set_bump + 1);
@@ -1380,11 +1376,11 @@ int scone_fused_plan_set(const scone_complex* cx, FusedState* f, int B, const in
         SCONE_CUDA(cudaMemsetAsync(f->d_set_bump + 1, 0, sizeof(unsigned long long), st));       // retry counter only: the arena keeps growing
         p.traj_ptr = traj_ptr + off; p.last_nodes = last_nodes + off; p.hdr = f->d_set_hdr + (size_t)off * kFusedHdrW;
         p.tier = 0; p.n_work = b; p.retry = f->two_tiers ? f->d_retry : nullptr;
-        p.HS = f->HS0; p.LC = f->LC0; p.LV = f->LV0; p.EC = f->EC0; p.hshift = f->hshift0;
+        p.HS = f->HS0; p.LV = f->LV0; p.EC = f->EC0; p.hshift = f->hshift0;
         fused_plan_kernel<256><<<b, 256, f->plan_smem0, st>>>(p);
         SCONE_LAUNCHED();
         if (f->two_tiers) {
-            p.tier = 1; p.HS = f->HS; p.LC = f->LC; p.LV = f->LV; p.EC = f->EC; p.hshift = f->hshift; p.retry = f->d_retry;
+            p.tier = 1; p.HS = f->HS; p.LV = f->LV; p.EC = f->EC; p.hshift = f->hshift; p.retry = f->d_retry;
             fused_plan_kernel<1024><<<std::min(b, cx->num_sms), 1024, f->plan_smem, st>>>(p);
             SCONE_LAUNCHED();
         }

@@ -48,8 +48,8 @@ def test_device_loss_accuracy_and_predictions_match_the_reference_fixture():
         net.weights = weights_of(fx, 'w_' + tag)
         assert abs(float(net.loss(net.weights, inputs, ds.targets, ds.train_mask)) - float(fx[tag + '_loss_train'])) <= 1e-5 * abs(float(fx[tag + '_loss_train']))
         assert abs(float(net.loss(net.weights, inputs, ds.targets, fx['batch_mask'])) - float(fx[tag + '_loss_batch'])) <= 1e-5 * abs(float(fx[tag + '_loss_batch']))
-        assert net.accuracy(net.shifts, inputs, ds.targets, ds.train_mask, n_nbrs) == pytest.approx(float(fx[tag + '_acc_train']), abs=1e-12)
-        assert net.accuracy(net.shifts, inputs, ds.targets, ds.test_mask, n_nbrs) == pytest.approx(float(fx[tag + '_acc_test']), abs=1e-12)
+        assert net.accuracy(net.shifts, inputs, ds.targets, ds.train_mask, n_nbrs) == pytest.approx(float(fx[tag + '_acc_train']), abs=1e-7)         # (the fixture stores float32)
+        assert net.accuracy(net.shifts, inputs, ds.targets, ds.test_mask, n_nbrs) == pytest.approx(float(fx[tag + '_acc_test']), abs=1e-7)
     # predictions: argmax with the -100 masking, first maximum, against NumPy on the reference's log-probs (ties included: at the
     # 0.01-scale init every logit of a row is ~0)
     p = net._prepared(inputs)

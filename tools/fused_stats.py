@@ -19,7 +19,7 @@ print('fused_info', net.fused_info())
 H = np.stack([net.fused_header(t) for t in range(B)])
 def pct(a):
     return ' '.join('%s=%d' % (k, np.percentile(a, q)) for k, q in (('p50', 50), ('p90', 90), ('p99', 99), ('p99.9', 99.9), ('max', 100))) + ' mean=%.1f' % a.mean()
-for name, col in (('n1', 1), ('n2', 2), ('n3', 3), ('hash', 11), ('listed', 12), ('pairs', 10), ('flows', 13)):
+for name, col in (('n1', 1), ('n2', 2), ('n3', 3), ('hash', 11), ('pairs', 10), ('flows', 13)):
     print(name, pct(H[:, col]))
 tot = H[:, 1] + H[:, 2] + H[:, 3]
 print('tot', pct(tot), 'frac tot>256: %.4f' % (tot > 256).mean(), 'flags nonzero:', int((H[:, 0] != 0).sum()))
