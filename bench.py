@@ -572,19 +572,37 @@ def dense_tile_roofline(L, cx, E, C, dev, stream, peak):
             torch.cuda.synchronize()
             best = min(best, a.elapsed_time(z))
         return best
-    f_ms = t_of(lambda: _lib.check(L.scone_layer_forward(cx.handle, 0, bd, C, C, _lib.dptr(Hd), _lib.dptr(Wd[0]), _lib.dptr(Wd[1]),
-                                                         _lib.dptr(Wd[2]), _lib.dptr(Od), None, None, None, stream)))
+    def fwd():
+        _lib.check(L.scone_layer_forward(cx.handle, 0, bd, C, C, _lib.dptr(Hd), _lib.dptr(Wd[0]), _lib.dptr(Wd[1]), _lib.dptr(Wd[2]), _lib.dptr(Od),
+                                         None, None, None, stream))
+    fwd_ms = {}
+    try:
+        for which, nme in ((1, 'slab (mma.sync 3xTF32)'), (3, 'tcgen05 tiles (TMEM operand, 3xTF32)')):
+            L.scone_set_dense_kernel(which)
+            fwd_ms[nme] = t_of(fwd)
+            if which == 3:
+                _lib.check(L.scone_umma_status(stream), 'scone_umma_status')
+    finally:
+        L.scone_set_dense_kernel(1)
+    best = min(fwd_ms, key=fwd_ms.get)
+    f_ms = fwd_ms[best]
     b_ms = t_of(lambda: _lib.check(L.scone_layer_backward(cx.handle, 0, bd, C, C, _lib.dptr(Hd), _lib.dptr(Od), _lib.dptr(Wd[0]),
                                                           _lib.dptr(Wd[1]), _lib.dptr(Wd[2]), _lib.dptr(Od), _lib.dptr(dWd), 0,
                                                           _lib.dptr(wsd), None, None, None, None, stream)))
     fa, ba = 4.0 * E * bd * 2 * C / f_ms / 1e6, 4.0 * E * bd * 3 * C / b_ms / 1e6
     del Hd, Od
     return {'bound': 'hbm', 'unit': 'GB/s', 'peak': peak, 'b': bd, 'tensor_bytes': 4.0 * E * bd * C,
-            'layer_fwd': {'ms': f_ms, 'achieved': fa, 'frac': fa / peak, 'algorithmic_bytes': 4.0 * E * bd * 2 * C},
-            'layer_bwd': {'ms': b_ms, 'achieved': ba, 'frac': ba / peak, 'algorithmic_bytes': 4.0 * E * bd * 3 * C},
+            'layer_fwd': {'kernel': best, 'ms': f_ms, 'achieved': fa, 'frac': fa / peak, 'algorithmic_bytes': 4.0 * E * bd * 2 * C,
+                          'all_kernels_ms': fwd_ms,
+                          'traffic': ncu_traffic('layer_fwd_umma_kernel', 'dense_umma_r2j') if 'tcgen05' in best else
+                          ncu_traffic('layer_fwd_slab_kernel', 'dense_slab_r2i')},
+            'layer_bwd': {'kernel': 'fp32 SIMT tile kernel', 'ms': b_ms, 'achieved': ba, 'frac': ba / peak, 'algorithmic_bytes': 4.0 * E * bd * 3 * C},
             'l2_policy': 'tensors of %.1f GB each: larger than L2' % (4.0 * E * bd * C / 1e9),
-            'note': 'one fused 32->32 layer on dense random features [E][64][32], every row computed (no flags / pruning), best of 3, '
-                    'CUDA events: forward = dense slab kernel, backward = dense tile kernel (DESIGN.md 4)'}
+            'note': 'one fused 32->32 layer on dense random features [E][64][32], every row computed (no flags / pruning), best of 3, CUDA '
+                    'events.  Both forward kernels share the gather (13 neighbour rows per output row through L1, 1.87x the compulsory DRAM '
+                    'reads, 16 warps per SM): with the product moved to tcgen05 the tensor pipe is 10 % busy and the time is unchanged — the '
+                    'bound is the latency of the gather loads at the occupancy 128 registers allow (profiles/prof_dense_*_r2*), not HBM and '
+                    'not the tensor cores'}
 
 
 def bench_bunch(args, cfg, sp, ds, hp, h2d_bytes, B, gb, world, rank, dev, stream, t_setup):

@@ -24,8 +24,10 @@ namespace {
 
 #include "slab_common.cuh"
 
-constexpr int kGatherWarps = 16, kGroupWarps = 8, kUmmaThreads = (kGatherWarps + 1) * 32;      // + one MMA-issuing warp
+constexpr int kGatherWarps = 16, kGroupWarps = 8, kUmmaThreads = kGatherWarps * 32;
+// (no dedicated MMA warp: a 17th warp would put 5 warps on one SM sub-partition and cap every thread at 96 registers)
 constexpr int kC = 32;
+constexpr int kGatherDepth = 4;            // neighbour rows in flight per warp: the gather is bound by load latency at 17 warps per SM
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColsAhi = 0, kColsAlo = 96, kColsD = 192, kColsGroup = 224;
 // f32 accumulate, tf32 x tf32, A / B K-major, N = 32, M = 128 (UMMA instruction descriptor, cute/arch/mma_sm100_desc.hpp)
@@ -91,12 +93,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {       // no-swiz
            ((uint64_t)1 << 46);
 }
 
-// Pipeline.  16 gather warps in two groups of 8 (group = one 128-row MMA tile = 8 consecutive edges x 16 trajectories) + 1 MMA warp.
-//   gather warp, per iteration:   [gather slab i+1 into registers]  while the tensor core works on tile i
-//                                 wait D_full(i) -> tcgen05.ld -> activation -> store          (its 16 rows of tile i)
-//                                 split + tcgen05.st slab i+1 into TMEM -> arrive on A_full    (8 arrivals complete a tile)
-//   MMA warp, per iteration and group:  wait A_full -> 36 tcgen05.mma -> tcgen05.commit -> D_full
-// D may be overwritten by tile i+1 only after all 8 warps read tile i: they arrive on A_full(i+1) after their tcgen05.ld completed.
+// Pipeline.  16 warps in two groups of 8 (group = one 128-row MMA tile = 8 consecutive edges x 16 trajectories).
+//   per warp and iteration:   [gather slab i+1 into registers]  while the tensor core works on tile i
+//                             wait D_full(i) -> tcgen05.ld -> activation -> store           (its 16 rows of tile i)
+//                             split + tcgen05.st slab i+1 into TMEM -> count itself in       (the 8th arrival issues the tile's
+//                                                                                             36 tcgen05.mma + tcgen05.commit -> D_full)
+// D may be overwritten by tile i+1 only after all 8 warps read tile i: each counts itself in for tile i+1 after its tcgen05.ld completed.
 // A may be overwritten by slab i+1 only after the MMAs of tile i finished: the warp waited on D_full(i) first.
 template <int ACT>
 __global__ void __launch_bounds__(kUmmaThreads, 1) layer_fwd_umma_kernel(const float* __restrict__ Hin, float* __restrict__ Hout,
@@ -109,7 +111,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) layer_fwd_umma_kernel(const f
     // B operand: [hi | lo][k-chunk 24][n-group 4][8 rows][4 floats]; element (n, k) of the stacked weights, k = 32 term + 8 s + kappa
     // <-> input channel chan(s, kappa) of W_term (the k order of the gather's fragments)
     __shared__ __align__(128) float Bs[2][24 * 4 * 32];
-    __shared__ __align__(8) uint64_t s_afull[2], s_dfull[2];
+    __shared__ __align__(8) uint64_t s_dfull[2];
+    __shared__ unsigned s_arrived[2];                     // warps of the group whose rows of the current tile are in TMEM
     __shared__ uint32_t s_tmem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tig = lane & 3;
 
@@ -118,8 +121,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) layer_fwd_umma_kernel(const f
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (threadIdx.x == 0) {
-        mbar_init(&s_afull[0], kGroupWarps);
-        mbar_init(&s_afull[1], kGroupWarps);
+        s_arrived[0] = s_arrived[1] = 0u;
         mbar_init(&s_dfull[0], 1);
         mbar_init(&s_dfull[1], 1);
     }
@@ -145,31 +147,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) layer_fwd_umma_kernel(const f
     const long long per = (n_tiles + gridDim.x - 1) / gridDim.x;
     const long long lo = (long long)blockIdx.x * per, hi = lo + per < n_tiles ? lo + per : n_tiles;
 
-    if (warp == kGatherWarps) {
-        // ---- MMA warp ----
-        const uint32_t bhi = smem_u32(&Bs[0][0]), blo = smem_u32(&Bs[1][0]);
-        uint32_t phase = 0;
-        for (long long tile = lo; tile < hi; ++tile) {
-#pragma unroll
-            for (int group = 0; group < 2; ++group) {
-                mbar_wait(&s_afull[group], phase, err);
-                tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t tbase = s_tmem + (uint32_t)group * kColsGroup;
-#pragma unroll
-                    for (int j = 0; j < 12; ++j) {         // K = 96 in steps of 8: two 16-byte k-chunks of B per step
-                        const uint64_t dh = umma_desc(bhi + (uint32_t)j * 2 * kLbo), dl = umma_desc(blo + (uint32_t)j * 2 * kLbo);
-                        umma_tf32_ts(tbase + kColsD, tbase + kColsAlo + 8 * j, dh, j > 0 ? 1u : 0u);
-                        umma_tf32_ts(tbase + kColsD, tbase + kColsAhi + 8 * j, dl, 1u);
-                        umma_tf32_ts(tbase + kColsD, tbase + kColsAhi + 8 * j, dh, 1u);
-                    }
-                    umma_commit(&s_dfull[group]);
-                }
-                __syncwarp();
-            }
-            phase ^= 1u;
-        }
-    } else {
+    {
         // ---- gather warps ----
         const int group = warp / kGroupWarps, gw = warp % kGroupWarps;
         const uint32_t tbase = s_tmem + (uint32_t)group * kColsGroup;
@@ -190,7 +168,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) layer_fwd_umma_kernel(const f
                 t0 = ts * TS;
                 live = e0 < E;                             // (a dead slab still takes part in the barriers; its rows are never stored)
                 if (live) {
-                    slab_gather<kC, TS>(Hin, rowbytes_in, mptr, ment, E, b, e0, t0, acc);
+                    slab_gather<kC, TS, kGatherDepth>(Hin, rowbytes_in, mptr, ment, E, b, e0, t0, acc);
                 } else {
 #pragma unroll
                     for (int k = 0; k < 3; ++k)
@@ -238,7 +216,27 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) layer_fwd_umma_kernel(const f
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&s_afull[group]);
+                // the LAST of the group's 8 warps to get here issues the tile's MMAs (acq_rel counter: the other warps' TMEM stores
+                // happen-before its tcgen05.mma); nobody waits for anybody
+                unsigned last_one = 0u;
+                if (lane == 0) {
+                    unsigned old;
+                    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(&s_arrived[group])) : "memory");
+                    last_one = (old % kGroupWarps) == (unsigned)(kGroupWarps - 1) ? 1u : 0u;     // (the counter runs on: no reset to order)
+                    if (last_one) {
+                        tc_fence_after();
+                        const uint32_t bhi = smem_u32(&Bs[0][0]), blo = smem_u32(&Bs[1][0]);
+#pragma unroll
+                        for (int j = 0; j < 12; ++j) {     // K = 96 in steps of 8: two 16-byte k-chunks of B per step
+                            const uint64_t dh = umma_desc(bhi + (uint32_t)j * 2 * kLbo), dl = umma_desc(blo + (uint32_t)j * 2 * kLbo);
+                            umma_tf32_ts(tbase + kColsD, tbase + kColsAlo + 8 * j, dh, j > 0 ? 1u : 0u);
+                            umma_tf32_ts(tbase + kColsD, tbase + kColsAhi + 8 * j, dl, 1u);
+                            umma_tf32_ts(tbase + kColsD, tbase + kColsAhi + 8 * j, dh, 1u);
+                        }
+                        umma_commit(&s_dfull[group]);
+                    }
+                }
+                __syncwarp();
                 pending = true;
                 plive = live;
                 pe0 = e0;

@@ -220,7 +220,7 @@ __device__ __forceinline__ void slab_accumulate(u64 (&acc)[3][SlabGeom<C, TS>::N
     }
 }
 
-template <int C, int TS>
+template <int C, int TS, int DEPTH = 2>
 __device__ __forceinline__ void slab_gather(const float* __restrict__ H, unsigned rowbytes, const int32_t* __restrict__ mptr,
                                             const int2* __restrict__ ment, int E, int b, int e0, int t0,
                                             u64 (&acc)[3][SlabGeom<C, TS>::NL][2]) {
@@ -255,6 +255,20 @@ __device__ __forceinline__ void slab_gather(const float* __restrict__ H, unsigne
             for (int j = 0; j < G::LPE; ++j)
                 ldg128(reinterpret_cast<const float*>(P[j] + r0), acc[0][x * G::LPE + j][0], acc[0][x * G::LPE + j][1]);
         }
+        if (DEPTH > 2)
+            for (; p + DEPTH <= p1; p += DEPTH) {        // DEPTH neighbour rows in flight (kernels with registers to spare)
+                int2 nd[DEPTH > 2 ? DEPTH : 1];
+                u64 vd[DEPTH > 2 ? DEPTH : 1][G::LPE][2];
+#pragma unroll
+                for (int u = 0; u < DEPTH; ++u) nd[u] = __ldg(ment + p + u);
+#pragma unroll
+                for (int u = 0; u < DEPTH; ++u)
+#pragma unroll
+                    for (int j = 0; j < G::LPE; ++j)
+                        ldg128(reinterpret_cast<const float*>(P[j] + (size_t)(unsigned)nd[u].x * rowbytes), vd[u][j][0], vd[u][j][1]);
+#pragma unroll
+                for (int u = 0; u < DEPTH; ++u) slab_accumulate<C, TS>(acc, x, nd[u].y, vd[u]);
+            }
         for (; p + 2 <= p1; p += 2) {                    // two neighbour rows in flight
             const int2 na = __ldg(ment + p), nb = __ldg(ment + p + 1);
             u64 va[G::LPE][2], vb[G::LPE][2];
