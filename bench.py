@@ -275,8 +275,14 @@ def main():
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU path)'
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    saved_stdout = None
     if world > 1:
-        os.environ['NCCL_DEBUG_FILE'] = '/dev/stderr'       # keep stdout to the one JSON line (NCCL prints its version banner)
+        # stdout carries exactly one JSON line: NCCL prints its version banner to fd 1 at the first collective, so fd 1 points at
+        # stderr until the result is printed
+        os.environ['NCCL_DEBUG_FILE'] = '/dev/stderr'
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group('nccl', device_id=dev)
     L = sg.lib()
 
@@ -542,6 +548,9 @@ def main():
                'roofline': roofline, 'roofline_dense': roofline_dense, 'plans_cached': plans_cached, 'e2e': e2e,
                'cpu_baseline': cpu_baseline, 'parity_check': parity, 'gpu_launches': int(launches),
                'clocks': clk, 'setup_s': setup_s, 'fused_info': info}
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
         print(json.dumps(out), flush=True)
         if parity is not None and not parity['ok']:
             sys.stderr.write('bench parity check FAILED: %s\n' % parity)
