@@ -256,7 +256,7 @@ int scone_model_set_weights_keep_state(scone_model* m, const float* weights_host
  * ring whose flows can reach it), [2] bound on |T_1| (rows a layer can have), [3] hash slots of tier 1, [4] trajectories per arena
  * chunk, [5] rows of the shared-memory row store, [6] / [7] KB of dynamic shared memory of the tier-1 plan / the compute kernel,
  * [8] / [9] hash slots / live rows per layer of tier 0 (tables that hold the cone of ~99 % of the nodes), [10] its KB, [11] two tiers in
- * use, [12] worst-case arena words per trajectory, [13] arena Mwords, [14] K entries of the per-complex cone table,
+ * use, [12] MB of the node table's operator rows (plans come from the table plan kernel; 0 = the hash plan: SCONE_FUSED_TABLE=0 or not enough memory), [13] arena Mwords, [14] K entries of the per-complex cone table,
  * [15] trajectories of the last chunk the first tier handed to the second (synchronises the device). */
 int scone_model_fused_info(const scone_model* m, int32_t* out /* [16] */);
 /* Plan of trajectory t of the LAST chunk run (synchronises the device): header (16 ints, layout in csrc/fused.cuh) and `words` 32-bit

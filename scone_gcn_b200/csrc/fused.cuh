@@ -13,6 +13,80 @@ constexpr int kFusedFlagRetry = 2;        // tier 0 of the plan kernel overflowe
 //   [7],[8] transposed programs of layers 2, 3 (rows = live rows of layer l - 1, entries = rows of layer l)
 //   [9] readout: rowptr[D + 1] then int2 {row of H_L | slot << 16, sign bits}   [10] pairs   [11] hash entries (flows + cone)
 //   [12] unused   [13] flow entries
+// Arguments of the plan kernels (both flavours: the hash plan of scone_fused.cu and the table plan of scone_plan_table.cu)
+struct PlanArgs {
+    const int32_t* traj_ptr;
+    const int32_t* flow_edge;
+    const float* flow_val;
+    const int32_t* last_nodes;
+    const int32_t* rank;
+    const int32_t* nbrhoods;
+    const int32_t* inc_ptr;
+    const int2* inc_ent;
+    const int32_t* mptr;
+    const int2* ment;
+    int N, D, E, L;
+    int HS, hshift;            // hash plan: hash slots (power of two): the flow edges and the cone T_0 of the trajectory
+    const unsigned* cone_ptr;  // cone table: entries of node n at cone_ent[cone_ptr[n] .. cone_ptr[n + 1]), ascending edge id
+    const uint32_t* cone_ent;  //   edge | level << 30
+    int LV;                    // live rows per layer
+    int EC;                    // hash plan: merged-row entries of the live rows of one layer (slot buffer)
+    // node table (table plan): the operator rows of the cone in LOCAL indices (position of the edge in the node's cone entries)
+    int M;                     // cone entries this tier's tables hold
+    const unsigned long long* node_off;   // [N + 1] first row entry of node n
+    const unsigned* tb_rowptr;            // m + 1 local offsets per node, at cone_ptr[n] + n
+    const int2* tb_ent;                   // {local column | own << 31, (c1 << 16) | c0}, ascending column
+    const unsigned* pair_ptr;             // [N + 1] readout pairs of node n
+    const int2* tb_pairs;                 // {local index | neighbour slot << 16, sign bits}
+    const int* pair_off;                  // [N][D + 1] first pair of every neighbour slot
+    int* hdr;
+    uint32_t* arena;
+    unsigned long long* bump;
+    unsigned long long arena_words;
+    int* overflow;
+    int tier;                  // 0: trajectory = work item, tables sized for ~99 % of the nodes; 1: the retry list, tables sized by the bounds
+    int n_work;                // tier 0: trajectories of the chunk
+    int* n_retry;              // device counter of the retry list
+    int* retry;                // [chunk]
+};
+
+#ifdef __CUDACC__
+// exclusive scan of a[0..n) in place (a[n] = total); every thread of the THREADS-thread CTA calls it
+template <int THREADS>
+__device__ inline int fused_block_scan_excl(int* a, int n, int* s_warp) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n + THREADS - 1) / THREADS;
+    const int lo = min(n, tid * per), hi = min(n, lo + per);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += a[i];
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    __syncthreads();                                      // (s_warp may still be read from a previous call)
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) {
+        const int v = s_warp[w];
+        if (w < warp) base += v;
+        total += v;
+    }
+    int run = base + inc - sum;
+    for (int i = lo; i < hi; ++i) {
+        const int v = a[i];
+        a[i] = run;
+        run += v;
+    }
+    if (tid == 0) a[n] = total;
+    __syncthreads();
+    return total;
+}
+#endif
+
 struct FusedState {
     int L = 0, C = 0;
     int64_t n_params = 0;
@@ -20,6 +94,19 @@ struct FusedState {
     unsigned* d_cone_ptr = nullptr;       // cone table: T_0 of every node, entries edge | level << 30
     uint32_t* d_cone_ent = nullptr;
     unsigned long long cone_entries = 0;
+    // node table (scone_plan_table.cu): operator rows of every node's cone in local indices + its readout pairs
+    bool tb_rows = false;                 // the table holds rows: plans come from table_plan_kernel (else: the hash plan)
+    unsigned long long* d_node_off = nullptr;
+    unsigned* d_tb_rowptr = nullptr;
+    int2* d_tb_ent = nullptr;
+    unsigned* d_pair_ptr = nullptr;
+    int2* d_tb_pairs = nullptr;
+    int* d_pair_off = nullptr;
+    unsigned long long tb_entries = 0, tb_bytes = 0;
+    int tbM0 = 0, tbLV0 = 0, tbM = 0, tbLV = 0;   // table plan tiers: cone entries / live rows per layer the tables hold
+    size_t tb_smem0 = 0, tb_smem = 0;
+    bool tb_two_tiers = false;
+    int quantile_cone = 0;                // |T_0| of ~99 % of the nodes
     int HS = 0, LV = 0, EC = 0, hshift = 0;        // plan tables, tier 1: sized by the bounds
     int HS0 = 0, LV0 = 0, EC0 = 0, hshift0 = 0;   // tier 0: sized for the cones of 99 % of the nodes
     bool two_tiers = false;
@@ -45,6 +132,11 @@ struct FusedState {
     unsigned long long set_arena_words = 0;
     int set_cap = 0, set_n = 0;
 };
+
+// scone_plan_table.cu
+int scone_table_build(const scone_complex* cx, FusedState* f, int L, bool* ok);
+int scone_table_plan_launch(const FusedState* f, PlanArgs p, int b, int num_sms, cudaStream_t st);
+void scone_table_destroy(FusedState* f);
 
 bool scone_fused_supported(const scone_complex* cx, int n_layers, const int32_t* hidden);
 int scone_fused_create(const scone_complex* cx, int L, int C, int mb, int64_t n_params, FusedState** out);

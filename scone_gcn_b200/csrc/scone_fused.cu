@@ -1,7 +1,8 @@
 // scone_fused.cu — pipeline 4: the TRAJECTORY-FUSED path behind the model-level entry points (uniform hidden width 16 / 32,
 // at most 3 conv layers).  Two kernels per micro-batch instead of the ~25 launches of the bitmap pipeline:
 //
-//   fused_plan_kernel   (weight-independent integer work, one CTA per trajectory)
+//   fused_plan_kernel   (weight-independent integer work, one CTA per trajectory; the HASH plan — the fallback of the table plan in
+//                        scone_plan_table.cu, which produces the same headers and programs from per-node operator rows)
 //        receptive cone of the readout (trajectory_experiments.py:151,298-303: the log-probs read H_L only at the edges incident
 //        to the neighbours of the last node; one merged-operator hop further down per layer), intersected layer by layer with the
 //        structural support of the flows (no bias, act(0) = 0: a row with no live neighbour below is exactly zero) -> per layer
@@ -16,7 +17,7 @@
 //        the weight gradients accumulated in mma accumulator REGISTERS across all trajectories of the CTA; one partial vector
 //        per CTA, reduced in CTA order by fused_reduce_kernel.  Activations and gradients of a trajectory never leave the SM.
 //
-// All capacities are STATIC bounds measured once per complex (fused_bound_kernel: the cone of every possible last node), so a
+// All capacities are STATIC bounds measured once per complex (scone_table_build: the cone of every possible last node), so a
 // micro-batch cannot overflow: the hash set holds |T_0| <= bound entries, a layer has at most |T_1| <= bound rows, the program
 // arena is sized for the worst case.  A trajectory whose rows do not fit the shared-memory row store runs in the BIG variant of
 // the same kernel (rows in a per-CTA global scratch).
@@ -29,11 +30,9 @@ namespace {
 
 #include "slab_common.cuh"
 
-constexpr int kPlanThreads = 256;
 constexpr int kTrajThreads = 256;
 constexpr int kFuMaxD = 128;
 constexpr uint32_t kNoRow = 0xFFFFu;
-constexpr int kBoundBuckets = 1024;
 
 template <int ACT>
 __device__ __forceinline__ float fu_act(float z) {
@@ -108,140 +107,6 @@ struct FuPairs {
     }
 };
 
-// exclusive scan of a[0..n) in place (a[n] = total); every thread of the 256-thread CTA calls it
-__device__ int block_scan_excl(int* a, int n, int* s_warp) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (n + kPlanThreads - 1) / kPlanThreads;
-    const int lo = min(n, tid * per), hi = min(n, lo + per);
-    int sum = 0;
-    for (int i = lo; i < hi; ++i) sum += a[i];
-    int inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += v;
-    }
-    __syncthreads();                                      // (s_warp may still be read from a previous call)
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    int base = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < kPlanThreads / 32; ++w) {
-        const int v = s_warp[w];
-        if (w < warp) base += v;
-        total += v;
-    }
-    int run = base + inc - sum;
-    for (int i = lo; i < hi; ++i) {
-        const int v = a[i];
-        a[i] = run;
-        run += v;
-    }
-    if (tid == 0) a[n] = total;
-    __syncthreads();
-    return total;
-}
-
-struct PlanArgs {
-    const int32_t* traj_ptr;
-    const int32_t* flow_edge;
-    const float* flow_val;
-    const int32_t* last_nodes;
-    const int32_t* rank;
-    const int32_t* nbrhoods;
-    const int32_t* inc_ptr;
-    const int2* inc_ent;
-    const int32_t* mptr;
-    const int2* ment;
-    int N, D, E, L;
-    int HS, hshift;            // hash slots (power of two): the flow edges and the cone T_1 of the trajectory
-    const unsigned* cone_ptr;  // cone table: entries of node n at cone_ent[cone_ptr[n] .. cone_ptr[n + 1])
-    const uint32_t* cone_ent;  //   edge | level << 30
-    int LV;                    // live rows per layer
-    int EC;                    // merged-row entries of the live rows of one layer (slot buffer)
-    int* hdr;
-    uint32_t* arena;
-    unsigned long long* bump;
-    unsigned long long arena_words;
-    int* overflow;
-    int tier;                  // 0: trajectory = work item, tables sized for ~99 % of the nodes; 1: the retry list, tables sized by the bounds
-    int n_work;                // tier 0: trajectories of the chunk
-    int* n_retry;              // device counter of the retry list
-    int* retry;                // [chunk]
-};
-
-// The receptive cone depends on the complex and the last node only: it is built ONCE per complex for every node (cone table) and a
-// plan just loads the cone of its last node.  blockIdx.x = node: level L = edges incident to its neighbours, one merged-row hop
-// further down per level, down to level 0 (T_0 = the edges whose flow value can reach a row of T_1).  Two passes:
-//   cone_ent == NULL   count: cnt[node] = |T_0|; stats[0] = max |T_0|, stats[1] = max |T_1| (rows a layer can have), stats[2] = 1 if
-//                      even the largest tables overflowed, histogram of |T_0| in buckets of 32 from stats[4] on
-//   cone_ent != NULL   fill: entries (edge | level << 30) at cone_ptr[node] .. (order = arrival order: nothing depends on it)
-__global__ void __launch_bounds__(kPlanThreads) fused_cone_kernel(const int32_t* __restrict__ nbrhoods, const int32_t* __restrict__ inc_ptr,
-                                                                 const int2* __restrict__ inc_ent, const int32_t* __restrict__ mptr,
-                                                                 const int2* __restrict__ ment, int N, int D, int L, int HS, int LC,
-                                                                 int hshift, int* __restrict__ stats, int* __restrict__ cnt,
-                                                                 const unsigned* __restrict__ cone_ptr, uint32_t* __restrict__ cone_ent) {
-    extern __shared__ __align__(16) unsigned char sm[];
-    int* keys = reinterpret_cast<int*>(sm);
-    int* list = keys + HS;
-    __shared__ FuPairs pairs;
-    __shared__ int s_nlist, s_nhash, s_n1, s_ovf, s_nat[kFusedMaxL + 2];
-    const int tid = threadIdx.x, ql = tid & 3;
-    for (int i = tid; i < HS; i += kPlanThreads) keys[i] = -1;
-    if (tid == 0) s_nlist = s_nhash = s_n1 = s_ovf = 0;
-    const int node = blockIdx.x;
-    const int total = pairs.setup(nbrhoods, inc_ptr, node, node < N, D);
-    EdgeSet set{keys, HS - 1, hshift};
-    uint32_t* out = cone_ent != nullptr ? cone_ent + cone_ptr[node] : nullptr;
-    auto add = [&](int e, int lv) {
-        bool is_new;
-        const int s = set.insert(e, is_new);
-        if (s < 0) {
-            s_ovf = 1;
-            return;
-        }
-        if (is_new) {
-            const int k = atomicAdd(&s_nhash, 1);
-            if (k >= (HS * 3) / 4) s_ovf = 1;
-            else if (out != nullptr) out[k] = (uint32_t)e | ((uint32_t)lv << 30);
-            if (lv >= 1) {                                  // level 0 edges are not expanded
-                atomicAdd(&s_n1, 1);
-                const int pos = atomicAdd(&s_nlist, 1);
-                if (pos < LC) list[pos] = e;
-                else s_ovf = 1;
-            }
-        }
-    };
-    for (int i = tid; i < total; i += kPlanThreads) {
-        const int j = pairs.slot_of(i, D);
-        add(inc_ent[pairs.s_ptr[j] + (i - pairs.s_off[j])].x, L);
-    }
-    __syncthreads();
-    if (tid == 0) s_nat[L] = min(s_nlist, LC);
-    __syncthreads();
-    int f0 = 0;
-    for (int lv = L - 1; lv >= 0; --lv) {
-        const int f1 = s_nat[lv + 1];
-        if (!s_ovf)
-            for (int i = f0 + (tid >> 2); i < f1; i += kPlanThreads / 4) {
-                const int e = list[i];
-                const int p1 = mptr[e + 1];
-                for (int q = mptr[e] + ql; q < p1; q += 4) add(ment[q].x, lv);
-            }
-        __syncthreads();
-        if (tid == 0) s_nat[lv] = min(s_nlist, LC);
-        __syncthreads();
-        f0 = f1;
-    }
-    if (tid == 0 && cone_ent == nullptr) {
-        cnt[node] = s_nhash;
-        atomicMax(&stats[0], s_nhash);
-        atomicMax(&stats[1], s_n1);
-        if (s_ovf) stats[2] = 1;
-        atomicAdd(&stats[4 + min(kBoundBuckets - 1, s_nhash / 32)], 1);
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
 // the plan of one trajectory (one CTA of THREADS threads)
 //
@@ -256,40 +121,6 @@ __global__ void __launch_bounds__(kPlanThreads) fused_cone_kernel(const int32_t*
 //                 entry is kept in shared memory (ebuf) and serves the layer's forward program (or the layer-1 scalars), the marking
 //                 of the next layer's live rows and the next layer's transposed program
 // ---------------------------------------------------------------------------------------------------------------------
-template <int THREADS>
-__device__ int block_scan_excl_t(int* a, int n, int* s_warp) {   // exclusive scan of a[0..n) in place (a[n] = total)
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (n + THREADS - 1) / THREADS;
-    const int lo = min(n, tid * per), hi = min(n, lo + per);
-    int sum = 0;
-    for (int i = lo; i < hi; ++i) sum += a[i];
-    int inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += v;
-    }
-    __syncthreads();                                      // (s_warp may still be read from a previous call)
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    int base = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < THREADS / 32; ++w) {
-        const int v = s_warp[w];
-        if (w < warp) base += v;
-        total += v;
-    }
-    int run = base + inc - sum;
-    for (int i = lo; i < hi; ++i) {
-        const int v = a[i];
-        a[i] = run;
-        run += v;
-    }
-    if (tid == 0) a[n] = total;
-    __syncthreads();
-    return total;
-}
-
 template <int THREADS>
 __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, unsigned char* sm) {
     constexpr int QUADS = THREADS / 4;
@@ -445,7 +276,7 @@ __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, 
             if (ql == 0) rowcnt[r] = c;
         }
         __syncthreads();
-        const int total = block_scan_excl_t<THREADS>(rowcnt, n_rows, s_warp);
+        const int total = fused_block_scan_excl<THREADS>(rowcnt, n_rows, s_warp);
         const unsigned off = alloc(align2(n_rows + 1) + 2 * total);
         if (!s_ovf) {
             int* pdst = reinterpret_cast<int*>(a.arena + off);
@@ -486,7 +317,7 @@ __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, 
             rowcnt[r] = a.mptr[e + 1] - a.mptr[e];
         }
         __syncthreads();
-        const int n_ent = block_scan_excl_t<THREADS>(rowcnt, n_cur, s_warp);
+        const int n_ent = fused_block_scan_excl<THREADS>(rowcnt, n_cur, s_warp);
         if (n_ent > EC) {                                  // (uniform) this tier's entry buffer is too small
             if (tid == 0) s_ovf = 1;
             __syncthreads();
@@ -1115,8 +946,9 @@ bool scone_fused_supported(const scone_complex* cx, int n_layers, const int32_t*
 
 void scone_fused_destroy(FusedState* f) {
     if (!f) return;
-    cudaFree(f->d_hdr); cudaFree(f->d_retry); cudaFree(f->d_arena); cudaFree(f->d_set_hdr); cudaFree(f->d_set_arena); cudaFree(f->d_set_bump); cudaFree(f->d_cone_ptr); cudaFree(f->d_cone_ent); cudaFree(f->d_bump); cudaFree(f->d_partial); cudaFree(f->d_scratch); cudaFree(f->d_stats);
+    cudaFree(f->d_hdr); cudaFree(f->d_retry); cudaFree(f->d_arena); cudaFree(f->d_set_hdr); cudaFree(f->d_set_arena); cudaFree(f->d_set_bump); cudaFree(f->d_bump); cudaFree(f->d_partial); cudaFree(f->d_scratch); cudaFree(f->d_stats);
     cudaFree(f->d_rows_done);
+    scone_table_destroy(f);
     delete f;
 }
 
@@ -1137,48 +969,15 @@ int scone_fused_create(const scone_complex* cx, int L, int C, int mb, int64_t n_
     f->L = L;
     f->C = C;
     f->n_params = n_params;
-    // ---- the cone table: T_0 of every node (weight- and data-independent geometry of the complex), built in two passes with the
-    // largest tables one CTA can hold; its sizes are the static bounds of the pipeline ----
-    const int n_stats = 4 + kBoundBuckets;
-    SCONE_CUDA(cudaMalloc((void**)&f->d_stats, n_stats * sizeof(int)));
-    SCONE_CUDA(cudaMemset(f->d_stats, 0, n_stats * sizeof(int)));
-    std::vector<int> st(n_stats, 0);
+    // ---- the node table: cone entries of every node (and, memory permitting, the operator rows of the cone in local indices: the
+    // table plan); weight- and data-independent geometry of the complex.  Its sizes are the static bounds of the pipeline ----
     {
-        const int HS = 32768, LC = 16384, hshift = 32 - 15;
-        const size_t smem = (size_t)HS * 4 + (size_t)LC * 4;
-        int* d_cnt = nullptr;
-        SCONE_CUDA(cudaMalloc((void**)&d_cnt, ((size_t)cx->N + 1) * sizeof(int)));
-        SCONE_CUDA(cudaFuncSetAttribute(fused_cone_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fused_cone_kernel<<<cx->N, kPlanThreads, smem>>>(cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, cx->d_mptr, cx->d_ment, cx->N, cx->D, L, HS, LC,
-                                                         hshift, f->d_stats, d_cnt, nullptr, nullptr);
-        SCONE_LAUNCHED();
-        SCONE_CUDA(cudaMemcpy(st.data(), f->d_stats, n_stats * sizeof(int), cudaMemcpyDeviceToHost));
-        std::vector<int> cnt((size_t)cx->N);
-        SCONE_CUDA(cudaMemcpy(cnt.data(), d_cnt, (size_t)cx->N * sizeof(int), cudaMemcpyDeviceToHost));
-        cudaFree(d_cnt);
-        unsigned long long total = 0;
-        for (int v : cnt) total += (unsigned long long)v;
-        if (st[2] || total >= (1ull << 32)) {             // cones larger than any table: not this pipeline's regime
+        bool ok = false;
+        const int rc = scone_table_build(cx, f, L, &ok);
+        if (rc || !ok) {                                   // cones larger than any table: not this pipeline's regime
             scone_fused_destroy(f);
-            return 0;
+            return rc;
         }
-        std::vector<unsigned> ptr((size_t)cx->N + 1);
-        unsigned run = 0;
-        for (int n = 0; n < cx->N; ++n) {
-            ptr[n] = run;
-            run += (unsigned)cnt[n];
-        }
-        ptr[cx->N] = run;
-        f->cone_entries = total;
-        SCONE_CUDA(cudaMalloc((void**)&f->d_cone_ptr, ptr.size() * sizeof(unsigned)));
-        SCONE_CUDA(cudaMalloc((void**)&f->d_cone_ent, (size_t)(total ? total : 1) * sizeof(uint32_t)));
-        SCONE_CUDA(cudaMemcpy(f->d_cone_ptr, ptr.data(), ptr.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
-        fused_cone_kernel<<<cx->N, kPlanThreads, smem>>>(cx->d_nbrhoods, cx->d_inc_ptr, cx->d_inc_ent, cx->d_mptr, cx->d_ment, cx->N, cx->D, L, HS, LC,
-                                                         hshift, f->d_stats, nullptr, f->d_cone_ptr, f->d_cone_ent);
-        SCONE_LAUNCHED();
-        SCONE_CUDA(cudaDeviceSynchronize());
-        f->bound_cone = st[0] > 0 ? st[0] : 1;            // |T_0|: hash entries
-        f->bound_list = st[1] > 0 ? st[1] : 1;            // |T_1|: rows a layer can have
     }
     int max_row = 1;
     {
@@ -1203,24 +1002,15 @@ int scone_fused_create(const scone_complex* cx, int L, int C, int mb, int64_t n_
             f->EC = (int)(((size_t)kMaxPlanSmem - fixed) / 2) & ~63;
     }
     f->plan_smem = plan_smem_bytes(f->HS, f->LV, f->EC);
-    if (f->plan_smem > (size_t)kMaxPlanSmem || f->bound_list >= 0xFFFF || f->HS > 32768) {
+    if (!f->tb_rows && (f->plan_smem > (size_t)kMaxPlanSmem || f->bound_list >= 0xFFFF || f->HS > 32768)) {   // neither plan kernel fits
         scone_fused_destroy(f);
         return 0;
     }
     {
-        long long acc = 0, want = ((long long)cx->N * 99 + 99) / 100;
-        int q0 = 32 * kBoundBuckets;
-        for (int b = 0; b < kBoundBuckets; ++b) {
-            acc += st[4 + b];
-            if (acc >= want) {
-                q0 = 32 * (b + 1);
-                break;
-            }
-        }
         // (tools/sweep_plan_tiers.sh on the 1M-edge bench complex: 1024 slots / 27 KB per CTA beat 2048 / 45 KB although twice as
         // many trajectories go to the second tier — occupancy is what the first tier lives on; 192 live rows / 3072 entries per
         // layer hold all but the trajectories the compute kernel sends to its big variant anyway)
-        table_shape(std::min(q0, f->bound_cone), &f->HS0, &f->hshift0);
+        table_shape(f->quantile_cone, &f->HS0, &f->hshift0);
         f->LV0 = std::min(192, f->LV);
         f->EC0 = std::min(3072, f->EC);
         f->two_tiers = f->HS0 < f->HS || f->LV0 < f->LV || f->EC0 < f->EC;
@@ -1288,6 +1078,24 @@ int scone_fused_create(const scone_complex* cx, int L, int C, int mb, int64_t n_
     return 0;
 }
 
+// Plan kernels over b trajectories (p: trajectories, outputs and the retry list set by the caller): the table plan when the node table
+// holds rows, else the hash plan; first tier, then the retry list.
+static int launch_plans(const scone_complex* cx, const FusedState* f, PlanArgs p, int b, cudaStream_t st) {
+    if (f->tb_rows) return scone_table_plan_launch(f, p, b, cx->num_sms, st);
+    p.tier = 0; p.n_work = b;
+    p.HS = f->HS0; p.LV = f->LV0; p.EC = f->EC0; p.hshift = f->hshift0;
+    int* retry = p.retry;
+    if (!f->two_tiers) p.retry = nullptr;
+    fused_plan_kernel<256><<<b, 256, f->plan_smem0, st>>>(p);
+    SCONE_LAUNCHED();
+    if (f->two_tiers) {                                    // the few trajectories whose cone overflowed the first tier's tables: 1024 threads each
+        p.tier = 1; p.HS = f->HS; p.LV = f->LV; p.EC = f->EC; p.hshift = f->hshift; p.retry = retry;
+        fused_plan_kernel<1024><<<std::min(b, cx->num_sms), 1024, f->plan_smem, st>>>(p);
+        SCONE_LAUNCHED();
+    }
+    return 0;
+}
+
 // One chunk (<= f->chunk trajectories, device pointers already offset to the chunk): plan + compute (+ partial reduce into grad).
 int scone_fused_run(const scone_complex* cx, FusedState* f, int act, int b, const int32_t* traj_ptr, const int32_t* flow_edge,
                     const float* flow_val, const int32_t* last_nodes, const float* W, const int64_t* w_off, float* logprobs,
@@ -1296,26 +1104,17 @@ int scone_fused_run(const scone_complex* cx, FusedState* f, int act, int b, cons
     SCONE_REQUIRE(b <= f->chunk, "scone_fused_run: chunk of %d trajectories exceeds the planned %d", b, f->chunk);
     const bool want_grad = grad != nullptr;
     SCONE_CUDA(cudaMemsetAsync(f->d_bump, 0, 2 * sizeof(unsigned long long), st));
-    PlanArgs p;
+    PlanArgs p{};
     p.traj_ptr = traj_ptr; p.flow_edge = flow_edge; p.flow_val = flow_val; p.last_nodes = last_nodes;
     p.rank = cx->d_rank; p.nbrhoods = cx->d_nbrhoods; p.inc_ptr = cx->d_inc_ptr; p.inc_ent = cx->d_inc_ent;
     p.mptr = cx->d_mptr; p.ment = cx->d_ment; p.cone_ptr = f->d_cone_ptr; p.cone_ent = f->d_cone_ent;
-    p.N = cx->N; p.D = cx->D; p.E = cx->E; p.L = f->L; p.HS = f->HS0; p.LV = f->LV0; p.EC = f->EC0; p.hshift = f->hshift0;
+    p.N = cx->N; p.D = cx->D; p.E = cx->E; p.L = f->L;
     p.hdr = f->d_hdr; p.arena = f->d_arena; p.bump = f->d_bump; p.arena_words = f->arena_words; p.overflow = overflow;
-    p.tier = 0; p.n_work = b; p.n_retry = reinterpret_cast<int*>(f->d_bump + 1); p.retry = f->two_tiers ? f->d_retry : nullptr;
+    p.n_retry = reinterpret_cast<int*>(f->d_bump + 1); p.retry = f->d_retry;
     {
         ScopedProf prof(SCONE_K_CONE, st);
-        if (f->two_tiers) {
-            fused_plan_kernel<256><<<b, 256, f->plan_smem0, st>>>(p);
-            SCONE_LAUNCHED();
-            // the few trajectories whose cone overflowed the first tier's tables: 1024 threads each
-            p.tier = 1; p.HS = f->HS; p.LV = f->LV; p.EC = f->EC; p.hshift = f->hshift; p.retry = f->d_retry;
-            fused_plan_kernel<1024><<<std::min(b, cx->num_sms), 1024, f->plan_smem, st>>>(p);
-            SCONE_LAUNCHED();
-        } else {
-            fused_plan_kernel<256><<<b, 256, f->plan_smem0, st>>>(p);
-            SCONE_LAUNCHED();
-        }
+        const int rc = launch_plans(cx, f, p, b, st);
+        if (rc) return rc;
     }
     TrajArgs t;
     t.hdr = f->d_hdr; t.arena = f->d_arena; t.rows = nullptr; t.W = W;
@@ -1363,27 +1162,20 @@ int scone_fused_plan_set(const scone_complex* cx, FusedState* f, int B, const in
     }
     f->set_n = 0;
     SCONE_CUDA(cudaMemsetAsync(f->d_set_bump, 0, 2 * sizeof(unsigned long long), st));
-    PlanArgs p;
+    PlanArgs p{};
     p.flow_edge = flow_edge; p.flow_val = flow_val;
     p.rank = cx->d_rank; p.nbrhoods = cx->d_nbrhoods; p.inc_ptr = cx->d_inc_ptr; p.inc_ent = cx->d_inc_ent;
     p.mptr = cx->d_mptr; p.ment = cx->d_ment; p.cone_ptr = f->d_cone_ptr; p.cone_ent = f->d_cone_ent;
     p.N = cx->N; p.D = cx->D; p.E = cx->E; p.L = f->L;
     p.arena = f->d_set_arena; p.bump = f->d_set_bump; p.arena_words = f->set_arena_words; p.overflow = overflow;
-    p.n_retry = reinterpret_cast<int*>(f->d_set_bump + 1);
+    p.n_retry = reinterpret_cast<int*>(f->d_set_bump + 1); p.retry = f->d_retry;
     ScopedProf prof(SCONE_K_CONE, st);
     for (int off = 0; off < B; off += f->chunk) {
         const int b = std::min(f->chunk, B - off);
         SCONE_CUDA(cudaMemsetAsync(f->d_set_bump + 1, 0, sizeof(unsigned long long), st));       // retry counter only: the arena keeps growing
         p.traj_ptr = traj_ptr + off; p.last_nodes = last_nodes + off; p.hdr = f->d_set_hdr + (size_t)off * kFusedHdrW;
-        p.tier = 0; p.n_work = b; p.retry = f->two_tiers ? f->d_retry : nullptr;
-        p.HS = f->HS0; p.LV = f->LV0; p.EC = f->EC0; p.hshift = f->hshift0;
-        fused_plan_kernel<256><<<b, 256, f->plan_smem0, st>>>(p);
-        SCONE_LAUNCHED();
-        if (f->two_tiers) {
-            p.tier = 1; p.HS = f->HS; p.LV = f->LV; p.EC = f->EC; p.hshift = f->hshift; p.retry = f->d_retry;
-            fused_plan_kernel<1024><<<std::min(b, cx->num_sms), 1024, f->plan_smem, st>>>(p);
-            SCONE_LAUNCHED();
-        }
+        const int rc = launch_plans(cx, f, p, b, st);
+        if (rc) return rc;
     }
     f->set_n = B;
     return 0;

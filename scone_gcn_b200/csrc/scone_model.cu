@@ -1078,7 +1078,7 @@ extern "C" int scone_model_fused_info(const scone_model* m, int32_t* out /* [16]
     out[0] = 1; out[1] = f->bound_cone; out[2] = f->bound_list; out[3] = f->HS; out[4] = f->chunk; out[5] = f->cap_rows;
     out[6] = (int32_t)(f->plan_smem / 1024); out[7] = (int32_t)(f->traj_smem_small / 1024);
     out[8] = f->HS0; out[9] = f->LV0; out[10] = (int32_t)(f->plan_smem0 / 1024); out[11] = f->two_tiers ? 1 : 0;
-    out[12] = (int32_t)std::min<unsigned long long>(f->worst_words, 0x7fffffffull); out[13] = (int32_t)(f->arena_words >> 20);
+    out[12] = f->tb_rows ? (int32_t)std::max<unsigned long long>(1, f->tb_bytes >> 20) : 0; out[13] = (int32_t)(f->arena_words >> 20);
     out[14] = (int32_t)std::min<unsigned long long>(f->cone_entries >> 10, 0x7fffffffull); out[15] = scone_fused_last_retries(m->fused);
     return 0;
 }

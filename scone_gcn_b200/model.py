@@ -50,7 +50,7 @@ class SconeModel:
         if not out[0]:
             return None
         keys = ['available', 'bound_cone', 'bound_list', 'hash_slots', 'chunk', 'cap_rows', 'plan_smem_kb', 'traj_smem_kb', 'hash_slots_tier0',
-                'live_rows_tier0', 'plan_smem_tier0_kb', 'two_tiers', 'worst_words', 'arena_mwords', 'cone_table_kentries', 'retries_last_chunk']
+                'live_rows_tier0', 'plan_smem_tier0_kb', 'two_tiers', 'table_plan_mb', 'arena_mwords', 'cone_table_kentries', 'retries_last_chunk']
         return dict(zip(keys, (int(v) for v in out)))
 
     def fused_header(self, t):

@@ -37,14 +37,26 @@ def cpu_live_rows(cx, n_layers, flows_row, last):
     return live
 
 
+@pytest.fixture(params=['table', 'hash'])
+def plan_kind(request, monkeypatch):
+    """Both plan kernels: the table plan (csrc/scone_plan_table.cu, the default) and the hash plan (SCONE_FUSED_TABLE=0, its fallback)."""
+    monkeypatch.setenv('SCONE_FUSED_TABLE', '1' if request.param == 'table' else '0')      # read when a model is created
+    return request.param
+
+
+def check_plan_kind(net, plan_kind):
+    assert (net.fused_info()['table_plan_mb'] > 0) == (plan_kind == 'table')
+
+
 @pytest.mark.parametrize('model,hidden', [('scone', [16, 16, 16]), ('scone', [32, 32]), ('ebli', [16, 16, 16]), ('scone', [32])])
-def test_plan_live_rows_match_cpu_sets(model, hidden):
+def test_plan_live_rows_match_cpu_sets(model, hidden, plan_kind):
     import scone_gcn_b200 as sg
     ds = Dataset('dataset_small.npz')
     cx = sg.SimplicialComplex.from_dense(ds.B1, ds.B2, model)
     B = 24
     net = sg.SconeModel(cx, hidden, micro_batch=B)
     assert net.pipeline == 4 and net.fused_info() is not None
+    check_plan_kind(net, plan_kind)
     rs = np.random.RandomState(0)
     net.set_weights([0.1 * rs.randn(*s) for s in net.shapes])
     ptr, fe, fv = sg.flows_to_csr(ds.flows[:B])
@@ -61,13 +73,14 @@ def test_plan_live_rows_match_cpu_sets(model, hidden):
 
 @pytest.mark.parametrize('model,hidden,mb,scale', [('scone', [16, 16, 16], 32, 0.1), ('scone', [32, 32, 32], 7, 0.1), ('ebli', [32, 32], 64, 0.02),
                                                    ('scone', [32], 16, 0.3), ('scone', [16, 16], 5, 0.3)])
-def test_fused_matches_row_list_pipeline_and_is_deterministic(model, hidden, mb, scale):
+def test_fused_matches_row_list_pipeline_and_is_deterministic(model, hidden, mb, scale, plan_kind):
     import scone_gcn_b200 as sg
     ds = Dataset('dataset_small.npz')
     cx = sg.SimplicialComplex.from_dense(ds.B1, ds.B2, model)
     ptr, fe, fv = sg.flows_to_csr(ds.flows)
     net = sg.SconeModel(cx, hidden, micro_batch=mb)
     assert net.pipeline == 4
+    check_plan_kind(net, plan_kind)
     rs = np.random.RandomState(len(hidden) * 10 + mb)
     net.set_weights([scale * rs.randn(*s_) for s_ in net.shapes])
     mask = (rs.rand(ds.n_traj) < 0.7).astype(np.float32)
@@ -113,7 +126,7 @@ def test_fused_results_do_not_depend_on_chunking():
     assert np.abs(outs[0] - fx['big_logprobs'][:, :, 0]).max() < 1e-5                # and they are the reference's
 
 
-def test_fused_big_trajectories_use_the_global_row_store():
+def test_fused_big_trajectories_use_the_global_row_store(plan_kind):
     """ebli on the small complex: three L1^2 hops cover the whole complex, every layer has ~E live rows -> far more rows than the
     shared-memory store holds; the BIG variant must give the oracle's numbers."""
     import scone_gcn_b200 as sg
@@ -141,7 +154,7 @@ def test_fused_big_trajectories_use_the_global_row_store():
         assert np.abs(a - r).max() <= 1e-4 * max(np.abs(r).max(), 1e-30)
 
 
-def test_fused_mixed_trajectories_with_empty_flows_and_invalid_last_node():
+def test_fused_mixed_trajectories_with_empty_flows_and_invalid_last_node(plan_kind):
     """Ragged inputs: a trajectory without flow entries (all logits 0 -> uniform log-probs over D slots) and one whose flows lie far
     from its last node, next to ordinary ones."""
     import scone_gcn_b200 as sg
@@ -165,7 +178,7 @@ def test_fused_mixed_trajectories_with_empty_flows_and_invalid_last_node():
     assert np.abs(lp - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
 
 
-def test_planned_set_gives_the_same_bits_as_planning_every_call():
+def test_planned_set_gives_the_same_bits_as_planning_every_call(plan_kind):
     """scone_model_plan_* + *_planned_*: plan the dataset once, run batches by row index — bit-identical to the unplanned entry points
     (the same kernels on the same programs), for arbitrary row subsets in arbitrary order."""
     import scone_gcn_b200 as sg
@@ -190,3 +203,31 @@ def test_planned_set_gives_the_same_bits_as_planning_every_call():
     assert np.array_equal(got, ref)
     # an intervening unplanned call (its own chunk arena) does not disturb the set
     assert np.array_equal(net.forward_planned(rows), ref_lp[rows])
+
+
+@pytest.mark.parametrize('model,hidden', [('scone', [32, 32, 32]), ('ebli', [16, 16]), ('scone', [16])])
+def test_table_plan_and_hash_plan_write_the_same_plans(model, hidden, monkeypatch):
+    """Headers (live rows per layer, pairs, cone entries, flow entries) equal, results bit-identical: same live sets, same row order,
+    same entry order, same layer-1 scalars."""
+    import scone_gcn_b200 as sg
+    ds = Dataset('dataset_small.npz')
+    cx = sg.SimplicialComplex.from_dense(ds.B1, ds.B2, model)
+    ptr, fe, fv = sg.flows_to_csr(ds.flows)
+    B = ds.n_traj
+    rs = np.random.RandomState(5)
+    out = {}
+    W = None
+    for kind in ('1', '0'):
+        monkeypatch.setenv('SCONE_FUSED_TABLE', kind)
+        net = sg.SconeModel(cx, hidden, micro_batch=B)
+        assert net.pipeline == 4 and (net.fused_info()['table_plan_mb'] > 0) == (kind == '1')
+        if W is None:
+            W = [0.2 * rs.randn(*s_) for s_ in net.shapes]
+        net.set_weights(W)
+        lp = net.forward(ptr, fe, fv, ds.last_nodes)
+        hdrs = np.stack([net.fused_header(t) for t in range(B)])
+        buf = net.loss_grad(ptr, fe, fv, ds.last_nodes, ds.raw['targets_argmax'], np.ones(B, np.float32))
+        out[kind] = (lp, hdrs, buf)
+    assert np.array_equal(out['1'][1][:, [0, 1, 2, 3, 10, 11, 13]], out['0'][1][:, [0, 1, 2, 3, 10, 11, 13]])
+    assert np.array_equal(out['1'][0], out['0'][0])
+    assert np.array_equal(out['1'][2], out['0'][2])
