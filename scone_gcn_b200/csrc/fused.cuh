@@ -125,6 +125,10 @@ struct FusedState {
     float* d_scratch = nullptr;
     int* d_stats = nullptr;
     unsigned long long* d_rows_done = nullptr;
+    uint32_t* d_sort = nullptr;           // cost-sorted batch: keys in / out, trajectories in / out
+    void* d_sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
+    int sort_cap = 0;
     // planned set (scone_fused_plan_set): headers + programs of a whole dataset, kept across calls
     int* d_set_hdr = nullptr;
     uint32_t* d_set_arena = nullptr;

@@ -23,6 +23,7 @@
 // the same kernel (rows in a per-CTA global scratch).
 #include <algorithm>
 #include <cstdlib>
+#include <cub/device/device_radix_sort.cuh>
 #include "common.cuh"
 #include "fused.cuh"
 
@@ -445,6 +446,8 @@ struct TrajArgs {
     const int* hdr;
     const uint32_t* arena;
     const int32_t* rows;                   // planned set: trajectory t of the batch is entry rows[t] of the set (NULL: t itself)
+    const uint32_t* okeys;                 // live rows of the batch's trajectories in descending order (0: flagged by the plan kernel)
+    const int32_t* order;                  //   and the trajectory each key belongs to (ties: ascending trajectory)
     const float* W;                        // flat weights
     int w_off[3 * kFusedMaxL + 1];
     int L, b, D, n_params;
@@ -658,9 +661,27 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
     unsigned long long n_fwd = 0, n_bwd = 0;
 
     float* rows = BIG ? a.scratch + (size_t)blockIdx.x * a.scratch_stride : rows_sm;
-    const int cap = BIG ? a.big_rows : a.cap_rows;
 
-    for (int t = blockIdx.x; t < a.b; t += gridDim.x) {
+    // The launch's trajectories: the range of the cost-sorted batch whose live rows fit this launch's row store and no smaller one
+    // (keys descending: BIG = the head, small = the tail).  They are dealt to the CTAs in snake order — heaviest first, every CTA gets
+    // one of each round — so that the CTAs finish together; the order depends on the data only: deterministic.
+    __shared__ int s_range[2];
+    if (tid == 0) {
+        int lo = 0, hi = a.b;
+        while (lo < hi) {                                  // first position with key <= cap_rows
+            const int mid = (lo + hi) >> 1;
+            if ((int)a.okeys[mid] > a.cap_rows) lo = mid + 1;
+            else hi = mid;
+        }
+        s_range[0] = BIG ? 0 : lo;
+        s_range[1] = BIG ? lo : a.b;
+    }
+    __syncthreads();
+    const int i_lo = s_range[0], i_hi = s_range[1];
+    for (int k = 0;; ++k) {
+        const int i = i_lo + k * (int)gridDim.x + ((k & 1) ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x);
+        if (i >= i_hi) break;
+        const int t = a.order[i];
         const int* h = a.hdr + (size_t)(a.rows != nullptr ? a.rows[t] : t) * kFusedHdrW;
         if (h[0] != 0) continue;                           // overflow reported by the plan kernel: skipped (host: error code 4)
         int n[kFusedMaxL + 1], hb[kFusedMaxL + 2];
@@ -673,9 +694,6 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
             hb[l] = tot;
             tot += n[l];
         }
-        const int need = tot;                             // G_l overwrites H_l in place (below): one stored row per live row
-        const bool big = need > a.cap_rows;
-        if (big != BIG || need > cap) continue;           // (block-uniform; need <= big_rows by construction of the bounds)
         const float* l1 = reinterpret_cast<const float*>(a.arena + (unsigned)h[4]);
         n_fwd += (unsigned long long)tot;
         if (3 * n[1] <= G::SL1) {                          // (block-uniform) the layer-1 scalars are read twice: stage them
@@ -874,6 +892,18 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
     }
 }
 
+// sort keys of a batch: live rows of trajectory t (0 when the plan kernel flagged it), value t
+__global__ void __launch_bounds__(256) fused_cost_kernel(const int* __restrict__ hdr, const int32_t* __restrict__ rows, int b, int L,
+                                                         uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= b) return;
+    const int* h = hdr + (size_t)(rows != nullptr ? rows[t] : t) * kFusedHdrW;
+    int tot = 0;
+    for (int l = 1; l <= L; ++l) tot += h[l];
+    keys[t] = h[0] != 0 ? 0u : (uint32_t)tot;
+    vals[t] = t;
+}
+
 // out[i] += sum over the CTAs' partial vectors in CTA order (deterministic); also rearms the arena bump pointer
 __global__ void __launch_bounds__(256) fused_reduce_kernel(const float* __restrict__ partial, int nparts, int n, float* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -932,6 +962,53 @@ int dispatch_traj(int act, const TrajArgs& a, int gs, int gb, size_t ss, size_t 
     return 2;
 }
 
+// Compute kernels over the plans t.hdr / t.arena describe (+ the fixed-order reduce of the CTAs' partial vectors into grad).  The
+// batch is first sorted by live rows (stable radix sort: the order depends on the data only).
+int run_traj(FusedState* f, int act, TrajArgs& t, float* grad, cudaStream_t st) {
+    const bool want_grad = grad != nullptr;
+    const int n = t.b;
+    if (n > f->sort_cap) {
+        cudaFree(f->d_sort);
+        cudaFree(f->d_sort_tmp);
+        f->d_sort = nullptr;
+        f->d_sort_tmp = nullptr;
+        f->sort_cap = 0;
+        uint32_t* k = nullptr;
+        int32_t* v = nullptr;
+        size_t bytes = 0;
+        SCONE_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, k, k, v, v, n, 0, 24, st));
+        SCONE_CUDA(cudaMalloc((void**)&f->d_sort, 4 * (size_t)n * sizeof(uint32_t)));
+        SCONE_CUDA(cudaMalloc((void**)&f->d_sort_tmp, bytes ? bytes : 16));
+        f->sort_tmp_bytes = bytes;
+        f->sort_cap = n;
+    }
+    uint32_t* k_in = f->d_sort;
+    uint32_t* k_out = k_in + f->sort_cap;
+    int32_t* v_in = reinterpret_cast<int32_t*>(k_out + f->sort_cap);
+    int32_t* v_out = v_in + f->sort_cap;
+    ScopedProf prof(want_grad ? SCONE_K_LAYER_BWD : SCONE_K_LAYER_FWD, st);
+    fused_cost_kernel<<<(n + 255) / 256, 256, 0, st>>>(t.hdr, t.rows, n, f->L, k_in, v_in);
+    SCONE_LAUNCHED();
+    size_t bytes = f->sort_tmp_bytes;
+    SCONE_CUDA(cub::DeviceRadixSort::SortPairsDescending(f->d_sort_tmp, bytes, k_in, k_out, v_in, v_out, n, 0, 24, st));
+    t.okeys = k_out;
+    t.order = v_out;
+    int rc;
+    if (f->C == 32)
+        rc = want_grad ? dispatch_traj<32, true>(act, t, f->grid_small, f->grid_big, f->traj_smem_small, f->traj_smem_big, st)
+                       : dispatch_traj<32, false>(act, t, f->grid_small, f->grid_big, f->traj_smem_small, f->traj_smem_big, st);
+    else
+        rc = want_grad ? dispatch_traj<16, true>(act, t, f->grid_small, f->grid_big, f->traj_smem_small, f->traj_smem_big, st)
+                       : dispatch_traj<16, false>(act, t, f->grid_small, f->grid_big, f->traj_smem_small, f->traj_smem_big, st);
+    if (rc) return rc;
+    if (want_grad) {
+        const int np = (int)f->n_params + 2;
+        fused_reduce_kernel<<<(np + 255) / 256, 256, 0, st>>>(f->d_partial, f->grid_small + f->grid_big, np, grad);
+        SCONE_LAUNCHED();
+    }
+    return 0;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -947,7 +1024,7 @@ bool scone_fused_supported(const scone_complex* cx, int n_layers, const int32_t*
 void scone_fused_destroy(FusedState* f) {
     if (!f) return;
     cudaFree(f->d_hdr); cudaFree(f->d_retry); cudaFree(f->d_arena); cudaFree(f->d_set_hdr); cudaFree(f->d_set_arena); cudaFree(f->d_set_bump); cudaFree(f->d_bump); cudaFree(f->d_partial); cudaFree(f->d_scratch); cudaFree(f->d_stats);
-    cudaFree(f->d_rows_done);
+    cudaFree(f->d_rows_done); cudaFree(f->d_sort); cudaFree(f->d_sort_tmp);
     scone_table_destroy(f);
     delete f;
 }
@@ -1102,7 +1179,6 @@ int scone_fused_run(const scone_complex* cx, FusedState* f, int act, int b, cons
                     const int32_t* target_idx, const float* mask, float* grad, int* overflow, bool count_rows, cudaStream_t st) {
     if (b <= 0) return 0;
     SCONE_REQUIRE(b <= f->chunk, "scone_fused_run: chunk of %d trajectories exceeds the planned %d", b, f->chunk);
-    const bool want_grad = grad != nullptr;
     SCONE_CUDA(cudaMemsetAsync(f->d_bump, 0, 2 * sizeof(unsigned long long), st));
     PlanArgs p{};
     p.traj_ptr = traj_ptr; p.flow_edge = flow_edge; p.flow_val = flow_val; p.last_nodes = last_nodes;
@@ -1124,23 +1200,7 @@ int scone_fused_run(const scone_complex* cx, FusedState* f, int act, int b, cons
     t.partial = f->d_partial; t.scratch = f->d_scratch; t.scratch_stride = f->scratch_stride;
     t.cap_rows = f->cap_rows; t.big_rows = f->big_rows;
     t.rows_done = count_rows ? f->d_rows_done : nullptr;
-    int rc;
-    {
-        ScopedProf prof(want_grad ? SCONE_K_LAYER_BWD : SCONE_K_LAYER_FWD, st);
-        if (f->C == 32)
-            rc = want_grad ? dispatch_traj<32, true>(act, t, f->grid_small, f->grid_big, f->traj_smem_small, f->traj_smem_big, st)
-                           : dispatch_traj<32, false>(act, t, f->grid_small, f->grid_big, f->traj_smem_small, f->traj_smem_big, st);
-        else
-            rc = want_grad ? dispatch_traj<16, true>(act, t, f->grid_small, f->grid_big, f->traj_smem_small, f->traj_smem_big, st)
-                           : dispatch_traj<16, false>(act, t, f->grid_small, f->grid_big, f->traj_smem_small, f->traj_smem_big, st);
-        if (rc) return rc;
-        if (want_grad) {
-            const int n = (int)f->n_params + 2;
-            fused_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(f->d_partial, f->grid_small + f->grid_big, n, grad);
-            SCONE_LAUNCHED();
-        }
-    }
-    return 0;
+    return run_traj(f, act, t, grad, st);
 }
 
 // ---- planned sets: the plan is weight-independent, so a dataset that is revisited every epoch is planned ONCE --------------------
@@ -1187,7 +1247,6 @@ int scone_fused_run_planned(const scone_complex* cx, FusedState* f, int act, int
     if (n <= 0) return 0;
     SCONE_REQUIRE(f->set_n > 0, "scone_fused_run_planned: no planned set (call scone_model_plan_* first)");
     SCONE_REQUIRE(rows_dev != nullptr || n <= f->set_n, "scone_fused_run_planned: %d trajectories requested, the planned set holds %d", n, f->set_n);
-    const bool want_grad = grad != nullptr;
     TrajArgs t;
     t.hdr = f->d_set_hdr; t.arena = f->d_set_arena; t.rows = rows_dev; t.W = W;
     for (int i = 0; i <= 3 * kFusedMaxL; ++i) t.w_off[i] = i <= 3 * f->L ? (int)w_off[i] : 0;
@@ -1196,21 +1255,7 @@ int scone_fused_run_planned(const scone_complex* cx, FusedState* f, int act, int
     t.partial = f->d_partial; t.scratch = f->d_scratch; t.scratch_stride = f->scratch_stride;
     t.cap_rows = f->cap_rows; t.big_rows = f->big_rows;
     t.rows_done = count_rows ? f->d_rows_done : nullptr;
-    ScopedProf prof(want_grad ? SCONE_K_LAYER_BWD : SCONE_K_LAYER_FWD, st);
-    int rc;
-    if (f->C == 32)
-        rc = want_grad ? dispatch_traj<32, true>(act, t, f->grid_small, f->grid_big, f->traj_smem_small, f->traj_smem_big, st)
-                       : dispatch_traj<32, false>(act, t, f->grid_small, f->grid_big, f->traj_smem_small, f->traj_smem_big, st);
-    else
-        rc = want_grad ? dispatch_traj<16, true>(act, t, f->grid_small, f->grid_big, f->traj_smem_small, f->traj_smem_big, st)
-                       : dispatch_traj<16, false>(act, t, f->grid_small, f->grid_big, f->traj_smem_small, f->traj_smem_big, st);
-    if (rc) return rc;
-    if (want_grad) {
-        const int np = (int)f->n_params + 2;
-        fused_reduce_kernel<<<(np + 255) / 256, 256, 0, st>>>(f->d_partial, f->grid_small + f->grid_big, np, grad);
-        SCONE_LAUNCHED();
-    }
-    return 0;
+    return run_traj(f, act, t, grad, st);
 }
 
 // debug / test access: header of trajectory t of the last chunk and `words` arena words from word offset `off`

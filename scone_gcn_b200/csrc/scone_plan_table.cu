@@ -764,6 +764,9 @@ int scone_table_build(const scone_complex* cx, FusedState* f, int L, bool* ok) {
         f->tbLV0 = std::min(f->tbLV, (env_int("SCONE_TABLE_LV0", 192) + 63) & ~63);
         f->tb_two_tiers = f->tbM0 < f->tbM || f->tbLV0 < f->tbLV;
         f->tb_smem0 = table_plan_smem(f->tbM0, f->tbLV0);
+        SCONE_CUDA(cudaFuncSetAttribute(table_plan_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTablePlanSmem));
+        SCONE_CUDA(cudaFuncSetAttribute(table_plan_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTablePlanSmem));
+        SCONE_CUDA(cudaFuncSetAttribute(table_plan_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTablePlanSmem));
         SCONE_CUDA(cudaFuncSetAttribute(table_plan_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTablePlanSmem));
         SCONE_CUDA(cudaFuncSetAttribute(table_plan_kernel<kTier1Threads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTablePlanSmem));
     }
@@ -779,11 +782,20 @@ int scone_table_plan_launch(const FusedState* f, PlanArgs p, int b, int num_sms,
     p.M = f->tbM0; p.LV = f->tbLV0;
     int* retry = p.retry;
     if (!f->tb_two_tiers) p.retry = nullptr;
-    table_plan_kernel<256><<<b, 256, f->tb_smem0, st>>>(p);
+    static const int t0 = [] { const char* v = getenv("SCONE_TABLE_T0"); return v && *v ? atoi(v) : 128; }();
+    static const int t1 = [] { const char* v = getenv("SCONE_TABLE_T1"); return v && *v ? atoi(v) : kTier1Threads; }();
+    if (t0 == 64) table_plan_kernel<64><<<b, 64, f->tb_smem0, st>>>(p);
+    else if (t0 == 128) table_plan_kernel<128><<<b, 128, f->tb_smem0, st>>>(p);
+    else if (t0 == 512) table_plan_kernel<512><<<b, 512, f->tb_smem0, st>>>(p);
+    else table_plan_kernel<256><<<b, 256, f->tb_smem0, st>>>(p);
     SCONE_LAUNCHED();
     if (f->tb_two_tiers) {
         p.tier = 1; p.M = f->tbM; p.LV = f->tbLV; p.retry = retry;
-        table_plan_kernel<kTier1Threads><<<std::min(b, 2 * num_sms), kTier1Threads, f->tb_smem, st>>>(p);
+        const int per_sm = std::max(1, (int)((size_t)220 * 1024 / (f->tb_smem + 1024)));
+        if (t1 == 128) table_plan_kernel<128><<<std::min(b, std::min(16, per_sm) * num_sms), 128, f->tb_smem, st>>>(p);
+        else if (t1 == 256) table_plan_kernel<256><<<std::min(b, std::min(8, per_sm) * num_sms), 256, f->tb_smem, st>>>(p);
+        else if (t1 == 1024) table_plan_kernel<1024><<<std::min(b, std::min(2, per_sm) * num_sms), 1024, f->tb_smem, st>>>(p);
+        else table_plan_kernel<512><<<std::min(b, std::min(4, per_sm) * num_sms), 512, f->tb_smem, st>>>(p);
         SCONE_LAUNCHED();
     }
     return 0;
