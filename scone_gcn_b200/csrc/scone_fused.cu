@@ -1173,25 +1173,35 @@ static int launch_plans(const scone_complex* cx, const FusedState* f, PlanArgs p
     return 0;
 }
 
-// One chunk (<= f->chunk trajectories, device pointers already offset to the chunk): plan + compute (+ partial reduce into grad).
-int scone_fused_run(const scone_complex* cx, FusedState* f, int act, int b, const int32_t* traj_ptr, const int32_t* flow_edge,
-                    const float* flow_val, const int32_t* last_nodes, const float* W, const int64_t* w_off, float* logprobs,
-                    const int32_t* target_idx, const float* mask, float* grad, int* overflow, bool count_rows, cudaStream_t st) {
-    if (b <= 0) return 0;
-    SCONE_REQUIRE(b <= f->chunk, "scone_fused_run: chunk of %d trajectories exceeds the planned %d", b, f->chunk);
+// One chunk (<= f->chunk trajectories) in three steps, so that a caller can plan the parts of a chunk as their inputs arrive
+// (scone_model_*_host: the H2D copy of part k + 1 runs under the plan kernels of part k):
+//   scone_fused_begin      rearms the chunk's program arena
+//   scone_fused_plan_part  plans trajectories off .. off + b of the chunk (traj_ptr / last_nodes: the CHUNK's arrays)
+//   scone_fused_compute    compute kernels over the b planned trajectories of the chunk (+ partial reduce into grad)
+int scone_fused_begin(FusedState* f, cudaStream_t st) {
     SCONE_CUDA(cudaMemsetAsync(f->d_bump, 0, 2 * sizeof(unsigned long long), st));
+    return 0;
+}
+
+int scone_fused_plan_part(const scone_complex* cx, FusedState* f, int off, int b, const int32_t* traj_ptr, const int32_t* flow_edge,
+                          const float* flow_val, const int32_t* last_nodes, int* overflow, cudaStream_t st) {
+    if (b <= 0) return 0;
+    SCONE_REQUIRE(off >= 0 && off + b <= f->chunk, "scone_fused_plan_part: trajectories %d .. %d exceed the planned chunk of %d", off, off + b, f->chunk);
+    if (off > 0) SCONE_CUDA(cudaMemsetAsync(f->d_bump + 1, 0, sizeof(unsigned long long), st));   // retry counter only: the arena keeps growing
     PlanArgs p{};
-    p.traj_ptr = traj_ptr; p.flow_edge = flow_edge; p.flow_val = flow_val; p.last_nodes = last_nodes;
+    p.traj_ptr = traj_ptr + off; p.flow_edge = flow_edge; p.flow_val = flow_val; p.last_nodes = last_nodes + off;
     p.rank = cx->d_rank; p.nbrhoods = cx->d_nbrhoods; p.inc_ptr = cx->d_inc_ptr; p.inc_ent = cx->d_inc_ent;
     p.mptr = cx->d_mptr; p.ment = cx->d_ment; p.cone_ptr = f->d_cone_ptr; p.cone_ent = f->d_cone_ent;
     p.N = cx->N; p.D = cx->D; p.E = cx->E; p.L = f->L;
-    p.hdr = f->d_hdr; p.arena = f->d_arena; p.bump = f->d_bump; p.arena_words = f->arena_words; p.overflow = overflow;
+    p.hdr = f->d_hdr + (size_t)off * kFusedHdrW; p.arena = f->d_arena; p.bump = f->d_bump; p.arena_words = f->arena_words; p.overflow = overflow;
     p.n_retry = reinterpret_cast<int*>(f->d_bump + 1); p.retry = f->d_retry;
-    {
-        ScopedProf prof(SCONE_K_CONE, st);
-        const int rc = launch_plans(cx, f, p, b, st);
-        if (rc) return rc;
-    }
+    ScopedProf prof(SCONE_K_CONE, st);
+    return launch_plans(cx, f, p, b, st);
+}
+
+int scone_fused_compute(const scone_complex* cx, FusedState* f, int act, int b, const float* W, const int64_t* w_off, float* logprobs,
+                        const int32_t* target_idx, const float* mask, float* grad, bool count_rows, cudaStream_t st) {
+    if (b <= 0) return 0;
     TrajArgs t;
     t.hdr = f->d_hdr; t.arena = f->d_arena; t.rows = nullptr; t.W = W;
     for (int i = 0; i <= 3 * kFusedMaxL; ++i) t.w_off[i] = i <= 3 * f->L ? (int)w_off[i] : 0;
@@ -1201,6 +1211,17 @@ int scone_fused_run(const scone_complex* cx, FusedState* f, int act, int b, cons
     t.cap_rows = f->cap_rows; t.big_rows = f->big_rows;
     t.rows_done = count_rows ? f->d_rows_done : nullptr;
     return run_traj(f, act, t, grad, st);
+}
+
+int scone_fused_run(const scone_complex* cx, FusedState* f, int act, int b, const int32_t* traj_ptr, const int32_t* flow_edge,
+                    const float* flow_val, const int32_t* last_nodes, const float* W, const int64_t* w_off, float* logprobs,
+                    const int32_t* target_idx, const float* mask, float* grad, int* overflow, bool count_rows, cudaStream_t st) {
+    if (b <= 0) return 0;
+    SCONE_REQUIRE(b <= f->chunk, "scone_fused_run: chunk of %d trajectories exceeds the planned %d", b, f->chunk);
+    int rc = scone_fused_begin(f, st);
+    if (!rc) rc = scone_fused_plan_part(cx, f, 0, b, traj_ptr, flow_edge, flow_val, last_nodes, overflow, st);
+    if (!rc) rc = scone_fused_compute(cx, f, act, b, W, w_off, logprobs, target_idx, mask, grad, count_rows, st);
+    return rc;
 }
 
 // ---- planned sets: the plan is weight-independent, so a dataset that is revisited every epoch is planned ONCE --------------------

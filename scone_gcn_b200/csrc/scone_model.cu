@@ -28,6 +28,8 @@ struct scone_model {
     cudaStream_t compute = nullptr;           // all kernels of a model-level call (highest priority), forked from / joined to the caller's stream
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_begin = nullptr;
+    cudaStream_t copy = nullptr;              // pipeline 4, *_host entry points: the flow arrays arrive in parts under the plan kernels
+    cudaEvent_t ev_copy0 = nullptr, ev_part[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> ev_fill;         // [2L]: H_1..H_L, G_{L-1}..G_0
     uint8_t* d_occS = nullptr;                // worklists / counters scratch (scone_occ_scratch_bytes)
     uint8_t* d_occX = nullptr;                // flags of the flows X
@@ -589,6 +591,9 @@ extern "C" int scone_model_destroy(scone_model* m) {
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
     if (m->ev_begin) cudaEventDestroy(m->ev_begin);
+    if (m->copy) cudaStreamDestroy(m->copy);
+    if (m->ev_copy0) cudaEventDestroy(m->ev_copy0);
+    for (auto e : m->ev_part) if (e) cudaEventDestroy(e);
     for (auto e : m->ev_fill) if (e) cudaEventDestroy(e);
     cudaFree(m->d_ptr); cudaFree(m->d_edge); cudaFree(m->d_last); cudaFree(m->d_tgt); cudaFree(m->d_val);
     cudaFree(m->d_mask); cudaFree(m->d_logp_all); cudaFree(m->d_nn); cudaFree(m->d_acc);
@@ -678,6 +683,49 @@ static int fused_call(scone_model* m, int32_t B, const int32_t* ptr, const int32
         if (rc) return rc;
     }
     return 0;
+}
+
+// pipeline 4 behind a *_host entry point, batch within one arena chunk: the flow arrays (all but a few hundred KB of the H2D bytes)
+// are copied in parts on a copy stream and every part is planned as soon as it has landed — the copy of part k + 1 runs under the
+// plan kernels of part k; one compute launch over the whole batch at the end.  ptr / last / tgt / mask: already enqueued on s.
+static bool fused_host_overlap_ok(const scone_model* m, int32_t B, int64_t nnz) {
+    const bool rows = m->pipeline >= 1 && !m->zero_fill;
+    return rows && m->pipeline == 4 && m->fused && B >= 512 && B <= m->fused->chunk && B <= m->mb && nnz >= (1 << 13);
+}
+
+static int fused_host_overlapped(scone_model* m, int32_t B, const int32_t* ptr, const int32_t* edge, const float* val, float* logprobs_dev,
+                                 bool grad, int32_t zero_first, cudaStream_t s) {
+    constexpr int kParts = 4;
+    if (!m->copy) {
+        SCONE_CUDA(cudaStreamCreateWithFlags(&m->copy, cudaStreamNonBlocking));
+        SCONE_CUDA(cudaEventCreateWithFlags(&m->ev_copy0, cudaEventDisableTiming));
+        for (auto& e : m->ev_part) SCONE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    // the staging buffers are free once everything enqueued on s so far has run (the previous call joined its kernels into s)
+    SCONE_CUDA(cudaEventRecord(m->ev_copy0, s));
+    SCONE_CUDA(cudaStreamWaitEvent(m->copy, m->ev_copy0, 0));
+    int32_t b0[kParts + 1];
+    for (int k = 0; k <= kParts; ++k) b0[k] = (int32_t)((int64_t)B * k / kParts);
+    for (int k = 0; k < kParts; ++k) {
+        const int64_t q0 = ptr[b0[k]], q1 = ptr[b0[k + 1]];
+        if (q1 > q0) {
+            SCONE_CUDA(cudaMemcpyAsync(m->d_edge + q0, edge + q0, (q1 - q0) * sizeof(int32_t), cudaMemcpyHostToDevice, m->copy));
+            SCONE_CUDA(cudaMemcpyAsync(m->d_val + q0, val + q0, (q1 - q0) * sizeof(float), cudaMemcpyHostToDevice, m->copy));
+        }
+        SCONE_CUDA(cudaEventRecord(m->ev_part[k], m->copy));
+    }
+    if (fork_to_compute(m, (void*)s)) return 1;
+    cudaStream_t c = m->compute;
+    if (grad && zero_first) SCONE_CUDA(cudaMemsetAsync(m->d_grad, 0, (m->n_params + 2) * sizeof(float), c));
+    int rc = scone_fused_begin(m->fused, c);
+    for (int k = 0; k < kParts && !rc; ++k) {
+        SCONE_CUDA(cudaStreamWaitEvent(c, m->ev_part[k], 0));
+        rc = scone_fused_plan_part(m->cx, m->fused, b0[k], b0[k + 1] - b0[k], m->d_ptr, m->d_edge, m->d_val, m->d_last, m->d_overflow, c);
+    }
+    if (!rc)
+        rc = scone_fused_compute(m->cx, m->fused, m->act, B, m->d_w, m->w_off.data(), logprobs_dev, grad ? m->d_tgt : nullptr,
+                                 grad ? m->d_mask : nullptr, grad ? m->d_grad : nullptr, g_scone_prof, c);
+    return finish_call(m, rc, (void*)s);
 }
 
 extern "C" int scone_model_forward_dev(scone_model* m, int32_t B, const int32_t* ptr, const int32_t* edge, const float* val,
@@ -788,10 +836,14 @@ extern "C" int scone_model_forward_host(scone_model* m, int32_t B, const int32_t
     int rc = ensure_staging(m, B, nnz);
     if (rc) return rc;
     SCONE_CUDA(cudaMemcpyAsync(m->d_ptr, ptr, (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    SCONE_CUDA(cudaMemcpyAsync(m->d_edge, edge, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    SCONE_CUDA(cudaMemcpyAsync(m->d_val, val, nnz * sizeof(float), cudaMemcpyHostToDevice, s));
     SCONE_CUDA(cudaMemcpyAsync(m->d_last, last, B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    rc = scone_model_forward_dev(m, B, m->d_ptr, m->d_edge, m->d_val, m->d_last, m->d_logp_all, st);
+    if (fused_host_overlap_ok(m, B, nnz)) {
+        rc = fused_host_overlapped(m, B, ptr, edge, val, m->d_logp_all, false, 0, s);
+    } else {
+        SCONE_CUDA(cudaMemcpyAsync(m->d_edge, edge, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        SCONE_CUDA(cudaMemcpyAsync(m->d_val, val, nnz * sizeof(float), cudaMemcpyHostToDevice, s));
+        rc = scone_model_forward_dev(m, B, m->d_ptr, m->d_edge, m->d_val, m->d_last, m->d_logp_all, st);
+    }
     if (rc) return rc;
     SCONE_CUDA(cudaMemcpyAsync(logprobs_out, m->d_logp_all, (size_t)B * m->cx->D * sizeof(float), cudaMemcpyDeviceToHost, s));
     int overflow = 0;
@@ -943,14 +995,15 @@ extern "C" int scone_model_loss_grad_host(scone_model* m, int32_t B, const int32
     int rc = ensure_staging(m, B, nnz);
     if (rc) return rc;
     SCONE_CUDA(cudaMemcpyAsync(m->d_ptr, ptr, (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    if (nnz) {
-        SCONE_CUDA(cudaMemcpyAsync(m->d_edge, edge, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-        SCONE_CUDA(cudaMemcpyAsync(m->d_val, val, nnz * sizeof(float), cudaMemcpyHostToDevice, s));
-    }
     if (B) {
         SCONE_CUDA(cudaMemcpyAsync(m->d_last, last, B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
         SCONE_CUDA(cudaMemcpyAsync(m->d_tgt, tgt, B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
         SCONE_CUDA(cudaMemcpyAsync(m->d_mask, mask, B * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
+    if (fused_host_overlap_ok(m, B, nnz)) return fused_host_overlapped(m, B, ptr, edge, val, nullptr, true, zero_first, s);
+    if (nnz) {
+        SCONE_CUDA(cudaMemcpyAsync(m->d_edge, edge, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        SCONE_CUDA(cudaMemcpyAsync(m->d_val, val, nnz * sizeof(float), cudaMemcpyHostToDevice, s));
     }
     return scone_model_loss_grad_dev(m, B, m->d_ptr, m->d_edge, m->d_val, m->d_last, m->d_tgt, m->d_mask, zero_first, st);
 }

@@ -231,3 +231,37 @@ def test_table_plan_and_hash_plan_write_the_same_plans(model, hidden, monkeypatc
     assert np.array_equal(out['1'][1][:, [0, 1, 2, 3, 10, 11, 13]], out['0'][1][:, [0, 1, 2, 3, 10, 11, 13]])
     assert np.array_equal(out['1'][0], out['0'][0])
     assert np.array_equal(out['1'][2], out['0'][2])
+
+
+def test_host_entry_points_plan_in_parts_under_the_copy():
+    """*_host entry points of a batch >= 512 trajectories: the flow arrays arrive in four parts on a copy stream, every part is planned
+    when it has landed, one compute launch at the end — same plans, same bits as the device-pointer entry points."""
+    import scone_gcn_b200 as sg
+    from scone_gcn_b200 import _lib
+    from scone_gcn_b200 import synthetic_data_gen as sdg
+    sp = sdg.generate_sparse_dataset(4000, 1500, seed=3, n_waypoints=16)
+    cx = sg.SimplicialComplex.from_simplices(int(sp.n_nodes), sp.edges, sp.faces, 'scone')
+    B = 1500
+    net = sg.SconeModel(cx, [16, 16, 16], micro_batch=2048)
+    assert net.pipeline == 4
+    rs = np.random.RandomState(4)
+    net.set_weights([0.3 * rs.randn(*s) for s in net.shapes])
+    nnz = int(sp.traj_ptr[B])
+    assert nnz >= 8192
+    ptr, fe, fv = sp.traj_ptr[:B + 1].astype(np.int32), sp.flow_edge[:nnz].astype(np.int32), sp.flow_val[:nnz].astype(np.float32)
+    last, tgt = sp.last_nodes[:B].astype(np.int32), sp.target_idx[:B].astype(np.int32)
+    mask = (rs.rand(B) < 0.8).astype(np.float32)
+    lp_host = net.forward(ptr, fe, fv, last)
+    g_host = net.loss_grad(ptr, fe, fv, last, tgt, mask)
+    d = {k: torch.from_numpy(v).cuda() for k, v in dict(ptr=ptr, fe=fe, fv=fv, last=last, tgt=tgt, mask=mask).items()}
+    lp_dev = torch.empty(B, cx.D, device='cuda')
+    L = _lib.lib()
+    _lib.check(L.scone_model_forward_dev(net.handle, B, _lib.dptr(d['ptr']), _lib.dptr(d['fe']), _lib.dptr(d['fv']), _lib.dptr(d['last']),
+                                         _lib.dptr(lp_dev), None), 'forward_dev')
+    _lib.check(L.scone_model_loss_grad_dev(net.handle, B, _lib.dptr(d['ptr']), _lib.dptr(d['fe']), _lib.dptr(d['fv']), _lib.dptr(d['last']),
+                                           _lib.dptr(d['tgt']), _lib.dptr(d['mask']), 1, None), 'loss_grad_dev')
+    g_dev = net.read_grads()
+    torch.cuda.synchronize()
+    assert np.array_equal(lp_host, lp_dev.cpu().numpy())
+    assert np.array_equal(g_host, g_dev)
+    assert g_host[-1] == mask.sum()
