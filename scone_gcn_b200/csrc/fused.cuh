@@ -12,7 +12,8 @@ constexpr int kFusedFlagRetry = 2;        // tier 0 of the plan kernel overflowe
 //   [5],[6] forward programs of layers 2, 3: rowptr[n_l + 1] then int2 entries {row below | own << 31, (c1 << 16) | c0}
 //   [7],[8] transposed programs of layers 2, 3 (rows = live rows of layer l - 1, entries = rows of layer l)
 //   [9] readout: rowptr[D + 1] then int2 {row of H_L | slot << 16, sign bits}   [10] pairs   [11] hash entries (flows + cone)
-//   [12] unused   [13] flow entries
+//   [12] / [14] entries of the forward programs of layers 2 / 3   [13] flow entries
+//   [15] entries of the transposed programs of layers 2 (low half) and 3 (high half), saturated at 0xFFFF
 // Arguments of the plan kernels (both flavours: the hash plan of scone_fused.cu and the table plan of scone_plan_table.cu)
 struct PlanArgs {
     const int32_t* traj_ptr;

@@ -261,10 +261,11 @@ __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, 
     }
     int n_l[kFusedMaxL + 1] = {0, 0, 0, 0};
     unsigned off_l1 = 0, off_f[kFusedMaxL + 1] = {0, 0, 0, 0}, off_b[kFusedMaxL + 1] = {0, 0, 0, 0};
+    int tot_f[kFusedMaxL + 1] = {0, 0, 0, 0}, tot_b[kFusedMaxL + 1] = {0, 0, 0, 0};
 
     // program of the n_cur scanned rows against the row indices `idx`: rowptr + entries {row | own << 31, coefficients} into the
     // arena, entries in column order (count pass, scan, fill pass — all over the shared-memory slot buffer)
-    auto emit_program = [&](const uint16_t* byrank, int n_rows, const uint16_t* idx) -> unsigned {
+    auto emit_program = [&](const uint16_t* byrank, int n_rows, const uint16_t* idx, int& total_out) -> unsigned {
         for (int r = tid >> 2; r < n_rows; r += QUADS) {
             const int b0 = erow[r], b1 = erow[r + 1];
             int c = 0;
@@ -278,6 +279,7 @@ __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, 
         }
         __syncthreads();
         const int total = fused_block_scan_excl<THREADS>(rowcnt, n_rows, s_warp);
+        total_out = total;
         const unsigned off = alloc(align2(n_rows + 1) + 2 * total);
         if (!s_ovf) {
             int* pdst = reinterpret_cast<int*>(a.arena + off);
@@ -368,7 +370,7 @@ __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, 
             }
             __syncthreads();
         } else {
-            off_f[l] = emit_program(rcur, n_cur, idx_prev);       // forward: rows of layer l, entries = live rows of layer l - 1
+            off_f[l] = emit_program(rcur, n_cur, idx_prev, tot_f[l]);       // forward: rows of layer l, entries = live rows of layer l - 1
         }
         if (l == L) break;
         // ---- live rows of layer l + 1: cone edges of level >= l + 1 among the scanned entries ----
@@ -381,7 +383,7 @@ __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, 
         }
         const int n_next = rank_live(idx_next, rnext);
         if (s_ovf) break;
-        off_b[l + 1] = emit_program(rcur, n_cur, idx_next);       // transposed program of layer l + 1: rows of layer l
+        off_b[l + 1] = emit_program(rcur, n_cur, idx_next, tot_b[l + 1]);       // transposed program of layer l + 1: rows of layer l
         uint16_t* tmp = rcur; rcur = rnext; rnext = tmp;
         n_cur = n_next;
     }
@@ -424,8 +426,10 @@ __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, 
         hdr[9] = (int)off_ro;
         hdr[10] = total_pairs;
         hdr[11] = s_nhash;
-        hdr[12] = 0;
+        hdr[12] = tot_f[2];
         hdr[13] = fp1 - fp0;
+        hdr[14] = tot_f[3];
+        hdr[15] = min(tot_b[2], 0xFFFF) | (min(tot_b[3], 0xFFFF) << 16);
     }
 }
 
@@ -469,7 +473,7 @@ struct FuGeom {
     static constexpr int LDW = C + 8;
     static constexpr int CH = 80;           // rows gathered per chunk (5 m-tiles)
     static constexpr int SE = 1024;         // program entries staged in shared memory per chunk
-    static constexpr int SP = 136;          // staged row pointers (CH + 1, or D + 1 for the readout pairs)
+    static constexpr int SP = 200;          // staged row pointers (a whole program of the small variant: <= 192 rows; D + 1 for the readout pairs)
     static constexpr int SL1 = 384;         // staged layer-1 scalars (3 per row: 128 rows)
     static constexpr int LPR = C / 4;       // lanes per row in the gather (one float4 each)
     static constexpr int NP = C / 16;       // pairs of n-tiles per row tile
@@ -512,6 +516,28 @@ __device__ __forceinline__ void fu_gather(float* __restrict__ tile, const float*
         *reinterpret_cast<ulonglong2*>(d + C) = make_ulonglong2(s0a, s0b);
         *reinterpret_cast<ulonglong2*>(d + 2 * C) = make_ulonglong2(s1a, s1b);
     }
+}
+
+__device__ __forceinline__ void cp_async_4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Asynchronous copy of a WHOLE program (row pointers + entries; also the readout pair list: D rows) into the staging buffers, issued
+// while the previous phase still computes (the staged loads were the top stall of this kernel).  false (nothing issued): the program
+// does not fit — the caller stages it chunk by chunk (fu_stage).  Completion: cp_async_wait_all() + barrier.
+template <int C>
+__device__ __forceinline__ bool fu_prefetch(const uint32_t* __restrict__ arena, unsigned off, int n_rows, int tot, int* sptr, int2* sent) {
+    using G = FuGeom<C>;
+    if (n_rows + 1 > G::SP || tot > G::SE) return false;   // (block-uniform)
+    const int* gptr = reinterpret_cast<const int*>(arena + off);
+    const int2* gent = reinterpret_cast<const int2*>(gptr + align2(n_rows + 1));
+    for (int i = threadIdx.x; i <= n_rows; i += kTrajThreads) cp_async_4(sptr + i, gptr + i);
+    for (int i = threadIdx.x; i < tot; i += kTrajThreads) cp_async_8(sent + i, gent + i);
+    return true;
 }
 
 // Stages the next chunk of a program (rows r0 ...) into shared memory: row pointers into sptr, entries into sent.  Returns the rows
@@ -696,11 +722,18 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
         }
         const float* l1 = reinterpret_cast<const float*>(a.arena + (unsigned)h[4]);
         n_fwd += (unsigned long long)tot;
-        if (3 * n[1] <= G::SL1) {                          // (block-uniform) the layer-1 scalars are read twice: stage them
-            for (int i = tid; i < 3 * n[1]; i += kTrajThreads) l1s[i] = __ldg(l1 + i);
-            __syncthreads();
-            l1 = l1s;
-        }
+        // entries of the programs (header): forward of layers 2 / 3, transposed of layers 2 / 3 (saturated at 0xFFFF: never fits then)
+        const int tot_f[kFusedMaxL + 1] = {0, 0, h[12], h[14]};
+        const int tot_b[kFusedMaxL + 1] = {0, 0, h[15] & 0xFFFF, (int)((unsigned)h[15] >> 16)};
+        // asynchronous staging: the layer-1 scalars (read twice) and the first program
+        const bool stage_l1 = 3 * n[1] <= G::SL1;          // (block-uniform)
+        if (stage_l1)
+            for (int i = tid; i < 3 * n[1]; i += kTrajThreads) cp_async_4(l1s + i, l1 + i);
+        bool pf = L >= 2 ? fu_prefetch<C>(a.arena, (unsigned)h[5], n[2], tot_f[2], sptr, sent)
+                         : fu_prefetch<C>(a.arena, (unsigned)h[9], D, h[10], sptr, sent);
+        cp_async_wait_all();
+        __syncthreads();
+        if (stage_l1) l1 = l1s;
 
         // ---- layer 1 ----
         for (int i = tid; i < n[1] * C; i += kTrajThreads) {
@@ -719,24 +752,46 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
             const float* hprev = rows + (size_t)hb[l - 1] * G::LDH;
             float* hout = rows + (size_t)hb[l] * G::LDH;
             const float* Wl = Wsm + (size_t)(l - 2) * 3 * C * G::LDW;
+            bool pf_next = false;
+            if (nl == 0)                                   // (no chunk below issues the next program's copy)
+                pf_next = l < L ? fu_prefetch<C>(a.arena, (unsigned)h[5 + (l - 1)], n[l + 1], tot_f[l < kFusedMaxL ? l + 1 : l], sptr, sent)
+                                : fu_prefetch<C>(a.arena, (unsigned)h[9], D, h[10], sptr, sent);
             for (int r0 = 0; r0 < nl;) {
-                bool staged;
-                const int nr = fu_stage<C>(ptr, ent, r0, nl, sptr, sent, &staged);
-                if (staged) fu_gather<C>(tile, hprev, sptr, sent, sptr[0], nr);
-                else fu_gather<C>(tile, hprev, sptr, ent, 0, nr);
+                int nr;
+                if (pf) {                                  // the whole program is in the staging buffers
+                    nr = min(G::CH, nl - r0);
+                    fu_gather<C>(tile, hprev, sptr + r0, sent, 0, nr);
+                } else {
+                    bool staged;
+                    nr = fu_stage<C>(ptr, ent, r0, nl, sptr, sent, &staged);
+                    if (staged) fu_gather<C>(tile, hprev, sptr, sent, sptr[0], nr);
+                    else fu_gather<C>(tile, hprev, sptr, ent, 0, nr);
+                }
                 __syncthreads();
+                if (r0 + nr >= nl)                         // the staging buffers are free: the next program flies under the product
+                    pf_next = l < L ? fu_prefetch<C>(a.arena, (unsigned)h[5 + (l - 1)], n[l + 1], tot_f[l < kFusedMaxL ? l + 1 : l], sptr, sent)
+                                    : fu_prefetch<C>(a.arena, (unsigned)h[9], D, h[10], sptr, sent);
                 fu_product<C, false>(tile, Wl, nr, [&](int r, int col, float v0, float v1) {
                     float* o = hout + (size_t)(r0 + r) * G::LDH + col;
                     *reinterpret_cast<float2*>(o) = make_float2(fu_act<ACT>(v0), fu_act<ACT>(v1));
                 });
+                cp_async_wait_all();
                 __syncthreads();
                 r0 += nr;
             }
+            if (nl == 0) {
+                cp_async_wait_all();
+                __syncthreads();
+            }
+            pf = pf_next;
         }
         // ---- readout: z_j = sum over the edges incident to neighbour j of sign * H_L[row]; logit_j = z_j . w_out ----
         const int* rptr = reinterpret_cast<const int*>(a.arena + (unsigned)h[9]);
         const int2* rent = reinterpret_cast<const int2*>(rptr + align2(D + 1));
-        if (h[10] <= G::SE) {                              // (block-uniform) stage the pair list: read by the logits and by dq
+        if (pf) {
+            rptr = sptr;
+            rent = sent;
+        } else if (h[10] <= G::SE) {                       // (block-uniform) stage the pair list: read by the logits and by dq
             for (int i = tid; i <= D; i += kTrajThreads) sptr[i] = __ldg(rptr + i);
             for (int i = tid; i < h[10]; i += kTrajThreads) sent[i] = __ldg(rent + i);
             __syncthreads();
@@ -807,10 +862,13 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
             }
         }
         __syncthreads();
+        // the pair list is done with: the transposed program of layer L flies under the elementwise pass
+        pf = L >= 2 ? fu_prefetch<C>(a.arena, (unsigned)h[7 + (L - 2)], n[L - 1], tot_b[L], sptr, sent) : false;
         for (int i = tid; i < nL * C; i += kTrajThreads) {
             const int r = i / C, c = i % C;
             gL[(size_t)r * G::LDH + c] = gL[(size_t)r * G::LDH + C] * wos[c] * fu_dact<ACT>(hL[(size_t)r * G::LDH + c]);
         }
+        cp_async_wait_all();
         __syncthreads();
         // ---- conv layers backward: AG = [G_l | S0 G_l | S1 G_l] on the live rows of layer l - 1 ----
 #pragma unroll
@@ -824,12 +882,21 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
             float* gprev = hprev;
             const float* Wl = Wsm + (size_t)(l - 2) * 3 * C * G::LDW;
             n_bwd += (unsigned long long)np_;
+            bool pf_next = false;
+            if (np_ == 0 && l > 2) pf_next = fu_prefetch<C>(a.arena, (unsigned)h[7 + (l - 3)], n[l - 2], tot_b[l - 1], sptr, sent);
             for (int r0 = 0; r0 < np_;) {
-                bool staged;
-                const int nr = fu_stage<C>(ptr, ent, r0, np_, sptr, sent, &staged);
-                if (staged) fu_gather<C>(tile, gl, sptr, sent, sptr[0], nr);
-                else fu_gather<C>(tile, gl, sptr, ent, 0, nr);
+                int nr;
+                if (pf) {
+                    nr = min(G::CH, np_ - r0);
+                    fu_gather<C>(tile, gl, sptr + r0, sent, 0, nr);
+                } else {
+                    bool staged;
+                    nr = fu_stage<C>(ptr, ent, r0, np_, sptr, sent, &staged);
+                    if (staged) fu_gather<C>(tile, gl, sptr, sent, sptr[0], nr);
+                    else fu_gather<C>(tile, gl, sptr, ent, 0, nr);
+                }
                 __syncthreads();
+                if (r0 + nr >= np_ && l > 2) pf_next = fu_prefetch<C>(a.arena, (unsigned)h[7 + (l - 3)], n[l - 2], tot_b[l - 1], sptr, sent);
                 fu_dw<C>(acc[l - 2], hprev + (size_t)r0 * G::LDH, tile, nr);
                 __syncthreads();                           // every warp has read H_{l-1} of this chunk: G_{l-1} may overwrite it
                 fu_product<C, true>(tile, Wl, nr, [&](int r, int col, float v0, float v1) {
@@ -837,9 +904,15 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
                     *reinterpret_cast<float2*>(gprev + (size_t)(r0 + r) * G::LDH + col) =
                         make_float2(v0 * fu_dact<ACT>(hv.x), v1 * fu_dact<ACT>(hv.y));
                 });
+                cp_async_wait_all();
                 __syncthreads();
                 r0 += nr;
             }
+            if (np_ == 0) {
+                cp_async_wait_all();
+                __syncthreads();
+            }
+            pf = pf_next;
         }
         // ---- first layer: dW_k[0][c] += sum_rows a_k[row] G_1[row][c] ----
         if (tid < 3 * C) {

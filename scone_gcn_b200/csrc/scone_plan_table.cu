@@ -520,16 +520,19 @@ __device__ __forceinline__ void table_plan_trajectory(const PlanArgs& a, const i
     const unsigned off_l1 = s_piece;
     const unsigned off_ro = off_l1 + (unsigned)align2(3 * n_l[1]);
     unsigned off_f[kFusedMaxL + 2] = {0, 0, 0, 0, 0}, off_b[kFusedMaxL + 2] = {0, 0, 0, 0, 0};
+    int tot_f[kFusedMaxL + 2] = {0, 0, 0, 0, 0}, tot_b[kFusedMaxL + 2] = {0, 0, 0, 0, 0};
     {
         unsigned o = off_ro + (unsigned)(align2(D + 1) + 2 * total_pairs);
         for (int s = 1; s <= L; ++s) {
             if (s >= 2) {
                 off_f[s] = o;
-                o += (unsigned)(align2(n_l[s] + 1) + 2 * (cnt[pbF[s] + n_l[s]] - cnt[pbF[s]]));
+                tot_f[s] = cnt[pbF[s] + n_l[s]] - cnt[pbF[s]];
+                o += (unsigned)(align2(n_l[s] + 1) + 2 * tot_f[s]);
             }
             if (s < L) {
                 off_b[s + 1] = o;
-                o += (unsigned)(align2(n_l[s] + 1) + 2 * (cnt[pbT[s] + n_l[s]] - cnt[pbT[s]]));
+                tot_b[s + 1] = cnt[pbT[s] + n_l[s]] - cnt[pbT[s]];
+                o += (unsigned)(align2(n_l[s] + 1) + 2 * tot_b[s + 1]);
             }
         }
     }
@@ -627,8 +630,10 @@ __device__ __forceinline__ void table_plan_trajectory(const PlanArgs& a, const i
         hdr[9] = (int)off_ro;
         hdr[10] = total_pairs;
         hdr[11] = m;
-        hdr[12] = 0;
+        hdr[12] = tot_f[2];
         hdr[13] = fp1 - fp0;
+        hdr[14] = tot_f[3];
+        hdr[15] = min(tot_b[2], 0xFFFF) | (min(tot_b[3], 0xFFFF) << 16);
     }
 }
 
