@@ -34,6 +34,7 @@ namespace {
 constexpr int kTrajThreads = 256;
 constexpr int kFuMaxD = 128;
 constexpr uint32_t kNoRow = 0xFFFFu;
+constexpr uint32_t kFlaggedKey = 0xFFFFFFu;   // sort key of a trajectory the plan kernel flagged (overflow): belongs to no launch
 
 template <int ACT>
 __device__ __forceinline__ float fu_act(float z) {
@@ -560,6 +561,9 @@ __device__ __forceinline__ int fu_stage(const int* __restrict__ gptr, const int2
     return nr;
 }
 
+// (3xTF32 splits: slab_common.cuh's round-to-nearest split_tf32.  A two-instruction split — hi = the value as is, truncated by the tensor
+// core, lo = a - trunc(a) — was measured: 3 % faster, but its one-sided truncations add up along K: 1.1e-5 on log-probs of magnitude
+// 12 and 1.1e-4 relative on the smallest weight gradients, both past the tolerances.  Not used.)
 // row tile product: D[nr x C] = tile[nr x 3C] * B, B = [W0; W1; W2] (forward) or [W0^T; W1^T; W2^T] (TRANSPOSED: the backward
 // data product); 3xTF32, fp32 accumulate.  A warp owns (m-tile, pair of n-tiles); epi(row, col, v0, v1) receives two adjacent columns.
 template <int C, bool TRANSPOSED, typename Epi>
@@ -663,8 +667,8 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
     float* dl = lg + ((D + 3) & ~3);                                 // [D] dlogits
     int2* sent = reinterpret_cast<int2*>(dl + ((D + 3) & ~3));       // [SE] staged program entries of the current chunk
     int* sptr = reinterpret_cast<int*>(sent + G::SE);                // [SP] staged row pointers
-    float* l1s = reinterpret_cast<float*>(sptr + G::SP);             // [SL1] staged layer-1 scalars
-    float* rows_sm = l1s + G::SL1;                                   // [cap_rows][LDH]  (small variant)
+    float* l1s = reinterpret_cast<float*>(sptr + G::SP);             // [2][SL1] staged layer-1 scalars of this / the next trajectory
+    float* rows_sm = l1s + 2 * G::SL1;                                   // [cap_rows][LDH]  (small variant)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int l = 2; l <= L; ++l)
@@ -691,25 +695,58 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
     // The launch's trajectories: the range of the cost-sorted batch whose live rows fit this launch's row store and no smaller one
     // (keys descending: BIG = the head, small = the tail).  They are dealt to the CTAs in snake order — heaviest first, every CTA gets
     // one of each round — so that the CTAs finish together; the order depends on the data only: deterministic.
+    // Trajectories are software-pipelined: while trajectory k computes, the header of trajectory k + 1 (order -> set row -> header: three
+    // dependent loads) is fetched in steps, and once the staging buffers are free its layer-1 scalars and first program follow.
     __shared__ int s_range[2];
+    __shared__ int s_hdr[2][kFusedHdrW];
     if (tid == 0) {
-        int lo = 0, hi = a.b;
+        // keys descending; plan-flagged trajectories carry the largest key: they head the list and belong to no launch
+        int f = 0, hi = a.b;
+        while (f < hi) {                                   // first position with key < kFlaggedKey
+            const int mid = (f + hi) >> 1;
+            if (a.okeys[mid] >= kFlaggedKey) f = mid + 1;
+            else hi = mid;
+        }
+        int lo = f;
+        hi = a.b;
         while (lo < hi) {                                  // first position with key <= cap_rows
             const int mid = (lo + hi) >> 1;
             if ((int)a.okeys[mid] > a.cap_rows) lo = mid + 1;
             else hi = mid;
         }
-        s_range[0] = BIG ? 0 : lo;
+        s_range[0] = BIG ? f : lo;
         s_range[1] = BIG ? lo : a.b;
     }
     __syncthreads();
     const int i_lo = s_range[0], i_hi = s_range[1];
-    for (int k = 0;; ++k) {
-        const int i = i_lo + k * (int)gridDim.x + ((k & 1) ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x);
-        if (i >= i_hi) break;
-        const int t = a.order[i];
-        const int* h = a.hdr + (size_t)(a.rows != nullptr ? a.rows[t] : t) * kFusedHdrW;
-        if (h[0] != 0) continue;                           // overflow reported by the plan kernel: skipped (host: error code 4)
+    auto index_of = [&](int kk) { return i_lo + kk * (int)gridDim.x + ((kk & 1) ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x); };
+    // asynchronous staging of the layer-1 scalars (read twice) and the first program of the trajectory whose header is hn
+    auto issue_first = [&](const int* hn, float* l1buf) -> bool {
+        const int n1 = hn[1];
+        if (3 * n1 <= G::SL1) {                            // (block-uniform)
+            const float* l1g = reinterpret_cast<const float*>(a.arena + (unsigned)hn[4]);
+            for (int i = tid; i < 3 * n1; i += kTrajThreads) cp_async_4(l1buf + i, l1g + i);
+        }
+        return L >= 2 ? fu_prefetch<C>(a.arena, (unsigned)hn[5], hn[2], hn[12], sptr, sent)
+                      : fu_prefetch<C>(a.arena, (unsigned)hn[9], D, hn[10], sptr, sent);
+    };
+    bool have = index_of(0) < i_hi, pf_first = false;
+    int t = 0;
+    if (have) {                                            // prologue: the first trajectory's header, synchronously
+        t = a.order[index_of(0)];
+        const int rid = a.rows != nullptr ? a.rows[t] : t;
+        if (tid < kFusedHdrW) s_hdr[0][tid] = a.hdr[(size_t)rid * kFusedHdrW + tid];
+        __syncthreads();
+        pf_first = issue_first(s_hdr[0], l1s);
+    }
+    for (int k = 0; have; ++k) {
+        const int* h = s_hdr[k & 1];
+        float* l1buf = l1s + (k & 1) * G::SL1;
+        const bool have_next = index_of(k + 1) < i_hi;
+        const int t_next = have_next ? a.order[index_of(k + 1)] : 0;      // (consumed after layer 1: the load flies meanwhile)
+        bool issued_next = false, pf_first_next = false;
+        cp_async_wait_all();
+        __syncthreads();
         int n[kFusedMaxL + 1], hb[kFusedMaxL + 2];
         int tot = 0;
         n[0] = 0;
@@ -725,15 +762,8 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
         // entries of the programs (header): forward of layers 2 / 3, transposed of layers 2 / 3 (saturated at 0xFFFF: never fits then)
         const int tot_f[kFusedMaxL + 1] = {0, 0, h[12], h[14]};
         const int tot_b[kFusedMaxL + 1] = {0, 0, h[15] & 0xFFFF, (int)((unsigned)h[15] >> 16)};
-        // asynchronous staging: the layer-1 scalars (read twice) and the first program
-        const bool stage_l1 = 3 * n[1] <= G::SL1;          // (block-uniform)
-        if (stage_l1)
-            for (int i = tid; i < 3 * n[1]; i += kTrajThreads) cp_async_4(l1s + i, l1 + i);
-        bool pf = L >= 2 ? fu_prefetch<C>(a.arena, (unsigned)h[5], n[2], tot_f[2], sptr, sent)
-                         : fu_prefetch<C>(a.arena, (unsigned)h[9], D, h[10], sptr, sent);
-        cp_async_wait_all();
-        __syncthreads();
-        if (stage_l1) l1 = l1s;
+        bool pf = pf_first;
+        if (3 * n[1] <= G::SL1) l1 = l1buf;                // (block-uniform) staged by issue_first
 
         // ---- layer 1 ----
         for (int i = tid; i < n[1] * C; i += kTrajThreads) {
@@ -741,6 +771,7 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
             const float z = fmaf(l1[3 * r + 2], w1s[2 * C + c], fmaf(l1[3 * r + 1], w1s[C + c], l1[3 * r] * w1s[c]));
             rows[(size_t)r * G::LDH + c] = fu_act<ACT>(z);
         }
+        const int rid_next = have_next ? (a.rows != nullptr ? a.rows[t_next] : t_next) : 0;   // (consumed after the conv layers)
         __syncthreads();
         // ---- conv layers ----
 #pragma unroll
@@ -785,6 +816,7 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
             }
             pf = pf_next;
         }
+        if (have_next && tid < kFusedHdrW) cp_async_4(&s_hdr[(k + 1) & 1][tid], a.hdr + (size_t)rid_next * kFusedHdrW + tid);
         // ---- readout: z_j = sum over the edges incident to neighbour j of sign * H_L[row]; logit_j = z_j . w_out ----
         const int* rptr = reinterpret_cast<const int*>(a.arena + (unsigned)h[9]);
         const int2* rent = reinterpret_cast<const int2*>(rptr + align2(D + 1));
@@ -837,7 +869,11 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
             if (GRAD && lane == 0) acc_cnt += mk;
         }
         if (!GRAD) {
-            __syncthreads();
+            cp_async_wait_all();
+            __syncthreads();                               // the next header has landed, the pair list is done with
+            if (have_next) pf_first = issue_first(s_hdr[(k + 1) & 1], l1s + ((k + 1) & 1) * G::SL1);
+            t = t_next;
+            have = have_next;
             continue;
         }
         // ---- backward of the readout: dq[row] = sum of sign * dl_j over its (at most two) pairs; G_L = dq w_out act'(H_L) ----
@@ -896,7 +932,14 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
                     else fu_gather<C>(tile, gl, sptr, ent, 0, nr);
                 }
                 __syncthreads();
-                if (r0 + nr >= np_ && l > 2) pf_next = fu_prefetch<C>(a.arena, (unsigned)h[7 + (l - 3)], n[l - 2], tot_b[l - 1], sptr, sent);
+                if (r0 + nr >= np_) {                      // the staging buffers are free
+                    if (l > 2) {
+                        pf_next = fu_prefetch<C>(a.arena, (unsigned)h[7 + (l - 3)], n[l - 2], tot_b[l - 1], sptr, sent);
+                    } else if (have_next) {                // last gather of this trajectory: the next one's first pieces
+                        pf_first_next = issue_first(s_hdr[(k + 1) & 1], l1s + ((k + 1) & 1) * G::SL1);
+                        issued_next = true;
+                    }
+                }
                 fu_dw<C>(acc[l - 2], hprev + (size_t)r0 * G::LDH, tile, nr);
                 __syncthreads();                           // every warp has read H_{l-1} of this chunk: G_{l-1} may overwrite it
                 fu_product<C, true>(tile, Wl, nr, [&](int r, int col, float v0, float v1) {
@@ -922,7 +965,14 @@ __global__ void __launch_bounds__(kTrajThreads, 2) fused_traj_kernel(const TrajA
             for (int r = 0; r < n[1]; ++r) s = fmaf(l1[3 * r + k], g1[(size_t)r * G::LDH + c], s);
             acc1 = s;
         }
-        __syncthreads();
+        if (have_next && !issued_next) {                   // (no conv layer / no live row in layer 1: nothing above issued it)
+            cp_async_wait_all();
+            __syncthreads();
+            pf_first_next = issue_first(s_hdr[(k + 1) & 1], l1s + ((k + 1) & 1) * G::SL1);
+        }
+        pf_first = pf_first_next;
+        t = t_next;
+        have = have_next;
     }
 
     if (a.rows_done != nullptr && tid == 0 && (n_fwd | n_bwd)) {
@@ -973,7 +1023,7 @@ __global__ void __launch_bounds__(256) fused_cost_kernel(const int* __restrict__
     const int* h = hdr + (size_t)(rows != nullptr ? rows[t] : t) * kFusedHdrW;
     int tot = 0;
     for (int l = 1; l <= L; ++l) tot += h[l];
-    keys[t] = h[0] != 0 ? 0u : (uint32_t)tot;
+    keys[t] = h[0] != 0 ? kFlaggedKey : min((uint32_t)tot, kFlaggedKey - 1u);
     vals[t] = t;
 }
 
@@ -1001,7 +1051,7 @@ template <int C>
 size_t traj_smem_bytes(int D, int cap_rows) {
     using G = FuGeom<C>;
     size_t fl = (size_t)(kFusedMaxL - 1) * 3 * C * G::LDW + 3 * C + C + (size_t)G::CH * G::LDA + (size_t)D * C + 2 * ((D + 3) & ~3) +
-                2 * (size_t)G::SE + G::SP + G::SL1 + (size_t)cap_rows * G::LDH;
+                2 * (size_t)G::SE + G::SP + 2 * G::SL1 + (size_t)cap_rows * G::LDH;
     return fl * sizeof(float);
 }
 
