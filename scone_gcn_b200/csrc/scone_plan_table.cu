@@ -374,10 +374,11 @@ __device__ __forceinline__ void table_plan_trajectory(const PlanArgs& a, const i
         return n;                                          // (the next phase starts with a barrier)
     };
 
-    // ---- 1: flows.  Only edges of T_0 can reach a cone row ----
-    for (int p = fp0 + (tid >> 2); p < fp1; p += QUADS) {
+    // ---- 1: flows (a thread per entry).  Only edges of T_0 can reach a cone row; a non-zero value marks the level >= 1 members of
+    // its row live in layer 1 ----
+    for (int p = fp0 + tid; p < fp1; p += THREADS) {
         const int eo = a.flow_edge[p];
-        if (eo < 0 || eo >= a.E) continue;                 // (same decision on the four lanes of the quad)
+        if (eo < 0 || eo >= a.E) continue;
         const uint32_t e = (uint32_t)a.rank[eo];
         int lo = 0, hi = m;
         while (lo < hi) {
@@ -387,82 +388,74 @@ __device__ __forceinline__ void table_plan_trajectory(const PlanArgs& a, const i
         }
         if (lo >= m || keys[lo] != e) continue;
         const float v = a.flow_val[p];
-        if (ql == 0) x[lo] = v;
+        x[lo] = v;
         if (v == 0.f) continue;
         const unsigned q1 = rp[lo + 1];
-        for (unsigned q = rp[lo] + ql; q < q1; q += 4) {
+        for (unsigned q = rp[lo]; q < q1; ++q) {
             const int j = ent[q].x & 0xFFFF;
             if (lv[j] >= 1) atomicOr(&bits[j >> 5], 1u << (j & 31));
         }
     }
-    // ---- 2: live rows layer by layer ----
+    // ---- 2: live rows layer by layer, and the entries per program row on the way.  Programs back to back in cnt: for s = 1 .. L the
+    // forward program of layer s (s >= 2), then the transposed program of layer s + 1 (s < L); both have the live rows of layer s as
+    // rows.  An entry of a live row of layer s belongs to the transposed program iff its column is live in layer s + 1, and that is
+    // the case iff the column lies in T_{s+1} (it has a live neighbour below: this row) — known before layer s + 1 is ranked. ----
     int n_l[kFusedMaxL + 2] = {0, 0, 0, 0, 0};
+    int pbF[kFusedMaxL + 2] = {0, 0, 0, 0, 0}, pbT[kFusedMaxL + 2] = {0, 0, 0, 0, 0}, rbase[kFusedMaxL + 2] = {0, 0, 0, 0, 0};
+    int n_prog_rows = 0, n_rows = 0, ptr_words = 0;
     n_l[1] = rank_live(1);
-    for (int s = 1; s < L && !s_ovf; ++s) {                // (s_ovf: uniform, written before the barrier inside rank_live)
+    for (int s = 1; s <= L && !s_ovf; ++s) {               // (s_ovf: uniform, written before a barrier inside rank_live)
         __syncthreads();
-        const uint16_t* brow = byr + (s - 1) * LV;
-        unsigned* bn = bits + s * W;
         const int ns = n_l[s];
+        rbase[s] = n_rows;
+        n_rows += ns;
+        if (s >= 2) {
+            pbF[s] = n_prog_rows;
+            n_prog_rows += ns;
+            ptr_words += align2(ns + 1);
+        }
+        if (s < L) {
+            pbT[s] = n_prog_rows;
+            n_prog_rows += ns;
+            ptr_words += align2(ns + 1);
+        }
+        if (s == 1 && L == 1) break;                       // (no program has the rows of layer 1 as rows, nothing to mark)
+        const uint16_t* brow = byr + (s - 1) * LV;
+        const uint16_t* idx_prev = idx + (s >= 2 ? s - 2 : 0) * M;
+        unsigned* bn = bits + (s < L ? s : 0) * W;
+        int* cF = cnt + pbF[s];
+        int* cT = cnt + pbT[s];
+        const int lnext = s + 1;
         for (int r = tid >> 2; r < ns; r += QUADS) {
             const int i = brow[r];
             const unsigned q1 = rp[i + 1];
+            int f = 0, tr = 0;
             for (unsigned q = rp[i] + ql; q < q1; q += 4) {
                 const int j = ent[q].x & 0xFFFF;
-                if (lv[j] >= s + 1) atomicOr(&bn[j >> 5], 1u << (j & 31));
+                if (s >= 2 && idx_prev[j] != (uint16_t)kNoRow) ++f;
+                if (s < L && lv[j] >= lnext) {
+                    ++tr;
+                    atomicOr(&bn[j >> 5], 1u << (j & 31));
+                }
+            }
+            f += __shfl_xor_sync(qmask, f, 1);
+            f += __shfl_xor_sync(qmask, f, 2);
+            tr += __shfl_xor_sync(qmask, tr, 1);
+            tr += __shfl_xor_sync(qmask, tr, 2);
+            if (ql == 0) {
+                if (s >= 2) cF[r] = f;
+                if (s < L) cT[r] = tr;
             }
         }
-        n_l[s + 1] = rank_live(s + 1);
+        if (s < L) n_l[s + 1] = rank_live(s + 1);
     }
     __syncthreads();
     if (s_ovf) {
         give_up();
         return;
     }
-    // ---- 3: entries per program row.  Programs back to back in cnt: for s = 1 .. L: forward program of layer s (s >= 2), then the
-    // transposed program of layer s + 1 (s < L); both have the live rows of layer s as rows ----
-    int pbF[kFusedMaxL + 2], pbT[kFusedMaxL + 2], rbase[kFusedMaxL + 2];
-    int n_prog_rows = 0, n_rows = 0, ptr_words = 0;
-    for (int s = 1; s <= kFusedMaxL; ++s) {
-        rbase[s] = n_rows;
-        pbF[s] = pbT[s] = 0;
-        if (s > L) continue;
-        n_rows += n_l[s];
-        if (s >= 2) {
-            pbF[s] = n_prog_rows;
-            n_prog_rows += n_l[s];
-            ptr_words += align2(n_l[s] + 1);
-        }
-        if (s < L) {
-            pbT[s] = n_prog_rows;
-            n_prog_rows += n_l[s];
-            ptr_words += align2(n_l[s] + 1);
-        }
-    }
-    rbase[kFusedMaxL + 1] = n_rows;
+    for (int s = L + 1; s <= kFusedMaxL + 1; ++s) rbase[s] = n_rows;
     auto layer_of = [&](int row) { return row < rbase[2] ? 1 : (row < rbase[3] ? 2 : 3); };
-    for (int row = tid >> 2; row < n_rows; row += QUADS) {
-        const int s = layer_of(row), r = row - rbase[s];
-        if (s == 1 && L == 1) continue;                    // (no program has the rows of layer 1 as rows)
-        const int i = byr[(s - 1) * LV + r];
-        const uint16_t* idx_prev = idx + (s >= 2 ? s - 2 : 0) * M;
-        const uint16_t* idx_next = idx + (s < L ? s : 0) * M;
-        const unsigned q1 = rp[i + 1];
-        int cF = 0, cT = 0;
-        for (unsigned q = rp[i] + ql; q < q1; q += 4) {
-            const int j = ent[q].x & 0xFFFF;
-            if (s >= 2 && idx_prev[j] != (uint16_t)kNoRow) ++cF;
-            if (s < L && idx_next[j] != (uint16_t)kNoRow) ++cT;
-        }
-        cF += __shfl_xor_sync(qmask, cF, 1);
-        cF += __shfl_xor_sync(qmask, cF, 2);
-        cT += __shfl_xor_sync(qmask, cT, 1);
-        cT += __shfl_xor_sync(qmask, cT, 2);
-        if (ql == 0) {
-            if (s >= 2) cnt[pbF[s] + r] = cF;
-            if (s < L) cnt[pbT[s] + r] = cT;
-        }
-    }
-    __syncthreads();
     const unsigned pp0 = last_ok ? a.pair_ptr[last] : 0u;
     const int total_pairs = last_ok ? (int)(a.pair_ptr[last + 1] - pp0) : 0;
     const int fixed_words = align2(3 * n_l[1]) + align2(D + 1) + 2 * total_pairs + ptr_words;
