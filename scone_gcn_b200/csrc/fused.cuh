@@ -45,10 +45,12 @@ struct PlanArgs {
     unsigned long long* bump;
     unsigned long long arena_words;
     int* overflow;
-    int tier;                  // 0: trajectory = work item, tables sized for ~99 % of the nodes; 1: the retry list, tables sized by the bounds
+    int tier;                  // 0: trajectory = work item, tables sized for ~99 % of the nodes; >= 1: the work list of the tier before
     int n_work;                // tier 0: trajectories of the chunk
-    int* n_retry;              // device counter of the retry list
-    int* retry;                // [chunk]
+    const int* n_in;           // tier >= 1: work list = the trajectories the tier before gave up on (device counter + list)
+    const int* in_list;
+    int* n_retry;              // trajectories this tier gives up on (tables too small): device counter + list; retry == NULL: last tier,
+    int* retry;                //   giving up = the overflow flag
 };
 
 #ifdef __CUDACC__
@@ -104,9 +106,9 @@ struct FusedState {
     int2* d_tb_pairs = nullptr;
     int* d_pair_off = nullptr;
     unsigned long long tb_entries = 0, tb_bytes = 0;
-    int tbM0 = 0, tbLV0 = 0, tbM = 0, tbLV = 0;   // table plan tiers: cone entries / live rows per layer the tables hold
-    size_t tb_smem0 = 0, tb_smem = 0;
-    bool tb_two_tiers = false;
+    int tbM0 = 0, tbLV0 = 0, tbM1 = 0, tbLV1 = 0, tbM = 0, tbLV = 0;   // table plan tiers: cone entries / live rows per layer the tables hold
+    size_t tb_smem0 = 0, tb_smem1 = 0, tb_smem = 0;
+    bool tb_two_tiers = false, tb_mid_tier = false;
     int quantile_cone = 0;                // |T_0| of ~99 % of the nodes
     int HS = 0, LV = 0, EC = 0, hshift = 0;        // plan tables, tier 1: sized by the bounds
     int HS0 = 0, LV0 = 0, EC0 = 0, hshift0 = 0;   // tier 0: sized for the cones of 99 % of the nodes
@@ -114,7 +116,7 @@ struct FusedState {
     int flow_room = 0;
     size_t plan_smem0 = 0;
     unsigned long long worst_words = 0;
-    int* d_retry = nullptr;
+    int* d_retry = nullptr;               // [2][chunk] work lists handed from tier to tier
     size_t plan_smem = 0, traj_smem_small = 0, traj_smem_big = 0;
     int cap_rows = 0, big_rows = 0, grid_small = 0, grid_big = 0, chunk = 0;
     size_t scratch_stride = 0;

@@ -148,7 +148,7 @@ __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, 
     // a table of this tier overflowed: tier 0 hands the trajectory to tier 1 (tables sized by the measured bounds)
     auto give_up = [&]() {
         if (tid == 0) {
-            if (a.tier == 0 && a.retry != nullptr) {
+            if (a.retry != nullptr) {
                 hdr[0] = kFusedFlagRetry;
                 a.retry[atomicAdd(a.n_retry, 1)] = t;
             } else {
@@ -437,9 +437,9 @@ __device__ __forceinline__ void plan_trajectory(const PlanArgs& a, const int t, 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) fused_plan_kernel(const PlanArgs a) {
     extern __shared__ __align__(16) unsigned char sm[];
-    const int n_work = a.tier == 0 ? a.n_work : *a.n_retry;
+    const int n_work = a.tier == 0 ? a.n_work : *a.n_in;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        plan_trajectory<THREADS>(a, a.tier == 0 ? w : a.retry[w], sm);
+        plan_trajectory<THREADS>(a, a.tier == 0 ? w : a.in_list[w], sm);
         __syncthreads();
     }
 }
@@ -1270,7 +1270,7 @@ int scone_fused_create(const scone_complex* cx, int L, int C, int mb, int64_t n_
     }
     SCONE_CUDA(cudaMalloc((void**)&f->d_arena, f->arena_words * sizeof(uint32_t)));
     SCONE_CUDA(cudaMalloc((void**)&f->d_hdr, (size_t)f->chunk * kFusedHdrW * sizeof(int)));
-    SCONE_CUDA(cudaMalloc((void**)&f->d_retry, (size_t)f->chunk * sizeof(int)));
+    SCONE_CUDA(cudaMalloc((void**)&f->d_retry, 2 * (size_t)f->chunk * sizeof(int)));
     SCONE_CUDA(cudaMalloc((void**)&f->d_bump, 2 * sizeof(unsigned long long)));  // [0] arena bump pointer, [1] retry counter (int)
     SCONE_CUDA(cudaMalloc((void**)&f->d_rows_done, 4 * sizeof(unsigned long long)));
     SCONE_CUDA(cudaMemset(f->d_rows_done, 0, 4 * sizeof(unsigned long long)));
@@ -1289,7 +1289,7 @@ static int launch_plans(const scone_complex* cx, const FusedState* f, PlanArgs p
     fused_plan_kernel<256><<<b, 256, f->plan_smem0, st>>>(p);
     SCONE_LAUNCHED();
     if (f->two_tiers) {                                    // the few trajectories whose cone overflowed the first tier's tables: 1024 threads each
-        p.tier = 1; p.HS = f->HS; p.LV = f->LV; p.EC = f->EC; p.hshift = f->hshift; p.retry = retry;
+        p.tier = 1; p.HS = f->HS; p.LV = f->LV; p.EC = f->EC; p.hshift = f->hshift; p.n_in = p.n_retry; p.in_list = retry; p.retry = nullptr;
         fused_plan_kernel<1024><<<std::min(b, cx->num_sms), 1024, f->plan_smem, st>>>(p);
         SCONE_LAUNCHED();
     }

@@ -305,7 +305,7 @@ __device__ __forceinline__ void table_plan_trajectory(const PlanArgs& a, const i
     int* hdr = a.hdr + (size_t)t * kFusedHdrW;
     auto give_up = [&]() {                                  // a table of this tier is too small: tier 0 hands the trajectory to tier 1
         if (tid == 0) {
-            if (a.tier == 0 && a.retry != nullptr) {
+            if (a.retry != nullptr) {
                 hdr[0] = kFusedFlagRetry;
                 a.retry[atomicAdd(a.n_retry, 1)] = t;
             } else {
@@ -633,9 +633,9 @@ __device__ __forceinline__ void table_plan_trajectory(const PlanArgs& a, const i
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) table_plan_kernel(const PlanArgs a) {
     extern __shared__ __align__(16) unsigned char sm[];
-    const int n_work = a.tier == 0 ? a.n_work : *a.n_retry;
+    const int n_work = a.tier == 0 ? a.n_work : *a.n_in;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        table_plan_trajectory<THREADS>(a, a.tier == 0 ? w : a.retry[w], sm);
+        table_plan_trajectory<THREADS>(a, a.tier == 0 ? w : a.in_list[w], sm);
         __syncthreads();
     }
 }
@@ -693,6 +693,7 @@ int scone_table_build(const scone_complex* cx, FusedState* f, int L, bool* ok) {
     if (st[2] || tm + (unsigned long long)N + 1 >= (1ull << 32) || tp >= (1ull << 32)) return 0;
     cone_ptr[N] = (unsigned)tm; node_off[N] = te; pair_ptr[N] = (unsigned)tp;
     f->cone_entries = tm;
+    int quantile999 = 0;
     f->bound_cone = st[0] > 0 ? st[0] : 1;
     f->bound_list = st[1] > 0 ? st[1] : 1;
     {
@@ -706,6 +707,16 @@ int scone_table_build(const scone_complex* cx, FusedState* f, int L, bool* ok) {
             }
         }
         f->quantile_cone = std::min(q0, f->bound_cone);
+        acc = 0;
+        want = ((long long)N * 999 + 999) / 1000;
+        quantile999 = f->bound_cone;
+        for (int b = 0; b < kTbBuckets; ++b) {
+            acc += st[4 + b];
+            if (acc >= want) {
+                quantile999 = std::min(32 * (b + 1), f->bound_cone);
+                break;
+            }
+        }
     }
     // rows in local indices: only if they fit comfortably (the hash plan needs none of it)
     const unsigned long long bytes = te * 8 + (tm + (unsigned long long)N + 1) * 4 + tp * 8 + (unsigned long long)N * (D + 1) * 4 + ((unsigned long long)N + 1) * 16;
@@ -762,9 +773,13 @@ int scone_table_build(const scone_complex* cx, FusedState* f, int L, bool* ok) {
         f->tbLV0 = std::min(f->tbLV, (env_int("SCONE_TABLE_LV0", 192) + 63) & ~63);
         f->tb_two_tiers = f->tbM0 < f->tbM || f->tbLV0 < f->tbLV;
         f->tb_smem0 = table_plan_smem(f->tbM0, f->tbLV0);
+        // middle tier: the cones of ~99.9 % of the nodes, 512 live rows per layer — a fraction of the last tier's shared memory
+        f->tbM1 = std::min(f->tbM, (env_int("SCONE_TABLE_M1", std::max(quantile999, 2 * f->tbM0)) + 63) & ~63);
+        f->tbLV1 = std::min(f->tbLV, (env_int("SCONE_TABLE_LV1", 512) + 63) & ~63);
+        f->tb_smem1 = table_plan_smem(f->tbM1, f->tbLV1);
+        f->tb_mid_tier = f->tb_two_tiers && (f->tbM1 > f->tbM0 || f->tbLV1 > f->tbLV0) && 2 * f->tb_smem1 <= f->tb_smem;
         SCONE_CUDA(cudaFuncSetAttribute(table_plan_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTablePlanSmem));
         SCONE_CUDA(cudaFuncSetAttribute(table_plan_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTablePlanSmem));
-        SCONE_CUDA(cudaFuncSetAttribute(table_plan_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTablePlanSmem));
         SCONE_CUDA(cudaFuncSetAttribute(table_plan_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTablePlanSmem));
         SCONE_CUDA(cudaFuncSetAttribute(table_plan_kernel<kTier1Threads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTablePlanSmem));
     }
@@ -774,27 +789,37 @@ int scone_table_build(const scone_complex* cx, FusedState* f, int L, bool* ok) {
 
 // Plans b trajectories (p: trajectories, outputs, retry list already set) with the table plan: first tier, then the retry list.
 int scone_table_plan_launch(const FusedState* f, PlanArgs p, int b, int num_sms, cudaStream_t st) {
+    const int f_chunk = f->chunk;
     p.cone_ptr = f->d_cone_ptr; p.cone_ent = f->d_cone_ent; p.node_off = f->d_node_off; p.tb_rowptr = f->d_tb_rowptr; p.tb_ent = f->d_tb_ent;
     p.pair_ptr = f->d_pair_ptr; p.tb_pairs = f->d_tb_pairs; p.pair_off = f->d_pair_off;
     p.tier = 0; p.n_work = b;
     p.M = f->tbM0; p.LV = f->tbLV0;
-    int* retry = p.retry;
-    if (!f->tb_two_tiers) p.retry = nullptr;
+    // up to three tiers; a tier hands the trajectories its tables cannot hold to the next one through a work list
+    int* list0 = p.retry;                                  // [2][chunk]
+    int* list1 = p.retry + f_chunk;
+    int* cnt0 = p.n_retry;                                 // two int counters (zeroed by the caller)
+    int* cnt1 = p.n_retry + 1;
+    p.retry = f->tb_two_tiers ? list0 : nullptr;
+    p.n_retry = cnt0;
     static const int t0 = [] { const char* v = getenv("SCONE_TABLE_T0"); return v && *v ? atoi(v) : 128; }();
-    static const int t1 = [] { const char* v = getenv("SCONE_TABLE_T1"); return v && *v ? atoi(v) : kTier1Threads; }();
     if (t0 == 64) table_plan_kernel<64><<<b, 64, f->tb_smem0, st>>>(p);
-    else if (t0 == 128) table_plan_kernel<128><<<b, 128, f->tb_smem0, st>>>(p);
-    else if (t0 == 512) table_plan_kernel<512><<<b, 512, f->tb_smem0, st>>>(p);
-    else table_plan_kernel<256><<<b, 256, f->tb_smem0, st>>>(p);
+    else if (t0 == 256) table_plan_kernel<256><<<b, 256, f->tb_smem0, st>>>(p);
+    else table_plan_kernel<128><<<b, 128, f->tb_smem0, st>>>(p);
     SCONE_LAUNCHED();
-    if (f->tb_two_tiers) {
-        p.tier = 1; p.M = f->tbM; p.LV = f->tbLV; p.retry = retry;
-        const int per_sm = std::max(1, (int)((size_t)220 * 1024 / (f->tb_smem + 1024)));
-        if (t1 == 128) table_plan_kernel<128><<<std::min(b, std::min(16, per_sm) * num_sms), 128, f->tb_smem, st>>>(p);
-        else if (t1 == 256) table_plan_kernel<256><<<std::min(b, std::min(8, per_sm) * num_sms), 256, f->tb_smem, st>>>(p);
-        else if (t1 == 1024) table_plan_kernel<1024><<<std::min(b, std::min(2, per_sm) * num_sms), 1024, f->tb_smem, st>>>(p);
-        else table_plan_kernel<512><<<std::min(b, std::min(4, per_sm) * num_sms), 512, f->tb_smem, st>>>(p);
+    if (!f->tb_two_tiers) return 0;
+    const int* n_in = cnt0;
+    const int* in_list = list0;
+    if (f->tb_mid_tier) {                                  // tables for all but the largest cones: 256 threads, several CTAs per SM
+        p.tier = 1; p.M = f->tbM1; p.LV = f->tbLV1; p.n_in = n_in; p.in_list = in_list; p.retry = list1; p.n_retry = cnt1;
+        const int per_sm = std::max(1, std::min(8, (int)((size_t)220 * 1024 / (f->tb_smem1 + 1024))));
+        table_plan_kernel<256><<<std::min(b, per_sm * num_sms), 256, f->tb_smem1, st>>>(p);
         SCONE_LAUNCHED();
+        n_in = cnt1;
+        in_list = list1;
     }
+    p.tier = 2; p.M = f->tbM; p.LV = f->tbLV; p.n_in = n_in; p.in_list = in_list; p.retry = nullptr; p.n_retry = cnt0;
+    const int per_sm = std::max(1, std::min(4, (int)((size_t)220 * 1024 / (f->tb_smem + 1024))));
+    table_plan_kernel<512><<<std::min(b, per_sm * num_sms), 512, f->tb_smem, st>>>(p);
+    SCONE_LAUNCHED();
     return 0;
 }
