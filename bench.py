@@ -624,7 +624,7 @@ def bench_bunch(args, cfg, sp, ds, hp, h2d_bytes, B, gb, world, rank, dev, strea
     L = sg.lib()
     cx = sg.SimplicialComplex.from_dense(ds.B1, ds.B2, 'scone')
     shifts = [CsrOperator(M) for M in compute_shift_matrices(ds.B1, ds.B2)]
-    net = BunchModel(shifts, np.array(cx.nbrhoods), [cfg['hidden']] * 3, micro_batch=min(B, 256))
+    net = BunchModel(shifts, np.array(cx.nbrhoods), [cfg['hidden']] * 3, micro_batch=min(B, 1024))
     rs = np.random.RandomState(1030)
     net.set_weights([0.01 * rs.randn(*s) for s in net.shapes])
     step_no = [0]

@@ -206,6 +206,15 @@ def main():
         onp.savez_compressed(os.path.join(OUT, 'model_default_scone_h16%s.npz' % tag), **fx)
         print('wrote default model fixture; init loss', fx['init_loss_train'])
 
+    # ---- -model bunch on the default complex (BASELINE config 3 on the reference's own default dataset) ----
+    if not args.skip_default_model and args.only in ('', 'default_bunch'):
+        fx = model_fixture(te, stm, 'default', 'bunch', [(7, 8), (7, 8), (7, 8)], epochs=0, batch_size=100, big_scale=0.3)
+        for k in list(fx):
+            if k.startswith('shift_'):
+                del fx[k]
+        onp.savez_compressed(os.path.join(OUT, 'model_default_bunch_h8%s.npz' % tag), **fx)
+        print('wrote default bunch fixture; init loss', fx['init_loss_train'])
+
 
 if __name__ == '__main__':
     main()

@@ -73,6 +73,64 @@ __global__ void __launch_bounds__(kBT) outer_reduce_kernel(const float* __restri
     if (threadIdx.x == 0) dW[ci * cout + co] += red[0];
 }
 
+// The same product for the common small widths, coalesced and with every row read once: a thread keeps an 8 x 8 tile of dW in
+// registers, walks rows m = global thread, + grid threads, ... (its 8 U and 8 G values are contiguous: two 32-byte loads), the
+// block folds its threads' tiles in a fixed order (shuffle tree, then warps in order) into partial[blockIdx.x][tile]; blockIdx.y
+// selects the tile of (ci, co).  outer_fold_kernel adds the blocks' partials in block order.  Deterministic.
+constexpr int kOT = 8;
+constexpr int kOuterBlocks = 296;
+constexpr int kOuterTilesMax = 16;         // widths up to 32 x 32
+__global__ void __launch_bounds__(kBT) outer_tile_kernel(const float* __restrict__ U, const float* __restrict__ G, float* __restrict__ partial,
+                                                        long long M, int cin, int cout) {
+    __shared__ float red[kBT / 32][kOT * kOT];
+    const int tiles_co = (cout + kOT - 1) / kOT;
+    const int ci0 = (blockIdx.y / tiles_co) * kOT, co0 = (blockIdx.y % tiles_co) * kOT;
+    float acc[kOT][kOT];
+#pragma unroll
+    for (int i = 0; i < kOT; ++i)
+#pragma unroll
+        for (int j = 0; j < kOT; ++j) acc[i][j] = 0.f;
+    const long long stride = (long long)gridDim.x * kBT;
+    for (long long m = (long long)blockIdx.x * kBT + threadIdx.x; m < M; m += stride) {
+        float u[kOT], g[kOT];
+#pragma unroll
+        for (int i = 0; i < kOT; ++i) u[i] = ci0 + i < cin ? U[m * cin + ci0 + i] : 0.f;
+#pragma unroll
+        for (int j = 0; j < kOT; ++j) g[j] = co0 + j < cout ? G[m * cout + co0 + j] : 0.f;
+#pragma unroll
+        for (int i = 0; i < kOT; ++i)
+#pragma unroll
+            for (int j = 0; j < kOT; ++j) acc[i][j] = fmaf(u[i], g[j], acc[i][j]);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < kOT; ++i)
+#pragma unroll
+        for (int j = 0; j < kOT; ++j) {
+            float v = acc[i][j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) red[warp][i * kOT + j] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < kOT * kOT) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < kBT / 32; ++w) v += red[w][threadIdx.x];
+        partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (kOT * kOT) + threadIdx.x] = v;
+    }
+}
+
+__global__ void outer_fold_kernel(const float* __restrict__ partial, int n_blocks, float* __restrict__ dW, int cin, int cout) {
+    const int tiles_co = (cout + kOT - 1) / kOT;
+    const int tile = blockIdx.x, e = threadIdx.x;          // one block of 64 threads per tile
+    const int ci = (tile / tiles_co) * kOT + e / kOT, co = (tile % tiles_co) * kOT + e % kOT;
+    if (ci >= cin || co >= cout) return;
+    float v = 0.f;
+    for (int b = 0; b < n_blocks; ++b) v += partial[((size_t)tile * n_blocks + b) * (kOT * kOT) + e];
+    dW[ci * cout + co] += v;
+}
+
 __global__ void relu_kernel(float* __restrict__ Z, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) Z[i] = fmaxf(Z[i], 0.f);
@@ -197,6 +255,7 @@ struct scone_bunch {
     float* d_G[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // dL/dZ ping-pong per level
     float* d_dX[3] = {nullptr, nullptr, nullptr};
     float *d_logp = nullptr, *d_partial = nullptr;
+    float* d_outer = nullptr;                 // [tiles][blocks][64] partial weight-gradient tiles
     int32_t *d_ptr = nullptr, *d_edge = nullptr, *d_last = nullptr, *d_tgt = nullptr;
     float *d_val = nullptr, *d_mask = nullptr, *d_logp_all = nullptr;
     int64_t cap_B = 0, cap_nnz = 0;
@@ -209,7 +268,7 @@ extern "C" int scone_bunch_destroy(scone_bunch* m) {
         for (float* p : m->act[lv]) cudaFree(p);
         cudaFree(m->d_G[0][lv]); cudaFree(m->d_G[1][lv]); cudaFree(m->d_dX[lv]);
     }
-    cudaFree(m->d_U); cudaFree(m->d_dU); cudaFree(m->d_logp); cudaFree(m->d_partial);
+    cudaFree(m->d_U); cudaFree(m->d_dU); cudaFree(m->d_logp); cudaFree(m->d_partial); cudaFree(m->d_outer);
     cudaFree(m->d_ptr); cudaFree(m->d_edge); cudaFree(m->d_last); cudaFree(m->d_tgt); cudaFree(m->d_val); cudaFree(m->d_mask);
     cudaFree(m->d_logp_all);
     delete m;
@@ -255,6 +314,7 @@ extern "C" int scone_bunch_create(const scone_csr* const* S7, int32_t N, int32_t
         alloc((void**)&m->d_dX[lv], (size_t)rows_of[lv] * mb * cmax * 4);
     }
     alloc((void**)&m->d_U, rmax * mb * cmax * 4); alloc((void**)&m->d_dU, rmax * mb * cmax * 4);
+    alloc((void**)&m->d_outer, (size_t)kOuterTilesMax * kOuterBlocks * kOT * kOT * 4);
     alloc((void**)&m->d_logp, mb * D * 4); alloc((void**)&m->d_partial, mb * 2 * 4);
     if (!rc) {
         cudaMemcpy(m->d_nbr, nbrhoods, (size_t)N * D * 4, cudaMemcpyHostToDevice);
@@ -413,8 +473,20 @@ extern "C" int scone_bunch_loss_grad_host(scone_bunch* m, int32_t B, const int32
                 csr_spmm_kernel<<<nblk((long long)S->rows * wdt), kBT, 0, st>>>(S->d_rowptr, S->d_col, S->d_val, m->act[il][i], m->d_U, S->rows,
                                                                                wdt, 0);
                 SCONE_LAUNCHED();
-                outer_reduce_kernel<<<cin * cout, kBT, 0, st>>>(m->d_U, m->d_G[cur][ol], m->d_grad + m->w_off[7 * i + k], M, cin, cout);
-                SCONE_LAUNCHED();
+                {
+                    // dW_k += U^T G over the M = rows x b stacked rows
+                    const int tiles = ((cin + kOT - 1) / kOT) * ((cout + kOT - 1) / kOT);
+                    const int nb = (int)std::min<long long>(kOuterBlocks, (M + kBT - 1) / kBT);
+                    if (tiles <= kOuterTilesMax) {
+                        outer_tile_kernel<<<dim3(nb, tiles), kBT, 0, st>>>(m->d_U, m->d_G[cur][ol], m->d_outer, M, cin, cout);
+                        SCONE_LAUNCHED();
+                        outer_fold_kernel<<<tiles, kOT * kOT, 0, st>>>(m->d_outer, nb, m->d_grad + m->w_off[7 * i + k], cin, cout);
+                        SCONE_LAUNCHED();
+                    } else {
+                        outer_reduce_kernel<<<cin * cout, kBT, 0, st>>>(m->d_U, m->d_G[cur][ol], m->d_grad + m->w_off[7 * i + k], M, cin, cout);
+                        SCONE_LAUNCHED();
+                    }
+                }
                 if (i > 0) {
                     rows_times_wt_kernel<<<nblk(M * cin), kBT, 0, st>>>(m->d_G[cur][ol], m->d_w + m->w_off[7 * i + k], m->d_dU, M, cin, cout);
                     SCONE_LAUNCHED();

@@ -275,7 +275,7 @@ class Scone_GCN():
             raise TypeError('setup(model_type="bunch") needs the 7 CsrOperator shifts returned by data_setup')
         self.shifts = shifts
         n = len(onp.asarray(inputs[1]))
-        mb = self.micro_batch or min(max(n, 1), 256)
+        mb = self.micro_batch or min(max(n, 1), 1024)
         self._net = BunchModel(shifts, onp.asarray(inputs[0]), [h[1] for h in hidden_layers], micro_batch=mb)
         self.model_single = model
 

@@ -15,11 +15,13 @@ def test_shift_matrices_match_reference_fixture():
 
 
 @pytest.mark.gpu
-def test_bunch_forward_grads_accuracy_vs_reference_golden():
+@pytest.mark.parametrize('which', ['small', 'default'])
+def test_bunch_forward_grads_accuracy_vs_reference_golden(which):
+    """small: the 120-node complex; default: the reference's own default dataset (400 nodes, 1000 trajectories; BASELINE config 3)."""
     import scone_gcn_b200 as sg
     from scone_gcn_b200.bunch import BunchModel, CsrOperator
-    ds = Dataset('dataset_small.npz')
-    fx = load('model_small_bunch_h8.npz')
+    ds = Dataset('dataset_%s.npz' % which)
+    fx = load('model_%s_bunch_h8.npz' % which)
     ops = [CsrOperator(M) for M in compute_shift_matrices(ds.B1, ds.B2)]
     net = BunchModel(ops, fx['nbrhoods'], [int(h[1]) for h in fx['hidden']], micro_batch=32)
     ptr, fe, fv = sg.flows_to_csr(ds.flows)

@@ -124,6 +124,18 @@ def test_default_complex_forward_vs_reference():
     assert np.allclose(lp, fx['big_logprobs'][::9], rtol=2e-5, atol=2e-5)
 
 
+def test_default_complex_bunch_forward_vs_reference():
+    """-model bunch on the reference's default dataset (400 nodes): the oracle against the reference's own run."""
+    ds = Dataset('dataset_default.npz')
+    fx = load('model_default_bunch_h8.npz')
+    orc = so.DenseOracle('bunch', so.shift_matrices(ds.B1, ds.B2, 'bunch'), ds.B1, ds.last_nodes, ds.flows, ds.targets)
+    W = weights_of(fx, 'w_big')
+    idx = torch.arange(0, 1000, 9)
+    with torch.no_grad():
+        lp = orc.forward(W, idx).numpy()
+    assert np.allclose(lp, fx['big_logprobs'][::9], rtol=2e-5, atol=2e-5)
+
+
 @pytest.mark.parametrize('model', ['scone', 'ebli'])
 def test_sparse_oracle_matches_dense(model):
     ds = Dataset('dataset_small.npz')
