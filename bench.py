@@ -151,9 +151,10 @@ class ClockSampler:
                 'samples': len(sm), 'source': self.source}
 
 
-def ncu_traffic(kernel_pattern, tag):
+def ncu_traffic(kernel_pattern, tag, launches_per_step=1):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full` capture
-    of this round (profiles/prof_<tag>_raw.csv) — only quoted when the capture was taken on the same launch shape."""
+    of this round (profiles/prof_<tag>_raw.csv) — only quoted when the capture was taken on the same launch shape.  A kernel that runs
+    as several launches per step (the fused compute kernel: its small and its big row-store class) is summed over them, like `achieved`."""
     path = os.path.join(ROOT, 'profiles', 'prof_%s_raw.csv' % tag)
     if not os.path.exists(path):
         return None
@@ -171,7 +172,7 @@ def ncu_traffic(kernel_pattern, tag):
                 i = hdr.index(name)
                 tot += float(val[i]) * scale[unit[i]]
             n += 1
-        return tot / n if n else None
+        return tot / (n / float(launches_per_step)) if n else None
     except Exception:
         return None
 
@@ -420,7 +421,9 @@ def main():
         if fam['layer_bwd'][0]:
             alg['layer_bwd'] = rows['layer_bwd'] * 4.0 * 3 * C / fam['layer_bwd'][0]
     tot_ms = sum(t for _, t in fam.values()) or 1.0
-    names = {'layer_bwd': 'fused_traj_kernel (+ fused_reduce_kernel)', 'cone': 'fused_plan_kernel'} if pipeline_id == 4 else {}
+    table_plan = pipeline_id == 4 and bool((net.fused_info() or {}).get('table_plan_mb'))
+    names = {'layer_bwd': 'fused_traj_kernel (small + big row-store launches; + cost sort, fused_reduce_kernel)',
+             'cone': 'table_plan_kernel (three tiers)' if table_plan else 'fused_plan_kernel (two tiers)'} if pipeline_id == 4 else {}
     kernels = {}
     for nme, (n_l, t_ms) in fam.items():
         if n_l:
@@ -435,7 +438,7 @@ def main():
     step_alg_bytes = (rows['layer_fwd'] * 4.0 * 2 * C + rows['layer_bwd'] * 4.0 * 3 * C) / prof_steps
     roofline = {'bound': 'hbm', 'kernel': kernels[dom]['kernel'], 'achieved': kernels[dom].get('achieved_gbs'), 'peak': peak, 'unit': 'GB/s',
                 'frac': kernels[dom].get('frac'),
-                'traffic': ncu_traffic('fused_traj_kernel', 'fused_r2_' + args.config) if pipeline_id == 4 else None,
+                'traffic': ncu_traffic('fused_traj_kernel', 'fused_r2_' + args.config, 2) if pipeline_id == 4 else None,
                 'peak_source': peak_src, 'largest_family': kernels[largest]['kernel'],
                 'algorithmic_bytes_per_launch': kernels[dom].get('algorithmic_bytes_per_launch'),
                 'whole_step': {'algorithmic_bytes': step_alg_bytes, 'achieved_gbs': step_alg_bytes / ms_per_step / 1e6,

@@ -131,6 +131,170 @@ __global__ void outer_fold_kernel(const float* __restrict__ partial, int n_block
     dW[ci * cout + co] += v;
 }
 
+// ---- fused layer kernels (widths 1 / 8 / 16): one launch per simplex level instead of spmm + product (+ accumulate) per operator ----
+// The operators that write (forward) / read (input gradient) one level, at most three.
+struct BunchOps {
+    int n;
+    const int32_t* rowptr[3];
+    const int32_t* col[3];
+    const float* val[3];
+    const float* X[3];                  // forward: state of the operator's input level [cols][b][CI]; backward: G of its output level [rows][b][CO]
+    const float* W[3];                  // [CI][CO]
+};
+
+// u[0..C) += v * x[0..C): 128-bit loads when the row has them (C = 8 / 16: rows are 32 / 64 bytes, aligned)
+template <int C>
+__device__ __forceinline__ void axpy_row(float (&u)[C], float v, const float* __restrict__ x) {
+    if (C % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < C / 4; ++q) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(x) + q);
+            u[4 * q + 0] = fmaf(v, w.x, u[4 * q + 0]);
+            u[4 * q + 1] = fmaf(v, w.y, u[4 * q + 1]);
+            u[4 * q + 2] = fmaf(v, w.z, u[4 * q + 2]);
+            u[4 * q + 3] = fmaf(v, w.w, u[4 * q + 3]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < C; ++i) u[i] = fmaf(v, __ldg(x + i), u[i]);
+    }
+}
+template <int C>
+__device__ __forceinline__ void store_row(float* __restrict__ dst, const float (&z)[C]) {
+    if (C % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < C / 4; ++q) reinterpret_cast<float4*>(dst)[q] = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < C; ++i) dst[i] = z[i];
+    }
+}
+
+// forward of one level: Z[r][t][:] = relu( sum_k (sum_p val_p X_k[col_p][t][:]) W_k ); one thread per (r, t)
+template <int CI, int CO>
+__global__ void __launch_bounds__(kBT) bunch_level_fwd_kernel(const BunchOps o, float* __restrict__ Z, int rows, int b) {
+    const long long idx = (long long)blockIdx.x * kBT + threadIdx.x;
+    if (idx >= (long long)rows * b) return;
+    const int r = (int)(idx / b), t = (int)(idx % b);
+    float z[CO];
+#pragma unroll
+    for (int j = 0; j < CO; ++j) z[j] = 0.f;
+    for (int k = 0; k < o.n; ++k) {
+        float u[CI];
+#pragma unroll
+        for (int i = 0; i < CI; ++i) u[i] = 0.f;
+        const int p1 = o.rowptr[k][r + 1];
+        for (int p = o.rowptr[k][r]; p < p1; ++p) {
+            axpy_row<CI>(u, o.val[k][p], o.X[k] + ((size_t)o.col[k][p] * b + t) * CI);
+        }
+        const float* W = o.W[k];
+#pragma unroll
+        for (int j = 0; j < CO; ++j) {
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < CI; ++i) acc = fmaf(u[i], W[i * CO + j], acc);
+            z[j] += acc;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < CO; ++j) z[j] = fmaxf(z[j], 0.f);
+    store_row<CO>(Z + (size_t)idx * CO, z);
+}
+
+// input gradient of one level: dX[c][t][:] = sum_k (sum_p val_p G_k[row_p][t][:]) W_k^T over the transposed operators; one thread per (c, t)
+template <int CI, int CO>
+__global__ void __launch_bounds__(kBT) bunch_level_bwd_kernel(const BunchOps o, float* __restrict__ dX, int cols, int b) {
+    const long long idx = (long long)blockIdx.x * kBT + threadIdx.x;
+    if (idx >= (long long)cols * b) return;
+    const int c = (int)(idx / b), t = (int)(idx % b);
+    float dx[CI];
+#pragma unroll
+    for (int i = 0; i < CI; ++i) dx[i] = 0.f;
+    for (int k = 0; k < o.n; ++k) {
+        float v[CO];
+#pragma unroll
+        for (int j = 0; j < CO; ++j) v[j] = 0.f;
+        const int p1 = o.rowptr[k][c + 1];
+        for (int p = o.rowptr[k][c]; p < p1; ++p) {
+            axpy_row<CO>(v, o.val[k][p], o.X[k] + ((size_t)o.col[k][p] * b + t) * CO);
+        }
+        const float* W = o.W[k];
+#pragma unroll
+        for (int i = 0; i < CI; ++i) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < CO; ++j) acc = fmaf(v[j], W[i * CO + j], acc);
+            dx[i] += acc;
+        }
+    }
+    store_row<CI>(dX + (size_t)idx * CI, dx);
+}
+
+// weight gradient of one operator with U = S X computed on the fly (outer_tile_kernel without the U round trip)
+__global__ void __launch_bounds__(kBT) outer_tile_spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                             const float* __restrict__ val, const float* __restrict__ X,
+                                                             const float* __restrict__ G, float* __restrict__ partial, int rows, int b, int cin,
+                                                             int cout) {
+    __shared__ float red[kBT / 32][kOT * kOT];
+    const int tiles_co = (cout + kOT - 1) / kOT;
+    const int ci0 = (blockIdx.y / tiles_co) * kOT, co0 = (blockIdx.y % tiles_co) * kOT;
+    float acc[kOT][kOT];
+#pragma unroll
+    for (int i = 0; i < kOT; ++i)
+#pragma unroll
+        for (int j = 0; j < kOT; ++j) acc[i][j] = 0.f;
+    const long long M = (long long)rows * b, stride = (long long)gridDim.x * kBT;
+    for (long long m = (long long)blockIdx.x * kBT + threadIdx.x; m < M; m += stride) {
+        const int r = (int)(m / b), t = (int)(m % b);
+        float u[kOT], g[kOT];
+#pragma unroll
+        for (int i = 0; i < kOT; ++i) u[i] = 0.f;
+        const int p1 = rowptr[r + 1];
+        for (int p = rowptr[r]; p < p1; ++p) {
+            const float v = val[p];
+            const float* x = X + ((size_t)col[p] * b + t) * cin + ci0;
+            if (cin % kOT == 0) {                          // (uniform) the tile is a whole, aligned 32-byte piece of the row
+                axpy_row<kOT>(u, v, x);
+            } else {
+#pragma unroll
+                for (int i = 0; i < kOT; ++i)
+                    if (ci0 + i < cin) u[i] = fmaf(v, x[i], u[i]);
+            }
+        }
+        if (cout % kOT == 0) {
+#pragma unroll
+            for (int q = 0; q < kOT / 4; ++q) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(G + m * cout + co0) + q);
+                g[4 * q] = w.x; g[4 * q + 1] = w.y; g[4 * q + 2] = w.z; g[4 * q + 3] = w.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kOT; ++j) g[j] = co0 + j < cout ? G[m * cout + co0 + j] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < kOT; ++i)
+#pragma unroll
+            for (int j = 0; j < kOT; ++j) acc[i][j] = fmaf(u[i], g[j], acc[i][j]);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < kOT; ++i)
+#pragma unroll
+        for (int j = 0; j < kOT; ++j) {
+            float v = acc[i][j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) red[warp][i * kOT + j] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < kOT * kOT) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < kBT / 32; ++w) v += red[w][threadIdx.x];
+        partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (kOT * kOT) + threadIdx.x] = v;
+    }
+}
+
 __global__ void relu_kernel(float* __restrict__ Z, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) Z[i] = fmaxf(Z[i], 0.f);
@@ -369,6 +533,25 @@ int ensure_staging(scone_bunch* m, int64_t B, int64_t nnz) {
     return 0;
 }
 
+bool fused_width(int c) { return c == 1 || c == 8 || c == 16; }
+
+template <bool FWD>
+int launch_level(const BunchOps& o, float* out, int rows, int b, int cin, int cout, cudaStream_t st) {
+    const unsigned grid = (unsigned)(((long long)rows * b + kBT - 1) / kBT);
+#define SCONE_BUNCH_CASE(CI, CO)                                                                          \
+    if (cin == CI && cout == CO) {                                                                       \
+        if (FWD) bunch_level_fwd_kernel<CI, CO><<<grid, kBT, 0, st>>>(o, out, rows, b);                   \
+        else bunch_level_bwd_kernel<CI, CO><<<grid, kBT, 0, st>>>(o, out, rows, b);                       \
+        SCONE_LAUNCHED();                                                                                \
+        return 0;                                                                                        \
+    }
+    SCONE_BUNCH_CASE(1, 8) SCONE_BUNCH_CASE(1, 16) SCONE_BUNCH_CASE(8, 8) SCONE_BUNCH_CASE(16, 16) SCONE_BUNCH_CASE(8, 16)
+    SCONE_BUNCH_CASE(16, 8) SCONE_BUNCH_CASE(8, 1) SCONE_BUNCH_CASE(16, 1) SCONE_BUNCH_CASE(1, 1)
+#undef SCONE_BUNCH_CASE
+    scone_set_error("scone_bunch: no fused layer kernel for widths %d -> %d", cin, cout);
+    return 1;
+}
+
 // forward of one micro-batch; states kept in m->act
 int bunch_forward_mb(scone_bunch* m, int b, const int32_t* ptr, const int32_t* edge, const float* val, cudaStream_t st) {
     for (int lv = 0; lv < 3; ++lv) SCONE_CUDA(cudaMemsetAsync(m->act[lv][0], 0, (size_t)m->n[lv] * b * 4, st));   // V_0 = T_0 = 0
@@ -376,6 +559,20 @@ int bunch_forward_mb(scone_bunch* m, int b, const int32_t* ptr, const int32_t* e
     SCONE_LAUNCHED();
     for (int i = 0; i < m->L; ++i) {
         const int cin = m->width[i], cout = m->width[i + 1];
+        if (fused_width(cin) && fused_width(cout)) {       // one launch per level: gather, products, relu
+            for (int lv = 0; lv < 3; ++lv) {
+                BunchOps o{};
+                for (int k = 0; k < 7; ++k)
+                    if (kOutLevel[k] == lv) {
+                        const scone_csr* S = m->S[k];
+                        o.rowptr[o.n] = S->d_rowptr; o.col[o.n] = S->d_col; o.val[o.n] = S->d_val;
+                        o.X[o.n] = m->act[kInLevel[k]][i]; o.W[o.n] = m->d_w + m->w_off[7 * i + k];
+                        ++o.n;
+                    }
+                if (launch_level<true>(o, m->act[lv][i + 1], m->n[lv], b, cin, cout, st)) return 1;
+            }
+            continue;
+        }
         bool first[3] = {true, true, true};
         for (int k = 0; k < 7; ++k) {
             const scone_csr* S = m->S[k];
@@ -462,6 +659,35 @@ extern "C" int scone_bunch_loss_grad_host(scone_bunch* m, int32_t B, const int32
                 const long long n = (long long)m->n[lv] * b * cout;
                 relu_bwd_kernel<<<nblk(n), kBT, 0, st>>>(m->d_dX[lv], m->act[lv][i + 1], m->d_G[cur][lv], n);
                 SCONE_LAUNCHED();
+            }
+            if (fused_width(cin) && fused_width(cout)) {
+                // weight gradients: U = S X on the fly; input gradients: one launch per level over the transposed operators
+                for (int k = 0; k < 7; ++k) {
+                    const scone_csr* S = m->S[k];
+                    const int ol = kOutLevel[k], il = kInLevel[k];
+                    const long long M = (long long)S->rows * b;
+                    const int tiles = ((cin + kOT - 1) / kOT) * ((cout + kOT - 1) / kOT);
+                    const int nb = (int)std::min<long long>(kOuterBlocks, (M + kBT - 1) / kBT);
+                    outer_tile_spmm_kernel<<<dim3(nb, tiles), kBT, 0, st>>>(S->d_rowptr, S->d_col, S->d_val, m->act[il][i], m->d_G[cur][ol],
+                                                                            m->d_outer, S->rows, b, cin, cout);
+                    SCONE_LAUNCHED();
+                    outer_fold_kernel<<<tiles, kOT * kOT, 0, st>>>(m->d_outer, nb, m->d_grad + m->w_off[7 * i + k], cin, cout);
+                    SCONE_LAUNCHED();
+                }
+                if (i > 0)
+                    for (int lv = 0; lv < 3; ++lv) {
+                        BunchOps o{};
+                        for (int k = 0; k < 7; ++k)
+                            if (kInLevel[k] == lv) {
+                                const scone_csr* S = m->S[k];
+                                o.rowptr[o.n] = S->d_t_rowptr; o.col[o.n] = S->d_t_col; o.val[o.n] = S->d_t_val;
+                                o.X[o.n] = m->d_G[cur][kOutLevel[k]]; o.W[o.n] = m->d_w + m->w_off[7 * i + k];
+                                ++o.n;
+                            }
+                        if (launch_level<false>(o, m->d_dX[lv], m->n[lv], b, cin, cout, st)) return 1;
+                    }
+                cur ^= 1;
+                continue;
             }
             if (i > 0)
                 for (int lv = 0; lv < 3; ++lv) SCONE_CUDA(cudaMemsetAsync(m->d_dX[lv], 0, (size_t)m->n[lv] * b * cin * 4, st));

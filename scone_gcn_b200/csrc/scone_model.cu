@@ -29,7 +29,7 @@ struct scone_model {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_begin = nullptr;
     cudaStream_t copy = nullptr;              // pipeline 4, *_host entry points: the flow arrays arrive in parts under the plan kernels
-    cudaEvent_t ev_copy0 = nullptr, ev_part[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_copy0 = nullptr, ev_part[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> ev_fill;         // [2L]: H_1..H_L, G_{L-1}..G_0
     uint8_t* d_occS = nullptr;                // worklists / counters scratch (scone_occ_scratch_bytes)
     uint8_t* d_occX = nullptr;                // flags of the flows X
@@ -686,7 +686,7 @@ static int fused_call(scone_model* m, int32_t B, const int32_t* ptr, const int32
 }
 
 // pipeline 4 behind a *_host entry point, batch within one arena chunk: the flow arrays (all but a few hundred KB of the H2D bytes)
-// are copied in parts on a copy stream and every part is planned as soon as it has landed — the copy of part k + 1 runs under the
+// are copied in four parts on a copy stream and every part is planned as soon as it has landed — the copy of part k + 1 runs under the
 // plan kernels of part k; one compute launch over the whole batch at the end.  ptr / last / tgt / mask: already enqueued on s.
 static bool fused_host_overlap_ok(const scone_model* m, int32_t B, int64_t nnz) {
     const bool rows = m->pipeline >= 1 && !m->zero_fill;
