@@ -533,9 +533,14 @@ def main():
         info = net.fused_info() if pipeline_id == 4 else None
         touched = 8.0 * nnz + 16.0 * B * 4 + (step_alg_bytes if pipeline_id != 4 else 0.0)
         if pipeline_id == 4:
-            l2_policy = ('no explicit flush; one step reads %.0f MB of flows / last nodes / targets and writes + re-reads the gather programs '
-                         'of all %d trajectories of the rank (~5-10 KB each) plus the merged operator rows it walks: %s the 126 MB L2'
-                         % (touched / 1e6, B, 'larger than' if B * 8e3 + touched > 126e6 else 'smaller than'))
+            # ncu (profiles/prof_r2*): the plan kernels read ~0.24 GB and write ~0.48 GB of DRAM per 32768 trajectories (node-table rows of
+            # 32768 random nodes out of a %d MB table; programs written), the compute kernel reads ~0.44 GB (programs back)
+            tb_mb = (info or {}).get('table_plan_mb', 0)
+            per_step = touched + B * 20e3 + B * 8e3
+            l2_policy = ('inputs larger than L2: a step reads %.0f MB of flows / last nodes / targets, the node-table rows of the %d last nodes '
+                         '(~20 KB each, random rows of a %d MB table) and writes + re-reads the gather programs (~8 KB per trajectory): ~%.0f MB per '
+                         'step, %s the 126 MB L2; no explicit flush'
+                         % (touched / 1e6, B, tb_mb, per_step / 1e6, 'larger than' if per_step > 126e6 else 'SMALLER than'))
         else:
             l2_policy = 'no explicit flush; compact row tensors of ~%.0f MB per step' % (touched / 1e6)
         out = {'metric': 'SCoNe train trajectories/sec', 'value': value, 'unit': 'trajectories/s', 'n_gpus': world,
@@ -659,10 +664,10 @@ def bench_bunch(args, cfg, sp, ds, hp, h2d_bytes, B, gb, world, rank, dev, strea
            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
            'dtype': 'f32', 'data': 'synthetic',
            'config': {'workload': args.config + ': ' + cfg['desc'], 'N': cx.N, 'E': cx.E, 'F': cx.F, 'D': cx.D, 'model': 'bunch',
-                      'global_batch': B, 'hidden': cfg['hidden'], 'layers': 4, 'l2_policy': 'working set L2-resident by size (E = %d)' % cx.E},
-           'roofline': {'bound': 'hbm', 'kernel': 'csr_spmm_kernel (generic CSR operators)', 'achieved': None, 'peak': peak, 'unit': 'GB/s', 'frac': None,
+                      'global_batch': B, 'hidden': cfg['hidden'], 'layers': 4, 'l2_policy': 'dense [rows][batch][C] tensors of %.0f MB each, ~30 of them per step: larger than L2' % (4e-6 * cx.E * min(B, 1024) * cfg['hidden'])},
+           'roofline': {'bound': 'hbm', 'kernel': 'bunch_level_fwd/bwd_kernel, outer_tile_spmm_kernel (generic CSR operators)', 'achieved': None, 'peak': peak, 'unit': 'GB/s', 'frac': None,
                         'traffic': None, 'peak_source': peak_src,
-                        'note': 'cfg3 complexes are L2-resident (E = 1001): launch-latency bound, no HBM roofline is meaningful'},
+                        'note': 'the bunch model runs dense (no pruning) on generic CSR operators; no per-kernel byte model is reported'},
            'e2e': {'value': value, 'unit': 'trajectories/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': int(4 * (net.n_params + 2)),
                    'steps': args.steps, 'last_loss': loss, 'note': 'the bunch model only has host-pointer entry points: value == e2e'},
            'cpu_baseline': None, 'gpu_launches': int(L.scone_launch_count() - launches0), 'clocks': clk, 'setup_s': time.time() - t_setup}

@@ -1027,20 +1027,19 @@ __global__ void __launch_bounds__(256) fused_cost_kernel(const int* __restrict__
     vals[t] = t;
 }
 
-// out[i] += sum over the CTAs' partial vectors in CTA order (deterministic); also rearms the arena bump pointer
+// out[i] += sum over the CTAs' partial vectors in a fixed order (deterministic): a block owns 32 consecutive elements (lane = element:
+// 128-byte reads), its 8 warps take the partials p = warp, warp + 8, ... and are folded in a fixed tree
 __global__ void __launch_bounds__(256) fused_reduce_kernel(const float* __restrict__ partial, int nparts, int n, float* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int p = 0;
-    for (; p + 3 < nparts; p += 4) {
-        s0 += partial[(size_t)p * n + i];
-        s1 += partial[(size_t)(p + 1) * n + i];
-        s2 += partial[(size_t)(p + 2) * n + i];
-        s3 += partial[(size_t)(p + 3) * n + i];
-    }
-    for (; p < nparts; ++p) s0 += partial[(size_t)p * n + i];
-    out[i] += (s0 + s1) + (s2 + s3);
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    float s = 0.f;
+    if (i < n)
+        for (int p = warp; p < nparts; p += 8) s += partial[(size_t)p * n + i];
+    red[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && i < n)
+        out[i] += ((red[0][lane] + red[1][lane]) + (red[2][lane] + red[3][lane])) + ((red[4][lane] + red[5][lane]) + (red[6][lane] + red[7][lane]));
 }
 
 size_t plan_smem_bytes(int HS, int LV, int EC) {
@@ -1126,7 +1125,7 @@ int run_traj(FusedState* f, int act, TrajArgs& t, float* grad, cudaStream_t st) 
     if (rc) return rc;
     if (want_grad) {
         const int np = (int)f->n_params + 2;
-        fused_reduce_kernel<<<(np + 255) / 256, 256, 0, st>>>(f->d_partial, f->grid_small + f->grid_big, np, grad);
+        fused_reduce_kernel<<<(np + 31) / 32, 256, 0, st>>>(f->d_partial, f->grid_small + f->grid_big, np, grad);
         SCONE_LAUNCHED();
     }
     return 0;
