@@ -117,6 +117,8 @@ int scone_readout_ws(const scone_complex* cx, int32_t act, int32_t b, int32_t C,
 bool scone_umma_supported(const scone_complex* cx, int cin, int cout, int b);
 int scone_umma_forward(const scone_complex* cx, int act, int b, const float* Hin, const float* W0, const float* W1, const float* W2,
                        float* Hout, cudaStream_t st);
+int scone_umma_backward(const scone_complex* cx, int act, int b, const float* G, const float* Hin, const float* W0, const float* W1,
+                        const float* W2, float* Gprev, float* dW, int accumulate, float* ws, cudaStream_t st);
 int scone_umma_check(cudaStream_t st);
 // slab kernels (scone_slab.cu): dense fused layer for widths 16 / 32, tensor-core product
 extern int g_scone_dense_kernel;

@@ -1622,6 +1622,11 @@ extern "C" int scone_layer_backward(const scone_complex* cx, int32_t act, int32_
     SCONE_REQUIRE(W0 && W1 && W2, "scone_layer_backward: NULL weights");
     SCONE_REQUIRE(width_ok(cin) && width_ok(cout),
                   "scone_layer_backward: hidden widths must be in {8,16,32,64} with |log2 ratio| <= 1 (got %d -> %d)", cin, cout);
+    if (g_scone_dense_kernel == 3 && occ_g == nullptr && scone_umma_supported(cx, cin, cout, b)) {      // tcgen05 / TMEM (scone_umma.cu)
+        ScopedProf prof(SCONE_K_LAYER_BWD, as_stream(stream));
+        if (Gprev && occ_prev) SCONE_CUDA(cudaMemsetAsync(occ_prev, 1, (size_t)cx->E * b, as_stream(stream)));
+        return scone_umma_backward(cx, act, b, G, Hin, W0, W1, W2, Gprev, dW, accumulate, (float*)workspace, as_stream(stream));
+    }
     SCONE_DISPATCH_WIDTHS(dispatch_bwd_act, cx, act, b, G, Hin, W0, W1, W2, Gprev, dW, accumulate, (float*)workspace, occ_g, occ_hin,
                           occ_prev, occ_scratch, as_stream(stream));
     scone_set_error("scone_layer_backward: unsupported width pair %d -> %d", cin, cout);

@@ -253,6 +253,277 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) layer_fwd_umma_kernel(const f
 
 int* g_umma_err = nullptr;
 
+// =================================================================================================================
+// Backward of the same layer (32 -> 32, dense [E][b][32] tensors):
+//
+//   AG      = [G | S0 G | S1 G]                          (the forward's gather, on G = dL/dZ; S0, S1 are symmetric)
+//   Gprev   = (AG [W0^T; W1^T; W2^T]) * act'(Hin)        per row
+//   dW_term = Hin^T AG_term                              summed over all E * b rows              scone_trajectory_model.py:307
+//
+// A warp owns a slab of 16 rows as in the forward kernels.  The row product AG W^T contracts over channels — the gathered
+// registers are its mma A fragments (3xTF32 mma.sync, the slab kernel's product with transposed weight fragments).  The weight
+// gradient contracts over ROWS, which no register fragment layout offers: the warp writes its slab of AG (96 columns) and of Hin
+// (32 columns), split hi / lo, into its private shared-memory buffers in the K-major canonical (no-swizzle) UMMA layout with
+// K = the 16 rows, and one lane issues 6 tcgen05.mma.kind::tf32 (M = 128: AG column, 96 used; N = 32: Hin channel; K = 8 rows
+// each; A_lo B_hi + A_hi B_lo + A_hi B_hi) that ACCUMULATE into the warp's own 32 TMEM columns for the whole kernel — the weight
+// gradient never touches registers or shared memory until the end, when warps 0..2 read term 0..2 (TMEM lanes 32 term .. + 31)
+// of every warp's accumulator, add them in warp order and write the CTA's partial; a second kernel folds the CTA partials in
+// CTA order.  Static slab -> warp -> CTA assignment: deterministic.  No CTA barrier in the slab loop: a warp only waits for its
+// own previous commit (one gather earlier) before it overwrites its buffers.
+// Buffer strides are padded (core-matrix pitch 144 B, k-chunk pitch = 8 words mod 32) so that the fragment-layout stores of a
+// warp hit 32 different banks.
+// =================================================================================================================
+constexpr int kBwdWarps = 10, kBwdThreads = kBwdWarps * 32;       // 10 x 18.4 KB of operand buffers + 24 KB of weight fragments
+constexpr int kBwdDepth = 4;
+constexpr int kDW = 3 * kC * kC;
+
+template <bool PAD>
+struct BwdBuf {
+    static constexpr uint32_t SBO_A = PAD ? 144u : 128u;            // bytes between core matrices adjacent in M (AG column / 8)
+    static constexpr uint32_t LBO_A = PAD ? 1824u : 1536u;          // ... adjacent in K (row / 4): 12 core matrices of M + padding
+    static constexpr uint32_t A_BYTES = 4u * LBO_A;                 // 16 rows = 4 k-chunks  (M rows 96..127 of the MMA read on into
+    static constexpr uint32_t SBO_B = 128u;                         //  the next buffer of the same warp: their D lanes are never read)
+    static constexpr uint32_t LBO_B = PAD ? 528u : 512u;
+    static constexpr uint32_t B_BYTES = 4u * LBO_B;
+    static constexpr uint32_t WARP_BYTES = 2u * A_BYTES + 2u * B_BYTES;      // [A_hi | A_lo | B_hi | B_lo]
+};
+constexpr uint32_t kBwdBfBytes = 3u * 4u * 4u * 32u * 16u;          // weight fragments of the transposed product: [3][KS][NT][32] uint4
+
+__device__ __forceinline__ uint64_t umma_desc2(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+           ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void umma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kIdesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {      // thread i <- TMEM lane base + i, 32 columns
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
+
+template <int ACT>
+__device__ __forceinline__ float umma_dact(float h) {               // derivative through the OUTPUT h = act(z)
+    if (ACT == SCONE_ACT_TANH) return 1.f - h * h;
+    if (ACT == SCONE_ACT_LEAKY_RELU) return h >= 0.f ? 1.f : 0.01f;
+    return h > 0.f ? 1.f : 0.f;
+}
+
+template <int ACT, bool WG, bool PAD>
+__global__ void __launch_bounds__(kBwdThreads, 1) layer_bwd_umma_kernel(const float* __restrict__ Gd, const float* Hin, float* Gprev,
+                                                                       const float* __restrict__ W0, const float* __restrict__ W1,
+                                                                       const float* __restrict__ W2, float* __restrict__ ws,
+                                                                       const int32_t* __restrict__ mptr, const int2* __restrict__ ment,
+                                                                       int E, int b, int* __restrict__ err) {
+    constexpr int TS = 16;
+    using G = SlabGeom<kC, TS>;
+    using L = BwdBuf<PAD>;
+    constexpr int NT = kC / 8;
+    extern __shared__ __align__(128) unsigned char bw_smem[];
+    __shared__ __align__(8) uint64_t s_bar[kBwdWarps];
+    __shared__ int s_used[kBwdWarps];
+    __shared__ uint32_t s_tmem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tig = lane & 3, g = lane >> 2;
+    uint4* Bf = reinterpret_cast<uint4*>(bw_smem);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (threadIdx.x < kBwdWarps) {
+        mbar_init(&s_bar[threadIdx.x], 1);
+        s_used[threadIdx.x] = 0;
+    }
+    if (WG) stage_weight_fragments<kC, kC, TS, true>(Bf, W0, W1, W2);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const uint32_t a_hi = smem_u32(bw_smem) + kBwdBfBytes + (uint32_t)warp * L::WARP_BYTES, a_lo = a_hi + L::A_BYTES;
+    const uint32_t b_hi = a_lo + L::A_BYTES, b_lo = b_hi + L::B_BYTES;
+    // fragment value (row g + 8 r, AG column 32 term + 16 h + 4 tig + s) -> k-chunk (g >> 2) + 2 r, core matrix 4 term + 2 h + (tig >> 1),
+    // row 4 (tig & 1) + s of the core matrix, word g & 3;   Hin value (row g + 8 r, channel 8 nt + 2 tig + j) likewise
+    const uint32_t lane_a = (uint32_t)(g >> 2) * L::LBO_A + (uint32_t)(tig >> 1) * L::SBO_A + (uint32_t)(tig & 1) * 64u + (uint32_t)(g & 3) * 4u;
+    const uint32_t lane_b = (uint32_t)(g >> 2) * L::LBO_B + (uint32_t)tig * 32u + (uint32_t)(g & 3) * 4u;
+    const uint32_t tmem_d = s_tmem + (uint32_t)warp * 32u;
+
+    const unsigned rowbytes = (unsigned)b * kC * 4u;
+    const size_t rowlen = (size_t)b * kC;
+    const int n_ts = b / TS;
+    const int tiles_per_ts = (E + kBwdWarps - 1) / kBwdWarps;            // a CTA tile = kBwdWarps consecutive edges x one slab of 16 trajectories
+    const long long n_tiles = (long long)n_ts * tiles_per_ts;
+    const long long per = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const long long lo = (long long)blockIdx.x * per, hi = lo + per < n_tiles ? lo + per : n_tiles;
+    uint32_t phase = 0;
+    bool issued = false;
+    for (long long tile = lo; tile < hi; ++tile) {
+        const int ts = (int)(tile / tiles_per_ts);
+        const int e0 = (int)(tile - (long long)ts * tiles_per_ts) * kBwdWarps + warp, t0 = ts * TS;
+        if (e0 >= E) continue;
+        float2 hv[2][NT];                                                // own rows of Hin in the mma C-fragment layout
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            int e, t;
+            slab_row<kC, TS>(r, e0, t0, e, t);
+            const float* src = Hin + (size_t)e * rowlen + (size_t)t * kC + 2 * tig;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) hv[r][nt] = *reinterpret_cast<const float2*>(src + nt * 8);
+        }
+        u64 acc[3][G::NL][2];
+        slab_gather<kC, TS, kBwdDepth>(Gd, rowbytes, mptr, ment, E, b, e0, t0, acc);
+        if (issued) {                                                    // the MMAs of the previous slab have read the buffers
+            mbar_wait(&s_bar[warp], phase, err);
+            phase ^= 1u;
+        }
+        float d[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) d[nt][0] = d[nt][1] = d[nt][2] = d[nt][3] = 0.f;
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+            float fr[G::KS][4];
+            slab_fragments<kC, TS>(acc[term], fr);
+            if (WG) slab_mma_term<G::KS, NT>(d, fr, Bf + term * G::KS * NT * 32);
+#pragma unroll
+            for (int s = 0; s < G::KS; ++s)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t vh, vl;
+                    split_tf32(fr[s][q], vh, vl);
+                    const uint32_t off = lane_a + (uint32_t)(q & 1) * 2u * L::LBO_A + (uint32_t)(4 * term + 2 * (q >> 1)) * L::SBO_A + (uint32_t)s * 16u;
+                    sts32(a_hi + off, vh);
+                    sts32(a_lo + off, vl);
+                }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                uint32_t xh, xl, yh, yl;
+                split_tf32(hv[r][nt].x, xh, xl);
+                split_tf32(hv[r][nt].y, yh, yl);
+                const uint32_t off = lane_b + (uint32_t)r * 2u * L::LBO_B + (uint32_t)nt * L::SBO_B;
+                sts32(b_hi + off, xh);
+                sts32(b_lo + off, xl);
+                sts32(b_hi + off + 16u, yh);
+                sts32(b_lo + off + 16u, yl);
+            }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {                             // K = 16 rows in two steps of 8 (two 16-byte k-chunks each)
+                const uint64_t dah = umma_desc2(a_hi + (uint32_t)ks * 2u * L::LBO_A, L::LBO_A, L::SBO_A);
+                const uint64_t dal = umma_desc2(a_lo + (uint32_t)ks * 2u * L::LBO_A, L::LBO_A, L::SBO_A);
+                const uint64_t dbh = umma_desc2(b_hi + (uint32_t)ks * 2u * L::LBO_B, L::LBO_B, L::SBO_B);
+                const uint64_t dbl = umma_desc2(b_lo + (uint32_t)ks * 2u * L::LBO_B, L::LBO_B, L::SBO_B);
+                umma_tf32_ss(tmem_d, dal, dbh, (issued || ks > 0) ? 1u : 0u);
+                umma_tf32_ss(tmem_d, dah, dbl, 1u);
+                umma_tf32_ss(tmem_d, dah, dbh, 1u);
+            }
+            umma_commit(&s_bar[warp]);
+        }
+        __syncwarp();
+        issued = true;
+        if (WG) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                int e, t;
+                slab_row<kC, TS>(r, e0, t0, e, t);
+                float* dst = Gprev + (size_t)e * rowlen + (size_t)t * kC + 2 * tig;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+                    *reinterpret_cast<float2*>(dst + nt * 8) =
+                        make_float2(d[nt][2 * r] * umma_dact<ACT>(hv[r][nt].x), d[nt][2 * r + 1] * umma_dact<ACT>(hv[r][nt].y));
+            }
+        }
+    }
+    if (issued) mbar_wait(&s_bar[warp], phase, err);                     // this warp's accumulator is complete
+    if (lane == 0) s_used[warp] = issued ? 1 : 0;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp < 3) {                                                      // term = warp: TMEM lanes 32 term + co, columns ci
+        float sum[kC];
+#pragma unroll
+        for (int j = 0; j < kC; ++j) sum[j] = 0.f;
+        for (int w = 0; w < kBwdWarps; ++w) {
+            if (!s_used[w]) continue;                                    // (warp-uniform)
+            uint32_t r[32];
+            tc_ld_32x32b_x32(s_tmem + (uint32_t)w * 32u + ((uint32_t)(32 * warp) << 16), r);
+#pragma unroll
+            for (int j = 0; j < kC; ++j) sum[j] += __uint_as_float(r[j]);
+        }
+        float* dst = ws + (size_t)blockIdx.x * kDW + warp * kC * kC + lane;      // dW[term][ci = j][co = lane]
+#pragma unroll
+        for (int j = 0; j < kC; ++j) dst[j * kC] = sum[j];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(kTmemCols));
+}
+
+// CTA partials -> dW in CTA order (8 slices of ascending parts, combined in slice order: a fixed tree)
+__global__ void __launch_bounds__(256) umma_reduce_partials_kernel(const float* __restrict__ partial, int nparts, int n,
+                                                                  float* __restrict__ out, int accumulate) {
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    const int per = (nparts + 7) / 8;
+    const int p0 = slice * per, p1 = min(nparts, p0 + per);
+    float s = 0.f;
+    if (i < n)
+        for (int p = p0; p < p1; ++p) s += partial[(size_t)p * n + i];
+    red[slice][lane] = s;
+    __syncthreads();
+    if (slice == 0 && i < n) {
+        float t = red[0][lane];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) t += red[k][lane];
+        out[i] = accumulate ? out[i] + t : t;
+    }
+}
+
+template <int ACT, bool WG, bool PAD>
+int launch_bwd_umma(const scone_complex* cx, int b, const float* G, const float* Hin, const float* W0, const float* W1, const float* W2,
+                    float* Gprev, float* ws, int grid, cudaStream_t st) {
+    const size_t smem = (size_t)kBwdBfBytes + (size_t)kBwdWarps * BwdBuf<PAD>::WARP_BYTES;
+    auto kern = layer_bwd_umma_kernel<ACT, WG, PAD>;
+    static bool configured = false;
+    if (!configured) {
+        SCONE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    kern<<<grid, kBwdThreads, smem, st>>>(G, Hin, Gprev, W0, W1, W2, ws, cx->d_mptr, cx->d_ment, cx->E, b, g_umma_err);
+    SCONE_LAUNCHED();
+    return 0;
+}
+
+template <int ACT, bool WG>
+int dispatch_bwd_umma_pad(const scone_complex* cx, int b, const float* G, const float* Hin, const float* W0, const float* W1,
+                          const float* W2, float* Gprev, float* ws, int grid, cudaStream_t st) {
+    static int pad = -1;
+    if (pad < 0) {
+        const char* e = getenv("SCONE_UMMA_BWD_PAD");                    // 0: canonical strides (bank-conflicting stores); experiments
+        pad = (e && e[0] == '0') ? 0 : 1;
+    }
+    return pad ? launch_bwd_umma<ACT, WG, true>(cx, b, G, Hin, W0, W1, W2, Gprev, ws, grid, st)
+               : launch_bwd_umma<ACT, WG, false>(cx, b, G, Hin, W0, W1, W2, Gprev, ws, grid, st);
+}
+
 }  // namespace
 
 bool scone_umma_supported(const scone_complex* cx, int cin, int cout, int b) {
@@ -284,6 +555,37 @@ int scone_umma_forward(const scone_complex* cx, int act, int b, const float* Hin
             scone_set_error("unknown activation %d", act);
             return 2;
     }
+    SCONE_LAUNCHED();
+    return 0;
+}
+
+// Gprev = (AG W^T) * act'(Hin) (skipped when Gprev == NULL), dW [3][32][32] (+)= Hin^T AG over dense [E][b][32] tensors; workspace:
+// grid x 3072 floats.  Asynchronous; a tcgen05 protocol time-out is reported by scone_umma_check like the forward kernel's.
+int scone_umma_backward(const scone_complex* cx, int act, int b, const float* G, const float* Hin, const float* W0, const float* W1,
+                        const float* W2, float* Gprev, float* dW, int accumulate, float* ws, cudaStream_t st) {
+    if (!g_umma_err) {
+        SCONE_CUDA(cudaMalloc((void**)&g_umma_err, sizeof(int)));
+        SCONE_CUDA(cudaMemset(g_umma_err, 0, sizeof(int)));
+    }
+    const long long n_tiles = (long long)(b / 16) * ((cx->E + kBwdWarps - 1) / kBwdWarps);
+    const int grid = (int)(n_tiles < cx->num_sms ? n_tiles : cx->num_sms);
+    int rc = 2;
+#define SCONE_UMMA_BWD(A)                                                                                                      \
+    case A:                                                                                                                    \
+        rc = Gprev ? dispatch_bwd_umma_pad<A, true>(cx, b, G, Hin, W0, W1, W2, Gprev, ws, grid, st)                            \
+                   : dispatch_bwd_umma_pad<A, false>(cx, b, G, Hin, W0, W1, W2, Gprev, ws, grid, st);                          \
+        break;
+    switch (act) {
+        SCONE_UMMA_BWD(SCONE_ACT_TANH)
+        SCONE_UMMA_BWD(SCONE_ACT_LEAKY_RELU)
+        SCONE_UMMA_BWD(SCONE_ACT_RELU)
+        default:
+            scone_set_error("unknown activation %d", act);
+            return 2;
+    }
+#undef SCONE_UMMA_BWD
+    if (rc) return rc;
+    umma_reduce_partials_kernel<<<(kDW + 31) / 32, 256, 0, st>>>(ws, grid, kDW, dW, accumulate);
     SCONE_LAUNCHED();
     return 0;
 }
