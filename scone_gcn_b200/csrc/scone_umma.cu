@@ -18,6 +18,7 @@
 // (mma.sync: once per 16 rows) and the tensor instruction stream is one thread's, not every warp's.
 // Every wait is bounded: a protocol error sets *err and the kernel runs on (wrong results, reported by the host) instead of hanging.
 #include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 
 namespace {
@@ -273,17 +274,20 @@ int* g_umma_err = nullptr;
 // Buffer strides are padded (core-matrix pitch 144 B, k-chunk pitch = 8 words mod 32) so that the fragment-layout stores of a
 // warp hit 32 different banks.
 // =================================================================================================================
-constexpr int kBwdWarps = 10, kBwdThreads = kBwdWarps * 32;       // 10 x 18.4 KB of operand buffers + 24 KB of weight fragments
-constexpr int kBwdDepth = 4;
+constexpr int kBwdMaxWarps = 12;
+constexpr int kFlushTiles = 32;            // slabs per warp between two flushes of the TMEM accumulators
 constexpr int kDW = 3 * kC * kC;
 
-template <bool PAD>
+// NW = 10 warps: fully padded strides (conflict-free stores, 18.4 KB per warp); NW = 12: k-chunk pitch padded only (2-way conflicts on
+// the A stores, 16.4 KB per warp) — either way NW buffers + 24 KB of weight fragments fill the 227 KB of shared memory
+template <int NW>
 struct BwdBuf {
-    static constexpr uint32_t SBO_A = PAD ? 144u : 128u;            // bytes between core matrices adjacent in M (AG column / 8)
-    static constexpr uint32_t LBO_A = PAD ? 1824u : 1536u;          // ... adjacent in K (row / 4): 12 core matrices of M + padding
+    static constexpr bool FULL = NW <= 10;
+    static constexpr uint32_t SBO_A = FULL ? 144u : 128u;           // bytes between core matrices adjacent in M (AG column / 8)
+    static constexpr uint32_t LBO_A = FULL ? 1824u : 1568u;         // ... adjacent in K (row / 4): 12 core matrices of M + padding
     static constexpr uint32_t A_BYTES = 4u * LBO_A;                 // 16 rows = 4 k-chunks  (M rows 96..127 of the MMA read on into
     static constexpr uint32_t SBO_B = 128u;                         //  the next buffer of the same warp: their D lanes are never read)
-    static constexpr uint32_t LBO_B = PAD ? 528u : 512u;
+    static constexpr uint32_t LBO_B = 528u;
     static constexpr uint32_t B_BYTES = 4u * LBO_B;
     static constexpr uint32_t WARP_BYTES = 2u * A_BYTES + 2u * B_BYTES;      // [A_hi | A_lo | B_hi | B_lo]
 };
@@ -321,19 +325,19 @@ __device__ __forceinline__ float umma_dact(float h) {               // derivativ
     return h > 0.f ? 1.f : 0.f;
 }
 
-template <int ACT, bool WG, bool PAD>
-__global__ void __launch_bounds__(kBwdThreads, 1) layer_bwd_umma_kernel(const float* __restrict__ Gd, const float* Hin, float* Gprev,
+template <int ACT, bool WG, int NW, int DEPTH>
+__global__ void __launch_bounds__(NW * 32, 1) layer_bwd_umma_kernel(const float* __restrict__ Gd, const float* Hin, float* Gprev,
                                                                        const float* __restrict__ W0, const float* __restrict__ W1,
                                                                        const float* __restrict__ W2, float* __restrict__ ws,
                                                                        const int32_t* __restrict__ mptr, const int2* __restrict__ ment,
                                                                        int E, int b, int* __restrict__ err) {
     constexpr int TS = 16;
     using G = SlabGeom<kC, TS>;
-    using L = BwdBuf<PAD>;
+    using L = BwdBuf<NW>;
     constexpr int NT = kC / 8;
     extern __shared__ __align__(128) unsigned char bw_smem[];
-    __shared__ __align__(8) uint64_t s_bar[kBwdWarps];
-    __shared__ int s_used[kBwdWarps];
+    __shared__ __align__(8) uint64_t s_bar[NW];
+    __shared__ int s_used[NW];
     __shared__ uint32_t s_tmem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tig = lane & 3, g = lane >> 2;
     uint4* Bf = reinterpret_cast<uint4*>(bw_smem);
@@ -342,7 +346,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) layer_bwd_umma_kernel(const fl
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    if (threadIdx.x < kBwdWarps) {
+    if (threadIdx.x < NW) {
         mbar_init(&s_bar[threadIdx.x], 1);
         s_used[threadIdx.x] = 0;
     }
@@ -363,16 +367,21 @@ __global__ void __launch_bounds__(kBwdThreads, 1) layer_bwd_umma_kernel(const fl
     const unsigned rowbytes = (unsigned)b * kC * 4u;
     const size_t rowlen = (size_t)b * kC;
     const int n_ts = b / TS;
-    const int tiles_per_ts = (E + kBwdWarps - 1) / kBwdWarps;            // a CTA tile = kBwdWarps consecutive edges x one slab of 16 trajectories
+    const int tiles_per_ts = (E + NW - 1) / NW;                          // a CTA tile = NW consecutive edges x one slab of 16 trajectories
     const long long n_tiles = (long long)n_ts * tiles_per_ts;
     const long long per = (n_tiles + gridDim.x - 1) / gridDim.x;
     const long long lo = (long long)blockIdx.x * per, hi = lo + per < n_tiles ? lo + per : n_tiles;
+    // this warp's share of the flushes: TMEM lane quarter q = warp & 3 (term q of the stacked gradient) of the accumulators
+    // j = warp >> 2, + nq, ... (nq = warps of this quarter); its running fp32 sums live in ws[cta][warp >> 2][term q][ci][co = lane]
+    const int fq = warp & 3, fidx = warp >> 2, fnq = (NW - fq + 3) / 4;
+    float* fdst = ws + ((size_t)blockIdx.x * 3 + fidx) * kDW + fq * kC * kC + lane;
+    for (int i = threadIdx.x; i < 3 * kDW; i += NW * 32) ws[(size_t)blockIdx.x * 3 * kDW + i] = 0.f;      // (visible after the flush's barrier)
     uint32_t phase = 0;
-    bool issued = false;
+    bool pending = false, fresh = true;                                  // MMAs not yet waited for / accumulator holds nothing
     for (long long tile = lo; tile < hi; ++tile) {
         const int ts = (int)(tile / tiles_per_ts);
-        const int e0 = (int)(tile - (long long)ts * tiles_per_ts) * kBwdWarps + warp, t0 = ts * TS;
-        if (e0 >= E) continue;
+        const int e0 = (int)(tile - (long long)ts * tiles_per_ts) * NW + warp, t0 = ts * TS;
+        if (e0 < E) {
         float2 hv[2][NT];                                                // own rows of Hin in the mma C-fragment layout
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
@@ -383,8 +392,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) layer_bwd_umma_kernel(const fl
             for (int nt = 0; nt < NT; ++nt) hv[r][nt] = *reinterpret_cast<const float2*>(src + nt * 8);
         }
         u64 acc[3][G::NL][2];
-        slab_gather<kC, TS, kBwdDepth>(Gd, rowbytes, mptr, ment, E, b, e0, t0, acc);
-        if (issued) {                                                    // the MMAs of the previous slab have read the buffers
+        slab_gather<kC, TS, DEPTH>(Gd, rowbytes, mptr, ment, E, b, e0, t0, acc);
+        if (pending) {                                                   // the MMAs of the previous slab have read the buffers
             mbar_wait(&s_bar[warp], phase, err);
             phase ^= 1u;
         }
@@ -430,14 +439,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) layer_bwd_umma_kernel(const fl
                 const uint64_t dal = umma_desc2(a_lo + (uint32_t)ks * 2u * L::LBO_A, L::LBO_A, L::SBO_A);
                 const uint64_t dbh = umma_desc2(b_hi + (uint32_t)ks * 2u * L::LBO_B, L::LBO_B, L::SBO_B);
                 const uint64_t dbl = umma_desc2(b_lo + (uint32_t)ks * 2u * L::LBO_B, L::LBO_B, L::SBO_B);
-                umma_tf32_ss(tmem_d, dal, dbh, (issued || ks > 0) ? 1u : 0u);
+                umma_tf32_ss(tmem_d, dal, dbh, (!fresh || ks > 0) ? 1u : 0u);
                 umma_tf32_ss(tmem_d, dah, dbl, 1u);
                 umma_tf32_ss(tmem_d, dah, dbh, 1u);
             }
             umma_commit(&s_bar[warp]);
         }
         __syncwarp();
-        issued = true;
+        pending = true;
+        fresh = false;
         if (WG) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
@@ -450,29 +460,40 @@ __global__ void __launch_bounds__(kBwdThreads, 1) layer_bwd_umma_kernel(const fl
                         make_float2(d[nt][2 * r] * umma_dact<ACT>(hv[r][nt].x), d[nt][2 * r + 1] * umma_dact<ACT>(hv[r][nt].y));
             }
         }
-    }
-    if (issued) mbar_wait(&s_bar[warp], phase, err);                     // this warp's accumulator is complete
-    if (lane == 0) s_used[warp] = issued ? 1 : 0;
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (warp < 3) {                                                      // term = warp: TMEM lanes 32 term + co, columns ci
-        float sum[kC];
-#pragma unroll
-        for (int j = 0; j < kC; ++j) sum[j] = 0.f;
-        for (int w = 0; w < kBwdWarps; ++w) {
-            if (!s_used[w]) continue;                                    // (warp-uniform)
-            uint32_t r[32];
-            tc_ld_32x32b_x32(s_tmem + (uint32_t)w * 32u + ((uint32_t)(32 * warp) << 16), r);
-#pragma unroll
-            for (int j = 0; j < kC; ++j) sum[j] += __uint_as_float(r[j]);
         }
-        float* dst = ws + (size_t)blockIdx.x * kDW + warp * kC * kC + lane;      // dW[term][ci = j][co = lane]
+        // Flush every kFlushTiles slabs: the tensor core's fp32 accumulation rounds towards zero, so a chain of n accumulations drifts
+        // by ~n ulp (measured: 6.6e-5 of max |dW| after 3600 accumulations, 4.6e-6 for the fp32 SIMT kernel); chains of 6 kFlushTiles
+        // accumulations are folded into fp32 sums with round-to-nearest adds.  CTA-uniform condition.
+        if ((tile - lo) % kFlushTiles == kFlushTiles - 1 || tile == hi - 1) {
+            if (pending) {
+                mbar_wait(&s_bar[warp], phase, err);
+                phase ^= 1u;
+                pending = false;
+            }
+            if (lane == 0) s_used[warp] = fresh ? 0 : 1;
+            tc_fence_before();
+            __syncthreads();
+            tc_fence_after();
+            if (fq < 3) {
+                float sum[kC];
 #pragma unroll
-        for (int j = 0; j < kC; ++j) dst[j * kC] = sum[j];
+                for (int j = 0; j < kC; ++j) sum[j] = 0.f;
+                for (int w = fidx; w < NW; w += fnq) {
+                    if (!s_used[w]) continue;                            // (warp-uniform)
+                    uint32_t r[32];
+                    tc_ld_32x32b_x32(s_tmem + (uint32_t)w * 32u + ((uint32_t)(32 * fq) << 16), r);
+#pragma unroll
+                    for (int j = 0; j < kC; ++j) sum[j] += __uint_as_float(r[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < kC; ++j) fdst[j * kC] += sum[j];     // dW[term][ci = j][co = lane]; this thread's own running sum
+            }
+            tc_fence_before();
+            __syncthreads();
+            tc_fence_after();
+            fresh = true;
+        }
     }
-    tc_fence_before();
-    __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(kTmemCols));
 }
 
@@ -497,31 +518,42 @@ __global__ void __launch_bounds__(256) umma_reduce_partials_kernel(const float* 
     }
 }
 
-template <int ACT, bool WG, bool PAD>
+template <int ACT, bool WG, int NW, int DEPTH>
 int launch_bwd_umma(const scone_complex* cx, int b, const float* G, const float* Hin, const float* W0, const float* W1, const float* W2,
-                    float* Gprev, float* ws, int grid, cudaStream_t st) {
-    const size_t smem = (size_t)kBwdBfBytes + (size_t)kBwdWarps * BwdBuf<PAD>::WARP_BYTES;
-    auto kern = layer_bwd_umma_kernel<ACT, WG, PAD>;
+                    float* Gprev, float* ws, int* grid_out, cudaStream_t st) {
+    const size_t smem = (size_t)kBwdBfBytes + (size_t)NW * BwdBuf<NW>::WARP_BYTES;
+    auto kern = layer_bwd_umma_kernel<ACT, WG, NW, DEPTH>;
     static bool configured = false;
     if (!configured) {
         SCONE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    kern<<<grid, kBwdThreads, smem, st>>>(G, Hin, Gprev, W0, W1, W2, ws, cx->d_mptr, cx->d_ment, cx->E, b, g_umma_err);
+    const long long n_tiles = (long long)(b / 16) * ((cx->E + NW - 1) / NW);
+    const int grid = (int)(n_tiles < cx->num_sms ? n_tiles : cx->num_sms);
+    *grid_out = grid;
+    kern<<<grid, NW * 32, smem, st>>>(G, Hin, Gprev, W0, W1, W2, ws, cx->d_mptr, cx->d_ment, cx->E, b, g_umma_err);
     SCONE_LAUNCHED();
     return 0;
 }
 
 template <int ACT, bool WG>
-int dispatch_bwd_umma_pad(const scone_complex* cx, int b, const float* G, const float* Hin, const float* W0, const float* W1,
-                          const float* W2, float* Gprev, float* ws, int grid, cudaStream_t st) {
-    static int pad = -1;
-    if (pad < 0) {
-        const char* e = getenv("SCONE_UMMA_BWD_PAD");                    // 0: canonical strides (bank-conflicting stores); experiments
-        pad = (e && e[0] == '0') ? 0 : 1;
+int dispatch_bwd_umma_cfg(const scone_complex* cx, int b, const float* G, const float* Hin, const float* W0, const float* W1,
+                          const float* W2, float* Gprev, float* ws, int* grid_out, cudaStream_t st) {
+    static int cfg = -1;
+    if (cfg < 0) {
+        const char* e = getenv("SCONE_UMMA_BWD_CFG");                    // "<warps>x<gather depth>" (experiments)
+        cfg = e ? atoi(e) * 100 + (strchr(e, 'x') ? atoi(strchr(e, 'x') + 1) : 4) : 1204;
     }
-    return pad ? launch_bwd_umma<ACT, WG, true>(cx, b, G, Hin, W0, W1, W2, Gprev, ws, grid, st)
-               : launch_bwd_umma<ACT, WG, false>(cx, b, G, Hin, W0, W1, W2, Gprev, ws, grid, st);
+#define SCONE_BWD_CFG(NW_, D_) \
+    if (cfg == NW_ * 100 + D_) return launch_bwd_umma<ACT, WG, NW_, D_>(cx, b, G, Hin, W0, W1, W2, Gprev, ws, grid_out, st);
+    SCONE_BWD_CFG(10, 4)
+    SCONE_BWD_CFG(10, 6)
+    SCONE_BWD_CFG(10, 8)
+    SCONE_BWD_CFG(12, 4)
+    SCONE_BWD_CFG(12, 6)
+#undef SCONE_BWD_CFG
+    scone_set_error("SCONE_UMMA_BWD_CFG: unknown configuration %d", cfg);
+    return 2;
 }
 
 }  // namespace
@@ -560,20 +592,18 @@ int scone_umma_forward(const scone_complex* cx, int act, int b, const float* Hin
 }
 
 // Gprev = (AG W^T) * act'(Hin) (skipped when Gprev == NULL), dW [3][32][32] (+)= Hin^T AG over dense [E][b][32] tensors; workspace:
-// grid x 3072 floats.  Asynchronous; a tcgen05 protocol time-out is reported by scone_umma_check like the forward kernel's.
+// 3 x grid x 3072 floats.  Asynchronous; a tcgen05 protocol time-out is reported by scone_umma_check like the forward kernel's.
 int scone_umma_backward(const scone_complex* cx, int act, int b, const float* G, const float* Hin, const float* W0, const float* W1,
                         const float* W2, float* Gprev, float* dW, int accumulate, float* ws, cudaStream_t st) {
     if (!g_umma_err) {
         SCONE_CUDA(cudaMalloc((void**)&g_umma_err, sizeof(int)));
         SCONE_CUDA(cudaMemset(g_umma_err, 0, sizeof(int)));
     }
-    const long long n_tiles = (long long)(b / 16) * ((cx->E + kBwdWarps - 1) / kBwdWarps);
-    const int grid = (int)(n_tiles < cx->num_sms ? n_tiles : cx->num_sms);
-    int rc = 2;
+    int rc = 2, grid = 0;
 #define SCONE_UMMA_BWD(A)                                                                                                      \
     case A:                                                                                                                    \
-        rc = Gprev ? dispatch_bwd_umma_pad<A, true>(cx, b, G, Hin, W0, W1, W2, Gprev, ws, grid, st)                            \
-                   : dispatch_bwd_umma_pad<A, false>(cx, b, G, Hin, W0, W1, W2, Gprev, ws, grid, st);                          \
+        rc = Gprev ? dispatch_bwd_umma_cfg<A, true>(cx, b, G, Hin, W0, W1, W2, Gprev, ws, &grid, st)                            \
+                   : dispatch_bwd_umma_cfg<A, false>(cx, b, G, Hin, W0, W1, W2, Gprev, ws, &grid, st);                          \
         break;
     switch (act) {
         SCONE_UMMA_BWD(SCONE_ACT_TANH)
@@ -585,7 +615,7 @@ int scone_umma_backward(const scone_complex* cx, int act, int b, const float* G,
     }
 #undef SCONE_UMMA_BWD
     if (rc) return rc;
-    umma_reduce_partials_kernel<<<(kDW + 31) / 32, 256, 0, st>>>(ws, grid, kDW, dW, accumulate);
+    umma_reduce_partials_kernel<<<(kDW + 31) / 32, 256, 0, st>>>(ws, 3 * grid, kDW, dW, accumulate);
     SCONE_LAUNCHED();
     return 0;
 }

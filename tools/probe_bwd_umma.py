@@ -21,7 +21,7 @@ E = cx.E
 dev = torch.device('cuda')
 st = torch.cuda.current_stream().cuda_stream
 PEAK = 6554.2
-print('complex: N=%d E=%d b=%d pad=%s' % (n, E, b, os.environ.get('SCONE_UMMA_BWD_PAD', '1')), flush=True)
+print('complex: N=%d E=%d b=%d cfg=%s' % (n, E, b, os.environ.get('SCONE_UMMA_BWD_CFG', '10x4')), flush=True)
 g = torch.Generator(device='cpu').manual_seed(1)
 H = torch.tanh(torch.randn(E, b, C, device=dev))
 G = torch.randn(E, b, C, device=dev)
@@ -55,6 +55,10 @@ def timeit(fn, iters=5, warm=2):
     return min(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))
 
 
+# float64 reference of the own-row term dW_0 = Hin^T G (the operator terms need no second opinion: same accumulation)
+ref0 = torch.zeros(C, C, dtype=torch.float64, device=dev)
+for lo_ in range(0, E, 8192):
+    ref0 += torch.einsum('ebi,ebo->io', H[lo_:lo_ + 8192].double(), G[lo_:lo_ + 8192].double())
 ok = True
 for act in (0, 1, 2):
     Gp0, dW0 = run(0, act)
@@ -65,6 +69,8 @@ for act in (0, 1, 2):
     same = bool(torch.equal(Gp3, Gp3b) and torch.equal(dW3, dW3b))
     _, dW3n = run(3, act, with_gprev=False)
     ewn = float((dW3n - dW0).abs().max()) / max(1e-30, float(dW0.abs().max()))
+    e64 = [float((x[0].double() - ref0).abs().max() / ref0.abs().max()) for x in (dW0, dW3)]
+    print('   dW_0 vs float64: SIMT kernel %.2e, tcgen05 kernel %.2e' % (e64[0], e64[1]))
     print('act %d: Gprev rel err %.2e, dW rel err %.2e (no-Gprev variant %.2e), run-to-run identical %s' % (act, eg, ew, ewn, same), flush=True)
     ok = ok and eg <= 2e-5 and ew <= 2e-5 and ewn <= 2e-5 and same
 print('PARITY', 'OK' if ok else 'FAIL', flush=True)
