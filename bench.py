@@ -603,9 +603,20 @@ def dense_tile_roofline(L, cx, E, C, dev, stream, peak):
         L.scone_set_dense_kernel(1)
     best = min(fwd_ms, key=fwd_ms.get)
     f_ms = fwd_ms[best]
-    b_ms = t_of(lambda: _lib.check(L.scone_layer_backward(cx.handle, 0, bd, C, C, _lib.dptr(Hd), _lib.dptr(Od), _lib.dptr(Wd[0]),
-                                                          _lib.dptr(Wd[1]), _lib.dptr(Wd[2]), _lib.dptr(Od), _lib.dptr(dWd), 0,
-                                                          _lib.dptr(wsd), None, None, None, None, stream)))
+    def bwd():
+        _lib.check(L.scone_layer_backward(cx.handle, 0, bd, C, C, _lib.dptr(Hd), _lib.dptr(Od), _lib.dptr(Wd[0]), _lib.dptr(Wd[1]), _lib.dptr(Wd[2]),
+                                          _lib.dptr(Od), _lib.dptr(dWd), 0, _lib.dptr(wsd), None, None, None, None, stream))
+    bwd_ms = {}
+    try:
+        for which, nme in ((1, 'fp32 SIMT tile kernel'), (3, 'tcgen05 (weight gradient accumulated in TMEM, 3xTF32)')):
+            L.scone_set_dense_kernel(which)
+            bwd_ms[nme] = t_of(bwd)
+            if which == 3:
+                _lib.check(L.scone_umma_status(stream), 'scone_umma_status')
+    finally:
+        L.scone_set_dense_kernel(1)
+    best_b = min(bwd_ms, key=bwd_ms.get)
+    b_ms = bwd_ms[best_b]
     fa, ba = 4.0 * E * bd * 2 * C / f_ms / 1e6, 4.0 * E * bd * 3 * C / b_ms / 1e6
     del Hd, Od
     return {'bound': 'hbm', 'unit': 'GB/s', 'peak': peak, 'b': bd, 'tensor_bytes': 4.0 * E * bd * C,
@@ -613,7 +624,8 @@ def dense_tile_roofline(L, cx, E, C, dev, stream, peak):
                           'all_kernels_ms': fwd_ms,
                           'traffic': ncu_traffic('layer_fwd_umma_kernel', 'dense_umma_r2j') if 'tcgen05' in best else
                           ncu_traffic('layer_fwd_slab_kernel', 'dense_slab_r2i')},
-            'layer_bwd': {'kernel': 'fp32 SIMT tile kernel', 'ms': b_ms, 'achieved': ba, 'frac': ba / peak, 'algorithmic_bytes': 4.0 * E * bd * 3 * C},
+            'layer_bwd': {'kernel': best_b, 'ms': b_ms, 'achieved': ba, 'frac': ba / peak, 'algorithmic_bytes': 4.0 * E * bd * 3 * C,
+                          'all_kernels_ms': bwd_ms, 'traffic': ncu_traffic('layer_bwd_umma_kernel', 'dense_bwd_umma_r2w')},
             'l2_policy': 'tensors of %.1f GB each: larger than L2' % (4.0 * E * bd * C / 1e9),
             'note': 'one fused 32->32 layer on dense random features [E][64][32], every row computed (no flags / pruning), best of 3, CUDA '
                     'events.  Both forward kernels share the gather (13 neighbour rows per output row through L1, 1.87x the compulsory DRAM '

@@ -308,7 +308,10 @@ int scone_get_zero_fill(void);
 int scone_set_dense_kernel(int32_t which);
 /* 3 = tcgen05 / TMEM tiles (csrc/scone_umma.cu) for 32 -> 32 layers with b % 16 == 0: the slab gather feeds 128-row tcgen05.mma.kind::tf32
  * tiles (A written to TMEM with tcgen05.st straight from the gather's registers, weights in shared memory, D read back with tcgen05.ld);
- * other shapes fall back to 1.  scone_umma_status synchronises the stream and returns 3 if a launch reported an mbarrier time-out. */
+ * other shapes fall back to 1.  With 3, scone_layer_backward (no occupancy flags, 32 -> 32, b % 16 == 0) also runs on tcgen05: the gather
+ * of G, the row product (AG W^T) * act'(Hin) on mma.sync, and the weight gradient Hin^T AG as tcgen05.mma over K = rows with both
+ * operands in shared memory, accumulated in TMEM and folded into fp32 sums every 32 slabs (deterministic; Gprev may alias Hin).
+ * scone_umma_status synchronises the stream and returns 3 if a launch reported an mbarrier time-out. */
 int scone_umma_status(void* stream);
 int scone_get_dense_kernel(void);
 

@@ -316,7 +316,6 @@ __device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[3
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
 
 template <int ACT>
 __device__ __forceinline__ float umma_dact(float h) {               // derivative through the OUTPUT h = act(z)
@@ -330,7 +329,7 @@ __global__ void __launch_bounds__(NW * 32, 1) layer_bwd_umma_kernel(const float*
                                                                        const float* __restrict__ W0, const float* __restrict__ W1,
                                                                        const float* __restrict__ W2, float* __restrict__ ws,
                                                                        const int32_t* __restrict__ mptr, const int2* __restrict__ ment,
-                                                                       int E, int b, int* __restrict__ err) {
+                                                                       int E, int b, int interleave, int* __restrict__ err) {
     constexpr int TS = 16;
     using G = SlabGeom<kC, TS>;
     using L = BwdBuf<NW>;
@@ -363,14 +362,26 @@ __global__ void __launch_bounds__(NW * 32, 1) layer_bwd_umma_kernel(const float*
     const uint32_t lane_a = (uint32_t)(g >> 2) * L::LBO_A + (uint32_t)(tig >> 1) * L::SBO_A + (uint32_t)(tig & 1) * 64u + (uint32_t)(g & 3) * 4u;
     const uint32_t lane_b = (uint32_t)(g >> 2) * L::LBO_B + (uint32_t)tig * 32u + (uint32_t)(g & 3) * 4u;
     const uint32_t tmem_d = s_tmem + (uint32_t)warp * 32u;
+    // the stores go through generic shared-memory pointers (one base register per buffer, immediate offsets)
+    unsigned char* const wbuf = bw_smem + kBwdBfBytes + (size_t)warp * L::WARP_BYTES;
+    unsigned char* const pa_hi = wbuf + lane_a;
+    unsigned char* const pa_lo = pa_hi + L::A_BYTES;
+    unsigned char* const pb_hi = wbuf + 2u * L::A_BYTES + lane_b;
+    unsigned char* const pb_lo = pb_hi + L::B_BYTES;
 
     const unsigned rowbytes = (unsigned)b * kC * 4u;
     const size_t rowlen = (size_t)b * kC;
     const int n_ts = b / TS;
     const int tiles_per_ts = (E + NW - 1) / NW;                          // a CTA tile = NW consecutive edges x one slab of 16 trajectories
     const long long n_tiles = (long long)n_ts * tiles_per_ts;
+    // Tile -> CTA.  Interleaved (default): CTA i takes tiles i, i + grid, ...: at any time the CTAs work on ~grid x NW consecutive edges
+    // of one trajectory slab, every neighbour row comes from DRAM once and is an L2 hit for its other ~13 uses (the operand buffers
+    // leave ~16 KB of L1: the forward kernels' contiguous ranges, which live on L1 reuse, gave L1 14 % / L2 54 % hits and 1.97 x the
+    // compulsory DRAM reads here).  Static either way.
     const long long per = (n_tiles + gridDim.x - 1) / gridDim.x;
-    const long long lo = (long long)blockIdx.x * per, hi = lo + per < n_tiles ? lo + per : n_tiles;
+    const long long lo = interleave ? (long long)blockIdx.x : (long long)blockIdx.x * per;
+    const long long hi = interleave ? n_tiles : (lo + per < n_tiles ? lo + per : n_tiles);
+    const long long step = interleave ? (long long)gridDim.x : 1;
     // this warp's share of the flushes: TMEM lane quarter q = warp & 3 (term q of the stacked gradient) of the accumulators
     // j = warp >> 2, + nq, ... (nq = warps of this quarter); its running fp32 sums live in ws[cta][warp >> 2][term q][ci][co = lane]
     const int fq = warp & 3, fidx = warp >> 2, fnq = (NW - fq + 3) / 4;
@@ -378,7 +389,8 @@ __global__ void __launch_bounds__(NW * 32, 1) layer_bwd_umma_kernel(const float*
     for (int i = threadIdx.x; i < 3 * kDW; i += NW * 32) ws[(size_t)blockIdx.x * 3 * kDW + i] = 0.f;      // (visible after the flush's barrier)
     uint32_t phase = 0;
     bool pending = false, fresh = true;                                  // MMAs not yet waited for / accumulator holds nothing
-    for (long long tile = lo; tile < hi; ++tile) {
+    int it = 0;
+    for (long long tile = lo; tile < hi; tile += step, ++it) {
         const int ts = (int)(tile / tiles_per_ts);
         const int e0 = (int)(tile - (long long)ts * tiles_per_ts) * NW + warp, t0 = ts * TS;
         if (e0 < E) {
@@ -411,9 +423,9 @@ __global__ void __launch_bounds__(NW * 32, 1) layer_bwd_umma_kernel(const float*
                 for (int q = 0; q < 4; ++q) {
                     uint32_t vh, vl;
                     split_tf32(fr[s][q], vh, vl);
-                    const uint32_t off = lane_a + (uint32_t)(q & 1) * 2u * L::LBO_A + (uint32_t)(4 * term + 2 * (q >> 1)) * L::SBO_A + (uint32_t)s * 16u;
-                    sts32(a_hi + off, vh);
-                    sts32(a_lo + off, vl);
+                    const uint32_t off = (uint32_t)(q & 1) * 2u * L::LBO_A + (uint32_t)(4 * term + 2 * (q >> 1)) * L::SBO_A + (uint32_t)s * 16u;
+                    *reinterpret_cast<uint32_t*>(pa_hi + off) = vh;
+                    *reinterpret_cast<uint32_t*>(pa_lo + off) = vl;
                 }
         }
 #pragma unroll
@@ -423,11 +435,11 @@ __global__ void __launch_bounds__(NW * 32, 1) layer_bwd_umma_kernel(const float*
                 uint32_t xh, xl, yh, yl;
                 split_tf32(hv[r][nt].x, xh, xl);
                 split_tf32(hv[r][nt].y, yh, yl);
-                const uint32_t off = lane_b + (uint32_t)r * 2u * L::LBO_B + (uint32_t)nt * L::SBO_B;
-                sts32(b_hi + off, xh);
-                sts32(b_lo + off, xl);
-                sts32(b_hi + off + 16u, yh);
-                sts32(b_lo + off + 16u, yl);
+                const uint32_t off = (uint32_t)r * 2u * L::LBO_B + (uint32_t)nt * L::SBO_B;
+                *reinterpret_cast<uint32_t*>(pb_hi + off) = xh;
+                *reinterpret_cast<uint32_t*>(pb_lo + off) = xl;
+                *reinterpret_cast<uint32_t*>(pb_hi + off + 16u) = yh;
+                *reinterpret_cast<uint32_t*>(pb_lo + off + 16u) = yl;
             }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> the tensor core's async proxy
         __syncwarp();
@@ -464,7 +476,7 @@ __global__ void __launch_bounds__(NW * 32, 1) layer_bwd_umma_kernel(const float*
         // Flush every kFlushTiles slabs: the tensor core's fp32 accumulation rounds towards zero, so a chain of n accumulations drifts
         // by ~n ulp (measured: 6.6e-5 of max |dW| after 3600 accumulations, 4.6e-6 for the fp32 SIMT kernel); chains of 6 kFlushTiles
         // accumulations are folded into fp32 sums with round-to-nearest adds.  CTA-uniform condition.
-        if ((tile - lo) % kFlushTiles == kFlushTiles - 1 || tile == hi - 1) {
+        if (it % kFlushTiles == kFlushTiles - 1 || tile + step >= hi) {
             if (pending) {
                 mbar_wait(&s_bar[warp], phase, err);
                 phase ^= 1u;
@@ -531,7 +543,12 @@ int launch_bwd_umma(const scone_complex* cx, int b, const float* G, const float*
     const long long n_tiles = (long long)(b / 16) * ((cx->E + NW - 1) / NW);
     const int grid = (int)(n_tiles < cx->num_sms ? n_tiles : cx->num_sms);
     *grid_out = grid;
-    kern<<<grid, NW * 32, smem, st>>>(G, Hin, Gprev, W0, W1, W2, ws, cx->d_mptr, cx->d_ment, cx->E, b, g_umma_err);
+    static int interleave = -1;
+    if (interleave < 0) {
+        const char* e = getenv("SCONE_UMMA_BWD_INTERLEAVE");             // 0: contiguous tile ranges per CTA (experiments)
+        interleave = (e && e[0] == '0') ? 0 : 1;
+    }
+    kern<<<grid, NW * 32, smem, st>>>(G, Hin, Gprev, W0, W1, W2, ws, cx->d_mptr, cx->d_ment, cx->E, b, interleave, g_umma_err);
     SCONE_LAUNCHED();
     return 0;
 }

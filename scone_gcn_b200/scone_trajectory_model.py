@@ -252,6 +252,11 @@ class Scone_GCN():
         cap = 4096 if all(w in (16, 32) for w in widths) and self._cx.E * 4096 < 2 ** 32 else 256
         mb = self.micro_batch or min(max(n, 1), cap)
         self._net = SconeModel(self._cx, widths, micro_batch=mb)
+        if self.micro_batch is None and mb > 512 and self._net.pipeline in (1, 2):
+            # complexes the cone pipelines cannot take (max degree > 32) run on whole-support row lists: ~8000 rows per
+            # trajectory against list capacities of 6 M / 32 M rows -> smaller micro-batches instead of error code 4
+            self._net = None
+            self._net = SconeModel(self._cx, widths, micro_batch=512)
         self.model_single = model
 
         def batched(weights, *args):
