@@ -274,17 +274,18 @@ int* g_umma_err = nullptr;
 // Buffer strides are padded (core-matrix pitch 144 B, k-chunk pitch = 8 words mod 32) so that the fragment-layout stores of a
 // warp hit 32 different banks.
 // =================================================================================================================
-constexpr int kBwdMaxWarps = 12;
+constexpr int kBwdMaxWarps = 12;   // (documentation: the operand buffers of 12 warps fill the shared memory)
 constexpr int kFlushTiles = 32;            // slabs per warp between two flushes of the TMEM accumulators
 constexpr int kDW = 3 * kC * kC;
 
-// NW = 10 warps: fully padded strides (conflict-free stores, 18.4 KB per warp); NW = 12: k-chunk pitch padded only (2-way conflicts on
-// the A stores, 16.4 KB per warp) — either way NW buffers + 24 KB of weight fragments fill the 227 KB of shared memory
+// Accumulator row m (TMEM lane) <-> AG column: m = 32 term + 8 s + 4 h + tig holds column co = 16 h + 4 tig + s of term `term` (the
+// fragment value a lane keeps for k-step s, half h): the four lanes of a quad write four consecutive rows of ONE core matrix, so
+// with the k-chunk pitch at 16 banks mod 32 every fragment store of a warp hits 32 different banks at the canonical 128-byte
+// core-matrix pitch (16.6 KB per warp: 12 warps + 24 KB of weight fragments fill the 227 KB of shared memory)
 template <int NW>
 struct BwdBuf {
-    static constexpr bool FULL = NW <= 10;
-    static constexpr uint32_t SBO_A = FULL ? 144u : 128u;           // bytes between core matrices adjacent in M (AG column / 8)
-    static constexpr uint32_t LBO_A = FULL ? 1824u : 1568u;         // ... adjacent in K (row / 4): 12 core matrices of M + padding
+    static constexpr uint32_t SBO_A = 128u;                         // bytes between core matrices adjacent in M (8 accumulator rows)
+    static constexpr uint32_t LBO_A = 1600u;                        // ... adjacent in K (row / 4): 12 core matrices of M + 64 B (16 banks)
     static constexpr uint32_t A_BYTES = 4u * LBO_A;                 // 16 rows = 4 k-chunks  (M rows 96..127 of the MMA read on into
     static constexpr uint32_t SBO_B = 128u;                         //  the next buffer of the same warp: their D lanes are never read)
     static constexpr uint32_t LBO_B = 528u;
@@ -357,9 +358,9 @@ __global__ void __launch_bounds__(NW * 32, 1) layer_bwd_umma_kernel(const float*
 
     const uint32_t a_hi = smem_u32(bw_smem) + kBwdBfBytes + (uint32_t)warp * L::WARP_BYTES, a_lo = a_hi + L::A_BYTES;
     const uint32_t b_hi = a_lo + L::A_BYTES, b_lo = b_hi + L::B_BYTES;
-    // fragment value (row g + 8 r, AG column 32 term + 16 h + 4 tig + s) -> k-chunk (g >> 2) + 2 r, core matrix 4 term + 2 h + (tig >> 1),
-    // row 4 (tig & 1) + s of the core matrix, word g & 3;   Hin value (row g + 8 r, channel 8 nt + 2 tig + j) likewise
-    const uint32_t lane_a = (uint32_t)(g >> 2) * L::LBO_A + (uint32_t)(tig >> 1) * L::SBO_A + (uint32_t)(tig & 1) * 64u + (uint32_t)(g & 3) * 4u;
+    // fragment value (row g + 8 r, AG column 16 h + 4 tig + s of term) -> k-chunk (g >> 2) + 2 r, core matrix 4 term + s, row 4 h + tig of
+    // the core matrix, word g & 3;   Hin value (row g + 8 r, channel 8 nt + 2 tig + j) -> core matrix nt, row 2 tig + j
+    const uint32_t lane_a = (uint32_t)(g >> 2) * L::LBO_A + (uint32_t)tig * 16u + (uint32_t)(g & 3) * 4u;
     const uint32_t lane_b = (uint32_t)(g >> 2) * L::LBO_B + (uint32_t)tig * 32u + (uint32_t)(g & 3) * 4u;
     const uint32_t tmem_d = s_tmem + (uint32_t)warp * 32u;
     // the stores go through generic shared-memory pointers (one base register per buffer, immediate offsets)
@@ -385,7 +386,8 @@ __global__ void __launch_bounds__(NW * 32, 1) layer_bwd_umma_kernel(const float*
     // this warp's share of the flushes: TMEM lane quarter q = warp & 3 (term q of the stacked gradient) of the accumulators
     // j = warp >> 2, + nq, ... (nq = warps of this quarter); its running fp32 sums live in ws[cta][warp >> 2][term q][ci][co = lane]
     const int fq = warp & 3, fidx = warp >> 2, fnq = (NW - fq + 3) / 4;
-    float* fdst = ws + ((size_t)blockIdx.x * 3 + fidx) * kDW + fq * kC * kC + lane;
+    // TMEM lane 32 fq + lane = accumulator row 8 s + 4 h + tig (s = lane >> 3, h = (lane >> 2) & 1, tig = lane & 3) of term fq
+    float* fdst = ws + ((size_t)blockIdx.x * 3 + fidx) * kDW + fq * kC * kC + (16 * ((lane >> 2) & 1) + 4 * (lane & 3) + (lane >> 3));
     for (int i = threadIdx.x; i < 3 * kDW; i += NW * 32) ws[(size_t)blockIdx.x * 3 * kDW + i] = 0.f;      // (visible after the flush's barrier)
     uint32_t phase = 0;
     bool pending = false, fresh = true;                                  // MMAs not yet waited for / accumulator holds nothing
@@ -423,7 +425,7 @@ __global__ void __launch_bounds__(NW * 32, 1) layer_bwd_umma_kernel(const float*
                 for (int q = 0; q < 4; ++q) {
                     uint32_t vh, vl;
                     split_tf32(fr[s][q], vh, vl);
-                    const uint32_t off = (uint32_t)(q & 1) * 2u * L::LBO_A + (uint32_t)(4 * term + 2 * (q >> 1)) * L::SBO_A + (uint32_t)s * 16u;
+                    const uint32_t off = (uint32_t)(q & 1) * 2u * L::LBO_A + (uint32_t)(4 * term + s) * L::SBO_A + (uint32_t)(q >> 1) * 64u;
                     *reinterpret_cast<uint32_t*>(pa_hi + off) = vh;
                     *reinterpret_cast<uint32_t*>(pa_lo + off) = vl;
                 }
@@ -498,7 +500,7 @@ __global__ void __launch_bounds__(NW * 32, 1) layer_bwd_umma_kernel(const float*
                     for (int j = 0; j < kC; ++j) sum[j] += __uint_as_float(r[j]);
                 }
 #pragma unroll
-                for (int j = 0; j < kC; ++j) fdst[j * kC] += sum[j];     // dW[term][ci = j][co = lane]; this thread's own running sum
+                for (int j = 0; j < kC; ++j) fdst[j * kC] += sum[j];     // dW[term][ci = j][co of this lane]; this thread's own running sum
             }
             tc_fence_before();
             __syncthreads();
@@ -564,8 +566,6 @@ int dispatch_bwd_umma_cfg(const scone_complex* cx, int b, const float* G, const 
 #define SCONE_BWD_CFG(NW_, D_) \
     if (cfg == NW_ * 100 + D_) return launch_bwd_umma<ACT, WG, NW_, D_>(cx, b, G, Hin, W0, W1, W2, Gprev, ws, grid_out, st);
     SCONE_BWD_CFG(10, 4)
-    SCONE_BWD_CFG(10, 6)
-    SCONE_BWD_CFG(10, 8)
     SCONE_BWD_CFG(12, 4)
     SCONE_BWD_CFG(12, 6)
 #undef SCONE_BWD_CFG
