@@ -313,6 +313,9 @@ int scone_set_dense_kernel(int32_t which);
  * operands in shared memory, accumulated in TMEM and folded into fp32 sums every 32 slabs (deterministic; Gprev may alias Hin).
  * scone_umma_status synchronises the stream and returns 3 if a launch reported an mbarrier time-out. */
 int scone_umma_status(void* stream);
+/* Tile order of the tcgen05 forward kernel: tiles (16 edges x 16 trajectories) are dealt to the CTAs in chunks of `tiles` consecutive
+ * tiles, round-robin; 0 = one contiguous range per CTA.  Also read from SCONE_DENSE_CHUNK when the first dense layer runs. */
+int scone_set_dense_chunk(int32_t tiles);
 int scone_get_dense_kernel(void);
 
 /* Optional per-kernel-family device timing (CUDA events recorded on the launching stream around each launch);

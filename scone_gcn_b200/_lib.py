@@ -46,6 +46,7 @@ SIGNATURES = {
     'scone_set_zero_fill': (C.c_int, [_i32]),
     'scone_get_zero_fill': (C.c_int, []),
     'scone_set_dense_kernel': (C.c_int, [_i32]),
+    'scone_set_dense_chunk': (C.c_int, [_i32]),
     'scone_get_dense_kernel': (C.c_int, []),
     'scone_umma_status': (C.c_int, [_vp]),
     'scone_csr_create': (C.c_int, [_i32, _i32, _vp, _vp, _vp, C.POINTER(_vp)]),

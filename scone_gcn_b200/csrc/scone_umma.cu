@@ -105,7 +105,7 @@ template <int ACT>
 __global__ void __launch_bounds__(kUmmaThreads, 1) layer_fwd_umma_kernel(const float* __restrict__ Hin, float* __restrict__ Hout,
                                                                         const float* __restrict__ W0, const float* __restrict__ W1,
                                                                         const float* __restrict__ W2, const int32_t* __restrict__ mptr,
-                                                                        const int2* __restrict__ ment, int E, int b, int* __restrict__ err) {
+                                                                        const int2* __restrict__ ment, int E, int b, int chunk, int* __restrict__ err) {
     constexpr int TS = 16;
     using G = SlabGeom<kC, TS>;
     constexpr int NT = kC / 8;
@@ -145,8 +145,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) layer_fwd_umma_kernel(const f
     const int n_ts = (b + TS - 1) / TS;
     const int tiles_per_ts = (E + kGatherWarps - 1) / kGatherWarps;      // a CTA tile = 16 consecutive edges x one slab of 16 trajectories
     const long long n_tiles = (long long)n_ts * tiles_per_ts;
+    // Tile sequence of this CTA: chunks of `cl` consecutive tiles dealt round-robin to the CTAs (chunk = 0: one chunk per CTA, i.e.
+    // contiguous ranges).  Inside a chunk the neighbour rows of consecutive edges are L1 hits; with small chunks all CTAs sweep
+    // the same region of the tensor and an L1 miss is an L2 hit instead of a DRAM read.
     const long long per = (n_tiles + gridDim.x - 1) / gridDim.x;
-    const long long lo = (long long)blockIdx.x * per, hi = lo + per < n_tiles ? lo + per : n_tiles;
+    const long long cl = chunk > 0 ? (long long)chunk : per;
 
     {
         // ---- gather warps ----
@@ -158,8 +161,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) layer_fwd_umma_kernel(const f
         uint32_t phase = 0;
         int pe0 = 0, pt0 = 0;                              // slab whose product is in flight
         bool pending = false, plive = false;
-        for (long long tile = lo; tile <= hi; ++tile) {
-            const bool have = tile < hi;
+        for (long long k = 0;; ++k) {
+            const long long tile = ((k / cl) * gridDim.x + blockIdx.x) * cl + k % cl;
+            const bool have = tile < n_tiles;
             int e0 = 0, t0 = 0;
             bool live = false;
             u64 acc[3][G::NL][2];
@@ -243,7 +247,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) layer_fwd_umma_kernel(const f
                 pe0 = e0;
                 pt0 = t0;
             } else {
-                pending = false;
+                break;
             }
         }
     }
@@ -253,6 +257,17 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) layer_fwd_umma_kernel(const f
 }
 
 int* g_umma_err = nullptr;
+
+int g_dense_chunk = -1;
+int scone_dense_chunk() {                 // tiles per chunk of the forward kernel's tile sequence (0 = contiguous ranges)
+    int& chunk = g_dense_chunk;
+    if (chunk < 0) {
+        const char* e = getenv("SCONE_DENSE_CHUNK");
+        chunk = e ? atoi(e) : 8;                      // measured: 9.34 ms at 8, 9.62 contiguous, 10.86 at 1 (tools/sweep_dense_chunk.py)
+        if (chunk < 0) chunk = 0;
+    }
+    return chunk;
+}
 
 // =================================================================================================================
 // Backward of the same layer (32 -> 32, dense [E][b][32] tensors):
@@ -590,15 +605,16 @@ int scone_umma_forward(const scone_complex* cx, int act, int b, const float* Hin
     const int n_ts = (b + 15) / 16;
     const long long n_tiles = (long long)n_ts * ((cx->E + kGatherWarps - 1) / kGatherWarps);
     const int grid = (int)(n_tiles < cx->num_sms ? n_tiles : cx->num_sms);
+    const int chunk = scone_dense_chunk();
     switch (act) {
         case SCONE_ACT_TANH:
-            layer_fwd_umma_kernel<SCONE_ACT_TANH><<<grid, kUmmaThreads, 0, st>>>(Hin, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, cx->E, b, g_umma_err);
+            layer_fwd_umma_kernel<SCONE_ACT_TANH><<<grid, kUmmaThreads, 0, st>>>(Hin, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, cx->E, b, chunk, g_umma_err);
             break;
         case SCONE_ACT_LEAKY_RELU:
-            layer_fwd_umma_kernel<SCONE_ACT_LEAKY_RELU><<<grid, kUmmaThreads, 0, st>>>(Hin, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, cx->E, b, g_umma_err);
+            layer_fwd_umma_kernel<SCONE_ACT_LEAKY_RELU><<<grid, kUmmaThreads, 0, st>>>(Hin, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, cx->E, b, chunk, g_umma_err);
             break;
         case SCONE_ACT_RELU:
-            layer_fwd_umma_kernel<SCONE_ACT_RELU><<<grid, kUmmaThreads, 0, st>>>(Hin, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, cx->E, b, g_umma_err);
+            layer_fwd_umma_kernel<SCONE_ACT_RELU><<<grid, kUmmaThreads, 0, st>>>(Hin, Hout, W0, W1, W2, cx->d_mptr, cx->d_ment, cx->E, b, chunk, g_umma_err);
             break;
         default:
             scone_set_error("unknown activation %d", act);
@@ -634,6 +650,12 @@ int scone_umma_backward(const scone_complex* cx, int act, int b, const float* G,
     if (rc) return rc;
     umma_reduce_partials_kernel<<<(kDW + 31) / 32, 256, 0, st>>>(ws, 3 * grid, kDW, dW, accumulate);
     SCONE_LAUNCHED();
+    return 0;
+}
+
+extern "C" int scone_set_dense_chunk(int32_t tiles) {
+    SCONE_REQUIRE(tiles >= 0, "scone_set_dense_chunk: tiles per chunk must be >= 0 (0 = contiguous tile ranges per CTA)");
+    g_dense_chunk = tiles;
     return 0;
 }
 
