@@ -1,6 +1,6 @@
 # Builds libscone_b200.so (sm_100a) in-tree.  `python __graft_entry__.py build` does the same.
 NVCC ?= nvcc
-SRC := scone_gcn_b200/csrc/scone_complex.cu scone_gcn_b200/csrc/scone_kernels.cu scone_gcn_b200/csrc/scone_model.cu scone_gcn_b200/csrc/scone_bunch.cu scone_gcn_b200/csrc/scone_slab.cu scone_gcn_b200/csrc/scone_rows.cu scone_gcn_b200/csrc/scone_fused.cu scone_gcn_b200/csrc/scone_plan_table.cu scone_gcn_b200/csrc/scone_umma.cu
+SRC := scone_gcn_b200/csrc/scone_complex.cu scone_gcn_b200/csrc/scone_kernels.cu scone_gcn_b200/csrc/scone_model.cu scone_gcn_b200/csrc/scone_bunch.cu scone_gcn_b200/csrc/scone_slab.cu scone_gcn_b200/csrc/scone_rows.cu scone_gcn_b200/csrc/scone_fused.cu scone_gcn_b200/csrc/scone_plan_table.cu scone_gcn_b200/csrc/scone_umma.cu scone_gcn_b200/csrc/scone_dp.cu
 OUT := scone_gcn_b200/libscone_b200.so
 FLAGS := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Iinclude -shared -Xptxas -v
 

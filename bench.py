@@ -257,6 +257,8 @@ def main():
     ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch')
     ap.add_argument('--micro-batch', type=int, default=0)
     ap.add_argument('--pipeline', type=int, default=-1, help='force a model-level pipeline (default: the library\'s choice)')
+    ap.add_argument('--exchange', default='peer', choices=['peer', 'nccl'],
+                    help='N > 1: gradient exchange fused with Adam over NVLink peer memory (one kernel), or NCCL all-reduce + Adam kernel')
     ap.add_argument('--e2e-steps', type=int, default=10)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', dest='extras', action='store_false', help='skip the dense-tile roofline measurement')
@@ -331,20 +333,28 @@ def main():
     d = {k: v.to(dev) for k, v in h.items()}
     gbuf = net.grads_tensor()
 
+    exchange = None
+    if world > 1 and args.exchange == 'peer':
+        os.environ.pop('SCONE_DP_EXCHANGE', None)
+        exchange = dp.make_exchange(net.n_params + 2, dev)   # None (with a message on stderr) if the peers cannot be mapped
+
+    def optimizer_step():
+        if exchange is not None:                           # sum over ranks + Adam: one kernel over NVLink peer memory
+            exchange.adam_step(net, step_no[0], lr, wd, stream)
+        else:
+            if world > 1:
+                dist.all_reduce(gbuf)
+            net.adam_step(step_no[0], lr, wd, stream)
+        step_no[0] += 1
+
     def step_dev():
         _lib.check(L.scone_model_loss_grad_dev(net.handle, B, _lib.dptr(d['ptr']), _lib.dptr(d['edge']), _lib.dptr(d['val']),
                                                _lib.dptr(d['last']), _lib.dptr(d['tgt']), _lib.dptr(d['mask']), 1, stream))
-        if world > 1:
-            dist.all_reduce(gbuf)
-        net.adam_step(step_no[0], lr, wd, stream)
-        step_no[0] += 1
+        optimizer_step()
 
     def step_e2e():
         net.loss_grad(hp['ptr'], hp['edge'], hp['val'], hp['last'], hp['tgt'], hp['mask'], zero_first=True, stream=stream, read=False)
-        if world > 1:
-            dist.all_reduce(gbuf)
-        net.adam_step(step_no[0], lr, wd, stream)
-        step_no[0] += 1
+        optimizer_step()
         buf = net.read_grads(stream)                       # D2H of [grads | nll_sum | count]: the step's loss
         return float(buf[-2] / buf[-1])
 
@@ -549,7 +559,9 @@ def main():
                'config': {'workload': args.config + ': ' + cfg['desc'] + (' (%d per GPU)' % B if world > 1 else ''),
                           'N': N, 'E': E, 'F': F, 'D': D, 'model': model, 'per_gpu_batch': B, 'global_batch': gb, 'hidden': C,
                           'layers': 3, 'micro_batch': mb,
-                          'parallelism': 'dp%d (trajectory shards, complex replicated, one all-reduce of %d floats per step)' % (world, net.n_params + 2),
+                          'parallelism': 'dp%d (trajectory shards, complex replicated, one sum of %d floats over ranks per step: %s)' % (
+                              world, net.n_params + 2, 'none at N = 1' if world == 1 else
+                              ('NVLink peer-memory push + Adam in one kernel (scone_dp.cu)' if exchange is not None else 'NCCL all-reduce, then the Adam kernel')),
                           'l2_policy': l2_policy, 'generator_seed': 1030, 'mean_flow_nnz': nnz / B,
                           'trajectories': ('prefixes of %d BEGIN->A->B->END walks cut at %d random points each' % (-(-gb // cfg['cuts']), cfg['cuts']))
                           if cfg['n_nodes'] > 1000 else 'the reference generator\'s 1000 trajectories (tests/golden/dataset_default.npz)'},

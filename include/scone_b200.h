@@ -229,6 +229,23 @@ int scone_model_read_grads(scone_model* m, float* out_host, void* stream);
  *   g = grads / count + 2 * weight_decay * W ;  m,v update ;  W -= lr * mhat / (sqrt(vhat) + eps)
  * step = 0-based iteration index i. */
 int scone_model_adam_step(scone_model* m, int32_t step, float lr, float weight_decay, void* stream);
+
+/* Data-parallel optimizer step over NVLink peer memory (one process per GPU of one node, <= 8 ranks): ONE kernel per rank pushes the
+ * rank's [grads | nll_sum | count] buffer into every peer's exchange buffer (CUDA IPC mappings), waits for the peers' pushes, sums
+ * the `world` vectors in rank order (bit-identical weights on every rank), writes the sums back into the gradient buffer and applies
+ * the Adam update — what `dist.all_reduce(scone_model_grads_dev)` + scone_model_adam_step do in two launches and an NCCL call
+ * (the update is scone_trajectory_model.py:264-357's).  If any rank's micro-batch overflowed a capacity, no rank updates.
+ *   scone_dp_create(rank, world, n_params + 2, &dp); scone_dp_get_handle -> all-gather the scone_dp_handle_bytes()-byte handles ->
+ *   scone_dp_open(dp, handles); then scone_model_dp_adam_step every step.  scone_dp_status synchronises the stream and returns 3 if
+ *   a peer did not arrive within ~10 s. */
+typedef struct scone_dp scone_dp;
+int scone_dp_create(int32_t rank, int32_t world, int64_t n_floats, scone_dp** out);
+int32_t scone_dp_handle_bytes(void);
+int scone_dp_get_handle(scone_dp* dp, void* handle_out);
+int scone_dp_open(scone_dp* dp, const void* handles_rank_major);
+int scone_model_dp_adam_step(scone_model* m, scone_dp* dp, int32_t step, float lr, float wd, void* stream);
+int scone_dp_status(scone_dp* dp, void* stream);
+void scone_dp_destroy(scone_dp* dp);
 /* Planned sets (pipeline 4).  The plan of a trajectory — receptive cone, live rows, gather programs — depends on the complex, the
  * flows and the last node, not on the weights: a dataset that is revisited every epoch (Scone_GCN.train samples its batches from the
  * same N trajectories for `epochs` epochs, scone_trajectory_model.py:318-322) is planned ONCE and every step runs only the compute

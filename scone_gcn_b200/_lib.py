@@ -82,6 +82,13 @@ SIGNATURES = {
     'scone_model_eval_host': (C.c_int, [_vp, _i32] + [_vp] * 10 + [_vp]),
     'scone_model_two_target_host': (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp]),
     'scone_model_adam_step': (C.c_int, [_vp, _i32, _f32, _f32, _vp]),
+    'scone_dp_create': (C.c_int, [_i32, _i32, _i64, C.POINTER(_vp)]),
+    'scone_dp_handle_bytes': (_i32, []),
+    'scone_dp_get_handle': (C.c_int, [_vp, _vp]),
+    'scone_dp_open': (C.c_int, [_vp, _vp]),
+    'scone_model_dp_adam_step': (C.c_int, [_vp, _vp, _i32, _f32, _f32, _vp]),
+    'scone_dp_status': (C.c_int, [_vp, _vp]),
+    'scone_dp_destroy': (None, [_vp]),
     'scone_model_check_overflow': (C.c_int, [_vp, _vp]),
     'scone_model_plan_host': (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     'scone_model_plan_dev': (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),

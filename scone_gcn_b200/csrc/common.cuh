@@ -113,6 +113,10 @@ int scone_readout_ws(const scone_complex* cx, int32_t act, int32_t b, int32_t C,
                      const int32_t* last_nodes, float* logprobs, const int32_t* target_idx, const float* mask,
                      float scale, float* GL, float* dwout, float* nll_sum, float* count, int32_t accumulate,
                      void* workspace, const uint8_t* occ_HL, uint8_t* occ_GL, void* stream);
+// data-parallel exchange fused with Adam (scone_dp.cu)
+struct scone_dp;
+int scone_dp_allreduce_adam(scone_dp* d, float* W, float* m, float* v, float* grad, int64_t n_params, const int* overflow_dev,
+                            int32_t step, float lr, float wd, cudaStream_t st);
 // tcgen05 dense layer (scone_umma.cu)
 bool scone_umma_supported(const scone_complex* cx, int cin, int cout, int b);
 int scone_umma_forward(const scone_complex* cx, int act, int b, const float* Hin, const float* W0, const float* W1, const float* W2,

@@ -1157,6 +1157,11 @@ extern "C" int scone_model_read_rows_done(scone_model* m, int64_t* out /* [2] */
 
 extern "C" int scone_umma_status(void* st) { return scone_umma_check(as_stream(st)); }
 
+extern "C" int scone_model_dp_adam_step(scone_model* m, scone_dp* dp, int32_t step, float lr, float wd, void* st) {
+    SCONE_REQUIRE(m && dp && step >= 0, "scone_model_dp_adam_step: bad arguments");
+    return scone_dp_allreduce_adam(dp, m->d_w, m->d_m, m->d_v, m->d_grad, m->n_params, m->d_overflow, step, lr, wd, as_stream(st));
+}
+
 extern "C" int scone_model_adam_step(scone_model* m, int32_t step, float lr, float wd, void* st) {
     SCONE_REQUIRE(m && step >= 0, "scone_model_adam_step: bad arguments");
     return scone_adam_launch(m->d_w, m->d_m, m->d_v, m->d_grad, m->n_params, step, lr, wd, st, m->d_overflow);

@@ -57,7 +57,8 @@ class Scone_GCN():
         (micro_batch / forward_all / data_parallel: B200-side knobs, not in the reference.  data_parallel=None: on when a
          torch.distributed process group with more than one rank exists — every rank runs the same script with the same RNG
          stream, computes the gradient of its contiguous share of each batch, and the flat [grads | nll | count] buffer is
-         all-reduced (NCCL over NVLink) before the replicated Adam step: SURVEY 8(e))
+         summed over ranks and the replicated Adam step applied by one kernel over NVLink peer memory (dp.PeerExchange;
+         SCONE_DP_EXCHANGE=nccl: NCCL all-reduce + Adam kernel): SURVEY 8(e))
         """
         self.random_targets = None
         self.trained = False
@@ -310,6 +311,11 @@ class Scone_GCN():
         use_dp = dp.is_distributed() if self.data_parallel is None else bool(self.data_parallel)
         if use_dp and not hasattr(self._net, 'grads_tensor'):
             raise NotImplementedError('data-parallel training is implemented for -model scone / ebli')
+        exchange = None
+        if use_dp and dp.is_distributed():                 # NVLink peer-memory exchange fused with Adam (None: NCCL all-reduce + Adam)
+            import torch
+            if torch.cuda.is_available():
+                exchange = dp.make_exchange(self._net.n_params + 2, torch.device('cuda', torch.cuda.current_device()))
         unshuffled_batch_mask = onp.array([1] * self.batch_size + [0] * (N - self.batch_size))
         train_loss = train_acc = test_loss = test_acc = None
 
@@ -331,9 +337,12 @@ class Scone_GCN():
             else:
                 ptr, fe, fv, last = p.select(rows)
                 self._net.loss_grad(ptr, fe, fv, last, target_idx[rows], m, zero_first=True, read=False)
-            if use_dp:                                     # the one exchange of the step: [grads | nll_sum | count], summed over ranks
-                dp.allreduce_sum_(self._net.grads_tensor())
-            self._net.adam_step(i, self.step_size, self.weight_decay)
+            if exchange is not None:                       # the one exchange of the step ([grads | nll_sum | count] summed over ranks)
+                exchange.adam_step(self._net, i, self.step_size, self.weight_decay)      # + Adam, one kernel over NVLink peer memory
+            else:
+                if use_dp:
+                    dp.allreduce_sum_(self._net.grads_tensor())
+                self._net.adam_step(i, self.step_size, self.weight_decay)
 
             if i % n_batches == n_batches - 1:
                 self.weights = self._net.get_weights()

@@ -33,13 +33,28 @@ def run(out, data_parallel):
     net._push(net.weights)
     ptr, fe, fv, last = p.select(mine)
     net._net.loss_grad(ptr, fe, fv, last, ds.raw['targets_argmax'][mine].astype(np.int32), np.ones(len(mine), np.float32), read=False)
+    ident = True
     if data_parallel:
-        dp.allreduce_sum_(net._net.grads_tensor())
+        if os.environ.get('SCONE_DP_EXCHANGE', 'peer') == 'peer':
+            # the fused exchange: sum over ranks (left in the gradient buffer) + one Adam step on a scratch copy of the weights
+            ex = dp.make_exchange(net._net.n_params + 2, torch.device('cuda', torch.cuda.current_device()))
+            assert ex is not None, 'peer exchange could not be set up'
+            w_before = net._net.get_weights()
+            ex.adam_step(net._net, 0, 1e-3, 5e-5)
+            ex.status()
+            wt = net._net.weights_tensor().clone()
+            both = [torch.empty_like(wt) for _ in range(world)]
+            torch.distributed.all_gather(both, wt)
+            ident = all(bool(torch.equal(both[0], b)) for b in both[1:])       # rank-ordered sums: bit-identical on every rank
+            net._net.set_weights(w_before, reset_adam=True)
+            ex.close()
+        else:
+            dp.allreduce_sum_(net._net.grads_tensor())
     grads = net._net.read_grads()
     n_nbrs = fx['n_nbrs']
     res = net.train(inputs, ds.targets, ds.train_mask, ds.test_mask, n_nbrs)
     if rank == 0:
-        np.savez(out, grads=grads, result=np.asarray(res, np.float64), world=world, **{'w%d' % i: w for i, w in enumerate(net.weights)})
+        np.savez(out, grads=grads, result=np.asarray(res, np.float64), world=world, ident=ident, **{'w%d' % i: w for i, w in enumerate(net.weights)})
     if data_parallel:
         torch.cuda.synchronize()
         torch.distributed.destroy_process_group()
