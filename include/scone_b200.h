@@ -224,6 +224,12 @@ int scone_model_two_target_host(scone_model* m, int32_t B, const int32_t* true_i
                                 void* stream);
 /* Read back [grads | nll_sum | count] (host, n_params + 2 floats); synchronises the stream. */
 int scone_model_read_grads(scone_model* m, float* out_host, void* stream);
+/* The same copy enqueued on the stream without synchronising (out_pinned: page-locked host memory, valid once the caller has
+ * synchronised with the stream, e.g. through an event recorded after this call).  Lets a caller enqueue step k + 1 before it looks at
+ * the loss of step k: the *_host entry points of the fused pipeline then copy the flow arrays of step k + 1 under the compute kernel
+ * of step k (their staging buffers are free once the plan kernels of step k are done).  Capacity overflow is not reported here:
+ * scone_model_check_overflow. */
+int scone_model_read_grads_async(scone_model* m, float* out_pinned, void* stream);
 
 /* Adam step on the accumulated buffer (upstream JAX `adam`, used at scone_trajectory_model.py:300,310):
  *   g = grads / count + 2 * weight_decay * W ;  m,v update ;  W -= lr * mhat / (sqrt(vhat) + eps)

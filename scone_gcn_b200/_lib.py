@@ -79,6 +79,7 @@ SIGNATURES = {
     'scone_accuracy_dev': (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     'scone_model_accuracy_host': (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'scone_model_read_grads': (C.c_int, [_vp, _vp, _vp]),
+    'scone_model_read_grads_async': (C.c_int, [_vp, _vp, _vp]),
     'scone_model_eval_host': (C.c_int, [_vp, _i32] + [_vp] * 10 + [_vp]),
     'scone_model_two_target_host': (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp]),
     'scone_model_adam_step': (C.c_int, [_vp, _i32, _f32, _f32, _vp]),

@@ -47,6 +47,7 @@ struct PlanArgs {
     int* overflow;
     int tier;                  // 0: trajectory = work item, tables sized for ~99 % of the nodes; >= 1: the work list of the tier before
     int n_work;                // tier 0: trajectories of the chunk
+    int t0;                    // tier 0: first trajectory of this launch (work item w = trajectory t0 + w)
     const int* n_in;           // tier >= 1: work list = the trajectories the tier before gave up on (device counter + list)
     const int* in_list;
     int* n_retry;              // trajectories this tier gives up on (tables too small): device counter + list; retry == NULL: last tier,
@@ -142,7 +143,7 @@ struct FusedState {
 
 // scone_plan_table.cu
 int scone_table_build(const scone_complex* cx, FusedState* f, int L, bool* ok);
-int scone_table_plan_launch(const FusedState* f, PlanArgs p, int b, int num_sms, cudaStream_t st);
+int scone_table_plan_launch(const FusedState* f, PlanArgs p, int b, int num_sms, cudaStream_t st, int phase = 2);
 void scone_table_destroy(FusedState* f);
 
 bool scone_fused_supported(const scone_complex* cx, int n_layers, const int32_t* hidden);
@@ -153,7 +154,10 @@ int scone_fused_run(const scone_complex* cx, FusedState* f, int act, int b, cons
                     const int32_t* target_idx, const float* mask, float* grad, int* overflow, bool count_rows, cudaStream_t st);
 int scone_fused_begin(FusedState* f, cudaStream_t st);
 int scone_fused_plan_part(const scone_complex* cx, FusedState* f, int off, int b, const int32_t* traj_ptr, const int32_t* flow_edge,
-                          const float* flow_val, const int32_t* last_nodes, int* overflow, cudaStream_t st);
+                          const float* flow_val, const int32_t* last_nodes, int* overflow, cudaStream_t st,
+                          bool defer_tiers = false);
+int scone_fused_plan_finish(const scone_complex* cx, FusedState* f, int B, const int32_t* traj_ptr, const int32_t* flow_edge,
+                            const float* flow_val, const int32_t* last_nodes, int* overflow, cudaStream_t st);
 int scone_fused_compute(const scone_complex* cx, FusedState* f, int act, int b, const float* W, const int64_t* w_off, float* logprobs,
                         const int32_t* target_idx, const float* mask, float* grad, bool count_rows, cudaStream_t st);
 int scone_fused_plan_set(const scone_complex* cx, FusedState* f, int B, const int32_t* traj_ptr, const int32_t* flow_edge,

@@ -1305,11 +1305,8 @@ int scone_fused_begin(FusedState* f, cudaStream_t st) {
     return 0;
 }
 
-int scone_fused_plan_part(const scone_complex* cx, FusedState* f, int off, int b, const int32_t* traj_ptr, const int32_t* flow_edge,
-                          const float* flow_val, const int32_t* last_nodes, int* overflow, cudaStream_t st) {
-    if (b <= 0) return 0;
-    SCONE_REQUIRE(off >= 0 && off + b <= f->chunk, "scone_fused_plan_part: trajectories %d .. %d exceed the planned chunk of %d", off, off + b, f->chunk);
-    if (off > 0) SCONE_CUDA(cudaMemsetAsync(f->d_bump + 1, 0, sizeof(unsigned long long), st));   // retry counter only: the arena keeps growing
+static PlanArgs plan_args(const scone_complex* cx, FusedState* f, int off, const int32_t* traj_ptr, const int32_t* flow_edge,
+                          const float* flow_val, const int32_t* last_nodes, int* overflow) {
     PlanArgs p{};
     p.traj_ptr = traj_ptr + off; p.flow_edge = flow_edge; p.flow_val = flow_val; p.last_nodes = last_nodes + off;
     p.rank = cx->d_rank; p.nbrhoods = cx->d_nbrhoods; p.inc_ptr = cx->d_inc_ptr; p.inc_ent = cx->d_inc_ent;
@@ -1317,8 +1314,32 @@ int scone_fused_plan_part(const scone_complex* cx, FusedState* f, int off, int b
     p.N = cx->N; p.D = cx->D; p.E = cx->E; p.L = f->L;
     p.hdr = f->d_hdr + (size_t)off * kFusedHdrW; p.arena = f->d_arena; p.bump = f->d_bump; p.arena_words = f->arena_words; p.overflow = overflow;
     p.n_retry = reinterpret_cast<int*>(f->d_bump + 1); p.retry = f->d_retry;
+    return p;
+}
+
+// defer_tiers (table plan only): run the first tier over this part and leave its give-ups on the chunk's work list; the later tiers
+// run once over all parts (scone_fused_plan_finish) instead of once per part — each of their launches lasts as long as its slowest
+// trajectory, whatever the number of trajectories.
+int scone_fused_plan_part(const scone_complex* cx, FusedState* f, int off, int b, const int32_t* traj_ptr, const int32_t* flow_edge,
+                          const float* flow_val, const int32_t* last_nodes, int* overflow, cudaStream_t st, bool defer_tiers) {
+    if (b <= 0) return 0;
+    SCONE_REQUIRE(off >= 0 && off + b <= f->chunk, "scone_fused_plan_part: trajectories %d .. %d exceed the planned chunk of %d", off, off + b, f->chunk);
     ScopedProf prof(SCONE_K_CONE, st);
-    return launch_plans(cx, f, p, b, st);
+    if (defer_tiers && f->tb_rows) {
+        PlanArgs p = plan_args(cx, f, 0, traj_ptr, flow_edge, flow_val, last_nodes, overflow);      // absolute trajectory numbers
+        p.t0 = off;
+        return scone_table_plan_launch(f, p, b, cx->num_sms, st, 0);
+    }
+    if (off > 0) SCONE_CUDA(cudaMemsetAsync(f->d_bump + 1, 0, sizeof(unsigned long long), st));   // retry counter only: the arena keeps growing
+    return launch_plans(cx, f, plan_args(cx, f, off, traj_ptr, flow_edge, flow_val, last_nodes, overflow), b, st);
+}
+
+// The later tiers of the parts planned with defer_tiers (no-op for the hash plan, which runs its tiers per part).
+int scone_fused_plan_finish(const scone_complex* cx, FusedState* f, int B, const int32_t* traj_ptr, const int32_t* flow_edge,
+                            const float* flow_val, const int32_t* last_nodes, int* overflow, cudaStream_t st) {
+    if (B <= 0 || !f->tb_rows) return 0;
+    ScopedProf prof(SCONE_K_CONE, st);
+    return scone_table_plan_launch(f, plan_args(cx, f, 0, traj_ptr, flow_edge, flow_val, last_nodes, overflow), B, cx->num_sms, st, 1);
 }
 
 int scone_fused_compute(const scone_complex* cx, FusedState* f, int act, int b, const float* W, const int64_t* w_off, float* logprobs,

@@ -30,6 +30,8 @@ struct scone_model {
     cudaEvent_t ev_begin = nullptr;
     cudaStream_t copy = nullptr;              // pipeline 4, *_host entry points: the flow arrays arrive in parts under the plan kernels
     cudaEvent_t ev_copy0 = nullptr, ev_part[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_plan_done = nullptr;       // the plan kernels of the last overlapped *_host call have read the flow staging buffers
+    long long staging_epoch = 0, plan_done_epoch = -1;      // ensure_staging calls so far / value when ev_plan_done was recorded
     std::vector<cudaEvent_t> ev_fill;         // [2L]: H_1..H_L, G_{L-1}..G_0
     uint8_t* d_occS = nullptr;                // worklists / counters scratch (scone_occ_scratch_bytes)
     uint8_t* d_occX = nullptr;                // flags of the flows X
@@ -71,6 +73,8 @@ struct scone_model {
 namespace {
 
 int ensure_staging(scone_model* m, int64_t B, int64_t nnz) {
+    m->staging_epoch += 1;
+    if (nnz > m->cap_nnz) m->plan_done_epoch = -1;       // (the buffers are about to be reallocated)
     if (B > m->cap_B) {
         cudaFree(m->d_ptr); cudaFree(m->d_last); cudaFree(m->d_tgt); cudaFree(m->d_mask); cudaFree(m->d_logp_all); cudaFree(m->d_nn);
         int64_t cap = B + B / 4 + 16;
@@ -593,6 +597,7 @@ extern "C" int scone_model_destroy(scone_model* m) {
     if (m->ev_begin) cudaEventDestroy(m->ev_begin);
     if (m->copy) cudaStreamDestroy(m->copy);
     if (m->ev_copy0) cudaEventDestroy(m->ev_copy0);
+    if (m->ev_plan_done) cudaEventDestroy(m->ev_plan_done);
     for (auto e : m->ev_part) if (e) cudaEventDestroy(e);
     for (auto e : m->ev_fill) if (e) cudaEventDestroy(e);
     cudaFree(m->d_ptr); cudaFree(m->d_edge); cudaFree(m->d_last); cudaFree(m->d_tgt); cudaFree(m->d_val);
@@ -695,16 +700,28 @@ static bool fused_host_overlap_ok(const scone_model* m, int32_t B, int64_t nnz) 
 
 static int fused_host_overlapped(scone_model* m, int32_t B, const int32_t* ptr, const int32_t* edge, const float* val, float* logprobs_dev,
                                  bool grad, int32_t zero_first, cudaStream_t s) {
-    constexpr int kParts = 4;
+    // parts of >= 4096 trajectories, at most 4: a part's first plan tier runs as soon as its flows have landed; the later tiers (a few
+    // heavy trajectories, each launch as long as its slowest one) run once over all parts.  Small batches are planned in one piece
+    // (their copy is short, and steps enqueued back to back copy under the previous compute)
+    constexpr int kMaxParts = 4;
+    const int kParts = B >= 4 * 4096 ? 4 : (B >= 2 * 4096 ? 2 : 1);
     if (!m->copy) {
         SCONE_CUDA(cudaStreamCreateWithFlags(&m->copy, cudaStreamNonBlocking));
         SCONE_CUDA(cudaEventCreateWithFlags(&m->ev_copy0, cudaEventDisableTiming));
+        SCONE_CUDA(cudaEventCreateWithFlags(&m->ev_plan_done, cudaEventDisableTiming));
         for (auto& e : m->ev_part) SCONE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
-    // the staging buffers are free once everything enqueued on s so far has run (the previous call joined its kernels into s)
-    SCONE_CUDA(cudaEventRecord(m->ev_copy0, s));
-    SCONE_CUDA(cudaStreamWaitEvent(m->copy, m->ev_copy0, 0));
-    int32_t b0[kParts + 1];
+    // The flow staging buffers are read by the plan kernels only.  If their last user was the previous overlapped call (exactly one
+    // ensure_staging since: this call's), they are free as soon as ITS plan kernels are done — the copy of this batch then runs
+    // under that call's compute kernel when the caller enqueues steps back to back.  Otherwise: once everything enqueued on s so
+    // far has run (every call joins its kernels into s).
+    if (m->plan_done_epoch >= 0 && m->plan_done_epoch == m->staging_epoch - 1) {
+        SCONE_CUDA(cudaStreamWaitEvent(m->copy, m->ev_plan_done, 0));
+    } else {
+        SCONE_CUDA(cudaEventRecord(m->ev_copy0, s));
+        SCONE_CUDA(cudaStreamWaitEvent(m->copy, m->ev_copy0, 0));
+    }
+    int32_t b0[kMaxParts + 1];
     for (int k = 0; k <= kParts; ++k) b0[k] = (int32_t)((int64_t)B * k / kParts);
     for (int k = 0; k < kParts; ++k) {
         const int64_t q0 = ptr[b0[k]], q1 = ptr[b0[k + 1]];
@@ -720,7 +737,15 @@ static int fused_host_overlapped(scone_model* m, int32_t B, const int32_t* ptr, 
     int rc = scone_fused_begin(m->fused, c);
     for (int k = 0; k < kParts && !rc; ++k) {
         SCONE_CUDA(cudaStreamWaitEvent(c, m->ev_part[k], 0));
-        rc = scone_fused_plan_part(m->cx, m->fused, b0[k], b0[k + 1] - b0[k], m->d_ptr, m->d_edge, m->d_val, m->d_last, m->d_overflow, c);
+        rc = scone_fused_plan_part(m->cx, m->fused, b0[k], b0[k + 1] - b0[k], m->d_ptr, m->d_edge, m->d_val, m->d_last, m->d_overflow, c,
+                                   kParts > 1);
+    }
+    if (!rc && kParts > 1) rc = scone_fused_plan_finish(m->cx, m->fused, B, m->d_ptr, m->d_edge, m->d_val, m->d_last, m->d_overflow, c);
+    if (!rc) {
+        SCONE_CUDA(cudaEventRecord(m->ev_plan_done, c));
+        m->plan_done_epoch = m->staging_epoch;
+    } else {
+        m->plan_done_epoch = -1;
     }
     if (!rc)
         rc = scone_fused_compute(m->cx, m->fused, m->act, B, m->d_w, m->w_off.data(), logprobs_dev, grad ? m->d_tgt : nullptr,
@@ -1006,6 +1031,12 @@ extern "C" int scone_model_loss_grad_host(scone_model* m, int32_t B, const int32
         SCONE_CUDA(cudaMemcpyAsync(m->d_val, val, nnz * sizeof(float), cudaMemcpyHostToDevice, s));
     }
     return scone_model_loss_grad_dev(m, B, m->d_ptr, m->d_edge, m->d_val, m->d_last, m->d_tgt, m->d_mask, zero_first, st);
+}
+
+extern "C" int scone_model_read_grads_async(scone_model* m, float* out_pinned, void* st) {
+    SCONE_REQUIRE(m && out_pinned, "scone_model_read_grads_async: NULL argument");
+    SCONE_CUDA(cudaMemcpyAsync(out_pinned, m->d_grad, (m->n_params + 2) * sizeof(float), cudaMemcpyDeviceToHost, as_stream(st)));
+    return 0;
 }
 
 extern "C" int scone_model_read_grads(scone_model* m, float* out, void* st) {

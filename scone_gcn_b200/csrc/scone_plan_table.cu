@@ -635,7 +635,7 @@ __global__ void __launch_bounds__(THREADS) table_plan_kernel(const PlanArgs a) {
     extern __shared__ __align__(16) unsigned char sm[];
     const int n_work = a.tier == 0 ? a.n_work : *a.n_in;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        table_plan_trajectory<THREADS>(a, a.tier == 0 ? w : a.in_list[w], sm);
+        table_plan_trajectory<THREADS>(a, a.tier == 0 ? a.t0 + w : a.in_list[w], sm);
         __syncthreads();
     }
 }
@@ -788,7 +788,9 @@ int scone_table_build(const scone_complex* cx, FusedState* f, int L, bool* ok) {
 }
 
 // Plans b trajectories (p: trajectories, outputs, retry list already set) with the table plan: first tier, then the retry list.
-int scone_table_plan_launch(const FusedState* f, PlanArgs p, int b, int num_sms, cudaStream_t st) {
+// phase 0: the first tier only, over trajectories p.t0 .. p.t0 + b (its give-ups are APPENDED to the work list: the counters are not
+// reset between launches); phase 1: the later tiers over the accumulated work list (b = trajectories of the whole chunk); 2: both.
+int scone_table_plan_launch(const FusedState* f, PlanArgs p, int b, int num_sms, cudaStream_t st, int phase) {
     const int f_chunk = f->chunk;
     p.cone_ptr = f->d_cone_ptr; p.cone_ent = f->d_cone_ent; p.node_off = f->d_node_off; p.tb_rowptr = f->d_tb_rowptr; p.tb_ent = f->d_tb_ent;
     p.pair_ptr = f->d_pair_ptr; p.tb_pairs = f->d_tb_pairs; p.pair_off = f->d_pair_off;
@@ -801,12 +803,14 @@ int scone_table_plan_launch(const FusedState* f, PlanArgs p, int b, int num_sms,
     int* cnt1 = p.n_retry + 1;
     p.retry = f->tb_two_tiers ? list0 : nullptr;
     p.n_retry = cnt0;
-    static const int t0 = [] { const char* v = getenv("SCONE_TABLE_T0"); return v && *v ? atoi(v) : 128; }();
-    if (t0 == 64) table_plan_kernel<64><<<b, 64, f->tb_smem0, st>>>(p);
-    else if (t0 == 256) table_plan_kernel<256><<<b, 256, f->tb_smem0, st>>>(p);
-    else table_plan_kernel<128><<<b, 128, f->tb_smem0, st>>>(p);
-    SCONE_LAUNCHED();
-    if (!f->tb_two_tiers) return 0;
+    if (phase != 1) {
+        static const int t0 = [] { const char* v = getenv("SCONE_TABLE_T0"); return v && *v ? atoi(v) : 128; }();
+        if (t0 == 64) table_plan_kernel<64><<<b, 64, f->tb_smem0, st>>>(p);
+        else if (t0 == 256) table_plan_kernel<256><<<b, 256, f->tb_smem0, st>>>(p);
+        else table_plan_kernel<128><<<b, 128, f->tb_smem0, st>>>(p);
+        SCONE_LAUNCHED();
+    }
+    if (!f->tb_two_tiers || phase == 0) return 0;
     const int* n_in = cnt0;
     const int* in_list = list0;
     if (f->tb_mid_tier) {                                  // tables for all but the largest cones: 256 threads, several CTAs per SM

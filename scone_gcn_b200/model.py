@@ -199,6 +199,12 @@ class SconeModel:
         _lib.check(_lib.lib().scone_model_read_grads(self.handle, _lib.ptr(buf), stream), 'scone_model_read_grads')
         return buf
 
+    def read_grads_async(self, pinned, stream=None):
+        """Enqueue the device -> host copy of [grads | nll_sum | count] into `pinned` (a pinned float32 torch tensor or NumPy view of
+        one, n_params + 2 elements) without synchronising; the caller waits on its own event before reading it."""
+        ptr = pinned.data_ptr() if hasattr(pinned, 'data_ptr') else pinned.ctypes.data
+        _lib.check(_lib.lib().scone_model_read_grads_async(self.handle, ptr, stream), 'scone_model_read_grads_async')
+
     def adam_step(self, step, lr, weight_decay, stream=None):
         _lib.check(_lib.lib().scone_model_adam_step(self.handle, int(step), float(lr), float(weight_decay), stream),
                    'scone_model_adam_step')

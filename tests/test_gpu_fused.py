@@ -233,17 +233,20 @@ def test_table_plan_and_hash_plan_write_the_same_plans(model, hidden, monkeypatc
     assert np.array_equal(out['1'][2], out['0'][2])
 
 
-def test_host_entry_points_plan_in_parts_under_the_copy():
-    """*_host entry points of a batch >= 512 trajectories: the flow arrays arrive in four parts on a copy stream, every part is planned
-    when it has landed, one compute launch at the end — same plans, same bits as the device-pointer entry points."""
+@pytest.mark.parametrize('cuts,B', [(1, 1500), (6, 9000), (12, 17500)])
+def test_host_entry_points_plan_in_parts_under_the_copy(cuts, B, plan_kind):
+    """*_host entry points of a batch >= 512 trajectories: the flow arrays arrive on a copy stream in 1 / 2 / 4 parts (batches below
+    8192 / below 16384 / larger); the first plan tier of a part runs when the part has landed, the later tiers once over all parts
+    (table plan; the hash plan runs its tiers per part), one compute launch at the end — same bits as the device-pointer entry points."""
     import scone_gcn_b200 as sg
     from scone_gcn_b200 import _lib
     from scone_gcn_b200 import synthetic_data_gen as sdg
-    sp = sdg.generate_sparse_dataset(4000, 1500, seed=3, n_waypoints=16)
+    sp = sdg.generate_sparse_dataset(4000, B, seed=3, n_waypoints=16, cuts_per_walk=cuts)
+    assert sp.n_traj >= B
     cx = sg.SimplicialComplex.from_simplices(int(sp.n_nodes), sp.edges, sp.faces, 'scone')
-    B = 1500
-    net = sg.SconeModel(cx, [16, 16, 16], micro_batch=2048)
+    net = sg.SconeModel(cx, [16, 16, 16], micro_batch=B)
     assert net.pipeline == 4
+    check_plan_kind(net, plan_kind)
     rs = np.random.RandomState(4)
     net.set_weights([0.3 * rs.randn(*s) for s in net.shapes])
     nnz = int(sp.traj_ptr[B])
@@ -265,3 +268,54 @@ def test_host_entry_points_plan_in_parts_under_the_copy():
     assert np.array_equal(lp_host, lp_dev.cpu().numpy())
     assert np.array_equal(g_host, g_dev)
     assert g_host[-1] == mask.sum()
+
+
+def test_host_steps_enqueued_back_to_back_copy_under_the_previous_compute():
+    """Three different batches through loss_grad_host + Adam + read_grads_async WITHOUT a host synchronisation in between (pinned host
+    buffers): the flow arrays of step k + 1 are copied while step k computes (the staging buffers are free once step k's plan
+    kernels are done).  Gradients of every step bit-identical to the same steps run one at a time with a synchronisation each."""
+    import scone_gcn_b200 as sg
+    from scone_gcn_b200 import synthetic_data_gen as sdg
+    sp = sdg.generate_sparse_dataset(4000, 1500, seed=3, n_waypoints=16)
+    cx = sg.SimplicialComplex.from_simplices(int(sp.n_nodes), sp.edges, sp.faces, 'scone')
+    rs = np.random.RandomState(5)
+    w0 = None
+    batches = []
+    for lo, hi in ((0, 700), (300, 1200), (700, 1500)):
+        p0, p1 = int(sp.traj_ptr[lo]), int(sp.traj_ptr[hi])
+        arrs = dict(ptr=(sp.traj_ptr[lo:hi + 1] - sp.traj_ptr[lo]).astype(np.int32), fe=sp.flow_edge[p0:p1].astype(np.int32),
+                    fv=sp.flow_val[p0:p1].astype(np.float32), last=sp.last_nodes[lo:hi].astype(np.int32),
+                    tgt=sp.target_idx[lo:hi].astype(np.int32), mask=(rs.rand(hi - lo) < 0.8).astype(np.float32))
+        pins = {k: torch.from_numpy(v).pin_memory() for k, v in arrs.items()}
+        batches.append({k: v.numpy() for k, v in pins.items()} | {'_keep': pins})
+
+    def run(pipelined):
+        nonlocal w0
+        net = sg.SconeModel(cx, [16, 16, 16], micro_batch=2048)
+        assert net.pipeline == 4
+        if w0 is None:
+            w0 = [0.3 * np.random.RandomState(6).randn(*s) for s in net.shapes]
+        net.set_weights(w0)
+        outs = []
+        if pipelined:
+            pinned = [torch.empty(net.n_params + 2, dtype=torch.float32).pin_memory() for _ in batches]
+            for k, b in enumerate(batches):
+                net.loss_grad(b['ptr'], b['fe'], b['fv'], b['last'], b['tgt'], b['mask'], zero_first=True, read=False)
+                net.read_grads_async(pinned[k])
+                net.adam_step(k, 1e-2, 5e-5)
+            torch.cuda.synchronize()
+            net.check_overflow()
+            outs = [p.numpy().copy() for p in pinned]
+        else:
+            for k, b in enumerate(batches):
+                outs.append(net.loss_grad(b['ptr'], b['fe'], b['fv'], b['last'], b['tgt'], b['mask'], zero_first=True))
+                net.adam_step(k, 1e-2, 5e-5)
+                torch.cuda.synchronize()
+        return outs, net.get_weights()
+
+    g_sync, w_sync = run(False)
+    g_pipe, w_pipe = run(True)
+    for a, b in zip(g_sync, g_pipe):
+        assert np.array_equal(a, b)
+    for a, b in zip(w_sync, w_pipe):
+        assert np.array_equal(a, b)
