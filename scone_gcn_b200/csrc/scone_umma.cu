@@ -58,9 +58,6 @@ __device__ __forceinline__ void tc_ld_16x256b_x4(uint32_t taddr, float (&d)[4][4
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
@@ -289,7 +286,6 @@ int scone_dense_chunk() {                 // tiles per chunk of the forward kern
 // Buffer strides are padded (core-matrix pitch 144 B, k-chunk pitch = 8 words mod 32) so that the fragment-layout stores of a
 // warp hit 32 different banks.
 // =================================================================================================================
-constexpr int kBwdMaxWarps = 12;   // (documentation: the operand buffers of 12 warps fill the shared memory)
 constexpr int kFlushTiles = 32;            // slabs per warp between two flushes of the TMEM accumulators
 constexpr int kDW = 3 * kC * kC;
 

@@ -1,6 +1,6 @@
 """Dense backward probe: tcgen05 backward kernel (scone_set_dense_kernel(3)) against the fp32 SIMT tile kernel (0) on the same
-dense random tensors — max differences of Gprev and dW, run-to-run bit-exactness, timing.  SCONE_UMMA_BWD_PAD=0|1 picks the
-operand-buffer strides.  Usage: python tools/probe_bwd_umma.py [n_nodes] [b]"""
+dense random tensors — max differences of Gprev and dW (and of dW_0 against float64), run-to-run bit-exactness, timing.
+SCONE_UMMA_BWD_CFG=<warps>x<gather depth> (10x4, 12x4, 12x6) picks the kernel variant.  Usage: python tools/probe_bwd_umma.py [n_nodes] [b]"""
 import os
 import sys
 
