@@ -408,6 +408,8 @@ def main():
     launches = L.scone_launch_count() - launches0
     clk = clocks.stop()
     net.check_overflow(stream)                             # a truncated step would have been timed silently otherwise
+    if exchange is not None:
+        exchange.status(stream)                            # ... and so would a step whose peers never delivered their gradients
     ms_per_step = ms_total / args.steps
     value = gb * args.steps / (ms_total / 1e3)
 

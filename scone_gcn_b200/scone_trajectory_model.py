@@ -345,6 +345,8 @@ class Scone_GCN():
                 self._net.adam_step(i, self.step_size, self.weight_decay)
 
             if i % n_batches == n_batches - 1:
+                if exchange is not None:
+                    exchange.status()                      # a rank that never delivered its gradients (time-out) is an error, not a hang
                 self.weights = self._net.get_weights()
                 preds = self._net.forward_planned()[:, :, None] if planned else self._forward(self.weights, inputs)
                 ridge = self._ridge(self.weights)
