@@ -646,7 +646,7 @@ def dense_tile_roofline(L, cx, E, C, dev, stream, peak):
             if which == 3:
                 _lib.check(L.scone_umma_status(stream), 'scone_umma_status')
     finally:
-        L.scone_set_dense_kernel(1)
+        L.scone_set_dense_kernel(_lib.DEFAULT_DENSE_KERNEL)
     best = min(fwd_ms, key=fwd_ms.get)
     f_ms = fwd_ms[best]
     def bwd():
@@ -660,7 +660,7 @@ def dense_tile_roofline(L, cx, E, C, dev, stream, peak):
             if which == 3:
                 _lib.check(L.scone_umma_status(stream), 'scone_umma_status')
     finally:
-        L.scone_set_dense_kernel(1)
+        L.scone_set_dense_kernel(_lib.DEFAULT_DENSE_KERNEL)
     best_b = min(bwd_ms, key=bwd_ms.get)
     b_ms = bwd_ms[best_b]
     fa, ba = 4.0 * E * bd * 2 * C / f_ms / 1e6, 4.0 * E * bd * 3 * C / b_ms / 1e6

@@ -324,7 +324,7 @@ int scone_bunch_adam_step(scone_bunch* m, int32_t step, float lr, float weight_d
 int scone_set_zero_fill(int32_t on);
 int scone_get_zero_fill(void);
 
-/* Dense (no occupancy flags) fused layer kernels: 1 (default) = slab kernels for widths 16 / 32 (merged-row gather straight
+/* Dense (no occupancy flags) fused layer kernels: 3 (default, see below) = tcgen05 / TMEM; 1 = slab kernels for widths 16 / 32 (merged-row gather straight
  * into mma.sync fragments, 3xTF32 tensor-core product, fp32-grade accuracy), a warp owning 16 trajectories of one edge;
  * 2 = the same with 8 trajectories of two edges per warp; 0 = the fp32 SIMT tile kernels for every width (bit-identical to
  * the flagged unit kernels; used by the tests that assert that identity). */

@@ -19,6 +19,7 @@ def library_path():
 
 
 _i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+DEFAULT_DENSE_KERNEL = 3          # scone_set_dense_kernel: tcgen05 / TMEM where the shape allows it, slab kernels elsewhere
 
 # name -> (restype, argtypes); every symbol include/scone_b200.h declares
 SIGNATURES = {

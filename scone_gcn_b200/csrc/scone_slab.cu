@@ -330,7 +330,7 @@ int scone_slab_forward_rows(const scone_complex* cx, int act, int b, int cin, in
     return 2;
 }
 
-int g_scone_dense_kernel = 1;   // 0: fp32 SIMT tile kernels; 1: slab kernels, 16 trajectories x 1 edge per slab; 2: slab, 8 x 2;
+int g_scone_dense_kernel = 3;   // 0: fp32 SIMT tile kernels; 1: slab kernels, 16 trajectories x 1 edge per slab; 2: slab, 8 x 2;
                                 // 3: tcgen05 tiles of 128 rows for 32 -> 32 with b % 16 == 0 (scone_umma.cu), slab 16 x 1 elsewhere
 
 bool scone_slab_supported(const scone_complex* cx, int cin, int cout) {

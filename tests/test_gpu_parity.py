@@ -290,7 +290,7 @@ def test_occupancy_flags_are_exact(small, cin, cout, family, b):
                                           _lib.dptr(occG) if flagged else None, _lib.dptr(occH) if flagged == 2 else None,
                                           _lib.dptr(occ_p), _lib.dptr(scratch) if flagged else None, st))
         outs.append((out.cpu(), occ_out.cpu(), Gp.cpu(), occ_p.cpu(), dW.cpu()))
-    L.scone_set_dense_kernel(1)
+    L.scone_set_dense_kernel(_lib.DEFAULT_DENSE_KERNEL)
     same_arith = family == 0 or cin == 64 or b % (128 // cin) == 0      # else: slab (3xTF32) vs unit (fp32 SIMT) kernels
     for k in (1, 2):
         if same_arith:
@@ -330,7 +330,7 @@ def test_slab_kernels_match_simt_dense_kernels(small, cin, cout, act, b):
                                              _lib.dptr(W[2]), _lib.dptr(out), None, None, None, st))
             outs.append(out.cpu().numpy())
     finally:
-        L.scone_set_dense_kernel(1)
+        L.scone_set_dense_kernel(_lib.DEFAULT_DENSE_KERNEL)
     scale = max(1.0, np.abs(outs[0]).max())
     for k in (1, 2):
         assert np.abs(outs[k] - outs[0]).max() <= 2e-5 * scale, (k, np.abs(outs[k] - outs[0]).max())

@@ -23,7 +23,7 @@ def _run(cx, act, b, H, W, which):
             _lib.check(L.scone_umma_status(st), 'scone_umma_status')
         return out.cpu().numpy()
     finally:
-        L.scone_set_dense_kernel(1)
+        L.scone_set_dense_kernel(_lib.DEFAULT_DENSE_KERNEL)
 
 
 @pytest.mark.parametrize('act', [0, 1, 2])
@@ -75,7 +75,7 @@ def _run_bwd(cx, act, b, G, H, W, which, with_gprev=True):
             _lib.check(L.scone_umma_status(st), 'scone_umma_status')
         return (Gp.cpu().numpy() if with_gprev else None), dW.cpu().numpy() - 0.5
     finally:
-        L.scone_set_dense_kernel(1)
+        L.scone_set_dense_kernel(_lib.DEFAULT_DENSE_KERNEL)
 
 
 @pytest.mark.parametrize('act', [0, 1, 2])
@@ -141,7 +141,7 @@ def test_umma_backward_many_slabs_per_warp_and_in_place():
                                           _lib.dptr(W[2]), _lib.dptr(Hc), _lib.dptr(dW), 0, _lib.dptr(ws), None, None, None, None, st))
         _lib.check(L.scone_umma_status(st), 'scone_umma_status')
     finally:
-        L.scone_set_dense_kernel(1)
+        L.scone_set_dense_kernel(_lib.DEFAULT_DENSE_KERNEL)
     assert np.array_equal(Hc.cpu().numpy(), Gp3) and np.array_equal(dW.cpu().numpy(), dW3)
 
 

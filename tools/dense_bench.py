@@ -36,6 +36,6 @@ for which in (1, 3):
     outs[which] = O[:4096].clone()
     gbs = 4.0 * E * b * 2 * C / best / 1e6
     res[which] = dict(ms=best, gbs=gbs, frac=gbs / peak)
-L.scone_set_dense_kernel(1)
+L.scone_set_dense_kernel(_lib.DEFAULT_DENSE_KERNEL)
 print(json.dumps({'E': E, 'b': b, 'C': C, 'peak_gbs': peak, 'slab_mma_sync': res[1], 'umma_tcgen05': res[3],
                   'max_abs_diff_first_rows': float((outs[1] - outs[3]).abs().max())}))

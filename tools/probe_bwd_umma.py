@@ -38,7 +38,7 @@ def run(which, act, with_gprev=True):
     if which == 3:
         _lib.check(L.scone_umma_status(st), 'scone_umma_status')
     torch.cuda.synchronize()
-    L.scone_set_dense_kernel(1)
+    L.scone_set_dense_kernel(_lib.DEFAULT_DENSE_KERNEL)
     return Gp, dW
 
 
@@ -82,4 +82,4 @@ for which in (0, 3):
                                                          _lib.dptr(W[2]), _lib.dptr(Gp), _lib.dptr(dW), 0, _lib.dptr(ws), None, None, None, None, st)))
     gbs = 4.0 * E * b * 3 * C / ms / 1e6
     print('bwd kernel=%d: %8.3f ms  %7.1f GB/s algorithmic  %.3f of %.0f' % (which, ms, gbs, gbs / PEAK, PEAK), flush=True)
-L.scone_set_dense_kernel(1)
+L.scone_set_dense_kernel(_lib.DEFAULT_DENSE_KERNEL)

@@ -68,7 +68,7 @@ for C in Cs:
             gbs = 4.0 * E * b * 3 * C / msb / 1e6
             print('bwd C=%d wscale=%.2f kernel=%d: %8.3f ms  %7.1f GB/s algorithmic  %.1f%% of %.0f' % (C, wscale, which, msb, gbs, 100 * gbs / PEAK, PEAK),
                   flush=True)
-    L.scone_set_dense_kernel(1)
+    L.scone_set_dense_kernel(_lib.DEFAULT_DENSE_KERNEL)
     del H, out, G, Gp
 a = torch.empty(E * b * 32, device=dev)
 c = torch.empty_like(a)

@@ -34,4 +34,4 @@ for chunk in (0, 1, 2, 4, 8, 16, 32, 64):
     same = bool(torch.equal(ref, O))
     print('chunk %3d: %.3f ms  %.3f of 6554 GB/s   identical to chunk 0: %s' % (chunk, best, 4.0 * E * b * 2 * C / best / 1e6 / 6554.2, same), flush=True)
 L.scone_set_dense_chunk(0)
-L.scone_set_dense_kernel(1)
+L.scone_set_dense_kernel(_lib.DEFAULT_DENSE_KERNEL)
