@@ -674,10 +674,9 @@ def dense_tile_roofline(L, cx, E, C, dev, stream, peak):
                           'all_kernels_ms': bwd_ms, 'traffic': ncu_traffic('layer_bwd_umma_kernel', 'dense_bwd_umma_r2w')},
             'l2_policy': 'tensors of %.1f GB each: larger than L2' % (4.0 * E * bd * C / 1e9),
             'note': 'one fused 32->32 layer on dense random features [E][64][32], every row computed (no flags / pruning), best of 3, CUDA '
-                    'events.  Both forward kernels share the gather (13 neighbour rows per output row through L1, 1.87x the compulsory DRAM '
-                    'reads, 16 warps per SM): with the product moved to tcgen05 the tensor pipe is 10 % busy and the time is unchanged — the '
-                    'bound is the latency of the gather loads at the occupancy 128 registers allow (profiles/prof_dense_*_r2*), not HBM and '
-                    'not the tensor cores'}
+                    'events.  All kernels share the gather (13 neighbour rows per output row): what binds is the L1 / shared-memory data '
+                    'pipe the gathered rows come through (backward kernel: 83 % of its peak, tensor pipe 33 %, DRAM 19 %; forward: 47-73 %), '
+                    'not HBM and not the tensor cores (profiles/prof_dense_*_r2*, DESIGN.md 4.2)'}
 
 
 def bench_bunch(args, cfg, sp, ds, hp, h2d_bytes, B, gb, world, rank, dev, stream, t_setup):
