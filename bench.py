@@ -110,13 +110,26 @@ class ClockSampler:
                 (getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20), 'sw_thermal_slowdown'),
                 (getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4), 'sw_power_cap')]
         get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
-        while self.running:
+
+        def once():
             try:
                 sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = int(get_reasons(self.h))
                 self.rows.append([sm, self.mx, 0.0] + ['Active' if r & bit else 'Not Active' for bit, _ in bits])
             except Exception:
                 pass
+        self._once = once
+        while self.running:
+            once()
+            time.sleep(0.001)
+
+    def sample_while(self, busy):
+        """Poll from the CALLING thread while busy() holds (the timed steps are enqueued and the GPU is working through them): the
+        background thread alone can be starved by the interpreter lock and leave a single sample."""
+        once = getattr(self, '_once', None)
+        while busy():
+            if once is not None and self.nv is not None:
+                once()
             time.sleep(0.001)
 
     def _read(self):
@@ -403,9 +416,10 @@ def main():
     for _ in range(args.steps):
         step_dev()
     ev1.record()
+    launches = L.scone_launch_count() - launches0
+    clocks.sample_while(lambda: not ev1.query())           # (host-side polling of NVML: nothing is enqueued on the GPU)
     barrier()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    launches = L.scone_launch_count() - launches0
     clk = clocks.stop()
     net.check_overflow(stream)                             # a truncated step would have been timed silently otherwise
     if exchange is not None:
